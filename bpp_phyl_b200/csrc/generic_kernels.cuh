@@ -1,0 +1,119 @@
+// Generic fallback for K2/K3: any S, any C, any arity; one launch per node.
+// Same arithmetic as walk_kernels.cuh (same references), no specialisation:
+// thread = (pattern, class, state).  All node CLVs live in the keep buffers.
+#pragma once
+#include "common.cuh"
+#include "walk_kernels.cuh"
+
+namespace bppgpu {
+
+struct GenericParams {
+  const Child* childs;  // children of this op
+  int nchild;
+  int out_idx;          // keep buffer index of the node
+  int S, C, ncodes, code_bytes;
+  long long N;
+  const double* P;       // [nn][C][S][S]
+  const double* tiptab;  // [nl][C][ncodes][S]
+  const void* codes;
+  double* keep;
+  int* keep_exp;
+};
+
+__global__ void generic_node_kernel(GenericParams p) {
+  const long long total = p.N * p.C * p.S;
+  const long long rows = p.N * p.C;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+       e += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(e % p.S);
+    const long long rc = e / p.S;
+    const int c = (int)(rc % p.C);
+    const long long pat = rc / p.C;
+    double acc = 1.0;
+    for (int j = 0; j < p.nchild; ++j) {
+      const Child ch = p.childs[j];
+      double t;
+      if (ch.kind == CHILD_TIP) {
+        const int code = load_code(p.codes, p.code_bytes, (long long)ch.idx * p.N + pat);
+        t = p.tiptab[(((size_t)ch.idx * p.C + c) * p.ncodes + code) * p.S + x];
+      } else {
+        const double* Pr = p.P + (((size_t)ch.pnode * p.C + c) * p.S + x) * p.S;
+        const double* l = p.keep + ((size_t)ch.idx * rows + rc) * p.S;
+        t = 0.0;
+        for (int y = 0; y < p.S; ++y) t = fma(Pr[y], l[y], t);
+      }
+      acc *= t;
+    }
+    p.keep[((size_t)p.out_idx * rows + rc) * p.S + x] = acc;
+  }
+}
+
+// thread = pattern: accumulate child exponents, rescale the node's C*S entries
+__global__ void generic_scale_kernel(GenericParams p) {
+  const long long pat = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (pat >= p.N) return;
+  int Ea = 0;
+  for (int j = 0; j < p.nchild; ++j) {
+    const Child ch = p.childs[j];
+    if (ch.kind != CHILD_TIP) Ea += p.keep_exp[(size_t)ch.idx * p.N + pat];
+  }
+  const int w = p.C * p.S;
+  double* v = p.keep + ((size_t)p.out_idx * p.N + pat) * w;
+  int m = 0;
+  for (int i = 0; i < w; ++i) m = max(m, hi_word(v[i]));
+  if (m < kScaleThresholdHi && m >= (1 << 20)) {
+    const int k = rescale_shift(m);
+    const double f = pow2(k);
+    for (int i = 0; i < w; ++i) v[i] *= f;
+    Ea += k;
+  }
+  p.keep_exp[(size_t)p.out_idx * p.N + pat] = Ea;
+}
+
+struct RootParams {
+  const double* root_clv;  // [N][C][S]
+  const int* root_exp;     // [N]
+  int S, C;
+  unsigned flags;
+  long long N;
+  const double* rootfreq;
+  const double* probs;
+  const double* weights;
+  double* SR;
+  int* rexp;
+  double* site_lnl;
+  double* partials;
+};
+
+__global__ void generic_root_kernel(RootParams p) {
+  __shared__ double red[32];
+  const long long pat = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  double contrib = 0.0;
+  if (pat < p.N) {
+    const bool rsem = p.flags & 1u;
+    const double* v = p.root_clv + (size_t)pat * p.C * p.S;
+    double L = 0.0;
+    for (int c = 0; c < p.C; ++c) {
+      double s = 0.0;
+      for (int x = 0; x < p.S; ++x) {
+        const double t = v[c * p.S + x] * p.rootfreq[x];
+        if (rsem) s += t > 0 ? t : 0.0;
+        else s += t;
+      }
+      const double lc = s * p.probs[c];
+      if (rsem) L += lc > 0 ? lc : 0.0;
+      else L += lc;
+    }
+    if (!rsem && L < 0) L = 0.0;
+    const int E = p.root_exp[pat];
+    const double lnl = log(L) - (double)E * kLn2;
+    p.SR[pat] = L;
+    p.rexp[pat] = E;
+    p.site_lnl[pat] = lnl;
+    contrib = p.weights[pat] * lnl;
+  }
+  const double bs = block_sum(contrib, red);
+  if (threadIdx.x == 0) p.partials[blockIdx.x] = bs;
+}
+
+}  // namespace bppgpu

@@ -1,0 +1,175 @@
+// K1: branch-batched transition-probability tables.
+//
+// One launch builds P, r_c*P', r_c^2*P'' for every (point, branch, rate class):
+//   pxy_[b][c] = P(l_b*r_c), dpxy_ = r_c*P'(l_b*r_c), d2pxy_ = r_c^2*P''(l_b*r_c)
+// (Likelihood/AbstractHomogeneousTreeLikelihood.cpp:354-414) from the HOST
+// eigendecomposition of Q:
+//   P   = V.diag(exp(lambda*rate*t)).V^-1                 Model/AbstractSubstitutionModel.cpp:436
+//   P'  = V.diag(rate*lambda*exp(..)).V^-1                :505
+//   P'' = V.diag((rate*lambda)^2*exp(..)).V^-1            :576
+// Conjugate eigen-pairs use the real 2x2 block form (:438-468, :507-537, :578-612):
+// V.T.V^-1 with T tridiagonal.  t == 0 gives the identity for P (:428-431).
+//
+// This file is the CUDA-core path used for small/medium S (one CTA per matrix,
+// one thread per element group).  The S>=32 DMMA path is in gemm_kernels.cuh.
+#pragma once
+#include "common.cuh"
+
+namespace bppgpu {
+
+struct ModelDev {
+  const double* V;     // [S][S] right eigenvectors (columns)
+  const double* Vinv;  // [S][S] left eigenvectors (rows)
+  const double* re;    // [S]
+  const double* im;    // [S] (zeros when real)
+  const int* role;     // [S] 0 real, 1 first of a conjugate pair, 2 second
+  const double* Q;     // [S][S] generator or nullptr
+  const double* Q2;    // [S][S] Q.Q or nullptr
+  double rate;
+  double eps;
+  unsigned flags;
+  int has_complex;
+};
+
+struct PtParams {
+  const ModelDev* models;
+  const int* branch_model;  // [npoints][nn]
+  const double* brlen;      // [npoints][nn]
+  const double* rates;      // [C]
+  int S, C, nn, root;
+  unsigned want;            // BPPGPU_WANT_*
+  double* P;                // [npoints][nn][C][S][S]
+  double* dP;
+  double* d2P;
+};
+
+// dynamic smem: 6*S doubles (dia/up for orders 0,1,2)
+__global__ void pt_eigen_kernel(PtParams p) {
+  extern __shared__ double sm[];
+  const int S = p.S;
+  double* dia0 = sm;
+  double* up0 = sm + S;
+  double* dia1 = sm + 2 * S;
+  double* up1 = sm + 3 * S;
+  double* dia2 = sm + 4 * S;
+  double* up2 = sm + 5 * S;
+
+  const int m = blockIdx.x;
+  const int c = m % p.C;
+  const int node = (m / p.C) % p.nn;
+  const int point = m / (p.C * p.nn);
+  if (node == p.root) return;
+  const ModelDev md = p.models[p.branch_model[point * p.nn + node]];
+  if (!((md.flags & 1u) || (md.flags & 2u))) return;  // handled by the series kernel
+  if (!(md.flags & 2u)) return;                       // singular -> series kernel
+  const double rc = p.rates[c];
+  const double t = p.brlen[point * p.nn + node] * rc;  // l_b * r_c
+  const double l = md.rate * t;
+
+  for (int k = threadIdx.x; k < S; k += blockDim.x) {
+    const double a = md.re[k];
+    const int role = md.has_complex ? md.role[k] : 0;
+    if (role == 0) {
+      const double ex = exp(a * l);
+      const double ra = md.rate * a;
+      dia0[k] = ex;
+      dia1[k] = rc * (ra * ex);
+      dia2[k] = rc * rc * (ra * ra * ex);
+      up0[k] = up1[k] = up2[k] = 0.0;
+    } else {
+      const int kf = role == 1 ? k : k - 1;  // first member holds +im
+      const double ar = md.re[kf], b = md.im[kf];
+      const double ex = exp(ar * l);
+      double s, cc;
+      sincos(b * l, &s, &cc);
+      const double r1 = md.rate, r2 = md.rate * md.rate;
+      dia0[k] = ex * cc;
+      dia1[k] = rc * (r1 * (ar * cc - b * s) * ex);
+      dia2[k] = rc * rc * (r2 * ((ar * ar - b * b) * cc - 2.0 * ar * b * s) * ex);
+      // T[kf][kf+1] = up, T[kf+1][kf] = -up ; stored at the FIRST index only
+      up0[k] = role == 1 ? ex * s : 0.0;
+      up1[k] = role == 1 ? rc * (r1 * (ar * s + b * cc) * ex) : 0.0;
+      up2[k] = role == 1 ? rc * rc * (r2 * ((ar * ar - b * b) * s + 2.0 * ar * b * cc) * ex) : 0.0;
+    }
+  }
+  __syncthreads();
+
+  const size_t base = (size_t)m * S * S;
+  const bool wP = p.want & 1u, wD = p.want & 2u, wD2 = p.want & 4u;
+  const bool clamp = md.flags & 4u;
+  for (int e = threadIdx.x; e < S * S; e += blockDim.x) {
+    const int x = e / S, y = e - x * S;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+    if (!md.has_complex) {
+      for (int k = 0; k < S; ++k) {
+        const double vv = md.V[x * S + k] * md.Vinv[k * S + y];
+        a0 = fma(vv, dia0[k], a0);
+        a1 = fma(vv, dia1[k], a1);
+        a2 = fma(vv, dia2[k], a2);
+      }
+    } else {
+      for (int k = 0; k < S; ++k) {
+        const int role = md.role[k];
+        const double vk = md.V[x * S + k];
+        double w0 = vk * dia0[k], w1 = vk * dia1[k], w2 = vk * dia2[k];
+        if (role == 2) {  // T[k-1][k] = up[k-1]
+          const double vm = md.V[x * S + k - 1];
+          w0 = fma(vm, up0[k - 1], w0);
+          w1 = fma(vm, up1[k - 1], w1);
+          w2 = fma(vm, up2[k - 1], w2);
+        } else if (role == 1) {  // T[k+1][k] = -up[k]
+          const double vp = md.V[x * S + k + 1];
+          w0 = fma(vp, -up0[k], w0);
+          w1 = fma(vp, -up1[k], w1);
+          w2 = fma(vp, -up2[k], w2);
+        }
+        const double u = md.Vinv[k * S + y];
+        a0 = fma(w0, u, a0);
+        a1 = fma(w1, u, a1);
+        a2 = fma(w2, u, a2);
+      }
+    }
+    if (wP) {
+      if (t == 0.0) a0 = (x == y) ? 1.0 : 0.0;
+      if (clamp) {  // ChromosomeSubstitutionModel.cpp:903-916
+        if (a0 < 0.0) a0 = 1e-20;
+        else if (a0 > 1.0) a0 = 1.0;
+      }
+      p.P[base + e] = a0;
+    }
+    if (wD) p.dP[base + e] = a1;
+    if (wD2) p.d2P[base + e] = a2;
+  }
+}
+
+// ---- tip lookup tables --------------------------------------------------------
+// tiptab[point][leaf][c][code][x] = sum_y P_leaf[c][x][y] * code_table[code][y]
+// i.e. the son contraction of RHomogeneousTreeLikelihood.cpp:851-856 evaluated once
+// per distinct tip code instead of once per pattern (tips are never expanded to S
+// doubles).
+struct TipTabParams {
+  const double* P;           // [npoints][nn][C][S][S]
+  const double* code_table;  // [ncodes][S]
+  const int* leaf_nodes;     // [nl] node id of each leaf slot
+  int S, C, nn, nl, ncodes;
+  double* tiptab;            // [npoints][nl][C][ncodes][S]
+};
+
+__global__ void tiptab_kernel(TipTabParams p) {
+  const int m = blockIdx.x;  // (point*nl + leaf)*C + c
+  const int c = m % p.C;
+  const int leaf = (m / p.C) % p.nl;
+  const int point = m / (p.C * p.nl);
+  const int S = p.S;
+  const double* Pm = p.P + ((size_t)(point * p.nn + p.leaf_nodes[leaf]) * p.C + c) * S * S;
+  double* out = p.tiptab + (size_t)m * p.ncodes * S;
+  for (int e = threadIdx.x; e < p.ncodes * S; e += blockDim.x) {
+    const int code = e / S, x = e - code * S;
+    const double* tv = p.code_table + (size_t)code * S;
+    double acc = 0.0;
+    for (int y = 0; y < S; ++y) acc = fma(Pm[x * S + y], tv[y], acc);
+    out[e] = acc;
+  }
+}
+
+}  // namespace bppgpu

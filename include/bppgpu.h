@@ -1,0 +1,183 @@
+/*
+ * bppgpu.h -- C ABI of the B200-native tree-likelihood hot path.
+ *
+ * This is the drop-in boundary: a C++ shim that keeps
+ * the reference's class surface (bpp::TransitionModel::getPij_t ...,
+ * bpp::R/DRHomogeneousTreeLikelihood, bpp::DRNonHomogeneousTreeLikelihood)
+ * binds exactly these entry points; see INTEGRATION.md.  All functions are
+ * extern "C", take plain pointers and sizes, never throw, and return a status
+ * code; bppgpu_last_error() gives the message for the calling thread.
+ *
+ * There is no CPU fallback: every entry point that computes fails with
+ * BPPGPU_E_CUDA when no sm_100a device is usable.
+ *
+ * Reference interfaces replaced (paths relative to src/Bpp/Phyl/ of
+ * anatshafir1/bpp-phyl):
+ *   Model/SubstitutionModel.h:233,240,247        getPij_t / getdPij_dt / getd2Pij_dt2
+ *   Model/AbstractSubstitutionModel.cpp:426-641  generic eigen / block / Taylor forms
+ *   Model/ChromosomeSubstitutionModel.cpp:808-1001  Chromosome P(t) family (clamp, P.Q, Q^2.P)
+ *   Likelihood/AbstractHomogeneousTreeLikelihood.cpp:341-414   pxy_/dpxy_/d2pxy_ tables
+ *   Likelihood/RHomogeneousTreeLikelihood.cpp:162-216,802-863  pruning + root reduction
+ *   Likelihood/DRHomogeneousTreeLikelihood.cpp:170-186,287-454,483-719  DR passes, d1/d2
+ *   Likelihood/DRNonHomogeneousTreeLikelihood.cpp:370-541,904-962      NH form, weighted root
+ */
+#ifndef BPPGPU_H
+#define BPPGPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- status codes (SURVEY.md 8b "Error conventions") ---------------------- */
+enum {
+  BPPGPU_OK = 0,
+  BPPGPU_E_INVALID = 1, /* bad argument / shape                                */
+  BPPGPU_E_STATE = 2,   /* call order: data, model, lengths not set yet ...    */
+  BPPGPU_E_CUDA = 3,    /* CUDA runtime error, or no usable device             */
+  BPPGPU_E_NCCL = 4,
+  BPPGPU_E_NUMERIC = 5, /* e.g. Taylor series did not converge                 */
+  BPPGPU_E_NOMEM = 6
+};
+
+/* message of the last failing call on this thread ("" if none) */
+const char* bppgpu_last_error(void);
+/* ABI version, bumped on incompatible change */
+int bppgpu_abi_version(void);
+/* number of visible CUDA devices (0 -> nothing below can compute) */
+int bppgpu_device_count(int* n);
+
+/* ---- model descriptor ------------------------------------------------------
+ * What bpp::SubstitutionModel exposes (Model/SubstitutionModel.h:468-525):
+ * getGenerator, getEigenValues, getIEigenValues, isDiagonalizable,
+ * isNonSingular, getRowLeftEigenVectors, getColumnRightEigenVectors, getRate.
+ * All matrices row-major S x S; x = from-state row, y = to-state column.     */
+enum {
+  BPPGPU_MODEL_DIAGONALIZABLE = 1u << 0, /* isDiagonalizable()                   */
+  BPPGPU_MODEL_NONSINGULAR = 1u << 1,    /* isNonSingular()                      */
+  BPPGPU_MODEL_CLAMP01 = 1u << 2,        /* Chromosome: P<0 -> 1e-20, P>1 -> 1   */
+  BPPGPU_MODEL_CHR_DERIV = 1u << 3,      /* Chromosome: dP = P.Q.rate, d2P = Q^2.P.rate^2 */
+  BPPGPU_MODEL_CHR_TAYLOR = 1u << 4,     /* Chromosome singular path: L1-norm scaling +
+                                            the reference's 1e-4 truncation rule          */
+  BPPGPU_MODEL_EXACT_EXPM = 1u << 5      /* singular path: run the series to FP64
+                                            convergence instead of the reference's cut   */
+};
+
+typedef struct bppgpu_model_desc {
+  int32_t n_states;
+  uint32_t flags;
+  double rate;               /* getRate()                                           */
+  const double* right_eigen; /* V   [S*S] columns = right eigenvectors              */
+  const double* left_eigen;  /* V^-1 [S*S] rows   = left eigenvectors               */
+  const double* eigen_re;    /* [S]                                                  */
+  const double* eigen_im;    /* [S] or NULL (all real)                               */
+  const double* generator;   /* Q [S*S]; required unless DIAGONALIZABLE|NONSINGULAR  */
+  double taylor_epsilon;     /* Chromosome truncation threshold (get_epsilon(), 1e-4)*/
+} bppgpu_model_desc;
+
+enum { BPPGPU_WANT_P = 1, BPPGPU_WANT_DP = 2, BPPGPU_WANT_D2P = 4 };
+
+/* Interface 1: batched P(t) family for one model, host in / host out.
+ * out arrays are [n_t][S][S]; pass NULL for tables not in `want`.
+ * getPij_t(t) for a single t is n_t = 1.                                      */
+int bppgpu_pt_batch(int device, const bppgpu_model_desc* model, int64_t n_t, const double* t,
+                    unsigned want, double* P, double* dP, double* d2P);
+
+/* ---- Interface 2: tree likelihood engine ----------------------------------- */
+typedef struct bppgpu_engine bppgpu_engine;
+
+enum {
+  BPPGPU_FLAG_KEEP_CLVS = 1u << 0,   /* keep every node's lower CLV in HBM (needed for
+                                        derivatives and bppgpu_get_clv)                 */
+  BPPGPU_FLAG_R_SEMANTICS = 1u << 1, /* root reduction drops non-positive terms like the
+                                        R classes (RHomogeneousTreeLikelihood.cpp:198,213);
+                                        default = DR semantics (clamp SR<0 to 0)        */
+  BPPGPU_FLAG_WEIGHTED_ROOT = 1u << 2, /* root frequencies = normalised per-state root
+                                        likelihood (DRNonHomogeneousTreeLikelihood.cpp:927-962) */
+  BPPGPU_FLAG_NH_DERIV = 1u << 3     /* derivative in the NH numerator/denominator form
+                                        (DRNonHomogeneousTreeLikelihood.cpp:370-413)    */
+};
+
+typedef struct bppgpu_config {
+  int32_t n_states;             /* S                                                   */
+  int32_t n_cats;               /* C rate classes                                      */
+  int64_t n_patterns;           /* N patterns held by THIS engine (a shard)            */
+  int32_t n_nodes;              /* nodes of the flattened tree                         */
+  int32_t root;                 /* id of the root node                                 */
+  const int32_t* child_offsets; /* [n_nodes+1] CSR; a node with no children is a leaf  */
+  const int32_t* children;      /* [child_offsets[n_nodes]] son ids in son order       */
+  int32_t n_points;             /* independent parameter points evaluated per call     */
+  int32_t n_models;             /* model slots (>=1)                                   */
+  int32_t n_codes;              /* rows of code_table                                  */
+  int32_t code_bytes;           /* 1 (uint8) or 2 (uint16) per tip code                */
+  const double* code_table;     /* [n_codes][S]: getInitValue(s, code) (0/1 or probs)  */
+  int32_t device;               /* CUDA device ordinal                                 */
+  uint32_t flags;
+} bppgpu_config;
+
+int bppgpu_create(const bppgpu_config* cfg, bppgpu_engine** out);
+int bppgpu_destroy(bppgpu_engine* e);
+
+/* tip data: codes[N] for leaf `node` (copied) */
+int bppgpu_set_tip_codes(bppgpu_engine* e, int32_t node, const void* codes);
+/* pattern weights (SitePatterns::getWeights, unsigned int) */
+int bppgpu_set_pattern_weights(bppgpu_engine* e, const uint32_t* w);
+/* rate classes: getCategory(c), getProbability(c) */
+int bppgpu_set_rates(bppgpu_engine* e, const double* rates, const double* probs);
+/* model slot (eigensystem copied to the device) */
+int bppgpu_set_model(bppgpu_engine* e, int32_t slot, const bppgpu_model_desc* m);
+/* per point: model slot of the branch above each node (default: slot 0, or slot
+ * `point` when n_models == n_points)                                           */
+int bppgpu_set_branch_models(bppgpu_engine* e, int32_t point, const int32_t* slot_of_node);
+/* per point: length of the branch above each node, indexed by node id; the
+ * root's entry is ignored                                                      */
+int bppgpu_set_branch_lengths(bppgpu_engine* e, int32_t point, const double* t);
+/* per point: root frequencies [S] */
+int bppgpu_set_root_freqs(bppgpu_engine* e, int32_t point, const double* pi);
+
+enum { BPPGPU_EVAL_LNL = 1, BPPGPU_EVAL_D1 = 2, BPPGPU_EVAL_D2 = 4 };
+
+/* One full evaluation for every point: P(t) tables for all branches, pruning,
+ * root reduction [, prefix pass and branch derivatives].
+ * lnl[n_points]; d1, d2 [n_points][n_nodes] = d(lnL)/dt and the reference's
+ * sum_i w_i (d2L_i/L_i - (dL_i/L_i)^2), i.e. derivatives of +lnL; the shim
+ * flips the sign for getFirstOrderDerivative (DRHomogeneousTreeLikelihood.cpp:367). */
+int bppgpu_eval(bppgpu_engine* e, unsigned want, double* lnl, double* d1, double* d2);
+
+/* Same, results left in device memory as [n_points][1 + 2*n_nodes] doubles
+ * (lnL, d1[n_nodes], d2[n_nodes]) at `dev_out`, enqueued on `cuda_stream`
+ * (a cudaStream_t; NULL = the engine's stream) without a host sync, so the
+ * caller can follow with an NCCL all-reduce on the same stream.               */
+int bppgpu_eval_device(bppgpu_engine* e, unsigned want, double* dev_out, void* cuda_stream);
+
+/* accessors (valid after an eval) */
+int bppgpu_get_site_lnl(bppgpu_engine* e, int32_t point, double* out /* [N] */);
+/* which: 0 = lower (subtree) CLV of `node`, 1 = upper (rest of tree, conditional on
+ * the father's state).  clv [N][C][S] in the reference's VVVdouble order, values
+ * are scaled: true = clv * 2^-scale_exp[i].  Needs BPPGPU_FLAG_KEEP_CLVS.       */
+int bppgpu_get_clv(bppgpu_engine* e, int32_t point, int32_t node, int32_t which, double* clv,
+                   int32_t* scale_exp);
+/* which: BPPGPU_WANT_P / _DP / _D2P; out [C][S][S] = pxy_[node][c][x][y] */
+int bppgpu_get_transition_probabilities(bppgpu_engine* e, int32_t point, int32_t node,
+                                        unsigned which, double* out);
+/* root frequencies actually used (differs from the input with WEIGHTED_ROOT) */
+int bppgpu_get_root_freqs(bppgpu_engine* e, int32_t point, double* out /* [S] */);
+
+/* introspection for benches/tests */
+typedef struct bppgpu_stats {
+  int64_t kernel_launches; /* kernels launched by the last eval                   */
+  int64_t clv_updates;     /* (node,pattern,cat,state) elements produced by it    */
+  double last_eval_ms;     /* device time of the last bppgpu_eval (CUDA events)   */
+  double prune_ms;         /* ... of its pruning kernel(s)                        */
+  int64_t hbm_bytes_resident;
+  int32_t stack_slots;
+  int32_t path;            /* which kernel family ran             */
+} bppgpu_stats;
+int bppgpu_get_stats(bppgpu_engine* e, bppgpu_stats* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BPPGPU_H */

@@ -1,0 +1,310 @@
+"""Oracle (TEST INFRASTRUCTURE): pruning, root reduction, branch derivatives.
+
+Vectorised NumPy restatement of (paths relative to
+/root/reference/src/Bpp/Phyl/Likelihood/):
+
+* RHomogeneousTreeLikelihood::computeSubtreeLikelihood     RHomogeneousTreeLikelihood.cpp:802-863
+* ... getLogLikelihood / ForASite / ForARateClass           :162-216
+* ... computeTreeDLikelihood / computeDownSubtreeDLikelihood (+D2)  :365-541, :615-791
+* DRHomogeneousTreeLikelihood::computeSubtreeLikelihoodPostfix / Prefix  DRHomogeneousTreeLikelihood.cpp:483-649
+* ... computeRootLikelihood :653-719, getLogLikelihood :170-186
+* ... computeTreeDLikelihoodAtNode / D2 :287-326, :373-411; reductions :340-368, :425-454
+* DRNonHomogeneousTreeLikelihood (per-branch models, NH derivative form :370-413,
+  weighted root frequencies :927-962)
+
+Arrays are indexed [pattern][class][state] like the reference's VVVdouble.
+``scaled=True`` adds the per-pattern power-of-two rescaling the GPU path uses
+(the reference has none, SURVEY.md finding 5); it is exact, so wherever the
+unscaled value is finite both agree to rounding of the final log.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+SCALE_THRESHOLD_EXP = -256   # rescale a pattern when max CLV < 2^-256 (same rule as the CUDA path)
+
+
+def _contract(P, L):
+    """sum_y P[c][x][y] * L[i][c][y] -> [i][c][x]   (:851-856)."""
+    return np.einsum("cxy,icy->icx", P, L)
+
+
+def _contract_T(P, L):
+    """root-side: sum_y P[c][y][x] * L[i][c][y]   (DRHomogeneousTreeLikelihood.cpp:934-940)."""
+    return np.einsum("cyx,icy->icx", P, L)
+
+
+def _rescale(A, E):
+    """Per-pattern power-of-two rescale: A[i] *= 2^k, E[i] += k when max(A[i]) < 2^-256."""
+    m = A.reshape(A.shape[0], -1).max(axis=1)
+    need = (m > 0) & (m < 2.0 ** SCALE_THRESHOLD_EXP)
+    if need.any():
+        _, ex = np.frexp(m[need])           # m = f * 2^ex, f in [0.5,1)
+        k = -ex
+        A[need] = np.ldexp(A[need], k[:, None, None])
+        E[need] += k
+    return A, E
+
+
+def leaf_array(codes_row, table, C):
+    """Tip CLV [N][C][S] from codes (DRASRTreeLikelihoodData.cpp:277-303)."""
+    L = table[codes_row.astype(np.int64)]            # [N][S]
+    return np.repeat(L[:, None, :], C, axis=1)
+
+
+# ----------------------------------------------------------------------------
+# single recursion (R classes)
+# ----------------------------------------------------------------------------
+def prune(flat, tip_codes, table, P, C, links=None, n_per_node=None, scaled=False, keep=False):
+    """computeSubtreeLikelihood.  tip_codes: dict leaf id -> code vector over that leaf's
+    own pattern list (recursive mode) or over the global list.  P[b][c][x][y] indexed by
+    node id.  links[father][son] = index vector (None -> identity).
+    Returns (root CLV [N][C][S], scale exponents [N], {node: (clv, exp)} if keep)."""
+    clv = {}
+    exps = {}
+    for nid in range(flat.n_nodes):                     # post-order ids
+        if flat.is_leaf[nid]:
+            clv[nid] = leaf_array(tip_codes[nid], table, C)
+            exps[nid] = np.zeros(clv[nid].shape[0], np.int64)
+            continue
+        A = None
+        E = None
+        for s in flat.children[nid]:
+            Ls, Es = clv[s], exps[s]
+            if links is not None:
+                idx = links[nid][s]
+                Ls, Es = Ls[idx], Es[idx]
+            t = _contract(P[s], Ls)
+            A = t if A is None else A * t
+            E = Es.copy() if E is None else E + Es
+            if not keep:
+                pass
+        if scaled:
+            A, E = _rescale(A, E)
+        clv[nid], exps[nid] = A, E
+    root = flat.root
+    if keep:
+        return clv[root], exps[root], (clv, exps)
+    return clv[root], exps[root], None
+
+
+def site_likelihoods_R(root_clv, root_freqs, probs):
+    """getLikelihoodForASiteForARateClass (:205-216, drops negative terms) and
+    getLogLikelihoodForASite (:192-201, drops non-positive class terms)."""
+    t = root_clv * root_freqs[None, None, :]
+    t = np.where(t > 0, t, 0.0)
+    lc = t.sum(axis=2) * probs[None, :]
+    lc = np.where(lc > 0, lc, 0.0)
+    return lc.sum(axis=1)
+
+
+def loglik_R(root_clv, root_exp, root_freqs, probs, root_links):
+    """getLogLikelihood (:162-176): per SITE (duplicates included) through
+    rootPatternLinks_, sorted, summed from the largest."""
+    with np.errstate(divide="ignore"):
+        lp = np.log(site_likelihoods_R(root_clv, root_freqs, probs)) - root_exp * np.log(2.0)
+    la = np.sort(lp[root_links])
+    return float(np.sum(la[::-1])), lp
+
+
+# ----------------------------------------------------------------------------
+# double recursion (DR classes), global patterns
+# ----------------------------------------------------------------------------
+class DRResult:
+    pass
+
+
+def dr_eval(flat, tip_codes, table, P, C, root_freqs, probs, weights,
+            dP=None, d2P=None, scaled=False, nh_form=False, weighted_root=False):
+    """computeTreeLikelihood (DRHomogeneousTreeLikelihood.cpp:474-479) + derivatives.
+
+    lower[n]  = likelihood of n's subtree given the state at n           (postfix :483-539)
+    upper[n]  = likelihood of everything else given the state at n's FATHER,
+                root frequencies folded in at the root's sons             (prefix :543-649)
+    """
+    N = len(weights)
+    nn = flat.n_nodes
+    lower, lexp = {}, {}
+    for nid in range(nn):
+        if flat.is_leaf[nid]:
+            lower[nid] = leaf_array(tip_codes[nid], table, C)
+            lexp[nid] = np.zeros(N, np.int64)
+        else:
+            A, E = None, np.zeros(N, np.int64)
+            for s in flat.children[nid]:
+                t = _contract(P[s], lower[s])
+                A = t if A is None else A * t
+                E = E + lexp[s]
+            if scaled:
+                A, E = _rescale(A, E)
+            lower[nid], lexp[nid] = A, E
+    root = flat.root
+    res = DRResult()
+    res.lower, res.lexp = lower, lexp
+    root_clv, root_e = lower[root], lexp[root]
+
+    if weighted_root:
+        # setWeightedRootFreq (DRNonHomogeneousTreeLikelihood.cpp:927-962):
+        # pi_x = sum_i sum_c p_c L_root[i][c][x] / sum_x(...)
+        # (scale exponents: per-pattern; with N=1 they cancel in the normalisation)
+        tot = np.einsum("icx,c->x", np.ldexp(root_clv, -(root_e - root_e.min())[:, None, None]), probs)
+        root_freqs = tot / tot.sum()
+    res.root_freqs = root_freqs
+
+    # computeRootLikelihood (:653-719)
+    S_ic = np.einsum("icx,x->ic", root_clv, root_freqs)
+    SR = S_ic @ probs
+    SR = np.where(SR < 0, 0.0, SR)
+    res.SR, res.SR_exp = SR, root_e
+    with np.errstate(divide="ignore"):
+        lp = np.log(SR) - root_e * np.log(2.0)
+    res.site_lnl = lp
+    la = np.sort(weights * lp)                    # getLogLikelihood (:170-186)
+    res.lnl = float(np.sum(la[::-1]))
+
+    if dP is None and d2P is None:
+        return res
+
+    # prefix pass
+    upper, uexp = {}, {}
+    order = list(range(nn - 1, -1, -1))           # fathers before sons
+    for nid in order:
+        if nid == root:
+            continue
+        f = int(flat.parent[nid])
+        A = None
+        E = np.zeros(N, np.int64)
+        for b in flat.children[f]:
+            if b == nid:
+                continue
+            t = _contract(P[b], lower[b])
+            A = t if A is None else A * t
+            E = E + lexp[b]
+        if f != root:
+            t = _contract_T(P[f], upper[f])
+            A = t if A is None else A * t
+            E = E + uexp[f]
+        else:
+            A = A * root_freqs[None, None, :]
+        if scaled:
+            A, E = _rescale(A, E)
+        upper[nid], uexp[nid] = A, E
+    res.upper, res.uexp = upper, uexp
+
+    nb = nn - 1
+    d1 = np.zeros(nb)
+    d2 = np.zeros(nb)
+    res.dL, res.d2L = {}, {}
+    for nid in range(nb):
+        U, D = upper[nid], lower[nid]
+        sh = (root_e - uexp[nid] - lexp[nid])       # true = stored * 2^-(e); ratio needs 2^(eR-eU-eD)
+        if nh_form:
+            # DRNonHomogeneousTreeLikelihood.cpp:370-413: larray = full conditional at the
+            # father INCLUDING this son; divide by (P.lower), 0 where the denominator is 0
+            den = _contract(P[nid], D)
+            full = U * den
+            num1 = _contract(dP[nid], D) if dP is not None else None
+            num2 = _contract(d2P[nid], D) if d2P is not None else None
+            with np.errstate(divide="ignore", invalid="ignore"):
+                if num1 is not None:
+                    q = np.where(den == 0, 0.0, full * num1 / den)
+                    dLi = np.ldexp(np.einsum("icx,c->i", q, probs), sh) / SR
+                if num2 is not None:
+                    q = np.where(den == 0, 0.0, full * num2 / den)
+                    d2Li = np.ldexp(np.einsum("icx,c->i", q, probs), sh) / SR
+        else:
+            if dP is not None:
+                dLi = np.ldexp(np.einsum("icx,icx,c->i", U, _contract(dP[nid], D), probs), sh) / SR
+            if d2P is not None:
+                d2Li = np.ldexp(np.einsum("icx,icx,c->i", U, _contract(d2P[nid], D), probs), sh) / SR
+        if dP is not None:
+            res.dL[nid] = dLi
+            d1[nid] = -float(np.sum(weights * dLi))                     # :340-368
+        if d2P is not None and dP is not None:
+            res.d2L[nid] = d2Li
+            d2[nid] = -float(np.sum(weights * (d2Li - dLi ** 2)))       # :425-454
+    res.d1, res.d2 = d1, d2
+    return res
+
+
+# ----------------------------------------------------------------------------
+# R-class derivatives (single recursion re-pruned along the path to the root)
+# ----------------------------------------------------------------------------
+def r_derivative(flat, tip_codes, table, P, dP, C, root_freqs, probs, weights, branch, order=1, d2P=None):
+    """computeTreeDLikelihood / computeDownSubtreeDLikelihood
+    (RHomogeneousTreeLikelihood.cpp:365-541; D2 :615-791) on the global pattern list:
+    substitute dP (d2P) on ``branch`` and re-prune the path to the root; then
+    getFirstOrderDerivative (:346-361) / getSecondOrderDerivative (:596-611)."""
+    N = len(weights)
+    clv = {}
+    for nid in range(flat.n_nodes):
+        if flat.is_leaf[nid]:
+            clv[nid] = leaf_array(tip_codes[nid], table, C)
+        else:
+            A = None
+            for s in flat.children[nid]:
+                t = _contract(P[s], clv[s])
+                A = t if A is None else A * t
+            clv[nid] = A
+    L = site_like_plain(clv[flat.root], root_freqs, probs)
+
+    def along(M):
+        path = set()
+        n = branch
+        while n != flat.root:
+            path.add(n)
+            n = int(flat.parent[n])
+        d = {}
+        for nid in range(flat.n_nodes):
+            if flat.is_leaf[nid]:
+                continue
+            hit = [s for s in flat.children[nid] if s in path]
+            if not hit:
+                continue
+            s0 = hit[0]
+            A = None
+            for s in flat.children[nid]:
+                if s == s0:
+                    t = _contract(M[s], clv[s]) if s == branch else _contract(P[s], d[s])
+                else:
+                    t = _contract(P[s], clv[s])
+                A = t if A is None else A * t
+            d[nid] = A
+        return site_like_plain(d[flat.root], root_freqs, probs)
+
+    dL = along(dP)
+    if order == 1:
+        return -float(np.sum(weights * dL / L))
+    d2L = along(d2P)
+    return -float(np.sum(weights * (d2L / L - (dL / L) ** 2)))
+
+
+def site_like_plain(root_clv, root_freqs, probs):
+    return np.einsum("icx,x,c->i", root_clv, root_freqs, probs)
+
+
+# ----------------------------------------------------------------------------
+# brute force over all internal-state assignments (structural check, tiny trees)
+# ----------------------------------------------------------------------------
+def brute_force_site(flat, tip_states_probs, P_c, root_freqs):
+    """Sum over every assignment of states to internal nodes for ONE pattern and ONE
+    rate class.  tip_states_probs: leaf id -> vector[S]; P_c[node] = S x S."""
+    import itertools
+    S = len(root_freqs)
+    internal = [i for i in range(flat.n_nodes) if not flat.is_leaf[i]]
+    total = 0.0
+    for assign in itertools.product(range(S), repeat=len(internal)):
+        st = dict(zip(internal, assign))
+        p = root_freqs[st[flat.root]]
+        for nid in range(flat.n_nodes):
+            if nid == flat.root:
+                continue
+            x = st[int(flat.parent[nid])]
+            if flat.is_leaf[nid]:
+                p *= float(P_c[nid][x] @ tip_states_probs[nid])
+            else:
+                p *= P_c[nid][x, st[nid]]
+            if p == 0:
+                break
+        total += p
+    return total
