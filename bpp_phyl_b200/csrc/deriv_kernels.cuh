@@ -1,0 +1,183 @@
+// K4 + K5, generic form (any S, any C, any arity): one launch per node.
+//
+//   upper[n][i][c][x] = likelihood of everything outside n's subtree given state x at
+//                       n's FATHER, root frequencies folded in below the root
+//                       (DRHomogeneousTreeLikelihood::computeSubtreeLikelihoodPrefix,
+//                        Likelihood/DRHomogeneousTreeLikelihood.cpp:543-649; the father-branch
+//                        contraction uses P transposed, :919-945)
+//   dL_i  = [sum_c p_c sum_x upper[n][i][c][x] sum_y dpxy[n][c][x][y] lower[n][i][c][y]] / SR_i
+//                       (computeTreeDLikelihoodAtNode :287-326, D2 :373-411)
+//   d1[n] = sum_i w_i dL_i ; d2[n] = sum_i w_i (d2L_i - dL_i^2)          (:340-368, :425-454)
+// The NH form (DRNonHomogeneousTreeLikelihood.cpp:370-413, :497-541) multiplies the full
+// conditional by dP.lower / P.lower with a `denominator == 0 -> 0` guard.
+//
+// This is the correctness/fallback path; the specialised fused down-walk for S = 4 / 20
+// lives in downwalk_kernels.cuh.
+#pragma once
+#include "common.cuh"
+#include "walk_kernels.cuh"
+
+namespace bppgpu {
+
+struct UpperParams {
+  const Child* sibs;  // siblings of the node (kinds TIP / KEEP), pnode = sibling node id
+  int nsib;
+  int father;         // node id of the father (its branch carries P^T), -1 if father is the root
+  int S, C, ncodes, code_bytes;
+  long long N;
+  const double* P;       // [nn][C][S][S]
+  const double* tiptab;  // [nl][C][ncodes][S]
+  const void* codes;
+  const double* keep;    // lower CLVs of internal nodes
+  const int* keep_exp;
+  const double* upper_f;  // father's upper [N][C][S] (father != root)
+  const int* uexp_f;
+  const double* rootfreq;
+  double* upper_out;
+  int* uexp_out;
+};
+
+__global__ void upper_node_kernel(UpperParams p) {
+  const long long total = p.N * p.C * p.S;
+  const long long rows = p.N * p.C;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+       e += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(e % p.S);
+    const long long rc = e / p.S;
+    const int c = (int)(rc % p.C);
+    const long long pat = rc / p.C;
+    double acc;
+    if (p.father < 0) {
+      acc = p.rootfreq[x];
+    } else {
+      // sum_y P_f[c][y][x] * upper_f[i][c][y]  (transposed contraction)
+      const double* Pf = p.P + ((size_t)p.father * p.C + c) * p.S * p.S;
+      const double* u = p.upper_f + (size_t)rc * p.S;
+      acc = 0.0;
+      for (int y = 0; y < p.S; ++y) acc = fma(Pf[(size_t)y * p.S + x], u[y], acc);
+    }
+    for (int j = 0; j < p.nsib; ++j) {
+      const Child ch = p.sibs[j];
+      double t;
+      if (ch.kind == CHILD_TIP) {
+        const int code = load_code(p.codes, p.code_bytes, (long long)ch.idx * p.N + pat);
+        t = p.tiptab[(((size_t)ch.idx * p.C + c) * p.ncodes + code) * p.S + x];
+      } else {
+        const double* Pr = p.P + (((size_t)ch.pnode * p.C + c) * p.S + x) * p.S;
+        const double* l = p.keep + ((size_t)ch.idx * rows + rc) * p.S;
+        t = 0.0;
+        for (int y = 0; y < p.S; ++y) t = fma(Pr[y], l[y], t);
+      }
+      acc *= t;
+    }
+    p.upper_out[e] = acc;
+  }
+}
+
+__global__ void upper_scale_kernel(UpperParams p) {
+  const long long pat = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (pat >= p.N) return;
+  int Ea = p.father < 0 ? 0 : p.uexp_f[pat];
+  for (int j = 0; j < p.nsib; ++j) {
+    const Child ch = p.sibs[j];
+    if (ch.kind != CHILD_TIP) Ea += p.keep_exp[(size_t)ch.idx * p.N + pat];
+  }
+  const int w = p.C * p.S;
+  double* v = p.upper_out + (size_t)pat * w;
+  int m = 0;
+  for (int i = 0; i < w; ++i) m = max(m, hi_word(v[i]));
+  if (m < kScaleThresholdHi && m >= (1 << 20)) {
+    const int k = rescale_shift(m);
+    const double f = pow2(k);
+    for (int i = 0; i < w; ++i) v[i] *= f;
+    Ea += k;
+  }
+  p.uexp_out[pat] = Ea;
+}
+
+struct DerivParams {
+  int node;
+  int is_tip;
+  int idx;  // leaf slot (tip) or keep index (internal)
+  int S, C, code_bytes;
+  int nh_form;
+  unsigned want;  // bit1: d1, bit2: d2
+  long long N;
+  const double* P;    // [C][S][S] of this branch
+  const double* dP;
+  const double* d2P;
+  const double* code_table;  // [ncodes][S]
+  const void* codes;
+  const double* keep;
+  const int* keep_exp;
+  const double* upper;  // [N][C][S]
+  const int* uexp;
+  const double* SR;
+  const int* rexp;
+  const double* probs;
+  const double* weights;
+  double* part1;  // [gridDim.x]
+  double* part2;
+};
+
+__global__ void deriv_node_kernel(DerivParams p) {
+  __shared__ double red[32];
+  const long long pat = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  double c1 = 0.0, c2 = 0.0;
+  if (pat < p.N) {
+    const int S = p.S;
+    const double* D0;
+    int le = 0;
+    if (p.is_tip) {
+      const int code = load_code(p.codes, p.code_bytes, (long long)p.idx * p.N + pat);
+      D0 = p.code_table + (size_t)code * S;
+    } else {
+      D0 = p.keep + ((size_t)p.idx * p.N + pat) * p.C * S;
+      le = p.keep_exp[(size_t)p.idx * p.N + pat];
+    }
+    double a1 = 0.0, a2 = 0.0;
+    for (int c = 0; c < p.C; ++c) {
+      const double* D = p.is_tip ? D0 : D0 + (size_t)c * S;
+      const double* U = p.upper + ((size_t)pat * p.C + c) * S;
+      double s1c = 0.0, s2c = 0.0;
+      for (int x = 0; x < S; ++x) {
+        const double* r0 = p.P + ((size_t)c * S + x) * S;
+        const double* r1 = p.dP + ((size_t)c * S + x) * S;
+        const double* r2 = p.d2P ? p.d2P + ((size_t)c * S + x) * S : nullptr;
+        double n1 = 0.0, n2 = 0.0, den = 0.0;
+        for (int y = 0; y < S; ++y) {
+          const double d = D[y];
+          n1 = fma(r1[y], d, n1);
+          if (r2) n2 = fma(r2[y], d, n2);
+          if (p.nh_form) den = fma(r0[y], d, den);
+        }
+        const double u = U[x];
+        if (p.nh_form) {
+          const double full = u * den;
+          s1c += den == 0.0 ? 0.0 : full * n1 / den;
+          s2c += den == 0.0 ? 0.0 : full * n2 / den;
+        } else {
+          s1c = fma(u, n1, s1c);
+          s2c = fma(u, n2, s2c);
+        }
+      }
+      a1 = fma(s1c, p.probs[c], a1);
+      a2 = fma(s2c, p.probs[c], a2);
+    }
+    const int sh = p.rexp[pat] - p.uexp[pat] - le;
+    const double sr = p.SR[pat];
+    const double dL = scalbn(a1, sh) / sr;
+    const double d2L = scalbn(a2, sh) / sr;
+    const double w = p.weights[pat];
+    c1 = w * dL;
+    c2 = w * (d2L - dL * dL);
+  }
+  const double b1 = block_sum(c1, red);
+  const double b2 = block_sum(c2, red);
+  if (threadIdx.x == 0) {
+    p.part1[blockIdx.x] = b1;
+    p.part2[blockIdx.x] = b2;
+  }
+}
+
+}  // namespace bppgpu

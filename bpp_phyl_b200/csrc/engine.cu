@@ -1,0 +1,1091 @@
+// libbppgpu: implementation of the C ABI in include/bppgpu.h (sm_100a only, no CPU fallback).
+//
+// Host planner: flattens the tree into a post-order walk program (Sethi-Ullman ordered so
+// the on-chip CLV stack stays logarithmic), owns all device buffers, and enqueues
+//   K1  pt_eigen_kernel / pt_series_kernel   P, r.P', r^2.P'' for every (point, branch, class)
+//   K2b tiptab_kernel                         tip-code lookup tables
+//   K2+K3 walk4 / walkS / generic             pruning + root reduction
+//   K4+K5 upper / deriv kernels               prefix pass and branch derivatives
+// on one stream; bppgpu_eval synchronises once at the end, bppgpu_eval_device not at all.
+#include "engine.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <functional>
+
+namespace bppgpu {
+
+std::string& last_error() {
+  static thread_local std::string s;
+  return s;
+}
+
+static int g_sm_count = 148;
+
+template <typename T>
+static cudaError_t dev_alloc(bppgpu_engine* e, T** p, size_t n) {
+  *p = nullptr;
+  if (n == 0) n = 1;
+  cudaError_t r = cudaMalloc((void**)p, n * sizeof(T));
+  if (r == cudaSuccess && e) e->bytes_resident += n * sizeof(T);
+  return r;
+}
+
+static bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
+static int ilog2(int v) {
+  int l = 0;
+  while ((1 << l) < v) ++l;
+  return l;
+}
+
+// ---- walk program -----------------------------------------------------------------
+// Children with the larger Sethi-Ullman label are evaluated first, so the number of
+// live intermediate CLVs (stack slots) is minimal; the multiplication order inside an
+// op stays the reference's son order (RHomogeneousTreeLikelihood.cpp:827-861).
+static void build_program(bppgpu_engine* e, Program& pr, bool all_keep) {
+  const int nn = e->nn;
+  std::vector<int> label(nn, 0);
+  // node ids are arbitrary: compute labels by an explicit post-order
+  std::vector<int> order;
+  order.reserve(nn);
+  {
+    std::vector<std::pair<int, int>> st;
+    st.push_back({e->root, 0});
+    while (!st.empty()) {
+      auto& top = st.back();
+      int n = top.first;
+      int nc = e->child_off[n + 1] - e->child_off[n];
+      if (top.second < nc) {
+        int ch = e->children[e->child_off[n] + top.second];
+        top.second++;
+        st.push_back({ch, 0});
+      } else {
+        order.push_back(n);
+        st.pop_back();
+      }
+    }
+  }
+  for (int n : order) {
+    int nc = e->child_off[n + 1] - e->child_off[n];
+    if (nc == 0) continue;
+    std::vector<int> ls;
+    for (int j = 0; j < nc; ++j) {
+      int ch = e->children[e->child_off[n] + j];
+      if (e->leaf_slot[ch] < 0) ls.push_back(label[ch]);
+    }
+    std::sort(ls.begin(), ls.end(), std::greater<int>());
+    int lab = 1;
+    for (size_t i = 0; i < ls.size(); ++i) lab = std::max(lab, ls[i] + (int)i);
+    label[n] = lab;
+  }
+  pr.ops.clear();
+  pr.childs.clear();
+  pr.nslots = 0;
+  std::vector<int> free_slots;
+  int next_slot = 0;
+  std::vector<int> slot_of(nn, -1);
+  std::vector<int> op_of(nn, -1);
+  // iterative emission
+  std::function<void(int)> emit = [&](int n) {
+    int nc = e->child_off[n + 1] - e->child_off[n];
+    std::vector<int> internal;
+    for (int j = 0; j < nc; ++j) {
+      int ch = e->children[e->child_off[n] + j];
+      if (e->leaf_slot[ch] < 0) internal.push_back(ch);
+    }
+    std::stable_sort(internal.begin(), internal.end(), [&](int a, int b) { return label[a] > label[b]; });
+    for (size_t i = 0; i < internal.size(); ++i) {
+      emit(internal[i]);
+      if (!all_keep && i + 1 < internal.size()) {
+        int s;
+        if (!free_slots.empty()) {
+          s = free_slots.back();
+          free_slots.pop_back();
+        } else {
+          s = next_slot++;
+        }
+        slot_of[internal[i]] = s;
+        pr.ops[op_of[internal[i]]].dst_slot = s;
+      }
+    }
+    Op op{};
+    op.node = n;
+    op.nchild = nc;
+    op.child_begin = (int)pr.childs.size();
+    op.dst_slot = -1;
+    op.keep_idx = (e->keep || all_keep) ? e->internal_idx[n] : -1;
+    op.is_root = n == e->root;
+    for (int j = 0; j < nc; ++j) {
+      int ch = e->children[e->child_off[n] + j];
+      Child c{};
+      c.pnode = ch;
+      if (e->leaf_slot[ch] >= 0) {
+        c.kind = CHILD_TIP;
+        c.idx = e->leaf_slot[ch];
+      } else if (all_keep) {
+        c.kind = CHILD_KEEP;
+        c.idx = e->internal_idx[ch];
+      } else if (slot_of[ch] >= 0) {
+        c.kind = CHILD_SLOT;
+        c.idx = slot_of[ch];
+      } else {
+        c.kind = CHILD_REG;
+        c.idx = 0;
+      }
+      pr.childs.push_back(c);
+    }
+    for (int ch : internal)
+      if (slot_of[ch] >= 0) {
+        free_slots.push_back(slot_of[ch]);
+        slot_of[ch] = -1;
+      }
+    op_of[n] = (int)pr.ops.size();
+    pr.ops.push_back(op);
+  };
+  if (e->leaf_slot[e->root] < 0) emit(e->root);
+  pr.nslots = next_slot;
+}
+
+static int upload_program(bppgpu_engine* e, Program& pr) {
+  BPP_CUDA(dev_alloc(e, &pr.d_ops, pr.ops.size()));
+  BPP_CUDA(dev_alloc(e, &pr.d_childs, pr.childs.size()));
+  if (!pr.ops.empty())
+    BPP_CUDA(cudaMemcpy(pr.d_ops, pr.ops.data(), pr.ops.size() * sizeof(Op), cudaMemcpyHostToDevice));
+  if (!pr.childs.empty())
+    BPP_CUDA(cudaMemcpy(pr.d_childs, pr.childs.data(), pr.childs.size() * sizeof(Child), cudaMemcpyHostToDevice));
+  return BPPGPU_OK;
+}
+
+static int check_device(int device) {
+  int n = 0;
+  cudaError_t r = cudaGetDeviceCount(&n);
+  if (r != cudaSuccess || n == 0)
+    BPP_FAIL(BPPGPU_E_CUDA, "no usable CUDA device (%s); libbppgpu has no CPU fallback",
+             r == cudaSuccess ? "device count is 0" : cudaGetErrorString(r));
+  if (device < 0 || device >= n) BPP_FAIL(BPPGPU_E_INVALID, "device %d out of range (0..%d)", device, n - 1);
+  BPP_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  BPP_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10) BPP_FAIL(BPPGPU_E_CUDA, "device %d is sm_%d%d; libbppgpu is built for sm_100a only", device, prop.major, prop.minor);
+  g_sm_count = prop.multiProcessorCount;
+  return BPPGPU_OK;
+}
+
+// ---- model upload -------------------------------------------------------------------
+static void free_model(DevModel& m) {
+  cudaFree(m.V); cudaFree(m.Vinv); cudaFree(m.re); cudaFree(m.im); cudaFree(m.Q); cudaFree(m.Q2); cudaFree(m.role);
+  m = DevModel{};
+}
+
+static int upload_model(DevModel& dm, const bppgpu_model_desc* m, int S) {
+  free_model(dm);
+  const size_t SS = (size_t)S * S;
+  const bool eigen = (m->flags & BPPGPU_MODEL_NONSINGULAR) != 0;
+  if (eigen && (!m->right_eigen || !m->left_eigen || !m->eigen_re))
+    BPP_FAIL(BPPGPU_E_INVALID, "model flagged NONSINGULAR needs right_eigen, left_eigen and eigen_re");
+  if (!eigen && !m->generator) BPP_FAIL(BPPGPU_E_INVALID, "singular model needs its generator");
+  if ((m->flags & BPPGPU_MODEL_CHR_DERIV) && !m->generator)
+    BPP_FAIL(BPPGPU_E_INVALID, "BPPGPU_MODEL_CHR_DERIV needs the generator");
+  dm.flags = m->flags;
+  dm.rate = m->rate;
+  dm.eps = m->taylor_epsilon > 0 ? m->taylor_epsilon : 1e-4;
+  if (eigen) {
+    BPP_CUDA(cudaMalloc(&dm.V, SS * 8));
+    BPP_CUDA(cudaMalloc(&dm.Vinv, SS * 8));
+    BPP_CUDA(cudaMalloc(&dm.re, S * 8));
+    BPP_CUDA(cudaMalloc(&dm.im, S * 8));
+    BPP_CUDA(cudaMalloc(&dm.role, S * 4));
+    BPP_CUDA(cudaMemcpy(dm.V, m->right_eigen, SS * 8, cudaMemcpyHostToDevice));
+    BPP_CUDA(cudaMemcpy(dm.Vinv, m->left_eigen, SS * 8, cudaMemcpyHostToDevice));
+    BPP_CUDA(cudaMemcpy(dm.re, m->eigen_re, S * 8, cudaMemcpyHostToDevice));
+    std::vector<double> im(S, 0.0);
+    std::vector<int> role(S, 0);
+    if (m->eigen_im) {
+      for (int k = 0; k < S; ++k) im[k] = m->eigen_im[k];
+      // conjugate pairs are adjacent, the +im member first (JAMA EigenValue convention,
+      // AbstractSubstitutionModel.cpp:438-468 walks them the same way)
+      for (int k = 0; k < S; ++k) {
+        if (im[k] != 0.0 && role[k] == 0) {
+          if (k + 1 >= S || im[k + 1] == 0.0) BPP_FAIL(BPPGPU_E_INVALID, "unpaired complex eigenvalue at index %d", k);
+          role[k] = 1;
+          role[k + 1] = 2;
+          dm.has_complex = 1;
+        }
+      }
+    }
+    BPP_CUDA(cudaMemcpy(dm.im, im.data(), S * 8, cudaMemcpyHostToDevice));
+    BPP_CUDA(cudaMemcpy(dm.role, role.data(), S * 4, cudaMemcpyHostToDevice));
+  }
+  if (m->generator) {
+    BPP_CUDA(cudaMalloc(&dm.Q, SS * 8));
+    BPP_CUDA(cudaMalloc(&dm.Q2, SS * 8));
+    BPP_CUDA(cudaMemcpy(dm.Q, m->generator, SS * 8, cudaMemcpyHostToDevice));
+    std::vector<double> q2(SS, 0.0);
+    double l1 = 0.0;
+    for (int i = 0; i < S; ++i)
+      for (int k = 0; k < S; ++k) {
+        const double a = m->generator[(size_t)i * S + k];
+        l1 += std::fabs(a);
+        if (a == 0.0) continue;
+        for (int j = 0; j < S; ++j) q2[(size_t)i * S + j] += a * m->generator[(size_t)k * S + j];
+      }
+    dm.q_l1 = l1;
+    BPP_CUDA(cudaMemcpy(dm.Q2, q2.data(), SS * 8, cudaMemcpyHostToDevice));
+  }
+  dm.set = true;
+  return BPPGPU_OK;
+}
+
+static ModelDev to_dev(const DevModel& m) {
+  ModelDev d{};
+  d.V = m.V; d.Vinv = m.Vinv; d.re = m.re; d.im = m.im; d.role = m.role; d.Q = m.Q; d.Q2 = m.Q2;
+  d.rate = m.rate; d.eps = m.eps; d.q_l1 = m.q_l1; d.flags = m.flags; d.has_complex = m.has_complex;
+  return d;
+}
+
+// enqueue K1 for `npts` points starting at `p0` (tables indexed from 0 within the chunk)
+static int launch_pt(cudaStream_t st, const ModelDev* d_models, bool any_series, bool any_chr_deriv,
+                     const int* d_branch_model, const double* d_brlen, const double* d_rates, int S, int C,
+                     int nn, int root, int npts, unsigned want, double* P, double* dP, double* d2P,
+                     double* scratch, int* d_status, long long* launches) {
+  PtParams pp{};
+  pp.models = d_models;
+  pp.branch_model = d_branch_model;
+  pp.brlen = d_brlen;
+  pp.rates = d_rates;
+  pp.S = S; pp.C = C; pp.nn = nn; pp.root = root;
+  pp.want = want;
+  pp.P = P; pp.dP = dP; pp.d2P = d2P;
+  pp.Pun = any_chr_deriv && (want & 6u) ? scratch : nullptr;
+  const int nmat = npts * nn * C;
+  if (nmat == 0) return BPPGPU_OK;
+  const int threads = S * S >= 256 ? 256 : (S * S >= 64 ? 64 : 32);
+  pt_eigen_kernel<<<nmat, threads, 6 * S * sizeof(double), st>>>(pp);
+  ++*launches;
+  if (any_chr_deriv && (want & 6u)) {
+    SeriesParams sp{};
+    sp.pt = pp;
+    sp.scratch = scratch;
+    sp.status = d_status;
+    pt_chr_deriv_kernel<<<nmat, threads, 0, st>>>(sp);
+    ++*launches;
+  }
+  if (any_series) {
+    SeriesParams sp{};
+    sp.pt = pp;
+    sp.scratch = scratch;
+    sp.status = d_status;
+    pt_series_kernel<<<nmat, threads, 0, st>>>(sp);
+    ++*launches;
+  }
+  BPP_CUDA(cudaGetLastError());
+  return BPPGPU_OK;
+}
+
+}  // namespace bppgpu
+
+using namespace bppgpu;
+
+// =====================================================================================
+// (C linkage comes from the declarations in include/bppgpu.h)
+
+const char* bppgpu_last_error(void) { return last_error().c_str(); }
+int bppgpu_abi_version(void) { return 1; }
+
+int bppgpu_device_count(int* n) {
+  if (!n) BPP_FAIL(BPPGPU_E_INVALID, "null argument");
+  int c = 0;
+  cudaError_t r = cudaGetDeviceCount(&c);
+  if (r != cudaSuccess) {
+    *n = 0;
+    cudaGetLastError();
+    return BPPGPU_OK;
+  }
+  *n = c;
+  return BPPGPU_OK;
+}
+
+// ---- Interface 1 ----------------------------------------------------------------------
+int bppgpu_pt_batch(int device, const bppgpu_model_desc* model, int64_t n_t, const double* t, unsigned want,
+                    double* P, double* dP, double* d2P) {
+  if (!model || !t || n_t < 0) BPP_FAIL(BPPGPU_E_INVALID, "null model / t or negative n_t");
+  const int S = model->n_states;
+  if (S <= 0) BPP_FAIL(BPPGPU_E_INVALID, "n_states must be positive");
+  if (((want & 1u) && !P) || ((want & 2u) && !dP) || ((want & 4u) && !d2P))
+    BPP_FAIL(BPPGPU_E_INVALID, "output pointer missing for a requested table");
+  int rc = check_device(device);
+  if (rc) return rc;
+  if (n_t == 0) return BPPGPU_OK;
+  DevModel dm;
+  rc = upload_model(dm, model, S);
+  if (rc) { free_model(dm); return rc; }
+  ModelDev md = to_dev(dm);
+  const size_t SS = (size_t)S * S;
+  ModelDev* d_md = nullptr;
+  int* d_bm = nullptr;
+  double *d_t = nullptr, *d_r = nullptr, *dPm = nullptr, *ddP = nullptr, *dd2P = nullptr, *scr = nullptr;
+  int* d_status = nullptr;
+  const bool series = !(model->flags & BPPGPU_MODEL_NONSINGULAR);
+  const bool chrd = (model->flags & BPPGPU_MODEL_CHR_DERIV) && !series;
+  auto cleanup = [&]() {
+    cudaFree(d_md); cudaFree(d_bm); cudaFree(d_t); cudaFree(d_r); cudaFree(dPm); cudaFree(ddP); cudaFree(dd2P);
+    cudaFree(scr); cudaFree(d_status);
+    free_model(dm);
+  };
+#define PT_CUDA(x)                                                                      \
+  do {                                                                                  \
+    cudaError_t _e = (x);                                                               \
+    if (_e != cudaSuccess) {                                                            \
+      cleanup();                                                                        \
+      BPP_FAIL(_e == cudaErrorMemoryAllocation ? BPPGPU_E_NOMEM : BPPGPU_E_CUDA, "CUDA error %s at %s:%d: %s", \
+               cudaGetErrorName(_e), __FILE__, __LINE__, cudaGetErrorString(_e));      \
+    }                                                                                   \
+  } while (0)
+  PT_CUDA(cudaMalloc(&d_md, sizeof(ModelDev)));
+  PT_CUDA(cudaMemcpy(d_md, &md, sizeof(ModelDev), cudaMemcpyHostToDevice));
+  PT_CUDA(cudaMalloc(&d_bm, n_t * sizeof(int)));
+  PT_CUDA(cudaMemset(d_bm, 0, n_t * sizeof(int)));
+  PT_CUDA(cudaMalloc(&d_t, n_t * 8));
+  PT_CUDA(cudaMemcpy(d_t, t, n_t * 8, cudaMemcpyHostToDevice));
+  const double one = 1.0;
+  PT_CUDA(cudaMalloc(&d_r, 8));
+  PT_CUDA(cudaMemcpy(d_r, &one, 8, cudaMemcpyHostToDevice));
+  PT_CUDA(cudaMalloc(&d_status, 4));
+  PT_CUDA(cudaMemset(d_status, 0, 4));
+  if (want & 1u) PT_CUDA(cudaMalloc(&dPm, n_t * SS * 8));
+  if (want & 2u) PT_CUDA(cudaMalloc(&ddP, n_t * SS * 8));
+  if (want & 4u) PT_CUDA(cudaMalloc(&dd2P, n_t * SS * 8));
+  if (series) PT_CUDA(cudaMalloc(&scr, n_t * 4 * SS * 8));
+  else if (chrd) PT_CUDA(cudaMalloc(&scr, n_t * SS * 8));
+  long long launches = 0;
+  rc = launch_pt(nullptr, d_md, series, chrd, d_bm, d_t, d_r, S, 1, (int)n_t, -1, 1, want, dPm, ddP, dd2P, scr,
+                 d_status, &launches);
+  if (rc) { cleanup(); return rc; }
+  PT_CUDA(cudaDeviceSynchronize());
+  if (want & 1u) PT_CUDA(cudaMemcpy(P, dPm, n_t * SS * 8, cudaMemcpyDeviceToHost));
+  if (want & 2u) PT_CUDA(cudaMemcpy(dP, ddP, n_t * SS * 8, cudaMemcpyDeviceToHost));
+  if (want & 4u) PT_CUDA(cudaMemcpy(d2P, dd2P, n_t * SS * 8, cudaMemcpyDeviceToHost));
+  int status = 0;
+  PT_CUDA(cudaMemcpy(&status, d_status, 4, cudaMemcpyDeviceToHost));
+  cleanup();
+#undef PT_CUDA
+  if (status) BPP_FAIL(BPPGPU_E_NUMERIC, "ChromosomeSubstitutionModel: Taylor series did not reach convergence!");
+  return BPPGPU_OK;
+}
+
+// ---- Interface 2 ----------------------------------------------------------------------
+int bppgpu_destroy(bppgpu_engine* e) {
+  if (!e) return BPPGPU_OK;
+  cudaSetDevice(e->dev);
+  if (e->stream) cudaStreamSynchronize(e->stream);
+  void* ptrs[] = {e->d_codes, e->d_code_table, e->d_weights, e->d_rates, e->d_probs, e->d_rootfreq,
+                  e->d_rootfreq_used, e->d_brlen, e->d_branch_model, e->d_leaf_nodes, e->d_models, e->d_P, e->d_dP,
+                  e->d_d2P, e->d_tiptab, e->d_keep, e->d_keep_exp, e->d_gstack, e->d_gstack_exp, e->d_upper,
+                  e->d_upper_exp, e->d_SR, e->d_rexp, e->d_site_lnl, e->d_partials, e->d_partials2, e->d_out,
+                  e->prog.d_ops, e->prog.d_childs, e->gprog.d_ops, e->gprog.d_childs, e->d_sibs, e->d_scratch,
+                  e->d_status};
+  for (void* p : ptrs) cudaFree(p);
+  for (auto& m : e->models) free_model(m);
+  if (e->ev0) cudaEventDestroy(e->ev0);
+  if (e->ev1) cudaEventDestroy(e->ev1);
+  if (e->ev2) cudaEventDestroy(e->ev2);
+  if (e->ev3) cudaEventDestroy(e->ev3);
+  if (e->stream) cudaStreamDestroy(e->stream);
+  delete e;
+  return BPPGPU_OK;
+}
+
+static int create_impl(const bppgpu_config* cfg, bppgpu_engine* e) {
+  e->dev = cfg->device;
+  e->S = cfg->n_states; e->C = cfg->n_cats; e->N = cfg->n_patterns; e->nn = cfg->n_nodes; e->root = cfg->root;
+  e->npoints = cfg->n_points; e->nmodels = cfg->n_models; e->ncodes = cfg->n_codes; e->code_bytes = cfg->code_bytes;
+  e->flags = cfg->flags;
+  e->keep = (cfg->flags & BPPGPU_FLAG_KEEP_CLVS) != 0;
+  const int nn = e->nn, S = e->S, C = e->C;
+  const long long N = e->N;
+  e->child_off.assign(cfg->child_offsets, cfg->child_offsets + nn + 1);
+  if (e->child_off[0] != 0) BPP_FAIL(BPPGPU_E_INVALID, "child_offsets[0] must be 0");
+  for (int i = 0; i < nn; ++i)
+    if (e->child_off[i + 1] < e->child_off[i]) BPP_FAIL(BPPGPU_E_INVALID, "child_offsets must be non-decreasing");
+  e->children.assign(cfg->children, cfg->children + e->child_off[nn]);
+  e->parent.assign(nn, -1);
+  for (int n = 0; n < nn; ++n)
+    for (int k = e->child_off[n]; k < e->child_off[n + 1]; ++k) {
+      int ch = e->children[k];
+      if (ch < 0 || ch >= nn || ch == e->root) BPP_FAIL(BPPGPU_E_INVALID, "bad child id %d of node %d", ch, n);
+      if (e->parent[ch] != -1) BPP_FAIL(BPPGPU_E_INVALID, "node %d has two fathers", ch);
+      e->parent[ch] = n;
+    }
+  for (int n = 0; n < nn; ++n)
+    if (n != e->root && e->parent[n] < 0) BPP_FAIL(BPPGPU_E_INVALID, "node %d is not connected to the root", n);
+  e->leaf_slot.assign(nn, -1);
+  e->internal_idx.assign(nn, -1);
+  for (int n = 0; n < nn; ++n) {
+    if (e->child_off[n + 1] == e->child_off[n]) {
+      e->leaf_slot[n] = e->nl++;
+      e->leaf_nodes.push_back(n);
+    } else {
+      e->internal_idx[n] = e->ni++;
+    }
+  }
+  if (e->leaf_slot[e->root] >= 0) BPP_FAIL(BPPGPU_E_INVALID, "the root must have sons");
+  // pre-order (fathers first), cycle check
+  {
+    std::vector<int> st{e->root};
+    while (!st.empty()) {
+      int n = st.back();
+      st.pop_back();
+      e->preorder.push_back(n);
+      for (int k = e->child_off[n + 1] - 1; k >= e->child_off[n]; --k) st.push_back(e->children[k]);
+    }
+    if ((int)e->preorder.size() != nn) BPP_FAIL(BPPGPU_E_INVALID, "topology is not a tree");
+  }
+  BPP_CUDA(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+  BPP_CUDA(cudaEventCreate(&e->ev0));
+  BPP_CUDA(cudaEventCreate(&e->ev1));
+  BPP_CUDA(cudaEventCreate(&e->ev2));
+  BPP_CUDA(cudaEventCreate(&e->ev3));
+
+  // ---- path selection ---------------------------------------------------------------
+  build_program(e, e->prog, false);
+  build_program(e, e->gprog, true);
+  const bool cpow = is_pow2(C) && C <= 8;
+  if (S == 4 && cpow && (size_t)e->prog.nslots * kWalkThreads * 36 <= 200 * 1024) e->path = PATH_WALK4;
+  else if (S == 20 && cpow) e->path = PATH_WALKS;
+  else e->path = PATH_GENERIC;
+  if (cfg->flags & BPPGPU_FLAG_FORCE_GENERIC) e->path = PATH_GENERIC;
+  if (e->path == PATH_GENERIC) e->keep = true;
+  if (e->keep) {
+    // the walk program must stream every node out
+    build_program(e, e->prog, false);
+  }
+  int rc = upload_program(e, e->prog);
+  if (rc) return rc;
+  rc = upload_program(e, e->gprog);
+  if (rc) return rc;
+  // siblings per node (generic kinds) for the prefix pass
+  e->sib_off.assign(nn + 1, 0);
+  std::vector<Child> allsibs;
+  for (int n = 0; n < nn; ++n) {
+    e->sib_off[n] = (int)allsibs.size();
+    if (n == e->root) continue;
+    int f = e->parent[n];
+    for (int k = e->child_off[f]; k < e->child_off[f + 1]; ++k) {
+      int b = e->children[k];
+      if (b == n) continue;
+      Child c{};
+      c.pnode = b;
+      if (e->leaf_slot[b] >= 0) { c.kind = CHILD_TIP; c.idx = e->leaf_slot[b]; }
+      else { c.kind = CHILD_KEEP; c.idx = e->internal_idx[b]; }
+      allsibs.push_back(c);
+    }
+  }
+  e->sib_off[nn] = (int)allsibs.size();
+  BPP_CUDA(dev_alloc(e, &e->d_sibs, allsibs.size()));
+  if (!allsibs.empty())
+    BPP_CUDA(cudaMemcpy(e->d_sibs, allsibs.data(), allsibs.size() * sizeof(Child), cudaMemcpyHostToDevice));
+
+  // ---- buffers ------------------------------------------------------------------------
+  const size_t SS = (size_t)S * S;
+  BPP_CUDA(dev_alloc(e, (unsigned char**)&e->d_codes, (size_t)e->nl * N * e->code_bytes));
+  BPP_CUDA(cudaMemset(e->d_codes, 0, std::max<size_t>(1, (size_t)e->nl * N * e->code_bytes)));
+  BPP_CUDA(dev_alloc(e, &e->d_code_table, (size_t)e->ncodes * S));
+  BPP_CUDA(cudaMemcpy(e->d_code_table, cfg->code_table, (size_t)e->ncodes * S * 8, cudaMemcpyHostToDevice));
+  BPP_CUDA(dev_alloc(e, &e->d_weights, (size_t)N));
+  BPP_CUDA(dev_alloc(e, &e->d_rates, (size_t)C));
+  BPP_CUDA(dev_alloc(e, &e->d_probs, (size_t)C));
+  BPP_CUDA(dev_alloc(e, &e->d_rootfreq, (size_t)e->npoints * S));
+  BPP_CUDA(dev_alloc(e, &e->d_rootfreq_used, (size_t)e->npoints * S));
+  BPP_CUDA(dev_alloc(e, &e->d_brlen, (size_t)e->npoints * nn));
+  BPP_CUDA(cudaMemset(e->d_brlen, 0, (size_t)e->npoints * nn * 8));
+  BPP_CUDA(dev_alloc(e, &e->d_branch_model, (size_t)e->npoints * nn));
+  BPP_CUDA(dev_alloc(e, &e->d_leaf_nodes, (size_t)e->nl));
+  BPP_CUDA(cudaMemcpy(e->d_leaf_nodes, e->leaf_nodes.data(), e->nl * sizeof(int), cudaMemcpyHostToDevice));
+  e->models.resize(e->nmodels);
+  BPP_CUDA(dev_alloc(e, &e->d_models, (size_t)e->nmodels));
+  e->h_brlen.assign((size_t)e->npoints * nn, 0.0);
+  e->h_branch_model.assign((size_t)e->npoints * nn, 0);
+  if (e->nmodels == e->npoints && e->npoints > 1)
+    for (int p = 0; p < e->npoints; ++p)
+      for (int n = 0; n < nn; ++n) e->h_branch_model[(size_t)p * nn + n] = p;
+  BPP_CUDA(cudaMemcpy(e->d_branch_model, e->h_branch_model.data(), e->h_branch_model.size() * sizeof(int),
+                      cudaMemcpyHostToDevice));
+  e->have_tip.assign(e->nl, 0);
+  e->have_brlen.assign(e->npoints, 0);
+  e->have_rootfreq.assign(e->npoints, 0);
+
+  // P tables: as many points per chunk as fit a 16 GiB budget
+  const size_t per_point = (size_t)nn * C * SS * 8;
+  size_t budget = (size_t)16 << 30;
+  e->pchunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)e->npoints, budget / std::max<size_t>(1, 3 * per_point)));
+  BPP_CUDA(dev_alloc(e, &e->d_P, (size_t)e->pchunk * nn * C * SS));
+  BPP_CUDA(dev_alloc(e, &e->d_tiptab, (size_t)e->pchunk * e->nl * C * e->ncodes * S));
+
+  const size_t clv = (size_t)N * C * S;
+  if (e->keep) {
+    BPP_CUDA(dev_alloc(e, &e->d_keep, (size_t)e->ni * clv));
+    BPP_CUDA(dev_alloc(e, &e->d_keep_exp, (size_t)e->ni * N));
+  }
+  if (e->path == PATH_WALKS && e->prog.nslots > 0) {
+    BPP_CUDA(dev_alloc(e, &e->d_gstack, (size_t)e->prog.nslots * clv));
+    BPP_CUDA(dev_alloc(e, &e->d_gstack_exp, (size_t)e->prog.nslots * N));
+  }
+  BPP_CUDA(dev_alloc(e, &e->d_SR, (size_t)N));
+  BPP_CUDA(dev_alloc(e, &e->d_rexp, (size_t)N));
+  BPP_CUDA(dev_alloc(e, &e->d_site_lnl, (size_t)e->npoints * N));
+  const long long rows = N * C;
+  e->n_partials = (int)std::max<long long>(1, std::max((rows + kWalkThreads - 1) / kWalkThreads, (N + 255) / 256));
+  BPP_CUDA(dev_alloc(e, &e->d_partials, (size_t)e->n_partials));
+  BPP_CUDA(dev_alloc(e, &e->d_partials2, (size_t)e->n_partials));
+  BPP_CUDA(dev_alloc(e, &e->d_out, (size_t)e->npoints * (1 + 2 * nn)));
+  BPP_CUDA(cudaMemset(e->d_out, 0, (size_t)e->npoints * (1 + 2 * nn) * 8));
+  BPP_CUDA(dev_alloc(e, &e->d_status, 1));
+  BPP_CUDA(cudaMemset(e->d_status, 0, sizeof(int)));
+
+  if (e->path == PATH_WALK4) {
+    size_t smem = (size_t)e->prog.nslots * kWalkThreads * 36;
+    switch (ilog2(C)) {
+      case 0: BPP_CUDA(cudaFuncSetAttribute(walk4_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); break;
+      case 1: BPP_CUDA(cudaFuncSetAttribute(walk4_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); break;
+      case 2: BPP_CUDA(cudaFuncSetAttribute(walk4_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); break;
+      default: BPP_CUDA(cudaFuncSetAttribute(walk4_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); break;
+    }
+  }
+  if (e->path == PATH_WALKS) {
+    size_t smem = (size_t)kMaxStagedChildren * C * (S * S + 2) * 8;
+    switch (ilog2(C)) {
+      case 0: BPP_CUDA(cudaFuncSetAttribute(walkS_kernel<20, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); break;
+      case 1: BPP_CUDA(cudaFuncSetAttribute(walkS_kernel<20, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); break;
+      case 2: BPP_CUDA(cudaFuncSetAttribute(walkS_kernel<20, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); break;
+      default: BPP_CUDA(cudaFuncSetAttribute(walkS_kernel<20, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); break;
+    }
+  }
+  e->stats.path = e->path;
+  e->stats.stack_slots = e->prog.nslots;
+  e->stats.hbm_bytes_resident = (int64_t)e->bytes_resident;
+  return BPPGPU_OK;
+}
+
+int bppgpu_create(const bppgpu_config* cfg, bppgpu_engine** out) {
+  if (!cfg || !out) BPP_FAIL(BPPGPU_E_INVALID, "null argument");
+  *out = nullptr;
+  if (cfg->n_states <= 0 || cfg->n_cats <= 0 || cfg->n_patterns < 0 || cfg->n_nodes <= 1 || cfg->n_points <= 0 ||
+      cfg->n_models <= 0 || cfg->n_codes <= 0)
+    BPP_FAIL(BPPGPU_E_INVALID, "non-positive dimension in bppgpu_config");
+  if (cfg->root < 0 || cfg->root >= cfg->n_nodes) BPP_FAIL(BPPGPU_E_INVALID, "root id out of range");
+  if (cfg->code_bytes != 1 && cfg->code_bytes != 2) BPP_FAIL(BPPGPU_E_INVALID, "code_bytes must be 1 or 2");
+  if (cfg->code_bytes == 1 && cfg->n_codes > 256) BPP_FAIL(BPPGPU_E_INVALID, "n_codes > 256 needs code_bytes = 2");
+  if (!cfg->child_offsets || !cfg->children || !cfg->code_table) BPP_FAIL(BPPGPU_E_INVALID, "null array in bppgpu_config");
+  int rc = check_device(cfg->device);
+  if (rc) return rc;
+  bppgpu_engine* e = new bppgpu_engine();
+  rc = create_impl(cfg, e);
+  if (rc) {
+    std::string msg = last_error();
+    bppgpu_destroy(e);
+    last_error() = msg;
+    return rc;
+  }
+  *out = e;
+  return BPPGPU_OK;
+}
+
+#define ENGINE_ENTER(e)                                                \
+  if (!(e)) BPP_FAIL(BPPGPU_E_INVALID, "null engine");                 \
+  BPP_CUDA(cudaSetDevice((e)->dev));
+
+int bppgpu_set_tip_codes(bppgpu_engine* e, int32_t node, const void* codes) {
+  ENGINE_ENTER(e);
+  if (node < 0 || node >= e->nn || e->leaf_slot[node] < 0) BPP_FAIL(BPPGPU_E_INVALID, "node %d is not a leaf", node);
+  if (!codes) BPP_FAIL(BPPGPU_E_INVALID, "null codes");
+  const size_t bytes = (size_t)e->N * e->code_bytes;
+  BPP_CUDA(cudaMemcpyAsync((unsigned char*)e->d_codes + (size_t)e->leaf_slot[node] * bytes, codes, bytes,
+                           cudaMemcpyHostToDevice, e->stream));
+  BPP_CUDA(cudaStreamSynchronize(e->stream));
+  e->have_tip[e->leaf_slot[node]] = 1;
+  e->last_point = -1;
+  return BPPGPU_OK;
+}
+
+int bppgpu_set_all_tip_codes(bppgpu_engine* e, const void* codes) {
+  ENGINE_ENTER(e);
+  if (!codes) BPP_FAIL(BPPGPU_E_INVALID, "null codes");
+  const size_t bytes = (size_t)e->N * e->code_bytes * e->nl;
+  BPP_CUDA(cudaMemcpyAsync(e->d_codes, codes, bytes, cudaMemcpyHostToDevice, e->stream));
+  BPP_CUDA(cudaStreamSynchronize(e->stream));
+  std::fill(e->have_tip.begin(), e->have_tip.end(), 1);
+  e->last_point = -1;
+  return BPPGPU_OK;
+}
+
+int bppgpu_leaf_slot(bppgpu_engine* e, int32_t node, int32_t* slot) {
+  if (!e || !slot) BPP_FAIL(BPPGPU_E_INVALID, "null argument");
+  if (node < 0 || node >= e->nn) BPP_FAIL(BPPGPU_E_INVALID, "node out of range");
+  *slot = e->leaf_slot[node];
+  return BPPGPU_OK;
+}
+
+int bppgpu_set_pattern_weights(bppgpu_engine* e, const uint32_t* w) {
+  ENGINE_ENTER(e);
+  if (!w && e->N > 0) BPP_FAIL(BPPGPU_E_INVALID, "null weights");
+  std::vector<double> wd((size_t)e->N);
+  for (long long i = 0; i < e->N; ++i) wd[i] = (double)w[i];
+  BPP_CUDA(cudaMemcpy(e->d_weights, wd.data(), (size_t)e->N * 8, cudaMemcpyHostToDevice));
+  e->have_weights = true;
+  e->last_point = -1;
+  return BPPGPU_OK;
+}
+
+int bppgpu_set_rates(bppgpu_engine* e, const double* rates, const double* probs) {
+  ENGINE_ENTER(e);
+  if (!rates || !probs) BPP_FAIL(BPPGPU_E_INVALID, "null rates / probs");
+  e->h_rates.assign(rates, rates + e->C);
+  e->h_probs.assign(probs, probs + e->C);
+  BPP_CUDA(cudaMemcpy(e->d_rates, rates, e->C * 8, cudaMemcpyHostToDevice));
+  BPP_CUDA(cudaMemcpy(e->d_probs, probs, e->C * 8, cudaMemcpyHostToDevice));
+  e->have_rates = true;
+  e->last_point = -1;
+  return BPPGPU_OK;
+}
+
+int bppgpu_set_model(bppgpu_engine* e, int32_t slot, const bppgpu_model_desc* m) {
+  ENGINE_ENTER(e);
+  if (!m) BPP_FAIL(BPPGPU_E_INVALID, "null model");
+  if (slot < 0 || slot >= e->nmodels) BPP_FAIL(BPPGPU_E_INVALID, "model slot %d out of range", slot);
+  if (m->n_states != e->S) BPP_FAIL(BPPGPU_E_INVALID, "model has %d states, engine %d", m->n_states, e->S);
+  BPP_CUDA(cudaStreamSynchronize(e->stream));
+  int rc = upload_model(e->models[slot], m, e->S);
+  if (rc) return rc;
+  e->models_dirty = true;
+  e->last_point = -1;
+  return BPPGPU_OK;
+}
+
+int bppgpu_set_branch_models(bppgpu_engine* e, int32_t point, const int32_t* slot_of_node) {
+  ENGINE_ENTER(e);
+  if (point < 0 || point >= e->npoints || !slot_of_node) BPP_FAIL(BPPGPU_E_INVALID, "bad point or null array");
+  for (int n = 0; n < e->nn; ++n) {
+    if (n != e->root && (slot_of_node[n] < 0 || slot_of_node[n] >= e->nmodels))
+      BPP_FAIL(BPPGPU_E_INVALID, "model slot %d of node %d out of range", slot_of_node[n], n);
+    e->h_branch_model[(size_t)point * e->nn + n] = n == e->root ? 0 : slot_of_node[n];
+  }
+  BPP_CUDA(cudaMemcpy(e->d_branch_model + (size_t)point * e->nn, &e->h_branch_model[(size_t)point * e->nn],
+                      e->nn * sizeof(int), cudaMemcpyHostToDevice));
+  e->last_point = -1;
+  return BPPGPU_OK;
+}
+
+int bppgpu_set_branch_lengths(bppgpu_engine* e, int32_t point, const double* t) {
+  ENGINE_ENTER(e);
+  if (point < 0 || point >= e->npoints || !t) BPP_FAIL(BPPGPU_E_INVALID, "bad point or null array");
+  std::copy(t, t + e->nn, e->h_brlen.begin() + (size_t)point * e->nn);
+  BPP_CUDA(cudaMemcpyAsync(e->d_brlen + (size_t)point * e->nn, t, e->nn * 8, cudaMemcpyHostToDevice, e->stream));
+  BPP_CUDA(cudaStreamSynchronize(e->stream));
+  e->have_brlen[point] = 1;
+  e->last_point = -1;
+  return BPPGPU_OK;
+}
+
+int bppgpu_set_root_freqs(bppgpu_engine* e, int32_t point, const double* pi) {
+  ENGINE_ENTER(e);
+  if (point < 0 || point >= e->npoints || !pi) BPP_FAIL(BPPGPU_E_INVALID, "bad point or null array");
+  BPP_CUDA(cudaMemcpyAsync(e->d_rootfreq + (size_t)point * e->S, pi, e->S * 8, cudaMemcpyHostToDevice, e->stream));
+  BPP_CUDA(cudaStreamSynchronize(e->stream));
+  e->have_rootfreq[point] = 1;
+  e->last_point = -1;
+  return BPPGPU_OK;
+}
+
+// ---- evaluation ---------------------------------------------------------------------------
+static int check_ready(bppgpu_engine* e) {
+  if (!e->have_weights) BPP_FAIL(BPPGPU_E_STATE, "pattern weights not set");
+  if (!e->have_rates) BPP_FAIL(BPPGPU_E_STATE, "rate classes not set");
+  for (int l = 0; l < e->nl; ++l)
+    if (!e->have_tip[l]) BPP_FAIL(BPPGPU_E_STATE, "tip codes of leaf node %d not set", e->leaf_nodes[l]);
+  for (int p = 0; p < e->npoints; ++p) {
+    if (!e->have_brlen[p]) BPP_FAIL(BPPGPU_E_STATE, "branch lengths of point %d not set", p);
+    if (!e->have_rootfreq[p] && !(e->flags & BPPGPU_FLAG_WEIGHTED_ROOT))
+      BPP_FAIL(BPPGPU_E_STATE, "root frequencies of point %d not set", p);
+  }
+  std::vector<char> used(e->nmodels, 0);
+  for (int p = 0; p < e->npoints; ++p)
+    for (int n = 0; n < e->nn; ++n)
+      if (n != e->root) used[e->h_branch_model[(size_t)p * e->nn + n]] = 1;
+  for (int m = 0; m < e->nmodels; ++m)
+    if (used[m] && !e->models[m].set) BPP_FAIL(BPPGPU_E_STATE, "model slot %d is used by a branch but not set", m);
+  return BPPGPU_OK;
+}
+
+static int ensure_deriv_buffers(bppgpu_engine* e, unsigned want) {
+  const size_t tab = (size_t)e->pchunk * e->nn * e->C * e->S * e->S;
+  if ((want & (BPPGPU_EVAL_D1 | BPPGPU_EVAL_D2)) && !e->d_dP) BPP_CUDA(dev_alloc(e, &e->d_dP, tab));
+  if ((want & BPPGPU_EVAL_D2) && !e->d_d2P) BPP_CUDA(dev_alloc(e, &e->d_d2P, tab));
+  if ((want & (BPPGPU_EVAL_D1 | BPPGPU_EVAL_D2)) && !e->d_upper) {
+    const size_t clv = (size_t)e->N * e->C * e->S;
+    BPP_CUDA(dev_alloc(e, &e->d_upper, (size_t)e->nn * clv));
+    BPP_CUDA(dev_alloc(e, &e->d_upper_exp, (size_t)e->nn * e->N));
+  }
+  return BPPGPU_OK;
+}
+
+static int ensure_scratch(bppgpu_engine* e, bool series, bool chrd) {
+  if (!series && !chrd) return BPPGPU_OK;
+  const size_t need = (size_t)e->pchunk * e->nn * e->C * e->S * e->S * (series ? 4 : 1);
+  if (e->scratch_elems < need) {
+    BPP_CUDA(cudaStreamSynchronize(e->stream));
+    cudaFree(e->d_scratch);
+    e->d_scratch = nullptr;
+    BPP_CUDA(dev_alloc(e, &e->d_scratch, need));
+    e->scratch_elems = need;
+  }
+  return BPPGPU_OK;
+}
+
+template <int CL>
+static void launch_walk4(const WalkParams& wp, int grid, size_t smem, cudaStream_t st) {
+  walk4_kernel<CL><<<grid, kWalkThreads, smem, st>>>(wp);
+}
+template <int CL>
+static void launch_walkS20(const WalkParams& wp, int grid, size_t smem, cudaStream_t st) {
+  walkS_kernel<20, CL><<<grid, kWalkThreads, smem, st>>>(wp);
+}
+
+// pruning + root reduction of one point (tables of chunk-local index `pl`)
+static int enqueue_prune(bppgpu_engine* e, int point, int pl, cudaStream_t st) {
+  const int S = e->S, C = e->C, nn = e->nn;
+  const long long N = e->N;
+  const size_t SS = (size_t)S * S;
+  const double* P = e->d_P + (size_t)pl * nn * C * SS;
+  const double* tiptab = e->d_tiptab + (size_t)pl * e->nl * C * e->ncodes * S;
+  const double* rootfreq = e->d_rootfreq_used + (size_t)point * S;
+  double* site_lnl = e->d_site_lnl + (size_t)point * N;
+  double* out = e->d_out + (size_t)point * (1 + 2 * nn);
+  const unsigned rflag = (e->flags & BPPGPU_FLAG_R_SEMANTICS) ? 1u : 0u;
+  int nparts = 0;
+  if (N == 0) {
+    BPP_CUDA(cudaMemsetAsync(out, 0, 8, st));
+    return BPPGPU_OK;
+  }
+  if (e->path == PATH_WALK4 || e->path == PATH_WALKS) {
+    if (e->flags & BPPGPU_FLAG_WEIGHTED_ROOT)
+      BPP_FAIL(BPPGPU_E_INVALID, "BPPGPU_FLAG_WEIGHTED_ROOT is served by the generic path only");
+    WalkParams wp{};
+    wp.ops = e->prog.d_ops;
+    wp.childs = e->prog.d_childs;
+    wp.n_ops = (int)e->prog.ops.size();
+    wp.C = C;
+    wp.ncodes = e->ncodes;
+    wp.code_bytes = e->code_bytes;
+    wp.nslots = e->prog.nslots;
+    wp.flags = rflag;
+    wp.N = N;
+    wp.P = P;
+    wp.tiptab = tiptab;
+    wp.codes = e->d_codes;
+    wp.keep = e->d_keep;
+    wp.keep_exp = e->d_keep_exp;
+    wp.gstack = e->d_gstack;
+    wp.gstack_exp = e->d_gstack_exp;
+    wp.rootfreq = rootfreq;
+    wp.probs = e->d_probs;
+    wp.weights = e->d_weights;
+    wp.SR = e->d_SR;
+    wp.rexp = e->d_rexp;
+    wp.site_lnl = site_lnl;
+    wp.partials = e->d_partials;
+    const long long rows = N * C;
+    const int grid = (int)((rows + kWalkThreads - 1) / kWalkThreads);
+    nparts = grid;
+    const int cl = ilog2(C);
+    if (e->path == PATH_WALK4) {
+      const size_t smem = (size_t)e->prog.nslots * kWalkThreads * 36;
+      if (cl == 0) launch_walk4<0>(wp, grid, smem, st);
+      else if (cl == 1) launch_walk4<1>(wp, grid, smem, st);
+      else if (cl == 2) launch_walk4<2>(wp, grid, smem, st);
+      else launch_walk4<3>(wp, grid, smem, st);
+    } else {
+      const size_t smem = (size_t)kMaxStagedChildren * C * (S * S + 2) * 8;
+      if (cl == 0) launch_walkS20<0>(wp, grid, smem, st);
+      else if (cl == 1) launch_walkS20<1>(wp, grid, smem, st);
+      else if (cl == 2) launch_walkS20<2>(wp, grid, smem, st);
+      else launch_walkS20<3>(wp, grid, smem, st);
+    }
+    e->stats.kernel_launches++;
+  } else {
+    const long long total = N * C * S;
+    const int grid_e = (int)std::min<long long>((total + 255) / 256, (long long)g_sm_count * 32);
+    const int grid_p = (int)((N + 255) / 256);
+    for (const Op& op : e->gprog.ops) {
+      GenericParams gp{};
+      gp.childs = e->gprog.d_childs + op.child_begin;
+      gp.nchild = op.nchild;
+      gp.out_idx = op.keep_idx;
+      gp.S = S; gp.C = C; gp.ncodes = e->ncodes; gp.code_bytes = e->code_bytes;
+      gp.N = N;
+      gp.P = P; gp.tiptab = tiptab; gp.codes = e->d_codes;
+      gp.keep = e->d_keep; gp.keep_exp = e->d_keep_exp;
+      generic_node_kernel<<<grid_e, 256, 0, st>>>(gp);
+      generic_scale_kernel<<<grid_p, 256, 0, st>>>(gp);
+      e->stats.kernel_launches += 2;
+    }
+    const int ridx = e->internal_idx[e->root];
+    if (e->flags & BPPGPU_FLAG_WEIGHTED_ROOT) {
+      WeightedRootParams wr{};
+      wr.root_clv = e->d_keep + (size_t)ridx * N * C * S;
+      wr.root_exp = e->d_keep_exp + (size_t)ridx * N;
+      wr.S = S; wr.C = C; wr.N = N;
+      wr.probs = e->d_probs;
+      wr.out = e->d_rootfreq_used + (size_t)point * S;
+      weighted_root_kernel<<<1, 256, 0, st>>>(wr);
+      e->stats.kernel_launches++;
+    }
+    RootParams rp{};
+    rp.root_clv = e->d_keep + (size_t)ridx * N * C * S;
+    rp.root_exp = e->d_keep_exp + (size_t)ridx * N;
+    rp.S = S; rp.C = C; rp.flags = rflag; rp.N = N;
+    rp.rootfreq = rootfreq; rp.probs = e->d_probs; rp.weights = e->d_weights;
+    rp.SR = e->d_SR; rp.rexp = e->d_rexp; rp.site_lnl = site_lnl; rp.partials = e->d_partials;
+    generic_root_kernel<<<grid_p, 256, 0, st>>>(rp);
+    e->stats.kernel_launches++;
+    nparts = grid_p;
+  }
+  finalize_sum_kernel<<<1, 256, 0, st>>>(e->d_partials, nparts, out);
+  e->stats.kernel_launches++;
+  BPP_CUDA(cudaGetLastError());
+  long long upd = 0;
+  for (const Op& op : e->prog.ops) (void)op, upd += N * C * S;
+  e->stats.clv_updates += upd;
+  return BPPGPU_OK;
+}
+
+// prefix pass + derivatives for one point, generic kernels (lower CLVs must be resident)
+static int enqueue_derivs(bppgpu_engine* e, int point, int pl, unsigned want, cudaStream_t st) {
+  const int S = e->S, C = e->C, nn = e->nn;
+  const long long N = e->N;
+  const size_t SS = (size_t)S * S;
+  const size_t clv = (size_t)N * C * S;
+  const double* P = e->d_P + (size_t)pl * nn * C * SS;
+  const double* dP = e->d_dP + (size_t)pl * nn * C * SS;
+  const double* d2P = (want & BPPGPU_EVAL_D2) ? e->d_d2P + (size_t)pl * nn * C * SS : nullptr;
+  const double* tiptab = e->d_tiptab + (size_t)pl * e->nl * C * e->ncodes * S;
+  double* out = e->d_out + (size_t)point * (1 + 2 * nn);
+  if (N == 0) return BPPGPU_OK;
+  const long long total = N * C * S;
+  const int grid_e = (int)std::min<long long>((total + 255) / 256, (long long)g_sm_count * 32);
+  const int grid_p = (int)((N + 255) / 256);
+  for (int n : e->preorder) {
+    if (n == e->root) continue;
+    const int f = e->parent[n];
+    UpperParams up{};
+    up.sibs = e->d_sibs + e->sib_off[n];
+    up.nsib = e->sib_off[n + 1] - e->sib_off[n];
+    up.father = f == e->root ? -1 : f;
+    up.S = S; up.C = C; up.ncodes = e->ncodes; up.code_bytes = e->code_bytes;
+    up.N = N;
+    up.P = P; up.tiptab = tiptab; up.codes = e->d_codes;
+    up.keep = e->d_keep; up.keep_exp = e->d_keep_exp;
+    up.upper_f = e->d_upper + (size_t)f * clv;
+    up.uexp_f = e->d_upper_exp + (size_t)f * N;
+    up.rootfreq = e->d_rootfreq_used + (size_t)point * S;
+    up.upper_out = e->d_upper + (size_t)n * clv;
+    up.uexp_out = e->d_upper_exp + (size_t)n * N;
+    upper_node_kernel<<<grid_e, 256, 0, st>>>(up);
+    upper_scale_kernel<<<grid_p, 256, 0, st>>>(up);
+    DerivParams dp{};
+    dp.node = n;
+    dp.is_tip = e->leaf_slot[n] >= 0;
+    dp.idx = dp.is_tip ? e->leaf_slot[n] : e->internal_idx[n];
+    dp.S = S; dp.C = C; dp.code_bytes = e->code_bytes;
+    dp.nh_form = (e->flags & BPPGPU_FLAG_NH_DERIV) ? 1 : 0;
+    dp.want = want;
+    dp.N = N;
+    dp.P = P + (size_t)n * C * SS;
+    dp.dP = dP + (size_t)n * C * SS;
+    dp.d2P = d2P ? d2P + (size_t)n * C * SS : nullptr;
+    dp.code_table = e->d_code_table;
+    dp.codes = e->d_codes;
+    dp.keep = e->d_keep; dp.keep_exp = e->d_keep_exp;
+    dp.upper = up.upper_out; dp.uexp = up.uexp_out;
+    dp.SR = e->d_SR; dp.rexp = e->d_rexp;
+    dp.probs = e->d_probs; dp.weights = e->d_weights;
+    dp.part1 = e->d_partials; dp.part2 = e->d_partials2;
+    deriv_node_kernel<<<grid_p, 256, 0, st>>>(dp);
+    finalize_sum_kernel<<<1, 256, 0, st>>>(e->d_partials, grid_p, out + 1 + n);
+    finalize_sum_kernel<<<1, 256, 0, st>>>(e->d_partials2, grid_p, out + 1 + nn + n);
+    e->stats.kernel_launches += 5;
+  }
+  BPP_CUDA(cudaGetLastError());
+  return BPPGPU_OK;
+}
+
+static int eval_impl(bppgpu_engine* e, unsigned want, cudaStream_t st, bool timed) {
+  int rc = check_ready(e);
+  if (rc) return rc;
+  if (want == 0) want = BPPGPU_EVAL_LNL;
+  if (want & BPPGPU_EVAL_D2) want |= BPPGPU_EVAL_D1;
+  const bool derivs = (want & (BPPGPU_EVAL_D1 | BPPGPU_EVAL_D2)) != 0;
+  if (derivs && !e->keep) BPP_FAIL(BPPGPU_E_STATE, "derivatives need an engine created with BPPGPU_FLAG_KEEP_CLVS");
+  rc = ensure_deriv_buffers(e, want);
+  if (rc) return rc;
+  bool any_series = false, any_chrd = false;
+  if (e->models_dirty) {
+    std::vector<ModelDev> md(e->nmodels);
+    for (int m = 0; m < e->nmodels; ++m) md[m] = to_dev(e->models[m]);
+    BPP_CUDA(cudaMemcpyAsync(e->d_models, md.data(), md.size() * sizeof(ModelDev), cudaMemcpyHostToDevice, st));
+    BPP_CUDA(cudaStreamSynchronize(st));
+    e->models_dirty = false;
+  }
+  for (int m = 0; m < e->nmodels; ++m) {
+    if (!e->models[m].set) continue;
+    if (!(e->models[m].flags & BPPGPU_MODEL_NONSINGULAR)) any_series = true;
+    else if (e->models[m].flags & BPPGPU_MODEL_CHR_DERIV) any_chrd = true;
+  }
+  rc = ensure_scratch(e, any_series, any_chrd && derivs);
+  if (rc) return rc;
+  e->stats.kernel_launches = 0;
+  e->stats.clv_updates = 0;
+  const int S = e->S, C = e->C, nn = e->nn;
+  const size_t SS = (size_t)S * S;
+  unsigned pt_want = BPPGPU_WANT_P | ((want & BPPGPU_EVAL_D1) ? BPPGPU_WANT_DP : 0) | ((want & BPPGPU_EVAL_D2) ? BPPGPU_WANT_D2P : 0);
+  if (timed) BPP_CUDA(cudaEventRecord(e->ev0, st));
+  BPP_CUDA(cudaMemcpyAsync(e->d_rootfreq_used, e->d_rootfreq, (size_t)e->npoints * S * 8, cudaMemcpyDeviceToDevice, st));
+  float prune_ms_total = 0.f;
+  for (int p0 = 0; p0 < e->npoints; p0 += e->pchunk) {
+    const int np = std::min(e->pchunk, e->npoints - p0);
+    long long launches = 0;
+    rc = launch_pt(st, e->d_models, any_series, any_chrd, e->d_branch_model + (size_t)p0 * nn,
+                   e->d_brlen + (size_t)p0 * nn, e->d_rates, S, C, nn, e->root, np, pt_want, e->d_P, e->d_dP, e->d_d2P,
+                   e->d_scratch, e->d_status, &launches);
+    if (rc) return rc;
+    e->stats.kernel_launches += launches;
+    TipTabParams tp{};
+    tp.P = e->d_P;
+    tp.code_table = e->d_code_table;
+    tp.leaf_nodes = e->d_leaf_nodes;
+    tp.S = S; tp.C = C; tp.nn = nn; tp.nl = e->nl; tp.ncodes = e->ncodes;
+    tp.tiptab = e->d_tiptab;
+    tiptab_kernel<<<np * e->nl * C, 128, 0, st>>>(tp);
+    e->stats.kernel_launches++;
+    BPP_CUDA(cudaGetLastError());
+    for (int pl = 0; pl < np; ++pl) {
+      const int point = p0 + pl;
+      if (timed && point == 0) BPP_CUDA(cudaEventRecord(e->ev2, st));
+      rc = enqueue_prune(e, point, pl, st);
+      if (rc) return rc;
+      if (timed && point == 0) BPP_CUDA(cudaEventRecord(e->ev3, st));
+      if (derivs) {
+        rc = enqueue_derivs(e, point, pl, want, st);
+        if (rc) return rc;
+      }
+      e->last_point = point;
+    }
+  }
+  (void)SS;
+  (void)prune_ms_total;
+  if (timed) BPP_CUDA(cudaEventRecord(e->ev1, st));
+  e->last_want = want;
+  return BPPGPU_OK;
+}
+
+int bppgpu_eval(bppgpu_engine* e, unsigned want, double* lnl, double* d1, double* d2) {
+  ENGINE_ENTER(e);
+  int rc = eval_impl(e, want, e->stream, true);
+  if (rc) return rc;
+  BPP_CUDA(cudaStreamSynchronize(e->stream));
+  float ms = 0.f;
+  BPP_CUDA(cudaEventElapsedTime(&ms, e->ev0, e->ev1));
+  e->stats.last_eval_ms = ms;
+  BPP_CUDA(cudaEventElapsedTime(&ms, e->ev2, e->ev3));
+  e->stats.prune_ms = ms;
+  const int nn = e->nn;
+  std::vector<double> h((size_t)e->npoints * (1 + 2 * nn));
+  BPP_CUDA(cudaMemcpy(h.data(), e->d_out, h.size() * 8, cudaMemcpyDeviceToHost));
+  int status = 0;
+  BPP_CUDA(cudaMemcpy(&status, e->d_status, 4, cudaMemcpyDeviceToHost));
+  if (status) {
+    cudaMemset(e->d_status, 0, 4);
+    BPP_FAIL(BPPGPU_E_NUMERIC, "ChromosomeSubstitutionModel: Taylor series did not reach convergence!");
+  }
+  for (int p = 0; p < e->npoints; ++p) {
+    const double* row = h.data() + (size_t)p * (1 + 2 * nn);
+    if (lnl) lnl[p] = row[0];
+    if (d1 && (e->last_want & BPPGPU_EVAL_D1)) std::copy(row + 1, row + 1 + nn, d1 + (size_t)p * nn);
+    if (d2 && (e->last_want & BPPGPU_EVAL_D2)) std::copy(row + 1 + nn, row + 1 + 2 * nn, d2 + (size_t)p * nn);
+  }
+  return BPPGPU_OK;
+}
+
+int bppgpu_eval_device(bppgpu_engine* e, unsigned want, double* dev_out, void* cuda_stream) {
+  ENGINE_ENTER(e);
+  if (!dev_out) BPP_FAIL(BPPGPU_E_INVALID, "null dev_out");
+  cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : e->stream;
+  int rc = eval_impl(e, want, st, false);
+  if (rc) return rc;
+  BPP_CUDA(cudaMemcpyAsync(dev_out, e->d_out, (size_t)e->npoints * (1 + 2 * e->nn) * 8, cudaMemcpyDeviceToDevice, st));
+  return BPPGPU_OK;
+}
+
+// ---- accessors -------------------------------------------------------------------------
+int bppgpu_get_site_lnl(bppgpu_engine* e, int32_t point, double* out) {
+  ENGINE_ENTER(e);
+  if (point < 0 || point >= e->npoints || !out) BPP_FAIL(BPPGPU_E_INVALID, "bad point or null out");
+  if (e->last_want == 0) BPP_FAIL(BPPGPU_E_STATE, "no evaluation yet");
+  BPP_CUDA(cudaStreamSynchronize(e->stream));
+  BPP_CUDA(cudaMemcpy(out, e->d_site_lnl + (size_t)point * e->N, (size_t)e->N * 8, cudaMemcpyDeviceToHost));
+  return BPPGPU_OK;
+}
+
+int bppgpu_get_clv(bppgpu_engine* e, int32_t point, int32_t node, int32_t which, double* clv, int32_t* scale_exp) {
+  ENGINE_ENTER(e);
+  if (!e->keep) BPP_FAIL(BPPGPU_E_STATE, "bppgpu_get_clv needs BPPGPU_FLAG_KEEP_CLVS");
+  if (node < 0 || node >= e->nn || !clv) BPP_FAIL(BPPGPU_E_INVALID, "bad node or null out");
+  if (point != e->last_point) BPP_FAIL(BPPGPU_E_STATE, "CLVs resident are those of point %d", e->last_point);
+  BPP_CUDA(cudaStreamSynchronize(e->stream));
+  const size_t clvn = (size_t)e->N * e->C * e->S;
+  if (which == 0) {
+    if (e->internal_idx[node] < 0) BPP_FAIL(BPPGPU_E_INVALID, "node %d is a leaf: its CLV is the code table row", node);
+    const int k = e->internal_idx[node];
+    BPP_CUDA(cudaMemcpy(clv, e->d_keep + (size_t)k * clvn, clvn * 8, cudaMemcpyDeviceToHost));
+    if (scale_exp) BPP_CUDA(cudaMemcpy(scale_exp, e->d_keep_exp + (size_t)k * e->N, (size_t)e->N * 4, cudaMemcpyDeviceToHost));
+  } else {
+    if (!(e->last_want & BPPGPU_EVAL_D1) || !e->d_upper) BPP_FAIL(BPPGPU_E_STATE, "upper CLVs exist after an eval with derivatives");
+    if (node == e->root) BPP_FAIL(BPPGPU_E_INVALID, "the root has no upper CLV");
+    BPP_CUDA(cudaMemcpy(clv, e->d_upper + (size_t)node * clvn, clvn * 8, cudaMemcpyDeviceToHost));
+    if (scale_exp) BPP_CUDA(cudaMemcpy(scale_exp, e->d_upper_exp + (size_t)node * e->N, (size_t)e->N * 4, cudaMemcpyDeviceToHost));
+  }
+  return BPPGPU_OK;
+}
+
+int bppgpu_get_transition_probabilities(bppgpu_engine* e, int32_t point, int32_t node, unsigned which, double* out) {
+  ENGINE_ENTER(e);
+  if (point < 0 || point >= e->npoints || node < 0 || node >= e->nn || node == e->root || !out)
+    BPP_FAIL(BPPGPU_E_INVALID, "bad point / node or null out");
+  if (e->last_want == 0) BPP_FAIL(BPPGPU_E_STATE, "no evaluation yet");
+  const int last_chunk0 = ((e->npoints - 1) / e->pchunk) * e->pchunk;
+  if (point < last_chunk0) BPP_FAIL(BPPGPU_E_STATE, "tables resident are those of points >= %d", last_chunk0);
+  const double* src = which == BPPGPU_WANT_P ? e->d_P : which == BPPGPU_WANT_DP ? e->d_dP : which == BPPGPU_WANT_D2P ? e->d_d2P : nullptr;
+  if (!src) BPP_FAIL(BPPGPU_E_STATE, "requested table was not built by the last eval");
+  if (which == BPPGPU_WANT_DP && !(e->last_want & BPPGPU_EVAL_D1)) BPP_FAIL(BPPGPU_E_STATE, "dP not built by the last eval");
+  if (which == BPPGPU_WANT_D2P && !(e->last_want & BPPGPU_EVAL_D2)) BPP_FAIL(BPPGPU_E_STATE, "d2P not built by the last eval");
+  BPP_CUDA(cudaStreamSynchronize(e->stream));
+  const size_t per = (size_t)e->C * e->S * e->S;
+  BPP_CUDA(cudaMemcpy(out, src + ((size_t)(point - last_chunk0) * e->nn + node) * per, per * 8, cudaMemcpyDeviceToHost));
+  return BPPGPU_OK;
+}
+
+int bppgpu_get_root_freqs(bppgpu_engine* e, int32_t point, double* out) {
+  ENGINE_ENTER(e);
+  if (point < 0 || point >= e->npoints || !out) BPP_FAIL(BPPGPU_E_INVALID, "bad point or null out");
+  BPP_CUDA(cudaStreamSynchronize(e->stream));
+  BPP_CUDA(cudaMemcpy(out, e->d_rootfreq_used + (size_t)point * e->S, e->S * 8, cudaMemcpyDeviceToHost));
+  return BPPGPU_OK;
+}
+
+int bppgpu_get_stats(bppgpu_engine* e, bppgpu_stats* out) {
+  if (!e || !out) BPP_FAIL(BPPGPU_E_INVALID, "null argument");
+  e->stats.hbm_bytes_resident = (int64_t)e->bytes_resident;
+  *out = e->stats;
+  return BPPGPU_OK;
+}
+

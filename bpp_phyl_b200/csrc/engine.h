@@ -6,6 +6,8 @@
 #include <vector>
 
 #include "../../include/bppgpu.h"
+#include "deriv_kernels.cuh"
+#include "generic_kernels.cuh"
 #include "pt_kernels.cuh"
 #include "walk_kernels.cuh"
 
@@ -20,16 +22,16 @@ struct DevModel {
   unsigned flags = 0;
   int has_complex = 0;
   bool set = false;
-  double q_max_abs_diag = 0.0, q_l1 = 0.0;
+  double q_l1 = 0.0;  // sum |Q_ij| (ChromosomeSubstitutionModel::getFirstNorm)
 };
 
+// Post-order "program" of the pruning recursion: one Op per internal node.
 struct Program {
   std::vector<Op> ops;
   std::vector<Child> childs;
   int nslots = 0;
   Op* d_ops = nullptr;
   Child* d_childs = nullptr;
-  bool built = false;
 };
 
 }  // namespace bppgpu
@@ -41,15 +43,19 @@ struct bppgpu_engine {
   long long N = 0;
   unsigned flags = 0;
   // topology (host)
-  std::vector<int> child_off, children, parent, leaf_slot, leaf_nodes, internal_idx;
+  std::vector<int> child_off, children, parent;
+  std::vector<int> leaf_slot;     // node id -> leaf slot or -1
+  std::vector<int> leaf_nodes;    // leaf slot -> node id
+  std::vector<int> internal_idx;  // node id -> keep index or -1
+  std::vector<int> preorder;      // fathers before sons
   int nl = 0, ni = 0;
   // device inputs
-  void* d_codes = nullptr;
-  double* d_code_table = nullptr;
-  double* d_weights = nullptr;
+  void* d_codes = nullptr;        // [nl][N] tip codes
+  double* d_code_table = nullptr; // [ncodes][S]
+  double* d_weights = nullptr;    // [N]
   double *d_rates = nullptr, *d_probs = nullptr;
-  double* d_rootfreq = nullptr;       // [npoints][S]
-  double* d_rootfreq_used = nullptr;  // [npoints][S]
+  double* d_rootfreq = nullptr;       // [npoints][S] as given
+  double* d_rootfreq_used = nullptr;  // [npoints][S] as used (WEIGHTED_ROOT overwrites)
   double* d_brlen = nullptr;          // [npoints][nn]
   int* d_branch_model = nullptr;      // [npoints][nn]
   int* d_leaf_nodes = nullptr;
@@ -59,34 +65,41 @@ struct bppgpu_engine {
   std::vector<double> h_rates, h_probs;
   std::vector<double> h_brlen;  // [npoints][nn]
   std::vector<int> h_branch_model;
-  // tables
+  // tables, sized for `pchunk` points
+  int pchunk = 1;
   double *d_P = nullptr, *d_dP = nullptr, *d_d2P = nullptr;
   double* d_tiptab = nullptr;
-  // CLV storage
+  // CLV storage (one point at a time)
   double* d_keep = nullptr;  // [ni][N][C][S]
-  int* d_keep_exp = nullptr;
+  int* d_keep_exp = nullptr; // [ni][N]
   double* d_gstack = nullptr;
   int* d_gstack_exp = nullptr;
-  double* d_upper = nullptr;  // derivative pass scratch
+  double* d_upper = nullptr;  // [nn][N][C][S] generic derivative pass
   int* d_upper_exp = nullptr;
-  int upper_slots = 0;
   // outputs
-  double* d_SR = nullptr;
+  double* d_SR = nullptr;        // [N] of the last evaluated point
   int* d_rexp = nullptr;
   double* d_site_lnl = nullptr;  // [npoints][N]
   double* d_partials = nullptr;
+  double* d_partials2 = nullptr;
   int n_partials = 0;
   double* d_out = nullptr;  // [npoints][1+2nn]
-  double* d_deriv_partials = nullptr;
+  double* d_scratch = nullptr;  // series / unclamped-P scratch
+  size_t scratch_elems = 0;
+  int* d_status = nullptr;
   // schedule
-  bppgpu::Program prog;
-  bppgpu::Program uprog;  // prefix/derivative program
+  bppgpu::Program prog;   // walk program (REG / SLOT children)
+  bppgpu::Program gprog;  // generic program (all internal children read from keep)
+  std::vector<std::vector<bppgpu::Child>> sibs;  // per node: siblings, generic kinds
+  bppgpu::Child* d_sibs = nullptr;
+  std::vector<int> sib_off;
   int path = bppgpu::PATH_NONE;
+  bool keep = false;
   // state flags
-  bool have_weights = false, have_rates = false, have_brlen = false, have_rootfreq = false;
-  std::vector<char> have_tip;
-  int cached_point = -1;
-  unsigned cached_want = 0;
+  bool have_weights = false, have_rates = false, have_codes_all = false;
+  std::vector<char> have_tip, have_brlen, have_rootfreq;
+  int last_point = -1;  // point whose CLVs / SR are currently resident
+  unsigned last_want = 0;
   // stats
   bppgpu_stats stats{};
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;

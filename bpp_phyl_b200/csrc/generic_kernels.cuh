@@ -116,4 +116,49 @@ __global__ void generic_root_kernel(RootParams p) {
   if (threadIdx.x == 0) p.partials[blockIdx.x] = bs;
 }
 
+// K3b: weighted root frequencies (fork): pi_x = sum_i sum_c p_c L_root[i][c][x], normalised
+// (DRNonHomogeneousTreeLikelihood::setWeightedRootFreq, DRNonHomogeneousTreeLikelihood.cpp:927-962).
+// Stored CLVs carry per-pattern exponents, so patterns are aligned on the smallest one first.
+// Single CTA: the fork only uses this with one character (N = 1).
+struct WeightedRootParams {
+  const double* root_clv;  // [N][C][S]
+  const int* root_exp;     // [N]
+  int S, C;
+  long long N;
+  const double* probs;
+  double* out;  // [S]
+};
+
+__global__ void weighted_root_kernel(WeightedRootParams p) {
+  __shared__ int emin_s;
+  __shared__ double tot_s;
+  __shared__ double red[32];
+  int em = 0x7fffffff;
+  for (long long i = threadIdx.x; i < p.N; i += blockDim.x) em = min(em, p.root_exp[i]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) em = min(em, __shfl_xor_sync(0xffffffffu, em, o));
+  if (threadIdx.x == 0) emin_s = 0x7fffffff;
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) atomicMin(&emin_s, em);
+  __syncthreads();
+  const int emin = emin_s;
+  double tot = 0.0;
+  for (int x = 0; x < p.S; ++x) {
+    double acc = 0.0;
+    for (long long i = threadIdx.x; i < p.N; i += blockDim.x) {
+      double a = 0.0;
+      for (int c = 0; c < p.C; ++c) a = fma(p.root_clv[((size_t)i * p.C + c) * p.S + x], p.probs[c], a);
+      acc += scalbn(a, -(p.root_exp[i] - emin));
+    }
+    const double s = block_sum(acc, red);
+    if (threadIdx.x == 0) {
+      p.out[x] = s;
+      tot += s;
+    }
+  }
+  if (threadIdx.x == 0) tot_s = tot;
+  __syncthreads();
+  for (int x = threadIdx.x; x < p.S; x += blockDim.x) p.out[x] /= tot_s;
+}
+
 }  // namespace bppgpu

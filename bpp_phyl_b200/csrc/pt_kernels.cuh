@@ -27,6 +27,7 @@ struct ModelDev {
   const double* Q2;    // [S][S] Q.Q or nullptr
   double rate;
   double eps;
+  double q_l1;         // sum_ij |Q_ij| (ChromosomeSubstitutionModel::getFirstNorm)
   unsigned flags;
   int has_complex;
 };
@@ -41,6 +42,7 @@ struct PtParams {
   double* P;                // [npoints][nn][C][S][S]
   double* dP;
   double* d2P;
+  double* Pun;              // [npoints][nn][C][S][S] unclamped P for CHR_DERIV models, or nullptr
 };
 
 // dynamic smem: 6*S doubles (dia/up for orders 0,1,2)
@@ -97,6 +99,7 @@ __global__ void pt_eigen_kernel(PtParams p) {
   const size_t base = (size_t)m * S * S;
   const bool wP = p.want & 1u, wD = p.want & 2u, wD2 = p.want & 4u;
   const bool clamp = md.flags & 4u;
+  const bool chr_deriv = md.flags & 8u;  // dP, d2P rebuilt from the unclamped P by pt_chr_deriv_kernel
   for (int e = threadIdx.x; e < S * S; e += blockDim.x) {
     const int x = e / S, y = e - x * S;
     double a0 = 0.0, a1 = 0.0, a2 = 0.0;
@@ -129,16 +132,17 @@ __global__ void pt_eigen_kernel(PtParams p) {
         a2 = fma(w2, u, a2);
       }
     }
+    if (t == 0.0) a0 = (x == y) ? 1.0 : 0.0;  // :428-431
+    if (chr_deriv && p.Pun) p.Pun[base + e] = a0;
     if (wP) {
-      if (t == 0.0) a0 = (x == y) ? 1.0 : 0.0;
       if (clamp) {  // ChromosomeSubstitutionModel.cpp:903-916
         if (a0 < 0.0) a0 = 1e-20;
         else if (a0 > 1.0) a0 = 1.0;
       }
       p.P[base + e] = a0;
     }
-    if (wD) p.dP[base + e] = a1;
-    if (wD2) p.d2P[base + e] = a2;
+    if (wD && !chr_deriv) p.dP[base + e] = a1;
+    if (wD2 && !chr_deriv) p.d2P[base + e] = a2;
   }
 }
 
@@ -169,6 +173,182 @@ __global__ void tiptab_kernel(TipTabParams p) {
     double acc = 0.0;
     for (int y = 0; y < S; ++y) acc = fma(Pm[x * S + y], tv[y], acc);
     out[e] = acc;
+  }
+}
+
+}  // namespace bppgpu
+
+namespace bppgpu {
+
+// ---- K1c: series + scaling-and-squaring for singular / non-diagonalisable Q -----
+// Generic model (AbstractSubstitutionModel.cpp:470-492): v = rate*t halved m times until
+// <= 0.5, P = sum_{k<30} v^k/k! Q^k, squared m times; derivatives rate*Q.P and rate^2*Q.Q.P
+// (:539-563, :614-638).  Chromosome variant (ChromosomeSubstitutionModel.cpp:852-899,
+// :934-946): halve until v*sum|Q_ij| <= 0.5, add terms until every |term_ij| <= eps and
+// P within [-eps, 1+eps] (at least 3 terms, at most 250), square back; then
+// dP = P.Q.rate (:966-982), d2P = Q^2.P.rate^2 (:986-1001) from the UNCLAMPED P, and the
+// clamp P<0 -> 1e-20, P>1 -> 1 (:903-916) on P itself.  BPPGPU_MODEL_EXACT_EXPM runs the
+// series to FP64 convergence instead of the reference's truncation.
+//
+// One CTA per matrix, scratch in global memory ([4][S][S] per matrix): a correctness
+// path for the rare singular case, not a throughput kernel.
+struct SeriesParams {
+  PtParams pt;
+  double* scratch;  // [nmat][4][S*S]
+  double q_l1_unused;
+  int* status;      // set to 1 if the chromosome series did not converge
+  int only_chr_deriv;  // 1: matrices of eigen-path models flagged CHR_DERIV: rebuild dP/d2P from P
+};
+
+__device__ __forceinline__ void mat_mul(const double* A, const double* B, double* O, int S, double scale) {
+  for (int e = threadIdx.x; e < S * S; e += blockDim.x) {
+    const int x = e / S, y = e - x * S;
+    double acc = 0.0;
+    for (int k = 0; k < S; ++k) acc = fma(A[x * S + k], B[k * S + y], acc);
+    O[e] = acc * scale;
+  }
+  __syncthreads();
+}
+
+__global__ void pt_series_kernel(SeriesParams sp) {
+  const PtParams& p = sp.pt;
+  __shared__ double red_max[32];
+  __shared__ int flag;
+  const int S = p.S;
+  const int m = blockIdx.x;
+  const int c = m % p.C;
+  const int node = (m / p.C) % p.nn;
+  const int point = m / (p.C * p.nn);
+  if (node == p.root) return;
+  const ModelDev md = p.models[p.branch_model[point * p.nn + node]];
+  const bool eigen_path = (md.flags & 2u) != 0;  // NONSINGULAR
+  const bool chr = (md.flags & 16u) != 0;        // CHR_TAYLOR
+  const bool chr_deriv = (md.flags & 8u) != 0;
+  if (eigen_path) return;  // built by pt_eigen_kernel (+ pt_chr_deriv_kernel)
+  const double rc = p.rates[c];
+  const double t = p.brlen[point * p.nn + node] * rc;
+  double* T = sp.scratch + (size_t)m * 4 * S * S;  // current term
+  double* A = T + S * S;                            // running sum / result
+  double* B = A + S * S;                            // temp
+  const double* Q = md.Q;
+  const size_t base = (size_t)m * S * S;
+  const bool wP = p.want & 1u, wD = p.want & 2u, wD2 = p.want & 4u;
+
+  double v = md.rate * t;
+  int k = 0;
+  if (chr) {
+    double norm = v * md.q_l1;
+    while (norm > 0.5) { ++k; v *= 0.5; norm *= 0.5; }
+  } else {
+    while (v > 0.5) { ++k; v *= 0.5; }
+  }
+  for (int e = threadIdx.x; e < S * S; e += blockDim.x) {
+    const double id = (e / S == e % S) ? 1.0 : 0.0;
+    T[e] = id;
+    A[e] = id;
+  }
+  __syncthreads();
+  if (t != 0.0) {
+    const bool exact = (md.flags & 32u) != 0;
+    const int max_terms = chr || exact ? 250 : 29;
+    for (int i = 1; i <= max_terms; ++i) {
+      mat_mul(T, Q, B, S, v / (double)i);  // term_i = term_{i-1}.Q.v/i
+      double mx = 0.0;
+      int bad = 0;
+      for (int e = threadIdx.x; e < S * S; e += blockDim.x) {
+        const double tv = B[e];
+        T[e] = tv;
+        const double a = A[e] + tv;
+        A[e] = a;
+        mx = fmax(mx, fabs(tv));
+        if (chr && !exact && (a + md.eps < 0.0 || a > 1.0 + md.eps)) bad = 1;
+      }
+      if (chr || exact) {
+        // block max of |term| and OR of the range test
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+          bad |= __shfl_xor_sync(0xffffffffu, bad, o);
+        }
+        if (threadIdx.x == 0) flag = 0;
+        __syncthreads();
+        if ((threadIdx.x & 31) == 0) {
+          red_max[threadIdx.x >> 5] = mx;
+          if (bad) atomicOr(&flag, 1);
+        }
+        __syncthreads();
+        double bm = 0.0;
+        for (int w = 0; w < (int)((blockDim.x + 31) >> 5); ++w) bm = fmax(bm, red_max[w]);
+        const int anybad = flag;
+        __syncthreads();
+        const double tol = exact ? 1e-18 : md.eps;
+        if (i >= 3 && bm <= tol && !anybad) break;
+        if (i == max_terms && !exact && threadIdx.x == 0) *sp.status = 1;
+      } else {
+        __syncthreads();
+      }
+    }
+    for (int j = 0; j < k; ++j) {  // square back
+      mat_mul(A, A, B, S, 1.0);
+      for (int e = threadIdx.x; e < S * S; e += blockDim.x) A[e] = B[e];
+      __syncthreads();
+    }
+  }
+  // A = unclamped P
+  if (wD) {
+    if (chr_deriv) mat_mul(A, Q, B, S, md.rate * rc);  // P.Q.rate
+    else mat_mul(Q, A, B, S, md.rate * rc);            // rate.Q.P
+    for (int e = threadIdx.x; e < S * S; e += blockDim.x) p.dP[base + e] = B[e];
+    __syncthreads();
+  }
+  if (wD2) {
+    mat_mul(md.Q2, A, B, S, md.rate * md.rate * rc * rc);  // rate^2.Q^2.P
+    for (int e = threadIdx.x; e < S * S; e += blockDim.x) p.d2P[base + e] = B[e];
+    __syncthreads();
+  }
+  if (wP) {
+    const bool clamp = md.flags & 4u;
+    for (int e = threadIdx.x; e < S * S; e += blockDim.x) {
+      double a = A[e];
+      if (clamp) {
+        if (a < 0.0) a = 1e-20;
+        else if (a > 1.0) a = 1.0;
+      }
+      p.P[base + e] = a;
+    }
+  }
+}
+
+// Chromosome models on the eigen path: dP = Pun.Q.rate, d2P = Q^2.Pun.rate^2 where Pun is the
+// UNCLAMPED P that pt_eigen_kernel left in `scratch` ([nmat][S*S]).
+__global__ void pt_chr_deriv_kernel(SeriesParams sp) {
+  const PtParams& p = sp.pt;
+  const int S = p.S;
+  const int m = blockIdx.x;
+  const int c = m % p.C;
+  const int node = (m / p.C) % p.nn;
+  const int point = m / (p.C * p.nn);
+  if (node == p.root) return;
+  const ModelDev md = p.models[p.branch_model[point * p.nn + node]];
+  if (!(md.flags & 2u) || !(md.flags & 8u)) return;
+  const double rc = p.rates[c];
+  const double* Pun = sp.scratch + (size_t)m * S * S;
+  const size_t base = (size_t)m * S * S;
+  if (p.want & 2u) {
+    for (int e = threadIdx.x; e < S * S; e += blockDim.x) {
+      const int x = e / S, y = e - x * S;
+      double acc = 0.0;
+      for (int k = 0; k < S; ++k) acc = fma(Pun[x * S + k], md.Q[k * S + y], acc);
+      p.dP[base + e] = acc * md.rate * rc;
+    }
+  }
+  if (p.want & 4u) {
+    for (int e = threadIdx.x; e < S * S; e += blockDim.x) {
+      const int x = e / S, y = e - x * S;
+      double acc = 0.0;
+      for (int k = 0; k < S; ++k) acc = fma(md.Q2[x * S + k], Pun[k * S + y], acc);
+      p.d2P[base + e] = acc * md.rate * md.rate * rc * rc;
+    }
   }
 }
 

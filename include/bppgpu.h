@@ -96,8 +96,10 @@ enum {
                                         default = DR semantics (clamp SR<0 to 0)        */
   BPPGPU_FLAG_WEIGHTED_ROOT = 1u << 2, /* root frequencies = normalised per-state root
                                         likelihood (DRNonHomogeneousTreeLikelihood.cpp:927-962) */
-  BPPGPU_FLAG_NH_DERIV = 1u << 3     /* derivative in the NH numerator/denominator form
+  BPPGPU_FLAG_NH_DERIV = 1u << 3,    /* derivative in the NH numerator/denominator form
                                         (DRNonHomogeneousTreeLikelihood.cpp:370-413)    */
+  BPPGPU_FLAG_FORCE_GENERIC = 1u << 4 /* run the unspecialised one-launch-per-node kernels
+                                        (cross-check of the specialised paths)          */
 };
 
 typedef struct bppgpu_config {
@@ -122,6 +124,10 @@ int bppgpu_destroy(bppgpu_engine* e);
 
 /* tip data: codes[N] for leaf `node` (copied) */
 int bppgpu_set_tip_codes(bppgpu_engine* e, int32_t node, const void* codes);
+/* all tips at once: codes[n_leaves][N], leaf rows in increasing node-id order
+ * (bppgpu_leaf_slot gives the row of a leaf node)                             */
+int bppgpu_set_all_tip_codes(bppgpu_engine* e, const void* codes);
+int bppgpu_leaf_slot(bppgpu_engine* e, int32_t node, int32_t* slot);
 /* pattern weights (SitePatterns::getWeights, unsigned int) */
 int bppgpu_set_pattern_weights(bppgpu_engine* e, const uint32_t* w);
 /* rate classes: getCategory(c), getProbability(c) */
