@@ -1,0 +1,277 @@
+"""ctypes binding of the C ABI in include/bppgpu.h (libbppgpu.so).
+
+This is plumbing for tests/, bench.py and __graft_entry__.py: it mirrors the
+header one to one (same names, same argument meaning, status codes turned into
+``BppGpuError``).  There is no fallback: if the shared library is missing the
+import of :func:`lib` raises, and every compute call fails with BPPGPU_E_CUDA
+when no sm_100a device is usable.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import pathlib
+
+import numpy as np
+
+PKG_DIR = pathlib.Path(__file__).resolve().parent
+LIB_PATH = PKG_DIR / "lib" / "libbppgpu.so"
+
+OK, E_INVALID, E_STATE, E_CUDA, E_NCCL, E_NUMERIC, E_NOMEM = range(7)
+
+MODEL_DIAGONALIZABLE = 1 << 0
+MODEL_NONSINGULAR = 1 << 1
+MODEL_CLAMP01 = 1 << 2
+MODEL_CHR_DERIV = 1 << 3
+MODEL_CHR_TAYLOR = 1 << 4
+MODEL_EXACT_EXPM = 1 << 5
+
+WANT_P, WANT_DP, WANT_D2P = 1, 2, 4
+EVAL_LNL, EVAL_D1, EVAL_D2 = 1, 2, 4
+
+FLAG_KEEP_CLVS = 1 << 0
+FLAG_R_SEMANTICS = 1 << 1
+FLAG_WEIGHTED_ROOT = 1 << 2
+FLAG_NH_DERIV = 1 << 3
+FLAG_FORCE_GENERIC = 1 << 4
+
+
+class BppGpuError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("bppgpu error %d: %s" % (code, msg))
+        self.code = code
+
+
+_dp = C.POINTER(C.c_double)
+
+
+class ModelDesc(C.Structure):
+    _fields_ = [
+        ("n_states", C.c_int32),
+        ("flags", C.c_uint32),
+        ("rate", C.c_double),
+        ("right_eigen", _dp),
+        ("left_eigen", _dp),
+        ("eigen_re", _dp),
+        ("eigen_im", _dp),
+        ("generator", _dp),
+        ("taylor_epsilon", C.c_double),
+    ]
+
+
+class Config(C.Structure):
+    _fields_ = [
+        ("n_states", C.c_int32),
+        ("n_cats", C.c_int32),
+        ("n_patterns", C.c_int64),
+        ("n_nodes", C.c_int32),
+        ("root", C.c_int32),
+        ("child_offsets", C.POINTER(C.c_int32)),
+        ("children", C.POINTER(C.c_int32)),
+        ("n_points", C.c_int32),
+        ("n_models", C.c_int32),
+        ("n_codes", C.c_int32),
+        ("code_bytes", C.c_int32),
+        ("code_table", _dp),
+        ("device", C.c_int32),
+        ("flags", C.c_uint32),
+    ]
+
+
+class Stats(C.Structure):
+    _fields_ = [
+        ("kernel_launches", C.c_int64),
+        ("clv_updates", C.c_int64),
+        ("last_eval_ms", C.c_double),
+        ("prune_ms", C.c_double),
+        ("hbm_bytes_resident", C.c_int64),
+        ("stack_slots", C.c_int32),
+        ("path", C.c_int32),
+    ]
+
+
+_lib = None
+
+
+def lib():
+    """The loaded libbppgpu.so (raises if it has not been built: no fallback)."""
+    global _lib
+    if _lib is None:
+        if not LIB_PATH.exists():
+            raise ImportError(
+                "%s not built; run `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(there is no CPU fallback)" % LIB_PATH)
+        _lib = C.CDLL(os.fspath(LIB_PATH))
+        _lib.bppgpu_last_error.restype = C.c_char_p
+    return _lib
+
+
+def _check(rc):
+    if rc != OK:
+        raise BppGpuError(rc, lib().bppgpu_last_error().decode())
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _ptr(a, t=C.c_double):
+    return a.ctypes.data_as(C.POINTER(t)) if a is not None else None
+
+
+def device_count():
+    n = C.c_int(0)
+    _check(lib().bppgpu_device_count(C.byref(n)))
+    return n.value
+
+
+class _ModelHolder:
+    """Keeps the numpy buffers a ModelDesc points at alive."""
+
+    def __init__(self, S, flags, rate=1.0, V=None, Vinv=None, ev_re=None, ev_im=None, Q=None, eps=1e-4):
+        self.arrays = [None if a is None else _f64(a) for a in (V, Vinv, ev_re, ev_im, Q)]
+        d = ModelDesc()
+        d.n_states = S
+        d.flags = flags
+        d.rate = rate
+        d.right_eigen, d.left_eigen, d.eigen_re, d.eigen_im, d.generator = [_ptr(a) for a in self.arrays]
+        d.taylor_epsilon = eps
+        self.desc = d
+
+
+def model_desc(S, flags, **kw):
+    return _ModelHolder(S, flags, **kw)
+
+
+def pt_batch(model: _ModelHolder, t, want=WANT_P, device=0):
+    """bppgpu_pt_batch: returns (P, dP, d2P) arrays [n_t][S][S] (None where not wanted)."""
+    t = _f64(t).ravel()
+    S = model.desc.n_states
+    outs = [np.empty((len(t), S, S)) if want & w else None for w in (WANT_P, WANT_DP, WANT_D2P)]
+    _check(lib().bppgpu_pt_batch(C.c_int(device), C.byref(model.desc), C.c_int64(len(t)), _ptr(t),
+                                 C.c_uint(want), *[_ptr(o) for o in outs]))
+    return outs
+
+
+class Engine:
+    """Owning wrapper of a ``bppgpu_engine*``."""
+
+    def __init__(self, n_states, n_cats, n_patterns, child_offsets, children, root, code_table,
+                 n_points=1, n_models=1, code_bytes=1, device=0, flags=0):
+        self._h = C.c_void_p()
+        self.child_offsets = np.ascontiguousarray(child_offsets, np.int32)
+        self.children = np.ascontiguousarray(children, np.int32)
+        self.code_table = _f64(code_table)
+        cfg = Config()
+        cfg.n_states, cfg.n_cats, cfg.n_patterns = n_states, n_cats, n_patterns
+        cfg.n_nodes = len(self.child_offsets) - 1
+        cfg.root = root
+        cfg.child_offsets = _ptr(self.child_offsets, C.c_int32)
+        cfg.children = _ptr(self.children, C.c_int32)
+        cfg.n_points, cfg.n_models = n_points, n_models
+        cfg.n_codes = self.code_table.shape[0]
+        cfg.code_bytes = code_bytes
+        cfg.code_table = _ptr(self.code_table)
+        cfg.device = device
+        cfg.flags = flags
+        self.S, self.C, self.N, self.nn = n_states, n_cats, n_patterns, cfg.n_nodes
+        self.n_points = n_points
+        self.code_bytes = code_bytes
+        _check(lib().bppgpu_create(C.byref(cfg), C.byref(self._h)))
+
+    def close(self):
+        if self._h:
+            lib().bppgpu_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # --- setters ---------------------------------------------------------------
+    def leaf_slot(self, node):
+        s = C.c_int32(-1)
+        _check(lib().bppgpu_leaf_slot(self._h, C.c_int32(node), C.byref(s)))
+        return s.value
+
+    def _codes(self, codes):
+        return np.ascontiguousarray(codes, np.uint8 if self.code_bytes == 1 else np.uint16)
+
+    def set_tip_codes(self, node, codes):
+        a = self._codes(codes)
+        _check(lib().bppgpu_set_tip_codes(self._h, C.c_int32(node), a.ctypes.data_as(C.c_void_p)))
+
+    def set_all_tip_codes(self, codes):
+        a = self._codes(codes)
+        _check(lib().bppgpu_set_all_tip_codes(self._h, a.ctypes.data_as(C.c_void_p)))
+
+    def set_pattern_weights(self, w):
+        a = np.ascontiguousarray(w, np.uint32)
+        _check(lib().bppgpu_set_pattern_weights(self._h, _ptr(a, C.c_uint32)))
+
+    def set_rates(self, rates, probs):
+        r, p = _f64(rates), _f64(probs)
+        _check(lib().bppgpu_set_rates(self._h, _ptr(r), _ptr(p)))
+
+    def set_model(self, slot, model: _ModelHolder):
+        _check(lib().bppgpu_set_model(self._h, C.c_int32(slot), C.byref(model.desc)))
+
+    def set_branch_models(self, point, slots):
+        a = np.ascontiguousarray(slots, np.int32)
+        _check(lib().bppgpu_set_branch_models(self._h, C.c_int32(point), _ptr(a, C.c_int32)))
+
+    def set_branch_lengths(self, point, t):
+        a = _f64(t)
+        assert a.size == self.nn
+        _check(lib().bppgpu_set_branch_lengths(self._h, C.c_int32(point), _ptr(a)))
+
+    def set_root_freqs(self, point, pi):
+        a = _f64(pi)
+        _check(lib().bppgpu_set_root_freqs(self._h, C.c_int32(point), _ptr(a)))
+
+    # --- evaluation --------------------------------------------------------------
+    def eval(self, want=EVAL_LNL):
+        lnl = np.zeros(self.n_points)
+        d1 = np.zeros((self.n_points, self.nn)) if want & (EVAL_D1 | EVAL_D2) else None
+        d2 = np.zeros((self.n_points, self.nn)) if want & EVAL_D2 else None
+        _check(lib().bppgpu_eval(self._h, C.c_uint(want), _ptr(lnl), _ptr(d1), _ptr(d2)))
+        return lnl, d1, d2
+
+    def eval_device(self, want, dev_ptr, stream=0):
+        _check(lib().bppgpu_eval_device(self._h, C.c_uint(want), C.c_void_p(dev_ptr), C.c_void_p(stream)))
+
+    def site_lnl(self, point=0):
+        out = np.empty(self.N)
+        _check(lib().bppgpu_get_site_lnl(self._h, C.c_int32(point), _ptr(out)))
+        return out
+
+    def clv(self, node, which=0, point=0):
+        out = np.empty((self.N, self.C, self.S))
+        ex = np.empty(self.N, np.int32)
+        _check(lib().bppgpu_get_clv(self._h, C.c_int32(point), C.c_int32(node), C.c_int32(which), _ptr(out),
+                                    _ptr(ex, C.c_int32)))
+        return out, ex
+
+    def transition_probabilities(self, node, which=WANT_P, point=0):
+        out = np.empty((self.C, self.S, self.S))
+        _check(lib().bppgpu_get_transition_probabilities(self._h, C.c_int32(point), C.c_int32(node),
+                                                         C.c_uint(which), _ptr(out)))
+        return out
+
+    def root_freqs(self, point=0):
+        out = np.empty(self.S)
+        _check(lib().bppgpu_get_root_freqs(self._h, C.c_int32(point), _ptr(out)))
+        return out
+
+    def stats(self):
+        s = Stats()
+        _check(lib().bppgpu_get_stats(self._h, C.byref(s)))
+        return {k: getattr(s, k) for k, _ in Stats._fields_}

@@ -292,6 +292,14 @@ using namespace bppgpu;
 
 const char* bppgpu_last_error(void) { return last_error().c_str(); }
 int bppgpu_abi_version(void) { return 1; }
+int bppgpu_sizeof(int which) {
+  switch (which) {
+    case 0: return (int)sizeof(bppgpu_model_desc);
+    case 1: return (int)sizeof(bppgpu_config);
+    case 2: return (int)sizeof(bppgpu_stats);
+    default: return -1;
+  }
+}
 
 int bppgpu_device_count(int* n) {
   if (!n) BPP_FAIL(BPPGPU_E_INVALID, "null argument");

@@ -48,6 +48,9 @@ const char* bppgpu_last_error(void);
 int bppgpu_abi_version(void);
 /* number of visible CUDA devices (0 -> nothing below can compute) */
 int bppgpu_device_count(int* n);
+/* sizeof of the ABI structs as this library was compiled: which = 0 bppgpu_model_desc,
+ * 1 bppgpu_config, 2 bppgpu_stats (lets a foreign-language binding verify its mirror) */
+int bppgpu_sizeof(int which);
 
 /* ---- model descriptor ------------------------------------------------------
  * What bpp::SubstitutionModel exposes (Model/SubstitutionModel.h:468-525):

@@ -1,0 +1,148 @@
+"""Shared builders for the parity tests: a *case* = tree + model + rate classes + tip codes,
+expressed once for the oracle (numpy arrays) and once for the C ABI (an Engine).
+
+Test infrastructure: uses oracle/ (allowed in tests/, smoke() and bench.py's cpu_baseline only).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from oracle import ref_likelihood as rl
+from oracle import ref_models as rm
+from oracle import ref_patterns as rp
+from oracle import ref_tree as rt
+
+
+class Case:
+    pass
+
+
+def model_flags(m: rm.Model):
+    from bpp_phyl_b200 import capi
+    f = 0
+    if m.diagonalizable:
+        f |= capi.MODEL_DIAGONALIZABLE
+    if m.nonsingular:
+        f |= capi.MODEL_NONSINGULAR
+    if m.chromosome:
+        f |= capi.MODEL_CLAMP01 | capi.MODEL_CHR_DERIV | capi.MODEL_CHR_TAYLOR
+    return f
+
+
+def to_model_desc(m: rm.Model, extra_flags=0):
+    from bpp_phyl_b200 import capi
+    return capi.model_desc(m.size, model_flags(m) | extra_flags, rate=m.rate, V=m.V, Vinv=m.Vinv,
+                           ev_re=m.ev_re, ev_im=m.ev_im, Q=m.Q)
+
+
+def simulate_tips(flat: rt.FlatTree, m: rm.Model, rates, n_sites, rng, root_freqs=None):
+    """Sample states down the tree (one rate class per site); returns [n_leaves(pre-order)][n_sites] states."""
+    S = m.size
+    pi = m.freq if root_freqs is None else root_freqs
+    pi = np.asarray(pi, float)
+    pi = pi / pi.sum()
+    cls = rng.integers(len(rates), size=n_sites)
+    st = {flat.root: rng.choice(S, size=n_sites, p=pi)}
+    Pc = {}
+    for nid in range(flat.n_nodes - 2, -1, -1):       # fathers have larger post-order ids
+        f = int(flat.parent[nid])
+        out = np.empty(n_sites, np.int64)
+        for c, r in enumerate(rates):
+            P = np.clip(rm.pij_t(m, flat.brlen[nid] * r), 0, None)
+            P = P / P.sum(axis=1, keepdims=True)
+            cum = np.cumsum(P, axis=1)
+            sel = np.where(cls == c)[0]
+            u = rng.random(len(sel))
+            out[sel] = (u[:, None] > cum[st[f][sel]]).sum(axis=1).clip(0, S - 1)
+        st[nid] = out
+    return np.stack([st[l] for l in flat.leaf_ids])
+
+
+def make_case(n_taxa, n_sites, model: rm.Model, rates, probs, seed, rooted=False, mean_brlen=0.05,
+              random_tips=False, ambiguity=0.0, compress=True):
+    """Random tree + simulated (or i.i.d.) tip states, globally compressed (DR layout)."""
+    rng = np.random.default_rng(seed)
+    root = rt.random_tree(n_taxa, rng, mean_brlen=mean_brlen, rooted=rooted)
+    flat = rt.FlatTree(root, check_rooted=not rooted)
+    S = model.size
+    if random_tips:
+        tips = rng.integers(S, size=(n_taxa, n_sites))
+    else:
+        tips = simulate_tips(flat, model, rates, n_sites, rng)
+    # code table: S plain states + one fully ambiguous code + (S>=4) one two-state ambiguity
+    table = np.eye(S)
+    table = np.vstack([table, np.ones((1, S))])
+    amb2 = np.zeros((1, S))
+    amb2[0, :2] = 1.0
+    table = np.vstack([table, amb2])
+    if ambiguity > 0:
+        mask = rng.random(tips.shape) < ambiguity
+        tips = np.where(mask, rng.integers(S, S + 2, size=tips.shape), tips)
+    code_dtype = np.uint8 if table.shape[0] <= 256 else np.uint16
+    cols = np.ascontiguousarray(tips.T.astype(code_dtype))             # [site][leaf]
+    if compress:
+        keys = [c.tobytes() for c in cols]
+        uniq, w, idx = rp.site_patterns(keys)
+        pat = np.frombuffer(b"".join(uniq), dtype=code_dtype).reshape(len(uniq), n_taxa)
+    else:
+        pat, w, idx = cols, np.ones(len(cols), np.uint32), np.arange(len(cols))
+    c = Case()
+    c.flat, c.model, c.rates, c.probs = flat, model, np.asarray(rates, float), np.asarray(probs, float)
+    c.table = table
+    c.N = pat.shape[0]
+    c.weights = w
+    c.site_index = idx
+    c.codes_by_leaf = {lid: np.ascontiguousarray(pat[:, k]) for k, lid in enumerate(flat.leaf_ids)}
+    c.code_dtype = code_dtype
+    c.root_freqs = np.asarray(model.freq, float)
+    return c
+
+
+def case_from_alignment(newick, seqs, model, rates, probs, check_rooted=True, states=rp.DNA_STATES,
+                        aliases=rp.DNA_ALIASES):
+    """The reference tests' way: Newick string + named sequences (test/test_likelihood.cpp:91-103)."""
+    flat = rt.FlatTree(rt.parse_newick(newick), check_rooted=check_rooted)
+    uniq, w, idx = rp.global_patterns(seqs, flat.leaf_names)
+    chars, table = rp.init_value_table(states, aliases)
+    codes = rp.encode_columns(uniq, chars)
+    c = Case()
+    c.flat, c.model, c.rates, c.probs = flat, model, np.asarray(rates, float), np.asarray(probs, float)
+    c.table = table
+    c.N = len(uniq)
+    c.weights = w
+    c.site_index = idx
+    c.codes_by_leaf = {lid: codes[k] for k, lid in enumerate(flat.leaf_ids)}
+    c.code_dtype = codes.dtype
+    c.root_freqs = np.asarray(model.freq, float)
+    c.patterns = uniq
+    return c
+
+
+def oracle_eval(c: Case, want_d1=False, want_d2=False, scaled=True, nh_form=False, weighted_root=False,
+                brlen=None, model=None):
+    m = c.model if model is None else model
+    bl = c.flat.brlen if brlen is None else brlen
+    P, dP, d2P = rm.transition_tables(m, bl, c.rates, want_d1 or want_d2, want_d2)
+    res = rl.dr_eval(c.flat, c.codes_by_leaf, c.table, P, len(c.rates), c.root_freqs, c.probs,
+                     c.weights.astype(float), dP=dP, d2P=d2P, scaled=scaled, nh_form=nh_form,
+                     weighted_root=weighted_root)
+    res.P, res.dP, res.d2P = P, dP, d2P
+    return res
+
+
+def make_engine(c: Case, flags=0, n_points=1, n_models=1, device=0):
+    from bpp_phyl_b200 import capi
+    off, ch = c.flat.csr()
+    e = capi.Engine(c.model.size, len(c.rates), c.N, off, ch, c.flat.root, c.table, n_points=n_points,
+                    n_models=n_models, code_bytes=np.dtype(c.code_dtype).itemsize, device=device, flags=flags)
+    for lid, codes in c.codes_by_leaf.items():
+        e.set_tip_codes(lid, codes)
+    e.set_pattern_weights(c.weights)
+    e.set_rates(c.rates, c.probs)
+    md = to_model_desc(c.model)
+    e._model_holders = [md]
+    e.set_model(0, md)
+    for p in range(n_points):
+        e.set_branch_lengths(p, c.flat.brlen)
+        e.set_root_freqs(p, c.root_freqs)
+    return e

@@ -1,0 +1,214 @@
+"""Parity of the CUDA path (through the C ABI) against the oracle.  Needs a B200: -m gpu."""
+import numpy as np
+import pytest
+
+import cases
+from oracle import ref_models as rm
+from test_oracle_golden import GOLD1, GOLD2, SEQS1, SEQS2, TREE1, TREE2
+
+pytestmark = pytest.mark.gpu
+
+REL = 1e-9      # north-star tolerance: log L within 1e-9 relative in FP64
+
+
+def _capi():
+    from bpp_phyl_b200 import capi
+    return capi
+
+
+def gtr():
+    return rm.gtr(1.2, 0.8, 0.6, 1.5, 0.9, (.3, .2, .25, .25))
+
+
+def check_value(c, flags=0, **okw):
+    capi = _capi()
+    res = cases.oracle_eval(c, **okw)
+    with cases.make_engine(c, flags=flags) as e:
+        lnl, _, _ = e.eval(capi.EVAL_LNL)
+        site = e.site_lnl()
+        st = e.stats()
+    assert abs(lnl[0] - res.lnl) <= REL * abs(res.lnl), (lnl[0], res.lnl)
+    np.testing.assert_allclose(site, res.site_lnl, rtol=1e-11, atol=1e-11)
+    return st
+
+
+@pytest.mark.parametrize("flags", [0, 2, 16, 1])
+def test_config1_golden_value_through_c_abi(flags):
+    """test/test_likelihood.cpp:108 through every kernel family (walk, R semantics, generic, keep)."""
+    r, p = rm.gamma_rates(4, 1.0)
+    c = cases.case_from_alignment(TREE1, SEQS1, rm.t92(3.0, 0.5), r, p)
+    with cases.make_engine(c, flags=flags) as e:
+        lnl, _, _ = e.eval()
+    assert abs(-lnl[0] - GOLD1) < 1e-9
+
+
+def test_clock_golden_value_rooted():
+    r, p = rm.constant_rate()
+    c = cases.case_from_alignment(TREE2, SEQS2, rm.t92(3.0, 0.5), r, p, check_rooted=False)
+    with cases.make_engine(c) as e:
+        lnl, _, _ = e.eval()
+    assert abs(-lnl[0] - GOLD2) < 1e-4
+
+
+@pytest.mark.parametrize("ncat", [1, 2, 4, 8])
+@pytest.mark.parametrize("flags", [0, 1, 16])
+def test_dna_random_trees(ncat, flags):
+    r, p = rm.gamma_rates(ncat, 0.5)
+    c = cases.make_case(64, 700, gtr(), r, p, seed=11 + ncat, ambiguity=0.02)
+    st = check_value(c, flags=flags)
+    assert st["path"] == (3 if flags & 16 else 1)
+
+
+@pytest.mark.parametrize("flags", [0, 1, 16])
+def test_protein_random_trees(flags):
+    r, p = rm.gamma_rates(4, 0.7)
+    c = cases.make_case(40, 300, rm.lg08(), r, p, seed=21, ambiguity=0.02)
+    st = check_value(c, flags=flags)
+    assert st["path"] == (3 if flags & 16 else 2)
+
+
+def test_codon_generic():
+    r, p = rm.constant_rate()
+    c = cases.make_case(12, 150, rm.yn98(2.0, 0.3), r, p, seed=31, mean_brlen=0.1)
+    check_value(c)
+
+
+def test_underflow_scaling_large_tree():
+    """i.i.d. tips on a long-branched 700-taxon tree: the unscaled reference arithmetic gives -inf."""
+    r, p = rm.gamma_rates(4, 0.5)
+    c = cases.make_case(700, 300, gtr(), r, p, seed=4, random_tips=True, mean_brlen=0.5)
+    check_value(c)
+    check_value(c, flags=16)
+
+
+def test_ragged_pattern_counts_and_multifurcation():
+    r, p = rm.gamma_rates(4, 0.5)
+    for n in (1, 2, 63, 65, 257):
+        c = cases.make_case(9, n, gtr(), r, p, seed=100 + n, random_tips=True, compress=False)
+        check_value(c)
+    # star tree: root with 5 sons
+    c = cases.case_from_alignment("(A:0.1,B:0.2,C:0.3,D:0.05,E:0.01);",
+                                  {"A": "ACGTNACG", "B": "ACGTRACC", "C": "AGGT-TCG", "D": "ACCTYACG", "E": "TCGTAACG"},
+                                  gtr(), r, p)
+    check_value(c)
+    check_value(c, flags=16)
+
+
+def test_empty_pattern_list():
+    r, p = rm.gamma_rates(4, 0.5)
+    c = cases.make_case(5, 0, gtr(), r, p, seed=1, random_tips=True, compress=False)
+    with cases.make_engine(c) as e:
+        lnl, _, _ = e.eval()
+    assert lnl[0] == 0.0
+
+
+@pytest.mark.parametrize("mk,ncat,ntaxa,nsites,flags", [
+    (gtr, 4, 30, 200, 0), (gtr, 4, 30, 200, 16), (rm.lg08, 4, 16, 80, 0), (rm.lg08, 2, 16, 80, 16),
+    (lambda: rm.yn98(2.0, 0.3), 1, 8, 40, 0)])
+def test_branch_derivatives(mk, ncat, ntaxa, nsites, flags):
+    capi = _capi()
+    r, p = rm.gamma_rates(ncat, 0.6) if ncat > 1 else rm.constant_rate()
+    c = cases.make_case(ntaxa, nsites, mk(), r, p, seed=41)
+    res = cases.oracle_eval(c, want_d1=True, want_d2=True)
+    with cases.make_engine(c, flags=flags | capi.FLAG_KEEP_CLVS) as e:
+        lnl, d1, d2 = e.eval(capi.EVAL_LNL | capi.EVAL_D1 | capi.EVAL_D2)
+        nb = c.flat.n_nodes - 1
+        assert abs(lnl[0] - res.lnl) <= REL * abs(res.lnl)
+        # the ABI returns derivatives of +lnL; the oracle (like getFirstOrderDerivative) of -lnL
+        np.testing.assert_allclose(-d1[0, :nb], res.d1, rtol=1e-8, atol=1e-8)
+        np.testing.assert_allclose(-d2[0, :nb], res.d2, rtol=1e-8, atol=1e-7)
+        # device-resident CLVs (getLikelihoodData consumers)
+        for nid in range(c.flat.n_nodes):
+            if c.flat.is_leaf[nid]:
+                continue
+            clv, ex = e.clv(nid, 0)
+            np.testing.assert_array_equal(ex, res.lexp[nid])
+            np.testing.assert_allclose(clv, res.lower[nid], rtol=1e-11, atol=1e-14 * res.lower[nid].max())
+        for nid in range(nb):
+            clv, ex = e.clv(nid, 1)
+            got = np.ldexp(clv, -ex[:, None, None].astype(np.int64))
+            exp = np.ldexp(res.upper[nid], -res.uexp[nid][:, None, None])
+            np.testing.assert_allclose(got, exp, rtol=1e-10, atol=1e-13 * exp.max())
+        # pxy_/dpxy_/d2pxy_ tables
+        for nid in (0, nb - 1):
+            np.testing.assert_allclose(e.transition_probabilities(nid, capi.WANT_P), res.P[nid], rtol=0, atol=1e-13)
+            np.testing.assert_allclose(e.transition_probabilities(nid, capi.WANT_DP), res.dP[nid], rtol=0, atol=1e-11)
+            np.testing.assert_allclose(e.transition_probabilities(nid, capi.WANT_D2P), res.d2P[nid], rtol=0, atol=1e-9)
+
+
+def test_nh_derivative_form():
+    capi = _capi()
+    r, p = rm.gamma_rates(4, 0.6)
+    c = cases.make_case(20, 100, gtr(), r, p, seed=43, rooted=True)
+    res = cases.oracle_eval(c, want_d1=True, want_d2=True, nh_form=True)
+    with cases.make_engine(c, flags=capi.FLAG_KEEP_CLVS | capi.FLAG_NH_DERIV) as e:
+        lnl, d1, d2 = e.eval(7)
+    nb = c.flat.n_nodes - 1
+    np.testing.assert_allclose(-d1[0, :nb], res.d1, rtol=1e-8, atol=1e-8)
+    np.testing.assert_allclose(-d2[0, :nb], res.d2, rtol=1e-8, atol=1e-7)
+
+
+@pytest.mark.parametrize("name", ["t92", "gtr", "lg08", "yn98", "chr_eigen", "chr_complex", "chr_singular", "nonrev4"])
+def test_pt_batch_interface(name):
+    """Interface 1: getPij_t / getdPij_dt / getd2Pij_dt2 for a batch of t."""
+    capi = _capi()
+    if name == "nonrev4":
+        Q = np.array([[0, .9, .05, .05], [.05, 0, .9, .05], [.05, .05, 0, .9], [.9, .05, .05, 0.]])
+        Q = rm._set_diagonal(Q)
+        m = rm.update_matrices(rm.Model("NR", Q, np.full(4, .25), reversible=False))
+        assert not m.diagonalizable and m.nonsingular          # complex pair -> block form
+    else:
+        m = {"t92": lambda: rm.t92(3.0, 0.5), "gtr": gtr, "lg08": rm.lg08, "yn98": lambda: rm.yn98(2.0, 0.3),
+             "chr_eigen": lambda: rm.chromosome(1, 40, gain=0.7, loss=0.4, dupl=0.2, demi=rm.DEMI_EQUAL_DUPL),
+             "chr_complex": lambda: rm.chromosome(1, 25, gain=1.5, loss=0.1, dupl=0.9, demi=0.4, gain_r=0.05),
+             "chr_singular": lambda: rm.chromosome(1, 20, gain=0.5, loss=0.0, dupl=0.0)}[name]()
+    ts = np.array([0.0, 1e-6, 0.013, 0.2, 1.0, 4.5])
+    P, dP, d2P = capi.pt_batch(cases.to_model_desc(m), ts, 7)
+    for k, t in enumerate(ts):
+        np.testing.assert_allclose(P[k], rm.pij_t(m, t), rtol=0, atol=2e-13, err_msg="P t=%g" % t)
+        np.testing.assert_allclose(dP[k], rm.dpij_dt(m, t), rtol=1e-10, atol=1e-11, err_msg="dP t=%g" % t)
+        np.testing.assert_allclose(d2P[k], rm.d2pij_dt2(m, t), rtol=1e-10, atol=1e-9, err_msg="d2P t=%g" % t)
+
+
+def test_chromosome_weighted_root_batched_points():
+    """ChromEvol shape: one character, C = 1, weighted root frequencies, many parameter points."""
+    capi = _capi()
+    rng = np.random.default_rng(7)
+    r, p = rm.constant_rate()
+    pts = [rm.chromosome(1, 30, gain=rng.uniform(0.2, 2), loss=rng.uniform(0.2, 2), dupl=rng.uniform(0.05, 1),
+                         demi=rm.DEMI_EQUAL_DUPL) for _ in range(5)]
+    c = cases.make_case(25, 1, pts[0], r, p, seed=51, rooted=True, mean_brlen=0.2, compress=False)
+    off, ch = c.flat.csr()
+    e = capi.Engine(30, 1, 1, off, ch, c.flat.root, c.table, n_points=len(pts), n_models=len(pts),
+                    flags=capi.FLAG_WEIGHTED_ROOT)
+    for lid, codes in c.codes_by_leaf.items():
+        e.set_tip_codes(lid, codes)
+    e.set_pattern_weights(c.weights)
+    e.set_rates(r, p)
+    holders = [cases.to_model_desc(m) for m in pts]
+    for k, h in enumerate(holders):
+        e.set_model(k, h)
+        e.set_branch_lengths(k, c.flat.brlen)
+    lnl, _, _ = e.eval()
+    for k, m in enumerate(pts):
+        res = cases.oracle_eval(c, model=m, weighted_root=True)
+        assert abs(lnl[k] - res.lnl) <= REL * abs(res.lnl)
+        np.testing.assert_allclose(e.root_freqs(k), res.root_freqs, rtol=1e-10, atol=1e-300)
+    e.close()
+
+
+def test_error_conventions():
+    capi = _capi()
+    r, p = rm.gamma_rates(4, 0.5)
+    c = cases.make_case(6, 10, gtr(), r, p, seed=1)
+    off, ch = c.flat.csr()
+    e = capi.Engine(4, 4, c.N, off, ch, c.flat.root, c.table)
+    with pytest.raises(capi.BppGpuError) as ei:
+        e.eval()
+    assert ei.value.code == capi.E_STATE
+    with pytest.raises(capi.BppGpuError) as ei:
+        e.set_tip_codes(c.flat.root, np.zeros(c.N, np.uint8))
+    assert ei.value.code == capi.E_INVALID
+    e.close()
+    with pytest.raises(capi.BppGpuError):
+        capi.Engine(4, 4, 10, np.array([0, 0, 0, 2], np.int32), np.array([0, 0], np.int32), 2, c.table)

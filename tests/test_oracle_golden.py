@@ -1,0 +1,159 @@
+"""The oracle against every known-answer value the reference's own tests hold for the path
+(SURVEY.md section 8c).  CPU only."""
+import numpy as np
+import pytest
+
+from oracle import ref_likelihood as rl
+from oracle import ref_models as rm
+from oracle import ref_patterns as rp
+from oracle import ref_tree as rt
+import cases
+
+# test/test_likelihood.cpp:91-108
+TREE1 = "((A:0.01, B:0.02):0.03,C:0.01,D:0.1);"
+SEQS1 = {"A": "AAATGGCTGTGCACGTC", "B": "GACTGGATCTGCACGTC", "C": "CTCTGGATGTGCACGTG", "D": "AAATGGCGGTGCGCCTA"}
+GOLD1 = 85.030942031997312824
+# test/test_likelihood_clock.cpp:99-115
+TREE2 = "(((A:0.01, B:0.01):0.02,C:0.03):0.01,D:0.04);"
+SEQS2 = {"A": "AAATGGCTGTGCACGTC", "B": "AACTGGATCTGCATGTC", "C": "ATCTGGACGTGCACGTG", "D": "CAACGGGAGTGCGCCTA"}
+GOLD2 = 94.3957
+
+
+def case1():
+    r, p = rm.gamma_rates(4, 1.0)
+    return cases.case_from_alignment(TREE1, SEQS1, rm.t92(3.0, 0.5), r, p)
+
+
+def test_gamma_class_means():
+    r, p = rm.gamma_rates(4, 1.0)
+    np.testing.assert_allclose(r, [0.13695378, 0.47675186, 1.0, 2.38629436], atol=5e-9)
+    np.testing.assert_allclose(p, 0.25)
+
+
+def test_pattern_order_matches_survey_appendix_c():
+    c = case1()
+    assert [u.decode() for u in c.patterns] == ["AAAG", "AATA", "ACCA", "AGCA", "CAAC", "CCCC", "CCGA", "GCGG",
+                                                "GGGC", "GGGG", "TTTG", "TTTT"]
+    assert int(c.weights.sum()) == 17
+    # indices_: site -> pattern reproduces every original column
+    flat = c.flat
+    cols = rp.columns_from_sequences([SEQS1[n] for n in flat.leaf_names])
+    assert [c.patterns[i] for i in c.site_index] == cols
+
+
+def test_golden_dr_class_value():
+    c = case1()
+    for scaled in (False, True):
+        res = cases.oracle_eval(c, scaled=scaled)
+        assert abs(-res.lnl - GOLD1) < 1e-9, (-res.lnl, GOLD1)
+
+
+def test_golden_r_class_value_recursive_patterns():
+    """R classes: per-subtree compression + per-site sum (RHomogeneousTreeLikelihood.cpp:162-176)."""
+    r, p = rm.gamma_rates(4, 1.0)
+    m = rm.t92(3.0, 0.5)
+    flat = rt.FlatTree(rt.parse_newick(TREE1))
+    rec = rp.recursive_patterns(flat, SEQS1)
+    chars, table = rp.init_value_table(rp.DNA_STATES, rp.DNA_ALIASES)
+    tip_codes = {lid: rp.encode_columns(rec["cols"][lid], chars)[0] for lid in flat.leaf_ids}
+    P, _, _ = rm.transition_tables(m, flat.brlen, r)
+    clv, ex, _ = rl.prune(flat, tip_codes, table, P, 4, links=rec["links"])
+    lnl, _ = rl.loglik_R(clv, ex, m.freq, p, rec["root_links"])
+    assert abs(-lnl - GOLD1) < 1e-9
+
+
+def test_golden_hky85_equals_t92():
+    """BASELINE.json config 1 says HKY85; the test uses T92(theta=.5) = HKY85(kappa=3, pi=1/4) (SURVEY finding 4)."""
+    r, p = rm.gamma_rates(4, 1.0)
+    c = cases.case_from_alignment(TREE1, SEQS1, rm.hky85(3.0), r, p)
+    assert abs(-cases.oracle_eval(c).lnl - GOLD1) < 1e-9
+
+
+def test_golden_clock_rooted_constant_rate():
+    r, p = rm.constant_rate()
+    c = cases.case_from_alignment(TREE2, SEQS2, rm.t92(3.0, 0.5), r, p, check_rooted=False)
+    assert len(c.flat.children[c.flat.root]) == 2
+    assert abs(-cases.oracle_eval(c).lnl - GOLD2) < 1e-4        # the reference prints 6 digits
+
+
+def test_r_vs_dr_derivatives_identity():
+    """test/test_likelihood.cpp:124-135: d1 from the single and the double recursion agree to 1e-6."""
+    c = case1()
+    res = cases.oracle_eval(c, want_d1=True, want_d2=True, scaled=False)
+    for b in range(c.flat.n_nodes - 1):
+        d1r = rl.r_derivative(c.flat, c.codes_by_leaf, c.table, res.P, res.dP, 4, c.root_freqs, c.probs,
+                              c.weights.astype(float), b, order=1)
+        d2r = rl.r_derivative(c.flat, c.codes_by_leaf, c.table, res.P, res.dP, 4, c.root_freqs, c.probs,
+                              c.weights.astype(float), b, order=2, d2P=res.d2P)
+        assert abs(d1r - res.d1[b]) < 1e-6
+        assert abs(d2r - res.d2[b]) < 1e-6 * max(1.0, abs(d2r))
+
+
+def test_derivatives_vs_finite_differences():
+    c = case1()
+    res = cases.oracle_eval(c, want_d1=True, want_d2=True)
+    h = 1e-5
+    for b in range(c.flat.n_nodes - 1):
+        bl = c.flat.brlen.copy()
+        bl[b] += h
+        fp = -cases.oracle_eval(c, brlen=bl).lnl
+        bl[b] -= 2 * h
+        fm = -cases.oracle_eval(c, brlen=bl).lnl
+        f0 = -res.lnl
+        assert abs((fp - fm) / (2 * h) - res.d1[b]) < 1e-5 * max(1, abs(res.d1[b]))
+        assert abs((fp - 2 * f0 + fm) / h ** 2 - res.d2[b]) < 2e-3 * max(1, abs(res.d2[b]))
+
+
+@pytest.mark.parametrize("name", ["gtr", "lg08", "yn98", "chromosome"])
+def test_pt_family_against_scipy_expm(name):
+    from scipy.linalg import expm
+    m = {"gtr": lambda: rm.gtr(1.2, 0.8, 0.6, 1.5, 0.9, (.3, .2, .25, .25)),
+         "lg08": rm.lg08,
+         "yn98": lambda: rm.yn98(2.0, 0.3),
+         "chromosome": lambda: rm.chromosome(1, 30, gain=0.7, loss=0.4, dupl=0.2, demi=rm.DEMI_EQUAL_DUPL)}[name]()
+    for t in (1e-6, 0.05, 0.7, 3.0):
+        E = expm(m.Q * m.rate * t)
+        P = rm.pij_t(m, t)
+        tol = 1e-10 if name != "chromosome" else 1e-8
+        np.testing.assert_allclose(P, np.where(m.chromosome & (E < 0), rm.VERY_TINY, E), atol=tol)
+        np.testing.assert_allclose(P.sum(axis=1), 1.0, atol=1e-9)
+        if not m.chromosome:
+            np.testing.assert_allclose(rm.dpij_dt(m, t), m.rate * m.Q @ E, atol=1e-9)
+            np.testing.assert_allclose(rm.d2pij_dt2(m, t), m.rate ** 2 * m.Q @ m.Q @ E, atol=1e-8)
+
+
+def test_reversible_models_detailed_balance_and_normalisation():
+    for m in (rm.gtr(1.2, 0.8, 0.6, 1.5, 0.9, (.3, .2, .25, .25)), rm.lg08(), rm.yn98(2.0, 0.3)):
+        F = m.freq[:, None] * m.Q
+        np.testing.assert_allclose(F, F.T, atol=1e-14)
+        assert abs(-np.dot(np.diag(m.Q), m.freq) - 1.0) < 1e-12
+
+
+@pytest.mark.parametrize("S,mk", [(4, lambda: rm.gtr(1.2, 0.8, 0.6, 1.5, 0.9, (.3, .2, .25, .25))),
+                                  (20, rm.lg08)])
+def test_pruning_against_brute_force(S, mk):
+    """Sum over all internal-state assignments on a 4-taxon tree (2 internal nodes)."""
+    m = mk()
+    rates, probs = rm.gamma_rates(2, 0.7)
+    c = cases.make_case(4, 3, m, rates, probs, seed=5, random_tips=True)
+    res = cases.oracle_eval(c, scaled=False)
+    for i in range(c.N):
+        L = 0.0
+        for ci, r in enumerate(rates):
+            Pc = {n: rm.pij_t(m, c.flat.brlen[n] * r) for n in range(c.flat.n_nodes - 1)}
+            tips = {l: c.table[c.codes_by_leaf[l][i]] for l in c.flat.leaf_ids}
+            L += probs[ci] * rl.brute_force_site(c.flat, tips, Pc, c.root_freqs)
+        assert abs(np.log(L) - res.site_lnl[i]) < 1e-12 * abs(np.log(L)) + 1e-13
+
+
+def test_scaled_equals_unscaled_where_finite_and_survives_underflow():
+    m = rm.gtr(1.2, 0.8, 0.6, 1.5, 0.9, (.3, .2, .25, .25))
+    rates, probs = rm.gamma_rates(4, 0.5)
+    c = cases.make_case(40, 30, m, rates, probs, seed=3)
+    a = cases.oracle_eval(c, scaled=False)
+    b = cases.oracle_eval(c, scaled=True)
+    assert abs(a.lnl - b.lnl) <= 1e-12 * abs(a.lnl)
+    big = cases.make_case(700, 4, m, rates, probs, seed=4, random_tips=True, mean_brlen=0.5)
+    assert not np.isfinite(cases.oracle_eval(big, scaled=False).lnl)      # the reference would return -inf
+    s = cases.oracle_eval(big, scaled=True)
+    assert np.isfinite(s.lnl) and s.SR_exp.max() > 256
