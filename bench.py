@@ -1,0 +1,362 @@
+#!/usr/bin/env python
+"""bench.py -- the hot path on the BASELINE.json workload, one JSON line on stdout (rank 0).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference] [--workload NAME]
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A *step* is one full log-likelihood evaluation of the workload (K1 P(t) tables for every branch x class,
+K2b tip tables, K2+K3 pruning + root reduction [+ K4/K5 derivatives], and for N > 1 the NCCL all-reduce of the
+per-shard scalars).  ``value`` = CLV updates per second (one update = one (node, pattern, class, state) element of
+an internal node's conditional likelihood vector), whole job, inputs resident in HBM.
+``e2e`` = the same through the C-ABI call sequence of one optimiser step with HOST buffers: branch lengths and the
+model eigensystem go host->device, log L (and derivatives) come back device->host, inside the timed region.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # BASELINE.json configs[1]: GTR+G4 DNA, 1024 taxa x 1M patterns
+    "dna_gtr_g4_1024x1M": dict(S=4, C=4, taxa=1024, patterns=1_000_000, alpha=0.5, derivs=False, seed=20260102),
+    # configs[2]: 20 states + G4, 500 taxa x 200k patterns with d1/d2
+    "protein_g4_500x200k_d2": dict(S=20, C=4, taxa=500, patterns=200_000, alpha=0.7, derivs=True, seed=20260103),
+    # configs[3]: 64-state codon (61 sense), 200 taxa x 100k patterns, C = 1
+    "codon_200x100k": dict(S=64, C=1, taxa=200, patterns=100_000, alpha=None, derivs=False, seed=20260104),
+}
+DEFAULT = "dna_gtr_g4_1024x1M"
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2])); pw.append(float(r[3]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def algorithmic_bytes(tree, N, C, S):
+    """per CLV update at a node with k sons of which k_t are tips: 8*(1 + k - k_t) bytes."""
+    tot = 0
+    for n in range(tree.nn):
+        sons = tree.sons(n)
+        if len(sons) == 0:
+            continue
+        k_int = int((~tree.is_leaf[sons]).sum())
+        tot += 8 * (1 + k_int)
+    return tot * N * C * S
+
+
+def model_for(w, rng):
+    from bpp_phyl_b200 import synth
+    if w["S"] == 4:
+        return synth.gtr()
+    return synth.random_reversible(w["S"], rng)
+
+
+def build_inputs(w, rank, world, device):
+    """Tree + model + this rank's contiguous pattern shard (strong scaling: the workload's patterns are split)."""
+    from bpp_phyl_b200 import synth
+    rng = np.random.default_rng(w["seed"])
+    tree = synth.random_tree(w["taxa"], rng, mean_brlen=0.05)
+    es = model_for(w, rng)
+    rates, probs = synth.gamma_rates(w["C"], w["alpha"]) if w["C"] > 1 else (np.ones(1), np.ones(1))
+    N = w["patterns"]
+    lo, hi = N * rank // world, N * (rank + 1) // world
+    t0 = time.time()
+    codes = synth.simulate_tip_codes(tree, es, rates, hi - lo, seed=w["seed"] + 7919 * rank, device=device)
+    log("[rank %d] simulated %d patterns x %d tips in %.1fs" % (rank, hi - lo, tree.n_leaves, time.time() - t0))
+    return tree, es, rates, probs, codes
+
+
+def make_engine(w, tree, es, rates, probs, codes, dev_index, flags):
+    from bpp_phyl_b200 import capi, synth
+    S = w["S"]
+    e = capi.Engine(S, w["C"], codes.shape[1], tree.child_off, tree.children, tree.root, np.eye(S), device=dev_index,
+                    flags=flags)
+    e.set_all_tip_codes(codes)
+    e.set_pattern_weights(np.ones(codes.shape[1], np.uint32))
+    e.set_rates(rates, probs)
+    md = synth.model_desc(es)
+    e.set_model(0, md)
+    e.set_branch_lengths(0, tree.brlen)
+    e.set_root_freqs(0, es["pi"])
+    return e, md
+
+
+def cpu_leg(w, tree, es, rates, probs, codes, threads, target_seconds=12.0, per_thread=512):
+    """The reference's CPU algorithm (oracle/ref_cpu.cpp, a port: the reference cannot be built here) on a bounded
+    sample of the same workload."""
+    from oracle import ref_cpu
+    ref_cpu.build()
+    n = min(codes.shape[1], per_thread * threads)
+    sub = np.ascontiguousarray(codes[:, :n])
+    want = 7 if w["derivs"] else 1
+    args = dict(S=w["S"], Ccat=w["C"], N=n, child_off=tree.child_off, children=tree.children, root=tree.root, codes=sub,
+                code_table=np.eye(w["S"]), weights=np.ones(n, np.uint32), rates=rates, probs=probs, V=es["V"],
+                Vinv=es["Vinv"], ev=es["ev"], model_rate=1.0, brlen=tree.brlen, rootfreq=es["pi"], scaled=True, want=want,
+                nthreads=threads)
+    r = ref_cpu.eval_raw(reps=1, **args)
+    reps = int(max(1, min(20, target_seconds / max(r["seconds"], 1e-3))))
+    if reps > 1:
+        r = ref_cpu.eval_raw(reps=reps, **args)
+    upd = tree.n_internal * n * w["C"] * w["S"]
+    return {"value": upd / r["seconds"], "unit": "CLV updates/s", "cores": threads, "kind": "port",
+            "sample": "%d of %d patterns, full tree, best of %d evals (%.2f s each), scaled arithmetic" %
+                      (n, w["patterns"], reps, r["seconds"]),
+            "evals_per_s_full_size_extrapolated": (upd / r["seconds"]) / (tree.n_internal * w["patterns"] * w["C"] * w["S"]),
+            "lnl_sample": r["lnl"]}, sub
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--workload", default=DEFAULT, choices=sorted(WORKLOADS))
+    ap.add_argument("--patterns", type=int, default=0, help="override the workload's pattern count (debug)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    a = ap.parse_args()
+    w = dict(WORKLOADS[a.workload])
+    if a.patterns:
+        w["patterns"] = a.patterns
+    W = max(a.warmup, 3) if a.impl == "native" else a.warmup
+    K = a.steps
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    metric = "CLV updates/s"
+    config = {"workload": a.workload, "states": w["S"], "rate_classes": w["C"], "taxa": w["taxa"],
+              "patterns": w["patterns"], "derivatives": w["derivs"], "sharding": "patterns/%d" % world,
+              "l2": "inputs larger than L2 (tip codes %.0f MB per rank; CLVs never re-read from a previous step)" %
+                    (w["taxa"] * w["patterns"] / world / 1e6)}
+
+    if a.impl == "reference":
+        if rank != 0:
+            return 0
+        from bpp_phyl_b200 import synth
+        rng = np.random.default_rng(w["seed"])
+        tree = synth.random_tree(w["taxa"], rng, mean_brlen=0.05)
+        es = model_for(w, rng)
+        rates, probs = synth.gamma_rates(w["C"], w["alpha"]) if w["C"] > 1 else (np.ones(1), np.ones(1))
+        threads = os.cpu_count() or 1
+        n = 512 * threads
+        codes = np.random.default_rng(1).integers(0, w["S"], size=(tree.n_leaves, n), dtype=np.uint8)
+        from oracle import ref_cpu
+        ref_cpu.build()
+        want = 7 if w["derivs"] else 1
+        args = dict(S=w["S"], Ccat=w["C"], N=n, child_off=tree.child_off, children=tree.children, root=tree.root,
+                    codes=codes, code_table=np.eye(w["S"]), weights=np.ones(n, np.uint32), rates=rates, probs=probs,
+                    V=es["V"], Vinv=es["Vinv"], ev=es["ev"], model_rate=1.0, brlen=tree.brlen, rootfreq=es["pi"],
+                    scaled=True, want=want, nthreads=threads)
+        for _ in range(a.warmup):
+            ref_cpu.eval_raw(reps=1, **args)
+        t0 = time.perf_counter()
+        for _ in range(K):
+            ref_cpu.eval_raw(reps=1, **args)
+        dt = time.perf_counter() - t0
+        upd = tree.n_internal * n * w["C"] * w["S"]
+        val = upd * K / dt
+        sample = "%d of %d patterns per step (full tree), %d host threads as independent pattern shards" % (n, w["patterns"], threads)
+        print(json.dumps({"impl": "reference", "metric": metric, "value": val, "unit": "CLV updates/s", "n_gpus": a.gpus,
+                          "steps": K, "warmup": a.warmup, "ms_per_step": 1e3 * dt / K, "higher_is_better": True,
+                          "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                          "config": config,
+                          "cpu_baseline": {"value": val, "unit": "CLV updates/s", "cores": threads, "kind": "port", "sample": sample},
+                          "e2e": {"value": val, "unit": "CLV updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return 0
+
+    # ---------------- native arm ----------------
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as g
+    from bpp_phyl_b200 import capi
+    if not capi.LIB_PATH.exists():
+        g.build_lib()
+    torch.cuda.set_device(local)
+    device = "cuda:%d" % local
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(device))
+    flags = capi.FLAG_KEEP_CLVS if w["derivs"] else 0
+    want = 7 if w["derivs"] else 1
+    tree, es, rates, probs, codes = build_inputs(w, rank, world, device)
+    e, md = make_engine(w, tree, es, rates, probs, codes, local, flags)
+    nn = tree.nn
+    out = torch.zeros(1 + 2 * nn, dtype=torch.float64, device=device)
+    # a real (non-NULL) stream: kernels, NCCL and the timing events all go on it
+    stream = torch.cuda.Stream(device=device)
+    torch.cuda.set_stream(stream)
+
+    def step_device():
+        e.eval_device(want, out.data_ptr(), stream.cuda_stream)
+        if world > 1:
+            dist.all_reduce(out)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(W):
+        step_device()
+    barrier()
+    st0 = e.stats()             # clears the kernel-timing ring
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record(stream)
+    for _ in range(K):
+        step_device()
+    ev1.record(stream)
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    st = e.stats()
+    lnl_dev = float(out[0].item())
+    tms = torch.tensor([ms], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    ms = float(tms.item())
+
+    # ---- e2e: one optimiser step through the C ABI with host buffers -----------------------------------------
+    brl = tree.brlen.copy()
+    host_out = torch.empty(1 + 2 * nn, dtype=torch.float64).pin_memory()
+    h2d = brl.nbytes + es["V"].nbytes + es["Vinv"].nbytes + es["ev"].nbytes + es["Q"].nbytes
+    d2h = 8 * (1 + (2 * nn if w["derivs"] else 0))
+
+    def step_e2e(i):
+        brl[0] = tree.brlen[0] * (1.0 + 1e-3 * ((i % 5) - 2))      # a branch-length probe, as an optimiser would send
+        e.set_model(0, md)                                          # eigensystem host -> device
+        e.set_branch_lengths(0, brl)                                # host -> device
+        if world == 1:
+            return e.eval(want)[0][0]                               # log L (d1, d2) device -> host
+        e.eval_device(want, out.data_ptr(), stream.cuda_stream)
+        dist.all_reduce(out)
+        host_out.copy_(out, non_blocking=False)
+        return float(host_out[0])
+
+    for i in range(W):
+        step_e2e(i)
+    barrier()
+    t0 = time.perf_counter()
+    ev0.record(stream)
+    for i in range(K):
+        step_e2e(i)
+    ev1.record(stream)
+    barrier()
+    e2e_ms = max(ev0.elapsed_time(ev1), 1e3 * (time.perf_counter() - t0))
+    tms = torch.tensor([e2e_ms], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    e2e_ms = float(tms.item())
+    clocks = sampler.stop() if rank == 0 else None
+    e.set_branch_lengths(0, tree.brlen)
+
+    upd_step = tree.n_internal * w["patterns"] * w["C"] * w["S"]         # whole job (all shards)
+    value = upd_step * K / (ms * 1e-3)
+    line = None
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except OSError:
+            pass
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        n_local = codes.shape[1]
+        alg = algorithmic_bytes(tree, n_local, w["C"], w["S"])
+        kms = st["prune_ms_sum"] / max(1, st["prune_count"])
+        achieved = alg / (kms * 1e-3) / 1e9 if kms > 0 else None
+        roofline = {"bound": "hbm", "kernel": {1: "walk4_kernel", 2: "walkS_kernel", 3: "generic_node_kernel"}.get(st["path"], "?"),
+                    "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak if achieved else None,
+                    "traffic": None, "kernel_ms": kms, "launches_timed": st["prune_count"],
+                    "algorithmic_bytes_per_launch": alg,
+                    "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
+                    "note": "algorithmic bytes = 8*(1+internal sons) per CLV element (SURVEY 8d), the traffic a level-scheduled "
+                            "kernel must move; this kernel keeps CLVs on chip, so frac > 1 is expected and DRAM traffic is "
+                            "the tip codes only (see profiles/)"}
+        line = {"metric": metric, "value": value, "unit": "CLV updates/s", "n_gpus": world, "steps": K, "warmup": W,
+                "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic (tips simulated down a random tree under the model; every site kept as a pattern, weight 1)",
+                "config": config, "logl_evals_per_s": K / (ms * 1e-3), "lnl": lnl_dev,
+                "e2e": {"value": upd_step * K / (e2e_ms * 1e-3), "unit": "CLV updates/s", "h2d_bytes_per_step": h2d,
+                        "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / K,
+                        "call": "bppgpu_set_model + bppgpu_set_branch_lengths + bppgpu_eval (host buffers)"},
+                "gpu_launches": int(st["kernel_launches"]) * K, "launches_per_step": int(st["kernel_launches"]),
+                "roofline": roofline, "clocks": clocks,
+                "hbm_resident_bytes": int(st["hbm_bytes_resident"])}
+        if world == 1 and not a.no_cpu:
+            t0 = time.time()
+            cb, sub = cpu_leg(w, tree, es, rates, probs, codes, threads=os.cpu_count() or 1)
+            # the same sample through the CUDA path: the checker, not the thing measured
+            e2, _ = make_engine(w, tree, es, rates, probs, sub, local, 0)
+            l2 = e2.eval(1)[0][0]
+            e2.close()
+            cb["gpu_lnl_same_sample"] = l2
+            cb["rel_diff_vs_gpu"] = abs(l2 - cb["lnl_sample"]) / abs(cb["lnl_sample"])
+            line["cpu_baseline"] = cb
+            log("cpu leg %.1fs" % (time.time() - t0))
+        print(json.dumps(line), flush=True)
+    e.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

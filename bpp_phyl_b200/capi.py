@@ -84,6 +84,8 @@ class Stats(C.Structure):
         ("clv_updates", C.c_int64),
         ("last_eval_ms", C.c_double),
         ("prune_ms", C.c_double),
+        ("prune_ms_sum", C.c_double),
+        ("prune_count", C.c_int64),
         ("hbm_bytes_resident", C.c_int64),
         ("stack_slots", C.c_int32),
         ("path", C.c_int32),
@@ -255,7 +257,7 @@ class Engine:
 
     def clv(self, node, which=0, point=0):
         out = np.empty((self.N, self.C, self.S))
-        ex = np.empty(self.N, np.int32)
+        ex = np.empty((self.N, self.C), np.int32)
         _check(lib().bppgpu_get_clv(self._h, C.c_int32(point), C.c_int32(node), C.c_int32(which), _ptr(out),
                                     _ptr(ex, C.c_int32)))
         return out, ex

@@ -55,6 +55,9 @@ __device__ __forceinline__ double pow2(int k) { return __hiloint2double((k + 102
 
 constexpr double kLn2 = 0.693147180559945309417232121458;
 
+// 2^-d for d >= 0 (aligning a class row to the pattern's smallest exponent); 0 once it would be subnormal
+__device__ __forceinline__ double align_factor(int d) { return d > 1000 ? 0.0 : pow2(-d); }
+
 // ---- deterministic block sum (fixed shuffle tree, then warp 0) ---------------
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll

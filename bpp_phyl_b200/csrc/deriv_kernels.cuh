@@ -75,24 +75,24 @@ __global__ void upper_node_kernel(UpperParams p) {
 }
 
 __global__ void upper_scale_kernel(UpperParams p) {
-  const long long pat = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (pat >= p.N) return;
-  int Ea = p.father < 0 ? 0 : p.uexp_f[pat];
+  const long long rows = p.N * p.C;
+  const long long rc = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (rc >= rows) return;
+  int Ea = p.father < 0 ? 0 : p.uexp_f[rc];
   for (int j = 0; j < p.nsib; ++j) {
     const Child ch = p.sibs[j];
-    if (ch.kind != CHILD_TIP) Ea += p.keep_exp[(size_t)ch.idx * p.N + pat];
+    if (ch.kind != CHILD_TIP) Ea += p.keep_exp[(size_t)ch.idx * rows + rc];
   }
-  const int w = p.C * p.S;
-  double* v = p.upper_out + (size_t)pat * w;
+  double* v = p.upper_out + (size_t)rc * p.S;
   int m = 0;
-  for (int i = 0; i < w; ++i) m = max(m, hi_word(v[i]));
+  for (int i = 0; i < p.S; ++i) m = max(m, hi_word(v[i]));
   if (m < kScaleThresholdHi && m >= (1 << 20)) {
     const int k = rescale_shift(m);
     const double f = pow2(k);
-    for (int i = 0; i < w; ++i) v[i] *= f;
+    for (int i = 0; i < p.S; ++i) v[i] *= f;
     Ea += k;
   }
-  p.uexp_out[pat] = Ea;
+  p.uexp_out[rc] = Ea;
 }
 
 struct DerivParams {
@@ -127,14 +127,15 @@ __global__ void deriv_node_kernel(DerivParams p) {
   if (pat < p.N) {
     const int S = p.S;
     const double* D0;
-    int le = 0;
+    const int* le = nullptr;
     if (p.is_tip) {
       const int code = load_code(p.codes, p.code_bytes, (long long)p.idx * p.N + pat);
       D0 = p.code_table + (size_t)code * S;
     } else {
       D0 = p.keep + ((size_t)p.idx * p.N + pat) * p.C * S;
-      le = p.keep_exp[(size_t)p.idx * p.N + pat];
+      le = p.keep_exp + ((size_t)p.idx * p.N + pat) * p.C;
     }
+    const int re = p.rexp[pat];
     double a1 = 0.0, a2 = 0.0;
     for (int c = 0; c < p.C; ++c) {
       const double* D = p.is_tip ? D0 : D0 + (size_t)c * S;
@@ -161,13 +162,13 @@ __global__ void deriv_node_kernel(DerivParams p) {
           s2c = fma(u, n2, s2c);
         }
       }
-      a1 = fma(s1c, p.probs[c], a1);
-      a2 = fma(s2c, p.probs[c], a2);
+      const int sh = re - p.uexp[(size_t)pat * p.C + c] - (le ? le[c] : 0);
+      a1 = fma(scalbn(s1c, sh), p.probs[c], a1);
+      a2 = fma(scalbn(s2c, sh), p.probs[c], a2);
     }
-    const int sh = p.rexp[pat] - p.uexp[pat] - le;
     const double sr = p.SR[pat];
-    const double dL = scalbn(a1, sh) / sr;
-    const double d2L = scalbn(a2, sh) / sr;
+    const double dL = a1 / sr;
+    const double d2L = a2 / sr;
     const double w = p.weights[pat];
     c1 = w * dL;
     c2 = w * (d2L - dL * dL);

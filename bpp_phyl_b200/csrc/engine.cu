@@ -11,6 +11,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <functional>
 
@@ -169,11 +170,16 @@ static int check_device(int device) {
   BPP_CUDA(cudaGetDeviceProperties(&prop, device));
   if (prop.major < 10) BPP_FAIL(BPPGPU_E_CUDA, "device %d is sm_%d%d; libbppgpu is built for sm_100a only", device, prop.major, prop.minor);
   g_sm_count = prop.multiProcessorCount;
+  // dynamic shared memory above 48 KB is opt-in
+  BPP_CUDA(cudaFuncSetAttribute(pt_dmma_kernel<8, 1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+  BPP_CUDA(cudaFuncSetAttribute(pt_dmma_kernel<8, 2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+  BPP_CUDA(cudaFuncSetAttribute(pt_dmma_kernel<8, 4, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
   return BPPGPU_OK;
 }
 
 // ---- model upload -------------------------------------------------------------------
 static void free_model(DevModel& m) {
+  if (m.Vp != m.V) { cudaFree(m.Vp); cudaFree(m.Vinvp); cudaFree(m.rep); }
   cudaFree(m.V); cudaFree(m.Vinv); cudaFree(m.re); cudaFree(m.im); cudaFree(m.Q); cudaFree(m.Q2); cudaFree(m.role);
   m = DevModel{};
 }
@@ -216,6 +222,24 @@ static int upload_model(DevModel& dm, const bppgpu_model_desc* m, int S) {
     }
     BPP_CUDA(cudaMemcpy(dm.im, im.data(), S * 8, cudaMemcpyHostToDevice));
     BPP_CUDA(cudaMemcpy(dm.role, role.data(), S * 4, cudaMemcpyHostToDevice));
+    const int Sp = (S + 7) & ~7;
+    if (Sp == S) {
+      dm.Vp = dm.V; dm.Vinvp = dm.Vinv; dm.rep = dm.re;
+    } else if (S >= 32) {  // padded copies for the DMMA kernel
+      std::vector<double> vp((size_t)Sp * Sp, 0.0), vip((size_t)Sp * Sp, 0.0), rp(Sp, 0.0);
+      for (int i = 0; i < S; ++i)
+        for (int j = 0; j < S; ++j) {
+          vp[(size_t)i * Sp + j] = m->right_eigen[(size_t)i * S + j];
+          vip[(size_t)i * Sp + j] = m->left_eigen[(size_t)i * S + j];
+        }
+      for (int k = 0; k < S; ++k) rp[k] = m->eigen_re[k];
+      BPP_CUDA(cudaMalloc(&dm.Vp, vp.size() * 8));
+      BPP_CUDA(cudaMalloc(&dm.Vinvp, vip.size() * 8));
+      BPP_CUDA(cudaMalloc(&dm.rep, Sp * 8));
+      BPP_CUDA(cudaMemcpy(dm.Vp, vp.data(), vp.size() * 8, cudaMemcpyHostToDevice));
+      BPP_CUDA(cudaMemcpy(dm.Vinvp, vip.data(), vip.size() * 8, cudaMemcpyHostToDevice));
+      BPP_CUDA(cudaMemcpy(dm.rep, rp.data(), Sp * 8, cudaMemcpyHostToDevice));
+    }
   }
   if (m->generator) {
     BPP_CUDA(cudaMalloc(&dm.Q, SS * 8));
@@ -240,12 +264,14 @@ static int upload_model(DevModel& dm, const bppgpu_model_desc* m, int S) {
 static ModelDev to_dev(const DevModel& m) {
   ModelDev d{};
   d.V = m.V; d.Vinv = m.Vinv; d.re = m.re; d.im = m.im; d.role = m.role; d.Q = m.Q; d.Q2 = m.Q2;
+  d.Vp = m.Vp; d.Vinvp = m.Vinvp; d.rep = m.rep;
   d.rate = m.rate; d.eps = m.eps; d.q_l1 = m.q_l1; d.flags = m.flags; d.has_complex = m.has_complex;
   return d;
 }
 
 // enqueue K1 for `npts` points starting at `p0` (tables indexed from 0 within the chunk)
-static int launch_pt(cudaStream_t st, const ModelDev* d_models, bool any_series, bool any_chr_deriv,
+static int launch_pt(cudaStream_t st, const ModelDev* d_models, bool any_series, bool any_chr_deriv, bool any_real_eigen,
+                     bool any_complex,
                      const int* d_branch_model, const double* d_brlen, const double* d_rates, int S, int C,
                      int nn, int root, int npts, unsigned want, double* P, double* dP, double* d2P,
                      double* scratch, int* d_status, long long* launches) {
@@ -261,8 +287,25 @@ static int launch_pt(cudaStream_t st, const ModelDev* d_models, bool any_series,
   const int nmat = npts * nn * C;
   if (nmat == 0) return BPPGPU_OK;
   const int threads = S * S >= 256 ? 256 : (S * S >= 64 ? 64 : 32);
-  pt_eigen_kernel<<<nmat, threads, 6 * S * sizeof(double), st>>>(pp);
-  ++*launches;
+  const int Sp = (S + 7) & ~7;
+  pp.dmma_real = 0;
+  if (S >= 32 && Sp <= 256 && any_real_eigen) {
+    // FP64 tensor-core GEMM for every real-spectrum matrix; the CUDA-core kernel keeps the complex ones
+    pp.dmma_real = 1;
+    const int nblk = Sp / 8;
+    if (nblk <= 8) {
+      pt_dmma_kernel<8, 1, 8><<<dim3(nmat, 1), 256, pt_dmma_smem_bytes(Sp, 8), st>>>(pp, Sp);
+    } else if (nblk <= 16) {
+      pt_dmma_kernel<8, 2, 8><<<dim3(nmat, (nblk + 7) / 8), 256, pt_dmma_smem_bytes(Sp, 8), st>>>(pp, Sp);
+    } else {
+      pt_dmma_kernel<8, 4, 5><<<dim3(nmat, (nblk + 4) / 5), 256, pt_dmma_smem_bytes(Sp, 5), st>>>(pp, Sp);
+    }
+    ++*launches;
+  }
+  if (!pp.dmma_real || any_complex) {
+    pt_eigen_kernel<<<nmat, threads, 6 * S * sizeof(double), st>>>(pp);
+    ++*launches;
+  }
   if (any_chr_deriv && (want & 6u)) {
     SeriesParams sp{};
     sp.pt = pp;
@@ -367,8 +410,8 @@ int bppgpu_pt_batch(int device, const bppgpu_model_desc* model, int64_t n_t, con
   if (series) PT_CUDA(cudaMalloc(&scr, n_t * 4 * SS * 8));
   else if (chrd) PT_CUDA(cudaMalloc(&scr, n_t * SS * 8));
   long long launches = 0;
-  rc = launch_pt(nullptr, d_md, series, chrd, d_bm, d_t, d_r, S, 1, (int)n_t, -1, 1, want, dPm, ddP, dd2P, scr,
-                 d_status, &launches);
+  rc = launch_pt(nullptr, d_md, series, chrd, !series && !dm.has_complex, !series && dm.has_complex, d_bm, d_t, d_r, S, 1,
+                 (int)n_t, -1, 1, want, dPm, ddP, dd2P, scr, d_status, &launches);
   if (rc) { cleanup(); return rc; }
   PT_CUDA(cudaDeviceSynchronize());
   if (want & 1u) PT_CUDA(cudaMemcpy(P, dPm, n_t * SS * 8, cudaMemcpyDeviceToHost));
@@ -392,17 +435,22 @@ int bppgpu_destroy(bppgpu_engine* e) {
                   e->d_d2P, e->d_tiptab, e->d_keep, e->d_keep_exp, e->d_gstack, e->d_gstack_exp, e->d_upper,
                   e->d_upper_exp, e->d_SR, e->d_rexp, e->d_site_lnl, e->d_partials, e->d_partials2, e->d_out,
                   e->prog.d_ops, e->prog.d_childs, e->gprog.d_ops, e->gprog.d_childs, e->d_sibs, e->d_scratch,
+                  e->d_w4_desc, e->d_w4_tip_order, e->d_w4_blocks, e->d_w4_stream, e->d_codesT,
                   e->d_status};
   for (void* p : ptrs) cudaFree(p);
   for (auto& m : e->models) free_model(m);
   if (e->ev0) cudaEventDestroy(e->ev0);
   if (e->ev1) cudaEventDestroy(e->ev1);
-  if (e->ev2) cudaEventDestroy(e->ev2);
-  if (e->ev3) cudaEventDestroy(e->ev3);
+  for (int i = 0; i < bppgpu_engine::kRing; ++i) {
+    if (e->ring_a[i]) cudaEventDestroy(e->ring_a[i]);
+    if (e->ring_b[i]) cudaEventDestroy(e->ring_b[i]);
+  }
   if (e->stream) cudaStreamDestroy(e->stream);
   delete e;
   return BPPGPU_OK;
 }
+
+static int walk4_dispatch(bppgpu_engine* e, const Walk4Params* wp, int grid, size_t, cudaStream_t st, bool attr_only);
 
 static int create_impl(const bppgpu_config* cfg, bppgpu_engine* e) {
   e->dev = cfg->device;
@@ -452,21 +500,53 @@ static int create_impl(const bppgpu_config* cfg, bppgpu_engine* e) {
   BPP_CUDA(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
   BPP_CUDA(cudaEventCreate(&e->ev0));
   BPP_CUDA(cudaEventCreate(&e->ev1));
-  BPP_CUDA(cudaEventCreate(&e->ev2));
-  BPP_CUDA(cudaEventCreate(&e->ev3));
+  for (int i = 0; i < bppgpu_engine::kRing; ++i) {
+    BPP_CUDA(cudaEventCreate(&e->ring_a[i]));
+    BPP_CUDA(cudaEventCreate(&e->ring_b[i]));
+  }
 
   // ---- path selection ---------------------------------------------------------------
   build_program(e, e->prog, false);
-  build_program(e, e->gprog, true);
+  // keep-buffer index of an internal node = its position in the walk (so the walk streams node o to slab o)
+  for (size_t o = 0; o < e->prog.ops.size(); ++o) e->internal_idx[e->prog.ops[o].node] = (int)o;
   const bool cpow = is_pow2(C) && C <= 8;
-  if (S == 4 && cpow && (size_t)e->prog.nslots * kWalkThreads * 36 <= 200 * 1024) e->path = PATH_WALK4;
+  bool w4ok = S == 4 && cpow && e->code_bytes == 1 && e->prog.nslots <= 63 &&
+              (size_t)e->prog.nslots * kWalk4Threads * 36 <= 200 * 1024;
+  for (const Op& op : e->prog.ops)
+    if (op.nchild > 6) w4ok = false;
+  if (w4ok) e->path = PATH_WALK4;
   else if (S == 20 && cpow) e->path = PATH_WALKS;
   else e->path = PATH_GENERIC;
   if (cfg->flags & BPPGPU_FLAG_FORCE_GENERIC) e->path = PATH_GENERIC;
   if (e->path == PATH_GENERIC) e->keep = true;
-  if (e->keep) {
-    // the walk program must stream every node out
-    build_program(e, e->prog, false);
+  build_program(e, e->prog, false);  // again: keep indices are known now
+  build_program(e, e->gprog, true);
+  if (e->path == PATH_WALK4) {
+    // packed descriptors, tip consumption order and table blocks, all in walk order
+    size_t off = 0;
+    for (const Op& op : e->prog.ops) {
+      unsigned long long d = (unsigned long long)op.nchild | ((unsigned long long)(op.dst_slot + 1) << 8);
+      for (int j = 0; j < op.nchild; ++j) {
+        const Child& ch = e->prog.childs[op.child_begin + j];
+        const unsigned tok = ((unsigned)ch.kind << 6) | (ch.kind == CHILD_SLOT ? (unsigned)ch.idx : 0u);
+        d |= (unsigned long long)tok << (16 + 8 * j);
+        PackBlock b{};
+        b.kind = ch.kind;
+        b.pnode = ch.pnode;
+        b.off = (long long)off;
+        e->w4_blocks.push_back(b);
+        if (ch.kind == CHILD_TIP) {
+          e->w4_tip_order.push_back(ch.idx);
+          off += (size_t)e->ncodes * C * 4;
+        } else {
+          off += (size_t)C * 16;
+        }
+      }
+      e->w4_desc.push_back(d);
+    }
+    e->w4_desc.push_back(0ull);  // sentinel read by the one-op-ahead prefetch
+    e->w4_stream_len = off;
+    e->w4_tstride = (int)(((e->w4_tip_order.size() + 7) / 8) * 8 + 16);
   }
   int rc = upload_program(e, e->prog);
   if (rc) return rc;
@@ -528,22 +608,33 @@ static int create_impl(const bppgpu_config* cfg, bppgpu_engine* e) {
   size_t budget = (size_t)16 << 30;
   e->pchunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)e->npoints, budget / std::max<size_t>(1, 3 * per_point)));
   BPP_CUDA(dev_alloc(e, &e->d_P, (size_t)e->pchunk * nn * C * SS));
-  BPP_CUDA(dev_alloc(e, &e->d_tiptab, (size_t)e->pchunk * e->nl * C * e->ncodes * S));
+  if (e->path == PATH_WALK4) {
+    BPP_CUDA(dev_alloc(e, &e->d_w4_desc, e->w4_desc.size()));
+    BPP_CUDA(cudaMemcpy(e->d_w4_desc, e->w4_desc.data(), e->w4_desc.size() * 8, cudaMemcpyHostToDevice));
+    BPP_CUDA(dev_alloc(e, &e->d_w4_tip_order, e->w4_tip_order.size()));
+    BPP_CUDA(cudaMemcpy(e->d_w4_tip_order, e->w4_tip_order.data(), e->w4_tip_order.size() * 4, cudaMemcpyHostToDevice));
+    BPP_CUDA(dev_alloc(e, &e->d_w4_blocks, e->w4_blocks.size()));
+    BPP_CUDA(cudaMemcpy(e->d_w4_blocks, e->w4_blocks.data(), e->w4_blocks.size() * sizeof(PackBlock), cudaMemcpyHostToDevice));
+    BPP_CUDA(dev_alloc(e, &e->d_w4_stream, (size_t)e->pchunk * e->w4_stream_len));
+    BPP_CUDA(dev_alloc(e, &e->d_codesT, (size_t)N * e->w4_tstride));
+  }
+  if (e->path != PATH_WALK4 || e->keep)
+    BPP_CUDA(dev_alloc(e, &e->d_tiptab, (size_t)e->pchunk * e->nl * C * e->ncodes * S));
 
   const size_t clv = (size_t)N * C * S;
   if (e->keep) {
     BPP_CUDA(dev_alloc(e, &e->d_keep, (size_t)e->ni * clv));
-    BPP_CUDA(dev_alloc(e, &e->d_keep_exp, (size_t)e->ni * N));
+    BPP_CUDA(dev_alloc(e, &e->d_keep_exp, (size_t)e->ni * N * C));
   }
   if (e->path == PATH_WALKS && e->prog.nslots > 0) {
     BPP_CUDA(dev_alloc(e, &e->d_gstack, (size_t)e->prog.nslots * clv));
-    BPP_CUDA(dev_alloc(e, &e->d_gstack_exp, (size_t)e->prog.nslots * N));
+    BPP_CUDA(dev_alloc(e, &e->d_gstack_exp, (size_t)e->prog.nslots * N * C));
   }
   BPP_CUDA(dev_alloc(e, &e->d_SR, (size_t)N));
   BPP_CUDA(dev_alloc(e, &e->d_rexp, (size_t)N));
   BPP_CUDA(dev_alloc(e, &e->d_site_lnl, (size_t)e->npoints * N));
   const long long rows = N * C;
-  e->n_partials = (int)std::max<long long>(1, std::max((rows + kWalkThreads - 1) / kWalkThreads, (N + 255) / 256));
+  e->n_partials = (int)std::max<long long>(1, std::max((rows + 127) / 128, (N + 255) / 256) + 1);
   BPP_CUDA(dev_alloc(e, &e->d_partials, (size_t)e->n_partials));
   BPP_CUDA(dev_alloc(e, &e->d_partials2, (size_t)e->n_partials));
   BPP_CUDA(dev_alloc(e, &e->d_out, (size_t)e->npoints * (1 + 2 * nn)));
@@ -552,13 +643,16 @@ static int create_impl(const bppgpu_config* cfg, bppgpu_engine* e) {
   BPP_CUDA(cudaMemset(e->d_status, 0, sizeof(int)));
 
   if (e->path == PATH_WALK4) {
-    size_t smem = (size_t)e->prog.nslots * kWalkThreads * 36;
-    switch (ilog2(C)) {
-      case 0: BPP_CUDA(cudaFuncSetAttribute(walk4_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); break;
-      case 1: BPP_CUDA(cudaFuncSetAttribute(walk4_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); break;
-      case 2: BPP_CUDA(cudaFuncSetAttribute(walk4_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); break;
-      default: BPP_CUDA(cudaFuncSetAttribute(walk4_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); break;
+    // patterns per thread: 4 when the stack still leaves >= 2 CTAs per SM, else fewer
+    e->w4_pt = 4;
+    while (e->w4_pt > 1 && (size_t)e->prog.nslots * e->w4_pt * kWalk4Threads * 36 > 100 * 1024) e->w4_pt >>= 1;
+    if (N * C < (long long)g_sm_count * 4 * kWalk4Threads * 4) e->w4_pt = 1;  // small inputs: more CTAs instead
+    if (const char* env = getenv("BPPGPU_WALK4_PT")) {  // tuning knob: 1, 2 or 4
+      const int v = atoi(env);
+      if ((v == 1 || v == 2 || v == 4) && (size_t)e->prog.nslots * v * kWalk4Threads * 36 <= 200 * 1024) e->w4_pt = v;
     }
+    int rc4 = walk4_dispatch(e, nullptr, 0, 0, nullptr, true);
+    if (rc4) return rc4;
   }
   if (e->path == PATH_WALKS) {
     size_t smem = (size_t)kMaxStagedChildren * C * (S * S + 2) * 8;
@@ -612,6 +706,7 @@ int bppgpu_set_tip_codes(bppgpu_engine* e, int32_t node, const void* codes) {
                            cudaMemcpyHostToDevice, e->stream));
   BPP_CUDA(cudaStreamSynchronize(e->stream));
   e->have_tip[e->leaf_slot[node]] = 1;
+  e->codesT_dirty = true;
   e->last_point = -1;
   return BPPGPU_OK;
 }
@@ -623,6 +718,7 @@ int bppgpu_set_all_tip_codes(bppgpu_engine* e, const void* codes) {
   BPP_CUDA(cudaMemcpyAsync(e->d_codes, codes, bytes, cudaMemcpyHostToDevice, e->stream));
   BPP_CUDA(cudaStreamSynchronize(e->stream));
   std::fill(e->have_tip.begin(), e->have_tip.end(), 1);
+  e->codesT_dirty = true;
   e->last_point = -1;
   return BPPGPU_OK;
 }
@@ -732,7 +828,7 @@ static int ensure_deriv_buffers(bppgpu_engine* e, unsigned want) {
   if ((want & (BPPGPU_EVAL_D1 | BPPGPU_EVAL_D2)) && !e->d_upper) {
     const size_t clv = (size_t)e->N * e->C * e->S;
     BPP_CUDA(dev_alloc(e, &e->d_upper, (size_t)e->nn * clv));
-    BPP_CUDA(dev_alloc(e, &e->d_upper_exp, (size_t)e->nn * e->N));
+    BPP_CUDA(dev_alloc(e, &e->d_upper_exp, (size_t)e->nn * e->N * e->C));
   }
   return BPPGPU_OK;
 }
@@ -750,9 +846,35 @@ static int ensure_scratch(bppgpu_engine* e, bool series, bool chrd) {
   return BPPGPU_OK;
 }
 
+template <int CL, int PT, bool KEEP>
+static int walk4_launch_one(const Walk4Params* wp, int grid, size_t smem, cudaStream_t st, bool attr_only) {
+  if (attr_only) {
+    BPP_CUDA(cudaFuncSetAttribute(walk4_kernel<CL, PT, KEEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    return BPPGPU_OK;
+  }
+  walk4_kernel<CL, PT, KEEP><<<grid, kWalk4Threads, smem, st>>>(*wp);
+  return BPPGPU_OK;
+}
+template <int CL, int PT>
+static int walk4_launch_k(bool keep, const Walk4Params* wp, int grid, size_t smem, cudaStream_t st, bool attr_only) {
+  return keep ? walk4_launch_one<CL, PT, true>(wp, grid, smem, st, attr_only)
+              : walk4_launch_one<CL, PT, false>(wp, grid, smem, st, attr_only);
+}
 template <int CL>
-static void launch_walk4(const WalkParams& wp, int grid, size_t smem, cudaStream_t st) {
-  walk4_kernel<CL><<<grid, kWalkThreads, smem, st>>>(wp);
+static int walk4_launch_pt(int pt, bool keep, const Walk4Params* wp, int grid, size_t smem, cudaStream_t st, bool attr_only) {
+  if (pt == 4) return walk4_launch_k<CL, 4>(keep, wp, grid, smem, st, attr_only);
+  if (pt == 2) return walk4_launch_k<CL, 2>(keep, wp, grid, smem, st, attr_only);
+  return walk4_launch_k<CL, 1>(keep, wp, grid, smem, st, attr_only);
+}
+// launches (or, with attr_only, just opts in to the dynamic shared memory of) the walk4 instantiation of this engine
+static int walk4_dispatch(bppgpu_engine* e, const Walk4Params* wp, int grid, size_t /*unused*/, cudaStream_t st, bool attr_only) {
+  const size_t smem = (size_t)e->prog.nslots * e->w4_pt * kWalk4Threads * 36;
+  switch (ilog2(e->C)) {
+    case 0: return walk4_launch_pt<0>(e->w4_pt, e->keep, wp, grid, smem, st, attr_only);
+    case 1: return walk4_launch_pt<1>(e->w4_pt, e->keep, wp, grid, smem, st, attr_only);
+    case 2: return walk4_launch_pt<2>(e->w4_pt, e->keep, wp, grid, smem, st, attr_only);
+    default: return walk4_launch_pt<3>(e->w4_pt, e->keep, wp, grid, smem, st, attr_only);
+  }
 }
 template <int CL>
 static void launch_walkS20(const WalkParams& wp, int grid, size_t smem, cudaStream_t st) {
@@ -775,7 +897,35 @@ static int enqueue_prune(bppgpu_engine* e, int point, int pl, cudaStream_t st) {
     BPP_CUDA(cudaMemsetAsync(out, 0, 8, st));
     return BPPGPU_OK;
   }
-  if (e->path == PATH_WALK4 || e->path == PATH_WALKS) {
+  if (e->path == PATH_WALK4) {
+    if (e->flags & BPPGPU_FLAG_WEIGHTED_ROOT)
+      BPP_FAIL(BPPGPU_E_INVALID, "BPPGPU_FLAG_WEIGHTED_ROOT is served by the generic path only");
+    Walk4Params wp{};
+    wp.desc = e->d_w4_desc;
+    wp.n_ops = (int)e->prog.ops.size();
+    wp.nslots = e->prog.nslots;
+    wp.ncodes = e->ncodes;
+    wp.tstride = e->w4_tstride;
+    wp.flags = rflag;
+    wp.N = N;
+    wp.stream = e->d_w4_stream + (size_t)pl * e->w4_stream_len;
+    wp.codesT = e->d_codesT;
+    wp.keep = e->d_keep;
+    wp.keep_exp = e->d_keep_exp;
+    wp.rootfreq = rootfreq;
+    wp.probs = e->d_probs;
+    wp.weights = e->d_weights;
+    wp.SR = e->d_SR;
+    wp.rexp = e->d_rexp;
+    wp.site_lnl = site_lnl;
+    wp.partials = e->d_partials;
+    const long long per_cta = (long long)(kWalk4Threads / C) * e->w4_pt;  // patterns per CTA
+    const int grid = (int)((N + per_cta - 1) / per_cta);
+    nparts = grid;
+    int rc4 = walk4_dispatch(e, &wp, grid, 0, st, false);
+    if (rc4) return rc4;
+    e->stats.kernel_launches++;
+  } else if (e->path == PATH_WALKS) {
     if (e->flags & BPPGPU_FLAG_WEIGHTED_ROOT)
       BPP_FAIL(BPPGPU_E_INVALID, "BPPGPU_FLAG_WEIGHTED_ROOT is served by the generic path only");
     WalkParams wp{};
@@ -806,13 +956,7 @@ static int enqueue_prune(bppgpu_engine* e, int point, int pl, cudaStream_t st) {
     const int grid = (int)((rows + kWalkThreads - 1) / kWalkThreads);
     nparts = grid;
     const int cl = ilog2(C);
-    if (e->path == PATH_WALK4) {
-      const size_t smem = (size_t)e->prog.nslots * kWalkThreads * 36;
-      if (cl == 0) launch_walk4<0>(wp, grid, smem, st);
-      else if (cl == 1) launch_walk4<1>(wp, grid, smem, st);
-      else if (cl == 2) launch_walk4<2>(wp, grid, smem, st);
-      else launch_walk4<3>(wp, grid, smem, st);
-    } else {
+    {
       const size_t smem = (size_t)kMaxStagedChildren * C * (S * S + 2) * 8;
       if (cl == 0) launch_walkS20<0>(wp, grid, smem, st);
       else if (cl == 1) launch_walkS20<1>(wp, grid, smem, st);
@@ -824,6 +968,7 @@ static int enqueue_prune(bppgpu_engine* e, int point, int pl, cudaStream_t st) {
     const long long total = N * C * S;
     const int grid_e = (int)std::min<long long>((total + 255) / 256, (long long)g_sm_count * 32);
     const int grid_p = (int)((N + 255) / 256);
+    const int grid_r = (int)((N * C + 255) / 256);
     for (const Op& op : e->gprog.ops) {
       GenericParams gp{};
       gp.childs = e->gprog.d_childs + op.child_begin;
@@ -834,14 +979,14 @@ static int enqueue_prune(bppgpu_engine* e, int point, int pl, cudaStream_t st) {
       gp.P = P; gp.tiptab = tiptab; gp.codes = e->d_codes;
       gp.keep = e->d_keep; gp.keep_exp = e->d_keep_exp;
       generic_node_kernel<<<grid_e, 256, 0, st>>>(gp);
-      generic_scale_kernel<<<grid_p, 256, 0, st>>>(gp);
+      generic_scale_kernel<<<grid_r, 256, 0, st>>>(gp);
       e->stats.kernel_launches += 2;
     }
     const int ridx = e->internal_idx[e->root];
     if (e->flags & BPPGPU_FLAG_WEIGHTED_ROOT) {
       WeightedRootParams wr{};
       wr.root_clv = e->d_keep + (size_t)ridx * N * C * S;
-      wr.root_exp = e->d_keep_exp + (size_t)ridx * N;
+      wr.root_exp = e->d_keep_exp + (size_t)ridx * N * C;
       wr.S = S; wr.C = C; wr.N = N;
       wr.probs = e->d_probs;
       wr.out = e->d_rootfreq_used + (size_t)point * S;
@@ -850,7 +995,7 @@ static int enqueue_prune(bppgpu_engine* e, int point, int pl, cudaStream_t st) {
     }
     RootParams rp{};
     rp.root_clv = e->d_keep + (size_t)ridx * N * C * S;
-    rp.root_exp = e->d_keep_exp + (size_t)ridx * N;
+    rp.root_exp = e->d_keep_exp + (size_t)ridx * N * C;
     rp.S = S; rp.C = C; rp.flags = rflag; rp.N = N;
     rp.rootfreq = rootfreq; rp.probs = e->d_probs; rp.weights = e->d_weights;
     rp.SR = e->d_SR; rp.rexp = e->d_rexp; rp.site_lnl = site_lnl; rp.partials = e->d_partials;
@@ -882,6 +1027,7 @@ static int enqueue_derivs(bppgpu_engine* e, int point, int pl, unsigned want, cu
   const long long total = N * C * S;
   const int grid_e = (int)std::min<long long>((total + 255) / 256, (long long)g_sm_count * 32);
   const int grid_p = (int)((N + 255) / 256);
+  const int grid_r = (int)((N * C + 255) / 256);
   for (int n : e->preorder) {
     if (n == e->root) continue;
     const int f = e->parent[n];
@@ -894,12 +1040,12 @@ static int enqueue_derivs(bppgpu_engine* e, int point, int pl, unsigned want, cu
     up.P = P; up.tiptab = tiptab; up.codes = e->d_codes;
     up.keep = e->d_keep; up.keep_exp = e->d_keep_exp;
     up.upper_f = e->d_upper + (size_t)f * clv;
-    up.uexp_f = e->d_upper_exp + (size_t)f * N;
+    up.uexp_f = e->d_upper_exp + (size_t)f * N * C;
     up.rootfreq = e->d_rootfreq_used + (size_t)point * S;
     up.upper_out = e->d_upper + (size_t)n * clv;
-    up.uexp_out = e->d_upper_exp + (size_t)n * N;
+    up.uexp_out = e->d_upper_exp + (size_t)n * N * C;
     upper_node_kernel<<<grid_e, 256, 0, st>>>(up);
-    upper_scale_kernel<<<grid_p, 256, 0, st>>>(up);
+    upper_scale_kernel<<<grid_r, 256, 0, st>>>(up);
     DerivParams dp{};
     dp.node = n;
     dp.is_tip = e->leaf_slot[n] >= 0;
@@ -936,7 +1082,7 @@ static int eval_impl(bppgpu_engine* e, unsigned want, cudaStream_t st, bool time
   if (derivs && !e->keep) BPP_FAIL(BPPGPU_E_STATE, "derivatives need an engine created with BPPGPU_FLAG_KEEP_CLVS");
   rc = ensure_deriv_buffers(e, want);
   if (rc) return rc;
-  bool any_series = false, any_chrd = false;
+  bool any_series = false, any_chrd = false, any_real = false, any_complex = false;
   if (e->models_dirty) {
     std::vector<ModelDev> md(e->nmodels);
     for (int m = 0; m < e->nmodels; ++m) md[m] = to_dev(e->models[m]);
@@ -947,7 +1093,11 @@ static int eval_impl(bppgpu_engine* e, unsigned want, cudaStream_t st, bool time
   for (int m = 0; m < e->nmodels; ++m) {
     if (!e->models[m].set) continue;
     if (!(e->models[m].flags & BPPGPU_MODEL_NONSINGULAR)) any_series = true;
-    else if (e->models[m].flags & BPPGPU_MODEL_CHR_DERIV) any_chrd = true;
+    else {
+      if (e->models[m].flags & BPPGPU_MODEL_CHR_DERIV) any_chrd = true;
+      if (e->models[m].has_complex) any_complex = true;
+      else any_real = true;
+    }
   }
   rc = ensure_scratch(e, any_series, any_chrd && derivs);
   if (rc) return rc;
@@ -962,26 +1112,45 @@ static int eval_impl(bppgpu_engine* e, unsigned want, cudaStream_t st, bool time
   for (int p0 = 0; p0 < e->npoints; p0 += e->pchunk) {
     const int np = std::min(e->pchunk, e->npoints - p0);
     long long launches = 0;
-    rc = launch_pt(st, e->d_models, any_series, any_chrd, e->d_branch_model + (size_t)p0 * nn,
+    rc = launch_pt(st, e->d_models, any_series, any_chrd, any_real, any_complex, e->d_branch_model + (size_t)p0 * nn,
                    e->d_brlen + (size_t)p0 * nn, e->d_rates, S, C, nn, e->root, np, pt_want, e->d_P, e->d_dP, e->d_d2P,
                    e->d_scratch, e->d_status, &launches);
     if (rc) return rc;
     e->stats.kernel_launches += launches;
-    TipTabParams tp{};
-    tp.P = e->d_P;
-    tp.code_table = e->d_code_table;
-    tp.leaf_nodes = e->d_leaf_nodes;
-    tp.S = S; tp.C = C; tp.nn = nn; tp.nl = e->nl; tp.ncodes = e->ncodes;
-    tp.tiptab = e->d_tiptab;
-    tiptab_kernel<<<np * e->nl * C, 128, 0, st>>>(tp);
-    e->stats.kernel_launches++;
+    if (e->path == PATH_WALK4) {
+      if (e->codesT_dirty && e->N > 0) {
+        transpose_codes_kernel<<<(unsigned)((e->N + 127) / 128), 128, 0, st>>>(
+            (const unsigned char*)e->d_codes, e->d_w4_tip_order, (int)e->w4_tip_order.size(), e->N, e->w4_tstride, e->d_codesT);
+        e->stats.kernel_launches++;
+        e->codesT_dirty = false;
+      }
+      for (int pl = 0; pl < np; ++pl)
+        pack_stream4_kernel<<<(unsigned)e->w4_blocks.size(), 64, 0, st>>>(
+            e->d_w4_blocks, e->d_P + (size_t)pl * nn * C * SS, e->d_code_table, C, e->ncodes,
+            e->d_w4_stream + (size_t)pl * e->w4_stream_len);
+      e->stats.kernel_launches += np;
+    }
+    if (e->d_tiptab) {
+      TipTabParams tp{};
+      tp.P = e->d_P;
+      tp.code_table = e->d_code_table;
+      tp.leaf_nodes = e->d_leaf_nodes;
+      tp.S = S; tp.C = C; tp.nn = nn; tp.nl = e->nl; tp.ncodes = e->ncodes;
+      tp.tiptab = e->d_tiptab;
+      tiptab_kernel<<<np * e->nl * C, 128, 0, st>>>(tp);
+      e->stats.kernel_launches++;
+    }
     BPP_CUDA(cudaGetLastError());
     for (int pl = 0; pl < np; ++pl) {
       const int point = p0 + pl;
-      if (timed && point == 0) BPP_CUDA(cudaEventRecord(e->ev2, st));
+      if (point == 0) BPP_CUDA(cudaEventRecord(e->ring_a[e->ring_head], st));
       rc = enqueue_prune(e, point, pl, st);
       if (rc) return rc;
-      if (timed && point == 0) BPP_CUDA(cudaEventRecord(e->ev3, st));
+      if (point == 0) {
+        BPP_CUDA(cudaEventRecord(e->ring_b[e->ring_head], st));
+        e->ring_head = (e->ring_head + 1) % bppgpu_engine::kRing;
+        e->ring_n = std::min(e->ring_n + 1, (int)bppgpu_engine::kRing);
+      }
       if (derivs) {
         rc = enqueue_derivs(e, point, pl, want, st);
         if (rc) return rc;
@@ -1004,8 +1173,10 @@ int bppgpu_eval(bppgpu_engine* e, unsigned want, double* lnl, double* d1, double
   float ms = 0.f;
   BPP_CUDA(cudaEventElapsedTime(&ms, e->ev0, e->ev1));
   e->stats.last_eval_ms = ms;
-  BPP_CUDA(cudaEventElapsedTime(&ms, e->ev2, e->ev3));
-  e->stats.prune_ms = ms;
+  {
+    const int last = (e->ring_head + bppgpu_engine::kRing - 1) % bppgpu_engine::kRing;
+    if (e->ring_n > 0 && cudaEventElapsedTime(&ms, e->ring_a[last], e->ring_b[last]) == cudaSuccess) e->stats.prune_ms = ms;
+  }
   const int nn = e->nn;
   std::vector<double> h((size_t)e->npoints * (1 + 2 * nn));
   BPP_CUDA(cudaMemcpy(h.data(), e->d_out, h.size() * 8, cudaMemcpyDeviceToHost));
@@ -1055,12 +1226,12 @@ int bppgpu_get_clv(bppgpu_engine* e, int32_t point, int32_t node, int32_t which,
     if (e->internal_idx[node] < 0) BPP_FAIL(BPPGPU_E_INVALID, "node %d is a leaf: its CLV is the code table row", node);
     const int k = e->internal_idx[node];
     BPP_CUDA(cudaMemcpy(clv, e->d_keep + (size_t)k * clvn, clvn * 8, cudaMemcpyDeviceToHost));
-    if (scale_exp) BPP_CUDA(cudaMemcpy(scale_exp, e->d_keep_exp + (size_t)k * e->N, (size_t)e->N * 4, cudaMemcpyDeviceToHost));
+    if (scale_exp) BPP_CUDA(cudaMemcpy(scale_exp, e->d_keep_exp + (size_t)k * e->N * e->C, (size_t)e->N * e->C * 4, cudaMemcpyDeviceToHost));
   } else {
     if (!(e->last_want & BPPGPU_EVAL_D1) || !e->d_upper) BPP_FAIL(BPPGPU_E_STATE, "upper CLVs exist after an eval with derivatives");
     if (node == e->root) BPP_FAIL(BPPGPU_E_INVALID, "the root has no upper CLV");
     BPP_CUDA(cudaMemcpy(clv, e->d_upper + (size_t)node * clvn, clvn * 8, cudaMemcpyDeviceToHost));
-    if (scale_exp) BPP_CUDA(cudaMemcpy(scale_exp, e->d_upper_exp + (size_t)node * e->N, (size_t)e->N * 4, cudaMemcpyDeviceToHost));
+    if (scale_exp) BPP_CUDA(cudaMemcpy(scale_exp, e->d_upper_exp + (size_t)node * e->N * e->C, (size_t)e->N * e->C * 4, cudaMemcpyDeviceToHost));
   }
   return BPPGPU_OK;
 }
@@ -1093,6 +1264,20 @@ int bppgpu_get_root_freqs(bppgpu_engine* e, int32_t point, double* out) {
 int bppgpu_get_stats(bppgpu_engine* e, bppgpu_stats* out) {
   if (!e || !out) BPP_FAIL(BPPGPU_E_INVALID, "null argument");
   e->stats.hbm_bytes_resident = (int64_t)e->bytes_resident;
+  // collect the pruning-kernel timings recorded since the last call (waits for them to complete)
+  e->stats.prune_ms_sum = 0.0;
+  e->stats.prune_count = 0;
+  cudaSetDevice(e->dev);
+  for (int k = 0; k < e->ring_n; ++k) {
+    const int i = (e->ring_head + bppgpu_engine::kRing - 1 - k) % bppgpu_engine::kRing;
+    float ms = 0.f;
+    if (cudaEventSynchronize(e->ring_b[i]) == cudaSuccess && cudaEventElapsedTime(&ms, e->ring_a[i], e->ring_b[i]) == cudaSuccess) {
+      e->stats.prune_ms_sum += ms;
+      e->stats.prune_count++;
+    }
+  }
+  e->ring_n = 0;
+  cudaGetLastError();
   *out = e->stats;
   return BPPGPU_OK;
 }

@@ -8,6 +8,7 @@
 #include "../../include/bppgpu.h"
 #include "deriv_kernels.cuh"
 #include "generic_kernels.cuh"
+#include "pt_dmma_kernels.cuh"
 #include "pt_kernels.cuh"
 #include "walk_kernels.cuh"
 
@@ -17,6 +18,7 @@ enum PathKind { PATH_NONE = 0, PATH_WALK4 = 1, PATH_WALKS = 2, PATH_GENERIC = 3,
 
 struct DevModel {
   double *V = nullptr, *Vinv = nullptr, *re = nullptr, *im = nullptr, *Q = nullptr, *Q2 = nullptr;
+  double *Vp = nullptr, *Vinvp = nullptr, *rep = nullptr;  // zero-padded to a multiple of 8 (own storage only if S % 8)
   int* role = nullptr;
   double rate = 1.0, eps = 1e-4;
   unsigned flags = 0;
@@ -69,9 +71,22 @@ struct bppgpu_engine {
   int pchunk = 1;
   double *d_P = nullptr, *d_dP = nullptr, *d_d2P = nullptr;
   double* d_tiptab = nullptr;
+  // walk4 artefacts (everything in walk order, see walk_kernels.cuh)
+  std::vector<unsigned long long> w4_desc;
+  std::vector<int> w4_tip_order;
+  std::vector<bppgpu::PackBlock> w4_blocks;
+  size_t w4_stream_len = 0;  // doubles per point
+  int w4_tstride = 0;
+  int w4_pt = 1;  // patterns per thread
+  unsigned long long* d_w4_desc = nullptr;
+  int* d_w4_tip_order = nullptr;
+  bppgpu::PackBlock* d_w4_blocks = nullptr;
+  double* d_w4_stream = nullptr;       // [pchunk][w4_stream_len]
+  unsigned char* d_codesT = nullptr;   // [N][w4_tstride]
+  bool codesT_dirty = true;
   // CLV storage (one point at a time)
   double* d_keep = nullptr;  // [ni][N][C][S]
-  int* d_keep_exp = nullptr; // [ni][N]
+  int* d_keep_exp = nullptr; // [ni][N][C]
   double* d_gstack = nullptr;
   int* d_gstack_exp = nullptr;
   double* d_upper = nullptr;  // [nn][N][C][S] generic derivative pass
@@ -102,6 +117,11 @@ struct bppgpu_engine {
   unsigned last_want = 0;
   // stats
   bppgpu_stats stats{};
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  // ring of event pairs bracketing the pruning kernel(s) of point 0 of each eval, on the launching stream
+  static constexpr int kRing = 64;
+  cudaEvent_t ring_a[kRing] = {}, ring_b[kRing] = {};
+  int ring_n = 0;  // pairs recorded since the last collection (capped at kRing)
+  int ring_head = 0;
   size_t bytes_resident = 0;
 };

@@ -48,31 +48,31 @@ __global__ void generic_node_kernel(GenericParams p) {
   }
 }
 
-// thread = pattern: accumulate child exponents, rescale the node's C*S entries
+// thread = (pattern, class) row: accumulate child exponents, rescale the row's S entries
 __global__ void generic_scale_kernel(GenericParams p) {
-  const long long pat = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (pat >= p.N) return;
+  const long long rows = p.N * p.C;
+  const long long rc = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (rc >= rows) return;
   int Ea = 0;
   for (int j = 0; j < p.nchild; ++j) {
     const Child ch = p.childs[j];
-    if (ch.kind != CHILD_TIP) Ea += p.keep_exp[(size_t)ch.idx * p.N + pat];
+    if (ch.kind != CHILD_TIP) Ea += p.keep_exp[(size_t)ch.idx * rows + rc];
   }
-  const int w = p.C * p.S;
-  double* v = p.keep + ((size_t)p.out_idx * p.N + pat) * w;
+  double* v = p.keep + ((size_t)p.out_idx * rows + rc) * p.S;
   int m = 0;
-  for (int i = 0; i < w; ++i) m = max(m, hi_word(v[i]));
+  for (int i = 0; i < p.S; ++i) m = max(m, hi_word(v[i]));
   if (m < kScaleThresholdHi && m >= (1 << 20)) {
     const int k = rescale_shift(m);
     const double f = pow2(k);
-    for (int i = 0; i < w; ++i) v[i] *= f;
+    for (int i = 0; i < p.S; ++i) v[i] *= f;
     Ea += k;
   }
-  p.keep_exp[(size_t)p.out_idx * p.N + pat] = Ea;
+  p.keep_exp[(size_t)p.out_idx * rows + rc] = Ea;
 }
 
 struct RootParams {
   const double* root_clv;  // [N][C][S]
-  const int* root_exp;     // [N]
+  const int* root_exp;     // [N][C]
   int S, C;
   unsigned flags;
   long long N;
@@ -92,6 +92,9 @@ __global__ void generic_root_kernel(RootParams p) {
   if (pat < p.N) {
     const bool rsem = p.flags & 1u;
     const double* v = p.root_clv + (size_t)pat * p.C * p.S;
+    const int* ex = p.root_exp + (size_t)pat * p.C;
+    int E = ex[0];
+    for (int c = 1; c < p.C; ++c) E = min(E, ex[c]);
     double L = 0.0;
     for (int c = 0; c < p.C; ++c) {
       double s = 0.0;
@@ -100,12 +103,11 @@ __global__ void generic_root_kernel(RootParams p) {
         if (rsem) s += t > 0 ? t : 0.0;
         else s += t;
       }
-      const double lc = s * p.probs[c];
+      const double lc = s * align_factor(ex[c] - E) * p.probs[c];
       if (rsem) L += lc > 0 ? lc : 0.0;
       else L += lc;
     }
     if (!rsem && L < 0) L = 0.0;
-    const int E = p.root_exp[pat];
     const double lnl = log(L) - (double)E * kLn2;
     p.SR[pat] = L;
     p.rexp[pat] = E;
@@ -122,7 +124,7 @@ __global__ void generic_root_kernel(RootParams p) {
 // Single CTA: the fork only uses this with one character (N = 1).
 struct WeightedRootParams {
   const double* root_clv;  // [N][C][S]
-  const int* root_exp;     // [N]
+  const int* root_exp;     // [N][C]
   int S, C;
   long long N;
   const double* probs;
@@ -134,7 +136,7 @@ __global__ void weighted_root_kernel(WeightedRootParams p) {
   __shared__ double tot_s;
   __shared__ double red[32];
   int em = 0x7fffffff;
-  for (long long i = threadIdx.x; i < p.N; i += blockDim.x) em = min(em, p.root_exp[i]);
+  for (long long i = threadIdx.x; i < p.N * p.C; i += blockDim.x) em = min(em, p.root_exp[i]);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) em = min(em, __shfl_xor_sync(0xffffffffu, em, o));
   if (threadIdx.x == 0) emin_s = 0x7fffffff;
@@ -147,8 +149,9 @@ __global__ void weighted_root_kernel(WeightedRootParams p) {
     double acc = 0.0;
     for (long long i = threadIdx.x; i < p.N; i += blockDim.x) {
       double a = 0.0;
-      for (int c = 0; c < p.C; ++c) a = fma(p.root_clv[((size_t)i * p.C + c) * p.S + x], p.probs[c], a);
-      acc += scalbn(a, -(p.root_exp[i] - emin));
+      for (int c = 0; c < p.C; ++c)
+        a = fma(p.root_clv[((size_t)i * p.C + c) * p.S + x] * align_factor(p.root_exp[i * p.C + c] - emin), p.probs[c], a);
+      acc += a;
     }
     const double s = block_sum(acc, red);
     if (threadIdx.x == 0) {

@@ -1,0 +1,163 @@
+// K1 on the FP64 tensor cores: branch-batched P(t) = (V . diag(f(lambda tau))) . V^-1 for S >= 32
+// (codon S = 64, chromosome S ~ 200), one batched GEMM launch for every (point, branch, class).
+//   f = exp(x)            -> pxy_    (Model/AbstractSubstitutionModel.cpp:436)
+//   f = r  (rate lambda)   exp(x)   -> dpxy_   (:505, times r_c: AbstractHomogeneousTreeLikelihood.cpp:389)
+//   f = r^2 (rate lambda)^2 exp(x)  -> d2pxy_  (:576, :409)
+// Real spectra only; conjugate pairs (block form, :438-468) and singular generators keep the CUDA-core
+// kernels of pt_kernels.cuh.
+//
+// Tiling: one CTA per (matrix, column panel).  WARPS warps, warp w owns MBW 8-row blocks (all of M = S =
+// WARPS*MBW*8 is covered by the CTA) times the panel's NB 8-column blocks: MBW*NB DMMA atoms per k-step
+// against MBW + NB fragment loads.  V and V^-1 are streamed through shared memory in k-slabs of 8 by a
+// 2-stage cp.async pipeline; the eigenvalue factor is applied to the A fragment on the way to the
+// registers.  Shared-memory row strides are = 4 (mod 16) doubles so that every fragment load is
+// conflict free (SURVEY/DESIGN: half-warp (g<4, q) -> bank pairs g*4+q).
+#pragma once
+#include "dmma.cuh"
+#include "pt_kernels.cuh"
+
+namespace bppgpu {
+
+constexpr int kPtKT = 8;        // k-slab
+constexpr int kPtAStride = 12;  // doubles per staged V row (8 + 4 pad)
+
+// Sp = S rounded up to a multiple of 8; Vp / Vinvp / rep are the model's arrays zero-padded to Sp
+// (ModelDev::Vp ...; identical to V / Vinv / re when S % 8 == 0).  Row block mb of warp w, slot i is
+// w + i*WARPS (interleaved, predicated on mb < Sp/8); the CTA covers all rows and NB column blocks.
+template <int NB>
+__host__ __device__ constexpr int pt_bstride() { return NB * 8 + 4; }
+
+inline size_t pt_dmma_smem_bytes(int Sp, int NB) {
+  return (size_t)(3 * Sp + 2 * Sp * kPtAStride + 2 * kPtKT * (NB * 8 + 4)) * sizeof(double);
+}
+
+template <int WARPS, int MBW, int NB>
+__global__ void __launch_bounds__(WARPS * 32) pt_dmma_kernel(PtParams p, int Sp) {
+  constexpr int NT = WARPS * 32;
+  constexpr int BStride = pt_bstride<NB>();
+  const int S = p.S;
+  const int kAStage = Sp * kPtAStride;
+  constexpr int kBStage = kPtKT * BStride;
+  extern __shared__ __align__(16) double sm_pt[];
+  double* dtab = sm_pt;               // [3][Sp]
+  double* As = dtab + 3 * Sp;         // [2][Sp][12]
+  double* Bs = As + 2 * kAStage;      // [2][8][BStride]
+
+  const int m = blockIdx.x;
+  const int c = m % p.C;
+  const int node = (m / p.C) % p.nn;
+  const int point = m / (p.C * p.nn);
+  if (node == p.root) return;
+  const ModelDev md = p.models[p.branch_model[point * p.nn + node]];
+  if (!(md.flags & 2u) || md.has_complex) return;  // singular / complex spectrum: CUDA-core kernels
+  const double rc = p.rates[c];
+  const double t = p.brlen[point * p.nn + node] * rc;
+  const double l = md.rate * t;
+  const int n0 = blockIdx.y * NB * 8;  // first column of this panel
+  const int nblk = Sp >> 3;
+
+  for (int k = threadIdx.x; k < Sp; k += NT) {
+    const double a = md.rep[k];
+    const double ex = exp(a * l);
+    const double ra = md.rate * a;
+    dtab[k] = ex;
+    dtab[Sp + k] = rc * (ra * ex);
+    dtab[2 * Sp + k] = rc * rc * (ra * ra * ex);
+  }
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, q = lane & 3;
+  const bool chr_deriv = md.flags & 8u;
+  const bool clamp = md.flags & 4u;
+  const size_t base = (size_t)m * S * S;
+
+  auto stage = [&](int ks, int buf) {
+    // Vp[:, ks*8 .. +8) : Sp rows x 64 B = 4 x 16 B chunks per row
+    double* a_dst = As + buf * kAStage;
+    for (int i = threadIdx.x; i < Sp * 4; i += NT) {
+      const int row = i >> 2, ch = i & 3;
+      cp_async16(a_dst + row * kPtAStride + ch * 2, md.Vp + (size_t)row * Sp + ks * kPtKT + ch * 2);
+    }
+    // Vinvp[ks*8 .. +8, n0 .. n0 + NB*8)
+    double* b_dst = Bs + buf * kBStage;
+    for (int i = threadIdx.x; i < kPtKT * NB * 4; i += NT) {
+      const int row = i / (NB * 4), ch = i - row * (NB * 4);
+      if (n0 + ch * 2 < Sp)
+        cp_async16(b_dst + row * BStride + ch * 2, md.Vinvp + (size_t)(ks * kPtKT + row) * Sp + n0 + ch * 2);
+    }
+    cp_async_commit();
+  };
+
+  for (int tab = 0; tab < 3; ++tab) {
+    const bool wanted = (p.want >> tab) & 1u;
+    // Chromosome models rebuild dP/d2P from the unclamped P (pt_chr_deriv_kernel): only P (+Pun) here
+    if (!wanted || (tab > 0 && chr_deriv)) continue;
+    double acc[MBW][NB][2];
+#pragma unroll
+    for (int i = 0; i < MBW; ++i)
+#pragma unroll
+      for (int j = 0; j < NB; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    const double* dt = dtab + tab * Sp;
+
+    __syncthreads();  // dtab ready / previous table's smem reads done
+    stage(0, 0);
+    const int NKS = Sp / kPtKT;
+    for (int ks = 0; ks < NKS; ++ks) {
+      const int buf = ks & 1;
+      if (ks + 1 < NKS) {
+        stage(ks + 1, buf ^ 1);
+        cp_async_wait<1>();
+      } else {
+        cp_async_wait<0>();
+      }
+      __syncthreads();
+      const double* a_src = As + buf * kAStage;
+      const double* b_src = Bs + buf * kBStage;
+#pragma unroll
+      for (int kb = 0; kb < kPtKT / 4; ++kb) {
+        const double dk = dt[ks * kPtKT + kb * 4 + q];
+        double a[MBW], b[NB];
+#pragma unroll
+        for (int i = 0; i < MBW; ++i) {
+          const int mb = warp + i * WARPS;
+          a[i] = mb < nblk ? a_src[(mb * 8 + g) * kPtAStride + kb * 4 + q] * dk : 0.0;
+        }
+#pragma unroll
+        for (int j = 0; j < NB; ++j) b[j] = b_src[(kb * 4 + q) * BStride + j * 8 + g];
+#pragma unroll
+        for (int i = 0; i < MBW; ++i) {
+          if (warp + i * WARPS < nblk) {  // warp-uniform
+#pragma unroll
+            for (int j = 0; j < NB; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+          }
+        }
+      }
+      __syncthreads();
+    }
+
+    double* out = tab == 0 ? p.P : tab == 1 ? p.dP : p.d2P;
+#pragma unroll
+    for (int i = 0; i < MBW; ++i) {
+      const int x = (warp + i * WARPS) * 8 + g;
+      if (x >= S) continue;
+#pragma unroll
+      for (int j = 0; j < NB; ++j) {
+        const int y = n0 + j * 8 + 2 * q;
+        double v[2] = {acc[i][j][0], acc[i][j][1]};
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          if (y + h >= S) continue;
+          double val = v[h];
+          if (tab == 0) {
+            if (t == 0.0) val = x == y + h ? 1.0 : 0.0;  // AbstractSubstitutionModel.cpp:428-431
+            if (chr_deriv && p.Pun) p.Pun[base + (size_t)x * S + y + h] = val;
+            if (clamp) val = val < 0.0 ? 1e-20 : (val > 1.0 ? 1.0 : val);  // ChromosomeSubstitutionModel.cpp:903-916
+          }
+          out[base + (size_t)x * S + y + h] = val;
+        }
+      }
+    }
+  }
+}
+
+}  // namespace bppgpu

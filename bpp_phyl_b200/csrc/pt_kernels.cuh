@@ -25,6 +25,9 @@ struct ModelDev {
   const int* role;     // [S] 0 real, 1 first of a conjugate pair, 2 second
   const double* Q;     // [S][S] generator or nullptr
   const double* Q2;    // [S][S] Q.Q or nullptr
+  const double* Vp;    // [Sp][Sp] V zero-padded to Sp = roundup(S, 8) (== V when S % 8 == 0)
+  const double* Vinvp; // [Sp][Sp]
+  const double* rep;   // [Sp]
   double rate;
   double eps;
   double q_l1;         // sum_ij |Q_ij| (ChromosomeSubstitutionModel::getFirstNorm)
@@ -43,6 +46,7 @@ struct PtParams {
   double* dP;
   double* d2P;
   double* Pun;              // [npoints][nn][C][S][S] unclamped P for CHR_DERIV models, or nullptr
+  int dmma_real;            // 1: real-spectrum eigen models are built by pt_dmma_kernel, skip them here
 };
 
 // dynamic smem: 6*S doubles (dia/up for orders 0,1,2)
@@ -64,6 +68,7 @@ __global__ void pt_eigen_kernel(PtParams p) {
   const ModelDev md = p.models[p.branch_model[point * p.nn + node]];
   if (!((md.flags & 1u) || (md.flags & 2u))) return;  // handled by the series kernel
   if (!(md.flags & 2u)) return;                       // singular -> series kernel
+  if (p.dmma_real && !md.has_complex) return;         // built on the tensor cores (pt_dmma_kernels.cuh)
   const double rc = p.rates[c];
   const double t = p.brlen[point * p.nn + node] * rc;  // l_b * r_c
   const double l = md.rate * t;

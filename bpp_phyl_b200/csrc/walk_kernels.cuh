@@ -53,9 +53,9 @@ struct WalkParams {
   const double* tiptab;     // [nl][C][ncodes][S] (this point)
   const void* codes;        // [nl][N]
   double* keep;             // [n_internal][N][C][S] or nullptr
-  int* keep_exp;            // [n_internal][N]
+  int* keep_exp;            // [n_internal][N][C]
   double* gstack;           // [nslots][N][C][S] (global-stack variant) or nullptr
-  int* gstack_exp;          // [nslots][N]
+  int* gstack_exp;          // [nslots][N][C]
   const double* rootfreq;   // [S]
   const double* probs;      // [C]
   const double* weights;    // [N]
@@ -72,109 +72,264 @@ __device__ __forceinline__ int load_code(const void* codes, int code_bytes, long
 }
 
 // ----------------------------------------------------------------------------
-// S = 4 (DNA): thread = (pattern, class); 4 doubles per row; stack in shared memory.
+// S = 4 (DNA): thread = (pattern, class) row, 4 doubles per row, stack in shared memory.
+//
+// Everything the walk touches is laid out in WALK ORDER so that no address depends on a
+// dependent load:
+//   * desc[o]   one packed 64-bit descriptor per op (byte 0 nchild, byte 1 dst_slot+1,
+//               bytes 2..7 child tokens kind<<6|slot), prefetched one op ahead;
+//   * stream    the P / tip tables of every child, concatenated in consumption order
+//               (pack_stream_kernel):  internal child -> [row x][class][4]  (a warp reads
+//               ONE 128-byte line per row),  tip child -> [code][class][4];
+//   * codesT    tip codes transposed to [pattern][tip in consumption order]; each thread
+//               streams its own row 8 bytes at a time, one 8-byte word ahead of use, so the
+//               only DRAM-latency load of the kernel is always in flight early.
+// Rescaling is per row (pattern, class): max over 4 high words on the integer pipe, no
+// shuffles inside the walk; classes are re-aligned once at the root.
 // ----------------------------------------------------------------------------
-template <int C_LOG2>
-__global__ void __launch_bounds__(kWalkThreads) walk4_kernel(WalkParams prm) {
+struct Walk4Params {
+  const unsigned long long* desc;  // [n_ops]
+  int n_ops;
+  int nslots;
+  int ncodes;
+  int tstride;                     // bytes per codesT row (multiple of 8, >= n_tips + 16)
+  unsigned flags;                  // bit0: R semantics at the root
+  long long N;
+  const double* stream;            // this point's packed tables
+  const unsigned char* codesT;     // [N][tstride]
+  double* keep;                    // [n_ops][N*C][4] or nullptr
+  int* keep_exp;                   // [n_ops][N*C]
+  const double* rootfreq;          // [4]
+  const double* probs;             // [C]
+  const double* weights;           // [N]
+  double* SR;                      // [N]
+  int* rexp;                       // [N]
+  double* site_lnl;                // [N]
+  double* partials;                // [gridDim.x]
+};
+
+__device__ __forceinline__ unsigned long long ldg_u64_nc(const unsigned char* p) {
+  unsigned long long v;
+  asm volatile("ld.global.nc.u64 %0, [%1];" : "=l"(v) : "l"(p));
+  return v;
+}
+
+// PT = patterns per thread.  The L1 data pipe delivers 128 B/clk/SM to the register file, and a thread needs
+// the whole 128-byte P block of its class for every internal child: with one pattern per thread the kernel is
+// bound by that pipe (ncu r1a: l1tex data-pipe wavefronts 77 %, FP64 pipe 18 %).  Holding PT patterns of the same
+// class in one thread re-uses every loaded P row PT times.
+constexpr int kWalk4Threads = 128;
+
+template <int C_LOG2, int PT, bool KEEP>
+__global__ void __launch_bounds__(kWalk4Threads) walk4_kernel(Walk4Params prm) {
   constexpr int C = 1 << C_LOG2;
+  constexpr int NTH = kWalk4Threads;
+  constexpr int GROUPS = NTH >> C_LOG2;  // pattern groups per CTA
   extern __shared__ __align__(32) unsigned char smem_raw[];
-  double4* st = reinterpret_cast<double4*>(smem_raw);                       // [nslots][256]
-  int* ste = reinterpret_cast<int*>(smem_raw + (size_t)prm.nslots * kWalkThreads * 32);  // [nslots][256]
+  double4* st = reinterpret_cast<double4*>(smem_raw);                                      // [nslots][PT][NTH]
+  int* ste = reinterpret_cast<int*>(smem_raw + (size_t)prm.nslots * PT * NTH * 32);        // [nslots][PT][NTH]
   __shared__ double red[32];
 
   const int tid = threadIdx.x;
+  const int c = tid & (C - 1);
+  const long long pat0 = ((long long)blockIdx.x * GROUPS + (tid >> C_LOG2)) * PT;
   const long long rows = prm.N << C_LOG2;
-  const long long r0 = (long long)blockIdx.x * kWalkThreads + tid;
-  const bool valid = r0 < rows;
-  const long long r = valid ? r0 : rows - 1;
-  const long long pat = r >> C_LOG2;
-  const int c = (int)(r & (C - 1));
 
-  double v0 = 1.0, v1 = 1.0, v2 = 1.0, v3 = 1.0;
-  int E = 0;
+  const unsigned char* crow[PT];
+  unsigned long long q[PT], qn[PT];
+#pragma unroll
+  for (int j = 0; j < PT; ++j) {
+    const long long pj = pat0 + j < prm.N ? pat0 + j : prm.N - 1;
+    crow[j] = prm.codesT + (size_t)pj * prm.tstride;
+    q[j] = ldg_u64_nc(crow[j]);
+    qn[j] = ldg_u64_nc(crow[j] + 8);
+  }
+  int tipk = 0;
+  const double* sp = prm.stream;  // uniform cursor into the packed tables
+  const int tip_block = (prm.ncodes << C_LOG2) * 4;
+
+  double v[PT][4];
+  int E[PT];
+#pragma unroll
+  for (int j = 0; j < PT; ++j) {
+    v[j][0] = v[j][1] = v[j][2] = v[j][3] = 1.0;
+    E[j] = 0;
+  }
+  unsigned long long d = prm.desc[0];
 
   for (int o = 0; o < prm.n_ops; ++o) {
-    const Op op = prm.ops[o];
-    double a0 = 1.0, a1 = 1.0, a2 = 1.0, a3 = 1.0;
-    int Ea = 0;
-    for (int j = 0; j < op.nchild; ++j) {
-      const Child ch = prm.childs[op.child_begin + j];
-      double t0, t1, t2, t3;
-      if (ch.kind == CHILD_TIP) {
-        const int code = load_code(prm.codes, prm.code_bytes, (long long)ch.idx * prm.N + pat);
-        const double* tt = prm.tiptab + (((size_t)ch.idx * C + c) * prm.ncodes + code) * 4;
-        ld256nc(tt, t0, t1, t2, t3);
-      } else {
-        double l0, l1, l2, l3;
-        int e;
-        if (ch.kind == CHILD_REG) {
-          l0 = v0; l1 = v1; l2 = v2; l3 = v3; e = E;
-        } else if (ch.kind == CHILD_SLOT) {
-          const double4 s = st[ch.idx * kWalkThreads + tid];
-          l0 = s.x; l1 = s.y; l2 = s.z; l3 = s.w;
-          e = ste[ch.idx * kWalkThreads + tid];
-        } else {
-          ld256(prm.keep + ((size_t)ch.idx * rows + r) * 4, l0, l1, l2, l3);
-          e = prm.keep_exp[(size_t)ch.idx * prm.N + pat];
-        }
-        const double* Pm = prm.P + ((size_t)ch.pnode * C + c) * 16;
-        double p0, p1, p2, p3;
-        ld256nc(Pm, p0, p1, p2, p3);
-        t0 = fma(p3, l3, fma(p2, l2, fma(p1, l1, p0 * l0)));
-        ld256nc(Pm + 4, p0, p1, p2, p3);
-        t1 = fma(p3, l3, fma(p2, l2, fma(p1, l1, p0 * l0)));
-        ld256nc(Pm + 8, p0, p1, p2, p3);
-        t2 = fma(p3, l3, fma(p2, l2, fma(p1, l1, p0 * l0)));
-        ld256nc(Pm + 12, p0, p1, p2, p3);
-        t3 = fma(p3, l3, fma(p2, l2, fma(p1, l1, p0 * l0)));
-        Ea += e;
-      }
-      a0 *= t0; a1 *= t1; a2 *= t2; a3 *= t3;
-    }
-    // per-pattern power-of-two rescale (max over states and classes)
-    int m = max(max(hi_word(a0), hi_word(a1)), max(hi_word(a2), hi_word(a3)));
+    const unsigned long long dn = prm.desc[o + 1];  // desc has a zero sentinel at [n_ops]
+    const int nchild = (int)(d & 0xffu);
+    const int dst = (int)((d >> 8) & 0xffu);
+    double a[PT][4];
+    int Ea[PT];
 #pragma unroll
-    for (int off = 1; off < C; off <<= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, off));
-    if (m < kScaleThresholdHi && m >= (1 << 20)) {
-      const int k = rescale_shift(m);
-      const double f = pow2(k);
-      a0 *= f; a1 *= f; a2 *= f; a3 *= f;
-      Ea += k;
+    for (int j = 0; j < PT; ++j) Ea[j] = 0;
+    unsigned long long toks = d >> 16;
+#pragma unroll 1
+    for (int ch = 0; ch < nchild; ++ch, toks >>= 8) {
+      const int kind = (int)(toks >> 6) & 3;
+      double t[PT][4];
+      if (kind == CHILD_TIP) {
+#pragma unroll
+        for (int j = 0; j < PT; ++j) {
+          const int code = (int)(q[j] & 0xffu);
+          q[j] >>= 8;
+          ld256nc(sp + (((code << C_LOG2) + c) << 2), t[j][0], t[j][1], t[j][2], t[j][3]);
+        }
+        if (((++tipk) & 7) == 0) {
+#pragma unroll
+          for (int j = 0; j < PT; ++j) {
+            q[j] = qn[j];
+            qn[j] = ldg_u64_nc(crow[j] + tipk + 8);
+          }
+        }
+        sp += tip_block;
+      } else {
+        double l[PT][4];
+        if (kind == CHILD_REG) {
+#pragma unroll
+          for (int j = 0; j < PT; ++j) {
+            l[j][0] = v[j][0]; l[j][1] = v[j][1]; l[j][2] = v[j][2]; l[j][3] = v[j][3];
+            Ea[j] += E[j];
+          }
+        } else {
+          const int slot = (int)toks & 63;
+#pragma unroll
+          for (int j = 0; j < PT; ++j) {
+            const double4 s = st[(slot * PT + j) * NTH + tid];
+            l[j][0] = s.x; l[j][1] = s.y; l[j][2] = s.z; l[j][3] = s.w;
+            Ea[j] += ste[(slot * PT + j) * NTH + tid];
+          }
+        }
+        const double* Pm = sp + (c << 2);
+#pragma unroll
+        for (int x = 0; x < 4; ++x) {
+          double p0, p1, p2, p3;
+          ld256nc(Pm + x * 4 * C, p0, p1, p2, p3);
+#pragma unroll
+          for (int j = 0; j < PT; ++j) t[j][x] = fma(p3, l[j][3], fma(p2, l[j][2], fma(p1, l[j][1], p0 * l[j][0])));
+        }
+        sp += 16 * C;
+      }
+      if (ch == 0) {
+#pragma unroll
+        for (int j = 0; j < PT; ++j) {
+          a[j][0] = t[j][0]; a[j][1] = t[j][1]; a[j][2] = t[j][2]; a[j][3] = t[j][3];
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < PT; ++j) {
+          a[j][0] *= t[j][0]; a[j][1] *= t[j][1]; a[j][2] *= t[j][2]; a[j][3] *= t[j][3];
+        }
+      }
     }
-    v0 = a0; v1 = a1; v2 = a2; v3 = a3;
-    E = Ea;
-    if (op.dst_slot >= 0) {
-      st[op.dst_slot * kWalkThreads + tid] = make_double4(v0, v1, v2, v3);
-      ste[op.dst_slot * kWalkThreads + tid] = E;
+#pragma unroll
+    for (int j = 0; j < PT; ++j) {
+      // power-of-two rescale of this row
+      const int m = max(max(hi_word(a[j][0]), hi_word(a[j][1])), max(hi_word(a[j][2]), hi_word(a[j][3])));
+      if (m < kScaleThresholdHi && m >= (1 << 20)) {
+        const int k = rescale_shift(m);
+        const double f = pow2(k);
+        a[j][0] *= f; a[j][1] *= f; a[j][2] *= f; a[j][3] *= f;
+        Ea[j] += k;
+      }
+      v[j][0] = a[j][0]; v[j][1] = a[j][1]; v[j][2] = a[j][2]; v[j][3] = a[j][3];
+      E[j] = Ea[j];
     }
-    if (op.keep_idx >= 0 && valid) {
-      st256(prm.keep + ((size_t)op.keep_idx * rows + r) * 4, v0, v1, v2, v3);
-      if (c == 0) prm.keep_exp[(size_t)op.keep_idx * prm.N + pat] = E;
+    if (dst) {
+#pragma unroll
+      for (int j = 0; j < PT; ++j) {
+        st[((dst - 1) * PT + j) * NTH + tid] = make_double4(v[j][0], v[j][1], v[j][2], v[j][3]);
+        ste[((dst - 1) * PT + j) * NTH + tid] = E[j];
+      }
     }
+    if (KEEP) {
+#pragma unroll
+      for (int j = 0; j < PT; ++j) {
+        if (pat0 + j < prm.N) {
+          const long long r = ((pat0 + j) << C_LOG2) + c;
+          st256(prm.keep + ((size_t)o * rows + r) * 4, v[j][0], v[j][1], v[j][2], v[j][3]);
+          prm.keep_exp[(size_t)o * rows + r] = E[j];
+        }
+      }
+    }
+    d = dn;
   }
 
-  // ---- root reduction: L_i = sum_c p_c sum_x pi_x CLV_root[i][c][x] ----------
+  // ---- root reduction: L_i = sum_c p_c 2^-(E_c - Emin) sum_x pi_x CLV_root[i][c][x] ----------
   const bool rsem = prm.flags & 1u;
-  const double t0 = v0 * prm.rootfreq[0], t1 = v1 * prm.rootfreq[1];
-  const double t2 = v2 * prm.rootfreq[2], t3 = v3 * prm.rootfreq[3];
-  double s;
-  if (rsem) s = (t0 > 0 ? t0 : 0.0) + (t1 > 0 ? t1 : 0.0) + (t2 > 0 ? t2 : 0.0) + (t3 > 0 ? t3 : 0.0);
-  else s = ((t0 + t1) + t2) + t3;
-  double L = s * prm.probs[c];
-  if (rsem && !(L > 0)) L = 0.0;
-#pragma unroll
-  for (int off = 1; off < C; off <<= 1) L += __shfl_xor_sync(0xffffffffu, L, off);
-  if (!rsem && L < 0) L = 0.0;
+  const double f0 = prm.rootfreq[0], f1 = prm.rootfreq[1], f2 = prm.rootfreq[2], f3 = prm.rootfreq[3];
+  const double pc = prm.probs[c];
   double contrib = 0.0;
-  if (valid && c == 0) {
-    const double lnl = log(L) - (double)E * kLn2;
-    prm.SR[pat] = L;
-    prm.rexp[pat] = E;
-    prm.site_lnl[pat] = lnl;
-    contrib = prm.weights[pat] * lnl;
+#pragma unroll
+  for (int j = 0; j < PT; ++j) {
+    int Emin = E[j];
+#pragma unroll
+    for (int off = 1; off < C; off <<= 1) Emin = min(Emin, __shfl_xor_sync(0xffffffffu, Emin, off));
+    const double t0 = v[j][0] * f0, t1 = v[j][1] * f1, t2 = v[j][2] * f2, t3 = v[j][3] * f3;
+    double s;
+    if (rsem) s = (t0 > 0 ? t0 : 0.0) + (t1 > 0 ? t1 : 0.0) + (t2 > 0 ? t2 : 0.0) + (t3 > 0 ? t3 : 0.0);
+    else s = ((t0 + t1) + t2) + t3;
+    double L = s * align_factor(E[j] - Emin) * pc;
+    if (rsem && !(L > 0)) L = 0.0;
+#pragma unroll
+    for (int off = 1; off < C; off <<= 1) L += __shfl_xor_sync(0xffffffffu, L, off);
+    if (!rsem && L < 0) L = 0.0;
+    if (pat0 + j < prm.N && c == 0) {
+      const long long pat = pat0 + j;
+      const double lnl = log(L) - (double)Emin * kLn2;
+      prm.SR[pat] = L;
+      prm.rexp[pat] = Emin;
+      prm.site_lnl[pat] = lnl;
+      contrib += prm.weights[pat] * lnl;
+    }
   }
   const double bs = block_sum(contrib, red);
   if (tid == 0) prm.partials[blockIdx.x] = bs;
+}
+
+// codes [nl][N] (leaf-slot major) -> codesT [N][tstride], column k = k-th tip the walk consumes
+__global__ void transpose_codes_kernel(const unsigned char* codes, const int* tip_order, int ntips, long long N,
+                                       int tstride, unsigned char* codesT) {
+  const long long pat = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (pat >= N) return;
+  unsigned char* row = codesT + (size_t)pat * tstride;
+  for (int k0 = 0; k0 < tstride; k0 += 8) {
+    unsigned long long w = 0;
+#pragma unroll
+    for (int b = 0; b < 8; ++b) {
+      const int k = k0 + b;
+      if (k < ntips) w |= (unsigned long long)codes[(size_t)tip_order[k] * N + pat] << (8 * b);
+    }
+    *reinterpret_cast<unsigned long long*>(row + k0) = w;
+  }
+}
+
+// stream packing for S = 4: one CTA per child block
+struct PackBlock {
+  int kind;       // CHILD_TIP or internal (anything else)
+  int pnode;      // node whose branch carries the child
+  long long off;  // offset of the block in the stream (doubles)
+};
+__global__ void pack_stream4_kernel(const PackBlock* blocks, const double* P /*[nn][C][4][4]*/, const double* code_table,
+                                    int C, int ncodes, double* stream) {
+  const PackBlock b = blocks[blockIdx.x];
+  const double* Pn = P + (size_t)b.pnode * C * 16;
+  double* out = stream + b.off;
+  if (b.kind == CHILD_TIP) {
+    for (int e = threadIdx.x; e < ncodes * C * 4; e += blockDim.x) {
+      const int x = e & 3, c = (e >> 2) % C, code = (e >> 2) / C;
+      const double* tv = code_table + code * 4;
+      const double* pr = Pn + c * 16 + x * 4;
+      out[e] = fma(pr[3], tv[3], fma(pr[2], tv[2], fma(pr[1], tv[1], pr[0] * tv[0])));
+    }
+  } else {
+    for (int e = threadIdx.x; e < C * 16; e += blockDim.x) {
+      const int y = e & 3, c = (e >> 2) % C, x = (e >> 2) / C;
+      out[e] = Pn[c * 16 + x * 4 + y];
+    }
+  }
 }
 
 // ----------------------------------------------------------------------------
@@ -264,10 +419,10 @@ __global__ void __launch_bounds__(kWalkThreads) walkS_kernel(WalkParams prm) {
           e = E;
         } else if (ch.kind == CHILD_SLOT) {
           load_row<S>(prm.gstack + ((size_t)ch.idx * rows + r) * S, l);
-          e = prm.gstack_exp[(size_t)ch.idx * prm.N + pat];
+          e = prm.gstack_exp[(size_t)ch.idx * rows + r];
         } else {
           load_row<S>(prm.keep + ((size_t)ch.idx * rows + r) * S, l);
-          e = prm.keep_exp[(size_t)ch.idx * prm.N + pat];
+          e = prm.keep_exp[(size_t)ch.idx * rows + r];
         }
         const double* pt = PT + (size_t)(j % kMaxStagedChildren) * L::kChildStride + c * L::kCStride;
 #pragma unroll
@@ -295,8 +450,6 @@ __global__ void __launch_bounds__(kWalkThreads) walkS_kernel(WalkParams prm) {
     int m = 0;
 #pragma unroll
     for (int x = 0; x < S; ++x) m = max(m, hi_word(a[x]));
-#pragma unroll
-    for (int off = 1; off < C; off <<= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, off));
     if (m < kScaleThresholdHi && m >= (1 << 20)) {
       const int k = rescale_shift(m);
       const double f = pow2(k);
@@ -309,11 +462,11 @@ __global__ void __launch_bounds__(kWalkThreads) walkS_kernel(WalkParams prm) {
     E = Ea;
     if (op.dst_slot >= 0 && valid) {
       store_row<S>(prm.gstack + ((size_t)op.dst_slot * rows + r) * S, v);
-      if (c == 0) prm.gstack_exp[(size_t)op.dst_slot * prm.N + pat] = E;
+      prm.gstack_exp[(size_t)op.dst_slot * rows + r] = E;
     }
     if (op.keep_idx >= 0 && valid) {
       store_row<S>(prm.keep + ((size_t)op.keep_idx * rows + r) * S, v);
-      if (c == 0) prm.keep_exp[(size_t)op.keep_idx * prm.N + pat] = E;
+      prm.keep_exp[(size_t)op.keep_idx * rows + r] = E;
     }
   }
 
@@ -325,16 +478,19 @@ __global__ void __launch_bounds__(kWalkThreads) walkS_kernel(WalkParams prm) {
     if (rsem) s += tx > 0 ? tx : 0.0;
     else s += tx;
   }
-  double Lk = s * prm.probs[c];
+  int Emin = E;
+#pragma unroll
+  for (int off = 1; off < C; off <<= 1) Emin = min(Emin, __shfl_xor_sync(0xffffffffu, Emin, off));
+  double Lk = s * align_factor(E - Emin) * prm.probs[c];
   if (rsem && !(Lk > 0)) Lk = 0.0;
 #pragma unroll
   for (int off = 1; off < C; off <<= 1) Lk += __shfl_xor_sync(0xffffffffu, Lk, off);
   if (!rsem && Lk < 0) Lk = 0.0;
   double contrib = 0.0;
   if (valid && c == 0) {
-    const double lnl = log(Lk) - (double)E * kLn2;
+    const double lnl = log(Lk) - (double)Emin * kLn2;
     prm.SR[pat] = Lk;
-    prm.rexp[pat] = E;
+    prm.rexp[pat] = Emin;
     prm.site_lnl[pat] = lnl;
     contrib = prm.weights[pat] * lnl;
   }

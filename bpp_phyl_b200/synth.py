@@ -1,0 +1,167 @@
+"""Synthetic inputs of the BASELINE.json shapes for bench.py: random trees in the flattened
+post-order layout the C ABI takes, model eigensystems, Gamma rate classes, and tip states simulated down the
+tree on the GPU with torch (plumbing) from P(t) tables produced by the product's own bppgpu_pt_batch.
+
+Not a port of the reference's model classes (those live in C++ under host/); this only has to produce
+well-formed inputs deterministically from a seed.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+class Tree:
+    """Flattened topology: node ids are post-order positions (root last), CSR children, branch lengths."""
+
+    def __init__(self, child_off, children, brlen):
+        self.child_off = np.asarray(child_off, np.int32)
+        self.children = np.asarray(children, np.int32)
+        self.brlen = np.asarray(brlen, np.float64)
+        self.nn = len(self.child_off) - 1
+        self.root = self.nn - 1
+        self.is_leaf = np.diff(self.child_off) == 0
+        self.n_leaves = int(self.is_leaf.sum())
+        self.n_internal = self.nn - self.n_leaves
+        self.parent = np.full(self.nn, -1, np.int32)
+        for n in range(self.nn):
+            self.parent[self.children[self.child_off[n]:self.child_off[n + 1]]] = n
+        self.leaf_nodes = np.where(self.is_leaf)[0]           # leaf slot -> node id (increasing id)
+
+    def sons(self, n):
+        return self.children[self.child_off[n]:self.child_off[n + 1]]
+
+
+def random_tree(n_taxa, rng, mean_brlen=0.05, rooted=False):
+    """Random binary topology by sequential random attachment, Exp(mean) lengths clamped to [1e-6, 1e4]
+    (AbstractHomogeneousTreeLikelihood.cpp:305-337).  Unrooted: 3-son root; rooted: 2-son root."""
+    sons = {0: []}          # node -> list of sons (temporary ids)
+    parent = {}
+    nxt = 1
+    edges = []
+    start = 2 if rooted or n_taxa < 3 else 3
+    for _ in range(start):
+        sons[0].append(nxt)
+        parent[nxt] = 0
+        sons[nxt] = []
+        edges.append(nxt)
+        nxt += 1
+    for _ in range(start, n_taxa):
+        e = edges[int(rng.integers(len(edges)))]
+        f = parent[e]
+        mid, leaf = nxt, nxt + 1
+        nxt += 2
+        sons[f][sons[f].index(e)] = mid
+        parent[mid] = f
+        sons[mid] = [e, leaf]
+        parent[e] = mid
+        parent[leaf] = mid
+        sons[leaf] = []
+        edges.extend([mid, leaf])
+    # post-order renumbering
+    order = []
+    st = [(0, 0)]
+    while st:
+        n, i = st.pop()
+        if i < len(sons[n]):
+            st.append((n, i + 1))
+            st.append((sons[n][i], 0))
+        else:
+            order.append(n)
+    new = {old: k for k, old in enumerate(order)}
+    child_off = [0]
+    children = []
+    for old in order:
+        children.extend(new[s] for s in sons[old])
+        child_off.append(len(children))
+    brlen = np.clip(rng.exponential(mean_brlen, size=len(order)), 1e-6, 1e4)
+    brlen[-1] = 0.0
+    return Tree(child_off, children, brlen)
+
+
+def gamma_rates(ncat, alpha):
+    """Equiprobable Gamma(alpha, alpha) classes, class value = class mean (bpp-core GammaDiscreteDistribution)."""
+    from scipy import special
+    if ncat == 1:
+        return np.ones(1), np.ones(1)
+    q = special.gammaincinv(alpha, np.arange(1, ncat) / ncat) / alpha
+    b = np.concatenate([[0.0], q, [np.inf]])
+    return ncat * np.diff(special.gammainc(alpha + 1.0, b * alpha)), np.full(ncat, 1.0 / ncat)
+
+
+def reversible_eigensystem(exch, pi):
+    """Q = exch * pi (off-diagonal), normalised to one substitution per unit time; eigensystem through the
+    symmetric similarity pi^1/2 Q pi^-1/2.  Returns dict(Q, V, Vinv, ev, pi)."""
+    pi = np.asarray(pi, float)
+    pi = pi / pi.sum()
+    Q = np.asarray(exch, float) * pi[None, :]
+    np.fill_diagonal(Q, 0.0)
+    np.fill_diagonal(Q, -Q.sum(axis=1))
+    Q = Q / -(np.diag(Q) @ pi)
+    s = np.sqrt(pi)
+    B = (s[:, None] * Q) / s[None, :]
+    w, U = np.linalg.eigh((B + B.T) / 2)
+    w[np.argmax(w)] = 0.0
+    return {"Q": Q, "V": U / s[:, None], "Vinv": U.T * s[None, :], "ev": w, "pi": pi}
+
+
+def gtr(a=1.2, b=0.8, c=0.6, d=1.5, e=0.9, pi=(.3, .2, .25, .25)):
+    """GTR exchangeabilities as in Model/Nucleotide/GTR.cpp:84-124 (AC=d AG=1 AT=b CG=e CT=a GT=c)."""
+    ex = np.zeros((4, 4))
+    ex[0, 1] = ex[1, 0] = d
+    ex[0, 2] = ex[2, 0] = 1.0
+    ex[0, 3] = ex[3, 0] = b
+    ex[1, 2] = ex[2, 1] = e
+    ex[1, 3] = ex[3, 1] = a
+    ex[2, 3] = ex[3, 2] = c
+    return reversible_eigensystem(ex, pi)
+
+
+def random_reversible(S, rng):
+    """A random reversible model with S states (stands in for LG08-shaped inputs where only the shape matters)."""
+    ex = rng.gamma(0.6, 1.0, size=(S, S)) + 1e-3
+    ex = (ex + ex.T) / 2
+    pi = rng.dirichlet(np.full(S, 5.0))
+    return reversible_eigensystem(ex, pi)
+
+
+def model_desc(es):
+    from . import capi
+    S = len(es["ev"])
+    return capi.model_desc(S, capi.MODEL_DIAGONALIZABLE | capi.MODEL_NONSINGULAR, rate=1.0, V=es["V"], Vinv=es["Vinv"],
+                           ev_re=es["ev"], Q=es["Q"])
+
+
+def simulate_tip_codes(tree: Tree, es, rates, n_sites, seed, device="cuda:0", chunk=1 << 20):
+    """Tip states [n_leaves][n_sites] uint8 (leaf slots in increasing node id), simulated down the tree on the GPU.
+    P(t) comes from bppgpu_pt_batch (the product's interface 1)."""
+    import torch
+    from . import capi
+    S = len(es["ev"])
+    C = len(rates)
+    md = model_desc(es)
+    t = (tree.brlen[:, None] * np.asarray(rates)[None, :]).ravel()
+    P, _, _ = capi.pt_batch(md, t, capi.WANT_P, device=int(str(device).split(":")[-1]) if ":" in str(device) else 0)
+    P = np.clip(P.reshape(tree.nn, C, S, S), 0, None)
+    cum = torch.tensor(np.cumsum(P / P.sum(-1, keepdims=True), axis=-1), device=device)     # [nn][C][S][S]
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    out = torch.empty((tree.n_leaves, n_sites), dtype=torch.uint8, device="cpu").pin_memory() if n_sites else \
+        torch.empty((tree.n_leaves, 0), dtype=torch.uint8)
+    leaf_slot = {int(n): k for k, n in enumerate(tree.leaf_nodes)}
+    picum = torch.tensor(np.cumsum(es["pi"]), device=device)
+    for s0 in range(0, n_sites, chunk):
+        n = min(chunk, n_sites - s0)
+        cls = torch.randint(C, (n,), device=device, generator=g)
+        st = {tree.root: torch.searchsorted(picum, torch.rand(n, device=device, generator=g, dtype=torch.float64)).clamp_(max=S - 1).to(torch.uint8)}
+        for node in range(tree.nn - 2, -1, -1):
+            f = int(tree.parent[node])
+            rows = cum[node][cls, st[f].long()]                                    # [n][S]
+            u = torch.rand(n, 1, device=device, generator=g, dtype=torch.float64)
+            child = (u > rows).sum(dim=1).clamp_(max=S - 1)
+            if tree.is_leaf[node]:
+                out[leaf_slot[node], s0:s0 + n] = child.to(torch.uint8).cpu()
+            else:
+                st[node] = child.to(torch.uint8)
+            # free fathers whose sons are all done
+        del st
+    return out.numpy()

@@ -165,7 +165,8 @@ int bppgpu_eval_device(bppgpu_engine* e, unsigned want, double* dev_out, void* c
 int bppgpu_get_site_lnl(bppgpu_engine* e, int32_t point, double* out /* [N] */);
 /* which: 0 = lower (subtree) CLV of `node`, 1 = upper (rest of tree, conditional on
  * the father's state).  clv [N][C][S] in the reference's VVVdouble order, values
- * are scaled: true = clv * 2^-scale_exp[i].  Needs BPPGPU_FLAG_KEEP_CLVS.       */
+ * are scaled per (pattern, class) row: true = clv[i][c][.] * 2^-scale_exp[i][c]
+ * (scale_exp is [N][C]).  Needs BPPGPU_FLAG_KEEP_CLVS.                          */
 int bppgpu_get_clv(bppgpu_engine* e, int32_t point, int32_t node, int32_t which, double* clv,
                    int32_t* scale_exp);
 /* which: BPPGPU_WANT_P / _DP / _D2P; out [C][S][S] = pxy_[node][c][x][y] */
@@ -179,7 +180,9 @@ typedef struct bppgpu_stats {
   int64_t kernel_launches; /* kernels launched by the last eval                   */
   int64_t clv_updates;     /* (node,pattern,cat,state) elements produced by it    */
   double last_eval_ms;     /* device time of the last bppgpu_eval (CUDA events)   */
-  double prune_ms;         /* ... of its pruning kernel(s)                        */
+  double prune_ms;         /* ... of its pruning kernel(s) (point 0)              */
+  double prune_ms_sum;     /* pruning-kernel device time summed over the evals    */
+  int64_t prune_count;     /* ... since the previous bppgpu_get_stats (max 64)    */
   int64_t hbm_bytes_resident;
   int32_t stack_slots;
   int32_t path;            /* which kernel family ran             */

@@ -13,7 +13,7 @@ Vectorised NumPy restatement of (paths relative to
   weighted root frequencies :927-962)
 
 Arrays are indexed [pattern][class][state] like the reference's VVVdouble.
-``scaled=True`` adds the per-pattern power-of-two rescaling the GPU path uses
+``scaled=True`` adds the per-(pattern, class) power-of-two rescaling the GPU path uses
 (the reference has none, SURVEY.md finding 5); it is exact, so wherever the
 unscaled value is finite both agree to rounding of the final log.
 """
@@ -35,15 +35,22 @@ def _contract_T(P, L):
 
 
 def _rescale(A, E):
-    """Per-pattern power-of-two rescale: A[i] *= 2^k, E[i] += k when max(A[i]) < 2^-256."""
-    m = A.reshape(A.shape[0], -1).max(axis=1)
-    need = (m > 0) & (m < 2.0 ** SCALE_THRESHOLD_EXP)
+    """Power-of-two rescale per (pattern, class) row: A[i][c] *= 2^k, E[i][c] += k when
+    0 < max_x A[i][c][x] < 2^-256, k chosen so that the max lands in [0.5, 1)."""
+    m = A.max(axis=2)
+    need = (m >= 2.0 ** -1022) & (m < 2.0 ** SCALE_THRESHOLD_EXP)
     if need.any():
         _, ex = np.frexp(m[need])           # m = f * 2^ex, f in [0.5,1)
         k = -ex
-        A[need] = np.ldexp(A[need], k[:, None, None])
+        A[need] = np.ldexp(A[need], k[:, None])
         E[need] += k
     return A, E
+
+
+def _align(root_clv, root_e):
+    """Bring the C rows of each pattern to the pattern's smallest exponent: returns (clv', Emin[N])."""
+    emin = root_e.min(axis=1)
+    return np.ldexp(root_clv, -(root_e - emin[:, None])[:, :, None]), emin
 
 
 def leaf_array(codes_row, table, C):
@@ -65,7 +72,7 @@ def prune(flat, tip_codes, table, P, C, links=None, n_per_node=None, scaled=Fals
     for nid in range(flat.n_nodes):                     # post-order ids
         if flat.is_leaf[nid]:
             clv[nid] = leaf_array(tip_codes[nid], table, C)
-            exps[nid] = np.zeros(clv[nid].shape[0], np.int64)
+            exps[nid] = np.zeros(clv[nid].shape[:2], np.int64)
             continue
         A = None
         E = None
@@ -101,8 +108,9 @@ def site_likelihoods_R(root_clv, root_freqs, probs):
 def loglik_R(root_clv, root_exp, root_freqs, probs, root_links):
     """getLogLikelihood (:162-176): per SITE (duplicates included) through
     rootPatternLinks_, sorted, summed from the largest."""
+    al, emin = _align(root_clv, root_exp)
     with np.errstate(divide="ignore"):
-        lp = np.log(site_likelihoods_R(root_clv, root_freqs, probs)) - root_exp * np.log(2.0)
+        lp = np.log(site_likelihoods_R(al, root_freqs, probs)) - emin * np.log(2.0)
     la = np.sort(lp[root_links])
     return float(np.sum(la[::-1])), lp
 
@@ -128,9 +136,9 @@ def dr_eval(flat, tip_codes, table, P, C, root_freqs, probs, weights,
     for nid in range(nn):
         if flat.is_leaf[nid]:
             lower[nid] = leaf_array(tip_codes[nid], table, C)
-            lexp[nid] = np.zeros(N, np.int64)
+            lexp[nid] = np.zeros((N, C), np.int64)
         else:
-            A, E = None, np.zeros(N, np.int64)
+            A, E = None, np.zeros((N, C), np.int64)
             for s in flat.children[nid]:
                 t = _contract(P[s], lower[s])
                 A = t if A is None else A * t
@@ -147,17 +155,18 @@ def dr_eval(flat, tip_codes, table, P, C, root_freqs, probs, weights,
         # setWeightedRootFreq (DRNonHomogeneousTreeLikelihood.cpp:927-962):
         # pi_x = sum_i sum_c p_c L_root[i][c][x] / sum_x(...)
         # (scale exponents: per-pattern; with N=1 they cancel in the normalisation)
-        tot = np.einsum("icx,c->x", np.ldexp(root_clv, -(root_e - root_e.min())[:, None, None]), probs)
+        tot = np.einsum("icx,c->x", np.ldexp(root_clv, -(root_e - root_e.min())[:, :, None]), probs)
         root_freqs = tot / tot.sum()
     res.root_freqs = root_freqs
 
     # computeRootLikelihood (:653-719)
-    S_ic = np.einsum("icx,x->ic", root_clv, root_freqs)
+    aligned, emin = _align(root_clv, root_e)
+    S_ic = np.einsum("icx,x->ic", aligned, root_freqs)
     SR = S_ic @ probs
     SR = np.where(SR < 0, 0.0, SR)
-    res.SR, res.SR_exp = SR, root_e
+    res.SR, res.SR_exp = SR, emin
     with np.errstate(divide="ignore"):
-        lp = np.log(SR) - root_e * np.log(2.0)
+        lp = np.log(SR) - emin * np.log(2.0)
     res.site_lnl = lp
     la = np.sort(weights * lp)                    # getLogLikelihood (:170-186)
     res.lnl = float(np.sum(la[::-1]))
@@ -173,7 +182,7 @@ def dr_eval(flat, tip_codes, table, P, C, root_freqs, probs, weights,
             continue
         f = int(flat.parent[nid])
         A = None
-        E = np.zeros(N, np.int64)
+        E = np.zeros((N, C), np.int64)
         for b in flat.children[f]:
             if b == nid:
                 continue
@@ -197,7 +206,7 @@ def dr_eval(flat, tip_codes, table, P, C, root_freqs, probs, weights,
     res.dL, res.d2L = {}, {}
     for nid in range(nb):
         U, D = upper[nid], lower[nid]
-        sh = (root_e - uexp[nid] - lexp[nid])       # true = stored * 2^-(e); ratio needs 2^(eR-eU-eD)
+        sh = (emin[:, None] - uexp[nid] - lexp[nid])   # [N][C]; true = stored * 2^-(e); ratio needs 2^(eR-eU-eD)
         if nh_form:
             # DRNonHomogeneousTreeLikelihood.cpp:370-413: larray = full conditional at the
             # father INCLUDING this son; divide by (P.lower), 0 where the denominator is 0
@@ -208,15 +217,15 @@ def dr_eval(flat, tip_codes, table, P, C, root_freqs, probs, weights,
             with np.errstate(divide="ignore", invalid="ignore"):
                 if num1 is not None:
                     q = np.where(den == 0, 0.0, full * num1 / den)
-                    dLi = np.ldexp(np.einsum("icx,c->i", q, probs), sh) / SR
+                    dLi = np.einsum("ic,c->i", np.ldexp(q.sum(axis=2), sh), probs) / SR
                 if num2 is not None:
                     q = np.where(den == 0, 0.0, full * num2 / den)
-                    d2Li = np.ldexp(np.einsum("icx,c->i", q, probs), sh) / SR
+                    d2Li = np.einsum("ic,c->i", np.ldexp(q.sum(axis=2), sh), probs) / SR
         else:
             if dP is not None:
-                dLi = np.ldexp(np.einsum("icx,icx,c->i", U, _contract(dP[nid], D), probs), sh) / SR
+                dLi = np.einsum("ic,c->i", np.ldexp(np.einsum("icx,icx->ic", U, _contract(dP[nid], D)), sh), probs) / SR
             if d2P is not None:
-                d2Li = np.ldexp(np.einsum("icx,icx,c->i", U, _contract(d2P[nid], D), probs), sh) / SR
+                d2Li = np.einsum("ic,c->i", np.ldexp(np.einsum("icx,icx->ic", U, _contract(d2P[nid], D)), sh), probs) / SR
         if dP is not None:
             res.dL[nid] = dLi
             d1[nid] = -float(np.sum(weights * dLi))                     # :340-368

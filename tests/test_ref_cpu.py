@@ -1,0 +1,37 @@
+"""The C++ CPU restatement (what bench.py times as cpu_baseline) against the numpy oracle and the golden value."""
+import numpy as np
+
+import cases
+from oracle import ref_cpu
+from oracle import ref_models as rm
+from test_oracle_golden import GOLD1, SEQS1, TREE1
+
+
+def test_cpp_port_reproduces_the_reference_golden_value():
+    r, p = rm.gamma_rates(4, 1.0)
+    c = cases.case_from_alignment(TREE1, SEQS1, rm.t92(3.0, 0.5), r, p)
+    for scaled in (False, True):
+        out = ref_cpu.eval_case(c, scaled=scaled)
+        assert abs(-out["lnl"] - GOLD1) < 1e-9
+
+
+def test_cpp_port_matches_numpy_oracle_with_derivatives_and_threads():
+    r, p = rm.gamma_rates(4, 0.5)
+    c = cases.make_case(40, 300, rm.gtr(1.2, 0.8, 0.6, 1.5, 0.9, (.3, .2, .25, .25)), r, p, seed=9)
+    res = cases.oracle_eval(c, want_d1=True, want_d2=True)
+    for nt in (1, 3):
+        out = ref_cpu.eval_case(c, want=7, nthreads=nt, site=True)
+        assert abs(out["lnl"] - res.lnl) < 1e-10 * abs(res.lnl)
+        nb = c.flat.n_nodes - 1
+        np.testing.assert_allclose(out["d1"][:nb], res.d1, rtol=1e-9, atol=1e-9)
+        np.testing.assert_allclose(out["d2"][:nb], res.d2, rtol=1e-9, atol=1e-8)
+        np.testing.assert_allclose(out["site_lnl"], res.site_lnl, rtol=1e-12)
+
+
+def test_cpp_port_protein_and_underflow():
+    r, p = rm.gamma_rates(4, 0.7)
+    c = cases.make_case(12, 60, rm.lg08(), r, p, seed=10)
+    assert abs(ref_cpu.eval_case(c)["lnl"] - cases.oracle_eval(c).lnl) < 1e-9
+    big = cases.make_case(700, 3, rm.gtr(), r, p, seed=4, random_tips=True, mean_brlen=0.5)
+    assert ref_cpu.eval_case(big, scaled=False)["lnl"] == -np.inf
+    assert abs(ref_cpu.eval_case(big, scaled=True)["lnl"] - cases.oracle_eval(big).lnl) < 1e-9 * 1e4
