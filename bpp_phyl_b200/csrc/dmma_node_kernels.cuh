@@ -1,0 +1,188 @@
+// K2 on the FP64 tensor cores: one pruning step  CLV_node = prod_sons (CLV_son . P_son^T)  for medium / large
+// state counts (protein S = 20, codon S = 64), CLVs resident in HBM in the reference's [pattern][class][state]
+// order (RHomogeneousTreeLikelihood::computeSubtreeLikelihood, Likelihood/RHomogeneousTreeLikelihood.cpp:802-863;
+// DR twin computeLikelihoodFromArrays, DRHomogeneousTreeLikelihood.cpp:819-864).
+//
+// GEMM view per son: T[row][x] = sum_y L[row][y] * B[y][x] with B[y][x] = P[x][y], i.e. the row-major pxy_ table
+// IS the column-major B operand of mma.sync.m8n8k4.  A CTA handles one rate class and a tile of patterns; its
+// 4 warps own RW 8-pattern row blocks each and all S columns.  The son's CLV rows go global -> registers as A
+// fragments (each element is read exactly once, full 32-byte sectors), P_son of this class is staged once per
+// CTA in shared memory with a row stride = 4 (mod 16) doubles so B-fragment loads are conflict free; tip sons are
+// a gather from the per-branch tip table.  The Hadamard product over sons, the per-row power-of-two rescale
+// (max over the row through two quad shuffles) and the exponent bookkeeping are fused into the epilogue.
+#pragma once
+#include "dmma.cuh"
+#include "walk_kernels.cuh"
+
+namespace bppgpu {
+
+struct DmmaNodeParams {
+  const Child* childs;  // sons of this node (kinds TIP / KEEP)
+  int nchild;
+  int out_idx;          // keep slab of the node
+  int S, C, ncodes, code_bytes;
+  long long N;
+  const double* P;       // [nn][C][S][S]
+  const double* tiptab;  // [nl][C][ncodes][S]
+  const void* codes;     // [nl][N]
+  double* keep;          // [ni][N][C][S]
+  int* keep_exp;         // [ni][N][C]
+};
+
+constexpr int kDmmaNodeWarps = 4;
+
+template <int KB>
+__host__ __device__ constexpr int dmma_pstride() {
+  // smallest stride >= 4*KB that is = 4 (mod 16) doubles
+  return ((4 * KB + 11) / 16) * 16 + 4;
+}
+template <int KB, int NBLK>
+constexpr size_t dmma_node_smem_per_child() {
+  return (size_t)NBLK * 8 * dmma_pstride<KB>() * sizeof(double);
+}
+
+// stage P[c] of one branch (row-major S x S) into shared memory, zero padded to [NBLK*8][stride]
+template <int KB, int NBLK, bool TRANSPOSE>
+__device__ __forceinline__ void stage_matrix(double* dst, const double* Pg, int S, int nthreads) {
+  constexpr int SB = dmma_pstride<KB>();
+  for (int e = threadIdx.x; e < NBLK * 8 * 4 * KB; e += nthreads) {
+    const int x = e / (4 * KB), y = e - x * (4 * KB);
+    double v = 0.0;
+    if (x < S && y < S) v = TRANSPOSE ? Pg[(size_t)y * S + x] : Pg[(size_t)x * S + y];
+    dst[x * SB + y] = v;
+  }
+}
+
+// acc[r][nb] += A(rows of block r) . B(staged matrix)   for the RW row blocks of this warp
+template <int KB, int NBLK, int RW>
+__device__ __forceinline__ void dmma_rows_times_matrix(double (&acc)[RW][NBLK][2], const double (&a)[RW][KB],
+                                                       const double* Ps, int g, int q) {
+  constexpr int SB = dmma_pstride<KB>();
+#pragma unroll
+  for (int kb = 0; kb < KB; ++kb) {
+#pragma unroll
+    for (int nb = 0; nb < NBLK; ++nb) {
+      const double b = Ps[(nb * 8 + g) * SB + kb * 4 + q];
+#pragma unroll
+      for (int r = 0; r < RW; ++r) dmma884(acc[r][nb][0], acc[r][nb][1], a[r][kb], b);
+    }
+  }
+}
+
+template <int KB, int NBLK, int RW>
+__global__ void __launch_bounds__(kDmmaNodeWarps * 32) dmma_node_kernel(DmmaNodeParams p) {
+  constexpr int NT = kDmmaNodeWarps * 32;
+  constexpr int SB = dmma_pstride<KB>();
+  extern __shared__ __align__(16) double sm_node[];
+  const int S = p.S, C = p.C;
+  const int c = blockIdx.y;
+
+  int nint = 0;
+  for (int j = 0; j < p.nchild; ++j) {
+    const Child ch = p.childs[j];
+    if (ch.kind == CHILD_TIP) continue;
+    stage_matrix<KB, NBLK, false>(sm_node + (size_t)nint * NBLK * 8 * SB, p.P + ((size_t)ch.pnode * C + c) * S * S, S, NT);
+    ++nint;
+  }
+  __syncthreads();
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, q = lane & 3;
+  const long long pat_base = ((long long)blockIdx.x * kDmmaNodeWarps + warp) * RW * 8;
+  if (pat_base >= p.N) return;
+  long long pat[RW];
+#pragma unroll
+  for (int r = 0; r < RW; ++r) {
+    const long long pp = pat_base + r * 8 + g;
+    pat[r] = pp < p.N ? pp : p.N - 1;
+  }
+
+  double prod[RW][NBLK][2];
+  int Ea[RW];
+#pragma unroll
+  for (int r = 0; r < RW; ++r) Ea[r] = 0;
+  nint = 0;
+  for (int j = 0; j < p.nchild; ++j) {
+    const Child ch = p.childs[j];
+    double acc[RW][NBLK][2];
+    if (ch.kind == CHILD_TIP) {
+#pragma unroll
+      for (int r = 0; r < RW; ++r) {
+        const int code = load_code(p.codes, p.code_bytes, (long long)ch.idx * p.N + pat[r]);
+        const double* tt = p.tiptab + (((size_t)ch.idx * C + c) * p.ncodes + code) * S;
+#pragma unroll
+        for (int nb = 0; nb < NBLK; ++nb) {
+          const int x = nb * 8 + 2 * q;
+          acc[r][nb][0] = x < S ? tt[x] : 0.0;
+          acc[r][nb][1] = x + 1 < S ? tt[x + 1] : 0.0;
+        }
+      }
+    } else {
+      double a[RW][KB];
+#pragma unroll
+      for (int r = 0; r < RW; ++r) {
+        const double* row = p.keep + (((size_t)ch.idx * p.N + pat[r]) * C + c) * S;
+#pragma unroll
+        for (int kb = 0; kb < KB; ++kb) {
+          const int y = kb * 4 + q;
+          a[r][kb] = y < S ? row[y] : 0.0;
+        }
+        Ea[r] += p.keep_exp[((size_t)ch.idx * p.N + pat[r]) * C + c];
+      }
+#pragma unroll
+      for (int r = 0; r < RW; ++r)
+#pragma unroll
+        for (int nb = 0; nb < NBLK; ++nb) acc[r][nb][0] = acc[r][nb][1] = 0.0;
+      dmma_rows_times_matrix<KB, NBLK, RW>(acc, a, sm_node + (size_t)nint * NBLK * 8 * SB, g, q);
+      ++nint;
+    }
+    if (j == 0) {
+#pragma unroll
+      for (int r = 0; r < RW; ++r)
+#pragma unroll
+        for (int nb = 0; nb < NBLK; ++nb) {
+          prod[r][nb][0] = acc[r][nb][0];
+          prod[r][nb][1] = acc[r][nb][1];
+        }
+    } else {
+#pragma unroll
+      for (int r = 0; r < RW; ++r)
+#pragma unroll
+        for (int nb = 0; nb < NBLK; ++nb) {
+          prod[r][nb][0] *= acc[r][nb][0];
+          prod[r][nb][1] *= acc[r][nb][1];
+        }
+    }
+  }
+
+#pragma unroll
+  for (int r = 0; r < RW; ++r) {
+    int m = 0;
+#pragma unroll
+    for (int nb = 0; nb < NBLK; ++nb) m = max(m, max(hi_word(prod[r][nb][0]), hi_word(prod[r][nb][1])));
+    m = max(m, __shfl_xor_sync(0xffffffffu, m, 1));
+    m = max(m, __shfl_xor_sync(0xffffffffu, m, 2));
+    if (m < kScaleThresholdHi && m >= (1 << 20)) {
+      const int k = rescale_shift(m);
+      const double f = pow2(k);
+#pragma unroll
+      for (int nb = 0; nb < NBLK; ++nb) {
+        prod[r][nb][0] *= f;
+        prod[r][nb][1] *= f;
+      }
+      Ea[r] += k;
+    }
+    if (pat_base + r * 8 + g < p.N) {
+      double* row = p.keep + (((size_t)p.out_idx * p.N + pat[r]) * C + c) * S;
+#pragma unroll
+      for (int nb = 0; nb < NBLK; ++nb) {
+        const int x = nb * 8 + 2 * q;
+        if (x < S) row[x] = prod[r][nb][0];
+        if (x + 1 < S) row[x + 1] = prod[r][nb][1];
+      }
+      if (q == 0) p.keep_exp[((size_t)p.out_idx * p.N + pat[r]) * C + c] = Ea[r];
+    }
+  }
+}
+
+}  // namespace bppgpu

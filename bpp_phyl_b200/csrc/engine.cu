@@ -174,6 +174,8 @@ static int check_device(int device) {
   BPP_CUDA(cudaFuncSetAttribute(pt_dmma_kernel<8, 1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
   BPP_CUDA(cudaFuncSetAttribute(pt_dmma_kernel<8, 2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
   BPP_CUDA(cudaFuncSetAttribute(pt_dmma_kernel<8, 4, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+  BPP_CUDA(cudaFuncSetAttribute(dmma_node_kernel<5, 3, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  BPP_CUDA(cudaFuncSetAttribute(dmma_node_kernel<16, 8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   return BPPGPU_OK;
 }
 
@@ -435,7 +437,7 @@ int bppgpu_destroy(bppgpu_engine* e) {
                   e->d_d2P, e->d_tiptab, e->d_keep, e->d_keep_exp, e->d_gstack, e->d_gstack_exp, e->d_upper,
                   e->d_upper_exp, e->d_SR, e->d_rexp, e->d_site_lnl, e->d_partials, e->d_partials2, e->d_out,
                   e->prog.d_ops, e->prog.d_childs, e->gprog.d_ops, e->gprog.d_childs, e->d_sibs, e->d_scratch,
-                  e->d_w4_desc, e->d_w4_tip_order, e->d_w4_blocks, e->d_w4_stream, e->d_codesT,
+                  e->d_w4_desc, e->d_w4_tip_order, e->d_w4_blocks, e->d_w4_stream, e->d_codesT, e->d_w4_tokens,
                   e->d_status};
   for (void* p : ptrs) cudaFree(p);
   for (auto& m : e->models) free_model(m);
@@ -517,8 +519,13 @@ static int create_impl(const bppgpu_config* cfg, bppgpu_engine* e) {
   if (w4ok) e->path = PATH_WALK4;
   else if (S == 20 && cpow) e->path = PATH_WALKS;
   else e->path = PATH_GENERIC;
+  if (e->path == PATH_GENERIC && ((S > 16 && S <= 20) || (S > 56 && S <= 64))) e->path = PATH_DMMA;
+  if (const char* env = getenv("BPPGPU_PATH")) {  // tuning knob
+    if (!strcmp(env, "generic")) e->path = PATH_GENERIC;
+    if (!strcmp(env, "dmma") && ((S > 16 && S <= 20) || (S > 56 && S <= 64))) e->path = PATH_DMMA;
+  }
   if (cfg->flags & BPPGPU_FLAG_FORCE_GENERIC) e->path = PATH_GENERIC;
-  if (e->path == PATH_GENERIC) e->keep = true;
+  if (e->path == PATH_GENERIC || e->path == PATH_DMMA) e->keep = true;
   build_program(e, e->prog, false);  // again: keep indices are known now
   build_program(e, e->gprog, true);
   if (e->path == PATH_WALK4) {
@@ -543,7 +550,17 @@ static int create_impl(const bppgpu_config* cfg, bppgpu_engine* e) {
         }
       }
       e->w4_desc.push_back(d);
+      for (int j = 0; j < op.nchild; ++j) {
+        const Child& ch = e->prog.childs[op.child_begin + j];
+        unsigned tok = ((unsigned)ch.kind << 6) | (ch.kind == CHILD_SLOT ? (unsigned)ch.idx : 0u);
+        if (j == 0) tok |= 1u << 8;
+        if (j == op.nchild - 1) tok |= (1u << 9) | ((unsigned)(op.dst_slot + 1) << 10);
+        e->w4_tokens.push_back((unsigned short)tok);
+      }
     }
+    if (e->w4_tokens.size() & 1) e->w4_tokens.push_back((unsigned short)(EV_NOP << 6));
+    e->w4_n_events = (int)e->w4_tokens.size();
+    for (int k = 0; k < 8; ++k) e->w4_tokens.push_back((unsigned short)(EV_NOP << 6));  // prefetch slack
     e->w4_desc.push_back(0ull);  // sentinel read by the one-op-ahead prefetch
     e->w4_stream_len = off;
     e->w4_tstride = (int)(((e->w4_tip_order.size() + 7) / 8) * 8 + 16);
@@ -615,7 +632,11 @@ static int create_impl(const bppgpu_config* cfg, bppgpu_engine* e) {
     BPP_CUDA(cudaMemcpy(e->d_w4_tip_order, e->w4_tip_order.data(), e->w4_tip_order.size() * 4, cudaMemcpyHostToDevice));
     BPP_CUDA(dev_alloc(e, &e->d_w4_blocks, e->w4_blocks.size()));
     BPP_CUDA(cudaMemcpy(e->d_w4_blocks, e->w4_blocks.data(), e->w4_blocks.size() * sizeof(PackBlock), cudaMemcpyHostToDevice));
-    BPP_CUDA(dev_alloc(e, &e->d_w4_stream, (size_t)e->pchunk * e->w4_stream_len));
+    BPP_CUDA(dev_alloc(e, &e->d_w4_tokens, e->w4_tokens.size()));
+    BPP_CUDA(cudaMemcpy(e->d_w4_tokens, e->w4_tokens.data(), e->w4_tokens.size() * 2, cudaMemcpyHostToDevice));
+    // slack behind the last block: the pipelined kernel fetches one event ahead
+    BPP_CUDA(dev_alloc(e, &e->d_w4_stream, (size_t)e->pchunk * e->w4_stream_len + (size_t)e->ncodes * C * 4 + 64));
+    BPP_CUDA(cudaMemset(e->d_w4_stream, 0, ((size_t)e->pchunk * e->w4_stream_len + (size_t)e->ncodes * C * 4 + 64) * 8));
     BPP_CUDA(dev_alloc(e, &e->d_codesT, (size_t)N * e->w4_tstride));
   }
   if (e->path != PATH_WALK4 || e->keep)
@@ -647,9 +668,12 @@ static int create_impl(const bppgpu_config* cfg, bppgpu_engine* e) {
     e->w4_pt = 4;
     while (e->w4_pt > 1 && (size_t)e->prog.nslots * e->w4_pt * kWalk4Threads * 36 > 100 * 1024) e->w4_pt >>= 1;
     if (N * C < (long long)g_sm_count * 4 * kWalk4Threads * 4) e->w4_pt = 1;  // small inputs: more CTAs instead
+    e->w4_pipe = e->w4_pt == 4;
+    if (const char* env = getenv("BPPGPU_WALK4_PIPE")) e->w4_pipe = atoi(env) != 0 && e->w4_pt == 4;  // tuning knob
     if (const char* env = getenv("BPPGPU_WALK4_PT")) {  // tuning knob: 1, 2 or 4
       const int v = atoi(env);
       if ((v == 1 || v == 2 || v == 4) && (size_t)e->prog.nslots * v * kWalk4Threads * 36 <= 200 * 1024) e->w4_pt = v;
+      if (e->w4_pt != 4) e->w4_pipe = false;
     }
     int rc4 = walk4_dispatch(e, nullptr, 0, 0, nullptr, true);
     if (rc4) return rc4;
@@ -867,8 +891,34 @@ static int walk4_launch_pt(int pt, bool keep, const Walk4Params* wp, int grid, s
   return walk4_launch_k<CL, 1>(keep, wp, grid, smem, st, attr_only);
 }
 // launches (or, with attr_only, just opts in to the dynamic shared memory of) the walk4 instantiation of this engine
+template <int CL, bool KEEP>
+static int walk4_pipe_one(bppgpu_engine* e, const Walk4Params* wp, int grid, size_t smem, cudaStream_t st, bool attr_only) {
+  if (attr_only) {
+    BPP_CUDA(cudaFuncSetAttribute(walk4_pipe_kernel<CL, KEEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    return BPPGPU_OK;
+  }
+  Walk4PipeParams pp{};
+  pp.w = *wp;
+  pp.tokens = e->d_w4_tokens;
+  pp.n_events = e->w4_n_events;
+  walk4_pipe_kernel<CL, KEEP><<<grid, kWalk4Threads, smem, st>>>(pp);
+  return BPPGPU_OK;
+}
+template <int CL>
+static int walk4_pipe_k(bppgpu_engine* e, const Walk4Params* wp, int grid, size_t smem, cudaStream_t st, bool attr_only) {
+  return e->keep ? walk4_pipe_one<CL, true>(e, wp, grid, smem, st, attr_only)
+                 : walk4_pipe_one<CL, false>(e, wp, grid, smem, st, attr_only);
+}
 static int walk4_dispatch(bppgpu_engine* e, const Walk4Params* wp, int grid, size_t /*unused*/, cudaStream_t st, bool attr_only) {
   const size_t smem = (size_t)e->prog.nslots * e->w4_pt * kWalk4Threads * 36;
+  if (e->w4_pipe) {
+    switch (ilog2(e->C)) {
+      case 0: return walk4_pipe_k<0>(e, wp, grid, smem, st, attr_only);
+      case 1: return walk4_pipe_k<1>(e, wp, grid, smem, st, attr_only);
+      case 2: return walk4_pipe_k<2>(e, wp, grid, smem, st, attr_only);
+      default: return walk4_pipe_k<3>(e, wp, grid, smem, st, attr_only);
+    }
+  }
   switch (ilog2(e->C)) {
     case 0: return walk4_launch_pt<0>(e->w4_pt, e->keep, wp, grid, smem, st, attr_only);
     case 1: return walk4_launch_pt<1>(e->w4_pt, e->keep, wp, grid, smem, st, attr_only);
@@ -978,9 +1028,29 @@ static int enqueue_prune(bppgpu_engine* e, int point, int pl, cudaStream_t st) {
       gp.N = N;
       gp.P = P; gp.tiptab = tiptab; gp.codes = e->d_codes;
       gp.keep = e->d_keep; gp.keep_exp = e->d_keep_exp;
-      generic_node_kernel<<<grid_e, 256, 0, st>>>(gp);
-      generic_scale_kernel<<<grid_r, 256, 0, st>>>(gp);
-      e->stats.kernel_launches += 2;
+      if (e->path == PATH_DMMA) {
+        DmmaNodeParams dp{};
+        dp.childs = gp.childs; dp.nchild = gp.nchild; dp.out_idx = gp.out_idx;
+        dp.S = S; dp.C = C; dp.ncodes = e->ncodes; dp.code_bytes = e->code_bytes; dp.N = N;
+        dp.P = P; dp.tiptab = tiptab; dp.codes = e->d_codes; dp.keep = e->d_keep; dp.keep_exp = e->d_keep_exp;
+        int nint = 0;
+        for (int j = 0; j < op.nchild; ++j)
+          if (e->gprog.childs[op.child_begin + j].kind != CHILD_TIP) ++nint;
+        if (S <= 20) {
+          constexpr int RW = 4;
+          const dim3 grid((unsigned)((N + 8 * RW * kDmmaNodeWarps - 1) / (8 * RW * kDmmaNodeWarps)), (unsigned)C);
+          dmma_node_kernel<5, 3, RW><<<grid, kDmmaNodeWarps * 32, nint * dmma_node_smem_per_child<5, 3>(), st>>>(dp);
+        } else {
+          constexpr int RW = 2;
+          const dim3 grid((unsigned)((N + 8 * RW * kDmmaNodeWarps - 1) / (8 * RW * kDmmaNodeWarps)), (unsigned)C);
+          dmma_node_kernel<16, 8, RW><<<grid, kDmmaNodeWarps * 32, nint * dmma_node_smem_per_child<16, 8>(), st>>>(dp);
+        }
+        e->stats.kernel_launches += 1;
+      } else {
+        generic_node_kernel<<<grid_e, 256, 0, st>>>(gp);
+        generic_scale_kernel<<<grid_r, 256, 0, st>>>(gp);
+        e->stats.kernel_launches += 2;
+      }
     }
     const int ridx = e->internal_idx[e->root];
     if (e->flags & BPPGPU_FLAG_WEIGHTED_ROOT) {

@@ -7,6 +7,7 @@
 
 #include "../../include/bppgpu.h"
 #include "deriv_kernels.cuh"
+#include "dmma_node_kernels.cuh"
 #include "generic_kernels.cuh"
 #include "pt_dmma_kernels.cuh"
 #include "pt_kernels.cuh"
@@ -78,6 +79,10 @@ struct bppgpu_engine {
   size_t w4_stream_len = 0;  // doubles per point
   int w4_tstride = 0;
   int w4_pt = 1;  // patterns per thread
+  bool w4_pipe = false;  // software-pipelined event kernel (PT = 4)
+  std::vector<unsigned short> w4_tokens;
+  int w4_n_events = 0;
+  unsigned short* d_w4_tokens = nullptr;
   unsigned long long* d_w4_desc = nullptr;
   int* d_w4_tip_order = nullptr;
   bppgpu::PackBlock* d_w4_blocks = nullptr;

@@ -59,6 +59,30 @@ def test_dna_random_trees(ncat, flags):
     assert st["path"] == (3 if flags & 16 else 1)
 
 
+@pytest.mark.parametrize("pt,pipe", [(1, 0), (2, 0), (4, 0), (4, 1)])
+@pytest.mark.parametrize("flags", [0, 1])
+def test_dna_walk_kernel_variants(monkeypatch, pt, pipe, flags):
+    """every instantiation of the DNA walk (patterns per thread, software-pipelined event kernel), with and
+    without streaming the CLVs out, on ragged sizes and a multifurcating root"""
+    monkeypatch.setenv("BPPGPU_WALK4_PT", str(pt))
+    monkeypatch.setenv("BPPGPU_WALK4_PIPE", str(pipe))
+    r, p = rm.gamma_rates(4, 0.5)
+    for ntaxa, nsites, seed in ((64, 700, 5), (9, 130, 6), (300, 65, 7)):
+        c = cases.make_case(ntaxa, nsites, gtr(), r, p, seed=seed, ambiguity=0.02, mean_brlen=0.3 if ntaxa == 300 else 0.05,
+                            random_tips=ntaxa == 300)
+        st = check_value(c, flags=flags)
+        assert st["path"] == 1
+    if flags & 1:
+        capi = _capi()
+        c = cases.make_case(30, 200, gtr(), r, p, seed=41)
+        res = cases.oracle_eval(c, want_d1=True, want_d2=True)
+        with cases.make_engine(c, flags=capi.FLAG_KEEP_CLVS) as e:
+            lnl, d1, d2 = e.eval(7)
+            nb = c.flat.n_nodes - 1
+            np.testing.assert_allclose(-d1[0, :nb], res.d1, rtol=1e-8, atol=1e-8)
+            np.testing.assert_allclose(-d2[0, :nb], res.d2, rtol=1e-8, atol=1e-7)
+
+
 @pytest.mark.parametrize("flags", [0, 1, 16])
 def test_protein_random_trees(flags):
     r, p = rm.gamma_rates(4, 0.7)
