@@ -176,6 +176,8 @@ static int check_device(int device) {
   BPP_CUDA(cudaFuncSetAttribute(pt_dmma_kernel<8, 4, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
   BPP_CUDA(cudaFuncSetAttribute(dmma_node_kernel<5, 3, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   BPP_CUDA(cudaFuncSetAttribute(dmma_node_kernel<16, 8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  BPP_CUDA(cudaFuncSetAttribute(dmma_upper_deriv_kernel<5, 3, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  BPP_CUDA(cudaFuncSetAttribute(dmma_upper_deriv_kernel<16, 8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   return BPPGPU_OK;
 }
 
@@ -437,7 +439,7 @@ int bppgpu_destroy(bppgpu_engine* e) {
                   e->d_d2P, e->d_tiptab, e->d_keep, e->d_keep_exp, e->d_gstack, e->d_gstack_exp, e->d_upper,
                   e->d_upper_exp, e->d_SR, e->d_rexp, e->d_site_lnl, e->d_partials, e->d_partials2, e->d_out,
                   e->prog.d_ops, e->prog.d_childs, e->gprog.d_ops, e->gprog.d_childs, e->d_sibs, e->d_scratch,
-                  e->d_w4_desc, e->d_w4_tip_order, e->d_w4_blocks, e->d_w4_stream, e->d_codesT, e->d_w4_tokens,
+                  e->d_dtiptab, e->d_d2tiptab, e->d_dLc, e->d_w4_desc, e->d_w4_tip_order, e->d_w4_blocks, e->d_w4_stream, e->d_codesT,
                   e->d_status};
   for (void* p : ptrs) cudaFree(p);
   for (auto& m : e->models) free_model(m);
@@ -532,7 +534,15 @@ static int create_impl(const bppgpu_config* cfg, bppgpu_engine* e) {
     // packed descriptors, tip consumption order and table blocks, all in walk order
     size_t off = 0;
     for (const Op& op : e->prog.ops) {
-      unsigned long long d = (unsigned long long)op.nchild | ((unsigned long long)(op.dst_slot + 1) << 8);
+      int shape = 0;
+      if (op.nchild == 2) {
+        const int ka = walk4_kind_index(e->prog.childs[op.child_begin].kind);
+        const int kb = walk4_kind_index(e->prog.childs[op.child_begin + 1].kind);
+        shape = 1 + 3 * ka + kb;
+        if (shape == 5 || shape == 9) shape = 0;  // (SLOT,SLOT) / (REG,REG) cannot come out of the planner
+      }
+      unsigned long long d = (unsigned long long)shape | ((unsigned long long)op.nchild << 4) |
+                             ((unsigned long long)(op.dst_slot + 1) << 8);
       for (int j = 0; j < op.nchild; ++j) {
         const Child& ch = e->prog.childs[op.child_begin + j];
         const unsigned tok = ((unsigned)ch.kind << 6) | (ch.kind == CHILD_SLOT ? (unsigned)ch.idx : 0u);
@@ -550,18 +560,9 @@ static int create_impl(const bppgpu_config* cfg, bppgpu_engine* e) {
         }
       }
       e->w4_desc.push_back(d);
-      for (int j = 0; j < op.nchild; ++j) {
-        const Child& ch = e->prog.childs[op.child_begin + j];
-        unsigned tok = ((unsigned)ch.kind << 6) | (ch.kind == CHILD_SLOT ? (unsigned)ch.idx : 0u);
-        if (j == 0) tok |= 1u << 8;
-        if (j == op.nchild - 1) tok |= (1u << 9) | ((unsigned)(op.dst_slot + 1) << 10);
-        e->w4_tokens.push_back((unsigned short)tok);
-      }
     }
-    if (e->w4_tokens.size() & 1) e->w4_tokens.push_back((unsigned short)(EV_NOP << 6));
-    e->w4_n_events = (int)e->w4_tokens.size();
-    for (int k = 0; k < 8; ++k) e->w4_tokens.push_back((unsigned short)(EV_NOP << 6));  // prefetch slack
-    e->w4_desc.push_back(0ull);  // sentinel read by the one-op-ahead prefetch
+    e->w4_desc.push_back(0ull);  // sentinels read by the one-op-ahead prefetch
+    e->w4_desc.push_back(0ull);
     e->w4_stream_len = off;
     e->w4_tstride = (int)(((e->w4_tip_order.size() + 7) / 8) * 8 + 16);
   }
@@ -587,6 +588,7 @@ static int create_impl(const bppgpu_config* cfg, bppgpu_engine* e) {
     }
   }
   e->sib_off[nn] = (int)allsibs.size();
+  e->sibs_flat = allsibs;
   BPP_CUDA(dev_alloc(e, &e->d_sibs, allsibs.size()));
   if (!allsibs.empty())
     BPP_CUDA(cudaMemcpy(e->d_sibs, allsibs.data(), allsibs.size() * sizeof(Child), cudaMemcpyHostToDevice));
@@ -632,11 +634,8 @@ static int create_impl(const bppgpu_config* cfg, bppgpu_engine* e) {
     BPP_CUDA(cudaMemcpy(e->d_w4_tip_order, e->w4_tip_order.data(), e->w4_tip_order.size() * 4, cudaMemcpyHostToDevice));
     BPP_CUDA(dev_alloc(e, &e->d_w4_blocks, e->w4_blocks.size()));
     BPP_CUDA(cudaMemcpy(e->d_w4_blocks, e->w4_blocks.data(), e->w4_blocks.size() * sizeof(PackBlock), cudaMemcpyHostToDevice));
-    BPP_CUDA(dev_alloc(e, &e->d_w4_tokens, e->w4_tokens.size()));
-    BPP_CUDA(cudaMemcpy(e->d_w4_tokens, e->w4_tokens.data(), e->w4_tokens.size() * 2, cudaMemcpyHostToDevice));
-    // slack behind the last block: the pipelined kernel fetches one event ahead
-    BPP_CUDA(dev_alloc(e, &e->d_w4_stream, (size_t)e->pchunk * e->w4_stream_len + (size_t)e->ncodes * C * 4 + 64));
-    BPP_CUDA(cudaMemset(e->d_w4_stream, 0, ((size_t)e->pchunk * e->w4_stream_len + (size_t)e->ncodes * C * 4 + 64) * 8));
+    BPP_CUDA(dev_alloc(e, &e->d_w4_stream, (size_t)e->pchunk * e->w4_stream_len + (size_t)e->ncodes * C * 4 + 64 + 8192));
+    BPP_CUDA(cudaMemset(e->d_w4_stream, 0, ((size_t)e->pchunk * e->w4_stream_len + (size_t)e->ncodes * C * 4 + 64 + 8192) * 8));
     BPP_CUDA(dev_alloc(e, &e->d_codesT, (size_t)N * e->w4_tstride));
   }
   if (e->path != PATH_WALK4 || e->keep)
@@ -664,16 +663,13 @@ static int create_impl(const bppgpu_config* cfg, bppgpu_engine* e) {
   BPP_CUDA(cudaMemset(e->d_status, 0, sizeof(int)));
 
   if (e->path == PATH_WALK4) {
-    // patterns per thread: 4 when the stack still leaves >= 2 CTAs per SM, else fewer
-    e->w4_pt = 4;
-    while (e->w4_pt > 1 && (size_t)e->prog.nslots * e->w4_pt * kWalk4Threads * 36 > 100 * 1024) e->w4_pt >>= 1;
+    // patterns per thread: 2 (4 CTAs of 128 threads per SM at 128 registers) while the stack leaves room for it
+    e->w4_pt = 2;
+    while (e->w4_pt > 1 && (size_t)e->prog.nslots * e->w4_pt * kWalk4Threads * 36 > 56 * 1024) e->w4_pt >>= 1;
     if (N * C < (long long)g_sm_count * 4 * kWalk4Threads * 4) e->w4_pt = 1;  // small inputs: more CTAs instead
-    e->w4_pipe = e->w4_pt == 4;
-    if (const char* env = getenv("BPPGPU_WALK4_PIPE")) e->w4_pipe = atoi(env) != 0 && e->w4_pt == 4;  // tuning knob
     if (const char* env = getenv("BPPGPU_WALK4_PT")) {  // tuning knob: 1, 2 or 4
       const int v = atoi(env);
       if ((v == 1 || v == 2 || v == 4) && (size_t)e->prog.nslots * v * kWalk4Threads * 36 <= 200 * 1024) e->w4_pt = v;
-      if (e->w4_pt != 4) e->w4_pipe = false;
     }
     int rc4 = walk4_dispatch(e, nullptr, 0, 0, nullptr, true);
     if (rc4) return rc4;
@@ -851,8 +847,20 @@ static int ensure_deriv_buffers(bppgpu_engine* e, unsigned want) {
   if ((want & BPPGPU_EVAL_D2) && !e->d_d2P) BPP_CUDA(dev_alloc(e, &e->d_d2P, tab));
   if ((want & (BPPGPU_EVAL_D1 | BPPGPU_EVAL_D2)) && !e->d_upper) {
     const size_t clv = (size_t)e->N * e->C * e->S;
-    BPP_CUDA(dev_alloc(e, &e->d_upper, (size_t)e->nn * clv));
-    BPP_CUDA(dev_alloc(e, &e->d_upper_exp, (size_t)e->nn * e->N * e->C));
+    // upper CLVs of tips are read by nobody on the DMMA path: keep them only while they are cheap (accessors/tests)
+    const bool all = e->path != PATH_DMMA || (double)e->nn * clv * 8 < 4e9;
+    e->upper_slab.assign(e->nn, -1);
+    e->n_upper_slabs = 0;
+    for (int n = 0; n < e->nn; ++n)
+      if (n != e->root && (all || e->leaf_slot[n] < 0)) e->upper_slab[n] = e->n_upper_slabs++;
+    BPP_CUDA(dev_alloc(e, &e->d_upper, (size_t)e->n_upper_slabs * clv));
+    BPP_CUDA(dev_alloc(e, &e->d_upper_exp, (size_t)e->n_upper_slabs * e->N * e->C));
+    if (e->path == PATH_DMMA) {
+      const size_t tt = (size_t)e->pchunk * e->nl * e->C * e->ncodes * e->S;
+      BPP_CUDA(dev_alloc(e, &e->d_dtiptab, tt));
+      BPP_CUDA(dev_alloc(e, &e->d_d2tiptab, tt));
+      BPP_CUDA(dev_alloc(e, &e->d_dLc, (size_t)e->N * e->C * 2));
+    }
   }
   return BPPGPU_OK;
 }
@@ -891,34 +899,8 @@ static int walk4_launch_pt(int pt, bool keep, const Walk4Params* wp, int grid, s
   return walk4_launch_k<CL, 1>(keep, wp, grid, smem, st, attr_only);
 }
 // launches (or, with attr_only, just opts in to the dynamic shared memory of) the walk4 instantiation of this engine
-template <int CL, bool KEEP>
-static int walk4_pipe_one(bppgpu_engine* e, const Walk4Params* wp, int grid, size_t smem, cudaStream_t st, bool attr_only) {
-  if (attr_only) {
-    BPP_CUDA(cudaFuncSetAttribute(walk4_pipe_kernel<CL, KEEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    return BPPGPU_OK;
-  }
-  Walk4PipeParams pp{};
-  pp.w = *wp;
-  pp.tokens = e->d_w4_tokens;
-  pp.n_events = e->w4_n_events;
-  walk4_pipe_kernel<CL, KEEP><<<grid, kWalk4Threads, smem, st>>>(pp);
-  return BPPGPU_OK;
-}
-template <int CL>
-static int walk4_pipe_k(bppgpu_engine* e, const Walk4Params* wp, int grid, size_t smem, cudaStream_t st, bool attr_only) {
-  return e->keep ? walk4_pipe_one<CL, true>(e, wp, grid, smem, st, attr_only)
-                 : walk4_pipe_one<CL, false>(e, wp, grid, smem, st, attr_only);
-}
 static int walk4_dispatch(bppgpu_engine* e, const Walk4Params* wp, int grid, size_t /*unused*/, cudaStream_t st, bool attr_only) {
   const size_t smem = (size_t)e->prog.nslots * e->w4_pt * kWalk4Threads * 36;
-  if (e->w4_pipe) {
-    switch (ilog2(e->C)) {
-      case 0: return walk4_pipe_k<0>(e, wp, grid, smem, st, attr_only);
-      case 1: return walk4_pipe_k<1>(e, wp, grid, smem, st, attr_only);
-      case 2: return walk4_pipe_k<2>(e, wp, grid, smem, st, attr_only);
-      default: return walk4_pipe_k<3>(e, wp, grid, smem, st, attr_only);
-    }
-  }
   switch (ilog2(e->C)) {
     case 0: return walk4_launch_pt<0>(e->w4_pt, e->keep, wp, grid, smem, st, attr_only);
     case 1: return walk4_launch_pt<1>(e->w4_pt, e->keep, wp, grid, smem, st, attr_only);
@@ -1109,11 +1091,55 @@ static int enqueue_derivs(bppgpu_engine* e, int point, int pl, unsigned want, cu
     up.N = N;
     up.P = P; up.tiptab = tiptab; up.codes = e->d_codes;
     up.keep = e->d_keep; up.keep_exp = e->d_keep_exp;
-    up.upper_f = e->d_upper + (size_t)f * clv;
-    up.uexp_f = e->d_upper_exp + (size_t)f * N * C;
+    const int fslab = f == e->root ? 0 : e->upper_slab[f];
+    const int nslab = e->upper_slab[n];
+    if (e->path == PATH_DMMA) {
+      DmmaUpperParams du{};
+      du.sibs = e->d_sibs + e->sib_off[n];
+      du.nsib = e->sib_off[n + 1] - e->sib_off[n];
+      du.father = f == e->root ? -1 : f;
+      du.father_upper = fslab;
+      du.node = n;
+      du.node_is_tip = e->leaf_slot[n] >= 0;
+      du.node_idx = du.node_is_tip ? e->leaf_slot[n] : e->internal_idx[n];
+      du.upper_out = nslab;
+      du.S = S; du.C = C; du.ncodes = e->ncodes; du.code_bytes = e->code_bytes;
+      du.nh_form = (e->flags & BPPGPU_FLAG_NH_DERIV) ? 1 : 0;
+      du.want = want;
+      du.N = N;
+      du.P = P; du.dP = dP; du.d2P = d2P;
+      du.tiptab = tiptab;
+      du.dtiptab = e->d_dtiptab + (size_t)pl * e->nl * C * e->ncodes * S;
+      du.d2tiptab = e->d_d2tiptab + (size_t)pl * e->nl * C * e->ncodes * S;
+      du.codes = e->d_codes;
+      du.keep = e->d_keep; du.keep_exp = e->d_keep_exp;
+      du.upper = e->d_upper; du.upper_exp = e->d_upper_exp;
+      du.rootfreq = e->d_rootfreq_used + (size_t)point * S;
+      du.probs = e->d_probs; du.SR = e->d_SR; du.rexp = e->d_rexp;
+      du.dLc = e->d_dLc;
+      int nmat = (du.father >= 0 ? 1 : 0);
+      for (int k = e->sib_off[n]; k < e->sib_off[n + 1]; ++k)
+        if (e->sibs_flat[k].kind != CHILD_TIP) ++nmat;
+      if (!du.node_is_tip) nmat += ((want & 2u) ? 1 : 0) + ((want & 4u) ? 1 : 0) + du.nh_form;
+      if (S <= 20) {
+        constexpr int RW = 4;
+        const dim3 grid((unsigned)((N + 8 * RW * kDmmaNodeWarps - 1) / (8 * RW * kDmmaNodeWarps)), (unsigned)C);
+        dmma_upper_deriv_kernel<5, 3, RW><<<grid, kDmmaNodeWarps * 32, nmat * dmma_node_smem_per_child<5, 3>(), st>>>(du);
+      } else {
+        constexpr int RW = 2;
+        const dim3 grid((unsigned)((N + 8 * RW * kDmmaNodeWarps - 1) / (8 * RW * kDmmaNodeWarps)), (unsigned)C);
+        dmma_upper_deriv_kernel<16, 8, RW><<<grid, kDmmaNodeWarps * 32, nmat * dmma_node_smem_per_child<16, 8>(), st>>>(du);
+      }
+      deriv_combine_kernel<<<grid_p, 256, 0, st>>>(e->d_dLc, e->d_weights, C, N, e->d_partials, e->d_partials2);
+      finalize_sum2_kernel<<<1, 256, 0, st>>>(e->d_partials, e->d_partials2, grid_p, out + 1 + n, out + 1 + nn + n);
+      e->stats.kernel_launches += 3;
+      continue;
+    }
+    up.upper_f = e->d_upper + (size_t)fslab * clv;
+    up.uexp_f = e->d_upper_exp + (size_t)fslab * N * C;
     up.rootfreq = e->d_rootfreq_used + (size_t)point * S;
-    up.upper_out = e->d_upper + (size_t)n * clv;
-    up.uexp_out = e->d_upper_exp + (size_t)n * N * C;
+    up.upper_out = e->d_upper + (size_t)nslab * clv;
+    up.uexp_out = e->d_upper_exp + (size_t)nslab * N * C;
     upper_node_kernel<<<grid_e, 256, 0, st>>>(up);
     upper_scale_kernel<<<grid_r, 256, 0, st>>>(up);
     DerivParams dp{};
@@ -1209,6 +1235,16 @@ static int eval_impl(bppgpu_engine* e, unsigned want, cudaStream_t st, bool time
       tp.tiptab = e->d_tiptab;
       tiptab_kernel<<<np * e->nl * C, 128, 0, st>>>(tp);
       e->stats.kernel_launches++;
+      if (e->path == PATH_DMMA && derivs) {
+        tp.P = e->d_dP; tp.tiptab = e->d_dtiptab;
+        tiptab_kernel<<<np * e->nl * C, 128, 0, st>>>(tp);
+        e->stats.kernel_launches++;
+        if (want & BPPGPU_EVAL_D2) {
+          tp.P = e->d_d2P; tp.tiptab = e->d_d2tiptab;
+          tiptab_kernel<<<np * e->nl * C, 128, 0, st>>>(tp);
+          e->stats.kernel_launches++;
+        }
+      }
     }
     BPP_CUDA(cudaGetLastError());
     for (int pl = 0; pl < np; ++pl) {
@@ -1300,8 +1336,10 @@ int bppgpu_get_clv(bppgpu_engine* e, int32_t point, int32_t node, int32_t which,
   } else {
     if (!(e->last_want & BPPGPU_EVAL_D1) || !e->d_upper) BPP_FAIL(BPPGPU_E_STATE, "upper CLVs exist after an eval with derivatives");
     if (node == e->root) BPP_FAIL(BPPGPU_E_INVALID, "the root has no upper CLV");
-    BPP_CUDA(cudaMemcpy(clv, e->d_upper + (size_t)node * clvn, clvn * 8, cudaMemcpyDeviceToHost));
-    if (scale_exp) BPP_CUDA(cudaMemcpy(scale_exp, e->d_upper_exp + (size_t)node * e->N * e->C, (size_t)e->N * e->C * 4, cudaMemcpyDeviceToHost));
+    const int slab = e->upper_slab[node];
+    if (slab < 0) BPP_FAIL(BPPGPU_E_STATE, "the upper CLV of tip %d is not materialised at this problem size", node);
+    BPP_CUDA(cudaMemcpy(clv, e->d_upper + (size_t)slab * clvn, clvn * 8, cudaMemcpyDeviceToHost));
+    if (scale_exp) BPP_CUDA(cudaMemcpy(scale_exp, e->d_upper_exp + (size_t)slab * e->N * e->C, (size_t)e->N * e->C * 4, cudaMemcpyDeviceToHost));
   }
   return BPPGPU_OK;
 }

@@ -7,6 +7,7 @@
 
 #include "../../include/bppgpu.h"
 #include "deriv_kernels.cuh"
+#include "dmma_deriv_kernels.cuh"
 #include "dmma_node_kernels.cuh"
 #include "generic_kernels.cuh"
 #include "pt_dmma_kernels.cuh"
@@ -72,6 +73,10 @@ struct bppgpu_engine {
   int pchunk = 1;
   double *d_P = nullptr, *d_dP = nullptr, *d_d2P = nullptr;
   double* d_tiptab = nullptr;
+  double *d_dtiptab = nullptr, *d_d2tiptab = nullptr;  // tip tables of dP, d2P (DMMA derivative path)
+  double* d_dLc = nullptr;                              // [N][C][2]
+  std::vector<int> upper_slab;                          // node id -> slab of d_upper, or -1
+  int n_upper_slabs = 0;
   // walk4 artefacts (everything in walk order, see walk_kernels.cuh)
   std::vector<unsigned long long> w4_desc;
   std::vector<int> w4_tip_order;
@@ -79,10 +84,6 @@ struct bppgpu_engine {
   size_t w4_stream_len = 0;  // doubles per point
   int w4_tstride = 0;
   int w4_pt = 1;  // patterns per thread
-  bool w4_pipe = false;  // software-pipelined event kernel (PT = 4)
-  std::vector<unsigned short> w4_tokens;
-  int w4_n_events = 0;
-  unsigned short* d_w4_tokens = nullptr;
   unsigned long long* d_w4_desc = nullptr;
   int* d_w4_tip_order = nullptr;
   bppgpu::PackBlock* d_w4_blocks = nullptr;
@@ -113,6 +114,7 @@ struct bppgpu_engine {
   std::vector<std::vector<bppgpu::Child>> sibs;  // per node: siblings, generic kinds
   bppgpu::Child* d_sibs = nullptr;
   std::vector<int> sib_off;
+  std::vector<bppgpu::Child> sibs_flat;
   int path = bppgpu::PATH_NONE;
   bool keep = false;
   // state flags

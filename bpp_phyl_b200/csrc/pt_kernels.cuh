@@ -165,7 +165,7 @@ struct TipTabParams {
 };
 
 __global__ void tiptab_kernel(TipTabParams p) {
-  const int m = blockIdx.x;  // (point*nl + leaf)*C + c
+  const int m = blockIdx.x;  // (point*nl + leaf)*C + c  (P may be pxy_, dpxy_ or d2pxy_)
   const int c = m % p.C;
   const int leaf = (m / p.C) % p.nl;
   const int point = m / (p.C * p.nl);

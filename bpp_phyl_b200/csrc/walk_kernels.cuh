@@ -118,7 +118,145 @@ __device__ __forceinline__ unsigned long long ldg_u64_nc(const unsigned char* p)
 // the whole 128-byte P block of its class for every internal child: with one pattern per thread the kernel is
 // bound by that pipe (ncu r1a: l1tex data-pipe wavefronts 77 %, FP64 pipe 18 %).  Holding PT patterns of the same
 // class in one thread re-uses every loaded P row PT times.
+//
+// Instruction overhead is the other limiter (ncu r1b: 128 issued instructions per pattern-op for 20 FP64 ones), so
+// the binary ops -- 99.9 % of a bifurcating tree -- are dispatched by a warp-uniform switch on a host-computed
+// SHAPE code to straight-line handlers specialised at compile time on the two child kinds; anything else (the
+// 3-son root, multifurcations) takes the generic child loop.
+//
+// Measured on the 1024-taxon x 1M-pattern config (ms per evaluation): PT=1 30.0, PT=2 18.7, PT=4 19.3.  Tried and
+// dropped because they measured slower (DESIGN.md has the numbers): a software-pipelined event loop, register
+// prefetch of the next op's tables (costs the occupancy it tries to replace) and prefetch.global.L1 of the stream.
 constexpr int kWalk4Threads = 128;
+
+// shape = 1 + 3*k(child0) + k(child1) with k: TIP 0, SLOT 1, REG 2;  0 = generic loop
+__host__ __device__ constexpr int walk4_kind_index(int kind) { return kind == CHILD_TIP ? 0 : (kind == CHILD_SLOT ? 1 : 2); }
+
+template <int C_LOG2, int PT>
+struct Walk4State {
+  static constexpr int C = 1 << C_LOG2;
+  static constexpr int NTH = kWalk4Threads;
+  double v[PT][4];
+  int E[PT];
+  unsigned long long q[PT], qn[PT];
+  const unsigned char* crow[PT];
+  int tipk;
+  const double* sp;
+  int tip_block;
+  int c, tid;
+  double4* st;
+  int* ste;
+
+  // t = tip vector of the next tip in consumption order
+  __device__ __forceinline__ void term_tip(double (&t)[PT][4]) {
+#pragma unroll
+    for (int j = 0; j < PT; ++j) {
+      const int code = (int)(q[j] & 0xffu);
+      q[j] >>= 8;
+      ld256nc(sp + (((code << C_LOG2) + c) << 2), t[j][0], t[j][1], t[j][2], t[j][3]);
+    }
+    if (((++tipk) & 7) == 0) {
+#pragma unroll
+      for (int j = 0; j < PT; ++j) {
+        q[j] = qn[j];
+        qn[j] = ldg_u64_nc(crow[j] + tipk + 8);
+      }
+    }
+    sp += tip_block;
+  }
+  // t = P . l for the next internal child, l = current registers (REG) or a stack slot
+  template <bool FROM_SLOT>
+  __device__ __forceinline__ void term_internal(int slot, double (&t)[PT][4], int (&e)[PT]) {
+    const double* Pm = sp + (c << 2);
+    double p[4][4];
+#pragma unroll
+    for (int x = 0; x < 4; ++x) ld256nc(Pm + x * 4 * C, p[x][0], p[x][1], p[x][2], p[x][3]);
+    sp += 16 * C;
+#pragma unroll
+    for (int j = 0; j < PT; ++j) {
+      double l0, l1, l2, l3;
+      if (FROM_SLOT) {
+        const double4 s = st[(slot * PT + j) * NTH + tid];
+        l0 = s.x; l1 = s.y; l2 = s.z; l3 = s.w;
+        e[j] += ste[(slot * PT + j) * NTH + tid];
+      } else {
+        l0 = v[j][0]; l1 = v[j][1]; l2 = v[j][2]; l3 = v[j][3];
+        e[j] += E[j];
+      }
+#pragma unroll
+      for (int x = 0; x < 4; ++x) t[j][x] = fma(p[x][3], l3, fma(p[x][2], l2, fma(p[x][1], l1, p[x][0] * l0)));
+    }
+  }
+  template <int K>
+  __device__ __forceinline__ void term(int slot, double (&t)[PT][4], int (&e)[PT]) {
+    if (K == 0) term_tip(t);
+    else if (K == 1) term_internal<true>(slot, t, e);
+    else term_internal<false>(slot, t, e);
+  }
+  // v = a, rescaled per row; E = e (+ shift)
+  __device__ __forceinline__ void commit(double (&a)[PT][4], int (&e)[PT]) {
+    int m[PT];
+    int mmin = 0x7fffffff;
+#pragma unroll
+    for (int j = 0; j < PT; ++j) {
+      m[j] = max(max(hi_word(a[j][0]), hi_word(a[j][1])), max(hi_word(a[j][2]), hi_word(a[j][3])));
+      mmin = min(mmin, m[j]);
+    }
+    if (mmin < kScaleThresholdHi) {  // rare: some row of this thread is small (or identically zero)
+#pragma unroll
+      for (int j = 0; j < PT; ++j) {
+        if (m[j] < kScaleThresholdHi && m[j] >= (1 << 20)) {
+          const int k = rescale_shift(m[j]);
+          const double f = pow2(k);
+          a[j][0] *= f; a[j][1] *= f; a[j][2] *= f; a[j][3] *= f;
+          e[j] += k;
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < PT; ++j) {
+      v[j][0] = a[j][0]; v[j][1] = a[j][1]; v[j][2] = a[j][2]; v[j][3] = a[j][3];
+      E[j] = e[j];
+    }
+  }
+  template <int KA, int KB>
+  __device__ __forceinline__ void op2(int slotA, int slotB) {
+    double ta[PT][4], tb[PT][4];
+    int e[PT];
+#pragma unroll
+    for (int j = 0; j < PT; ++j) e[j] = 0;
+    term<KA>(slotA, ta, e);
+    term<KB>(slotB, tb, e);
+#pragma unroll
+    for (int j = 0; j < PT; ++j) {
+      ta[j][0] *= tb[j][0]; ta[j][1] *= tb[j][1]; ta[j][2] *= tb[j][2]; ta[j][3] *= tb[j][3];
+    }
+    commit(ta, e);
+  }
+  __device__ __forceinline__ void op_generic(int nchild, unsigned long long toks) {
+    double a[PT][4];
+    int e[PT];
+#pragma unroll
+    for (int j = 0; j < PT; ++j) e[j] = 0;
+#pragma unroll 1
+    for (int ch = 0; ch < nchild; ++ch, toks >>= 8) {
+      const int kind = (int)(toks >> 6) & 3;
+      double t[PT][4];
+      if (kind == CHILD_TIP) term_tip(t);
+      else if (kind == CHILD_SLOT) term_internal<true>((int)toks & 63, t, e);
+      else term_internal<false>(0, t, e);
+#pragma unroll
+      for (int j = 0; j < PT; ++j) {
+        if (ch == 0) {
+          a[j][0] = t[j][0]; a[j][1] = t[j][1]; a[j][2] = t[j][2]; a[j][3] = t[j][3];
+        } else {
+          a[j][0] *= t[j][0]; a[j][1] *= t[j][1]; a[j][2] *= t[j][2]; a[j][3] *= t[j][3];
+        }
+      }
+    }
+    commit(a, e);
+  }
+};
 
 template <int C_LOG2, int PT, bool KEEP>
 __global__ void __launch_bounds__(kWalk4Threads) walk4_kernel(Walk4Params prm) {
@@ -126,122 +264,51 @@ __global__ void __launch_bounds__(kWalk4Threads) walk4_kernel(Walk4Params prm) {
   constexpr int NTH = kWalk4Threads;
   constexpr int GROUPS = NTH >> C_LOG2;  // pattern groups per CTA
   extern __shared__ __align__(32) unsigned char smem_raw[];
-  double4* st = reinterpret_cast<double4*>(smem_raw);                                      // [nslots][PT][NTH]
-  int* ste = reinterpret_cast<int*>(smem_raw + (size_t)prm.nslots * PT * NTH * 32);        // [nslots][PT][NTH]
   __shared__ double red[32];
 
+  Walk4State<C_LOG2, PT> s;
+  s.st = reinterpret_cast<double4*>(smem_raw);                                      // [nslots][PT][NTH]
+  s.ste = reinterpret_cast<int*>(smem_raw + (size_t)prm.nslots * PT * NTH * 32);    // [nslots][PT][NTH]
   const int tid = threadIdx.x;
+  s.tid = tid;
   const int c = tid & (C - 1);
+  s.c = c;
   const long long pat0 = ((long long)blockIdx.x * GROUPS + (tid >> C_LOG2)) * PT;
   const long long rows = prm.N << C_LOG2;
-
-  const unsigned char* crow[PT];
-  unsigned long long q[PT], qn[PT];
 #pragma unroll
   for (int j = 0; j < PT; ++j) {
     const long long pj = pat0 + j < prm.N ? pat0 + j : prm.N - 1;
-    crow[j] = prm.codesT + (size_t)pj * prm.tstride;
-    q[j] = ldg_u64_nc(crow[j]);
-    qn[j] = ldg_u64_nc(crow[j] + 8);
+    s.crow[j] = prm.codesT + (size_t)pj * prm.tstride;
+    s.q[j] = ldg_u64_nc(s.crow[j]);
+    s.qn[j] = ldg_u64_nc(s.crow[j] + 8);
+    s.v[j][0] = s.v[j][1] = s.v[j][2] = s.v[j][3] = 1.0;
+    s.E[j] = 0;
   }
-  int tipk = 0;
-  const double* sp = prm.stream;  // uniform cursor into the packed tables
-  const int tip_block = (prm.ncodes << C_LOG2) * 4;
+  s.tipk = 0;
+  s.sp = prm.stream;
+  s.tip_block = (prm.ncodes << C_LOG2) * 4;
 
-  double v[PT][4];
-  int E[PT];
-#pragma unroll
-  for (int j = 0; j < PT; ++j) {
-    v[j][0] = v[j][1] = v[j][2] = v[j][3] = 1.0;
-    E[j] = 0;
-  }
   unsigned long long d = prm.desc[0];
-
   for (int o = 0; o < prm.n_ops; ++o) {
     const unsigned long long dn = prm.desc[o + 1];  // desc has a zero sentinel at [n_ops]
-    const int nchild = (int)(d & 0xffu);
+    const int shape = (int)(d & 0xfu);
     const int dst = (int)((d >> 8) & 0xffu);
-    double a[PT][4];
-    int Ea[PT];
-#pragma unroll
-    for (int j = 0; j < PT; ++j) Ea[j] = 0;
-    unsigned long long toks = d >> 16;
-#pragma unroll 1
-    for (int ch = 0; ch < nchild; ++ch, toks >>= 8) {
-      const int kind = (int)(toks >> 6) & 3;
-      double t[PT][4];
-      if (kind == CHILD_TIP) {
-#pragma unroll
-        for (int j = 0; j < PT; ++j) {
-          const int code = (int)(q[j] & 0xffu);
-          q[j] >>= 8;
-          ld256nc(sp + (((code << C_LOG2) + c) << 2), t[j][0], t[j][1], t[j][2], t[j][3]);
-        }
-        if (((++tipk) & 7) == 0) {
-#pragma unroll
-          for (int j = 0; j < PT; ++j) {
-            q[j] = qn[j];
-            qn[j] = ldg_u64_nc(crow[j] + tipk + 8);
-          }
-        }
-        sp += tip_block;
-      } else {
-        double l[PT][4];
-        if (kind == CHILD_REG) {
-#pragma unroll
-          for (int j = 0; j < PT; ++j) {
-            l[j][0] = v[j][0]; l[j][1] = v[j][1]; l[j][2] = v[j][2]; l[j][3] = v[j][3];
-            Ea[j] += E[j];
-          }
-        } else {
-          const int slot = (int)toks & 63;
-#pragma unroll
-          for (int j = 0; j < PT; ++j) {
-            const double4 s = st[(slot * PT + j) * NTH + tid];
-            l[j][0] = s.x; l[j][1] = s.y; l[j][2] = s.z; l[j][3] = s.w;
-            Ea[j] += ste[(slot * PT + j) * NTH + tid];
-          }
-        }
-        const double* Pm = sp + (c << 2);
-#pragma unroll
-        for (int x = 0; x < 4; ++x) {
-          double p0, p1, p2, p3;
-          ld256nc(Pm + x * 4 * C, p0, p1, p2, p3);
-#pragma unroll
-          for (int j = 0; j < PT; ++j) t[j][x] = fma(p3, l[j][3], fma(p2, l[j][2], fma(p1, l[j][1], p0 * l[j][0])));
-        }
-        sp += 16 * C;
-      }
-      if (ch == 0) {
-#pragma unroll
-        for (int j = 0; j < PT; ++j) {
-          a[j][0] = t[j][0]; a[j][1] = t[j][1]; a[j][2] = t[j][2]; a[j][3] = t[j][3];
-        }
-      } else {
-#pragma unroll
-        for (int j = 0; j < PT; ++j) {
-          a[j][0] *= t[j][0]; a[j][1] *= t[j][1]; a[j][2] *= t[j][2]; a[j][3] *= t[j][3];
-        }
-      }
-    }
-#pragma unroll
-    for (int j = 0; j < PT; ++j) {
-      // power-of-two rescale of this row
-      const int m = max(max(hi_word(a[j][0]), hi_word(a[j][1])), max(hi_word(a[j][2]), hi_word(a[j][3])));
-      if (m < kScaleThresholdHi && m >= (1 << 20)) {
-        const int k = rescale_shift(m);
-        const double f = pow2(k);
-        a[j][0] *= f; a[j][1] *= f; a[j][2] *= f; a[j][3] *= f;
-        Ea[j] += k;
-      }
-      v[j][0] = a[j][0]; v[j][1] = a[j][1]; v[j][2] = a[j][2]; v[j][3] = a[j][3];
-      E[j] = Ea[j];
+    const int slotA = (int)(d >> 16) & 63, slotB = (int)(d >> 24) & 63;
+    switch (shape) {
+      case 1: s.template op2<0, 0>(slotA, slotB); break;
+      case 2: s.template op2<0, 1>(slotA, slotB); break;
+      case 3: s.template op2<0, 2>(slotA, slotB); break;
+      case 4: s.template op2<1, 0>(slotA, slotB); break;
+      case 6: s.template op2<1, 2>(slotA, slotB); break;
+      case 7: s.template op2<2, 0>(slotA, slotB); break;
+      case 8: s.template op2<2, 1>(slotA, slotB); break;
+      default: s.op_generic((int)(d >> 4) & 0xf, d >> 16); break;
     }
     if (dst) {
 #pragma unroll
       for (int j = 0; j < PT; ++j) {
-        st[((dst - 1) * PT + j) * NTH + tid] = make_double4(v[j][0], v[j][1], v[j][2], v[j][3]);
-        ste[((dst - 1) * PT + j) * NTH + tid] = E[j];
+        s.st[((dst - 1) * PT + j) * NTH + tid] = make_double4(s.v[j][0], s.v[j][1], s.v[j][2], s.v[j][3]);
+        s.ste[((dst - 1) * PT + j) * NTH + tid] = s.E[j];
       }
     }
     if (KEEP) {
@@ -249,8 +316,8 @@ __global__ void __launch_bounds__(kWalk4Threads) walk4_kernel(Walk4Params prm) {
       for (int j = 0; j < PT; ++j) {
         if (pat0 + j < prm.N) {
           const long long r = ((pat0 + j) << C_LOG2) + c;
-          st256(prm.keep + ((size_t)o * rows + r) * 4, v[j][0], v[j][1], v[j][2], v[j][3]);
-          prm.keep_exp[(size_t)o * rows + r] = E[j];
+          st256(prm.keep + ((size_t)o * rows + r) * 4, s.v[j][0], s.v[j][1], s.v[j][2], s.v[j][3]);
+          prm.keep_exp[(size_t)o * rows + r] = s.E[j];
         }
       }
     }
@@ -264,225 +331,14 @@ __global__ void __launch_bounds__(kWalk4Threads) walk4_kernel(Walk4Params prm) {
   double contrib = 0.0;
 #pragma unroll
   for (int j = 0; j < PT; ++j) {
-    int Emin = E[j];
+    int Emin = s.E[j];
 #pragma unroll
     for (int off = 1; off < C; off <<= 1) Emin = min(Emin, __shfl_xor_sync(0xffffffffu, Emin, off));
-    const double t0 = v[j][0] * f0, t1 = v[j][1] * f1, t2 = v[j][2] * f2, t3 = v[j][3] * f3;
-    double s;
-    if (rsem) s = (t0 > 0 ? t0 : 0.0) + (t1 > 0 ? t1 : 0.0) + (t2 > 0 ? t2 : 0.0) + (t3 > 0 ? t3 : 0.0);
-    else s = ((t0 + t1) + t2) + t3;
-    double L = s * align_factor(E[j] - Emin) * pc;
-    if (rsem && !(L > 0)) L = 0.0;
-#pragma unroll
-    for (int off = 1; off < C; off <<= 1) L += __shfl_xor_sync(0xffffffffu, L, off);
-    if (!rsem && L < 0) L = 0.0;
-    if (pat0 + j < prm.N && c == 0) {
-      const long long pat = pat0 + j;
-      const double lnl = log(L) - (double)Emin * kLn2;
-      prm.SR[pat] = L;
-      prm.rexp[pat] = Emin;
-      prm.site_lnl[pat] = lnl;
-      contrib += prm.weights[pat] * lnl;
-    }
-  }
-  const double bs = block_sum(contrib, red);
-  if (tid == 0) prm.partials[blockIdx.x] = bs;
-}
-
-// ----------------------------------------------------------------------------
-// Software-pipelined variant (PT = 4): the walk is flattened into one stream of child EVENTS
-// (16-bit tokens: slot | kind<<6 | first<<8 | last<<9 | (dst_slot+1)<<10) and the table data of event e+1
-// (the 128-byte P block of this thread's class, or the PT tip vectors selected by the already-resident codes)
-// is loaded into registers while event e is being computed.  With only 2 resident warps per scheduler
-// (the shared-memory stack bounds the rows in flight per SM) this is what hides the L1/L2 latency.
-// ----------------------------------------------------------------------------
-enum { EV_NOP = 3 };
-
-struct Walk4PipeParams {
-  Walk4Params w;
-  const unsigned short* tokens;  // [n_events + pad], pad tokens are EV_NOP
-  int n_events;                  // multiple of 2
-};
-
-template <int C_LOG2, bool KEEP>
-__global__ void __launch_bounds__(kWalk4Threads) walk4_pipe_kernel(Walk4PipeParams pp) {
-  constexpr int PT = 4;
-  constexpr int C = 1 << C_LOG2;
-  constexpr int NTH = kWalk4Threads;
-  constexpr int GROUPS = NTH >> C_LOG2;
-  const Walk4Params& prm = pp.w;
-  extern __shared__ __align__(32) unsigned char smem_raw[];
-  double4* st = reinterpret_cast<double4*>(smem_raw);                                // [nslots][PT][NTH]
-  int* ste = reinterpret_cast<int*>(smem_raw + (size_t)prm.nslots * PT * NTH * 32);  // [nslots][PT][NTH]
-  __shared__ double red[32];
-
-  const int tid = threadIdx.x;
-  const int c = tid & (C - 1);
-  const long long pat0 = ((long long)blockIdx.x * GROUPS + (tid >> C_LOG2)) * PT;
-  const long long rows = prm.N << C_LOG2;
-
-  const unsigned char* crow[PT];
-  unsigned long long q[PT], qn[PT];
-#pragma unroll
-  for (int j = 0; j < PT; ++j) {
-    const long long pj = pat0 + j < prm.N ? pat0 + j : prm.N - 1;
-    crow[j] = prm.codesT + (size_t)pj * prm.tstride;
-    q[j] = ldg_u64_nc(crow[j]);
-    qn[j] = ldg_u64_nc(crow[j] + 8);
-  }
-  int tipk = 0;                   // tips whose vectors have been fetched
-  const double* sp = prm.stream;  // fetch cursor (one event ahead of the compute)
-  const int tip_block = (prm.ncodes << C_LOG2) * 4;
-
-  double v[PT][4], a[PT][4];
-  int E[PT], Ea[PT];
-#pragma unroll
-  for (int j = 0; j < PT; ++j) {
-    v[j][0] = v[j][1] = v[j][2] = v[j][3] = 1.0;
-    a[j][0] = a[j][1] = a[j][2] = a[j][3] = 1.0;
-    E[j] = 0;
-    Ea[j] = 0;
-  }
-  int op_index = 0;
-
-  // fetch the table data of an event into buf[16]
-  auto fetch = [&](unsigned tok, double (&buf)[16]) {
-    const unsigned kind = (tok >> 6) & 3u;
-    if (kind == CHILD_TIP) {
-#pragma unroll
-      for (int j = 0; j < PT; ++j) {
-        const int code = (int)(q[j] & 0xffu);
-        q[j] >>= 8;
-        ld256nc(sp + (((code << C_LOG2) + c) << 2), buf[4 * j], buf[4 * j + 1], buf[4 * j + 2], buf[4 * j + 3]);
-      }
-      if (((++tipk) & 7) == 0) {
-#pragma unroll
-        for (int j = 0; j < PT; ++j) {
-          q[j] = qn[j];
-          qn[j] = ldg_u64_nc(crow[j] + tipk + 8);
-        }
-      }
-      sp += tip_block;
-    } else if (kind != EV_NOP) {
-      const double* Pm = sp + (c << 2);
-#pragma unroll
-      for (int x = 0; x < 4; ++x) ld256nc(Pm + x * 4 * C, buf[4 * x], buf[4 * x + 1], buf[4 * x + 2], buf[4 * x + 3]);
-      sp += 16 * C;
-    }
-  };
-
-  // consume an event whose table data sits in buf[16]
-  auto compute = [&](unsigned tok, const double (&buf)[16]) {
-    const unsigned kind = (tok >> 6) & 3u;
-    if (kind == EV_NOP) return;
-    const bool first = (tok >> 8) & 1u, last = (tok >> 9) & 1u;
-    double t[PT][4];
-    if (kind == CHILD_TIP) {
-#pragma unroll
-      for (int j = 0; j < PT; ++j) {
-        t[j][0] = buf[4 * j]; t[j][1] = buf[4 * j + 1]; t[j][2] = buf[4 * j + 2]; t[j][3] = buf[4 * j + 3];
-      }
-    } else {
-      double l[PT][4];
-      int el[PT];
-      if (kind == CHILD_REG) {
-#pragma unroll
-        for (int j = 0; j < PT; ++j) {
-          l[j][0] = v[j][0]; l[j][1] = v[j][1]; l[j][2] = v[j][2]; l[j][3] = v[j][3];
-          el[j] = E[j];
-        }
-      } else {
-        const int slot = (int)tok & 63;
-#pragma unroll
-        for (int j = 0; j < PT; ++j) {
-          const double4 s = st[(slot * PT + j) * NTH + tid];
-          l[j][0] = s.x; l[j][1] = s.y; l[j][2] = s.z; l[j][3] = s.w;
-          el[j] = ste[(slot * PT + j) * NTH + tid];
-        }
-      }
-#pragma unroll
-      for (int j = 0; j < PT; ++j) {
-#pragma unroll
-        for (int x = 0; x < 4; ++x)
-          t[j][x] = fma(buf[4 * x + 3], l[j][3], fma(buf[4 * x + 2], l[j][2], fma(buf[4 * x + 1], l[j][1], buf[4 * x] * l[j][0])));
-        Ea[j] = first ? el[j] : Ea[j] + el[j];
-      }
-    }
-    if (kind == CHILD_TIP && first) {
-#pragma unroll
-      for (int j = 0; j < PT; ++j) Ea[j] = 0;
-    }
-#pragma unroll
-    for (int j = 0; j < PT; ++j) {
-      if (first) {
-        a[j][0] = t[j][0]; a[j][1] = t[j][1]; a[j][2] = t[j][2]; a[j][3] = t[j][3];
-      } else {
-        a[j][0] *= t[j][0]; a[j][1] *= t[j][1]; a[j][2] *= t[j][2]; a[j][3] *= t[j][3];
-      }
-    }
-    if (last) {
-#pragma unroll
-      for (int j = 0; j < PT; ++j) {
-        const int m = max(max(hi_word(a[j][0]), hi_word(a[j][1])), max(hi_word(a[j][2]), hi_word(a[j][3])));
-        if (m < kScaleThresholdHi && m >= (1 << 20)) {
-          const int k = rescale_shift(m);
-          const double f = pow2(k);
-          a[j][0] *= f; a[j][1] *= f; a[j][2] *= f; a[j][3] *= f;
-          Ea[j] += k;
-        }
-        v[j][0] = a[j][0]; v[j][1] = a[j][1]; v[j][2] = a[j][2]; v[j][3] = a[j][3];
-        E[j] = Ea[j];
-      }
-      const int dst = (int)(tok >> 10) & 63;
-      if (dst) {
-#pragma unroll
-        for (int j = 0; j < PT; ++j) {
-          st[((dst - 1) * PT + j) * NTH + tid] = make_double4(v[j][0], v[j][1], v[j][2], v[j][3]);
-          ste[((dst - 1) * PT + j) * NTH + tid] = E[j];
-        }
-      }
-      if (KEEP) {
-#pragma unroll
-        for (int j = 0; j < PT; ++j) {
-          if (pat0 + j < prm.N) {
-            const long long r = ((pat0 + j) << C_LOG2) + c;
-            st256(prm.keep + ((size_t)op_index * rows + r) * 4, v[j][0], v[j][1], v[j][2], v[j][3]);
-            prm.keep_exp[(size_t)op_index * rows + r] = E[j];
-          }
-        }
-      }
-      ++op_index;
-    }
-  };
-
-  double bufA[16], bufB[16];
-  const unsigned* tok32 = reinterpret_cast<const unsigned*>(pp.tokens);  // two tokens per word
-  unsigned w = tok32[0];
-  fetch(w & 0xffffu, bufA);
-  for (int ev = 0; ev < pp.n_events; ev += 2) {
-    const unsigned wn = tok32[(ev >> 1) + 1];  // padded: always readable
-    fetch(w >> 16, bufB);
-    compute(w & 0xffffu, bufA);
-    fetch(wn & 0xffffu, bufA);
-    compute(w >> 16, bufB);
-    w = wn;
-  }
-
-  // ---- root reduction (same as walk4_kernel) --------------------------------------------------
-  const bool rsem = prm.flags & 1u;
-  const double f0 = prm.rootfreq[0], f1 = prm.rootfreq[1], f2 = prm.rootfreq[2], f3 = prm.rootfreq[3];
-  const double pc = prm.probs[c];
-  double contrib = 0.0;
-#pragma unroll
-  for (int j = 0; j < PT; ++j) {
-    int Emin = E[j];
-#pragma unroll
-    for (int off = 1; off < C; off <<= 1) Emin = min(Emin, __shfl_xor_sync(0xffffffffu, Emin, off));
-    const double t0 = v[j][0] * f0, t1 = v[j][1] * f1, t2 = v[j][2] * f2, t3 = v[j][3] * f3;
-    double s;
-    if (rsem) s = (t0 > 0 ? t0 : 0.0) + (t1 > 0 ? t1 : 0.0) + (t2 > 0 ? t2 : 0.0) + (t3 > 0 ? t3 : 0.0);
-    else s = ((t0 + t1) + t2) + t3;
-    double L = s * align_factor(E[j] - Emin) * pc;
+    const double t0 = s.v[j][0] * f0, t1 = s.v[j][1] * f1, t2 = s.v[j][2] * f2, t3 = s.v[j][3] * f3;
+    double sum;
+    if (rsem) sum = (t0 > 0 ? t0 : 0.0) + (t1 > 0 ? t1 : 0.0) + (t2 > 0 ? t2 : 0.0) + (t3 > 0 ? t3 : 0.0);
+    else sum = ((t0 + t1) + t2) + t3;
+    double L = sum * align_factor(s.E[j] - Emin) * pc;
     if (rsem && !(L > 0)) L = 0.0;
 #pragma unroll
     for (int off = 1; off < C; off <<= 1) L += __shfl_xor_sync(0xffffffffu, L, off);

@@ -59,7 +59,7 @@ def test_dna_random_trees(ncat, flags):
     assert st["path"] == (3 if flags & 16 else 1)
 
 
-@pytest.mark.parametrize("pt,pipe", [(1, 0), (2, 0), (4, 0), (4, 1)])
+@pytest.mark.parametrize("pt,pipe", [(1, 0), (2, 0), (4, 0)])
 @pytest.mark.parametrize("flags", [0, 1])
 def test_dna_walk_kernel_variants(monkeypatch, pt, pipe, flags):
     """every instantiation of the DNA walk (patterns per thread, software-pipelined event kernel), with and
