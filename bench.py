@@ -115,7 +115,8 @@ def build_inputs(w, rank, world, device):
     es = model_for(w, rng)
     rates, probs = synth.gamma_rates(w["C"], w["alpha"]) if w["C"] > 1 else (np.ones(1), np.ones(1))
     N = w["patterns"]
-    lo, hi = N * rank // world, N * (rank + 1) // world
+    from bpp_phyl_b200.shard import shard_range
+    lo, hi = shard_range(N, rank, world)
     t0 = time.time()
     codes = synth.simulate_tip_codes(tree, es, rates, hi - lo, seed=w["seed"] + 7919 * rank, device=device)
     log("[rank %d] simulated %d patterns x %d tips in %.1fs" % (rank, hi - lo, tree.n_leaves, time.time() - t0))
@@ -170,12 +171,15 @@ def main():
     ap.add_argument("--workload", default=DEFAULT, choices=sorted(WORKLOADS))
     ap.add_argument("--patterns", type=int, default=0, help="override the workload's pattern count (debug)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--profile", action="store_true", help="1 warm-up + 1 timed step, no e2e / CPU legs (for ncu only)")
     a = ap.parse_args()
     w = dict(WORKLOADS[a.workload])
     if a.patterns:
         w["patterns"] = a.patterns
     W = max(a.warmup, 3) if a.impl == "native" else a.warmup
     K = a.steps
+    if a.profile:
+        W, K, a.no_cpu = 1, 1, True
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -224,7 +228,7 @@ def main():
     import torch
     import torch.distributed as dist
     import __graft_entry__ as g
-    from bpp_phyl_b200 import capi
+    from bpp_phyl_b200 import capi, shard
     if not capi.LIB_PATH.exists():
         g.build_lib()
     torch.cuda.set_device(local)
@@ -243,17 +247,18 @@ def main():
 
     def step_device():
         e.eval_device(want, out.data_ptr(), stream.cuda_stream)
-        if world > 1:
-            dist.all_reduce(out)
+        shard.combine(out)          # NCCL all-reduce(sum) of (lnL, d1, d2) on the same stream; no-op at N = 1
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    log("[rank %d] engine ready, path %d" % (rank, e.stats()["path"]))
     for _ in range(W):
         step_device()
     barrier()
+    log("[rank %d] warm-up done" % rank)
     st0 = e.stats()             # clears the kernel-timing ring
     sampler = ClockSampler(local)
     if rank == 0:
@@ -266,6 +271,7 @@ def main():
     ev1.record(stream)
     barrier()
     ms = ev0.elapsed_time(ev1)
+    log("[rank %d] timed region done: %.3f ms/step" % (rank, ms / K))
     st = e.stats()
     lnl_dev = float(out[0].item())
     tms = torch.tensor([ms], dtype=torch.float64, device=device)
@@ -286,16 +292,16 @@ def main():
         if world == 1:
             return e.eval(want)[0][0]                               # log L (d1, d2) device -> host
         e.eval_device(want, out.data_ptr(), stream.cuda_stream)
-        dist.all_reduce(out)
+        shard.combine(out)
         host_out.copy_(out, non_blocking=False)
         return float(host_out[0])
 
-    for i in range(W):
+    for i in range(0 if a.profile else W):
         step_e2e(i)
     barrier()
     t0 = time.perf_counter()
     ev0.record(stream)
-    for i in range(K):
+    for i in range(0 if a.profile else K):
         step_e2e(i)
     ev1.record(stream)
     barrier()
@@ -304,6 +310,7 @@ def main():
     if world > 1:
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
     e2e_ms = float(tms.item())
+    log("[rank %d] e2e region done: %.3f ms/step" % (rank, e2e_ms / K))
     clocks = sampler.stop() if rank == 0 else None
     e.set_branch_lengths(0, tree.brlen)
 
@@ -351,6 +358,7 @@ def main():
             line["cpu_baseline"] = cb
             log("cpu leg %.1fs" % (time.time() - t0))
         print(json.dumps(line), flush=True)
+        log("[rank 0] JSON line printed")
     e.close()
     if world > 1:
         dist.barrier()
@@ -359,4 +367,12 @@ def main():
 
 
 if __name__ == "__main__":
-    sys.exit(main())
+    try:
+        rc = main()
+    except BaseException:
+        import traceback
+        traceback.print_exc()
+        sys.stderr.flush()
+        raise
+    sys.stdout.flush()
+    sys.exit(rc)

@@ -85,8 +85,10 @@ __global__ void __launch_bounds__(kDmmaNodeWarps * 32) dmma_upper_deriv_kernel(D
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, q = lane & 3;
-  const long long pat_base = ((long long)blockIdx.x * kDmmaNodeWarps + warp) * RW * 8;
-  if (pat_base >= p.N) return;
+  const long long tile_rows = (long long)kDmmaNodeWarps * RW * 8;
+  for (long long tile = blockIdx.x; tile * tile_rows < p.N; tile += gridDim.x) {
+  const long long pat_base = (tile * kDmmaNodeWarps + warp) * RW * 8;
+  if (pat_base >= p.N) break;
   long long pat[RW];
 #pragma unroll
   for (int r = 0; r < RW; ++r) {
@@ -102,12 +104,7 @@ __global__ void __launch_bounds__(kDmmaNodeWarps * 32) dmma_upper_deriv_kernel(D
   if (p.father >= 0) {
 #pragma unroll
     for (int r = 0; r < RW; ++r) {
-      const double* row = p.upper + (((size_t)p.father_upper * p.N + pat[r]) * C + c) * S;
-#pragma unroll
-      for (int kb = 0; kb < KB; ++kb) {
-        const int y = kb * 4 + q;
-        a[r][kb] = y < S ? row[y] : 0.0;
-      }
+      load_a_row<KB>(p.upper + (((size_t)p.father_upper * p.N + pat[r]) * C + c) * S, S, q, a[r]);
       Eu[r] = p.upper_exp[((size_t)p.father_upper * p.N + pat[r]) * C + c];
 #pragma unroll
       for (int nb = 0; nb < NBLK; ++nb) U[r][nb][0] = U[r][nb][1] = 0.0;
@@ -143,12 +140,7 @@ __global__ void __launch_bounds__(kDmmaNodeWarps * 32) dmma_upper_deriv_kernel(D
     } else {
 #pragma unroll
       for (int r = 0; r < RW; ++r) {
-        const double* row = p.keep + (((size_t)ch.idx * p.N + pat[r]) * C + c) * S;
-#pragma unroll
-        for (int kb = 0; kb < KB; ++kb) {
-          const int y = kb * 4 + q;
-          a[r][kb] = y < S ? row[y] : 0.0;
-        }
+        load_a_row<KB>(p.keep + (((size_t)ch.idx * p.N + pat[r]) * C + c) * S, S, q, a[r]);
         Eu[r] += p.keep_exp[((size_t)ch.idx * p.N + pat[r]) * C + c];
 #pragma unroll
         for (int nb = 0; nb < NBLK; ++nb) acc[r][nb][0] = acc[r][nb][1] = 0.0;
@@ -194,7 +186,7 @@ __global__ void __launch_bounds__(kDmmaNodeWarps * 32) dmma_upper_deriv_kernel(D
   }
 
   // ---- derivatives of branch n -----------------------------------------------------------------------------------
-  if (!(p.want & 6u)) return;
+  if (!(p.want & 6u)) continue;
   int El[RW];
   size_t tipoff[RW];
   if (p.node_is_tip) {
@@ -208,12 +200,7 @@ __global__ void __launch_bounds__(kDmmaNodeWarps * 32) dmma_upper_deriv_kernel(D
 #pragma unroll
     for (int r = 0; r < RW; ++r) {
       tipoff[r] = 0;
-      const double* row = p.keep + (((size_t)p.node_idx * p.N + pat[r]) * C + c) * S;
-#pragma unroll
-      for (int kb = 0; kb < KB; ++kb) {
-        const int y = kb * 4 + q;
-        a[r][kb] = y < S ? row[y] : 0.0;
-      }
+      load_a_row<KB>(p.keep + (((size_t)p.node_idx * p.N + pat[r]) * C + c) * S, S, q, a[r]);
       El[r] = p.keep_exp[((size_t)p.node_idx * p.N + pat[r]) * C + c];
     }
   }
@@ -301,6 +288,7 @@ __global__ void __launch_bounds__(kDmmaNodeWarps * 32) dmma_upper_deriv_kernel(D
       o[1] = scalbn(sres[1][r], sh) * pc / sr;
     }
   }
+  }  // tiles
 }
 
 // thread = pattern: dL_i = sum_c dLc, d2L_i = sum_c d2Lc;  partial sums of w dL and w (d2L - dL^2)

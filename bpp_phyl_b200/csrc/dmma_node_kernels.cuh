@@ -41,15 +41,40 @@ constexpr size_t dmma_node_smem_per_child() {
   return (size_t)NBLK * 8 * dmma_pstride<KB>() * sizeof(double);
 }
 
-// stage P[c] of one branch (row-major S x S) into shared memory, zero padded to [NBLK*8][stride]
+// The MMA sums over k, so WHICH state y sits at k-position (kb, q) is free as long as A and B agree.  The choice
+// below lets a lane fetch its A elements with 32-byte vector loads (the 4 lanes of a row then read one contiguous
+// 128-byte line): for the 16-state chunks j = 0 .. S/16-1, k-block kb = 4j+e of lane q holds y = 16j + 4q + e;
+// the remaining S mod 16 states are taken 4 at a time, y = 16*(S/16) + 4*kb' + q.
+template <int KB>
+__host__ __device__ __forceinline__ int dmma_ymap(int kb, int q) {
+  constexpr int J = KB / 4;  // full 16-state chunks
+  return kb < 4 * J ? 16 * (kb >> 2) + 4 * q + (kb & 3) : 16 * J + 4 * (kb - 4 * J) + q;
+}
+
+// the A fragments of one CLV row (S doubles, 32-byte aligned): a[kb] = row[ymap(kb, q)]
+template <int KB>
+__device__ __forceinline__ void load_a_row(const double* row, int S, int q, double (&a)[KB]) {
+  constexpr int J = KB / 4;
+#pragma unroll
+  for (int j = 0; j < J; ++j) ld256(row + 16 * j + 4 * q, a[4 * j], a[4 * j + 1], a[4 * j + 2], a[4 * j + 3]);
+#pragma unroll
+  for (int kb = 4 * J; kb < KB; ++kb) {
+    const int y = 16 * J + 4 * (kb - 4 * J) + q;
+    a[kb] = y < S ? row[y] : 0.0;
+  }
+}
+
+// stage P[c] of one branch (row-major S x S) into shared memory as [x][kb*4+q] = P[x][ymap(kb,q)] (or the transpose),
+// zero padded to [NBLK*8][stride]
 template <int KB, int NBLK, bool TRANSPOSE>
 __device__ __forceinline__ void stage_matrix(double* dst, const double* Pg, int S, int nthreads) {
   constexpr int SB = dmma_pstride<KB>();
   for (int e = threadIdx.x; e < NBLK * 8 * 4 * KB; e += nthreads) {
-    const int x = e / (4 * KB), y = e - x * (4 * KB);
+    const int x = e / (4 * KB), col = e - x * (4 * KB);
+    const int y = dmma_ymap<KB>(col >> 2, col & 3);
     double v = 0.0;
     if (x < S && y < S) v = TRANSPOSE ? Pg[(size_t)y * S + x] : Pg[(size_t)x * S + y];
-    dst[x * SB + y] = v;
+    dst[x * SB + col] = v;
   }
 }
 
@@ -88,8 +113,11 @@ __global__ void __launch_bounds__(kDmmaNodeWarps * 32) dmma_node_kernel(DmmaNode
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, q = lane & 3;
-  const long long pat_base = ((long long)blockIdx.x * kDmmaNodeWarps + warp) * RW * 8;
-  if (pat_base >= p.N) return;
+  // persistent over pattern tiles: the staged matrices serve every tile of this CTA
+  const long long tile_rows = (long long)kDmmaNodeWarps * RW * 8;
+  for (long long tile = blockIdx.x; tile * tile_rows < p.N; tile += gridDim.x) {
+  const long long pat_base = (tile * kDmmaNodeWarps + warp) * RW * 8;
+  if (pat_base >= p.N) break;
   long long pat[RW];
 #pragma unroll
   for (int r = 0; r < RW; ++r) {
@@ -121,12 +149,7 @@ __global__ void __launch_bounds__(kDmmaNodeWarps * 32) dmma_node_kernel(DmmaNode
       double a[RW][KB];
 #pragma unroll
       for (int r = 0; r < RW; ++r) {
-        const double* row = p.keep + (((size_t)ch.idx * p.N + pat[r]) * C + c) * S;
-#pragma unroll
-        for (int kb = 0; kb < KB; ++kb) {
-          const int y = kb * 4 + q;
-          a[r][kb] = y < S ? row[y] : 0.0;
-        }
+        load_a_row<KB>(p.keep + (((size_t)ch.idx * p.N + pat[r]) * C + c) * S, S, q, a[r]);
         Ea[r] += p.keep_exp[((size_t)ch.idx * p.N + pat[r]) * C + c];
       }
 #pragma unroll
@@ -183,6 +206,7 @@ __global__ void __launch_bounds__(kDmmaNodeWarps * 32) dmma_node_kernel(DmmaNode
       if (q == 0) p.keep_exp[((size_t)p.out_idx * p.N + pat[r]) * C + c] = Ea[r];
     }
   }
+  }  // tiles
 }
 
 }  // namespace bppgpu

@@ -174,10 +174,10 @@ static int check_device(int device) {
   BPP_CUDA(cudaFuncSetAttribute(pt_dmma_kernel<8, 1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
   BPP_CUDA(cudaFuncSetAttribute(pt_dmma_kernel<8, 2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
   BPP_CUDA(cudaFuncSetAttribute(pt_dmma_kernel<8, 4, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-  BPP_CUDA(cudaFuncSetAttribute(dmma_node_kernel<5, 3, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  BPP_CUDA(cudaFuncSetAttribute(dmma_node_kernel<5, 3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   BPP_CUDA(cudaFuncSetAttribute(dmma_node_kernel<16, 8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-  BPP_CUDA(cudaFuncSetAttribute(dmma_upper_deriv_kernel<5, 3, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-  BPP_CUDA(cudaFuncSetAttribute(dmma_upper_deriv_kernel<16, 8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  BPP_CUDA(cudaFuncSetAttribute(dmma_upper_deriv_kernel<5, 3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  BPP_CUDA(cudaFuncSetAttribute(dmma_upper_deriv_kernel<16, 8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   return BPPGPU_OK;
 }
 
@@ -519,7 +519,7 @@ static int create_impl(const bppgpu_config* cfg, bppgpu_engine* e) {
   for (const Op& op : e->prog.ops)
     if (op.nchild > 6) w4ok = false;
   if (w4ok) e->path = PATH_WALK4;
-  else if (S == 20 && cpow) e->path = PATH_WALKS;
+  else if (S == 20 && cpow && !e->keep) e->path = PATH_WALKS;   // value-only protein: register walk
   else e->path = PATH_GENERIC;
   if (e->path == PATH_GENERIC && ((S > 16 && S <= 20) || (S > 56 && S <= 64))) e->path = PATH_DMMA;
   if (const char* env = getenv("BPPGPU_PATH")) {  // tuning knob
@@ -1019,12 +1019,14 @@ static int enqueue_prune(bppgpu_engine* e, int point, int pl, cudaStream_t st) {
         for (int j = 0; j < op.nchild; ++j)
           if (e->gprog.childs[op.child_begin + j].kind != CHILD_TIP) ++nint;
         if (S <= 20) {
-          constexpr int RW = 4;
-          const dim3 grid((unsigned)((N + 8 * RW * kDmmaNodeWarps - 1) / (8 * RW * kDmmaNodeWarps)), (unsigned)C);
+          constexpr int RW = 2;
+          const long long tiles = (N + 8 * RW * kDmmaNodeWarps - 1) / (8 * RW * kDmmaNodeWarps);
+          const dim3 grid((unsigned)std::min<long long>(tiles, std::max(1, g_sm_count * 8 / C)), (unsigned)C);
           dmma_node_kernel<5, 3, RW><<<grid, kDmmaNodeWarps * 32, nint * dmma_node_smem_per_child<5, 3>(), st>>>(dp);
         } else {
           constexpr int RW = 2;
-          const dim3 grid((unsigned)((N + 8 * RW * kDmmaNodeWarps - 1) / (8 * RW * kDmmaNodeWarps)), (unsigned)C);
+          const long long tiles = (N + 8 * RW * kDmmaNodeWarps - 1) / (8 * RW * kDmmaNodeWarps);
+          const dim3 grid((unsigned)std::min<long long>(tiles, std::max(1, g_sm_count * 4 / C)), (unsigned)C);
           dmma_node_kernel<16, 8, RW><<<grid, kDmmaNodeWarps * 32, nint * dmma_node_smem_per_child<16, 8>(), st>>>(dp);
         }
         e->stats.kernel_launches += 1;
@@ -1122,12 +1124,14 @@ static int enqueue_derivs(bppgpu_engine* e, int point, int pl, unsigned want, cu
         if (e->sibs_flat[k].kind != CHILD_TIP) ++nmat;
       if (!du.node_is_tip) nmat += ((want & 2u) ? 1 : 0) + ((want & 4u) ? 1 : 0) + du.nh_form;
       if (S <= 20) {
-        constexpr int RW = 4;
-        const dim3 grid((unsigned)((N + 8 * RW * kDmmaNodeWarps - 1) / (8 * RW * kDmmaNodeWarps)), (unsigned)C);
+        constexpr int RW = 2;
+        const long long tiles = (N + 8 * RW * kDmmaNodeWarps - 1) / (8 * RW * kDmmaNodeWarps);
+        const dim3 grid((unsigned)std::min<long long>(tiles, std::max(1, g_sm_count * 8 / C)), (unsigned)C);
         dmma_upper_deriv_kernel<5, 3, RW><<<grid, kDmmaNodeWarps * 32, nmat * dmma_node_smem_per_child<5, 3>(), st>>>(du);
       } else {
-        constexpr int RW = 2;
-        const dim3 grid((unsigned)((N + 8 * RW * kDmmaNodeWarps - 1) / (8 * RW * kDmmaNodeWarps)), (unsigned)C);
+        constexpr int RW = 1;
+        const long long tiles = (N + 8 * RW * kDmmaNodeWarps - 1) / (8 * RW * kDmmaNodeWarps);
+        const dim3 grid((unsigned)std::min<long long>(tiles, std::max(1, g_sm_count * 4 / C)), (unsigned)C);
         dmma_upper_deriv_kernel<16, 8, RW><<<grid, kDmmaNodeWarps * 32, nmat * dmma_node_smem_per_child<16, 8>(), st>>>(du);
       }
       deriv_combine_kernel<<<grid_p, 256, 0, st>>>(e->d_dLc, e->d_weights, C, N, e->d_partials, e->d_partials2);

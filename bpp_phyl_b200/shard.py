@@ -1,0 +1,24 @@
+"""Pattern sharding across the GPUs of one box.
+
+Given P(t) (replicated, tiny) every site pattern's recursion is independent, so rank g owns the contiguous block
+[g*N/G, (g+1)*N/G) of the compressed, sorted pattern list (fixed boundaries -> the result is deterministic for a
+given G) and only the per-shard scalars are combined: one all-reduce(sum) of the (1 + 2*n_nodes)-vector
+(lnL, d1[.], d2[.]) per evaluation, NCCL on GPUs, gloo in the CPU tests.  torch.distributed is plumbing here.
+"""
+from __future__ import annotations
+
+
+def shard_range(n_patterns: int, rank: int, world: int):
+    """[lo, hi) of the patterns owned by `rank`."""
+    if not (0 <= rank < world):
+        raise ValueError("rank %d outside world of %d" % (rank, world))
+    return n_patterns * rank // world, n_patterns * (rank + 1) // world
+
+
+def combine(out_tensor):
+    """Sum the per-shard (lnL, d1, d2) vectors in place over the default process group (no-op for world 1).
+    Enqueued on the current stream for CUDA tensors: follow bppgpu_eval_device with it, no host sync in between."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(out_tensor, op=dist.ReduceOp.SUM)
+    return out_tensor

@@ -88,13 +88,53 @@ def test_protein_random_trees(flags):
     r, p = rm.gamma_rates(4, 0.7)
     c = cases.make_case(40, 300, rm.lg08(), r, p, seed=21, ambiguity=0.02)
     st = check_value(c, flags=flags)
-    assert st["path"] == (3 if flags & 16 else 2)
+    assert st["path"] == (3 if flags & 16 else (4 if flags & 1 else 2))
 
 
 def test_codon_generic():
     r, p = rm.constant_rate()
     c = cases.make_case(12, 150, rm.yn98(2.0, 0.3), r, p, seed=31, mean_brlen=0.1)
     check_value(c)
+
+
+@pytest.mark.parametrize("which,ncat", [("lg08", 4), ("lg08", 1), ("yn98", 1), ("yn98", 2)])
+def test_dmma_tensor_core_path(monkeypatch, which, ncat):
+    """FP64 tensor-core (mma.sync DMMA) node / upper / derivative kernels: S = 20 (forced) and S = 64 (default)."""
+    capi = _capi()
+    monkeypatch.setenv("BPPGPU_PATH", "dmma")
+    m = rm.lg08() if which == "lg08" else rm.yn98(2.0, 0.3)
+    r, p = rm.gamma_rates(ncat, 0.7) if ncat > 1 else rm.constant_rate()
+    for ntaxa, nsites, seed, nh in ((14, 150, 61, False), (9, 37, 62, True)):
+        c = cases.make_case(ntaxa, nsites, m, r, p, seed=seed, mean_brlen=0.1, ambiguity=0.03, rooted=nh)
+        res = cases.oracle_eval(c, want_d1=True, want_d2=True, nh_form=nh)
+        flags = capi.FLAG_KEEP_CLVS | (capi.FLAG_NH_DERIV if nh else 0)
+        with cases.make_engine(c, flags=flags) as e:
+            lnl, d1, d2 = e.eval(7)
+            assert e.stats()["path"] == 4
+            nb = c.flat.n_nodes - 1
+            assert abs(lnl[0] - res.lnl) <= REL * abs(res.lnl)
+            np.testing.assert_allclose(e.site_lnl(), res.site_lnl, rtol=1e-11, atol=1e-11)
+            np.testing.assert_allclose(-d1[0, :nb], res.d1, rtol=1e-8, atol=1e-8)
+            np.testing.assert_allclose(-d2[0, :nb], res.d2, rtol=1e-8, atol=1e-7)
+            for nid in range(c.flat.n_nodes - 1):
+                if c.flat.is_leaf[nid]:
+                    continue
+                clv, ex = e.clv(nid, 0)
+                np.testing.assert_array_equal(ex, res.lexp[nid])
+                np.testing.assert_allclose(clv, res.lower[nid], rtol=1e-10, atol=1e-14 * res.lower[nid].max())
+                clv, ex = e.clv(nid, 1)
+                got = np.ldexp(clv, -ex[:, :, None].astype(np.int64))
+                exp = np.ldexp(res.upper[nid], -res.uexp[nid][:, :, None])
+                np.testing.assert_allclose(got, exp, rtol=1e-9, atol=1e-13 * exp.max())
+
+
+def test_dmma_underflow_scaling():
+    r, p = rm.constant_rate()
+    c = cases.make_case(150, 40, rm.yn98(2.0, 0.3), r, p, seed=63, mean_brlen=0.8)     # simulated: no stop codons
+    res = cases.oracle_eval(c)
+    assert res.SR_exp.max() > 256 and np.isfinite(res.lnl)
+    st = check_value(c)
+    assert st["path"] == 4
 
 
 def test_underflow_scaling_large_tree():

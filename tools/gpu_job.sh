@@ -1,2 +1,3 @@
-python -m pytest tests -m gpu -q -x 2>&1 | tail -30 > gpurun_out/t7.log
-for pf in 1 0; do for pt in 1 2 4; do BPPGPU_WALK4_PREFETCH=$pf BPPGPU_WALK4_PT=$pt python bench.py --steps 10 --warmup 3 --no-cpu > gpurun_out/bench7_pf${pf}_pt$pt.json 2> gpurun_out/bench7.err; done; done
+python -m pytest tests -m gpu -q 2>&1 | tail -15 > gpurun_out/t10.log
+python bench.py --workload codon_200x100k --steps 5 --warmup 3 --no-cpu > gpurun_out/b_codon2.json 2> gpurun_out/b_codon2.err
+python bench.py --workload protein_g4_500x200k_d2 --steps 3 --warmup 3 --no-cpu > gpurun_out/b_prot2.json 2> gpurun_out/b_prot2.err
