@@ -127,6 +127,20 @@ def device_count():
     return n.value
 
 
+def site_patterns(columns):
+    """bppgpu_site_patterns.  ``columns``: uint8 array [n_sites][col_bytes].  Returns (pattern_site, weights, indices)."""
+    cols = np.ascontiguousarray(columns, np.uint8)
+    n, w = cols.shape
+    ps = np.empty(n, np.int64)
+    wt = np.empty(n, np.uint32)
+    ix = np.empty(n, np.int64)
+    npat = C.c_int64(0)
+    _check(lib().bppgpu_site_patterns(cols.ctypes.data_as(C.POINTER(C.c_uint8)), C.c_int64(n), C.c_int32(max(w, 1)),
+                                      _ptr(ps, C.c_int64), _ptr(wt, C.c_uint32), _ptr(ix, C.c_int64), C.byref(npat)))
+    k = npat.value
+    return ps[:k].copy(), wt[:k].copy(), ix
+
+
 class _ModelHolder:
     """Keeps the numpy buffers a ModelDesc points at alive."""
 

@@ -361,6 +361,41 @@ int bppgpu_device_count(int* n) {
   return BPPGPU_OK;
 }
 
+// ---- site patterns (host) ---------------------------------------------------------------
+int bppgpu_site_patterns(const uint8_t* columns, int64_t n_sites, int32_t col_bytes, int64_t* pattern_site,
+                         uint32_t* weights, int64_t* indices, int64_t* n_patterns) {
+  if (n_sites < 0 || col_bytes <= 0 || !n_patterns || (n_sites > 0 && (!columns || !pattern_site || !weights || !indices)))
+    BPP_FAIL(BPPGPU_E_INVALID, "bad argument to bppgpu_site_patterns");
+  *n_patterns = 0;
+  if (n_sites == 0) return BPPGPU_OK;
+  std::vector<int64_t> order((size_t)n_sites);
+  for (int64_t i = 0; i < n_sites; ++i) order[(size_t)i] = i;
+  const size_t w = (size_t)col_bytes;
+  // std::sort like the reference; ties are identical columns, so their relative order cannot change the result
+  // except for WHICH identical site represents the pattern -- we take the smallest original position
+  std::sort(order.begin(), order.end(), [&](int64_t a, int64_t b) {
+    const int c = memcmp(columns + (size_t)a * w, columns + (size_t)b * w, w);
+    return c != 0 ? c < 0 : a < b;
+  });
+  int64_t np = 0;
+  pattern_site[0] = order[0];
+  weights[0] = 1;
+  indices[order[0]] = 0;
+  for (int64_t k = 1; k < n_sites; ++k) {
+    const int64_t cur = order[(size_t)k], prev = order[(size_t)k - 1];
+    if (memcmp(columns + (size_t)cur * w, columns + (size_t)prev * w, w) == 0) {
+      weights[np]++;
+    } else {
+      ++np;
+      pattern_site[np] = cur;
+      weights[np] = 1;
+    }
+    indices[cur] = np;
+  }
+  *n_patterns = np + 1;
+  return BPPGPU_OK;
+}
+
 // ---- Interface 1 ----------------------------------------------------------------------
 int bppgpu_pt_batch(int device, const bppgpu_model_desc* model, int64_t n_t, const double* t, unsigned want,
                     double* P, double* dP, double* d2P) {
@@ -518,8 +553,10 @@ static int create_impl(const bppgpu_config* cfg, bppgpu_engine* e) {
               (size_t)e->prog.nslots * kWalk4Threads * 36 <= 200 * 1024;
   for (const Op& op : e->prog.ops)
     if (op.nchild > 6) w4ok = false;
+  const bool wroot = (cfg->flags & BPPGPU_FLAG_WEIGHTED_ROOT) != 0;  // needs the root CLV in HBM: node-kernel paths
+  if (wroot) w4ok = false;
   if (w4ok) e->path = PATH_WALK4;
-  else if (S == 20 && cpow && !e->keep) e->path = PATH_WALKS;   // value-only protein: register walk
+  else if (S == 20 && cpow && !e->keep && !wroot) e->path = PATH_WALKS;   // value-only protein: register walk
   else e->path = PATH_GENERIC;
   if (e->path == PATH_GENERIC && ((S > 16 && S <= 20) || (S > 56 && S <= 64))) e->path = PATH_DMMA;
   if (const char* env = getenv("BPPGPU_PATH")) {  // tuning knob

@@ -52,6 +52,17 @@ int bppgpu_device_count(int* n);
  * 1 bppgpu_config, 2 bppgpu_stats (lets a foreign-language binding verify its mirror) */
 int bppgpu_sizeof(int which);
 
+/* ---- site-pattern compression (host side, integer work, bit-exact) -------------
+ * bpp::SitePatterns::SitePatterns (SitePatterns.cpp:52-106): sort the alignment columns by their
+ * character string (Site::toString(), here the `col_bytes` bytes of each column in the sequence order
+ * of the container), merge identical neighbours.  Outputs (caller-allocated, capacity n_sites):
+ *   pattern_site[k]  original position of the site that represents pattern k (sites_)
+ *   weights[k]       number of sites with pattern k (weights_)
+ *   indices[i]       pattern of site i (indices_)
+ * Patterns come out in lexicographic (memcmp) order of their column strings.                  */
+int bppgpu_site_patterns(const uint8_t* columns, int64_t n_sites, int32_t col_bytes, int64_t* pattern_site,
+                         uint32_t* weights, int64_t* indices, int64_t* n_patterns);
+
 /* ---- model descriptor ------------------------------------------------------
  * What bpp::SubstitutionModel exposes (Model/SubstitutionModel.h:468-525):
  * getGenerator, getEigenValues, getIEigenValues, isDiagonalizable,

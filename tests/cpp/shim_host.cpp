@@ -1,0 +1,108 @@
+// Host-side (no GPU) checks of the C++ shim: prints one JSON document that tests/test_cpp_shim.py compares with the oracle.
+#include <cstdio>
+#include <iostream>
+#include <memory>
+
+#include "../../bpp_phyl_b200/host/bppgpu_shim.hpp"
+
+using namespace bppshim;
+using namespace std;
+
+static void print_vec(const char* key, const Vdouble& v, bool comma = true) {
+  printf("\"%s\": [", key);
+  for (size_t i = 0; i < v.size(); ++i) printf("%s%.17g", i ? ", " : "", v[i]);
+  printf("]%s\n", comma ? "," : "");
+}
+static void print_mat(const char* key, const RowMatrix<double>& m, bool comma = true) {
+  printf("\"%s\": [", key);
+  for (size_t i = 0; i < m.getNumberOfRows(); ++i) {
+    printf("%s[", i ? ", " : "");
+    for (size_t j = 0; j < m.getNumberOfColumns(); ++j) printf("%s%.17g", j ? ", " : "", m(i, j));
+    printf("]");
+  }
+  printf("]%s\n", comma ? "," : "");
+}
+static void print_model(const char* name, const SubstitutionModel& m, bool comma = true) {
+  printf("\"%s\": {\n", name);
+  print_mat("Q", m.getGenerator());
+  print_mat("V", m.getColumnRightEigenVectors());
+  print_mat("Vinv", m.getRowLeftEigenVectors());
+  print_vec("re", m.getEigenValues());
+  print_vec("im", m.getIEigenValues());
+  print_vec("freq", m.getFrequencies());
+  printf("\"diagonalizable\": %d, \"nonsingular\": %d, \"rate\": %.17g\n}%s\n", (int)m.isDiagonalizable(), (int)m.isNonSingular(), m.getRate(),
+         comma ? "," : "");
+}
+
+int main() {
+  printf("{\n");
+  {
+    GammaDiscreteRateDistribution g41(4, 1.0), g405(4, 0.5), g8(8, 2.3), g1(1, 0.7);
+    Vdouble r;
+    for (size_t i = 0; i < 4; ++i) r.push_back(g41.getCategory(i));
+    print_vec("gamma_4_1", r);
+    r.clear();
+    for (size_t i = 0; i < 4; ++i) r.push_back(g405.getCategory(i));
+    print_vec("gamma_4_0.5", r);
+    r.clear();
+    for (size_t i = 0; i < 8; ++i) r.push_back(g8.getCategory(i));
+    print_vec("gamma_8_2.3", r);
+    r.clear();
+    r.push_back(g1.getCategory(0));
+    print_vec("gamma_1_0.7", r);
+  }
+  const DNA* dna = &AlphabetTools::DNA_ALPHABET();
+  {
+    T92 t92(dna, 3.0, 0.5);
+    print_model("T92", t92);
+    GTR gtr(dna, 1.2, 0.8, 0.6, 1.5, 0.9, .3, .2, .25, .25);
+    print_model("GTR", gtr);
+    LG08 lg(&AlphabetTools::PROTEIN_ALPHABET());
+    print_model("LG08", lg);
+    YN98 yn(&AlphabetTools::CODON_ALPHABET(), 2.0, 0.3);
+    print_model("YN98", yn);
+    ChromosomeAlphabet chr(1, 40);
+    ChromosomeSubstitutionModel c1(&chr, 0.7, 0.4, 0.2, ChromosomeSubstitutionModel::DemiEqualDupl);
+    print_model("CHR_REAL", c1);
+    ChromosomeAlphabet chr2(1, 25);
+    ChromosomeSubstitutionModel c2(&chr2, 1.5, 0.1, 0.9, 0.4, 0.05);
+    print_model("CHR_COMPLEX", c2);
+    ChromosomeAlphabet chr3(1, 20);
+    ChromosomeSubstitutionModel c3(&chr3, 0.5, 0.0, 0.0, ChromosomeSubstitutionModel::IgnoreParam);
+    print_model("CHR_SINGULAR", c3);
+    // getInitValue / aliases
+    printf("\"init_R\": [%g, %g, %g, %g],\n", t92.getInitValue(0, "R"), t92.getInitValue(1, "R"), t92.getInitValue(2, "R"), t92.getInitValue(3, "R"));
+  }
+  {
+    // tree flattening: unrooting, post-order BrLen indexing, pre-order leaf order
+    unique_ptr<Tree> t(TreeTemplateTools::parenthesisToTree("(((A:0.01, B:0.01):0.02,C:0.03):0.01,(D:0.04,E:0.05):0.06);"));
+    t->unroot();
+    t->resetNodesId();
+    printf("\"unrooted_postorder\": [");
+    bool first = true;
+    for (Node* n : t->getNodes()) {
+      printf("%s[\"%s\", %.17g, %d]", first ? "" : ", ", n->hasName() ? n->getName().c_str() : "", n->hasDistanceToFather() ? n->getDistanceToFather() : -1.0,
+             n->hasFather() ? n->getFather()->getId() : -1);
+      first = false;
+    }
+    printf("],\n\"leaves\": [");
+    first = true;
+    for (const string& s : t->getLeavesNames()) { printf("%s\"%s\"", first ? "" : ", ", s.c_str()); first = false; }
+    printf("],\n");
+  }
+  {
+    VectorSiteContainer sites(dna);
+    sites.addSequence(BasicSequence("A", "AAATGGCTGTGCACGTC", dna));
+    sites.addSequence(BasicSequence("B", "GACTGGATCTGCACGTC", dna));
+    sites.addSequence(BasicSequence("C", "CTCTGGATGTGCACGTG", dna));
+    sites.addSequence(BasicSequence("D", "AAATGGCGGTGCGCCTA", dna));
+    SitePatterns sp(sites, {"A", "B", "C", "D"});
+    printf("\"pattern_weights\": [");
+    for (size_t i = 0; i < sp.getWeights().size(); ++i) printf("%s%u", i ? ", " : "", sp.getWeights()[i]);
+    printf("],\n\"pattern_indices\": [");
+    for (size_t i = 0; i < sp.getIndices().size(); ++i) printf("%s%ld", i ? ", " : "", (long)sp.getIndices()[i]);
+    printf("]\n");
+  }
+  printf("}\n");
+  return 0;
+}

@@ -1,0 +1,181 @@
+// Mirrors the reference's own likelihood tests through the C++ host shim (GPU required):
+//   test/test_likelihood.cpp:90-136        T92(kappa=3)+Gamma4 on 4 taxa x 17 sites, R and DR classes, -lnL = 85.030942031997312824,
+//                                          first derivatives of the two classes agree to 1e-6
+//   test/test_likelihood_clock.cpp:99-115  rooted tree kept rooted (checkRooted=false), constant rate: 94.3957
+// plus derivative-vs-finite-difference checks and the error conventions of SURVEY.md 8b.  Exit code 0 = success
+// (the reference's CTest convention).  Extra cases print "name value" lines that tests/test_cpp_shim.py compares with the oracle.
+#include <cmath>
+#include <cstdio>
+#include <iostream>
+#include <memory>
+
+#include "../../bpp_phyl_b200/host/bppgpu_shim.hpp"
+
+using namespace bppshim;
+using namespace std;
+
+static int fails = 0;
+#define EXPECT(cond, msg)                                     \
+  do {                                                        \
+    if (!(cond)) { cerr << "FAILED: " << msg << endl; ++fails; } \
+  } while (0)
+
+template <class LIK>
+void fitModel(SubstitutionModel* model, DiscreteDistribution* rdist, const Tree& tree, const VectorSiteContainer& sites, double initialValue,
+              const char* label) {
+  LIK tl(tree, sites, model, rdist);
+  tl.initialize();
+  printf("%s %.15f\n", label, tl.getValue());
+  EXPECT(fabs(tl.getValue() - initialValue) < 1e-9, "Incorrect initial value (" << label << "): " << tl.getValue());
+}
+
+int main() {
+  try {
+    unique_ptr<Tree> tree(TreeTemplateTools::parenthesisToTree("((A:0.01, B:0.02):0.03,C:0.01,D:0.1);"));
+    const DNA* alphabet = &AlphabetTools::DNA_ALPHABET();
+    VectorSiteContainer sites(alphabet);
+    sites.addSequence(BasicSequence("A", "AAATGGCTGTGCACGTC", alphabet));
+    sites.addSequence(BasicSequence("B", "GACTGGATCTGCACGTC", alphabet));
+    sites.addSequence(BasicSequence("C", "CTCTGGATGTGCACGTG", alphabet));
+    sites.addSequence(BasicSequence("D", "AAATGGCGGTGCGCCTA", alphabet));
+
+    unique_ptr<SubstitutionModel> model(new T92(alphabet, 3.));
+    unique_ptr<DiscreteDistribution> rdist(new GammaDiscreteRateDistribution(4, 1.0));
+    cout << "Testing Single Tree Traversal likelihood class..." << endl;
+    fitModel<RHomogeneousTreeLikelihood>(model.get(), rdist.get(), *tree, sites, 85.030942031997312824, "R_T92_G4");
+    cout << "Testing Double Tree Traversal likelihood class..." << endl;
+    fitModel<DRHomogeneousTreeLikelihood>(model.get(), rdist.get(), *tree, sites, 85.030942031997312824, "DR_T92_G4");
+
+    // Let's compare the derivatives (test_likelihood.cpp:124-135) and check them against finite differences
+    RHomogeneousTreeLikelihood tlsr(*tree, sites, model.get(), rdist.get());
+    tlsr.initialize();
+    DRHomogeneousTreeLikelihood tldr(*tree, sites, model.get(), rdist.get());
+    tldr.initialize();
+    ParameterList params = tlsr.getBranchLengthsParameters();
+    EXPECT(params.size() == 5, "an unrooted 4-taxon tree has 5 branch-length parameters, got " << params.size());
+    for (const Parameter& p : params) {
+      const double d1sr = tlsr.getFirstOrderDerivative(p.name), d1dr = tldr.getFirstOrderDerivative(p.name);
+      const double d2dr = tldr.getSecondOrderDerivative(p.name);
+      printf("%s\t%.12g\t%.12g\t%.12g\n", p.name.c_str(), d1sr, d1dr, d2dr);
+      EXPECT(fabs(d1sr - d1dr) <= 0.000001, "R and DR first derivatives differ for " << p.name);
+      const double h = 1e-6, f0 = tldr.getValue();
+      tldr.setParameterValue(p.name, p.value + h);
+      const double fp = tldr.getValue();
+      tldr.setParameterValue(p.name, p.value - h);
+      const double fm = tldr.getValue();
+      tldr.setParameterValue(p.name, p.value);
+      EXPECT(fabs((fp - fm) / (2 * h) - d1dr) < 1e-4 * max(1.0, fabs(d1dr)), "first derivative vs finite difference, " << p.name);
+      EXPECT(fabs(tldr.getValue() - f0) < 1e-12, "value restored");
+      (void)d2dr;
+    }
+    // per-site accessors: sum over sites of log L_site = log L, duplicated columns share a pattern
+    double s = 0;
+    for (size_t i = 0; i < tldr.getNumberOfSites(); ++i) s += tldr.getLogLikelihoodForASite(i);
+    EXPECT(fabs(s - tldr.getLogLikelihood()) < 1e-10, "sum of per-site log-likelihoods");
+    EXPECT(tldr.getNumberOfSites() == 17 && tldr.getNumberOfDistinctSites() == 12, "17 sites, 12 patterns");
+
+    // getPij_t interface (Interface 1): rows sum to one, P(0) = I, dP rows sum to zero
+    const RowMatrix<double>& P = model->getPij_t(0.1);
+    for (size_t i = 0; i < 4; ++i) {
+      double r = 0;
+      for (size_t j = 0; j < 4; ++j) r += P(i, j);
+      EXPECT(fabs(r - 1.0) < 1e-14, "row sum of P(t)");
+    }
+    EXPECT(fabs(model->Pij_t(2, 2, 0.0) - 1.0) < 1e-15 && fabs(model->Pij_t(2, 1, 0.0)) < 1e-15, "P(0) = I");
+
+    // clock test: rooted tree, kept rooted, constant rate (test_likelihood_clock.cpp:99-115)
+    {
+      unique_ptr<Tree> t2(TreeTemplateTools::parenthesisToTree("(((A:0.01, B:0.01):0.02,C:0.03):0.01,D:0.04);"));
+      VectorSiteContainer s2(alphabet);
+      s2.addSequence(BasicSequence("A", "AAATGGCTGTGCACGTC", alphabet));
+      s2.addSequence(BasicSequence("B", "AACTGGATCTGCATGTC", alphabet));
+      s2.addSequence(BasicSequence("C", "ATCTGGACGTGCACGTG", alphabet));
+      s2.addSequence(BasicSequence("D", "CAACGGGAGTGCGCCTA", alphabet));
+      ConstantRateDistribution cst;
+      RHomogeneousTreeLikelihood tl(*t2, s2, model.get(), &cst, false, false);
+      tl.initialize();
+      printf("CLOCK_T92_CONST %.15f\n", tl.getValue());
+      EXPECT(fabs(tl.getValue() - 94.3957) < 1e-4, "Incorrect initial value (clock): " << tl.getValue());
+    }
+
+    // error conventions
+    {
+      RHomogeneousTreeLikelihood tl(*tree, sites, model.get(), rdist.get());
+      bool thrown = false;
+      try { tl.getValue(); } catch (Exception&) { thrown = true; }
+      EXPECT(thrown, "getValue() before initialize() must throw");
+      tl.initialize();
+      thrown = false;
+      try { tl.initialize(); } catch (Exception&) { thrown = true; }
+      EXPECT(thrown, "second initialize() must throw");
+      thrown = false;
+      try { tl.getFirstOrderDerivative("T92.kappa"); } catch (Exception&) { thrown = true; }
+      EXPECT(thrown, "derivative w.r.t. a model parameter must throw");
+      thrown = false;
+      try { tl.getFirstOrderDerivative("BrLen99"); } catch (ParameterNotFoundException&) { thrown = true; }
+      EXPECT(thrown, "unknown parameter must throw ParameterNotFoundException");
+      // a model parameter change re-evaluates everything (fireParameterChanged)
+      const double before = tl.getValue();
+      tl.setParameterValue("T92.kappa", 2.0);
+      EXPECT(fabs(tl.getValue() - before) > 1e-3, "kappa change must move the likelihood");
+      tl.setParameterValue("T92.kappa", 3.0);
+      EXPECT(fabs(tl.getValue() - before) < 1e-10, "kappa restored");
+      model->setParameterValue("kappa", 3.0);
+    }
+
+    // other state spaces: values printed for the oracle comparison in tests/test_cpp_shim.py
+    {
+      const ProteicAlphabet* prot = &AlphabetTools::PROTEIN_ALPHABET();
+      unique_ptr<Tree> t3(TreeTemplateTools::parenthesisToTree("((a:0.1,b:0.2):0.05,(c:0.3,d:0.02):0.07,e:0.15);"));
+      VectorSiteContainer s3(prot);
+      s3.addSequence(BasicSequence("a", "ARNDCQEGHILKMFPSTWYVAAX", prot));
+      s3.addSequence(BasicSequence("b", "ARNDCQEGHILKMFPSTWYVLK-", prot));
+      s3.addSequence(BasicSequence("c", "ARNECQDGHLIKMFPTSWYVAKB", prot));
+      s3.addSequence(BasicSequence("d", "GRNDCQEGHILRMYPSTWFVAAZ", prot));
+      s3.addSequence(BasicSequence("e", "ARNDCQEGHVLKMFPSTWYIVAA", prot));
+      LG08 lg(prot);
+      GammaDiscreteRateDistribution g4(4, 0.7);
+      DRHomogeneousTreeLikelihood tl(*t3, s3, &lg, &g4);
+      tl.initialize();
+      printf("LG08_G4 %.15f\n", tl.getValue());
+      for (const Parameter& p : tl.getBranchLengthsParameters())
+        printf("LG08_G4_d %s %.12g %.12g\n", p.name.c_str(), tl.getFirstOrderDerivative(p.name), tl.getSecondOrderDerivative(p.name));
+    }
+    {
+      const CodonAlphabet* cod = &AlphabetTools::CODON_ALPHABET();
+      unique_ptr<Tree> t4(TreeTemplateTools::parenthesisToTree("((a:0.1,b:0.2):0.05,c:0.3,d:0.02);"));
+      VectorSiteContainer s4(cod);
+      s4.addSequence(BasicSequence("a", "ATGGCTAAATTTGGGCCC", cod));
+      s4.addSequence(BasicSequence("b", "ATGGCCAAATTCGGGCCA", cod));
+      s4.addSequence(BasicSequence("c", "ATGGCTAAGTTTGGACCC", cod));
+      s4.addSequence(BasicSequence("d", "ATGTCTAAATTTGGGCCC", cod));
+      YN98 yn(cod, 2.0, 0.3);
+      ConstantRateDistribution cst;
+      DRHomogeneousTreeLikelihood tl(*t4, s4, &yn, &cst);
+      tl.initialize();
+      printf("YN98_CONST %.15f\n", tl.getValue());
+    }
+    {
+      ChromosomeAlphabet chr(1, 30);
+      unique_ptr<Tree> t5(TreeTemplateTools::parenthesisToTree("(((a:0.3,b:0.2):0.4,c:0.5):0.1,(d:0.3,e:0.6):0.2);"));
+      VectorSiteContainer s5(&chr);
+      s5.addSequence(BasicSequence("a", "7", &chr));
+      s5.addSequence(BasicSequence("b", "8", &chr));
+      s5.addSequence(BasicSequence("c", "14", &chr));
+      s5.addSequence(BasicSequence("d", "9", &chr));
+      s5.addSequence(BasicSequence("e", "X", &chr));
+      ChromosomeSubstitutionModel cm(&chr, 0.7, 0.4, 0.2, ChromosomeSubstitutionModel::DemiEqualDupl);
+      ConstantRateDistribution cst;
+      DRNonHomogeneousTreeLikelihood tl(*t5, s5, true, false, &cm, &cst);
+      tl.initialize();
+      printf("CHR_WEIGHTED %.15f\n", tl.getValue());
+      cm.setParameterValue("Chromosome.gain", 1.1);
+    }
+  } catch (exception& ex) {
+    cerr << "EXCEPTION: " << ex.what() << endl;
+    return 1;
+  }
+  if (fails) { cerr << fails << " check(s) failed" << endl; return 1; }
+  cout << "OK" << endl;
+  return 0;
+}

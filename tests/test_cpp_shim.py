@@ -1,0 +1,165 @@
+"""The C++ host shim (bpp_phyl_b200/host/bppgpu_shim.hpp: the reference's class surface above the C ABI).
+
+CPU part: the shim compiles, and its host-side pieces (rate classes, generators + host eigen-decomposition, tree
+flattening, site patterns) agree with the oracle.  GPU part: tests/cpp/test_likelihood.cpp -- the reference's own
+test_likelihood.cpp / test_likelihood_clock.cpp rewritten against the shim -- exits 0, and the values it prints for
+the other state spaces match the oracle."""
+import json
+import pathlib
+import subprocess
+
+import numpy as np
+import pytest
+
+import cases
+from oracle import ref_models as rm
+from oracle import ref_patterns as rp
+from oracle import ref_tree as rt
+
+ROOT = pathlib.Path(__file__).resolve().parent.parent
+BUILD = ROOT / "tests" / "cpp" / "_build"
+
+
+def compile_cpp(name, built_lib):
+    BUILD.mkdir(exist_ok=True)
+    src = ROOT / "tests" / "cpp" / (name + ".cpp")
+    exe = BUILD / name
+    hdr = ROOT / "bpp_phyl_b200" / "host" / "bppgpu_shim.hpp"
+    lib = ROOT / "bpp_phyl_b200" / "lib"
+    if not exe.exists() or exe.stat().st_mtime < max(src.stat().st_mtime, hdr.stat().st_mtime):
+        subprocess.check_call(["g++", "-std=c++17", "-O2", "-Wall", "-Wno-unused", "-I", str(ROOT), "-o", str(exe), str(src),
+                               "-L", str(lib), "-lbppgpu", "-Wl,-rpath," + str(lib)])
+    return exe
+
+
+@pytest.fixture(scope="module")
+def host_doc(built_lib):
+    exe = compile_cpp("shim_host", built_lib)
+    return json.loads(subprocess.check_output([str(exe)]))
+
+
+def test_shim_and_reference_style_test_compile(built_lib):
+    compile_cpp("test_likelihood", built_lib)
+
+
+def test_gamma_rate_classes(host_doc):
+    for key, (n, a) in {"gamma_4_1": (4, 1.0), "gamma_4_0.5": (4, 0.5), "gamma_8_2.3": (8, 2.3), "gamma_1_0.7": (1, 0.7)}.items():
+        np.testing.assert_allclose(host_doc[key], rm.gamma_rates(n, a)[0], rtol=1e-13)
+
+
+def _block_diag(re, im):
+    n = len(re)
+    D = np.zeros((n, n))
+    i = 0
+    while i < n:
+        if im[i] != 0:
+            D[i, i] = D[i + 1, i + 1] = re[i]
+            D[i, i + 1], D[i + 1, i] = im[i], -im[i]
+            i += 2
+        else:
+            D[i, i] = re[i]
+            i += 1
+    return D
+
+
+@pytest.mark.parametrize("key", ["T92", "GTR", "LG08", "YN98", "CHR_REAL", "CHR_COMPLEX", "CHR_SINGULAR"])
+def test_models_generator_and_eigensystem(host_doc, key):
+    m = {"T92": lambda: rm.t92(3.0, 0.5), "GTR": lambda: rm.gtr(1.2, 0.8, 0.6, 1.5, 0.9, (.3, .2, .25, .25)), "LG08": rm.lg08,
+         "YN98": lambda: rm.yn98(2.0, 0.3),
+         "CHR_REAL": lambda: rm.chromosome(1, 40, gain=0.7, loss=0.4, dupl=0.2, demi=rm.DEMI_EQUAL_DUPL),
+         "CHR_COMPLEX": lambda: rm.chromosome(1, 25, gain=1.5, loss=0.1, dupl=0.9, demi=0.4, gain_r=0.05),
+         "CHR_SINGULAR": lambda: rm.chromosome(1, 20, gain=0.5, loss=0.0, dupl=0.0)}[key]()
+    c = host_doc[key]
+    Q = np.array(c["Q"])
+    np.testing.assert_allclose(Q, m.Q, rtol=0, atol=1e-14 * np.abs(m.Q).max())          # generator: same numbers
+    np.testing.assert_allclose(c["freq"], m.freq, rtol=0, atol=1e-15)
+    assert bool(c["nonsingular"]) == m.nonsingular and bool(c["diagonalizable"]) == m.diagonalizable
+    if c["nonsingular"]:
+        # only V f(D) V^-1 matters: the shim's eigen form must reproduce the generator
+        V, Vi = np.array(c["V"]), np.array(c["Vinv"])
+        R = V @ _block_diag(c["re"], c["im"]) @ Vi
+        assert np.abs(R - Q).max() <= 1e-10 * np.abs(Q).max()
+        np.testing.assert_allclose(np.sort(c["re"]), np.sort(m.ev_re), rtol=0, atol=1e-10 * np.abs(Q).max())
+
+
+def test_alias_init_values(host_doc):
+    assert host_doc["init_R"] == [1, 0, 1, 0]          # R = A or G
+
+
+def test_tree_flattening_matches_oracle(host_doc):
+    flat = rt.FlatTree(rt.parse_newick("(((A:0.01, B:0.01):0.02,C:0.03):0.01,(D:0.04,E:0.05):0.06);"))
+    got = host_doc["unrooted_postorder"]
+    assert len(got) == flat.n_nodes
+    for i, (name, length, father) in enumerate(got):
+        assert (name or None) == flat.nodes[i].name
+        assert father == flat.parent[i]
+        if i < flat.n_nodes - 1:
+            assert abs(length - flat.brlen[i]) < 1e-15
+    assert host_doc["leaves"] == flat.leaf_names
+
+
+def test_site_patterns_through_the_shim(host_doc):
+    seqs = {"A": "AAATGGCTGTGCACGTC", "B": "GACTGGATCTGCACGTC", "C": "CTCTGGATGTGCACGTG", "D": "AAATGGCGGTGCGCCTA"}
+    _, w, idx = rp.global_patterns(seqs, ["A", "B", "C", "D"])
+    assert host_doc["pattern_weights"] == list(map(int, w))
+    assert host_doc["pattern_indices"] == list(map(int, idx))
+
+
+@pytest.mark.gpu
+def test_reference_likelihood_tests_through_the_shim(built_lib):
+    exe = compile_cpp("test_likelihood", built_lib)
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    vals = {}
+    derivs = {}
+    for line in r.stdout.splitlines():
+        f = line.split()
+        if len(f) == 2 and f[0].isupper() or (len(f) == 2 and "_" in f[0]):
+            try:
+                vals[f[0]] = float(f[1])
+            except ValueError:
+                pass
+        if len(f) == 4 and f[0] == "LG08_G4_d":
+            derivs[f[1]] = (float(f[2]), float(f[3]))
+    assert abs(vals["R_T92_G4"] - 85.030942031997312824) < 1e-9
+    assert abs(vals["DR_T92_G4"] - 85.030942031997312824) < 1e-9
+    assert abs(vals["CLOCK_T92_CONST"] - 94.3957) < 1e-4
+    # protein: LG08 + Gamma4(0.7) with ambiguity characters, value and both derivatives against the oracle
+    r4, p4 = rm.gamma_rates(4, 0.7)
+    c = cases.case_from_alignment("((a:0.1,b:0.2):0.05,(c:0.3,d:0.02):0.07,e:0.15);",
+                                  {"a": "ARNDCQEGHILKMFPSTWYVAAX", "b": "ARNDCQEGHILKMFPSTWYVLK-", "c": "ARNECQDGHLIKMFPTSWYVAKB",
+                                   "d": "GRNDCQEGHILRMYPSTWFVAAZ", "e": "ARNDCQEGHVLKMFPSTWYIVAA"}, rm.lg08(), r4, p4,
+                                  states=rp.PROTEIN_STATES, aliases=rp.PROTEIN_ALIASES)
+    res = cases.oracle_eval(c, want_d1=True, want_d2=True)
+    assert abs(vals["LG08_G4"] + res.lnl) <= 1e-9 * abs(res.lnl)
+    for b in range(c.flat.n_nodes - 1):
+        d1, d2 = derivs["BrLen%d" % b]
+        assert abs(d1 - res.d1[b]) <= 1e-8 * max(1, abs(res.d1[b]))
+        assert abs(d2 - res.d2[b]) <= 1e-8 * max(1, abs(res.d2[b]))
+    # codon: YN98(kappa 2, omega 0.3), constant rate
+    cod_states = [a + b + c_ for a in "ACGT" for b in "ACGT" for c_ in "ACGT"]
+    flat = rt.FlatTree(rt.parse_newick("((a:0.1,b:0.2):0.05,c:0.3,d:0.02);"))
+    seqs = {"a": "ATGGCTAAATTTGGGCCC", "b": "ATGGCCAAATTCGGGCCA", "c": "ATGGCTAAGTTTGGACCC", "d": "ATGTCTAAATTTGGGCCC"}
+    uniq, w, idx = rp.global_patterns(seqs, flat.leaf_names, width=3)
+    codes = rp.encode_columns(uniq, cod_states, width=3)
+    cc = cases.Case()
+    m = rm.yn98(2.0, 0.3)
+    cc.flat, cc.model, cc.rates, cc.probs = flat, m, np.ones(1), np.ones(1)
+    cc.table, cc.N, cc.weights = np.eye(64), len(uniq), w
+    cc.codes_by_leaf = {lid: codes[k] for k, lid in enumerate(flat.leaf_ids)}
+    cc.root_freqs = m.freq
+    res = cases.oracle_eval(cc)
+    assert abs(vals["YN98_CONST"] + res.lnl) <= 1e-9 * abs(res.lnl)
+    # chromosome: one character, weighted root frequencies, unknown count at one tip
+    flat = rt.FlatTree(rt.parse_newick("(((a:0.3,b:0.2):0.4,c:0.5):0.1,(d:0.3,e:0.6):0.2);"), check_rooted=False)
+    m = rm.chromosome(1, 30, gain=0.7, loss=0.4, dupl=0.2, demi=rm.DEMI_EQUAL_DUPL)
+    table = np.vstack([np.eye(30), np.ones((1, 30))])
+    counts = {"a": 7, "b": 8, "c": 14, "d": 9, "e": None}
+    ch = cases.Case()
+    ch.flat, ch.model, ch.rates, ch.probs = flat, m, np.ones(1), np.ones(1)
+    ch.table, ch.N, ch.weights = table, 1, np.ones(1, np.uint32)
+    ch.codes_by_leaf = {lid: np.array([30 if counts[flat.nodes[lid].name] is None else counts[flat.nodes[lid].name] - 1], np.uint8)
+                        for lid in flat.leaf_ids}
+    ch.root_freqs = m.freq
+    res = cases.oracle_eval(ch, weighted_root=True)
+    assert abs(vals["CHR_WEIGHTED"] + res.lnl) <= 1e-9 * abs(res.lnl)
