@@ -171,9 +171,9 @@ static int check_device(int device) {
   if (prop.major < 10) BPP_FAIL(BPPGPU_E_CUDA, "device %d is sm_%d%d; libbppgpu is built for sm_100a only", device, prop.major, prop.minor);
   g_sm_count = prop.multiProcessorCount;
   // dynamic shared memory above 48 KB is opt-in
-  BPP_CUDA(cudaFuncSetAttribute(pt_dmma_kernel<8, 1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-  BPP_CUDA(cudaFuncSetAttribute(pt_dmma_kernel<8, 2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-  BPP_CUDA(cudaFuncSetAttribute(pt_dmma_kernel<8, 4, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+  BPP_CUDA(cudaFuncSetAttribute(pt_dmma_kernel<8, 1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
+  BPP_CUDA(cudaFuncSetAttribute(pt_dmma_kernel<8, 2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
+  BPP_CUDA(cudaFuncSetAttribute(pt_dmma_kernel<8, 4, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
   BPP_CUDA(cudaFuncSetAttribute(dmma_node_kernel<5, 3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   BPP_CUDA(cudaFuncSetAttribute(dmma_node_kernel<16, 8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   BPP_CUDA(cudaFuncSetAttribute(dmma_upper_deriv_kernel<5, 3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -184,6 +184,7 @@ static int check_device(int device) {
 // ---- model upload -------------------------------------------------------------------
 static void free_model(DevModel& m) {
   if (m.Vp != m.V) { cudaFree(m.Vp); cudaFree(m.Vinvp); cudaFree(m.rep); }
+  cudaFree(m.imp);
   cudaFree(m.V); cudaFree(m.Vinv); cudaFree(m.re); cudaFree(m.im); cudaFree(m.Q); cudaFree(m.Q2); cudaFree(m.role);
   m = DevModel{};
 }
@@ -227,22 +228,34 @@ static int upload_model(DevModel& dm, const bppgpu_model_desc* m, int S) {
     BPP_CUDA(cudaMemcpy(dm.im, im.data(), S * 8, cudaMemcpyHostToDevice));
     BPP_CUDA(cudaMemcpy(dm.role, role.data(), S * 4, cudaMemcpyHostToDevice));
     const int Sp = (S + 7) & ~7;
-    if (Sp == S) {
+    if (Sp == S && !dm.has_complex) {
       dm.Vp = dm.V; dm.Vinvp = dm.Vinv; dm.rep = dm.re;
-    } else if (S >= 32) {  // padded copies for the DMMA kernel
-      std::vector<double> vp((size_t)Sp * Sp, 0.0), vip((size_t)Sp * Sp, 0.0), rp(Sp, 0.0);
-      for (int i = 0; i < S; ++i)
-        for (int j = 0; j < S; ++j) {
-          vp[(size_t)i * Sp + j] = m->right_eigen[(size_t)i * S + j];
-          vip[(size_t)i * Sp + j] = m->left_eigen[(size_t)i * S + j];
+    } else if (S >= 32) {
+      // copies for the DMMA kernel: zero-padded to Sp, eigen-columns permuted so that every conjugate pair starts at an
+      // even index (pairs first, then the real eigenvalues)
+      std::vector<int> order;
+      for (int k = 0; k < S; ++k)
+        if (role[k] == 1) { order.push_back(k); order.push_back(k + 1); }
+      for (int k = 0; k < S; ++k)
+        if (role[k] == 0) order.push_back(k);
+      std::vector<double> vp((size_t)Sp * Sp, 0.0), vip((size_t)Sp * Sp, 0.0), rp(Sp, 0.0), ip(Sp, 0.0);
+      for (int j = 0; j < S; ++j) {
+        const int k = order[j];
+        rp[j] = m->eigen_re[k];
+        ip[j] = im[k];
+        for (int i = 0; i < S; ++i) {
+          vp[(size_t)i * Sp + j] = m->right_eigen[(size_t)i * S + k];
+          vip[(size_t)j * Sp + i] = m->left_eigen[(size_t)k * S + i];
         }
-      for (int k = 0; k < S; ++k) rp[k] = m->eigen_re[k];
+      }
       BPP_CUDA(cudaMalloc(&dm.Vp, vp.size() * 8));
       BPP_CUDA(cudaMalloc(&dm.Vinvp, vip.size() * 8));
       BPP_CUDA(cudaMalloc(&dm.rep, Sp * 8));
       BPP_CUDA(cudaMemcpy(dm.Vp, vp.data(), vp.size() * 8, cudaMemcpyHostToDevice));
       BPP_CUDA(cudaMemcpy(dm.Vinvp, vip.data(), vip.size() * 8, cudaMemcpyHostToDevice));
       BPP_CUDA(cudaMemcpy(dm.rep, rp.data(), Sp * 8, cudaMemcpyHostToDevice));
+      BPP_CUDA(cudaMalloc(&dm.imp, Sp * 8));
+      BPP_CUDA(cudaMemcpy(dm.imp, ip.data(), Sp * 8, cudaMemcpyHostToDevice));
     }
   }
   if (m->generator) {
@@ -268,7 +281,7 @@ static int upload_model(DevModel& dm, const bppgpu_model_desc* m, int S) {
 static ModelDev to_dev(const DevModel& m) {
   ModelDev d{};
   d.V = m.V; d.Vinv = m.Vinv; d.re = m.re; d.im = m.im; d.role = m.role; d.Q = m.Q; d.Q2 = m.Q2;
-  d.Vp = m.Vp; d.Vinvp = m.Vinvp; d.rep = m.rep;
+  d.Vp = m.Vp; d.Vinvp = m.Vinvp; d.rep = m.rep; d.imp = m.imp;
   d.rate = m.rate; d.eps = m.eps; d.q_l1 = m.q_l1; d.flags = m.flags; d.has_complex = m.has_complex;
   return d;
 }
@@ -293,8 +306,8 @@ static int launch_pt(cudaStream_t st, const ModelDev* d_models, bool any_series,
   const int threads = S * S >= 256 ? 256 : (S * S >= 64 ? 64 : 32);
   const int Sp = (S + 7) & ~7;
   pp.dmma_real = 0;
-  if (S >= 32 && Sp <= 256 && any_real_eigen) {
-    // FP64 tensor-core GEMM for every real-spectrum matrix; the CUDA-core kernel keeps the complex ones
+  if (S >= 32 && Sp <= 256 && (any_real_eigen || any_complex)) {
+    // FP64 tensor-core GEMM for every eigen-path matrix (real spectra and conjugate-pair block form)
     pp.dmma_real = 1;
     const int nblk = Sp / 8;
     if (nblk <= 8) {
@@ -306,7 +319,7 @@ static int launch_pt(cudaStream_t st, const ModelDev* d_models, bool any_series,
     }
     ++*launches;
   }
-  if (!pp.dmma_real || any_complex) {
+  if (!pp.dmma_real) {
     pt_eigen_kernel<<<nmat, threads, 6 * S * sizeof(double), st>>>(pp);
     ++*launches;
   }
@@ -469,7 +482,7 @@ int bppgpu_destroy(bppgpu_engine* e) {
   if (!e) return BPPGPU_OK;
   cudaSetDevice(e->dev);
   if (e->stream) cudaStreamSynchronize(e->stream);
-  void* ptrs[] = {e->d_codes, e->d_code_table, e->d_weights, e->d_rates, e->d_probs, e->d_rootfreq,
+  void* ptrs[] = {e->d_codes, e->d_code_table, e->d_code_single, e->d_weights, e->d_rates, e->d_probs, e->d_rootfreq,
                   e->d_rootfreq_used, e->d_brlen, e->d_branch_model, e->d_leaf_nodes, e->d_models, e->d_P, e->d_dP,
                   e->d_d2P, e->d_tiptab, e->d_keep, e->d_keep_exp, e->d_gstack, e->d_gstack_exp, e->d_upper,
                   e->d_upper_exp, e->d_SR, e->d_rexp, e->d_site_lnl, e->d_partials, e->d_partials2, e->d_out,
@@ -564,7 +577,9 @@ static int create_impl(const bppgpu_config* cfg, bppgpu_engine* e) {
     if (!strcmp(env, "dmma") && ((S > 16 && S <= 20) || (S > 56 && S <= 64))) e->path = PATH_DMMA;
   }
   if (cfg->flags & BPPGPU_FLAG_FORCE_GENERIC) e->path = PATH_GENERIC;
-  if (e->path == PATH_GENERIC || e->path == PATH_DMMA) e->keep = true;
+  // many parameter points on few patterns (ChromEvol): one launch per node covers every point of a chunk
+  if (e->npoints > 1 && N * C <= 64 && !(cfg->flags & BPPGPU_FLAG_FORCE_GENERIC)) e->path = PATH_POINTS;
+  if (e->path == PATH_GENERIC || e->path == PATH_DMMA || e->path == PATH_POINTS) e->keep = true;
   build_program(e, e->prog, false);  // again: keep indices are known now
   build_program(e, e->gprog, true);
   if (e->path == PATH_WALK4) {
@@ -636,6 +651,20 @@ static int create_impl(const bppgpu_config* cfg, bppgpu_engine* e) {
   BPP_CUDA(cudaMemset(e->d_codes, 0, std::max<size_t>(1, (size_t)e->nl * N * e->code_bytes)));
   BPP_CUDA(dev_alloc(e, &e->d_code_table, (size_t)e->ncodes * S));
   BPP_CUDA(cudaMemcpy(e->d_code_table, cfg->code_table, (size_t)e->ncodes * S * 8, cudaMemcpyHostToDevice));
+  {
+    std::vector<int> single(e->ncodes, -1);
+    for (int k = 0; k < e->ncodes; ++k) {
+      int ones = 0, other = 0, pos = -1;
+      for (int x = 0; x < S; ++x) {
+        const double v = cfg->code_table[(size_t)k * S + x];
+        if (v == 1.0) { ++ones; pos = x; }
+        else if (v != 0.0) ++other;
+      }
+      if (ones == 1 && other == 0) single[k] = pos;
+    }
+    BPP_CUDA(dev_alloc(e, &e->d_code_single, (size_t)e->ncodes));
+    BPP_CUDA(cudaMemcpy(e->d_code_single, single.data(), e->ncodes * sizeof(int), cudaMemcpyHostToDevice));
+  }
   BPP_CUDA(dev_alloc(e, &e->d_weights, (size_t)N));
   BPP_CUDA(dev_alloc(e, &e->d_rates, (size_t)C));
   BPP_CUDA(dev_alloc(e, &e->d_probs, (size_t)C));
@@ -662,7 +691,11 @@ static int create_impl(const bppgpu_config* cfg, bppgpu_engine* e) {
   // P tables: as many points per chunk as fit a 16 GiB budget
   const size_t per_point = (size_t)nn * C * SS * 8;
   size_t budget = (size_t)16 << 30;
-  e->pchunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)e->npoints, budget / std::max<size_t>(1, 3 * per_point)));
+  if (e->path == PATH_POINTS) {
+    size_t fr = 0, tot = 0;
+    if (cudaMemGetInfo(&fr, &tot) == cudaSuccess) budget = std::max(budget, fr / 2);
+  }
+  e->pchunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)e->npoints, budget / std::max<size_t>(1, (e->path == PATH_POINTS ? 1 : 3) * per_point)));
   BPP_CUDA(dev_alloc(e, &e->d_P, (size_t)e->pchunk * nn * C * SS));
   if (e->path == PATH_WALK4) {
     BPP_CUDA(dev_alloc(e, &e->d_w4_desc, e->w4_desc.size()));
@@ -675,13 +708,14 @@ static int create_impl(const bppgpu_config* cfg, bppgpu_engine* e) {
     BPP_CUDA(cudaMemset(e->d_w4_stream, 0, ((size_t)e->pchunk * e->w4_stream_len + (size_t)e->ncodes * C * 4 + 64 + 8192) * 8));
     BPP_CUDA(dev_alloc(e, &e->d_codesT, (size_t)N * e->w4_tstride));
   }
-  if (e->path != PATH_WALK4 || e->keep)
+  if ((e->path != PATH_WALK4 || e->keep) && e->path != PATH_POINTS)
     BPP_CUDA(dev_alloc(e, &e->d_tiptab, (size_t)e->pchunk * e->nl * C * e->ncodes * S));
 
   const size_t clv = (size_t)N * C * S;
   if (e->keep) {
-    BPP_CUDA(dev_alloc(e, &e->d_keep, (size_t)e->ni * clv));
-    BPP_CUDA(dev_alloc(e, &e->d_keep_exp, (size_t)e->ni * N * C));
+    const size_t mult = e->path == PATH_POINTS ? (size_t)e->pchunk : 1;
+    BPP_CUDA(dev_alloc(e, &e->d_keep, mult * e->ni * clv));
+    BPP_CUDA(dev_alloc(e, &e->d_keep_exp, mult * e->ni * N * C));
   }
   if (e->path == PATH_WALKS && e->prog.nslots > 0) {
     BPP_CUDA(dev_alloc(e, &e->d_gstack, (size_t)e->prog.nslots * clv));
@@ -1288,6 +1322,44 @@ static int eval_impl(bppgpu_engine* e, unsigned want, cudaStream_t st, bool time
       }
     }
     BPP_CUDA(cudaGetLastError());
+    if (e->path == PATH_POINTS) {
+      if (derivs) BPP_FAIL(BPPGPU_E_INVALID, "branch derivatives are not available on the batched-points path (n_points > 1)");
+      if (p0 == 0) BPP_CUDA(cudaEventRecord(e->ring_a[e->ring_head], st));
+      const long long rows = e->N * C;
+      for (const Op& op : e->gprog.ops) {
+        PointsNodeParams pp{};
+        pp.childs = e->gprog.d_childs + op.child_begin;
+        pp.nchild = op.nchild;
+        pp.out_idx = op.keep_idx;
+        pp.S = S; pp.C = C; pp.nn = nn; pp.nl = e->nl; pp.ni = e->ni; pp.ncodes = e->ncodes; pp.code_bytes = e->code_bytes;
+        pp.N = e->N;
+        pp.P = e->d_P; pp.code_table = e->d_code_table; pp.code_single = e->d_code_single; pp.codes = e->d_codes;
+        pp.keep = e->d_keep; pp.keep_exp = e->d_keep_exp;
+        points_node_kernel<<<dim3((unsigned)np, (unsigned)std::min<long long>(rows, 64)), 256, (2 * S + 32) * sizeof(double), st>>>(pp);
+        e->stats.kernel_launches++;
+      }
+      PointsRootParams pr{};
+      pr.root_idx = e->internal_idx[e->root]; pr.S = S; pr.C = C; pr.ni = e->ni;
+      pr.flags = ((e->flags & BPPGPU_FLAG_R_SEMANTICS) ? 1u : 0u) | ((e->flags & BPPGPU_FLAG_WEIGHTED_ROOT) ? 2u : 0u);
+      pr.N = e->N;
+      pr.keep = e->d_keep; pr.keep_exp = e->d_keep_exp; pr.probs = e->d_probs; pr.weights = e->d_weights;
+      pr.rootfreq_in = e->d_rootfreq + (size_t)p0 * S;
+      pr.rootfreq_used = e->d_rootfreq_used + (size_t)p0 * S;
+      pr.site_lnl = e->d_site_lnl + (size_t)p0 * e->N;
+      pr.out = e->d_out + (size_t)p0 * (1 + 2 * nn);
+      pr.out_stride = 1 + 2 * nn;
+      points_root_kernel<<<np, 256, S * sizeof(double), st>>>(pr);
+      e->stats.kernel_launches++;
+      BPP_CUDA(cudaGetLastError());
+      e->stats.clv_updates += (long long)np * e->ni * rows * S;
+      if (p0 + np >= e->npoints) {
+        BPP_CUDA(cudaEventRecord(e->ring_b[e->ring_head], st));
+        e->ring_head = (e->ring_head + 1) % bppgpu_engine::kRing;
+        e->ring_n = std::min(e->ring_n + 1, (int)bppgpu_engine::kRing);
+      }
+      e->last_point = p0 + np - 1;
+      continue;
+    }
     for (int pl = 0; pl < np; ++pl) {
       const int point = p0 + pl;
       if (point == 0) BPP_CUDA(cudaEventRecord(e->ring_a[e->ring_head], st));
@@ -1366,14 +1438,22 @@ int bppgpu_get_clv(bppgpu_engine* e, int32_t point, int32_t node, int32_t which,
   ENGINE_ENTER(e);
   if (!e->keep) BPP_FAIL(BPPGPU_E_STATE, "bppgpu_get_clv needs BPPGPU_FLAG_KEEP_CLVS");
   if (node < 0 || node >= e->nn || !clv) BPP_FAIL(BPPGPU_E_INVALID, "bad node or null out");
-  if (point != e->last_point) BPP_FAIL(BPPGPU_E_STATE, "CLVs resident are those of point %d", e->last_point);
-  BPP_CUDA(cudaStreamSynchronize(e->stream));
   const size_t clvn = (size_t)e->N * e->C * e->S;
+  size_t pt_off = 0;  // slab offset of the point inside the resident chunk (batched-points path)
+  if (e->path == PATH_POINTS) {
+    const int chunk0 = ((e->npoints - 1) / e->pchunk) * e->pchunk;
+    if (e->last_point < 0 || point < chunk0 || point >= e->npoints)
+      BPP_FAIL(BPPGPU_E_STATE, "CLVs resident are those of points >= %d", chunk0);
+    pt_off = (size_t)(point - chunk0) * e->ni;
+  } else if (point != e->last_point) {
+    BPP_FAIL(BPPGPU_E_STATE, "CLVs resident are those of point %d", e->last_point);
+  }
+  BPP_CUDA(cudaStreamSynchronize(e->stream));
   if (which == 0) {
     if (e->internal_idx[node] < 0) BPP_FAIL(BPPGPU_E_INVALID, "node %d is a leaf: its CLV is the code table row", node);
-    const int k = e->internal_idx[node];
-    BPP_CUDA(cudaMemcpy(clv, e->d_keep + (size_t)k * clvn, clvn * 8, cudaMemcpyDeviceToHost));
-    if (scale_exp) BPP_CUDA(cudaMemcpy(scale_exp, e->d_keep_exp + (size_t)k * e->N * e->C, (size_t)e->N * e->C * 4, cudaMemcpyDeviceToHost));
+    const size_t k = pt_off + (size_t)e->internal_idx[node];
+    BPP_CUDA(cudaMemcpy(clv, e->d_keep + k * clvn, clvn * 8, cudaMemcpyDeviceToHost));
+    if (scale_exp) BPP_CUDA(cudaMemcpy(scale_exp, e->d_keep_exp + k * e->N * e->C, (size_t)e->N * e->C * 4, cudaMemcpyDeviceToHost));
   } else {
     if (!(e->last_want & BPPGPU_EVAL_D1) || !e->d_upper) BPP_FAIL(BPPGPU_E_STATE, "upper CLVs exist after an eval with derivatives");
     if (node == e->root) BPP_FAIL(BPPGPU_E_INVALID, "the root has no upper CLV");

@@ -10,6 +10,7 @@
 #include "dmma_deriv_kernels.cuh"
 #include "dmma_node_kernels.cuh"
 #include "generic_kernels.cuh"
+#include "points_kernels.cuh"
 #include "pt_dmma_kernels.cuh"
 #include "pt_kernels.cuh"
 #include "walk_kernels.cuh"
@@ -20,7 +21,7 @@ enum PathKind { PATH_NONE = 0, PATH_WALK4 = 1, PATH_WALKS = 2, PATH_GENERIC = 3,
 
 struct DevModel {
   double *V = nullptr, *Vinv = nullptr, *re = nullptr, *im = nullptr, *Q = nullptr, *Q2 = nullptr;
-  double *Vp = nullptr, *Vinvp = nullptr, *rep = nullptr;  // zero-padded to a multiple of 8 (own storage only if S % 8)
+  double *Vp = nullptr, *Vinvp = nullptr, *rep = nullptr, *imp = nullptr;  // zero-padded to a multiple of 8 (own storage only if S % 8)
   int* role = nullptr;
   double rate = 1.0, eps = 1e-4;
   unsigned flags = 0;
@@ -56,6 +57,7 @@ struct bppgpu_engine {
   // device inputs
   void* d_codes = nullptr;        // [nl][N] tip codes
   double* d_code_table = nullptr; // [ncodes][S]
+  int* d_code_single = nullptr;   // [ncodes] state of an indicator row or -1
   double* d_weights = nullptr;    // [N]
   double *d_rates = nullptr, *d_probs = nullptr;
   double* d_rootfreq = nullptr;       // [npoints][S] as given

@@ -3,8 +3,11 @@
 //   f = exp(x)            -> pxy_    (Model/AbstractSubstitutionModel.cpp:436)
 //   f = r  (rate lambda)   exp(x)   -> dpxy_   (:505, times r_c: AbstractHomogeneousTreeLikelihood.cpp:389)
 //   f = r^2 (rate lambda)^2 exp(x)  -> d2pxy_  (:576, :409)
-// Real spectra only; conjugate pairs (block form, :438-468) and singular generators keep the CUDA-core
-// kernels of pt_kernels.cuh.
+// Conjugate eigen-pairs use the real block form (:438-468, :507-537, :578-612): P = V.T.V^-1 with 2x2 blocks
+// [[dia, up], [-up, dia]], i.e. column k of the left factor is dia_k V[:,k] + off_k V[:,k^1] with off = -up for the
+// first and +up for the second member.  The engine uploads the eigen-columns permuted so that every pair starts at an
+// even index (ModelDev::Vp / Vinvp / rep / imp), which keeps a pair inside one k-block.  Singular generators keep the
+// series kernel of pt_kernels.cuh.
 //
 // Tiling: one CTA per (matrix, column panel).  WARPS warps, warp w owns MBW 8-row blocks (all of M = S =
 // WARPS*MBW*8 is covered by the CTA) times the panel's NB 8-column blocks: MBW*NB DMMA atoms per k-step
@@ -28,7 +31,7 @@ template <int NB>
 __host__ __device__ constexpr int pt_bstride() { return NB * 8 + 4; }
 
 inline size_t pt_dmma_smem_bytes(int Sp, int NB) {
-  return (size_t)(3 * Sp + 2 * Sp * kPtAStride + 2 * kPtKT * (NB * 8 + 4)) * sizeof(double);
+  return (size_t)(6 * Sp + 2 * Sp * kPtAStride + 2 * kPtKT * (NB * 8 + 4)) * sizeof(double);
 }
 
 template <int WARPS, int MBW, int NB>
@@ -39,8 +42,9 @@ __global__ void __launch_bounds__(WARPS * 32) pt_dmma_kernel(PtParams p, int Sp)
   const int kAStage = Sp * kPtAStride;
   constexpr int kBStage = kPtKT * BStride;
   extern __shared__ __align__(16) double sm_pt[];
-  double* dtab = sm_pt;               // [3][Sp]
-  double* As = dtab + 3 * Sp;         // [2][Sp][12]
+  double* dtab = sm_pt;               // [3][Sp] diagonal factors
+  double* otab = dtab + 3 * Sp;       // [3][Sp] partner-column factors (0 for real eigenvalues)
+  double* As = otab + 3 * Sp;         // [2][Sp][12]
   double* Bs = As + 2 * kAStage;      // [2][8][BStride]
 
   const int m = blockIdx.x;
@@ -49,7 +53,7 @@ __global__ void __launch_bounds__(WARPS * 32) pt_dmma_kernel(PtParams p, int Sp)
   const int point = m / (p.C * p.nn);
   if (node == p.root) return;
   const ModelDev md = p.models[p.branch_model[point * p.nn + node]];
-  if (!(md.flags & 2u) || md.has_complex) return;  // singular / complex spectrum: CUDA-core kernels
+  if (!(md.flags & 2u)) return;  // singular generator: series kernel
   const double rc = p.rates[c];
   const double t = p.brlen[point * p.nn + node] * rc;
   const double l = md.rate * t;
@@ -57,12 +61,30 @@ __global__ void __launch_bounds__(WARPS * 32) pt_dmma_kernel(PtParams p, int Sp)
   const int nblk = Sp >> 3;
 
   for (int k = threadIdx.x; k < Sp; k += NT) {
-    const double a = md.rep[k];
-    const double ex = exp(a * l);
-    const double ra = md.rate * a;
-    dtab[k] = ex;
-    dtab[Sp + k] = rc * (ra * ex);
-    dtab[2 * Sp + k] = rc * rc * (ra * ra * ex);
+    const double bk = md.has_complex ? md.imp[k] : 0.0;
+    if (bk == 0.0) {
+      const double a = md.rep[k];
+      const double ex = exp(a * l);
+      const double ra = md.rate * a;
+      dtab[k] = ex;
+      dtab[Sp + k] = rc * (ra * ex);
+      dtab[2 * Sp + k] = rc * rc * (ra * ra * ex);
+      otab[k] = otab[Sp + k] = otab[2 * Sp + k] = 0.0;
+    } else {
+      const int kf = k & ~1;  // first member holds +im
+      const double ar = md.rep[kf], b = md.imp[kf];
+      const double ex = exp(ar * l);
+      double sn, cs;
+      sincos(b * l, &sn, &cs);
+      const double r1 = md.rate, r2 = md.rate * md.rate;
+      const double sg = (k & 1) ? 1.0 : -1.0;
+      dtab[k] = ex * cs;
+      dtab[Sp + k] = rc * (r1 * (ar * cs - b * sn) * ex);
+      dtab[2 * Sp + k] = rc * rc * (r2 * ((ar * ar - b * b) * cs - 2.0 * ar * b * sn) * ex);
+      otab[k] = sg * ex * sn;
+      otab[Sp + k] = sg * rc * (r1 * (ar * sn + b * cs) * ex);
+      otab[2 * Sp + k] = sg * rc * rc * (r2 * ((ar * ar - b * b) * sn + 2.0 * ar * b * cs) * ex);
+    }
   }
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -98,6 +120,8 @@ __global__ void __launch_bounds__(WARPS * 32) pt_dmma_kernel(PtParams p, int Sp)
 #pragma unroll
       for (int j = 0; j < NB; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
     const double* dt = dtab + tab * Sp;
+    const double* ot = otab + tab * Sp;
+    const bool cplx = md.has_complex != 0;
 
     __syncthreads();  // dtab ready / previous table's smem reads done
     stage(0, 0);
@@ -116,11 +140,18 @@ __global__ void __launch_bounds__(WARPS * 32) pt_dmma_kernel(PtParams p, int Sp)
 #pragma unroll
       for (int kb = 0; kb < kPtKT / 4; ++kb) {
         const double dk = dt[ks * kPtKT + kb * 4 + q];
+        const double ok = cplx ? ot[ks * kPtKT + kb * 4 + q] : 0.0;
         double a[MBW], b[NB];
 #pragma unroll
         for (int i = 0; i < MBW; ++i) {
           const int mb = warp + i * WARPS;
-          a[i] = mb < nblk ? a_src[(mb * 8 + g) * kPtAStride + kb * 4 + q] * dk : 0.0;
+          double av = 0.0;
+          if (mb < nblk) {
+            const double* ar = a_src + (mb * 8 + g) * kPtAStride + kb * 4;
+            av = ar[q] * dk;
+            if (cplx) av = fma(ar[q ^ 1], ok, av);
+          }
+          a[i] = av;
         }
 #pragma unroll
         for (int j = 0; j < NB; ++j) b[j] = b_src[(kb * 4 + q) * BStride + j * 8 + g];

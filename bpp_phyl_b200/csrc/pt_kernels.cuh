@@ -28,6 +28,7 @@ struct ModelDev {
   const double* Vp;    // [Sp][Sp] V zero-padded to Sp = roundup(S, 8) (== V when S % 8 == 0)
   const double* Vinvp; // [Sp][Sp]
   const double* rep;   // [Sp]
+  const double* imp;   // [Sp] imaginary parts in the permuted order (pairs first, each at an even index)
   double rate;
   double eps;
   double q_l1;         // sum_ij |Q_ij| (ChromosomeSubstitutionModel::getFirstNorm)
@@ -68,7 +69,7 @@ __global__ void pt_eigen_kernel(PtParams p) {
   const ModelDev md = p.models[p.branch_model[point * p.nn + node]];
   if (!((md.flags & 1u) || (md.flags & 2u))) return;  // handled by the series kernel
   if (!(md.flags & 2u)) return;                       // singular -> series kernel
-  if (p.dmma_real && !md.has_complex) return;         // built on the tensor cores (pt_dmma_kernels.cuh)
+  if (p.dmma_real) return;                            // built on the tensor cores (pt_dmma_kernels.cuh)
   const double rc = p.rates[c];
   const double t = p.brlen[point * p.nn + node] * rc;  // l_b * r_c
   const double l = md.rate * t;

@@ -124,6 +124,64 @@ def random_reversible(S, rng):
     return reversible_eigensystem(ex, pi)
 
 
+def chromosome_generator(n_states, gain, loss, dupl, demi):
+    """ChromEvol generator on counts 1..n_states (Model/ChromosomeSubstitutionModel.cpp:431-577, constant rates, no base
+    number): +1 gain, -1 loss, x2 duplication, x1.5 demi-duplication (split between floor/ceil for odd counts), overflow to
+    the maximum state.  Not normalised."""
+    n = n_states
+    Q = np.zeros((n, n))
+    for i in range(1, n + 1):
+        r = i - 1
+        if i + 1 <= n:
+            Q[r, r + 1] += gain
+        if i - 1 >= 1:
+            Q[r, r - 1] += loss
+        if 2 * i <= n:
+            Q[r, 2 * i - 1] += dupl
+        elif i != n:
+            Q[r, n - 1] += dupl
+        if i != n:
+            if i % 2 == 0 and int(i * 1.5) <= n:
+                Q[r, int(i * 1.5) - 1] += demi
+            elif i % 2 != 0 and int(np.ceil(i * 1.5)) <= n:
+                if i == 1:
+                    Q[r, int(np.ceil(i * 1.5)) - 1] += demi
+                else:
+                    Q[r, int(np.ceil(i * 1.5)) - 1] += demi / 2
+                    Q[r, int(np.floor(i * 1.5)) - 1] += demi / 2
+            else:
+                Q[r, n - 1] += demi
+    np.fill_diagonal(Q, 0.0)
+    np.fill_diagonal(Q, -Q.sum(axis=1))
+    return Q
+
+
+def chromosome_eigensystem(args):
+    """Host eigendecomposition of one parameter point (what ChromosomeSubstitutionModel::updateEigenMatrices does per
+    likelihood object); returns None when the spectrum is not real / the basis unusable (those points take other kernels)."""
+    n, gain, loss, dupl, demi = args
+    Q = chromosome_generator(n, gain, loss, dupl, demi)
+    w, V = np.linalg.eig(Q)
+    if np.abs(w.imag).max() > 1e-12:
+        return None
+    w, V = w.real, V.real
+    try:
+        Vinv = np.linalg.inv(V)
+    except np.linalg.LinAlgError:
+        return None
+    if np.abs(V @ np.diag(w) @ Vinv - Q).max() > 1e-9 * np.abs(Q).max():
+        return None
+    w[np.argmin(np.abs(w))] = 0.0
+    return {"Q": Q, "V": V, "Vinv": Vinv, "ev": w, "pi": np.full(n, 1.0 / n)}
+
+
+def chromosome_model_desc(es):
+    from . import capi
+    S = len(es["ev"])
+    return capi.model_desc(S, capi.MODEL_DIAGONALIZABLE | capi.MODEL_NONSINGULAR | capi.MODEL_CLAMP01 | capi.MODEL_CHR_DERIV |
+                           capi.MODEL_CHR_TAYLOR, rate=1.0, V=es["V"], Vinv=es["Vinv"], ev_re=es["ev"], Q=es["Q"])
+
+
 def model_desc(es):
     from . import capi
     S = len(es["ev"])

@@ -212,7 +212,8 @@ def test_nh_derivative_form():
     np.testing.assert_allclose(-d2[0, :nb], res.d2, rtol=1e-8, atol=1e-7)
 
 
-@pytest.mark.parametrize("name", ["t92", "gtr", "lg08", "yn98", "chr_eigen", "chr_complex", "chr_singular", "nonrev4"])
+@pytest.mark.parametrize("name", ["t92", "gtr", "lg08", "yn98", "chr_eigen", "chr_complex", "chr_complex50", "chr_real200",
+                                  "chr_complex200", "chr_singular", "nonrev4"])
 def test_pt_batch_interface(name):
     """Interface 1: getPij_t / getdPij_dt / getd2Pij_dt2 for a batch of t."""
     capi = _capi()
@@ -225,7 +226,12 @@ def test_pt_batch_interface(name):
         m = {"t92": lambda: rm.t92(3.0, 0.5), "gtr": gtr, "lg08": rm.lg08, "yn98": lambda: rm.yn98(2.0, 0.3),
              "chr_eigen": lambda: rm.chromosome(1, 40, gain=0.7, loss=0.4, dupl=0.2, demi=rm.DEMI_EQUAL_DUPL),
              "chr_complex": lambda: rm.chromosome(1, 25, gain=1.5, loss=0.1, dupl=0.9, demi=0.4, gain_r=0.05),
+             "chr_complex50": lambda: rm.chromosome(1, 50, gain=1.02, loss=1.90, dupl=0.14, demi=0.95),
+             "chr_real200": lambda: rm.chromosome(1, 104, gain=1.0, loss=1.0, dupl=0.01),     # real spectrum, S % 8 == 0
+             "chr_complex200": lambda: rm.chromosome(1, 200, gain=0.08, loss=1.06, dupl=0.46, demi=0.06),
              "chr_singular": lambda: rm.chromosome(1, 20, gain=0.5, loss=0.0, dupl=0.0)}[name]()
+        if name in ("chr_complex50", "chr_complex200"):
+            assert m.nonsingular and not m.diagonalizable       # conjugate pairs -> block form on the tensor cores
     ts = np.array([0.0, 1e-6, 0.013, 0.2, 1.0, 4.5])
     P, dP, d2P = capi.pt_batch(cases.to_model_desc(m), ts, 7)
     for k, t in enumerate(ts):
@@ -261,6 +267,48 @@ def test_chromosome_weighted_root_batched_points():
         res = cases.oracle_eval(c, model=m, weighted_root=True)
         assert abs(lnl[k] - res.lnl) <= REL * abs(res.lnl)
         np.testing.assert_allclose(e.root_freqs(k), res.root_freqs, rtol=1e-10, atol=1e-14)
+    e.close()
+
+
+def test_batched_points_path_general_shapes():
+    """n_points > 1 on a small pattern set: per-point models AND branch lengths, several patterns and classes,
+    ambiguity codes, rescaling, device-resident CLVs of a point."""
+    capi = _capi()
+    rng = np.random.default_rng(17)
+    r, p = rm.gamma_rates(2, 0.8)
+    base = rm.lg08()
+    c = cases.make_case(110, 9, base, r, p, seed=71, mean_brlen=0.6, ambiguity=0.05, compress=False)
+    npts = 7
+    off, ch = c.flat.csr()
+    models = [rm.lg08()] + [rm._reversible("R%d" % k, np.triu(rng.gamma(0.6, 1.0, (20, 20)), 1) + np.triu(rng.gamma(0.6, 1.0, (20, 20)), 1).T
+                                           if False else (lambda a: (a + a.T) / 2)(rng.gamma(0.6, 1.0, (20, 20)) + 1e-3),
+                                           rng.dirichlet(np.full(20, 5.0))) for k in range(npts - 1)]
+    brl = [c.flat.brlen * rng.uniform(0.5, 1.5, size=c.flat.n_nodes) for _ in range(npts)]
+    e = capi.Engine(20, 2, c.N, off, ch, c.flat.root, c.table, n_points=npts, n_models=npts)
+    for lid, codes in c.codes_by_leaf.items():
+        e.set_tip_codes(lid, codes)
+    e.set_pattern_weights(c.weights)
+    e.set_rates(r, p)
+    holders = [cases.to_model_desc(m) for m in models]
+    for k in range(npts):
+        e.set_model(k, holders[k])
+        e.set_branch_lengths(k, brl[k])
+        e.set_root_freqs(k, models[k].freq)
+    lnl, _, _ = e.eval()
+    assert e.stats()["path"] == 5
+    for k in range(npts):
+        cc = cases.Case()
+        cc.__dict__.update(c.__dict__)
+        cc.root_freqs = models[k].freq
+        res = cases.oracle_eval(cc, model=models[k], brlen=brl[k])
+        assert abs(lnl[k] - res.lnl) <= REL * abs(res.lnl), k
+        np.testing.assert_allclose(e.site_lnl(k), res.site_lnl, rtol=1e-11)
+        assert res.SR_exp.max() > 0          # rescaling really happened on this tree
+    clv, ex = e.clv(c.flat.root, 0, point=npts - 1)
+    np.testing.assert_array_equal(ex, res.lexp[c.flat.root])
+    np.testing.assert_allclose(clv, res.lower[c.flat.root], rtol=1e-10, atol=1e-14 * res.lower[c.flat.root].max())
+    with pytest.raises(capi.BppGpuError):
+        e.eval(7)                            # no branch derivatives on this path
     e.close()
 
 
