@@ -33,6 +33,8 @@ WORKLOADS = {
     "protein_g4_500x200k_d2": dict(S=20, C=4, taxa=500, patterns=200_000, alpha=0.7, derivs=True, seed=20260103),
     # configs[3]: 64-state codon (61 sense), 200 taxa x 100k patterns, C = 1
     "codon_200x100k": dict(S=64, C=1, taxa=200, patterns=100_000, alpha=None, derivs=False, seed=20260104),
+    # configs[4]: ChromEvol-style chromosome-number model, 200 states, 500 taxa, one character, 4096 parameter points
+    "chromosome_500x4096pts": dict(S=200, C=1, taxa=500, patterns=1, points=4096, alpha=None, derivs=False, seed=20260105),
 }
 DEFAULT = "dna_gtr_g4_1024x1M"
 
@@ -162,6 +164,159 @@ def cpu_leg(w, tree, es, rates, probs, codes, threads, target_seconds=12.0, per_
             "lnl_sample": r["lnl"]}, sub
 
 
+def flops_per_eval(tree, rows, S):
+    """pruning contraction flops: 2 S^2 per (row, internal son) + S per extra son"""
+    tot = 0
+    for n in range(tree.nn):
+        sons = tree.sons(n)
+        if len(sons) == 0:
+            continue
+        k_int = int((~tree.is_leaf[sons]).sum())
+        tot += k_int * 2 * S * S + (len(sons) - 1) * S
+    return tot * rows
+
+
+def run_points(a, w, rank, world, local, K, W, metric, config):
+    """configs[4]: many parameter points on one character.  Points are an independent batch axis: each rank takes a
+    contiguous block of them, no collective."""
+    import torch
+    import torch.distributed as dist
+    from bpp_phyl_b200 import capi, synth
+    from bpp_phyl_b200.shard import shard_range
+    device = "cuda:%d" % local
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(device))
+    S = w["S"]
+    npts_total = a.points or w["points"]
+    lo, hi = shard_range(npts_total, rank, world)
+    npts = hi - lo
+    rng = np.random.default_rng(w["seed"])
+    tree = synth.random_tree(w["taxa"], rng, mean_brlen=0.02, rooted=True)
+    t0 = time.time()
+    pts = synth.chromosome_points(S, npts, seed=w["seed"] + 1000 * rank)
+    log("[rank %d] %d parameter points (host eigendecompositions) in %.1fs" % (rank, npts, time.time() - t0))
+    mds = [synth.chromosome_model_desc(es) for es in pts]
+    P0, _, _ = capi.pt_batch(mds[0], tree.brlen, capi.WANT_P, device=local)
+    codes = synth.simulate_single_character(tree, P0, root_state=23, seed=w["seed"])
+    e = capi.Engine(S, 1, 1, tree.child_off, tree.children, tree.root, np.eye(S), n_points=npts, n_models=npts, device=local,
+                    flags=capi.FLAG_WEIGHTED_ROOT)
+    e.set_all_tip_codes(codes)
+    e.set_pattern_weights(np.ones(1, np.uint32))
+    e.set_rates(np.ones(1), np.ones(1))
+    for k in range(npts):
+        e.set_model(k, mds[k])
+        e.set_branch_lengths(k, tree.brlen)
+    nn = tree.nn
+    out = torch.zeros(npts * (1 + 2 * nn), dtype=torch.float64, device=device)
+    stream = torch.cuda.Stream(device=device)
+    torch.cuda.set_stream(stream)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    log("[rank %d] engine ready, path %d" % (rank, e.stats()["path"]))
+    for _ in range(W):
+        e.eval_device(1, out.data_ptr(), stream.cuda_stream)
+    barrier()
+    e.stats()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record(stream)
+    for _ in range(K):
+        e.eval_device(1, out.data_ptr(), stream.cuda_stream)
+    ev1.record(stream)
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    st = e.stats()
+    log("[rank %d] timed region done: %.3f ms/step, P(t) %.3f ms, pruning %.3f ms" % (rank, ms / K, st["pt_ms_sum"] / K, st["prune_ms_sum"] / max(1, st["prune_count"])))
+    lnl0 = float(out[0].item())
+    # e2e: every point's model (host eigensystem) and branch lengths go host -> device, log L of every point comes back
+    h2d = npts * (4 * S * S * 8 + 2 * S * 8 + nn * 8)
+    d2h = npts * 8
+
+    def step_e2e():
+        for k in range(npts):
+            e.set_model(k, mds[k])
+            e.set_branch_lengths(k, tree.brlen)
+        return e.eval(1)[0]
+
+    n_e2e = 0 if a.profile else max(1, min(K, 2))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(n_e2e):
+        lnl_host = step_e2e()
+    barrier()
+    e2e_ms = 1e3 * (time.perf_counter() - t0) / max(1, n_e2e)
+    tms = torch.tensor([ms, e2e_ms], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    ms, e2e_ms = float(tms[0]), float(tms[1])
+    clocks = sampler.stop() if rank == 0 else None
+    upd_step = tree.n_internal * npts_total * S          # CLV updates of the whole job per step
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.loads(open(os.path.join(ROOT, "profiles", "r1_fp64_peaks.json")).readline())
+        except (OSError, ValueError, AttributeError):
+            pass
+        dmma_peak = peaks.get("dmma_m8n8k4_tflops", 37.1)
+        n_mat = npts * (nn - 1)
+        flops = n_mat * (2.0 * S ** 3 + S * S)
+        pt_ms = st["pt_ms_sum"] / max(1, K)              # all chunks of one evaluation
+        ach = flops / (pt_ms * 1e-3) / 1e12 if pt_ms > 0 else None
+        line = {"metric": metric, "value": upd_step * K / (ms * 1e-3), "unit": "CLV updates/s", "n_gpus": world, "steps": K,
+                "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic (one chromosome count per taxon simulated down a random rooted tree; parameter points "
+                                        "drawn uniformly, numerically defective generators redrawn)",
+                "config": dict(config, points=npts_total, sharding="points/%d (replicas, no collective)" % world),
+                "logl_evals_per_s": npts_total * K / (ms * 1e-3), "lnl_point0": lnl0,
+                "e2e": {"value": upd_step / (e2e_ms * 1e-3) if e2e_ms > 0 else None, "unit": "CLV updates/s",
+                        "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms,
+                        "logl_evals_per_s": npts_total / (e2e_ms * 1e-3) if e2e_ms > 0 else None,
+                        "call": "bppgpu_set_model + bppgpu_set_branch_lengths per point, one bppgpu_eval (host buffers)"},
+                "gpu_launches": int(st["kernel_launches"]) * K, "launches_per_step": int(st["kernel_launches"]),
+                "roofline": {"bound": "tensor", "kernel": "pt_dmma_kernel", "achieved": ach, "peak": dmma_peak, "unit": "TFLOP/s",
+                             "frac": ach / dmma_peak if ach else None, "traffic": None, "kernel_ms": pt_ms,
+                             "flops_per_eval": flops,
+                             "peak_source": "FP64 mma.sync m8n8k4 measured with tools/fp64_peak.cu (profiles/r1_fp64_peaks.json); "
+                                            "MEASURED_PEAKS.json has no FP64 figure",
+                             "pruning_ms": st["prune_ms_sum"] / max(1, st["prune_count"])},
+                "clocks": clocks, "hbm_resident_bytes": int(st["hbm_bytes_resident"])}
+        if world == 1 and not a.no_cpu:
+            # the reference's CPU algorithm on a few points, one point per host thread
+            from concurrent.futures import ThreadPoolExecutor
+            from oracle import ref_cpu
+            ref_cpu.build()
+            threads = min(os.cpu_count() or 1, npts, 16)
+
+            def one(k):
+                es = pts[k]
+                return ref_cpu.eval_raw(S, 1, 1, tree.child_off, tree.children, tree.root, codes, np.eye(S), np.ones(1, np.uint32),
+                                        np.ones(1), np.ones(1), es["V"], es["Vinv"], es["ev"], 1.0, tree.brlen, es["pi"], scaled=True,
+                                        want=1, nthreads=1, reps=1, ev_im=es["ev_im"], chr_clamp=True, weighted_root=True)
+            t0 = time.perf_counter()
+            with ThreadPoolExecutor(threads) as ex:
+                res = list(ex.map(one, range(threads)))
+            dt = time.perf_counter() - t0
+            rel = max(abs(res[k]["lnl"] - lnl_host[k]) / abs(res[k]["lnl"]) for k in range(threads))
+            line["cpu_baseline"] = {"value": tree.n_internal * threads * S / dt, "unit": "CLV updates/s", "cores": threads, "kind": "port",
+                                    "sample": "%d of %d points, full tree, one point per thread, %.1f s" % (threads, npts_total, dt),
+                                    "logl_evals_per_s": threads / dt, "rel_diff_vs_gpu": rel}
+        print(json.dumps(line), flush=True)
+        log("[rank 0] JSON line printed")
+    e.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -170,6 +325,7 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--workload", default=DEFAULT, choices=sorted(WORKLOADS))
     ap.add_argument("--patterns", type=int, default=0, help="override the workload's pattern count (debug)")
+    ap.add_argument("--points", type=int, default=0, help="override the number of parameter points (chromosome workload)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--profile", action="store_true", help="1 warm-up + 1 timed step, no e2e / CPU legs (for ncu only)")
     a = ap.parse_args()
@@ -189,6 +345,12 @@ def main():
               "l2": "inputs larger than L2 (tip codes %.0f MB per rank; CLVs never re-read from a previous step)" %
                     (w["taxa"] * w["patterns"] / world / 1e6)}
 
+    if "points" in w and a.impl == "native":
+        import __graft_entry__ as g
+        from bpp_phyl_b200 import capi
+        if not capi.LIB_PATH.exists():
+            g.build_lib()
+        return run_points(a, w, rank, world, local, K, W, metric, config)
     if a.impl == "reference":
         if rank != 0:
             return 0

@@ -86,6 +86,8 @@ class Stats(C.Structure):
         ("prune_ms", C.c_double),
         ("prune_ms_sum", C.c_double),
         ("prune_count", C.c_int64),
+        ("pt_ms_sum", C.c_double),
+        ("pt_count", C.c_int64),
         ("hbm_bytes_resident", C.c_int64),
         ("stack_slots", C.c_int32),
         ("path", C.c_int32),

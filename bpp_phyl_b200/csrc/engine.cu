@@ -190,8 +190,43 @@ static void free_model(DevModel& m) {
 }
 
 static int upload_model(DevModel& dm, const bppgpu_model_desc* m, int S) {
-  free_model(dm);
   const size_t SS = (size_t)S * S;
+  // fast path (an optimiser re-sending a model of the same kind every step): same arrays present, real spectrum both
+  // times -> overwrite in place, no allocation
+  {
+    const bool eigen_new = (m->flags & BPPGPU_MODEL_NONSINGULAR) != 0;
+    bool cplx_new = false;
+    if (eigen_new && m->eigen_im)
+      for (int k = 0; k < S; ++k) cplx_new |= m->eigen_im[k] != 0.0;
+    const int Sp0 = (S + 7) & ~7;
+    if (dm.set && dm.S == S && eigen_new && dm.V && !cplx_new && !dm.has_complex && (Sp0 == S || S < 32) &&
+        ((m->generator != nullptr) == (dm.Q != nullptr)) && m->right_eigen && m->left_eigen && m->eigen_re) {
+      dm.flags = m->flags;
+      dm.rate = m->rate;
+      dm.eps = m->taylor_epsilon > 0 ? m->taylor_epsilon : 1e-4;
+      BPP_CUDA(cudaMemcpy(dm.V, m->right_eigen, SS * 8, cudaMemcpyHostToDevice));
+      BPP_CUDA(cudaMemcpy(dm.Vinv, m->left_eigen, SS * 8, cudaMemcpyHostToDevice));
+      BPP_CUDA(cudaMemcpy(dm.re, m->eigen_re, S * 8, cudaMemcpyHostToDevice));
+      if (m->generator) {
+        BPP_CUDA(cudaMemcpy(dm.Q, m->generator, SS * 8, cudaMemcpyHostToDevice));
+        if (m->flags & (BPPGPU_MODEL_CHR_DERIV | 0u) || !(m->flags & BPPGPU_MODEL_NONSINGULAR)) {
+          std::vector<double> q2(SS, 0.0);
+          double l1 = 0.0;
+          for (int i = 0; i < S; ++i)
+            for (int k = 0; k < S; ++k) {
+              const double a = m->generator[(size_t)i * S + k];
+              l1 += std::fabs(a);
+              if (a == 0.0) continue;
+              for (int j = 0; j < S; ++j) q2[(size_t)i * S + j] += a * m->generator[(size_t)k * S + j];
+            }
+          dm.q_l1 = l1;
+          BPP_CUDA(cudaMemcpy(dm.Q2, q2.data(), SS * 8, cudaMemcpyHostToDevice));
+        }
+      }
+      return BPPGPU_OK;
+    }
+  }
+  free_model(dm);
   const bool eigen = (m->flags & BPPGPU_MODEL_NONSINGULAR) != 0;
   if (eigen && (!m->right_eigen || !m->left_eigen || !m->eigen_re))
     BPP_FAIL(BPPGPU_E_INVALID, "model flagged NONSINGULAR needs right_eigen, left_eigen and eigen_re");
@@ -275,6 +310,7 @@ static int upload_model(DevModel& dm, const bppgpu_model_desc* m, int S) {
     BPP_CUDA(cudaMemcpy(dm.Q2, q2.data(), SS * 8, cudaMemcpyHostToDevice));
   }
   dm.set = true;
+  dm.S = S;
   return BPPGPU_OK;
 }
 
@@ -496,6 +532,8 @@ int bppgpu_destroy(bppgpu_engine* e) {
   for (int i = 0; i < bppgpu_engine::kRing; ++i) {
     if (e->ring_a[i]) cudaEventDestroy(e->ring_a[i]);
     if (e->ring_b[i]) cudaEventDestroy(e->ring_b[i]);
+    if (e->ptring_a[i]) cudaEventDestroy(e->ptring_a[i]);
+    if (e->ptring_b[i]) cudaEventDestroy(e->ptring_b[i]);
   }
   if (e->stream) cudaStreamDestroy(e->stream);
   delete e;
@@ -555,6 +593,8 @@ static int create_impl(const bppgpu_config* cfg, bppgpu_engine* e) {
   for (int i = 0; i < bppgpu_engine::kRing; ++i) {
     BPP_CUDA(cudaEventCreate(&e->ring_a[i]));
     BPP_CUDA(cudaEventCreate(&e->ring_b[i]));
+    BPP_CUDA(cudaEventCreate(&e->ptring_a[i]));
+    BPP_CUDA(cudaEventCreate(&e->ptring_b[i]));
   }
 
   // ---- path selection ---------------------------------------------------------------
@@ -1283,10 +1323,14 @@ static int eval_impl(bppgpu_engine* e, unsigned want, cudaStream_t st, bool time
   for (int p0 = 0; p0 < e->npoints; p0 += e->pchunk) {
     const int np = std::min(e->pchunk, e->npoints - p0);
     long long launches = 0;
+    BPP_CUDA(cudaEventRecord(e->ptring_a[e->ptring_head], st));
     rc = launch_pt(st, e->d_models, any_series, any_chrd, any_real, any_complex, e->d_branch_model + (size_t)p0 * nn,
                    e->d_brlen + (size_t)p0 * nn, e->d_rates, S, C, nn, e->root, np, pt_want, e->d_P, e->d_dP, e->d_d2P,
                    e->d_scratch, e->d_status, &launches);
     if (rc) return rc;
+    BPP_CUDA(cudaEventRecord(e->ptring_b[e->ptring_head], st));
+    e->ptring_head = (e->ptring_head + 1) % bppgpu_engine::kRing;
+    e->ptring_n = std::min(e->ptring_n + 1, (int)bppgpu_engine::kRing);
     e->stats.kernel_launches += launches;
     if (e->path == PATH_WALK4) {
       if (e->codesT_dirty && e->N > 0) {
@@ -1506,6 +1550,17 @@ int bppgpu_get_stats(bppgpu_engine* e, bppgpu_stats* out) {
     }
   }
   e->ring_n = 0;
+  e->stats.pt_ms_sum = 0.0;
+  e->stats.pt_count = 0;
+  for (int k = 0; k < e->ptring_n; ++k) {
+    const int i = (e->ptring_head + bppgpu_engine::kRing - 1 - k) % bppgpu_engine::kRing;
+    float ms = 0.f;
+    if (cudaEventSynchronize(e->ptring_b[i]) == cudaSuccess && cudaEventElapsedTime(&ms, e->ptring_a[i], e->ptring_b[i]) == cudaSuccess) {
+      e->stats.pt_ms_sum += ms;
+      e->stats.pt_count++;
+    }
+  }
+  e->ptring_n = 0;
   cudaGetLastError();
   *out = e->stats;
   return BPPGPU_OK;

@@ -27,6 +27,7 @@ struct DevModel {
   unsigned flags = 0;
   int has_complex = 0;
   bool set = false;
+  int S = 0;
   double q_l1 = 0.0;  // sum |Q_ij| (ChromosomeSubstitutionModel::getFirstNorm)
 };
 
@@ -132,5 +133,8 @@ struct bppgpu_engine {
   cudaEvent_t ring_a[kRing] = {}, ring_b[kRing] = {};
   int ring_n = 0;  // pairs recorded since the last collection (capped at kRing)
   int ring_head = 0;
+  // same for the K1 P(t) launches (one pair per chunk of points)
+  cudaEvent_t ptring_a[kRing] = {}, ptring_b[kRing] = {};
+  int ptring_n = 0, ptring_head = 0;
   size_t bytes_resident = 0;
 };

@@ -156,30 +156,101 @@ def chromosome_generator(n_states, gain, loss, dupl, demi):
     return Q
 
 
+def real_block_form(w, U):
+    """Complex eigenpairs -> the real form bpp-core's EigenValue<double> presents: eigenvalues (re, im), real V with
+    A V = V D, D block diagonal [[re, im], [-im, re]] per conjugate pair, the +im member first."""
+    n = len(w)
+    re, im, V = np.zeros(n), np.zeros(n), np.zeros((n, n))
+    used = np.zeros(n, bool)
+    k = 0
+    for i in np.argsort(-w.real, kind="stable"):
+        if used[i]:
+            continue
+        if abs(w[i].imag) <= 1e-13 * max(1.0, abs(w[i])):
+            re[k], V[:, k] = w[i].real, U[:, i].real
+            used[i] = True
+            k += 1
+        else:
+            cand = [j for j in range(n) if not used[j] and j != i]
+            j = min(cand, key=lambda jj: abs(w[jj] - np.conj(w[i])))
+            ip = i if w[i].imag > 0 else j
+            re[k] = re[k + 1] = w[ip].real
+            im[k], im[k + 1] = w[ip].imag, -w[ip].imag
+            V[:, k], V[:, k + 1] = U[:, ip].real, U[:, ip].imag
+            used[i] = used[j] = True
+            k += 2
+    return re, im, V
+
+
 def chromosome_eigensystem(args):
     """Host eigendecomposition of one parameter point (what ChromosomeSubstitutionModel::updateEigenMatrices does per
-    likelihood object); returns None when the spectrum is not real / the basis unusable (those points take other kernels)."""
+    likelihood object: Model/ChromosomeSubstitutionModel.cpp:589-802).  Returns None when the eigen form does not
+    reproduce the generator (numerically defective Q: the reference then uses its Taylor series; such points are not part
+    of the throughput workload)."""
     n, gain, loss, dupl, demi = args
     Q = chromosome_generator(n, gain, loss, dupl, demi)
-    w, V = np.linalg.eig(Q)
-    if np.abs(w.imag).max() > 1e-12:
-        return None
-    w, V = w.real, V.real
+    w, U = np.linalg.eig(Q)
+    re, im, V = real_block_form(w, U)
     try:
         Vinv = np.linalg.inv(V)
     except np.linalg.LinAlgError:
         return None
-    if np.abs(V @ np.diag(w) @ Vinv - Q).max() > 1e-9 * np.abs(Q).max():
+    D = np.diag(re)
+    for k in range(n - 1):
+        if im[k] > 0:
+            D[k, k + 1], D[k + 1, k] = im[k], -im[k]
+    if not np.all(np.isfinite(Vinv)) or np.abs(V @ D @ Vinv - Q).max() > 1e-9 * np.abs(Q).max():
         return None
-    w[np.argmin(np.abs(w))] = 0.0
-    return {"Q": Q, "V": V, "Vinv": Vinv, "ev": w, "pi": np.full(n, 1.0 / n)}
+    z = np.argmin(np.abs(re) + np.abs(im))
+    re[z] = 0.0
+    return {"Q": Q, "V": V, "Vinv": Vinv, "ev": re, "ev_im": im, "pi": np.full(n, 1.0 / n), "params": (gain, loss, dupl, demi)}
 
 
 def chromosome_model_desc(es):
     from . import capi
     S = len(es["ev"])
     return capi.model_desc(S, capi.MODEL_DIAGONALIZABLE | capi.MODEL_NONSINGULAR | capi.MODEL_CLAMP01 | capi.MODEL_CHR_DERIV |
-                           capi.MODEL_CHR_TAYLOR, rate=1.0, V=es["V"], Vinv=es["Vinv"], ev_re=es["ev"], Q=es["Q"])
+                           capi.MODEL_CHR_TAYLOR if not np.any(es["ev_im"]) else
+                           capi.MODEL_NONSINGULAR | capi.MODEL_CLAMP01 | capi.MODEL_CHR_DERIV | capi.MODEL_CHR_TAYLOR,
+                           rate=1.0, V=es["V"], Vinv=es["Vinv"], ev_re=es["ev"], ev_im=es["ev_im"], Q=es["Q"])
+
+
+def _single_thread_blas():
+    try:
+        import threadpoolctl
+        threadpoolctl.threadpool_limits(1)
+    except Exception:
+        pass
+
+
+def chromosome_points(n_states, n_points, seed, workers=None):
+    """`n_points` usable parameter points (gain, loss ~ U(0,2); dupl, demi ~ U(0,1)), eigensystems computed in parallel."""
+    import concurrent.futures as cf
+    import os
+    rng = np.random.default_rng(seed)
+    out = []
+    with cf.ProcessPoolExecutor(max_workers=workers or (os.cpu_count() or 1), initializer=_single_thread_blas) as ex:
+        while len(out) < n_points:
+            need = n_points - len(out)
+            args = [(n_states, rng.uniform(0, 2), rng.uniform(0, 2), rng.uniform(0, 1), rng.uniform(0, 1)) for _ in range(int(need * 1.3) + 8)]
+            for es in ex.map(chromosome_eigensystem, args, chunksize=8):
+                if es is not None and len(out) < n_points:
+                    out.append(es)
+    return out
+
+
+def simulate_single_character(tree: Tree, P, root_state, seed):
+    """One character down the tree: P[node] is the S x S transition matrix of the branch above node."""
+    rng = np.random.default_rng(seed)
+    st = {tree.root: root_state}
+    codes = np.zeros((tree.n_leaves, 1), np.uint8)
+    slot = {int(n): k for k, n in enumerate(tree.leaf_nodes)}
+    for node in range(tree.nn - 2, -1, -1):
+        row = np.clip(P[node][st[int(tree.parent[node])]], 0, None)
+        st[node] = int(rng.choice(len(row), p=row / row.sum()))
+        if tree.is_leaf[node]:
+            codes[slot[node], 0] = st[node]
+    return codes
 
 
 def model_desc(es):

@@ -194,6 +194,8 @@ typedef struct bppgpu_stats {
   double prune_ms;         /* ... of its pruning kernel(s) (point 0)              */
   double prune_ms_sum;     /* pruning-kernel device time summed over the evals    */
   int64_t prune_count;     /* ... since the previous bppgpu_get_stats (max 64)    */
+  double pt_ms_sum;        /* device time of the K1 P(t) launches, same window    */
+  int64_t pt_count;        /* number of K1 launch groups timed (one per chunk)    */
   int64_t hbm_bytes_resident;
   int32_t stack_slots;
   int32_t path;            /* which kernel family ran             */

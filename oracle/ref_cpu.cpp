@@ -43,9 +43,29 @@ struct Problem {
   const void* codes;  // [nl][N], leaf slots in increasing node id
   const double* code_table;
   const unsigned* weights;
-  const double *rates, *probs, *V, *Vinv, *ev, *brlen, *rootfreq;
+  const double *rates, *probs, *V, *Vinv, *ev, *ev_im, *brlen, *rootfreq;
   double model_rate;
+  int chr_clamp, weighted_root;
 };
+
+// MatrixTools::mult(A, dia, up, lo, B, O): O = A . T . B with T tridiagonal (bpp-core); the complex-pair block form of
+// AbstractSubstitutionModel::getPij_t (Model/AbstractSubstitutionModel.cpp:438-468)
+void mult_tridiag(const double* A, const Vdouble& dia, const Vdouble& up, const Vdouble& lo, const double* B, int S, VVdouble& O) {
+  VVdouble AT(S, Vdouble(S));
+  for (int i = 0; i < S; i++)
+    for (int k = 0; k < S; k++) {
+      double s = A[i * S + k] * dia[k];
+      if (k > 0) s += A[i * S + k - 1] * up[k - 1];
+      if (k < S - 1) s += A[i * S + k + 1] * lo[k];
+      AT[i][k] = s;
+    }
+  for (int i = 0; i < S; i++)
+    for (int j = 0; j < S; j++) {
+      double s = 0;
+      for (int k = 0; k < S; k++) s += AT[i][k] * B[k * S + j];
+      O[i][j] = s;
+    }
+}
 
 // MatrixTools::mult(A, D, B, O): O = A . diag(D) . B  (bpp-core), then copied out as a RowMatrix
 void mult_diag(const double* A, const Vdouble& D, const double* B, int S, VVdouble& O) {
@@ -110,10 +130,32 @@ struct Shard {
         if (t == 0) {
           for (int x = 0; x < S; x++)
             for (int y = 0; y < S; y++) Q[x][y] = x == y ? 1. : 0.;
+        } else if (P.ev_im) {
+          Vdouble dia(S), up(S - 1 > 0 ? S - 1 : 1, 0.), lo(S - 1 > 0 ? S - 1 : 1, 0.);
+          const double lt = P.model_rate * t;
+          for (int k = 0; k < S; k++) {
+            const double ex = std::exp(P.ev[k] * lt);
+            if (P.ev_im[k] != 0. && k + 1 < S) {
+              const double c = std::cos(P.ev_im[k] * lt), sn = std::sin(P.ev_im[k] * lt);
+              dia[k] = dia[k + 1] = ex * c;
+              up[k] = ex * sn;
+              lo[k] = -ex * sn;
+              k++;
+            } else {
+              dia[k] = ex;
+            }
+          }
+          mult_tridiag(P.V, dia, up, lo, P.Vinv, S, Q);
         } else {
           for (int k = 0; k < S; k++) D[k] = std::exp(P.ev[k] * (P.model_rate * t));
           mult_diag(P.V, D, P.Vinv, S, Q);
         }
+        if (P.chr_clamp)  // ChromosomeSubstitutionModel.cpp:903-916
+          for (int x = 0; x < S; x++)
+            for (int y = 0; y < S; y++) {
+              if (Q[x][y] < 0) Q[x][y] = 1e-20;
+              else if (Q[x][y] > 1) Q[x][y] = 1;
+            }
         VVdouble Qc = Q;  // "RowMatrix<double> Q = model_->getPij_t(...)" copies
         for (int x = 0; x < S; x++)
           for (int y = 0; y < S; y++) pxy[v][c][x][y] = Qc[x][y];
@@ -197,13 +239,29 @@ struct Shard {
   void root_likelihood() {
     const Problem& P = *p;
     const VVVdouble& r = lik[P.root];
+    Vdouble wfreq;
+    const double* rootfreq = P.rootfreq;
+    if (P.weighted_root) {  // setWeightedRootFreq (DRNonHomogeneousTreeLikelihood.cpp:927-962), one shard only
+      int em = ex[P.root][0][0];
+      for (long i = 0; i < n; i++)
+        for (int c = 0; c < P.C; c++) em = std::min(em, ex[P.root][i][c]);
+      wfreq.assign(P.S, 0.);
+      double tot = 0;
+      for (int x = 0; x < P.S; x++) {
+        for (long i = 0; i < n; i++)
+          for (int c = 0; c < P.C; c++) wfreq[x] += std::ldexp(r[i][c][x], -(ex[P.root][i][c] - em)) * P.probs[c];
+        tot += wfreq[x];
+      }
+      for (int x = 0; x < P.S; x++) wfreq[x] /= tot;
+      rootfreq = wfreq.data();
+    }
     for (long i = 0; i < n; i++) {
       int emin = ex[P.root][i][0];
       for (int c = 1; c < P.C; c++) emin = std::min(emin, ex[P.root][i][c]);
       double sr = 0;
       for (int c = 0; c < P.C; c++) {
         double s = 0;
-        for (int x = 0; x < P.S; x++) s += r[i][c][x] * P.rootfreq[x];
+        for (int x = 0; x < P.S; x++) s += r[i][c][x] * rootfreq[x];
         sr += std::ldexp(s, -(ex[P.root][i][c] - emin)) * P.probs[c];
       }
       if (sr < 0) sr = 0;
@@ -313,14 +371,16 @@ struct Shard {
 extern "C" int refcpu_eval(int S, int C, long N, int nn, int root, const int* child_off, const int* children,
                            const void* codes, int code_bytes, int ncodes, const double* code_table,
                            const unsigned* weights, const double* rates, const double* probs, const double* V,
-                           const double* Vinv, const double* ev, double model_rate, const double* brlen,
+                           const double* Vinv, const double* ev, const double* ev_im /*NULL = real*/, int chr_clamp,
+                           int weighted_root, double model_rate, const double* brlen,
                            const double* rootfreq, int scaled, int want, int nthreads, int reps, double* lnl_out,
                            double* d1_out /*[nn] or NULL*/, double* d2_out /*[nn] or NULL*/,
                            double* site_lnl_out /*[N] or NULL*/, double* best_seconds) {
   Problem P;
   P.S = S; P.C = C; P.N = N; P.nn = nn; P.root = root; P.child_off = child_off; P.children = children;
   P.codes = codes; P.code_bytes = code_bytes; P.ncodes = ncodes; P.code_table = code_table; P.weights = weights;
-  P.rates = rates; P.probs = probs; P.V = V; P.Vinv = Vinv; P.ev = ev; P.model_rate = model_rate; P.brlen = brlen;
+  P.rates = rates; P.probs = probs; P.V = V; P.Vinv = Vinv; P.ev = ev; P.ev_im = ev_im; P.chr_clamp = chr_clamp;
+  P.weighted_root = weighted_root; P.model_rate = model_rate; P.brlen = brlen;
   P.rootfreq = rootfreq; P.scaled = scaled; P.want = want;
   if (nthreads < 1) nthreads = 1;
   if (nthreads > N && N > 0) nthreads = (int)N;

@@ -39,7 +39,8 @@ def _p(a, t=C.c_double):
 
 
 def eval_raw(S, Ccat, N, child_off, children, root, codes, code_table, weights, rates, probs, V, Vinv, ev,
-             model_rate, brlen, rootfreq, scaled=True, want=1, nthreads=1, reps=1, site=False):
+             model_rate, brlen, rootfreq, scaled=True, want=1, nthreads=1, reps=1, site=False, ev_im=None, chr_clamp=False,
+             weighted_root=False):
     """codes: [n_leaves][N] rows in increasing leaf node id."""
     f64 = lambda a: np.ascontiguousarray(a, np.float64)
     child_off = np.ascontiguousarray(child_off, np.int32)
@@ -49,6 +50,10 @@ def eval_raw(S, Ccat, N, child_off, children, root, codes, code_table, weights, 
     code_table, rates, probs, V, Vinv, ev, brlen, rootfreq = map(f64, (code_table, rates, probs, V, Vinv, ev, brlen, rootfreq))
     weights = np.ascontiguousarray(weights, np.uint32)
     nn = len(child_off) - 1
+    if ev_im is not None:
+        ev_im = f64(ev_im)
+        if not np.any(ev_im):
+            ev_im = None
     lnl = C.c_double(0)
     sec = C.c_double(0)
     d1 = np.zeros(nn) if want & 6 else None
@@ -57,7 +62,8 @@ def eval_raw(S, Ccat, N, child_off, children, root, codes, code_table, weights, 
     rc = lib().refcpu_eval(C.c_int(S), C.c_int(Ccat), C.c_long(N), C.c_int(nn), C.c_int(root), _p(child_off, C.c_int),
                            _p(children, C.c_int), codes.ctypes.data_as(C.c_void_p), C.c_int(codes.dtype.itemsize),
                            C.c_int(code_table.shape[0]), _p(code_table), _p(weights, C.c_uint), _p(rates), _p(probs),
-                           _p(V), _p(Vinv), _p(ev), C.c_double(model_rate), _p(brlen), _p(rootfreq),
+                           _p(V), _p(Vinv), _p(ev), _p(ev_im), C.c_int(int(chr_clamp)), C.c_int(int(weighted_root)),
+                           C.c_double(model_rate), _p(brlen), _p(rootfreq),
                            C.c_int(int(scaled)), C.c_int(want), C.c_int(nthreads), C.c_int(reps), C.byref(lnl),
                            _p(d1), _p(d2), _p(sl), C.byref(sec))
     assert rc == 0
@@ -67,7 +73,9 @@ def eval_raw(S, Ccat, N, child_off, children, root, codes, code_table, weights, 
 def eval_case(case, **kw):
     """``case`` as built by tests/cases.py (diagonalisable models only)."""
     flat, m = case.flat, case.model
-    assert m.nonsingular and m.diagonalizable
+    assert m.nonsingular
+    kw.setdefault("ev_im", m.ev_im)
+    kw.setdefault("chr_clamp", m.chromosome)
     off, ch = flat.csr()
     leaf_ids = [i for i in range(flat.n_nodes) if flat.is_leaf[i]]
     codes = np.stack([case.codes_by_leaf[l] for l in leaf_ids]) if case.N else np.zeros((len(leaf_ids), 0), np.uint8)

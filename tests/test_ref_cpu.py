@@ -35,3 +35,14 @@ def test_cpp_port_protein_and_underflow():
     big = cases.make_case(700, 3, rm.gtr(), r, p, seed=4, random_tips=True, mean_brlen=0.5)
     assert ref_cpu.eval_case(big, scaled=False)["lnl"] == -np.inf
     assert abs(ref_cpu.eval_case(big, scaled=True)["lnl"] - cases.oracle_eval(big).lnl) < 1e-9 * 1e4
+
+
+def test_cpp_port_chromosome_block_form_and_weighted_root():
+    """conjugate eigen-pairs (block form), the Chromosome clamp and the fork's weighted root frequencies"""
+    r, p = rm.constant_rate()
+    m = rm.chromosome(1, 50, gain=1.02, loss=1.90, dupl=0.14, demi=0.95)
+    assert m.nonsingular and not m.diagonalizable
+    c = cases.make_case(15, 1, m, r, p, seed=12, rooted=True, mean_brlen=0.2, compress=False)
+    res = cases.oracle_eval(c, weighted_root=True)
+    out = ref_cpu.eval_case(c, weighted_root=True)
+    assert abs(out["lnl"] - res.lnl) < 1e-10 * abs(res.lnl)
