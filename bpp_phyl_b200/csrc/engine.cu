@@ -171,9 +171,10 @@ static int check_device(int device) {
   if (prop.major < 10) BPP_FAIL(BPPGPU_E_CUDA, "device %d is sm_%d%d; libbppgpu is built for sm_100a only", device, prop.major, prop.minor);
   g_sm_count = prop.multiProcessorCount;
   // dynamic shared memory above 48 KB is opt-in
-  BPP_CUDA(cudaFuncSetAttribute(pt_dmma_kernel<8, 1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
-  BPP_CUDA(cudaFuncSetAttribute(pt_dmma_kernel<8, 2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
-  BPP_CUDA(cudaFuncSetAttribute(pt_dmma_kernel<8, 4, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
+  BPP_CUDA(cudaFuncSetAttribute(pt_dmma_kernel<8, 1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
+  BPP_CUDA(cudaFuncSetAttribute(pt_dmma_kernel<8, 2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
+  BPP_CUDA(cudaFuncSetAttribute(pt_dmma_kernel<8, 4, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
+  BPP_CUDA(cudaFuncSetAttribute(pt_dmma_stacked_kernel<8, 4, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
   BPP_CUDA(cudaFuncSetAttribute(dmma_node_kernel<5, 3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   BPP_CUDA(cudaFuncSetAttribute(dmma_node_kernel<16, 8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   BPP_CUDA(cudaFuncSetAttribute(dmma_upper_deriv_kernel<5, 3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -324,7 +325,7 @@ static ModelDev to_dev(const DevModel& m) {
 
 // enqueue K1 for `npts` points starting at `p0` (tables indexed from 0 within the chunk)
 static int launch_pt(cudaStream_t st, const ModelDev* d_models, bool any_series, bool any_chr_deriv, bool any_real_eigen,
-                     bool any_complex,
+                     bool any_complex, bool stacked_ok,
                      const int* d_branch_model, const double* d_brlen, const double* d_rates, int S, int C,
                      int nn, int root, int npts, unsigned want, double* P, double* dP, double* d2P,
                      double* scratch, int* d_status, long long* launches) {
@@ -346,7 +347,13 @@ static int launch_pt(cudaStream_t st, const ModelDev* d_models, bool any_series,
     // FP64 tensor-core GEMM for every eigen-path matrix (real spectra and conjugate-pair block form)
     pp.dmma_real = 1;
     const int nblk = Sp / 8;
-    if (nblk <= 8) {
+    if (stacked_ok && nblk > 16 && nblk * 1 >= 6 && !any_series) {
+      // one model per point: stack the row blocks of the point's matrices (perfect balance, see pt_dmma_kernels.cuh)
+      constexpr int RB = 32;
+      const long long total_rb = (long long)nn * C * nblk;
+      const dim3 grid((unsigned)((total_rb + RB - 1) / RB), (unsigned)((nblk + 4) / 5), (unsigned)npts);
+      pt_dmma_stacked_kernel<8, 4, 5><<<grid, 256, pt_dmma_stacked_smem_bytes(Sp, 5), st>>>(pp, Sp);
+    } else if (nblk <= 8) {
       pt_dmma_kernel<8, 1, 8><<<dim3(nmat, 1), 256, pt_dmma_smem_bytes(Sp, 8), st>>>(pp, Sp);
     } else if (nblk <= 16) {
       pt_dmma_kernel<8, 2, 8><<<dim3(nmat, (nblk + 7) / 8), 256, pt_dmma_smem_bytes(Sp, 8), st>>>(pp, Sp);
@@ -498,7 +505,7 @@ int bppgpu_pt_batch(int device, const bppgpu_model_desc* model, int64_t n_t, con
   if (series) PT_CUDA(cudaMalloc(&scr, n_t * 4 * SS * 8));
   else if (chrd) PT_CUDA(cudaMalloc(&scr, n_t * SS * 8));
   long long launches = 0;
-  rc = launch_pt(nullptr, d_md, series, chrd, !series && !dm.has_complex, !series && dm.has_complex, d_bm, d_t, d_r, S, 1,
+  rc = launch_pt(nullptr, d_md, series, chrd, !series && !dm.has_complex, !series && dm.has_complex, false, d_bm, d_t, d_r, S, 1,
                  (int)n_t, -1, 1, want, dPm, ddP, dd2P, scr, d_status, &launches);
   if (rc) { cleanup(); return rc; }
   PT_CUDA(cudaDeviceSynchronize());
@@ -915,7 +922,8 @@ int bppgpu_set_branch_lengths(bppgpu_engine* e, int32_t point, const double* t) 
   ENGINE_ENTER(e);
   if (point < 0 || point >= e->npoints || !t) BPP_FAIL(BPPGPU_E_INVALID, "bad point or null array");
   std::copy(t, t + e->nn, e->h_brlen.begin() + (size_t)point * e->nn);
-  BPP_CUDA(cudaMemcpyAsync(e->d_brlen + (size_t)point * e->nn, t, e->nn * 8, cudaMemcpyHostToDevice, e->stream));
+  e->h_brlen[(size_t)point * e->nn + e->root] = 0.0;  // the root has no branch: its table slot is the identity
+  BPP_CUDA(cudaMemcpyAsync(e->d_brlen + (size_t)point * e->nn, &e->h_brlen[(size_t)point * e->nn], e->nn * 8, cudaMemcpyHostToDevice, e->stream));
   BPP_CUDA(cudaStreamSynchronize(e->stream));
   e->have_brlen[point] = 1;
   e->last_point = -1;
@@ -944,9 +952,15 @@ static int check_ready(bppgpu_engine* e) {
       BPP_FAIL(BPPGPU_E_STATE, "root frequencies of point %d not set", p);
   }
   std::vector<char> used(e->nmodels, 0);
-  for (int p = 0; p < e->npoints; ++p)
+  e->homogeneous_points = true;
+  for (int p = 0; p < e->npoints; ++p) {
+    const int first = e->h_branch_model[(size_t)p * e->nn + (e->root == 0 ? 1 : 0)];
     for (int n = 0; n < e->nn; ++n)
-      if (n != e->root) used[e->h_branch_model[(size_t)p * e->nn + n]] = 1;
+      if (n != e->root) {
+        used[e->h_branch_model[(size_t)p * e->nn + n]] = 1;
+        if (e->h_branch_model[(size_t)p * e->nn + n] != first) e->homogeneous_points = false;
+      }
+  }
   for (int m = 0; m < e->nmodels; ++m)
     if (used[m] && !e->models[m].set) BPP_FAIL(BPPGPU_E_STATE, "model slot %d is used by a branch but not set", m);
   return BPPGPU_OK;
@@ -1324,7 +1338,7 @@ static int eval_impl(bppgpu_engine* e, unsigned want, cudaStream_t st, bool time
     const int np = std::min(e->pchunk, e->npoints - p0);
     long long launches = 0;
     BPP_CUDA(cudaEventRecord(e->ptring_a[e->ptring_head], st));
-    rc = launch_pt(st, e->d_models, any_series, any_chrd, any_real, any_complex, e->d_branch_model + (size_t)p0 * nn,
+    rc = launch_pt(st, e->d_models, any_series, any_chrd, any_real, any_complex, e->homogeneous_points, e->d_branch_model + (size_t)p0 * nn,
                    e->d_brlen + (size_t)p0 * nn, e->d_rates, S, C, nn, e->root, np, pt_want, e->d_P, e->d_dP, e->d_d2P,
                    e->d_scratch, e->d_status, &launches);
     if (rc) return rc;

@@ -69,6 +69,7 @@ struct bppgpu_engine {
   std::vector<bppgpu::DevModel> models;
   bppgpu::ModelDev* d_models = nullptr;
   bool models_dirty = true;
+  bool homogeneous_points = true;  // every branch of a point uses the same model slot
   std::vector<double> h_rates, h_probs;
   std::vector<double> h_brlen;  // [npoints][nn]
   std::vector<int> h_branch_model;

@@ -243,16 +243,22 @@ def test_pt_batch_interface(name):
         np.testing.assert_allclose(d2P[k], rm.d2pij_dt2(m, t), rtol=1e-10, atol=(2e-15 * kap + 1e-12) * q * q * 10, err_msg="d2P t=%g" % t)
 
 
-def test_chromosome_weighted_root_batched_points():
-    """ChromEvol shape: one character, C = 1, weighted root frequencies, many parameter points."""
+@pytest.mark.parametrize("S,npts,ntaxa", [(30, 5, 25), (144, 3, 12)])
+def test_chromosome_weighted_root_batched_points(S, npts, ntaxa):
+    """ChromEvol shape: one character, C = 1, weighted root frequencies, many parameter points.  S = 144 takes the
+    stacked tensor-core P(t) kernel (row blocks of a point's matrices stacked along M), conjugate eigen-pairs included."""
     capi = _capi()
     rng = np.random.default_rng(7)
     r, p = rm.constant_rate()
-    pts = [rm.chromosome(1, 30, gain=rng.uniform(0.2, 2), loss=rng.uniform(0.2, 2), dupl=rng.uniform(0.05, 1),
-                         demi=rm.DEMI_EQUAL_DUPL) for _ in range(5)]
-    c = cases.make_case(25, 1, pts[0], r, p, seed=51, rooted=True, mean_brlen=0.2, compress=False)
+    pts = []
+    while len(pts) < npts:
+        m = rm.chromosome(1, S, gain=rng.uniform(0.2, 2), loss=rng.uniform(0.2, 2), dupl=rng.uniform(0.05, 1),
+                          demi=rm.DEMI_EQUAL_DUPL if S == 30 else rng.uniform(0.05, 1))
+        if m.nonsingular and np.linalg.cond(m.V) < 1e6:
+            pts.append(m)
+    c = cases.make_case(ntaxa, 1, pts[0], r, p, seed=51, rooted=True, mean_brlen=0.2 if S == 30 else 0.05, compress=False)
     off, ch = c.flat.csr()
-    e = capi.Engine(30, 1, 1, off, ch, c.flat.root, c.table, n_points=len(pts), n_models=len(pts),
+    e = capi.Engine(S, 1, 1, off, ch, c.flat.root, c.table, n_points=len(pts), n_models=len(pts),
                     flags=capi.FLAG_WEIGHTED_ROOT)
     for lid, codes in c.codes_by_leaf.items():
         e.set_tip_codes(lid, codes)

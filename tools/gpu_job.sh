@@ -1,2 +1,1 @@
-python bench.py --workload chromosome_500x4096pts --points 256 --steps 3 --warmup 3 > gpurun_out/b_chr256.json 2> gpurun_out/b_chr256.err
-python bench.py --workload chromosome_500x4096pts --steps 3 --warmup 3 > gpurun_out/b_chr.json 2> gpurun_out/b_chr.err
+python -m pytest tests -m gpu -q 2>&1 | tail -12 > gpurun_out/t15.log
