@@ -94,6 +94,31 @@ __device__ __forceinline__ void dmma_rows_times_matrix(double (&acc)[RW][NBLK][2
   }
 }
 
+// two doubles of a row at an even column: one 16-byte access when the row is 16-byte aligned there (S even)
+__device__ __forceinline__ void ld2(const double* row, int x, int S, bool vec, double& v0, double& v1) {
+  if (vec && x + 1 < S) {
+    const double2 t = *reinterpret_cast<const double2*>(row + x);
+    v0 = t.x; v1 = t.y;
+  } else {
+    v0 = x < S ? row[x] : 0.0;
+    v1 = x + 1 < S ? row[x + 1] : 0.0;
+  }
+}
+__device__ __forceinline__ void st2(double* row, int x, int S, bool vec, double v0, double v1) {
+  if (vec && x + 1 < S) {
+    *reinterpret_cast<double2*>(row + x) = make_double2(v0, v1);
+  } else {
+    if (x < S) row[x] = v0;
+    if (x + 1 < S) row[x + 1] = v1;
+  }
+}
+
+constexpr int kNodePrefetch = 2;  // sons whose inputs are fetched one tile ahead (a third son, the root's, is fetched in place)
+
+// Persistent CTA = (pattern tiles, class).  The inputs of tile t+1 (A fragments of the internal sons, tip codes,
+// exponents) are requested before tile t is computed, and those of the first tile before the P matrices are staged, so
+// HBM latency overlaps the tensor-core work instead of preceding it (ncu r1a: long-scoreboard on the first DMMA of every
+// tile and on the staging stores dominated this kernel).
 template <int KB, int NBLK, int RW>
 __global__ void __launch_bounds__(kDmmaNodeWarps * 32) dmma_node_kernel(DmmaNodeParams p) {
   constexpr int NT = kDmmaNodeWarps * 32;
@@ -101,6 +126,43 @@ __global__ void __launch_bounds__(kDmmaNodeWarps * 32) dmma_node_kernel(DmmaNode
   extern __shared__ __align__(16) double sm_node[];
   const int S = p.S, C = p.C;
   const int c = blockIdx.y;
+  const bool vec = (S & 1) == 0;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, q = lane & 3;
+  const long long tile_rows = (long long)kDmmaNodeWarps * RW * 8;
+
+  struct In {
+    double a[kNodePrefetch][RW][KB];
+    int e[kNodePrefetch][RW];
+    int code[kNodePrefetch][RW];
+  };
+  auto pattern_of = [&](long long tile, int r) {
+    const long long pp = (tile * kDmmaNodeWarps + warp) * RW * 8 + r * 8 + g;
+    return pp < p.N ? pp : p.N - 1;
+  };
+  auto fetch = [&](long long tile, In& in) {
+#pragma unroll
+    for (int j = 0; j < kNodePrefetch; ++j) {
+      if (j < p.nchild) {
+        const Child ch = p.childs[j];
+#pragma unroll
+        for (int r = 0; r < RW; ++r) {
+          const long long pat = pattern_of(tile, r);
+          if (ch.kind == CHILD_TIP) {
+            in.code[j][r] = load_code(p.codes, p.code_bytes, (long long)ch.idx * p.N + pat);
+          } else {
+            load_a_row<KB>(p.keep + (((size_t)ch.idx * p.N + pat) * C + c) * S, S, q, in.a[j][r]);
+            in.e[j][r] = p.keep_exp[((size_t)ch.idx * p.N + pat) * C + c];
+          }
+        }
+      }
+    }
+  };
+
+  In nxt;
+  long long tile = blockIdx.x;
+  const bool any = tile * tile_rows < p.N;
+  if (any) fetch(tile, nxt);
 
   int nint = 0;
   for (int j = 0; j < p.nchild; ++j) {
@@ -111,63 +173,74 @@ __global__ void __launch_bounds__(kDmmaNodeWarps * 32) dmma_node_kernel(DmmaNode
   }
   __syncthreads();
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int g = lane >> 2, q = lane & 3;
-  // persistent over pattern tiles: the staged matrices serve every tile of this CTA
-  const long long tile_rows = (long long)kDmmaNodeWarps * RW * 8;
-  for (long long tile = blockIdx.x; tile * tile_rows < p.N; tile += gridDim.x) {
-  const long long pat_base = (tile * kDmmaNodeWarps + warp) * RW * 8;
-  if (pat_base >= p.N) break;
-  long long pat[RW];
-#pragma unroll
-  for (int r = 0; r < RW; ++r) {
-    const long long pp = pat_base + r * 8 + g;
-    pat[r] = pp < p.N ? pp : p.N - 1;
-  }
+  for (; tile * tile_rows < p.N; tile += gridDim.x) {
+    const long long pat_base = (tile * kDmmaNodeWarps + warp) * RW * 8;
+    In cur = nxt;
+    if ((tile + gridDim.x) * tile_rows < p.N) fetch(tile + gridDim.x, nxt);
+    if (pat_base >= p.N) continue;  // this warp's rows are past the end (other warps of the CTA may still have rows)
 
-  double prod[RW][NBLK][2];
-  int Ea[RW];
+    double prod[RW][NBLK][2];
+    int Ea[RW];
 #pragma unroll
-  for (int r = 0; r < RW; ++r) Ea[r] = 0;
-  nint = 0;
-  for (int j = 0; j < p.nchild; ++j) {
-    const Child ch = p.childs[j];
-    double acc[RW][NBLK][2];
-    if (ch.kind == CHILD_TIP) {
+    for (int r = 0; r < RW; ++r) Ea[r] = 0;
+    nint = 0;
+    // sons 0 .. kNodePrefetch-1: inputs already in registers (compile-time indices keep them there)
 #pragma unroll
-      for (int r = 0; r < RW; ++r) {
-        const int code = load_code(p.codes, p.code_bytes, (long long)ch.idx * p.N + pat[r]);
-        const double* tt = p.tiptab + (((size_t)ch.idx * C + c) * p.ncodes + code) * S;
+    for (int j = 0; j < kNodePrefetch; ++j) {
+      if (j < p.nchild) {
+        const Child ch = p.childs[j];
+        double acc[RW][NBLK][2];
+        if (ch.kind == CHILD_TIP) {
 #pragma unroll
-        for (int nb = 0; nb < NBLK; ++nb) {
-          const int x = nb * 8 + 2 * q;
-          acc[r][nb][0] = x < S ? tt[x] : 0.0;
-          acc[r][nb][1] = x + 1 < S ? tt[x + 1] : 0.0;
+          for (int r = 0; r < RW; ++r) {
+            const double* tt = p.tiptab + (((size_t)ch.idx * C + c) * p.ncodes + cur.code[j][r]) * S;
+#pragma unroll
+            for (int nb = 0; nb < NBLK; ++nb) ld2(tt, nb * 8 + 2 * q, S, vec, acc[r][nb][0], acc[r][nb][1]);
+          }
+        } else {
+#pragma unroll
+          for (int r = 0; r < RW; ++r) {
+            Ea[r] += cur.e[j][r];
+#pragma unroll
+            for (int nb = 0; nb < NBLK; ++nb) acc[r][nb][0] = acc[r][nb][1] = 0.0;
+          }
+          dmma_rows_times_matrix<KB, NBLK, RW>(acc, cur.a[j], sm_node + (size_t)nint * NBLK * 8 * SB, g, q);
+          ++nint;
         }
+#pragma unroll
+        for (int r = 0; r < RW; ++r)
+#pragma unroll
+          for (int nb = 0; nb < NBLK; ++nb) {
+            prod[r][nb][0] = j == 0 ? acc[r][nb][0] : prod[r][nb][0] * acc[r][nb][0];
+            prod[r][nb][1] = j == 0 ? acc[r][nb][1] : prod[r][nb][1] * acc[r][nb][1];
+          }
       }
-    } else {
-      double a[RW][KB];
-#pragma unroll
-      for (int r = 0; r < RW; ++r) {
-        load_a_row<KB>(p.keep + (((size_t)ch.idx * p.N + pat[r]) * C + c) * S, S, q, a[r]);
-        Ea[r] += p.keep_exp[((size_t)ch.idx * p.N + pat[r]) * C + c];
-      }
-#pragma unroll
-      for (int r = 0; r < RW; ++r)
-#pragma unroll
-        for (int nb = 0; nb < NBLK; ++nb) acc[r][nb][0] = acc[r][nb][1] = 0.0;
-      dmma_rows_times_matrix<KB, NBLK, RW>(acc, a, sm_node + (size_t)nint * NBLK * 8 * SB, g, q);
-      ++nint;
     }
-    if (j == 0) {
+    // further sons (multifurcations, the unrooted tree's third root son): fetched in place
+    for (int j = kNodePrefetch; j < p.nchild; ++j) {
+      const Child ch = p.childs[j];
+      double acc[RW][NBLK][2];
+      if (ch.kind == CHILD_TIP) {
 #pragma unroll
-      for (int r = 0; r < RW; ++r)
+        for (int r = 0; r < RW; ++r) {
+          const int code = load_code(p.codes, p.code_bytes, (long long)ch.idx * p.N + pattern_of(tile, r));
+          const double* tt = p.tiptab + (((size_t)ch.idx * C + c) * p.ncodes + code) * S;
 #pragma unroll
-        for (int nb = 0; nb < NBLK; ++nb) {
-          prod[r][nb][0] = acc[r][nb][0];
-          prod[r][nb][1] = acc[r][nb][1];
+          for (int nb = 0; nb < NBLK; ++nb) ld2(tt, nb * 8 + 2 * q, S, vec, acc[r][nb][0], acc[r][nb][1]);
         }
-    } else {
+      } else {
+        double a[RW][KB];
+#pragma unroll
+        for (int r = 0; r < RW; ++r) {
+          const long long pat = pattern_of(tile, r);
+          load_a_row<KB>(p.keep + (((size_t)ch.idx * p.N + pat) * C + c) * S, S, q, a[r]);
+          Ea[r] += p.keep_exp[((size_t)ch.idx * p.N + pat) * C + c];
+#pragma unroll
+          for (int nb = 0; nb < NBLK; ++nb) acc[r][nb][0] = acc[r][nb][1] = 0.0;
+        }
+        dmma_rows_times_matrix<KB, NBLK, RW>(acc, a, sm_node + (size_t)nint * NBLK * 8 * SB, g, q);
+        ++nint;
+      }
 #pragma unroll
       for (int r = 0; r < RW; ++r)
 #pragma unroll
@@ -176,37 +249,33 @@ __global__ void __launch_bounds__(kDmmaNodeWarps * 32) dmma_node_kernel(DmmaNode
           prod[r][nb][1] *= acc[r][nb][1];
         }
     }
-  }
 
 #pragma unroll
-  for (int r = 0; r < RW; ++r) {
-    int m = 0;
+    for (int r = 0; r < RW; ++r) {
+      int m = 0;
 #pragma unroll
-    for (int nb = 0; nb < NBLK; ++nb) m = max(m, max(hi_word(prod[r][nb][0]), hi_word(prod[r][nb][1])));
-    m = max(m, __shfl_xor_sync(0xffffffffu, m, 1));
-    m = max(m, __shfl_xor_sync(0xffffffffu, m, 2));
-    if (m < kScaleThresholdHi && m >= (1 << 20)) {
-      const int k = rescale_shift(m);
-      const double f = pow2(k);
+      for (int nb = 0; nb < NBLK; ++nb) m = max(m, max(hi_word(prod[r][nb][0]), hi_word(prod[r][nb][1])));
+      m = max(m, __shfl_xor_sync(0xffffffffu, m, 1));
+      m = max(m, __shfl_xor_sync(0xffffffffu, m, 2));
+      if (m < kScaleThresholdHi && m >= (1 << 20)) {
+        const int k = rescale_shift(m);
+        const double f = pow2(k);
 #pragma unroll
-      for (int nb = 0; nb < NBLK; ++nb) {
-        prod[r][nb][0] *= f;
-        prod[r][nb][1] *= f;
+        for (int nb = 0; nb < NBLK; ++nb) {
+          prod[r][nb][0] *= f;
+          prod[r][nb][1] *= f;
+        }
+        Ea[r] += k;
       }
-      Ea[r] += k;
-    }
-    if (pat_base + r * 8 + g < p.N) {
-      double* row = p.keep + (((size_t)p.out_idx * p.N + pat[r]) * C + c) * S;
+      if (pat_base + r * 8 + g < p.N) {
+        const long long pat = pat_base + r * 8 + g;
+        double* row = p.keep + (((size_t)p.out_idx * p.N + pat) * C + c) * S;
 #pragma unroll
-      for (int nb = 0; nb < NBLK; ++nb) {
-        const int x = nb * 8 + 2 * q;
-        if (x < S) row[x] = prod[r][nb][0];
-        if (x + 1 < S) row[x + 1] = prod[r][nb][1];
+        for (int nb = 0; nb < NBLK; ++nb) st2(row, nb * 8 + 2 * q, S, vec, prod[r][nb][0], prod[r][nb][1]);
+        if (q == 0) p.keep_exp[((size_t)p.out_idx * p.N + pat) * C + c] = Ea[r];
       }
-      if (q == 0) p.keep_exp[((size_t)p.out_idx * p.N + pat[r]) * C + c] = Ea[r];
     }
   }
-  }  // tiles
 }
 
 }  // namespace bppgpu

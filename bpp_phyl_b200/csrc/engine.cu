@@ -177,6 +177,9 @@ static int check_device(int device) {
   BPP_CUDA(cudaFuncSetAttribute(pt_dmma_stacked_kernel<8, 4, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
   BPP_CUDA(cudaFuncSetAttribute(dmma_node_kernel<5, 3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   BPP_CUDA(cudaFuncSetAttribute(dmma_node_kernel<16, 8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  BPP_CUDA(cudaFuncSetAttribute(dmma_node_kernel<16, 8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  BPP_CUDA(cudaFuncSetAttribute(dmma_node_kernel<5, 3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  BPP_CUDA(cudaFuncSetAttribute(dmma_node_kernel<5, 3, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   BPP_CUDA(cudaFuncSetAttribute(dmma_upper_deriv_kernel<5, 3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   BPP_CUDA(cudaFuncSetAttribute(dmma_upper_deriv_kernel<16, 8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   return BPPGPU_OK;
@@ -1143,16 +1146,23 @@ static int enqueue_prune(bppgpu_engine* e, int point, int pl, cudaStream_t st) {
         int nint = 0;
         for (int j = 0; j < op.nchild; ++j)
           if (e->gprog.childs[op.child_begin + j].kind != CHILD_TIP) ++nint;
+        static const int rw_env = getenv("BPPGPU_DMMA_RW") ? atoi(getenv("BPPGPU_DMMA_RW")) : 0;   // tuning knob
+        static const int cta_env = getenv("BPPGPU_DMMA_CTAS") ? atoi(getenv("BPPGPU_DMMA_CTAS")) : 0;
+        auto launch = [&](auto kern, int RW, size_t smem, int ctas_per_sm) {
+          const long long tiles = (N + 8 * RW * kDmmaNodeWarps - 1) / (8 * RW * kDmmaNodeWarps);
+          if (cta_env > 0) ctas_per_sm = cta_env;
+          const dim3 grid((unsigned)std::min<long long>(tiles, std::max(1, g_sm_count * ctas_per_sm / C)), (unsigned)C);
+          kern<<<grid, kDmmaNodeWarps * 32, smem, st>>>(dp);
+        };
         if (S <= 20) {
-          constexpr int RW = 2;
-          const long long tiles = (N + 8 * RW * kDmmaNodeWarps - 1) / (8 * RW * kDmmaNodeWarps);
-          const dim3 grid((unsigned)std::min<long long>(tiles, std::max(1, g_sm_count * 8 / C)), (unsigned)C);
-          dmma_node_kernel<5, 3, RW><<<grid, kDmmaNodeWarps * 32, nint * dmma_node_smem_per_child<5, 3>(), st>>>(dp);
+          const size_t smem = nint * dmma_node_smem_per_child<5, 3>();
+          if (rw_env == 1) launch(dmma_node_kernel<5, 3, 1>, 1, smem, 12);
+          else if (rw_env == 4) launch(dmma_node_kernel<5, 3, 4>, 4, smem, 4);
+          else launch(dmma_node_kernel<5, 3, 2>, 2, smem, 8);
         } else {
-          constexpr int RW = 2;
-          const long long tiles = (N + 8 * RW * kDmmaNodeWarps - 1) / (8 * RW * kDmmaNodeWarps);
-          const dim3 grid((unsigned)std::min<long long>(tiles, std::max(1, g_sm_count * 4 / C)), (unsigned)C);
-          dmma_node_kernel<16, 8, RW><<<grid, kDmmaNodeWarps * 32, nint * dmma_node_smem_per_child<16, 8>(), st>>>(dp);
+          const size_t smem = nint * dmma_node_smem_per_child<16, 8>();
+          if (rw_env == 2) launch(dmma_node_kernel<16, 8, 2>, 2, smem, 2);
+          else launch(dmma_node_kernel<16, 8, 1>, 1, smem, 2);
         }
         e->stats.kernel_launches += 1;
       } else {
