@@ -31,6 +31,8 @@ WORKLOADS = {
     "dna_gtr_g4_1024x1M": dict(S=4, C=4, taxa=1024, patterns=1_000_000, alpha=0.5, derivs=False, seed=20260102),
     # configs[2]: 20 states + G4, 500 taxa x 200k patterns with d1/d2
     "protein_g4_500x200k_d2": dict(S=20, C=4, taxa=500, patterns=200_000, alpha=0.7, derivs=True, seed=20260103),
+    # configs[2] without the derivatives (value-only protein evaluation)
+    "protein_g4_500x200k": dict(S=20, C=4, taxa=500, patterns=200_000, alpha=0.7, derivs=False, seed=20260103),
     # configs[3]: 64-state codon (61 sense), 200 taxa x 100k patterns, C = 1
     "codon_200x100k": dict(S=64, C=1, taxa=200, patterns=100_000, alpha=None, derivs=False, seed=20260104),
     # configs[4]: ChromEvol-style chromosome-number model, 200 states, 500 taxa, one character, 4096 parameter points

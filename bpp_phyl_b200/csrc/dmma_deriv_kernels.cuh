@@ -176,11 +176,7 @@ __global__ void __launch_bounds__(kDmmaNodeWarps * 32) dmma_upper_deriv_kernel(D
     if (p.upper_out >= 0 && pat_base + r * 8 + g < p.N) {
       double* row = p.upper + (((size_t)p.upper_out * p.N + pat[r]) * C + c) * S;
 #pragma unroll
-      for (int nb = 0; nb < NBLK; ++nb) {
-        const int x = nb * 8 + 2 * q;
-        if (x < S) row[x] = U[r][nb][0];
-        if (x + 1 < S) row[x + 1] = U[r][nb][1];
-      }
+      for (int nb = 0; nb < NBLK; ++nb) st2(row, nb * 8 + 2 * q, S, (S & 1) == 0, U[r][nb][0], U[r][nb][1]);
       if (q == 0) p.upper_exp[((size_t)p.upper_out * p.N + pat[r]) * C + c] = Eu[r];
     }
   }

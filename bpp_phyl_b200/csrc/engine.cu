@@ -181,6 +181,7 @@ static int check_device(int device) {
   BPP_CUDA(cudaFuncSetAttribute(dmma_node_kernel<5, 3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   BPP_CUDA(cudaFuncSetAttribute(dmma_node_kernel<5, 3, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   BPP_CUDA(cudaFuncSetAttribute(dmma_upper_deriv_kernel<5, 3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  BPP_CUDA(cudaFuncSetAttribute(dmma_upper_deriv_kernel<5, 3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   BPP_CUDA(cudaFuncSetAttribute(dmma_upper_deriv_kernel<16, 8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   return BPPGPU_OK;
 }
@@ -619,11 +620,15 @@ static int create_impl(const bppgpu_config* cfg, bppgpu_engine* e) {
   const bool wroot = (cfg->flags & BPPGPU_FLAG_WEIGHTED_ROOT) != 0;  // needs the root CLV in HBM: node-kernel paths
   if (wroot) w4ok = false;
   if (w4ok) e->path = PATH_WALK4;
-  else if (S == 20 && cpow && !e->keep && !wroot) e->path = PATH_WALKS;   // value-only protein: register walk
   else e->path = PATH_GENERIC;
+  // S = 20 register walk (walkS_kernel): measured 77 ms vs 41 ms for the tensor-core node kernels on the 500-taxon x 200k
+  // config, so it is no longer a default; BPPGPU_PATH=walk selects it (value-only, no weighted root)
+  const bool walks_ok = S == 20 && cpow && !e->keep && !wroot;
+  (void)walks_ok;
   if (e->path == PATH_GENERIC && ((S > 16 && S <= 20) || (S > 56 && S <= 64))) e->path = PATH_DMMA;
   if (const char* env = getenv("BPPGPU_PATH")) {  // tuning knob
     if (!strcmp(env, "generic")) e->path = PATH_GENERIC;
+    if (!strcmp(env, "walk") && walks_ok) e->path = PATH_WALKS;
     if (!strcmp(env, "dmma") && ((S > 16 && S <= 20) || (S > 56 && S <= 64))) e->path = PATH_DMMA;
   }
   if (cfg->flags & BPPGPU_FLAG_FORCE_GENERIC) e->path = PATH_GENERIC;
@@ -1258,16 +1263,18 @@ static int enqueue_derivs(bppgpu_engine* e, int point, int pl, unsigned want, cu
       for (int k = e->sib_off[n]; k < e->sib_off[n + 1]; ++k)
         if (e->sibs_flat[k].kind != CHILD_TIP) ++nmat;
       if (!du.node_is_tip) nmat += ((want & 2u) ? 1 : 0) + ((want & 4u) ? 1 : 0) + du.nh_form;
+      static const int drw_env = getenv("BPPGPU_DERIV_RW") ? atoi(getenv("BPPGPU_DERIV_RW")) : 0;   // tuning knob
+      auto launch = [&](auto kern, int RW, size_t smem, int ctas_per_sm) {
+        const long long tiles = (N + 8 * RW * kDmmaNodeWarps - 1) / (8 * RW * kDmmaNodeWarps);
+        const dim3 grid((unsigned)std::min<long long>(tiles, std::max(1, g_sm_count * ctas_per_sm / C)), (unsigned)C);
+        kern<<<grid, kDmmaNodeWarps * 32, smem, st>>>(du);
+      };
       if (S <= 20) {
-        constexpr int RW = 2;
-        const long long tiles = (N + 8 * RW * kDmmaNodeWarps - 1) / (8 * RW * kDmmaNodeWarps);
-        const dim3 grid((unsigned)std::min<long long>(tiles, std::max(1, g_sm_count * 8 / C)), (unsigned)C);
-        dmma_upper_deriv_kernel<5, 3, RW><<<grid, kDmmaNodeWarps * 32, nmat * dmma_node_smem_per_child<5, 3>(), st>>>(du);
+        const size_t smem = nmat * dmma_node_smem_per_child<5, 3>();
+        if (drw_env == 2) launch(dmma_upper_deriv_kernel<5, 3, 2>, 2, smem, 8);
+        else launch(dmma_upper_deriv_kernel<5, 3, 1>, 1, smem, 16);
       } else {
-        constexpr int RW = 1;
-        const long long tiles = (N + 8 * RW * kDmmaNodeWarps - 1) / (8 * RW * kDmmaNodeWarps);
-        const dim3 grid((unsigned)std::min<long long>(tiles, std::max(1, g_sm_count * 4 / C)), (unsigned)C);
-        dmma_upper_deriv_kernel<16, 8, RW><<<grid, kDmmaNodeWarps * 32, nmat * dmma_node_smem_per_child<16, 8>(), st>>>(du);
+        launch(dmma_upper_deriv_kernel<16, 8, 1>, 1, nmat * dmma_node_smem_per_child<16, 8>(), 4);
       }
       deriv_combine_kernel<<<grid_p, 256, 0, st>>>(e->d_dLc, e->d_weights, C, N, e->d_partials, e->d_partials2);
       finalize_sum2_kernel<<<1, 256, 0, st>>>(e->d_partials, e->d_partials2, grid_p, out + 1 + n, out + 1 + nn + n);

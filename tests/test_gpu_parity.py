@@ -83,12 +83,15 @@ def test_dna_walk_kernel_variants(monkeypatch, pt, pipe, flags):
             np.testing.assert_allclose(-d2[0, :nb], res.d2, rtol=1e-8, atol=1e-7)
 
 
-@pytest.mark.parametrize("flags", [0, 1, 16])
-def test_protein_random_trees(flags):
+@pytest.mark.parametrize("flags,env,path", [(0, None, 4), (1, None, 4), (16, None, 3), (0, "walk", 2)])
+def test_protein_random_trees(monkeypatch, flags, env, path):
+    """S = 20: tensor-core node kernels (default), the generic kernels, and the register walk (BPPGPU_PATH=walk)"""
+    if env:
+        monkeypatch.setenv("BPPGPU_PATH", env)
     r, p = rm.gamma_rates(4, 0.7)
     c = cases.make_case(40, 300, rm.lg08(), r, p, seed=21, ambiguity=0.02)
     st = check_value(c, flags=flags)
-    assert st["path"] == (3 if flags & 16 else (4 if flags & 1 else 2))
+    assert st["path"] == path
 
 
 def test_codon_generic():
@@ -316,6 +319,48 @@ def test_batched_points_path_general_shapes():
     with pytest.raises(capi.BppGpuError):
         e.eval(7)                            # no branch derivatives on this path
     e.close()
+
+
+def test_odd_class_counts_two_byte_codes_and_impossible_sites():
+    capi = _capi()
+    # C = 3 (not a power of two) -> generic kernels for DNA
+    r, p = rm.gamma_rates(3, 0.9)
+    c = cases.make_case(20, 120, gtr(), r, p, seed=81, ambiguity=0.05)
+    st = check_value(c)
+    assert st["path"] == 3
+    # C = 8 on the DNA walk
+    r8, p8 = rm.gamma_rates(8, 0.4)
+    c = cases.make_case(33, 257, gtr(), r8, p8, seed=82)
+    assert check_value(c)["path"] == 1
+    # more than 256 distinct tip codes -> 2-byte codes (composite states carry probabilities, like chromosome counts)
+    rng = np.random.default_rng(83)
+    r4, p4 = rm.gamma_rates(4, 0.7)
+    c = cases.make_case(10, 90, rm.lg08(), r4, p4, seed=83)
+    extra = rng.dirichlet(np.ones(20), size=300)
+    c.table = np.vstack([c.table, extra])
+    for lid in c.codes_by_leaf:
+        codes = c.codes_by_leaf[lid].astype(np.uint16)
+        mask = rng.random(c.N) < 0.3
+        codes[mask] = rng.integers(22, 322, size=int(mask.sum()))
+        c.codes_by_leaf[lid] = codes
+    c.code_dtype = np.uint16
+    st = check_value(c)
+    assert st["path"] == 4
+    # a site that is impossible under the model (all-zero tip vector): log L = -inf like the reference
+    # ("Likelihood will be 0 for site", DRASRTreeLikelihoodData.cpp:305-306), the other sites are unaffected
+    c = cases.make_case(8, 30, gtr(), r4, p4, seed=84, compress=False)
+    c.table = np.vstack([c.table, np.zeros((1, 4))])
+    first = c.flat.leaf_ids[0]
+    c.codes_by_leaf[first] = c.codes_by_leaf[first].copy()
+    c.codes_by_leaf[first][5] = c.table.shape[0] - 1
+    res = cases.oracle_eval(c)
+    with cases.make_engine(c) as e:
+        lnl, _, _ = e.eval()
+        site = e.site_lnl()
+    assert lnl[0] == -np.inf and res.lnl == -np.inf
+    assert site[5] == -np.inf
+    keep = np.arange(c.N) != 5
+    np.testing.assert_allclose(site[keep], res.site_lnl[keep], rtol=1e-11)
 
 
 def test_error_conventions():
