@@ -166,6 +166,29 @@ def cpu_leg(w, tree, es, rates, probs, codes, threads, target_seconds=12.0, per_
             "lnl_sample": r["lnl"]}, sub
 
 
+def ncu_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of `kernel`, from the committed ncu summaries (profiles/);
+    None when no capture of that kernel on this workload is committed."""
+    import csv
+    import glob
+    best = None
+    for f in sorted(glob.glob(os.path.join(ROOT, "profiles", "*_ncu_summary.csv"))):
+        rd = wr = None
+        try:
+            for row in csv.reader(open(f)):
+                if len(row) == 4 and kernel.split("_kernel")[0] in row[0]:
+                    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(row[2])
+                    if row[1] == "dram__bytes_read.sum" and scale and rd is None:
+                        rd = float(row[3]) * scale
+                    if row[1] == "dram__bytes_write.sum" and scale and wr is None:
+                        wr = float(row[3]) * scale
+        except OSError:
+            continue
+        if rd is not None and wr is not None and kernel == "walk4_kernel":
+            best = rd + wr          # the walk4 captures are of the default (1M-pattern) workload
+    return best
+
+
 def flops_per_eval(tree, rows, S):
     """pruning contraction flops: 2 S^2 per (row, internal son) + S per extra son"""
     tot = 0
@@ -491,15 +514,40 @@ def main():
         n_local = codes.shape[1]
         alg = algorithmic_bytes(tree, n_local, w["C"], w["S"])
         kms = st["prune_ms_sum"] / max(1, st["prune_count"])
-        achieved = alg / (kms * 1e-3) / 1e9 if kms > 0 else None
-        roofline = {"bound": "hbm", "kernel": {1: "walk4_kernel", 2: "walkS_kernel", 3: "generic_node_kernel"}.get(st["path"], "?"),
-                    "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak if achieved else None,
-                    "traffic": None, "kernel_ms": kms, "launches_timed": st["prune_count"],
-                    "algorithmic_bytes_per_launch": alg,
-                    "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
-                    "note": "algorithmic bytes = 8*(1+internal sons) per CLV element (SURVEY 8d), the traffic a level-scheduled "
-                            "kernel must move; this kernel keeps CLVs on chip, so frac > 1 is expected and DRAM traffic is "
-                            "the tip codes only (see profiles/)"}
+        kname = {1: "walk4_kernel", 2: "walkS_kernel", 3: "generic_node_kernel", 4: "dmma_node_kernel"}.get(st["path"], "?")
+        if st["path"] == 4 and w["S"] >= 32:
+            # dense contraction on the FP64 tensor cores (mma.sync DMMA; tcgen05 has no f64 kind)
+            try:
+                fp = json.loads(open(os.path.join(ROOT, "profiles", "r1_fp64_peaks.json")).readline())
+            except (OSError, ValueError):
+                fp = {}
+            dmma_peak = fp.get("dmma_m8n8k4_tflops", 37.1)
+            rows = n_local * w["C"]
+            alg_flops = sum((2 * w["S"] * len(tree.sons(n)) + len(tree.sons(n)) - 1) * w["S"] for n in range(tree.nn)
+                            if len(tree.sons(n))) * rows                  # every son contracted, tips included
+            exe_flops = flops_per_eval(tree, rows, w["S"])                # DMMA flops issued: tip sons are table gathers
+            ach = alg_flops / (kms * 1e-3) / 1e12 if kms > 0 else None
+            roofline = {"bound": "tensor", "kernel": kname + " (one launch per node; all launches of an evaluation timed together)",
+                        "achieved": ach, "peak": dmma_peak, "unit": "TFLOP/s", "frac": ach / dmma_peak if ach else None, "traffic": None,
+                        "kernel_ms": kms, "launches_timed": st["prune_count"], "algorithmic_flops_per_eval": alg_flops,
+                        "executed_dmma_tflops": exe_flops / (kms * 1e-3) / 1e12 if kms > 0 else None,
+                        "peak_source": "FP64 mma.sync m8n8k4 measured with tools/fp64_peak.cu (profiles/r1_fp64_peaks.json); "
+                                       "MEASURED_PEAKS.json has no FP64 figure",
+                        "note": "algorithmic flops = (2 S k + k - 1) per CLV element with k sons (SURVEY 8d, the reference contracts "
+                                "tip sons too); tip sons are gathers here, so executed_dmma_tflops is the tensor-pipe figure"}
+        else:
+            achieved = alg / (kms * 1e-3) / 1e9 if kms > 0 else None
+            roofline = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                        "frac": achieved / hbm_peak if achieved else None,
+                        "traffic": ncu_traffic(kname) if (a.workload == DEFAULT and not a.patterns and world == 1) else None,
+                        "kernel_ms": kms,
+                        "launches_timed": st["prune_count"], "algorithmic_bytes_per_launch": alg,
+                        "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
+                        "note": ("algorithmic bytes = 8*(1+internal sons) per CLV element (SURVEY 8d), the traffic a level-scheduled "
+                                 "kernel must move; this kernel keeps CLVs on chip, so frac > 1 is expected and DRAM traffic is "
+                                 "the tip codes only (traffic = dram bytes of one launch, ncu, profiles/)") if st["path"] == 1 else
+                                "algorithmic bytes = 8*(1+internal sons) per CLV element (SURVEY 8d); one launch per node, all "
+                                "launches of an evaluation timed together"}
         line = {"metric": metric, "value": value, "unit": "CLV updates/s", "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic (tips simulated down a random tree under the model; every site kept as a pattern, weight 1)",
