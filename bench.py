@@ -25,6 +25,8 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# stdout carries exactly one JSON line: keep NCCL's banner ("NCCL version ...") and any debug output on stderr
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
 WORKLOADS = {
     # BASELINE.json configs[1]: GTR+G4 DNA, 1024 taxa x 1M patterns
@@ -33,6 +35,8 @@ WORKLOADS = {
     "protein_g4_500x200k_d2": dict(S=20, C=4, taxa=500, patterns=200_000, alpha=0.7, derivs=True, seed=20260103),
     # configs[2] without the derivatives (value-only protein evaluation)
     "protein_g4_500x200k": dict(S=20, C=4, taxa=500, patterns=200_000, alpha=0.7, derivs=False, seed=20260103),
+    # layout experiment: the same CLV bytes as protein_g4_500x200k with one class (rows contiguous)
+    "protein_c1_500x800k": dict(S=20, C=1, taxa=500, patterns=800_000, alpha=None, derivs=False, seed=20260103),
     # configs[3]: 64-state codon (61 sense), 200 taxa x 100k patterns, C = 1
     "codon_200x100k": dict(S=64, C=1, taxa=200, patterns=100_000, alpha=None, derivs=False, seed=20260104),
     # configs[4]: ChromEvol-style chromosome-number model, 200 states, 500 taxa, one character, 4096 parameter points
@@ -213,7 +217,7 @@ def run_points(a, w, rank, world, local, K, W, metric, config):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device(device))
     S = w["S"]
-    npts_total = a.points or w["points"]
+    npts_total = (a.points or w["points"]) * (world if a.scaling == "weak" else 1)
     lo, hi = shard_range(npts_total, rank, world)
     npts = hi - lo
     rng = np.random.default_rng(w["seed"])
@@ -296,7 +300,7 @@ def run_points(a, w, rank, world, local, K, W, metric, config):
         pt_ms = st["pt_ms_sum"] / max(1, K)              # all chunks of one evaluation
         ach = flops / (pt_ms * 1e-3) / 1e12 if pt_ms > 0 else None
         line = {"metric": metric, "value": upd_step * K / (ms * 1e-3), "unit": "CLV updates/s", "n_gpus": world, "steps": K,
-                "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": a.scaling, "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic (one chromosome count per taxon simulated down a random rooted tree; parameter points "
                                         "drawn uniformly, numerically defective generators redrawn)",
                 "config": dict(config, points=npts_total, sharding="points/%d (replicas, no collective)" % world),
@@ -351,6 +355,9 @@ def main():
     ap.add_argument("--workload", default=DEFAULT, choices=sorted(WORKLOADS))
     ap.add_argument("--patterns", type=int, default=0, help="override the workload's pattern count (debug)")
     ap.add_argument("--points", type=int, default=0, help="override the number of parameter points (chromosome workload)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="N > 1: weak = every GPU gets the workload's pattern count (patterns are an independent axis, no data-path "
+                         "collective); strong = the workload's patterns are split across the GPUs")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--profile", action="store_true", help="1 warm-up + 1 timed step, no e2e / CPU legs (for ncu only)")
     a = ap.parse_args()
@@ -364,9 +371,13 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    per_gpu_patterns = w["patterns"]
+    if a.scaling == "weak" and "points" not in w:
+        w["patterns"] = per_gpu_patterns * world        # whole job; each rank still owns a contiguous 1/world block
     metric = "CLV updates/s"
     config = {"workload": a.workload, "states": w["S"], "rate_classes": w["C"], "taxa": w["taxa"],
-              "patterns": w["patterns"], "derivatives": w["derivs"], "sharding": "patterns/%d" % world,
+              "patterns": w["patterns"], "patterns_per_gpu": w["patterns"] // world, "derivatives": w["derivs"],
+              "sharding": "contiguous pattern blocks, one per GPU; all-reduce of (lnL, d1, d2) only",
               "l2": "inputs larger than L2 (tip codes %.0f MB per rank; CLVs never re-read from a previous step)" %
                     (w["taxa"] * w["patterns"] / world / 1e6)}
 
@@ -405,7 +416,7 @@ def main():
         sample = "%d of %d patterns per step (full tree), %d host threads as independent pattern shards" % (n, w["patterns"], threads)
         print(json.dumps({"impl": "reference", "metric": metric, "value": val, "unit": "CLV updates/s", "n_gpus": a.gpus,
                           "steps": K, "warmup": a.warmup, "ms_per_step": 1e3 * dt / K, "higher_is_better": True,
-                          "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                          "scaling": a.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                           "config": config,
                           "cpu_baseline": {"value": val, "unit": "CLV updates/s", "cores": threads, "kind": "port", "sample": sample},
                           "e2e": {"value": val, "unit": "CLV updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
@@ -549,7 +560,7 @@ def main():
                                 "algorithmic bytes = 8*(1+internal sons) per CLV element (SURVEY 8d); one launch per node, all "
                                 "launches of an evaluation timed together"}
         line = {"metric": metric, "value": value, "unit": "CLV updates/s", "n_gpus": world, "steps": K, "warmup": W,
-                "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+                "ms_per_step": ms / K, "higher_is_better": True, "scaling": a.scaling, "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic (tips simulated down a random tree under the model; every site kept as a pattern, weight 1)",
                 "config": config, "logl_evals_per_s": K / (ms * 1e-3), "lnl": lnl_dev,
                 "e2e": {"value": upd_step * K / (e2e_ms * 1e-3), "unit": "CLV updates/s", "h2d_bytes_per_step": h2d,
