@@ -795,7 +795,7 @@ static int create_impl(const bppgpu_config* cfg, bppgpu_engine* e) {
     if (N * C < (long long)g_sm_count * 4 * kWalk4Threads * 4) e->w4_pt = 1;  // small inputs: more CTAs instead
     if (const char* env = getenv("BPPGPU_WALK4_PT")) {  // tuning knob: 1, 2 or 4
       const int v = atoi(env);
-      if ((v == 1 || v == 2 || v == 4) && (size_t)e->prog.nslots * v * kWalk4Threads * 36 <= 200 * 1024) e->w4_pt = v;
+      if (v >= 1 && v <= 4 && (size_t)e->prog.nslots * v * kWalk4Threads * 36 <= 200 * 1024) e->w4_pt = v;
     }
     int rc4 = walk4_dispatch(e, nullptr, 0, 0, nullptr, true);
     if (rc4) return rc4;
@@ -1028,6 +1028,7 @@ static int walk4_launch_k(bool keep, const Walk4Params* wp, int grid, size_t sme
 template <int CL>
 static int walk4_launch_pt(int pt, bool keep, const Walk4Params* wp, int grid, size_t smem, cudaStream_t st, bool attr_only) {
   if (pt == 4) return walk4_launch_k<CL, 4>(keep, wp, grid, smem, st, attr_only);
+  if (pt == 3) return walk4_launch_k<CL, 3>(keep, wp, grid, smem, st, attr_only);
   if (pt == 2) return walk4_launch_k<CL, 2>(keep, wp, grid, smem, st, attr_only);
   return walk4_launch_k<CL, 1>(keep, wp, grid, smem, st, attr_only);
 }

@@ -375,7 +375,7 @@ extern "C" int refcpu_eval(int S, int C, long N, int nn, int root, const int* ch
                            int weighted_root, double model_rate, const double* brlen,
                            const double* rootfreq, int scaled, int want, int nthreads, int reps, double* lnl_out,
                            double* d1_out /*[nn] or NULL*/, double* d2_out /*[nn] or NULL*/,
-                           double* site_lnl_out /*[N] or NULL*/, double* best_seconds) {
+                           double* site_lnl_out /*[N] or NULL*/, double* best_seconds, double* sum_seconds /*all reps, or NULL*/) {
   Problem P;
   P.S = S; P.C = C; P.N = N; P.nn = nn; P.root = root; P.child_off = child_off; P.children = children;
   P.codes = codes; P.code_bytes = code_bytes; P.ncodes = ncodes; P.code_table = code_table; P.weights = weights;
@@ -395,7 +395,7 @@ extern "C" int refcpu_eval(int S, int C, long N, int nn, int root, const int* ch
     for (int t = 0; t < nthreads; t++) th.emplace_back([&sh, t] { sh[t].alloc(); });
     for (auto& x : th) x.join();
   }
-  double best = 1e300, lnl = 0;
+  double best = 1e300, lnl = 0, total = 0;
   Vdouble la(N);
   for (int r = 0; r < reps; r++) {
     auto t0 = std::chrono::steady_clock::now();
@@ -428,11 +428,13 @@ extern "C" int refcpu_eval(int S, int C, long N, int nn, int root, const int* ch
     }
     double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     best = std::min(best, sec);
+    total += sec;
   }
   *lnl_out = lnl;
   if (site_lnl_out)
     for (int t = 0; t < nthreads; t++)
       for (long i = 0; i < sh[t].n; i++) site_lnl_out[sh[t].i0 + i] = sh[t].site_lnl[i];
   if (best_seconds) *best_seconds = best;
+  if (sum_seconds) *sum_seconds = total;
   return 0;
 }

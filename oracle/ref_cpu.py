@@ -56,6 +56,7 @@ def eval_raw(S, Ccat, N, child_off, children, root, codes, code_table, weights, 
             ev_im = None
     lnl = C.c_double(0)
     sec = C.c_double(0)
+    tot = C.c_double(0)
     d1 = np.zeros(nn) if want & 6 else None
     d2 = np.zeros(nn) if want & 4 else None
     sl = np.zeros(N) if site else None
@@ -65,9 +66,9 @@ def eval_raw(S, Ccat, N, child_off, children, root, codes, code_table, weights, 
                            _p(V), _p(Vinv), _p(ev), _p(ev_im), C.c_int(int(chr_clamp)), C.c_int(int(weighted_root)),
                            C.c_double(model_rate), _p(brlen), _p(rootfreq),
                            C.c_int(int(scaled)), C.c_int(want), C.c_int(nthreads), C.c_int(reps), C.byref(lnl),
-                           _p(d1), _p(d2), _p(sl), C.byref(sec))
+                           _p(d1), _p(d2), _p(sl), C.byref(sec), C.byref(tot))
     assert rc == 0
-    return {"lnl": lnl.value, "d1": d1, "d2": d2, "site_lnl": sl, "seconds": sec.value}
+    return {"lnl": lnl.value, "d1": d1, "d2": d2, "site_lnl": sl, "seconds": sec.value, "total_seconds": tot.value}
 
 
 def eval_case(case, **kw):

@@ -1,1 +1,1 @@
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus 8 --steps 20 --warmup 3 > gpurun_out/scale8.json 2> gpurun_out/scale8.err; echo "rc=$?" >> gpurun_out/scale8.err
+for pt in 3; do BPPGPU_WALK4_PT=$pt python bench.py --steps 10 --warmup 3 --no-cpu 2>&1 >/dev/null | grep "timed region" | sed "s/^/pt=$pt /" >> gpurun_out/sweep_pt3.log; done
