@@ -534,7 +534,7 @@ int bppgpu_destroy(bppgpu_engine* e) {
                   e->d_d2P, e->d_tiptab, e->d_keep, e->d_keep_exp, e->d_gstack, e->d_gstack_exp, e->d_upper,
                   e->d_upper_exp, e->d_SR, e->d_rexp, e->d_site_lnl, e->d_partials, e->d_partials2, e->d_out,
                   e->prog.d_ops, e->prog.d_childs, e->gprog.d_ops, e->gprog.d_childs, e->d_sibs, e->d_scratch,
-                  e->d_dtiptab, e->d_d2tiptab, e->d_dLc, e->d_w4_desc, e->d_w4_tip_order, e->d_w4_blocks, e->d_w4_stream, e->d_codesT,
+                  e->d_dtiptab, e->d_d2tiptab, e->d_dLc, e->d_fam_mask, e->d_fam_part, e->d_fam_packA, e->d_fam_packS, e->d_fam_packT, e->d_w4_desc, e->d_w4_tip_order, e->d_w4_blocks, e->d_w4_stream, e->d_codesT,
                   e->d_status};
   for (void* p : ptrs) cudaFree(p);
   for (auto& m : e->models) free_model(m);
@@ -625,11 +625,11 @@ static int create_impl(const bppgpu_config* cfg, bppgpu_engine* e) {
   // config, so it is no longer a default; BPPGPU_PATH=walk selects it (value-only, no weighted root)
   const bool walks_ok = S == 20 && cpow && !e->keep && !wroot;
   (void)walks_ok;
-  if (e->path == PATH_GENERIC && ((S > 16 && S <= 20) || (S > 56 && S <= 64))) e->path = PATH_DMMA;
+  if (e->path == PATH_GENERIC && S % 4 == 0 && ((S > 16 && S <= 20) || (S > 56 && S <= 64))) e->path = PATH_DMMA;
   if (const char* env = getenv("BPPGPU_PATH")) {  // tuning knob
     if (!strcmp(env, "generic")) e->path = PATH_GENERIC;
     if (!strcmp(env, "walk") && walks_ok) e->path = PATH_WALKS;
-    if (!strcmp(env, "dmma") && ((S > 16 && S <= 20) || (S > 56 && S <= 64))) e->path = PATH_DMMA;
+    if (!strcmp(env, "dmma") && S % 4 == 0 && ((S > 16 && S <= 20) || (S > 56 && S <= 64))) e->path = PATH_DMMA;
   }
   if (cfg->flags & BPPGPU_FLAG_FORCE_GENERIC) e->path = PATH_GENERIC;
   // many parameter points on few patterns (ChromEvol): one launch per node covers every point of a chunk
@@ -993,6 +993,44 @@ static int ensure_deriv_buffers(bppgpu_engine* e, unsigned want) {
       BPP_CUDA(dev_alloc(e, &e->d_dtiptab, tt));
       BPP_CUDA(dev_alloc(e, &e->d_d2tiptab, tt));
       BPP_CUDA(dev_alloc(e, &e->d_dLc, (size_t)e->N * e->C * 2));
+      // per-father fused pass (S = 20): every father with <= 3 sons; BPPGPU_FAMILY=0 keeps the per-branch kernels
+      const char* fenv = getenv("BPPGPU_FAMILY");
+      e->family = e->S == 20 && e->C <= kFamMaxClasses && e->N > 0 && !(fenv && atoi(fenv) == 0);
+      if (e->family) {
+        e->fam_mask.assign(e->nn, 0);
+        for (int f = 0; f < e->nn; ++f) {
+          const int k = e->child_off[f + 1] - e->child_off[f];
+          if (k >= 1 && k <= kFamMaxSons)
+            for (int j = e->child_off[f]; j < e->child_off[f + 1]; ++j) e->fam_mask[e->children[j]] = 1;
+        }
+        BPP_CUDA(dev_alloc(e, &e->d_fam_mask, (size_t)e->nn));
+        BPP_CUDA(cudaMemcpy(e->d_fam_mask, e->fam_mask.data(), e->nn * sizeof(int), cudaMemcpyHostToDevice));
+        {
+          auto attr = [](auto k, size_t smem) { return cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); };
+          BPP_CUDA(attr(dmma_family_kernel<5, 0>, dmma_family_smem<0>(e->C)));
+          BPP_CUDA(attr(dmma_family_kernel<5, 1>, dmma_family_smem<1>(e->C)));
+          BPP_CUDA(attr(dmma_family_kernel<5, 2>, dmma_family_smem<2>(e->C)));
+          BPP_CUDA(attr(dmma_family_kernel<5, 3>, dmma_family_smem<3>(e->C)));
+          BPP_CUDA(attr(dmma_family_kernel<5, 4>, dmma_family_smem<4>(e->C)));
+          BPP_CUDA(attr(dmma_family_kernel<8, 0>, dmma_family_smem<0>(e->C)));
+          BPP_CUDA(attr(dmma_family_kernel<8, 1>, dmma_family_smem<1>(e->C)));
+          BPP_CUDA(attr(dmma_family_kernel<8, 2>, dmma_family_smem<2>(e->C)));
+          BPP_CUDA(attr(dmma_family_kernel<8, 3>, dmma_family_smem<3>(e->C)));
+          BPP_CUDA(attr(dmma_family_kernel<8, 4>, dmma_family_smem<4>(e->C)));
+        }
+        const int per_sm = 1;  // persistent: one CTA per SM (registers and shared memory both say so)
+        long long slots = (long long)g_sm_count * std::max(1, per_sm);
+        if (const char* env = getenv("BPPGPU_FAMILY_GRID")) slots = std::max(1, atoi(env));  // test knob: few CTAs, many chunks
+        long long ppc = (e->N + slots - 1) / slots;
+        ppc = std::max<long long>(8, (ppc + 7) / 8 * 8);
+        e->fam_ppc = (int)ppc;
+        e->fam_grid = (int)((e->N + ppc - 1) / ppc);
+        BPP_CUDA(dev_alloc(e, &e->d_fam_part, (size_t)e->nn * 2 * e->fam_grid));
+        BPP_CUDA(cudaMemset(e->d_fam_part, 0, (size_t)e->nn * 2 * e->fam_grid * 8));
+        BPP_CUDA(dev_alloc(e, &e->d_fam_packA, (size_t)e->nn * e->C * kFamPackA));
+        BPP_CUDA(dev_alloc(e, &e->d_fam_packS, (size_t)e->nn * e->C * kFamPackS));
+        BPP_CUDA(dev_alloc(e, &e->d_fam_packT, (size_t)e->nl * e->C * e->ncodes * 64));
+      }
     }
   }
   return BPPGPU_OK;
@@ -1223,8 +1261,73 @@ static int enqueue_derivs(bppgpu_engine* e, int point, int pl, unsigned want, cu
   const int grid_e = (int)std::min<long long>((total + 255) / 256, (long long)g_sm_count * 32);
   const int grid_p = (int)((N + 255) / 256);
   const int grid_r = (int)((N * C + 255) / 256);
-  for (int n : e->preorder) {
-    if (n == e->root) continue;
+  const bool family = e->path == PATH_DMMA && e->family;
+  auto launch_family = [&](int f) {
+    DmmaFamilyParams fp{};
+    const size_t clvN = (size_t)N * C * S, expN = (size_t)N * C;
+    fp.nson = e->child_off[f + 1] - e->child_off[f];
+    int kind = fp.nson == 2 ? 0 : 4;
+    for (int j = 0; j < fp.nson; ++j) {
+      const int s = e->children[e->child_off[f] + j];
+      const bool tip = e->leaf_slot[s] >= 0;
+      FamilySon& fs = fp.sons[j];
+      fs.kind = tip ? CHILD_TIP : CHILD_KEEP;
+      fs.node = s;
+      if (tip) {
+        const int slot = e->leaf_slot[s];
+        fs.codes = (const char*)e->d_codes + (size_t)slot * N * e->code_bytes;
+        fs.tpack = e->d_fam_packT + (size_t)slot * C * e->ncodes * 64;
+        if (kind != 4) kind |= 1 << j;
+      } else {
+        fs.clv = e->d_keep + (size_t)e->internal_idx[s] * clvN;
+        fs.exp = e->d_keep_exp + (size_t)e->internal_idx[s] * expN;
+      }
+      if (e->upper_slab[s] >= 0) {
+        fs.up = e->d_upper + (size_t)e->upper_slab[s] * clvN;
+        fs.upexp = e->d_upper_exp + (size_t)e->upper_slab[s] * expN;
+      }
+    }
+    fp.father = f == e->root ? -1 : f;
+    if (f != e->root) {
+      fp.fup = e->d_upper + (size_t)e->upper_slab[f] * clvN;
+      fp.fupexp = e->d_upper_exp + (size_t)e->upper_slab[f] * expN;
+    }
+    fp.S = S; fp.C = C; fp.ncodes = e->ncodes; fp.code_bytes = e->code_bytes;
+    fp.nh_form = (e->flags & BPPGPU_FLAG_NH_DERIV) ? 1 : 0;
+    fp.ppc = e->fam_ppc;
+    fp.N = N;
+    fp.packA = e->d_fam_packA; fp.packS = e->d_fam_packS;
+    fp.rootfreq = e->d_rootfreq_used + (size_t)point * S;
+    fp.probs = e->d_probs; fp.SR = e->d_SR; fp.weights = e->d_weights; fp.rexp = e->d_rexp;
+    fp.part = e->d_fam_part;
+    const bool d2 = (want & BPPGPU_EVAL_D2) != 0;
+    const int G = e->fam_grid;
+#define BPP_FAM(NBv, Kv) dmma_family_kernel<NBv, Kv><<<G, fam_threads(Kv == 4 ? 3 : 2), dmma_family_smem<Kv>(C), st>>>(fp)
+    switch (kind) {
+      case 0: if (d2) BPP_FAM(8, 0); else BPP_FAM(5, 0); break;
+      case 1: if (d2) BPP_FAM(8, 1); else BPP_FAM(5, 1); break;
+      case 2: if (d2) BPP_FAM(8, 2); else BPP_FAM(5, 2); break;
+      case 3: if (d2) BPP_FAM(8, 3); else BPP_FAM(5, 3); break;
+      default: if (d2) BPP_FAM(8, 4); else BPP_FAM(5, 4); break;
+    }
+#undef BPP_FAM
+    e->stats.kernel_launches++;
+  };
+  if (family) {
+    FamilyPackParams pk{};
+    pk.P = P; pk.dP = dP; pk.d2P = d2P;
+    pk.packA = e->d_fam_packA; pk.packS = e->d_fam_packS;
+    pk.tt = tiptab;
+    pk.dtt = e->d_dtiptab + (size_t)pl * e->nl * C * e->ncodes * S;
+    pk.d2tt = (want & BPPGPU_EVAL_D2) ? e->d_d2tiptab + (size_t)pl * e->nl * C * e->ncodes * S : nullptr;
+    pk.packT = e->d_fam_packT;
+    pk.S = S;
+    pk.nbc = nn * C;
+    pk.ntc = e->nl * C * e->ncodes;
+    family_pack_kernel<<<pk.nbc + (pk.ntc + 3) / 4, 256, 0, st>>>(pk);
+    e->stats.kernel_launches++;
+  }
+  auto launch_branch = [&](int n) {
     const int f = e->parent[n];
     UpperParams up{};
     up.sibs = e->d_sibs + e->sib_off[n];
@@ -1280,7 +1383,7 @@ static int enqueue_derivs(bppgpu_engine* e, int point, int pl, unsigned want, cu
       deriv_combine_kernel<<<grid_p, 256, 0, st>>>(e->d_dLc, e->d_weights, C, N, e->d_partials, e->d_partials2);
       finalize_sum2_kernel<<<1, 256, 0, st>>>(e->d_partials, e->d_partials2, grid_p, out + 1 + n, out + 1 + nn + n);
       e->stats.kernel_launches += 3;
-      continue;
+      return;
     }
     up.upper_f = e->d_upper + (size_t)fslab * clv;
     up.uexp_f = e->d_upper_exp + (size_t)fslab * N * C;
@@ -1311,6 +1414,18 @@ static int enqueue_derivs(bppgpu_engine* e, int point, int pl, unsigned want, cu
     finalize_sum_kernel<<<1, 256, 0, st>>>(e->d_partials, grid_p, out + 1 + n);
     finalize_sum_kernel<<<1, 256, 0, st>>>(e->d_partials2, grid_p, out + 1 + nn + n);
     e->stats.kernel_launches += 5;
+  };
+  for (int n : e->preorder) {
+    if (n != e->root && !(family && e->fam_mask[n])) launch_branch(n);
+    if (family) {
+      // the sons of n in one launch (upper[n] is complete: n's own launch precedes this one in pre-order)
+      const int k = e->child_off[n + 1] - e->child_off[n];
+      if (k >= 1 && k <= kFamMaxSons) launch_family(n);
+    }
+  }
+  if (family) {
+    finalize_family_kernel<<<nn, 128, 0, st>>>(e->d_fam_part, e->d_fam_mask, e->fam_grid, nn, out, want);
+    e->stats.kernel_launches++;
   }
   BPP_CUDA(cudaGetLastError());
   return BPPGPU_OK;

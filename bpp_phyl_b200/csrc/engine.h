@@ -8,6 +8,7 @@
 #include "../../include/bppgpu.h"
 #include "deriv_kernels.cuh"
 #include "dmma_deriv_kernels.cuh"
+#include "dmma_family_kernels.cuh"
 #include "dmma_node_kernels.cuh"
 #include "generic_kernels.cuh"
 #include "points_kernels.cuh"
@@ -80,6 +81,13 @@ struct bppgpu_engine {
   double *d_dtiptab = nullptr, *d_d2tiptab = nullptr;  // tip tables of dP, d2P (DMMA derivative path)
   double* d_dLc = nullptr;                              // [N][C][2]
   std::vector<int> upper_slab;                          // node id -> slab of d_upper, or -1
+  // per-father fused upper + derivative pass (dmma_family_kernels.cuh)
+  bool family = false;
+  std::vector<int> fam_mask;   // node id -> 1 when its branch is served by its father's family launch
+  int* d_fam_mask = nullptr;
+  double* d_fam_part = nullptr;  // [nn][2][fam_grid]
+  double *d_fam_packA = nullptr, *d_fam_packS = nullptr, *d_fam_packT = nullptr;  // B operands in fragment order (family_pack_kernel)
+  int fam_grid = 0, fam_ppc = 0;
   int n_upper_slabs = 0;
   // walk4 artefacts (everything in walk order, see walk_kernels.cuh)
   std::vector<unsigned long long> w4_desc;

@@ -131,6 +131,73 @@ def test_dmma_tensor_core_path(monkeypatch, which, ncat):
                 np.testing.assert_allclose(got, exp, rtol=1e-9, atol=1e-13 * exp.max())
 
 
+def _check_derivs_and_uppers(c, e, res, want=7, uppers=True):
+    capi = _capi()
+    lnl, d1, d2 = e.eval(want)
+    nb = c.flat.n_nodes - 1
+    assert abs(lnl[0] - res.lnl) <= REL * abs(res.lnl)
+    np.testing.assert_allclose(-d1[0, :nb], res.d1, rtol=1e-8, atol=1e-8)
+    if want & capi.EVAL_D2:
+        np.testing.assert_allclose(-d2[0, :nb], res.d2, rtol=1e-8, atol=1e-7)
+    if not uppers:
+        return
+    for nid in range(nb):
+        clv, ex = e.clv(nid, 1)
+        got = np.ldexp(clv, -ex[:, :, None].astype(np.int64))
+        exp = np.ldexp(res.upper[nid], -res.uexp[nid][:, :, None])
+        np.testing.assert_allclose(got, exp, rtol=1e-9, atol=1e-13 * exp.max())
+
+
+@pytest.mark.parametrize("family", ["1", "0"])
+@pytest.mark.parametrize("want", [7, 3])
+def test_family_kernel_vs_per_branch(monkeypatch, family, want):
+    """S = 20 prefix + derivative pass: the per-father fused kernel (default) and the per-branch kernels it replaces,
+    value+d1 only (5 column blocks) and value+d1+d2 (8), rooted NH form and unrooted DR form, ragged pattern counts."""
+    capi = _capi()
+    monkeypatch.setenv("BPPGPU_FAMILY", family)
+    r, p = rm.gamma_rates(4, 0.7)
+    for ntaxa, nsites, seed, nh in ((14, 150, 71, False), (9, 37, 72, True), (6, 3, 73, False)):
+        c = cases.make_case(ntaxa, nsites, rm.lg08(), r, p, seed=seed, mean_brlen=0.1, ambiguity=0.03, rooted=nh,
+                            compress=False)
+        res = cases.oracle_eval(c, want_d1=True, want_d2=True, nh_form=nh)
+        with cases.make_engine(c, flags=capi.FLAG_KEEP_CLVS | (capi.FLAG_NH_DERIV if nh else 0)) as e:
+            assert e.stats()["path"] == 4
+            _check_derivs_and_uppers(c, e, res, want)
+            launches = e.stats()["kernel_launches"]
+        # one launch per father instead of three per branch
+        if family == "1":
+            assert launches < 3 * (c.flat.n_nodes - 1)
+
+
+def test_family_kernel_chunks_multifurcation_and_underflow(monkeypatch):
+    """Few CTAs (several 512-pattern accumulation chunks per CTA), a father with 4 sons (falls back to the per-branch
+    kernels inside the same pass), a 3-son father below the root, and upper CLVs that need rescaling."""
+    capi = _capi()
+    r, p = rm.gamma_rates(2, 0.5)
+    monkeypatch.setenv("BPPGPU_FAMILY_GRID", "2")
+    c = cases.make_case(8, 1300, rm.lg08(), r, p, seed=74, random_tips=True, compress=False)
+    res = cases.oracle_eval(c, want_d1=True, want_d2=True)
+    with cases.make_engine(c, flags=capi.FLAG_KEEP_CLVS) as e:
+        _check_derivs_and_uppers(c, e, res)
+    monkeypatch.delenv("BPPGPU_FAMILY_GRID")
+    aa = "ARNDCQEGHILKMFPSTWYV"
+    rng = np.random.default_rng(75)
+    names = list("ABCDEFGHIJ")
+    seqs = {n: "".join(rng.choice(list(aa), size=23)) for n in names}
+    nwk = "((A:0.1,B:0.2,C:0.3,D:0.05):0.1,(E:0.01,F:0.2,(G:0.1,H:0.1):0.05):0.2,I:0.3,J:0.1);"
+    c = cases.case_from_alignment(nwk, seqs, rm.lg08(), r, p, states=aa, aliases={ch: [ch] for ch in aa})
+    res = cases.oracle_eval(c, want_d1=True, want_d2=True)
+    with cases.make_engine(c, flags=capi.FLAG_KEEP_CLVS) as e:
+        assert e.stats()["path"] == 4
+        _check_derivs_and_uppers(c, e, res)
+    # long branches, i.i.d. tips, 300 taxa: lower and upper rows are rescaled many times
+    c = cases.make_case(300, 24, rm.lg08(), r, p, seed=76, random_tips=True, mean_brlen=0.6, compress=False)
+    res = cases.oracle_eval(c, want_d1=True, want_d2=True)
+    assert res.SR_exp.max() > 256
+    with cases.make_engine(c, flags=capi.FLAG_KEEP_CLVS) as e:
+        _check_derivs_and_uppers(c, e, res, uppers=False)
+
+
 def test_dmma_underflow_scaling():
     r, p = rm.constant_rate()
     c = cases.make_case(150, 40, rm.yn98(2.0, 0.3), r, p, seed=63, mean_brlen=0.8)     # simulated: no stop codons
