@@ -17,10 +17,11 @@
 // blocks instead of 3 x 3), so a binary father costs 15 + 2 x 40 DMMAs per 8 rows instead of 2 x 60.
 //
 // Column ownership: in the m8n8k4 accumulator lane q of a quad owns columns 2q, 2q+1 of every 8-column block.  The
-// staged B operand is permuted so that lane q owns states x = 4 i + q (i = 0..4) of ALL three matrices: slot
-// t = 5 mat + i lives in block t / 2, half t % 2.  M, dM, d2M, A_f and the rescaled upper row are therefore
-// element-aligned in registers and every product / dot product of the epilogue is lane-local.
-//
+// staged B operand is permuted so that lane q owns the SAME five states of all three matrices -- x = 4q .. 4q+3 and
+// 16 + q, i.e. exactly the states whose A fragments it loads -- slot t = 5 mat + i living in block t / 2, half t % 2.
+// M, dM, d2M, A_f and the rescaled upper row are therefore element-aligned in registers, every product / dot product
+// of the epilogue is lane-local, a row is stored with one 32-byte and one 8-byte access per lane (a quad writes 128
+// contiguous bytes), and tip sons read their rows of the ordinary [code][state] tip tables the same way.
 // One persistent CTA per SM owns a contiguous range of patterns; its warps take 8-pattern row blocks round-robin and
 // run the rate classes of a block back to back.  The operands of ALL classes stay in shared memory for the whole
 // launch (C <= 4: 25.6 KB per class for a binary father), so there is no barrier after the prologue, the class sums
@@ -46,7 +47,7 @@ struct FamilySon {
   const double* clv;     // lower CLV slab [N][C][S]            (internal son)
   const int* exp;        // its exponents  [N][C]
   const void* codes;     // tip codes      [N]                  (tip son)
-  const double* tpack;   // tip tables of P | dP | d2P in lane order [C][ncodes][4][16]   (tip son)
+  const double *tt, *dtt, *d2tt;  // this leaf's tip tables of P, dP, d2P  [C][ncodes][S]   (tip son)
   double* up;            // slab that receives upper[son], or null
   int* upexp;
 };
@@ -78,46 +79,40 @@ struct DmmaFamilyParams {
 constexpr int kFamPackA = kFamKB * 2 * 64;  // doubles per (branch, class)
 constexpr int kFamPackS = kFamKB * 4 * 64;
 
+// state owned by lane q in slot i (0..4)
+__host__ __device__ __forceinline__ int fam_state(int i, int q) { return i < 4 ? 4 * q + i : 16 + q; }
+
 struct FamilyPackParams {
   const double *P, *dP, *d2P;  // [nn][C][S][S]; d2P may be null
   double *packA, *packS;
-  const double *tt, *dtt, *d2tt;  // [nl][C][ncodes][S] tip tables; d2tt may be null
-  double* packT;                  // [nl][C][ncodes][4][16]: lane q of a quad reads its 15 values (slot t = 5 mat + i <-> x = 4 i + q) contiguously
-  int S, nbc, ntc;                // nbc = nn * C operand blocks, then ntc = nl * C * ncodes tip rows
+  double* packL;                  // [nn][C][kFamPackA]  P alone (pruning pass); packA/packS are skipped when dP is null
+  int S;
 };
 
 __global__ void family_pack_kernel(FamilyPackParams p) {
   const int S = p.S;
-  if ((int)blockIdx.x >= p.nbc) {
-    // tip rows: 64 threads per (leaf, class, code)
-    const size_t row = (size_t)(blockIdx.x - p.nbc) * (blockDim.x / 64) + threadIdx.x / 64;
-    if (row >= (size_t)p.ntc) return;
-    const int e = threadIdx.x & 63, q = e >> 4, t = e & 15, mat = t / 5, i = t - 5 * mat, x = 4 * i + q;
-    const double* tab = mat == 0 ? p.tt : (mat == 1 ? p.dtt : (mat == 2 ? p.d2tt : nullptr));
-    p.packT[row * 64 + e] = (tab != nullptr && x < S) ? tab[row * S + x] : 0.0;
-    return;
-  }
   const size_t SS = (size_t)S * S;
   const size_t bc = blockIdx.x;  // branch * C + class
   const double* m[3] = {p.P + bc * SS, p.dP ? p.dP + bc * SS : nullptr, p.d2P ? p.d2P + bc * SS : nullptr};
-  for (int e = threadIdx.x; e < kFamPackA + kFamPackS; e += blockDim.x) {
-    const bool isA = e < kFamPackA;
-    const int ee = isA ? e : e - kFamPackA;
-    const int NP = isA ? 2 : 4;
+  const int total = p.dP ? 2 * kFamPackA + kFamPackS : kFamPackA;  // [packL][packA][packS]
+  for (int e = threadIdx.x; e < total; e += blockDim.x) {
+    const int which = e < kFamPackA ? 0 : (e < 2 * kFamPackA ? 1 : 2);  // L, A, S
+    const int ee = which == 0 ? e : (which == 1 ? e - kFamPackA : e - 2 * kFamPackA);
+    const int NP = which == 2 ? 4 : 2;
     const int h = ee & 1, lane = (ee >> 1) & 31, kp = ee >> 6, pi = kp % NP, kb = kp / NP;
     const int g = lane >> 2, q = lane & 3;
     const int y = dmma_ymap<kFamKB>(kb, q);  // k index
     const int nb = 2 * pi + h, qq = g >> 1, hh = g & 1, t = 2 * nb + hh;  // column n = 8 nb + g
-    const int mat = t / 5, i = t - 5 * mat, x = 4 * i + qq;
+    const int mat = t / 5, i = t - 5 * mat, x = fam_state(i, qq);
     double v = 0.0;
     if (x < S && y < S) {
-      if (isA) {
-        if (mat == 0) v = m[0][(size_t)y * S + x];
-      } else if (mat < 3 && m[mat]) {
-        v = m[mat][(size_t)x * S + y];
+      if (which == 2) {
+        if (mat < 3 && m[mat]) v = m[mat][(size_t)x * S + y];
+      } else if (mat == 0) {
+        v = which == 1 ? m[0][(size_t)y * S + x] : m[0][(size_t)x * S + y];
       }
     }
-    (isA ? p.packA + bc * kFamPackA : p.packS + bc * kFamPackS)[ee] = v;
+    (which == 0 ? p.packL + bc * kFamPackA : (which == 1 ? p.packA + bc * kFamPackA : p.packS + bc * kFamPackS))[ee] = v;
   }
 }
 
@@ -329,18 +324,18 @@ __global__ void __launch_bounds__(fam_threads(KIND == 4 ? 3 : 2), 1) dmma_family
 #pragma unroll
       for (int j = 0; j < MS; ++j) {
         if (has(j) && tip(j)) {
-          const double* tp = p.sons[j].tpack + (size_t)(((c * p.ncodes + pcur.code[j]) << 2) + q) * 16;
-#pragma unroll
-          for (int k = 0; k < (2 * NB + 3) / 4; ++k) {
-            double v0, v1, v2, v3;
-            ld256nc(tp + 4 * k, v0, v1, v2, v3);
-            R[j][2 * k][0] = v0;
-            R[j][2 * k][1] = v1;
-            if (2 * k + 1 < NB) {
-              R[j][2 * k + 1][0] = v2;
-              R[j][2 * k + 1][1] = v3;
-            }
+          const int toff = (c * p.ncodes + pcur.code[j]) * S;
+          double v[15];
+          ld256nc(p.sons[j].tt + toff + 4 * q, v[0], v[1], v[2], v[3]);
+          v[4] = __ldg(p.sons[j].tt + toff + 16 + q);
+          ld256nc(p.sons[j].dtt + toff + 4 * q, v[5], v[6], v[7], v[8]);
+          v[9] = __ldg(p.sons[j].dtt + toff + 16 + q);
+          if (NMAT > 2) {
+            ld256nc(p.sons[j].d2tt + toff + 4 * q, v[10], v[11], v[12], v[13]);
+            v[14] = __ldg(p.sons[j].d2tt + toff + 16 + q);
           }
+#pragma unroll
+          for (int t = 0; t < 2 * NB; ++t) R[j][t >> 1][t & 1] = t < 5 * NMAT ? v[t] : 0.0;
         }
       }
       // ---- A_f -----------------------------------------------------------------------------------------------------
@@ -352,7 +347,7 @@ __global__ void __launch_bounds__(fam_threads(KIND == 4 ? 3 : 2), 1) dmma_family
         family_contract<3, 2>(A, a, matA, lane);
       } else {
 #pragma unroll
-        for (int t = 0; t < 6; ++t) A[t >> 1][t & 1] = (t < 5 && 4 * t + q < S) ? p.rootfreq[4 * t + q] : 0.0;
+        for (int t = 0; t < 6; ++t) A[t >> 1][t & 1] = t < 5 ? p.rootfreq[fam_state(t, q)] : 0.0;
       }
       // ---- M, dM, d2M of internal sons ---------------------------------------------------------------------------------
 #pragma unroll
@@ -366,7 +361,7 @@ __global__ void __launch_bounds__(fam_threads(KIND == 4 ? 3 : 2), 1) dmma_family
       }
       // ---- per son: upper row, rescale, store, derivative dots --------------------------------------------------------
       const double rinv = sprobs[c] * inv_sr;
-      const int ooff = (r0 + g) * CS + c * S + q;  // (only dereferenced when valid)
+      const int ooff = (r0 + g) * CS + c * S;  // (only dereferenced when valid)
       const int oexp = (r0 + g) * C + c;
 #pragma unroll
       for (int j = 0; j < MS; ++j) {
@@ -397,9 +392,8 @@ __global__ void __launch_bounds__(fam_threads(KIND == 4 ? 3 : 2), 1) dmma_family
           }
           if (p.sons[j].up != nullptr && valid) {
             double* row = p.sons[j].up + cta0 * CS + ooff;
-#pragma unroll
-            for (int i = 0; i < 5; ++i)
-              if (4 * i + q < S) row[4 * i] = U[i];
+            st256(row + 4 * q, U[0], U[1], U[2], U[3]);
+            row[16 + q] = U[4];
             if (q == 0) p.sons[j].upexp[cta0 * C + oexp] = Eu;
           }
           double s1 = 0.0, s2 = 0.0;
@@ -459,6 +453,192 @@ __global__ void finalize_family_kernel(const double* part, const int* mask, int 
   if (threadIdx.x == 0) {
     out[1 + n] = s1;
     if (want & 4u) out[1 + nn + n] = s2;
+  }
+}
+
+
+// ----------------------------------------------------------------------------------------------------------------------
+// K2 for S = 20 with the same machinery: one pruning step  CLV_n = prod_sons (P_son . CLV_son)  per launch
+// (RHomogeneousTreeLikelihood::computeSubtreeLikelihood, Likelihood/RHomogeneousTreeLikelihood.cpp:802-863;
+// DRHomogeneousTreeLikelihood::computeLikelihoodFromArrays :819-864), per-row power-of-two rescaling fused.
+// An item is light here (15 DMMAs per internal son), so the kernel lives on HBM: 16 warps per SM, each with a 3-deep
+// cp.async ring of son rows, operands of every class resident, nothing but the output row and its exponent written.
+struct PruneSon {
+  int kind, node;
+  const double* clv;   // internal son: lower CLV slab, exponents
+  const int* exp;
+  const void* codes;   // tip son: codes, this leaf's tip table [C][ncodes][S]
+  const double* tt;
+};
+struct DmmaPruneParams {
+  PruneSon sons[kFamMaxSons];
+  int nson;
+  int S, C, ncodes, code_bytes;
+  int ppc;
+  long long N;
+  const double* packL;  // [nn][C][kFamPackA]
+  double* out;          // CLV slab of the node
+  int* out_exp;
+};
+
+__host__ __device__ constexpr int prune_threads(int KIND) { return KIND == 4 ? 256 : 512; }  // (three sons: 50 % more shared memory per warp)
+constexpr int kPruneStages = 3;
+__host__ __device__ constexpr int prune_rowstage(int KIND) { return fam_msi(KIND) * (kFamRowArr + 4); }
+template <int KIND>
+constexpr size_t dmma_prune_smem(int C) {
+  return (size_t)(C * fam_msi(KIND) * kFamPackA + (prune_threads(KIND) / 32) * kPruneStages * prune_rowstage(KIND)) * sizeof(double);
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(prune_threads(KIND), 1) dmma_prune_kernel(DmmaPruneParams p) {
+  constexpr bool GEN = KIND == 4;
+  constexpr int MS = GEN ? 3 : 2;
+  constexpr int NT = prune_threads(KIND);
+  constexpr int NW = NT / 32;
+  constexpr int MSI = fam_msi(KIND);
+  constexpr int MATS = MSI * kFamPackA;
+  constexpr int NST = kPruneStages;
+  constexpr int ROWSTAGE = prune_rowstage(KIND);
+  constexpr int EXPOFF = MSI * kFamRowArr;
+  extern __shared__ __align__(16) double sm_pr[];  // [C][MATS] operands, then [warp][NST][ROWSTAGE]
+
+  auto has = [&](int j) { return GEN ? j < p.nson : true; };
+  auto tip = [&](int j) { return GEN ? p.sons[j].kind == CHILD_TIP : ((KIND >> j) & 1) != 0; };
+  auto slot = [&](int j) { return GEN ? j : (j == 1 && !(KIND & 1) ? 1 : 0); };
+
+  const int S = p.S, C = p.C;
+  const int CS = C * S;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, q = lane & 3;
+  double* rows = sm_pr + (size_t)C * MATS + (size_t)warp * NST * ROWSTAGE;
+  const long long cta0 = (long long)blockIdx.x * p.ppc;
+  const int ncta = (int)(cta0 + p.ppc < p.N ? p.ppc : p.N - cta0);
+
+  int cp_r[3], cp_src[3], cp_dst[3];
+#pragma unroll
+  for (int it = 0; it < 3; ++it) {
+    const int e = lane + 32 * it;
+    cp_r[it] = e / 10;
+    cp_src[it] = 2 * (e - cp_r[it] * 10);
+    cp_dst[it] = cp_r[it] * kFamRowStride + cp_src[it];
+  }
+  const int* exp_src = nullptr;
+#pragma unroll
+  for (int j = 0; j < MS; ++j)
+    if (has(j) && !tip(j) && (lane >> 3) == slot(j)) exp_src = p.sons[j].exp + cta0 * C;
+
+  auto fetch_rows = [&](int r0, int c, int st) {
+    double* dst = rows + (size_t)st * ROWSTAGE;
+    const int rmax = ncta - 1 - r0;
+    const int cS = c * S;
+    if (MSI > 0) {
+#pragma unroll
+      for (int it = 0; it < 3; ++it) {
+        if (it < 2 || lane < 16) {
+          const int off = (r0 + min(cp_r[it], rmax)) * CS + cS + cp_src[it];
+          double* d = dst + cp_dst[it];
+#pragma unroll
+          for (int j = 0; j < MS; ++j)
+            if (has(j) && !tip(j)) cp_async16(d + slot(j) * kFamRowArr, p.sons[j].clv + cta0 * CS + off);
+        }
+      }
+      if (exp_src != nullptr)
+        cp_async4(reinterpret_cast<int*>(dst + EXPOFF) + lane, exp_src + (r0 + min(lane & 7, rmax)) * C + c);
+    }
+  };
+  int fr0 = warp * 8, fc = 0;
+  auto fetch_next = [&](int st) {
+    if (fr0 < ncta) {
+      fetch_rows(fr0, fc, st);
+      if (++fc == C) {
+        fc = 0;
+        fr0 += NW * 8;
+      }
+    }
+    cp_async_commit();
+  };
+  auto load_frag = [&](const double* arr, double (&a)[kFamKB]) {
+    const double* row = arr + g * kFamRowStride;
+    const double2 v0 = *reinterpret_cast<const double2*>(row + 4 * q);
+    const double2 v1 = *reinterpret_cast<const double2*>(row + 4 * q + 2);
+    a[0] = v0.x; a[1] = v0.y; a[2] = v1.x; a[3] = v1.y;
+    a[4] = row[16 + q];
+  };
+  auto load_codes = [&](int r0, int (&code)[MS]) {
+    const long long pat = cta0 + min(r0 + g, ncta - 1);
+#pragma unroll
+    for (int j = 0; j < MS; ++j) code[j] = (has(j) && tip(j)) ? load_code(p.sons[j].codes, p.code_bytes, pat) : 0;
+  };
+
+#pragma unroll
+  for (int s0 = 0; s0 < NST - 1; ++s0) fetch_next(s0);
+  for (int c = 0; c < C; ++c)
+#pragma unroll
+    for (int j = 0; j < MS; ++j)
+      if (has(j) && !tip(j))
+        family_stage_async<NT>(sm_pr + (size_t)c * MATS + (size_t)slot(j) * kFamPackA,
+                               p.packL + ((size_t)p.sons[j].node * C + c) * kFamPackA, kFamPackA);
+  cp_async_commit();
+  int ccur[MS], cnxt[MS];
+  load_codes(warp * 8, cnxt);
+  cp_async_wait<0>();
+  __syncthreads();
+
+  int st = 0;
+  for (int r0 = warp * 8; r0 < ncta; r0 += NW * 8) {
+    const bool valid = r0 + g < ncta;
+#pragma unroll
+    for (int j = 0; j < MS; ++j) ccur[j] = cnxt[j];
+    if (r0 + NW * 8 < ncta) load_codes(r0 + NW * 8, cnxt);
+    for (int c = 0; c < C; ++c) {
+      __syncwarp();
+      fetch_next(st == 0 ? NST - 1 : st - 1);
+      cp_async_wait<NST - 1>();
+      __syncwarp();
+      const double* rs = rows + (size_t)st * ROWSTAGE;
+      const int* ex = reinterpret_cast<const int*>(rs + EXPOFF);
+      st = st + 1 == NST ? 0 : st + 1;
+      const double* mats = sm_pr + (size_t)c * MATS;
+
+      double prod[5];
+      int Ea = 0;
+      bool firstson = true;
+#pragma unroll
+      for (int j = 0; j < MS; ++j) {
+        if (has(j)) {
+          double v[5];
+          if (tip(j)) {
+            const double* tp = p.sons[j].tt + (c * p.ncodes + ccur[j]) * S;
+            ld256nc(tp + 4 * q, v[0], v[1], v[2], v[3]);
+            v[4] = __ldg(tp + 16 + q);
+          } else {
+            double a[kFamKB], acc[3][2];
+            load_frag(rs + slot(j) * kFamRowArr, a);
+            Ea += ex[slot(j) * 8 + g];
+            family_contract<3, 2>(acc, a, mats + (size_t)slot(j) * kFamPackA, lane);
+#pragma unroll
+            for (int i = 0; i < 5; ++i) v[i] = acc[i >> 1][i & 1];
+          }
+#pragma unroll
+          for (int i = 0; i < 5; ++i) prod[i] = firstson ? v[i] : prod[i] * v[i];
+          firstson = false;
+        }
+      }
+      int m = 0;
+#pragma unroll
+      for (int i = 0; i < 5; ++i) m = max(m, hi_word(prod[i]));
+      m = max(m, __shfl_xor_sync(0xffffffffu, m, 1));
+      m = max(m, __shfl_xor_sync(0xffffffffu, m, 2));
+      const int k = (m < kScaleThresholdHi && m >= (1 << 20)) ? rescale_shift(m) : 0;
+      const double f = pow2(k);
+      Ea += k;
+      if (valid) {
+        double* row = p.out + cta0 * CS + (r0 + g) * CS + c * S;
+        st256(row + 4 * q, prod[0] * f, prod[1] * f, prod[2] * f, prod[3] * f);
+        row[16 + q] = prod[4] * f;
+        if (q == 0) p.out_exp[cta0 * C + (r0 + g) * C + c] = Ea;
+      }
+    }
   }
 }
 

@@ -534,7 +534,7 @@ int bppgpu_destroy(bppgpu_engine* e) {
                   e->d_d2P, e->d_tiptab, e->d_keep, e->d_keep_exp, e->d_gstack, e->d_gstack_exp, e->d_upper,
                   e->d_upper_exp, e->d_SR, e->d_rexp, e->d_site_lnl, e->d_partials, e->d_partials2, e->d_out,
                   e->prog.d_ops, e->prog.d_childs, e->gprog.d_ops, e->gprog.d_childs, e->d_sibs, e->d_scratch,
-                  e->d_dtiptab, e->d_d2tiptab, e->d_dLc, e->d_fam_mask, e->d_fam_part, e->d_fam_packA, e->d_fam_packS, e->d_fam_packT, e->d_w4_desc, e->d_w4_tip_order, e->d_w4_blocks, e->d_w4_stream, e->d_codesT,
+                  e->d_dtiptab, e->d_d2tiptab, e->d_dLc, e->d_fam_mask, e->d_fam_part, e->d_fam_packA, e->d_fam_packS, e->d_fam_packL, e->d_w4_desc, e->d_w4_tip_order, e->d_w4_blocks, e->d_w4_stream, e->d_codesT,
                   e->d_status};
   for (void* p : ptrs) cudaFree(p);
   for (auto& m : e->models) free_model(m);
@@ -788,6 +788,28 @@ static int create_impl(const bppgpu_config* cfg, bppgpu_engine* e) {
   BPP_CUDA(dev_alloc(e, &e->d_status, 1));
   BPP_CUDA(cudaMemset(e->d_status, 0, sizeof(int)));
 
+  // S = 20 on the FP64 tensor cores: fragment-order operands, one persistent CTA per SM (dmma_family_kernels.cuh);
+  // BPPGPU_FAMILY=0 keeps the older per-node / per-branch kernels
+  {
+    const char* fenv = getenv("BPPGPU_FAMILY");
+    e->family = e->path == PATH_DMMA && S == 20 && C <= kFamMaxClasses && N > 0 && e->npoints == 1 && !(fenv && atoi(fenv) == 0);
+  }
+  if (e->family) {
+    long long slots = g_sm_count;
+    if (const char* env = getenv("BPPGPU_FAMILY_GRID")) slots = std::max(1, atoi(env));  // test knob: few CTAs, long ranges
+    long long ppc = (N + slots - 1) / slots;
+    ppc = std::max<long long>(8, (ppc + 7) / 8 * 8);
+    e->fam_ppc = (int)ppc;
+    e->fam_grid = (int)((N + ppc - 1) / ppc);
+    BPP_CUDA(dev_alloc(e, &e->d_fam_packL, (size_t)nn * C * kFamPackA));
+    auto attr = [](auto k, size_t smem) { return cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); };
+    BPP_CUDA(attr(dmma_prune_kernel<0>, dmma_prune_smem<0>(C)));
+    BPP_CUDA(attr(dmma_prune_kernel<1>, dmma_prune_smem<1>(C)));
+    BPP_CUDA(attr(dmma_prune_kernel<2>, dmma_prune_smem<2>(C)));
+    BPP_CUDA(attr(dmma_prune_kernel<3>, dmma_prune_smem<3>(C)));
+    BPP_CUDA(attr(dmma_prune_kernel<4>, dmma_prune_smem<4>(C)));
+  }
+
   if (e->path == PATH_WALK4) {
     // patterns per thread: 2 (4 CTAs of 128 threads per SM at 128 registers) while the stack leaves room for it
     e->w4_pt = 2;
@@ -993,9 +1015,7 @@ static int ensure_deriv_buffers(bppgpu_engine* e, unsigned want) {
       BPP_CUDA(dev_alloc(e, &e->d_dtiptab, tt));
       BPP_CUDA(dev_alloc(e, &e->d_d2tiptab, tt));
       BPP_CUDA(dev_alloc(e, &e->d_dLc, (size_t)e->N * e->C * 2));
-      // per-father fused pass (S = 20): every father with <= 3 sons; BPPGPU_FAMILY=0 keeps the per-branch kernels
-      const char* fenv = getenv("BPPGPU_FAMILY");
-      e->family = e->S == 20 && e->C <= kFamMaxClasses && e->N > 0 && !(fenv && atoi(fenv) == 0);
+      // per-father fused pass (S = 20): every father with <= 3 sons
       if (e->family) {
         e->fam_mask.assign(e->nn, 0);
         for (int f = 0; f < e->nn; ++f) {
@@ -1018,18 +1038,10 @@ static int ensure_deriv_buffers(bppgpu_engine* e, unsigned want) {
           BPP_CUDA(attr(dmma_family_kernel<8, 3>, dmma_family_smem<3>(e->C)));
           BPP_CUDA(attr(dmma_family_kernel<8, 4>, dmma_family_smem<4>(e->C)));
         }
-        const int per_sm = 1;  // persistent: one CTA per SM (registers and shared memory both say so)
-        long long slots = (long long)g_sm_count * std::max(1, per_sm);
-        if (const char* env = getenv("BPPGPU_FAMILY_GRID")) slots = std::max(1, atoi(env));  // test knob: few CTAs, many chunks
-        long long ppc = (e->N + slots - 1) / slots;
-        ppc = std::max<long long>(8, (ppc + 7) / 8 * 8);
-        e->fam_ppc = (int)ppc;
-        e->fam_grid = (int)((e->N + ppc - 1) / ppc);
         BPP_CUDA(dev_alloc(e, &e->d_fam_part, (size_t)e->nn * 2 * e->fam_grid));
         BPP_CUDA(cudaMemset(e->d_fam_part, 0, (size_t)e->nn * 2 * e->fam_grid * 8));
         BPP_CUDA(dev_alloc(e, &e->d_fam_packA, (size_t)e->nn * e->C * kFamPackA));
         BPP_CUDA(dev_alloc(e, &e->d_fam_packS, (size_t)e->nn * e->C * kFamPackS));
-        BPP_CUDA(dev_alloc(e, &e->d_fam_packT, (size_t)e->nl * e->C * e->ncodes * 64));
       }
     }
   }
@@ -1182,7 +1194,40 @@ static int enqueue_prune(bppgpu_engine* e, int point, int pl, cudaStream_t st) {
       gp.N = N;
       gp.P = P; gp.tiptab = tiptab; gp.codes = e->d_codes;
       gp.keep = e->d_keep; gp.keep_exp = e->d_keep_exp;
-      if (e->path == PATH_DMMA) {
+      if (e->path == PATH_DMMA && e->family && op.nchild <= kFamMaxSons) {
+        DmmaPruneParams pp{};
+        pp.nson = op.nchild;
+        int kind = op.nchild == 2 ? 0 : 4;
+        for (int j = 0; j < op.nchild; ++j) {
+          const Child& ch = e->gprog.childs[op.child_begin + j];
+          PruneSon& ps = pp.sons[j];
+          ps.kind = ch.kind == CHILD_TIP ? CHILD_TIP : CHILD_KEEP;
+          ps.node = ch.pnode;
+          if (ch.kind == CHILD_TIP) {
+            ps.codes = (const char*)e->d_codes + (size_t)ch.idx * N * e->code_bytes;
+            ps.tt = tiptab + (size_t)ch.idx * C * e->ncodes * S;
+            if (kind != 4) kind |= 1 << j;
+          } else {
+            ps.clv = e->d_keep + (size_t)ch.idx * N * C * S;
+            ps.exp = e->d_keep_exp + (size_t)ch.idx * N * C;
+          }
+        }
+        pp.S = S; pp.C = C; pp.ncodes = e->ncodes; pp.code_bytes = e->code_bytes;
+        pp.ppc = e->fam_ppc;
+        pp.N = N;
+        pp.packL = e->d_fam_packL;
+        pp.out = e->d_keep + (size_t)op.keep_idx * N * C * S;
+        pp.out_exp = e->d_keep_exp + (size_t)op.keep_idx * N * C;
+        const int G = e->fam_grid;
+        switch (kind) {
+          case 0: dmma_prune_kernel<0><<<G, prune_threads(0), dmma_prune_smem<0>(C), st>>>(pp); break;
+          case 1: dmma_prune_kernel<1><<<G, prune_threads(1), dmma_prune_smem<1>(C), st>>>(pp); break;
+          case 2: dmma_prune_kernel<2><<<G, prune_threads(2), dmma_prune_smem<2>(C), st>>>(pp); break;
+          case 3: dmma_prune_kernel<3><<<G, prune_threads(3), dmma_prune_smem<3>(C), st>>>(pp); break;
+          default: dmma_prune_kernel<4><<<G, prune_threads(4), dmma_prune_smem<4>(C), st>>>(pp); break;
+        }
+        e->stats.kernel_launches += 1;
+      } else if (e->path == PATH_DMMA) {
         DmmaNodeParams dp{};
         dp.childs = gp.childs; dp.nchild = gp.nchild; dp.out_idx = gp.out_idx;
         dp.S = S; dp.C = C; dp.ncodes = e->ncodes; dp.code_bytes = e->code_bytes; dp.N = N;
@@ -1276,7 +1321,10 @@ static int enqueue_derivs(bppgpu_engine* e, int point, int pl, unsigned want, cu
       if (tip) {
         const int slot = e->leaf_slot[s];
         fs.codes = (const char*)e->d_codes + (size_t)slot * N * e->code_bytes;
-        fs.tpack = e->d_fam_packT + (size_t)slot * C * e->ncodes * 64;
+        const size_t ttN = (size_t)C * e->ncodes * S;
+        fs.tt = tiptab + slot * ttN;
+        fs.dtt = e->d_dtiptab + ((size_t)pl * e->nl + slot) * ttN;
+        fs.d2tt = e->d_d2tiptab + ((size_t)pl * e->nl + slot) * ttN;
         if (kind != 4) kind |= 1 << j;
       } else {
         fs.clv = e->d_keep + (size_t)e->internal_idx[s] * clvN;
@@ -1313,20 +1361,6 @@ static int enqueue_derivs(bppgpu_engine* e, int point, int pl, unsigned want, cu
 #undef BPP_FAM
     e->stats.kernel_launches++;
   };
-  if (family) {
-    FamilyPackParams pk{};
-    pk.P = P; pk.dP = dP; pk.d2P = d2P;
-    pk.packA = e->d_fam_packA; pk.packS = e->d_fam_packS;
-    pk.tt = tiptab;
-    pk.dtt = e->d_dtiptab + (size_t)pl * e->nl * C * e->ncodes * S;
-    pk.d2tt = (want & BPPGPU_EVAL_D2) ? e->d_d2tiptab + (size_t)pl * e->nl * C * e->ncodes * S : nullptr;
-    pk.packT = e->d_fam_packT;
-    pk.S = S;
-    pk.nbc = nn * C;
-    pk.ntc = e->nl * C * e->ncodes;
-    family_pack_kernel<<<pk.nbc + (pk.ntc + 3) / 4, 256, 0, st>>>(pk);
-    e->stats.kernel_launches++;
-  }
   auto launch_branch = [&](int n) {
     const int f = e->parent[n];
     UpperParams up{};
@@ -1511,6 +1545,17 @@ static int eval_impl(bppgpu_engine* e, unsigned want, cudaStream_t st, bool time
           e->stats.kernel_launches++;
         }
       }
+    }
+    if (e->family) {
+      // operands in fragment order for the S = 20 tensor-core kernels (single-point engines only)
+      FamilyPackParams pk{};
+      pk.P = e->d_P;
+      pk.dP = derivs ? e->d_dP : nullptr;
+      pk.d2P = (want & BPPGPU_EVAL_D2) ? e->d_d2P : nullptr;
+      pk.packA = e->d_fam_packA; pk.packS = e->d_fam_packS; pk.packL = e->d_fam_packL;
+      pk.S = S;
+      family_pack_kernel<<<nn * C, 256, 0, st>>>(pk);
+      e->stats.kernel_launches++;
     }
     BPP_CUDA(cudaGetLastError());
     if (e->path == PATH_POINTS) {
