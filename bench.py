@@ -193,6 +193,28 @@ def ncu_traffic(kernel):
     return best
 
 
+def ncu_traffic_per_eval(workload, kernel):
+    """DRAM bytes of all launches of `kernel` in one evaluation of `workload` (profiles/r1e_traffic.json, written by
+    tools/traffic_from_launches.py from the committed ncu launch list), or None."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "r1e_traffic.json")))
+        return t[workload][kernel]["dram_bytes_per_eval"]
+    except (OSError, ValueError, KeyError):
+        return None
+
+
+def family_dmma_flops(tree, rows):
+    """FP64 tensor-core flops the per-father derivative kernel issues (S = 20, d1 + d2): per 8 rows and class, 15 DMMAs
+    (m8n8k4, 512 flop) for the father contraction of every non-root father and 40 per internal son (P | dP | d2P stacked)."""
+    dmma = 0
+    for n in range(tree.nn):
+        sons = tree.sons(n)
+        if not len(sons):
+            continue
+        dmma += (15 if n != tree.root else 0) + 40 * sum(1 for s in sons if len(tree.sons(s)))
+    return dmma * 512.0 * rows / 8
+
+
 def flops_per_eval(tree, rows, S):
     """pruning contraction flops: 2 S^2 per (row, internal son) + S per extra son"""
     tot = 0
@@ -525,6 +547,9 @@ def main():
         alg = algorithmic_bytes(tree, n_local, w["C"], w["S"])
         kms = st["prune_ms_sum"] / max(1, st["prune_count"])
         kname = {1: "walk4_kernel", 2: "walkS_kernel", 3: "generic_node_kernel", 4: "dmma_node_kernel"}.get(st["path"], "?")
+        fam20 = st["path"] == 4 and w["S"] == 20 and w["C"] <= 4 and os.environ.get("BPPGPU_FAMILY", "1") != "0"
+        if fam20:
+            kname = "dmma_prune_kernel"
         if st["path"] == 4 and w["S"] >= 32:
             # dense contraction on the FP64 tensor cores (mma.sync DMMA; tcgen05 has no f64 kind)
             try:
@@ -549,7 +574,8 @@ def main():
             achieved = alg / (kms * 1e-3) / 1e9 if kms > 0 else None
             roofline = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                         "frac": achieved / hbm_peak if achieved else None,
-                        "traffic": ncu_traffic(kname) if (a.workload == DEFAULT and not a.patterns and world == 1) else None,
+                        "traffic": (ncu_traffic(kname) if a.workload == DEFAULT else ncu_traffic_per_eval(a.workload, kname))
+                        if (not a.patterns and world == 1) else None,
                         "kernel_ms": kms,
                         "launches_timed": st["prune_count"], "algorithmic_bytes_per_launch": alg,
                         "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
@@ -558,6 +584,21 @@ def main():
                                  "the tip codes only (traffic = dram bytes of one launch, ncu, profiles/)") if st["path"] == 1 else
                                 "algorithmic bytes = 8*(1+internal sons) per CLV element (SURVEY 8d); one launch per node, all "
                                 "launches of an evaluation timed together"}
+        if fam20 and w["derivs"]:
+            # second kernel family of this workload: the per-father upper + d1/d2 pass, bound by the FP64 tensor pipe
+            try:
+                fp = json.loads(open(os.path.join(ROOT, "profiles", "r1_fp64_peaks.json")).readline())
+            except (OSError, ValueError):
+                fp = {}
+            dmma_peak = fp.get("dmma_m8n8k4_tflops", 37.1)
+            dms = ms / K - kms - st["pt_ms_sum"] / max(1, K)
+            fl = family_dmma_flops(tree, n_local * w["C"])
+            roofline["derivative_pass"] = {
+                "kernel": "dmma_family_kernel (one launch per father)", "bound": "tensor", "ms": dms,
+                "executed_dmma_flops": fl, "achieved": fl / (dms * 1e-3) / 1e12 if dms > 0 else None, "peak": dmma_peak,
+                "unit": "TFLOP/s", "frac": fl / (dms * 1e-3) / 1e12 / dmma_peak if dms > 0 else None,
+                "traffic": ncu_traffic_per_eval(a.workload, "dmma_family_kernel") if (not a.patterns and world == 1) else None,
+                "note": "ms = step - pruning - P(t) (event timed); flops = DMMAs issued x 512"}
         line = {"metric": metric, "value": value, "unit": "CLV updates/s", "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": ms / K, "higher_is_better": True, "scaling": a.scaling, "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic (tips simulated down a random tree under the model; every site kept as a pattern, weight 1)",

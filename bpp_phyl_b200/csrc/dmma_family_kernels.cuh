@@ -47,7 +47,7 @@ struct FamilySon {
   const double* clv;     // lower CLV slab [N][C][S]            (internal son)
   const int* exp;        // its exponents  [N][C]
   const void* codes;     // tip codes      [N]                  (tip son)
-  const double *tt, *dtt, *d2tt;  // this leaf's tip tables of P, dP, d2P  [C][ncodes][S]   (tip son)
+  const double* tpack;   // this leaf's tip tables of P | dP | d2P in lane order [C][ncodes][4][4][4]   (tip son)
   double* up;            // slab that receives upper[son], or null
   int* upexp;
 };
@@ -86,11 +86,24 @@ struct FamilyPackParams {
   const double *P, *dP, *d2P;  // [nn][C][S][S]; d2P may be null
   double *packA, *packS;
   double* packL;                  // [nn][C][kFamPackA]  P alone (pruning pass); packA/packS are skipped when dP is null
-  int S;
+  // tip tables [nl][C][ncodes][S] (dtt / d2tt may be null) -> packT [nl][C][ncodes][k = 4][q = 4][4]: the 16 slots of lane q
+  // (t = 4k + e = 5 mat + i <-> state fam_state(i, q)) in four 32-byte pieces, piece k of the four lanes of a quad
+  // contiguous, so that one 256-bit load per lane fetches a full 128-byte line per row
+  const double *tt, *dtt, *d2tt;
+  double* packT;
+  int S, nbc, ntc;  // nbc = nn * C operand blocks, then ntc = nl * C * ncodes tip rows (0: none)
 };
 
 __global__ void family_pack_kernel(FamilyPackParams p) {
   const int S = p.S;
+  if ((int)blockIdx.x >= p.nbc) {
+    const size_t row = (size_t)(blockIdx.x - p.nbc) * (blockDim.x / 64) + threadIdx.x / 64;
+    if (row >= (size_t)p.ntc) return;
+    const int e = threadIdx.x & 63, k = e >> 4, q = (e >> 2) & 3, t = 4 * k + (e & 3), mat = t / 5, i = t - 5 * mat;
+    const double* tab = mat == 0 ? p.tt : (mat == 1 ? p.dtt : (mat == 2 ? p.d2tt : nullptr));
+    p.packT[row * 64 + e] = tab != nullptr ? tab[row * S + fam_state(i, q)] : 0.0;
+    return;
+  }
   const size_t SS = (size_t)S * S;
   const size_t bc = blockIdx.x;  // branch * C + class
   const double* m[3] = {p.P + bc * SS, p.dP ? p.dP + bc * SS : nullptr, p.d2P ? p.d2P + bc * SS : nullptr};
@@ -324,18 +337,18 @@ __global__ void __launch_bounds__(fam_threads(KIND == 4 ? 3 : 2), 1) dmma_family
 #pragma unroll
       for (int j = 0; j < MS; ++j) {
         if (has(j) && tip(j)) {
-          const int toff = (c * p.ncodes + pcur.code[j]) * S;
-          double v[15];
-          ld256nc(p.sons[j].tt + toff + 4 * q, v[0], v[1], v[2], v[3]);
-          v[4] = __ldg(p.sons[j].tt + toff + 16 + q);
-          ld256nc(p.sons[j].dtt + toff + 4 * q, v[5], v[6], v[7], v[8]);
-          v[9] = __ldg(p.sons[j].dtt + toff + 16 + q);
-          if (NMAT > 2) {
-            ld256nc(p.sons[j].d2tt + toff + 4 * q, v[10], v[11], v[12], v[13]);
-            v[14] = __ldg(p.sons[j].d2tt + toff + 16 + q);
-          }
+          const double* tp = p.sons[j].tpack + (size_t)(c * p.ncodes + pcur.code[j]) * 64 + 4 * q;
 #pragma unroll
-          for (int t = 0; t < 2 * NB; ++t) R[j][t >> 1][t & 1] = t < 5 * NMAT ? v[t] : 0.0;
+          for (int k = 0; k < (2 * NB + 3) / 4; ++k) {
+            double v0, v1, v2, v3;
+            ld256nc(tp + 16 * k, v0, v1, v2, v3);
+            R[j][2 * k][0] = v0;
+            R[j][2 * k][1] = v1;
+            if (2 * k + 1 < NB) {
+              R[j][2 * k + 1][0] = v2;
+              R[j][2 * k + 1][1] = v3;
+            }
+          }
         }
       }
       // ---- A_f -----------------------------------------------------------------------------------------------------

@@ -534,7 +534,7 @@ int bppgpu_destroy(bppgpu_engine* e) {
                   e->d_d2P, e->d_tiptab, e->d_keep, e->d_keep_exp, e->d_gstack, e->d_gstack_exp, e->d_upper,
                   e->d_upper_exp, e->d_SR, e->d_rexp, e->d_site_lnl, e->d_partials, e->d_partials2, e->d_out,
                   e->prog.d_ops, e->prog.d_childs, e->gprog.d_ops, e->gprog.d_childs, e->d_sibs, e->d_scratch,
-                  e->d_dtiptab, e->d_d2tiptab, e->d_dLc, e->d_fam_mask, e->d_fam_part, e->d_fam_packA, e->d_fam_packS, e->d_fam_packL, e->d_w4_desc, e->d_w4_tip_order, e->d_w4_blocks, e->d_w4_stream, e->d_codesT,
+                  e->d_dtiptab, e->d_d2tiptab, e->d_dLc, e->d_fam_mask, e->d_fam_part, e->d_fam_packA, e->d_fam_packS, e->d_fam_packL, e->d_fam_packT, e->d_w4_desc, e->d_w4_tip_order, e->d_w4_blocks, e->d_w4_stream, e->d_codesT,
                   e->d_status};
   for (void* p : ptrs) cudaFree(p);
   for (auto& m : e->models) free_model(m);
@@ -1042,6 +1042,7 @@ static int ensure_deriv_buffers(bppgpu_engine* e, unsigned want) {
         BPP_CUDA(cudaMemset(e->d_fam_part, 0, (size_t)e->nn * 2 * e->fam_grid * 8));
         BPP_CUDA(dev_alloc(e, &e->d_fam_packA, (size_t)e->nn * e->C * kFamPackA));
         BPP_CUDA(dev_alloc(e, &e->d_fam_packS, (size_t)e->nn * e->C * kFamPackS));
+        BPP_CUDA(dev_alloc(e, &e->d_fam_packT, (size_t)e->nl * e->C * e->ncodes * 64));
       }
     }
   }
@@ -1321,10 +1322,7 @@ static int enqueue_derivs(bppgpu_engine* e, int point, int pl, unsigned want, cu
       if (tip) {
         const int slot = e->leaf_slot[s];
         fs.codes = (const char*)e->d_codes + (size_t)slot * N * e->code_bytes;
-        const size_t ttN = (size_t)C * e->ncodes * S;
-        fs.tt = tiptab + slot * ttN;
-        fs.dtt = e->d_dtiptab + ((size_t)pl * e->nl + slot) * ttN;
-        fs.d2tt = e->d_d2tiptab + ((size_t)pl * e->nl + slot) * ttN;
+        fs.tpack = e->d_fam_packT + (size_t)slot * C * e->ncodes * 64;
         if (kind != 4) kind |= 1 << j;
       } else {
         fs.clv = e->d_keep + (size_t)e->internal_idx[s] * clvN;
@@ -1554,7 +1552,15 @@ static int eval_impl(bppgpu_engine* e, unsigned want, cudaStream_t st, bool time
       pk.d2P = (want & BPPGPU_EVAL_D2) ? e->d_d2P : nullptr;
       pk.packA = e->d_fam_packA; pk.packS = e->d_fam_packS; pk.packL = e->d_fam_packL;
       pk.S = S;
-      family_pack_kernel<<<nn * C, 256, 0, st>>>(pk);
+      pk.nbc = nn * C;
+      pk.ntc = derivs ? e->nl * C * e->ncodes : 0;
+      if (derivs) {
+        pk.tt = e->d_tiptab;
+        pk.dtt = e->d_dtiptab;
+        pk.d2tt = (want & BPPGPU_EVAL_D2) ? e->d_d2tiptab : nullptr;
+        pk.packT = e->d_fam_packT;
+      }
+      family_pack_kernel<<<pk.nbc + (pk.ntc + 3) / 4, 256, 0, st>>>(pk);
       e->stats.kernel_launches++;
     }
     BPP_CUDA(cudaGetLastError());

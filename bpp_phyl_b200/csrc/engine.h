@@ -86,7 +86,7 @@ struct bppgpu_engine {
   std::vector<int> fam_mask;   // node id -> 1 when its branch is served by its father's family launch
   int* d_fam_mask = nullptr;
   double* d_fam_part = nullptr;  // [nn][2][fam_grid]
-  double *d_fam_packA = nullptr, *d_fam_packS = nullptr, *d_fam_packL = nullptr;  // B operands in fragment order (family_pack_kernel)
+  double *d_fam_packA = nullptr, *d_fam_packS = nullptr, *d_fam_packL = nullptr, *d_fam_packT = nullptr;  // B operands in fragment order (family_pack_kernel)
   int fam_grid = 0, fam_ppc = 0;
   int n_upper_slabs = 0;
   // walk4 artefacts (everything in walk order, see walk_kernels.cuh)
