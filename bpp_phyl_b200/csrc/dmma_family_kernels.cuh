@@ -35,9 +35,9 @@ namespace bppgpu {
 constexpr int kFamMaxSons = 3;
 constexpr int kFamMaxClasses = 4; // operands of every class are resident in shared memory
 constexpr int kFamKB = 5;        // k blocks: S = 20
-// binary fathers (all but the unrooted root): 12 warps per SM; three sons need 32 more accumulator registers and
-// 10 KB more operands per class: 6 warps
-__host__ __device__ constexpr int fam_threads(int MS) { return MS == 2 ? 384 : 192; }
+// warps per SM by kernel kind: binary fathers 12 (16 warps at 128 registers measured 8 % slower); the run-time kind (up to three sons:
+// 32 more accumulator registers and 10 KB more operands per class) 6
+__host__ __device__ constexpr int fam_threads_kind(int KIND) { return KIND == 4 ? 192 : 384; }
 
 // Everything the kernel dereferences is a ready-made pointer (the host folds slab indices in): the first version
 // rebuilt 64-bit slab offsets per access and spent more issue slots on IMAD than on DMMA.
@@ -61,6 +61,7 @@ struct DmmaFamilyParams {
   int S, C, ncodes, code_bytes;
   int nh_form;
   int ppc;               // patterns per CTA (multiple of 8)
+  int prow, crow;        // CLV row of (pattern i, class c) = i * prow + c * crow  ([i][c]: C, 1;  class-major [c][i]: 1, N)
   long long N;
   const double* packA;   // [nn][C][kFamPackA]  P^T of every branch in fragment order
   const double* packS;   // [nn][C][kFamPackS]  stacked P | dP | d2P in fragment order
@@ -176,18 +177,18 @@ __host__ __device__ constexpr int fam_rowstage(int KIND) { return (1 + fam_msi(K
 template <int KIND>
 constexpr size_t dmma_family_smem(int C) {
   return (size_t)(C * (kFamPackA + fam_msi(KIND) * kFamPackS) +
-                  (fam_threads(KIND == 4 ? 3 : 2) / 32) * fam_stages(KIND) * fam_rowstage(KIND)) * sizeof(double);
+                  (fam_threads_kind(KIND) / 32) * fam_stages(KIND) * fam_rowstage(KIND)) * sizeof(double);
 }
 
 // NB = 5 (d1) or 8 (d1, d2) column blocks per son.
 // KIND 0..3: a binary father whose son j is a tip iff bit j is set (straight-line code, 12 warps);  KIND 4: one to three
 // sons of any kind decided at run time (the unrooted root, unary nodes; 6 warps).
 template <int NB, int KIND>
-__global__ void __launch_bounds__(fam_threads(KIND == 4 ? 3 : 2), 1) dmma_family_kernel(DmmaFamilyParams p) {
+__global__ void __launch_bounds__(fam_threads_kind(KIND), 1) dmma_family_kernel(DmmaFamilyParams p) {
   constexpr bool GEN = KIND == 4;
   constexpr int MS = GEN ? 3 : 2;
   constexpr int NMAT = NB == 5 ? 2 : 3;
-  constexpr int NT = fam_threads(MS);
+  constexpr int NT = fam_threads_kind(KIND);
   constexpr int NW = NT / 32;
   constexpr int MSI = fam_msi(KIND);                     // sons that can be internal: operand / row slots
   constexpr int MATS = kFamPackA + MSI * kFamPackS;      // doubles per class
@@ -204,7 +205,6 @@ __global__ void __launch_bounds__(fam_threads(KIND == 4 ? 3 : 2), 1) dmma_family
   auto slot = [&](int j) { return GEN ? j : (j == 1 && !(KIND & 1) ? 1 : 0); };  // operand / row slot of internal son j
 
   const int S = p.S, C = p.C;
-  const int CS = C * S;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, q = lane & 3;
   double* rows = sm_fam + (size_t)C * MATS + (size_t)warp * NST * ROWSTAGE;
@@ -212,8 +212,10 @@ __global__ void __launch_bounds__(fam_threads(KIND == 4 ? 3 : 2), 1) dmma_family
   const long long cta0 = (long long)blockIdx.x * p.ppc;
   const int ncta = (int)(cta0 + p.ppc < p.N ? p.ppc : p.N - cta0);
   const bool root = p.father < 0;
-  const double* fup = p.fup + (root ? 0 : cta0 * CS);
-  const int* fupexp = p.fupexp + (root ? 0 : cta0 * C);
+  const double* fup = p.fup;
+  const int* fupexp = p.fupexp;
+  const int prow = p.prow, crow = p.crow;
+  const int rowbase = (int)cta0 * prow;  // CLV row of (CTA pattern r, class c) = rowbase + r * prow + c * crow  (< 2^31 / S, host-checked)
 
   // per-lane constants of the row copy: piece e = lane + 32 it of the 8 x 10 16-byte pieces of an array
   int cp_r[3], cp_src[3], cp_dst[3];
@@ -231,27 +233,26 @@ __global__ void __launch_bounds__(fam_threads(KIND == 4 ? 3 : 2), 1) dmma_family
   } else {
 #pragma unroll
     for (int j = 0; j < MS; ++j)
-      if (has(j) && !tip(j) && (lane >> 3) == 1 + slot(j)) exp_src = p.sons[j].exp + cta0 * C;
+      if (has(j) && !tip(j) && (lane >> 3) == 1 + slot(j)) exp_src = p.sons[j].exp;
   }
 
   // rows [r0, r0 + 8) (relative to the CTA) of class c and their exponents -> stage st of this warp (asynchronous)
   auto fetch_rows = [&](int r0, int c, int st) {
     double* dst = rows + (size_t)st * ROWSTAGE;
     const int rmax = ncta - 1 - r0;  // rows past the CTA's range re-read its last row
-    const int cS = c * S;
+    const int row0 = rowbase + r0 * prow + c * crow;
 #pragma unroll
     for (int it = 0; it < 3; ++it) {
       if (it < 2 || lane < 16) {
-        const int off = (r0 + min(cp_r[it], rmax)) * CS + cS + cp_src[it];
+        const int off = (row0 + min(cp_r[it], rmax) * prow) * S + cp_src[it];
         double* d = dst + cp_dst[it];
         if (!root) cp_async16(d, fup + off);
 #pragma unroll
         for (int j = 0; j < MS; ++j)
-          if (has(j) && !tip(j)) cp_async16(d + (1 + slot(j)) * kFamRowArr, p.sons[j].clv + cta0 * CS + off);
+          if (has(j) && !tip(j)) cp_async16(d + (1 + slot(j)) * kFamRowArr, p.sons[j].clv + off);
       }
     }
-    if (exp_src != nullptr)
-      cp_async4(reinterpret_cast<int*>(dst + EXPOFF) + lane, exp_src + (r0 + min(lane & 7, rmax)) * C + c);
+    if (exp_src != nullptr) cp_async4(reinterpret_cast<int*>(dst + EXPOFF) + lane, exp_src + row0 + min(lane & 7, rmax) * prow);
   };
   // the fetch cursor runs NST - 1 items ahead of the compute cursor through the same (row block, class) sequence
   int fr0 = warp * 8, fc = 0;
@@ -374,8 +375,8 @@ __global__ void __launch_bounds__(fam_threads(KIND == 4 ? 3 : 2), 1) dmma_family
       }
       // ---- per son: upper row, rescale, store, derivative dots --------------------------------------------------------
       const double rinv = sprobs[c] * inv_sr;
-      const int ooff = (r0 + g) * CS + c * S;  // (only dereferenced when valid)
-      const int oexp = (r0 + g) * C + c;
+      const int oexp = rowbase + (r0 + g) * prow + c * crow;  // output row (only dereferenced when valid)
+      const int ooff = oexp * S;
 #pragma unroll
       for (int j = 0; j < MS; ++j) {
         if (has(j)) {
@@ -404,10 +405,10 @@ __global__ void __launch_bounds__(fam_threads(KIND == 4 ? 3 : 2), 1) dmma_family
             Eu += k;
           }
           if (p.sons[j].up != nullptr && valid) {
-            double* row = p.sons[j].up + cta0 * CS + ooff;
+            double* row = p.sons[j].up + ooff;
             st256(row + 4 * q, U[0], U[1], U[2], U[3]);
             row[16 + q] = U[4];
-            if (q == 0) p.sons[j].upexp[cta0 * C + oexp] = Eu;
+            if (q == 0) p.sons[j].upexp[oexp] = Eu;
           }
           double s1 = 0.0, s2 = 0.0;
 #pragma unroll
@@ -488,6 +489,7 @@ struct DmmaPruneParams {
   int nson;
   int S, C, ncodes, code_bytes;
   int ppc;
+  int prow, crow;       // CLV row of (pattern i, class c) = i * prow + c * crow
   long long N;
   const double* packL;  // [nn][C][kFamPackA]
   double* out;          // CLV slab of the node
@@ -520,12 +522,13 @@ __global__ void __launch_bounds__(prune_threads(KIND), 1) dmma_prune_kernel(Dmma
   auto slot = [&](int j) { return GEN ? j : (j == 1 && !(KIND & 1) ? 1 : 0); };
 
   const int S = p.S, C = p.C;
-  const int CS = C * S;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, q = lane & 3;
   double* rows = sm_pr + (size_t)C * MATS + (size_t)warp * NST * ROWSTAGE;
   const long long cta0 = (long long)blockIdx.x * p.ppc;
   const int ncta = (int)(cta0 + p.ppc < p.N ? p.ppc : p.N - cta0);
+  const int prow = p.prow, crow = p.crow;
+  const int rowbase = (int)cta0 * prow;
 
   int cp_r[3], cp_src[3], cp_dst[3];
 #pragma unroll
@@ -538,25 +541,24 @@ __global__ void __launch_bounds__(prune_threads(KIND), 1) dmma_prune_kernel(Dmma
   const int* exp_src = nullptr;
 #pragma unroll
   for (int j = 0; j < MS; ++j)
-    if (has(j) && !tip(j) && (lane >> 3) == slot(j)) exp_src = p.sons[j].exp + cta0 * C;
+    if (has(j) && !tip(j) && (lane >> 3) == slot(j)) exp_src = p.sons[j].exp;
 
   auto fetch_rows = [&](int r0, int c, int st) {
     double* dst = rows + (size_t)st * ROWSTAGE;
     const int rmax = ncta - 1 - r0;
-    const int cS = c * S;
+    const int row0 = rowbase + r0 * prow + c * crow;
     if (MSI > 0) {
 #pragma unroll
       for (int it = 0; it < 3; ++it) {
         if (it < 2 || lane < 16) {
-          const int off = (r0 + min(cp_r[it], rmax)) * CS + cS + cp_src[it];
+          const int off = (row0 + min(cp_r[it], rmax) * prow) * S + cp_src[it];
           double* d = dst + cp_dst[it];
 #pragma unroll
           for (int j = 0; j < MS; ++j)
-            if (has(j) && !tip(j)) cp_async16(d + slot(j) * kFamRowArr, p.sons[j].clv + cta0 * CS + off);
+            if (has(j) && !tip(j)) cp_async16(d + slot(j) * kFamRowArr, p.sons[j].clv + off);
         }
       }
-      if (exp_src != nullptr)
-        cp_async4(reinterpret_cast<int*>(dst + EXPOFF) + lane, exp_src + (r0 + min(lane & 7, rmax)) * C + c);
+      if (exp_src != nullptr) cp_async4(reinterpret_cast<int*>(dst + EXPOFF) + lane, exp_src + row0 + min(lane & 7, rmax) * prow);
     }
   };
   int fr0 = warp * 8, fc = 0;
@@ -646,10 +648,11 @@ __global__ void __launch_bounds__(prune_threads(KIND), 1) dmma_prune_kernel(Dmma
       const double f = pow2(k);
       Ea += k;
       if (valid) {
-        double* row = p.out + cta0 * CS + (r0 + g) * CS + c * S;
+        const int orow = rowbase + (r0 + g) * prow + c * crow;
+        double* row = p.out + orow * S;
         st256(row + 4 * q, prod[0] * f, prod[1] * f, prod[2] * f, prod[3] * f);
         row[16 + q] = prod[4] * f;
-        if (q == 0) p.out_exp[cta0 * C + (r0 + g) * C + c] = Ea;
+        if (q == 0) p.out_exp[orow] = Ea;
       }
     }
   }

@@ -795,6 +795,17 @@ static int create_impl(const bppgpu_config* cfg, bppgpu_engine* e) {
     e->family = e->path == PATH_DMMA && S == 20 && C <= kFamMaxClasses && N > 0 && e->npoints == 1 && !(fenv && atoi(fenv) == 0);
   }
   if (e->family) {
+    // The S = 20 kernels own their CLV slabs, so when no node needs the first-generation kernels (every father has <= 3
+    // sons) the slabs are CLASS-MAJOR [class][pattern][state]: the 8 rows of an item are then 1280 contiguous bytes instead
+    // of 160-byte pieces at a 160 C stride.  Accessors transpose back to the reference's [pattern][class][state].
+    bool wide = false;
+    for (int n = 0; n < nn; ++n)
+      if (e->child_off[n + 1] - e->child_off[n] > kFamMaxSons) wide = true;
+    const char* lenv = getenv("BPPGPU_CLV_LAYOUT");  // "pattern" keeps the reference order (A/B measurements)
+    e->clv_class_major = !wide && !wroot && (double)N * C * S < 2.0e9 && !(lenv && !strcmp(lenv, "pattern"));
+    if ((double)N * C * S >= 2.0e9) e->family = false;  // 32-bit row offsets inside the kernels
+  }
+  if (e->family) {
     long long slots = g_sm_count;
     if (const char* env = getenv("BPPGPU_FAMILY_GRID")) slots = std::max(1, atoi(env));  // test knob: few CTAs, long ranges
     long long ppc = (N + slots - 1) / slots;
@@ -1215,6 +1226,8 @@ static int enqueue_prune(bppgpu_engine* e, int point, int pl, cudaStream_t st) {
         }
         pp.S = S; pp.C = C; pp.ncodes = e->ncodes; pp.code_bytes = e->code_bytes;
         pp.ppc = e->fam_ppc;
+        pp.prow = e->clv_class_major ? 1 : C;
+        pp.crow = e->clv_class_major ? (int)N : 1;
         pp.N = N;
         pp.packL = e->d_fam_packL;
         pp.out = e->d_keep + (size_t)op.keep_idx * N * C * S;
@@ -1276,6 +1289,8 @@ static int enqueue_prune(bppgpu_engine* e, int point, int pl, cudaStream_t st) {
     rp.root_clv = e->d_keep + (size_t)ridx * N * C * S;
     rp.root_exp = e->d_keep_exp + (size_t)ridx * N * C;
     rp.S = S; rp.C = C; rp.flags = rflag; rp.N = N;
+    rp.prow = e->clv_class_major ? 1 : C;
+    rp.crow = e->clv_class_major ? N : 1;
     rp.rootfreq = rootfreq; rp.probs = e->d_probs; rp.weights = e->d_weights;
     rp.SR = e->d_SR; rp.rexp = e->d_rexp; rp.site_lnl = site_lnl; rp.partials = e->d_partials;
     generic_root_kernel<<<grid_p, 256, 0, st>>>(rp);
@@ -1341,6 +1356,8 @@ static int enqueue_derivs(bppgpu_engine* e, int point, int pl, unsigned want, cu
     fp.S = S; fp.C = C; fp.ncodes = e->ncodes; fp.code_bytes = e->code_bytes;
     fp.nh_form = (e->flags & BPPGPU_FLAG_NH_DERIV) ? 1 : 0;
     fp.ppc = e->fam_ppc;
+    fp.prow = e->clv_class_major ? 1 : C;
+    fp.crow = e->clv_class_major ? (int)N : 1;
     fp.N = N;
     fp.packA = e->d_fam_packA; fp.packS = e->d_fam_packS;
     fp.rootfreq = e->d_rootfreq_used + (size_t)point * S;
@@ -1348,7 +1365,7 @@ static int enqueue_derivs(bppgpu_engine* e, int point, int pl, unsigned want, cu
     fp.part = e->d_fam_part;
     const bool d2 = (want & BPPGPU_EVAL_D2) != 0;
     const int G = e->fam_grid;
-#define BPP_FAM(NBv, Kv) dmma_family_kernel<NBv, Kv><<<G, fam_threads(Kv == 4 ? 3 : 2), dmma_family_smem<Kv>(C), st>>>(fp)
+#define BPP_FAM(NBv, Kv) dmma_family_kernel<NBv, Kv><<<G, fam_threads_kind(Kv), dmma_family_smem<Kv>(C), st>>>(fp)
     switch (kind) {
       case 0: if (d2) BPP_FAM(8, 0); else BPP_FAM(5, 0); break;
       case 1: if (d2) BPP_FAM(8, 1); else BPP_FAM(5, 1); break;
@@ -1676,6 +1693,20 @@ int bppgpu_get_site_lnl(bppgpu_engine* e, int32_t point, double* out) {
   return BPPGPU_OK;
 }
 
+// class-major device slabs -> the reference's VVVdouble order [pattern][class][state] (host side, accessor only)
+static void to_reference_order(bppgpu_engine* e, double* clv, int32_t* ex) {
+  if (!e->clv_class_major || e->C == 1) return;
+  const size_t N = (size_t)e->N, C = (size_t)e->C, S = (size_t)e->S;
+  std::vector<double> t(clv, clv + N * C * S);
+  for (size_t c = 0; c < C; ++c)
+    for (size_t i = 0; i < N; ++i) memcpy(clv + (i * C + c) * S, t.data() + (c * N + i) * S, S * sizeof(double));
+  if (ex) {
+    std::vector<int32_t> te(ex, ex + N * C);
+    for (size_t c = 0; c < C; ++c)
+      for (size_t i = 0; i < N; ++i) ex[i * C + c] = te[c * N + i];
+  }
+}
+
 int bppgpu_get_clv(bppgpu_engine* e, int32_t point, int32_t node, int32_t which, double* clv, int32_t* scale_exp) {
   ENGINE_ENTER(e);
   if (!e->keep) BPP_FAIL(BPPGPU_E_STATE, "bppgpu_get_clv needs BPPGPU_FLAG_KEEP_CLVS");
@@ -1696,6 +1727,7 @@ int bppgpu_get_clv(bppgpu_engine* e, int32_t point, int32_t node, int32_t which,
     const size_t k = pt_off + (size_t)e->internal_idx[node];
     BPP_CUDA(cudaMemcpy(clv, e->d_keep + k * clvn, clvn * 8, cudaMemcpyDeviceToHost));
     if (scale_exp) BPP_CUDA(cudaMemcpy(scale_exp, e->d_keep_exp + k * e->N * e->C, (size_t)e->N * e->C * 4, cudaMemcpyDeviceToHost));
+    to_reference_order(e, clv, scale_exp);
   } else {
     if (!(e->last_want & BPPGPU_EVAL_D1) || !e->d_upper) BPP_FAIL(BPPGPU_E_STATE, "upper CLVs exist after an eval with derivatives");
     if (node == e->root) BPP_FAIL(BPPGPU_E_INVALID, "the root has no upper CLV");
@@ -1703,6 +1735,7 @@ int bppgpu_get_clv(bppgpu_engine* e, int32_t point, int32_t node, int32_t which,
     if (slab < 0) BPP_FAIL(BPPGPU_E_STATE, "the upper CLV of tip %d is not materialised at this problem size", node);
     BPP_CUDA(cudaMemcpy(clv, e->d_upper + (size_t)slab * clvn, clvn * 8, cudaMemcpyDeviceToHost));
     if (scale_exp) BPP_CUDA(cudaMemcpy(scale_exp, e->d_upper_exp + (size_t)slab * e->N * e->C, (size_t)e->N * e->C * 4, cudaMemcpyDeviceToHost));
+    to_reference_order(e, clv, scale_exp);
   }
   return BPPGPU_OK;
 }

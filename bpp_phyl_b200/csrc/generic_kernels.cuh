@@ -71,8 +71,9 @@ __global__ void generic_scale_kernel(GenericParams p) {
 }
 
 struct RootParams {
-  const double* root_clv;  // [N][C][S]
-  const int* root_exp;     // [N][C]
+  const double* root_clv;  // row of (pattern i, class c) = i * prow + c * crow:  [N][C][S] (prow = C, crow = 1) or class-major
+  const int* root_exp;     // same rows
+  long long prow, crow;
   int S, C;
   unsigned flags;
   long long N;
@@ -91,19 +92,20 @@ __global__ void generic_root_kernel(RootParams p) {
   double contrib = 0.0;
   if (pat < p.N) {
     const bool rsem = p.flags & 1u;
-    const double* v = p.root_clv + (size_t)pat * p.C * p.S;
-    const int* ex = p.root_exp + (size_t)pat * p.C;
+    const double* v = p.root_clv + (size_t)pat * p.prow * p.S;
+    const int* ex = p.root_exp + (size_t)pat * p.prow;
+    const size_t cs = (size_t)p.crow;
     int E = ex[0];
-    for (int c = 1; c < p.C; ++c) E = min(E, ex[c]);
+    for (int c = 1; c < p.C; ++c) E = min(E, ex[c * cs]);
     double L = 0.0;
     for (int c = 0; c < p.C; ++c) {
       double s = 0.0;
       for (int x = 0; x < p.S; ++x) {
-        const double t = v[c * p.S + x] * p.rootfreq[x];
+        const double t = v[c * cs * p.S + x] * p.rootfreq[x];
         if (rsem) s += t > 0 ? t : 0.0;
         else s += t;
       }
-      const double lc = s * align_factor(ex[c] - E) * p.probs[c];
+      const double lc = s * align_factor(ex[c * cs] - E) * p.probs[c];
       if (rsem) L += lc > 0 ? lc : 0.0;
       else L += lc;
     }

@@ -198,6 +198,29 @@ def test_family_kernel_chunks_multifurcation_and_underflow(monkeypatch):
         _check_derivs_and_uppers(c, e, res, uppers=False)
 
 
+def test_s20_fallbacks_eight_classes_and_two_points():
+    """The S = 20 fragment-order kernels hold the operands of <= 4 rate classes and serve single-point engines; 8 classes
+    and 2-point engines must take the per-node / per-branch tensor-core kernels and agree with the oracle all the same."""
+    capi = _capi()
+    r, p = rm.gamma_rates(8, 0.8)
+    c = cases.make_case(11, 90, rm.lg08(), r, p, seed=81, mean_brlen=0.1, ambiguity=0.02, compress=False)
+    res = cases.oracle_eval(c, want_d1=True, want_d2=True)
+    with cases.make_engine(c, flags=capi.FLAG_KEEP_CLVS) as e:
+        assert e.stats()["path"] == 4
+        _check_derivs_and_uppers(c, e, res)
+    r, p = rm.gamma_rates(4, 0.8)
+    c = cases.make_case(9, 70, rm.lg08(), r, p, seed=82, mean_brlen=0.1, compress=False)
+    res = cases.oracle_eval(c)
+    bl2 = c.flat.brlen * 1.7
+    res2 = cases.oracle_eval(c, brlen=bl2)
+    with cases.make_engine(c, n_points=2) as e:
+        e.set_branch_lengths(1, bl2)
+        lnl, _, _ = e.eval(capi.EVAL_LNL)
+        assert e.stats()["path"] == 4
+    assert abs(lnl[0] - res.lnl) <= REL * abs(res.lnl)
+    assert abs(lnl[1] - res2.lnl) <= REL * abs(res2.lnl)
+
+
 def test_dmma_underflow_scaling():
     r, p = rm.constant_rate()
     c = cases.make_case(150, 40, rm.yn98(2.0, 0.3), r, p, seed=63, mean_brlen=0.8)     # simulated: no stop codons
