@@ -126,7 +126,18 @@ def build_inputs(w, rank, world, device):
     from bpp_phyl_b200.shard import shard_range
     lo, hi = shard_range(N, rank, world)
     t0 = time.time()
-    codes = synth.simulate_tip_codes(tree, es, rates, hi - lo, seed=w["seed"] + 7919 * rank, device=device)
+    nblk = 16
+    if N % nblk == 0 and nblk % world == 0 and N >= nblk:
+        # world-size invariant data: the job's patterns are 16 independently seeded blocks and a rank simulates the blocks
+        # of its range, so strong-scaling runs at 1, 2, 4, 8 GPUs evaluate the SAME alignment (equal lnL is then a full-size
+        # check of the sharding)
+        B = N // nblk
+        b0 = lo // B
+        parts = [synth.simulate_tip_codes(tree, es, rates, B, seed=w["seed"] + 7919 * (b0 + k + 1), device=device)
+                 for k in range((hi - lo) // B)]
+        codes = np.concatenate(parts, axis=1) if len(parts) > 1 else parts[0]
+    else:
+        codes = synth.simulate_tip_codes(tree, es, rates, hi - lo, seed=w["seed"] + 7919 * rank, device=device)
     log("[rank %d] simulated %d patterns x %d tips in %.1fs" % (rank, hi - lo, tree.n_leaves, time.time() - t0))
     return tree, es, rates, probs, codes
 

@@ -1,1 +1,4 @@
-ncu --metrics gpu__time_duration.sum,sm__inst_executed_pipe_tensor_subpipe_dmma.avg.pct_of_peak_sustained_active,l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:"family|prune" -c 2100 --csv --log-file gpurun_out/launches_prot_cm.csv python bench.py --workload protein_g4_500x200k_d2 --profile > gpurun_out/ncu_prot_cm.log 2>&1
+python bench.py --steps 3 --warmup 3 --workload protein_g4_500x200k_d2 --no-cpu > gpurun_out/inv1_prot.json 2> gpurun_out/inv1_prot.err
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29542 bench.py --gpus 2 --steps 3 --warmup 3 --workload protein_g4_500x200k_d2 --scaling strong --no-cpu > gpurun_out/inv2_prot.json 2> gpurun_out/inv2_prot.err
+python bench.py --steps 5 --warmup 3 --no-cpu > gpurun_out/inv1_dna.json 2> gpurun_out/inv1_dna.err
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29544 bench.py --gpus 2 --steps 5 --warmup 3 --scaling strong --no-cpu > gpurun_out/inv2_dna.json 2> gpurun_out/inv2_dna.err
