@@ -1452,7 +1452,7 @@ class AbstractHomogeneousTreeLikelihood {
     bppgpu_config cfg;
     std::memset(&cfg, 0, sizeof(cfg));
     cfg.n_states = (int32_t)S; cfg.n_cats = (int32_t)C; cfg.n_patterns = nPatterns_; cfg.n_nodes = nn; cfg.root = nn - 1;
-    cfg.child_offsets = off.data(); cfg.children = children.data(); cfg.n_points = 1; cfg.n_models = 1;
+    cfg.child_offsets = off.data(); cfg.children = children.data(); cfg.n_points = nPoints_; cfg.n_models = nPoints_;
     cfg.n_codes = (int32_t)chars.size(); cfg.code_bytes = chars.size() > 256 ? 2 : 1; cfg.code_table = table.data();
     cfg.device = device_; cfg.flags = engineFlags_ | BPPGPU_FLAG_KEEP_CLVS;
     if (engine_) { bppgpu_destroy(engine_); engine_ = nullptr; }
@@ -1473,7 +1473,7 @@ class AbstractHomogeneousTreeLikelihood {
 
   virtual Vdouble rootFrequencies() const { return model_->getFrequencies(); }
 
-  void uploadModel() {
+  virtual void uploadModel() {
     if (!engine_) return;
     bppgpu_model_desc d;
     model_->fillModelDesc(d);
@@ -1486,7 +1486,7 @@ class AbstractHomogeneousTreeLikelihood {
   }
 
   // computeAllTransitionProbabilities + computeTreeLikelihood (+ the DR derivative passes) in one device evaluation
-  void fireParameterChanged() {
+  virtual void fireParameterChanged() {
     Vdouble t(nodes_.size(), 0.0);
     for (size_t i = 0; i < brLen_.size(); ++i) t[i] = brLen_[i];
     check(bppgpu_set_branch_lengths(engine_, 0, t.data()), "applyParameters");
@@ -1543,6 +1543,7 @@ class AbstractHomogeneousTreeLikelihood {
   mutable Vdouble d1_, d2_;
   mutable bool derivsValid_;
   long numOfLikelihoodCalculations_;
+  int nPoints_ = 1;  // parameter points evaluated per device call (LikelihoodPointBatch)
 };
 
 // Likelihood/RHomogeneousTreeLikelihood.h:108-138.  `usePatterns` (recursive per-subtree compression) changes only the
@@ -1586,6 +1587,82 @@ class DRNonHomogeneousTreeLikelihood : public AbstractHomogeneousTreeLikelihood 
 
  private:
   Vdouble fixedRootFreqs_;
+};
+
+// ---- batched front-end ------------------------------------------------------------------------------------------
+// ChromosomeNumberOptimizer keeps a vector of DRNonHomogeneousTreeLikelihood objects, one per starting point, and evaluates
+// and line-searches them one after the other (Likelihood/ChromosomeNumberOptimizer.cpp:58, :141-153, :472-517).  This class
+// is that vector as ONE device object: same tree and data, one substitution model (and optionally one set of branch lengths)
+// per point, every point's -lnL from a single bppgpu_eval (batched P(t) + one launch per node covering all points).
+// Values are identical to what a DRNonHomogeneousTreeLikelihood built on models[k] returns.
+class LikelihoodPointBatch : public AbstractHomogeneousTreeLikelihood {
+ public:
+  LikelihoodPointBatch(const Tree& tree, const VectorSiteContainer& data, bool weightedRootFreq,
+                       const std::vector<SubstitutionModel*>& models, DiscreteDistribution* rDist, int device = 0)
+      : AbstractHomogeneousTreeLikelihood(tree, models.at(0), rDist, false,
+                                          BPPGPU_FLAG_NH_DERIV | (weightedRootFreq ? BPPGPU_FLAG_WEIGHTED_ROOT : 0u), device),
+        models_(models) {
+    nPoints_ = (int)models.size();
+    computeDerivatives_ = false;
+    pointBrLen_.assign(models.size(), brLen_);
+    values_.assign(models.size(), 0.0);
+    setData(data);
+  }
+  size_t getNumberOfPoints() const { return models_.size(); }
+  // a model parameter of point k moved (the caller changed models[k]): its eigensystem is re-uploaded before the next evaluation
+  void modelChanged(size_t k) { dirty_.at(k) = 1; if (initialized_) fireParameterChanged(); }
+  void setBranchLengths(size_t k, const Vdouble& brlen) {
+    if (brlen.size() != brLen_.size()) throw Exception("LikelihoodPointBatch::setBranchLengths: wrong number of branch lengths");
+    for (size_t i = 0; i < brlen.size(); ++i) pointBrLen_.at(k)[i] = std::min(std::max(brlen[i], minimumBrLen_), maximumBrLen_);
+    if (initialized_) fireParameterChanged();
+  }
+  // -lnL of every point (getValue() of the k-th likelihood of the reference's vector)
+  const Vdouble& getValues() const { requireInit(); return values_; }
+  double getValue(size_t k) const { requireInit(); return values_.at(k); }
+  // index of the best point (the reference sorts its vector with compareLikValues, ChromosomeNumberOptimizer.cpp:156)
+  size_t getBestPoint() const {
+    requireInit();
+    size_t b = 0;
+    for (size_t k = 1; k < values_.size(); ++k) if (values_[k] < values_[b]) b = k;
+    return b;
+  }
+
+ protected:
+  void uploadModel() override {
+    if (!engine_) return;
+    if (dirty_.size() != models_.size()) dirty_.assign(models_.size(), 1);
+    Vdouble r(rDist_->getNumberOfCategories()), p(r.size());
+    for (size_t c = 0; c < r.size(); ++c) { r[c] = rDist_->getCategory(c); p[c] = rDist_->getProbability(c); }
+    check(bppgpu_set_rates(engine_, r.data(), p.data()), "setRates");
+    for (size_t k = 0; k < models_.size(); ++k) {
+      if (!dirty_[k]) continue;
+      bppgpu_model_desc d;
+      models_[k]->fillModelDesc(d);
+      check(bppgpu_set_model(engine_, (int32_t)k, &d), "setModel");
+      const Vdouble f = models_[k]->getFrequencies();
+      check(bppgpu_set_root_freqs(engine_, (int32_t)k, f.data()), "setRootFreqs");
+      dirty_[k] = 0;
+    }
+  }
+  void fireParameterChanged() override {
+    uploadModel();
+    for (size_t k = 0; k < models_.size(); ++k) {
+      Vdouble t(nodes_.size(), 0.0);
+      for (size_t i = 0; i < brLen_.size(); ++i) t[i] = pointBrLen_[k][i];
+      check(bppgpu_set_branch_lengths(engine_, (int32_t)k, t.data()), "applyParameters");
+    }
+    Vdouble lnl(models_.size(), 0.0);
+    check(bppgpu_eval(engine_, BPPGPU_EVAL_LNL, lnl.data(), nullptr, nullptr), "computeTreeLikelihood");
+    numOfLikelihoodCalculations_ += (long)models_.size();
+    for (size_t k = 0; k < models_.size(); ++k) values_[k] = -lnl[k];
+    minusLogLik_ = values_[0];
+  }
+
+ private:
+  std::vector<SubstitutionModel*> models_;  // not owned
+  std::vector<Vdouble> pointBrLen_;
+  std::vector<char> dirty_;
+  Vdouble values_;
 };
 
 }  // namespace bppshim

@@ -170,6 +170,33 @@ int main() {
       tl.initialize();
       printf("CHR_WEIGHTED %.15f\n", tl.getValue());
       cm.setParameterValue("Chromosome.gain", 1.1);
+      // the batched front-end: ChromosomeNumberOptimizer's vector of likelihoods (one starting point each) as one device object
+      const double pts[5][4] = {{0.7, 0.4, 0.2, 0.1}, {1.1, 0.4, 0.2, 0.05}, {0.2, 1.3, 0.6, 0.3}, {2.0, 2.0, 0.01, 0.4}, {0.05, 0.05, 0.9, 0.0}};
+      vector<unique_ptr<ChromosomeSubstitutionModel> > owned;
+      vector<SubstitutionModel*> models;
+      for (int k = 0; k < 5; ++k) {
+        owned.emplace_back(new ChromosomeSubstitutionModel(&chr, pts[k][0], pts[k][1], pts[k][2], pts[k][3]));
+        models.push_back(owned.back().get());
+      }
+      LikelihoodPointBatch batch(*t5, s5, true, models, &cst);
+      batch.initialize();
+      double maxrel = 0;
+      for (int k = 0; k < 5; ++k) {
+        DRNonHomogeneousTreeLikelihood one(*t5, s5, true, false, models[k], &cst);
+        one.initialize();
+        const double rel = fabs(batch.getValue(k) - one.getValue()) / fabs(one.getValue());
+        if (rel > maxrel) maxrel = rel;
+        printf("CHR_BATCH_%d %.15f\n", k, batch.getValue(k));
+      }
+      printf("CHR_BATCH_MAXREL %.3e\n", maxrel);
+      // a Brent-style probe of one point: change a parameter of point 2, re-evaluate everything in one call
+      owned[2]->setParameterValue("Chromosome.loss", 0.9);
+      batch.modelChanged(2);
+      DRNonHomogeneousTreeLikelihood probe(*t5, s5, true, false, models[2], &cst);
+      probe.initialize();
+      printf("CHR_BATCH_PROBE_REL %.3e\n", fabs(batch.getValue(2) - probe.getValue()) / fabs(probe.getValue()));
+      printf("CHR_BATCH_BEST %zu\n", batch.getBestPoint());
+      if (maxrel > 1e-12) { cerr << "batched points differ from single-point likelihoods" << endl; fails++; }
     }
   } catch (exception& ex) {
     cerr << "EXCEPTION: " << ex.what() << endl;

@@ -163,3 +163,11 @@ def test_reference_likelihood_tests_through_the_shim(built_lib):
     ch.root_freqs = m.freq
     res = cases.oracle_eval(ch, weighted_root=True)
     assert abs(vals["CHR_WEIGHTED"] + res.lnl) <= 1e-9 * abs(res.lnl)
+    # batched front-end (LikelihoodPointBatch): five parameter points in one device evaluation, each against the oracle
+    pts = [(0.7, 0.4, 0.2, 0.1), (1.1, 0.4, 0.2, 0.05), (0.2, 1.3, 0.6, 0.3), (2.0, 2.0, 0.01, 0.4), (0.05, 0.05, 0.9, 0.0)]
+    for k, (g, l, du, de) in enumerate(pts):
+        mk = rm.chromosome(1, 30, gain=g, loss=l, dupl=du, demi=de)
+        ch.model, ch.root_freqs = mk, mk.freq
+        rk = cases.oracle_eval(ch, weighted_root=True)
+        assert abs(vals["CHR_BATCH_%d" % k] + rk.lnl) <= 1e-9 * abs(rk.lnl), k
+    assert vals["CHR_BATCH_MAXREL"] <= 1e-12 and vals["CHR_BATCH_PROBE_REL"] <= 1e-12
