@@ -278,6 +278,16 @@ class Engine:
                                     _ptr(ex, C.c_int32)))
         return out, ex
 
+    def node_posteriors(self, node, point=0, full=True):
+        """(likelihood at node [N][C][S], its exponents [N][C], posterior probabilities [N][C][S]); full=False asks for
+        the posteriors alone (leaves of large problems)."""
+        la = np.empty((self.N, self.C, self.S)) if full else None
+        ex = np.empty((self.N, self.C), np.int32) if full else None
+        post = np.empty((self.N, self.C, self.S))
+        _check(lib().bppgpu_get_node_posteriors(self._h, C.c_int32(point), C.c_int32(node), _ptr(la), _ptr(ex, C.c_int32),
+                                                _ptr(post)))
+        return la, ex, post
+
     def transition_probabilities(self, node, which=WANT_P, point=0):
         out = np.empty((self.C, self.S, self.S))
         _check(lib().bppgpu_get_transition_probabilities(self._h, C.c_int32(point), C.c_int32(node),

@@ -181,4 +181,93 @@ __global__ void deriv_node_kernel(DerivParams p) {
   }
 }
 
+
+// ---- consumers of the DR arrays ---------------------------------------------------------------------------
+// DRTreeLikelihood::computeLikelihoodAtNode (DRHomogeneousTreeLikelihood::computeLikelihoodAtNode_,
+// Likelihood/DRHomogeneousTreeLikelihood.cpp:723-815):  full[i][c][x] = sub[i][c][x] * sum_y P_n[c][y][x] upper_n[i][c][y]
+// (sub = the node's lower CLV, or its leaf likelihoods), times the root frequencies at the root; the arrays never leave
+// the device.  Element = (pattern, class, state); rows of the device slabs follow prow / crow (class-major or not), the
+// output is always in the reference's [pattern][class][state] order.
+struct NodeFullParams {
+  int is_leaf, is_root;
+  int S, C, code_bytes;
+  long long N;
+  long long prow, crow;
+  const double* P;           // [C][S][S] of this node's branch
+  const double* lower;       // slab of the node (internal)
+  const int* lower_exp;
+  const void* codes;         // this leaf's codes [N] and the code table [ncodes][S]
+  const double* code_table;
+  const double* upper;       // slab of upper[node] (non-root)
+  const int* upper_exp;
+  const double* rootfreq;
+  double* out;               // [N][C][S]
+  int* out_exp;              // [N][C]
+};
+
+__global__ void node_full_kernel(NodeFullParams p) {
+  const long long total = p.N * p.C * p.S;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(e % p.S);
+    const long long rc = e / p.S;
+    const int c = (int)(rc % p.C);
+    const long long i = rc / p.C;
+    const size_t row = (size_t)(i * p.prow + c * p.crow);
+    double sub;
+    int ex = 0;
+    if (p.is_leaf) {
+      const int code = p.code_bytes == 1 ? (int)((const unsigned char*)p.codes)[i] : (int)((const unsigned short*)p.codes)[i];
+      sub = p.code_table[(size_t)code * p.S + x];
+    } else {
+      sub = p.lower[row * p.S + x];
+      ex = p.lower_exp[row];
+    }
+    double v;
+    if (p.is_root) {
+      v = sub * p.rootfreq[x];
+    } else {
+      const double* U = p.upper + row * p.S;
+      const double* Pc = p.P + (size_t)c * p.S * p.S;
+      double acc = 0.0;
+      for (int y = 0; y < p.S; ++y) acc = fma(Pc[(size_t)y * p.S + x], U[y], acc);
+      v = sub * acc;
+      ex += p.upper_exp[row];
+    }
+    p.out[e] = v;
+    if (x == 0) p.out_exp[rc] = ex;
+  }
+}
+
+// DRTreeLikelihoodTools::getPosteriorProbabilitiesForEachStateForEachRate (Likelihood/DRTreeLikelihoodTools.cpp:46-119):
+// internal node: full / sum_{c,x} full (classes aligned on the pattern's smallest exponent first; like the reference, no class
+// probabilities); leaf: leaf likelihoods[x] * p_c / sum_x leaf likelihoods.  thread = pattern.
+__global__ void node_posterior_kernel(const double* full, const int* full_exp, int is_leaf, const void* codes, int code_bytes,
+                                      const double* code_table, const double* probs, int S, int C, long long N, double* post) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  double* o = post + (size_t)i * C * S;
+  if (is_leaf) {
+    const int code = code_bytes == 1 ? (int)((const unsigned char*)codes)[i] : (int)((const unsigned short*)codes)[i];
+    const double* t = code_table + (size_t)code * S;
+    double sum = 0.0;
+    for (int x = 0; x < S; ++x) sum += t[x];
+    for (int c = 0; c < C; ++c)
+      for (int x = 0; x < S; ++x) o[c * S + x] = t[x] * probs[c] / sum;
+    return;
+  }
+  const double* f = full + (size_t)i * C * S;
+  const int* ex = full_exp + (size_t)i * C;
+  int E = ex[0];
+  for (int c = 1; c < C; ++c) E = min(E, ex[c]);
+  double sum = 0.0;
+  for (int c = 0; c < C; ++c) {
+    const double a = align_factor(ex[c] - E);
+    for (int x = 0; x < S; ++x) sum += f[c * S + x] * a;
+  }
+  for (int c = 0; c < C; ++c) {
+    const double a = align_factor(ex[c] - E);
+    for (int x = 0; x < S; ++x) o[c * S + x] = f[c * S + x] * a / sum;
+  }
+}
+
 }  // namespace bppgpu

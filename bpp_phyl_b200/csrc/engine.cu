@@ -1740,6 +1740,74 @@ int bppgpu_get_clv(bppgpu_engine* e, int32_t point, int32_t node, int32_t which,
   return BPPGPU_OK;
 }
 
+int bppgpu_get_node_posteriors(bppgpu_engine* e, int32_t point, int32_t node, double* full_out, int32_t* exp_out, double* post_out) {
+  ENGINE_ENTER(e);
+  if (!e->keep) BPP_FAIL(BPPGPU_E_STATE, "bppgpu_get_node_posteriors needs BPPGPU_FLAG_KEEP_CLVS");
+  if (node < 0 || node >= e->nn) BPP_FAIL(BPPGPU_E_INVALID, "bad node");
+  if (e->path == PATH_POINTS) BPP_FAIL(BPPGPU_E_STATE, "not available on the batched-points path");
+  if (point != e->last_point) BPP_FAIL(BPPGPU_E_STATE, "CLVs resident are those of point %d", e->last_point);
+  const bool leaf = e->leaf_slot[node] >= 0, root = node == e->root;
+  const int S = e->S, C = e->C;
+  const long long N = e->N;
+  if (N == 0) return BPPGPU_OK;
+  const size_t clvn = (size_t)N * C * S, rows = (size_t)N * C;
+  const bool need_full = full_out || exp_out || (post_out && !leaf);
+  const int uslab = root ? -1 : (e->d_upper ? e->upper_slab[node] : -1);
+  if (need_full && !root) {
+    if (!(e->last_want & BPPGPU_EVAL_D1) || !e->d_upper) BPP_FAIL(BPPGPU_E_STATE, "upper CLVs exist after an eval with derivatives");
+    if (uslab < 0) BPP_FAIL(BPPGPU_E_STATE, "the upper CLV of tip %d is not materialised at this problem size", node);
+  }
+  cudaStream_t st = e->stream;
+  double *d_full = nullptr, *d_post = nullptr;
+  int* d_fexp = nullptr;
+  auto cleanup = [&]() { cudaFree(d_full); cudaFree(d_post); cudaFree(d_fexp); };
+  if (need_full) {
+    if (cudaMalloc(&d_full, clvn * 8) != cudaSuccess || cudaMalloc(&d_fexp, rows * 4) != cudaSuccess) {
+      cleanup();
+      BPP_FAIL(BPPGPU_E_NOMEM, "out of device memory for the likelihood array of node %d", node);
+    }
+    NodeFullParams np{};
+    np.is_leaf = leaf; np.is_root = root;
+    np.S = S; np.C = C; np.code_bytes = e->code_bytes; np.N = N;
+    np.prow = e->clv_class_major ? 1 : C;
+    np.crow = e->clv_class_major ? N : 1;
+    const int pl = e->path == PATH_POINTS ? 0 : (point % e->pchunk);
+    np.P = e->d_P + ((size_t)pl * e->nn + node) * C * S * S;
+    if (leaf) {
+      np.codes = (const char*)e->d_codes + (size_t)e->leaf_slot[node] * N * e->code_bytes;
+      np.code_table = e->d_code_table;
+    } else {
+      np.lower = e->d_keep + (size_t)e->internal_idx[node] * clvn;
+      np.lower_exp = e->d_keep_exp + (size_t)e->internal_idx[node] * rows;
+    }
+    if (!root) {
+      np.upper = e->d_upper + (size_t)uslab * clvn;
+      np.upper_exp = e->d_upper_exp + (size_t)uslab * rows;
+    }
+    np.rootfreq = e->d_rootfreq_used + (size_t)point * S;
+    np.out = d_full; np.out_exp = d_fexp;
+    const int grid = (int)std::min<long long>(((long long)clvn + 255) / 256, (long long)g_sm_count * 32);
+    node_full_kernel<<<grid, 256, 0, st>>>(np);
+  }
+  if (post_out) {
+    if (cudaMalloc(&d_post, clvn * 8) != cudaSuccess) {
+      cleanup();
+      BPP_FAIL(BPPGPU_E_NOMEM, "out of device memory for the posteriors of node %d", node);
+    }
+    const void* codes = leaf ? (const void*)((const char*)e->d_codes + (size_t)e->leaf_slot[node] * N * e->code_bytes) : nullptr;
+    node_posterior_kernel<<<(unsigned)((N + 127) / 128), 128, 0, st>>>(d_full, d_fexp, leaf ? 1 : 0, codes, e->code_bytes,
+                                                                       e->d_code_table, e->d_probs, S, C, N, d_post);
+  }
+  cudaError_t err = cudaGetLastError();
+  if (err == cudaSuccess && full_out) err = cudaMemcpyAsync(full_out, d_full, clvn * 8, cudaMemcpyDeviceToHost, st);
+  if (err == cudaSuccess && exp_out) err = cudaMemcpyAsync(exp_out, d_fexp, rows * 4, cudaMemcpyDeviceToHost, st);
+  if (err == cudaSuccess && post_out) err = cudaMemcpyAsync(post_out, d_post, clvn * 8, cudaMemcpyDeviceToHost, st);
+  if (err == cudaSuccess) err = cudaStreamSynchronize(st);
+  cleanup();
+  BPP_CUDA(err);
+  return BPPGPU_OK;
+}
+
 int bppgpu_get_transition_probabilities(bppgpu_engine* e, int32_t point, int32_t node, unsigned which, double* out) {
   ENGINE_ENTER(e);
   if (point < 0 || point >= e->npoints || node < 0 || node >= e->nn || node == e->root || !out)

@@ -1397,6 +1397,52 @@ class AbstractHomogeneousTreeLikelihood {
         for (size_t x = 0; x < S; ++x) likelihoodArray[i][c][x] = buf[(i * C + c) * S + x];
       }
   }
+  // DRTreeLikelihood::computeLikelihoodAtNode(nodeId, VVVdouble&) (Likelihood/DRTreeLikelihood.h:92-102): the conditional
+  // likelihood of ALL the data given the state at the node, computed on the device from the resident lower / upper
+  // arrays; true value = likelihoodArray[i][c][x] * 2^-scale[i][c] (scale may be null: values are then de-scaled)
+  void computeLikelihoodAtNode(int nodeId, VVVdouble& likelihoodArray, std::vector<std::vector<int> >* scale = nullptr) const {
+    requireInit();
+    ensureDerivativePass();
+    const size_t S = getNumberOfStates(), C = getNumberOfClasses(), N = (size_t)nPatterns_;
+    std::vector<double> buf(N * C * S);
+    std::vector<int32_t> ex(N * C);
+    check(bppgpu_get_node_posteriors(engine_, 0, nodeId, buf.data(), ex.data(), nullptr), "computeLikelihoodAtNode");
+    likelihoodArray.assign(N, VVdouble(C, Vdouble(S)));
+    if (scale) scale->assign(N, std::vector<int>(C));
+    for (size_t i = 0; i < N; ++i)
+      for (size_t c = 0; c < C; ++c) {
+        if (scale) (*scale)[i][c] = ex[i * C + c];
+        for (size_t x = 0; x < S; ++x)
+          likelihoodArray[i][c][x] = scale ? buf[(i * C + c) * S + x] : std::ldexp(buf[(i * C + c) * S + x], -ex[i * C + c]);
+      }
+  }
+  // DRTreeLikelihoodTools::getPosteriorProbabilitiesForEachStateForEachRate(drl, nodeId) (DRTreeLikelihoodTools.cpp:46-119)
+  VVVdouble getPosteriorProbabilitiesForEachStateForEachRate(int nodeId) const {
+    requireInit();
+    ensureDerivativePass();
+    const size_t S = getNumberOfStates(), C = getNumberOfClasses(), N = (size_t)nPatterns_;
+    std::vector<double> buf(N * C * S);
+    check(bppgpu_get_node_posteriors(engine_, 0, nodeId, nullptr, nullptr, buf.data()), "getPosteriorProbabilities");
+    VVVdouble p(N, VVdouble(C, Vdouble(S)));
+    for (size_t i = 0; i < N; ++i)
+      for (size_t c = 0; c < C; ++c)
+        for (size_t x = 0; x < S; ++x) p[i][c][x] = buf[(i * C + c) * S + x];
+    return p;
+  }
+  // MarginalAncestralStateReconstruction::getAncestralStatesForNode: argmax_x sum_c posterior, one state per distinct site
+  std::vector<size_t> getAncestralStatesForNode(int nodeId) const {
+    const VVVdouble p = getPosteriorProbabilitiesForEachStateForEachRate(nodeId);
+    std::vector<size_t> best(p.size(), 0);
+    for (size_t i = 0; i < p.size(); ++i) {
+      double bv = -1;
+      for (size_t x = 0; x < p[i][0].size(); ++x) {
+        double v = 0;
+        for (size_t c = 0; c < p[i].size(); ++c) v += p[i][c][x];
+        if (v > bv) { bv = v; best[i] = x; }
+      }
+    }
+    return best;
+  }
   long getNumberOfLikelihoodCalculations() const { return numOfLikelihoodCalculations_; }  // fork: DRNonHomogeneousTreeLikelihood.h:75
 
  protected:
@@ -1500,6 +1546,15 @@ class AbstractHomogeneousTreeLikelihood {
     derivsValid_ = false;
   }
 
+  // the prefix (upper) arrays exist after an evaluation with derivatives
+  void ensureDerivativePass() const {
+    if (derivsValid_) return;
+    d1_.assign(nodes_.size(), 0.0);
+    d2_.assign(nodes_.size(), 0.0);
+    double lnl = 0;
+    check(bppgpu_eval(engine_, BPPGPU_EVAL_LNL | BPPGPU_EVAL_D1 | BPPGPU_EVAL_D2, &lnl, d1_.data(), d2_.data()), "computeTreeDLikelihoods");
+    derivsValid_ = true;
+  }
   double derivative(const std::string& variable, int order) const {
     requireInit();
     const int b = brlenIndex(variable);

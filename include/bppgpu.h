@@ -180,6 +180,17 @@ int bppgpu_get_site_lnl(bppgpu_engine* e, int32_t point, double* out /* [N] */);
  * (scale_exp is [N][C]).  Needs BPPGPU_FLAG_KEEP_CLVS.                          */
 int bppgpu_get_clv(bppgpu_engine* e, int32_t point, int32_t node, int32_t which, double* clv,
                    int32_t* scale_exp);
+/* Consumers of the device-resident DR arrays (ancestral reconstruction, posterior rates), valid after an eval with
+ * derivatives (the prefix pass must have run; the root needs only the value pass):
+ *   likelihood_at_node [N][C][S] + scale_exp [N][C] = DRTreeLikelihood::computeLikelihoodAtNode(nodeId, VVVdouble&)
+ *       (Likelihood/DRTreeLikelihood.h:92-102; DRHomogeneousTreeLikelihood::computeLikelihoodAtNode_,
+ *        DRHomogeneousTreeLikelihood.cpp:723-815): true = value * 2^-scale_exp[i][c];
+ *   posterior [N][C][S] = DRTreeLikelihoodTools::getPosteriorProbabilitiesForEachStateForEachRate(drl, nodeId)
+ *       (Likelihood/DRTreeLikelihoodTools.cpp:46-119), as read by MarginalAncestralStateReconstruction.
+ * Any of the three outputs may be NULL.  For a leaf whose upper CLV is not materialised (large problems) only
+ * `posterior` is available (the reference's leaf formula needs the leaf likelihoods alone).                      */
+int bppgpu_get_node_posteriors(bppgpu_engine* e, int32_t point, int32_t node, double* likelihood_at_node,
+                               int32_t* scale_exp, double* posterior);
 /* which: BPPGPU_WANT_P / _DP / _D2P; out [C][S][S] = pxy_[node][c][x][y] */
 int bppgpu_get_transition_probabilities(bppgpu_engine* e, int32_t point, int32_t node,
                                         unsigned which, double* out);

@@ -237,6 +237,35 @@ def dr_eval(flat, tip_codes, table, P, C, root_freqs, probs, weights,
 
 
 # ----------------------------------------------------------------------------
+# Consumers of the DR arrays: computeLikelihoodAtNode + posterior probabilities
+def likelihood_at_node(flat, res, P, nid):
+    """DRTreeLikelihood::computeLikelihoodAtNode(nodeId, VVVdouble&)
+    (DRHomogeneousTreeLikelihood::computeLikelihoodAtNode_, Likelihood/DRHomogeneousTreeLikelihood.cpp:723-815):
+    the conditional likelihood of ALL the data given the state at `nid`,
+        leaf / subtree part  x  sum_y P_nid[y][x] upper_nid[y]      (P transposed, :919-945),
+    times the root frequencies at the root (:797-813).  ``res`` is a dr_eval result with the
+    prefix pass done.  Returns (array [N][C][S], exponents [N][C]): true = array * 2^-exp."""
+    L, E = res.lower[nid], res.lexp[nid]
+    if nid == flat.root:
+        return L * res.root_freqs[None, None, :], E.copy()
+    return L * _contract_T(P[nid], res.upper[nid]), E + res.uexp[nid]
+
+
+def posterior_probabilities(flat, res, P, nid, probs, tip_codes=None, table=None):
+    """DRTreeLikelihoodTools::getPosteriorProbabilitiesForEachStateForEachRate
+    (Likelihood/DRTreeLikelihoodTools.cpp:46-119), [N][C][S].
+    Internal node: computeLikelihoodAtNode / sum over (c, x) -- as in the reference the class
+    probabilities are NOT applied (they cancel for the equiprobable classes of the Gamma law).
+    Leaf: leaf likelihoods[x] * p_c / sum_x leaf likelihoods (the rest of the tree is ignored, :58-79)."""
+    if flat.is_leaf[nid]:
+        la = table[np.asarray(tip_codes[nid], dtype=np.int64)]          # [N][S]
+        return la[:, None, :] * np.asarray(probs)[None, :, None] / la.sum(axis=1)[:, None, None]
+    A, E = likelihood_at_node(flat, res, P, nid)
+    al = np.ldexp(A, -(E - E.min(axis=1, keepdims=True))[:, :, None])
+    return al / al.sum(axis=(1, 2))[:, None, None]
+
+
+# ----------------------------------------------------------------------------
 # R-class derivatives (single recursion re-pruned along the path to the root)
 # ----------------------------------------------------------------------------
 def r_derivative(flat, tip_codes, table, P, dP, C, root_freqs, probs, weights, branch, order=1, d2P=None):

@@ -156,6 +156,41 @@ int main() {
       printf("YN98_CONST %.15f\n", tl.getValue());
     }
     {
+      // consumers of the DR arrays: posterior probabilities at every node sum to one, computeLikelihoodAtNode integrates to the
+      // site likelihood at every node (DRTreeLikelihoodTools / MarginalAncestralStateReconstruction)
+      const DNA dna2;
+      unique_ptr<Tree> t6(TreeTemplateTools::parenthesisToTree("((A:0.01, B:0.02):0.03,C:0.01,D:0.1);"));
+      VectorSiteContainer s6(&dna2);
+      s6.addSequence(BasicSequence("A", "AAATGGCTGTGCACGTC", &dna2));
+      s6.addSequence(BasicSequence("B", "GACTGGATCTGCACGTC", &dna2));
+      s6.addSequence(BasicSequence("C", "CTCTGGATGTGCACGTG", &dna2));
+      s6.addSequence(BasicSequence("D", "AAATGGCGGTGCGCCTA", &dna2));
+      T92 m6(&dna2, 3.);
+      GammaDiscreteRateDistribution g6(4, 1.0);
+      DRHomogeneousTreeLikelihood tl(*t6, s6, &m6, &g6);
+      tl.initialize();
+      double worst = 0, worstL = 0;
+      for (int nid = 0; nid < 6; ++nid) {
+        VVVdouble post = tl.getPosteriorProbabilitiesForEachStateForEachRate(nid);
+        VVVdouble full;
+        tl.computeLikelihoodAtNode(nid, full);
+        for (size_t i = 0; i < post.size(); ++i) {
+          double sp = 0, sl = 0;
+          for (size_t c = 0; c < post[i].size(); ++c)
+            for (size_t x = 0; x < post[i][c].size(); ++x) { sp += post[i][c][x]; sl += full[i][c][x] * g6.getProbability(c); }
+          worst = max(worst, fabs(sp - 1.0));
+          size_t site = 0;
+          while (tl.getSiteIndex(site) != i) ++site;
+          worstL = max(worstL, fabs(log(sl) - tl.getLogLikelihoodForASite(site)));
+        }
+      }
+      printf("POSTERIOR_SUM_ERR %.3e\n", worst);
+      printf("ATNODE_LNL_ERR %.3e\n", worstL);
+      vector<size_t> anc = tl.getAncestralStatesForNode(5);
+      printf("ANCESTRAL_ROOT_SITE0 %zu\n", anc[0]);
+      if (worst > 1e-12 || worstL > 1e-10) { cerr << "posterior / computeLikelihoodAtNode checks failed" << endl; fails++; }
+    }
+    {
       ChromosomeAlphabet chr(1, 30);
       unique_ptr<Tree> t5(TreeTemplateTools::parenthesisToTree("(((a:0.3,b:0.2):0.4,c:0.5):0.1,(d:0.3,e:0.6):0.2);"));
       VectorSiteContainer s5(&chr);

@@ -221,6 +221,33 @@ def test_s20_fallbacks_eight_classes_and_two_points():
     assert abs(lnl[1] - res2.lnl) <= REL * abs(res2.lnl)
 
 
+@pytest.mark.parametrize("mk,ncat,rooted", [(gtr, 4, False), (rm.lg08, 4, False), (rm.lg08, 2, True),
+                                            (lambda: rm.yn98(2.0, 0.3), 1, False)])
+def test_likelihood_at_node_and_posteriors(mk, ncat, rooted):
+    """SURVEY 8f-2: DRTreeLikelihood::computeLikelihoodAtNode and DRTreeLikelihoodTools' posterior probabilities per state
+    and rate class, computed from the device-resident lower / upper arrays, for every node (leaves, internal nodes, root)."""
+    capi = _capi()
+    r, p = rm.gamma_rates(ncat, 0.6) if ncat > 1 else rm.constant_rate()
+    c = cases.make_case(12, 60, mk(), r, p, seed=91, rooted=rooted, ambiguity=0.05, compress=False, mean_brlen=0.2)
+    res = cases.oracle_eval(c, want_d1=True)
+    from oracle import ref_likelihood as rl
+    with cases.make_engine(c, flags=capi.FLAG_KEEP_CLVS) as e:
+        e.eval(capi.EVAL_LNL | capi.EVAL_D1)
+        for nid in range(c.flat.n_nodes):
+            la, ex, post = e.node_posteriors(nid)
+            exp_post = rl.posterior_probabilities(c.flat, res, res.P, nid, c.probs, c.codes_by_leaf, c.table)
+            np.testing.assert_allclose(post, exp_post, rtol=1e-9, atol=1e-14)
+            np.testing.assert_allclose(post.sum(axis=(1, 2)), 1.0, rtol=1e-12)
+            A, E = rl.likelihood_at_node(c.flat, res, res.P, nid)
+            got = np.ldexp(la, -ex[:, :, None].astype(np.int64))
+            want = np.ldexp(A, -E[:, :, None])
+            np.testing.assert_allclose(got, want, rtol=1e-9, atol=1e-13 * want.max())
+            # every node sees all the data: sum_x full[i][c][x] is the class likelihood of the site, whatever the node
+            site_c = np.einsum("icx->ic", got)
+            root_c = np.einsum("icx->ic", np.ldexp(res.lower[c.flat.root] * res.root_freqs, -res.lexp[c.flat.root][:, :, None]))
+            np.testing.assert_allclose(site_c, root_c, rtol=1e-8)
+
+
 def test_dmma_underflow_scaling():
     r, p = rm.constant_rate()
     c = cases.make_case(150, 40, rm.yn98(2.0, 0.3), r, p, seed=63, mean_brlen=0.8)     # simulated: no stop codons

@@ -1,1 +1,1 @@
-python -m pytest tests/test_cpp_shim.py -x -q -m gpu > gpurun_out/t33.log 2>&1; echo "rc=$?" >> gpurun_out/t33.log
+python -m pytest tests -x -q -m gpu -k "posteriors or shim" > gpurun_out/t34.log 2>&1; echo "rc=$?" >> gpurun_out/t34.log
