@@ -157,3 +157,40 @@ def test_scaled_equals_unscaled_where_finite_and_survives_underflow():
     assert not np.isfinite(cases.oracle_eval(big, scaled=False).lnl)      # the reference would return -inf
     s = cases.oracle_eval(big, scaled=True)
     assert np.isfinite(s.lnl) and s.SR_exp.max() > 256
+
+
+def test_posterior_probabilities_against_brute_force_enumeration():
+    """likelihood_at_node / posterior_probabilities (the restatement of computeLikelihoodAtNode_ and
+    DRTreeLikelihoodTools.cpp:46-119) equal the marginals obtained by enumerating every assignment of the internal states."""
+    import itertools
+    import cases
+    from oracle import ref_likelihood as rl
+    r, p = rm.gamma_rates(2, 0.7)
+    m = rm.gtr(1.2, 0.8, 0.6, 1.5, 0.9, (.3, .2, .25, .25))
+    c = cases.make_case(5, 6, m, r, p, seed=5, compress=False, ambiguity=0.1)
+    res = cases.oracle_eval(c, want_d1=True)
+    flat, S = c.flat, 4
+    internals = [n for n in range(flat.n_nodes) if not flat.is_leaf[n]]
+    for i in (0, 2, 5):
+        tot = {n: np.zeros((len(r), S)) for n in internals}
+        for cc in range(len(r)):
+            for states in itertools.product(range(S), repeat=len(internals)):
+                st = dict(zip(internals, states))
+                pr = c.root_freqs[st[flat.root]]
+                for n in range(flat.n_nodes - 1):
+                    f = int(flat.parent[n])
+                    if flat.is_leaf[n]:
+                        pr *= (res.P[n][cc][st[f]] * c.table[c.codes_by_leaf[n][i]]).sum()
+                    else:
+                        pr *= res.P[n][cc][st[f]][st[n]]
+                for n in internals:
+                    tot[n][cc, st[n]] += pr
+        for n in internals:
+            post = rl.posterior_probabilities(flat, res, res.P, n, c.probs)
+            np.testing.assert_allclose(post[i], tot[n] / tot[n].sum(), rtol=1e-12, atol=1e-16)
+            A, E = rl.likelihood_at_node(flat, res, res.P, n)
+            np.testing.assert_allclose(np.ldexp(A[i], -E[i][:, None]), tot[n], rtol=1e-12, atol=1e-300)
+    # leaves: the reference's formula uses the leaf likelihoods alone
+    leaf = flat.leaf_ids[0]
+    post = rl.posterior_probabilities(flat, res, res.P, leaf, c.probs, c.codes_by_leaf, c.table)
+    np.testing.assert_allclose(post.sum(axis=(1, 2)), 1.0, rtol=1e-14)
