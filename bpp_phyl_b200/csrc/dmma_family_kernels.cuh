@@ -496,23 +496,26 @@ struct DmmaPruneParams {
   int* out_exp;
 };
 
-__host__ __device__ constexpr int prune_threads(int KIND) { return KIND == 4 ? 256 : 512; }  // (three sons: 50 % more shared memory per warp)
-constexpr int kPruneStages = 3;
+// CFG picks warps x ring depth of the binary kinds: 0 = 16 x 3 (default), 1 = 12 x 4, 2 = 8 x 6 (BPPGPU_PRUNE_CFG, A/B runs);
+// the run-time kind (three sons: 50 % more shared memory per warp) is always 8 x 3
+__host__ __device__ constexpr int prune_threads(int KIND, int CFG) { return KIND == 4 ? 256 : (CFG == 0 ? 512 : (CFG == 1 ? 384 : 256)); }
+__host__ __device__ constexpr int prune_stages(int KIND, int CFG) { return KIND == 4 ? 3 : (CFG == 0 ? 3 : (CFG == 1 ? 4 : 6)); }
 __host__ __device__ constexpr int prune_rowstage(int KIND) { return fam_msi(KIND) * (kFamRowArr + 4); }
-template <int KIND>
+template <int KIND, int CFG>
 constexpr size_t dmma_prune_smem(int C) {
-  return (size_t)(C * fam_msi(KIND) * kFamPackA + (prune_threads(KIND) / 32) * kPruneStages * prune_rowstage(KIND)) * sizeof(double);
+  return (size_t)(C * fam_msi(KIND) * kFamPackA + (prune_threads(KIND, CFG) / 32) * prune_stages(KIND, CFG) * prune_rowstage(KIND)) *
+         sizeof(double);
 }
 
-template <int KIND>
-__global__ void __launch_bounds__(prune_threads(KIND), 1) dmma_prune_kernel(DmmaPruneParams p) {
+template <int KIND, int CFG>
+__global__ void __launch_bounds__(prune_threads(KIND, CFG), 1) dmma_prune_kernel(DmmaPruneParams p) {
   constexpr bool GEN = KIND == 4;
   constexpr int MS = GEN ? 3 : 2;
-  constexpr int NT = prune_threads(KIND);
+  constexpr int NT = prune_threads(KIND, CFG);
   constexpr int NW = NT / 32;
   constexpr int MSI = fam_msi(KIND);
   constexpr int MATS = MSI * kFamPackA;
-  constexpr int NST = kPruneStages;
+  constexpr int NST = prune_stages(KIND, CFG);
   constexpr int ROWSTAGE = prune_rowstage(KIND);
   constexpr int EXPOFF = MSI * kFamRowArr;
   extern __shared__ __align__(16) double sm_pr[];  // [C][MATS] operands, then [warp][NST][ROWSTAGE]

@@ -814,11 +814,14 @@ static int create_impl(const bppgpu_config* cfg, bppgpu_engine* e) {
     e->fam_grid = (int)((N + ppc - 1) / ppc);
     BPP_CUDA(dev_alloc(e, &e->d_fam_packL, (size_t)nn * C * kFamPackA));
     auto attr = [](auto k, size_t smem) { return cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); };
-    BPP_CUDA(attr(dmma_prune_kernel<0>, dmma_prune_smem<0>(C)));
-    BPP_CUDA(attr(dmma_prune_kernel<1>, dmma_prune_smem<1>(C)));
-    BPP_CUDA(attr(dmma_prune_kernel<2>, dmma_prune_smem<2>(C)));
-    BPP_CUDA(attr(dmma_prune_kernel<3>, dmma_prune_smem<3>(C)));
-    BPP_CUDA(attr(dmma_prune_kernel<4>, dmma_prune_smem<4>(C)));
+    if (const char* env = getenv("BPPGPU_PRUNE_CFG")) e->prune_cfg = std::min(2, std::max(0, atoi(env)));
+#define BPP_PRUNE_ATTR(Kv) \
+    BPP_CUDA(attr(dmma_prune_kernel<Kv, 0>, dmma_prune_smem<Kv, 0>(C))); \
+    BPP_CUDA(attr(dmma_prune_kernel<Kv, 1>, dmma_prune_smem<Kv, 1>(C))); \
+    BPP_CUDA(attr(dmma_prune_kernel<Kv, 2>, dmma_prune_smem<Kv, 2>(C)));
+    BPP_PRUNE_ATTR(0) BPP_PRUNE_ATTR(1) BPP_PRUNE_ATTR(2) BPP_PRUNE_ATTR(3)
+#undef BPP_PRUNE_ATTR
+    BPP_CUDA(attr(dmma_prune_kernel<4, 0>, dmma_prune_smem<4, 0>(C)));
   }
 
   if (e->path == PATH_WALK4) {
@@ -1234,11 +1237,15 @@ static int enqueue_prune(bppgpu_engine* e, int point, int pl, cudaStream_t st) {
         pp.out_exp = e->d_keep_exp + (size_t)op.keep_idx * N * C;
         const int G = e->fam_grid;
         switch (kind) {
-          case 0: dmma_prune_kernel<0><<<G, prune_threads(0), dmma_prune_smem<0>(C), st>>>(pp); break;
-          case 1: dmma_prune_kernel<1><<<G, prune_threads(1), dmma_prune_smem<1>(C), st>>>(pp); break;
-          case 2: dmma_prune_kernel<2><<<G, prune_threads(2), dmma_prune_smem<2>(C), st>>>(pp); break;
-          case 3: dmma_prune_kernel<3><<<G, prune_threads(3), dmma_prune_smem<3>(C), st>>>(pp); break;
-          default: dmma_prune_kernel<4><<<G, prune_threads(4), dmma_prune_smem<4>(C), st>>>(pp); break;
+#define BPP_PRUNE(Kv, Cv) dmma_prune_kernel<Kv, Cv><<<G, prune_threads(Kv, Cv), dmma_prune_smem<Kv, Cv>(C), st>>>(pp)
+#define BPP_PRUNE_K(Kv) if (e->prune_cfg == 0) BPP_PRUNE(Kv, 0); else if (e->prune_cfg == 1) BPP_PRUNE(Kv, 1); else BPP_PRUNE(Kv, 2)
+          case 0: BPP_PRUNE_K(0); break;
+          case 1: BPP_PRUNE_K(1); break;
+          case 2: BPP_PRUNE_K(2); break;
+          case 3: BPP_PRUNE_K(3); break;
+          default: BPP_PRUNE(4, 0); break;
+#undef BPP_PRUNE_K
+#undef BPP_PRUNE
         }
         e->stats.kernel_launches += 1;
       } else if (e->path == PATH_DMMA) {

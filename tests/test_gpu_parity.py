@@ -495,3 +495,29 @@ def test_error_conventions():
     e.close()
     with pytest.raises(capi.BppGpuError):
         capi.Engine(4, 4, 10, np.array([0, 0, 0, 2], np.int32), np.array([0, 0], np.int32), 2, c.table)
+
+
+def test_node_posteriors_error_conventions():
+    """bppgpu_get_node_posteriors: needs kept CLVs, needs the prefix pass for non-root nodes (the root works after a value-only
+    evaluation), rejects bad node ids; a leaf's posteriors need no upper array."""
+    capi = _capi()
+    r, p = rm.gamma_rates(4, 0.5)
+    c = cases.make_case(6, 10, gtr(), r, p, seed=3)
+    with cases.make_engine(c) as e:                      # no KEEP_CLVS
+        e.eval()
+        with pytest.raises(capi.BppGpuError) as ei:
+            e.node_posteriors(c.flat.root)
+        assert ei.value.code == capi.E_STATE
+    with cases.make_engine(c, flags=capi.FLAG_KEEP_CLVS) as e:
+        e.eval(capi.EVAL_LNL)
+        la, ex, post = e.node_posteriors(c.flat.root)    # root: lower array and root frequencies only
+        np.testing.assert_allclose(post.sum(axis=(1, 2)), 1.0, rtol=1e-12)
+        inner = next(n for n in range(c.flat.n_nodes - 1) if not c.flat.is_leaf[n])
+        with pytest.raises(capi.BppGpuError) as ei:
+            e.node_posteriors(inner)
+        assert ei.value.code == capi.E_STATE
+        _, _, post = e.node_posteriors(c.flat.leaf_ids[0], full=False)
+        np.testing.assert_allclose(post.sum(axis=(1, 2)), 1.0, rtol=1e-12)
+        with pytest.raises(capi.BppGpuError) as ei:
+            e.node_posteriors(c.flat.n_nodes)
+        assert ei.value.code == capi.E_INVALID

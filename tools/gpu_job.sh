@@ -1,2 +1,2 @@
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29551 bench.py --gpus 8 --steps 20 --warmup 3 > gpurun_out/w8_default.json 2> gpurun_out/w8_default.err; echo "rc=$?" >> gpurun_out/w8_default.err
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29552 bench.py --gpus 8 --steps 20 --warmup 3 --scaling strong --no-cpu > gpurun_out/s8_default.json 2> gpurun_out/s8_default.err; echo "rc=$?" >> gpurun_out/s8_default.err
+python -m pytest tests -x -q -m gpu -k "posteriors_error or family_kernel_vs" > gpurun_out/t35.log 2>&1; echo "rc=$?" >> gpurun_out/t35.log
+for cfg in 0 1 2; do BPPGPU_PRUNE_CFG=$cfg python bench.py --workload protein_g4_500x200k --steps 10 --warmup 3 --no-cpu 2>&1 >/dev/null | grep "timed region" | sed "s/^/cfg=$cfg /" >> gpurun_out/sweep_prune_cfg.log; done
