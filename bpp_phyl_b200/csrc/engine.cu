@@ -1601,7 +1601,11 @@ static int eval_impl(bppgpu_engine* e, unsigned want, cudaStream_t st, bool time
         pp.N = e->N;
         pp.P = e->d_P; pp.code_table = e->d_code_table; pp.code_single = e->d_code_single; pp.codes = e->d_codes;
         pp.keep = e->d_keep; pp.keep_exp = e->d_keep_exp;
-        points_node_kernel<<<dim3((unsigned)np, (unsigned)std::min<long long>(rows, 64)), 256, (2 * S + 32) * sizeof(double), st>>>(pp);
+        // a chunk holds only a few hundred points (one CTA each per row): large alphabets get 16 warps per CTA so that enough
+        // of the point's P rows are in flight to stream them at HBM speed
+        static const int pts_threads_env = getenv("BPPGPU_POINTS_THREADS") ? atoi(getenv("BPPGPU_POINTS_THREADS")) : 0;
+        const int pts_threads = pts_threads_env > 0 ? pts_threads_env : (S >= 128 ? 512 : 256);  // S = 200, 256 points: 27.0 ms (256 threads), 16.7 (512), 19.4 (1024)
+        points_node_kernel<<<dim3((unsigned)np, (unsigned)std::min<long long>(rows, 64)), pts_threads, (2 * S + 32) * sizeof(double), st>>>(pp);
         e->stats.kernel_launches++;
       }
       PointsRootParams pr{};

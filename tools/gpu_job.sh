@@ -1,2 +1,2 @@
-python -m pytest tests -x -q -m gpu -k "posteriors_error or family_kernel_vs" > gpurun_out/t35.log 2>&1; echo "rc=$?" >> gpurun_out/t35.log
-for cfg in 0 1 2; do BPPGPU_PRUNE_CFG=$cfg python bench.py --workload protein_g4_500x200k --steps 10 --warmup 3 --no-cpu 2>&1 >/dev/null | grep "timed region" | sed "s/^/cfg=$cfg /" >> gpurun_out/sweep_prune_cfg.log; done
+python -m pytest tests -x -q -m gpu -k "chromosome or points" > gpurun_out/t37.log 2>&1; echo "rc=$?" >> gpurun_out/t37.log
+for th in 256 512 1024; do BPPGPU_POINTS_THREADS=$th python bench.py --workload chromosome_500x4096pts --points 256 --steps 2 --warmup 1 --no-cpu 2>&1 >/dev/null | grep "timed region" | sed "s/^/threads=$th /" >> gpurun_out/sweep_points_threads.log; done
