@@ -198,6 +198,31 @@ def test_family_kernel_chunks_multifurcation_and_underflow(monkeypatch):
         _check_derivs_and_uppers(c, e, res, uppers=False)
 
 
+def test_s20_three_classes_two_byte_codes_with_derivatives():
+    """fragment-order S = 20 kernels with an odd class count (class-major rows: crow = N) and 2-byte tip codes, d1 + d2"""
+    capi = _capi()
+    rng = np.random.default_rng(85)
+    r, p = rm.gamma_rates(3, 0.9)
+    c = cases.make_case(13, 75, rm.lg08(), r, p, seed=85, compress=False, mean_brlen=0.15)
+    extra = rng.dirichlet(np.ones(20), size=300)
+    c.table = np.vstack([c.table, extra])
+    for lid in c.codes_by_leaf:
+        codes = c.codes_by_leaf[lid].astype(np.uint16)
+        mask = rng.random(c.N) < 0.3
+        codes[mask] = rng.integers(22, 322, size=int(mask.sum()))
+        c.codes_by_leaf[lid] = codes
+    c.code_dtype = np.uint16
+    res = cases.oracle_eval(c, want_d1=True, want_d2=True)
+    with cases.make_engine(c, flags=capi.FLAG_KEEP_CLVS) as e:
+        assert e.stats()["path"] == 4
+        _check_derivs_and_uppers(c, e, res)
+        for nid in range(c.flat.n_nodes):
+            if not c.flat.is_leaf[nid]:
+                clv, ex = e.clv(nid, 0)
+                np.testing.assert_array_equal(ex, res.lexp[nid])
+                np.testing.assert_allclose(clv, res.lower[nid], rtol=1e-10, atol=1e-14 * res.lower[nid].max())
+
+
 def test_s20_fallbacks_eight_classes_and_two_points():
     """The S = 20 fragment-order kernels hold the operands of <= 4 rate classes and serve single-point engines; 8 classes
     and 2-point engines must take the per-node / per-branch tensor-core kernels and agree with the oracle all the same."""
