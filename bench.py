@@ -559,7 +559,7 @@ def main():
         kms = st["prune_ms_sum"] / max(1, st["prune_count"])
         kname = {1: "walk4_kernel", 2: "walkS_kernel", 3: "generic_node_kernel", 4: "dmma_node_kernel"}.get(st["path"], "?")
         fam20 = st["path"] == 4 and w["S"] == 20 and w["C"] <= 4 and os.environ.get("BPPGPU_FAMILY", "1") != "0"
-        if fam20:
+        if fam20 or (st["path"] == 4 and w["S"] == 64 and w["C"] == 1 and os.environ.get("BPPGPU_FAMILY", "1") != "0"):
             kname = "dmma_prune_kernel"
         if st["path"] == 4 and w["S"] >= 32:
             # dense contraction on the FP64 tensor cores (mma.sync DMMA; tcgen05 has no f64 kind)

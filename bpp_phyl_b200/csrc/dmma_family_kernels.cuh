@@ -472,11 +472,14 @@ __global__ void finalize_family_kernel(const double* part, const int* mask, int 
 
 
 // ----------------------------------------------------------------------------------------------------------------------
-// K2 for S = 20 with the same machinery: one pruning step  CLV_n = prod_sons (P_son . CLV_son)  per launch
-// (RHomogeneousTreeLikelihood::computeSubtreeLikelihood, Likelihood/RHomogeneousTreeLikelihood.cpp:802-863;
-// DRHomogeneousTreeLikelihood::computeLikelihoodFromArrays :819-864), per-row power-of-two rescaling fused.
-// An item is light here (15 DMMAs per internal son), so the kernel lives on HBM: 16 warps per SM, each with a 3-deep
-// cp.async ring of son rows, operands of every class resident, nothing but the output row and its exponent written.
+// K2 with the same machinery, for S = 20 (protein) and S = 64 (codon): one pruning step
+// CLV_n = prod_sons (P_son . CLV_son)  per launch (RHomogeneousTreeLikelihood::computeSubtreeLikelihood,
+// Likelihood/RHomogeneousTreeLikelihood.cpp:802-863; DRHomogeneousTreeLikelihood::computeLikelihoodFromArrays :819-864),
+// per-row power-of-two rescaling fused.  Lane q of a quad owns the S/4 states dmma_ymap(t, q), t = 0 .. S/4 - 1, in its
+// accumulator columns -- the states whose A fragments it loads -- so rows are stored 32 bytes per lane and tip sons read
+// their table rows the same way.  S = 20: an item is light (15 DMMAs per internal son), the kernel lives on HBM: 16 warps
+// per SM with a 3-deep cp.async ring.  S = 64: 128 DMMAs per internal son and item, FP64-tensor bound: 8 warps, 2-deep ring,
+// the 32 KB operand of each son resident.
 struct PruneSon {
   int kind, node;
   const double* clv;   // internal son: lower CLV slab, exponents
@@ -491,40 +494,105 @@ struct DmmaPruneParams {
   int ppc;
   int prow, crow;       // CLV row of (pattern i, class c) = i * prow + c * crow
   long long N;
-  const double* packL;  // [nn][C][kFamPackA]
+  const double* packL;  // [nn][C][prune_pack(S)]
   double* out;          // CLV slab of the node
   int* out_exp;
 };
 
-// CFG picks warps x ring depth of the binary kinds: 0 = 16 x 3 (default), 1 = 12 x 4, 2 = 8 x 6 (BPPGPU_PRUNE_CFG, A/B runs);
-// the run-time kind (three sons: 50 % more shared memory per warp) is always 8 x 3
-__host__ __device__ constexpr int prune_threads(int KIND, int CFG) { return KIND == 4 ? 256 : (CFG == 0 ? 512 : (CFG == 1 ? 384 : 256)); }
-__host__ __device__ constexpr int prune_stages(int KIND, int CFG) { return KIND == 4 ? 3 : (CFG == 0 ? 3 : (CFG == 1 ? 4 : 6)); }
-__host__ __device__ constexpr int prune_rowstage(int KIND) { return fam_msi(KIND) * (kFamRowArr + 4); }
-template <int KIND, int CFG>
-constexpr size_t dmma_prune_smem(int C) {
-  return (size_t)(C * fam_msi(KIND) * kFamPackA + (prune_threads(KIND, CFG) / 32) * prune_stages(KIND, CFG) * prune_rowstage(KIND)) *
-         sizeof(double);
+__host__ __device__ constexpr int prune_kb(int S) { return S / 4; }                       // k blocks = states per lane
+__host__ __device__ constexpr int prune_nb(int S) { return (S + 7) / 8; }                 // column blocks
+__host__ __device__ constexpr int prune_np(int S) { return (prune_nb(S) + 1) / 2; }       // 16-byte operand pairs per k block
+__host__ __device__ constexpr int prune_pack(int S) { return prune_kb(S) * prune_np(S) * 64; }  // operand doubles per (branch, class)
+__host__ __device__ constexpr int prune_rowstride(int S) { return S + 2; }                // = 2 (mod 4): conflict-free 16-byte fragment reads
+__host__ __device__ constexpr int prune_rowarr(int S) { return 8 * prune_rowstride(S); }
+
+// P of every (branch, class) in fragment order for the pruning kernels (block = branch * C + class):
+//   pack[((kb * NP + pi) * 32 + lane) * 2 + h] = P[x][y],  y = ymap(kb, q), column n = 8 (2 pi + h) + g  <->  slot t = 2 nb + (g & 1)
+//   of lane q' = g >> 1, x = ymap(t, q')
+template <int S_>
+__global__ void prune_pack_kernel(const double* P, double* packL) {
+  constexpr int KB = prune_kb(S_), NP = prune_np(S_), PACK = prune_pack(S_);
+  const size_t bc = blockIdx.x;
+  const double* m = P + bc * S_ * S_;
+  for (int e = threadIdx.x; e < PACK; e += blockDim.x) {
+    const int h = e & 1, lane = (e >> 1) & 31, kp = e >> 6, pi = kp % NP, kb = kp / NP;
+    const int g = lane >> 2, q = lane & 3;
+    const int y = dmma_ymap<KB>(kb, q);
+    const int nb = 2 * pi + h, t = 2 * nb + (g & 1);
+    double v = 0.0;
+    if (t < KB) {
+      const int x = dmma_ymap<KB>(t, g >> 1);
+      if (x < S_ && y < S_) v = m[(size_t)x * S_ + y];
+    }
+    packL[bc * PACK + e] = v;
+  }
 }
 
-template <int KIND, int CFG>
-__global__ void __launch_bounds__(prune_threads(KIND, CFG), 1) dmma_prune_kernel(DmmaPruneParams p) {
+// acc[nb] = A-fragments x packed operand, KB k blocks
+template <int KB, int NB, int NP>
+__device__ __forceinline__ void prune_contract(double (&acc)[NB][2], const double (&a)[KB], const double* Ms, int lane) {
+#pragma unroll
+  for (int nb = 0; nb < NB; ++nb) acc[nb][0] = acc[nb][1] = 0.0;
+#pragma unroll
+  for (int kb = 0; kb < KB; ++kb)
+#pragma unroll
+    for (int pi = 0; pi < (NB + 1) / 2; ++pi) {
+      const double2 b = *reinterpret_cast<const double2*>(Ms + ((kb * NP + pi) * 32 + lane) * 2);
+      dmma884(acc[2 * pi][0], acc[2 * pi][1], a[kb], b.x);
+      if (2 * pi + 1 < NB) dmma884(acc[2 * pi + 1][0], acc[2 * pi + 1][1], a[kb], b.y);
+    }
+}
+
+// the S/4 values of a row owned by lane q: v[t] <-> state ymap(t, q); 32-byte accesses for the full 16-state chunks
+template <int S_, bool NC>
+__device__ __forceinline__ void prune_load_states(const double* row, int q, double (&v)[S_ / 4]) {
+  constexpr int KB = S_ / 4, J = S_ / 16;
+#pragma unroll
+  for (int j = 0; j < J; ++j) {
+    if (NC) ld256nc(row + 16 * j + 4 * q, v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    else ld256(row + 16 * j + 4 * q, v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+  }
+#pragma unroll
+  for (int t = 4 * J; t < KB; ++t) v[t] = NC ? __ldg(row + 16 * J + 4 * (t - 4 * J) + q) : row[16 * J + 4 * (t - 4 * J) + q];
+}
+
+// CFG picks warps x ring depth of the binary S = 20 kinds: 0 = 16 x 3 (default), 1 = 12 x 4, 2 = 8 x 6 (BPPGPU_PRUNE_CFG, A/B
+// runs); the run-time kind (three sons: 50 % more shared memory per warp) is 8 x 3; S = 64 is always 8 x 2 (run-time kind 4 x 2)
+__host__ __device__ constexpr int prune_threads(int S, int KIND, int CFG) {
+  return S > 32 ? (KIND == 4 ? 128 : 256) : (KIND == 4 ? 256 : (CFG == 0 ? 512 : (CFG == 1 ? 384 : 256)));
+}
+__host__ __device__ constexpr int prune_stages(int S, int KIND, int CFG) {
+  return S > 32 ? 2 : (KIND == 4 ? 3 : (CFG == 0 ? 3 : (CFG == 1 ? 4 : 6)));
+}
+__host__ __device__ constexpr int prune_rowstage(int S, int KIND) { return fam_msi(KIND) * (prune_rowarr(S) + 4); }
+template <int S_, int KIND, int CFG>
+constexpr size_t dmma_prune_smem(int C) {
+  return (size_t)(C * fam_msi(KIND) * prune_pack(S_) +
+                  (prune_threads(S_, KIND, CFG) / 32) * prune_stages(S_, KIND, CFG) * prune_rowstage(S_, KIND)) * sizeof(double);
+}
+
+template <int S_, int KIND, int CFG>
+__global__ void __launch_bounds__(prune_threads(S_, KIND, CFG), 1) dmma_prune_kernel(DmmaPruneParams p) {
   constexpr bool GEN = KIND == 4;
   constexpr int MS = GEN ? 3 : 2;
-  constexpr int NT = prune_threads(KIND, CFG);
+  constexpr int KB = prune_kb(S_), NB = prune_nb(S_), NP = prune_np(S_), PACK = prune_pack(S_);
+  constexpr int RSTRIDE = prune_rowstride(S_), RARR = prune_rowarr(S_);
+  constexpr int NT = prune_threads(S_, KIND, CFG);
   constexpr int NW = NT / 32;
   constexpr int MSI = fam_msi(KIND);
-  constexpr int MATS = MSI * kFamPackA;
-  constexpr int NST = prune_stages(KIND, CFG);
-  constexpr int ROWSTAGE = prune_rowstage(KIND);
-  constexpr int EXPOFF = MSI * kFamRowArr;
-  extern __shared__ __align__(16) double sm_pr[];  // [C][MATS] operands, then [warp][NST][ROWSTAGE]
+  constexpr int MATS = MSI * PACK;
+  constexpr int NST = prune_stages(S_, KIND, CFG);
+  constexpr int ROWSTAGE = prune_rowstage(S_, KIND);
+  constexpr int EXPOFF = MSI * RARR;
+  constexpr int PIECES = S_ / 2;                    // 16-byte pieces of a row
+  constexpr int NIT = (8 * PIECES + 31) / 32;       // copy instructions per lane and array
+  extern __shared__ __align__(16) double sm_pr[];   // [C][MATS] operands, then [warp][NST][ROWSTAGE]
 
   auto has = [&](int j) { return GEN ? j < p.nson : true; };
   auto tip = [&](int j) { return GEN ? p.sons[j].kind == CHILD_TIP : ((KIND >> j) & 1) != 0; };
   auto slot = [&](int j) { return GEN ? j : (j == 1 && !(KIND & 1) ? 1 : 0); };
 
-  const int S = p.S, C = p.C;
+  const int C = p.C;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, q = lane & 3;
   double* rows = sm_pr + (size_t)C * MATS + (size_t)warp * NST * ROWSTAGE;
@@ -533,13 +601,13 @@ __global__ void __launch_bounds__(prune_threads(KIND, CFG), 1) dmma_prune_kernel
   const int prow = p.prow, crow = p.crow;
   const int rowbase = (int)cta0 * prow;
 
-  int cp_r[3], cp_src[3], cp_dst[3];
+  int cp_r[NIT], cp_src[NIT], cp_dst[NIT];
 #pragma unroll
-  for (int it = 0; it < 3; ++it) {
+  for (int it = 0; it < NIT; ++it) {
     const int e = lane + 32 * it;
-    cp_r[it] = e / 10;
-    cp_src[it] = 2 * (e - cp_r[it] * 10);
-    cp_dst[it] = cp_r[it] * kFamRowStride + cp_src[it];
+    cp_r[it] = e / PIECES;
+    cp_src[it] = 2 * (e - cp_r[it] * PIECES);
+    cp_dst[it] = cp_r[it] * RSTRIDE + cp_src[it];
   }
   const int* exp_src = nullptr;
 #pragma unroll
@@ -552,13 +620,13 @@ __global__ void __launch_bounds__(prune_threads(KIND, CFG), 1) dmma_prune_kernel
     const int row0 = rowbase + r0 * prow + c * crow;
     if (MSI > 0) {
 #pragma unroll
-      for (int it = 0; it < 3; ++it) {
-        if (it < 2 || lane < 16) {
-          const int off = (row0 + min(cp_r[it], rmax) * prow) * S + cp_src[it];
+      for (int it = 0; it < NIT; ++it) {
+        if (lane + 32 * it < 8 * PIECES) {
+          const int off = (row0 + min(cp_r[it], rmax) * prow) * S_ + cp_src[it];
           double* d = dst + cp_dst[it];
 #pragma unroll
           for (int j = 0; j < MS; ++j)
-            if (has(j) && !tip(j)) cp_async16(d + slot(j) * kFamRowArr, p.sons[j].clv + off);
+            if (has(j) && !tip(j)) cp_async16(d + slot(j) * RARR, p.sons[j].clv + off);
         }
       }
       if (exp_src != nullptr) cp_async4(reinterpret_cast<int*>(dst + EXPOFF) + lane, exp_src + row0 + min(lane & 7, rmax) * prow);
@@ -575,12 +643,18 @@ __global__ void __launch_bounds__(prune_threads(KIND, CFG), 1) dmma_prune_kernel
     }
     cp_async_commit();
   };
-  auto load_frag = [&](const double* arr, double (&a)[kFamKB]) {
-    const double* row = arr + g * kFamRowStride;
-    const double2 v0 = *reinterpret_cast<const double2*>(row + 4 * q);
-    const double2 v1 = *reinterpret_cast<const double2*>(row + 4 * q + 2);
-    a[0] = v0.x; a[1] = v0.y; a[2] = v1.x; a[3] = v1.y;
-    a[4] = row[16 + q];
+  // the A fragments of row g from a staged array: a[kb] = row[ymap(kb, q)]
+  auto load_frag = [&](const double* arr, double (&a)[KB]) {
+    const double* row = arr + g * RSTRIDE;
+    constexpr int J = S_ / 16;
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+      const double2 v0 = *reinterpret_cast<const double2*>(row + 16 * j + 4 * q);
+      const double2 v1 = *reinterpret_cast<const double2*>(row + 16 * j + 4 * q + 2);
+      a[4 * j] = v0.x; a[4 * j + 1] = v0.y; a[4 * j + 2] = v1.x; a[4 * j + 3] = v1.y;
+    }
+#pragma unroll
+    for (int kb = 4 * J; kb < KB; ++kb) a[kb] = row[16 * J + 4 * (kb - 4 * J) + q];
   };
   auto load_codes = [&](int r0, int (&code)[MS]) {
     const long long pat = cta0 + min(r0 + g, ncta - 1);
@@ -594,8 +668,7 @@ __global__ void __launch_bounds__(prune_threads(KIND, CFG), 1) dmma_prune_kernel
 #pragma unroll
     for (int j = 0; j < MS; ++j)
       if (has(j) && !tip(j))
-        family_stage_async<NT>(sm_pr + (size_t)c * MATS + (size_t)slot(j) * kFamPackA,
-                               p.packL + ((size_t)p.sons[j].node * C + c) * kFamPackA, kFamPackA);
+        family_stage_async<NT>(sm_pr + (size_t)c * MATS + (size_t)slot(j) * PACK, p.packL + ((size_t)p.sons[j].node * C + c) * PACK, PACK);
   cp_async_commit();
   int ccur[MS], cnxt[MS];
   load_codes(warp * 8, cnxt);
@@ -618,33 +691,31 @@ __global__ void __launch_bounds__(prune_threads(KIND, CFG), 1) dmma_prune_kernel
       st = st + 1 == NST ? 0 : st + 1;
       const double* mats = sm_pr + (size_t)c * MATS;
 
-      double prod[5];
+      double prod[KB];
       int Ea = 0;
       bool firstson = true;
 #pragma unroll
       for (int j = 0; j < MS; ++j) {
         if (has(j)) {
-          double v[5];
           if (tip(j)) {
-            const double* tp = p.sons[j].tt + (c * p.ncodes + ccur[j]) * S;
-            ld256nc(tp + 4 * q, v[0], v[1], v[2], v[3]);
-            v[4] = __ldg(tp + 16 + q);
+            double v[KB];
+            prune_load_states<S_, true>(p.sons[j].tt + (size_t)(c * p.ncodes + ccur[j]) * S_, q, v);
+#pragma unroll
+            for (int i = 0; i < KB; ++i) prod[i] = firstson ? v[i] : prod[i] * v[i];
           } else {
-            double a[kFamKB], acc[3][2];
-            load_frag(rs + slot(j) * kFamRowArr, a);
+            double a[KB], acc[NB][2];
+            load_frag(rs + slot(j) * RARR, a);
             Ea += ex[slot(j) * 8 + g];
-            family_contract<3, 2>(acc, a, mats + (size_t)slot(j) * kFamPackA, lane);
+            prune_contract<KB, NB, NP>(acc, a, mats + (size_t)slot(j) * PACK, lane);
 #pragma unroll
-            for (int i = 0; i < 5; ++i) v[i] = acc[i >> 1][i & 1];
+            for (int i = 0; i < KB; ++i) prod[i] = firstson ? acc[i >> 1][i & 1] : prod[i] * acc[i >> 1][i & 1];
           }
-#pragma unroll
-          for (int i = 0; i < 5; ++i) prod[i] = firstson ? v[i] : prod[i] * v[i];
           firstson = false;
         }
       }
       int m = 0;
 #pragma unroll
-      for (int i = 0; i < 5; ++i) m = max(m, hi_word(prod[i]));
+      for (int i = 0; i < KB; ++i) m = max(m, hi_word(prod[i]));
       m = max(m, __shfl_xor_sync(0xffffffffu, m, 1));
       m = max(m, __shfl_xor_sync(0xffffffffu, m, 2));
       const int k = (m < kScaleThresholdHi && m >= (1 << 20)) ? rescale_shift(m) : 0;
@@ -652,9 +723,13 @@ __global__ void __launch_bounds__(prune_threads(KIND, CFG), 1) dmma_prune_kernel
       Ea += k;
       if (valid) {
         const int orow = rowbase + (r0 + g) * prow + c * crow;
-        double* row = p.out + orow * S;
-        st256(row + 4 * q, prod[0] * f, prod[1] * f, prod[2] * f, prod[3] * f);
-        row[16 + q] = prod[4] * f;
+        double* row = p.out + (size_t)orow * S_;
+        constexpr int J = S_ / 16;
+#pragma unroll
+        for (int j = 0; j < J; ++j)
+          st256(row + 16 * j + 4 * q, prod[4 * j] * f, prod[4 * j + 1] * f, prod[4 * j + 2] * f, prod[4 * j + 3] * f);
+#pragma unroll
+        for (int t = 4 * J; t < KB; ++t) row[16 * J + 4 * (t - 4 * J) + q] = prod[t] * f;
         if (q == 0) p.out_exp[orow] = Ea;
       }
     }

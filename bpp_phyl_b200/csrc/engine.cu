@@ -805,23 +805,38 @@ static int create_impl(const bppgpu_config* cfg, bppgpu_engine* e) {
     e->clv_class_major = !wide && !wroot && (double)N * C * S < 2.0e9 && !(lenv && !strcmp(lenv, "pattern"));
     if ((double)N * C * S >= 2.0e9) e->family = false;  // 32-bit row offsets inside the kernels
   }
-  if (e->family) {
+  {
+    // S = 64 (codon), one rate class: the same fragment-order pruning kernel (the derivative pass keeps the first-generation
+    // kernels, which share the reference-order slabs: with C = 1 both orders coincide)
+    const char* fenv = getenv("BPPGPU_FAMILY");
+    e->prune64 = e->path == PATH_DMMA && S == 64 && C == 1 && N > 0 && e->npoints == 1 && (double)N * C * S < 2.0e9 &&
+                 !(fenv && atoi(fenv) == 0);
+  }
+  if (e->family || e->prune64) {
     long long slots = g_sm_count;
     if (const char* env = getenv("BPPGPU_FAMILY_GRID")) slots = std::max(1, atoi(env));  // test knob: few CTAs, long ranges
     long long ppc = (N + slots - 1) / slots;
     ppc = std::max<long long>(8, (ppc + 7) / 8 * 8);
     e->fam_ppc = (int)ppc;
     e->fam_grid = (int)((N + ppc - 1) / ppc);
-    BPP_CUDA(dev_alloc(e, &e->d_fam_packL, (size_t)nn * C * kFamPackA));
+    BPP_CUDA(dev_alloc(e, &e->d_fam_packL, (size_t)nn * C * prune_pack(S)));
     auto attr = [](auto k, size_t smem) { return cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); };
-    if (const char* env = getenv("BPPGPU_PRUNE_CFG")) e->prune_cfg = std::min(2, std::max(0, atoi(env)));
+    if (e->family) {
+      if (const char* env = getenv("BPPGPU_PRUNE_CFG")) e->prune_cfg = std::min(2, std::max(0, atoi(env)));
 #define BPP_PRUNE_ATTR(Kv) \
-    BPP_CUDA(attr(dmma_prune_kernel<Kv, 0>, dmma_prune_smem<Kv, 0>(C))); \
-    BPP_CUDA(attr(dmma_prune_kernel<Kv, 1>, dmma_prune_smem<Kv, 1>(C))); \
-    BPP_CUDA(attr(dmma_prune_kernel<Kv, 2>, dmma_prune_smem<Kv, 2>(C)));
-    BPP_PRUNE_ATTR(0) BPP_PRUNE_ATTR(1) BPP_PRUNE_ATTR(2) BPP_PRUNE_ATTR(3)
+      BPP_CUDA(attr(dmma_prune_kernel<20, Kv, 0>, dmma_prune_smem<20, Kv, 0>(C))); \
+      BPP_CUDA(attr(dmma_prune_kernel<20, Kv, 1>, dmma_prune_smem<20, Kv, 1>(C))); \
+      BPP_CUDA(attr(dmma_prune_kernel<20, Kv, 2>, dmma_prune_smem<20, Kv, 2>(C)));
+      BPP_PRUNE_ATTR(0) BPP_PRUNE_ATTR(1) BPP_PRUNE_ATTR(2) BPP_PRUNE_ATTR(3)
 #undef BPP_PRUNE_ATTR
-    BPP_CUDA(attr(dmma_prune_kernel<4, 0>, dmma_prune_smem<4, 0>(C)));
+      BPP_CUDA(attr(dmma_prune_kernel<20, 4, 0>, dmma_prune_smem<20, 4, 0>(C)));
+    } else {
+      BPP_CUDA(attr(dmma_prune_kernel<64, 0, 0>, dmma_prune_smem<64, 0, 0>(C)));
+      BPP_CUDA(attr(dmma_prune_kernel<64, 1, 0>, dmma_prune_smem<64, 1, 0>(C)));
+      BPP_CUDA(attr(dmma_prune_kernel<64, 2, 0>, dmma_prune_smem<64, 2, 0>(C)));
+      BPP_CUDA(attr(dmma_prune_kernel<64, 3, 0>, dmma_prune_smem<64, 3, 0>(C)));
+      BPP_CUDA(attr(dmma_prune_kernel<64, 4, 0>, dmma_prune_smem<64, 4, 0>(C)));
+    }
   }
 
   if (e->path == PATH_WALK4) {
@@ -1209,7 +1224,7 @@ static int enqueue_prune(bppgpu_engine* e, int point, int pl, cudaStream_t st) {
       gp.N = N;
       gp.P = P; gp.tiptab = tiptab; gp.codes = e->d_codes;
       gp.keep = e->d_keep; gp.keep_exp = e->d_keep_exp;
-      if (e->path == PATH_DMMA && e->family && op.nchild <= kFamMaxSons) {
+      if (e->path == PATH_DMMA && (e->family || e->prune64) && op.nchild <= kFamMaxSons) {
         DmmaPruneParams pp{};
         pp.nson = op.nchild;
         int kind = op.nchild == 2 ? 0 : 4;
@@ -1237,13 +1252,14 @@ static int enqueue_prune(bppgpu_engine* e, int point, int pl, cudaStream_t st) {
         pp.out_exp = e->d_keep_exp + (size_t)op.keep_idx * N * C;
         const int G = e->fam_grid;
         switch (kind) {
-#define BPP_PRUNE(Kv, Cv) dmma_prune_kernel<Kv, Cv><<<G, prune_threads(Kv, Cv), dmma_prune_smem<Kv, Cv>(C), st>>>(pp)
-#define BPP_PRUNE_K(Kv) if (e->prune_cfg == 0) BPP_PRUNE(Kv, 0); else if (e->prune_cfg == 1) BPP_PRUNE(Kv, 1); else BPP_PRUNE(Kv, 2)
+#define BPP_PRUNE(Sv, Kv, Cv) dmma_prune_kernel<Sv, Kv, Cv><<<G, prune_threads(Sv, Kv, Cv), dmma_prune_smem<Sv, Kv, Cv>(C), st>>>(pp)
+#define BPP_PRUNE_K(Kv) if (S == 64) BPP_PRUNE(64, Kv, 0); else if (e->prune_cfg == 0) BPP_PRUNE(20, Kv, 0); \
+                        else if (e->prune_cfg == 1) BPP_PRUNE(20, Kv, 1); else BPP_PRUNE(20, Kv, 2)
           case 0: BPP_PRUNE_K(0); break;
           case 1: BPP_PRUNE_K(1); break;
           case 2: BPP_PRUNE_K(2); break;
           case 3: BPP_PRUNE_K(3); break;
-          default: BPP_PRUNE(4, 0); break;
+          default: if (S == 64) BPP_PRUNE(64, 4, 0); else BPP_PRUNE(20, 4, 0); break;
 #undef BPP_PRUNE_K
 #undef BPP_PRUNE
         }
@@ -1567,6 +1583,10 @@ static int eval_impl(bppgpu_engine* e, unsigned want, cudaStream_t st, bool time
           e->stats.kernel_launches++;
         }
       }
+    }
+    if (e->prune64) {
+      prune_pack_kernel<64><<<nn * C, 256, 0, st>>>(e->d_P, e->d_fam_packL);
+      e->stats.kernel_launches++;
     }
     if (e->family) {
       // operands in fragment order for the S = 20 tensor-core kernels (single-point engines only)

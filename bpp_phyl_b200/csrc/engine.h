@@ -83,6 +83,7 @@ struct bppgpu_engine {
   std::vector<int> upper_slab;                          // node id -> slab of d_upper, or -1
   // per-father fused upper + derivative pass (dmma_family_kernels.cuh)
   bool family = false;
+  bool prune64 = false;          // S = 64, C = 1: fragment-order pruning kernel (dmma_prune_kernel<64, ...>)
   int prune_cfg = 0;             // warps x ring depth of dmma_prune_kernel (BPPGPU_PRUNE_CFG)
   bool clv_class_major = false;  // CLV slabs are [class][pattern][state] (S = 20 fragment-order kernels only)
   std::vector<int> fam_mask;   // node id -> 1 when its branch is served by its father's family launch
