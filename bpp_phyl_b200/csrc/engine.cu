@@ -1538,7 +1538,6 @@ static int eval_impl(bppgpu_engine* e, unsigned want, cudaStream_t st, bool time
   unsigned pt_want = BPPGPU_WANT_P | ((want & BPPGPU_EVAL_D1) ? BPPGPU_WANT_DP : 0) | ((want & BPPGPU_EVAL_D2) ? BPPGPU_WANT_D2P : 0);
   if (timed) BPP_CUDA(cudaEventRecord(e->ev0, st));
   BPP_CUDA(cudaMemcpyAsync(e->d_rootfreq_used, e->d_rootfreq, (size_t)e->npoints * S * 8, cudaMemcpyDeviceToDevice, st));
-  float prune_ms_total = 0.f;
   for (int p0 = 0; p0 < e->npoints; p0 += e->pchunk) {
     const int np = std::min(e->pchunk, e->npoints - p0);
     long long launches = 0;
@@ -1668,7 +1667,6 @@ static int eval_impl(bppgpu_engine* e, unsigned want, cudaStream_t st, bool time
     }
   }
   (void)SS;
-  (void)prune_ms_total;
   if (timed) BPP_CUDA(cudaEventRecord(e->ev1, st));
   e->last_want = want;
   return BPPGPU_OK;
