@@ -20,6 +20,7 @@
 #pragma once
 #include <algorithm>
 #include <cmath>
+#include <limits>
 #include <complex>
 #include <cstdint>
 #include <cstring>
@@ -1653,9 +1654,10 @@ class DRNonHomogeneousTreeLikelihood : public AbstractHomogeneousTreeLikelihood 
 class LikelihoodPointBatch : public AbstractHomogeneousTreeLikelihood {
  public:
   LikelihoodPointBatch(const Tree& tree, const VectorSiteContainer& data, bool weightedRootFreq,
-                       const std::vector<SubstitutionModel*>& models, DiscreteDistribution* rDist, int device = 0)
-      : AbstractHomogeneousTreeLikelihood(tree, models.at(0), rDist, false,
-                                          BPPGPU_FLAG_NH_DERIV | (weightedRootFreq ? BPPGPU_FLAG_WEIGHTED_ROOT : 0u), device),
+                       const std::vector<SubstitutionModel*>& models, DiscreteDistribution* rDist, int device = 0,
+                       bool checkRooted = false, unsigned engineFlags = BPPGPU_FLAG_NH_DERIV)
+      : AbstractHomogeneousTreeLikelihood(tree, models.at(0), rDist, checkRooted,
+                                          engineFlags | (weightedRootFreq ? BPPGPU_FLAG_WEIGHTED_ROOT : 0u), device),
         models_(models) {
     nPoints_ = (int)models.size();
     computeDerivatives_ = false;
@@ -1718,6 +1720,54 @@ class LikelihoodPointBatch : public AbstractHomogeneousTreeLikelihood {
   std::vector<Vdouble> pointBrLen_;
   std::vector<char> dirty_;
   Vdouble values_;
+};
+
+// ---- mixture of substitution models ------------------------------------------------------------------------------
+// RHomogeneousMixedTreeLikelihood keeps one RHomogeneousTreeLikelihood per sub-model of a MixedSubstitutionModel and combines
+// them per site and rate class with the sub-model probabilities, L_site = sum_k probas_k L_k,site
+// (Likelihood/RHomogeneousMixedTreeLikelihood.cpp:191-212; YNGP M-series, RELAX).  Here the sub-likelihoods are the points of one
+// device object and the combination is a log-sum-exp over their per-site log-likelihoods.
+class RHomogeneousMixedTreeLikelihood : public LikelihoodPointBatch {
+ public:
+  RHomogeneousMixedTreeLikelihood(const Tree& tree, const VectorSiteContainer& data, const std::vector<SubstitutionModel*>& subModels,
+                                  const Vdouble& probas, DiscreteDistribution* rDist, int device = 0)
+      : LikelihoodPointBatch(tree, data, false, subModels, rDist, device, /*checkRooted=*/true, /*engineFlags=*/0u), probas_(probas) {
+    if (probas_.size() != subModels.size()) throw Exception("RHomogeneousMixedTreeLikelihood: one probability per sub-model");
+  }
+  void setProbabilities(const Vdouble& p) { probas_ = p; if (initialized_) combine(); }
+  double getValue() const { requireInit(); return mixedMinusLogLik_; }
+  double getLogLikelihood() const { return -getValue(); }
+  double getLogLikelihoodForASite(size_t site) const { requireInit(); return mixedSiteLnl_[(size_t)siteIndex_[site]]; }
+
+ protected:
+  void fireParameterChanged() override {
+    LikelihoodPointBatch::fireParameterChanged();
+    combine();
+  }
+
+ private:
+  void combine() {
+    const size_t K = getNumberOfPoints(), N = (size_t)nPatterns_;
+    std::vector<Vdouble> sl(K, Vdouble(N));
+    for (size_t k = 0; k < K; ++k) check(bppgpu_get_site_lnl(engine_, (int32_t)k, sl[k].data()), "getLogLikelihoodForEachSite");
+    mixedSiteLnl_.assign(N, 0.0);
+    for (size_t i = 0; i < N; ++i) {
+      double m = -std::numeric_limits<double>::infinity();
+      for (size_t k = 0; k < K; ++k) if (probas_[k] > 0) m = std::max(m, sl[k][i]);
+      double s = 0;
+      for (size_t k = 0; k < K; ++k) if (probas_[k] > 0) s += probas_[k] * std::exp(sl[k][i] - m);
+      mixedSiteLnl_[i] = std::isfinite(m) ? m + std::log(s) : m;
+    }
+    // getLogLikelihood (RHomogeneousTreeLikelihood.cpp:162-176): every site, sorted, summed
+    Vdouble la(siteIndex_.size());
+    for (size_t j = 0; j < la.size(); ++j) la[j] = mixedSiteLnl_[(size_t)siteIndex_[j]];
+    std::sort(la.begin(), la.end());
+    double ll = 0;
+    for (size_t j = la.size(); j > 0; --j) ll += la[j - 1];
+    mixedMinusLogLik_ = -ll;
+  }
+  Vdouble probas_, mixedSiteLnl_;
+  double mixedMinusLogLik_ = 0;
 };
 
 }  // namespace bppshim

@@ -191,6 +191,31 @@ int main() {
       if (worst > 1e-12 || worstL > 1e-10) { cerr << "posterior / computeLikelihoodAtNode checks failed" << endl; fails++; }
     }
     {
+      // mixture of sub-models (RHomogeneousMixedTreeLikelihood): three T92 with different kappa, probabilities .2 / .5 / .3
+      const DNA dna3;
+      unique_ptr<Tree> t7(TreeTemplateTools::parenthesisToTree("((A:0.01, B:0.02):0.03,C:0.01,D:0.1);"));
+      VectorSiteContainer s7(&dna3);
+      s7.addSequence(BasicSequence("A", "AAATGGCTGTGCACGTC", &dna3));
+      s7.addSequence(BasicSequence("B", "GACTGGATCTGCACGTC", &dna3));
+      s7.addSequence(BasicSequence("C", "CTCTGGATGTGCACGTG", &dna3));
+      s7.addSequence(BasicSequence("D", "AAATGGCGGTGCGCCTA", &dna3));
+      T92 ma(&dna3, 1.), mb(&dna3, 3.), mc(&dna3, 8.);
+      GammaDiscreteRateDistribution g7(4, 1.0);
+      vector<SubstitutionModel*> subs;
+      subs.push_back(&ma); subs.push_back(&mb); subs.push_back(&mc);
+      Vdouble pr(3);
+      pr[0] = 0.2; pr[1] = 0.5; pr[2] = 0.3;
+      RHomogeneousMixedTreeLikelihood mix(*t7, s7, subs, pr, &g7);
+      mix.initialize();
+      printf("MIXED_T92_G4 %.15f\n", mix.getValue());
+      // a degenerate mixture is the plain likelihood
+      Vdouble one(3, 0.0);
+      one[1] = 1.0;
+      mix.setProbabilities(one);
+      printf("MIXED_DEGENERATE %.15f\n", mix.getValue());
+      if (fabs(mix.getValue() - 85.030942031997312824) > 1e-9) { cerr << "degenerate mixture != golden value" << endl; fails++; }
+    }
+    {
       ChromosomeAlphabet chr(1, 30);
       unique_ptr<Tree> t5(TreeTemplateTools::parenthesisToTree("(((a:0.3,b:0.2):0.4,c:0.5):0.1,(d:0.3,e:0.6):0.2);"));
       VectorSiteContainer s5(&chr);

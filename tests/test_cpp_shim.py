@@ -171,3 +171,14 @@ def test_reference_likelihood_tests_through_the_shim(built_lib):
         rk = cases.oracle_eval(ch, weighted_root=True)
         assert abs(vals["CHR_BATCH_%d" % k] + rk.lnl) <= 1e-9 * abs(rk.lnl), k
     assert vals["CHR_BATCH_MAXREL"] <= 1e-12 and vals["CHR_BATCH_PROBE_REL"] <= 1e-12
+    # mixture of sub-models: L_site = sum_k p_k L_k,site (RHomogeneousMixedTreeLikelihood.cpp:191-212)
+    seqs1 = {"A": "AAATGGCTGTGCACGTC", "B": "GACTGGATCTGCACGTC", "C": "CTCTGGATGTGCACGTG", "D": "AAATGGCGGTGCGCCTA"}
+    rg, pg = rm.gamma_rates(4, 1.0)
+    site_l = []
+    for kappa in (1.0, 3.0, 8.0):
+        ck = cases.case_from_alignment("((A:0.01, B:0.02):0.03,C:0.01,D:0.1);", seqs1, rm.t92(kappa, 0.5), rg, pg)
+        site_l.append(cases.oracle_eval(ck).site_lnl)
+    mixed = np.log(0.2 * np.exp(site_l[0]) + 0.5 * np.exp(site_l[1]) + 0.3 * np.exp(site_l[2]))
+    expect = -float(np.sum(ck.weights * mixed))
+    assert abs(vals["MIXED_T92_G4"] - expect) <= 1e-9 * abs(expect)
+    assert abs(vals["MIXED_DEGENERATE"] - 85.030942031997312824) < 1e-9
