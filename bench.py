@@ -574,7 +574,8 @@ def main():
             exe_flops = flops_per_eval(tree, rows, w["S"])                # DMMA flops issued: tip sons are table gathers
             ach = alg_flops / (kms * 1e-3) / 1e12 if kms > 0 else None
             roofline = {"bound": "tensor", "kernel": kname + " (one launch per node; all launches of an evaluation timed together)",
-                        "achieved": ach, "peak": dmma_peak, "unit": "TFLOP/s", "frac": ach / dmma_peak if ach else None, "traffic": None,
+                        "achieved": ach, "peak": dmma_peak, "unit": "TFLOP/s", "frac": ach / dmma_peak if ach else None,
+                        "traffic": ncu_traffic_per_eval(a.workload, kname) if (not a.patterns and world == 1) else None,
                         "kernel_ms": kms, "launches_timed": st["prune_count"], "algorithmic_flops_per_eval": alg_flops,
                         "executed_dmma_tflops": exe_flops / (kms * 1e-3) / 1e12 if kms > 0 else None,
                         "peak_source": "FP64 mma.sync m8n8k4 measured with tools/fp64_peak.cu (profiles/r1_fp64_peaks.json); "
