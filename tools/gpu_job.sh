@@ -1,2 +1,5 @@
-ncu --metrics gpu__time_duration.sum,sm__inst_executed_pipe_tensor_subpipe_dmma.avg.pct_of_peak_sustained_active,l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:"prune|dmma_node|generic_root|tiptab|pt_dmma|pt_eigen|finalize" -c 900 --csv --log-file gpurun_out/launches_codon.csv python bench.py --workload codon_200x100k --profile > gpurun_out/ncu_codon_l.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:"dmma_prune" -s 300 -c 4 -f -o gpurun_out/prune64_r1e python bench.py --workload codon_200x100k --profile > gpurun_out/ncu_prune64_full.log 2>&1
+# last verification of the tree as committed: GPU parity suite, smoke, default bench, a short codon bench
+python -m pytest tests -m gpu -x -q > gpurun_out/t44.log 2>&1; echo "rc=$?" >> gpurun_out/t44.log
+python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke4.log 2>&1; echo "rc=$?" >> gpurun_out/smoke4.log
+timeout 600 python bench.py > gpurun_out/h_default.json 2> gpurun_out/h_default.err
+timeout 300 python bench.py --workload codon_200x100k --steps 5 --warmup 3 --no-cpu > gpurun_out/h_codon.json 2> gpurun_out/h_codon.err
