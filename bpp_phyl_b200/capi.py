@@ -288,6 +288,12 @@ class Engine:
                                                 _ptr(post)))
         return la, ex, post
 
+    def root_reparam_derivatives(self, point=0):
+        """(d lnL/d BrLenRoot, d lnL/d RootPosition, d2 lnL/d BrLenRoot^2, d2 lnL/d RootPosition^2) after an eval with D2"""
+        out = np.zeros(4)
+        _check(lib().bppgpu_get_root_reparam_derivatives(self._h, C.c_int32(point), _ptr(out)))
+        return out
+
     def transition_probabilities(self, node, which=WANT_P, point=0):
         out = np.empty((self.C, self.S, self.S))
         _check(lib().bppgpu_get_transition_probabilities(self._h, C.c_int32(point), C.c_int32(node),

@@ -270,4 +270,105 @@ __global__ void node_posterior_kernel(const double* full, const int* full_exp, i
   }
 }
 
+
+// ---- BrLenRoot / RootPosition (re-parametrised root branches of a rooted tree) ---------------------------------------------
+// DRNonHomogeneousTreeLikelihood::getFirstOrderDerivative / getSecondOrderDerivative for the two parameters that replace the
+// root branches l1 = len * pos, l2 = len * (1 - pos) (Likelihood/DRNonHomogeneousTreeLikelihood.cpp:445-478, :576-867;
+// AbstractNonHomogeneousTreeLikelihood.cpp:319-330, :386-389).  The second derivatives need the cross term
+// (dP_1 L_1)(dP_2 L_2), which the per-branch derivative pass does not produce, so everything is rebuilt at the root from the
+// two sons' lower arrays:  per root state x
+//   d_len   = pos dl1 l2 + (1 - pos) dl2 l1                    d_pos   = len (dl1 l2 - dl2 l1)
+//   d2_len  = pos^2 d2l1 l2 + (1 - pos)^2 d2l2 l1 + 2 pos (1 - pos) dl1 dl2        (:662-663)
+//   d2_pos  = len^2 (d2l1 l2 + d2l2 l1 - 2 dl1 dl2)
+// times the other root sons' P.L, pi_x and p_c, over SR_i; the four weighted sums  sum_i w_i D_i  and
+// sum_i w_i (D2_i - D_i^2)  come back as per-block partials (derivatives of +lnL; the reference returns those of -lnL).
+// thread = pattern; accessor-grade CUDA-core kernel (6 S^2 multiply-adds per class and pattern).
+struct RootReparamSon {
+  int is_leaf;
+  const double* lower;    // internal: lower slab + exponents (rows follow prow / crow)
+  const int* lower_exp;
+  const void* codes;      // leaf: codes [N]
+  const double *P, *dP, *d2P;  // [C][S][S] of the son's branch (dP / d2P unused for the "other" sons)
+};
+struct RootReparamParams {
+  RootReparamSon sons[4];   // [0] = root1, [1] = root2, then up to two other root sons
+  int nson;
+  int S, C, code_bytes;
+  long long N, prow, crow;
+  double pos, len;
+  const double* code_table;
+  const double *rootfreq, *probs, *weights, *SR;
+  const int* rexp;
+  double* part;   // [4][gridDim.x]
+};
+
+__global__ void root_reparam_kernel(RootReparamParams p) {
+  __shared__ double red[32];
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int S = p.S;
+  double D[4] = {0.0, 0.0, 0.0, 0.0};  // d_len, d_pos, d2_len, d2_pos of this pattern (already / SR)
+  if (i < p.N) {
+    for (int c = 0; c < p.C; ++c) {
+      const size_t row = (size_t)(i * p.prow + c * p.crow);
+      const double* L[4];
+      int e = 0;
+      for (int j = 0; j < p.nson; ++j) {
+        if (p.sons[j].is_leaf) {
+          const int code = p.code_bytes == 1 ? (int)((const unsigned char*)p.sons[j].codes)[i] : (int)((const unsigned short*)p.sons[j].codes)[i];
+          L[j] = p.code_table + (size_t)code * S;
+        } else {
+          L[j] = p.sons[j].lower + row * S;
+          e += p.sons[j].lower_exp[row];
+        }
+      }
+      const size_t mo = (size_t)c * S * S;
+      double a[4] = {0.0, 0.0, 0.0, 0.0};
+      for (int x = 0; x < S; ++x) {
+        double l1 = 0, l2 = 0, dl1 = 0, dl2 = 0, d2l1 = 0, d2l2 = 0;
+        const size_t ro = mo + (size_t)x * S;
+        for (int y = 0; y < S; ++y) {
+          const double v1 = L[0][y], v2 = L[1][y];
+          l1 = fma(p.sons[0].P[ro + y], v1, l1);
+          dl1 = fma(p.sons[0].dP[ro + y], v1, dl1);
+          d2l1 = fma(p.sons[0].d2P[ro + y], v1, d2l1);
+          l2 = fma(p.sons[1].P[ro + y], v2, l2);
+          dl2 = fma(p.sons[1].dP[ro + y], v2, dl2);
+          d2l2 = fma(p.sons[1].d2P[ro + y], v2, d2l2);
+        }
+        double o = p.rootfreq[x];
+        for (int j = 2; j < p.nson; ++j) {
+          double t = 0;
+          for (int y = 0; y < S; ++y) t = fma(p.sons[j].P[ro + y], L[j][y], t);
+          o *= t;
+        }
+        a[0] = fma(o, p.pos * dl1 * l2 + (1.0 - p.pos) * dl2 * l1, a[0]);
+        a[1] = fma(o, p.len * (dl1 * l2 - dl2 * l1), a[1]);
+        a[2] = fma(o, p.pos * p.pos * d2l1 * l2 + (1.0 - p.pos) * (1.0 - p.pos) * d2l2 * l1 + 2.0 * p.pos * (1.0 - p.pos) * dl1 * dl2, a[2]);
+        a[3] = fma(o, p.len * p.len * (d2l1 * l2 + d2l2 * l1 - 2.0 * dl1 * dl2), a[3]);
+      }
+      const int sh = p.rexp[i] - e;
+      const double f = p.probs[c] / p.SR[i];
+      for (int k = 0; k < 4; ++k) D[k] += scalbn(a[k], sh) * f;
+    }
+  }
+  const double w = i < p.N ? p.weights[i] : 0.0;
+  const double c0 = w * D[0], c1 = w * D[1], c2 = w * (D[2] - D[0] * D[0]), c3 = w * (D[3] - D[1] * D[1]);
+  const double b0 = block_sum(c0, red), b1 = block_sum(c1, red), b2 = block_sum(c2, red), b3 = block_sum(c3, red);
+  if (threadIdx.x == 0) {
+    p.part[0 * gridDim.x + blockIdx.x] = b0;
+    p.part[1 * gridDim.x + blockIdx.x] = b1;
+    p.part[2 * gridDim.x + blockIdx.x] = b2;
+    p.part[3 * gridDim.x + blockIdx.x] = b3;
+  }
+}
+
+// one block per output: out[k] = sum of part[k][0 .. n)
+__global__ void root_reparam_finalize_kernel(const double* part, int n, double* out) {
+  __shared__ double red[32];
+  double a = 0.0;
+  for (int j = threadIdx.x; j < n; j += blockDim.x) a += part[(size_t)blockIdx.x * n + j];
+  const double s = block_sum(a, red);
+  if (threadIdx.x == 0) out[blockIdx.x] = s;
+}
+
 }  // namespace bppgpu

@@ -1837,6 +1837,68 @@ int bppgpu_get_node_posteriors(bppgpu_engine* e, int32_t point, int32_t node, do
   return BPPGPU_OK;
 }
 
+int bppgpu_get_root_reparam_derivatives(bppgpu_engine* e, int32_t point, double out[4]) {
+  ENGINE_ENTER(e);
+  if (!out) BPP_FAIL(BPPGPU_E_INVALID, "null out");
+  if (!e->keep) BPP_FAIL(BPPGPU_E_STATE, "bppgpu_get_root_reparam_derivatives needs BPPGPU_FLAG_KEEP_CLVS");
+  if (e->path == PATH_POINTS) BPP_FAIL(BPPGPU_E_STATE, "not available on the batched-points path");
+  if (point != e->last_point) BPP_FAIL(BPPGPU_E_STATE, "CLVs resident are those of point %d", e->last_point);
+  if (!(e->last_want & BPPGPU_EVAL_D2) || !e->d_dP || !e->d_d2P)
+    BPP_FAIL(BPPGPU_E_STATE, "BrLenRoot / RootPosition derivatives need an eval with BPPGPU_EVAL_D2");
+  const int root = e->root;
+  const int ns = e->child_off[root + 1] - e->child_off[root];
+  if (ns < 2 || ns > 4) BPP_FAIL(BPPGPU_E_INVALID, "the root must have 2 to 4 sons (it has %d)", ns);
+  const int S = e->S, C = e->C;
+  const long long N = e->N;
+  for (int k = 0; k < 4; ++k) out[k] = 0.0;
+  if (N == 0) return BPPGPU_OK;
+  const size_t clvn = (size_t)N * C * S, rows = (size_t)N * C, SS = (size_t)S * S;
+  const int pl = point % e->pchunk;
+  RootReparamParams rp{};
+  rp.nson = ns;
+  double l1 = 0, l2 = 0;
+  for (int j = 0; j < ns; ++j) {
+    const int s = e->children[e->child_off[root] + j];
+    RootReparamSon& rs = rp.sons[j];
+    rs.is_leaf = e->leaf_slot[s] >= 0;
+    if (rs.is_leaf) {
+      rs.codes = (const char*)e->d_codes + (size_t)e->leaf_slot[s] * N * e->code_bytes;
+    } else {
+      rs.lower = e->d_keep + (size_t)e->internal_idx[s] * clvn;
+      rs.lower_exp = e->d_keep_exp + (size_t)e->internal_idx[s] * rows;
+    }
+    const size_t mo = ((size_t)pl * e->nn + s) * C * SS;
+    rs.P = e->d_P + mo; rs.dP = e->d_dP + mo; rs.d2P = e->d_d2P + mo;
+    if (j == 0) l1 = e->h_brlen[(size_t)point * e->nn + s];
+    if (j == 1) l2 = e->h_brlen[(size_t)point * e->nn + s];
+  }
+  if (!(l1 + l2 > 0)) BPP_FAIL(BPPGPU_E_INVALID, "the two root branches have zero total length");
+  rp.S = S; rp.C = C; rp.code_bytes = e->code_bytes; rp.N = N;
+  rp.prow = e->clv_class_major ? 1 : C;
+  rp.crow = e->clv_class_major ? N : 1;
+  rp.len = l1 + l2;
+  rp.pos = l1 / (l1 + l2);
+  rp.code_table = e->d_code_table;
+  rp.rootfreq = e->d_rootfreq_used + (size_t)point * S;
+  rp.probs = e->d_probs; rp.weights = e->d_weights; rp.SR = e->d_SR; rp.rexp = e->d_rexp;
+  const int grid = (int)((N + 127) / 128);
+  double *d_part = nullptr, *d_out = nullptr;
+  if (cudaMalloc(&d_part, (size_t)4 * grid * 8) != cudaSuccess || cudaMalloc(&d_out, 4 * 8) != cudaSuccess) {
+    cudaFree(d_part); cudaFree(d_out);
+    BPP_FAIL(BPPGPU_E_NOMEM, "out of device memory");
+  }
+  rp.part = d_part;
+  cudaStream_t st = e->stream;
+  root_reparam_kernel<<<grid, 128, 0, st>>>(rp);
+  root_reparam_finalize_kernel<<<4, 256, 0, st>>>(d_part, grid, d_out);
+  cudaError_t err = cudaGetLastError();
+  if (err == cudaSuccess) err = cudaMemcpyAsync(out, d_out, 4 * 8, cudaMemcpyDeviceToHost, st);
+  if (err == cudaSuccess) err = cudaStreamSynchronize(st);
+  cudaFree(d_part); cudaFree(d_out);
+  BPP_CUDA(err);
+  return BPPGPU_OK;
+}
+
 int bppgpu_get_transition_probabilities(bppgpu_engine* e, int32_t point, int32_t node, unsigned which, double* out) {
   ENGINE_ENTER(e);
   if (point < 0 || point >= e->npoints || node < 0 || node >= e->nn || node == e->root || !out)

@@ -1333,7 +1333,14 @@ class AbstractHomogeneousTreeLikelihood {
   // "BrLen<i>": i-th node of the post-order list with the root dropped (init_ :155-157)
   ParameterList getBranchLengthsParameters() const {
     ParameterList pl;
-    for (size_t i = 0; i < brLen_.size(); ++i) pl.push_back({"BrLen" + std::to_string(i), brLen_[i]});
+    for (size_t i = 0; i < brLen_.size(); ++i) {
+      if (reparametrizeRoot_ && ((int)i == root1_ || (int)i == root2_)) continue;
+      pl.push_back({"BrLen" + std::to_string(i), brLen_[i]});
+    }
+    if (reparametrizeRoot_) {  // AbstractNonHomogeneousTreeLikelihood::initBranchLengthsParameters (:386-389)
+      pl.push_back({"BrLenRoot", brLen_[(size_t)root1_] + brLen_[(size_t)root2_]});
+      pl.push_back({"RootPosition", brLen_[(size_t)root1_] / (brLen_[(size_t)root1_] + brLen_[(size_t)root2_])});
+    }
     return pl;
   }
   ParameterList getSubstitutionModelParameters() const {
@@ -1342,6 +1349,8 @@ class AbstractHomogeneousTreeLikelihood {
     return pl;
   }
   double getParameterValue(const std::string& name) const {
+    if (reparametrizeRoot_ && name == "BrLenRoot") return brLen_[(size_t)root1_] + brLen_[(size_t)root2_];
+    if (reparametrizeRoot_ && name == "RootPosition") return brLen_[(size_t)root1_] / (brLen_[(size_t)root1_] + brLen_[(size_t)root2_]);
     int b = brlenIndex(name);
     if (b < 0) throw ParameterNotFoundException("ParameterNotFoundException: " + name);
     return brLen_[(size_t)b];
@@ -1352,6 +1361,14 @@ class AbstractHomogeneousTreeLikelihood {
   void setParametersValues(const ParameterList& pl) {
     bool modelChanged = false;
     for (const Parameter& p : pl) {
+      if (reparametrizeRoot_ && (p.name == "BrLenRoot" || p.name == "RootPosition")) {
+        // applyParameters (AbstractNonHomogeneousTreeLikelihood.cpp:319-330): l1 = len * pos, l2 = len * (1 - pos)
+        double len = brLen_[(size_t)root1_] + brLen_[(size_t)root2_], pos = brLen_[(size_t)root1_] / len;
+        if (p.name == "BrLenRoot") len = p.value; else pos = p.value;
+        brLen_[(size_t)root1_] = len * pos;
+        brLen_[(size_t)root2_] = len * (1.0 - pos);
+        continue;
+      }
       const int b = brlenIndex(p.name);
       if (b >= 0) brLen_[(size_t)b] = std::min(std::max(p.value, minimumBrLen_), maximumBrLen_);
       else {
@@ -1558,6 +1575,15 @@ class AbstractHomogeneousTreeLikelihood {
   }
   double derivative(const std::string& variable, int order) const {
     requireInit();
+    if (reparametrizeRoot_ && (variable == "BrLenRoot" || variable == "RootPosition")) {
+      // DRNonHomogeneousTreeLikelihood.cpp:445-478 (first order), :576-867 (second order: needs the cross term of the two
+      // root branches, rebuilt on the device)
+      ensureDerivativePass();
+      double o[4];
+      check(bppgpu_get_root_reparam_derivatives(engine_, 0, o), "getSecondOrderDerivative");
+      const int k = (order == 1 ? 0 : 2) + (variable == "BrLenRoot" ? 0 : 1);
+      return -o[k];
+    }
     const int b = brlenIndex(variable);
     if (b < 0) {
       for (const std::string& n : model_->getParameterNames())
@@ -1600,6 +1626,8 @@ class AbstractHomogeneousTreeLikelihood {
   mutable bool derivsValid_;
   long numOfLikelihoodCalculations_;
   int nPoints_ = 1;  // parameter points evaluated per device call (LikelihoodPointBatch)
+  bool reparametrizeRoot_ = false;  // BrLenRoot / RootPosition replace the two root branches (NH classes, rooted trees)
+  int root1_ = -1, root2_ = -1;     // ids (= BrLen indices) of the root's first two sons
 };
 
 // Likelihood/RHomogeneousTreeLikelihood.h:108-138.  `usePatterns` (recursive per-subtree compression) changes only the
@@ -1629,10 +1657,17 @@ class DRNonHomogeneousTreeLikelihood : public AbstractHomogeneousTreeLikelihood 
  public:
   DRNonHomogeneousTreeLikelihood(const Tree& tree, const VectorSiteContainer& data, bool weightedRootFreq, bool calculateDerivatives,
                                  SubstitutionModel* model, DiscreteDistribution* rDist, const Vdouble* rootFreqs = nullptr,
-                                 bool verbose = true, int device = 0)
+                                 bool verbose = true, int device = 0, bool reparametrizeRoot = false)
       : AbstractHomogeneousTreeLikelihood(tree, model, rDist, false,
                                           BPPGPU_FLAG_NH_DERIV | (weightedRootFreq ? BPPGPU_FLAG_WEIGHTED_ROOT : 0u), device) {
     (void)verbose;
+    if (reparametrizeRoot) {  // AbstractNonHomogeneousTreeLikelihood::init_ (:162-189): root1_ / root2_ = the root's two sons
+      const Node* root = nodes_.back();
+      if (root->getNumberOfSons() != 2) throw Exception("reparametrizeRoot needs a rooted tree (a root with two sons)");
+      root1_ = root->getSon(0)->getId();
+      root2_ = root->getSon(1)->getId();
+      reparametrizeRoot_ = true;
+    }
     computeDerivatives_ = calculateDerivatives;
     if (rootFreqs) fixedRootFreqs_ = *rootFreqs;
     setData(data);

@@ -191,6 +191,13 @@ int bppgpu_get_clv(bppgpu_engine* e, int32_t point, int32_t node, int32_t which,
  * `posterior` is available (the reference's leaf formula needs the leaf likelihoods alone).                      */
 int bppgpu_get_node_posteriors(bppgpu_engine* e, int32_t point, int32_t node, double* likelihood_at_node,
                                int32_t* scale_exp, double* posterior);
+/* Derivatives of lnL with respect to "BrLenRoot" = l1 + l2 and "RootPosition" = l1 / (l1 + l2), the re-parametrisation of
+ * the two root branches of a rooted tree (reparametrizeRoot; AbstractNonHomogeneousTreeLikelihood.cpp:319-330, :386-389):
+ *   out[0..3] = d lnL / d BrLenRoot, d lnL / d RootPosition, d2 lnL / d BrLenRoot^2, d2 lnL / d RootPosition^2
+ * = minus DRNonHomogeneousTreeLikelihood::getFirstOrderDerivative / getSecondOrderDerivative of those two names
+ * (DRNonHomogeneousTreeLikelihood.cpp:445-478, :576-867).  The root's first two sons are root1, root2; valid after an
+ * eval with BPPGPU_EVAL_D2 (dP, d2P and the lower arrays resident).                                                   */
+int bppgpu_get_root_reparam_derivatives(bppgpu_engine* e, int32_t point, double out[4]);
 /* which: BPPGPU_WANT_P / _DP / _D2P; out [C][S][S] = pxy_[node][c][x][y] */
 int bppgpu_get_transition_probabilities(bppgpu_engine* e, int32_t point, int32_t node,
                                         unsigned which, double* out);

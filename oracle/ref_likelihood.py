@@ -265,6 +265,46 @@ def posterior_probabilities(flat, res, P, nid, probs, tip_codes=None, table=None
     return al / al.sum(axis=(1, 2))[:, None, None]
 
 
+def root_reparam_derivatives(flat, res, P, dP, d2P, probs, weights):
+    """Derivatives of -lnL with respect to ``BrLenRoot`` (l1 + l2) and ``RootPosition`` (l1 / (l1 + l2)), the
+    re-parametrisation of the two root branches of a rooted tree
+    (AbstractNonHomogeneousTreeLikelihood::initBranchLengthsParameters, .cpp:386-389; applyParameters :319-330).
+    First order: DRNonHomogeneousTreeLikelihood::getFirstOrderDerivative (.cpp:445-478) -- combinations of the two
+    branches' derivatives.  Second order: getSecondOrderDerivative (.cpp:576-867) -- the cross term
+    dP_1 L_1 . dP_2 L_2 cannot be deduced from the per-branch values and is rebuilt at the root:
+        dl  = pos dl1 l2 + (1 - pos) dl2 l1,   d2l = pos^2 d2l1 l2 + (1 - pos)^2 d2l2 l1 + 2 pos (1 - pos) dl1 dl2   (:662-663)
+    per root state, times the other root sons, the root frequencies and the class probabilities, then
+    -sum_i w_i (d2l_i / SR_i - (dl_i / SR_i)^2)  (:705-720).  Returns dict d1_len, d1_pos, d2_len, d2_pos."""
+    root = flat.root
+    sons = list(flat.children[root])
+    r1, r2 = sons[0], sons[1]
+    l1b, l2b = flat.brlen[r1], flat.brlen[r2]
+    length, pos = l1b + l2b, l1b / (l1b + l2b)
+    L1, L2 = res.lower[r1], res.lower[r2]
+    e = res.lexp[r1] + res.lexp[r2]
+    others = np.ones_like(_contract(P[r1], L1))
+    for s in sons[2:]:
+        others = others * _contract(P[s], res.lower[s])
+        e = e + res.lexp[s]
+    l1, l2 = _contract(P[r1], L1), _contract(P[r2], L2)
+    dl1, dl2 = _contract(dP[r1], L1), _contract(dP[r2], L2)
+    d2l1, d2l2 = _contract(d2P[r1], L1), _contract(d2P[r2], L2)
+    sh = (res.SR_exp[:, None] - e)                       # [N][C]
+
+    def site(v):                                        # sum_c p_c sum_x pi_x others v / SR
+        t = np.einsum("icx,x->ic", others * v, res.root_freqs)
+        return np.einsum("ic,c->i", np.ldexp(t, sh), probs) / res.SR
+
+    d_len = site(pos * dl1 * l2 + (1 - pos) * dl2 * l1)
+    d_pos = site(length * (dl1 * l2 - dl2 * l1))
+    d2_len = site(pos * pos * d2l1 * l2 + (1 - pos) ** 2 * d2l2 * l1 + 2 * pos * (1 - pos) * dl1 * dl2)
+    d2_pos = site(length * length * (d2l1 * l2 + d2l2 * l1 - 2 * dl1 * dl2))
+    w = np.asarray(weights, float)
+    return {"d1_len": -float(np.sum(w * d_len)), "d1_pos": -float(np.sum(w * d_pos)),
+            "d2_len": -float(np.sum(w * (d2_len - d_len ** 2))), "d2_pos": -float(np.sum(w * (d2_pos - d_pos ** 2))),
+            "length": length, "pos": pos, "root1": r1, "root2": r2}
+
+
 # ----------------------------------------------------------------------------
 # R-class derivatives (single recursion re-pruned along the path to the root)
 # ----------------------------------------------------------------------------

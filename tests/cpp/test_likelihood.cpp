@@ -216,6 +216,39 @@ int main() {
       if (fabs(mix.getValue() - 85.030942031997312824) > 1e-9) { cerr << "degenerate mixture != golden value" << endl; fails++; }
     }
     {
+      // BrLenRoot / RootPosition (reparametrizeRoot, test_likelihood_nh.cpp:57-58): derivatives against central differences
+      const DNA dna4;
+      unique_ptr<Tree> t8(TreeTemplateTools::parenthesisToTree("(((A:0.01, B:0.01):0.02,C:0.03):0.01,D:0.04);"));
+      VectorSiteContainer s8(&dna4);
+      s8.addSequence(BasicSequence("A", "AAATGGCTGTGCACGTC", &dna4));
+      s8.addSequence(BasicSequence("B", "AACTGGATCTGCATGTC", &dna4));
+      s8.addSequence(BasicSequence("C", "ATCTGGACGTGCACGTG", &dna4));
+      s8.addSequence(BasicSequence("D", "CAACGGGAGTGCGCCTA", &dna4));
+      T92 m8(&dna4, 3.);
+      GammaDiscreteRateDistribution g8(4, 1.0);
+      Vdouble rf(4);
+      rf[0] = 0.1; rf[1] = 0.4; rf[2] = 0.3; rf[3] = 0.2;   // non-stationary root: the root position matters
+      DRNonHomogeneousTreeLikelihood tl(*t8, s8, false, true, &m8, &g8, &rf, false, 0, true);
+      tl.initialize();
+      const char* names[2] = {"BrLenRoot", "RootPosition"};
+      for (int k = 0; k < 2; ++k) {
+        const double v0 = tl.getParameterValue(names[k]), h = 1e-5 * (k == 0 ? 1.0 : 1.0);
+        const double d1 = tl.getFirstOrderDerivative(names[k]), d2 = tl.getSecondOrderDerivative(names[k]);
+        const double f0 = tl.getValue();
+        tl.setParameterValue(names[k], v0 + h);
+        const double fp = tl.getValue();
+        tl.setParameterValue(names[k], v0 - h);
+        const double fm = tl.getValue();
+        tl.setParameterValue(names[k], v0);
+        const double fd1 = (fp - fm) / (2 * h), fd2 = (fp - 2 * f0 + fm) / (h * h);
+        printf("REPARAM_%s %.12f %.12f %.9f %.9f\n", names[k], d1, fd1, d2, fd2);
+        if (fabs(d1 - fd1) > 1e-5 * max(1.0, fabs(d1)) || fabs(d2 - fd2) > 2e-3 * max(1.0, fabs(d2))) {
+          cerr << "BrLenRoot / RootPosition derivative differs from finite differences" << endl;
+          fails++;
+        }
+      }
+    }
+    {
       ChromosomeAlphabet chr(1, 30);
       unique_ptr<Tree> t5(TreeTemplateTools::parenthesisToTree("(((a:0.3,b:0.2):0.4,c:0.5):0.1,(d:0.3,e:0.6):0.2);"));
       VectorSiteContainer s5(&chr);

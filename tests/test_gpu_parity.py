@@ -546,3 +546,27 @@ def test_node_posteriors_error_conventions():
         with pytest.raises(capi.BppGpuError) as ei:
             e.node_posteriors(c.flat.n_nodes)
         assert ei.value.code == capi.E_INVALID
+
+
+@pytest.mark.parametrize("mk,ncat", [(gtr, 4), (rm.lg08, 3), (lambda: rm.yn98(2.0, 0.3), 1)])
+def test_root_reparametrisation_derivatives(mk, ncat):
+    """BrLenRoot / RootPosition (reparametrizeRoot): first and second derivatives rebuilt at the root on the device, against
+    the oracle's restatement of DRNonHomogeneousTreeLikelihood.cpp:445-478 / :576-867 (itself checked by finite differences)."""
+    capi = _capi()
+    from oracle import ref_likelihood as rl
+    r, p = rm.gamma_rates(ncat, 0.7) if ncat > 1 else rm.constant_rate()
+    m = mk()
+    c = cases.make_case(9, 50, m, r, p, seed=95, rooted=True, ambiguity=0.04, mean_brlen=0.2, compress=False)
+    rng = np.random.default_rng(96)
+    c.root_freqs = rng.dirichlet(np.ones(m.size))            # non-stationary root: the root position matters
+    res = cases.oracle_eval(c, want_d1=True, want_d2=True, nh_form=True)
+    g = rl.root_reparam_derivatives(c.flat, res, res.P, res.dP, res.d2P, c.probs, c.weights)
+    with cases.make_engine(c, flags=capi.FLAG_KEEP_CLVS | capi.FLAG_NH_DERIV) as e:
+        e.eval(7)
+        out = e.root_reparam_derivatives()
+        np.testing.assert_allclose(-out, [g["d1_len"], g["d1_pos"], g["d2_len"], g["d2_pos"]], rtol=1e-8, atol=1e-8)
+    with cases.make_engine(c, flags=capi.FLAG_KEEP_CLVS) as e:
+        e.eval(capi.EVAL_LNL | capi.EVAL_D1)
+        with pytest.raises(capi.BppGpuError) as ei:          # d2P is not resident
+            e.root_reparam_derivatives()
+        assert ei.value.code == capi.E_STATE

@@ -194,3 +194,33 @@ def test_posterior_probabilities_against_brute_force_enumeration():
     leaf = flat.leaf_ids[0]
     post = rl.posterior_probabilities(flat, res, res.P, leaf, c.probs, c.codes_by_leaf, c.table)
     np.testing.assert_allclose(post.sum(axis=(1, 2)), 1.0, rtol=1e-14)
+
+
+def test_root_reparametrisation_derivatives_against_finite_differences():
+    """root_reparam_derivatives (BrLenRoot / RootPosition, DRNonHomogeneousTreeLikelihood.cpp:445-478, :576-867): first order equals
+    the reference's combination of the two root branches' derivatives, both orders equal central differences of -lnL; with
+    a reversible model and stationary root frequencies the root position is not identifiable (pulley principle): zero derivative."""
+    import cases
+    from oracle import ref_likelihood as rl
+    r, p = rm.gamma_rates(3, 0.7)
+    m = rm.gtr(1.2, 0.8, 0.6, 1.5, 0.9, (.3, .2, .25, .25))
+    c = cases.make_case(7, 40, m, r, p, seed=11, rooted=True, ambiguity=0.05, mean_brlen=0.2)
+    res = cases.oracle_eval(c, want_d1=True, want_d2=True)
+    g = rl.root_reparam_derivatives(c.flat, res, res.P, res.dP, res.d2P, c.probs, c.weights)
+    assert abs(g["d1_pos"]) < 1e-10 and abs(g["d2_pos"]) < 1e-10
+    c.root_freqs = np.array([.1, .4, .3, .2])
+    res = cases.oracle_eval(c, want_d1=True, want_d2=True)
+    g = rl.root_reparam_derivatives(c.flat, res, res.P, res.dP, res.d2P, c.probs, c.weights)
+    r1, r2, L, pos = g["root1"], g["root2"], g["length"], g["pos"]
+    assert abs(g["d1_len"] - (pos * res.d1[r1] + (1 - pos) * res.d1[r2])) < 1e-9        # :445-463
+    assert abs(g["d1_pos"] - L * (res.d1[r1] - res.d1[r2])) < 1e-9                      # :464-478
+
+    def nll(length, q):
+        bl = np.array(c.flat.brlen)
+        bl[r1], bl[r2] = length * q, length * (1 - q)
+        return -cases.oracle_eval(c, brlen=bl).lnl
+    h, f0 = 1e-5, nll(L, pos)
+    assert abs((nll(L + h, pos) - nll(L - h, pos)) / (2 * h) - g["d1_len"]) < 1e-6
+    assert abs((nll(L, pos + h) - nll(L, pos - h)) / (2 * h) - g["d1_pos"]) < 1e-6
+    assert abs((nll(L + h, pos) - 2 * f0 + nll(L - h, pos)) / h ** 2 - g["d2_len"]) < 2e-3 * abs(g["d2_len"])
+    assert abs((nll(L, pos + h) - 2 * f0 + nll(L, pos - h)) / h ** 2 - g["d2_pos"]) < 2e-3 * abs(g["d2_pos"])
