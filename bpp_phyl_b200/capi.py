@@ -288,6 +288,14 @@ class Engine:
                                                 _ptr(post)))
         return la, ex, post
 
+    def marginal_posteriors(self, node, point=0, joint=True):
+        """MarginalNonRevAncestralStateReconstruction for one node: (posterior [N][S], joint with the father's state
+        [N][S][S] indexed [i][node state][father state], or None)."""
+        post = np.empty((self.N, self.S))
+        jt = np.empty((self.N, self.S, self.S)) if joint else None
+        _check(lib().bppgpu_get_marginal_posteriors(self._h, C.c_int32(point), C.c_int32(node), _ptr(post), _ptr(jt)))
+        return post, jt
+
     def root_reparam_derivatives(self, point=0):
         """(d lnL/d BrLenRoot, d lnL/d RootPosition, d2 lnL/d BrLenRoot^2, d2 lnL/d RootPosition^2) after an eval with D2"""
         out = np.zeros(4)

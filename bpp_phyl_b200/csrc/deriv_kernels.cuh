@@ -271,6 +271,73 @@ __global__ void node_posterior_kernel(const double* full, const int* full_exp, i
 }
 
 
+// MarginalNonRevAncestralStateReconstruction (fork; Likelihood/MarginalNonRevAncestralStateReconstruction.cpp:10-136): per
+// distinct site the posterior of every state x at a node and the joint posterior of (x, father state y).  The reference sums,
+// over the S root states r, pi_r times a prefix pass conditional on r (DRNonHomogeneousTreeLikelihood.cpp:1026-1162); that sum
+// IS the ordinary prefix array (root frequencies folded in at the root's sons), so the resident upper slab gives it in one pass:
+//   joint[i][x][y] = sum_c p_c upper[i][c][y] P[c][y][x] sub[i][c][x] / L_i     post[i][x] = sum_y joint[i][x][y]
+//   root:            post[i][x] = sum_c p_c pi_x lower[i][c][x] / L_i           (:104-115)
+// thread = (pattern, node state); accessor-grade CUDA-core kernel.  joint may be null.
+struct MarginalParams {
+  int is_leaf, is_root;
+  int S, C, code_bytes;
+  long long N, prow, crow;
+  const double* P;           // [C][S][S] of this node's branch
+  const double* lower;       // slab of the node (internal) + exponents
+  const int* lower_exp;
+  const void* codes;         // leaf: codes [N]
+  const double* code_table;
+  const double* upper;       // slab of upper[node] (non-root) + exponents
+  const int* upper_exp;
+  const double *rootfreq, *probs, *SR;
+  const int* rexp;
+  double* post;              // [N][S]
+  double* joint;             // [N][S][S]  (x = node state, y = father state) or null
+};
+
+__global__ void marginal_posterior_kernel(MarginalParams p) {
+  const long long total = p.N * p.S;
+  const int S = p.S;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(e % S);
+    const long long i = e / S;
+    const double sr = p.SR[i];
+    const int re = p.rexp[i];
+    double leafv = 0.0;
+    if (p.is_leaf) {
+      const int code = p.code_bytes == 1 ? (int)((const unsigned char*)p.codes)[i] : (int)((const unsigned short*)p.codes)[i];
+      leafv = p.code_table[(size_t)code * S + x];
+    }
+    if (p.is_root) {
+      double acc = 0.0;
+      for (int c = 0; c < p.C; ++c) {
+        const size_t row = (size_t)(i * p.prow + c * p.crow);
+        const double sub = p.is_leaf ? leafv : p.lower[row * S + x];
+        const int sh = re - (p.is_leaf ? 0 : p.lower_exp[row]);
+        acc += scalbn(sub * p.rootfreq[x], sh) * p.probs[c];
+      }
+      p.post[e] = acc / sr;
+      continue;
+    }
+    double tot = 0.0;
+    for (int y = 0; y < S; ++y) {
+      double acc = 0.0;
+      for (int c = 0; c < p.C; ++c) {
+        const size_t row = (size_t)(i * p.prow + c * p.crow);
+        const double sub = p.is_leaf ? leafv : p.lower[row * S + x];
+        const int sh = re - (p.is_leaf ? 0 : p.lower_exp[row]) - p.upper_exp[row];
+        const double t = p.upper[row * S + y] * p.P[((size_t)c * S + y) * S + x] * sub;
+        acc += scalbn(t, sh) * p.probs[c];
+      }
+      acc /= sr;
+      if (p.joint) p.joint[((size_t)i * S + x) * S + y] = acc;
+      tot += acc;
+    }
+    p.post[e] = tot;
+  }
+}
+
+
 // ---- BrLenRoot / RootPosition (re-parametrised root branches of a rooted tree) ---------------------------------------------
 // DRNonHomogeneousTreeLikelihood::getFirstOrderDerivative / getSecondOrderDerivative for the two parameters that replace the
 // root branches l1 = len * pos, l2 = len * (1 - pos) (Likelihood/DRNonHomogeneousTreeLikelihood.cpp:445-478, :576-867;

@@ -1837,6 +1837,65 @@ int bppgpu_get_node_posteriors(bppgpu_engine* e, int32_t point, int32_t node, do
   return BPPGPU_OK;
 }
 
+int bppgpu_get_marginal_posteriors(bppgpu_engine* e, int32_t point, int32_t node, double* post_out, double* joint_out) {
+  ENGINE_ENTER(e);
+  if (!e->keep) BPP_FAIL(BPPGPU_E_STATE, "bppgpu_get_marginal_posteriors needs BPPGPU_FLAG_KEEP_CLVS");
+  if (node < 0 || node >= e->nn || !post_out) BPP_FAIL(BPPGPU_E_INVALID, "bad node or null out");
+  if (e->path == PATH_POINTS) BPP_FAIL(BPPGPU_E_STATE, "not available on the batched-points path");
+  if (e->last_want == 0) BPP_FAIL(BPPGPU_E_STATE, "no evaluation yet");
+  if (point != e->last_point) BPP_FAIL(BPPGPU_E_STATE, "CLVs resident are those of point %d", e->last_point);
+  const bool leaf = e->leaf_slot[node] >= 0, root = node == e->root;
+  if (root && joint_out) BPP_FAIL(BPPGPU_E_INVALID, "the root has no father: no joint posterior");
+  const int S = e->S, C = e->C;
+  const long long N = e->N;
+  if (N == 0) return BPPGPU_OK;
+  const size_t clvn = (size_t)N * C * S, rows = (size_t)N * C;
+  int uslab = -1;
+  if (!root) {
+    if (!(e->last_want & BPPGPU_EVAL_D1) || !e->d_upper) BPP_FAIL(BPPGPU_E_STATE, "upper CLVs exist after an eval with derivatives");
+    uslab = e->upper_slab[node];
+    if (uslab < 0) BPP_FAIL(BPPGPU_E_STATE, "the upper CLV of tip %d is not materialised at this problem size", node);
+  }
+  double *d_post = nullptr, *d_joint = nullptr;
+  auto cleanup = [&]() { cudaFree(d_post); cudaFree(d_joint); };
+  if (cudaMalloc(&d_post, (size_t)N * S * 8) != cudaSuccess ||
+      (joint_out && cudaMalloc(&d_joint, (size_t)N * S * S * 8) != cudaSuccess)) {
+    cleanup();
+    cudaGetLastError();
+    BPP_FAIL(BPPGPU_E_NOMEM, "out of device memory for the marginal posteriors of node %d", node);
+  }
+  MarginalParams mp{};
+  mp.is_leaf = leaf; mp.is_root = root;
+  mp.S = S; mp.C = C; mp.code_bytes = e->code_bytes; mp.N = N;
+  mp.prow = e->clv_class_major ? 1 : C;
+  mp.crow = e->clv_class_major ? N : 1;
+  mp.P = e->d_P + ((size_t)(point % e->pchunk) * e->nn + node) * C * S * S;
+  if (leaf) {
+    mp.codes = (const char*)e->d_codes + (size_t)e->leaf_slot[node] * N * e->code_bytes;
+    mp.code_table = e->d_code_table;
+  } else {
+    mp.lower = e->d_keep + (size_t)e->internal_idx[node] * clvn;
+    mp.lower_exp = e->d_keep_exp + (size_t)e->internal_idx[node] * rows;
+  }
+  if (!root) {
+    mp.upper = e->d_upper + (size_t)uslab * clvn;
+    mp.upper_exp = e->d_upper_exp + (size_t)uslab * rows;
+  }
+  mp.rootfreq = e->d_rootfreq_used + (size_t)point * S;
+  mp.probs = e->d_probs; mp.SR = e->d_SR; mp.rexp = e->d_rexp;
+  mp.post = d_post; mp.joint = d_joint;
+  cudaStream_t st = e->stream;
+  const int grid = (int)std::min<long long>((N * S + 127) / 128, (long long)g_sm_count * 32);
+  marginal_posterior_kernel<<<grid, 128, 0, st>>>(mp);
+  cudaError_t err = cudaGetLastError();
+  if (err == cudaSuccess) err = cudaMemcpyAsync(post_out, d_post, (size_t)N * S * 8, cudaMemcpyDeviceToHost, st);
+  if (err == cudaSuccess && joint_out) err = cudaMemcpyAsync(joint_out, d_joint, (size_t)N * S * S * 8, cudaMemcpyDeviceToHost, st);
+  if (err == cudaSuccess) err = cudaStreamSynchronize(st);
+  cleanup();
+  BPP_CUDA(err);
+  return BPPGPU_OK;
+}
+
 int bppgpu_get_root_reparam_derivatives(bppgpu_engine* e, int32_t point, double out[4]) {
   ENGINE_ENTER(e);
   if (!out) BPP_FAIL(BPPGPU_E_INVALID, "null out");

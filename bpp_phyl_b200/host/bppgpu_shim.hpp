@@ -672,6 +672,8 @@ class TreeTemplate {
     return n;
   }
   std::vector<int> getNodesId() const { std::vector<int> v; for (N* n : getNodes()) v.push_back(n->getId()); return v; }
+  N* getNode(int id) const { for (N* n : getNodes()) if (n->getId() == id) return n; throw Exception("NodeNotFoundException: TreeTemplate::getNode(): Node with id not found."); }
+  int getFatherId(int id) const { return getNode(id)->getFather()->getId(); }
   void resetNodesId() { int i = 0; for (N* n : getNodes()) n->setId(i++); }
   // TreeTemplate::unroot (TreeTemplate.h:244-284): keep son 0 as the new root, hang son 1 under it, sum the lengths
   bool unroot() {
@@ -1461,6 +1463,31 @@ class AbstractHomogeneousTreeLikelihood {
     }
     return best;
   }
+  // MarginalNonRevAncestralStateReconstruction's per-node tables (fork, MarginalNonRev...cpp:10-136) from the device-resident
+  // arrays: post[i][x] = P(node = x | site i), joint[i][x][y] = P(node = x, father = y | site i) (null / ignored at the root)
+  void getMarginalPosteriors(int nodeId, VVdouble& post, VVVdouble* joint) const {
+    requireInit();
+    const size_t S = getNumberOfStates(), N = (size_t)nPatterns_;
+    const bool isRoot = nodeId == (int)nodes_.size() - 1;
+    if (!isRoot) ensureDerivativePass();
+    std::vector<double> pb(N * S), jb(joint && !isRoot ? N * S * S : 0);
+    check(bppgpu_get_marginal_posteriors(engine_, 0, nodeId, pb.data(), jb.empty() ? nullptr : jb.data()), "MarginalNonRevAncestralStateReconstruction");
+    post.assign(N, Vdouble(S));
+    for (size_t i = 0; i < N; ++i)
+      for (size_t x = 0; x < S; ++x) post[i][x] = pb[i * S + x];
+    if (joint) {
+      joint->assign(N, VVdouble(S, Vdouble(S, 0.0)));
+      if (!isRoot)
+        for (size_t i = 0; i < N; ++i)
+          for (size_t x = 0; x < S; ++x)
+            for (size_t y = 0; y < S; ++y) (*joint)[i][x][y] = jb[(i * S + x) * S + y];
+    }
+  }
+  std::vector<int> getNodesId() const {
+    std::vector<int> ids;
+    for (const Node* n : nodes_) ids.push_back(n->getId());
+    return ids;
+  }
   long getNumberOfLikelihoodCalculations() const { return numOfLikelihoodCalculations_; }  // fork: DRNonHomogeneousTreeLikelihood.h:75
 
  protected:
@@ -1803,6 +1830,67 @@ class RHomogeneousMixedTreeLikelihood : public LikelihoodPointBatch {
   }
   Vdouble probas_, mixedSiteLnl_;
   double mixedMinusLogLik_ = 0;
+};
+
+// ---- marginal ancestral reconstruction for non-reversible models (fork) --------------------------------------------------------
+// Likelihood/MarginalNonRevAncestralStateReconstruction.h:66-207.  The reference re-runs the prefix pass once per root state
+// (DRNonHomogeneousTreeLikelihood::computeLikelihoodPrefixConditionalOnRoot, .cpp:1026-1162: S full passes, S^2 work per
+// (node, site, state) on top); the device computes the same tables in one pass per node from the resident arrays
+// (bppgpu_get_marginal_posteriors).  Map keys follow the reference: node id -> distinct-site index -> state vector.
+class MarginalNonRevAncestralStateReconstruction {
+ public:
+  explicit MarginalNonRevAncestralStateReconstruction(AbstractHomogeneousTreeLikelihood* drl)
+      : likelihood_(drl), nbSites_(drl->getNumberOfSites()), nbDistinctSites_(drl->getNumberOfDistinctSites()),
+        nbClasses_(drl->getNumberOfClasses()), nbStates_(drl->getNumberOfStates()) {}
+
+  void computePosteriorProbabilitiesOfNodesForEachStatePerSite() {
+    postProbNode_.reset(new std::map<int, std::map<size_t, std::vector<double> > >);
+    jointProbabilities_.reset(new std::map<int, std::map<size_t, VVdouble> >);
+    for (int id : likelihood_->getNodesId()) {
+      VVdouble post;
+      VVVdouble joint;
+      likelihood_->getMarginalPosteriors(id, post, &joint);
+      for (size_t i = 0; i < nbDistinctSites_; ++i) {
+        (*postProbNode_)[id][i] = post[i];
+        (*jointProbabilities_)[id][i] = joint[i];   // [nodeState][fatherState]; all zero at the root, like the reference
+      }
+    }
+  }
+  std::map<int, std::map<size_t, VVdouble> > getAllJointFatherNodeProbabilities() {
+    if (!jointProbabilities_) computePosteriorProbabilitiesOfNodesForEachStatePerSite();
+    return *jointProbabilities_;
+  }
+  std::map<int, std::map<size_t, std::vector<double> > >* getPosteriorProbForAllNodesAndStatesPerSite() {
+    if (!postProbNode_) computePosteriorProbabilitiesOfNodesForEachStatePerSite();
+    return postProbNode_.get();
+  }
+  // argmax state per SITE (.cpp:155-167).  The reference indexes the distinct-site tables with the site number, which is
+  // only right when every site is its own pattern (ChromEvol: one site); here a site reads its pattern's entry.
+  const std::map<int, std::vector<size_t> > getAllAncestralStates() const {
+    if (!postProbNode_) throw Exception("MarginalNonRevAncestralStateReconstruction: posterior probabilities not computed");
+    std::map<int, std::vector<size_t> > ancestors;
+    for (const auto& kv : *postProbNode_) {
+      std::vector<size_t>& a = ancestors[kv.first];
+      a.reserve(nbSites_);
+      for (size_t s = 0; s < nbSites_; ++s) {
+        const std::vector<double>& p = kv.second.at(likelihood_->getSiteIndex(s));
+        a.push_back((size_t)(std::max_element(p.begin(), p.end()) - p.begin()));   // VectorTools::whichMax: first maximum
+      }
+    }
+    return ancestors;
+  }
+  // posterior of the root state at distinct site 0 (.cpp:139-153)
+  std::vector<double> getRootPosteriorProb() const {
+    VVdouble post;
+    likelihood_->getMarginalPosteriors(likelihood_->getNodesId().back(), post, nullptr);
+    return post.at(0);
+  }
+
+ private:
+  AbstractHomogeneousTreeLikelihood* likelihood_;   // not owned
+  size_t nbSites_, nbDistinctSites_, nbClasses_, nbStates_;
+  std::unique_ptr<std::map<int, std::map<size_t, std::vector<double> > > > postProbNode_;
+  std::unique_ptr<std::map<int, std::map<size_t, VVdouble> > > jointProbabilities_;
 };
 
 }  // namespace bppshim

@@ -191,6 +191,17 @@ int bppgpu_get_clv(bppgpu_engine* e, int32_t point, int32_t node, int32_t which,
  * `posterior` is available (the reference's leaf formula needs the leaf likelihoods alone).                      */
 int bppgpu_get_node_posteriors(bppgpu_engine* e, int32_t point, int32_t node, double* likelihood_at_node,
                                int32_t* scale_exp, double* posterior);
+/* MarginalNonRevAncestralStateReconstruction (fork; Likelihood/MarginalNonRevAncestralStateReconstruction.h:66-207, .cpp:10-136)
+ * for one node, from the device-resident lower / upper arrays:
+ *   posterior [N][S]    = postProbNode_[node][i][x]: P(state at node = x | data of distinct site i)
+ *       (computePosteriorProbabilitiesOfNodesForEachStatePerSite, .cpp:10-48; root: getRootPosteriorProb, :139-153)
+ *   joint [N][S][S]     = jointProbabilities_[node][i][x][y]: P(node = x, father = y | data)
+ *       (getJointLikelihoodFatherNode, .cpp:52-88, summed over the root states); NULL to skip; must be NULL at the root.
+ * The reference's loop over the S root states with DRNonHomogeneousTreeLikelihood::computeLikelihoodPrefixConditionalOnRoot
+ * (DRNonHomogeneousTreeLikelihood.cpp:1026-1162) collapses to the ordinary prefix arrays (linearity in the root state), so this
+ * is one pass.  Valid after an eval with BPPGPU_EVAL_D1 on an engine created with BPPGPU_FLAG_KEEP_CLVS (the root needs
+ * the value pass only).                                                                                              */
+int bppgpu_get_marginal_posteriors(bppgpu_engine* e, int32_t point, int32_t node, double* posterior, double* joint);
 /* Derivatives of lnL with respect to "BrLenRoot" = l1 + l2 and "RootPosition" = l1 / (l1 + l2), the re-parametrisation of
  * the two root branches of a rooted tree (reparametrizeRoot; AbstractNonHomogeneousTreeLikelihood.cpp:319-330, :386-389):
  *   out[0..3] = d lnL / d BrLenRoot, d lnL / d RootPosition, d2 lnL / d BrLenRoot^2, d2 lnL / d RootPosition^2

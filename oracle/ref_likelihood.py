@@ -265,6 +265,78 @@ def posterior_probabilities(flat, res, P, nid, probs, tip_codes=None, table=None
     return al / al.sum(axis=(1, 2))[:, None, None]
 
 
+def marginal_posteriors(flat, res, P, nid, probs):
+    """MarginalNonRevAncestralStateReconstruction (fork): posterior probability of every state at a node, and the joint
+    posterior of (node state x, father state y), per distinct site.
+
+    The reference loops over the S root states, re-runs the prefix pass conditional on each
+    (DRNonHomogeneousTreeLikelihood::computeLikelihoodPrefixConditionalOnRoot, .cpp:1026-1162) and adds
+        FatherTerm_y(r) P[c][y][x] lower[x] p_c pi_r / L_site     (getJointLikelihoodFatherNode, MarginalNonRev...cpp:52-88)
+    over r (computePosteriorProbabilitiesOfNodesForEachStatePerSite, :10-48).  The conditional prefix arrays are linear in
+    the indicator of the root state, so their pi_r-weighted sum over r is the ordinary prefix array (root frequencies folded
+    in at the root's sons, DRHomogeneousTreeLikelihood.cpp:625-640) and ONE pass suffices:
+        joint[i][x][y] = sum_c p_c upper[i][c][y] P[c][y][x] sub[i][c][x] / L_i ,   post[i][x] = sum_y joint[i][x][y]
+    (root: post[i][x] = sum_c p_c pi_x lower[i][c][x] / L_i, :112-122).  ``sub`` is the node's lower array (leaf likelihoods
+    for a leaf).  ``marginal_posteriors_by_root_state`` below is the literal S-pass form; tests hold the two equal.
+    Returns (post [N][S], joint [N][S][S] or None at the root)."""
+    probs = np.asarray(probs, float)
+    sub, esub = res.lower[nid], res.lexp[nid]
+    if nid == flat.root:
+        sh = res.SR_exp[:, None] - esub
+        post = np.einsum("icx,c->ix", np.ldexp(sub * res.root_freqs[None, None, :], sh[:, :, None]), probs) / res.SR[:, None]
+        return post, None
+    U, eU = res.upper[nid], res.uexp[nid]
+    sh = res.SR_exp[:, None] - esub - eU
+    t = np.einsum("icy,cyx,icx->icxy", U, P[nid], sub)          # U[i][c][y] P[c][y][x] sub[i][c][x]
+    joint = np.einsum("icxy,c->ixy", np.ldexp(t, sh[:, :, None, None]), probs) / res.SR[:, None, None]
+    return joint.sum(axis=2), joint
+
+
+def marginal_posteriors_by_root_state(flat, res, P, probs):
+    """The reference's own S-pass algorithm, statement by statement, on UNSCALED arrays (small cases only):
+    for every root state r: computeLikelihoodPrefixConditionalOnRoot(root, r) (DRNonHomogeneousTreeLikelihood.cpp:1026-1117;
+    at a root son only father state r survives and NO root frequency is applied, computeLikelihoodRootSonConditionalOnState
+    :1119-1162), then getPosteriorProbabilitiesOfNodesForEachRootStatePerSite (MarginalNonRev...cpp:91-136) adds
+    getJointLikelihoodFatherNode = FatherTerm_y P[c][y][x] lower[x] r_c pi_r / l_i (:52-88) into jointProbabilities_ and
+    postProbNode_.  ``res`` must come from dr_eval(scaled=False).  Returns ({node: post [N][S]}, {node: joint [N][S][S]})."""
+    probs = np.asarray(probs, float)
+    nn, root = flat.n_nodes, flat.root
+    lower = res.lower
+    N, C, S = lower[root].shape
+    l_site = res.SR * np.ldexp(1.0, -res.SR_exp)            # getRootRateSiteLikelihoodArray
+    post = {n: np.zeros((N, S)) for n in range(nn)}
+    joint = {n: np.zeros((N, S, S)) for n in range(nn) if n != root}
+    for r in range(S):
+        cond = {}
+        for nid in range(nn - 1, -1, -1):                    # fathers before sons (pre-order recursion of the reference)
+            if nid == root:
+                continue
+            f = int(flat.parent[nid])
+            A = np.ones((N, C, S))                           # resetLikelihoodArray
+            if f != root:
+                for b in flat.children[f]:
+                    if b != nid:
+                        A = A * _contract(P[b], lower[b])
+                A = A * _contract_T(P[f], cond[f])           # computeLikelihoodFromArrays, root-side overload
+            else:
+                ind = np.zeros(S)
+                ind[r] = 1.0                                 # "if (x == initState)" (:1147), else the product is 0
+                for b in flat.children[f]:
+                    if b != nid:
+                        A = A * (_contract(P[b], lower[b]) * ind[None, None, :])
+            cond[nid] = A
+        pi_r = res.root_freqs[r]
+        for nid in range(nn):
+            if nid == root:                                  # :104-115
+                post[nid][:, r] += pi_r * np.einsum("ic,c->i", lower[root][:, :, r], probs) / l_site
+                continue
+            # joint[i][x][y] += sum_c cond[i][c][y] P[c][y][x] lower[i][c][x] r_c pi_r / l_i
+            j = np.einsum("icy,cyx,icx,c->ixy", cond[nid], P[nid], lower[nid], probs) * pi_r / l_site[:, None, None]
+            joint[nid] += j
+            post[nid] += j.sum(axis=2)
+    return post, joint
+
+
 def root_reparam_derivatives(flat, res, P, dP, d2P, probs, weights):
     """Derivatives of -lnL with respect to ``BrLenRoot`` (l1 + l2) and ``RootPosition`` (l1 / (l1 + l2)), the
     re-parametrisation of the two root branches of a rooted tree

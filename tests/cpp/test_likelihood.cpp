@@ -262,6 +262,50 @@ int main() {
       DRNonHomogeneousTreeLikelihood tl(*t5, s5, true, false, &cm, &cst);
       tl.initialize();
       printf("CHR_WEIGHTED %.15f\n", tl.getValue());
+      {
+        // marginal reconstruction for non-reversible models (fork: MarginalNonRevAncestralStateReconstruction), as
+        // ChromosomeNumberMng::runChromEvol does after the optimisation
+        MarginalNonRevAncestralStateReconstruction asr(&tl);
+        asr.computePosteriorProbabilitiesOfNodesForEachStatePerSite();
+        auto* post = asr.getPosteriorProbForAllNodesAndStatesPerSite();
+        auto joint = asr.getAllJointFatherNodeProbabilities();
+        const map<int, vector<size_t> > anc = asr.getAllAncestralStates();
+        double sumErr = 0, jointErr = 0, fatherErr = 0;
+        const int rootId = (int)post->size() - 1;
+        for (auto& kv : *post) {
+          const vector<double>& p = kv.second[0];
+          double s = 0;
+          for (double v : p) s += v;
+          sumErr = max(sumErr, fabs(s - 1.0));
+          printf("CHR_ANC_%d %zu\n", kv.first, anc.at(kv.first)[0]);
+          printf("CHR_POSTMAX_%d %.15g\n", kv.first, p[anc.at(kv.first)[0]]);
+          if (kv.first == rootId) continue;
+          const VVdouble& j = joint[kv.first][0];
+          const int father = tl.getTree().getNode(kv.first)->getFather()->getId();
+          const vector<double>& pf = (*post)[father][0];
+          for (size_t x = 0; x < p.size(); ++x) {
+            double r = 0;
+            for (size_t y = 0; y < p.size(); ++y) r += j[x][y];
+            jointErr = max(jointErr, fabs(r - p[x]));
+          }
+          for (size_t y = 0; y < p.size(); ++y) {
+            double cs = 0;
+            for (size_t x = 0; x < p.size(); ++x) cs += j[x][y];
+            fatherErr = max(fatherErr, fabs(cs - pf[y]));
+          }
+        }
+        const vector<double> rp = asr.getRootPosteriorProb();
+        double rootErr = 0;
+        for (size_t x = 0; x < rp.size(); ++x) rootErr = max(rootErr, fabs(rp[x] - (*post)[rootId][0][x]));
+        printf("CHR_MARG_SUM_ERR %.3e\n", sumErr);
+        printf("CHR_MARG_JOINT_ERR %.3e\n", jointErr);
+        printf("CHR_MARG_FATHER_ERR %.3e\n", fatherErr);
+        printf("CHR_MARG_ROOT_ERR %.3e\n", rootErr);
+        if (sumErr > 1e-10 || jointErr > 1e-12 || fatherErr > 1e-10 || rootErr > 1e-15) {
+          cerr << "MarginalNonRevAncestralStateReconstruction consistency checks failed" << endl;
+          fails++;
+        }
+      }
       cm.setParameterValue("Chromosome.gain", 1.1);
       // the batched front-end: ChromosomeNumberOptimizer's vector of likelihoods (one starting point each) as one device object
       const double pts[5][4] = {{0.7, 0.4, 0.2, 0.1}, {1.1, 0.4, 0.2, 0.05}, {0.2, 1.3, 0.6, 0.3}, {2.0, 2.0, 0.01, 0.4}, {0.05, 0.05, 0.9, 0.0}};

@@ -163,6 +163,14 @@ def test_reference_likelihood_tests_through_the_shim(built_lib):
     ch.root_freqs = m.freq
     res = cases.oracle_eval(ch, weighted_root=True)
     assert abs(vals["CHR_WEIGHTED"] + res.lnl) <= 1e-9 * abs(res.lnl)
+    # MarginalNonRevAncestralStateReconstruction on that likelihood: best state and its posterior at every node
+    from oracle import ref_likelihood as rl
+    res_m = cases.oracle_eval(ch, weighted_root=True, want_d1=True)
+    for n in range(flat.n_nodes):
+        post, _ = rl.marginal_posteriors(flat, res_m, res_m.P, n, ch.probs)
+        assert int(vals["CHR_ANC_%d" % n]) == int(np.argmax(post[0])), n
+        assert abs(vals["CHR_POSTMAX_%d" % n] - post[0].max()) <= 1e-9, n
+    assert vals["CHR_MARG_SUM_ERR"] <= 1e-10 and vals["CHR_MARG_JOINT_ERR"] <= 1e-12 and vals["CHR_MARG_FATHER_ERR"] <= 1e-10
     # batched front-end (LikelihoodPointBatch): five parameter points in one device evaluation, each against the oracle
     pts = [(0.7, 0.4, 0.2, 0.1), (1.1, 0.4, 0.2, 0.05), (0.2, 1.3, 0.6, 0.3), (2.0, 2.0, 0.01, 0.4), (0.05, 0.05, 0.9, 0.0)]
     for k, (g, l, du, de) in enumerate(pts):

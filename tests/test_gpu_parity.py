@@ -548,6 +548,70 @@ def test_node_posteriors_error_conventions():
         assert ei.value.code == capi.E_INVALID
 
 
+@pytest.mark.parametrize("mk,ncat,rooted,nsites", [
+    (gtr, 4, True, 70), (rm.lg08, 4, False, 40), (rm.lg08, 2, True, 40), (lambda: rm.yn98(2.0, 0.3), 1, True, 12),
+    (lambda: rm.chromosome(1, 40, gain=0.7, loss=0.4, dupl=0.2, demi=rm.DEMI_EQUAL_DUPL), 1, True, 1),
+    (lambda: rm.chromosome(1, 25, gain=1.5, loss=0.1, dupl=0.9, demi=0.4, gain_r=0.05), 2, True, 3)])
+def test_marginal_nonrev_ancestral_posteriors(mk, ncat, rooted, nsites):
+    """MarginalNonRevAncestralStateReconstruction (fork): node posteriors and (node, father) joint posteriors of every node
+    from the device-resident arrays against the oracle (itself held to the reference's S-pass form and to brute-force
+    enumeration on CPU); non-stationary root frequencies so that the non-reversible case is exercised."""
+    capi = _capi()
+    from oracle import ref_likelihood as rl
+    r, p = rm.gamma_rates(ncat, 0.6) if ncat > 1 else rm.constant_rate()
+    m = mk()
+    c = cases.make_case(9, nsites, m, r, p, seed=23, rooted=rooted, ambiguity=0.05, compress=False,
+                        mean_brlen=0.2 if m.size <= 64 else 0.05)
+    rng = np.random.default_rng(5)
+    c.root_freqs = rng.dirichlet(np.ones(m.size))
+    res = cases.oracle_eval(c, want_d1=True)
+    flat = c.flat
+    with cases.make_engine(c, flags=capi.FLAG_KEEP_CLVS) as e:
+        lnl, _, _ = e.eval(capi.EVAL_LNL | capi.EVAL_D1)
+        assert abs(lnl[0] - res.lnl) <= REL * abs(res.lnl)
+        posts = {}
+        for nid in range(flat.n_nodes):
+            is_root = nid == flat.root
+            post, joint = e.marginal_posteriors(nid, joint=not is_root)
+            want_post, want_joint = rl.marginal_posteriors(flat, res, res.P, nid, c.probs)
+            np.testing.assert_allclose(post, want_post, rtol=1e-9, atol=1e-14)
+            np.testing.assert_allclose(post.sum(axis=1), 1.0, rtol=1e-9)
+            posts[nid] = post
+            if not is_root:
+                np.testing.assert_allclose(joint, want_joint, rtol=1e-9, atol=1e-14)
+                post_only, none = e.marginal_posteriors(nid, joint=False)
+                assert none is None
+                np.testing.assert_array_equal(post_only, post)
+        # marginalising the node's state out of the joint table gives the father's posterior
+        for nid in range(flat.n_nodes - 1):
+            _, joint = e.marginal_posteriors(nid)
+            np.testing.assert_allclose(joint.sum(axis=1), posts[int(flat.parent[nid])], rtol=1e-8, atol=1e-13)
+
+
+def test_marginal_posteriors_error_conventions():
+    """bppgpu_get_marginal_posteriors: needs kept CLVs and an evaluation, the prefix pass for non-root nodes, no joint table at
+    the root, valid node ids."""
+    capi = _capi()
+    r, p = rm.gamma_rates(2, 0.5)
+    c = cases.make_case(6, 20, gtr(), r, p, seed=3, rooted=True)
+    with cases.make_engine(c) as e:
+        e.eval(capi.EVAL_LNL)
+        with pytest.raises(capi.BppGpuError):
+            e.marginal_posteriors(c.flat.root, joint=False)
+    with cases.make_engine(c, flags=capi.FLAG_KEEP_CLVS) as e:
+        with pytest.raises(capi.BppGpuError):
+            e.marginal_posteriors(c.flat.root, joint=False)          # no evaluation yet
+        e.eval(capi.EVAL_LNL)
+        post, _ = e.marginal_posteriors(c.flat.root, joint=False)    # the root needs the value pass only
+        np.testing.assert_allclose(post.sum(axis=1), 1.0, rtol=1e-12)
+        with pytest.raises(capi.BppGpuError):
+            e.marginal_posteriors(c.flat.root, joint=True)
+        with pytest.raises(capi.BppGpuError):
+            e.marginal_posteriors(0, joint=False)                    # no prefix pass yet
+        with pytest.raises(capi.BppGpuError):
+            e.marginal_posteriors(c.flat.n_nodes, joint=False)
+
+
 @pytest.mark.parametrize("mk,ncat", [(gtr, 4), (rm.lg08, 3), (lambda: rm.yn98(2.0, 0.3), 1)])
 def test_root_reparametrisation_derivatives(mk, ncat):
     """BrLenRoot / RootPosition (reparametrizeRoot): first and second derivatives rebuilt at the root on the device, against

@@ -224,3 +224,62 @@ def test_root_reparametrisation_derivatives_against_finite_differences():
     assert abs((nll(L, pos + h) - nll(L, pos - h)) / (2 * h) - g["d1_pos"]) < 1e-6
     assert abs((nll(L + h, pos) - 2 * f0 + nll(L - h, pos)) / h ** 2 - g["d2_len"]) < 2e-3 * abs(g["d2_len"])
     assert abs((nll(L, pos + h) - 2 * f0 + nll(L, pos - h)) / h ** 2 - g["d2_pos"]) < 2e-3 * abs(g["d2_pos"])
+
+
+def test_marginal_nonrev_posteriors_one_pass_equals_reference_s_pass_form_and_enumeration():
+    """MarginalNonRevAncestralStateReconstruction (fork): the one-pass restatement (ordinary prefix arrays) equals the
+    reference's S-pass algorithm restated literally (prefix pass conditional on every root state,
+    DRNonHomogeneousTreeLikelihood.cpp:1026-1162 + MarginalNonRev...cpp:10-136) and, independently, the node and
+    (node, father) marginals obtained by enumerating every assignment of the internal states.  Non-reversible model
+    (chromosome gains / losses / duplications), non-stationary root frequencies, rooted tree: nothing cancels."""
+    import itertools
+    import cases
+    from oracle import ref_likelihood as rl
+    r, p = rm.gamma_rates(2, 0.7)
+    m = rm.chromosome(1, 5, gain=0.9, loss=0.4, dupl=0.3)
+    S = m.size
+    c = cases.make_case(5, 4, m, r, p, seed=17, rooted=True, compress=False, mean_brlen=0.3)
+    c.root_freqs = np.array([.1, .3, .2, .25, .15])
+    res = cases.oracle_eval(c, want_d1=True, scaled=False)
+    flat = c.flat
+    post_ref, joint_ref = rl.marginal_posteriors_by_root_state(flat, res, res.P, c.probs)
+    for n in range(flat.n_nodes):
+        post, joint = rl.marginal_posteriors(flat, res, res.P, n, c.probs)
+        np.testing.assert_allclose(post, post_ref[n], rtol=1e-12, atol=1e-16)
+        np.testing.assert_allclose(post.sum(axis=1), 1.0, rtol=1e-12)
+        if n != flat.root:
+            np.testing.assert_allclose(joint, joint_ref[n], rtol=1e-12, atol=1e-16)
+    # the scaled arrays (what the device holds) give the same posteriors
+    res_s = cases.oracle_eval(c, want_d1=True, scaled=True)
+    for n in range(flat.n_nodes):
+        np.testing.assert_allclose(rl.marginal_posteriors(flat, res_s, res_s.P, n, c.probs)[0], post_ref[n], rtol=1e-12, atol=1e-16)
+    # brute force: P(node = x, father = y | data) by enumeration of the internal states
+    internals = [n for n in range(flat.n_nodes) if not flat.is_leaf[n]]
+    for i in (0, 3):
+        tot = {n: np.zeros((S, S)) for n in range(flat.n_nodes) if n != flat.root}
+        rootm = np.zeros(S)
+        for cc in range(len(r)):
+            for states in itertools.product(range(S), repeat=len(internals)):
+                st = dict(zip(internals, states))
+                pr = c.probs[cc] * c.root_freqs[st[flat.root]]
+                leaf_terms = {}
+                for n in range(flat.n_nodes - 1):
+                    f = int(flat.parent[n])
+                    if flat.is_leaf[n]:
+                        leaf_terms[n] = res.P[n][cc][st[f]] * c.table[c.codes_by_leaf[n][i]]     # over the leaf's state x
+                        pr *= leaf_terms[n].sum()
+                    else:
+                        pr *= res.P[n][cc][st[f]][st[n]]
+                rootm[st[flat.root]] += pr
+                for n in tot:
+                    f = int(flat.parent[n])
+                    if flat.is_leaf[n]:
+                        s = leaf_terms[n].sum()
+                        if s > 0:
+                            tot[n][:, st[f]] += pr * leaf_terms[n] / s
+                    else:
+                        tot[n][st[n], st[f]] += pr
+        L = rootm.sum()
+        np.testing.assert_allclose(rl.marginal_posteriors(flat, res, res.P, flat.root, c.probs)[0][i], rootm / L, rtol=1e-11)
+        for n in tot:
+            np.testing.assert_allclose(joint_ref[n][i], tot[n] / L, rtol=1e-10, atol=1e-16)
