@@ -808,6 +808,8 @@ class SubstitutionModel {
   virtual void setParameterValue(const std::string& name, double v) = 0;
   virtual std::vector<std::string> getParameterNames() const = 0;
   virtual void fillModelDesc(bppgpu_model_desc& d) const = 0;
+  virtual SubstitutionModel* clone() const = 0;
+  virtual double getParameterValue(const std::string& name) const { throw ParameterNotFoundException(name); }
 };
 
 class AbstractSubstitutionModel : public SubstitutionModel {
@@ -1055,6 +1057,7 @@ class GTR : public AbstractReversibleSubstitutionModel {
     freq_[0] = piA; freq_[1] = piC; freq_[2] = piG; freq_[3] = piT;
     update();
   }
+  GTR* clone() const { return new GTR(*this); }
   std::string getName() const { return "GTR"; }
   std::vector<std::string> getParameterNames() const { return {"GTR.a", "GTR.b", "GTR.c", "GTR.d", "GTR.e"}; }
   void setParameterValue(const std::string& name, double v) {
@@ -1083,8 +1086,13 @@ class HKY85 : public AbstractReversibleSubstitutionModel {
     freq_[0] = piA; freq_[1] = piC; freq_[2] = piG; freq_[3] = piT;
     update();
   }
+  HKY85* clone() const { return new HKY85(*this); }
   std::string getName() const { return name_; }
   std::vector<std::string> getParameterNames() const { return {name_ + ".kappa"}; }
+  double getParameterValue(const std::string& name) const {
+    if (name == "kappa" || name == name_ + ".kappa") return kappa_;
+    throw ParameterNotFoundException(name);
+  }
   void setParameterValue(const std::string& name, double v) {
     if (name != "kappa" && name != name_ + ".kappa") throw ParameterNotFoundException(name);
     kappa_ = v;
@@ -1107,15 +1115,35 @@ class HKY85 : public AbstractReversibleSubstitutionModel {
 // Model/Nucleotide/T92.cpp:81-187: HKY85 with pi = ((1-theta)/2, theta/2, theta/2, (1-theta)/2)
 class T92 : public HKY85 {
  public:
-  T92(const Alphabet* alpha, double kappa = 1., double theta = 0.5) : HKY85(alpha, kappa, (1 - theta) / 2, theta / 2, theta / 2, (1 - theta) / 2, "T92") {}
+  T92(const Alphabet* alpha, double kappa = 1., double theta = 0.5)
+      : HKY85(alpha, kappa, (1 - theta) / 2, theta / 2, theta / 2, (1 - theta) / 2, "T92"), theta_(theta) {}
+  T92* clone() const { return new T92(*this); }
+  std::vector<std::string> getParameterNames() const { return {"T92.kappa", "T92.theta"}; }
+  double getParameterValue(const std::string& name) const {
+    if (name == "theta" || name == "T92.theta") return theta_;
+    return HKY85::getParameterValue(name);
+  }
+  void setParameterValue(const std::string& name, double v) {
+    if (name == "theta" || name == "T92.theta") {   // T92::updateMatrices (T92.cpp:81-94): piA = piT = (1 - theta) / 2, piC = piG = theta / 2
+      theta_ = v;
+      freq_[0] = freq_[3] = (1 - v) / 2;
+      freq_[1] = freq_[2] = v / 2;
+      update();
+    } else HKY85::setParameterValue(name, v);
+  }
+
+ private:
+  double theta_;
 };
 class K80 : public HKY85 {
  public:
   K80(const Alphabet* alpha, double kappa = 1.) : HKY85(alpha, kappa, .25, .25, .25, .25, "K80") {}
+  K80* clone() const { return new K80(*this); }
 };
 class JCnuc : public HKY85 {
  public:
   explicit JCnuc(const Alphabet* alpha) : HKY85(alpha, 1.0, .25, .25, .25, .25, "JC69") {}
+  JCnuc* clone() const { return new JCnuc(*this); }
 };
 
 // Model/Protein/LG08.cpp:53-62 + the published Le & Gascuel 2008 constants
@@ -1129,6 +1157,7 @@ class LG08 : public AbstractReversibleSubstitutionModel {
     for (int i = 0; i < 20; ++i) freq_[i] = LG08_FREQ[i];
     updateReversible();
   }
+  LG08* clone() const { return new LG08(*this); }
   std::string getName() const { return "LG08"; }
   std::vector<std::string> getParameterNames() const { return {}; }
   void setParameterValue(const std::string& name, double) { throw ParameterNotFoundException(name); }
@@ -1149,7 +1178,13 @@ class YN98 : public AbstractSubstitutionModel {
     reversible_ = false;  // the reference runs the general EigenValue path for word models
     update();
   }
+  YN98* clone() const { return new YN98(*this); }
   std::string getName() const { return "YN98"; }
+  double getParameterValue(const std::string& name) const {
+    if (name == "kappa" || name == "YN98.kappa") return kappa_;
+    if (name == "omega" || name == "YN98.omega") return omega_;
+    throw ParameterNotFoundException(name);
+  }
   std::vector<std::string> getParameterNames() const { return {"YN98.kappa", "YN98.omega"}; }
   void setParameterValue(const std::string& name, double v) {
     if (name == "kappa" || name == "YN98.kappa") kappa_ = v;
@@ -1201,6 +1236,7 @@ class ChromosomeSubstitutionModel : public AbstractSubstitutionModel {
     extraFlags_ = BPPGPU_MODEL_CLAMP01 | BPPGPU_MODEL_CHR_DERIV | BPPGPU_MODEL_CHR_TAYLOR;
     update();
   }
+  ChromosomeSubstitutionModel* clone() const { return new ChromosomeSubstitutionModel(*this); }
   std::string getName() const { return "Chromosome"; }
   std::vector<std::string> getParameterNames() const { return {"Chromosome.gain", "Chromosome.loss", "Chromosome.dupl", "Chromosome.demi"}; }
   void setParameterValue(const std::string& name, double v) {
@@ -1256,6 +1292,168 @@ class ChromosomeSubstitutionModel : public AbstractSubstitutionModel {
   unsigned maxChrRange_;
   rateChangeFunc rc_;
 };
+
+// ---- root frequency sets and non-homogeneous model sets ---------------------------------------------------------------------------
+// Model/FrequencySet/NucleotideFrequencySet.h: GCFrequencySet (one parameter theta = G+C content), FixedFrequencySet
+class FrequencySet {
+ public:
+  virtual ~FrequencySet() {}
+  virtual FrequencySet* clone() const = 0;
+  virtual const Vdouble& getFrequencies() const = 0;
+  virtual std::vector<std::string> getParameterNames() const = 0;
+  virtual double getParameterValue(const std::string& name) const = 0;
+  virtual void setParameterValue(const std::string& name, double v) = 0;
+};
+class GCFrequencySet : public FrequencySet {
+ public:
+  explicit GCFrequencySet(const Alphabet* = nullptr, double theta = 0.5) : freq_(4) { set(theta); }
+  GCFrequencySet* clone() const { return new GCFrequencySet(*this); }
+  const Vdouble& getFrequencies() const { return freq_; }
+  std::vector<std::string> getParameterNames() const { return {"GC.theta"}; }
+  double getParameterValue(const std::string& name) const { if (name != "GC.theta" && name != "theta") throw ParameterNotFoundException(name); return theta_; }
+  void setParameterValue(const std::string& name, double v) { if (name != "GC.theta" && name != "theta") throw ParameterNotFoundException(name); set(v); }
+
+ private:
+  void set(double theta) { theta_ = theta; freq_[0] = freq_[3] = (1 - theta) / 2; freq_[1] = freq_[2] = theta / 2; }
+  double theta_;
+  Vdouble freq_;
+};
+class FixedFrequencySet : public FrequencySet {
+ public:
+  explicit FixedFrequencySet(const Vdouble& f) : freq_(f) {}
+  FixedFrequencySet* clone() const { return new FixedFrequencySet(*this); }
+  const Vdouble& getFrequencies() const { return freq_; }
+  std::vector<std::string> getParameterNames() const { return {}; }
+  double getParameterValue(const std::string& name) const { throw ParameterNotFoundException(name); }
+  void setParameterValue(const std::string& name, double) { throw ParameterNotFoundException(name); }
+
+ private:
+  Vdouble freq_;
+};
+
+// Model/SubstitutionModelSet.h: models attached to the branches above given node ids, root frequencies, parameters named
+// "<model parameter>_<model index + 1>" with aliases (SubstitutionModelSet::aliasParameters).  The set owns its models and
+// its root frequency set, like the reference.
+class SubstitutionModelSet {
+ public:
+  explicit SubstitutionModelSet(const Alphabet* alpha) : alphabet_(alpha) {}
+  SubstitutionModelSet(const SubstitutionModelSet& o) : alphabet_(o.alphabet_), nodeToModel_(o.nodeToModel_), aliases_(o.aliases_) {
+    for (const auto& m : o.models_) models_.emplace_back(m->clone());
+    if (o.rootFreqs_) rootFreqs_.reset(o.rootFreqs_->clone());
+  }
+  SubstitutionModelSet& operator=(const SubstitutionModelSet&) = delete;
+  SubstitutionModelSet* clone() const { return new SubstitutionModelSet(*this); }
+  const Alphabet* getAlphabet() const { return alphabet_; }
+  void setRootFrequencies(FrequencySet* f) { rootFreqs_.reset(f); }
+  const FrequencySet* getRootFrequencySet() const { return rootFreqs_.get(); }
+  bool isStationary() const { return !rootFreqs_; }
+  // SubstitutionModelSet::getRootFrequencies: the root set, or (stationary sets) the first model's equilibrium frequencies
+  Vdouble getRootFrequencies() const { return rootFreqs_ ? rootFreqs_->getFrequencies() : models_.at(0)->getFrequencies(); }
+  void addModel(SubstitutionModel* model, const std::vector<int>& nodesId) {
+    std::unique_ptr<SubstitutionModel> own(model);
+    if (!models_.empty() && model->getNumberOfStates() != models_[0]->getNumberOfStates())
+      throw Exception("SubstitutionModelSet::addModel. A Substitution Model cannot be added to a Model Set if it does not have the same number of states.");
+    for (int id : nodesId) {
+      if (nodeToModel_.count(id)) throw Exception("SubstitutionModelSet::addModel. Node " + std::to_string(id) + " already has a model.");
+      nodeToModel_[id] = models_.size();
+    }
+    models_.push_back(std::move(own));
+  }
+  size_t getNumberOfModels() const { return models_.size(); }
+  size_t getNumberOfStates() const { return models_.at(0)->getNumberOfStates(); }
+  SubstitutionModel* getModel(size_t i) const { return models_.at(i).get(); }
+  size_t getModelIndexForNode(int nodeId) const {
+    std::map<int, size_t>::const_iterator it = nodeToModel_.find(nodeId);
+    if (it == nodeToModel_.end()) throw Exception("SubstitutionModelSet::getModelIndexForNode(). No model associated to node with id " + std::to_string(nodeId));
+    return it->second;
+  }
+  SubstitutionModel* getModelForNode(int nodeId) const { return getModel(getModelIndexForNode(nodeId)); }
+  std::vector<int> getNodesWithModel(size_t i) const {
+    std::vector<int> v;
+    for (const auto& kv : nodeToModel_) if (kv.second == i) v.push_back(kv.first);
+    return v;
+  }
+  // every node of the tree but the root has a model, and only those (SubstitutionModelSet::isFullySetUpFor)
+  bool isFullySetUpFor(const Tree& tree) const {
+    const std::vector<Node*> nodes = tree.getNodes();
+    for (size_t i = 0; i + 1 < nodes.size(); ++i) if (!nodeToModel_.count(nodes[i]->getId())) return false;
+    return !models_.empty();
+  }
+  // `to` follows `from` from now on (both full names, e.g. "T92.kappa_1", "T92.kappa_2")
+  void aliasParameters(const std::string& from, const std::string& to) {
+    aliases_[from].push_back(to);
+    setParameterValue(to, getParameterValue(from));
+  }
+  // independent parameters: root frequencies first, then the model parameters that are not aliased to another one
+  std::vector<std::string> getParameterNames() const {
+    std::vector<std::string> names;
+    std::map<std::string, bool> follower;
+    for (const auto& kv : aliases_) for (const std::string& t : kv.second) follower[t] = true;
+    if (rootFreqs_) for (const std::string& n : rootFreqs_->getParameterNames()) if (!follower.count(n)) names.push_back(n);
+    for (size_t k = 0; k < models_.size(); ++k)
+      for (const std::string& n : models_[k]->getParameterNames()) {
+        const std::string full = n + "_" + std::to_string(k + 1);
+        if (!follower.count(full)) names.push_back(full);
+      }
+    return names;
+  }
+  double getParameterValue(const std::string& name) const {
+    size_t k;
+    std::string base;
+    if (splitName(name, base, k)) return models_[k]->getParameterValue(base);
+    if (rootFreqs_) return rootFreqs_->getParameterValue(name);
+    throw ParameterNotFoundException("ParameterNotFoundException: " + name);
+  }
+  void setParameterValue(const std::string& name, double v) {
+    size_t k;
+    std::string base;
+    if (splitName(name, base, k)) models_[k]->setParameterValue(base, v);
+    else if (rootFreqs_) rootFreqs_->setParameterValue(name, v);
+    else throw ParameterNotFoundException("ParameterNotFoundException: " + name);
+    std::map<std::string, std::vector<std::string> >::const_iterator it = aliases_.find(name);
+    if (it != aliases_.end()) for (const std::string& t : it->second) setParameterValue(t, v);
+  }
+
+ private:
+  bool splitName(const std::string& name, std::string& base, size_t& k) const {
+    const size_t u = name.rfind('_');
+    if (u == std::string::npos || u + 1 >= name.size()) return false;
+    char* end = nullptr;
+    const long idx = std::strtol(name.c_str() + u + 1, &end, 10);
+    if (*end != 0 || idx < 1 || (size_t)idx > models_.size()) return false;
+    base = name.substr(0, u);
+    k = (size_t)idx - 1;
+    return true;
+  }
+  const Alphabet* alphabet_;
+  std::vector<std::unique_ptr<SubstitutionModel> > models_;
+  std::map<int, size_t> nodeToModel_;
+  std::unique_ptr<FrequencySet> rootFreqs_;
+  std::map<std::string, std::vector<std::string> > aliases_;
+};
+
+namespace SubstitutionModelSetTools {
+// Model/SubstitutionModelSetTools.cpp:78-183: one copy of `model` per branch (model k + 1 on the k-th node of
+// tree.getNodesId() with the root removed), the listed global parameters aliased to the first copy's; takes ownership of
+// `model` (deleted, like the reference) and of `rootFreqs`.
+inline SubstitutionModelSet* createNonHomogeneousModelSet(SubstitutionModel* model, FrequencySet* rootFreqs, const Tree* tree,
+                                                          const std::vector<std::string>& globalParameterNames) {
+  std::unique_ptr<SubstitutionModel> tmpl(model);
+  const std::vector<std::string> modelParams = model->getParameterNames();
+  for (const std::string& g : globalParameterNames)
+    if (std::find(modelParams.begin(), modelParams.end(), g) == modelParams.end())
+      throw Exception("SubstitutionModelSetTools::createNonHomogeneousModelSet. Parameter '" + g + "' is not valid.");
+  SubstitutionModelSet* set = new SubstitutionModelSet(model->getAlphabet());
+  if (rootFreqs) set->setRootFrequencies(rootFreqs);
+  std::vector<int> ids = tree->getNodesId();
+  const int rootId = tree->getRootNode()->getId();
+  ids.erase(std::find(ids.begin(), ids.end(), rootId));
+  for (int id : ids) set->addModel(model->clone(), std::vector<int>(1, id));
+  for (const std::string& g : globalParameterNames)
+    for (size_t i = 1; i < ids.size(); ++i) set->aliasParameters(g + "_1", g + "_" + std::to_string(i + 1));
+  return set;
+}
+}  // namespace SubstitutionModelSetTools
 
 // ---- site patterns (SitePatterns.cpp:52-106 through the C ABI) -----------------------------------------------------------------
 class SitePatterns {
@@ -1347,9 +1545,11 @@ class AbstractHomogeneousTreeLikelihood {
   }
   ParameterList getSubstitutionModelParameters() const {
     ParameterList pl;
-    for (const std::string& n : model_->getParameterNames()) pl.push_back({n, 0.0});
+    if (modelSet_) for (const std::string& n : modelSet_->getParameterNames()) pl.push_back({n, modelSet_->getParameterValue(n)});
+    else for (const std::string& n : model_->getParameterNames()) pl.push_back({n, 0.0});
     return pl;
   }
+  const SubstitutionModelSet* getSubstitutionModelSet() const { return modelSet_; }
   double getParameterValue(const std::string& name) const {
     if (reparametrizeRoot_ && name == "BrLenRoot") return brLen_[(size_t)root1_] + brLen_[(size_t)root2_];
     if (reparametrizeRoot_ && name == "RootPosition") return brLen_[(size_t)root1_] / (brLen_[(size_t)root1_] + brLen_[(size_t)root2_]);
@@ -1374,7 +1574,7 @@ class AbstractHomogeneousTreeLikelihood {
       const int b = brlenIndex(p.name);
       if (b >= 0) brLen_[(size_t)b] = std::min(std::max(p.value, minimumBrLen_), maximumBrLen_);
       else {
-        try { model_->setParameterValue(p.name, p.value); }
+        try { if (modelSet_) modelSet_->setParameterValue(p.name, p.value); else model_->setParameterValue(p.name, p.value); }
         catch (ParameterNotFoundException&) { rDist_->setParameterValue(p.name, p.value); }
         modelChanged = true;
       }
@@ -1543,7 +1743,8 @@ class AbstractHomogeneousTreeLikelihood {
     bppgpu_config cfg;
     std::memset(&cfg, 0, sizeof(cfg));
     cfg.n_states = (int32_t)S; cfg.n_cats = (int32_t)C; cfg.n_patterns = nPatterns_; cfg.n_nodes = nn; cfg.root = nn - 1;
-    cfg.child_offsets = off.data(); cfg.children = children.data(); cfg.n_points = nPoints_; cfg.n_models = nPoints_;
+    cfg.child_offsets = off.data(); cfg.children = children.data(); cfg.n_points = nPoints_;
+    cfg.n_models = modelSet_ ? (int32_t)modelSet_->getNumberOfModels() : nPoints_;
     cfg.n_codes = (int32_t)chars.size(); cfg.code_bytes = chars.size() > 256 ? 2 : 1; cfg.code_table = table.data();
     cfg.device = device_; cfg.flags = engineFlags_ | BPPGPU_FLAG_KEEP_CLVS;
     if (engine_) { bppgpu_destroy(engine_); engine_ = nullptr; }
@@ -1562,13 +1763,25 @@ class AbstractHomogeneousTreeLikelihood {
     uploadModel();
   }
 
-  virtual Vdouble rootFrequencies() const { return model_->getFrequencies(); }
+  virtual Vdouble rootFrequencies() const { return modelSet_ ? modelSet_->getRootFrequencies() : model_->getFrequencies(); }
 
   virtual void uploadModel() {
     if (!engine_) return;
     bppgpu_model_desc d;
-    model_->fillModelDesc(d);
-    check(bppgpu_set_model(engine_, 0, &d), "setModel");
+    if (modelSet_) {
+      // AbstractNonHomogeneousTreeLikelihood::computeTransitionProbabilitiesForNode (.cpp:410-468): the branch above a node
+      // uses modelSet_->getModelForNode(node id); one device slot per model of the set
+      for (size_t k = 0; k < modelSet_->getNumberOfModels(); ++k) {
+        modelSet_->getModel(k)->fillModelDesc(d);
+        check(bppgpu_set_model(engine_, (int32_t)k, &d), "setModel");
+      }
+      std::vector<int32_t> slot(nodes_.size(), 0);
+      for (size_t i = 0; i + 1 < nodes_.size(); ++i) slot[i] = (int32_t)modelSet_->getModelIndexForNode(nodes_[i]->getId());
+      check(bppgpu_set_branch_models(engine_, 0, slot.data()), "setBranchModels");
+    } else {
+      model_->fillModelDesc(d);
+      check(bppgpu_set_model(engine_, 0, &d), "setModel");
+    }
     Vdouble r(rDist_->getNumberOfCategories()), p(r.size());
     for (size_t c = 0; c < r.size(); ++c) { r[c] = rDist_->getCategory(c); p[c] = rDist_->getProbability(c); }
     check(bppgpu_set_rates(engine_, r.data(), p.data()), "setRates");
@@ -1613,7 +1826,7 @@ class AbstractHomogeneousTreeLikelihood {
     }
     const int b = brlenIndex(variable);
     if (b < 0) {
-      for (const std::string& n : model_->getParameterNames())
+      for (const std::string& n : modelSet_ ? modelSet_->getParameterNames() : model_->getParameterNames())
         if (n == variable) throw Exception("Derivatives respective to substitution model parameters are not implemented.");
       throw ParameterNotFoundException("ParameterNotFoundException: " + variable);
     }
@@ -1637,6 +1850,7 @@ class AbstractHomogeneousTreeLikelihood {
 
   std::unique_ptr<Tree> tree_;
   SubstitutionModel* model_;      // not owned (like the reference)
+  SubstitutionModelSet* modelSet_ = nullptr;  // not owned; non-homogeneous classes: one model per branch group
   DiscreteDistribution* rDist_;   // not owned
   bppgpu_engine* engine_;
   unsigned engineFlags_;
@@ -1700,11 +1914,44 @@ class DRNonHomogeneousTreeLikelihood : public AbstractHomogeneousTreeLikelihood 
     setData(data);
   }
 
+  // Likelihood/DRNonHomogeneousTreeLikelihood.h:93-111: (tree, data, SubstitutionModelSet*, rDist, verbose, reparametrizeRoot)
+  DRNonHomogeneousTreeLikelihood(const Tree& tree, const VectorSiteContainer& data, SubstitutionModelSet* modelSet,
+                                 DiscreteDistribution* rDist, bool verbose = true, bool reparametrizeRoot = false, int device = 0,
+                                 unsigned extraFlags = 0)
+      : AbstractHomogeneousTreeLikelihood(tree, modelSet->getModel(0), rDist, false, BPPGPU_FLAG_NH_DERIV | extraFlags, device) {
+    (void)verbose;
+    // AbstractNonHomogeneousTreeLikelihood::setSubstitutionModelSet (.cpp:193-216)
+    if (!modelSet->isFullySetUpFor(*tree_)) throw Exception("AbstractNonHomogeneousTreeLikelihood::init_(). Model set is not fully specified.");
+    modelSet_ = modelSet;
+    if (reparametrizeRoot) {
+      const Node* root = nodes_.back();
+      if (root->getNumberOfSons() != 2) throw Exception("reparametrizeRoot needs a rooted tree (a root with two sons)");
+      root1_ = root->getSon(0)->getId();
+      root2_ = root->getSon(1)->getId();
+      reparametrizeRoot_ = true;
+    }
+    setData(data);
+  }
+
  protected:
-  Vdouble rootFrequencies() const { return fixedRootFreqs_.empty() ? model_->getFrequencies() : fixedRootFreqs_; }
+  Vdouble rootFrequencies() const {
+    if (modelSet_) return modelSet_->getRootFrequencies();
+    return fixedRootFreqs_.empty() ? model_->getFrequencies() : fixedRootFreqs_;
+  }
 
  private:
   Vdouble fixedRootFreqs_;
+};
+// Likelihood/RNonHomogeneousTreeLikelihood.h: (tree, data, modelSet, rDist, verbose, usePatterns, reparametrizeRoot); the R
+// classes' root reduction (non-positive terms dropped), same device path
+class RNonHomogeneousTreeLikelihood : public DRNonHomogeneousTreeLikelihood {
+ public:
+  RNonHomogeneousTreeLikelihood(const Tree& tree, const VectorSiteContainer& data, SubstitutionModelSet* modelSet,
+                                DiscreteDistribution* rDist, bool verbose = true, bool usePatterns = true, bool reparametrizeRoot = false,
+                                int device = 0)
+      : DRNonHomogeneousTreeLikelihood(tree, data, modelSet, rDist, verbose, reparametrizeRoot, device, BPPGPU_FLAG_R_SEMANTICS) {
+    (void)usePatterns;
+  }
 };
 
 // ---- batched front-end ------------------------------------------------------------------------------------------

@@ -130,6 +130,20 @@ def oracle_eval(c: Case, want_d1=False, want_d2=False, scaled=True, nh_form=Fals
     return res
 
 
+def oracle_eval_nh(c: Case, models, slot_of_node, want_d1=False, want_d2=False, nh_form=True, scaled=True):
+    """Non-homogeneous evaluation: the branch above node n uses models[slot_of_node[n]]
+    (AbstractNonHomogeneousTreeLikelihood::computeTransitionProbabilitiesForNode, .cpp:410-468: the node's own model from the
+    SubstitutionModelSet); root frequencies are c.root_freqs (the set's root FrequencySet)."""
+    tabs = [rm.transition_tables(m, c.flat.brlen, c.rates, want_d1 or want_d2, want_d2) for m in models]
+    nb = len(c.flat.brlen)
+    pick = lambda k: None if tabs[0][k] is None else np.stack([tabs[slot_of_node[n]][k][n] for n in range(nb)])
+    P, dP, d2P = pick(0), pick(1), pick(2)
+    res = rl.dr_eval(c.flat, c.codes_by_leaf, c.table, P, len(c.rates), c.root_freqs, c.probs, c.weights.astype(float),
+                     dP=dP, d2P=d2P, scaled=scaled, nh_form=nh_form)
+    res.P, res.dP, res.d2P = P, dP, d2P
+    return res
+
+
 def make_engine(c: Case, flags=0, n_points=1, n_models=1, device=0):
     from bpp_phyl_b200 import capi
     off, ch = c.flat.csr()

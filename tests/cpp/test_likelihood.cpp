@@ -249,6 +249,41 @@ int main() {
       }
     }
     {
+      // test/test_likelihood_nh.cpp:73-110: one T92 per branch (kappa shared, theta free), GC root frequencies, Gamma(4, 1);
+      // the statistical recovery loop of that test is the optimiser's business, the likelihood of the set is checked here
+      const DNA dna4;
+      unique_ptr<Tree> t8(TreeTemplateTools::parenthesisToTree("(((A:0.1, B:0.2):0.3,C:0.1):0.2,(D:0.3,(E:0.2,F:0.05):0.1):0.1);"));
+      VectorSiteContainer s8(&dna4);
+      s8.addSequence(BasicSequence("A", "ATGTTATCCCGTCGAATCATATGGAATCGTCTAGAACTCA", &dna4));
+      s8.addSequence(BasicSequence("B", "ATGGTATCTCGCCTAATCATGTGGCATCGTCAAAAAATCA", &dna4));
+      s8.addSequence(BasicSequence("C", "TTGGTGTGTCCCTTAATCGTGTGGTATCGTCCGGATATAG", &dna4));
+      s8.addSequence(BasicSequence("D", "ATGGAATCTCCCCTATTCAAGTGGTAACGTCTAGAAATAA", &dna4));
+      s8.addSequence(BasicSequence("E", "CTGGTATCTCCCATTATCATGTGCTATAGTCGAAAAACAA", &dna4));
+      s8.addSequence(BasicSequence("F", "ATGGTTTCTCCCCTAATAGTTCGGCAACGTCAAGACATCA", &dna4));
+      FrequencySet* rootFreqs = new GCFrequencySet(&dna4);
+      SubstitutionModel* model = new T92(&dna4, 3.);
+      unique_ptr<SubstitutionModelSet> modelSet(SubstitutionModelSetTools::createNonHomogeneousModelSet(model, rootFreqs, t8.get(), {"T92.kappa"}));
+      const size_t nmodels = modelSet->getNumberOfModels();
+      for (size_t i = 0; i < nmodels; ++i) modelSet->setParameterValue("T92.theta_" + to_string(i + 1), 0.15 + 0.07 * (double)i);
+      GammaDiscreteRateDistribution g8(4, 1.0);
+      unique_ptr<SubstitutionModelSet> modelSet2(modelSet->clone());
+      DRNonHomogeneousTreeLikelihood tl(*t8, s8, modelSet.get(), &g8, false, false);
+      tl.initialize();
+      RNonHomogeneousTreeLikelihood tlR(*t8, s8, modelSet2.get(), &g8, false, true, false);
+      tlR.initialize();
+      printf("NH_NMODELS %zu\n", nmodels);
+      printf("NH_DR_T92_G4 %.15f\n", tl.getValue());
+      printf("NH_R_T92_G4 %.15f\n", tlR.getValue());
+      printf("NH_NPARAMS %zu\n", tl.getSubstitutionModelParameters().size());
+      for (const Parameter& p : tl.getBranchLengthsParameters())
+        printf("NH_T92_G4_d %s %.12g %.12g\n", p.name.c_str(), tl.getFirstOrderDerivative(p.name), tl.getSecondOrderDerivative(p.name));
+      if (fabs(tl.getValue() - tlR.getValue()) > 1e-9) { cerr << "R and DR non-homogeneous likelihoods differ" << endl; fails++; }
+      // move the shared kappa (all ten models follow), one branch's theta and the root GC content
+      tl.setParametersValues({{"T92.kappa_1", 2.0}, {"T92.theta_3", 0.6}, {"GC.theta", 0.3}});
+      printf("NH_DR_T92_G4_MOVED %.15f\n", tl.getValue());
+      printf("NH_KAPPA_7 %.15f\n", modelSet->getParameterValue("T92.kappa_7"));
+    }
+    {
       ChromosomeAlphabet chr(1, 30);
       unique_ptr<Tree> t5(TreeTemplateTools::parenthesisToTree("(((a:0.3,b:0.2):0.4,c:0.5):0.1,(d:0.3,e:0.6):0.2);"));
       VectorSiteContainer s5(&chr);

@@ -112,6 +112,7 @@ def test_reference_likelihood_tests_through_the_shim(built_lib):
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     vals = {}
     derivs = {}
+    nh_derivs = {}
     for line in r.stdout.splitlines():
         f = line.split()
         if len(f) == 2 and f[0].isupper() or (len(f) == 2 and "_" in f[0]):
@@ -121,6 +122,8 @@ def test_reference_likelihood_tests_through_the_shim(built_lib):
                 pass
         if len(f) == 4 and f[0] == "LG08_G4_d":
             derivs[f[1]] = (float(f[2]), float(f[3]))
+        if len(f) == 4 and f[0] == "NH_T92_G4_d":
+            nh_derivs[f[1]] = (float(f[2]), float(f[3]))
     assert abs(vals["R_T92_G4"] - 85.030942031997312824) < 1e-9
     assert abs(vals["DR_T92_G4"] - 85.030942031997312824) < 1e-9
     assert abs(vals["CLOCK_T92_CONST"] - 94.3957) < 1e-4
@@ -150,6 +153,29 @@ def test_reference_likelihood_tests_through_the_shim(built_lib):
     cc.root_freqs = m.freq
     res = cases.oracle_eval(cc)
     assert abs(vals["YN98_CONST"] + res.lnl) <= 1e-9 * abs(res.lnl)
+    # non-homogeneous model set (test/test_likelihood_nh.cpp's construction): one T92 per branch, kappa shared, GC root frequencies
+    r1, p1 = rm.gamma_rates(4, 1.0)
+    seqs_nh = {"A": "ATGTTATCCCGTCGAATCATATGGAATCGTCTAGAACTCA", "B": "ATGGTATCTCGCCTAATCATGTGGCATCGTCAAAAAATCA",
+               "C": "TTGGTGTGTCCCTTAATCGTGTGGTATCGTCCGGATATAG", "D": "ATGGAATCTCCCCTATTCAAGTGGTAACGTCTAGAAATAA",
+               "E": "CTGGTATCTCCCATTATCATGTGCTATAGTCGAAAAACAA", "F": "ATGGTTTCTCCCCTAATAGTTCGGCAACGTCAAGACATCA"}
+    cn = cases.case_from_alignment("(((A:0.1, B:0.2):0.3,C:0.1):0.2,(D:0.3,(E:0.2,F:0.05):0.1):0.1);", seqs_nh, rm.t92(3.0, 0.5),
+                                   r1, p1, check_rooted=False)
+    nb = cn.flat.n_nodes - 1
+    assert int(vals["NH_NMODELS"]) == nb == 10 and int(vals["NH_NPARAMS"]) == 1 + 1 + nb      # GC.theta, kappa_1, ten thetas
+    thetas = [0.15 + 0.07 * i for i in range(nb)]
+    cn.root_freqs = np.array([.25, .25, .25, .25])
+    resn = cases.oracle_eval_nh(cn, [rm.t92(3.0, th) for th in thetas], np.arange(nb + 1) % nb, want_d1=True, want_d2=True)
+    assert abs(vals["NH_DR_T92_G4"] + resn.lnl) <= 1e-9 * abs(resn.lnl)
+    assert abs(vals["NH_R_T92_G4"] + resn.lnl) <= 1e-9 * abs(resn.lnl)
+    for b in range(nb):
+        d1, d2 = nh_derivs["BrLen%d" % b]
+        assert abs(d1 - resn.d1[b]) <= 1e-8 * max(1, abs(resn.d1[b])), b
+        assert abs(d2 - resn.d2[b]) <= 1e-8 * max(1, abs(resn.d2[b])), b
+    thetas[2] = 0.6
+    cn.root_freqs = np.array([.35, .15, .15, .35])
+    resn = cases.oracle_eval_nh(cn, [rm.t92(2.0, th) for th in thetas], np.arange(nb + 1) % nb)
+    assert abs(vals["NH_DR_T92_G4_MOVED"] + resn.lnl) <= 1e-9 * abs(resn.lnl)
+    assert vals["NH_KAPPA_7"] == 2.0
     # chromosome: one character, weighted root frequencies, unknown count at one tip
     flat = rt.FlatTree(rt.parse_newick("(((a:0.3,b:0.2):0.4,c:0.5):0.1,(d:0.3,e:0.6):0.2);"), check_rooted=False)
     m = rm.chromosome(1, 30, gain=0.7, loss=0.4, dupl=0.2, demi=rm.DEMI_EQUAL_DUPL)

@@ -357,6 +357,61 @@ def test_nh_derivative_form():
     np.testing.assert_allclose(-d2[0, :nb], res.d2, rtol=1e-8, atol=1e-7)
 
 
+def _nh_models(kind):
+    if kind == "dna":
+        return [rm.t92(3.0, th) for th in (0.2, 0.5, 0.8)] + [gtr()]
+    if kind == "protein":
+        lg = rm.lg08()
+        rng = np.random.default_rng(8)
+        other = []
+        exch = lg.Q / lg.freq[None, :]
+        np.fill_diagonal(exch, 0.0)
+        for _ in range(2):        # LG exchangeabilities with other equilibrium frequencies (LG08+F style)
+            f = rng.dirichlet(np.ones(20) * 5)
+            other.append(rm._reversible("LG08F", exch, f))
+        return [lg] + other
+    return [rm.yn98(2.0, 0.3), rm.yn98(1.0, 1.7), rm.yn98(4.0, 0.05)]
+
+
+@pytest.mark.parametrize("kind,ncat,ntaxa,nsites", [("dna", 4, 14, 150), ("protein", 4, 10, 60), ("protein", 3, 10, 60), ("codon", 1, 8, 30),
+                                                    ("codon", 2, 6, 20)])
+def test_nonhomogeneous_model_set_per_branch_models(kind, ncat, ntaxa, nsites):
+    """SubstitutionModelSet semantics (AbstractNonHomogeneousTreeLikelihood.cpp:394-468): every branch takes P, dP, d2P from the
+    model of its own node (bppgpu_set_branch_models), rooted tree, free root frequencies; value, per-site values, NH-form
+    derivatives and the P tables against the oracle."""
+    capi = _capi()
+    models = _nh_models(kind)
+    r, p = rm.gamma_rates(ncat, 0.8) if ncat > 1 else rm.constant_rate()
+    c = cases.make_case(ntaxa, nsites, models[0], r, p, seed=61, rooted=True, ambiguity=0.03, mean_brlen=0.15)
+    rng = np.random.default_rng(12)
+    nn = c.flat.n_nodes
+    slots = rng.integers(len(models), size=nn).astype(np.int32)
+    slots[:len(models)] = np.arange(len(models))             # every model used at least once
+    c.root_freqs = rng.dirichlet(np.ones(models[0].size) * 3)
+    res = cases.oracle_eval_nh(c, models, slots, want_d1=True, want_d2=True)
+    with cases.make_engine(c, flags=capi.FLAG_KEEP_CLVS | capi.FLAG_NH_DERIV, n_models=len(models)) as e:
+        holders = [cases.to_model_desc(m) for m in models]
+        e._model_holders = holders
+        for k, md in enumerate(holders):
+            e.set_model(k, md)
+        e.set_branch_models(0, slots)
+        lnl, d1, d2 = e.eval(7)
+        assert abs(lnl[0] - res.lnl) <= REL * abs(res.lnl)
+        np.testing.assert_allclose(e.site_lnl(), res.site_lnl, rtol=1e-11, atol=1e-11)
+        nb = nn - 1
+        np.testing.assert_allclose(-d1[0, :nb], res.d1, rtol=1e-8, atol=1e-7)
+        np.testing.assert_allclose(-d2[0, :nb], res.d2, rtol=1e-8, atol=1e-6)
+        for nid in (0, nb // 2, nb - 1):
+            np.testing.assert_allclose(e.transition_probabilities(nid), res.P[nid], rtol=0, atol=1e-12)
+        # value-only evaluation after the derivative one, and back to a homogeneous assignment
+        lnl2, _, _ = e.eval(capi.EVAL_LNL)
+        assert lnl2[0] == lnl[0]
+        e.set_branch_models(0, np.zeros(nn, np.int32))
+        c0 = cases.oracle_eval_nh(c, models, np.zeros(nn, np.int64))
+        lnl3, _, _ = e.eval(capi.EVAL_LNL)
+        assert abs(lnl3[0] - c0.lnl) <= REL * abs(c0.lnl)
+
+
 @pytest.mark.parametrize("name", ["t92", "gtr", "lg08", "yn98", "chr_eigen", "chr_complex", "chr_complex50", "chr_real200",
                                   "chr_complex200", "chr_singular", "nonrev4"])
 def test_pt_batch_interface(name):
