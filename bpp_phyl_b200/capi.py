@@ -143,6 +143,32 @@ def site_patterns(columns):
     return ps[:k].copy(), wt[:k].copy(), ix
 
 
+def site_patterns_device(columns, code_bytes=1, tip_codes=True, device=0):
+    """bppgpu_site_patterns_device: the same compression on the GPU.  ``columns``: uint8 array [n_sites][col_bytes] (for
+    2-byte codes: the little-endian bytes of a uint16 array [n_sites][n_leaves]).  Returns (pattern_site, weights, indices,
+    tip codes [n_leaves][n_patterns] or None)."""
+    cols = np.ascontiguousarray(columns)
+    if cols.dtype == np.uint16:
+        code_bytes = 2
+        cols = cols.view(np.uint8)
+    cols = np.ascontiguousarray(cols, np.uint8)
+    n, w = cols.shape
+    ps = np.empty(n, np.int64)
+    wt = np.empty(n, np.uint32)
+    ix = np.empty(n, np.int64)
+    tip = np.empty(max(n * w, 1), np.uint8) if tip_codes else None
+    npat = C.c_int64(0)
+    _check(lib().bppgpu_site_patterns_device(C.c_int(device), cols.ctypes.data_as(C.POINTER(C.c_uint8)), C.c_int64(n),
+                                             C.c_int32(max(w, 1)), C.c_int32(code_bytes), _ptr(ps, C.c_int64),
+                                             _ptr(wt, C.c_uint32), _ptr(ix, C.c_int64), C.byref(npat),
+                                             None if tip is None else tip.ctypes.data_as(C.c_void_p)))
+    k = npat.value
+    codes = None
+    if tip is not None:
+        codes = tip[:k * w].view(np.uint8 if code_bytes == 1 else np.uint16).reshape(w // code_bytes, k).copy()
+    return ps[:k].copy(), wt[:k].copy(), ix, codes
+
+
 class _ModelHolder:
     """Keeps the numpy buffers a ModelDesc points at alive."""
 

@@ -1,0 +1,208 @@
+// libbppgpu: site-pattern compression on the device (the input side of the hot path).
+//
+// bpp::SitePatterns::SitePatterns (SitePatterns.cpp:52-106) sorts the alignment columns by their character string and merges
+// identical neighbours; bppgpu_site_patterns (engine.cu) is that rule on the host.  Here the same result -- bit for bit: the
+// patterns in memcmp order of their columns, each represented by its first site, weights, site -> pattern indices -- is
+// produced on the GPU, together with the transposed tip codes the engine consumes, so that a 1M-site x 1024-taxon alignment
+// never goes through an O(N log N) string sort on one host core.
+//
+// Integer / byte work, HBM-bound: nothing here is shaped into a GEMM.
+//   1. LSD radix sort of the column permutation, one stable 64-bit pass per 8-byte word of the column from the last word to the
+//      first (keys are the word's bytes in big-endian order so that integer order = memcmp order).  The per-pass sort of
+//      (key, position) pairs is cub::DeviceRadixSort (a library primitive, like cuBLAS for a plain GEMM); the key gather,
+//      run detection, numbering and transposition kernels are below.
+//   2. run heads: column[perm[k]] != column[perm[k-1]] (one warp per pair, early exit), inclusive scan -> pattern number.
+//   3. scatter: indices[site], pattern_site[pattern] (the run head = smallest original position, the sort being stable),
+//      weights[pattern] (integer atomics: order independent).
+//   4. tip codes: tip[leaf][pattern] = column[pattern_site[pattern]][leaf] through a shared-memory tile transpose.
+#include "common.cuh"
+#include "bppgpu.h"
+
+#include <cub/cub.cuh>
+
+#include <algorithm>
+
+namespace bppgpu {
+namespace {
+
+// key of position i in this pass: bytes [8w, 8w+8) of column perm[i], first byte most significant, zero padded past the end
+__global__ void pattern_key_kernel(const uint8_t* __restrict__ cols, const uint32_t* __restrict__ perm, long long n, int col_bytes,
+                                   int word, int aligned8, unsigned long long* __restrict__ keys) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint8_t* c = cols + (size_t)perm[i] * col_bytes + (size_t)word * 8;
+  const int rem = col_bytes - word * 8;
+  unsigned long long k = 0;
+  if (aligned8 && rem >= 8) {
+    const unsigned long long v = *reinterpret_cast<const unsigned long long*>(c);   // little-endian load
+    const unsigned lo = (unsigned)v, hi = (unsigned)(v >> 32);
+    k = ((unsigned long long)__byte_perm(lo, 0, 0x0123) << 32) | (unsigned long long)__byte_perm(hi, 0, 0x0123);
+  } else {
+    for (int b = 0; b < 8; ++b) k = (k << 8) | (unsigned long long)(b < rem ? c[b] : 0);
+  }
+  keys[i] = k;
+}
+
+__global__ void pattern_iota_kernel(uint32_t* perm, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) perm[i] = (uint32_t)i;
+}
+
+// one warp per sorted position k: head[k] = 1 when the column differs from its predecessor (k = 0: always)
+__global__ void pattern_head_kernel(const uint8_t* __restrict__ cols, const uint32_t* __restrict__ perm, long long n, int col_bytes,
+                                    uint32_t* __restrict__ head) {
+  const long long k = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (k >= n) return;
+  if (k == 0) {
+    if (lane == 0) head[0] = 1u;
+    return;
+  }
+  const uint8_t* a = cols + (size_t)perm[k] * col_bytes;
+  const uint8_t* b = cols + (size_t)perm[k - 1] * col_bytes;
+  int differ = 0;
+  for (int o = 0; o < col_bytes; o += 32) {
+    const int j = o + lane;
+    const int d = (j < col_bytes) && (a[j] != b[j]);
+    if (__any_sync(0xffffffffu, d)) { differ = 1; break; }
+  }
+  if (lane == 0) head[k] = (uint32_t)differ;
+}
+
+// number[k] = inclusive scan of head = 1-based pattern number of sorted position k
+__global__ void pattern_scatter_kernel(const uint32_t* __restrict__ perm, const uint32_t* __restrict__ head,
+                                       const uint32_t* __restrict__ number, long long n, long long* __restrict__ pattern_site,
+                                       uint32_t* __restrict__ weights, long long* __restrict__ indices) {
+  const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const uint32_t p = number[k] - 1u;
+  const uint32_t site = perm[k];
+  indices[site] = (long long)p;
+  if (head[k]) pattern_site[p] = (long long)site;
+  atomicAdd(&weights[p], 1u);
+}
+
+// tip[leaf][pattern] = column[pattern_site[pattern]][leaf], elements of eb bytes; 32 x 32 tiles through shared memory so that
+// both the column reads (along the leaf) and the tip-row writes (along the pattern) are contiguous
+template <typename T>
+__global__ void pattern_tip_codes_kernel(const T* __restrict__ cols, const long long* __restrict__ pattern_site, long long np,
+                                         int n_leaves, T* __restrict__ tip) {
+  __shared__ T tile[32][33];
+  const long long p0 = (long long)blockIdx.x * 32;
+  const int l0 = blockIdx.y * 32;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {   // r = pattern within the tile, threadIdx.x = leaf within the tile
+    const long long p = p0 + r;
+    const int l = l0 + threadIdx.x;
+    if (p < np && l < n_leaves) tile[r][threadIdx.x] = cols[(size_t)pattern_site[p] * n_leaves + l];
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {   // r = leaf within the tile, threadIdx.x = pattern within the tile
+    const int l = l0 + r;
+    const long long p = p0 + threadIdx.x;
+    if (p < np && l < n_leaves) tip[(size_t)l * np + p] = tile[threadIdx.x][r];
+  }
+}
+
+struct DevBufs {
+  uint8_t* cols = nullptr;
+  unsigned long long *keys_a = nullptr, *keys_b = nullptr;
+  uint32_t *perm_a = nullptr, *perm_b = nullptr, *head = nullptr, *number = nullptr, *weights = nullptr;
+  long long *pattern_site = nullptr, *indices = nullptr;
+  void* temp = nullptr;
+  uint8_t* tip = nullptr;
+  ~DevBufs() {
+    cudaFree(cols); cudaFree(keys_a); cudaFree(keys_b); cudaFree(perm_a); cudaFree(perm_b); cudaFree(head); cudaFree(number);
+    cudaFree(weights); cudaFree(pattern_site); cudaFree(indices); cudaFree(temp); cudaFree(tip);
+  }
+};
+
+}  // namespace
+}  // namespace bppgpu
+
+using namespace bppgpu;
+
+int bppgpu_site_patterns_device(int device, const uint8_t* columns, int64_t n_sites, int32_t col_bytes, int32_t code_bytes,
+                                int64_t* pattern_site, uint32_t* weights, int64_t* indices, int64_t* n_patterns,
+                                void* tip_codes) {
+  if (n_sites < 0 || col_bytes <= 0 || !n_patterns || (n_sites > 0 && (!columns || !pattern_site || !weights || !indices)))
+    BPP_FAIL(BPPGPU_E_INVALID, "bad argument to bppgpu_site_patterns_device");
+  if (tip_codes && ((code_bytes != 1 && code_bytes != 2) || col_bytes % code_bytes != 0))
+    BPP_FAIL(BPPGPU_E_INVALID, "tip codes need code_bytes 1 or 2 dividing col_bytes");
+  if (n_sites >= (int64_t)1 << 31) BPP_FAIL(BPPGPU_E_INVALID, "more than 2^31 - 1 sites");
+  int ndev = 0;
+  cudaError_t r = cudaGetDeviceCount(&ndev);
+  if (r != cudaSuccess || ndev == 0)
+    BPP_FAIL(BPPGPU_E_CUDA, "no usable CUDA device (%s); libbppgpu has no CPU fallback", r == cudaSuccess ? "device count is 0" : cudaGetErrorString(r));
+  if (device < 0 || device >= ndev) BPP_FAIL(BPPGPU_E_INVALID, "device %d out of range (0..%d)", device, ndev - 1);
+  BPP_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  BPP_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10) BPP_FAIL(BPPGPU_E_CUDA, "device %d is sm_%d%d; libbppgpu is built for sm_100a only", device, prop.major, prop.minor);
+  *n_patterns = 0;
+  if (n_sites == 0) return BPPGPU_OK;
+
+  const long long n = n_sites;
+  const size_t bytes = (size_t)n * (size_t)col_bytes;
+  DevBufs d;
+  BPP_CUDA(cudaMalloc(&d.cols, bytes + 8));   // + 8: the aligned fast path never reads past the end, the slack is for safety
+  BPP_CUDA(cudaMalloc(&d.keys_a, (size_t)n * 8));
+  BPP_CUDA(cudaMalloc(&d.keys_b, (size_t)n * 8));
+  BPP_CUDA(cudaMalloc(&d.perm_a, (size_t)n * 4));
+  BPP_CUDA(cudaMalloc(&d.perm_b, (size_t)n * 4));
+  BPP_CUDA(cudaMalloc(&d.head, (size_t)n * 4));
+  BPP_CUDA(cudaMalloc(&d.number, (size_t)n * 4));
+  BPP_CUDA(cudaMalloc(&d.weights, (size_t)n * 4));
+  BPP_CUDA(cudaMalloc(&d.pattern_site, (size_t)n * 8));
+  BPP_CUDA(cudaMalloc(&d.indices, (size_t)n * 8));
+  size_t temp_sort = 0, temp_scan = 0;
+  BPP_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, temp_sort, d.keys_a, d.keys_b, d.perm_a, d.perm_b, (int)n));
+  BPP_CUDA(cub::DeviceScan::InclusiveSum(nullptr, temp_scan, d.head, d.number, (int)n));
+  const size_t temp_bytes = std::max(temp_sort, temp_scan);
+  BPP_CUDA(cudaMalloc(&d.temp, std::max<size_t>(temp_bytes, 16)));
+
+  cudaStream_t st = 0;
+  BPP_CUDA(cudaMemcpyAsync(d.cols, columns, bytes, cudaMemcpyHostToDevice, st));
+  const unsigned blocks = (unsigned)((n + 255) / 256);
+  pattern_iota_kernel<<<blocks, 256, 0, st>>>(d.perm_a, n);
+  const int nwords = (col_bytes + 7) / 8;
+  const int aligned8 = col_bytes % 8 == 0;
+  uint32_t *pin = d.perm_a, *pout = d.perm_b;
+  for (int w = nwords - 1; w >= 0; --w) {
+    pattern_key_kernel<<<blocks, 256, 0, st>>>(d.cols, pin, n, col_bytes, w, aligned8, d.keys_a);
+    size_t tb = temp_bytes;
+    BPP_CUDA(cub::DeviceRadixSort::SortPairs(d.temp, tb, d.keys_a, d.keys_b, pin, pout, (int)n, 0, 64, st));
+    std::swap(pin, pout);
+  }
+  const uint32_t* perm = pin;   // sorted positions -> original site
+  pattern_head_kernel<<<(unsigned)((n * 32 + 255) / 256), 256, 0, st>>>(d.cols, perm, n, col_bytes, d.head);
+  {
+    size_t tb = temp_bytes;
+    BPP_CUDA(cub::DeviceScan::InclusiveSum(d.temp, tb, d.head, d.number, (int)n, st));
+  }
+  BPP_CUDA(cudaMemsetAsync(d.weights, 0, (size_t)n * 4, st));
+  pattern_scatter_kernel<<<blocks, 256, 0, st>>>(perm, d.head, d.number, n, d.pattern_site, d.weights, d.indices);
+  BPP_CUDA(cudaGetLastError());
+  uint32_t np32 = 0;
+  BPP_CUDA(cudaMemcpyAsync(&np32, d.number + (n - 1), 4, cudaMemcpyDeviceToHost, st));
+  BPP_CUDA(cudaStreamSynchronize(st));
+  const long long np = (long long)np32;
+  BPP_CUDA(cudaMemcpyAsync(pattern_site, d.pattern_site, (size_t)np * 8, cudaMemcpyDeviceToHost, st));
+  BPP_CUDA(cudaMemcpyAsync(weights, d.weights, (size_t)np * 4, cudaMemcpyDeviceToHost, st));
+  BPP_CUDA(cudaMemcpyAsync(indices, d.indices, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+  if (tip_codes) {
+    const int n_leaves = col_bytes / code_bytes;
+    BPP_CUDA(cudaMalloc(&d.tip, (size_t)np * (size_t)col_bytes));
+    const dim3 grid((unsigned)((np + 31) / 32), (unsigned)((n_leaves + 31) / 32)), block(32, 8);
+    if (grid.y > 65535u) BPP_FAIL(BPPGPU_E_INVALID, "too many leaves for the tip-code transpose");
+    if (code_bytes == 1)
+      pattern_tip_codes_kernel<uint8_t><<<grid, block, 0, st>>>(d.cols, d.pattern_site, np, n_leaves, d.tip);
+    else
+      pattern_tip_codes_kernel<uint16_t><<<grid, block, 0, st>>>(reinterpret_cast<const uint16_t*>(d.cols), d.pattern_site, np, n_leaves,
+                                                                 reinterpret_cast<uint16_t*>(d.tip));
+    BPP_CUDA(cudaGetLastError());
+    BPP_CUDA(cudaMemcpyAsync(tip_codes, d.tip, (size_t)np * (size_t)col_bytes, cudaMemcpyDeviceToHost, st));
+  }
+  BPP_CUDA(cudaStreamSynchronize(st));
+  *n_patterns = np;
+  return BPPGPU_OK;
+}

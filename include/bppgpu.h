@@ -63,6 +63,16 @@ int bppgpu_sizeof(int which);
 int bppgpu_site_patterns(const uint8_t* columns, int64_t n_sites, int32_t col_bytes, int64_t* pattern_site,
                          uint32_t* weights, int64_t* indices, int64_t* n_patterns);
 
+/* The same compression on the device: columns are copied to the GPU, sorted there (one stable radix pass per
+ * 8-byte word of the column, last word first), runs of identical columns numbered, and -- optionally -- the tip codes the
+ * engine consumes extracted: tip_codes[l * n_patterns + k] = element l of the column of pattern k (elements of `code_bytes`
+ * = 1 or 2 bytes, col_bytes / code_bytes leaves; caller-allocated, capacity n_sites * col_bytes bytes; NULL to skip), i.e.
+ * row l is what bppgpu_set_tip_codes takes for leaf l.  Results are identical, bit for bit, to bppgpu_site_patterns.
+ * No CPU fallback: BPPGPU_E_CUDA without a usable sm_100a device.                                                   */
+int bppgpu_site_patterns_device(int device, const uint8_t* columns, int64_t n_sites, int32_t col_bytes, int32_t code_bytes,
+                                int64_t* pattern_site, uint32_t* weights, int64_t* indices, int64_t* n_patterns,
+                                void* tip_codes);
+
 /* ---- model descriptor ------------------------------------------------------
  * What bpp::SubstitutionModel exposes (Model/SubstitutionModel.h:468-525):
  * getGenerator, getEigenValues, getIEigenValues, isDiagonalizable,

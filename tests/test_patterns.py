@@ -1,5 +1,6 @@
 """Site-pattern compression (bit-exact integer work): the product's host routine against the oracle's restatement of
-SitePatterns::SitePatterns (SitePatterns.cpp:52-106).  CPU only: no device is needed for this entry point."""
+SitePatterns::SitePatterns (SitePatterns.cpp:52-106): CPU only, no device is needed for that entry point.  GPU part:
+bppgpu_site_patterns_device (radix sort of the columns on the device + tip-code extraction) returns the same arrays bit for bit."""
 import numpy as np
 import pytest
 
@@ -47,3 +48,84 @@ def test_empty_and_all_identical(built_lib):
     cols = np.full((100, 6), ord("A"), np.uint8)
     ps, w, idx = capi.site_patterns(cols)
     assert list(w) == [100] and list(ps) == [0] and not idx.any()
+
+
+def test_device_entry_has_no_cpu_fallback(built_lib):
+    """Without a GPU the device routine refuses (E_CUDA) instead of silently running the host one."""
+    import torch
+    from bpp_phyl_b200 import capi
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(capi.BppGpuError) as ei:
+        capi.site_patterns_device(np.zeros((4, 3), np.uint8))
+    assert ei.value.code == capi.E_CUDA
+
+
+def check_device(cols, code_bytes=1):
+    from bpp_phyl_b200 import capi
+    raw = cols.view(np.uint8) if cols.dtype == np.uint16 else cols
+    ps, w, idx = capi.site_patterns(raw)                        # the host routine (itself held to the oracle above)
+    ps2, w2, idx2, tips = capi.site_patterns_device(cols, code_bytes=code_bytes)
+    np.testing.assert_array_equal(ps2, ps)
+    np.testing.assert_array_equal(w2, w)
+    np.testing.assert_array_equal(idx2, idx)
+    np.testing.assert_array_equal(tips, cols[ps].T)             # row l = bppgpu_set_tip_codes input of leaf l
+    return len(ps)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,ntaxa,nstates,seed", [(1, 3, 4, 0), (2, 1, 2, 1), (500, 5, 2, 2), (5000, 7, 4, 3), (3000, 40, 20, 4),
+                                                   (257, 300, 4, 5), (4000, 8, 2, 6), (2500, 16, 3, 7), (1000, 33, 4, 8),
+                                                   (70000, 64, 4, 9)])
+def test_device_patterns_equal_host_patterns(built_lib, n, ntaxa, nstates, seed):
+    rng = np.random.default_rng(seed)
+    alphabet = np.frombuffer(b"ACGTRYKMSWBDHVN-?XQZ", np.uint8)[:nstates]
+    cols = alphabet[rng.integers(nstates, size=(n, ntaxa))]
+    check_device(cols)
+    # realistic redundancy: few distinct columns, many repeats, bytes above 127 (unsigned comparison like memcmp)
+    base = rng.integers(0, 256, size=(max(2, n // 50), ntaxa)).astype(np.uint8)
+    cols = base[rng.integers(len(base), size=n)]
+    assert check_device(cols) <= len(base)
+
+
+@pytest.mark.gpu
+def test_device_patterns_reference_alignment_two_byte_codes_and_edges(built_lib):
+    from bpp_phyl_b200 import capi
+    seqs = ["AAATGGCTGTGCACGTC", "GACTGGATCTGCACGTC", "CTCTGGATGTGCACGTG", "AAATGGCGGTGCGCCTA"]
+    cols = _cols(seqs)
+    ps, w, idx, tips = capi.site_patterns_device(cols)
+    assert ["".join(chr(x) for x in cols[i]) for i in ps] == ["AAAG", "AATA", "ACCA", "AGCA", "CAAC", "CCCC", "CCGA",
+                                                               "GCGG", "GGGC", "GGGG", "TTTG", "TTTT"]
+    assert int(w.sum()) == 17
+    rng = np.random.default_rng(3)
+    cols16 = rng.integers(0, 700, size=(3000, 21)).astype(np.uint16)          # chromosome-style counts above 255
+    cols16[rng.integers(3000, size=1500)] = cols16[rng.integers(3000, size=1500)]
+    check_device(cols16)
+    ps, w, idx, tips = capi.site_patterns_device(np.zeros((0, 4), np.uint8))
+    assert len(ps) == 0 and len(w) == 0
+    allsame = np.full((1000, 9), ord("A"), np.uint8)
+    ps, w, idx, tips = capi.site_patterns_device(allsame)
+    assert list(w) == [1000] and list(ps) == [0] and not idx.any() and tips.shape == (9, 1)
+
+
+@pytest.mark.gpu
+def test_device_patterns_feed_the_engine(built_lib):
+    """Ingestion straight to tip codes: the device routine's rows go to bppgpu_set_tip_codes unchanged and the evaluation
+    equals the one fed by the oracle's compression."""
+    import cases
+    from bpp_phyl_b200 import capi
+    from oracle import ref_models as rm
+    r, p = rm.gamma_rates(4, 0.5)
+    m = rm.gtr(1.2, 0.8, 0.6, 1.5, 0.9, (.3, .2, .25, .25))
+    c = cases.make_case(12, 3000, m, r, p, seed=5, compress=False)                # one column per site
+    cols = np.stack([c.codes_by_leaf[l] for l in c.flat.leaf_ids], axis=1)      # [site][leaf]
+    ps, w, idx, tips = capi.site_patterns_device(cols)
+    c2 = cases.make_case(12, 3000, m, r, p, seed=5, compress=True)
+    assert len(ps) == c2.N
+    np.testing.assert_array_equal(w, c2.weights)
+    res = cases.oracle_eval(c2)
+    c.N, c.weights = len(ps), w
+    c.codes_by_leaf = {l: np.ascontiguousarray(tips[k]) for k, l in enumerate(c.flat.leaf_ids)}
+    with cases.make_engine(c) as e:
+        lnl, _, _ = e.eval(capi.EVAL_LNL)
+    assert abs(lnl[0] - res.lnl) <= 1e-9 * abs(res.lnl)
