@@ -1,0 +1,39 @@
+"""Times the site-pattern compression (SitePatterns.cpp:52-106) of one synthetic alignment on the host routine
+(bppgpu_site_patterns: std::sort + memcmp, one core -- what the reference does) and on the device routine
+(bppgpu_site_patterns_device, H2D copy of the columns and D2H copy of every output included), checks that the
+outputs are identical and prints one JSON line.   python tools/bench_patterns.py [n_sites] [n_taxa]"""
+import json
+import pathlib
+import sys
+import time
+
+import numpy as np
+
+sys.path.insert(0, str(pathlib.Path(__file__).resolve().parent.parent))
+from bpp_phyl_b200 import capi  # noqa: E402
+
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 1_000_000
+taxa = int(sys.argv[2]) if len(sys.argv) > 2 else 1024
+rng = np.random.default_rng(20260104)
+# columns that share long prefixes, like a real alignment: one ancestral character per site, 4 % of the cells mutated,
+# and a pool of sites 4x smaller than the alignment so that most patterns repeat
+pool = max(1, n // 4)
+base = rng.integers(4, size=pool, dtype=np.uint8)
+cols = np.repeat(base[:, None], taxa, axis=1)
+mut = rng.random((pool, taxa), dtype=np.float32) < 0.04
+cols[mut] = rng.integers(4, size=int(mut.sum()), dtype=np.uint8)
+cols = np.frombuffer(b"ACGT", np.uint8)[cols][rng.integers(pool, size=n)]
+cols = np.ascontiguousarray(cols)
+
+capi.site_patterns_device(cols[:1000])                 # context + module load outside the timed region
+t0 = time.perf_counter()
+ps_d, w_d, ix_d, tips = capi.site_patterns_device(cols)
+t_dev = time.perf_counter() - t0
+t0 = time.perf_counter()
+ps_h, w_h, ix_h = capi.site_patterns(cols)
+t_host = time.perf_counter() - t0
+same = bool(np.array_equal(ps_d, ps_h) and np.array_equal(w_d, w_h) and np.array_equal(ix_d, ix_h)
+            and np.array_equal(tips, cols[ps_h].T))
+print(json.dumps({"workload": "site patterns %d sites x %d taxa" % (n, taxa), "n_patterns": int(len(ps_h)),
+                  "host_s": round(t_host, 4), "device_s_incl_copies": round(t_dev, 4),
+                  "alignment_bytes": int(cols.nbytes), "identical": same}))
