@@ -322,6 +322,13 @@ class Engine:
         _check(lib().bppgpu_get_marginal_posteriors(self._h, C.c_int32(point), C.c_int32(node), _ptr(post), _ptr(jt)))
         return post, jt
 
+    def ml_ancestral_states(self, point=0):
+        """MLAncestralStateReconstruction: (states [n_nodes][N] int32, log joint likelihood of the best assignment [N])"""
+        st = np.empty((self.nn, self.N), np.int32)
+        best = np.empty(self.N)
+        _check(lib().bppgpu_ml_ancestral_states(self._h, C.c_int32(point), _ptr(st, C.c_int32), _ptr(best)))
+        return st, best
+
     def root_reparam_derivatives(self, point=0):
         """(d lnL/d BrLenRoot, d lnL/d RootPosition, d2 lnL/d BrLenRoot^2, d2 lnL/d RootPosition^2) after an eval with D2"""
         out = np.zeros(4)

@@ -338,6 +338,118 @@ __global__ void marginal_posterior_kernel(MarginalParams p) {
 }
 
 
+// ---- joint ML ancestral reconstruction (fork) ------------------------------------------------------------------------------
+// MLAncestralStateReconstruction (Likelihood/MLAncestralStateReconstruction.cpp:6-188; leaf arrays
+// DRASRTreeLikelihoodData.cpp:265-300): Pupko's max-product recursion.  Per (pattern i, class c), indexed by the FATHER's state x:
+//   leaf with observed state s (the first state whose init value is 1):  L[x] = P[c][x][s],  anc[x] = s
+//       (no such state -- composite / probabilistic tips: L[x] = 1, anc[x] = 0, as the reference leaves them)
+//   internal node:   L[x] = max_y P[c][x][y] prod_sons L_son[y],  anc[x] = the first y reaching the (positive) maximum
+//   root:            L[x] = pi_x prod_sons L_son[x]
+// anc is the table of the LAST class (the reference overwrites it class after class); the root's state is the first maximum of
+// class 0 (:151-160).  The reference has no rescaling and underflows to 0 on large trees; here every (i, c) row carries a
+// power-of-two exponent (max-product is invariant under a per-row scale), so the tables equal the reference's wherever it is
+// finite.  One warp per (pattern, class) row; accessor-grade CUDA-core kernels.
+struct MLNodeParams {
+  int kind;                  // 0 leaf, 1 internal, 2 root
+  int S, C, code_bytes, nson;
+  long long N;
+  const double* P;           // [C][S][S] of this node's branch (leaf, internal)
+  const void* codes;         // leaf
+  const double* code_table;
+  const double* son_L[4];    // [N][C][S] of every son (internal, root)
+  const int* son_E[4];
+  const double* rootfreq;
+  double* L;                 // [N][C][S]
+  int* E;                    // [N][C]
+  unsigned short* anc;       // [N][S]  (leaf, internal)
+};
+
+__global__ void ml_node_kernel(MLNodeParams p) {
+  extern __shared__ double ml_sm[];        // [warps per block][S]
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + wib;
+  if (row >= p.N * p.C) return;
+  const int S = p.S;
+  const int c = (int)(row % p.C);
+  const long long i = row / p.C;
+  double* prod = ml_sm + (size_t)wib * S;
+  double* Lrow = p.L + (size_t)row * S;
+  const bool last_class = c == p.C - 1;
+  if (p.kind == 0) {
+    const int code = p.code_bytes == 1 ? (int)((const unsigned char*)p.codes)[i] : (int)((const unsigned short*)p.codes)[i];
+    const double* t = p.code_table + (size_t)code * S;
+    int s = -1;
+    for (int y = 0; y < S; ++y)
+      if (t[y] == 1.0) { s = y; break; }
+    const double* Pc = p.P + (size_t)c * S * S;
+    for (int x = lane; x < S; x += 32) {
+      Lrow[x] = s >= 0 ? Pc[(size_t)x * S + s] : 1.0;
+      if (last_class) p.anc[(size_t)i * S + x] = (unsigned short)(s >= 0 ? s : 0);
+    }
+    if (lane == 0) p.E[row] = 0;
+    return;
+  }
+  int e = 0;
+  for (int j = 0; j < p.nson; ++j) e += p.son_E[j][row];
+  for (int y = lane; y < S; y += 32) {
+    double v = p.son_L[0][(size_t)row * S + y];
+    for (int j = 1; j < p.nson; ++j) v *= p.son_L[j][(size_t)row * S + y];
+    prod[y] = v;
+  }
+  __syncwarp();
+  double mx = 0.0;
+  if (p.kind == 2) {
+    for (int x = lane; x < S; x += 32) {
+      const double v = p.rootfreq[x] * prod[x];
+      Lrow[x] = v;
+      mx = fmax(mx, v);
+    }
+  } else {
+    const double* Pc = p.P + (size_t)c * S * S;
+    for (int x = lane; x < S; x += 32) {
+      double best = 0.0;
+      int arg = 0;
+      const double* Px = Pc + (size_t)x * S;
+      for (int y = 0; y < S; ++y) {
+        const double v = prod[y] * Px[y];
+        if (v > best) { best = v; arg = y; }
+      }
+      Lrow[x] = best;
+      if (last_class) p.anc[(size_t)i * S + x] = (unsigned short)arg;
+      mx = fmax(mx, best);
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  const int mh = hi_word(mx);
+  if (mx > 0.0 && mh < kScaleThresholdHi && mh >= (1 << 20)) {   // same rule as the pruning kernels
+    const int k = rescale_shift(mh);
+    const double f = pow2(k);
+    for (int x = lane; x < S; x += 32) Lrow[x] *= f;            // each lane re-reads what it wrote
+    e += k;
+  }
+  if (lane == 0) p.E[row] = e;
+}
+
+// state of the root: first maximum of class 0 (:151-160); best_lnl = log of that joint likelihood.  thread = pattern
+__global__ void ml_root_state_kernel(const double* L, const int* E, int S, int C, long long N, int* state, double* best_lnl) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  const double* l = L + (size_t)i * C * S;
+  double best = 0.0;
+  int arg = 0;
+  for (int x = 0; x < S; ++x)
+    if (l[x] > best) { best = l[x]; arg = x; }
+  state[i] = arg;
+  if (best_lnl) best_lnl[i] = log(best) - E[(size_t)i * C] * kLn2;
+}
+
+// trace back: state[node][i] = anc[node][i][state[father][i]] (:162-167; a leaf's table is constant in the father's state)
+__global__ void ml_traceback_kernel(const unsigned short* anc, const int* father_state, int S, long long N, int* state) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < N) state[i] = (int)anc[(size_t)i * S + father_state[i]];
+}
+
+
 // ---- BrLenRoot / RootPosition (re-parametrised root branches of a rooted tree) ---------------------------------------------
 // DRNonHomogeneousTreeLikelihood::getFirstOrderDerivative / getSecondOrderDerivative for the two parameters that replace the
 // root branches l1 = len * pos, l2 = len * (1 - pos) (Likelihood/DRNonHomogeneousTreeLikelihood.cpp:445-478, :576-867;

@@ -1896,6 +1896,96 @@ int bppgpu_get_marginal_posteriors(bppgpu_engine* e, int32_t point, int32_t node
   return BPPGPU_OK;
 }
 
+int bppgpu_ml_ancestral_states(bppgpu_engine* e, int32_t point, int32_t* states, double* best_lnl) {
+  ENGINE_ENTER(e);
+  if (!states) BPP_FAIL(BPPGPU_E_INVALID, "null states");
+  if (e->path == PATH_POINTS) BPP_FAIL(BPPGPU_E_STATE, "not available on the batched-points path");
+  if (e->last_want == 0) BPP_FAIL(BPPGPU_E_STATE, "no evaluation yet (the transition probabilities of the last evaluation are used)");
+  if (point != e->last_point) BPP_FAIL(BPPGPU_E_STATE, "tables resident are those of point %d", e->last_point);
+  const int S = e->S, C = e->C, nn = e->nn;
+  const long long N = e->N;
+  if (S > 65535) BPP_FAIL(BPPGPU_E_INVALID, "more than 65535 states");
+  for (int n = 0; n < nn; ++n)
+    if (e->child_off[n + 1] - e->child_off[n] > 4) BPP_FAIL(BPPGPU_E_INVALID, "node %d has more than 4 sons", n);
+  if (N == 0) return BPPGPU_OK;
+  const size_t clvn = (size_t)N * C * S, rows = (size_t)N * C;
+  // slabs: the arrays of a node live until its father is done; the traceback tables of every node stay
+  std::vector<double*> L(nn, nullptr);
+  std::vector<int*> E(nn, nullptr);
+  std::vector<double*> freeL;
+  std::vector<int*> freeE;
+  unsigned short* d_anc = nullptr;
+  int* d_state = nullptr;
+  double* d_best = nullptr;
+  auto cleanup = [&]() {
+    for (double* q : L) cudaFree(q);
+    for (int* q : E) cudaFree(q);
+    for (double* q : freeL) cudaFree(q);
+    for (int* q : freeE) cudaFree(q);
+    cudaFree(d_anc); cudaFree(d_state); cudaFree(d_best);
+    cudaGetLastError();
+  };
+#define ML_TRY(expr)                                                                         \
+  do {                                                                                       \
+    cudaError_t _r = (expr);                                                                 \
+    if (_r != cudaSuccess) {                                                                 \
+      cleanup();                                                                             \
+      BPP_FAIL(_r == cudaErrorMemoryAllocation ? BPPGPU_E_NOMEM : BPPGPU_E_CUDA,            \
+               "joint ML reconstruction: %s", cudaGetErrorString(_r));                       \
+    }                                                                                        \
+  } while (0)
+  ML_TRY(cudaMalloc(&d_anc, (size_t)nn * N * S * sizeof(unsigned short)));
+  ML_TRY(cudaMalloc(&d_state, (size_t)nn * N * sizeof(int)));
+  if (best_lnl) ML_TRY(cudaMalloc(&d_best, (size_t)N * 8));
+  cudaStream_t st = e->stream;
+  const int pl = point % e->pchunk;
+  const int wpb = 4;   // warps (rows) per block
+  const unsigned grid = (unsigned)((rows + wpb - 1) / wpb);
+  const size_t smem = (size_t)wpb * S * sizeof(double);
+  for (int k = nn - 1; k >= 0; --k) {   // reverse pre-order: sons before fathers
+    const int n = e->preorder[k];
+    if (!freeL.empty()) { L[n] = freeL.back(); freeL.pop_back(); E[n] = freeE.back(); freeE.pop_back(); }
+    else { ML_TRY(cudaMalloc(&L[n], clvn * 8)); ML_TRY(cudaMalloc(&E[n], rows * 4)); }
+    MLNodeParams mp{};
+    const bool leaf = e->leaf_slot[n] >= 0;
+    mp.kind = leaf ? 0 : (n == e->root ? 2 : 1);
+    mp.S = S; mp.C = C; mp.code_bytes = e->code_bytes; mp.N = N;
+    mp.P = e->d_P + ((size_t)pl * nn + n) * C * S * S;
+    mp.code_table = e->d_code_table;
+    mp.rootfreq = e->d_rootfreq_used + (size_t)point * S;
+    if (leaf) mp.codes = (const char*)e->d_codes + (size_t)e->leaf_slot[n] * N * e->code_bytes;
+    mp.nson = e->child_off[n + 1] - e->child_off[n];
+    for (int j = 0; j < mp.nson; ++j) {
+      const int sn = e->children[e->child_off[n] + j];
+      mp.son_L[j] = L[sn];
+      mp.son_E[j] = E[sn];
+    }
+    mp.L = L[n]; mp.E = E[n];
+    mp.anc = d_anc + (size_t)n * N * S;
+    ml_node_kernel<<<grid, wpb * 32, smem, st>>>(mp);
+    ML_TRY(cudaGetLastError());
+    for (int j = 0; j < mp.nson; ++j) {   // stream order keeps the slab valid until the kernel above has read it
+      const int sn = e->children[e->child_off[n] + j];
+      freeL.push_back(L[sn]); freeE.push_back(E[sn]);
+      L[sn] = nullptr; E[sn] = nullptr;
+    }
+  }
+  const unsigned gridN = (unsigned)((N + 127) / 128);
+  ml_root_state_kernel<<<gridN, 128, 0, st>>>(L[e->root], E[e->root], S, C, N, d_state + (size_t)e->root * N, d_best);
+  for (int k = 0; k < nn; ++k) {   // fathers before sons
+    const int n = e->preorder[k];
+    if (n == e->root) continue;
+    ml_traceback_kernel<<<gridN, 128, 0, st>>>(d_anc + (size_t)n * N * S, d_state + (size_t)e->parent[n] * N, S, N, d_state + (size_t)n * N);
+  }
+  ML_TRY(cudaGetLastError());
+  ML_TRY(cudaMemcpyAsync(states, d_state, (size_t)nn * N * sizeof(int), cudaMemcpyDeviceToHost, st));
+  if (best_lnl) ML_TRY(cudaMemcpyAsync(best_lnl, d_best, (size_t)N * 8, cudaMemcpyDeviceToHost, st));
+  ML_TRY(cudaStreamSynchronize(st));
+#undef ML_TRY
+  cleanup();
+  return BPPGPU_OK;
+}
+
 int bppgpu_get_root_reparam_derivatives(bppgpu_engine* e, int32_t point, double out[4]) {
   ENGINE_ENTER(e);
   if (!out) BPP_FAIL(BPPGPU_E_INVALID, "null out");

@@ -26,6 +26,7 @@
 #include <cstring>
 #include <map>
 #include <memory>
+#include <random>
 #include <sstream>
 #include <stdexcept>
 #include <string>
@@ -1571,6 +1572,7 @@ class AbstractHomogeneousTreeLikelihood {
         brLen_[(size_t)root2_] = len * (1.0 - pos);
         continue;
       }
+      if (applyBranchParameter(p.name, p.value)) continue;
       const int b = brlenIndex(p.name);
       if (b >= 0) brLen_[(size_t)b] = std::min(std::max(p.value, minimumBrLen_), maximumBrLen_);
       else {
@@ -1601,6 +1603,73 @@ class AbstractHomogeneousTreeLikelihood {
         for (size_t y = 0; y < S; ++y) p[c][x][y] = buf[(c * S + x) * S + y];
     return p;
   }
+  // ---- DiscreteRatesAcrossSitesTreeLikelihood accessors (DiscreteRatesAcrossSitesTreeLikelihood.h:70-203) ---------------------------
+  // All of them read the root arrays of the last evaluation (DRHomogeneousTreeLikelihood.cpp:203-227: rootSiteLikelihoods_[i][c] =
+  // sum_x pi_x rootLikelihoods_[i][c][x]); they stay on the device until one of these is called, then come back once, scaled:
+  // true value = array * 2^-exponent, and everything below is combined in log space so that sites under 1e-308 stay finite.
+  double getLogLikelihoodForASiteForARateClass(size_t site, size_t rateClass) const {
+    ensureRootArrays();
+    return rootLogS_[(size_t)siteIndex_[site] * getNumberOfClasses() + rateClass];
+  }
+  double getLikelihoodForASiteForARateClass(size_t site, size_t rateClass) const { return std::exp(getLogLikelihoodForASiteForARateClass(site, rateClass)); }
+  double getLogLikelihoodForASiteForARateClassForAState(size_t site, size_t rateClass, int state) const {
+    ensureRootArrays();
+    const size_t C = getNumberOfClasses(), S = getNumberOfStates(), row = (size_t)siteIndex_[site] * C + rateClass;
+    return std::log(rootL_[row * S + (size_t)state]) - rootExp_[row] * 0.693147180559945309417232121458;
+  }
+  double getLikelihoodForASiteForARateClassForAState(size_t site, size_t rateClass, int state) const {
+    ensureRootArrays();
+    const size_t C = getNumberOfClasses(), S = getNumberOfStates(), row = (size_t)siteIndex_[site] * C + rateClass;
+    return std::ldexp(rootL_[row * S + (size_t)state], -rootExp_[row]);
+  }
+  // AbstractDiscreteRatesAcrossSitesTreeLikelihood.cpp:110-133: sum_c p_c L[site][c][state]
+  double getLikelihoodForASiteForAState(size_t site, int state) const {
+    double l = 0;
+    for (size_t c = 0; c < getNumberOfClasses(); ++c) l += getLikelihoodForASiteForARateClassForAState(site, c, state) * rDist_->getProbability(c);
+    return l;
+  }
+  double getLogLikelihoodForASiteForAState(size_t site, int state) const { return std::log(getLikelihoodForASiteForAState(site, state)); }
+  VVdouble getLikelihoodForEachSiteForEachRateClass() const { return eachSiteEachClass(false); }       // :92-106
+  VVdouble getLogLikelihoodForEachSiteForEachRateClass() const { return eachSiteEachClass(true); }     // :137-151
+  VVVdouble getLikelihoodForEachSiteForEachRateClassForEachState() const { return eachSiteEachClassEachState(false); }     // :155-174
+  VVVdouble getLogLikelihoodForEachSiteForEachRateClassForEachState() const { return eachSiteEachClassEachState(true); }   // :178-197
+  // :201-215  pb[i][c] = L[i][c] p_c / L[i]
+  VVdouble getPosteriorProbabilitiesOfEachRate() const {
+    ensureRootArrays();
+    const size_t C = getNumberOfClasses();
+    VVdouble pb(siteIndex_.size(), Vdouble(C));
+    for (size_t i = 0; i < pb.size(); ++i) {
+      const size_t k = (size_t)siteIndex_[i];
+      for (size_t c = 0; c < C; ++c) pb[i][c] = std::exp(rootLogS_[k * C + c] - siteLnl_[k]) * rDist_->getProbability(c);
+    }
+    return pb;
+  }
+  // :219-234  sum_c (L[i][c] / L[i]) p_c r_c
+  Vdouble getPosteriorRateOfEachSite() const {
+    const VVdouble pb = getPosteriorProbabilitiesOfEachRate();
+    Vdouble rates(pb.size(), 0.0);
+    for (size_t i = 0; i < pb.size(); ++i)
+      for (size_t c = 0; c < pb[i].size(); ++c) rates[i] += pb[i][c] * rDist_->getCategory(c);
+    return rates;
+  }
+  // :238-248  whichMax of L[i][.] (first maximum; NOT weighted by p_c, like the reference)
+  std::vector<size_t> getRateClassWithMaxPostProbOfEachSite() const {
+    ensureRootArrays();
+    const size_t C = getNumberOfClasses();
+    std::vector<size_t> classes(siteIndex_.size(), 0);
+    for (size_t i = 0; i < classes.size(); ++i) {
+      const double* l = &rootLogS_[(size_t)siteIndex_[i] * C];
+      for (size_t c = 1; c < C; ++c) if (l[c] > l[classes[i]]) classes[i] = c;
+    }
+    return classes;
+  }
+  Vdouble getRateWithMaxPostProbOfEachSite() const {   // :252-262
+    const std::vector<size_t> cl = getRateClassWithMaxPostProbOfEachSite();
+    Vdouble rates(cl.size());
+    for (size_t i = 0; i < cl.size(); ++i) rates[i] = rDist_->getCategory(cl[i]);
+    return rates;
+  }
+
   // DRTreeLikelihood::computeLikelihoodAtNode-style access to the device-resident conditional likelihoods of an internal
   // node (subtree below it): true value = likelihoodArray[i][c][x] * 2^-scale[i][c]
   void getLikelihoodArray(int nodeId, VVVdouble& likelihoodArray, std::vector<std::vector<int> >& scale) const {
@@ -1683,6 +1752,19 @@ class AbstractHomogeneousTreeLikelihood {
             for (size_t y = 0; y < S; ++y) (*joint)[i][x][y] = jb[(i * S + x) * S + y];
     }
   }
+  // MLAncestralStateReconstruction's result (fork): states[node][distinct site] of the joint ML assignment, computed on the
+  // device with the transition probabilities and root frequencies of the last evaluation; bestLogLik[i] = its log joint likelihood
+  void getJointMLAncestralStates(std::vector<std::vector<size_t> >& states, Vdouble* bestLogLik = nullptr) const {
+    requireInit();
+    const size_t N = (size_t)nPatterns_, nn = nodes_.size();
+    std::vector<int32_t> buf(nn * N);
+    Vdouble best(N);
+    check(bppgpu_ml_ancestral_states(engine_, 0, buf.data(), best.data()), "MLAncestralStateReconstruction");
+    states.assign(nn, std::vector<size_t>(N));
+    for (size_t n = 0; n < nn; ++n)
+      for (size_t i = 0; i < N; ++i) states[n][i] = (size_t)buf[n * N + i];
+    if (bestLogLik) *bestLogLik = best;
+  }
   std::vector<int> getNodesId() const {
     std::vector<int> ids;
     for (const Node* n : nodes_) ids.push_back(n->getId());
@@ -1763,6 +1845,8 @@ class AbstractHomogeneousTreeLikelihood {
     uploadModel();
   }
 
+  // hook for classes whose branch lengths are functions of other parameters (clock heights): true = name consumed
+  virtual bool applyBranchParameter(const std::string&, double) { return false; }
   virtual Vdouble rootFrequencies() const { return modelSet_ ? modelSet_->getRootFrequencies() : model_->getFrequencies(); }
 
   virtual void uploadModel() {
@@ -1802,6 +1886,7 @@ class AbstractHomogeneousTreeLikelihood {
     check(bppgpu_get_site_lnl(engine_, 0, siteLnl_.data()), "getLogLikelihoodForEachSite");
     if (engineFlags_ & BPPGPU_FLAG_WEIGHTED_ROOT) check(bppgpu_get_root_freqs(engine_, 0, rootFreqs_.data()), "getRootFrequencies");
     derivsValid_ = false;
+    rootArraysValid_ = false;
   }
 
   // the prefix (upper) arrays exist after an evaluation with derivatives
@@ -1847,6 +1932,43 @@ class AbstractHomogeneousTreeLikelihood {
     return (int)i;
   }
   void requireInit() const { if (!initialized_) throw Exception("Instance is not initialized."); }
+  // root arrays of the last evaluation: rootL_[i][c][x] (scaled), rootExp_[i][c], rootLogS_[i][c] = log sum_x pi_x L - exp ln 2
+  void ensureRootArrays() const {
+    requireInit();
+    if (rootArraysValid_) return;
+    const size_t S = getNumberOfStates(), C = getNumberOfClasses(), N = (size_t)nPatterns_;
+    rootL_.resize(N * C * S);
+    std::vector<int32_t> ex(N * C);
+    check(bppgpu_get_clv(engine_, 0, (int32_t)nodes_.size() - 1, 0, rootL_.data(), ex.data()), "getRootLikelihoodArray");
+    rootExp_.assign(ex.begin(), ex.end());
+    rootLogS_.resize(N * C);
+    for (size_t r = 0; r < N * C; ++r) {
+      double s = 0;
+      for (size_t x = 0; x < S; ++x) s += rootFreqs_[x] * rootL_[r * S + x];
+      rootLogS_[r] = std::log(s) - rootExp_[r] * 0.693147180559945309417232121458;
+    }
+    rootArraysValid_ = true;
+  }
+  VVdouble eachSiteEachClass(bool logs) const {
+    ensureRootArrays();
+    const size_t C = getNumberOfClasses();
+    VVdouble l(siteIndex_.size(), Vdouble(C));
+    for (size_t i = 0; i < l.size(); ++i)
+      for (size_t c = 0; c < C; ++c) {
+        const double v = rootLogS_[(size_t)siteIndex_[i] * C + c];
+        l[i][c] = logs ? v : std::exp(v);
+      }
+    return l;
+  }
+  VVVdouble eachSiteEachClassEachState(bool logs) const {
+    const size_t C = getNumberOfClasses(), S = getNumberOfStates();
+    VVVdouble l(siteIndex_.size(), VVdouble(C, Vdouble(S)));
+    for (size_t i = 0; i < l.size(); ++i)
+      for (size_t c = 0; c < C; ++c)
+        for (size_t x = 0; x < S; ++x)
+          l[i][c][x] = logs ? getLogLikelihoodForASiteForARateClassForAState(i, c, (int)x) : getLikelihoodForASiteForARateClassForAState(i, c, (int)x);
+    return l;
+  }
 
   std::unique_ptr<Tree> tree_;
   SubstitutionModel* model_;      // not owned (like the reference)
@@ -1865,6 +1987,9 @@ class AbstractHomogeneousTreeLikelihood {
   Vdouble siteLnl_, rootFreqs_;
   mutable Vdouble d1_, d2_;
   mutable bool derivsValid_;
+  mutable bool rootArraysValid_ = false;
+  mutable Vdouble rootL_, rootLogS_;
+  mutable std::vector<int> rootExp_;
   long numOfLikelihoodCalculations_;
   int nPoints_ = 1;  // parameter points evaluated per device call (LikelihoodPointBatch)
   bool reparametrizeRoot_ = false;  // BrLenRoot / RootPosition replace the two root branches (NH classes, rooted trees)
@@ -1881,6 +2006,77 @@ class RHomogeneousTreeLikelihood : public AbstractHomogeneousTreeLikelihood {
     (void)verbose; (void)usePatterns;
     setData(data);
   }
+};
+// Likelihood/RHomogeneousClockTreeLikelihood.{h,cpp}: the same likelihood with the branch lengths of a rooted, bifurcating tree
+// driven by node heights -- "TotalHeight" (height of the root: the longest path to a leaf, TreeTemplateTools::getHeights,
+// TreeTemplateTools.cpp:173-186) and "HeightP<id>" (height / father's height) for every internal non-root node
+// (initBranchLengthsParameters :121-157, computeBranchLengthsFromHeights :161-179, minimum branch length 0 :87).  No branch
+// derivatives (getDerivableParameters is empty, :183-187).
+class RHomogeneousClockTreeLikelihood : public RHomogeneousTreeLikelihood {
+ public:
+  RHomogeneousClockTreeLikelihood(const Tree& tree, const VectorSiteContainer& data, SubstitutionModel* model, DiscreteDistribution* rDist,
+                                  bool checkRooted = true, bool verbose = true, int device = 0)
+      : RHomogeneousTreeLikelihood(tree, data, model, rDist, false, verbose, true, device) {
+    (void)checkRooted;
+    if (!tree_->isRooted()) throw Exception("RHomogeneousClockTreeLikelihood::init_(). Tree is unrooted!");
+    for (const Node* n : nodes_)
+      if (n->getNumberOfSons() > 2) throw Exception("HomogeneousClockTreeLikelihood::init_(). Tree is multifurcating.");
+    minimumBrLen_ = 0.0;
+    std::vector<double> h(nodes_.size(), 0.0);
+    for (size_t i = 0; i < nodes_.size(); ++i)   // post-order: sons first
+      for (size_t k = 0; k < nodes_[i]->getNumberOfSons(); ++k) {
+        const int s = nodes_[i]->getSon(k)->getId();
+        h[i] = std::max(h[i], h[(size_t)s] + brLen_[(size_t)s]);
+      }
+    totalHeight_ = h.back();
+    for (size_t i = 0; i + 1 < nodes_.size(); ++i)
+      if (!nodes_[i]->isLeaf()) heightP_[(int)i] = h[i] / h[(size_t)nodes_[i]->getFather()->getId()];
+    computeBranchLengthsFromHeights(nodes_.back(), totalHeight_);
+  }
+  ParameterList getBranchLengthsParameters() const {
+    ParameterList pl;
+    pl.push_back({"TotalHeight", totalHeight_});
+    for (const auto& kv : heightP_) pl.push_back({"HeightP" + std::to_string(kv.first), kv.second});
+    return pl;
+  }
+  double getParameterValue(const std::string& name) const {
+    if (name == "TotalHeight") return totalHeight_;
+    if (name.compare(0, 7, "HeightP") == 0) {
+      std::map<int, double>::const_iterator it = heightP_.find(std::atoi(name.c_str() + 7));
+      if (it != heightP_.end()) return it->second;
+    }
+    throw ParameterNotFoundException("ParameterNotFoundException: " + name);
+  }
+  ParameterList getDerivableParameters() const { requireInit(); return ParameterList(); }
+  double getFirstOrderDerivative(const std::string& variable) const {
+    throw Exception("RHomogeneousClockTreeLikelihood: no derivative with respect to " + variable + " (all parameters are non-derivable).");
+  }
+  double getSecondOrderDerivative(const std::string& variable) const { return getFirstOrderDerivative(variable); }
+
+ protected:
+  bool applyBranchParameter(const std::string& name, double value) override {
+    if (name == "TotalHeight") totalHeight_ = value;
+    else if (name.compare(0, 7, "HeightP") == 0 && heightP_.count(std::atoi(name.c_str() + 7))) heightP_[std::atoi(name.c_str() + 7)] = value;
+    else if (name.compare(0, 5, "BrLen") == 0) throw ParameterNotFoundException("ParameterNotFoundException: " + name);
+    else return false;
+    computeBranchLengthsFromHeights(nodes_.back(), totalHeight_);
+    return true;
+  }
+
+ private:
+  void computeBranchLengthsFromHeights(const Node* node, double height) {
+    for (size_t i = 0; i < node->getNumberOfSons(); ++i) {
+      const Node* son = node->getSon(i);
+      if (son->isLeaf()) brLen_[(size_t)son->getId()] = std::max(minimumBrLen_, height);
+      else {
+        const double sonHeight = heightP_.at(son->getId()) * height;
+        brLen_[(size_t)son->getId()] = std::max(minimumBrLen_, height - sonHeight);
+        computeBranchLengthsFromHeights(son, sonHeight);
+      }
+    }
+  }
+  double totalHeight_ = 0;
+  std::map<int, double> heightP_;
 };
 // Likelihood/DRHomogeneousTreeLikelihood.h
 class DRHomogeneousTreeLikelihood : public AbstractHomogeneousTreeLikelihood {
@@ -2022,6 +2218,8 @@ class LikelihoodPointBatch : public AbstractHomogeneousTreeLikelihood {
     numOfLikelihoodCalculations_ += (long)models_.size();
     for (size_t k = 0; k < models_.size(); ++k) values_[k] = -lnl[k];
     minusLogLik_ = values_[0];
+    derivsValid_ = false;
+    rootArraysValid_ = false;
   }
 
  private:
@@ -2077,6 +2275,106 @@ class RHomogeneousMixedTreeLikelihood : public LikelihoodPointBatch {
   }
   Vdouble probas_, mixedSiteLnl_;
   double mixedMinusLogLik_ = 0;
+};
+
+// ---- joint ML ancestral reconstruction (fork: Likelihood/MLAncestralStateReconstruction.{h,cpp}, Pupko et al. 2000) -------------
+// The reference constructor takes the likelihood, its model, the root frequencies and its pxy_ map
+// (MLAncestralStateReconstruction.h:88-103); here the device already holds that likelihood's tables, so `model` and `Pijt` are
+// accepted for source compatibility only and `rootFrequencies` must be the likelihood's own.
+class MLAncestralStateReconstruction {
+ public:
+  MLAncestralStateReconstruction(const AbstractHomogeneousTreeLikelihood* drl, const SubstitutionModel* model, const std::vector<double>& rootFrequencies,
+                                 const void* Pijt = nullptr)
+      : likelihood_(drl) {
+    (void)model; (void)Pijt;
+    const Vdouble& rf = drl->getRootFrequencies();
+    if (rootFrequencies.size() != rf.size()) throw Exception("MLAncestralStateReconstruction: wrong number of root frequencies");
+    for (size_t x = 0; x < rf.size(); ++x)
+      if (std::fabs(rf[x] - rootFrequencies[x]) > 1e-12)
+        throw Exception("MLAncestralStateReconstruction: root frequencies other than the likelihood's own are not supported");
+  }
+  void computeJointLikelihood() { likelihood_->getJointMLAncestralStates(states_, &bestLogLik_); computed_ = true; }
+  // node id -> best state per distinct site (getAllAncestralStates, .cpp:136-141)
+  std::map<int, std::vector<size_t> > getAllAncestralStates() const {
+    if (!computed_) throw Exception("MLAncestralStateReconstruction: computeJointLikelihood() was not called");
+    std::map<int, std::vector<size_t> > ancestors;
+    const std::vector<int> ids = likelihood_->getNodesId();
+    for (size_t n = 0; n < ids.size(); ++n) ancestors[ids[n]] = states_[n];
+    return ancestors;
+  }
+  const Vdouble& getBestJointLogLikelihoodPerSite() const { return bestLogLik_; }   // not in the reference: log max joint likelihood
+
+ private:
+  const AbstractHomogeneousTreeLikelihood* likelihood_;   // not owned
+  std::vector<std::vector<size_t> > states_;
+  Vdouble bestLogLik_;
+  bool computed_ = false;
+};
+
+// ---- marginal ancestral reconstruction (Likelihood/MarginalAncestralStateReconstruction.{h,cpp}) ---------------------------------
+// getAncestralStatesForNode (.cpp:47-102): probs[i][x] = sum_c computeLikelihoodAtNode[i][c][x] r_c / l_i at an internal node --
+// the device's marginal posterior table -- and the best (or a sampled) state per distinct site; a leaf gets the first maximum
+// of its leaf likelihoods with probability one (:53-65).
+class MarginalAncestralStateReconstruction {
+ public:
+  explicit MarginalAncestralStateReconstruction(const AbstractHomogeneousTreeLikelihood* drl)
+      : likelihood_(drl), nbSites_(drl->getNumberOfSites()), nbDistinctSites_(drl->getNumberOfDistinctSites()),
+        nbStates_(drl->getNumberOfStates()) {}
+  std::vector<size_t> getAncestralStatesForNode(int nodeId, VVdouble& probs, bool sample = false) const {
+    std::vector<size_t> ancestors(nbDistinctSites_, 0);
+    if (likelihood_->getTree().getNode(nodeId)->isLeaf()) {
+      const VVVdouble leaf = likelihood_->getPosteriorProbabilitiesForEachStateForEachRate(nodeId);   // leaf likelihoods x p_c / sum
+      probs.assign(nbDistinctSites_, Vdouble(nbStates_, 0.0));
+      for (size_t i = 0; i < nbDistinctSites_; ++i) {
+        size_t j = 0;
+        for (size_t x = 1; x < nbStates_; ++x) if (leaf[i][0][x] > leaf[i][0][j]) j = x;
+        ancestors[i] = j;
+        probs[i][j] = 1.0;
+      }
+      return ancestors;
+    }
+    likelihood_->getMarginalPosteriors(nodeId, probs, nullptr);
+    for (size_t i = 0; i < nbDistinctSites_; ++i) {
+      if (sample) {
+        const double r = std::generate_canonical<double, 53>(rng_);
+        double cum = 0;
+        for (size_t j = 0; j < nbStates_; ++j) {
+          cum += probs[i][j];
+          if (r <= cum) { ancestors[i] = j; break; }
+        }
+      } else {
+        ancestors[i] = (size_t)(std::max_element(probs[i].begin(), probs[i].end()) - probs[i].begin());
+      }
+    }
+    return ancestors;
+  }
+  std::vector<size_t> getAncestralStatesForNode(int nodeId) const {
+    VVdouble probs;
+    return getAncestralStatesForNode(nodeId, probs, false);
+  }
+  // one state per distinct site for every node of the tree (recursiveMarginalAncestralStates)
+  std::map<int, std::vector<size_t> > getAllAncestralStates() const {
+    std::map<int, std::vector<size_t> > ancestors;
+    for (int id : likelihood_->getNodesId()) ancestors[id] = getAncestralStatesForNode(id);
+    return ancestors;
+  }
+  // the node's states site by site (getAncestralSequenceForNode without the Sequence wrapper): site -> pattern via getSiteIndex
+  std::vector<size_t> getAncestralStatesPerSiteForNode(int nodeId, VVdouble* probs = nullptr, bool sample = false) const {
+    VVdouble patterned;
+    const std::vector<size_t> states = getAncestralStatesForNode(nodeId, patterned, sample);
+    std::vector<size_t> all(nbSites_);
+    if (probs) probs->resize(nbSites_);
+    for (size_t i = 0; i < nbSites_; ++i) {
+      all[i] = states[likelihood_->getSiteIndex(i)];
+      if (probs) (*probs)[i] = patterned[likelihood_->getSiteIndex(i)];
+    }
+    return all;
+  }
+
+ private:
+  const AbstractHomogeneousTreeLikelihood* likelihood_;   // not owned
+  size_t nbSites_, nbDistinctSites_, nbStates_;
+  mutable std::mt19937_64 rng_{20260101};
 };
 
 // ---- marginal ancestral reconstruction for non-reversible models (fork) --------------------------------------------------------

@@ -212,6 +212,15 @@ int bppgpu_get_node_posteriors(bppgpu_engine* e, int32_t point, int32_t node, do
  * is one pass.  Valid after an eval with BPPGPU_EVAL_D1 on an engine created with BPPGPU_FLAG_KEEP_CLVS (the root needs
  * the value pass only).                                                                                              */
 int bppgpu_get_marginal_posteriors(bppgpu_engine* e, int32_t point, int32_t node, double* posterior, double* joint);
+/* MLAncestralStateReconstruction (fork; Likelihood/MLAncestralStateReconstruction.h, .cpp:6-188, leaf arrays
+ * DRASRTreeLikelihoodData.cpp:265-300): joint maximum-likelihood reconstruction (Pupko et al. 2000) with the transition
+ * probabilities and root frequencies of the last evaluation -- a max-product pass up the tree, the best root state of class 0,
+ * and the trace back (getAllAncestralStates, .cpp:136-186), all on the device.
+ *   states [n_nodes][N] int32   state of every node (a leaf: its observed state) per distinct site
+ *   best_lnl [N] or NULL        log of the joint likelihood of that assignment (class 0): log max_x pi_x prod ...
+ * Like the reference the traceback tables are those of the LAST rate class and the root uses class 0 (it "assumes one class");
+ * unlike it, rows are rescaled by powers of two, so large trees do not underflow.                                          */
+int bppgpu_ml_ancestral_states(bppgpu_engine* e, int32_t point, int32_t* states, double* best_lnl);
 /* Derivatives of lnL with respect to "BrLenRoot" = l1 + l2 and "RootPosition" = l1 / (l1 + l2), the re-parametrisation of
  * the two root branches of a rooted tree (reparametrizeRoot; AbstractNonHomogeneousTreeLikelihood.cpp:319-330, :386-389):
  *   out[0..3] = d lnL / d BrLenRoot, d lnL / d RootPosition, d2 lnL / d BrLenRoot^2, d2 lnL / d RootPosition^2

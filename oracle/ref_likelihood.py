@@ -337,6 +337,47 @@ def marginal_posteriors_by_root_state(flat, res, P, probs):
     return post, joint
 
 
+def ml_joint_reconstruction(flat, tip_codes, table, P, root_freqs):
+    """MLAncestralStateReconstruction (fork; Likelihood/MLAncestralStateReconstruction.cpp:6-188): joint ML reconstruction by
+    Pupko's max-product recursion, arrays indexed by the FATHER's state.
+      leaf with observed state s (first state whose init value is 1; DRASRTreeLikelihoodData.cpp:283-292):
+          L[i][c][x] = P[c][x][s], anc[i][x] = s   (no such state: L = 1, anc = 0)
+      internal (fillLikelihoodsArrays :101-134):  L[i][c][x] = max_y P[c][x][y] prod_sons L_son[i][c][y], anc[i][x] = first y
+          with a strictly larger (positive) value; the table of the LAST class survives
+      root (fillRootLikelihoodsArrays :66-98):    L[i][c][x] = pi_x prod_sons L_son[i][c][x]
+      trace back (getAllAncestralStatesRec :143-186): root = first maximum of class 0, node = anc[node][i][father's state].
+    Unscaled, like the reference.  Returns (states [n_nodes][N] int, L_root [N][C][S])."""
+    nn = flat.n_nodes
+    C, S = P.shape[1], P.shape[2]
+    N = len(next(iter(tip_codes.values())))
+    L, anc = {}, {}
+    for nid in range(nn):
+        if flat.is_leaf[nid]:
+            t = table[np.asarray(tip_codes[nid], dtype=np.int64)]              # [N][S]
+            has = (t == 1.0).any(axis=1)
+            s = np.argmax(t == 1.0, axis=1)
+            A = np.transpose(P[nid][:, :, s], (2, 0, 1)).copy()                 # [N][C][x] = P[c][x][s_i]
+            A[~has] = 1.0
+            L[nid] = A
+            anc[nid] = np.repeat(np.where(has, s, 0)[:, None], S, axis=1)
+            continue
+        prod = np.ones((N, C, S))
+        for son in flat.children[nid]:
+            prod = prod * L[son]
+        if nid == flat.root:
+            L[nid] = prod * np.asarray(root_freqs)[None, None, :]
+            continue
+        cand = prod[:, :, None, :] * P[nid][None, :, :, :]                     # [i][c][x][y]
+        L[nid] = cand.max(axis=3)
+        anc[nid] = np.argmax(cand[:, C - 1], axis=2)                            # first maximum; all-zero row -> 0
+    states = np.zeros((nn, N), np.int64)
+    states[flat.root] = np.argmax(L[flat.root][:, 0, :], axis=1)
+    for nid in range(nn - 2, -1, -1):                                           # fathers (larger ids) first
+        f = int(flat.parent[nid])
+        states[nid] = anc[nid][np.arange(N), states[f]]
+    return states, L[flat.root]
+
+
 def root_reparam_derivatives(flat, res, P, dP, d2P, probs, weights):
     """Derivatives of -lnL with respect to ``BrLenRoot`` (l1 + l2) and ``RootPosition`` (l1 / (l1 + l2)), the
     re-parametrisation of the two root branches of a rooted tree

@@ -167,6 +167,36 @@ class FlatTree:
         return off, np.array(flat, np.int32)
 
 
+def clock_parameters(flat: FlatTree):
+    """RHomogeneousClockTreeLikelihood::initBranchLengthsParameters (Likelihood/RHomogeneousClockTreeLikelihood.cpp:121-157):
+    heights by TreeTemplateTools::getHeights (TreeTemplateTools.cpp:173-186: the LONGEST path to a leaf below the node),
+    ``TotalHeight`` = height of the root, ``HeightP<id>`` = height / father's height for every internal non-root node.
+    Returns (total_height, {node id: height proportion})."""
+    h = np.zeros(flat.n_nodes)
+    for nid in range(flat.n_nodes):                      # post-order: sons first
+        for s in flat.children[nid]:
+            h[nid] = max(h[nid], h[s] + flat.brlen[s])
+    hp = {nid: h[nid] / h[int(flat.parent[nid])] for nid in range(flat.n_nodes - 1) if not flat.is_leaf[nid]}
+    return float(h[flat.root]), hp
+
+
+def clock_branch_lengths(flat: FlatTree, total_height: float, height_p: dict, min_brlen: float = 0.0):
+    """RHomogeneousClockTreeLikelihood::computeBranchLengthsFromHeights (:161-179): a leaf son hangs at the height of its
+    father, an internal son at HeightP * father's height; lengths are floored at minimumBrLen_ (0 for the clock class, :87)."""
+    bl = np.zeros(flat.n_nodes)
+    height = {flat.root: total_height}
+    for nid in range(flat.n_nodes - 1, -1, -1):          # fathers before sons
+        if nid not in height:
+            continue
+        for s in flat.children[nid]:
+            if flat.is_leaf[s]:
+                bl[s] = max(min_brlen, height[nid])
+            else:
+                height[s] = height_p[s] * height[nid]
+                bl[s] = max(min_brlen, height[nid] - height[s])
+    return bl
+
+
 def random_tree(n_taxa: int, rng: np.random.Generator, mean_brlen: float = 0.05, rooted: bool = False) -> Node:
     """Random binary topology by sequential random attachment; Exp(mean) lengths.
     Unrooted: 3-son root (what init_ produces after unroot()); rooted: 2-son root."""

@@ -184,6 +184,59 @@ int main() {
           worstL = max(worstL, fabs(log(sl) - tl.getLogLikelihoodForASite(site)));
         }
       }
+      // MarginalAncestralStateReconstruction::getAncestralStatesForNode: probs = sum_c computeLikelihoodAtNode r_c / l_i (.cpp:70-83),
+      // here from another device kernel (the marginal posterior table) than computeLikelihoodAtNode
+      MarginalAncestralStateReconstruction masr(&tl);
+      double masrErr = 0;
+      for (int nid : {2, 4, 5}) {   // an internal node, a leaf, the root
+        VVdouble probs;
+        const vector<size_t> st = masr.getAncestralStatesForNode(nid, probs);
+        VVVdouble full;
+        tl.computeLikelihoodAtNode(nid, full);
+        for (size_t i = 0; i < probs.size(); ++i) {
+          size_t site = 0;
+          while (tl.getSiteIndex(site) != i) ++site;
+          size_t arg = 0;
+          for (size_t x = 0; x < 4; ++x) {
+            double v = 0;
+            for (size_t c = 0; c < 4; ++c) v += full[i][c][x] * g6.getProbability(c);
+            v /= tl.getLikelihoodForASite(site);
+            masrErr = max(masrErr, fabs(v - probs[i][x]));
+            if (probs[i][x] > probs[i][arg]) arg = x;
+          }
+          if (arg != st[i]) masrErr = 1;
+        }
+      }
+      VVdouble leafProbs;
+      const vector<size_t> leafStates = masr.getAncestralStatesForNode(0, leafProbs);   // leaf A: its own characters
+      const string seqA = "AAATGGCTGTGCACGTC";
+      for (size_t site = 0; site < seqA.size(); ++site)
+        if (string("ACGT")[leafStates[tl.getSiteIndex(site)]] != seqA[site]) masrErr = 1;
+      // DiscreteRatesAcrossSitesTreeLikelihood accessors (posterior rates per site etc.) from the root arrays of the device
+      {
+        const Vdouble pr = tl.getPosteriorRateOfEachSite();
+        const vector<size_t> mc = tl.getRateClassWithMaxPostProbOfEachSite();
+        const VVdouble pb = tl.getPosteriorProbabilitiesOfEachRate();
+        double drasErr = 0;
+        for (size_t i = 0; i < pr.size(); ++i) {
+          printf("POSTRATE_%zu %.15g\n", i, pr[i]);
+          printf("MAXCLASS_%zu %zu\n", i, mc[i]);
+          double sp = 0, sl = 0, ss = 0;
+          for (size_t c = 0; c < 4; ++c) {
+            sp += pb[i][c];
+            sl += tl.getLikelihoodForASiteForARateClass(i, c) * g6.getProbability(c);
+          }
+          for (int x = 0; x < 4; ++x) ss += tl.getLikelihoodForASiteForAState(i, x) * tl.getRootFrequencies()[x];
+          drasErr = max(drasErr, fabs(sp - 1.0));
+          drasErr = max(drasErr, fabs(sl / tl.getLikelihoodForASite(i) - 1.0));   // sum_c p_c L[i][c] = L[i]
+          drasErr = max(drasErr, fabs(ss / tl.getLikelihoodForASite(i) - 1.0));   // sum_x pi_x sum_c p_c L[i][c][x] = L[i]
+        }
+        printf("DRAS_ERR %.3e\n", drasErr);
+        if (drasErr > 1e-12) { cerr << "DiscreteRatesAcrossSites accessor identities failed" << endl; fails++; }
+      }
+      printf("MASR_ERR %.3e\n", masrErr);
+      printf("MASR_NNODES %zu\n", masr.getAllAncestralStates().size());
+      if (masrErr > 1e-12) { cerr << "MarginalAncestralStateReconstruction check failed" << endl; fails++; }
       printf("POSTERIOR_SUM_ERR %.3e\n", worst);
       printf("ATNODE_LNL_ERR %.3e\n", worstL);
       vector<size_t> anc = tl.getAncestralStatesForNode(5);
@@ -247,6 +300,60 @@ int main() {
           fails++;
         }
       }
+    }
+    {
+      // test/test_likelihood_clock.cpp:80-93, 113-121: the clock class starts at the unconstrained value (the tree is ultrametric;
+      // the reference's 92.3295 is that start with the model parameters its first fit left behind) and, at the clock-constrained
+      // optimum, must give the reference's final value 71.2657 (tolerance 0.001 there; argmin from tests/golden/clock_optimum.json)
+      const DNA dna5;
+      unique_ptr<Tree> t9(TreeTemplateTools::parenthesisToTree("(((A:0.01, B:0.01):0.02,C:0.03):0.01,D:0.04);"));
+      VectorSiteContainer s9(&dna5);
+      s9.addSequence(BasicSequence("A", "AAATGGCTGTGCACGTC", &dna5));
+      s9.addSequence(BasicSequence("B", "AACTGGATCTGCATGTC", &dna5));
+      s9.addSequence(BasicSequence("C", "ATCTGGACGTGCACGTG", &dna5));
+      s9.addSequence(BasicSequence("D", "CAACGGGAGTGCGCCTA", &dna5));
+      T92 m9(&dna5, 3.);
+      ConstantRateDistribution c9;
+      RHomogeneousClockTreeLikelihood tl(*t9, s9, &m9, &c9);
+      tl.initialize();
+      printf("CLOCK_INIT %.15f\n", tl.getValue());
+      printf("CLOCK_TOTALHEIGHT %.15f\n", tl.getParameterValue("TotalHeight"));
+      printf("CLOCK_NPARAMS %zu\n", tl.getBranchLengthsParameters().size());
+      tl.setParametersValues({{"TotalHeight", 0.448120364718}, {"HeightP2", 0.818792488373}, {"HeightP4", 0.390971377099},
+                              {"T92.kappa", 0.996348825463}, {"T92.theta", 0.579945474376}});
+      printf("CLOCK_OPTIMUM %.15f\n", tl.getValue());
+      if (fabs(tl.getValue() - 71.2657) > 0.001) { cerr << "Incorrect final value (clock)." << endl; fails++; }
+      // a crude clock-constrained descent from the reference's starting point must also come down to it: cyclic golden-section
+      // line searches over the five parameters (the surface is smooth; this is not the reference's optimiser)
+      m9.setParameterValue("kappa", 3.0);   // the model object is shared with tl, which left it at the optimum
+      m9.setParameterValue("theta", 0.5);
+      RHomogeneousClockTreeLikelihood tl2(*t9, s9, &m9, &c9);
+      tl2.initialize();
+      const char* names[5] = {"TotalHeight", "HeightP2", "HeightP4", "T92.kappa", "T92.theta"};
+      double x[5] = {0.04, 1.0 / 3.0, 0.75, 3.0, 0.5};
+      const double lo[5] = {1e-6, 1e-6, 1e-6, 1e-3, 1e-3}, hi[5] = {2.0, 1 - 1e-6, 1 - 1e-6, 20.0, 0.999};
+      double best = tl2.getValue();
+      for (int sweep = 0; sweep < 60; ++sweep) {
+        const double before = best;
+        for (int k = 0; k < 5; ++k) {
+          double a = lo[k], b = hi[k];
+          const double g = 0.6180339887498949;
+          double c1 = b - g * (b - a), c2 = a + g * (b - a);
+          tl2.setParameterValue(names[k], c1); double f1 = tl2.getValue();
+          tl2.setParameterValue(names[k], c2); double f2 = tl2.getValue();
+          for (int it = 0; it < 60; ++it) {
+            if (f1 < f2) { b = c2; c2 = c1; f2 = f1; c1 = b - g * (b - a); tl2.setParameterValue(names[k], c1); f1 = tl2.getValue(); }
+            else { a = c1; c1 = c2; f1 = f2; c2 = a + g * (b - a); tl2.setParameterValue(names[k], c2); f2 = tl2.getValue(); }
+          }
+          const double xm = 0.5 * (a + b);
+          tl2.setParameterValue(names[k], xm);
+          if (tl2.getValue() <= best) { best = tl2.getValue(); x[k] = xm; }
+          else tl2.setParameterValue(names[k], x[k]);
+        }
+        if (before - best < 1e-9) break;
+      }
+      printf("CLOCK_DESCENT %.15f\n", best);
+      if (fabs(best - 71.2657) > 0.001) { cerr << "clock-constrained descent did not reach the reference optimum" << endl; fails++; }
     }
     {
       // test/test_likelihood_nh.cpp:73-110: one T92 per branch (kappa shared, theta free), GC root frequencies, Gamma(4, 1);
@@ -329,6 +436,12 @@ int main() {
             fatherErr = max(fatherErr, fabs(cs - pf[y]));
           }
         }
+        // joint ML reconstruction (fork: MLAncestralStateReconstruction), also called by runChromEvol
+        MLAncestralStateReconstruction mlasr(&tl, &cm, tl.getRootFrequencies());
+        mlasr.computeJointLikelihood();
+        const map<int, vector<size_t> > mlStates = mlasr.getAllAncestralStates();
+        for (auto& kv : mlStates) printf("CHR_ML_%d %zu\n", kv.first, kv.second[0]);
+        printf("CHR_ML_BEST %.15g\n", mlasr.getBestJointLogLikelihoodPerSite()[0]);
         const vector<double> rp = asr.getRootPosteriorProb();
         double rootErr = 0;
         for (size_t x = 0; x < rp.size(); ++x) rootErr = max(rootErr, fabs(rp[x] - (*post)[rootId][0][x]));

@@ -153,6 +153,30 @@ def test_reference_likelihood_tests_through_the_shim(built_lib):
     cc.root_freqs = m.freq
     res = cases.oracle_eval(cc)
     assert abs(vals["YN98_CONST"] + res.lnl) <= 1e-9 * abs(res.lnl)
+    assert vals["MASR_ERR"] <= 1e-12 and int(vals["MASR_NNODES"]) == 6
+    # posterior rate of each site / best rate class (AbstractDiscreteRatesAcrossSitesTreeLikelihood.cpp:201-248) against the oracle
+    rg4, pg4 = rm.gamma_rates(4, 1.0)
+    cg = cases.case_from_alignment("((A:0.01, B:0.02):0.03,C:0.01,D:0.1);",
+                                   {"A": "AAATGGCTGTGCACGTC", "B": "GACTGGATCTGCACGTC", "C": "CTCTGGATGTGCACGTG", "D": "AAATGGCGGTGCGCCTA"},
+                                   rm.t92(3.0, 0.5), rg4, pg4)
+    rg = cases.oracle_eval(cg)
+    root = cg.flat.root
+    S_ic = np.ldexp(np.einsum("icx,x->ic", rg.lower[root], cg.root_freqs), -rg.lexp[root])
+    post = S_ic * np.asarray(pg4)[None, :]
+    post /= post.sum(axis=1, keepdims=True)
+    for site in range(17):
+        k = cg.site_index[site]
+        assert abs(vals["POSTRATE_%d" % site] - float(post[k] @ np.asarray(rg4))) <= 1e-12, site
+        assert int(vals["MAXCLASS_%d" % site]) == int(np.argmax(S_ic[k])), site
+    assert vals["DRAS_ERR"] <= 1e-12
+    # clock class (test/test_likelihood_clock.cpp): start = the unconstrained value, optimum = the reference's 71.2657, both by
+    # evaluation at the stored argmin and by a descent run through the shim on the device
+    import json
+    clock = json.loads((ROOT / "tests" / "golden" / "clock_optimum.json").read_text())
+    assert abs(vals["CLOCK_INIT"] - 94.3957) < 5e-5 and abs(vals["CLOCK_TOTALHEIGHT"] - 0.04) < 1e-12 and int(vals["CLOCK_NPARAMS"]) == 3
+    assert abs(vals["CLOCK_OPTIMUM"] - clock["oracle_minus_lnl"]) <= 1e-9 * clock["oracle_minus_lnl"]
+    assert abs(vals["CLOCK_OPTIMUM"] - clock["reference_minus_lnl"]) <= 1e-4
+    assert abs(vals["CLOCK_DESCENT"] - clock["reference_minus_lnl"]) <= 1e-4 and vals["CLOCK_DESCENT"] >= vals["CLOCK_OPTIMUM"] - 1e-7
     # non-homogeneous model set (test/test_likelihood_nh.cpp's construction): one T92 per branch, kappa shared, GC root frequencies
     r1, p1 = rm.gamma_rates(4, 1.0)
     seqs_nh = {"A": "ATGTTATCCCGTCGAATCATATGGAATCGTCTAGAACTCA", "B": "ATGGTATCTCGCCTAATCATGTGGCATCGTCAAAAAATCA",
@@ -196,6 +220,10 @@ def test_reference_likelihood_tests_through_the_shim(built_lib):
         post, _ = rl.marginal_posteriors(flat, res_m, res_m.P, n, ch.probs)
         assert int(vals["CHR_ANC_%d" % n]) == int(np.argmax(post[0])), n
         assert abs(vals["CHR_POSTMAX_%d" % n] - post[0].max()) <= 1e-9, n
+    ml_states, ml_root = rl.ml_joint_reconstruction(flat, ch.codes_by_leaf, ch.table, res_m.P, res_m.root_freqs)
+    for n in range(flat.n_nodes):
+        assert int(vals["CHR_ML_%d" % n]) == int(ml_states[n][0]), n
+    assert abs(vals["CHR_ML_BEST"] - np.log(ml_root[0, 0].max())) <= 1e-10
     assert vals["CHR_MARG_SUM_ERR"] <= 1e-10 and vals["CHR_MARG_JOINT_ERR"] <= 1e-12 and vals["CHR_MARG_FATHER_ERR"] <= 1e-10
     # batched front-end (LikelihoodPointBatch): five parameter points in one device evaluation, each against the oracle
     pts = [(0.7, 0.4, 0.2, 0.1), (1.1, 0.4, 0.2, 0.05), (0.2, 1.3, 0.6, 0.3), (2.0, 2.0, 0.01, 0.4), (0.05, 0.05, 0.9, 0.0)]

@@ -97,3 +97,54 @@ def test_cuda_path_reproduces_oracle_fixtures(v):
         np.testing.assert_allclose(-d2[0, :nb], v["d2"], rtol=1e-8, atol=1e-7)
     if rf is not None:
         np.testing.assert_allclose(rf, v["root_freqs"], rtol=1e-9, atol=1e-15)
+
+
+# ---- the clock-constrained optimum of test/test_likelihood_clock.cpp (a second known-answer value, at other parameters) ----
+CLOCK = json.loads((GOLD / "clock_optimum.json").read_text())
+_cspec = importlib.util.spec_from_file_location("make_clock_optimum", GOLD / "make_clock_optimum.py")
+_ck = importlib.util.module_from_spec(_cspec)
+_cspec.loader.exec_module(_ck)
+
+
+def test_clock_parametrisation_round_trip():
+    """TotalHeight / HeightP<id> of the test tree (RHomogeneousClockTreeLikelihood.cpp:121-157) and back (:161-179): the tree is
+    ultrametric, so the clock branch lengths are its own and the clock likelihood starts at the unconstrained 94.3957."""
+    from oracle import ref_tree as rt
+    c = _ck.clock_case()
+    h, hp = rt.clock_parameters(c.flat)
+    assert abs(h - 0.04) < 1e-15 and set(hp) == {2, 4}
+    assert abs(hp[4] - 0.75) < 1e-12 and abs(hp[2] - 1.0 / 3.0) < 1e-12
+    np.testing.assert_allclose(rt.clock_branch_lengths(c.flat, h, hp), c.flat.brlen, rtol=0, atol=1e-15)
+    assert abs(_ck.minus_lnl(c, h, hp, 3.0, 0.5) - 94.3957) < 5e-5
+
+
+def test_oracle_reaches_the_reference_clock_optimum():
+    """Minimising the ORACLE's -lnL under the clock constraint, from the reference test's starting point, lands on the value the
+    reference test demands (71.2657 +- 0.001, test/test_likelihood_clock.cpp:91-92,121) -- in fact on all its printed digits; the
+    stored argmin reproduces the stored oracle value."""
+    c = _ck.clock_case()
+    ids, x, fx = _ck.optimise(c)
+    assert abs(fx - CLOCK["reference_minus_lnl"]) <= 1e-4
+    a = CLOCK["argmin"]
+    v = _ck.minus_lnl(c, a["TotalHeight"], {int(k): w for k, w in a["HeightP"].items()}, a["kappa"], a["theta"])
+    assert abs(v - CLOCK["oracle_minus_lnl"]) <= 1e-12 * v
+    assert abs(v - CLOCK["reference_minus_lnl"]) <= 1e-4 and fx >= v - 1e-9
+
+
+@pytest.mark.gpu
+def test_cuda_path_at_the_reference_clock_optimum():
+    """the CUDA path evaluated at the stored argmin: the reference's known-answer optimum within the reference's tolerance (and
+    to its last printed digit), the stored oracle value to 1e-9 relative"""
+    from bpp_phyl_b200 import capi
+    from oracle import ref_tree as rt
+    c = _ck.clock_case()
+    a = CLOCK["argmin"]
+    bl = rt.clock_branch_lengths(c.flat, a["TotalHeight"], {int(k): w for k, w in a["HeightP"].items()})
+    m = rm.t92(a["kappa"], a["theta"])
+    c.model, c.root_freqs = m, np.asarray(m.freq)
+    for flags in (0, capi.FLAG_R_SEMANTICS, capi.FLAG_FORCE_GENERIC):
+        with cases.make_engine(c, flags=flags) as e:
+            e.set_branch_lengths(0, bl)
+            lnl, _, _ = e.eval(capi.EVAL_LNL)
+        assert abs(-lnl[0] - CLOCK["reference_minus_lnl"]) <= 1e-4
+        assert abs(-lnl[0] - CLOCK["oracle_minus_lnl"]) <= 1e-9 * CLOCK["oracle_minus_lnl"]

@@ -643,6 +643,44 @@ def test_marginal_nonrev_ancestral_posteriors(mk, ncat, rooted, nsites):
             np.testing.assert_allclose(joint.sum(axis=1), posts[int(flat.parent[nid])], rtol=1e-8, atol=1e-13)
 
 
+@pytest.mark.parametrize("mk,ncat,rooted,ntaxa,nsites,amb", [
+    (gtr, 1, True, 12, 80, 0.05), (gtr, 4, False, 10, 50, 0.0), (rm.lg08, 1, True, 9, 40, 0.03),
+    (lambda: rm.chromosome(1, 40, gain=0.7, loss=0.4, dupl=0.2, demi=rm.DEMI_EQUAL_DUPL), 1, True, 14, 2, 0.0),
+    (lambda: rm.chromosome(1, 70, gain=1.5, loss=0.1, dupl=0.9, demi=0.4, gain_r=0.05), 1, True, 9, 1, 0.0)])
+def test_ml_joint_ancestral_reconstruction(mk, ncat, rooted, ntaxa, nsites, amb):
+    """MLAncestralStateReconstruction (fork): the device's max-product pass and trace back against the oracle (held to brute-force
+    enumeration on CPU).  Ties are compared through the value: the joint likelihood of the returned assignment and, where the
+    maximiser is unique, the states themselves."""
+    capi = _capi()
+    from oracle import ref_likelihood as rl
+    r, p = rm.gamma_rates(ncat, 0.6) if ncat > 1 else rm.constant_rate()
+    m = mk()
+    c = cases.make_case(ntaxa, nsites, m, r, p, seed=37, rooted=rooted, ambiguity=amb, compress=False,
+                        mean_brlen=0.2 if m.size <= 20 else 0.05)
+    c.root_freqs = np.random.default_rng(6).dirichlet(np.ones(m.size) * 2)
+    res = cases.oracle_eval(c)
+    want, Lroot = rl.ml_joint_reconstruction(c.flat, c.codes_by_leaf, c.table, res.P, c.root_freqs)
+    with cases.make_engine(c) as e:
+        e.eval(capi.EVAL_LNL)
+        got, best = e.ml_ancestral_states()
+    np.testing.assert_allclose(best, np.log(Lroot[:, 0, :].max(axis=1)), rtol=1e-10, atol=1e-10)
+    np.testing.assert_array_equal(got, want)
+
+
+def test_ml_joint_reconstruction_does_not_underflow_on_a_large_tree():
+    """700 taxa, long branches: the reference's unscaled arrays are all zero here (its reconstruction degenerates to state 0
+    everywhere); the device rows carry exponents, so the leaves come back as observed and the joint likelihood is finite."""
+    capi = _capi()
+    r, p = rm.constant_rate()
+    c = cases.make_case(700, 3, gtr(), r, p, seed=4, random_tips=True, mean_brlen=0.5, compress=False)
+    with cases.make_engine(c) as e:
+        lnl, _, _ = e.eval(capi.EVAL_LNL)
+        got, best = e.ml_ancestral_states()
+    assert np.all(np.isfinite(best)) and np.all(best < -708)          # below the smallest double: the reference returns zeros
+    for l in c.flat.leaf_ids:
+        np.testing.assert_array_equal(got[l], c.codes_by_leaf[l])
+
+
 def test_marginal_posteriors_error_conventions():
     """bppgpu_get_marginal_posteriors: needs kept CLVs and an evaluation, the prefix pass for non-root nodes, no joint table at
     the root, valid node ids."""

@@ -283,3 +283,35 @@ def test_marginal_nonrev_posteriors_one_pass_equals_reference_s_pass_form_and_en
         np.testing.assert_allclose(rl.marginal_posteriors(flat, res, res.P, flat.root, c.probs)[0][i], rootm / L, rtol=1e-11)
         for n in tot:
             np.testing.assert_allclose(joint_ref[n][i], tot[n] / L, rtol=1e-10, atol=1e-16)
+
+
+def test_ml_joint_reconstruction_against_enumeration():
+    """ml_joint_reconstruction (the restatement of MLAncestralStateReconstruction's max-product recursion and trace back): the
+    assignment it returns has the largest joint probability among ALL assignments of the internal states, and the root array's
+    maximum is that probability.  One rate class (the reference assumes it), non-reversible model, free root frequencies."""
+    import itertools
+    import cases
+    from oracle import ref_likelihood as rl
+    r, p = rm.constant_rate()
+    m = rm.chromosome(1, 5, gain=0.9, loss=0.4, dupl=0.3)
+    S = m.size
+    c = cases.make_case(6, 5, m, r, p, seed=29, rooted=True, compress=False, mean_brlen=0.4)
+    c.root_freqs = np.array([.1, .3, .2, .25, .15])
+    res = cases.oracle_eval(c)
+    flat = c.flat
+    states, Lroot = rl.ml_joint_reconstruction(flat, c.codes_by_leaf, c.table, res.P, c.root_freqs)
+    internals = [n for n in range(flat.n_nodes) if not flat.is_leaf[n]]
+    for i in range(c.N):
+        def joint(st):
+            pr = c.root_freqs[st[flat.root]]
+            for n in range(flat.n_nodes - 1):
+                f = int(flat.parent[n])
+                pr *= res.P[n][0][st[f]][st[n]]
+            return pr
+        obs = {l: int(c.codes_by_leaf[l][i]) for l in flat.leaf_ids}
+        assert all(v < S for v in obs.values())                      # no ambiguity in this case
+        best = max(joint({**obs, **dict(zip(internals, s))}) for s in itertools.product(range(S), repeat=len(internals)))
+        got = joint({n: int(states[n][i]) for n in range(flat.n_nodes)})
+        assert all(states[l][i] == obs[l] for l in flat.leaf_ids)
+        assert abs(got - best) <= 1e-13 * best
+        assert abs(Lroot[i, 0].max() - best) <= 1e-13 * best
