@@ -2438,4 +2438,90 @@ class MarginalNonRevAncestralStateReconstruction {
   std::unique_ptr<std::map<int, std::map<size_t, VVdouble> > > jointProbabilities_;
 };
 
+// ---- Newton-Raphson on the branch lengths --------------------------------------------------------------------------
+// Likelihood/PseudoNewtonOptimizer.cpp:100-193, the optimiser OptimizationTools::optimizeNumericalParameters puts on the branch
+// lengths (OptimizationTools.cpp:187-188): every parameter moves by d1 / d2 at once (the other way when d2 < 0, not at all when
+// d2 = 0 or the ratio is NaN), and the whole step is halved -- the Felsenstein-Churchill correction -- up to maxCorrection_ times
+// while the function is worse than before; stop when |f - f_previous| < tolerance (FunctionStopCondition).  This is the variant
+// with disableCG() (PseudoNewtonOptimizer.h:125): no conjugate-gradient detour at the fourth correction.
+// One step costs the reference 2 B per-branch derivative passes + the probes; here it is ONE device evaluation with
+// BPPGPU_EVAL_D1 | D2 (all B first and second derivatives) + one value evaluation per probe.
+class PseudoNewtonOptimizer {
+ public:
+  explicit PseudoNewtonOptimizer(AbstractHomogeneousTreeLikelihood* function)
+      : f_(function), tolerance_(1e-6), maxCorrection_(10), nbEvalMax_(1000000), nbEval_(0), currentValue_(0), previousValue_(0) {}
+  void setMaximumNumberOfCorrections(unsigned mx) { maxCorrection_ = mx; }
+  void setMaximumNumberOfEvaluations(unsigned n) { nbEvalMax_ = n; }
+  void setTolerance(double t) { tolerance_ = t; }
+  void disableCG() {}
+  void init(const ParameterList& params) {
+    params_ = params;
+    f_->setParametersValues(params_);
+    currentValue_ = f_->getValue();
+    previousValue_ = currentValue_;
+    nbEval_ = 0;
+  }
+  double step() {
+    const size_t n = params_.size();
+    std::vector<double> movements(n);
+    ParameterList newPoint = params_;
+    for (size_t i = 0; i < n; ++i) {
+      const double d1 = f_->getFirstOrderDerivative(params_[i].name), d2 = f_->getSecondOrderDerivative(params_[i].name);
+      if (d2 == 0) movements[i] = 0;
+      else if (d2 < 0) movements[i] = -d1 / d2;   // "Moving in the other direction" (:121-127)
+      else movements[i] = d1 / d2;
+      if (std::isnan(movements[i])) movements[i] = 0;
+      newPoint[i].value = params_[i].value - movements[i];
+    }
+    double newValue = probe(newPoint, &movements);
+    unsigned count = 0;
+    while (count < maxCorrection_ && (newValue > currentValue_ + tolerance_ || std::isnan(newValue))) {
+      for (size_t i = 0; i < n; ++i) {
+        movements[i] /= 2;
+        newPoint[i].value = params_[i].value - movements[i];
+      }
+      newValue = probe(newPoint, nullptr);
+      ++count;
+    }
+    if (newValue > currentValue_ + tolerance_) {   // "Value could not be ameliorated!"
+      f_->setParametersValues(params_);
+      newValue = currentValue_;
+      previousValue_ = currentValue_;
+    } else {
+      previousValue_ = currentValue_;
+      params_ = newPoint;
+      currentValue_ = newValue;
+    }
+    return newValue;
+  }
+  unsigned optimize() {
+    for (;;) {
+      step();
+      if (std::fabs(currentValue_ - previousValue_) < tolerance_ || nbEval_ >= nbEvalMax_) break;
+    }
+    return nbEval_;
+  }
+  double getFunctionValue() const { return currentValue_; }
+  unsigned getNumberOfEvaluations() const { return nbEval_; }
+  const ParameterList& getParameters() const { return params_; }
+
+ private:
+  // f(newPoint) with the function's own constraints applied (AUTO policy): the point actually reached is read back, and the
+  // movement corrected to it like :139-141
+  double probe(ParameterList& point, std::vector<double>* movements) {
+    f_->setParametersValues(point);
+    ++nbEval_;
+    for (size_t i = 0; i < point.size(); ++i) {
+      point[i].value = f_->getParameterValue(point[i].name);
+      if (movements) (*movements)[i] = params_[i].value - point[i].value;
+    }
+    return f_->getValue();
+  }
+  AbstractHomogeneousTreeLikelihood* f_;
+  ParameterList params_;
+  double tolerance_;
+  unsigned maxCorrection_, nbEvalMax_, nbEval_;
+  double currentValue_, previousValue_;
+};
+
 }  // namespace bppshim

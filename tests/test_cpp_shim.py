@@ -244,3 +244,68 @@ def test_reference_likelihood_tests_through_the_shim(built_lib):
     expect = -float(np.sum(ck.weights * mixed))
     assert abs(vals["MIXED_T92_G4"] - expect) <= 1e-9 * abs(expect)
     assert abs(vals["MIXED_DEGENERATE"] - 85.030942031997312824) < 1e-9
+
+
+def oracle_pseudo_newton(c, tol=1e-6, max_correction=10, max_steps=200):
+    """PseudoNewtonOptimizer::doStep (Likelihood/PseudoNewtonOptimizer.cpp:100-193, CG disabled) on the ORACLE's -lnL and its
+    branch derivatives: the trajectory the shim's optimiser must follow on the device."""
+    from oracle import ref_tree as rt
+    nb = c.flat.n_nodes - 1
+
+    def evaluate(bl, derivs):
+        res = cases.oracle_eval(c, brlen=np.concatenate([bl, [0.0]]), want_d1=derivs, want_d2=derivs)
+        return -res.lnl, (res.d1, res.d2) if derivs else None
+    x = np.asarray(c.flat.brlen[:nb], float).copy()
+    cur, (d1, d2) = evaluate(x, True)
+    values = [cur]
+    for _ in range(max_steps):
+        with np.errstate(divide="ignore", invalid="ignore"):
+            mv = np.where(d2 == 0, 0.0, np.where(d2 < 0, -d1 / d2, d1 / d2))
+        mv = np.where(np.isnan(mv), 0.0, mv)
+        new = np.clip(x - mv, rt.MIN_BRLEN, rt.MAX_BRLEN)
+        mv = x - new
+        val, _ = evaluate(new, False)
+        count = 0
+        while count < max_correction and (val > cur + tol or np.isnan(val)):
+            mv = mv / 2
+            new = np.clip(x - mv, rt.MIN_BRLEN, rt.MAX_BRLEN)
+            val, _ = evaluate(new, False)
+            count += 1
+        prev = cur
+        if val > cur + tol:
+            val = cur
+        else:
+            x, cur = new, val
+            _, (d1, d2) = evaluate(x, True)
+        values.append(val)
+        if abs(cur - prev) < tol:
+            break
+    return values, x
+
+
+@pytest.mark.gpu
+def test_pseudo_newton_branch_lengths_follow_the_oracle_trajectory(built_lib):
+    """the reference's Newton-Raphson branch-length optimiser on top of the device's d1 / d2 (all branches from one
+    evaluation per step).  Same start, same rule => the same sequence of -lnL values as the oracle-driven run, step by step."""
+    exe = compile_cpp("test_newton", built_lib)
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    vals = {f[0]: float(f[1]) for f in (line.split() for line in r.stdout.splitlines()) if len(f) == 2}
+    r4, p4 = rm.gamma_rates(4, 1.0)
+    dna = cases.case_from_alignment("((A:0.01, B:0.02):0.03,C:0.01,D:0.1);",
+                                    {"A": "AAATGGCTGTGCACGTC", "B": "GACTGGATCTGCACGTC", "C": "CTCTGGATGTGCACGTG", "D": "AAATGGCGGTGCGCCTA"},
+                                    rm.t92(3.0, 0.5), r4, p4)
+    r7, p7 = rm.gamma_rates(4, 0.7)
+    prot = cases.case_from_alignment("((a:0.1,b:0.2):0.05,(c:0.3,d:0.02):0.07,e:0.15);",
+                                     {"a": "ARNDCQEGHILKMFPSTWYVAAX", "b": "ARNDCQEGHILKMFPSTWYVLK-", "c": "ARNECQDGHLIKMFPTSWYVAKB",
+                                      "d": "GRNDCQEGHILRMYPSTWFVAAZ", "e": "ARNDCQEGHVLKMFPSTWYIVAA"}, rm.lg08(), r7, p7,
+                                     states=rp.PROTEIN_STATES, aliases=rp.PROTEIN_ALIASES)
+    for tag, c in (("PN_T92", dna), ("PN_LG08", prot)):
+        values, x = oracle_pseudo_newton(c)
+        assert abs(vals[tag + "_START"] - values[0]) <= 1e-9 * values[0]
+        assert int(vals[tag + "_NSTEPS"]) == len(values) - 1, tag
+        for k, v in enumerate(values[1:]):
+            assert abs(vals["%s_STEP_%d" % (tag, k)] - v) <= 1e-7 * abs(v), (tag, k)
+        assert vals[tag + "_FINAL"] < vals[tag + "_START"] - 1.0            # it did optimise
+        for b in range(len(x)):
+            assert abs(vals["%s_BrLen%d" % (tag, b)] - x[b]) <= 1e-5 * max(1.0, x[b]), (tag, b)
