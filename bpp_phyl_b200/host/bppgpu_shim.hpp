@@ -1294,6 +1294,140 @@ class ChromosomeSubstitutionModel : public AbstractSubstitutionModel {
   rateChangeFunc rc_;
 };
 
+// ---- mixtures of one model over a parameter (Model/MixedSubstitutionModel.h, MixtureOfASubstitutionModel) ---------------------------
+class MixedSubstitutionModel {
+ public:
+  virtual ~MixedSubstitutionModel() {}
+  virtual std::string getName() const = 0;
+  virtual size_t getNumberOfModels() const = 0;
+  virtual SubstitutionModel* getNModel(size_t i) const = 0;
+  virtual double getNProbability(size_t i) const = 0;
+  virtual std::vector<std::string> getParameterNames() const = 0;
+  virtual double getParameterValue(const std::string& name) const = 0;
+  virtual void setParameterValue(const std::string& name, double v) = 0;
+  Vdouble getProbabilities() const {
+    Vdouble p(getNumberOfModels());
+    for (size_t i = 0; i < p.size(); ++i) p[i] = getNProbability(i);
+    return p;
+  }
+};
+
+// The omega mixtures of the YNGP wrappers: three YN98 that differ in omega, class probabilities from the simplex parameters
+// theta1, theta2 (SimpleDiscreteDistribution: p0 = theta1, p1 = (1 - theta1) theta2, p2 = the rest), and the homogenisation of the
+// synonymous rate (YNGP_M2::updateMatrices, Model/Codon/YNGP_M2.cpp:134-146): sub-model k gets the relative rate
+// 1 / Q_k(synfrom, synto) for the first synonymous pair with non-zero rates, normalised to mean 1 under the probabilities
+// (MixtureOfASubstitutionModel::setVRates).
+class OmegaMixture_ : public MixedSubstitutionModel {
+ public:
+  size_t getNumberOfModels() const { return 3; }
+  SubstitutionModel* getNModel(size_t i) const { return sub_.at(i).get(); }
+  double getNProbability(size_t i) const { return probs_.at(i); }
+
+ protected:
+  OmegaMixture_(const Alphabet* alpha, const Vdouble* codonFreq) : alpha_(alpha) { if (codonFreq) codonFreq_ = *codonFreq; }
+  void rebuild(double kappa, const double omega[3], double theta1, double theta2) {
+    probs_ = {theta1, (1 - theta1) * theta2, (1 - theta1) * (1 - theta2)};
+    sub_.clear();
+    for (int k = 0; k < 3; ++k) sub_.emplace_back(new YN98(alpha_, kappa, omega[k], codonFreq_.empty() ? nullptr : &codonFreq_));
+    size_t from = 0, to = 0;
+    bool found = false;
+    for (size_t f = 1; f < 64 && !found; ++f)
+      for (size_t t = 0; t < f && !found; ++t)
+        if (CodonAlphabet::aminoAcid((int)f) == CodonAlphabet::aminoAcid((int)t) && !CodonAlphabet::isStop((int)f) &&
+            sub_[0]->getGenerator()(f, t) != 0 && sub_[1]->getGenerator()(f, t) != 0) {
+          from = f;
+          to = t;
+          found = true;
+        }
+    if (!found) throw Exception("Impossible to find synonymous codons");
+    double r[3], mean = 0;
+    for (int k = 0; k < 3; ++k) { r[k] = 1.0 / sub_[k]->getGenerator()(from, to); mean += probs_[k] * r[k]; }
+    for (int k = 0; k < 3; ++k) sub_[k]->setRate(r[k] / mean);
+  }
+  const Alphabet* alpha_;
+  Vdouble codonFreq_;
+  std::vector<std::unique_ptr<YN98> > sub_;
+  Vdouble probs_;
+};
+// Model/Codon/YNGP_M2.cpp:52-146: omega in {omega0 < 1, 1, omega2 > 1}
+class YNGP_M2 : public OmegaMixture_ {
+ public:
+  YNGP_M2(const Alphabet* alpha, double kappa = 1., double omega0 = 0.5, double omega2 = 2., double theta1 = 0.333333, double theta2 = 0.5,
+          const Vdouble* codonFreq = nullptr)
+      : OmegaMixture_(alpha, codonFreq), kappa_(kappa), omega0_(omega0), omega2_(omega2), theta1_(theta1), theta2_(theta2) { update(); }
+  std::string getName() const { return "YNGP_M2"; }
+  std::vector<std::string> getParameterNames() const { return {"YNGP_M2.kappa", "YNGP_M2.omega0", "YNGP_M2.omega2", "YNGP_M2.theta1", "YNGP_M2.theta2"}; }
+  double getParameterValue(const std::string& name) const { return *slot(name); }
+  void setParameterValue(const std::string& name, double v) { *const_cast<double*>(slot(name)) = v; update(); }
+
+ private:
+  const double* slot(const std::string& name) const {
+    const std::string n = name.substr(name.find('.') == std::string::npos ? 0 : name.find('.') + 1);
+    const std::map<std::string, const double*> m = {{"kappa", &kappa_}, {"omega0", &omega0_}, {"omega2", &omega2_}, {"theta1", &theta1_}, {"theta2", &theta2_}};
+    if (!m.count(n)) throw ParameterNotFoundException(name);
+    return m.at(n);
+  }
+  void update() { const double w[3] = {omega0_, 1.0, omega2_}; rebuild(kappa_, w, theta1_, theta2_); }
+  double kappa_, omega0_, omega2_, theta1_, theta2_;
+};
+// fork, Model/Codon/RELAX.cpp:52-218: omegas ((p omega1)^k, omega1^k, omega2^k), floored at 0.001 / capped at 999 (:176-205)
+class RELAX : public OmegaMixture_ {
+ public:
+  RELAX(const Alphabet* alpha, double kappa = 1., double p = 0.5, double omega1 = 1., double omega2 = 2., double k = 1.,
+        double theta1 = 0.333333, double theta2 = 0.5, const Vdouble* codonFreq = nullptr)
+      : OmegaMixture_(alpha, codonFreq), kappa_(kappa), p_(p), omega1_(omega1), omega2_(omega2), k_(k), theta1_(theta1), theta2_(theta2) { update(); }
+  std::string getName() const { return "RELAX"; }
+  std::vector<std::string> getParameterNames() const {
+    return {"RELAX.kappa", "RELAX.p", "RELAX.omega1", "RELAX.omega2", "RELAX.k", "RELAX.theta1", "RELAX.theta2"};
+  }
+  double getParameterValue(const std::string& name) const { return *slot(name); }
+  void setParameterValue(const std::string& name, double v) { *const_cast<double*>(slot(name)) = v; update(); }
+
+ private:
+  const double* slot(const std::string& name) const {
+    const std::string n = name.substr(name.find('.') == std::string::npos ? 0 : name.find('.') + 1);
+    const std::map<std::string, const double*> m = {{"kappa", &kappa_}, {"p", &p_}, {"omega1", &omega1_}, {"omega2", &omega2_},
+                                                     {"k", &k_}, {"theta1", &theta1_}, {"theta2", &theta2_}};
+    if (!m.count(n)) throw ParameterNotFoundException(name);
+    return m.at(n);
+  }
+  void update() {
+    const double w[3] = {std::max(std::pow(p_ * omega1_, k_), 0.001), std::max(std::pow(omega1_, k_), 0.001), std::min(std::pow(omega2_, k_), 999.0)};
+    rebuild(kappa_, w, theta1_, theta2_);
+  }
+  double kappa_, p_, omega1_, omega2_, k_, theta1_, theta2_;
+};
+
+// Model/MixedSubstitutionModelSet.h: mixed models on groups of branches; the site paths ("hyper-nodes") supported here are the
+// ones test/test_relax.cpp:100-102 sets up -- sub-model k of every model travels together, with the first model's probability.
+class MixedSubstitutionModelSet {
+ public:
+  explicit MixedSubstitutionModelSet(const Alphabet* alpha) : alphabet_(alpha) {}
+  void addModel(MixedSubstitutionModel* model, const std::vector<int>& nodesId) {   // owns the model
+    if (!models_.empty() && model->getNumberOfModels() != models_[0]->getNumberOfModels()) {
+      delete model;
+      throw Exception("MixedSubstitutionModelSet: every model needs the same number of sub-models for linked site paths");
+    }
+    for (int id : nodesId) nodeToModel_[id] = models_.size();
+    models_.emplace_back(model);
+  }
+  size_t getNumberOfModels() const { return models_.size(); }
+  MixedSubstitutionModel* getModel(size_t i) const { return models_.at(i).get(); }
+  size_t getNumberOfPaths() const { return models_.at(0)->getNumberOfModels(); }
+  double getPathProbability(size_t k) const { return models_.at(0)->getNProbability(k); }
+  size_t getModelIndexForNode(int nodeId) const {
+    std::map<int, size_t>::const_iterator it = nodeToModel_.find(nodeId);
+    if (it == nodeToModel_.end()) throw Exception("MixedSubstitutionModelSet: no model associated to node with id " + std::to_string(nodeId));
+    return it->second;
+  }
+  const Alphabet* getAlphabet() const { return alphabet_; }
+
+ private:
+  const Alphabet* alphabet_;
+  std::vector<std::unique_ptr<MixedSubstitutionModel> > models_;
+  std::map<int, size_t> nodeToModel_;
+};
+
 // ---- root frequency sets and non-homogeneous model sets ---------------------------------------------------------------------------
 // Model/FrequencySet/NucleotideFrequencySet.h: GCFrequencySet (one parameter theta = G+C content), FixedFrequencySet
 class FrequencySet {
@@ -1826,7 +1960,7 @@ class AbstractHomogeneousTreeLikelihood {
     std::memset(&cfg, 0, sizeof(cfg));
     cfg.n_states = (int32_t)S; cfg.n_cats = (int32_t)C; cfg.n_patterns = nPatterns_; cfg.n_nodes = nn; cfg.root = nn - 1;
     cfg.child_offsets = off.data(); cfg.children = children.data(); cfg.n_points = nPoints_;
-    cfg.n_models = modelSet_ ? (int32_t)modelSet_->getNumberOfModels() : nPoints_;
+    cfg.n_models = modelSet_ ? (int32_t)modelSet_->getNumberOfModels() : (nModelSlots_ > 0 ? nModelSlots_ : nPoints_);
     cfg.n_codes = (int32_t)chars.size(); cfg.code_bytes = chars.size() > 256 ? 2 : 1; cfg.code_table = table.data();
     cfg.device = device_; cfg.flags = engineFlags_ | BPPGPU_FLAG_KEEP_CLVS;
     if (engine_) { bppgpu_destroy(engine_); engine_ = nullptr; }
@@ -1992,6 +2126,7 @@ class AbstractHomogeneousTreeLikelihood {
   mutable std::vector<int> rootExp_;
   long numOfLikelihoodCalculations_;
   int nPoints_ = 1;  // parameter points evaluated per device call (LikelihoodPointBatch)
+  int nModelSlots_ = 0;  // device model slots when they are not one per point (RNonHomogeneousMixedTreeLikelihood)
   bool reparametrizeRoot_ = false;  // BrLenRoot / RootPosition replace the two root branches (NH classes, rooted trees)
   int root1_ = -1, root2_ = -1;     // ids (= BrLen indices) of the root's first two sons
 };
@@ -2241,6 +2376,16 @@ class RHomogeneousMixedTreeLikelihood : public LikelihoodPointBatch {
       : LikelihoodPointBatch(tree, data, false, subModels, rDist, device, /*checkRooted=*/true, /*engineFlags=*/0u), probas_(probas) {
     if (probas_.size() != subModels.size()) throw Exception("RHomogeneousMixedTreeLikelihood: one probability per sub-model");
   }
+  // Likelihood/RHomogeneousMixedTreeLikelihood.h: (tree, data, model, rDist, checkRooted, verbose, usePatterns) with a mixed model
+  RHomogeneousMixedTreeLikelihood(const Tree& tree, const VectorSiteContainer& data, MixedSubstitutionModel* model, DiscreteDistribution* rDist,
+                                  bool checkRooted = true, bool verbose = true, bool usePatterns = true, int device = 0)
+      : LikelihoodPointBatch(tree, data, false, subModelsOf(model), rDist, device, checkRooted, /*engineFlags=*/0u),
+        probas_(model->getProbabilities()) { (void)verbose; (void)usePatterns; }
+  static std::vector<SubstitutionModel*> subModelsOf(const MixedSubstitutionModel* m) {
+    std::vector<SubstitutionModel*> v;
+    for (size_t k = 0; k < m->getNumberOfModels(); ++k) v.push_back(m->getNModel(k));
+    return v;
+  }
   void setProbabilities(const Vdouble& p) { probas_ = p; if (initialized_) combine(); }
   double getValue() const { requireInit(); return mixedMinusLogLik_; }
   double getLogLikelihood() const { return -getValue(); }
@@ -2436,6 +2581,97 @@ class MarginalNonRevAncestralStateReconstruction {
   size_t nbSites_, nbDistinctSites_, nbClasses_, nbStates_;
   std::unique_ptr<std::map<int, std::map<size_t, std::vector<double> > > > postProbNode_;
   std::unique_ptr<std::map<int, std::map<size_t, VVdouble> > > jointProbabilities_;
+};
+
+// Likelihood/RNonHomogeneousMixedTreeLikelihood.{h,cpp}: mixed models on groups of branches.  The reference expands the set into one
+// RNonHomogeneousTreeLikelihood per site path ("hyper-node") and adds their site likelihoods with the path probabilities
+// (RNonHomogeneousMixedTreeLikelihood.cpp: getLikelihoodForASite = sum_paths p_path L_path); here every path is one point of a
+// single device object: K x M model slots (path k, model m), one branch -> slot map per point, one evaluation for all paths.
+class RNonHomogeneousMixedTreeLikelihood : public AbstractHomogeneousTreeLikelihood {
+ public:
+  RNonHomogeneousMixedTreeLikelihood(const Tree& tree, const VectorSiteContainer& data, MixedSubstitutionModelSet* modelSet,
+                                     DiscreteDistribution* rDist, bool verbose = true, bool usePatterns = true, int device = 0)
+      : AbstractHomogeneousTreeLikelihood(tree, modelSet->getModel(0)->getNModel(0), rDist, false, BPPGPU_FLAG_R_SEMANTICS, device),
+        mixedSet_(modelSet) {
+    (void)verbose; (void)usePatterns;
+    for (size_t i = 0; i + 1 < nodes_.size(); ++i) mixedSet_->getModelIndexForNode(nodes_[i]->getId());   // throws if a branch has no model
+    nPoints_ = (int)mixedSet_->getNumberOfPaths();
+    nModelSlots_ = nPoints_ * (int)mixedSet_->getNumberOfModels();
+    computeDerivatives_ = false;
+    setData(data);
+  }
+  double getValue() const { requireInit(); return mixedMinusLogLik_; }
+  double getLogLikelihood() const { return -getValue(); }
+  double getLogLikelihoodForASite(size_t site) const { requireInit(); return mixedSiteLnl_[(size_t)siteIndex_[site]]; }
+  void computeTreeLikelihood() { fireParameterChanged(); }
+
+ protected:
+  // "<Model>.<param>_<m>": parameter of the m-th mixed model of the set (1-based, like SubstitutionModelSet)
+  bool applyBranchParameter(const std::string& name, double value) override {
+    const size_t u = name.rfind('_');
+    if (u == std::string::npos || name.compare(0, 5, "BrLen") == 0) return false;
+    char* end = nullptr;
+    const long m = std::strtol(name.c_str() + u + 1, &end, 10);
+    if (*end != 0 || m < 1 || (size_t)m > mixedSet_->getNumberOfModels()) return false;
+    mixedSet_->getModel((size_t)m - 1)->setParameterValue(name.substr(0, u), value);
+    return true;
+  }
+  void uploadModel() override {
+    if (!engine_) return;
+    const size_t K = mixedSet_->getNumberOfPaths(), M = mixedSet_->getNumberOfModels();
+    Vdouble r(rDist_->getNumberOfCategories()), p(r.size());
+    for (size_t c = 0; c < r.size(); ++c) { r[c] = rDist_->getCategory(c); p[c] = rDist_->getProbability(c); }
+    check(bppgpu_set_rates(engine_, r.data(), p.data()), "setRates");
+    for (size_t k = 0; k < K; ++k) {
+      for (size_t m = 0; m < M; ++m) {
+        bppgpu_model_desc d;
+        mixedSet_->getModel(m)->getNModel(k)->fillModelDesc(d);
+        check(bppgpu_set_model(engine_, (int32_t)(k * M + m), &d), "setModel");
+      }
+      std::vector<int32_t> slot(nodes_.size(), 0);
+      for (size_t i = 0; i + 1 < nodes_.size(); ++i) slot[i] = (int32_t)(k * M + mixedSet_->getModelIndexForNode(nodes_[i]->getId()));
+      check(bppgpu_set_branch_models(engine_, (int32_t)k, slot.data()), "setBranchModels");
+      // stationary set (nonhomogeneous.stationarity = yes): the root uses the equilibrium frequencies of the models
+      const Vdouble f = mixedSet_->getModel(0)->getNModel(k)->getFrequencies();
+      check(bppgpu_set_root_freqs(engine_, (int32_t)k, f.data()), "setRootFreqs");
+    }
+    rootFreqs_ = mixedSet_->getModel(0)->getNModel(0)->getFrequencies();
+  }
+  void fireParameterChanged() override {
+    uploadModel();
+    const size_t K = mixedSet_->getNumberOfPaths(), N = (size_t)nPatterns_;
+    Vdouble t(nodes_.size(), 0.0);
+    for (size_t i = 0; i < brLen_.size(); ++i) t[i] = brLen_[i];
+    for (size_t k = 0; k < K; ++k) check(bppgpu_set_branch_lengths(engine_, (int32_t)k, t.data()), "applyParameters");
+    Vdouble lnl(K, 0.0);
+    check(bppgpu_eval(engine_, BPPGPU_EVAL_LNL, lnl.data(), nullptr, nullptr), "computeTreeLikelihood");
+    numOfLikelihoodCalculations_ += (long)K;
+    std::vector<Vdouble> sl(K, Vdouble(N));
+    for (size_t k = 0; k < K; ++k) check(bppgpu_get_site_lnl(engine_, (int32_t)k, sl[k].data()), "getLogLikelihoodForEachSite");
+    mixedSiteLnl_.assign(N, 0.0);
+    for (size_t i = 0; i < N; ++i) {
+      double mx = -std::numeric_limits<double>::infinity();
+      for (size_t k = 0; k < K; ++k) if (mixedSet_->getPathProbability(k) > 0) mx = std::max(mx, sl[k][i]);
+      double sum = 0;
+      for (size_t k = 0; k < K; ++k) if (mixedSet_->getPathProbability(k) > 0) sum += mixedSet_->getPathProbability(k) * std::exp(sl[k][i] - mx);
+      mixedSiteLnl_[i] = std::isfinite(mx) ? mx + std::log(sum) : mx;
+    }
+    Vdouble la(siteIndex_.size());   // getLogLikelihood (RHomogeneousTreeLikelihood.cpp:162-176): every site, sorted, summed
+    for (size_t j = 0; j < la.size(); ++j) la[j] = mixedSiteLnl_[(size_t)siteIndex_[j]];
+    std::sort(la.begin(), la.end());
+    double ll = 0;
+    for (size_t j = la.size(); j > 0; --j) ll += la[j - 1];
+    mixedMinusLogLik_ = -ll;
+    minusLogLik_ = mixedMinusLogLik_;
+    siteLnl_ = mixedSiteLnl_;
+    derivsValid_ = false;
+    rootArraysValid_ = false;
+  }
+
+ private:
+  MixedSubstitutionModelSet* mixedSet_;   // not owned
+  Vdouble mixedSiteLnl_;
+  double mixedMinusLogLik_ = 0;
 };
 
 // ---- Newton-Raphson on the branch lengths --------------------------------------------------------------------------

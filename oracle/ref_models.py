@@ -371,6 +371,43 @@ def yn98(kappa=1., omega=1., codon_freq=None):
     return update_matrices(m, compute_freq=False)
 
 
+def _simple_distribution_probs(thetas):
+    """SimpleDiscreteDistribution's simplex parameters (bpp-core): p_1 = theta1, p_2 = (1 - theta1) theta2, ...,
+    the last class takes the rest (YNGP_M2.cpp / RELAX.cpp: "theta1 = p0, theta2 = p1 / (p1 + p2)")."""
+    probs, rest = [], 1.0
+    for th in thetas:
+        probs.append(rest * th)
+        rest *= 1.0 - th
+    return np.array(probs + [rest])
+
+
+def _omega_mixture(kappa, omegas, probs, codon_freq=None):
+    """MixtureOfASubstitutionModel over YN98's omega + the synonymous-rate homogenisation of the YNGP / RELAX wrappers
+    (YNGP_M2::updateMatrices, Model/Codon/YNGP_M2.cpp:134-146; RELAX.cpp:212-218): sub-model k gets the relative rate
+    1 / Q_k(synfrom, synto) -- the first synonymous pair with a non-zero rate, AAG -> AAA in the 64-state order -- and
+    MixtureOfASubstitutionModel::setVRates normalises the rates to mean 1 under the class probabilities."""
+    models = [yn98(kappa, w, codon_freq) for w in omegas]
+    rates = np.array([1.0 / m.Q[2, 0] for m in models])
+    rates = rates / float(np.dot(probs, rates))
+    for m, r in zip(models, rates):
+        m.rate = float(r)
+    return models, np.asarray(probs, float)
+
+
+def yngp_m2(kappa=1., omega0=0.5, omega2=2., theta1=0.333333, theta2=0.5, codon_freq=None):
+    """YNGP_M2 (Model/Codon/YNGP_M2.cpp:52-146): three YN98 with omega in {omega0 < 1, 1, omega2 > 1}."""
+    return _omega_mixture(kappa, [omega0, 1.0, omega2], _simple_distribution_probs([theta1, theta2]), codon_freq)
+
+
+def relax(kappa=1., p=0.5, omega1=1., omega2=2., k=1., theta1=0.333333, theta2=0.5, codon_freq=None):
+    """RELAX (fork; Model/Codon/RELAX.cpp:52-218): omegas ((p omega1)^k, omega1^k, omega2^k), the first two floored at 0.001 and
+    the last capped at 999 (:176-205)."""
+    w0 = max((p * omega1) ** k, 0.001)
+    w1 = max(omega1 ** k, 0.001)
+    w2 = min(omega2 ** k, 999.0)
+    return _omega_mixture(kappa, [w0, w1, w2], _simple_distribution_probs([theta1, theta2]), codon_freq)
+
+
 # ---- chromosome number (fork) -------------------------------------------------
 IGNORE_PARAM = -999.0      # Model/ChromosomeSubstitutionModel.h:15-23
 DEMI_EQUAL_DUPL = -2.0

@@ -70,6 +70,37 @@ int main() {
     ChromosomeAlphabet chr3(1, 20);
     ChromosomeSubstitutionModel c3(&chr3, 0.5, 0.0, 0.0, ChromosomeSubstitutionModel::IgnoreParam);
     print_model("CHR_SINGULAR", c3);
+    // omega mixtures (YNGP_M2, RELAX): class probabilities, omegas and the synonymous-rate homogenisation, all host side
+    {
+      YNGP_M2 m2(&AlphabetTools::CODON_ALPHABET(), 2.0, 0.1, 2.0, 0.5, 0.8);
+      RELAX rx(&AlphabetTools::CODON_ALPHABET(), 2.0, 0.1, 1.0, 2.0, 2.0, 0.5, 0.8);
+      Vdouble r2, rr, q2;
+      for (size_t k = 0; k < 3; ++k) {
+        r2.push_back(m2.getNModel(k)->getRate());
+        rr.push_back(rx.getNModel(k)->getRate());
+        q2.push_back(m2.getNModel(k)->getGenerator()(2, 0));
+      }
+      print_vec("M2_rates", r2);
+      print_vec("M2_probs", m2.getProbabilities());
+      print_vec("M2_Q_AAG_AAA", q2);
+      print_vec("RELAX_k2_rates", rr);
+      SubstitutionModelSet* set = SubstitutionModelSetTools::createNonHomogeneousModelSet(
+          new T92(&AlphabetTools::DNA_ALPHABET(), 3.), new GCFrequencySet(&AlphabetTools::DNA_ALPHABET()),
+          unique_ptr<Tree>(TreeTemplateTools::parenthesisToTree("((A:0.1,B:0.2):0.3,(C:0.1,D:0.2):0.1);")).get(), {"T92.kappa"});
+      set->setParameterValue("T92.kappa_1", 5.0);      // every copy follows through the aliases
+      set->setParameterValue("T92.theta_4", 0.7);
+      set->setParameterValue("GC.theta", 0.2);
+      Vdouble kap, the;
+      for (size_t k = 0; k < set->getNumberOfModels(); ++k) {
+        kap.push_back(set->getModel(k)->getParameterValue("kappa"));
+        the.push_back(set->getModel(k)->getParameterValue("theta"));
+      }
+      print_vec("NHSET_kappas", kap);
+      print_vec("NHSET_thetas", the);
+      print_vec("NHSET_rootfreqs", set->getRootFrequencies());
+      printf("\"NHSET_nparams\": %zu,\n", set->getParameterNames().size());
+      delete set;
+    }
     // getInitValue / aliases
     printf("\"init_R\": [%g, %g, %g, %g],\n", t92.getInitValue(0, "R"), t92.getInitValue(1, "R"), t92.getInitValue(2, "R"), t92.getInitValue(3, "R"));
   }

@@ -82,6 +82,21 @@ def test_models_generator_and_eigensystem(host_doc, key):
         np.testing.assert_allclose(np.sort(c["re"]), np.sort(m.ev_re), rtol=0, atol=1e-10 * np.abs(Q).max())
 
 
+def test_omega_mixtures_and_model_set_parameters_host_side(host_doc):
+    """YNGP_M2 / RELAX sub-model rates and probabilities (host logic of the shim) equal the oracle's restatement of
+    YNGP_M2.cpp:134-146 / RELAX.cpp:176-218; SubstitutionModelSet naming, aliasing and root frequency set."""
+    m2, p2 = rm.yngp_m2(2.0, 0.1, 2.0, 0.5, 0.8)
+    np.testing.assert_allclose(host_doc["M2_rates"], [m.rate for m in m2], rtol=1e-10)
+    np.testing.assert_allclose(host_doc["M2_probs"], p2, rtol=0, atol=1e-15)
+    np.testing.assert_allclose(host_doc["M2_Q_AAG_AAA"], [m.Q[2, 0] for m in m2], rtol=1e-10)
+    rx, _ = rm.relax(2.0, 0.1, 1.0, 2.0, 2.0, 0.5, 0.8)
+    np.testing.assert_allclose(host_doc["RELAX_k2_rates"], [m.rate for m in rx], rtol=1e-10)
+    assert host_doc["NHSET_kappas"] == [5.0] * 6
+    assert host_doc["NHSET_thetas"] == [0.5, 0.5, 0.5, 0.7, 0.5, 0.5]
+    np.testing.assert_allclose(host_doc["NHSET_rootfreqs"], [0.4, 0.1, 0.1, 0.4], rtol=0, atol=1e-15)
+    assert host_doc["NHSET_nparams"] == 1 + 1 + 6            # GC.theta, the shared kappa, six thetas
+
+
 def test_alias_init_values(host_doc):
     assert host_doc["init_R"] == [1, 0, 1, 0]          # R = A or G
 
@@ -309,3 +324,29 @@ def test_pseudo_newton_branch_lengths_follow_the_oracle_trajectory(built_lib):
         assert vals[tag + "_FINAL"] < vals[tag + "_START"] - 1.0            # it did optimise
         for b in range(len(x)):
             assert abs(vals["%s_BrLen%d" % (tag, b)] - x[b]) <= 1e-5 * max(1.0, x[b]), (tag, b)
+
+
+@pytest.mark.gpu
+def test_relax_and_yngp_m2_through_the_shim(built_lib):
+    """test/test_relax.cpp's three equalities through the shim on the device (RNonHomogeneousMixedTreeLikelihood: every site path is a
+    point of one engine, K x M model slots, one branch -> slot map per point), and every value against the oracle's mixture."""
+    import test_oracle_golden as tog
+    exe = compile_cpp("test_relax", built_lib)
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    vals = {f[0]: float(f[1]) for f in (line.split() for line in r.stdout.splitlines()) if len(f) == 2}
+    c = tog._relax_case()
+    nn = c.flat.n_nodes
+    m2, p2 = rm.yngp_m2(2.0, 0.1, 2.0, 0.5, 0.8)
+    for k in range(3):
+        assert abs(vals["M2_RATE_%d" % k] - m2[k].rate) <= 1e-10 * m2[k].rate
+        assert abs(vals["M2_PROB_%d" % k] - p2[k]) <= 1e-15
+    ref = tog._mixture_minus_lnl(c, [([m], np.zeros(nn, np.int64)) for m in m2], p2)
+    for key in ("M2", "RELAX_PARTITION_A", "RELAX_PARTITION_B"):
+        assert abs(-vals[key] - ref) <= 1e-9 * ref, key
+    m2b, _ = rm.yngp_m2(2.0, 0.01, 4.0, 0.5, 0.8)
+    slots = np.array([1 if n == 0 else 0 for n in range(nn)])                # model 2 (k = 2) on node 0
+    ref2 = tog._mixture_minus_lnl(c, [([a, b], slots) for a, b in zip(m2, m2b)], p2)
+    for key in ("RELAX_K2", "DOUBLE_M2"):
+        assert abs(-vals[key] - ref2) <= 1e-9 * ref2, key
+    assert abs(ref - ref2) > 1e-4

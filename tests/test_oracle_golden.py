@@ -315,3 +315,55 @@ def test_ml_joint_reconstruction_against_enumeration():
         assert all(states[l][i] == obs[l] for l in flat.leaf_ids)
         assert abs(got - best) <= 1e-13 * best
         assert abs(Lroot[i, 0].max() - best) <= 1e-13 * best
+
+
+def _relax_case():
+    import cases
+    from oracle import ref_patterns as rp
+    from oracle import ref_tree as rt
+    cod_states = [a + b + c_ for a in "ACGT" for b in "ACGT" for c_ in "ACGT"]
+    flat = rt.FlatTree(rt.parse_newick("(((A:0.01, B:0.01):0.02,C:0.03):0.01,D:0.04);"), check_rooted=False)
+    seqs = {"A": "AAATGGCTGTGCACGTCT", "B": "AACTGGATCTGCATGTCT", "C": "ATCTGGACGTGCACGTGT", "D": "CAACGGGAGTGCGCCTAT"}
+    uniq, w, idx = rp.global_patterns(seqs, flat.leaf_names, width=3)
+    codes = rp.encode_columns(uniq, cod_states, width=3)
+    c = cases.Case()
+    c.flat, c.rates, c.probs = flat, np.ones(1), np.ones(1)
+    c.table, c.N, c.weights = np.eye(64), len(uniq), w
+    c.codes_by_leaf = {lid: codes[k] for k, lid in enumerate(flat.leaf_ids)}
+    c.code_dtype = codes.dtype
+    return c
+
+
+def _mixture_minus_lnl(c, paths, probs):
+    """sum over the sites of -log sum_k p_k L_k(site); paths[k] = (models, slot_of_node) of component k"""
+    import cases
+    site = []
+    for models, slots in paths:
+        c.root_freqs = np.asarray(models[0].freq)
+        site.append(cases.oracle_eval_nh(c, models, slots, nh_form=False).site_lnl)
+    mixed = np.log(np.sum(np.asarray(probs)[:, None] * np.exp(np.asarray(site)), axis=0))
+    return -float(np.sum(c.weights * mixed))
+
+
+def test_relax_equals_m2_when_k_is_one_and_partitions_do_not_matter():
+    """The assertions of test/test_relax.cpp:104-141 on the oracle: RELAX(kappa=2, p=0.1, omega1=1, omega2=2, k=1, theta1=0.5,
+    theta2=0.8) on any partition of the branches into two model groups gives the likelihood of YNGP_M2(kappa=2, omega0=0.1,
+    omega2=2, theta1=0.5, theta2=0.8); with k != 1 on one group it does not."""
+    c = _relax_case()
+    nn = c.flat.n_nodes
+    m2, p2 = rm.yngp_m2(2.0, 0.1, 2.0, 0.5, 0.8)
+    np.testing.assert_allclose(p2, [0.5, 0.4, 0.1])
+    assert abs(float(np.dot(p2, [m.rate for m in m2])) - 1.0) < 1e-14
+    # equal synonymous rates across the components (the point of the homogenisation)
+    syn = [m.rate * m.Q[2, 0] for m in m2]
+    assert max(syn) - min(syn) < 1e-15
+    ref = _mixture_minus_lnl(c, [([m], np.zeros(nn, np.int64)) for m in m2], p2)
+    r1, pr = rm.relax(2.0, 0.1, 1.0, 2.0, 1.0, 0.5, 0.8)
+    for group0 in ([0], [1, 2, 3, 4, 5]):                                      # model1.nodes_id of the two partitions
+        slots = np.array([0 if n in group0 else 1 for n in range(nn)])
+        v = _mixture_minus_lnl(c, [([a, b], slots) for a, b in zip(r1, r1)], pr)
+        assert abs(v - ref) < 1e-9
+    r2, _ = rm.relax(2.0, 0.1, 1.0, 2.0, 0.3, 0.5, 0.8)
+    slots = np.array([0 if n == 0 else 1 for n in range(nn)])
+    v = _mixture_minus_lnl(c, [([a, b], slots) for a, b in zip(r2, r1)], pr)
+    assert abs(v - ref) > 1e-4
