@@ -367,3 +367,31 @@ def test_relax_equals_m2_when_k_is_one_and_partitions_do_not_matter():
     slots = np.array([0 if n == 0 else 1 for n in range(nn)])
     v = _mixture_minus_lnl(c, [([a, b], slots) for a, b in zip(r2, r1)], pr)
     assert abs(v - ref) > 1e-4
+
+
+def test_lg08_tables_are_the_reference_s_own_numbers():
+    """The committed LG08 tables (oracle/lg08_data.py and the shim's lg08_data.inc) against the assignment lists the reference
+    includes (Model/Protein/__LG08ExchangeabilityCode, __LG08FrequenciesCode; LG08.cpp:53-62).  Runs where /root/reference exists
+    (the build container); skipped elsewhere -- the GPU box never reads the reference."""
+    import pathlib
+    import re
+    d = pathlib.Path("/root/reference/src/Bpp/Phyl/Model/Protein")
+    if not (d / "__LG08ExchangeabilityCode").exists():
+        pytest.skip("reference sources not present")
+    from oracle.lg08_data import LG08_FREQ, LG08_LOWER
+    ex = np.zeros((20, 20))
+    for i, j, v in re.findall(r"\((\d+),(\d+)\)\s*=\s*([0-9.eE+-]+)", (d / "__LG08ExchangeabilityCode").read_text()):
+        ex[int(i), int(j)] = float(v)
+    fr = np.zeros(20)
+    for i, v in re.findall(r"\[(\d+)\]\s*=\s*([0-9.eE+-]+)", (d / "__LG08FrequenciesCode").read_text()):
+        fr[int(i)] = float(v)
+    assert np.array_equal(ex, ex.T) and np.count_nonzero(ex - np.diag(np.diag(ex))) == 380      # the file also lists a diagonal
+    for i in range(1, 20):
+        assert list(ex[i, :i]) == list(LG08_LOWER[i - 1])
+    assert list(fr) == list(LG08_FREQ)
+    inc = (pathlib.Path(__file__).resolve().parent.parent / "bpp_phyl_b200" / "host" / "lg08_data.inc").read_text()
+    nums = [float(x) for x in re.findall(r"(?<![\w.])\d+\.\d+(?:[eE][+-]?\d+)?", inc.split("LG08_LOWER[190]")[1])]
+    assert nums[:190] == [ex[i, j] for i in range(1, 20) for j in range(i)] and nums[190:210] == list(fr)
+    # the exchangeabilities and frequencies define the generator the oracle builds
+    m = rm.lg08()
+    np.testing.assert_allclose(m.freq, fr / fr.sum(), rtol=1e-12)
