@@ -101,6 +101,39 @@ int main() {
       printf("\"NHSET_nparams\": %zu,\n", set->getParameterNames().size());
       delete set;
     }
+    // BatchedBrent (the lockstep line searches of the multi-start optimiser) on analytic functions: no device involved
+    {
+      struct Analytic {
+        std::vector<double> x, y, val, a, b;
+        unsigned calls = 0;
+        size_t size() const { return x.size(); }
+        double parameter(size_t k, const std::string& n) const { return n == "x" ? x[k] : y[k]; }
+        void setParameter(size_t k, const std::string& n, double v) { (n == "x" ? x[k] : y[k]) = v; }
+        void evaluate() {
+          ++calls;
+          for (size_t k = 0; k < x.size(); ++k)
+            val[k] = (x[k] - a[k]) * (x[k] - a[k]) + 0.5 * std::pow(y[k] - b[k], 4) + 0.3 * std::sin(0.05 * x[k] * y[k]) + std::fabs(x[k] - 2 * a[k]);
+        }
+        double value(size_t k) const { return val[k]; }
+      } fn;
+      fn.a = {0.5, 3.0, 7.5, 20.0, 99.0};
+      fn.b = {1.0, 0.2, 42.0, 5.5, 0.01};
+      fn.x.assign(5, 10.0); fn.y.assign(5, 10.0); fn.val.assign(5, 0.0);
+      fn.evaluate();
+      Vdouble start = fn.val;
+      BatchedBrent<Analytic> bb(&fn);
+      std::vector<char> active = {1, 1, 1, 0, 1};        // point 3 is not searched: it must not move
+      unsigned evals = 0;
+      for (int round = 0; round < 12; ++round) {
+        evals += bb.search("x", 1e-10, 100.0, 1e-8, active);
+        evals += bb.search("y", 1e-10, 100.0, 1e-8, active);
+      }
+      print_vec("BRENT_x", fn.x);
+      print_vec("BRENT_y", fn.y);
+      print_vec("BRENT_val", fn.val);
+      print_vec("BRENT_start", start);
+      printf("\"BRENT_batch_evals\": %u, \"BRENT_calls\": %u,\n", evals, fn.calls);
+    }
     // getInitValue / aliases
     printf("\"init_R\": [%g, %g, %g, %g],\n", t92.getInitValue(0, "R"), t92.getInitValue(1, "R"), t92.getInitValue(2, "R"), t92.getInitValue(3, "R"));
   }

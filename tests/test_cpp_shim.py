@@ -97,6 +97,33 @@ def test_omega_mixtures_and_model_set_parameters_host_side(host_doc):
     assert host_doc["NHSET_nparams"] == 1 + 1 + 6            # GC.theta, the shared kappa, six thetas
 
 
+def test_batched_brent_line_searches_host_side(host_doc):
+    """BatchedBrent (every point's probe of a line search in ONE batched evaluation) on five analytic, non-smooth,
+    coupled 2-d functions: every searched point ends at a local minimum of its own function along both coordinates (checked
+    against scipy on the same function), never above its start; the point left inactive does not move; the number of batched
+    evaluations is that of the slowest point, not the sum over the points."""
+    from scipy.optimize import minimize_scalar
+    a = [0.5, 3.0, 7.5, 20.0, 99.0]
+    b = [1.0, 0.2, 42.0, 5.5, 0.01]
+    f = lambda k, x, y: (x - a[k]) ** 2 + 0.5 * (y - b[k]) ** 4 + 0.3 * np.sin(0.05 * x * y) + abs(x - 2 * a[k])
+    X, Y, V, S = host_doc["BRENT_x"], host_doc["BRENT_y"], host_doc["BRENT_val"], host_doc["BRENT_start"]
+    for k in range(5):
+        assert abs(V[k] - f(k, X[k], Y[k])) <= 1e-12 * max(1.0, abs(V[k]))
+        if k == 3:
+            assert X[k] == 10.0 and Y[k] == 10.0 and V[k] == S[k]
+            continue
+        assert V[k] <= S[k]
+        # coordinate-wise optimality: nothing better nearby along x or along y
+        for d in (1e-3, 1e-2, 0.1):
+            for sx, sy in ((d, 0), (-d, 0), (0, d), (0, -d)):
+                x, y = min(max(X[k] + sx, 1e-10), 100.0), min(max(Y[k] + sy, 1e-10), 100.0)
+                assert f(k, x, y) >= V[k] - 1e-5, (k, sx, sy)
+        best_x = minimize_scalar(lambda x: f(k, x, Y[k]), bounds=(1e-10, 100.0), method="bounded", options={"xatol": 1e-10})
+        assert V[k] <= best_x.fun + 1e-5 or abs(X[k] - best_x.x) > 1e-3      # same basin -> same value
+    assert host_doc["BRENT_calls"] == host_doc["BRENT_batch_evals"] + 1
+    assert host_doc["BRENT_batch_evals"] < 24 * 80                             # 24 searches, each bounded by its slowest point
+
+
 def test_alias_init_values(host_doc):
     assert host_doc["init_R"] == [1, 0, 1, 0]          # R = A or G
 

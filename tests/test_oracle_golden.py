@@ -395,3 +395,17 @@ def test_lg08_tables_are_the_reference_s_own_numbers():
     # the exchangeabilities and frequencies define the generator the oracle builds
     m = rm.lg08()
     np.testing.assert_allclose(m.freq, fr / fr.sum(), rtol=1e-12)
+
+
+def test_chromosome_pijt_rows_sum_to_one_like_test_chr_model():
+    """test/test_chr_model.cpp:100-114,141,152-168: ChromosomeSubstitutionModel(1..25; gain 2, loss 1, dupl 3, demi 1.3) -- every row
+    of getPij_t sums to 1 within 1e-4 for the tree's branch lengths (the tree file is not in the repository: a spread of lengths),
+    through the eigen path and through the model's own Taylor rule, and the two agree within the rule's 1e-4 test."""
+    m = rm.chromosome(1, 25, gain=2.0, loss=1.0, dupl=3.0, demi=1.3)
+    for t in (1e-6, 0.003, 0.05, 0.3, 1.0, 3.6):
+        P = rm.pij_t(m, t)
+        assert np.all(np.abs(P.sum(axis=1) - 1.0) <= 1e-4)
+        assert P.min() >= 0.0 and P.max() <= 1.0
+        T = rm._chr_pij_t(m, t, False)
+        assert np.all(np.abs(T.sum(axis=1) - 1.0) <= 1e-4)
+        assert np.abs(T - P).max() <= 2e-4
