@@ -53,9 +53,13 @@ int main() {
     MLAncestralStateReconstruction ml(&tl, opt.getBestModel(), tl.getRootFrequencies());
     ml.computeJointLikelihood();
     for (auto& kv : ml.getAllAncestralStates()) printf("OPT_ML_%d %zu\n", kv.first, kv.second[0]);
+    printf("OPT_ML_BEST_LNL %.15g\n", ml.getBestJointLogLikelihoodPerSite()[0]);
     MarginalNonRevAncestralStateReconstruction asr(&tl);
     asr.computePosteriorProbabilitiesOfNodesForEachStatePerSite();
-    for (auto& kv : asr.getAllAncestralStates()) printf("OPT_MARG_%d %zu\n", kv.first, kv.second[0]);
+    for (auto& kv : asr.getAllAncestralStates()) {
+      printf("OPT_MARG_%d %zu\n", kv.first, kv.second[0]);
+      printf("OPT_MARGP_%d %.15g\n", kv.first, (*asr.getPosteriorProbForAllNodesAndStatesPerSite())[kv.first][0][kv.second[0]]);
+    }
   } catch (std::exception& e) {
     cerr << e.what() << endl;
     return 1;
