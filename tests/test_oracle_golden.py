@@ -409,3 +409,65 @@ def test_chromosome_pijt_rows_sum_to_one_like_test_chr_model():
         T = rm._chr_pij_t(m, t, False)
         assert np.all(np.abs(T.sum(axis=1) - 1.0) <= 1e-4)
         assert np.abs(T - P).max() <= 2e-4
+
+
+def test_t92_generator_and_closed_form_transition_probabilities():
+    """The oracle's generic route for T92 (generator -> eigen-decomposition -> V exp(D t) V^-1) against the reference's analytic T92:
+    generator and normalisation r_ (Model/Nucleotide/T92.cpp:81-116) and the closed-form getPij_t (:355-386) with its t-derivatives
+    (getdPij_dt / getd2Pij_dt2 differentiate the same expressions), for several kappa, theta, t and a model rate != 1."""
+    for kappa, theta in ((3.0, 0.5), (0.7, 0.2), (8.0, 0.83)):
+        pi = np.array([(1 - theta) / 2, theta / 2, theta / 2, (1 - theta) / 2])
+        k = (kappa + 1.0) / 2.0
+        r = 2.0 / (1.0 + 2.0 * theta * kappa - 2.0 * theta * theta * kappa)
+        G = np.zeros((4, 4))
+        G[0, 0] = G[3, 3] = -(1.0 + theta * kappa) / 2
+        G[1, 1] = G[2, 2] = -(1.0 + (1.0 - theta) * kappa) / 2
+        G[1, 0] = G[3, 0] = G[0, 3] = G[2, 3] = (1.0 - theta) / 2
+        G[0, 1] = G[2, 1] = G[1, 2] = G[3, 2] = theta / 2
+        G[2, 0] = G[1, 3] = kappa * (1.0 - theta) / 2
+        G[3, 1] = G[0, 2] = kappa * theta / 2
+        m = rm.t92(kappa, theta)
+        np.testing.assert_allclose(m.Q, G * r, rtol=0, atol=1e-14)
+        np.testing.assert_allclose(m.freq, pi, rtol=0, atol=1e-15)
+        for rate in (1.0, 0.37):
+            m.rate = rate
+            for t in (1e-6, 0.01, 0.3, 2.5):
+                def closed(order):
+                    s = rate * r                                     # l_ = rate_ * r_ * d
+                    e1 = (-s) ** order * np.exp(-s * t)
+                    e2 = (-k * s) ** order * np.exp(-k * s * t)
+                    one = 1.0 if order == 0 else 0.0
+                    P = np.empty((4, 4))
+                    P[0] = [pi[0] * (one + e1) + theta * e2, pi[1] * (one - e1), pi[2] * (one + e1) - theta * e2, pi[3] * (one - e1)]
+                    P[1] = [pi[0] * (one - e1), pi[1] * (one + e1) + (1 - theta) * e2, pi[2] * (one - e1), pi[3] * (one + e1) - (1 - theta) * e2]
+                    P[2] = [pi[0] * (one + e1) - (1 - theta) * e2, pi[1] * (one - e1), pi[2] * (one + e1) + (1 - theta) * e2, pi[3] * (one - e1)]
+                    P[3] = [pi[0] * (one - e1), pi[1] * (one + e1) - theta * e2, pi[2] * (one - e1), pi[3] * (one + e1) + theta * e2]
+                    return P
+                np.testing.assert_allclose(rm.pij_t(m, t), closed(0), rtol=0, atol=2e-15)
+                np.testing.assert_allclose(rm.dpij_dt(m, t), closed(1), rtol=0, atol=2e-14 * (1 + kappa))
+                np.testing.assert_allclose(rm.d2pij_dt2(m, t), closed(2), rtol=0, atol=2e-13 * (1 + kappa) ** 2)
+
+
+def test_gtr_generator_is_the_reference_s_exchangeability_formula():
+    """GTR::updateMatrices (Model/Nucleotide/GTR.cpp:84-124): exchangeabilities / p_ with p_ = 2(a piC piT + b piA piT + c piG piT +
+    d piA piC + e piC piG + piA piG), generator = exchangeability x pi (AbstractReversibleSubstitutionModel::updateMatrices,
+    AbstractSubstitutionModel.cpp:694-703): one expected substitution per unit time.  The benchmark's cfg2 model."""
+    a, b, c, d, e = 1.2, 0.8, 0.6, 1.5, 0.9
+    pi = np.array([.3, .2, .25, .25])
+    pA, pC, pG, pT = pi
+    p = 2 * (a * pC * pT + b * pA * pT + c * pG * pT + d * pA * pC + e * pC * pG + pA * pG)
+    ex = np.zeros((4, 4))
+    ex[0, 0] = (-b * pT - pG - d * pC) / (pA * p)
+    ex[1, 0] = ex[0, 1] = d / p
+    ex[2, 0] = ex[0, 2] = 1 / p
+    ex[3, 0] = ex[0, 3] = b / p
+    ex[1, 1] = (-a * pT - e * pG - d * pA) / (pC * p)
+    ex[1, 2] = ex[2, 1] = e / p
+    ex[1, 3] = ex[3, 1] = a / p
+    ex[2, 2] = (-c * pT - e * pC - pA) / (pG * p)
+    ex[2, 3] = ex[3, 2] = c / p
+    ex[3, 3] = (-c * pG - a * pC - b * pA) / (pT * p)
+    Q = ex * pi[None, :]
+    m = rm.gtr(a, b, c, d, e, tuple(pi))
+    np.testing.assert_allclose(m.Q, Q, rtol=0, atol=1e-15)
+    assert abs(-(pi * np.diag(Q)).sum() - 1.0) < 1e-15 and np.abs(Q.sum(axis=1)).max() < 1e-15
