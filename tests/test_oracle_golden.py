@@ -471,3 +471,27 @@ def test_gtr_generator_is_the_reference_s_exchangeability_formula():
     m = rm.gtr(a, b, c, d, e, tuple(pi))
     np.testing.assert_allclose(m.Q, Q, rtol=0, atol=1e-15)
     assert abs(-(pi * np.diag(Q)).sum() - 1.0) < 1e-15 and np.abs(Q.sum(axis=1)).max() < 1e-15
+
+
+def test_hky85_generator_and_closed_form_transition_probabilities():
+    """HKY85 (BASELINE configs[0]): generator and normalisation (Model/Nucleotide/HKY85.cpp:80-125) and the closed-form getPij_t
+    (:351-383) with unequal base frequencies, against the oracle's generic eigen route."""
+    kappa = 2.7
+    pi = np.array([.31, .19, .22, .28])
+    pA, pC, pG, pT = pi
+    pR, pY = pA + pG, pT + pC
+    k1, k2 = kappa * pY + pR, kappa * pR + pY
+    G = np.array([[0, pC, kappa * pG, pT], [pA, 0, pG, kappa * pT], [kappa * pA, pC, 0, pT], [pA, kappa * pC, pG, 0]], float)
+    np.fill_diagonal(G, -G.sum(axis=1))
+    r = 1.0 / (2.0 * (pA * pC + pC * pG + pA * pT + pG * pT + kappa * (pC * pT + pA * pG)))
+    m = rm.hky85(kappa, tuple(pi))
+    np.testing.assert_allclose(m.Q, G * r, rtol=0, atol=1e-15)
+    for t in (1e-6, 0.02, 0.4, 3.0):
+        l = r * t
+        e1, e22, e21 = np.exp(-l), np.exp(-k2 * l), np.exp(-k1 * l)
+        P = np.empty((4, 4))
+        P[0] = [pA * (1 + pY / pR * e1) + pG / pR * e22, pC * (1 - e1), pG * (1 + pY / pR * e1) - pG / pR * e22, pT * (1 - e1)]
+        P[1] = [pA * (1 - e1), pC * (1 + pR / pY * e1) + pT / pY * e21, pG * (1 - e1), pT * (1 + pR / pY * e1) - pT / pY * e21]
+        P[2] = [pA * (1 + pY / pR * e1) - pA / pR * e22, pC * (1 - e1), pG * (1 + pY / pR * e1) + pA / pR * e22, pT * (1 - e1)]
+        P[3] = [pA * (1 - e1), pC * (1 + pR / pY * e1) - pC / pY * e21, pG * (1 - e1), pT * (1 + pR / pY * e1) + pC / pY * e21]
+        np.testing.assert_allclose(rm.pij_t(m, t), P, rtol=0, atol=3e-15)
