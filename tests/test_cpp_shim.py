@@ -24,9 +24,9 @@ def compile_cpp(name, built_lib):
     BUILD.mkdir(exist_ok=True)
     src = ROOT / "tests" / "cpp" / (name + ".cpp")
     exe = BUILD / name
-    hdr = ROOT / "bpp_phyl_b200" / "host" / "bppgpu_shim.hpp"
+    hdrs = [h for h in (ROOT / "bpp_phyl_b200" / "host").rglob("*") if h.is_file()] + [ROOT / "include" / "bppgpu.h"]
     lib = ROOT / "bpp_phyl_b200" / "lib"
-    if not exe.exists() or exe.stat().st_mtime < max(src.stat().st_mtime, hdr.stat().st_mtime):
+    if not exe.exists() or exe.stat().st_mtime < max([src.stat().st_mtime] + [h.stat().st_mtime for h in hdrs]):
         subprocess.check_call(["g++", "-std=c++17", "-O2", "-Wall", "-Wno-unused", "-I", str(ROOT), "-o", str(exe), str(src),
                                "-L", str(lib), "-lbppgpu", "-Wl,-rpath," + str(lib)])
     return exe
