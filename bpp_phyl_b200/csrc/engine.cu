@@ -1904,7 +1904,7 @@ int bppgpu_ml_ancestral_states(bppgpu_engine* e, int32_t point, int32_t* states,
   if (point != e->last_point) BPP_FAIL(BPPGPU_E_STATE, "tables resident are those of point %d", e->last_point);
   const int S = e->S, C = e->C, nn = e->nn;
   const long long N = e->N;
-  if (S > 65535) BPP_FAIL(BPPGPU_E_INVALID, "more than 65535 states");
+  if ((size_t)4 * S * sizeof(double) > 48 * 1024) BPP_FAIL(BPPGPU_E_INVALID, "joint ML reconstruction supports up to 1536 states (%d given)", S);
   for (int n = 0; n < nn; ++n)
     if (e->child_off[n + 1] - e->child_off[n] > 4) BPP_FAIL(BPPGPU_E_INVALID, "node %d has more than 4 sons", n);
   if (N == 0) return BPPGPU_OK;
