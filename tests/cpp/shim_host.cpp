@@ -165,6 +165,19 @@ int main() {
     for (size_t i = 0; i < sp.getWeights().size(); ++i) printf("%s%u", i ? ", " : "", sp.getWeights()[i]);
     printf("],\n\"pattern_indices\": [");
     for (size_t i = 0; i < sp.getIndices().size(); ++i) printf("%s%ld", i ? ", " : "", (long)sp.getIndices()[i]);
+    printf("],\n");
+    // three-letter states: the codon alignment of test/test_relax.cpp with two columns repeated
+    const CodonAlphabet* cod = &AlphabetTools::CODON_ALPHABET();
+    VectorSiteContainer cs(cod);
+    cs.addSequence(BasicSequence("A", "AAATGGCTGTGCACGTCTTGGAAA", cod));
+    cs.addSequence(BasicSequence("B", "AACTGGATCTGCATGTCTTGGAAC", cod));
+    cs.addSequence(BasicSequence("C", "ATCTGGACGTGCACGTGTTGGATC", cod));
+    cs.addSequence(BasicSequence("D", "CAACGGGAGTGCGCCTATCGGCAA", cod));
+    SitePatterns cp(cs, {"A", "B", "C", "D"});
+    printf("\"codon_pattern_weights\": [");
+    for (size_t i = 0; i < cp.getWeights().size(); ++i) printf("%s%u", i ? ", " : "", cp.getWeights()[i]);
+    printf("],\n\"codon_pattern_indices\": [");
+    for (size_t i = 0; i < cp.getIndices().size(); ++i) printf("%s%ld", i ? ", " : "", (long)cp.getIndices()[i]);
     printf("]\n");
   }
   printf("}\n");

@@ -145,6 +145,10 @@ def test_site_patterns_through_the_shim(host_doc):
     _, w, idx = rp.global_patterns(seqs, ["A", "B", "C", "D"])
     assert host_doc["pattern_weights"] == list(map(int, w))
     assert host_doc["pattern_indices"] == list(map(int, idx))
+    cod = {"A": "AAATGGCTGTGCACGTCTTGGAAA", "B": "AACTGGATCTGCATGTCTTGGAAC", "C": "ATCTGGACGTGCACGTGTTGGATC", "D": "CAACGGGAGTGCGCCTATCGGCAA"}
+    _, w, idx = rp.global_patterns(cod, ["A", "B", "C", "D"], width=3)       # three-letter states (codons)
+    assert host_doc["codon_pattern_weights"] == list(map(int, w)) and sum(w) == 8 and len(w) == 6
+    assert host_doc["codon_pattern_indices"] == list(map(int, idx))
 
 
 @pytest.mark.gpu
