@@ -218,6 +218,17 @@ class AbstractHomogeneousTreeLikelihood {
     return rates;
   }
 
+  // TreeLikelihood::getTransitionProbabilities(nodeId, siteIndex): the class tables averaged with the class probabilities
+  // (AbstractDiscreteRatesAcrossSitesTreeLikelihood.cpp:310-329)
+  VVdouble getTransitionProbabilities(int nodeId, size_t siteIndex = 0) const {
+    const VVVdouble p3 = getTransitionProbabilitiesPerRateClass(nodeId, siteIndex);
+    const size_t S = getNumberOfStates();
+    VVdouble p2(S, Vdouble(S, 0.0));
+    for (size_t i = 0; i < S; ++i)
+      for (size_t j = 0; j < S; ++j)
+        for (size_t k = 0; k < p3.size(); ++k) p2[i][j] += p3[k][i][j] * rDist_->getProbability(k);
+    return p2;
+  }
   // DRTreeLikelihood::computeLikelihoodAtNode-style access to the device-resident conditional likelihoods of an internal
   // node (subtree below it): true value = likelihoodArray[i][c][x] * 2^-scale[i][c]
   void getLikelihoodArray(int nodeId, VVVdouble& likelihoodArray, std::vector<std::vector<int> >& scale) const {
