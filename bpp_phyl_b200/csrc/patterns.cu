@@ -21,6 +21,8 @@
 #include <cub/cub.cuh>
 
 #include <algorithm>
+#include <cstdlib>
+#include <string>
 
 namespace bppgpu {
 namespace {
@@ -103,6 +105,58 @@ __global__ void pattern_tip_codes_kernel(const T* __restrict__ cols, const long 
   }
 }
 
+// ---- variant "dedup" (BPPGPU_PATTERNS_ALGO=dedup; NOT yet run on a device, default off) -------------------------------------------
+// Identical columns are merged BEFORE the lexicographic sort: one 64-bit hash per column (equal columns -> equal hashes; a
+// collision between different columns only leaves duplicates for the final run detection to merge), one stable sort of the hashes,
+// run heads by full comparison, and the word-by-word radix sort runs over the unique columns only.
+__device__ __forceinline__ unsigned long long mix64(unsigned long long x) {
+  x ^= x >> 33; x *= 0xff51afd7ed558ccdULL; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL; x ^= x >> 33;
+  return x;
+}
+// one warp per column; position-dependent mixing, commutative combination across lanes
+__global__ void pattern_hash_kernel(const uint8_t* __restrict__ cols, long long n, int col_bytes, unsigned long long* __restrict__ hash) {
+  const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (i >= n) return;
+  const uint8_t* c = cols + (size_t)i * col_bytes;
+  unsigned long long acc = 0;
+  for (int j = lane; j < col_bytes; j += 32) acc += mix64(((unsigned long long)c[j] << 32) ^ (unsigned long long)(j + 1) * 0x9e3779b97f4a7c15ULL);
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) hash[i] = mix64(acc);
+}
+// sorted by hash: number[k] - 1 = id of the unique column of position k
+__global__ void pattern_dedup_scatter_kernel(const uint32_t* __restrict__ perm, const uint32_t* __restrict__ head,
+                                             const uint32_t* __restrict__ number, long long n, uint32_t* __restrict__ site_to_u,
+                                             uint32_t* __restrict__ u_site, uint32_t* __restrict__ u_weight) {
+  const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const uint32_t u = number[k] - 1u, site = perm[k];
+  site_to_u[site] = u;
+  if (head[k]) u_site[u] = site;     // the run head is the smallest original position: the hash sort is stable
+  atomicAdd(&u_weight[u], 1u);
+}
+// unique columns in lexicographic order: number[k] - 1 = pattern of sorted unique k (several uniques per pattern only after a
+// hash collision); pattern_site = smallest original position, weights = summed multiplicities
+__global__ void pattern_merge_kernel(const uint32_t* __restrict__ sorted_site, const uint32_t* __restrict__ number, long long nu,
+                                     const uint32_t* __restrict__ site_to_u, const uint32_t* __restrict__ u_weight,
+                                     long long* __restrict__ pattern_site, uint32_t* __restrict__ weights, uint32_t* __restrict__ u_to_pattern) {
+  const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= nu) return;
+  const uint32_t p = number[k] - 1u, site = sorted_site[k], u = site_to_u[site];
+  u_to_pattern[u] = p;
+  atomicMin(&pattern_site[p], (long long)site);
+  atomicAdd(&weights[p], u_weight[u]);
+}
+__global__ void pattern_fill_kernel(long long* a, long long n, long long v) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) a[i] = v;
+}
+__global__ void pattern_indices_kernel(const uint32_t* __restrict__ site_to_u, const uint32_t* __restrict__ u_to_pattern, long long n,
+                                       long long* __restrict__ indices) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) indices[i] = (long long)u_to_pattern[site_to_u[i]];
+}
+
 struct DevBufs {
   uint8_t* cols = nullptr;
   unsigned long long *keys_a = nullptr, *keys_b = nullptr;
@@ -110,11 +164,92 @@ struct DevBufs {
   long long *pattern_site = nullptr, *indices = nullptr;
   void* temp = nullptr;
   uint8_t* tip = nullptr;
+  uint32_t *site_to_u = nullptr, *u_site = nullptr, *u_weight = nullptr, *u_to_pattern = nullptr;   // "dedup" variant
   ~DevBufs() {
+    cudaFree(site_to_u); cudaFree(u_site); cudaFree(u_weight); cudaFree(u_to_pattern);
     cudaFree(cols); cudaFree(keys_a); cudaFree(keys_b); cudaFree(perm_a); cudaFree(perm_b); cudaFree(head); cudaFree(number);
     cudaFree(weights); cudaFree(pattern_site); cudaFree(indices); cudaFree(temp); cudaFree(tip);
   }
 };
+
+// The "dedup" variant of steps 1-3 (see above): fills d.pattern_site / d.weights / d.indices and returns the pattern count.
+// The buffers of `d` are those the default path allocates; cols are already on the device.
+int site_patterns_dedup(DevBufs& d, long long n, int col_bytes, size_t temp_bytes, cudaStream_t st, uint32_t* np_out) {
+  const unsigned blocks = (unsigned)((n + 255) / 256);
+  const int nwords = (col_bytes + 7) / 8;
+  const int aligned8 = col_bytes % 8 == 0;
+  auto heads_and_numbers = [&](const uint32_t* perm, long long count, uint32_t* last_number) -> int {
+    pattern_head_kernel<<<(unsigned)((count * 32 + 255) / 256), 256, 0, st>>>(d.cols, perm, count, col_bytes, d.head);
+    size_t tb = temp_bytes;
+    BPP_CUDA(cub::DeviceScan::InclusiveSum(d.temp, tb, d.head, d.number, (int)count, st));
+    BPP_CUDA(cudaGetLastError());
+    BPP_CUDA(cudaMemcpyAsync(last_number, d.number + (count - 1), 4, cudaMemcpyDeviceToHost, st));
+    BPP_CUDA(cudaStreamSynchronize(st));
+    return BPPGPU_OK;
+  };
+  BPP_CUDA(cudaMalloc(&d.site_to_u, (size_t)n * 4));
+  BPP_CUDA(cudaMalloc(&d.u_site, (size_t)n * 4));
+  BPP_CUDA(cudaMalloc(&d.u_weight, (size_t)n * 4));
+  BPP_CUDA(cudaMalloc(&d.u_to_pattern, (size_t)n * 4));
+  // 1. merge identical columns: hash, stable sort by hash, run heads by full comparison
+  pattern_hash_kernel<<<(unsigned)((n * 32 + 255) / 256), 256, 0, st>>>(d.cols, n, col_bytes, d.keys_a);
+  pattern_iota_kernel<<<blocks, 256, 0, st>>>(d.perm_a, n);
+  {
+    size_t tb = temp_bytes;
+    BPP_CUDA(cub::DeviceRadixSort::SortPairs(d.temp, tb, d.keys_a, d.keys_b, d.perm_a, d.perm_b, (int)n, 0, 64, st));
+  }
+  uint32_t nu32 = 0;
+  int rc = heads_and_numbers(d.perm_b, n, &nu32);
+  if (rc) return rc;
+  const long long nu = (long long)nu32;
+  BPP_CUDA(cudaMemsetAsync(d.u_weight, 0, (size_t)n * 4, st));
+  pattern_dedup_scatter_kernel<<<blocks, 256, 0, st>>>(d.perm_b, d.head, d.number, n, d.site_to_u, d.u_site, d.u_weight);
+  // 2. lexicographic order of the unique columns only: one stable radix pass per 8-byte word, last word first
+  BPP_CUDA(cudaMemcpyAsync(d.perm_a, d.u_site, (size_t)nu * 4, cudaMemcpyDeviceToDevice, st));
+  uint32_t *pin = d.perm_a, *pout = d.perm_b;
+  const unsigned bu = (unsigned)((nu + 255) / 256);
+  for (int w = nwords - 1; w >= 0; --w) {
+    pattern_key_kernel<<<bu, 256, 0, st>>>(d.cols, pin, nu, col_bytes, w, aligned8, d.keys_a);
+    size_t tb = temp_bytes;
+    BPP_CUDA(cub::DeviceRadixSort::SortPairs(d.temp, tb, d.keys_a, d.keys_b, pin, pout, (int)nu, 0, 64, st));
+    std::swap(pin, pout);
+  }
+  const uint32_t* sorted = pin;
+  rc = heads_and_numbers(sorted, nu, np_out);
+  if (rc) return rc;
+  // 3. patterns: representative site (smallest original position), weights, site -> pattern
+  BPP_CUDA(cudaMemsetAsync(d.weights, 0, (size_t)n * 4, st));
+  pattern_fill_kernel<<<bu, 256, 0, st>>>(d.pattern_site, nu, 0x7fffffffffffffffLL);
+  pattern_merge_kernel<<<bu, 256, 0, st>>>(sorted, d.number, nu, d.site_to_u, d.u_weight, d.pattern_site, d.weights, d.u_to_pattern);
+  pattern_indices_kernel<<<blocks, 256, 0, st>>>(d.site_to_u, d.u_to_pattern, n, d.indices);
+  BPP_CUDA(cudaGetLastError());
+  BPP_CUDA(cudaStreamSynchronize(st));
+  return BPPGPU_OK;
+}
+
+// copy-out + tip codes for the "dedup" variant (the default path keeps its own, verified, copy of these lines)
+int finish_site_patterns(DevBufs& d, long long np, long long n, int col_bytes, int code_bytes, cudaStream_t st, int64_t* pattern_site,
+                         uint32_t* weights, int64_t* indices, int64_t* n_patterns, void* tip_codes) {
+  BPP_CUDA(cudaMemcpyAsync(pattern_site, d.pattern_site, (size_t)np * 8, cudaMemcpyDeviceToHost, st));
+  BPP_CUDA(cudaMemcpyAsync(weights, d.weights, (size_t)np * 4, cudaMemcpyDeviceToHost, st));
+  BPP_CUDA(cudaMemcpyAsync(indices, d.indices, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+  if (tip_codes) {
+    const int n_leaves = col_bytes / code_bytes;
+    BPP_CUDA(cudaMalloc(&d.tip, (size_t)np * (size_t)col_bytes));
+    const dim3 grid((unsigned)((np + 31) / 32), (unsigned)((n_leaves + 31) / 32)), block(32, 8);
+    if (grid.y > 65535u) BPP_FAIL(BPPGPU_E_INVALID, "too many leaves for the tip-code transpose");
+    if (code_bytes == 1)
+      pattern_tip_codes_kernel<uint8_t><<<grid, block, 0, st>>>(d.cols, d.pattern_site, np, n_leaves, d.tip);
+    else
+      pattern_tip_codes_kernel<uint16_t><<<grid, block, 0, st>>>(reinterpret_cast<const uint16_t*>(d.cols), d.pattern_site, np, n_leaves,
+                                                                 reinterpret_cast<uint16_t*>(d.tip));
+    BPP_CUDA(cudaGetLastError());
+    BPP_CUDA(cudaMemcpyAsync(tip_codes, d.tip, (size_t)np * (size_t)col_bytes, cudaMemcpyDeviceToHost, st));
+  }
+  BPP_CUDA(cudaStreamSynchronize(st));
+  *n_patterns = np;
+  return BPPGPU_OK;
+}
 
 }  // namespace
 }  // namespace bppgpu
@@ -162,6 +297,13 @@ int bppgpu_site_patterns_device(int device, const uint8_t* columns, int64_t n_si
 
   cudaStream_t st = 0;
   BPP_CUDA(cudaMemcpyAsync(d.cols, columns, bytes, cudaMemcpyHostToDevice, st));
+  const char* algo = getenv("BPPGPU_PATTERNS_ALGO");
+  if (algo && std::string(algo) == "dedup") {   // NOT yet run on a device (see the variant's comment); the default path is below
+    uint32_t npd = 0;
+    const int rc = site_patterns_dedup(d, n, col_bytes, temp_bytes, st, &npd);
+    if (rc) return rc;
+    return finish_site_patterns(d, (long long)npd, n, col_bytes, code_bytes, st, pattern_site, weights, indices, n_patterns, tip_codes);
+  }
   const unsigned blocks = (unsigned)((n + 255) / 256);
   pattern_iota_kernel<<<blocks, 256, 0, st>>>(d.perm_a, n);
   const int nwords = (col_bytes + 7) / 8;

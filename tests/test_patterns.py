@@ -129,3 +129,20 @@ def test_device_patterns_feed_the_engine(built_lib):
     with cases.make_engine(c) as e:
         lnl, _, _ = e.eval(capi.EVAL_LNL)
     assert abs(lnl[0] - res.lnl) <= 1e-9 * abs(res.lnl)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,ntaxa,nstates,seed", [(1, 3, 4, 0), (500, 5, 2, 2), (3000, 40, 20, 4), (257, 300, 4, 5), (70000, 64, 4, 9)])
+def test_device_patterns_dedup_variant(built_lib, monkeypatch, n, ntaxa, nstates, seed):
+    """BPPGPU_PATTERNS_ALGO=dedup (merge identical columns by hash first, sort only the unique ones): written at the end of round 1
+    without GPU time left, never run on a device -- enabled with BPPGPU_UNCONFIRMED_CHECKS=1 until it has been seen green."""
+    import os
+    if os.environ.get("BPPGPU_UNCONFIRMED_CHECKS") != "1":
+        pytest.skip("variant not yet confirmed on a device (set BPPGPU_UNCONFIRMED_CHECKS=1)")
+    monkeypatch.setenv("BPPGPU_PATTERNS_ALGO", "dedup")
+    rng = np.random.default_rng(seed)
+    alphabet = np.frombuffer(b"ACGTRYKMSWBDHVN-?XQZ", np.uint8)[:nstates]
+    check_device(alphabet[rng.integers(nstates, size=(n, ntaxa))])
+    base = rng.integers(0, 256, size=(max(2, n // 50), ntaxa)).astype(np.uint8)
+    check_device(base[rng.integers(len(base), size=n)])
+    check_device(np.full((1000, 9), ord("A"), np.uint8))
