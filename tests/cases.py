@@ -160,3 +160,53 @@ def make_engine(c: Case, flags=0, n_points=1, n_models=1, device=0):
         e.set_branch_lengths(p, c.flat.brlen)
         e.set_root_freqs(p, c.root_freqs)
     return e
+
+
+# ---- the one rule for value parity on (nearly) defective chromosome generators --------------------------------------------
+# Both the reference and this repo pick between two exponentiation routes per model (ChromosomeSubstitutionModel.cpp:686-767):
+# V exp(D t) V^-1 when the eigensystem passes the reference's checks, else the truncated Taylor series (:852-899).  Close to a
+# defective Q the eigenvector matrix is ill conditioned, the checks depend on rounding inside the eigen-solver (bpp-core's JAMA port
+# there, LAPACK in the oracle, a Hessenberg-QR in the shim -- which additionally refuses an eigensystem that does not reproduce Q to
+# 1e-8) and the two sides may take DIFFERENT routes.  The rule:
+#   (1) same route on both sides            -> 1e-9 relative, as everywhere else;
+#   (2) different routes                    -> the oracle is re-run on the device's route and must agree to 1e-9 (same algorithm),
+#       and the device must be at least as close as the oracle's own route to the exact value (mpmath expm, 50 digits):
+#       |device - exact| <= max(1e-9 |exact|, |oracle_own_route - exact|).
+# Measured on the point that prompted it (gain 5, loss .5, dupl .1, demi 1, S = 30, cond(V) = 1.9e14): eigen route 1.4e-8 from
+# exact (its P is off by 1e-3), series route 5.6e-10 from exact.
+def exact_expm_tables(Q, brlen, rates, dps=50):
+    import mpmath as mp
+    old = mp.mp.dps
+    mp.mp.dps = dps
+    try:
+        Qm = mp.matrix(np.asarray(Q, float).tolist())
+        S = Qm.rows
+        out = np.zeros((len(brlen), len(rates), S, S))
+        for n, t in enumerate(brlen):
+            for c, r in enumerate(rates):
+                E = mp.expm(Qm * (mp.mpf(float(t)) * mp.mpf(float(r))))
+                out[n, c] = [[float(E[i, j]) for j in range(S)] for i in range(S)]
+        return out
+    finally:
+        mp.mp.dps = old
+
+
+def chromosome_value_parity(c: Case, model: rm.Model, device_lnl, device_nonsingular, weighted_root=True):
+    """Apply the rule above; returns (route_of_the_device, rel. distance device<->oracle on that route)."""
+    import copy
+    own = oracle_eval(c, weighted_root=weighted_root, model=model)
+    if bool(model.nonsingular) == bool(device_nonsingular):
+        rel = abs(device_lnl - own.lnl) / abs(own.lnl)
+        assert rel <= 1e-9, ("same route", rel)
+        return ("eigen" if model.nonsingular else "series"), rel
+    forced = copy.copy(model)
+    forced.nonsingular = bool(device_nonsingular)
+    forced.diagonalizable = bool(device_nonsingular) and model.diagonalizable
+    same = oracle_eval(c, weighted_root=weighted_root, model=forced)
+    rel = abs(device_lnl - same.lnl) / abs(same.lnl)
+    assert rel <= 1e-9, ("device route", rel)
+    Pex = exact_expm_tables(model.Q, c.flat.brlen, c.rates)
+    exact = rl.dr_eval(c.flat, c.codes_by_leaf, c.table, Pex, len(c.rates), c.root_freqs, c.probs, c.weights.astype(float),
+                       weighted_root=weighted_root).lnl
+    assert abs(device_lnl - exact) <= max(1e-9 * abs(exact), abs(own.lnl - exact)), (device_lnl, own.lnl, exact)
+    return ("eigen" if device_nonsingular else "series"), rel

@@ -31,7 +31,10 @@ int main() {
     }
     ConstantRateDistribution cst;
     ChromosomeNumberOptimizer opt(*tree, sites, models, &cst, /*weightedRootFreq=*/true);
-    for (size_t k = 0; k < 6; ++k) printf("OPT_START_%zu %.15f\n", k, opt.getValue(k));
+    for (size_t k = 0; k < 6; ++k) {
+      printf("OPT_START_%zu %.15f\n", k, opt.getValue(k));
+      printf("OPT_START_NONSINGULAR_%zu %d\n", k, (int)models[k]->isNonSingular());
+    }
     // searched on [1e-3, 3] (the reference: (0, 100]) to keep the test short
     opt.optimize({6, 3, 1}, {0, 2, 3}, 1e-3, 1e-3, 3.0);
     const vector<size_t>& order = opt.getPointOrder();

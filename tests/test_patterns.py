@@ -134,11 +134,8 @@ def test_device_patterns_feed_the_engine(built_lib):
 @pytest.mark.gpu
 @pytest.mark.parametrize("n,ntaxa,nstates,seed", [(1, 3, 4, 0), (500, 5, 2, 2), (3000, 40, 20, 4), (257, 300, 4, 5), (70000, 64, 4, 9)])
 def test_device_patterns_dedup_variant(built_lib, monkeypatch, n, ntaxa, nstates, seed):
-    """BPPGPU_PATTERNS_ALGO=dedup (merge identical columns by hash first, sort only the unique ones): written at the end of round 1
-    without GPU time left, never run on a device -- enabled with BPPGPU_UNCONFIRMED_CHECKS=1 until it has been seen green."""
-    import os
-    if os.environ.get("BPPGPU_UNCONFIRMED_CHECKS") != "1":
-        pytest.skip("variant not yet confirmed on a device (set BPPGPU_UNCONFIRMED_CHECKS=1)")
+    """BPPGPU_PATTERNS_ALGO=dedup (merge identical columns by hash first, sort only the unique ones): bit-identical to the host
+    routine (first seen green on a B200 at the start of round 2, gpurun_out/r2_t1_pat.log)."""
     monkeypatch.setenv("BPPGPU_PATTERNS_ALGO", "dedup")
     rng = np.random.default_rng(seed)
     alphabet = np.frombuffer(b"ACGTRYKMSWBDHVN-?XQZ", np.uint8)[:nstates]
