@@ -44,7 +44,9 @@ static int ilog2(int v) {
 // Children with the larger Sethi-Ullman label are evaluated first, so the number of
 // live intermediate CLVs (stack slots) is minimal; the multiplication order inside an
 // op stays the reference's son order (RHomogeneousTreeLikelihood.cpp:827-861).
-static void build_program(bppgpu_engine* e, Program& pr, bool all_keep) {
+// reg_slot (walk4c): a push whose lifetime contains no other push -- the sibling evaluated next has label 1, i.e. is a
+// caterpillar -- goes to the kernel's register slot (dst_slot = -2, child kind CHILD_RSLOT) instead of a shared-memory slot.
+static void build_program(bppgpu_engine* e, Program& pr, bool all_keep, bool reg_slot = false) {
   const int nn = e->nn;
   std::vector<int> label(nn, 0);
   // node ids are arbitrary: compute labels by an explicit post-order
@@ -98,7 +100,10 @@ static void build_program(bppgpu_engine* e, Program& pr, bool all_keep) {
     std::stable_sort(internal.begin(), internal.end(), [&](int a, int b) { return label[a] > label[b]; });
     for (size_t i = 0; i < internal.size(); ++i) {
       emit(internal[i]);
-      if (!all_keep && i + 1 < internal.size()) {
+      if (!all_keep && reg_slot && i + 2 == internal.size() && label[internal[i + 1]] == 1) {
+        slot_of[internal[i]] = -2;
+        pr.ops[op_of[internal[i]]].dst_slot = -2;
+      } else if (!all_keep && i + 1 < internal.size()) {
         int s;
         if (!free_slots.empty()) {
           s = free_slots.back();
@@ -130,17 +135,19 @@ static void build_program(bppgpu_engine* e, Program& pr, bool all_keep) {
       } else if (slot_of[ch] >= 0) {
         c.kind = CHILD_SLOT;
         c.idx = slot_of[ch];
+      } else if (slot_of[ch] == -2) {
+        c.kind = CHILD_RSLOT;
+        c.idx = 0;
       } else {
         c.kind = CHILD_REG;
         c.idx = 0;
       }
       pr.childs.push_back(c);
     }
-    for (int ch : internal)
-      if (slot_of[ch] >= 0) {
-        free_slots.push_back(slot_of[ch]);
-        slot_of[ch] = -1;
-      }
+    for (int ch : internal) {
+      if (slot_of[ch] >= 0) free_slots.push_back(slot_of[ch]);
+      slot_of[ch] = -1;
+    }
     op_of[n] = (int)pr.ops.size();
     pr.ops.push_back(op);
   };
@@ -534,7 +541,7 @@ int bppgpu_destroy(bppgpu_engine* e) {
                   e->d_d2P, e->d_tiptab, e->d_keep, e->d_keep_exp, e->d_gstack, e->d_gstack_exp, e->d_upper,
                   e->d_upper_exp, e->d_SR, e->d_rexp, e->d_site_lnl, e->d_partials, e->d_partials2, e->d_out,
                   e->prog.d_ops, e->prog.d_childs, e->gprog.d_ops, e->gprog.d_childs, e->d_sibs, e->d_scratch,
-                  e->d_dtiptab, e->d_d2tiptab, e->d_dLc, e->d_fam_mask, e->d_fam_part, e->d_fam_packA, e->d_fam_packS, e->d_fam_packL, e->d_fam_packT, e->d_w4_desc, e->d_w4_tip_order, e->d_w4_blocks, e->d_w4_stream, e->d_codesT,
+                  e->d_dtiptab, e->d_d2tiptab, e->d_dLc, e->d_fam_mask, e->d_fam_part, e->d_fam_packA, e->d_fam_packS, e->d_fam_packL, e->d_fam_packT, e->d_w4c_stream, e->d_w4c_blocks, e->d_w4c_tip_order, e->d_codes8, e->d_w4_desc, e->d_w4_tip_order, e->d_w4_blocks, e->d_w4_stream, e->d_codesT,
                   e->d_status};
   for (void* p : ptrs) cudaFree(p);
   for (auto& m : e->models) free_model(m);
@@ -552,6 +559,7 @@ int bppgpu_destroy(bppgpu_engine* e) {
 }
 
 static int walk4_dispatch(bppgpu_engine* e, const Walk4Params* wp, int grid, size_t, cudaStream_t st, bool attr_only);
+static int walk4c_dispatch(bppgpu_engine* e, const Walk4cParams* wp, int grid, size_t smem, cudaStream_t st, bool attr_only);
 
 static int create_impl(const bppgpu_config* cfg, bppgpu_engine* e) {
   e->dev = cfg->device;
@@ -673,6 +681,84 @@ static int create_impl(const bppgpu_config* cfg, bppgpu_engine* e) {
     e->w4_stream_len = off;
     e->w4_tstride = (int)(((e->w4_tip_order.size() + 7) / 8) * 8 + 16);
   }
+  if (e->path == PATH_WALK4 && !e->keep && !(getenv("BPPGPU_WALK4C") && atoi(getenv("BPPGPU_WALK4C")) == 0)) {
+    // walk4c: the same walk with leaf pushes in the register slot, tables cut into fixed-size chunks in walk order
+    build_program(e, e->prog4c, false, true);
+    const int blk_int = C * 128, blk_tip = C * e->ncodes * 32;
+    int max_op = 0;
+    bool ok = e->prog4c.nslots <= 61;
+    for (const Op& op : e->prog4c.ops) {
+      int b = 0;
+      for (int j = 0; j < op.nchild; ++j) b += e->prog4c.childs[op.child_begin + j].kind == CHILD_TIP ? blk_tip : blk_int;
+      max_op = std::max(max_op, b);
+    }
+    int CH = 8192;
+    while (CH - kW4cHeader < max_op) CH *= 2;
+    e->w4c_pt = 2;
+    if (N * C < (long long)g_sm_count * 2 * kW4cThreads * 2) e->w4c_pt = 1;  // small inputs: more CTAs instead
+    if (const char* env = getenv("BPPGPU_WALK4_PT")) {
+      const int v = atoi(env);
+      if (v == 1 || v == 2 || v == 4) e->w4c_pt = v;
+    }
+    while (e->w4c_pt > 1 && walk4c_smem_bytes(CH, e->prog4c.nslots, e->w4c_pt) > 200 * 1024) e->w4c_pt >>= 1;
+    if (walk4c_smem_bytes(CH, e->prog4c.nslots, e->w4c_pt) > 200 * 1024) ok = false;
+    if (ok) {
+      e->w4c = true;
+      e->w4c_CH = CH;
+      std::vector<unsigned char>& T = e->w4c_template;
+      int nops_in = 0;
+      size_t chunk0 = 0, used = 0;   // byte offset of the open chunk, table bytes used in it
+      auto open_chunk = [&]() {
+        chunk0 = T.size();
+        T.resize(T.size() + (size_t)CH, 0);
+        nops_in = 0;
+        used = 0;
+      };
+      open_chunk();
+      for (const Op& op : e->prog4c.ops) {
+        int b = 0;
+        for (int j = 0; j < op.nchild; ++j) b += e->prog4c.childs[op.child_begin + j].kind == CHILD_TIP ? blk_tip : blk_int;
+        if (nops_in == kW4cMaxOpsPerChunk || used + (size_t)b > (size_t)(CH - kW4cHeader)) open_chunk();
+        auto kind4c = [](int k) { return k == CHILD_TIP ? W4C_TIP : k == CHILD_SLOT ? W4C_SLOT : k == CHILD_RSLOT ? W4C_RSL : W4C_REG; };
+        int shape = W4C_GENERIC;
+        if (op.nchild == 2) {
+          const int ka = kind4c(e->prog4c.childs[op.child_begin].kind), kb = kind4c(e->prog4c.childs[op.child_begin + 1].kind);
+          if (ka == W4C_TIP && kb == W4C_TIP) shape = W4C_TT;
+          else if (ka == W4C_TIP && kb == W4C_REG) shape = W4C_TR;
+          else if (ka == W4C_REG && kb == W4C_TIP) shape = W4C_RT;
+          else if (ka == W4C_SLOT && kb == W4C_REG) shape = W4C_SR;
+          else if (ka == W4C_REG && kb == W4C_SLOT) shape = W4C_RS;
+          else if (ka == W4C_RSL && kb == W4C_REG) shape = W4C_WR;
+          else if (ka == W4C_REG && kb == W4C_RSL) shape = W4C_RW;
+        }
+        const int dst = op.dst_slot == -2 ? kW4cRegSlot : op.dst_slot + 1;
+        unsigned long long d = (unsigned long long)shape | (op.dst_slot == -2 ? 8ull : 0ull) | ((unsigned long long)op.nchild << 4) |
+                               ((unsigned long long)dst << 8);
+        for (int j = 0; j < op.nchild; ++j) {
+          const Child& ch = e->prog4c.childs[op.child_begin + j];
+          const unsigned tok = ((unsigned)kind4c(ch.kind) << 6) | (ch.kind == CHILD_SLOT ? (unsigned)ch.idx : 0u);
+          d |= (unsigned long long)tok << (16 + 8 * j);
+          Pack4cBlock pb{};
+          pb.kind = kind4c(ch.kind);
+          pb.pnode = ch.pnode;
+          pb.off = (long long)(chunk0 + kW4cHeader + used);
+          e->w4c_blocks.push_back(pb);
+          if (ch.kind == CHILD_TIP) {
+            e->w4c_tip_order.push_back(ch.idx);
+            used += (size_t)blk_tip;
+          } else {
+            used += (size_t)blk_int;
+          }
+        }
+        memcpy(&T[chunk0 + 8 + 8 * (size_t)nops_in], &d, 8);
+        ++nops_in;
+        memcpy(&T[chunk0], &nops_in, 4);
+      }
+      e->w4c_nchunks = (int)(T.size() / (size_t)CH);
+      e->w4c_ngroups = (int)((e->w4c_tip_order.size() + 7) / 8);
+      e->w4c_Npad = (N + 31) & ~31LL;
+    }
+  }
   int rc = upload_program(e, e->prog);
   if (rc) return rc;
   rc = upload_program(e, e->gprog);
@@ -752,7 +838,7 @@ static int create_impl(const bppgpu_config* cfg, bppgpu_engine* e) {
   }
   e->pchunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)e->npoints, budget / std::max<size_t>(1, (e->path == PATH_POINTS ? 1 : 3) * per_point)));
   BPP_CUDA(dev_alloc(e, &e->d_P, (size_t)e->pchunk * nn * C * SS));
-  if (e->path == PATH_WALK4) {
+  if (e->path == PATH_WALK4 && !e->w4c) {
     BPP_CUDA(dev_alloc(e, &e->d_w4_desc, e->w4_desc.size()));
     BPP_CUDA(cudaMemcpy(e->d_w4_desc, e->w4_desc.data(), e->w4_desc.size() * 8, cudaMemcpyHostToDevice));
     BPP_CUDA(dev_alloc(e, &e->d_w4_tip_order, e->w4_tip_order.size()));
@@ -762,6 +848,18 @@ static int create_impl(const bppgpu_config* cfg, bppgpu_engine* e) {
     BPP_CUDA(dev_alloc(e, &e->d_w4_stream, (size_t)e->pchunk * e->w4_stream_len + (size_t)e->ncodes * C * 4 + 64 + 8192));
     BPP_CUDA(cudaMemset(e->d_w4_stream, 0, ((size_t)e->pchunk * e->w4_stream_len + (size_t)e->ncodes * C * 4 + 64 + 8192) * 8));
     BPP_CUDA(dev_alloc(e, &e->d_codesT, (size_t)N * e->w4_tstride));
+  }
+  if (e->w4c) {
+    BPP_CUDA(dev_alloc(e, &e->d_w4c_stream, (size_t)e->pchunk * e->w4c_template.size()));
+    for (int pl = 0; pl < e->pchunk; ++pl)
+      BPP_CUDA(cudaMemcpy(e->d_w4c_stream + (size_t)pl * e->w4c_template.size(), e->w4c_template.data(), e->w4c_template.size(),
+                          cudaMemcpyHostToDevice));
+    BPP_CUDA(dev_alloc(e, &e->d_w4c_blocks, e->w4c_blocks.size()));
+    BPP_CUDA(cudaMemcpy(e->d_w4c_blocks, e->w4c_blocks.data(), e->w4c_blocks.size() * sizeof(Pack4cBlock), cudaMemcpyHostToDevice));
+    BPP_CUDA(dev_alloc(e, &e->d_w4c_tip_order, e->w4c_tip_order.size()));
+    BPP_CUDA(cudaMemcpy(e->d_w4c_tip_order, e->w4c_tip_order.data(), e->w4c_tip_order.size() * 4, cudaMemcpyHostToDevice));
+    BPP_CUDA(dev_alloc(e, &e->d_codes8, (size_t)(e->w4c_ngroups + 2) * std::max<long long>(e->w4c_Npad, 32)));
+    BPP_CUDA(cudaMemset(e->d_codes8, 0, (size_t)(e->w4c_ngroups + 2) * std::max<long long>(e->w4c_Npad, 32) * 8));
   }
   if ((e->path != PATH_WALK4 || e->keep) && e->path != PATH_POINTS)
     BPP_CUDA(dev_alloc(e, &e->d_tiptab, (size_t)e->pchunk * e->nl * C * e->ncodes * S));
@@ -839,7 +937,12 @@ static int create_impl(const bppgpu_config* cfg, bppgpu_engine* e) {
     }
   }
 
-  if (e->path == PATH_WALK4) {
+  if (e->w4c) {
+    const size_t smem = walk4c_smem_bytes(e->w4c_CH, e->prog4c.nslots, e->w4c_pt);
+    int rc4 = walk4c_dispatch(e, nullptr, 0, smem, nullptr, true);
+    if (rc4) return rc4;
+    e->stats.stack_slots = e->prog4c.nslots;
+  } else if (e->path == PATH_WALK4) {
     // patterns per thread: 2 (4 CTAs of 128 threads per SM at 128 registers) while the stack leaves room for it
     e->w4_pt = 2;
     while (e->w4_pt > 1 && (size_t)e->prog.nslots * e->w4_pt * kWalk4Threads * 36 > 56 * 1024) e->w4_pt >>= 1;
@@ -861,7 +964,7 @@ static int create_impl(const bppgpu_config* cfg, bppgpu_engine* e) {
     }
   }
   e->stats.path = e->path;
-  e->stats.stack_slots = e->prog.nslots;
+  if (!e->w4c) e->stats.stack_slots = e->prog.nslots;
   e->stats.hbm_bytes_resident = (int64_t)e->bytes_resident;
   return BPPGPU_OK;
 }
@@ -1122,6 +1225,29 @@ static int walk4_dispatch(bppgpu_engine* e, const Walk4Params* wp, int grid, siz
     default: return walk4_launch_pt<3>(e->w4_pt, e->keep, wp, grid, smem, st, attr_only);
   }
 }
+template <int CL, int PT>
+static int walk4c_launch_one(const Walk4cParams* wp, int grid, size_t smem, cudaStream_t st, bool attr_only) {
+  if (attr_only) {
+    BPP_CUDA(cudaFuncSetAttribute(walk4c_kernel<CL, PT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    return BPPGPU_OK;
+  }
+  walk4c_kernel<CL, PT><<<grid, kW4cThreads, smem, st>>>(*wp);
+  return BPPGPU_OK;
+}
+template <int CL>
+static int walk4c_launch_pt(int pt, const Walk4cParams* wp, int grid, size_t smem, cudaStream_t st, bool attr_only) {
+  if (pt == 4) return walk4c_launch_one<CL, 4>(wp, grid, smem, st, attr_only);
+  if (pt == 2) return walk4c_launch_one<CL, 2>(wp, grid, smem, st, attr_only);
+  return walk4c_launch_one<CL, 1>(wp, grid, smem, st, attr_only);
+}
+static int walk4c_dispatch(bppgpu_engine* e, const Walk4cParams* wp, int grid, size_t smem, cudaStream_t st, bool attr_only) {
+  switch (ilog2(e->C)) {
+    case 0: return walk4c_launch_pt<0>(e->w4c_pt, wp, grid, smem, st, attr_only);
+    case 1: return walk4c_launch_pt<1>(e->w4c_pt, wp, grid, smem, st, attr_only);
+    case 2: return walk4c_launch_pt<2>(e->w4c_pt, wp, grid, smem, st, attr_only);
+    default: return walk4c_launch_pt<3>(e->w4c_pt, wp, grid, smem, st, attr_only);
+  }
+}
 template <int CL>
 static void launch_walkS20(const WalkParams& wp, int grid, size_t smem, cudaStream_t st) {
   walkS_kernel<20, CL><<<grid, kWalkThreads, smem, st>>>(wp);
@@ -1143,7 +1269,31 @@ static int enqueue_prune(bppgpu_engine* e, int point, int pl, cudaStream_t st) {
     BPP_CUDA(cudaMemsetAsync(out, 0, 8, st));
     return BPPGPU_OK;
   }
-  if (e->path == PATH_WALK4) {
+  if (e->w4c) {
+    Walk4cParams wp{};
+    wp.stream = e->d_w4c_stream + (size_t)pl * e->w4c_template.size();
+    wp.nchunks = e->w4c_nchunks;
+    wp.CH = e->w4c_CH;
+    wp.nslots = e->prog4c.nslots;
+    wp.ncodes = e->ncodes;
+    wp.flags = rflag;
+    wp.N = N;
+    wp.Npad = e->w4c_Npad;
+    wp.codes8 = e->d_codes8;
+    wp.rootfreq = rootfreq;
+    wp.probs = e->d_probs;
+    wp.weights = e->d_weights;
+    wp.SR = e->d_SR;
+    wp.rexp = e->d_rexp;
+    wp.site_lnl = site_lnl;
+    wp.partials = e->d_partials;
+    const long long per_cta = (long long)(kW4cWarps / C) * 32 * e->w4c_pt;
+    const int grid = (int)((N + per_cta - 1) / per_cta);
+    nparts = grid;
+    int rc4 = walk4c_dispatch(e, &wp, grid, walk4c_smem_bytes(e->w4c_CH, e->prog4c.nslots, e->w4c_pt), st, false);
+    if (rc4) return rc4;
+    e->stats.kernel_launches++;
+  } else if (e->path == PATH_WALK4) {
     if (e->flags & BPPGPU_FLAG_WEIGHTED_ROOT)
       BPP_FAIL(BPPGPU_E_INVALID, "BPPGPU_FLAG_WEIGHTED_ROOT is served by the generic path only");
     Walk4Params wp{};
@@ -1550,7 +1700,20 @@ static int eval_impl(bppgpu_engine* e, unsigned want, cudaStream_t st, bool time
     e->ptring_head = (e->ptring_head + 1) % bppgpu_engine::kRing;
     e->ptring_n = std::min(e->ptring_n + 1, (int)bppgpu_engine::kRing);
     e->stats.kernel_launches += launches;
-    if (e->path == PATH_WALK4) {
+    if (e->w4c) {
+      if (e->codesT_dirty && e->N > 0) {
+        pack_codes8_kernel<<<(unsigned)((e->w4c_Npad + 127) / 128), 128, 0, st>>>(
+            (const unsigned char*)e->d_codes, e->d_w4c_tip_order, (int)e->w4c_tip_order.size(), e->N, e->w4c_Npad, e->w4c_ngroups,
+            e->d_codes8);
+        e->stats.kernel_launches++;
+        e->codesT_dirty = false;
+      }
+      for (int pl = 0; pl < np; ++pl)
+        pack_stream4c_kernel<<<(unsigned)e->w4c_blocks.size(), 64, 0, st>>>(
+            e->d_w4c_blocks, e->d_P + (size_t)pl * nn * C * SS, e->d_code_table, C, e->ncodes,
+            e->d_w4c_stream + (size_t)pl * e->w4c_template.size());
+      e->stats.kernel_launches += np;
+    } else if (e->path == PATH_WALK4) {
       if (e->codesT_dirty && e->N > 0) {
         transpose_codes_kernel<<<(unsigned)((e->N + 127) / 128), 128, 0, st>>>(
             (const unsigned char*)e->d_codes, e->d_w4_tip_order, (int)e->w4_tip_order.size(), e->N, e->w4_tstride, e->d_codesT);

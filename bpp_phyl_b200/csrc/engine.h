@@ -15,6 +15,7 @@
 #include "pt_dmma_kernels.cuh"
 #include "pt_kernels.cuh"
 #include "walk_kernels.cuh"
+#include "walk4c_kernels.cuh"
 
 namespace bppgpu {
 
@@ -105,6 +106,18 @@ struct bppgpu_engine {
   double* d_w4_stream = nullptr;       // [pchunk][w4_stream_len]
   unsigned char* d_codesT = nullptr;   // [N][w4_tstride]
   bool codesT_dirty = true;
+  // walk4c (class-uniform, chunk-streamed walk; value-only engines): see walk4c_kernels.cuh
+  bool w4c = false;
+  bppgpu::Program prog4c;                  // walk program whose leaf pushes use the register slot
+  std::vector<unsigned char> w4c_template; // [nchunks][CH]: headers + descriptors, tables zero
+  std::vector<bppgpu::Pack4cBlock> w4c_blocks;
+  std::vector<int> w4c_tip_order;
+  int w4c_CH = 0, w4c_nchunks = 0, w4c_pt = 2, w4c_ngroups = 0;
+  long long w4c_Npad = 0;
+  unsigned char* d_w4c_stream = nullptr;   // [pchunk][nchunks][CH]
+  bppgpu::Pack4cBlock* d_w4c_blocks = nullptr;
+  int* d_w4c_tip_order = nullptr;
+  unsigned long long* d_codes8 = nullptr;  // [ngroups + 2][Npad]
   // CLV storage (one point at a time)
   double* d_keep = nullptr;  // [ni][N][C][S]
   int* d_keep_exp = nullptr; // [ni][N][C]

@@ -20,7 +20,7 @@
 
 namespace bppgpu {
 
-enum ChildKind { CHILD_TIP = 0, CHILD_SLOT = 1, CHILD_REG = 2, CHILD_KEEP = 3 };
+enum ChildKind { CHILD_TIP = 0, CHILD_SLOT = 1, CHILD_REG = 2, CHILD_KEEP = 3, CHILD_RSLOT = 4 /* register slot (walk4c) */ };
 
 struct Child {
   int kind;   // ChildKind

@@ -83,6 +83,35 @@ def test_dna_walk_kernel_variants(monkeypatch, pt, pipe, flags):
             np.testing.assert_allclose(-d2[0, :nb], res.d2, rtol=1e-8, atol=1e-7)
 
 
+@pytest.mark.parametrize("ncat", [1, 2, 4, 8])
+def test_dna_chunk_streamed_walk_equals_register_walk(monkeypatch, ncat):
+    """walk4c_kernel (class-uniform warps, TMA-streamed table chunks, register slot) against walk4_kernel (BPPGPU_WALK4C=0):
+    same arithmetic in the same order, so the per-site log-likelihoods agree to the last bits (2 ulp: the compiler may contract
+    log(L) - E ln2 differently in the two kernels); trees deep enough to need several
+    chunks and shared-memory stack slots, ambiguity codes (wide tip tables), ragged pattern counts, a star tree."""
+    capi = _capi()
+    r, p = rm.gamma_rates(ncat, 0.5) if ncat > 1 else rm.constant_rate()
+    todo = [cases.make_case(ntaxa, nsites, gtr(), r, p, seed=seed, ambiguity=amb, random_tips=rt_, mean_brlen=bl)
+            for ntaxa, nsites, seed, amb, rt_, bl in ((200, 333, 71, 0.05, False, 0.05), (700, 130, 72, 0.0, True, 0.5),
+                                                       (5, 1, 73, 0.3, False, 0.1), (33, 64, 74, 0.0, False, 0.05))]
+    todo.append(cases.case_from_alignment("(A:0.1,B:0.2,C:0.3,D:0.05,E:0.01);",
+                                          {"A": "ACGTNACG", "B": "ACGTRACC", "C": "AGGT-TCG", "D": "ACCTYACG", "E": "TCGTAACG"},
+                                          gtr(), r, p))
+    for c in todo:
+        out = {}
+        for mode in ("1", "0"):
+            monkeypatch.setenv("BPPGPU_WALK4C", mode)
+            for pt in ("1", "2", "4"):
+                monkeypatch.setenv("BPPGPU_WALK4_PT", pt)
+                with cases.make_engine(c) as e:
+                    lnl, _, _ = e.eval(capi.EVAL_LNL)
+                    out[mode, pt] = (lnl[0], e.site_lnl().copy())
+        res = cases.oracle_eval(c)
+        for k, (lnl, site) in out.items():
+            np.testing.assert_allclose(site, out["0", "2"][1], rtol=5e-16, atol=0, err_msg=str(k))
+            assert abs(lnl - res.lnl) <= REL * abs(res.lnl), k
+
+
 @pytest.mark.parametrize("flags,env,path", [(0, None, 4), (1, None, 4), (16, None, 3), (0, "walk", 2)])
 def test_protein_random_trees(monkeypatch, flags, env, path):
     """S = 20: tensor-core node kernels (default), the generic kernels, and the register walk (BPPGPU_PATH=walk)"""
