@@ -541,7 +541,7 @@ int bppgpu_destroy(bppgpu_engine* e) {
                   e->d_d2P, e->d_tiptab, e->d_keep, e->d_keep_exp, e->d_gstack, e->d_gstack_exp, e->d_upper,
                   e->d_upper_exp, e->d_SR, e->d_rexp, e->d_site_lnl, e->d_partials, e->d_partials2, e->d_out,
                   e->prog.d_ops, e->prog.d_childs, e->gprog.d_ops, e->gprog.d_childs, e->d_sibs, e->d_scratch,
-                  e->d_dtiptab, e->d_d2tiptab, e->d_dLc, e->d_fam_mask, e->d_fam_part, e->d_fam_packA, e->d_fam_packS, e->d_fam_packL, e->d_fam_packT, e->d_w4c_stream, e->d_w4c_blocks, e->d_w4c_tip_order, e->d_codes8, e->d_w4_desc, e->d_w4_tip_order, e->d_w4_blocks, e->d_w4_stream, e->d_codesT,
+                  e->d_dtiptab, e->d_d2tiptab, e->d_dLc, e->d_fam_mask, e->d_fam_part, e->d_fam_packA, e->d_fam_packS, e->d_fam_packL, e->d_fam_packT, e->d_w4c_stream, e->d_w4c_blocks, e->d_w4c_tip_order, e->d_codesC, e->d_w4_desc, e->d_w4_tip_order, e->d_w4_blocks, e->d_w4_stream, e->d_codesT,
                   e->d_status};
   for (void* p : ptrs) cudaFree(p);
   for (auto& m : e->models) free_model(m);
@@ -682,66 +682,84 @@ static int create_impl(const bppgpu_config* cfg, bppgpu_engine* e) {
     e->w4_tstride = (int)(((e->w4_tip_order.size() + 7) / 8) * 8 + 16);
   }
   if (e->path == PATH_WALK4 && !e->keep && !(getenv("BPPGPU_WALK4C") && atoi(getenv("BPPGPU_WALK4C")) == 0)) {
-    // walk4c: the same walk with leaf pushes in the register slot, tables cut into fixed-size chunks in walk order
+    // walk4c: the same walk with leaf pushes in the register slot, tables cut into fixed-size chunks in walk order, the
+    // program (descriptor words + chunk records) in the kernel-parameter block
     build_program(e, e->prog4c, false, true);
     const int blk_int = C * 128, blk_tip = C * e->ncodes * 32;
     int max_op = 0;
-    bool ok = e->prog4c.nslots <= 61;
+    bool ok = e->prog4c.nslots <= 63;
     for (const Op& op : e->prog4c.ops) {
-      int b = 0;
-      for (int j = 0; j < op.nchild; ++j) b += e->prog4c.childs[op.child_begin + j].kind == CHILD_TIP ? blk_tip : blk_int;
+      int b = 0, nt = 0;
+      for (int j = 0; j < op.nchild; ++j) {
+        const bool tip = e->prog4c.childs[op.child_begin + j].kind == CHILD_TIP;
+        b += tip ? blk_tip : blk_int;
+        nt += tip;
+      }
       max_op = std::max(max_op, b);
+      if (op.nchild > 6 || nt > kW4cMaxTipsPerChunk) ok = false;
     }
     int CH = 8192;
-    while (CH - kW4cHeader < max_op) CH *= 2;
+    while (CH < max_op) CH *= 2;
     e->w4c_pt = 2;
     if (N * C < (long long)g_sm_count * 2 * kW4cThreads * 2) e->w4c_pt = 1;  // small inputs: more CTAs instead
     if (const char* env = getenv("BPPGPU_WALK4_PT")) {
       const int v = atoi(env);
       if (v == 1 || v == 2 || v == 4) e->w4c_pt = v;
     }
-    while (e->w4c_pt > 1 && walk4c_smem_bytes(CH, e->prog4c.nslots, e->w4c_pt) > 200 * 1024) e->w4c_pt >>= 1;
-    if (walk4c_smem_bytes(CH, e->prog4c.nslots, e->w4c_pt) > 200 * 1024) ok = false;
+    while (e->w4c_pt > 1 && walk4c_smem_bytes(CH, e->prog4c.nslots, C, e->w4c_pt) > 200 * 1024) e->w4c_pt >>= 1;
+    if (walk4c_smem_bytes(CH, e->prog4c.nslots, C, e->w4c_pt) > 200 * 1024) ok = false;
     if (ok) {
-      e->w4c = true;
-      e->w4c_CH = CH;
-      std::vector<unsigned char>& T = e->w4c_template;
-      int nops_in = 0;
-      size_t chunk0 = 0, used = 0;   // byte offset of the open chunk, table bytes used in it
-      auto open_chunk = [&]() {
-        chunk0 = T.size();
-        T.resize(T.size() + (size_t)CH, 0);
-        nops_in = 0;
+      W4cProgram& W = e->w4c_prog;
+      memset(&W, 0, sizeof(W));
+      int nwords = 0, nchunks = 0, nops_in = 0, ntips_in = 0, tip0 = 0;
+      size_t used = 0;
+      auto close_chunk = [&]() {
+        if (nchunks < kW4cMaxChunks) W.chunk[nchunks] = (unsigned)tip0 | ((unsigned)ntips_in << 16) | ((unsigned)nops_in << 21);
+        ++nchunks;
+        tip0 += ntips_in;
+        nops_in = ntips_in = 0;
         used = 0;
       };
-      open_chunk();
       for (const Op& op : e->prog4c.ops) {
-        int b = 0;
-        for (int j = 0; j < op.nchild; ++j) b += e->prog4c.childs[op.child_begin + j].kind == CHILD_TIP ? blk_tip : blk_int;
-        if (nops_in == kW4cMaxOpsPerChunk || used + (size_t)b > (size_t)(CH - kW4cHeader)) open_chunk();
+        int b = 0, nt = 0;
+        for (int j = 0; j < op.nchild; ++j) {
+          const bool tip = e->prog4c.childs[op.child_begin + j].kind == CHILD_TIP;
+          b += tip ? blk_tip : blk_int;
+          nt += tip;
+        }
+        if (nops_in == 31 || used + (size_t)b > (size_t)CH || ntips_in + nt > kW4cMaxTipsPerChunk) close_chunk();
         auto kind4c = [](int k) { return k == CHILD_TIP ? W4C_TIP : k == CHILD_SLOT ? W4C_SLOT : k == CHILD_RSLOT ? W4C_RSL : W4C_REG; };
         int shape = W4C_GENERIC;
+        int order[8] = {0, 1, 2, 3, 4, 5, 6, 7};   // order in which the handler consumes the children's table blocks
+        unsigned jslot = 0;
         if (op.nchild == 2) {
-          const int ka = kind4c(e->prog4c.childs[op.child_begin].kind), kb = kind4c(e->prog4c.childs[op.child_begin + 1].kind);
+          const Child& ca = e->prog4c.childs[op.child_begin];
+          const Child& cb2 = e->prog4c.childs[op.child_begin + 1];
+          const int ka = kind4c(ca.kind), kb = kind4c(cb2.kind);
           if (ka == W4C_TIP && kb == W4C_TIP) shape = W4C_TT;
-          else if (ka == W4C_TIP && kb == W4C_REG) shape = W4C_TR;
-          else if (ka == W4C_REG && kb == W4C_TIP) shape = W4C_RT;
-          else if (ka == W4C_SLOT && kb == W4C_REG) shape = W4C_SR;
-          else if (ka == W4C_REG && kb == W4C_SLOT) shape = W4C_RS;
-          else if (ka == W4C_RSL && kb == W4C_REG) shape = W4C_WR;
-          else if (ka == W4C_REG && kb == W4C_RSL) shape = W4C_RW;
+          else if (ka == W4C_TIP && kb == W4C_REG) shape = W4C_TS;
+          else if (ka == W4C_REG && kb == W4C_TIP) { shape = W4C_TS; order[0] = 1; order[1] = 0; }
+          else if (ka == W4C_RSL && kb == W4C_REG) shape = W4C_JW;
+          else if (ka == W4C_REG && kb == W4C_RSL) { shape = W4C_JW; order[0] = 1; order[1] = 0; }
+          else if (ka == W4C_SLOT && kb == W4C_REG) { shape = W4C_JS; jslot = (unsigned)ca.idx; }
+          else if (ka == W4C_REG && kb == W4C_SLOT) { shape = W4C_JS; jslot = (unsigned)cb2.idx; order[0] = 1; order[1] = 0; }
         }
-        const int dst = op.dst_slot == -2 ? kW4cRegSlot : op.dst_slot + 1;
-        unsigned long long d = (unsigned long long)shape | (op.dst_slot == -2 ? 8ull : 0ull) | ((unsigned long long)op.nchild << 4) |
-                               ((unsigned long long)dst << 8);
-        for (int j = 0; j < op.nchild; ++j) {
+        unsigned d = (unsigned)shape | (op.dst_slot == -2 ? (unsigned)W4C_DSTW : 0u) | ((unsigned)op.nchild << 24);
+        if (op.dst_slot >= 0) d |= ((unsigned)op.dst_slot << 8) | 0x4000u;
+        unsigned d2 = 0;
+        int nslot_tok = 0;
+        if (shape != W4C_GENERIC) d |= jslot << 16;
+        for (int jj = 0; jj < op.nchild; ++jj) {
+          const int j = order[jj];
           const Child& ch = e->prog4c.childs[op.child_begin + j];
-          const unsigned tok = ((unsigned)kind4c(ch.kind) << 6) | (ch.kind == CHILD_SLOT ? (unsigned)ch.idx : 0u);
-          d |= (unsigned long long)tok << (16 + 8 * j);
+          if (shape == W4C_GENERIC) {
+            d2 |= (unsigned)kind4c(ch.kind) << (2 * j);
+            if (ch.kind == CHILD_SLOT) d2 |= (unsigned)ch.idx << (12 + 6 * nslot_tok++);
+          }
           Pack4cBlock pb{};
           pb.kind = kind4c(ch.kind);
           pb.pnode = ch.pnode;
-          pb.off = (long long)(chunk0 + kW4cHeader + used);
+          pb.off = (long long)((size_t)nchunks * CH + used);
           e->w4c_blocks.push_back(pb);
           if (ch.kind == CHILD_TIP) {
             e->w4c_tip_order.push_back(ch.idx);
@@ -750,13 +768,18 @@ static int create_impl(const bppgpu_config* cfg, bppgpu_engine* e) {
             used += (size_t)blk_int;
           }
         }
-        memcpy(&T[chunk0 + 8 + 8 * (size_t)nops_in], &d, 8);
+        if (nslot_tok > 3) ok = false;
+        if (nwords < kW4cMaxOps) W.desc[nwords] = make_uint2(d, d2);
+        ++nwords;
         ++nops_in;
-        memcpy(&T[chunk0], &nops_in, 4);
+        ntips_in += nt;
       }
-      e->w4c_nchunks = (int)(T.size() / (size_t)CH);
-      e->w4c_ngroups = (int)((e->w4c_tip_order.size() + 7) / 8);
-      e->w4c_Npad = (N + 31) & ~31LL;
+      close_chunk();
+      if (nwords > kW4cMaxOps || nchunks > kW4cMaxChunks || e->w4c_tip_order.size() > 65535) ok = false;
+      e->w4c_nchunks = nchunks;
+      e->w4c_CH = CH;
+      e->w4c_stream_bytes = (size_t)nchunks * CH;
+      e->w4c = ok;
     }
   }
   int rc = upload_program(e, e->prog);
@@ -850,16 +873,15 @@ static int create_impl(const bppgpu_config* cfg, bppgpu_engine* e) {
     BPP_CUDA(dev_alloc(e, &e->d_codesT, (size_t)N * e->w4_tstride));
   }
   if (e->w4c) {
-    BPP_CUDA(dev_alloc(e, &e->d_w4c_stream, (size_t)e->pchunk * e->w4c_template.size()));
-    for (int pl = 0; pl < e->pchunk; ++pl)
-      BPP_CUDA(cudaMemcpy(e->d_w4c_stream + (size_t)pl * e->w4c_template.size(), e->w4c_template.data(), e->w4c_template.size(),
-                          cudaMemcpyHostToDevice));
+    BPP_CUDA(dev_alloc(e, &e->d_w4c_stream, (size_t)e->pchunk * e->w4c_stream_bytes));
+    BPP_CUDA(cudaMemset(e->d_w4c_stream, 0, (size_t)e->pchunk * e->w4c_stream_bytes));
     BPP_CUDA(dev_alloc(e, &e->d_w4c_blocks, e->w4c_blocks.size()));
     BPP_CUDA(cudaMemcpy(e->d_w4c_blocks, e->w4c_blocks.data(), e->w4c_blocks.size() * sizeof(Pack4cBlock), cudaMemcpyHostToDevice));
     BPP_CUDA(dev_alloc(e, &e->d_w4c_tip_order, e->w4c_tip_order.size()));
     BPP_CUDA(cudaMemcpy(e->d_w4c_tip_order, e->w4c_tip_order.data(), e->w4c_tip_order.size() * 4, cudaMemcpyHostToDevice));
-    BPP_CUDA(dev_alloc(e, &e->d_codes8, (size_t)(e->w4c_ngroups + 2) * std::max<long long>(e->w4c_Npad, 32)));
-    BPP_CUDA(cudaMemset(e->d_codes8, 0, (size_t)(e->w4c_ngroups + 2) * std::max<long long>(e->w4c_Npad, 32) * 8));
+    const long long ppc = (long long)(kW4cWarps / C) * 32 * e->w4c_pt;
+    e->w4c_grid = (int)((N + ppc - 1) / ppc);
+    BPP_CUDA(dev_alloc(e, &e->d_codesC, (size_t)std::max(1, e->w4c_grid) * e->w4c_tip_order.size() * (size_t)ppc + 16));
   }
   if ((e->path != PATH_WALK4 || e->keep) && e->path != PATH_POINTS)
     BPP_CUDA(dev_alloc(e, &e->d_tiptab, (size_t)e->pchunk * e->nl * C * e->ncodes * S));
@@ -938,7 +960,7 @@ static int create_impl(const bppgpu_config* cfg, bppgpu_engine* e) {
   }
 
   if (e->w4c) {
-    const size_t smem = walk4c_smem_bytes(e->w4c_CH, e->prog4c.nslots, e->w4c_pt);
+    const size_t smem = walk4c_smem_bytes(e->w4c_CH, e->prog4c.nslots, C, e->w4c_pt);
     int rc4 = walk4c_dispatch(e, nullptr, 0, smem, nullptr, true);
     if (rc4) return rc4;
     e->stats.stack_slots = e->prog4c.nslots;
@@ -1225,13 +1247,14 @@ static int walk4_dispatch(bppgpu_engine* e, const Walk4Params* wp, int grid, siz
     default: return walk4_launch_pt<3>(e->w4_pt, e->keep, wp, grid, smem, st, attr_only);
   }
 }
+static thread_local const W4cProgram* g_w4c_prog = nullptr;   // the launching engine's program (copied into the launch)
 template <int CL, int PT>
 static int walk4c_launch_one(const Walk4cParams* wp, int grid, size_t smem, cudaStream_t st, bool attr_only) {
   if (attr_only) {
     BPP_CUDA(cudaFuncSetAttribute(walk4c_kernel<CL, PT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     return BPPGPU_OK;
   }
-  walk4c_kernel<CL, PT><<<grid, kW4cThreads, smem, st>>>(*wp);
+  walk4c_kernel<CL, PT><<<grid, kW4cThreads, smem, st>>>(*wp, *g_w4c_prog);
   return BPPGPU_OK;
 }
 template <int CL>
@@ -1241,6 +1264,7 @@ static int walk4c_launch_pt(int pt, const Walk4cParams* wp, int grid, size_t sme
   return walk4c_launch_one<CL, 1>(wp, grid, smem, st, attr_only);
 }
 static int walk4c_dispatch(bppgpu_engine* e, const Walk4cParams* wp, int grid, size_t smem, cudaStream_t st, bool attr_only) {
+  g_w4c_prog = &e->w4c_prog;
   switch (ilog2(e->C)) {
     case 0: return walk4c_launch_pt<0>(e->w4c_pt, wp, grid, smem, st, attr_only);
     case 1: return walk4c_launch_pt<1>(e->w4c_pt, wp, grid, smem, st, attr_only);
@@ -1271,15 +1295,15 @@ static int enqueue_prune(bppgpu_engine* e, int point, int pl, cudaStream_t st) {
   }
   if (e->w4c) {
     Walk4cParams wp{};
-    wp.stream = e->d_w4c_stream + (size_t)pl * e->w4c_template.size();
+    wp.stream = e->d_w4c_stream + (size_t)pl * e->w4c_stream_bytes;
+    wp.codesC = e->d_codesC;
     wp.nchunks = e->w4c_nchunks;
     wp.CH = e->w4c_CH;
     wp.nslots = e->prog4c.nslots;
     wp.ncodes = e->ncodes;
+    wp.ntips = (int)e->w4c_tip_order.size();
     wp.flags = rflag;
     wp.N = N;
-    wp.Npad = e->w4c_Npad;
-    wp.codes8 = e->d_codes8;
     wp.rootfreq = rootfreq;
     wp.probs = e->d_probs;
     wp.weights = e->d_weights;
@@ -1287,10 +1311,9 @@ static int enqueue_prune(bppgpu_engine* e, int point, int pl, cudaStream_t st) {
     wp.rexp = e->d_rexp;
     wp.site_lnl = site_lnl;
     wp.partials = e->d_partials;
-    const long long per_cta = (long long)(kW4cWarps / C) * 32 * e->w4c_pt;
-    const int grid = (int)((N + per_cta - 1) / per_cta);
+    const int grid = e->w4c_grid;
     nparts = grid;
-    int rc4 = walk4c_dispatch(e, &wp, grid, walk4c_smem_bytes(e->w4c_CH, e->prog4c.nslots, e->w4c_pt), st, false);
+    int rc4 = walk4c_dispatch(e, &wp, grid, walk4c_smem_bytes(e->w4c_CH, e->prog4c.nslots, C, e->w4c_pt), st, false);
     if (rc4) return rc4;
     e->stats.kernel_launches++;
   } else if (e->path == PATH_WALK4) {
@@ -1702,16 +1725,16 @@ static int eval_impl(bppgpu_engine* e, unsigned want, cudaStream_t st, bool time
     e->stats.kernel_launches += launches;
     if (e->w4c) {
       if (e->codesT_dirty && e->N > 0) {
-        pack_codes8_kernel<<<(unsigned)((e->w4c_Npad + 127) / 128), 128, 0, st>>>(
-            (const unsigned char*)e->d_codes, e->d_w4c_tip_order, (int)e->w4c_tip_order.size(), e->N, e->w4c_Npad, e->w4c_ngroups,
-            e->d_codes8);
+        pack_codesC_kernel<<<(unsigned)e->w4c_grid, 256, 0, st>>>(
+            (const unsigned char*)e->d_codes, e->d_w4c_tip_order, (int)e->w4c_tip_order.size(), e->N,
+            (kW4cWarps / C) * 32 * e->w4c_pt, e->d_codesC);
         e->stats.kernel_launches++;
         e->codesT_dirty = false;
       }
       for (int pl = 0; pl < np; ++pl)
         pack_stream4c_kernel<<<(unsigned)e->w4c_blocks.size(), 64, 0, st>>>(
             e->d_w4c_blocks, e->d_P + (size_t)pl * nn * C * SS, e->d_code_table, C, e->ncodes,
-            e->d_w4c_stream + (size_t)pl * e->w4c_template.size());
+            e->d_w4c_stream + (size_t)pl * e->w4c_stream_bytes);
       e->stats.kernel_launches += np;
     } else if (e->path == PATH_WALK4) {
       if (e->codesT_dirty && e->N > 0) {

@@ -109,15 +109,16 @@ struct bppgpu_engine {
   // walk4c (class-uniform, chunk-streamed walk; value-only engines): see walk4c_kernels.cuh
   bool w4c = false;
   bppgpu::Program prog4c;                  // walk program whose leaf pushes use the register slot
-  std::vector<unsigned char> w4c_template; // [nchunks][CH]: headers + descriptors, tables zero
+  bppgpu::W4cProgram w4c_prog;             // descriptor words + chunk records (passed as a kernel parameter)
+  size_t w4c_stream_bytes = 0;             // nchunks * CH
+  int w4c_grid = 0;
   std::vector<bppgpu::Pack4cBlock> w4c_blocks;
   std::vector<int> w4c_tip_order;
-  int w4c_CH = 0, w4c_nchunks = 0, w4c_pt = 2, w4c_ngroups = 0;
-  long long w4c_Npad = 0;
+  int w4c_CH = 0, w4c_nchunks = 0, w4c_pt = 2;
   unsigned char* d_w4c_stream = nullptr;   // [pchunk][nchunks][CH]
   bppgpu::Pack4cBlock* d_w4c_blocks = nullptr;
   int* d_w4c_tip_order = nullptr;
-  unsigned long long* d_codes8 = nullptr;  // [ngroups + 2][Npad]
+  unsigned char* d_codesC = nullptr;       // [grid][ntips][PPC] tip codes as the CTAs stage them
   // CLV storage (one point at a time)
   double* d_keep = nullptr;  // [ni][N][C][S]
   int* d_keep_exp = nullptr; // [ni][N][C]

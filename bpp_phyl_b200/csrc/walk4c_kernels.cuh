@@ -28,22 +28,34 @@ namespace bppgpu {
 constexpr int kW4cThreads = 256;
 constexpr int kW4cWarps = kW4cThreads / 32;
 constexpr int kW4cStages = 3;
-constexpr int kW4cHeader = 128;        // bytes at the head of a chunk: u32 n_ops, u32 pad, up to 15 descriptors
-constexpr int kW4cMaxOpsPerChunk = 15;
-constexpr int kW4cRegSlot = 63;        // dst code of the register slot
+constexpr int kW4cMaxTipsPerChunk = 16;   // tip-code rows staged with a chunk
+constexpr int kW4cMaxOps = 3072;          // descriptors (8 bytes each) that fit the kernel-parameter block
+constexpr int kW4cMaxChunks = 1024;
 
 enum W4cKind { W4C_TIP = 0, W4C_SLOT = 1, W4C_REG = 2, W4C_RSL = 3 };
 // binary shapes (the only ones a bifurcating tree's planner emits); 0 = generic child loop
-enum W4cShape { W4C_GENERIC = 0, W4C_TT = 1, W4C_TR = 2, W4C_RT = 3, W4C_SR = 4, W4C_RS = 5, W4C_WR = 6, W4C_RW = 7 };
+// one-hot shape bits (tested one by one: the dispatch stays a chain of uniform branches)
+enum W4cShape { W4C_GENERIC = 0, W4C_TS = 1 /* tip + current rows */, W4C_TT = 2, W4C_JW = 4 /* register slot + current rows */,
+                W4C_JS = 8 /* shared-memory slot + current rows */, W4C_DSTW = 16 /* result goes to the register slot */ };
 
-// descriptor: bits 0-2 shape, bit 3 result goes to the register slot, bits 4-7 nchild, bits 8-15 dst (0 none, s+1 shared slot,
-// 63 register slot), byte 2+j child token kind<<6 | slot
+// The walk program lives in the KERNEL PARAMETER block (constant bank, up to 32 KB since CUDA 12.1): descriptors and chunk
+// records are read with warp-uniform loads and the per-op dispatch runs on the uniform datapath -- no convergence barriers, no
+// shared-memory round trip for the descriptor.
+//   descriptor .x: bits 0-3 one-hot shape (none = generic), bit 4 result goes to the register slot, bits 8-13 shared slot that
+//   also receives the result when bit 14 is set, bits 16-21 the shared slot read by W4C_JS, bits 24-27 nchild;
+//   .y (generic ops): bits 0-11 child kinds (2 bits each, son order), bits 12-31 the slots of its W4C_SLOT children (6 bits each)
+//   chunk record: bits 0-15 first tip (consumption order) of the chunk, bits 16-20 number of tips, bits 21-25 number of ops
+struct W4cProgram {
+  uint2 desc[kW4cMaxOps];
+  unsigned chunk[kW4cMaxChunks];
+};
+
 struct Walk4cParams {
-  const unsigned char* stream;       // [nchunks][CH] this point's chunks
-  int nchunks, CH, nslots, ncodes;
+  const unsigned char* stream;       // [nchunks][CH] this point's table chunks
+  const unsigned char* codesC;       // [gridDim.x][ntips][PPC] tip codes, consumption order, one byte per pattern
+  int nchunks, CH, nslots, ncodes, ntips;
   unsigned flags;                    // bit0: R semantics at the root
-  long long N, Npad;
-  const unsigned long long* codes8;  // [ntip8 + 2][Npad]
+  long long N;
   const double* rootfreq;            // [4]
   const double* probs;               // [C]
   const double* weights;             // [N]
@@ -104,39 +116,38 @@ __device__ __forceinline__ unsigned long long lds64u(unsigned a) {
   return r;
 }
 
+__device__ __forceinline__ unsigned lds_u8(unsigned a) {
+  unsigned r;
+  asm volatile("ld.shared.u8 %0, [%1];" : "=r"(r) : "r"(a));
+  return r;
+}
+
 template <int C_LOG2, int PT>
 struct W4cState {
   static constexpr int C = 1 << C_LOG2;
   static constexpr int NTH = kW4cThreads;
+  static constexpr int PPC = (kW4cWarps >> C_LOG2) * 32 * PT;
   double v[PT][4], w[PT][4];   // current CLV rows / register slot
   int E[PT], EW[PT];
-  unsigned long long q[PT], qn[PT];
-  const unsigned long long* crow[PT];
-  long long Npad;
-  int tipk;
-  unsigned sp;                 // shared address of the next table block of the current chunk
+  unsigned ca;                 // shared address of this thread's code byte of the next tip (pattern j: + 32 j)
+  unsigned sp;                 // shared address of the next table block of the current chunk (warp-uniform)
   int tip_off;                 // c * ncodes * 32 bytes
   int tip_block;               // C * ncodes * 32 bytes
-  int c, tid;
+  int c;
   unsigned stA, stB, ste;      // shared addresses of the stack planes, already offset by this thread's lane
 
   __device__ __forceinline__ void term_tip(double (&t)[PT][4]) {
     const unsigned tb = sp + tip_off;
+    unsigned code[PT];
+#pragma unroll
+    for (int j = 0; j < PT; ++j) code[j] = lds_u8(ca + 32 * j);
 #pragma unroll
     for (int j = 0; j < PT; ++j) {
-      const unsigned code = (unsigned)(q[j] & 0xffu);
-      q[j] >>= 8;
-      const double2 a = lds128(tb + (code << 5));
-      const double2 b = lds128(tb + (code << 5) + 16);
+      const double2 a = lds128(tb + (code[j] << 5));
+      const double2 b = lds128(tb + (code[j] << 5) + 16);
       t[j][0] = a.x; t[j][1] = a.y; t[j][2] = b.x; t[j][3] = b.y;
     }
-    if (((++tipk) & 7) == 0) {
-#pragma unroll
-      for (int j = 0; j < PT; ++j) {
-        q[j] = qn[j];
-        qn[j] = __ldg(crow[j] + (size_t)((tipk >> 3) + 1) * Npad);
-      }
-    }
+    ca += PPC;
     sp += tip_block;
   }
   // t = P . l, l from: the current rows (W4C_REG), the register slot (W4C_RSL) or a shared-memory slot (W4C_SLOT)
@@ -167,11 +178,6 @@ struct W4cState {
 #pragma unroll
       for (int j = 0; j < PT; ++j) t[j][x] = fma(p23.y, l[j][3], fma(p23.x, l[j][2], fma(p01.y, l[j][1], p01.x * l[j][0])));
     }
-  }
-  template <int K>
-  __device__ __forceinline__ void term(int slot, double (&t)[PT][4], int (&e)[PT]) {
-    if (K == W4C_TIP) term_tip(t);
-    else term_internal<K>(slot, t, e);
   }
   // rescale per row, then store to v (or to the register slot)
   template <bool DSTW>
@@ -205,31 +211,64 @@ struct W4cState {
       }
     }
   }
-  template <int KA, int KB, bool DSTW>
-  __device__ __forceinline__ void op2(int slotA, int slotB) {
+  // the four binary shapes.  IEEE multiplication commutes exactly, so (tip, reg) and (reg, tip) -- and the two orders of a
+  // join -- are one handler each; the host lays the op's table blocks out in the handler's order (tip block first / the
+  // stacked operand's P first).
+  template <bool DSTW>
+  __device__ __forceinline__ void op_tt() {
     double ta[PT][4], tb[PT][4];
     int e[PT];
 #pragma unroll
     for (int j = 0; j < PT; ++j) e[j] = 0;
-    term<KA>(slotA, ta, e);
-    term<KB>(slotB, tb, e);
+    term_tip(ta);
+    term_tip(tb);
 #pragma unroll
     for (int j = 0; j < PT; ++j) {
       ta[j][0] *= tb[j][0]; ta[j][1] *= tb[j][1]; ta[j][2] *= tb[j][2]; ta[j][3] *= tb[j][3];
     }
     commit<DSTW>(ta, e);
   }
-  __device__ __forceinline__ void op_generic(int nchild, unsigned long long toks, bool dstw) {
+  template <bool DSTW>
+  __device__ __forceinline__ void op_ts() {
+    double ta[PT][4], tb[PT][4];
+    int e[PT];
+#pragma unroll
+    for (int j = 0; j < PT; ++j) e[j] = 0;
+    term_tip(ta);
+    term_internal<W4C_REG>(0, tb, e);
+#pragma unroll
+    for (int j = 0; j < PT; ++j) {
+      ta[j][0] *= tb[j][0]; ta[j][1] *= tb[j][1]; ta[j][2] *= tb[j][2]; ta[j][3] *= tb[j][3];
+    }
+    commit<DSTW>(ta, e);
+  }
+  template <int SRC, bool DSTW>
+  __device__ __forceinline__ void op_join(int slot) {
+    double ta[PT][4], tb[PT][4];
+    int e[PT];
+#pragma unroll
+    for (int j = 0; j < PT; ++j) e[j] = 0;
+    term_internal<SRC>(slot, ta, e);
+    term_internal<W4C_REG>(0, tb, e);
+#pragma unroll
+    for (int j = 0; j < PT; ++j) {
+      ta[j][0] *= tb[j][0]; ta[j][1] *= tb[j][1]; ta[j][2] *= tb[j][2]; ta[j][3] *= tb[j][3];
+    }
+    commit<DSTW>(ta, e);
+  }
+  // any number of sons in the reference's son order; toks: 2 bits per child (kind), slots: 6 bits per W4C_SLOT child in order
+  // of appearance
+  __device__ __forceinline__ void op_generic(int nchild, unsigned toks, unsigned slots, bool dstw) {
     double a[PT][4];
     int e[PT];
 #pragma unroll
     for (int j = 0; j < PT; ++j) e[j] = 0;
 #pragma unroll 1
-    for (int ch = 0; ch < nchild; ++ch, toks >>= 8) {
-      const int kind = (int)(toks >> 6) & 3;
+    for (int ch = 0; ch < nchild; ++ch, toks >>= 2) {
+      const int kind = (int)toks & 3;
       double t[PT][4];
       if (kind == W4C_TIP) term_tip(t);
-      else if (kind == W4C_SLOT) term_internal<W4C_SLOT>((int)toks & 63, t, e);
+      else if (kind == W4C_SLOT) { term_internal<W4C_SLOT>((int)slots & 63, t, e); slots >>= 6; }
       else if (kind == W4C_RSL) term_internal<W4C_RSL>(0, t, e);
       else term_internal<W4C_REG>(0, t, e);
 #pragma unroll
@@ -246,13 +285,19 @@ struct W4cState {
   }
 };
 
+// bytes of one ring stage: the table chunk + the tip-code rows of the chunk's tips
+__host__ __device__ inline size_t walk4c_stage_bytes(int CH, int C, int PT) {
+  return (size_t)CH + (size_t)kW4cMaxTipsPerChunk * (kW4cWarps / C) * 32 * PT;
+}
 // dynamic shared memory of one CTA
-__host__ __device__ inline size_t walk4c_smem_bytes(int CH, int nslots, int PT) {
-  return (size_t)kW4cStages * CH + (size_t)(nslots > 0 ? nslots : 0) * PT * kW4cThreads * 36 + (size_t)PT * kW4cThreads * 12 + 128;
+__host__ __device__ inline size_t walk4c_smem_bytes(int CH, int nslots, int C, int PT) {
+  return (size_t)kW4cStages * walk4c_stage_bytes(CH, C, PT) + (size_t)(nslots > 0 ? nslots : 0) * PT * kW4cThreads * 36 +
+         (size_t)PT * kW4cThreads * 12 + 128;
 }
 
 template <int C_LOG2, int PT>
-__global__ void __launch_bounds__(kW4cThreads, (PT <= 2 ? 2 : 1)) walk4c_kernel(Walk4cParams prm) {
+__global__ void __launch_bounds__(kW4cThreads, (PT <= 2 ? 2 : 1))
+walk4c_kernel(const __grid_constant__ Walk4cParams prm, const __grid_constant__ W4cProgram prog) {
   constexpr int C = 1 << C_LOG2;
   constexpr int NTH = kW4cThreads;
   constexpr int G = kW4cWarps >> C_LOG2;   // pattern groups (of 32 * PT patterns) per CTA
@@ -261,9 +306,10 @@ __global__ void __launch_bounds__(kW4cThreads, (PT <= 2 ? 2 : 1)) walk4c_kernel(
   __shared__ double red[32];
 
   const int CH = prm.CH;
+  const unsigned SB = (unsigned)CH + kW4cMaxTipsPerChunk * PPC;   // stage bytes
   unsigned char* ring = smem_raw;
   const unsigned ring_s = smem_u32(smem_raw);
-  unsigned char* q0 = smem_raw + (size_t)kW4cStages * CH;
+  unsigned char* q0 = smem_raw + (size_t)kW4cStages * SB;
   const size_t plane = (size_t)(prm.nslots > 0 ? prm.nslots : 0) * PT * NTH;
   W4cState<C_LOG2, PT> s;
   s.stA = smem_u32(q0) + threadIdx.x * 16;
@@ -275,25 +321,17 @@ __global__ void __launch_bounds__(kW4cThreads, (PT <= 2 ? 2 : 1)) walk4c_kernel(
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int c = warp & (C - 1), g = warp >> C_LOG2;
-  s.tid = tid;
   s.c = c;
-  s.Npad = prm.Npad;
   s.tip_off = c * prm.ncodes * 32;
   s.tip_block = C * prm.ncodes * 32;
-  const long long pat0 = (long long)blockIdx.x * PPC + g * (32 * PT) + lane;   // pattern j: pat0 + 32 j
+  const unsigned my_code_off = (unsigned)(g * (32 * PT) + lane);
 #pragma unroll
   for (int j = 0; j < PT; ++j) {
-    long long pj = pat0 + 32 * j;
-    if (pj >= prm.N) pj = prm.N - 1;
-    s.crow[j] = prm.codes8 + pj;
-    s.q[j] = __ldg(s.crow[j]);
-    s.qn[j] = __ldg(s.crow[j] + prm.Npad);
     s.v[j][0] = s.v[j][1] = s.v[j][2] = s.v[j][3] = 1.0;
     s.w[j][0] = s.w[j][1] = s.w[j][2] = s.w[j][3] = 1.0;
     s.E[j] = 0;
     s.EW[j] = 0;
   }
-  s.tipk = 0;
 
   unsigned long long* full = bars;
   unsigned long long* empty = bars + kW4cStages;
@@ -308,49 +346,50 @@ __global__ void __launch_bounds__(kW4cThreads, (PT <= 2 ? 2 : 1)) walk4c_kernel(
   }
   __syncthreads();
   const int nchunks = prm.nchunks;
-  if (tid == 0) {
-    for (int k = 0; k < kW4cStages && k < nchunks; ++k) {
-      mbar_expect_tx(full + k, (unsigned)CH);
-      bulk_g2s(ring + (size_t)k * CH, prm.stream + (size_t)k * CH, (unsigned)CH, full + k);
-    }
-  }
+  const unsigned char* my_codes = prm.codesC + (size_t)blockIdx.x * prm.ntips * PPC;
+  // producer (thread 0): the tables of chunk k and the code rows of its tips, both completing on full[stage]
+  auto issue = [&](int k, int st) {
+    const unsigned rec = prog.chunk[k];
+    const unsigned tip0 = rec & 0xffffu, ntc = (rec >> 16) & 31u;
+    mbar_expect_tx(full + st, (unsigned)CH + ntc * PPC);
+    bulk_g2s(ring + (size_t)st * SB, prm.stream + (size_t)k * CH, (unsigned)CH, full + st);
+    if (ntc) bulk_g2s(ring + (size_t)st * SB + CH, my_codes + (size_t)tip0 * PPC, ntc * PPC, full + st);
+  };
+  if (tid == 0)
+    for (int k = 0; k < kW4cStages && k < nchunks; ++k) issue(k, k);
 
   int stage = 0;
   unsigned phase = 0;
+  int opi = 0;   // next descriptor
   for (int k = 0; k < nchunks; ++k) {
+    const int n_ops = (int)(prog.chunk[k] >> 21) & 31;
     mbar_wait(full + stage, phase);
-    const unsigned cb = ring_s + (unsigned)stage * (unsigned)CH;
-    const int n_ops = lds32(cb);
-    s.sp = cb + kW4cHeader;
+    s.sp = ring_s + (unsigned)stage * SB;
+    s.ca = s.sp + (unsigned)CH + my_code_off;
     for (int o = 0; o < n_ops; ++o) {
-      const unsigned long long d = lds64u(cb + 8 + 8 * o);
-      const int shape = (int)(d & 0xfu);   // bit 3 = result to the register slot
-      const int dst = (int)((d >> 8) & 0xffu);
-      const int slotA = (int)(d >> 16) & 63, slotB = (int)(d >> 24) & 63;
-      switch (shape) {
-        case W4C_TT: s.template op2<W4C_TIP, W4C_TIP, false>(0, 0); break;
-        case W4C_TR: s.template op2<W4C_TIP, W4C_REG, false>(0, 0); break;
-        case W4C_RT: s.template op2<W4C_REG, W4C_TIP, false>(0, 0); break;
-        case W4C_SR: s.template op2<W4C_SLOT, W4C_REG, false>(slotA, 0); break;
-        case W4C_RS: s.template op2<W4C_REG, W4C_SLOT, false>(0, slotB); break;
-        case W4C_WR: s.template op2<W4C_RSL, W4C_REG, false>(0, 0); break;
-        case W4C_RW: s.template op2<W4C_REG, W4C_RSL, false>(0, 0); break;
-        case 8 + W4C_TT: s.template op2<W4C_TIP, W4C_TIP, true>(0, 0); break;
-        case 8 + W4C_TR: s.template op2<W4C_TIP, W4C_REG, true>(0, 0); break;
-        case 8 + W4C_RT: s.template op2<W4C_REG, W4C_TIP, true>(0, 0); break;
-        case 8 + W4C_SR: s.template op2<W4C_SLOT, W4C_REG, true>(slotA, 0); break;
-        case 8 + W4C_RS: s.template op2<W4C_REG, W4C_SLOT, true>(0, slotB); break;
-        case 8 + W4C_WR: s.template op2<W4C_RSL, W4C_REG, true>(0, 0); break;
-        case 8 + W4C_RW: s.template op2<W4C_REG, W4C_RSL, true>(0, 0); break;
-        default: s.op_generic((int)(d >> 4) & 0xf, d >> 16, (shape & 8) != 0); break;
+      const uint2 dd = prog.desc[opi + o];
+      const unsigned d = dd.x;
+      if (!(d & W4C_DSTW)) {
+        if (d & W4C_TS) s.template op_ts<false>();
+        else if (d & W4C_TT) s.template op_tt<false>();
+        else if (d & W4C_JW) s.template op_join<W4C_RSL, false>(0);
+        else if (d & W4C_JS) s.template op_join<W4C_SLOT, false>((int)(d >> 16) & 63);
+        else s.op_generic((int)(d >> 24) & 0xf, dd.y & 0xfffu, dd.y >> 12, false);
+      } else {
+        if (d & W4C_TS) s.template op_ts<true>();
+        else if (d & W4C_TT) s.template op_tt<true>();
+        else if (d & W4C_JW) s.template op_join<W4C_RSL, true>(0);
+        else if (d & W4C_JS) s.template op_join<W4C_SLOT, true>((int)(d >> 16) & 63);
+        else s.op_generic((int)(d >> 24) & 0xf, dd.y & 0xfffu, dd.y >> 12, true);
       }
-      if (dst && dst != kW4cRegSlot) {
+      if (d & 0x4000u) {                            // bit 14: the result is also pushed to a shared-memory slot
+        const int dst = (int)(d >> 8) & 0x3f;
 #pragma unroll
         for (int j = 0; j < PT; ++j) {
-          const unsigned k = (unsigned)(((dst - 1) * PT + j) * NTH);
-          sts128(s.stA + k * 16, s.v[j][0], s.v[j][1]);
-          sts128(s.stB + k * 16, s.v[j][2], s.v[j][3]);
-          sts32(s.ste + k * 4, s.E[j]);
+          const unsigned kk = (unsigned)((dst * PT + j) * NTH);
+          sts128(s.stA + kk * 16, s.v[j][0], s.v[j][1]);
+          sts128(s.stB + kk * 16, s.v[j][2], s.v[j][3]);
+          sts32(s.ste + kk * 4, s.E[j]);
         }
       }
     }
@@ -362,9 +401,9 @@ __global__ void __launch_bounds__(kW4cThreads, (PT <= 2 ? 2 : 1)) walk4c_kernel(
       const int ps = stage == 0 ? kW4cStages - 1 : stage - 1;          // stage of chunk k-1
       const unsigned pph = stage == 0 ? phase ^ 1u : phase;             // its phase
       mbar_wait(empty + ps, pph);
-      mbar_expect_tx(full + ps, (unsigned)CH);
-      bulk_g2s(ring + (size_t)ps * CH, prm.stream + (size_t)(k - 1 + kW4cStages) * CH, (unsigned)CH, full + ps);
+      issue(k - 1 + kW4cStages, ps);
     }
+    opi += n_ops;
     if (++stage == kW4cStages) { stage = 0; phase ^= 1u; }
   }
 
@@ -412,21 +451,14 @@ __global__ void __launch_bounds__(kW4cThreads, (PT <= 2 ? 2 : 1)) walk4c_kernel(
   if (tid == 0) prm.partials[blockIdx.x] = bs;
 }
 
-// codes [nl][N] (leaf-slot major) -> codes8 [group][Npad] (one 8-byte word = the 8 tips k0..k0+7 of the consumption order)
-__global__ void pack_codes8_kernel(const unsigned char* codes, const int* tip_order, int ntips, long long N, long long Npad,
-                                   int ngroups, unsigned long long* codes8) {
-  const long long pat = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (pat >= Npad) return;
-  for (int g = 0; g < ngroups; ++g) {
-    unsigned long long wv = 0;
-    if (pat < N) {
-#pragma unroll
-      for (int b = 0; b < 8; ++b) {
-        const int k = g * 8 + b;
-        if (k < ntips) wv |= (unsigned long long)codes[(size_t)tip_order[k] * N + pat] << (8 * b);
-      }
-    }
-    codes8[(size_t)g * Npad + pat] = wv;
+// codes [nl][N] (leaf-slot major) -> codesC [cta][tip in consumption order][PPC]: the rows a CTA stages with its chunks
+__global__ void pack_codesC_kernel(const unsigned char* codes, const int* tip_order, int ntips, long long N, int PPC,
+                                   unsigned char* codesC) {
+  const size_t cta = blockIdx.x;
+  for (int i = threadIdx.x; i < ntips * PPC; i += blockDim.x) {
+    const int k = i / PPC, p = i - k * PPC;
+    const long long pat = (long long)cta * PPC + p;
+    codesC[(cta * ntips + k) * PPC + p] = pat < N ? codes[(size_t)tip_order[k] * N + pat] : (unsigned char)0;
   }
 }
 
