@@ -37,8 +37,9 @@ WORKLOADS = {
     "protein_g4_500x200k": dict(S=20, C=4, taxa=500, patterns=200_000, alpha=0.7, derivs=False, seed=20260103),
     # layout experiment: the same CLV bytes as protein_g4_500x200k with one class (rows contiguous)
     "protein_c1_500x800k": dict(S=20, C=1, taxa=500, patterns=800_000, alpha=None, derivs=False, seed=20260103),
-    # configs[3]: 64-state codon (61 sense), 200 taxa x 100k patterns, C = 1
-    "codon_200x100k": dict(S=64, C=1, taxa=200, patterns=100_000, alpha=None, derivs=False, seed=20260104),
+    # configs[3]: 64-state codon (61 sense + 3 inert stop lines), 200 taxa x 100k patterns, C = 1: YN98 and GY94
+    "codon_200x100k": dict(S=64, C=1, taxa=200, patterns=100_000, alpha=None, derivs=False, seed=20260104, model="YN98"),
+    "codon_gy94_200x100k": dict(S=64, C=1, taxa=200, patterns=100_000, alpha=None, derivs=False, seed=20260104, model="GY94"),
     # configs[4]: ChromEvol-style chromosome-number model, 200 states, 500 taxa, one character, 4096 parameter points
     "chromosome_500x4096pts": dict(S=200, C=1, taxa=500, patterns=1, points=4096, alpha=None, derivs=False, seed=20260105),
 }
@@ -109,10 +110,16 @@ def algorithmic_bytes(tree, N, C, S):
 
 
 def model_for(w, rng):
-    from bpp_phyl_b200 import synth
+    """The workload's substitution model, built by the product's own C++ host code (bppgpu_host_model: generator +
+    updateMatrices): GTR for DNA, LG08 for protein, YN98 / GY94 (64 states, three inert stop lines) for codons."""
+    from bpp_phyl_b200 import capi
     if w["S"] == 4:
-        return synth.gtr()
-    return synth.random_reversible(w["S"], rng)
+        return capi.host_model("GTR", 1.2, 0.8, 0.6, 1.5, 0.9, .3, .2, .25, .25)
+    if w["S"] == 20:
+        return capi.host_model("LG08")
+    if w.get("model") == "GY94":
+        return capi.host_model("GY94", 2.0, 80.0)
+    return capi.host_model("YN98", 2.0, 0.3)
 
 
 def build_inputs(w, rank, world, device):
@@ -157,28 +164,66 @@ def make_engine(w, tree, es, rates, probs, codes, dev_index, flags):
     return e, md
 
 
-def cpu_leg(w, tree, es, rates, probs, codes, threads, target_seconds=12.0, per_thread=512):
-    """The reference's CPU algorithm (oracle/ref_cpu.cpp, a port: the reference cannot be built here) on a bounded
-    sample of the same workload."""
+def _cpu_args(w, tree, es, rates, probs, sub, want, threads):
+    n = sub.shape[1]
+    return dict(S=w["S"], Ccat=w["C"], N=n, child_off=tree.child_off, children=tree.children, root=tree.root, codes=sub,
+                code_table=np.eye(w["S"]), weights=np.ones(n, np.uint32), rates=rates, probs=probs, V=es["V"],
+                Vinv=es["Vinv"], ev=es["ev"], model_rate=es.get("rate", 1.0), brlen=tree.brlen, rootfreq=es["pi"], scaled=True,
+                want=want, nthreads=threads)
+
+
+def cpu_leg(w, tree, es, rates, probs, codes, lnl_gpu_full, budget_s=60.0):
+    """The reference's CPU algorithm (oracle/ref_cpu.cpp, a port: the reference cannot be built here) on the SAME simulated
+    data as the GPU run, three ways: one thread (what the reference is), 8 threads and all host threads as
+    independent pattern shards -- each on a bounded sample -- and, inside the time budget, the FULL input in blocks for the
+    full-size parity check (lnL summed over the blocks against the GPU's lnL of the whole input)."""
     from oracle import ref_cpu
     ref_cpu.build()
-    n = min(codes.shape[1], per_thread * threads)
-    sub = np.ascontiguousarray(codes[:, :n])
+    cores = os.cpu_count() or 1
+    N = codes.shape[1]
     want = 7 if w["derivs"] else 1
-    args = dict(S=w["S"], Ccat=w["C"], N=n, child_off=tree.child_off, children=tree.children, root=tree.root, codes=sub,
-                code_table=np.eye(w["S"]), weights=np.ones(n, np.uint32), rates=rates, probs=probs, V=es["V"],
-                Vinv=es["Vinv"], ev=es["ev"], model_rate=1.0, brlen=tree.brlen, rootfreq=es["pi"], scaled=True, want=want,
-                nthreads=threads)
-    r = ref_cpu.eval_raw(reps=1, **args)
-    reps = int(max(1, min(20, target_seconds / max(r["seconds"], 1e-3))))
-    if reps > 1:
-        r = ref_cpu.eval_raw(reps=reps, **args)
-    upd = tree.n_internal * n * w["C"] * w["S"]
-    return {"value": upd / r["seconds"], "unit": "CLV updates/s", "cores": threads, "kind": "port",
-            "sample": "%d of %d patterns, full tree, best of %d evals (%.2f s each), scaled arithmetic" %
-                      (n, w["patterns"], reps, r["seconds"]),
-            "evals_per_s_full_size_extrapolated": (upd / r["seconds"]) / (tree.n_internal * w["patterns"] * w["C"] * w["S"]),
-            "lnl_sample": r["lnl"]}, sub
+    per_upd = tree.n_internal * w["C"] * w["S"]
+    out = {"unit": "CLV updates/s", "kind": "port", "cores": cores}
+
+    def run(n, threads, wnt):
+        sub = np.ascontiguousarray(codes[:, :n])
+        r = ref_cpu.eval_raw(reps=1, **_cpu_args(w, tree, es, rates, probs, sub, wnt, threads))
+        return r, sub
+
+    per_thread = 256 if w["S"] >= 20 else 512
+    r1, _ = run(min(N, per_thread), 1, want)
+    out["one_thread"] = {"value": per_upd * min(N, per_thread) / r1["seconds"], "cores": 1,
+                         "sample": "%d patterns, full tree, %.2f s" % (min(N, per_thread), r1["seconds"])}
+    if cores >= 8:
+        n8 = min(N, per_thread * 8)
+        r8, _ = run(n8, 8, want)
+        out["eight_shards"] = {"value": per_upd * n8 / r8["seconds"], "cores": 8,
+                               "sample": "%d patterns as 8 independent pattern shards, %.2f s" % (n8, r8["seconds"])}
+    nall = min(N, per_thread * cores)
+    rall, sub = run(nall, cores, want)
+    out["value"] = per_upd * nall / rall["seconds"]
+    out["sample"] = "%d of %d patterns (the GPU run's own data), full tree, %d host threads as independent pattern shards, " \
+                    "%.2f s, scaled arithmetic%s" % (nall, N, cores, rall["seconds"], ", with d1/d2" if w["derivs"] else "")
+    out["lnl_sample"] = rall["lnl"]
+    # full-size parity, value only: whole input in blocks of `blk` patterns, if the extrapolated time fits the budget
+    t_full = rall["seconds"] * N / nall * (0.45 if w["derivs"] else 1.0)
+    parity = {"lnl_gpu_full": lnl_gpu_full, "patterns": N}
+    if t_full <= budget_s or os.environ.get("BPPGPU_BENCH_FULL_PARITY") == "1":
+        blk = per_thread * cores * 2
+        tot, secs = 0.0, 0.0
+        for b0 in range(0, N, blk):
+            subb = np.ascontiguousarray(codes[:, b0:b0 + blk])
+            r = ref_cpu.eval_raw(reps=1, **_cpu_args(w, tree, es, rates, probs, subb, 1, cores))
+            tot += r["lnl"]
+            secs += r["seconds"]
+        parity.update({"lnl_cpu_full": tot, "rel_diff_full": abs(tot - lnl_gpu_full) / abs(tot), "cpu_seconds_full": secs,
+                       "cpu_updates_per_s_full": per_upd * N / secs,
+                       "note": "CPU port over the whole input in blocks of %d patterns on %d threads; lnL summed over blocks" % (blk, cores)})
+    else:
+        parity.update({"lnl_cpu_full": None, "rel_diff_full": None,
+                       "note": "full input would take %.0f s on %d threads (> %.0f s budget): sample parity only; "
+                               "set BPPGPU_BENCH_FULL_PARITY=1 to force" % (t_full, cores, budget_s)})
+    return out, sub, parity
 
 
 def ncu_traffic(kernel):
@@ -199,8 +244,8 @@ def ncu_traffic(kernel):
                         wr = float(row[3]) * scale
         except OSError:
             continue
-        if rd is not None and wr is not None and kernel == "walk4_kernel":
-            best = rd + wr          # the walk4 captures are of the default (1M-pattern) workload
+        if rd is not None and wr is not None and kernel in ("walk4_kernel", "walk4c_kernel"):
+            best = rd + wr          # the walk captures are of the default (1M-pattern) workload; the latest file wins
     return best
 
 
@@ -388,10 +433,12 @@ def main():
     ap.add_argument("--workload", default=DEFAULT, choices=sorted(WORKLOADS))
     ap.add_argument("--patterns", type=int, default=0, help="override the workload's pattern count (debug)")
     ap.add_argument("--points", type=int, default=0, help="override the number of parameter points (chromosome workload)")
-    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
-                    help="N > 1: weak = every GPU gets the workload's pattern count (patterns are an independent axis, no data-path "
-                         "collective); strong = the workload's patterns are split across the GPUs")
+    ap.add_argument("--scaling", default="strong", choices=["weak", "strong"],
+                    help="N > 1: strong (default, BASELINE's north-star) = the workload's patterns are split across the GPUs; "
+                         "weak = every GPU gets the workload's pattern count.  A strong run also times the weak job and reports it "
+                         "under the key `weak` of the same line.")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-weak", action="store_true", help="N > 1: skip the weak-scaling job timed after the strong one")
     ap.add_argument("--profile", action="store_true", help="1 warm-up + 1 timed step, no e2e / CPU legs (for ncu only)")
     a = ap.parse_args()
     w = dict(WORKLOADS[a.workload])
@@ -426,31 +473,35 @@ def main():
         from bpp_phyl_b200 import synth
         rng = np.random.default_rng(w["seed"])
         tree = synth.random_tree(w["taxa"], rng, mean_brlen=0.05)
-        es = model_for(w, rng)
+        es = model_for(w, rng)         # host code only (bppgpu_host_model launches nothing)
         rates, probs = synth.gamma_rates(w["C"], w["alpha"]) if w["C"] > 1 else (np.ones(1), np.ones(1))
         threads = os.cpu_count() or 1
-        n = 512 * threads
-        codes = np.random.default_rng(1).integers(0, w["S"], size=(tree.n_leaves, n), dtype=np.uint8)
+        n = (256 if w["S"] >= 20 else 512) * threads
+        # the native arm's data-generating process (tips simulated down the tree under the model), sampled on the CPU
+        codes = synth.simulate_tip_codes(tree, es, rates, n, seed=w["seed"] + 7919, device="cpu")
         from oracle import ref_cpu
         ref_cpu.build()
         want = 7 if w["derivs"] else 1
-        args = dict(S=w["S"], Ccat=w["C"], N=n, child_off=tree.child_off, children=tree.children, root=tree.root,
-                    codes=codes, code_table=np.eye(w["S"]), weights=np.ones(n, np.uint32), rates=rates, probs=probs,
-                    V=es["V"], Vinv=es["Vinv"], ev=es["ev"], model_rate=1.0, brlen=tree.brlen, rootfreq=es["pi"],
-                    scaled=True, want=want, nthreads=threads)
+        args = _cpu_args(w, tree, es, rates, probs, codes, want, threads)
         # one call: W + K evaluations on the same likelihood object (setData-style allocation is not part of a step);
         # the C side times every evaluation, the last K are the timed steps
-        r_all = ref_cpu.eval_raw(reps=max(1, a.warmup), **args) if a.warmup else None
+        if a.warmup:
+            ref_cpu.eval_raw(reps=max(1, a.warmup), **args)
         r = ref_cpu.eval_raw(reps=K, **args)
         dt = r["total_seconds"]
         upd = tree.n_internal * n * w["C"] * w["S"]
         val = upd * K / dt
-        sample = "%d of %d patterns per step (full tree), %d host threads as independent pattern shards" % (n, w["patterns"], threads)
+        r1 = ref_cpu.eval_raw(reps=1, **_cpu_args(w, tree, es, rates, probs, np.ascontiguousarray(codes[:, :n // threads]), want, 1))
+        one = tree.n_internal * (n // threads) * w["C"] * w["S"] / r1["seconds"]
+        sample = "%d of %d patterns per step (full tree, tips simulated under the model like the native arm's), %d host threads as " \
+                 "independent pattern shards" % (n, w["patterns"], threads)
         print(json.dumps({"impl": "reference", "metric": metric, "value": val, "unit": "CLV updates/s", "n_gpus": a.gpus,
                           "steps": K, "warmup": a.warmup, "ms_per_step": 1e3 * dt / K, "higher_is_better": True,
                           "scaling": a.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                           "config": config,
-                          "cpu_baseline": {"value": val, "unit": "CLV updates/s", "cores": threads, "kind": "port", "sample": sample},
+                          "cpu_baseline": {"value": val, "unit": "CLV updates/s", "cores": threads, "kind": "port", "sample": sample,
+                                           "one_thread": {"value": one, "cores": 1,
+                                                          "sample": "%d patterns, %.2f s" % (n // threads, r1["seconds"])}},
                           "e2e": {"value": val, "unit": "CLV updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return 0
 
@@ -541,11 +592,37 @@ def main():
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
     e2e_ms = float(tms.item())
     log("[rank %d] e2e region done: %.3f ms/step" % (rank, e2e_ms / K))
-    clocks = sampler.stop() if rank == 0 else None
     e.set_branch_lengths(0, tree.brlen)
 
     upd_step = tree.n_internal * w["patterns"] * w["C"] * w["S"]         # whole job (all shards)
     value = upd_step * K / (ms * 1e-3)
+    # FP64 ceilings of this GPU, measured now, while the clock sampler of the timed region is still running
+    dfma_peak, dmma_peak = capi.measure_fp64_peak(local) if rank == 0 else (None, None)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- the weak-scaling job of the same run (every GPU gets the workload's full pattern count) -------------------
+    weak = None
+    if world > 1 and a.scaling == "strong" and not a.profile and not a.no_weak:
+        e.close()
+        e = None
+        ww = dict(w, patterns=w["patterns"] * world)
+        t2, es2, r2, p2, codes2 = build_inputs(ww, rank, world, device)
+        e, md = make_engine(ww, t2, es2, r2, p2, codes2, local, flags)
+        for _ in range(W):
+            step_device()
+        barrier()
+        ev0.record(stream)
+        for _ in range(K):
+            step_device()
+        ev1.record(stream)
+        barrier()
+        tmsw = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=device)
+        dist.all_reduce(tmsw, op=dist.ReduceOp.MAX)
+        wms = float(tmsw.item())
+        weak = {"value": tree.n_internal * ww["patterns"] * w["C"] * w["S"] * K / (wms * 1e-3), "unit": "CLV updates/s",
+                "ms_per_step": wms / K, "patterns": ww["patterns"], "patterns_per_gpu": w["patterns"], "lnl": float(out[0].item())}
+        del codes2
+
     line = None
     if rank == 0:
         peaks = {}
@@ -557,52 +634,65 @@ def main():
         n_local = codes.shape[1]
         alg = algorithmic_bytes(tree, n_local, w["C"], w["S"])
         kms = st["prune_ms_sum"] / max(1, st["prune_count"])
-        kname = {1: "walk4_kernel", 2: "walkS_kernel", 3: "generic_node_kernel", 4: "dmma_node_kernel"}.get(st["path"], "?")
+        w4c = st["path"] == 1 and not w["derivs"] and os.environ.get("BPPGPU_WALK4C", "1") != "0"
+        kname = {1: "walk4c_kernel" if w4c else "walk4_kernel", 2: "walkS_kernel", 3: "generic_node_kernel", 4: "dmma_node_kernel"}.get(st["path"], "?")
         fam20 = st["path"] == 4 and w["S"] == 20 and w["C"] <= 4 and os.environ.get("BPPGPU_FAMILY", "1") != "0"
         if fam20 or (st["path"] == 4 and w["S"] == 64 and w["C"] == 1 and os.environ.get("BPPGPU_FAMILY", "1") != "0"):
             kname = "dmma_prune_kernel"
+        fp64_src = "measured in this run with bppgpu_measure_fp64_peak, under the clocks recorded in `clocks` (MEASURED_PEAKS.json has no FP64 figure)"
+        rows = n_local * w["C"]
         if st["path"] == 4 and w["S"] >= 32:
-            # dense contraction on the FP64 tensor cores (mma.sync DMMA; tcgen05 has no f64 kind)
-            try:
-                fp = json.loads(open(os.path.join(ROOT, "profiles", "r1_fp64_peaks.json")).readline())
-            except (OSError, ValueError):
-                fp = {}
-            dmma_peak = fp.get("dmma_m8n8k4_tflops", 37.1)
-            rows = n_local * w["C"]
+            # dense contraction on the FP64 tensor cores (mma.sync DMMA; tcgen05 has no f64 kind).  frac = the DMMAs actually
+            # issued (tip sons are table gathers) over the measured DMMA peak
             alg_flops = sum((2 * w["S"] * len(tree.sons(n)) + len(tree.sons(n)) - 1) * w["S"] for n in range(tree.nn)
                             if len(tree.sons(n))) * rows                  # every son contracted, tips included
-            exe_flops = flops_per_eval(tree, rows, w["S"])                # DMMA flops issued: tip sons are table gathers
-            ach = alg_flops / (kms * 1e-3) / 1e12 if kms > 0 else None
+            exe_flops = flops_per_eval(tree, rows, w["S"])                # DMMA flops issued
+            ach = exe_flops / (kms * 1e-3) / 1e12 if kms > 0 else None
             roofline = {"bound": "tensor", "kernel": kname + " (one launch per node; all launches of an evaluation timed together)",
                         "achieved": ach, "peak": dmma_peak, "unit": "TFLOP/s", "frac": ach / dmma_peak if ach else None,
                         "traffic": ncu_traffic_per_eval(a.workload, kname) if (not a.patterns and world == 1) else None,
-                        "kernel_ms": kms, "launches_timed": st["prune_count"], "algorithmic_flops_per_eval": alg_flops,
-                        "executed_dmma_tflops": exe_flops / (kms * 1e-3) / 1e12 if kms > 0 else None,
-                        "peak_source": "FP64 mma.sync m8n8k4 measured with tools/fp64_peak.cu (profiles/r1_fp64_peaks.json); "
-                                       "MEASURED_PEAKS.json has no FP64 figure",
-                        "note": "algorithmic flops = (2 S k + k - 1) per CLV element with k sons (SURVEY 8d, the reference contracts "
-                                "tip sons too); tip sons are gathers here, so executed_dmma_tflops is the tensor-pipe figure"}
+                        "kernel_ms": kms, "launches_timed": st["prune_count"], "executed_dmma_flops_per_eval": exe_flops,
+                        "algorithmic_flops_per_eval": alg_flops,
+                        "algorithmic_tflops": alg_flops / (kms * 1e-3) / 1e12 if kms > 0 else None,
+                        "peak_source": "FP64 mma.sync m8n8k4 " + fp64_src,
+                        "note": "achieved = DMMA flops ISSUED per evaluation / pruning time (tip sons are table gathers and issue none); "
+                                "algorithmic_flops counts (2 S k + k - 1) per CLV element with k sons as the reference does (SURVEY 8d)"}
+        elif st["path"] == 1:
+            # DNA register walk: every CLV stays on chip, HBM sees the tip codes only, the binding pipe is FP64 (CUDA cores)
+            S = w["S"]
+            fl = 0
+            for n in range(tree.nn):
+                sons = tree.sons(n)
+                if len(sons):
+                    fl += int((~tree.is_leaf[sons]).sum()) * (2 * S * S - S) + (len(sons) - 1) * S
+            exe_flops = fl * rows
+            ach = exe_flops / (kms * 1e-3) / 1e12 if kms > 0 else None
+            traffic = ncu_traffic(kname) if (a.workload == DEFAULT and not a.patterns and world == 1) else None
+            roofline = {"bound": "fp64", "kernel": kname, "achieved": ach, "peak": dfma_peak, "unit": "TFLOP/s",
+                        "frac": ach / dfma_peak if ach else None, "traffic": traffic, "kernel_ms": kms,
+                        "launches_timed": st["prune_count"], "executed_flops_per_launch": exe_flops,
+                        "peak_source": "DFMA (CUDA-core FP64 pipe) " + fp64_src,
+                        "hbm": {"bytes_moved_per_launch": traffic, "tip_code_bytes": int(tree.n_leaves) * n_local,
+                                "achieved_gbs": traffic / (kms * 1e-3) / 1e9 if traffic and kms > 0 else None, "peak_gbs": hbm_peak,
+                                "frac": traffic / (kms * 1e-3) / 1e9 / hbm_peak if traffic and kms > 0 else None},
+                        "vs_level_scheduled": {"algorithmic_bytes_per_launch": alg, "hbm_floor_ms": alg / (hbm_peak * 1e9) * 1e3,
+                                               "speedup_over_floor": alg / (hbm_peak * 1e9) * 1e3 / kms if kms > 0 else None,
+                                               "note": "time a perfect level-scheduled kernel needs to stream 8*(1+internal sons) bytes per "
+                                                       "CLV element (SURVEY 8d) at the measured HBM peak; this kernel does not move them"},
+                        "note": "executed flops = (2 S^2 - S) per internal son + S per extra son, per (pattern, class) row: the DFMA/DMUL "
+                                "the walk issues; CLVs never leave the SM, so the HBM roofline does not bound this kernel"}
         else:
             achieved = alg / (kms * 1e-3) / 1e9 if kms > 0 else None
             roofline = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                         "frac": achieved / hbm_peak if achieved else None,
-                        "traffic": (ncu_traffic(kname) if a.workload == DEFAULT else ncu_traffic_per_eval(a.workload, kname))
-                        if (not a.patterns and world == 1) else None,
+                        "traffic": ncu_traffic_per_eval(a.workload, kname) if (not a.patterns and world == 1) else None,
                         "kernel_ms": kms,
                         "launches_timed": st["prune_count"], "algorithmic_bytes_per_launch": alg,
                         "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
-                        "note": ("algorithmic bytes = 8*(1+internal sons) per CLV element (SURVEY 8d), the traffic a level-scheduled "
-                                 "kernel must move; this kernel keeps CLVs on chip, so frac > 1 is expected and DRAM traffic is "
-                                 "the tip codes only (traffic = dram bytes of one launch, ncu, profiles/)") if st["path"] == 1 else
-                                "algorithmic bytes = 8*(1+internal sons) per CLV element (SURVEY 8d); one launch per node, all "
+                        "note": "algorithmic bytes = 8*(1+internal sons) per CLV element (SURVEY 8d); one launch per node, all "
                                 "launches of an evaluation timed together"}
         if fam20 and w["derivs"]:
             # second kernel family of this workload: the per-father upper + d1/d2 pass, bound by the FP64 tensor pipe
-            try:
-                fp = json.loads(open(os.path.join(ROOT, "profiles", "r1_fp64_peaks.json")).readline())
-            except (OSError, ValueError):
-                fp = {}
-            dmma_peak = fp.get("dmma_m8n8k4_tflops", 37.1)
             dms = ms / K - kms - st["pt_ms_sum"] / max(1, K)
             fl = family_dmma_flops(tree, n_local * w["C"])
             roofline["derivative_pass"] = {
@@ -619,18 +709,22 @@ def main():
                         "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / K,
                         "call": "bppgpu_set_model + bppgpu_set_branch_lengths + bppgpu_eval (host buffers)"},
                 "gpu_launches": int(st["kernel_launches"]) * K, "launches_per_step": int(st["kernel_launches"]),
-                "roofline": roofline, "clocks": clocks,
+                "roofline": roofline, "clocks": clocks, "fp64_peaks_measured": {"dfma_tflops": dfma_peak, "dmma_m8n8k4_tflops": dmma_peak},
                 "hbm_resident_bytes": int(st["hbm_bytes_resident"])}
+        if weak is not None:
+            line["weak"] = weak
         if world == 1 and not a.no_cpu:
             t0 = time.time()
-            cb, sub = cpu_leg(w, tree, es, rates, probs, codes, threads=os.cpu_count() or 1)
+            cb, sub, parity = cpu_leg(w, tree, es, rates, probs, codes, lnl_dev)
             # the same sample through the CUDA path: the checker, not the thing measured
-            e2, _ = make_engine(w, tree, es, rates, probs, sub, local, 0)
-            l2 = e2.eval(1)[0][0]
+            e2, _ = make_engine(w, tree, es, rates, probs, sub, local, flags)
+            r2 = e2.eval(want)
             e2.close()
-            cb["gpu_lnl_same_sample"] = l2
-            cb["rel_diff_vs_gpu"] = abs(l2 - cb["lnl_sample"]) / abs(cb["lnl_sample"])
+            cb["gpu_lnl_same_sample"] = float(r2[0][0])
+            cb["rel_diff_vs_gpu"] = abs(r2[0][0] - cb["lnl_sample"]) / abs(cb["lnl_sample"])
+            parity["rel_diff_sample"] = cb["rel_diff_vs_gpu"]
             line["cpu_baseline"] = cb
+            line["parity"] = parity
             log("cpu leg %.1fs" % (time.time() - t0))
         print(json.dumps(line), flush=True)
         log("[rank 0] JSON line printed")

@@ -119,6 +119,30 @@ def _f64(a):
     return np.ascontiguousarray(a, dtype=np.float64)
 
 
+def host_model(name, *params):
+    """bppgpu_host_model: a named model built by the library's C++ host code (generator + updateMatrices).  Returns a dict with
+    Q, V, Vinv, ev (real parts), ev_im, pi (frequencies), flags, rate."""
+    pr = _f64(list(params)) if params else np.zeros(0)
+    n = C.c_int32(0)
+    _check(lib().bppgpu_host_model(name.encode(), pr.ctypes.data_as(_dp), C.c_int32(len(pr)), C.byref(n), None, None,
+                                   None, None, None, None, None, None))
+    S = n.value
+    out = {k: np.zeros((S, S)) for k in ("Q", "V", "Vinv")}
+    out.update({k: np.zeros(S) for k in ("ev", "ev_im", "pi")})
+    flags, rate = C.c_uint32(0), C.c_double(0)
+    _check(lib().bppgpu_host_model(name.encode(), pr.ctypes.data_as(_dp), C.c_int32(len(pr)), C.byref(n), C.byref(flags),
+                                   C.byref(rate), *(out[k].ctypes.data_as(_dp) for k in ("Q", "V", "Vinv", "ev", "ev_im", "pi"))))
+    out["flags"], out["rate"], out["name"] = flags.value, rate.value, name
+    return out
+
+
+def measure_fp64_peak(device=0):
+    """bppgpu_measure_fp64_peak: (DFMA TFLOP/s, DMMA m8n8k4 TFLOP/s) of the device, measured now."""
+    a, b = C.c_double(0), C.c_double(0)
+    _check(lib().bppgpu_measure_fp64_peak(C.c_int(device), C.byref(a), C.byref(b)))
+    return a.value, b.value
+
+
 def _ptr(a, t=C.c_double):
     return a.ctypes.data_as(C.POINTER(t)) if a is not None else None
 

@@ -701,13 +701,18 @@ static int create_impl(const bppgpu_config* cfg, bppgpu_engine* e) {
     int CH = 8192;
     while (CH < max_op) CH *= 2;
     e->w4c_pt = 2;
-    if (N * C < (long long)g_sm_count * 2 * kW4cThreads * 2) e->w4c_pt = 1;  // small inputs: more CTAs instead
+    e->w4c_nw = C <= 4 ? 4 : 8;
+    if (const char* env = getenv("BPPGPU_WALK4_NW")) {
+      const int v = atoi(env);
+      if ((v == 4 || v == 8) && v >= C) e->w4c_nw = v;
+    }
+    if (N * C < (long long)g_sm_count * 2 * 256 * 2) e->w4c_pt = 1;  // small inputs: more CTAs instead
     if (const char* env = getenv("BPPGPU_WALK4_PT")) {
       const int v = atoi(env);
       if (v == 1 || v == 2 || v == 4) e->w4c_pt = v;
     }
-    while (e->w4c_pt > 1 && walk4c_smem_bytes(CH, e->prog4c.nslots, C, e->w4c_pt) > 200 * 1024) e->w4c_pt >>= 1;
-    if (walk4c_smem_bytes(CH, e->prog4c.nslots, C, e->w4c_pt) > 200 * 1024) ok = false;
+    while (e->w4c_pt > 1 && walk4c_smem_bytes(CH, e->prog4c.nslots, C, e->w4c_pt, e->w4c_nw) > 200 * 1024) e->w4c_pt >>= 1;
+    if (walk4c_smem_bytes(CH, e->prog4c.nslots, C, e->w4c_pt, e->w4c_nw) > 200 * 1024) ok = false;
     if (ok) {
       W4cProgram& W = e->w4c_prog;
       memset(&W, 0, sizeof(W));
@@ -879,7 +884,7 @@ static int create_impl(const bppgpu_config* cfg, bppgpu_engine* e) {
     BPP_CUDA(cudaMemcpy(e->d_w4c_blocks, e->w4c_blocks.data(), e->w4c_blocks.size() * sizeof(Pack4cBlock), cudaMemcpyHostToDevice));
     BPP_CUDA(dev_alloc(e, &e->d_w4c_tip_order, e->w4c_tip_order.size()));
     BPP_CUDA(cudaMemcpy(e->d_w4c_tip_order, e->w4c_tip_order.data(), e->w4c_tip_order.size() * 4, cudaMemcpyHostToDevice));
-    const long long ppc = (long long)(kW4cWarps / C) * 32 * e->w4c_pt;
+    const long long ppc = (long long)(e->w4c_nw / C) * 32 * e->w4c_pt;
     e->w4c_grid = (int)((N + ppc - 1) / ppc);
     BPP_CUDA(dev_alloc(e, &e->d_codesC, (size_t)std::max(1, e->w4c_grid) * e->w4c_tip_order.size() * (size_t)ppc + 16));
   }
@@ -960,7 +965,7 @@ static int create_impl(const bppgpu_config* cfg, bppgpu_engine* e) {
   }
 
   if (e->w4c) {
-    const size_t smem = walk4c_smem_bytes(e->w4c_CH, e->prog4c.nslots, C, e->w4c_pt);
+    const size_t smem = walk4c_smem_bytes(e->w4c_CH, e->prog4c.nslots, C, e->w4c_pt, e->w4c_nw);
     int rc4 = walk4c_dispatch(e, nullptr, 0, smem, nullptr, true);
     if (rc4) return rc4;
     e->stats.stack_slots = e->prog4c.nslots;
@@ -1248,28 +1253,36 @@ static int walk4_dispatch(bppgpu_engine* e, const Walk4Params* wp, int grid, siz
   }
 }
 static thread_local const W4cProgram* g_w4c_prog = nullptr;   // the launching engine's program (copied into the launch)
-template <int CL, int PT>
+template <int CL, int PT, int NW>
 static int walk4c_launch_one(const Walk4cParams* wp, int grid, size_t smem, cudaStream_t st, bool attr_only) {
   if (attr_only) {
-    BPP_CUDA(cudaFuncSetAttribute(walk4c_kernel<CL, PT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    BPP_CUDA(cudaFuncSetAttribute(walk4c_kernel<CL, PT, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     return BPPGPU_OK;
   }
-  walk4c_kernel<CL, PT><<<grid, kW4cThreads, smem, st>>>(*wp, *g_w4c_prog);
+  walk4c_kernel<CL, PT, NW><<<grid, NW * 32, smem, st>>>(*wp, *g_w4c_prog);
   return BPPGPU_OK;
 }
-template <int CL>
+template <int CL, int NW>
 static int walk4c_launch_pt(int pt, const Walk4cParams* wp, int grid, size_t smem, cudaStream_t st, bool attr_only) {
-  if (pt == 4) return walk4c_launch_one<CL, 4>(wp, grid, smem, st, attr_only);
-  if (pt == 2) return walk4c_launch_one<CL, 2>(wp, grid, smem, st, attr_only);
-  return walk4c_launch_one<CL, 1>(wp, grid, smem, st, attr_only);
+  if (pt == 4) return walk4c_launch_one<CL, 4, NW>(wp, grid, smem, st, attr_only);
+  if (pt == 2) return walk4c_launch_one<CL, 2, NW>(wp, grid, smem, st, attr_only);
+  return walk4c_launch_one<CL, 1, NW>(wp, grid, smem, st, attr_only);
 }
 static int walk4c_dispatch(bppgpu_engine* e, const Walk4cParams* wp, int grid, size_t smem, cudaStream_t st, bool attr_only) {
   g_w4c_prog = &e->w4c_prog;
+  const int pt = e->w4c_pt;
+  if (e->w4c_nw == 4) {
+    switch (ilog2(e->C)) {
+      case 0: return walk4c_launch_pt<0, 4>(pt, wp, grid, smem, st, attr_only);
+      case 1: return walk4c_launch_pt<1, 4>(pt, wp, grid, smem, st, attr_only);
+      default: return walk4c_launch_pt<2, 4>(pt, wp, grid, smem, st, attr_only);
+    }
+  }
   switch (ilog2(e->C)) {
-    case 0: return walk4c_launch_pt<0>(e->w4c_pt, wp, grid, smem, st, attr_only);
-    case 1: return walk4c_launch_pt<1>(e->w4c_pt, wp, grid, smem, st, attr_only);
-    case 2: return walk4c_launch_pt<2>(e->w4c_pt, wp, grid, smem, st, attr_only);
-    default: return walk4c_launch_pt<3>(e->w4c_pt, wp, grid, smem, st, attr_only);
+    case 0: return walk4c_launch_pt<0, 8>(pt, wp, grid, smem, st, attr_only);
+    case 1: return walk4c_launch_pt<1, 8>(pt, wp, grid, smem, st, attr_only);
+    case 2: return walk4c_launch_pt<2, 8>(pt, wp, grid, smem, st, attr_only);
+    default: return walk4c_launch_pt<3, 8>(pt, wp, grid, smem, st, attr_only);
   }
 }
 template <int CL>
@@ -1313,7 +1326,7 @@ static int enqueue_prune(bppgpu_engine* e, int point, int pl, cudaStream_t st) {
     wp.partials = e->d_partials;
     const int grid = e->w4c_grid;
     nparts = grid;
-    int rc4 = walk4c_dispatch(e, &wp, grid, walk4c_smem_bytes(e->w4c_CH, e->prog4c.nslots, C, e->w4c_pt), st, false);
+    int rc4 = walk4c_dispatch(e, &wp, grid, walk4c_smem_bytes(e->w4c_CH, e->prog4c.nslots, C, e->w4c_pt, e->w4c_nw), st, false);
     if (rc4) return rc4;
     e->stats.kernel_launches++;
   } else if (e->path == PATH_WALK4) {
@@ -1727,7 +1740,7 @@ static int eval_impl(bppgpu_engine* e, unsigned want, cudaStream_t st, bool time
       if (e->codesT_dirty && e->N > 0) {
         pack_codesC_kernel<<<(unsigned)e->w4c_grid, 256, 0, st>>>(
             (const unsigned char*)e->d_codes, e->d_w4c_tip_order, (int)e->w4c_tip_order.size(), e->N,
-            (kW4cWarps / C) * 32 * e->w4c_pt, e->d_codesC);
+            (e->w4c_nw / C) * 32 * e->w4c_pt, e->d_codesC);
         e->stats.kernel_launches++;
         e->codesT_dirty = false;
       }

@@ -114,7 +114,7 @@ struct bppgpu_engine {
   int w4c_grid = 0;
   std::vector<bppgpu::Pack4cBlock> w4c_blocks;
   std::vector<int> w4c_tip_order;
-  int w4c_CH = 0, w4c_nchunks = 0, w4c_pt = 2;
+  int w4c_CH = 0, w4c_nchunks = 0, w4c_pt = 2, w4c_nw = 8;
   unsigned char* d_w4c_stream = nullptr;   // [pchunk][nchunks][CH]
   bppgpu::Pack4cBlock* d_w4c_blocks = nullptr;
   int* d_w4c_tip_order = nullptr;

@@ -25,8 +25,7 @@
 
 namespace bppgpu {
 
-constexpr int kW4cThreads = 256;
-constexpr int kW4cWarps = kW4cThreads / 32;
+constexpr int kW4cMaxWarps = 8;           // warps per CTA: 8 (two CTAs per SM at 128 registers) or 4 (three at 168)
 constexpr int kW4cStages = 3;
 constexpr int kW4cMaxTipsPerChunk = 16;   // tip-code rows staged with a chunk
 constexpr int kW4cMaxOps = 3072;          // descriptors (8 bytes each) that fit the kernel-parameter block
@@ -122,11 +121,11 @@ __device__ __forceinline__ unsigned lds_u8(unsigned a) {
   return r;
 }
 
-template <int C_LOG2, int PT>
+template <int C_LOG2, int PT, int NW>
 struct W4cState {
   static constexpr int C = 1 << C_LOG2;
-  static constexpr int NTH = kW4cThreads;
-  static constexpr int PPC = (kW4cWarps >> C_LOG2) * 32 * PT;
+  static constexpr int NTH = NW * 32;
+  static constexpr int PPC = (NW >> C_LOG2) * 32 * PT;
   double v[PT][4], w[PT][4];   // current CLV rows / register slot
   int E[PT], EW[PT];
   unsigned ca;                 // shared address of this thread's code byte of the next tip (pattern j: + 32 j)
@@ -286,21 +285,22 @@ struct W4cState {
 };
 
 // bytes of one ring stage: the table chunk + the tip-code rows of the chunk's tips
-__host__ __device__ inline size_t walk4c_stage_bytes(int CH, int C, int PT) {
-  return (size_t)CH + (size_t)kW4cMaxTipsPerChunk * (kW4cWarps / C) * 32 * PT;
+__host__ __device__ inline size_t walk4c_stage_bytes(int CH, int C, int PT, int NW) {
+  return (size_t)CH + (size_t)kW4cMaxTipsPerChunk * (NW / C) * 32 * PT;
 }
 // dynamic shared memory of one CTA
-__host__ __device__ inline size_t walk4c_smem_bytes(int CH, int nslots, int C, int PT) {
-  return (size_t)kW4cStages * walk4c_stage_bytes(CH, C, PT) + (size_t)(nslots > 0 ? nslots : 0) * PT * kW4cThreads * 36 +
-         (size_t)PT * kW4cThreads * 12 + 128;
+__host__ __device__ inline size_t walk4c_smem_bytes(int CH, int nslots, int C, int PT, int NW) {
+  return (size_t)kW4cStages * walk4c_stage_bytes(CH, C, PT, NW) + (size_t)(nslots > 0 ? nslots : 0) * PT * NW * 32 * 36 +
+         (size_t)PT * NW * 32 * 12 + 128;
 }
+__host__ __device__ constexpr int walk4c_min_ctas(int PT, int NW) { return NW == 8 ? (PT <= 2 ? 2 : 1) : (PT <= 2 ? 3 : 2); }
 
-template <int C_LOG2, int PT>
-__global__ void __launch_bounds__(kW4cThreads, (PT <= 2 ? 2 : 1))
+template <int C_LOG2, int PT, int NW>
+__global__ void __launch_bounds__(NW * 32, walk4c_min_ctas(PT, NW))
 walk4c_kernel(const __grid_constant__ Walk4cParams prm, const __grid_constant__ W4cProgram prog) {
   constexpr int C = 1 << C_LOG2;
-  constexpr int NTH = kW4cThreads;
-  constexpr int G = kW4cWarps >> C_LOG2;   // pattern groups (of 32 * PT patterns) per CTA
+  constexpr int NTH = NW * 32;
+  constexpr int G = NW >> C_LOG2;          // pattern groups (of 32 * PT patterns) per CTA
   constexpr int PPC = G * 32 * PT;         // patterns per CTA
   extern __shared__ __align__(32) unsigned char smem_raw[];
   __shared__ double red[32];
@@ -311,7 +311,7 @@ walk4c_kernel(const __grid_constant__ Walk4cParams prm, const __grid_constant__ 
   const unsigned ring_s = smem_u32(smem_raw);
   unsigned char* q0 = smem_raw + (size_t)kW4cStages * SB;
   const size_t plane = (size_t)(prm.nslots > 0 ? prm.nslots : 0) * PT * NTH;
-  W4cState<C_LOG2, PT> s;
+  W4cState<C_LOG2, PT, NW> s;
   s.stA = smem_u32(q0) + threadIdx.x * 16;
   s.stB = smem_u32(q0 + plane * 16) + threadIdx.x * 16;
   s.ste = smem_u32(q0 + plane * 32) + threadIdx.x * 4;
@@ -339,7 +339,7 @@ walk4c_kernel(const __grid_constant__ Walk4cParams prm, const __grid_constant__ 
 #pragma unroll
     for (int i = 0; i < kW4cStages; ++i) {
       mbar_init(full + i, 1);
-      mbar_init(empty + i, kW4cWarps);
+      mbar_init(empty + i, NW);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");

@@ -488,6 +488,103 @@ class YN98 : public AbstractSubstitutionModel {
   double kappa_, omega_;
 };
 
+// Grantham (1974) amino-acid distances, what bpp-seq's GranthamAAChemicalDistance::getIndex returns in its default symmetric
+// mode (GY94.h:45,88).  bpp-seq is not under /root/reference, so the published table is restated here in Grantham's own order
+// (Ser Arg Leu Pro Thr Ala Val Gly Ile Phe Tyr Cys His Gln Asn Lys Asp Glu Met Trp), upper triangle by rows.
+inline double granthamDistance(char a, char b) {
+  static const char* order = "SRLPTAVGIFYCHQNKDEMW";
+  static const int upper[190] = {
+      110, 145, 74, 58, 99, 124, 56, 142, 155, 144, 112, 89, 68, 46, 121, 65, 80, 135, 177,
+      102, 103, 71, 112, 96, 125, 97, 97, 77, 180, 29, 43, 86, 26, 96, 54, 91, 101,
+      98, 92, 96, 32, 138, 5, 22, 36, 198, 99, 113, 153, 107, 172, 138, 15, 61,
+      38, 27, 68, 42, 95, 114, 110, 169, 77, 76, 91, 103, 108, 93, 87, 147,
+      58, 69, 59, 89, 103, 92, 149, 47, 42, 65, 78, 85, 65, 81, 128,
+      64, 60, 94, 113, 112, 195, 86, 91, 111, 106, 126, 107, 84, 148,
+      109, 29, 50, 55, 192, 84, 96, 133, 97, 152, 121, 21, 88,
+      135, 153, 147, 159, 98, 87, 80, 127, 94, 98, 127, 184,
+      21, 33, 198, 94, 109, 149, 102, 168, 134, 10, 61,
+      22, 205, 100, 116, 158, 102, 177, 140, 28, 40,
+      194, 83, 99, 143, 85, 160, 122, 36, 37,
+      174, 154, 139, 202, 154, 170, 196, 215,
+      24, 68, 32, 81, 40, 87, 115,
+      46, 53, 61, 29, 101, 130,
+      94, 23, 42, 142, 174,
+      101, 56, 95, 110,
+      45, 160, 181,
+      126, 152,
+      67};
+  int i = -1, j = -1;
+  for (int k = 0; k < 20; ++k) {
+    if (order[k] == a) i = k;
+    if (order[k] == b) j = k;
+  }
+  if (i < 0 || j < 0) throw Exception("granthamDistance: not an amino acid");
+  if (i == j) return 0.0;
+  if (i > j) std::swap(i, j);
+  // row i starts after sum_{r<i} (19 - r) entries
+  return (double)upper[i * 19 - i * (i - 1) / 2 + (j - i - 1)];
+}
+
+// Model/Codon/GY94.cpp:49-71 = CodonDistanceFrequenciesSubstitutionModel over K80 with the Grantham distance:
+// K80 rate / 3 on single-nucleotide changes (AbstractWordSubstitutionModel::fillBasicGenerator), x exp(-d(aa_i, aa_j) / V) when
+// non-synonymous (beta = gamma = 1, AbstractCodonDistanceSubstitutionModel.cpp:80-88), x target codon frequency, stop codons
+// zeroed (AbstractCodonSubstitutionModel.cpp:174-191), then normalised.  Parameters "GY94.kappa" (1) and "GY94.V" (10000).
+class GY94 : public AbstractSubstitutionModel {
+ public:
+  GY94(const Alphabet* alpha, double kappa = 1., double V = 10000., const Vdouble* codonFreq = nullptr)
+      : AbstractSubstitutionModel(alpha, 64), kappa_(kappa), V_(V) {
+    if (codonFreq) freq_ = *codonFreq;
+    else {
+      double n = 0;
+      for (int i = 0; i < 64; ++i) { freq_[i] = CodonAlphabet::isStop(i) ? 0.0 : 1.0; n += freq_[i]; }
+      for (int i = 0; i < 64; ++i) freq_[i] /= n;
+    }
+    reversible_ = false;
+    update();
+  }
+  GY94* clone() const { return new GY94(*this); }
+  std::string getName() const { return "GY94"; }
+  double getParameterValue(const std::string& name) const {
+    if (name == "kappa" || name == "GY94.kappa") return kappa_;
+    if (name == "V" || name == "GY94.V") return V_;
+    throw ParameterNotFoundException(name);
+  }
+  std::vector<std::string> getParameterNames() const { return {"GY94.kappa", "GY94.V"}; }
+  void setParameterValue(const std::string& name, double v) {
+    if (name == "kappa" || name == "GY94.kappa") kappa_ = v;
+    else if (name == "V" || name == "GY94.V") V_ = v;
+    else throw ParameterNotFoundException(name);
+    update();
+  }
+  double getCodonsMulRate(size_t i, size_t j) const {
+    const char ai = CodonAlphabet::aminoAcid((int)i), aj = CodonAlphabet::aminoAcid((int)j);
+    return ai == aj ? 1.0 : std::exp(-granthamDistance(ai, aj) / V_);
+  }
+
+ private:
+  void update() {
+    for (int i = 0; i < 64; ++i)
+      for (int j = 0; j < 64; ++j) {
+        generator_(i, j) = 0.0;
+        if (i == j) continue;
+        const int di[3] = {i / 16, (i / 4) % 4, i % 4}, dj[3] = {j / 16, (j / 4) % 4, j % 4};
+        int ndiff = 0, p = -1;
+        for (int k = 0; k < 3; ++k)
+          if (di[k] != dj[k]) { ++ndiff; p = k; }
+        if (ndiff != 1 || CodonAlphabet::isStop(i) || CodonAlphabet::isStop(j)) continue;
+        const bool ts = (di[p] == 0 && dj[p] == 2) || (di[p] == 2 && dj[p] == 0) || (di[p] == 1 && dj[p] == 3) || (di[p] == 3 && dj[p] == 1);
+        generator_(i, j) = (ts ? kappa_ : 1.0) / (kappa_ + 2.0) / 3.0 * getCodonsMulRate(i, j) * freq_[j];
+      }
+    setDiagonal();
+    const Vdouble keep = freq_;
+    reversible_ = true;   // reversible w.r.t. the codon frequencies: symmetric solver on the sense codons
+    updateMatrices(false);
+    reversible_ = false;
+    freq_ = keep;
+  }
+  double kappa_, V_;
+};
+
 // Model/ChromosomeSubstitutionModel.cpp:431-802 (gain / loss / duplication / demi-duplication / base number)
 class ChromosomeSubstitutionModel : public AbstractSubstitutionModel {
  public:

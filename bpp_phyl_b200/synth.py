@@ -256,26 +256,35 @@ def simulate_single_character(tree: Tree, P, root_state, seed):
 def model_desc(es):
     from . import capi
     S = len(es["ev"])
-    return capi.model_desc(S, capi.MODEL_DIAGONALIZABLE | capi.MODEL_NONSINGULAR, rate=1.0, V=es["V"], Vinv=es["Vinv"],
-                           ev_re=es["ev"], Q=es["Q"])
+    return capi.model_desc(S, es.get("flags", capi.MODEL_DIAGONALIZABLE | capi.MODEL_NONSINGULAR), rate=es.get("rate", 1.0),
+                           V=es["V"], Vinv=es["Vinv"], ev_re=es["ev"], Q=es["Q"])
+
+
+def host_pt(es, t):
+    """P(t) = V exp(ev rate t) V^-1 on the host (real spectra), for callers that must not touch the device."""
+    t = np.asarray(t, float)
+    return np.einsum("ik,tk,kj->tij", es["V"], np.exp(np.outer(t * es.get("rate", 1.0), es["ev"])), es["Vinv"])
 
 
 def simulate_tip_codes(tree: Tree, es, rates, n_sites, seed, device="cuda:0", chunk=1 << 20):
-    """Tip states [n_leaves][n_sites] uint8 (leaf slots in increasing node id), simulated down the tree on the GPU.
-    P(t) comes from bppgpu_pt_batch (the product's interface 1)."""
+    """Tip states [n_leaves][n_sites] uint8 (leaf slots in increasing node id), simulated down the tree with torch on `device`.
+    On a GPU, P(t) comes from bppgpu_pt_batch (the product's interface 1); with device="cpu" from host_pt (no library call)."""
     import torch
-    from . import capi
     S = len(es["ev"])
     C = len(rates)
-    md = model_desc(es)
     t = (tree.brlen[:, None] * np.asarray(rates)[None, :]).ravel()
-    P, _, _ = capi.pt_batch(md, t, capi.WANT_P, device=int(str(device).split(":")[-1]) if ":" in str(device) else 0)
+    if str(device) == "cpu":
+        P = host_pt(es, t)
+    else:
+        from . import capi
+        P, _, _ = capi.pt_batch(model_desc(es), t, capi.WANT_P, device=int(str(device).split(":")[-1]) if ":" in str(device) else 0)
     P = np.clip(P.reshape(tree.nn, C, S, S), 0, None)
     cum = torch.tensor(np.cumsum(P / P.sum(-1, keepdims=True), axis=-1), device=device)     # [nn][C][S][S]
     g = torch.Generator(device=device)
     g.manual_seed(seed)
-    out = torch.empty((tree.n_leaves, n_sites), dtype=torch.uint8, device="cpu").pin_memory() if n_sites else \
-        torch.empty((tree.n_leaves, 0), dtype=torch.uint8)
+    out = torch.empty((tree.n_leaves, n_sites), dtype=torch.uint8, device="cpu")
+    if n_sites and str(device) != "cpu":
+        out = out.pin_memory()
     leaf_slot = {int(n): k for k, n in enumerate(tree.leaf_nodes)}
     picum = torch.tensor(np.cumsum(es["pi"]), device=device)
     for s0 in range(0, n_sites, chunk):

@@ -250,6 +250,22 @@ typedef struct bppgpu_stats {
 } bppgpu_stats;
 int bppgpu_get_stats(bppgpu_engine* e, bppgpu_stats* out);
 
+/* ---- host-side utilities (not on the evaluation path) ----------------------------------------------------------------
+ * bppgpu_host_model: build a named model with the C++ host code of this library -- the generator of the model class and
+ * AbstractSubstitutionModel::updateMatrices (Model/AbstractSubstitutionModel.cpp:175-421; Chromosome:
+ * Model/ChromosomeSubstitutionModel.cpp:431-802) -- and copy out what bppgpu_model_desc needs.  Names and parameter lists:
+ *   "GTR" a b c d e piA piC piG piT (Model/Nucleotide/GTR.cpp:84-124)   "HKY85" kappa piA piC piG piT   "T92" kappa theta
+ *   "K80" kappa   "JC69"   "LG08" (Model/Protein/LG08.cpp)   "YN98" kappa omega (Model/Codon/YN98.cpp:51-77)
+ *   "GY94" kappa V (Model/Codon/GY94.cpp:49-71, Grantham distances)
+ *   "Chromosome" min max gain loss dupl demi [gainR lossR duplR baseNum baseNumR maxChrRange]
+ * Missing trailing parameters take the class defaults.  Output arrays are caller-allocated ([S*S] / [S]); any may be NULL.
+ * Call once with all arrays NULL to learn *n_states.                                                                  */
+int bppgpu_host_model(const char* name, const double* params, int32_t n_params, int32_t* n_states, uint32_t* flags, double* rate,
+                      double* Q, double* V, double* Vinv, double* eigen_re, double* eigen_im, double* freq);
+/* FP64 ceilings of `device` measured now: DFMA (CUDA-core FP64 pipe) and DMMA mma.sync m8n8k4 (the FP64 tensor path of
+ * sm_100a), in TFLOP/s.  About 0.2 s.                                                                                   */
+int bppgpu_measure_fp64_peak(int device, double* dfma_tflops, double* dmma_tflops);
+
 #ifdef __cplusplus
 }
 #endif

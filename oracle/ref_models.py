@@ -371,6 +371,82 @@ def yn98(kappa=1., omega=1., codon_freq=None):
     return update_matrices(m, compute_freq=False)
 
 
+# Grantham (1974) distances = bpp-seq GranthamAAChemicalDistance::getIndex (symmetric mode), the index GY94 is built on
+# (Model/Codon/GY94.h:45,88).  bpp-seq is not under /root/reference: the published table is restated (Grantham's order, upper
+# triangle by rows) and checked in tests against Grantham's own formula from composition / polarity / volume.
+GRANTHAM_ORDER = "SRLPTAVGIFYCHQNKDEMW"
+_GRANTHAM_UPPER = """
+110 145 74 58 99 124 56 142 155 144 112 89 68 46 121 65 80 135 177
+102 103 71 112 96 125 97 97 77 180 29 43 86 26 96 54 91 101
+98 92 96 32 138 5 22 36 198 99 113 153 107 172 138 15 61
+38 27 68 42 95 114 110 169 77 76 91 103 108 93 87 147
+58 69 59 89 103 92 149 47 42 65 78 85 65 81 128
+64 60 94 113 112 195 86 91 111 106 126 107 84 148
+109 29 50 55 192 84 96 133 97 152 121 21 88
+135 153 147 159 98 87 80 127 94 98 127 184
+21 33 198 94 109 149 102 168 134 10 61
+22 205 100 116 158 102 177 140 28 40
+194 83 99 143 85 160 122 36 37
+174 154 139 202 154 170 196 215
+24 68 32 81 40 87 115
+46 53 61 29 101 130
+94 23 42 142 174
+101 56 95 110
+45 160 181
+126 152
+67
+"""
+# composition, polarity, molecular volume (Grantham 1974, table 1)
+GRANTHAM_PROPERTIES = {"S": (1.42, 9.2, 32), "R": (0.65, 10.5, 124), "L": (0, 4.9, 111), "P": (0.39, 8.0, 32.5), "T": (0.71, 8.6, 61),
+                       "A": (0, 8.1, 31), "V": (0, 5.9, 84), "G": (0.74, 9.0, 3), "I": (0, 5.2, 111), "F": (0, 5.2, 132),
+                       "Y": (0.20, 6.2, 136), "C": (2.75, 5.5, 55), "H": (0.58, 10.4, 96), "Q": (0.89, 10.5, 85),
+                       "N": (1.33, 11.6, 56), "K": (0.33, 11.3, 119), "D": (1.38, 13.0, 54), "E": (0.92, 12.3, 83),
+                       "M": (0, 5.7, 105), "W": (0.13, 5.4, 170)}
+
+
+def grantham_matrix():
+    """dict (a, b) -> distance, both orders, zero diagonal"""
+    rows = [list(map(float, line.split())) for line in _GRANTHAM_UPPER.strip().splitlines()]
+    d = {}
+    for i, row in enumerate(rows):
+        for k, v in enumerate(row):
+            a, b = GRANTHAM_ORDER[i], GRANTHAM_ORDER[i + 1 + k]
+            d[a, b] = d[b, a] = v
+    for a in GRANTHAM_ORDER:
+        d[a, a] = 0.0
+    return d
+
+
+def gy94(kappa=1., V=10000., codon_freq=None):
+    """GY94 (Model/Codon/GY94.cpp:49-71) = CodonDistanceFrequenciesSubstitutionModel over K80 with the Grantham index:
+    like yn98() with the non-synonymous factor exp(-d(aa_i, aa_j) / V) (beta = gamma = 1,
+    AbstractCodonDistanceSubstitutionModel.cpp:80-88; V is the model's `alpha`, GY94.cpp:66)."""
+    aa = standard_genetic_code()
+    dist = grantham_matrix()
+    if codon_freq is None:
+        codon_freq = np.array([0.0 if aa[i] == "*" else 1.0 for i in range(64)])
+        codon_freq /= codon_freq.sum()
+    codon_freq = np.asarray(codon_freq, float)
+    ts = {(0, 2), (2, 0), (1, 3), (3, 1)}
+    Q = np.zeros((64, 64))
+    for i in range(64):
+        for j in range(64):
+            if i == j:
+                continue
+            di = [(i // m) % 4 for m in (16, 4, 1)]
+            dj = [(j // m) % 4 for m in (16, 4, 1)]
+            diff = [p for p in range(3) if di[p] != dj[p]]
+            if len(diff) != 1 or aa[i] == "*" or aa[j] == "*":
+                continue
+            p = diff[0]
+            r = (kappa if (di[p], dj[p]) in ts else 1.0) / (kappa + 2.0) / 3.0
+            r *= (1.0 if aa[i] == aa[j] else math.exp(-dist[aa[i], aa[j]] / V)) * codon_freq[j]
+            Q[i, j] = r
+    Q = _set_diagonal(Q)
+    m = Model("GY94", Q, codon_freq.copy(), reversible=False)
+    return update_matrices(m, compute_freq=False)
+
+
 def _simple_distribution_probs(thetas):
     """SimpleDiscreteDistribution's simplex parameters (bpp-core): p_1 = theta1, p_2 = (1 - theta1) theta2, ...,
     the last class takes the rest (YNGP_M2.cpp / RELAX.cpp: "theta1 = p0, theta2 = p1 / (p1 + p2)")."""

@@ -61,6 +61,8 @@ int main() {
     print_model("LG08", lg);
     YN98 yn(&AlphabetTools::CODON_ALPHABET(), 2.0, 0.3);
     print_model("YN98", yn);
+    GY94 gy(&AlphabetTools::CODON_ALPHABET(), 2.0, 50.0);
+    print_model("GY94", gy);
     ChromosomeAlphabet chr(1, 40);
     ChromosomeSubstitutionModel c1(&chr, 0.7, 0.4, 0.2, ChromosomeSubstitutionModel::DemiEqualDupl);
     print_model("CHR_REAL", c1);

@@ -62,10 +62,10 @@ def _block_diag(re, im):
     return D
 
 
-@pytest.mark.parametrize("key", ["T92", "GTR", "LG08", "YN98", "CHR_REAL", "CHR_COMPLEX", "CHR_SINGULAR"])
+@pytest.mark.parametrize("key", ["T92", "GTR", "LG08", "YN98", "GY94", "CHR_REAL", "CHR_COMPLEX", "CHR_SINGULAR"])
 def test_models_generator_and_eigensystem(host_doc, key):
     m = {"T92": lambda: rm.t92(3.0, 0.5), "GTR": lambda: rm.gtr(1.2, 0.8, 0.6, 1.5, 0.9, (.3, .2, .25, .25)), "LG08": rm.lg08,
-         "YN98": lambda: rm.yn98(2.0, 0.3),
+         "YN98": lambda: rm.yn98(2.0, 0.3), "GY94": lambda: rm.gy94(2.0, 50.0),
          "CHR_REAL": lambda: rm.chromosome(1, 40, gain=0.7, loss=0.4, dupl=0.2, demi=rm.DEMI_EQUAL_DUPL),
          "CHR_COMPLEX": lambda: rm.chromosome(1, 25, gain=1.5, loss=0.1, dupl=0.9, demi=0.4, gain_r=0.05),
          "CHR_SINGULAR": lambda: rm.chromosome(1, 20, gain=0.5, loss=0.0, dupl=0.0)}[key]()

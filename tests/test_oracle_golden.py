@@ -104,12 +104,39 @@ def test_derivatives_vs_finite_differences():
         assert abs((fp - 2 * f0 + fm) / h ** 2 - res.d2[b]) < 2e-3 * max(1, abs(res.d2[b]))
 
 
-@pytest.mark.parametrize("name", ["gtr", "lg08", "yn98", "chromosome"])
+def test_grantham_table_against_grantham_s_formula_and_gy94_structure():
+    """The restated Grantham (1974) table (GY94's index; bpp-seq is not under /root/reference) against the paper's own formula
+    D = 50.723 sqrt(1.833 dc^2 + 0.1018 dp^2 + 0.000399 dv^2) from composition, polarity and volume: every entry within rounding
+    except the two entries the published table is known to carry off-formula (Asn-Glu 42, Asp-Trp 181).  GY94 itself: V -> inf
+    gives YN98 with omega = 1, small V suppresses radical changes most, frequencies are the codon frequencies."""
+    import math
+    d = rm.grantham_matrix()
+    assert len(d) == 400 and d["L", "I"] == 5 and d["C", "W"] == 215 and d["S", "R"] == 110
+    for a in rm.GRANTHAM_ORDER:
+        for b in rm.GRANTHAM_ORDER:
+            (ca, pa, va), (cb, pb, vb) = rm.GRANTHAM_PROPERTIES[a], rm.GRANTHAM_PROPERTIES[b]
+            f = 50.723 * math.sqrt(1.833 * (ca - cb) ** 2 + 0.1018 * (pa - pb) ** 2 + 0.000399 * (va - vb) ** 2)
+            if {a, b} in ({"N", "E"}, {"D", "W"}):
+                assert abs(f - d[a, b]) < 10
+            else:
+                assert abs(f - d[a, b]) <= 1.01, (a, b, f, d[a, b])
+    big, yn = rm.gy94(2.0, 1e12), rm.yn98(2.0, 1.0)
+    np.testing.assert_allclose(big.Q, yn.Q, atol=1e-10)
+    m = rm.gy94(2.0, 50.0)
+    aa = rm.standard_genetic_code()
+    i, j_cons, j_rad = 16 * 3 + 4 * 3 + 3, 16 * 3 + 4 * 3 + 1, 16 * 3 + 4 * 2 + 3        # TTT(F) -> TTC(F) syn, -> TGT(C) radical
+    assert aa[i] == "F" and aa[j_cons] == "F" and aa[j_rad] == "C"
+    assert m.Q[i, j_rad] / m.Q[i, j_cons] == pytest.approx(math.exp(-205 / 50.0) / 2.0, rel=1e-12)   # transversion vs transition(kappa=2)
+    F = m.freq[:, None] * m.Q
+    np.testing.assert_allclose(F, F.T, atol=1e-14)
+
+
+@pytest.mark.parametrize("name", ["gtr", "lg08", "yn98", "gy94", "chromosome"])
 def test_pt_family_against_scipy_expm(name):
     from scipy.linalg import expm
     m = {"gtr": lambda: rm.gtr(1.2, 0.8, 0.6, 1.5, 0.9, (.3, .2, .25, .25)),
          "lg08": rm.lg08,
-         "yn98": lambda: rm.yn98(2.0, 0.3),
+         "yn98": lambda: rm.yn98(2.0, 0.3), "gy94": lambda: rm.gy94(2.0, 50.0),
          "chromosome": lambda: rm.chromosome(1, 30, gain=0.7, loss=0.4, dupl=0.2, demi=rm.DEMI_EQUAL_DUPL)}[name]()
     for t in (1e-6, 0.05, 0.7, 3.0):
         E = expm(m.Q * m.rate * t)
