@@ -457,7 +457,7 @@ def main():
     metric = "CLV updates/s"
     config = {"workload": a.workload, "states": w["S"], "rate_classes": w["C"], "taxa": w["taxa"],
               "patterns": w["patterns"], "patterns_per_gpu": w["patterns"] // world, "derivatives": w["derivs"],
-              "sharding": "contiguous pattern blocks, one per GPU; all-reduce of (lnL, d1, d2) only",
+              "sharding": "contiguous pattern blocks, one per GPU; NCCL all-reduce of (lnL, d1, d2) inside the engine (bppgpu_comm_init)",
               "l2": "inputs larger than L2 (tip codes %.0f MB per rank; CLVs never re-read from a previous step)" %
                     (w["taxa"] * w["patterns"] / world / 1e6)}
 
@@ -526,9 +526,11 @@ def main():
     stream = torch.cuda.Stream(device=device)
     torch.cuda.set_stream(stream)
 
+    if world > 1:
+        shard.join_engine(e, device)   # bppgpu_comm_init: the engine all-reduces (lnL, d1, d2) itself, on the evaluation's stream
+
     def step_device():
         e.eval_device(want, out.data_ptr(), stream.cuda_stream)
-        shard.combine(out)          # NCCL all-reduce(sum) of (lnL, d1, d2) on the same stream; no-op at N = 1
 
     def barrier():
         if world > 1:
@@ -573,7 +575,6 @@ def main():
         if world == 1:
             return e.eval(want)[0][0]                               # log L (d1, d2) device -> host
         e.eval_device(want, out.data_ptr(), stream.cuda_stream)
-        shard.combine(out)
         host_out.copy_(out, non_blocking=False)
         return float(host_out[0])
 
@@ -608,6 +609,7 @@ def main():
         ww = dict(w, patterns=w["patterns"] * world)
         t2, es2, r2, p2, codes2 = build_inputs(ww, rank, world, device)
         e, md = make_engine(ww, t2, es2, r2, p2, codes2, local, flags)
+        shard.join_engine(e, device)
         for _ in range(W):
             step_device()
         barrier()

@@ -136,6 +136,53 @@ def host_model(name, *params):
     return out
 
 
+def subtree_patterns(columns, child_off, children, root, leaf_seq):
+    """bppgpu_subtree_patterns.  columns: [n_sites][n_seqs] array of fixed-width elements (uint8 / S<k> / uint16 ...).
+    Returns (n_patterns[n_nodes], {node: links array} for non-root nodes, root_links, root_weights)."""
+    cols = np.ascontiguousarray(columns)
+    n_sites, n_seqs = cols.shape
+    elem = cols.dtype.itemsize
+    child_off = np.ascontiguousarray(child_off, np.int32)
+    children = np.ascontiguousarray(children, np.int32)
+    leaf_seq = np.ascontiguousarray(leaf_seq, np.int32)
+    nn = len(child_off) - 1
+    npat = np.zeros(nn, np.int64)
+    off = np.zeros(nn + 1, np.int64)
+    i64 = C.POINTER(C.c_int64)
+    args = (cols.ctypes.data_as(C.POINTER(C.c_uint8)), C.c_int64(n_sites), C.c_int32(n_seqs), C.c_int32(elem), C.c_int32(nn),
+            child_off.ctypes.data_as(C.POINTER(C.c_int32)), children.ctypes.data_as(C.POINTER(C.c_int32)), C.c_int32(root),
+            leaf_seq.ctypes.data_as(C.POINTER(C.c_int32)), npat.ctypes.data_as(i64), off.ctypes.data_as(i64))
+    _check(lib().bppgpu_subtree_patterns(*args, None, None, None))
+    links = np.zeros(max(1, int(off[nn])), np.int64)
+    rl = np.zeros(max(1, n_sites), np.int64)
+    rw = np.zeros(max(1, n_sites), np.uint32)
+    _check(lib().bppgpu_subtree_patterns(*args, links.ctypes.data_as(i64), rl.ctypes.data_as(i64),
+                                         rw.ctypes.data_as(C.POINTER(C.c_uint32))))
+    per = {n: links[off[n]:off[n + 1]].copy() for n in range(nn) if n != root}
+    return npat, per, rl[:n_sites], rw[:int(npat[root])]
+
+
+UNIQUE_ID_BYTES = 128
+
+
+def comm_unique_id() -> bytes:
+    """bppgpu_comm_unique_id: the 128-byte NCCL id rank 0 hands to the other ranks."""
+    buf = C.create_string_buffer(UNIQUE_ID_BYTES)
+    _check(lib().bppgpu_comm_unique_id(buf))
+    return buf.raw
+
+
+def eval_multi(engines, want=EVAL_LNL):
+    """bppgpu_eval_multi: one process, one engine per device over contiguous pattern shards; returns the summed (lnL, d1, d2)."""
+    e0 = engines[0]
+    arr = (C.c_void_p * len(engines))(*[e._h for e in engines])
+    lnl = np.zeros(e0.n_points)
+    d1 = np.zeros((e0.n_points, e0.nn)) if want & (EVAL_D1 | EVAL_D2) else None
+    d2 = np.zeros((e0.n_points, e0.nn)) if want & EVAL_D2 else None
+    _check(lib().bppgpu_eval_multi(arr, C.c_int32(len(engines)), C.c_uint(want), _ptr(lnl), _ptr(d1), _ptr(d2)))
+    return lnl, d1, d2
+
+
 def measure_fp64_peak(device=0):
     """bppgpu_measure_fp64_peak: (DFMA TFLOP/s, DMMA m8n8k4 TFLOP/s) of the device, measured now."""
     a, b = C.c_double(0), C.c_double(0)
@@ -315,6 +362,21 @@ class Engine:
 
     def eval_device(self, want, dev_ptr, stream=0):
         _check(lib().bppgpu_eval_device(self._h, C.c_uint(want), C.c_void_p(dev_ptr), C.c_void_p(stream)))
+
+    def eval_status(self):
+        """Waits for the last (possibly asynchronous) evaluation; raises BppGpuError(E_NUMERIC) where the reference throws."""
+        st = C.c_int32(0)
+        _check(lib().bppgpu_eval_status(self._h, C.byref(st)))
+        return st.value
+
+    # --- multi-GPU (pattern shards) -------------------------------------------
+    def comm_init(self, rank, nranks, unique_id: bytes):
+        """Join the NCCL job: from now on eval / eval_device return the whole alignment's lnL, d1, d2 on every rank."""
+        assert len(unique_id) == UNIQUE_ID_BYTES
+        _check(lib().bppgpu_comm_init(self._h, C.c_int32(rank), C.c_int32(nranks), C.c_char_p(unique_id)))
+
+    def comm_finalize(self):
+        _check(lib().bppgpu_comm_finalize(self._h))
 
     def site_lnl(self, point=0):
         out = np.empty(self.N)

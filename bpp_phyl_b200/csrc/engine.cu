@@ -15,7 +15,45 @@
 #include <cstring>
 #include <functional>
 
+#include <dlfcn.h>
+#include <nccl.h>   // declarations only: the library is dlopen()ed at bppgpu_comm_init, so libbppgpu has no link-time NCCL dependency
+
 namespace bppgpu {
+
+// NCCL entry points, resolved on first use.  In a process that already holds an NCCL (e.g. torch's bundled copy) dlopen by
+// SONAME returns that one, so the engine and the host program share one NCCL runtime.
+struct NcclApi {
+  void* handle = nullptr;
+  decltype(&ncclGetUniqueId) GetUniqueId = nullptr;
+  decltype(&ncclCommInitRank) CommInitRank = nullptr;
+  decltype(&ncclCommDestroy) CommDestroy = nullptr;
+  decltype(&ncclAllReduce) AllReduce = nullptr;
+  decltype(&ncclAllGather) AllGather = nullptr;
+  decltype(&ncclGetErrorString) GetErrorString = nullptr;
+  bool ok = false;
+};
+static NcclApi& nccl_api() {
+  static NcclApi api;
+  if (api.handle) return api;
+  for (const char* name : {"libnccl.so.2", "libnccl.so"}) {
+    api.handle = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+    if (api.handle) break;
+  }
+  if (!api.handle) return api;
+  api.GetUniqueId = (decltype(api.GetUniqueId))dlsym(api.handle, "ncclGetUniqueId");
+  api.CommInitRank = (decltype(api.CommInitRank))dlsym(api.handle, "ncclCommInitRank");
+  api.CommDestroy = (decltype(api.CommDestroy))dlsym(api.handle, "ncclCommDestroy");
+  api.AllReduce = (decltype(api.AllReduce))dlsym(api.handle, "ncclAllReduce");
+  api.AllGather = (decltype(api.AllGather))dlsym(api.handle, "ncclAllGather");
+  api.GetErrorString = (decltype(api.GetErrorString))dlsym(api.handle, "ncclGetErrorString");
+  api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllReduce && api.AllGather && api.GetErrorString;
+  return api;
+}
+#define BPP_NCCL(expr)                                                                                  \
+  do {                                                                                                  \
+    ncclResult_t _r = (expr);                                                                           \
+    if (_r != ncclSuccess) BPP_FAIL(BPPGPU_E_NCCL, "NCCL error at %s:%d: %s", __FILE__, __LINE__, nccl_api().GetErrorString(_r)); \
+  } while (0)
 
 std::string& last_error() {
   static thread_local std::string s;
@@ -542,9 +580,12 @@ int bppgpu_destroy(bppgpu_engine* e) {
                   e->d_upper_exp, e->d_SR, e->d_rexp, e->d_site_lnl, e->d_partials, e->d_partials2, e->d_out,
                   e->prog.d_ops, e->prog.d_childs, e->gprog.d_ops, e->gprog.d_childs, e->d_sibs, e->d_scratch,
                   e->d_dtiptab, e->d_d2tiptab, e->d_dLc, e->d_fam_mask, e->d_fam_part, e->d_fam_packA, e->d_fam_packS, e->d_fam_packL, e->d_fam_packT, e->d_w4c_stream, e->d_w4c_blocks, e->d_w4c_tip_order, e->d_codesC, e->d_w4_desc, e->d_w4_tip_order, e->d_w4_blocks, e->d_w4_stream, e->d_codesT,
-                  e->d_status};
+                  e->d_status, e->d_wr_recs};
   for (void* p : ptrs) cudaFree(p);
   for (auto& m : e->models) free_model(m);
+  if (e->comm && nccl_api().ok) nccl_api().CommDestroy((ncclComm_t)e->comm);
+  e->comm = nullptr;
+  if (e->eval_done) cudaEventDestroy(e->eval_done);
   if (e->ev0) cudaEventDestroy(e->ev0);
   if (e->ev1) cudaEventDestroy(e->ev1);
   for (int i = 0; i < bppgpu_engine::kRing; ++i) {
@@ -912,6 +953,8 @@ static int create_impl(const bppgpu_config* cfg, bppgpu_engine* e) {
   BPP_CUDA(cudaMemset(e->d_out, 0, (size_t)e->npoints * (1 + 2 * nn) * 8));
   BPP_CUDA(dev_alloc(e, &e->d_status, 1));
   BPP_CUDA(cudaMemset(e->d_status, 0, sizeof(int)));
+  BPP_CUDA(dev_alloc(e, &e->d_wr_recs, (size_t)S + 1));
+  BPP_CUDA(cudaEventCreateWithFlags(&e->eval_done, cudaEventDisableTiming));
 
   // S = 20 on the FP64 tensor cores: fragment-order operands, one persistent CTA per SM (dmma_family_kernels.cuh);
   // BPPGPU_FAMILY=0 keeps the older per-node / per-branch kernels
@@ -1023,11 +1066,37 @@ int bppgpu_create(const bppgpu_config* cfg, bppgpu_engine** out) {
 #define ENGINE_ENTER(e)                                                \
   if (!(e)) BPP_FAIL(BPPGPU_E_INVALID, "null engine");                 \
   BPP_CUDA(cudaSetDevice((e)->dev));
+// setters and accessors: additionally wait for the last evaluation, whatever stream it was enqueued on (bppgpu_eval_device
+// does not synchronise), before engine buffers are read or overwritten
+#define ENGINE_SYNC(e)                                                 \
+  ENGINE_ENTER(e);                                                     \
+  if ((e)->eval_done) BPP_CUDA(cudaEventSynchronize((e)->eval_done));
+
+// tip codes index the per-branch tip tables directly: reject anything outside [0, n_codes) at upload, naming leaf and pattern
+static int check_codes(bppgpu_engine* e, const void* codes, long long n, int leaf_node_or_minus1) {
+  long long bad = -1;
+  if (e->code_bytes == 1) {
+    if (e->ncodes < 256) {
+      const unsigned char* c = (const unsigned char*)codes;
+      for (long long i = 0; i < n; ++i)
+        if (c[i] >= e->ncodes) { bad = i; break; }
+    }
+  } else {
+    const unsigned short* c = (const unsigned short*)codes;
+    for (long long i = 0; i < n; ++i)
+      if (c[i] >= e->ncodes) { bad = i; break; }
+  }
+  if (bad < 0) return BPPGPU_OK;
+  const int leaf = leaf_node_or_minus1 >= 0 ? leaf_node_or_minus1 : e->leaf_nodes[(size_t)(bad / std::max<long long>(1, e->N))];
+  BPP_FAIL(BPPGPU_E_INVALID, "tip code out of range at leaf node %d, pattern %lld: the code table has %d rows", leaf,
+           bad % std::max<long long>(1, e->N), e->ncodes);
+}
 
 int bppgpu_set_tip_codes(bppgpu_engine* e, int32_t node, const void* codes) {
-  ENGINE_ENTER(e);
+  ENGINE_SYNC(e);
   if (node < 0 || node >= e->nn || e->leaf_slot[node] < 0) BPP_FAIL(BPPGPU_E_INVALID, "node %d is not a leaf", node);
   if (!codes) BPP_FAIL(BPPGPU_E_INVALID, "null codes");
+  if (int rc = check_codes(e, codes, e->N, node)) return rc;
   const size_t bytes = (size_t)e->N * e->code_bytes;
   BPP_CUDA(cudaMemcpyAsync((unsigned char*)e->d_codes + (size_t)e->leaf_slot[node] * bytes, codes, bytes,
                            cudaMemcpyHostToDevice, e->stream));
@@ -1039,8 +1108,9 @@ int bppgpu_set_tip_codes(bppgpu_engine* e, int32_t node, const void* codes) {
 }
 
 int bppgpu_set_all_tip_codes(bppgpu_engine* e, const void* codes) {
-  ENGINE_ENTER(e);
+  ENGINE_SYNC(e);
   if (!codes) BPP_FAIL(BPPGPU_E_INVALID, "null codes");
+  if (int rc = check_codes(e, codes, e->N * e->nl, -1)) return rc;
   const size_t bytes = (size_t)e->N * e->code_bytes * e->nl;
   BPP_CUDA(cudaMemcpyAsync(e->d_codes, codes, bytes, cudaMemcpyHostToDevice, e->stream));
   BPP_CUDA(cudaStreamSynchronize(e->stream));
@@ -1058,7 +1128,7 @@ int bppgpu_leaf_slot(bppgpu_engine* e, int32_t node, int32_t* slot) {
 }
 
 int bppgpu_set_pattern_weights(bppgpu_engine* e, const uint32_t* w) {
-  ENGINE_ENTER(e);
+  ENGINE_SYNC(e);
   if (!w && e->N > 0) BPP_FAIL(BPPGPU_E_INVALID, "null weights");
   std::vector<double> wd((size_t)e->N);
   for (long long i = 0; i < e->N; ++i) wd[i] = (double)w[i];
@@ -1069,7 +1139,7 @@ int bppgpu_set_pattern_weights(bppgpu_engine* e, const uint32_t* w) {
 }
 
 int bppgpu_set_rates(bppgpu_engine* e, const double* rates, const double* probs) {
-  ENGINE_ENTER(e);
+  ENGINE_SYNC(e);
   if (!rates || !probs) BPP_FAIL(BPPGPU_E_INVALID, "null rates / probs");
   e->h_rates.assign(rates, rates + e->C);
   e->h_probs.assign(probs, probs + e->C);
@@ -1081,7 +1151,7 @@ int bppgpu_set_rates(bppgpu_engine* e, const double* rates, const double* probs)
 }
 
 int bppgpu_set_model(bppgpu_engine* e, int32_t slot, const bppgpu_model_desc* m) {
-  ENGINE_ENTER(e);
+  ENGINE_SYNC(e);
   if (!m) BPP_FAIL(BPPGPU_E_INVALID, "null model");
   if (slot < 0 || slot >= e->nmodels) BPP_FAIL(BPPGPU_E_INVALID, "model slot %d out of range", slot);
   if (m->n_states != e->S) BPP_FAIL(BPPGPU_E_INVALID, "model has %d states, engine %d", m->n_states, e->S);
@@ -1094,7 +1164,7 @@ int bppgpu_set_model(bppgpu_engine* e, int32_t slot, const bppgpu_model_desc* m)
 }
 
 int bppgpu_set_branch_models(bppgpu_engine* e, int32_t point, const int32_t* slot_of_node) {
-  ENGINE_ENTER(e);
+  ENGINE_SYNC(e);
   if (point < 0 || point >= e->npoints || !slot_of_node) BPP_FAIL(BPPGPU_E_INVALID, "bad point or null array");
   for (int n = 0; n < e->nn; ++n) {
     if (n != e->root && (slot_of_node[n] < 0 || slot_of_node[n] >= e->nmodels))
@@ -1108,7 +1178,7 @@ int bppgpu_set_branch_models(bppgpu_engine* e, int32_t point, const int32_t* slo
 }
 
 int bppgpu_set_branch_lengths(bppgpu_engine* e, int32_t point, const double* t) {
-  ENGINE_ENTER(e);
+  ENGINE_SYNC(e);
   if (point < 0 || point >= e->npoints || !t) BPP_FAIL(BPPGPU_E_INVALID, "bad point or null array");
   std::copy(t, t + e->nn, e->h_brlen.begin() + (size_t)point * e->nn);
   e->h_brlen[(size_t)point * e->nn + e->root] = 0.0;  // the root has no branch: its table slot is the identity
@@ -1120,7 +1190,7 @@ int bppgpu_set_branch_lengths(bppgpu_engine* e, int32_t point, const double* t) 
 }
 
 int bppgpu_set_root_freqs(bppgpu_engine* e, int32_t point, const double* pi) {
-  ENGINE_ENTER(e);
+  ENGINE_SYNC(e);
   if (point < 0 || point >= e->npoints || !pi) BPP_FAIL(BPPGPU_E_INVALID, "bad point or null array");
   BPP_CUDA(cudaMemcpyAsync(e->d_rootfreq + (size_t)point * e->S, pi, e->S * 8, cudaMemcpyHostToDevice, e->stream));
   BPP_CUDA(cudaStreamSynchronize(e->stream));
@@ -1491,8 +1561,13 @@ static int enqueue_prune(bppgpu_engine* e, int point, int pl, cudaStream_t st) {
       wr.S = S; wr.C = C; wr.N = N;
       wr.probs = e->d_probs;
       wr.out = e->d_rootfreq_used + (size_t)point * S;
-      weighted_root_kernel<<<1, 256, 0, st>>>(wr);
-      e->stats.kernel_launches++;
+      // partial record of this shard, exchanged between the GPUs of the job (one all-gather of S + 1 doubles), combined
+      weighted_root_partial_kernel<<<1, 256, 0, st>>>(wr, e->d_wr_recs + (size_t)e->comm_rank * (S + 1));
+      if (e->comm && e->comm_nranks > 1)
+        BPP_NCCL(nccl_api().AllGather(e->d_wr_recs + (size_t)e->comm_rank * (S + 1), e->d_wr_recs, (size_t)(S + 1), ncclDouble,
+                                      (ncclComm_t)e->comm, st));
+      weighted_root_combine_kernel<<<1, 256, 0, st>>>(e->d_wr_recs, e->comm_nranks, S, wr.out);
+      e->stats.kernel_launches += 2;
     }
     RootParams rp{};
     rp.root_clv = e->d_keep + (size_t)ridx * N * C * S;
@@ -1690,12 +1765,19 @@ static int enqueue_derivs(bppgpu_engine* e, int point, int pl, unsigned want, cu
 }
 
 static int eval_impl(bppgpu_engine* e, unsigned want, cudaStream_t st, bool timed) {
+  e->last_point = -1;   // nothing is resident until this evaluation has been enqueued completely
+  e->last_want = 0;
   int rc = check_ready(e);
   if (rc) return rc;
   if (want == 0) want = BPPGPU_EVAL_LNL;
   if (want & BPPGPU_EVAL_D2) want |= BPPGPU_EVAL_D1;
   const bool derivs = (want & (BPPGPU_EVAL_D1 | BPPGPU_EVAL_D2)) != 0;
   if (derivs && !e->keep) BPP_FAIL(BPPGPU_E_STATE, "derivatives need an engine created with BPPGPU_FLAG_KEEP_CLVS");
+  if (derivs && e->path == PATH_POINTS)
+    BPP_FAIL(BPPGPU_E_INVALID, "branch derivatives are not available on the batched-points path (n_points > 1)");
+  // an evaluation enqueued on another stream (bppgpu_eval_device) must have finished with the engine's buffers
+  if (e->eval_done && e->last_stream && e->last_stream != st) BPP_CUDA(cudaStreamWaitEvent(st, e->eval_done, 0));
+  BPP_CUDA(cudaMemsetAsync(e->d_status, 0, sizeof(int), st));
   rc = ensure_deriv_buffers(e, want);
   if (rc) return rc;
   bool any_series = false, any_chrd = false, any_real = false, any_complex = false;
@@ -1807,7 +1889,6 @@ static int eval_impl(bppgpu_engine* e, unsigned want, cudaStream_t st, bool time
     }
     BPP_CUDA(cudaGetLastError());
     if (e->path == PATH_POINTS) {
-      if (derivs) BPP_FAIL(BPPGPU_E_INVALID, "branch derivatives are not available on the batched-points path (n_points > 1)");
       if (p0 == 0) BPP_CUDA(cudaEventRecord(e->ring_a[e->ring_head], st));
       const long long rows = e->N * C;
       for (const Op& op : e->gprog.ops) {
@@ -1866,7 +1947,11 @@ static int eval_impl(bppgpu_engine* e, unsigned want, cudaStream_t st, bool time
     }
   }
   (void)SS;
+  if (e->comm && e->comm_nranks > 1)   // pattern shards: every rank ends up with the whole alignment's lnL, d1, d2
+    BPP_NCCL(nccl_api().AllReduce(e->d_out, e->d_out, (size_t)e->npoints * (1 + 2 * nn), ncclDouble, ncclSum, (ncclComm_t)e->comm, st));
   if (timed) BPP_CUDA(cudaEventRecord(e->ev1, st));
+  BPP_CUDA(cudaEventRecord(e->eval_done, st));
+  e->last_stream = st;
   e->last_want = want;
   return BPPGPU_OK;
 }
@@ -1888,10 +1973,7 @@ int bppgpu_eval(bppgpu_engine* e, unsigned want, double* lnl, double* d1, double
   BPP_CUDA(cudaMemcpy(h.data(), e->d_out, h.size() * 8, cudaMemcpyDeviceToHost));
   int status = 0;
   BPP_CUDA(cudaMemcpy(&status, e->d_status, 4, cudaMemcpyDeviceToHost));
-  if (status) {
-    cudaMemset(e->d_status, 0, 4);
-    BPP_FAIL(BPPGPU_E_NUMERIC, "ChromosomeSubstitutionModel: Taylor series did not reach convergence!");
-  }
+  if (status) BPP_FAIL(BPPGPU_E_NUMERIC, "ChromosomeSubstitutionModel: Taylor series did not reach convergence!");
   for (int p = 0; p < e->npoints; ++p) {
     const double* row = h.data() + (size_t)p * (1 + 2 * nn);
     if (lnl) lnl[p] = row[0];
@@ -1913,7 +1995,7 @@ int bppgpu_eval_device(bppgpu_engine* e, unsigned want, double* dev_out, void* c
 
 // ---- accessors -------------------------------------------------------------------------
 int bppgpu_get_site_lnl(bppgpu_engine* e, int32_t point, double* out) {
-  ENGINE_ENTER(e);
+  ENGINE_SYNC(e);
   if (point < 0 || point >= e->npoints || !out) BPP_FAIL(BPPGPU_E_INVALID, "bad point or null out");
   if (e->last_want == 0) BPP_FAIL(BPPGPU_E_STATE, "no evaluation yet");
   BPP_CUDA(cudaStreamSynchronize(e->stream));
@@ -1936,9 +2018,9 @@ static void to_reference_order(bppgpu_engine* e, double* clv, int32_t* ex) {
 }
 
 int bppgpu_get_clv(bppgpu_engine* e, int32_t point, int32_t node, int32_t which, double* clv, int32_t* scale_exp) {
-  ENGINE_ENTER(e);
+  ENGINE_SYNC(e);
   if (!e->keep) BPP_FAIL(BPPGPU_E_STATE, "bppgpu_get_clv needs BPPGPU_FLAG_KEEP_CLVS");
-  if (node < 0 || node >= e->nn || !clv) BPP_FAIL(BPPGPU_E_INVALID, "bad node or null out");
+  if (node < 0 || node >= e->nn || !clv || point < 0 || point >= e->npoints) BPP_FAIL(BPPGPU_E_INVALID, "bad node / point or null out");
   const size_t clvn = (size_t)e->N * e->C * e->S;
   size_t pt_off = 0;  // slab offset of the point inside the resident chunk (batched-points path)
   if (e->path == PATH_POINTS) {
@@ -1969,9 +2051,9 @@ int bppgpu_get_clv(bppgpu_engine* e, int32_t point, int32_t node, int32_t which,
 }
 
 int bppgpu_get_node_posteriors(bppgpu_engine* e, int32_t point, int32_t node, double* full_out, int32_t* exp_out, double* post_out) {
-  ENGINE_ENTER(e);
+  ENGINE_SYNC(e);
   if (!e->keep) BPP_FAIL(BPPGPU_E_STATE, "bppgpu_get_node_posteriors needs BPPGPU_FLAG_KEEP_CLVS");
-  if (node < 0 || node >= e->nn) BPP_FAIL(BPPGPU_E_INVALID, "bad node");
+  if (node < 0 || node >= e->nn || point < 0 || point >= e->npoints) BPP_FAIL(BPPGPU_E_INVALID, "bad node or point");
   if (e->path == PATH_POINTS) BPP_FAIL(BPPGPU_E_STATE, "not available on the batched-points path");
   if (point != e->last_point) BPP_FAIL(BPPGPU_E_STATE, "CLVs resident are those of point %d", e->last_point);
   const bool leaf = e->leaf_slot[node] >= 0, root = node == e->root;
@@ -2037,9 +2119,9 @@ int bppgpu_get_node_posteriors(bppgpu_engine* e, int32_t point, int32_t node, do
 }
 
 int bppgpu_get_marginal_posteriors(bppgpu_engine* e, int32_t point, int32_t node, double* post_out, double* joint_out) {
-  ENGINE_ENTER(e);
+  ENGINE_SYNC(e);
   if (!e->keep) BPP_FAIL(BPPGPU_E_STATE, "bppgpu_get_marginal_posteriors needs BPPGPU_FLAG_KEEP_CLVS");
-  if (node < 0 || node >= e->nn || !post_out) BPP_FAIL(BPPGPU_E_INVALID, "bad node or null out");
+  if (node < 0 || node >= e->nn || !post_out || point < 0 || point >= e->npoints) BPP_FAIL(BPPGPU_E_INVALID, "bad node / point or null out");
   if (e->path == PATH_POINTS) BPP_FAIL(BPPGPU_E_STATE, "not available on the batched-points path");
   if (e->last_want == 0) BPP_FAIL(BPPGPU_E_STATE, "no evaluation yet");
   if (point != e->last_point) BPP_FAIL(BPPGPU_E_STATE, "CLVs resident are those of point %d", e->last_point);
@@ -2096,8 +2178,8 @@ int bppgpu_get_marginal_posteriors(bppgpu_engine* e, int32_t point, int32_t node
 }
 
 int bppgpu_ml_ancestral_states(bppgpu_engine* e, int32_t point, int32_t* states, double* best_lnl) {
-  ENGINE_ENTER(e);
-  if (!states) BPP_FAIL(BPPGPU_E_INVALID, "null states");
+  ENGINE_SYNC(e);
+  if (!states || point < 0 || point >= e->npoints) BPP_FAIL(BPPGPU_E_INVALID, "null states or bad point");
   if (e->path == PATH_POINTS) BPP_FAIL(BPPGPU_E_STATE, "not available on the batched-points path");
   if (e->last_want == 0) BPP_FAIL(BPPGPU_E_STATE, "no evaluation yet (the transition probabilities of the last evaluation are used)");
   if (point != e->last_point) BPP_FAIL(BPPGPU_E_STATE, "tables resident are those of point %d", e->last_point);
@@ -2186,8 +2268,8 @@ int bppgpu_ml_ancestral_states(bppgpu_engine* e, int32_t point, int32_t* states,
 }
 
 int bppgpu_get_root_reparam_derivatives(bppgpu_engine* e, int32_t point, double out[4]) {
-  ENGINE_ENTER(e);
-  if (!out) BPP_FAIL(BPPGPU_E_INVALID, "null out");
+  ENGINE_SYNC(e);
+  if (!out || point < 0 || point >= e->npoints) BPP_FAIL(BPPGPU_E_INVALID, "null out or bad point");
   if (!e->keep) BPP_FAIL(BPPGPU_E_STATE, "bppgpu_get_root_reparam_derivatives needs BPPGPU_FLAG_KEEP_CLVS");
   if (e->path == PATH_POINTS) BPP_FAIL(BPPGPU_E_STATE, "not available on the batched-points path");
   if (point != e->last_point) BPP_FAIL(BPPGPU_E_STATE, "CLVs resident are those of point %d", e->last_point);
@@ -2248,7 +2330,7 @@ int bppgpu_get_root_reparam_derivatives(bppgpu_engine* e, int32_t point, double 
 }
 
 int bppgpu_get_transition_probabilities(bppgpu_engine* e, int32_t point, int32_t node, unsigned which, double* out) {
-  ENGINE_ENTER(e);
+  ENGINE_SYNC(e);
   if (point < 0 || point >= e->npoints || node < 0 || node >= e->nn || node == e->root || !out)
     BPP_FAIL(BPPGPU_E_INVALID, "bad point / node or null out");
   if (e->last_want == 0) BPP_FAIL(BPPGPU_E_STATE, "no evaluation yet");
@@ -2265,10 +2347,103 @@ int bppgpu_get_transition_probabilities(bppgpu_engine* e, int32_t point, int32_t
 }
 
 int bppgpu_get_root_freqs(bppgpu_engine* e, int32_t point, double* out) {
-  ENGINE_ENTER(e);
+  ENGINE_SYNC(e);
   if (point < 0 || point >= e->npoints || !out) BPP_FAIL(BPPGPU_E_INVALID, "bad point or null out");
   BPP_CUDA(cudaStreamSynchronize(e->stream));
   BPP_CUDA(cudaMemcpy(out, e->d_rootfreq_used + (size_t)point * e->S, e->S * 8, cudaMemcpyDeviceToHost));
+  return BPPGPU_OK;
+}
+
+// ---- multi-GPU ------------------------------------------------------------------------------
+int bppgpu_comm_unique_id(void* id_out) {
+  if (!id_out) BPP_FAIL(BPPGPU_E_INVALID, "null id_out");
+  NcclApi& api = nccl_api();
+  if (!api.ok) BPP_FAIL(BPPGPU_E_NCCL, "libnccl.so.2 could not be loaded: %s", dlerror() ? dlerror() : "missing symbols");
+  ncclUniqueId id;
+  BPP_NCCL(api.GetUniqueId(&id));
+  static_assert(sizeof(ncclUniqueId) == BPPGPU_UNIQUE_ID_BYTES, "unique id size");
+  memcpy(id_out, &id, sizeof(id));
+  return BPPGPU_OK;
+}
+
+int bppgpu_comm_init(bppgpu_engine* e, int32_t rank, int32_t nranks, const void* unique_id) {
+  ENGINE_SYNC(e);
+  if (!unique_id || nranks < 1 || rank < 0 || rank >= nranks) BPP_FAIL(BPPGPU_E_INVALID, "bad rank / nranks or null id");
+  if (e->comm) BPP_FAIL(BPPGPU_E_STATE, "the engine already has a communicator");
+  NcclApi& api = nccl_api();
+  if (!api.ok) BPP_FAIL(BPPGPU_E_NCCL, "libnccl.so.2 could not be loaded: %s", dlerror() ? dlerror() : "missing symbols");
+  ncclUniqueId id;
+  memcpy(&id, unique_id, sizeof(id));
+  ncclComm_t comm = nullptr;
+  BPP_NCCL(api.CommInitRank(&comm, nranks, id, rank));
+  e->comm = comm;
+  e->comm_rank = rank;
+  e->comm_nranks = nranks;
+  if (nranks > 1) {
+    cudaFree(e->d_wr_recs);
+    e->d_wr_recs = nullptr;
+    BPP_CUDA(dev_alloc(e, &e->d_wr_recs, (size_t)nranks * (e->S + 1)));
+  }
+  e->last_point = -1;
+  return BPPGPU_OK;
+}
+
+int bppgpu_comm_finalize(bppgpu_engine* e) {
+  ENGINE_SYNC(e);
+  if (e->comm) BPP_NCCL(nccl_api().CommDestroy((ncclComm_t)e->comm));
+  e->comm = nullptr;
+  e->comm_rank = 0;
+  e->comm_nranks = 1;
+  return BPPGPU_OK;
+}
+
+int bppgpu_eval_status(bppgpu_engine* e, int32_t* numeric_failure) {
+  ENGINE_SYNC(e);
+  if (!numeric_failure) BPP_FAIL(BPPGPU_E_INVALID, "null argument");
+  int status = 0;
+  BPP_CUDA(cudaMemcpy(&status, e->d_status, 4, cudaMemcpyDeviceToHost));
+  *numeric_failure = status;
+  if (status) BPP_FAIL(BPPGPU_E_NUMERIC, "ChromosomeSubstitutionModel: Taylor series did not reach convergence!");
+  return BPPGPU_OK;
+}
+
+int bppgpu_eval_multi(bppgpu_engine* const* engines, int32_t n_engines, unsigned want, double* lnl, double* d1, double* d2) {
+  if (!engines || n_engines < 1 || !engines[0]) BPP_FAIL(BPPGPU_E_INVALID, "no engines");
+  const int nn = engines[0]->nn, np = engines[0]->npoints;
+  for (int k = 0; k < n_engines; ++k) {
+    if (!engines[k] || engines[k]->nn != nn || engines[k]->npoints != np)
+      BPP_FAIL(BPPGPU_E_INVALID, "engine %d does not share the topology / number of points of engine 0", k);
+    if (engines[k]->comm && engines[k]->comm_nranks > 1)
+      BPP_FAIL(BPPGPU_E_STATE, "engine %d belongs to an NCCL job: its evaluations already return the job's totals", k);
+    if (engines[k]->flags & BPPGPU_FLAG_WEIGHTED_ROOT)
+      BPP_FAIL(BPPGPU_E_INVALID, "weighted root frequencies over pattern shards need the NCCL job form (bppgpu_comm_init)");
+  }
+  // enqueue every shard on its own device and stream, then collect: the shards run concurrently
+  for (int k = 0; k < n_engines; ++k) {
+    bppgpu_engine* e = engines[k];
+    BPP_CUDA(cudaSetDevice(e->dev));
+    int rc = eval_impl(e, want, e->stream, false);
+    if (rc) return rc;
+  }
+  const size_t row = (size_t)(1 + 2 * nn);
+  std::vector<double> tot((size_t)np * row, 0.0), h((size_t)np * row);
+  for (int k = 0; k < n_engines; ++k) {
+    bppgpu_engine* e = engines[k];
+    BPP_CUDA(cudaSetDevice(e->dev));
+    BPP_CUDA(cudaStreamSynchronize(e->stream));
+    BPP_CUDA(cudaMemcpy(h.data(), e->d_out, h.size() * 8, cudaMemcpyDeviceToHost));
+    int status = 0;
+    BPP_CUDA(cudaMemcpy(&status, e->d_status, 4, cudaMemcpyDeviceToHost));
+    if (status) BPP_FAIL(BPPGPU_E_NUMERIC, "ChromosomeSubstitutionModel: Taylor series did not reach convergence!");
+    for (size_t i = 0; i < tot.size(); ++i) tot[i] += h[i];   // shard order: deterministic
+  }
+  const unsigned lw = engines[0]->last_want;
+  for (int p = 0; p < np; ++p) {
+    const double* r = tot.data() + (size_t)p * row;
+    if (lnl) lnl[p] = r[0];
+    if (d1 && (lw & BPPGPU_EVAL_D1)) std::copy(r + 1, r + 1 + nn, d1 + (size_t)p * nn);
+    if (d2 && (lw & BPPGPU_EVAL_D2)) std::copy(r + 1 + nn, r + 1 + 2 * nn, d2 + (size_t)p * nn);
+  }
   return BPPGPU_OK;
 }
 

@@ -163,4 +163,10 @@ struct bppgpu_engine {
   cudaEvent_t ptring_a[kRing] = {}, ptring_b[kRing] = {};
   int ptring_n = 0, ptring_head = 0;
   size_t bytes_resident = 0;
+  // multi-GPU (pattern shards, one engine per GPU): NCCL communicator of the job, set by bppgpu_comm_init
+  void* comm = nullptr;           // ncclComm_t
+  int comm_rank = 0, comm_nranks = 1;
+  double* d_wr_recs = nullptr;    // [nranks][S + 1] weighted-root records (exponent, S sums), all-gathered
+  cudaEvent_t eval_done = nullptr;  // recorded at the end of every evaluation on the evaluation's stream
+  cudaStream_t last_stream = nullptr;
 };

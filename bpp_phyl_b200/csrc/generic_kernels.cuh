@@ -133,9 +133,11 @@ struct WeightedRootParams {
   double* out;  // [S]
 };
 
-__global__ void weighted_root_kernel(WeightedRootParams p) {
+// DRNonHomogeneousTreeLikelihood::setWeightedRootFreq (DRNonHomogeneousTreeLikelihood.cpp:927-962): freq_x proportional to
+// sum_i sum_c p_c L_root[i][c][x]; 1 / nbStates when every term is zero.  Written as partial + combine so that pattern shards on
+// several GPUs can exchange their (exponent, S sums) records in between: rec = [emin, s_0 .. s_{S-1}].
+__global__ void weighted_root_partial_kernel(WeightedRootParams p, double* rec) {
   __shared__ int emin_s;
-  __shared__ double tot_s;
   __shared__ double red[32];
   int em = 0x7fffffff;
   for (long long i = threadIdx.x; i < p.N * p.C; i += blockDim.x) em = min(em, p.root_exp[i]);
@@ -146,7 +148,6 @@ __global__ void weighted_root_kernel(WeightedRootParams p) {
   if ((threadIdx.x & 31) == 0) atomicMin(&emin_s, em);
   __syncthreads();
   const int emin = emin_s;
-  double tot = 0.0;
   for (int x = 0; x < p.S; ++x) {
     double acc = 0.0;
     for (long long i = threadIdx.x; i < p.N; i += blockDim.x) {
@@ -156,14 +157,30 @@ __global__ void weighted_root_kernel(WeightedRootParams p) {
       acc += a;
     }
     const double s = block_sum(acc, red);
-    if (threadIdx.x == 0) {
-      p.out[x] = s;
+    if (threadIdx.x == 0) rec[1 + x] = s;
+  }
+  if (threadIdx.x == 0) rec[0] = p.N > 0 ? (double)emin : 1e300;   // an empty shard contributes nothing
+}
+// recs [nrec][S + 1] (one record per pattern shard, rank order) -> out[S]
+__global__ void weighted_root_combine_kernel(const double* recs, int nrec, int S, double* out) {
+  __shared__ double tot_s;
+  double em = 1e300;
+  for (int r = 0; r < nrec; ++r) em = fmin(em, recs[(size_t)r * (S + 1)]);
+  if (threadIdx.x == 0) {
+    double tot = 0.0;
+    for (int x = 0; x < S; ++x) {
+      double s = 0.0;
+      for (int r = 0; r < nrec; ++r) {
+        const double er = recs[(size_t)r * (S + 1)];
+        if (er < 1e299) s += recs[(size_t)r * (S + 1) + 1 + x] * align_factor((int)(er - em));
+      }
+      out[x] = s;
       tot += s;
     }
+    tot_s = tot;
   }
-  if (threadIdx.x == 0) tot_s = tot;
   __syncthreads();
-  for (int x = threadIdx.x; x < p.S; x += blockDim.x) p.out[x] /= tot_s;
+  for (int x = threadIdx.x; x < S; x += blockDim.x) out[x] = tot_s == 0.0 ? 1.0 / S : out[x] / tot_s;
 }
 
 }  // namespace bppgpu

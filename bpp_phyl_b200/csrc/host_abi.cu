@@ -7,9 +7,12 @@
 //                             run under the same clocks.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cstring>
 #include <memory>
+#include <numeric>
 #include <string>
+#include <vector>
 
 #include "../../include/bppgpu.h"
 #include "../host/bppgpu_shim.hpp"
@@ -130,5 +133,103 @@ int bppgpu_host_model(const char* name, const double* params, int32_t n_params, 
   } catch (std::exception& ex) {
     BPP_FAIL(BPPGPU_E_INVALID, "%s", ex.what());
   }
+  return BPPGPU_OK;
+}
+
+// ---- a4: the R classes' recursive per-subtree compression (bit-exact integer work, host side) -------------------------
+// DRASRTreeLikelihoodData::initLikelihoodsWithPatterns (Likelihood/DRASRTreeLikelihoodData.cpp:218-332): at every node the
+// incoming container (the father's unique columns) is cut down to the node's own leaves (PatternTools::getSequenceSubset,
+// PatternTools.cpp:59-70: the leaves in tree order), compressed again (SitePatterns, SitePatterns.cpp:52-106) and handed to the
+// sons; the son's `indices_` is patternLinks_[father][son] (:323-325, DRASRTreeLikelihoodData.h:145).
+namespace {
+struct SubtreeCtx {
+  int elem;                       // bytes per sequence element
+  const int32_t *child_off, *children, *leaf_seq;
+  int64_t* n_patterns;
+  std::vector<std::vector<int64_t>> links;   // per node: father pattern -> this node's pattern
+};
+// unique sorted columns of `cols` (each `w` bytes); idx[i] = pattern of column i; weights optional
+static void compress_columns(const std::vector<std::string>& cols, std::vector<std::string>& uniq, std::vector<int64_t>& idx,
+                             std::vector<uint32_t>* weights) {
+  const size_t n = cols.size();
+  std::vector<int64_t> order(n);
+  std::iota(order.begin(), order.end(), 0);
+  std::sort(order.begin(), order.end(), [&](int64_t a, int64_t b) {
+    const int c = cols[(size_t)a].compare(cols[(size_t)b]);
+    return c != 0 ? c < 0 : a < b;
+  });
+  uniq.clear();
+  idx.assign(n, 0);
+  if (weights) weights->clear();
+  for (size_t k = 0; k < n; ++k) {
+    const std::string& c = cols[(size_t)order[k]];
+    if (k == 0 || c != uniq.back()) {
+      uniq.push_back(c);
+      if (weights) weights->push_back(0);
+    }
+    if (weights) weights->back()++;
+    idx[(size_t)order[k]] = (int64_t)uniq.size() - 1;
+  }
+}
+static void leaves_of(const SubtreeCtx& cx, int node, std::vector<int>& out) {
+  if (cx.child_off[node + 1] == cx.child_off[node]) { out.push_back(node); return; }
+  for (int k = cx.child_off[node]; k < cx.child_off[node + 1]; ++k) leaves_of(cx, cx.children[k], out);
+}
+// `order`: the leaf nodes whose elements make up a column of `cols`, in column order
+static void subtree_rec(SubtreeCtx& cx, int node, const std::vector<int>& order, const std::vector<std::string>& cols,
+                        std::vector<int64_t>& idx_out, std::vector<uint32_t>* weights) {
+  std::vector<int> lv;
+  leaves_of(cx, node, lv);
+  std::vector<int> pos(lv.size());
+  for (size_t k = 0; k < lv.size(); ++k) pos[k] = (int)(std::find(order.begin(), order.end(), lv[k]) - order.begin());
+  std::vector<std::string> sub(cols.size());
+  for (size_t i = 0; i < cols.size(); ++i) {
+    sub[i].reserve(lv.size() * cx.elem);
+    for (int p : pos) sub[i].append(cols[i], (size_t)p * cx.elem, (size_t)cx.elem);
+  }
+  std::vector<std::string> uniq;
+  compress_columns(sub, uniq, idx_out, weights);
+  cx.n_patterns[node] = (int64_t)uniq.size();
+  for (int k = cx.child_off[node]; k < cx.child_off[node + 1]; ++k) {
+    const int son = cx.children[k];
+    subtree_rec(cx, son, lv, uniq, cx.links[(size_t)son], nullptr);
+  }
+}
+}  // namespace
+
+int bppgpu_subtree_patterns(const uint8_t* columns, int64_t n_sites, int32_t n_seqs, int32_t elem_bytes, int32_t n_nodes,
+                            const int32_t* child_offsets, const int32_t* children, int32_t root, const int32_t* leaf_seq,
+                            int64_t* n_patterns, int64_t* link_offsets, int64_t* links, int64_t* root_links,
+                            uint32_t* root_weights) {
+  if (n_sites < 0 || n_seqs <= 0 || elem_bytes <= 0 || n_nodes <= 0 || !child_offsets || !children || !leaf_seq || !n_patterns ||
+      !link_offsets || (n_sites > 0 && !columns) || root < 0 || root >= n_nodes)
+    BPP_FAIL(BPPGPU_E_INVALID, "bad argument to bppgpu_subtree_patterns");
+  for (int n = 0; n < n_nodes; ++n) {
+    const bool leaf = child_offsets[n + 1] == child_offsets[n];
+    if (leaf && (leaf_seq[n] < 0 || leaf_seq[n] >= n_seqs)) BPP_FAIL(BPPGPU_E_INVALID, "leaf node %d has no sequence", n);
+  }
+  SubtreeCtx cx{elem_bytes, child_offsets, children, leaf_seq, n_patterns, {}};
+  cx.links.resize((size_t)n_nodes);
+  // the incoming container of the root: every sequence, in container order; pseudo leaf ids = -(seq + 1) are resolved through
+  // `order0`, which lists the leaf NODE of every sequence position (sequences without a leaf never match)
+  std::vector<int> order0((size_t)n_seqs, -1);
+  for (int n = 0; n < n_nodes; ++n)
+    if (child_offsets[n + 1] == child_offsets[n]) order0[(size_t)leaf_seq[n]] = n;
+  const size_t w = (size_t)n_seqs * elem_bytes;
+  std::vector<std::string> cols((size_t)n_sites);
+  for (int64_t i = 0; i < n_sites; ++i) cols[(size_t)i].assign((const char*)columns + (size_t)i * w, w);
+  std::vector<int64_t> ridx;
+  std::vector<uint32_t> rw;
+  subtree_rec(cx, root, order0, cols, ridx, &rw);
+  if (root_links) std::copy(ridx.begin(), ridx.end(), root_links);
+  if (root_weights) std::copy(rw.begin(), rw.end(), root_weights);
+  int64_t off = 0;
+  for (int n = 0; n < n_nodes; ++n) {
+    link_offsets[n] = off;
+    off += (int64_t)cx.links[(size_t)n].size();
+  }
+  link_offsets[n_nodes] = off;
+  if (links)
+    for (int n = 0; n < n_nodes; ++n) std::copy(cx.links[(size_t)n].begin(), cx.links[(size_t)n].end(), links + link_offsets[n]);
   return BPPGPU_OK;
 }

@@ -144,7 +144,8 @@ __global__ void points_root_kernel(PointsRootParams p) {
     __shared__ double tot_s;
     if (threadIdx.x == 0) tot_s = t;
     __syncthreads();
-    for (int x = threadIdx.x; x < S; x += blockDim.x) freq[x] /= tot_s;
+    // all-zero root arrays: 1 / nbStates, like setWeightedRootFreq (DRNonHomogeneousTreeLikelihood.cpp:950-953)
+    for (int x = threadIdx.x; x < S; x += blockDim.x) freq[x] = tot_s == 0.0 ? 1.0 / S : freq[x] / tot_s;
   } else {
     for (int x = threadIdx.x; x < S; x += blockDim.x) freq[x] = p.rootfreq_in[(size_t)pt * S + x];
   }

@@ -15,6 +15,21 @@ def shard_range(n_patterns: int, rank: int, world: int):
     return n_patterns * rank // world, n_patterns * (rank + 1) // world
 
 
+def join_engine(engine, device):
+    """Put `engine` (this rank's pattern shard) into the NCCL job of the default process group: rank 0 draws the id
+    (bppgpu_comm_unique_id), torch.distributed carries its 128 bytes, every rank calls bppgpu_comm_init.  Afterwards
+    bppgpu_eval / bppgpu_eval_device all-reduce (lnL, d1, d2) inside the engine, on the evaluation's stream."""
+    import torch
+    import torch.distributed as dist
+    from . import capi
+    rank, world = dist.get_rank(), dist.get_world_size()
+    t = torch.zeros(capi.UNIQUE_ID_BYTES, dtype=torch.uint8, device=device)
+    if rank == 0:
+        t.copy_(torch.frombuffer(bytearray(capi.comm_unique_id()), dtype=torch.uint8))
+    dist.broadcast(t, 0)
+    engine.comm_init(rank, world, t.cpu().numpy().tobytes())
+
+
 def combine(out_tensor):
     """Sum the per-shard (lnL, d1, d2) vectors in place over the default process group (no-op for world 1).
     Enqueued on the current stream for CUDA tensors: follow bppgpu_eval_device with it, no host sync in between."""

@@ -73,6 +73,22 @@ int bppgpu_site_patterns_device(int device, const uint8_t* columns, int64_t n_si
                                 int64_t* pattern_site, uint32_t* weights, int64_t* indices, int64_t* n_patterns,
                                 void* tip_codes);
 
+/* The R classes' recursive per-subtree compression (host side, bit-exact integer work):
+ * DRASRTreeLikelihoodData::initLikelihoodsWithPatterns (Likelihood/DRASRTreeLikelihoodData.cpp:218-332).  At every node the
+ * father's unique columns are cut down to the node's own leaves (tree order) and compressed again; what comes out is
+ *   n_patterns[n]                       number of distinct columns of the subtree below n (its likelihood-array length)
+ *   links[link_offsets[s] + i]          pattern of son s that father pattern i reads = patternLinks_[father][s][i]
+ *                                       (DRASRTreeLikelihoodData.h:145, getArrayPositions :231); n_patterns[father] entries,
+ *                                       none for the root
+ *   root_links[site], root_weights[k]   SitePatterns::getIndices / getWeights of the root's own compression.
+ * columns: n_sites columns of n_seqs elements of elem_bytes bytes, in CONTAINER order; leaf_seq[node] = position of the
+ * leaf's sequence inside a column (-1 for internal nodes).  n_patterns [n_nodes] and link_offsets [n_nodes + 1] are always
+ * written; links / root_links / root_weights may be NULL (call once for the sizes, again with link_offsets[n_nodes] slots). */
+int bppgpu_subtree_patterns(const uint8_t* columns, int64_t n_sites, int32_t n_seqs, int32_t elem_bytes, int32_t n_nodes,
+                            const int32_t* child_offsets, const int32_t* children, int32_t root, const int32_t* leaf_seq,
+                            int64_t* n_patterns, int64_t* link_offsets, int64_t* links, int64_t* root_links,
+                            uint32_t* root_weights);
+
 /* ---- model descriptor ------------------------------------------------------
  * What bpp::SubstitutionModel exposes (Model/SubstitutionModel.h:468-525):
  * getGenerator, getEigenValues, getIEigenValues, isDiagonalizable,
@@ -249,6 +265,29 @@ typedef struct bppgpu_stats {
   int32_t path;            /* which kernel family ran             */
 } bppgpu_stats;
 int bppgpu_get_stats(bppgpu_engine* e, bppgpu_stats* out);
+
+/* ---- multi-GPU: site patterns shard, nothing else does ---------------------------------------------------
+ * The pattern loop of RHomogeneousTreeLikelihood::computeSubtreeLikelihood (RHomogeneousTreeLikelihood.cpp:839-861) has no
+ * dependence between patterns, so every GPU holds one engine over a contiguous block of the compressed pattern list (its own
+ * tip codes and weights; tree, models, rates and branch lengths replicated) and the only exchange is the sum of the per-shard
+ * (lnL, d1[], d2[]) rows -- plus, with BPPGPU_FLAG_WEIGHTED_ROOT, one (exponent, S sums) record per shard before the root
+ * reduction (DRNonHomogeneousTreeLikelihood.cpp:927-962 sums over ALL sites).
+ *
+ * (a) one process per GPU (MPI / torchrun): NCCL inside the engine.  Rank 0 calls bppgpu_comm_unique_id and distributes
+ *     the 128 bytes by its own means; every rank calls bppgpu_comm_init on its engine.  From then on bppgpu_eval and
+ *     bppgpu_eval_device all-reduce their result rows on the evaluation's stream (all ranks must call them in the same
+ *     order) and return the whole alignment's lnL / d1 / d2 on every rank.  libnccl.so.2 is loaded at the first call; a
+ *     process that already has an NCCL (torch) shares it.  Errors: BPPGPU_E_NCCL.
+ * (b) one process driving several GPUs: create one engine per device and call bppgpu_eval_multi, which enqueues every
+ *     shard on its own device and stream, waits, and adds the rows on the host in shard order.                          */
+#define BPPGPU_UNIQUE_ID_BYTES 128
+int bppgpu_comm_unique_id(void* id_out /* [BPPGPU_UNIQUE_ID_BYTES] */);
+int bppgpu_comm_init(bppgpu_engine* e, int32_t rank, int32_t nranks, const void* unique_id);
+int bppgpu_comm_finalize(bppgpu_engine* e);
+int bppgpu_eval_multi(bppgpu_engine* const* engines, int32_t n_engines, unsigned want, double* lnl, double* d1, double* d2);
+/* After bppgpu_eval_device (which never synchronises): waits for that evaluation and reports its numeric status -- 0, or
+ * BPPGPU_E_NUMERIC with *numeric_failure = 1 where the reference throws "Taylor series did not reach convergence".        */
+int bppgpu_eval_status(bppgpu_engine* e, int32_t* numeric_failure);
 
 /* ---- host-side utilities (not on the evaluation path) ----------------------------------------------------------------
  * bppgpu_host_model: build a named model with the C++ host code of this library -- the generator of the model class and

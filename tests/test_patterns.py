@@ -143,3 +143,38 @@ def test_device_patterns_dedup_variant(built_lib, monkeypatch, n, ntaxa, nstates
     base = rng.integers(0, 256, size=(max(2, n // 50), ntaxa)).astype(np.uint8)
     check_device(base[rng.integers(len(base), size=n)])
     check_device(np.full((1000, 9), ord("A"), np.uint8))
+
+
+@pytest.mark.parametrize("ntaxa,nsites,nstates,seed,width", [(4, 17, 4, 0, 1), (9, 300, 2, 1, 1), (25, 800, 4, 2, 1), (12, 200, 4, 3, 3),
+                                                         (6, 0, 4, 4, 1), (2, 50, 3, 5, 1)])
+def test_recursive_subtree_patterns_are_bit_exact(built_lib, ntaxa, nsites, nstates, seed, width):
+    """SURVEY 8 a4 through the C ABI (host integer routine): bppgpu_subtree_patterns against the oracle's restatement of
+    DRASRTreeLikelihoodData::initLikelihoodsWithPatterns (:218-332) -- array length of every node, patternLinks_[father][son] for
+    every branch, root indices and weights, all IDENTICAL; container order differs from the tree's leaf order on purpose;
+    codon-width elements, an empty alignment and a two-leaf tree included."""
+    from bpp_phyl_b200 import capi
+    from oracle import ref_tree as rt
+    rng = np.random.default_rng(seed)
+    root = rt.random_tree(ntaxa, rng, rooted=ntaxa < 3 or bool(seed % 2))
+    flat = rt.FlatTree(root, check_rooted=False)
+    names = list(flat.leaf_names)
+    rng.shuffle(names)                                              # container order != tree order
+    alphabet = "ACGT"[:nstates]
+    base = ["".join(alphabet[k] for k in rng.integers(nstates, size=width * max(1, nsites // 6))) for _ in names]
+    pick = rng.integers(max(1, nsites // 6), size=nsites)            # many repeated columns
+    seqs = {nm: "".join(b[width * i:width * (i + 1)] for i in pick) for nm, b in zip(names, base)}
+    rec = rp.recursive_patterns(flat, seqs, width=width)
+    cols = np.array([[seqs[nm][width * i:width * (i + 1)].encode() for nm in names] for i in range(nsites)],
+                    dtype="S%d" % width).reshape(nsites, len(names))
+    off, ch = flat.csr()
+    leaf_seq = np.full(flat.n_nodes, -1, np.int32)
+    for lid, nm in zip(flat.leaf_ids, flat.leaf_names):
+        leaf_seq[lid] = names.index(nm)
+    npat, links, rl, rw = capi.subtree_patterns(cols, off, ch, flat.root, leaf_seq)
+    for n in range(flat.n_nodes):
+        assert npat[n] == rec["n"][n], n
+    for f, sons in rec["links"].items():
+        for s_, idx in sons.items():
+            np.testing.assert_array_equal(links[s_], idx)
+    np.testing.assert_array_equal(rl, rec["root_links"])
+    np.testing.assert_array_equal(rw, rec["weights"])
