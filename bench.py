@@ -209,16 +209,15 @@ def cpu_leg(w, tree, es, rates, probs, codes, lnl_gpu_full, budget_s=60.0):
     t_full = rall["seconds"] * N / nall * (0.45 if w["derivs"] else 1.0)
     parity = {"lnl_gpu_full": lnl_gpu_full, "patterns": N}
     if t_full <= budget_s or os.environ.get("BPPGPU_BENCH_FULL_PARITY") == "1":
-        blk = per_thread * cores * 2
-        tot, secs = 0.0, 0.0
-        for b0 in range(0, N, blk):
-            subb = np.ascontiguousarray(codes[:, b0:b0 + blk])
-            r = ref_cpu.eval_raw(reps=1, **_cpu_args(w, tree, es, rates, probs, subb, 1, cores))
-            tot += r["lnl"]
-            secs += r["seconds"]
+        blk = per_thread * cores
+        t0 = time.time()
+        tot, secs = ref_cpu.eval_blocks(w["S"], w["C"], N, blk, tree.child_off, tree.children, tree.root, codes, np.eye(w["S"]),
+                                        np.ones(N, np.uint32), rates, probs, es["V"], es["Vinv"], es["ev"], es.get("rate", 1.0),
+                                        tree.brlen, es["pi"], scaled=True, nthreads=cores)
+        log("full-size CPU parity: %.1f s evaluation, %.1f s wall" % (secs, time.time() - t0))
         parity.update({"lnl_cpu_full": tot, "rel_diff_full": abs(tot - lnl_gpu_full) / abs(tot), "cpu_seconds_full": secs,
                        "cpu_updates_per_s_full": per_upd * N / secs,
-                       "note": "CPU port over the whole input in blocks of %d patterns on %d threads; lnL summed over blocks" % (blk, cores)})
+                       "note": "CPU port over the whole input in blocks of %d patterns on %d threads (arrays allocated once); lnL summed over blocks" % (blk, cores)})
     else:
         parity.update({"lnl_cpu_full": None, "rel_diff_full": None,
                        "note": "full input would take %.0f s on %d threads (> %.0f s budget): sample parity only; "

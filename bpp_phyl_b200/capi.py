@@ -383,6 +383,13 @@ class Engine:
         _check(lib().bppgpu_get_site_lnl(self._h, C.c_int32(point), _ptr(out)))
         return out
 
+    def site_derivatives(self, node, point=0, second=True):
+        """bppgpu_get_site_derivatives: ((dL_i/dt)/L_i, (d2L_i/dt2)/L_i) of the branch above `node`, per pattern."""
+        a = np.empty(self.N)
+        b = np.empty(self.N) if second else None
+        _check(lib().bppgpu_get_site_derivatives(self._h, C.c_int32(point), C.c_int32(node), _ptr(a), _ptr(b)))
+        return a, b
+
     def clv(self, node, which=0, point=0):
         out = np.empty((self.N, self.C, self.S))
         ex = np.empty((self.N, self.C), np.int32)

@@ -182,6 +182,65 @@ __global__ void deriv_node_kernel(DerivParams p) {
 }
 
 
+// Per-site relative derivatives of one branch from the resident DR arrays -- DRASDRTreeLikelihoodData::getDLikelihoodArray /
+// getD2LikelihoodArray (DRHomogeneousTreeLikelihood::computeTreeDLikelihoodAtNode, DRHomogeneousTreeLikelihood.cpp:287-326,
+// :373-411): dL_i / L_i and d2L_i / L_i for every pattern.  Accessor-grade (one thread per pattern); slabs follow prow / crow.
+struct SiteDerivParams {
+  int is_tip, S, C, code_bytes, nh_form;
+  long long N, prow, crow;
+  const double *P, *dP, *d2P;      // [C][S][S] of this branch (d2P may be null)
+  const double* code_table;
+  const void* codes;               // this leaf's codes
+  const double* lower;             // slab of the node (internal)
+  const int* lower_exp;
+  const double* upper;             // slab of the node's upper array
+  const int* upper_exp;
+  const double* SR;
+  const int* rexp;
+  const double* probs;
+  double *d1, *d2;                 // [N]
+};
+__global__ void site_deriv_kernel(SiteDerivParams p) {
+  const long long pat = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (pat >= p.N) return;
+  const int S = p.S;
+  const int re = p.rexp[pat];
+  double a1 = 0.0, a2 = 0.0;
+  for (int c = 0; c < p.C; ++c) {
+    const long long row = pat * p.prow + c * p.crow;
+    const double* D = p.is_tip ? p.code_table + (size_t)load_code(p.codes, p.code_bytes, pat) * S : p.lower + (size_t)row * S;
+    const double* U = p.upper + (size_t)row * S;
+    double s1c = 0.0, s2c = 0.0;
+    for (int x = 0; x < S; ++x) {
+      const double* r0 = p.P + ((size_t)c * S + x) * S;
+      const double* r1 = p.dP + ((size_t)c * S + x) * S;
+      const double* r2 = p.d2P ? p.d2P + ((size_t)c * S + x) * S : nullptr;
+      double n1 = 0.0, n2 = 0.0, den = 0.0;
+      for (int y = 0; y < S; ++y) {
+        const double d = D[y];
+        n1 = fma(r1[y], d, n1);
+        if (r2) n2 = fma(r2[y], d, n2);
+        if (p.nh_form) den = fma(r0[y], d, den);
+      }
+      const double u = U[x];
+      if (p.nh_form) {
+        const double full = u * den;
+        s1c += den == 0.0 ? 0.0 : full * n1 / den;
+        s2c += den == 0.0 ? 0.0 : full * n2 / den;
+      } else {
+        s1c = fma(u, n1, s1c);
+        s2c = fma(u, n2, s2c);
+      }
+    }
+    const int sh = re - p.upper_exp[row] - (p.is_tip ? 0 : p.lower_exp[row]);
+    a1 = fma(scalbn(s1c, sh), p.probs[c], a1);
+    a2 = fma(scalbn(s2c, sh), p.probs[c], a2);
+  }
+  const double sr = p.SR[pat];
+  p.d1[pat] = a1 / sr;
+  if (p.d2) p.d2[pat] = a2 / sr;
+}
+
 // ---- consumers of the DR arrays ---------------------------------------------------------------------------
 // DRTreeLikelihood::computeLikelihoodAtNode (DRHomogeneousTreeLikelihood::computeLikelihoodAtNode_,
 // Likelihood/DRHomogeneousTreeLikelihood.cpp:723-815):  full[i][c][x] = sub[i][c][x] * sum_y P_n[c][y][x] upper_n[i][c][y]

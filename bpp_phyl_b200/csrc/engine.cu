@@ -741,13 +741,18 @@ static int create_impl(const bppgpu_config* cfg, bppgpu_engine* e) {
     }
     int CH = 8192;
     while (CH < max_op) CH *= 2;
-    e->w4c_pt = 2;
+    // patterns per thread: 4 (P rows re-used four times; two 4-warp CTAs per SM) once the input fills a wave of such CTAs
+    // -- measured 10.4 / 11.3 / 15.2 ms at PT = 4 / 2 / 1 on 1M patterns, 1.50 / 1.59 / 2.02 ms on 125k --, fewer below
     e->w4c_nw = C <= 4 ? 4 : 8;
     if (const char* env = getenv("BPPGPU_WALK4_NW")) {
       const int v = atoi(env);
       if ((v == 4 || v == 8) && v >= C) e->w4c_nw = v;
     }
-    if (N * C < (long long)g_sm_count * 2 * 256 * 2) e->w4c_pt = 1;  // small inputs: more CTAs instead
+    {
+      const long long groups = (N + 31) / 32;                                  // 32-pattern lane groups
+      const long long per_wave = (long long)g_sm_count * 2 * (e->w4c_nw / C);  // groups one wave of PT = 1 CTAs (2 per SM) covers
+      e->w4c_pt = groups >= 4 * per_wave ? 4 : (groups >= 2 * per_wave ? 2 : 1);
+    }
     if (const char* env = getenv("BPPGPU_WALK4_PT")) {
       const int v = atoi(env);
       if (v == 1 || v == 2 || v == 4) e->w4c_pt = v;
@@ -2325,6 +2330,57 @@ int bppgpu_get_root_reparam_derivatives(bppgpu_engine* e, int32_t point, double 
   if (err == cudaSuccess) err = cudaMemcpyAsync(out, d_out, 4 * 8, cudaMemcpyDeviceToHost, st);
   if (err == cudaSuccess) err = cudaStreamSynchronize(st);
   cudaFree(d_part); cudaFree(d_out);
+  BPP_CUDA(err);
+  return BPPGPU_OK;
+}
+
+int bppgpu_get_site_derivatives(bppgpu_engine* e, int32_t point, int32_t node, double* d1_out, double* d2_out) {
+  ENGINE_SYNC(e);
+  if (!d1_out || point < 0 || point >= e->npoints || node < 0 || node >= e->nn || node == e->root)
+    BPP_FAIL(BPPGPU_E_INVALID, "bad point / node or null out");
+  if (!e->keep) BPP_FAIL(BPPGPU_E_STATE, "bppgpu_get_site_derivatives needs BPPGPU_FLAG_KEEP_CLVS");
+  if (e->path == PATH_POINTS) BPP_FAIL(BPPGPU_E_STATE, "not available on the batched-points path");
+  if (point != e->last_point) BPP_FAIL(BPPGPU_E_STATE, "CLVs resident are those of point %d", e->last_point);
+  if (!(e->last_want & BPPGPU_EVAL_D1) || !e->d_upper || !e->d_dP) BPP_FAIL(BPPGPU_E_STATE, "upper CLVs exist after an eval with derivatives");
+  if (d2_out && (!(e->last_want & BPPGPU_EVAL_D2) || !e->d_d2P)) BPP_FAIL(BPPGPU_E_STATE, "second derivatives need an eval with BPPGPU_EVAL_D2");
+  const int uslab = e->upper_slab[node];
+  if (uslab < 0) BPP_FAIL(BPPGPU_E_STATE, "the upper CLV of tip %d is not materialised at this problem size", node);
+  const int S = e->S, C = e->C;
+  const long long N = e->N;
+  if (N == 0) return BPPGPU_OK;
+  const size_t clvn = (size_t)N * C * S, rows = (size_t)N * C, SS = (size_t)S * S;
+  double *d_1 = nullptr, *d_2 = nullptr;
+  if (cudaMalloc(&d_1, (size_t)N * 8) != cudaSuccess || (d2_out && cudaMalloc(&d_2, (size_t)N * 8) != cudaSuccess)) {
+    cudaFree(d_1); cudaFree(d_2);
+    cudaGetLastError();
+    BPP_FAIL(BPPGPU_E_NOMEM, "out of device memory");
+  }
+  SiteDerivParams sp{};
+  const bool leaf = e->leaf_slot[node] >= 0;
+  sp.is_tip = leaf; sp.S = S; sp.C = C; sp.code_bytes = e->code_bytes;
+  sp.nh_form = (e->flags & BPPGPU_FLAG_NH_DERIV) ? 1 : 0;
+  sp.N = N;
+  sp.prow = e->clv_class_major ? 1 : C;
+  sp.crow = e->clv_class_major ? N : 1;
+  const size_t mo = ((size_t)(point % e->pchunk) * e->nn + node) * C * SS;
+  sp.P = e->d_P + mo; sp.dP = e->d_dP + mo; sp.d2P = d2_out ? e->d_d2P + mo : nullptr;
+  sp.code_table = e->d_code_table;
+  if (leaf) sp.codes = (const char*)e->d_codes + (size_t)e->leaf_slot[node] * N * e->code_bytes;
+  else {
+    sp.lower = e->d_keep + (size_t)e->internal_idx[node] * clvn;
+    sp.lower_exp = e->d_keep_exp + (size_t)e->internal_idx[node] * rows;
+  }
+  sp.upper = e->d_upper + (size_t)uslab * clvn;
+  sp.upper_exp = e->d_upper_exp + (size_t)uslab * rows;
+  sp.SR = e->d_SR; sp.rexp = e->d_rexp; sp.probs = e->d_probs;
+  sp.d1 = d_1; sp.d2 = d_2;
+  cudaStream_t st = e->stream;
+  site_deriv_kernel<<<(unsigned)((N + 127) / 128), 128, 0, st>>>(sp);
+  cudaError_t err = cudaGetLastError();
+  if (err == cudaSuccess) err = cudaMemcpyAsync(d1_out, d_1, (size_t)N * 8, cudaMemcpyDeviceToHost, st);
+  if (err == cudaSuccess && d2_out) err = cudaMemcpyAsync(d2_out, d_2, (size_t)N * 8, cudaMemcpyDeviceToHost, st);
+  if (err == cudaSuccess) err = cudaStreamSynchronize(st);
+  cudaFree(d_1); cudaFree(d_2);
   BPP_CUDA(err);
   return BPPGPU_OK;
 }

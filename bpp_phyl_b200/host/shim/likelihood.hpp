@@ -71,6 +71,7 @@ class AbstractHomogeneousTreeLikelihood {
     for (size_t i = 0; i < v.size(); ++i) v[i] = siteLnl_[(size_t)siteIndex_[i]];
     return v;
   }
+  const Vdouble& getLogLikelihoodForEachDistinctSite() const { requireInit(); return siteLnl_; }
   size_t getNumberOfSites() const { return siteIndex_.size(); }
   size_t getNumberOfDistinctSites() const { return (size_t)nPatterns_; }
   size_t getSiteIndex(size_t site) const { return (size_t)siteIndex_[site]; }
@@ -95,7 +96,7 @@ class AbstractHomogeneousTreeLikelihood {
   ParameterList getSubstitutionModelParameters() const {
     ParameterList pl;
     if (modelSet_) for (const std::string& n : modelSet_->getParameterNames()) pl.push_back({n, modelSet_->getParameterValue(n)});
-    else for (const std::string& n : model_->getParameterNames()) pl.push_back({n, 0.0});
+    else for (const std::string& n : model_->getParameterNames()) pl.push_back({n, model_->getParameterValue(n)});
     return pl;
   }
   const SubstitutionModelSet* getSubstitutionModelSet() const { return modelSet_; }
@@ -133,11 +134,18 @@ class AbstractHomogeneousTreeLikelihood {
     if (initialized_) fireParameterChanged();
   }
   void setParameters(const ParameterList& pl) { setParametersValues(pl); }
+  // the model object was changed from outside (a mixed model re-deriving its sub-models): re-upload and re-evaluate
+  void modelParametersChanged() { uploadModel(); if (initialized_) fireParameterChanged(); }
 
   // derivatives w.r.t. branch lengths of -lnL (RHomogeneousTreeLikelihood.cpp:346-361, DRHomogeneousTreeLikelihood.cpp:340-368)
   double getFirstOrderDerivative(const std::string& variable) const { return derivative(variable, 1); }
   double getSecondOrderDerivative(const std::string& variable) const { return derivative(variable, 2); }
   void enableDerivatives(bool yn) { computeDerivatives_ = yn; }
+  // DRASDRTreeLikelihoodData::getDLikelihoodArray / getD2LikelihoodArray (nodeId): (dL_i / dt) / L_i and (d2L_i / dt2) / L_i per
+  // distinct site, computed on the device from the resident DR arrays
+  Vdouble getDLikelihoodArray(int nodeId) const { return siteDerivatives(nodeId, 1); }
+  Vdouble getD2LikelihoodArray(int nodeId) const { return siteDerivatives(nodeId, 2); }
+  const std::vector<unsigned int>& getWeights() const { return patternWeights_; }
 
   // pxy_[node][class][x][y] (getTransitionProbabilitiesPerRateClass)
   VVVdouble getTransitionProbabilitiesPerRateClass(int nodeId, size_t /*siteIndex*/ = 0) const {
@@ -400,6 +408,7 @@ class AbstractHomogeneousTreeLikelihood {
       }
     }
     check(bppgpu_set_pattern_weights(engine_, patterns.getWeights().data()), "setData");
+    patternWeights_ = patterns.getWeights();
     hasData_ = true;
     uploadModel();
   }
@@ -483,6 +492,13 @@ class AbstractHomogeneousTreeLikelihood {
     }
     return order == 1 ? -d1_[(size_t)b] : -d2_[(size_t)b];
   }
+  Vdouble siteDerivatives(int nodeId, int order) const {
+    requireInit();
+    ensureDerivativePass();
+    Vdouble a((size_t)nPatterns_), b((size_t)nPatterns_);
+    check(bppgpu_get_site_derivatives(engine_, 0, nodeId, a.data(), order == 2 ? b.data() : nullptr), "getDLikelihoodArray");
+    return order == 1 ? a : b;
+  }
   int brlenIndex(const std::string& name) const {
     if (name.compare(0, 5, "BrLen") != 0) return -1;
     char* end = nullptr;
@@ -535,6 +551,7 @@ class AbstractHomogeneousTreeLikelihood {
   DiscreteDistribution* rDist_;   // not owned
   bppgpu_engine* engine_;
   unsigned engineFlags_;
+  std::vector<unsigned int> patternWeights_;
   int device_;
   bool initialized_, hasData_, computeDerivatives_;
   double minusLogLik_;
@@ -848,6 +865,126 @@ class RHomogeneousMixedTreeLikelihood : public LikelihoodPointBatch {
   }
   Vdouble probas_, mixedSiteLnl_;
   double mixedMinusLogLik_ = 0;
+};
+
+// Likelihood/DRHomogeneousMixedTreeLikelihood.{h,cpp}: one DRHomogeneousTreeLikelihood per sub-model of a mixed model
+// (treeLikelihoodsContainer_, .cpp:60-78), combined with the sub-model probabilities:
+//   L_i            = sum_j p_j L_j,i                                                   (getLogLikelihood :239-268)
+//   d(-lnL)/dt_b   = - sum_i w_i sum_j p_j dL_j[i]                                      (getFirstOrderDerivative :399-437)
+//   d2(-lnL)/dt_b2 = - sum_i w_i ( sum_j p_j d2L_j[i] - (sum_j p_j dL_j[i])^2 )         (getSecondOrderDerivative :462-508)
+// where dL_j / d2L_j are sub-likelihood j's OWN relative arrays (getDLikelihoodArray: already divided by L_j,i) -- the
+// reference's combination, reproduced literally.  Each sub-likelihood owns a device engine; per-site arrays come from
+// bppgpu_get_site_lnl / bppgpu_get_site_derivatives.
+class DRHomogeneousMixedTreeLikelihood {
+ public:
+  DRHomogeneousMixedTreeLikelihood(const Tree& tree, const VectorSiteContainer& data, MixedSubstitutionModel* model,
+                                   DiscreteDistribution* rDist, bool checkRooted = true, bool verbose = true, bool rootArray = false,
+                                   int device = 0)
+      : model_(model) {
+    (void)verbose; (void)rootArray;
+    if (!model) throw Exception("Bad model: DRHomogeneousMixedTreeLikelihood needs a MixedTransitionModel.");
+    for (size_t k = 0; k < model->getNumberOfModels(); ++k)
+      subs_.emplace_back(new DRHomogeneousTreeLikelihood(tree, data, model->getNModel(k), rDist, checkRooted, false, device));
+    probas_ = model->getProbabilities();
+  }
+  void initialize() {
+    for (auto& s : subs_) s->initialize();
+    initialized_ = true;
+  }
+  size_t getNumberOfModels() const { return subs_.size(); }
+  const DRHomogeneousTreeLikelihood* getSubLikelihood(size_t k) const { return subs_.at(k).get(); }
+  // parameters shared by every sub-likelihood (branch lengths, rate distribution); model parameters go through the mixed model
+  void setParameterValue(const std::string& name, double value) {
+    for (auto& s : subs_) s->setParameterValue(name, value);
+  }
+  void setParametersValues(const ParameterList& pl) {
+    for (auto& s : subs_) s->setParametersValues(pl);
+  }
+  // fireParameterChanged (:170-192): the probabilities are re-read from the mixed model
+  void modelChanged() {
+    probas_ = model_->getProbabilities();
+    for (size_t k = 0; k < subs_.size(); ++k) subs_[k]->modelParametersChanged();
+  }
+  ParameterList getBranchLengthsParameters() const { return subs_.at(0)->getBranchLengthsParameters(); }
+  size_t getNumberOfSites() const { return subs_.at(0)->getNumberOfSites(); }
+  double getLikelihoodForASite(size_t site) const {
+    double r = 0;
+    for (size_t k = 0; k < subs_.size(); ++k) r += subs_[k]->getLikelihoodForASite(site) * probas_[k];
+    return r;
+  }
+  double getLogLikelihoodForASite(size_t site) const {
+    double x = getLikelihoodForASite(site);
+    if (x < 0) x = 0;
+    return std::log(x);
+  }
+  double getLikelihoodForASiteForARateClass(size_t site, size_t rateClass) const {
+    double r = 0;
+    for (size_t k = 0; k < subs_.size(); ++k) r += subs_[k]->getLikelihoodForASiteForARateClass(site, rateClass) * probas_[k];
+    return r;
+  }
+  double getLogLikelihood() const {
+    requireInit();
+    const std::vector<unsigned int>& w = subs_[0]->getWeights();
+    const size_t N = w.size(), K = subs_.size();
+    std::vector<Vdouble> sl(K);
+    for (size_t k = 0; k < K; ++k) sl[k] = subs_[k]->getLogLikelihoodForEachDistinctSite();
+    Vdouble la(N);
+    for (size_t i = 0; i < N; ++i) {
+      // log sum_j p_j L_j,i through the largest term: the per-site likelihoods of large trees are far below 1e-308
+      double m = -std::numeric_limits<double>::infinity();
+      for (size_t k = 0; k < K; ++k) if (probas_[k] > 0) m = std::max(m, sl[k][i]);
+      double x = 0;
+      for (size_t k = 0; k < K; ++k) if (probas_[k] > 0) x += probas_[k] * std::exp(sl[k][i] - m);
+      la[i] = w[i] * (std::isfinite(m) ? m + std::log(x) : m);
+    }
+    std::sort(la.begin(), la.end());
+    double ll = 0;
+    for (size_t i = N; i > 0; --i) ll += la[i - 1];
+    return ll;
+  }
+  double getValue() const { return -getLogLikelihood(); }
+  double getFirstOrderDerivative(const std::string& variable) const {
+    const int b = branch(variable);
+    const std::vector<unsigned int>& w = subs_[0]->getWeights();
+    std::vector<Vdouble> dl(subs_.size());
+    for (size_t k = 0; k < subs_.size(); ++k) dl[k] = subs_[k]->getDLikelihoodArray(b);
+    double d = 0;
+    for (size_t i = 0; i < w.size(); ++i) {
+      double x = 0;
+      for (size_t k = 0; k < subs_.size(); ++k) x += dl[k][i] * probas_[k];
+      d += w[i] * x;
+    }
+    return -d;
+  }
+  double getSecondOrderDerivative(const std::string& variable) const {
+    const int b = branch(variable);
+    const std::vector<unsigned int>& w = subs_[0]->getWeights();
+    std::vector<Vdouble> dl(subs_.size()), d2l(subs_.size());
+    for (size_t k = 0; k < subs_.size(); ++k) { dl[k] = subs_[k]->getDLikelihoodArray(b); d2l[k] = subs_[k]->getD2LikelihoodArray(b); }
+    double d = 0;
+    for (size_t i = 0; i < w.size(); ++i) {
+      double x = 0, x2 = 0;
+      for (size_t k = 0; k < subs_.size(); ++k) { x += dl[k][i] * probas_[k]; x2 += d2l[k][i] * probas_[k]; }
+      d += w[i] * (x2 - x * x);
+    }
+    return -d;
+  }
+
+ private:
+  void requireInit() const { if (!initialized_) throw Exception("Instance is not initialized."); }
+  int branch(const std::string& variable) const {
+    requireInit();
+    if (variable.compare(0, 5, "BrLen") != 0) {
+      for (const std::string& n : model_->getParameterNames())
+        if (n == variable) throw Exception("Derivatives respective to substitution model parameters are not implemented.");
+      throw ParameterNotFoundException("ParameterNotFoundException: " + variable);
+    }
+    return std::atoi(variable.c_str() + 5);
+  }
+  MixedSubstitutionModel* model_;
+  std::vector<std::unique_ptr<DRHomogeneousTreeLikelihood> > subs_;
+  Vdouble probas_;
+  bool initialized_ = false;
 };
 
 }  // namespace bppshim

@@ -328,6 +328,13 @@ class GTR : public AbstractReversibleSubstitutionModel {
   GTR* clone() const { return new GTR(*this); }
   std::string getName() const { return "GTR"; }
   std::vector<std::string> getParameterNames() const { return {"GTR.a", "GTR.b", "GTR.c", "GTR.d", "GTR.e"}; }
+  double getParameterValue(const std::string& name) const {
+    const std::string n = name.substr(name.find('.') == std::string::npos ? 0 : name.find('.') + 1);
+    const std::map<std::string, const double*> m = {{"a", &a_}, {"b", &b_}, {"c", &c_}, {"d", &d_}, {"e", &e_}};
+    const auto it = m.find(n);
+    if (it == m.end()) throw ParameterNotFoundException(name);
+    return *it->second;
+  }
   void setParameterValue(const std::string& name, double v) {
     const std::string n = name.substr(name.find('.') == std::string::npos ? 0 : name.find('.') + 1);
     if (n == "a") a_ = v; else if (n == "b") b_ = v; else if (n == "c") c_ = v; else if (n == "d") d_ = v; else if (n == "e") e_ = v;

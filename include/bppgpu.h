@@ -244,6 +244,11 @@ int bppgpu_ml_ancestral_states(bppgpu_engine* e, int32_t point, int32_t* states,
  * (DRNonHomogeneousTreeLikelihood.cpp:445-478, :576-867).  The root's first two sons are root1, root2; valid after an
  * eval with BPPGPU_EVAL_D2 (dP, d2P and the lower arrays resident).                                                   */
 int bppgpu_get_root_reparam_derivatives(bppgpu_engine* e, int32_t point, double out[4]);
+/* DRASDRTreeLikelihoodData::getDLikelihoodArray(nodeId) / getD2LikelihoodArray(nodeId) (filled by
+ * DRHomogeneousTreeLikelihood::computeTreeDLikelihoodAtNode / computeTreeD2LikelihoodAtNode, DRHomogeneousTreeLikelihood.cpp:
+ * 287-326, :373-411): per pattern, (dL_i / d t_node) / L_i and (d2L_i / d t_node^2) / L_i, computed on the device from the
+ * resident lower / upper arrays after an eval with derivatives.  d2_out may be NULL.                                      */
+int bppgpu_get_site_derivatives(bppgpu_engine* e, int32_t point, int32_t node, double* d1_out /* [N] */, double* d2_out /* [N] */);
 /* which: BPPGPU_WANT_P / _DP / _D2P; out [C][S][S] = pxy_[node][c][x][y] */
 int bppgpu_get_transition_probabilities(bppgpu_engine* e, int32_t point, int32_t node,
                                         unsigned which, double* out);

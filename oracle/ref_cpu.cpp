@@ -99,7 +99,19 @@ struct Shard {
       lik[v].assign(n, VVdouble(P.C, Vdouble(P.S, 1.)));
       ex[v].assign(n, std::vector<int>(P.C, 0));
     }
-    // leaf initialisation (getInitValue through the code table), done once like setData()
+    init_leaves();
+    pxy.assign(P.nn, VVVdouble(P.C, VVdouble(P.S, Vdouble(P.S))));
+    if (P.want & 2) dpxy = pxy;
+    if (P.want & 4) d2pxy = pxy;
+    site_lnl.assign(n, 0.);
+    SR.assign(n, 0.);
+    SRe.assign(n, 0);
+  }
+
+  // leaf initialisation (getInitValue through the code table), done once like setData(); the blocked driver
+  // (refcpu_eval_blocks) re-points the same arrays at the next block of patterns with it
+  void init_leaves() {
+    const Problem& P = *p;
     for (int v = 0; v < P.nn; v++) {
       if (leaf_slot[v] < 0) continue;
       for (long i = 0; i < n; i++) {
@@ -109,12 +121,6 @@ struct Shard {
           for (int x = 0; x < P.S; x++) lik[v][i][c][x] = P.code_table[code * P.S + x];
       }
     }
-    pxy.assign(P.nn, VVVdouble(P.C, VVdouble(P.S, Vdouble(P.S))));
-    if (P.want & 2) dpxy = pxy;
-    if (P.want & 4) d2pxy = pxy;
-    site_lnl.assign(n, 0.);
-    SR.assign(n, 0.);
-    SRe.assign(n, 0);
   }
 
   void transition_probabilities() {
@@ -435,6 +441,77 @@ extern "C" int refcpu_eval(int S, int C, long N, int nn, int root, const int* ch
     for (int t = 0; t < nthreads; t++)
       for (long i = 0; i < sh[t].n; i++) site_lnl_out[sh[t].i0 + i] = sh[t].site_lnl[i];
   if (best_seconds) *best_seconds = best;
+  if (sum_seconds) *sum_seconds = total;
+  return 0;
+}
+
+// The whole of a large alignment in blocks of `block` patterns: the nested arrays are allocated ONCE (the reference allocates
+// them in setData, outside any evaluation; re-allocating them per block would cost far more than the arithmetic) and re-pointed
+// at the next block by the leaf initialisation; value only.  lnl_out = sum over blocks of the block's sorted sum;
+// sum_seconds = evaluation time only (P(t) + pruning + root), like refcpu_eval.
+extern "C" int refcpu_eval_blocks(int S, int C, long N, long block, int nn, int root, const int* child_off, const int* children,
+                                  const void* codes, int code_bytes, int ncodes, const double* code_table,
+                                  const unsigned* weights, const double* rates, const double* probs, const double* V,
+                                  const double* Vinv, const double* ev, const double* ev_im, int chr_clamp, double model_rate,
+                                  const double* brlen, const double* rootfreq, int scaled, int nthreads, double* lnl_out,
+                                  double* sum_seconds) {
+  Problem P;
+  P.S = S; P.C = C; P.N = N; P.nn = nn; P.root = root; P.child_off = child_off; P.children = children;
+  P.codes = codes; P.code_bytes = code_bytes; P.ncodes = ncodes; P.code_table = code_table; P.weights = weights;
+  P.rates = rates; P.probs = probs; P.V = V; P.Vinv = Vinv; P.ev = ev; P.ev_im = ev_im; P.chr_clamp = chr_clamp;
+  P.weighted_root = 0; P.model_rate = model_rate; P.brlen = brlen;
+  P.rootfreq = rootfreq; P.scaled = scaled; P.want = 1;
+  if (block > N) block = N;
+  if (nthreads < 1) nthreads = 1;
+  if (nthreads > block && block > 0) nthreads = (int)block;
+  std::vector<Shard> sh(nthreads);
+  std::vector<long> cap(nthreads);
+  for (int t = 0; t < nthreads; t++) {
+    sh[t].p = &P;
+    sh[t].i0 = block * t / nthreads;
+    sh[t].n = cap[t] = block * (t + 1) / nthreads - sh[t].i0;
+  }
+  {
+    std::vector<std::thread> th;
+    for (int t = 0; t < nthreads; t++) th.emplace_back([&sh, t] { sh[t].alloc(); });
+    for (auto& x : th) x.join();
+  }
+  double lnl = 0, total = 0;
+  for (long b0 = 0; b0 < N; b0 += block) {
+    const long nb = std::min(block, N - b0);
+    for (int t = 0; t < nthreads; t++) {
+      const long lo = nb * t / nthreads, hi = nb * (t + 1) / nthreads;
+      sh[t].i0 = b0 + lo;
+      sh[t].n = std::min(hi - lo, cap[t]);
+    }
+    // the remainder of a short last block that does not fit a shard's capacity goes to the shards in turn (never
+    // happens for block sizes that are multiples of the thread count; kept for safety)
+    {
+      std::vector<std::thread> th;
+      for (int t = 0; t < nthreads; t++) th.emplace_back([&sh, t] { if (sh[t].n > 0) sh[t].init_leaves(); });
+      for (auto& x : th) x.join();
+    }
+    auto t0 = std::chrono::steady_clock::now();
+    {
+      std::vector<std::thread> th;
+      for (int t = 0; t < nthreads; t++) th.emplace_back([&sh, t] { if (sh[t].n > 0) sh[t].run(); });
+      for (auto& x : th) x.join();
+    }
+    Vdouble la;
+    la.reserve(nb);
+    long covered = 0;
+    for (int t = 0; t < nthreads; t++) {
+      for (long i = 0; i < sh[t].n; i++) la.push_back(weights[sh[t].i0 + i] * sh[t].site_lnl[i]);
+      covered += sh[t].n;
+    }
+    if (covered != nb) return 2;
+    std::sort(la.begin(), la.end());
+    double bl = 0;
+    for (long i = (long)la.size(); i > 0; i--) bl += la[i - 1];
+    lnl += bl;
+    total += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  }
+  *lnl_out = lnl;
   if (sum_seconds) *sum_seconds = total;
   return 0;
 }

@@ -71,6 +71,32 @@ def eval_raw(S, Ccat, N, child_off, children, root, codes, code_table, weights, 
     return {"lnl": lnl.value, "d1": d1, "d2": d2, "site_lnl": sl, "seconds": sec.value, "total_seconds": tot.value}
 
 
+def eval_blocks(S, Ccat, N, block, child_off, children, root, codes, code_table, weights, rates, probs, V, Vinv, ev, model_rate,
+                brlen, rootfreq, scaled=True, nthreads=1, ev_im=None, chr_clamp=False):
+    """Value-only evaluation of a large alignment in blocks of `block` patterns (arrays allocated once): (lnL, seconds)."""
+    f64 = lambda a: np.ascontiguousarray(a, np.float64)
+    child_off = np.ascontiguousarray(child_off, np.int32)
+    children = np.ascontiguousarray(children, np.int32)
+    codes = np.ascontiguousarray(codes)
+    assert codes.dtype in (np.uint8, np.uint16) and codes.shape[1] == N
+    code_table, rates, probs, V, Vinv, ev, brlen, rootfreq = map(f64, (code_table, rates, probs, V, Vinv, ev, brlen, rootfreq))
+    weights = np.ascontiguousarray(weights, np.uint32)
+    nn = len(child_off) - 1
+    if ev_im is not None:
+        ev_im = f64(ev_im)
+        if not np.any(ev_im):
+            ev_im = None
+    lnl, tot = C.c_double(0), C.c_double(0)
+    rc = lib().refcpu_eval_blocks(C.c_int(S), C.c_int(Ccat), C.c_long(N), C.c_long(block), C.c_int(nn), C.c_int(root),
+                                  _p(child_off, C.c_int), _p(children, C.c_int), codes.ctypes.data_as(C.c_void_p),
+                                  C.c_int(codes.dtype.itemsize), C.c_int(code_table.shape[0]), _p(code_table), _p(weights, C.c_uint),
+                                  _p(rates), _p(probs), _p(V), _p(Vinv), _p(ev), _p(ev_im), C.c_int(int(chr_clamp)),
+                                  C.c_double(model_rate), _p(brlen), _p(rootfreq), C.c_int(int(scaled)), C.c_int(nthreads),
+                                  C.byref(lnl), C.byref(tot))
+    assert rc == 0, rc
+    return lnl.value, tot.value
+
+
 def eval_case(case, **kw):
     """``case`` as built by tests/cases.py (diagonalisable models only)."""
     flat, m = case.flat, case.model

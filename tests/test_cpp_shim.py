@@ -381,3 +381,51 @@ def test_relax_and_yngp_m2_through_the_shim(built_lib):
     for key in ("RELAX_K2", "DOUBLE_M2"):
         assert abs(-vals[key] - ref2) <= 1e-9 * ref2, key
     assert abs(ref - ref2) > 1e-4
+
+
+@pytest.mark.gpu
+def test_dr_homogeneous_mixed_tree_likelihood_through_the_shim(built_lib):
+    """DRHomogeneousMixedTreeLikelihood (SURVEY 8f-3 names R and DR): YNGP_M2 on test_relax's data.  Value = the R class's = the
+    oracle's mixture; derivatives = the reference's own combination of the sub-likelihoods' RELATIVE per-site arrays
+    (DRHomogeneousMixedTreeLikelihood.cpp:399-508), rebuilt from the oracle's dL / d2L arrays; a branch move, a model move."""
+    import test_oracle_golden as tog
+    import cases
+    exe = compile_cpp("test_dr_mixed", built_lib)
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    vals = {f[0]: float(f[1]) for f in (line.split() for line in r.stdout.splitlines()) if len(f) == 2}
+    c = tog._relax_case()
+    nn = c.flat.n_nodes
+
+    def oracle(models, probs, brlen=None):
+        res = []
+        for m in models:
+            c.model, c.root_freqs = m, np.asarray(m.freq)
+            res.append(cases.oracle_eval(c, want_d1=True, want_d2=True, brlen=brlen))
+        mixed = np.log(np.sum(np.asarray(probs)[:, None] * np.exp(np.asarray([q.site_lnl for q in res])), axis=0))
+        d1, d2 = {}, {}
+        for b in range(nn - 1):
+            x = sum(p * q.dL[b] for p, q in zip(probs, res))
+            x2 = sum(p * q.d2L[b] for p, q in zip(probs, res))
+            d1[b] = -float(np.sum(c.weights * x))
+            d2[b] = -float(np.sum(c.weights * (x2 - x * x)))
+        return -float(np.sum(c.weights * mixed)), mixed, d1, d2
+
+    m2, p2 = rm.yngp_m2(2.0, 0.1, 2.0, 0.5, 0.8)
+    v, mixed, d1, d2 = oracle(m2, p2)
+    assert abs(vals["DRM_VALUE"] - v) <= 1e-9 * v and abs(vals["RM_VALUE"] - v) <= 1e-9 * v
+    assert int(vals["DRM_NBRANCH"]) == nn - 1
+    for b in range(nn - 1):
+        assert abs(vals["DRM_D1_%d" % b] - d1[b]) <= 1e-8 * max(1.0, abs(d1[b])), b
+        assert abs(vals["DRM_D2_%d" % b] - d2[b]) <= 1e-7 * max(1.0, abs(d2[b])), b
+    for i, k in enumerate(c.site_index if hasattr(c, "site_index") else range(c.N)):
+        pass
+    bl = c.flat.brlen.copy()
+    bl[1] = 0.2
+    v2, _, d1b, _ = oracle(m2, p2, brlen=bl)
+    assert abs(vals["DRM_VALUE_MOVED"] - v2) <= 1e-9 * v2
+    assert abs(vals["DRM_D1_MOVED_1"] - d1b[1]) <= 1e-8 * max(1.0, abs(d1b[1]))
+    m3, p3 = rm.yngp_m2(2.0, 0.3, 2.0, 0.5, 0.8)
+    v3, _, _, _ = oracle(m3, p3, brlen=bl)
+    assert abs(vals["DRM_VALUE_OMEGA"] - v3) <= 1e-9 * v3
+    assert int(vals["DRM_MODEL_DERIV_THROWS"]) == 1

@@ -374,6 +374,28 @@ def test_branch_derivatives(mk, ncat, ntaxa, nsites, flags):
             np.testing.assert_allclose(e.transition_probabilities(nid, capi.WANT_D2P), res.d2P[nid], rtol=0, atol=1e-9)
 
 
+@pytest.mark.parametrize("mk,ncat,flags", [(gtr, 4, 1), (rm.lg08, 4, 1), (rm.lg08, 3, 1 | 8), (lambda: rm.yn98(2.0, 0.3), 1, 1)])
+def test_per_site_derivative_arrays(mk, ncat, flags):
+    """bppgpu_get_site_derivatives = DRASDRTreeLikelihoodData::getDLikelihoodArray / getD2LikelihoodArray: (dL_i/dt)/L_i and
+    (d2L_i/dt2)/L_i of every branch, per pattern, against the oracle's arrays (both slab layouts, tips and internal nodes, the NH
+    form), and their weighted sums against the evaluation's own d1 / d2."""
+    capi = _capi()
+    r, p = rm.gamma_rates(ncat, 0.6) if ncat > 1 else rm.constant_rate()
+    c = cases.make_case(10, 60, mk(), r, p, seed=123, ambiguity=0.03)
+    res = cases.oracle_eval(c, want_d1=True, want_d2=True, nh_form=bool(flags & 8))
+    w = c.weights.astype(float)
+    with cases.make_engine(c, flags=flags) as e:
+        lnl, d1, d2 = e.eval(7)
+        for n in range(c.flat.n_nodes - 1):
+            a, b = e.site_derivatives(n)
+            np.testing.assert_allclose(a, res.dL[n], rtol=1e-8, atol=1e-10)
+            np.testing.assert_allclose(b, res.d2L[n], rtol=1e-8, atol=1e-9)
+            assert abs(np.sum(w * a) - d1[0, n]) <= 1e-9 * max(1.0, abs(d1[0, n]))
+            assert abs(np.sum(w * (b - a * a)) - d2[0, n]) <= 1e-8 * max(1.0, abs(d2[0, n]))
+        with pytest.raises(capi.BppGpuError):
+            e.site_derivatives(c.flat.root)
+
+
 def test_nh_derivative_form():
     capi = _capi()
     r, p = rm.gamma_rates(4, 0.6)

@@ -46,3 +46,20 @@ def test_cpp_port_chromosome_block_form_and_weighted_root():
     res = cases.oracle_eval(c, weighted_root=True)
     out = ref_cpu.eval_case(c, weighted_root=True)
     assert abs(out["lnl"] - res.lnl) < 1e-10 * abs(res.lnl)
+
+
+def test_blocked_driver_equals_the_single_call():
+    """refcpu_eval_blocks (arrays allocated once, re-pointed block by block: what bench.py's full-size parity leg runs) returns
+    the same lnL as one refcpu_eval over everything, for block sizes that do and do not divide the input."""
+    import cases
+    from oracle import ref_models as rm
+    r, p = rm.gamma_rates(4, 0.5)
+    c = cases.make_case(20, 700, rm.gtr(1.2, 0.8, 0.6, 1.5, 0.9, (.3, .2, .25, .25)), r, p, seed=3, compress=False)
+    ref = ref_cpu.eval_case(c, nthreads=2)["lnl"]
+    off, ch = c.flat.csr()
+    codes = np.stack([c.codes_by_leaf[l] for l in range(c.flat.n_nodes) if c.flat.is_leaf[l]])
+    m = c.model
+    for blk, th in ((700, 1), (128, 4), (96, 3), (333, 8)):
+        lnl, sec = ref_cpu.eval_blocks(4, 4, c.N, blk, off, ch, c.flat.root, codes, c.table, c.weights, c.rates, c.probs, m.V, m.Vinv,
+                                       m.ev_re, m.rate, c.flat.brlen, c.root_freqs, nthreads=th)
+        assert abs(lnl - ref) <= 1e-13 * abs(ref) and sec > 0
