@@ -600,7 +600,7 @@ int bppgpu_destroy(bppgpu_engine* e) {
 }
 
 static int walk4_dispatch(bppgpu_engine* e, const Walk4Params* wp, int grid, size_t, cudaStream_t st, bool attr_only);
-static int walk4c_dispatch(bppgpu_engine* e, const Walk4cParams* wp, int grid, size_t smem, cudaStream_t st, bool attr_only);
+static int walk4c_dispatch(bppgpu_engine* e, int pt, const Walk4cParams* wp, int grid, size_t smem, cudaStream_t st, bool attr_only);
 
 static int create_impl(const bppgpu_config* cfg, bppgpu_engine* e) {
   e->dev = cfg->device;
@@ -741,24 +741,70 @@ static int create_impl(const bppgpu_config* cfg, bppgpu_engine* e) {
     }
     int CH = 8192;
     while (CH < max_op) CH *= 2;
-    // patterns per thread: 4 (P rows re-used four times; two 4-warp CTAs per SM) once the input fills a wave of such CTAs
-    // -- measured 10.4 / 11.3 / 15.2 ms at PT = 4 / 2 / 1 on 1M patterns, 1.50 / 1.59 / 2.02 ms on 125k --, fewer below
+    // launch plan.  Patterns per thread PT = 4 / 2 / 1 run 2 / 3 / 4 CTAs (of NW warps, 32 PT NW / C patterns) per SM; measured
+    // on the 1024-taxon tree (ms per evaluation): 10.4 / 11.3 / 15.2 at 1M patterns, 1.47 / 1.56 / 1.98 at 125k -- PT = 4 wins at
+    // every size that fills the GPU, so the default is ONE segment at the widest PT that has enough CTAs.  A launch is a
+    // whole number of waves; BPPGPU_WALK4_PLAN=split walks k full waves at PT = 4 and the remainder with narrower CTAs
+    // (measured on 125k patterns: 1.483 vs 1.469 ms -- the partial last wave of wide CTAs already runs at one CTA per SM and
+    // is cheaper than a wave of narrow ones, so the split is not the default).  BPPGPU_WALK4_PT forces one segment.
     e->w4c_nw = C <= 4 ? 4 : 8;
     if (const char* env = getenv("BPPGPU_WALK4_NW")) {
       const int v = atoi(env);
       if ((v == 4 || v == 8) && v >= C) e->w4c_nw = v;
     }
-    {
-      const long long groups = (N + 31) / 32;                                  // 32-pattern lane groups
-      const long long per_wave = (long long)g_sm_count * 2 * (e->w4c_nw / C);  // groups one wave of PT = 1 CTAs (2 per SM) covers
-      e->w4c_pt = groups >= 4 * per_wave ? 4 : (groups >= 2 * per_wave ? 2 : 1);
-    }
+    int forced_pt = 0;
     if (const char* env = getenv("BPPGPU_WALK4_PT")) {
       const int v = atoi(env);
-      if (v == 1 || v == 2 || v == 4) e->w4c_pt = v;
+      if (v >= 1 && v <= 4) forced_pt = v;
     }
-    while (e->w4c_pt > 1 && walk4c_smem_bytes(CH, e->prog4c.nslots, C, e->w4c_pt, e->w4c_nw) > 200 * 1024) e->w4c_pt >>= 1;
-    if (walk4c_smem_bytes(CH, e->prog4c.nslots, C, e->w4c_pt, e->w4c_nw) > 200 * 1024) ok = false;
+    auto fits = [&](int pt) { return walk4c_smem_bytes(CH, e->prog4c.nslots, C, pt, e->w4c_nw) <= 200 * 1024; };
+    if (!fits(1)) ok = false;
+    if (ok) {
+      const int G = e->w4c_nw / C;
+      auto ppc = [&](int pt) { return (long long)G * 32 * pt; };
+      auto ctas_per_sm = [&](int pt) {
+        const size_t smem = walk4c_smem_bytes(CH, e->prog4c.nslots, C, pt, e->w4c_nw) + 1024;
+        const int by_regs = e->w4c_nw == 8 ? (pt <= 2 ? 2 : 1) : (pt <= 1 ? 4 : pt <= 3 ? 3 : 2);
+        return std::max(1, std::min<int>(by_regs, (int)(227 * 1024 / smem)));
+      };
+      const double wave_ms[5] = {0, 0.287, 0.315, 0.36, 0.386};   // relative cost of one wave (only ratios matter)
+      auto waves = [&](long long n, int pt) { const long long ctas = (n + ppc(pt) - 1) / ppc(pt); const long long slots = (long long)g_sm_count * ctas_per_sm(pt); return (ctas + slots - 1) / slots; };
+      e->w4c_segs.clear();
+      auto add_seg = [&](int pt, long long a, long long b) {
+        if (b <= a) return;
+        bppgpu_engine::W4cSeg sg{};
+        sg.pt = pt; sg.pat0 = a; sg.pat_end = b;
+        sg.grid = (int)((b - a + ppc(pt) - 1) / ppc(pt));
+        e->w4c_segs.push_back(sg);
+      };
+      if (forced_pt) {
+        int pt = forced_pt;
+        while (pt > 1 && !fits(pt)) --pt;
+        add_seg(pt, 0, N);
+      } else if (N > 0 && !(getenv("BPPGPU_WALK4_PLAN") && !strcmp(getenv("BPPGPU_WALK4_PLAN"), "split"))) {
+        int big = 4;
+        while (big > 1 && (!fits(big) || N < (long long)g_sm_count * ctas_per_sm(big) * ppc(big))) big >>= 1;   // at least one wave
+        add_seg(big, 0, N);
+      } else if (N > 0) {
+        int big = 4;
+        while (big > 1 && !fits(big)) big >>= 1;
+        const long long per_wave = (long long)g_sm_count * ctas_per_sm(big) * ppc(big);   // patterns in one full wave of the wide CTAs
+        double best = 1e300;
+        long long best_k = 0;
+        int best_pt = 1;
+        const long long kmax = N / per_wave;
+        for (long long k = std::max<long long>(0, kmax - 1); k <= kmax; ++k)
+          for (int pt : {1, 2, 4}) {
+            if (pt > big || !fits(pt)) continue;
+            const long long rem = N - k * per_wave;
+            const double t = k * wave_ms[big] + (rem > 0 ? waves(rem, pt) * wave_ms[pt] : 0.0);
+            if (t < best - 1e-12) { best = t; best_k = k; best_pt = pt; }
+          }
+        if (best_pt == big) add_seg(big, 0, N);
+        else { add_seg(big, 0, best_k * per_wave); add_seg(best_pt, best_k * per_wave, N); }
+      }
+      e->w4c_pt = e->w4c_segs.empty() ? 1 : e->w4c_segs[0].pt;
+    }
     if (ok) {
       W4cProgram& W = e->w4c_prog;
       memset(&W, 0, sizeof(W));
@@ -930,9 +976,16 @@ static int create_impl(const bppgpu_config* cfg, bppgpu_engine* e) {
     BPP_CUDA(cudaMemcpy(e->d_w4c_blocks, e->w4c_blocks.data(), e->w4c_blocks.size() * sizeof(Pack4cBlock), cudaMemcpyHostToDevice));
     BPP_CUDA(dev_alloc(e, &e->d_w4c_tip_order, e->w4c_tip_order.size()));
     BPP_CUDA(cudaMemcpy(e->d_w4c_tip_order, e->w4c_tip_order.data(), e->w4c_tip_order.size() * 4, cudaMemcpyHostToDevice));
-    const long long ppc = (long long)(e->w4c_nw / C) * 32 * e->w4c_pt;
-    e->w4c_grid = (int)((N + ppc - 1) / ppc);
-    BPP_CUDA(dev_alloc(e, &e->d_codesC, (size_t)std::max(1, e->w4c_grid) * e->w4c_tip_order.size() * (size_t)ppc + 16));
+    size_t codes_bytes = 0;
+    int parts = 0;
+    for (auto& sg : e->w4c_segs) {
+      sg.codes_off = codes_bytes;
+      sg.part0 = parts;
+      codes_bytes += (size_t)sg.grid * e->w4c_tip_order.size() * (size_t)(e->w4c_nw / C) * 32 * sg.pt;
+      codes_bytes = (codes_bytes + 127) & ~(size_t)127;
+      parts += sg.grid;
+    }
+    BPP_CUDA(dev_alloc(e, &e->d_codesC, codes_bytes + 128));
   }
   if ((e->path != PATH_WALK4 || e->keep) && e->path != PATH_POINTS)
     BPP_CUDA(dev_alloc(e, &e->d_tiptab, (size_t)e->pchunk * e->nl * C * e->ncodes * S));
@@ -1013,9 +1066,12 @@ static int create_impl(const bppgpu_config* cfg, bppgpu_engine* e) {
   }
 
   if (e->w4c) {
-    const size_t smem = walk4c_smem_bytes(e->w4c_CH, e->prog4c.nslots, C, e->w4c_pt, e->w4c_nw);
-    int rc4 = walk4c_dispatch(e, nullptr, 0, smem, nullptr, true);
-    if (rc4) return rc4;
+    for (int pt = 1; pt <= 4; ++pt) {   // opt in to the dynamic shared memory of every instantiation a plan may use
+      const size_t smem = walk4c_smem_bytes(e->w4c_CH, e->prog4c.nslots, C, pt, e->w4c_nw);
+      if (smem > 200 * 1024) continue;
+      int rc4 = walk4c_dispatch(e, pt, nullptr, 0, smem, nullptr, true);
+      if (rc4) return rc4;
+    }
     e->stats.stack_slots = e->prog4c.nslots;
   } else if (e->path == PATH_WALK4) {
     // patterns per thread: 2 (4 CTAs of 128 threads per SM at 128 registers) while the stack leaves room for it
@@ -1340,12 +1396,12 @@ static int walk4c_launch_one(const Walk4cParams* wp, int grid, size_t smem, cuda
 template <int CL, int NW>
 static int walk4c_launch_pt(int pt, const Walk4cParams* wp, int grid, size_t smem, cudaStream_t st, bool attr_only) {
   if (pt == 4) return walk4c_launch_one<CL, 4, NW>(wp, grid, smem, st, attr_only);
+  if (pt == 3) return walk4c_launch_one<CL, 3, NW>(wp, grid, smem, st, attr_only);
   if (pt == 2) return walk4c_launch_one<CL, 2, NW>(wp, grid, smem, st, attr_only);
   return walk4c_launch_one<CL, 1, NW>(wp, grid, smem, st, attr_only);
 }
-static int walk4c_dispatch(bppgpu_engine* e, const Walk4cParams* wp, int grid, size_t smem, cudaStream_t st, bool attr_only) {
+static int walk4c_dispatch(bppgpu_engine* e, int pt, const Walk4cParams* wp, int grid, size_t smem, cudaStream_t st, bool attr_only) {
   g_w4c_prog = &e->w4c_prog;
-  const int pt = e->w4c_pt;
   if (e->w4c_nw == 4) {
     switch (ilog2(e->C)) {
       case 0: return walk4c_launch_pt<0, 4>(pt, wp, grid, smem, st, attr_only);
@@ -1384,14 +1440,12 @@ static int enqueue_prune(bppgpu_engine* e, int point, int pl, cudaStream_t st) {
   if (e->w4c) {
     Walk4cParams wp{};
     wp.stream = e->d_w4c_stream + (size_t)pl * e->w4c_stream_bytes;
-    wp.codesC = e->d_codesC;
     wp.nchunks = e->w4c_nchunks;
     wp.CH = e->w4c_CH;
     wp.nslots = e->prog4c.nslots;
     wp.ncodes = e->ncodes;
     wp.ntips = (int)e->w4c_tip_order.size();
     wp.flags = rflag;
-    wp.N = N;
     wp.rootfreq = rootfreq;
     wp.probs = e->d_probs;
     wp.weights = e->d_weights;
@@ -1399,11 +1453,16 @@ static int enqueue_prune(bppgpu_engine* e, int point, int pl, cudaStream_t st) {
     wp.rexp = e->d_rexp;
     wp.site_lnl = site_lnl;
     wp.partials = e->d_partials;
-    const int grid = e->w4c_grid;
-    nparts = grid;
-    int rc4 = walk4c_dispatch(e, &wp, grid, walk4c_smem_bytes(e->w4c_CH, e->prog4c.nslots, C, e->w4c_pt, e->w4c_nw), st, false);
-    if (rc4) return rc4;
-    e->stats.kernel_launches++;
+    for (const auto& sg : e->w4c_segs) {
+      wp.codesC = e->d_codesC + sg.codes_off;
+      wp.pat0 = sg.pat0;
+      wp.pat_end = sg.pat_end;
+      wp.part0 = sg.part0;
+      int rc4 = walk4c_dispatch(e, sg.pt, &wp, sg.grid, walk4c_smem_bytes(e->w4c_CH, e->prog4c.nslots, C, sg.pt, e->w4c_nw), st, false);
+      if (rc4) return rc4;
+      nparts += sg.grid;
+      e->stats.kernel_launches++;
+    }
   } else if (e->path == PATH_WALK4) {
     if (e->flags & BPPGPU_FLAG_WEIGHTED_ROOT)
       BPP_FAIL(BPPGPU_E_INVALID, "BPPGPU_FLAG_WEIGHTED_ROOT is served by the generic path only");
@@ -1825,10 +1884,12 @@ static int eval_impl(bppgpu_engine* e, unsigned want, cudaStream_t st, bool time
     e->stats.kernel_launches += launches;
     if (e->w4c) {
       if (e->codesT_dirty && e->N > 0) {
-        pack_codesC_kernel<<<(unsigned)e->w4c_grid, 256, 0, st>>>(
-            (const unsigned char*)e->d_codes, e->d_w4c_tip_order, (int)e->w4c_tip_order.size(), e->N,
-            (e->w4c_nw / C) * 32 * e->w4c_pt, e->d_codesC);
-        e->stats.kernel_launches++;
+        for (const auto& sg : e->w4c_segs) {
+          pack_codesC_kernel<<<(unsigned)sg.grid, 256, 0, st>>>(
+              (const unsigned char*)e->d_codes, e->d_w4c_tip_order, (int)e->w4c_tip_order.size(), e->N, sg.pat0, sg.pat_end,
+              (e->w4c_nw / C) * 32 * sg.pt, e->d_codesC + sg.codes_off);
+          e->stats.kernel_launches++;
+        }
         e->codesT_dirty = false;
       }
       for (int pl = 0; pl < np; ++pl)

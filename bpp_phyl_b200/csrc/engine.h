@@ -111,7 +111,10 @@ struct bppgpu_engine {
   bppgpu::Program prog4c;                  // walk program whose leaf pushes use the register slot
   bppgpu::W4cProgram w4c_prog;             // descriptor words + chunk records (passed as a kernel parameter)
   size_t w4c_stream_bytes = 0;             // nchunks * CH
-  int w4c_grid = 0;
+  // launch plan: the pattern list is walked in one or two segments -- full waves of the widest CTAs, then the remainder with
+  // narrower ones (fewer patterns per thread, more CTAs per SM) so that the last wave is short
+  struct W4cSeg { int pt; long long pat0, pat_end; int grid; size_t codes_off; int part0; };
+  std::vector<W4cSeg> w4c_segs;
   std::vector<bppgpu::Pack4cBlock> w4c_blocks;
   std::vector<int> w4c_tip_order;
   int w4c_CH = 0, w4c_nchunks = 0, w4c_pt = 2, w4c_nw = 8;

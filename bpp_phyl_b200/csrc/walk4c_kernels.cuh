@@ -54,7 +54,8 @@ struct Walk4cParams {
   const unsigned char* codesC;       // [gridDim.x][ntips][PPC] tip codes, consumption order, one byte per pattern
   int nchunks, CH, nslots, ncodes, ntips;
   unsigned flags;                    // bit0: R semantics at the root
-  long long N;
+  long long pat0, pat_end;           // this launch covers patterns [pat0, pat_end) (a segment of the engine's pattern list)
+  int part0;                         // first slot of `partials` of this launch
   const double* rootfreq;            // [4]
   const double* probs;               // [C]
   const double* weights;             // [N]
@@ -293,7 +294,7 @@ __host__ __device__ inline size_t walk4c_smem_bytes(int CH, int nslots, int C, i
   return (size_t)kW4cStages * walk4c_stage_bytes(CH, C, PT, NW) + (size_t)(nslots > 0 ? nslots : 0) * PT * NW * 32 * 36 +
          (size_t)PT * NW * 32 * 12 + 128;
 }
-__host__ __device__ constexpr int walk4c_min_ctas(int PT, int NW) { return NW == 8 ? (PT <= 2 ? 2 : 1) : (PT <= 2 ? 3 : 2); }
+__host__ __device__ constexpr int walk4c_min_ctas(int PT, int NW) { return NW == 8 ? (PT <= 2 ? 2 : 1) : (PT <= 3 ? 3 : 2); }
 
 template <int C_LOG2, int PT, int NW>
 __global__ void __launch_bounds__(NW * 32, walk4c_min_ctas(PT, NW))
@@ -423,8 +424,8 @@ walk4c_kernel(const __grid_constant__ Walk4cParams prm, const __grid_constant__ 
   __syncthreads();
   double contrib = 0.0;
   for (int lp = tid; lp < PPC; lp += NTH) {
-    const long long pat = (long long)blockIdx.x * PPC + lp;
-    if (pat >= prm.N) continue;
+    const long long pat = prm.pat0 + (long long)blockIdx.x * PPC + lp;
+    if (pat >= prm.pat_end) continue;
     int Emin = rexpn[lp];
 #pragma unroll
     for (int cc = 1; cc < C; ++cc) Emin = min(Emin, rexpn[cc * PPC + lp]);
@@ -448,17 +449,18 @@ walk4c_kernel(const __grid_constant__ Walk4cParams prm, const __grid_constant__ 
     contrib += prm.weights[pat] * lnl;
   }
   const double bs = block_sum(contrib, red);
-  if (tid == 0) prm.partials[blockIdx.x] = bs;
+  if (tid == 0) prm.partials[prm.part0 + blockIdx.x] = bs;
 }
 
 // codes [nl][N] (leaf-slot major) -> codesC [cta][tip in consumption order][PPC]: the rows a CTA stages with its chunks
-__global__ void pack_codesC_kernel(const unsigned char* codes, const int* tip_order, int ntips, long long N, int PPC,
-                                   unsigned char* codesC) {
+// (of one segment [pat0, pat_end) of the pattern list, walked by CTAs of PPC patterns)
+__global__ void pack_codesC_kernel(const unsigned char* codes, const int* tip_order, int ntips, long long N, long long pat0,
+                                   long long pat_end, int PPC, unsigned char* codesC) {
   const size_t cta = blockIdx.x;
   for (int i = threadIdx.x; i < ntips * PPC; i += blockDim.x) {
     const int k = i / PPC, p = i - k * PPC;
-    const long long pat = (long long)cta * PPC + p;
-    codesC[(cta * ntips + k) * PPC + p] = pat < N ? codes[(size_t)tip_order[k] * N + pat] : (unsigned char)0;
+    const long long pat = pat0 + (long long)cta * PPC + p;
+    codesC[(cta * ntips + k) * PPC + p] = pat < pat_end ? codes[(size_t)tip_order[k] * N + pat] : (unsigned char)0;
   }
 }
 

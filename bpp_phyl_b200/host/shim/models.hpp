@@ -705,8 +705,17 @@ class OmegaMixture_ : public MixedSubstitutionModel {
   OmegaMixture_(const Alphabet* alpha, const Vdouble* codonFreq) : alpha_(alpha) { if (codonFreq) codonFreq_ = *codonFreq; }
   void rebuild(double kappa, const double omega[3], double theta1, double theta2) {
     probs_ = {theta1, (1 - theta1) * theta2, (1 - theta1) * (1 - theta2)};
-    sub_.clear();
-    for (int k = 0; k < 3; ++k) sub_.emplace_back(new YN98(alpha_, kappa, omega[k], codonFreq_.empty() ? nullptr : &codonFreq_));
+    // the sub-model OBJECTS are kept over parameter moves: likelihood objects hold pointers to them (getNModel)
+    if (sub_.size() != 3) {
+      sub_.clear();
+      for (int k = 0; k < 3; ++k) sub_.emplace_back(new YN98(alpha_, kappa, omega[k], codonFreq_.empty() ? nullptr : &codonFreq_));
+    } else {
+      for (int k = 0; k < 3; ++k) {
+        sub_[k]->setRate(1.0);
+        sub_[k]->setParameterValue("kappa", kappa);
+        sub_[k]->setParameterValue("omega", omega[k]);
+      }
+    }
     size_t from = 0, to = 0;
     bool found = false;
     for (size_t f = 1; f < 64 && !found; ++f)

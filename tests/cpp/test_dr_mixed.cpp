@@ -22,7 +22,7 @@ int main() {
     sites.addSequence(BasicSequence("D", "CAACGGGAGTGCGCCTAT", alphabet));
     ConstantRateDistribution rdist;
     YNGP_M2 m2(alphabet, 2.0, 0.1, 2.0, 0.5, 0.8);
-    DRHomogeneousMixedTreeLikelihood dr(*tree, sites, &m2, &rdist, true, false);
+    DRHomogeneousMixedTreeLikelihood dr(*tree, sites, &m2, &rdist, /*checkRooted=*/false, false);
     dr.initialize();
     RHomogeneousMixedTreeLikelihood r(*tree, sites, &m2, &rdist, true, false);
     r.initialize();
