@@ -363,37 +363,48 @@ def run_points(a, w, rank, world, local, K, W, metric, config):
     if world > 1:
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
     ms, e2e_ms = float(tms[0]), float(tms[1])
+    dfma_now, dmma_now = capi.measure_fp64_peak(local) if rank == 0 else (None, None)
     clocks = sampler.stop() if rank == 0 else None
     upd_step = tree.n_internal * npts_total * S          # CLV updates of the whole job per step
     if rank == 0:
-        peaks = {}
-        try:
-            peaks = json.loads(open(os.path.join(ROOT, "profiles", "r1_fp64_peaks.json")).readline())
-        except (OSError, ValueError, AttributeError):
-            pass
-        dmma_peak = peaks.get("dmma_m8n8k4_tflops", 37.1)
-        n_mat = npts * (nn - 1)
-        flops = n_mat * (2.0 * S ** 3 + S * S)
-        pt_ms = st["pt_ms_sum"] / max(1, K)              # all chunks of one evaluation
-        ach = flops / (pt_ms * 1e-3) / 1e12 if pt_ms > 0 else None
+        dmma_peak = dmma_now
+        kms = st["prune_ms_sum"] / max(1, st["prune_count"])      # level kernels + root (factored) or node kernels (tables)
+        pt_ms = st["pt_ms_sum"] / max(1, K)                        # guard (factored) or all P(t) chunks (tables)
+        nfac, ntab = int(st["factored_points"]), int(st["table_points"])
+        if nfac > 0:
+            K8 = (S + 7) // 8 * 8
+            dm_flops = nfac * (st["chr_tiles_tip"] + 2 * st["chr_tiles_dense"]) * (K8 // 8) * 4 * (K8 // 4) * 512.0
+            ach = dm_flops / (kms * 1e-3) / 1e12 if kms > 0 else None
+            roofline = {"bound": "tensor", "kernel": "chr_level_kernel (one launch per tree level; all levels + root timed together)",
+                        "achieved": ach, "peak": dmma_peak, "unit": "TFLOP/s", "frac": ach / dmma_peak if ach else None, "traffic": None,
+                        "kernel_ms": kms, "executed_dmma_flops_per_eval": dm_flops, "guard_ms": pt_ms,
+                        "peak_source": "FP64 mma.sync m8n8k4 measured in this run (bppgpu_measure_fp64_peak)",
+                        "note": "P(t) is applied in factored form V T(t) V^-1 x, tree level by tree level, as skinny tensor-core GEMMs; "
+                                "flops = DMMAs issued x 512 (column tiles are padded to 32 columns)"}
+        else:
+            n_mat = npts * (nn - 1)
+            flops = n_mat * (2.0 * S ** 3 + S * S)
+            ach = flops / (pt_ms * 1e-3) / 1e12 if pt_ms > 0 else None
+            roofline = {"bound": "tensor", "kernel": "pt_dmma_kernel", "achieved": ach, "peak": dmma_peak, "unit": "TFLOP/s",
+                        "frac": ach / dmma_peak if ach else None, "traffic": None, "kernel_ms": pt_ms, "flops_per_eval": flops,
+                        "node_kernels_ms": kms,
+                        "peak_source": "FP64 mma.sync m8n8k4 measured in this run (bppgpu_measure_fp64_peak)"}
         line = {"metric": metric, "value": upd_step * K / (ms * 1e-3), "unit": "CLV updates/s", "n_gpus": world, "steps": K,
                 "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": a.scaling, "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic (one chromosome count per taxon simulated down a random rooted tree; parameter points "
                                         "drawn uniformly, numerically defective generators redrawn)",
                 "config": dict(config, points=npts_total, sharding="points/%d (replicas, no collective)" % world),
                 "logl_evals_per_s": npts_total * K / (ms * 1e-3), "lnl_point0": lnl0,
+                "routes": {"factored_points": nfac, "table_points": ntab,
+                           "note": "points whose probe tables leave [0, 1] by more than 1e-8 (where the reference's per-entry clamp would matter) "
+                                   "and singular generators take the P-table route"},
                 "e2e": {"value": upd_step / (e2e_ms * 1e-3) if e2e_ms > 0 else None, "unit": "CLV updates/s",
                         "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms,
                         "logl_evals_per_s": npts_total / (e2e_ms * 1e-3) if e2e_ms > 0 else None,
                         "call": "bppgpu_set_model + bppgpu_set_branch_lengths per point, one bppgpu_eval (host buffers)"},
                 "gpu_launches": int(st["kernel_launches"]) * K, "launches_per_step": int(st["kernel_launches"]),
-                "roofline": {"bound": "tensor", "kernel": "pt_dmma_kernel", "achieved": ach, "peak": dmma_peak, "unit": "TFLOP/s",
-                             "frac": ach / dmma_peak if ach else None, "traffic": None, "kernel_ms": pt_ms,
-                             "flops_per_eval": flops,
-                             "peak_source": "FP64 mma.sync m8n8k4 measured with tools/fp64_peak.cu (profiles/r1_fp64_peaks.json); "
-                                            "MEASURED_PEAKS.json has no FP64 figure",
-                             "pruning_ms": st["prune_ms_sum"] / max(1, st["prune_count"])},
-                "clocks": clocks, "hbm_resident_bytes": int(st["hbm_bytes_resident"])}
+                "roofline": roofline, "clocks": clocks, "fp64_peaks_measured": {"dfma_tflops": dfma_now, "dmma_m8n8k4_tflops": dmma_now},
+                "hbm_resident_bytes": int(st["hbm_bytes_resident"])}
         if world == 1 and not a.no_cpu:
             # the reference's CPU algorithm on a few points, one point per host thread
             from concurrent.futures import ThreadPoolExecutor

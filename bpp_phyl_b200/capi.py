@@ -91,6 +91,10 @@ class Stats(C.Structure):
         ("hbm_bytes_resident", C.c_int64),
         ("stack_slots", C.c_int32),
         ("path", C.c_int32),
+        ("factored_points", C.c_int64),
+        ("table_points", C.c_int64),
+        ("chr_tiles_tip", C.c_int32),
+        ("chr_tiles_dense", C.c_int32),
     ]
 
 

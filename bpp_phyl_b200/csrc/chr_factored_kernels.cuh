@@ -1,0 +1,320 @@
+// Batched-points path WITHOUT transition-probability tables (BASELINE config 5: ChromEvol-style chromosome-number models,
+// S ~ 200 states, one character, thousands of parameter points on one tree).
+//
+// With one (pattern, class) row per point the pruning step of a branch is a matrix-VECTOR product, P_b . CLV_son
+// (RHomogeneousTreeLikelihood.cpp:851-856; DRNonHomogeneousTreeLikelihood::computeSubtreeLikelihoodPostfix), and building
+// P_b = V exp(L t_b) V^-1 (ChromosomeSubstitutionModel.cpp:808-851) first costs 2 S^3 flop and S^2 doubles of HBM traffic per
+// branch for the sake of 2 S^2 useful flop.  Here the product is applied in factored form,
+//     term_b = V . ( T(t_b) . ( V^-1 . x_b ) ),        T = exp(L t) with the 2x2 rotation blocks of conjugate pairs
+// (the reference's own block form, :821-850), and the branches of one tree LEVEL (sons of equal subtree height) are the
+// columns of two skinny GEMMs per point on the FP64 tensor cores (mma.sync m8n8k4): A = V^-1 / V straight from L2 (a point's
+// 2 S^2 doubles are re-used by every column tile of every level), B = the level's column tile in shared memory.
+// Tip sons with an observed count k need no first GEMM: V^-1 e_k is a column of V^-1.
+//   flops per point ~ 4 S^2 (#internal sons) + 2 S^2 (#tips)  vs  2 S^3 (#branches):  ~ 100x fewer at S = 200.
+//
+// What this route cannot reproduce is the reference's per-ENTRY clamp of P (P < 0 -> 1e-20, P > 1 -> 1, :903-916): it never
+// sees the entries.  The engine therefore evaluates a guard per point (P at the shortest, the geometric-mean and the longest
+// branch through the tensor-core table kernel, entries outside [-1e-8, 1 + 1e-8] counted) and sends points that fail it,
+// and singular generators (Taylor route), through the table path (points_kernels.cuh).
+#pragma once
+#include "dmma.cuh"
+#include "pt_kernels.cuh"
+
+namespace bppgpu {
+
+constexpr int kChrCols = 32;      // columns (branches) per tile
+constexpr int kChrLD = 36;        // leading dimension of the shared column tiles (= 4 mod 16 doubles: conflict-free B fragments)
+constexpr int kChrWarps = 8;
+constexpr int kChrMaxRB = 4;      // row blocks of 8 per warp -> S <= 8 * 8 * 4 = 256
+// Guard: a point takes the factored route when no entry of its probe tables leaves [0, 1] by more than this; entries that do
+// are the ones the reference clamps (ChromosomeSubstitutionModel.cpp:903-916).  Observed tips are exact whatever the guard says
+// (their term is a column of P and is clamped entry by entry); the guard is about internal branches, where the clamp cannot be
+// applied.  Measured on the benchmark's points (S = 200, 500 taxa; tools/chr_guard_sweep.py, profiles/r2_chr_guard_sweep.json):
+// with violations up to 1e-8 the factored lnL is within 1e-13 relative of the table route's, i.e. four orders below the 1e-9
+// parity bar, so 1e-8 is the threshold: tol 1e-12 sends 74 % of those points to the tables, 1e-10 12 %, 1e-9 0.2 %, 1e-8 none.
+constexpr double kChrGuardTol = 1e-8;
+
+struct ChrLevelParams {
+  const ModelDev* models;
+  const int* branch_model;   // [npts][nn] (homogeneous points: every branch of a point has the same slot)
+  const double* brlen;       // [npts][nn]
+  double rate0;              // the single rate class
+  int S, nn, p0;             // p0: first point of this launch (blockIdx.y is relative to it)
+  int tile0;                 // first tile of the level
+  const int* tile_edges;     // [ntiles][kChrCols] son node ids, -1 = unused column
+  const int* tile_kind;      // [ntiles] 0: tip sons with an observed state (first GEMM skipped), 1: dense columns
+  const int* child_off;      // CSR sons of every node
+  const int* children;
+  const int* leaf_state;     // [nn] observed state of a leaf, -1 = dense leaf (leaf_vec), -2 = internal node
+  const double* leaf_vec;    // [nn][S] getInitValue row of a dense leaf (ambiguity / unknown), unused otherwise
+  double* term;              // [points of this launch][nn][S] term of the branch above node n, rescaled
+  int* term_exp;             // [points of this launch][nn]
+  const int* skip;           // [npts] 1 = the point goes through the table route (guard), or nullptr
+};
+
+inline size_t chr_level_smem(int S) {
+  const int K4 = (S + 7) & ~7;
+  return (size_t)K4 * kChrLD * sizeof(double) + 3 * kChrCols * sizeof(double) + 2 * kChrCols * sizeof(int);
+}
+
+// C[rb][cb] += A[rows of rb][k] . Bs[k][cols of cb]   for this warp's row blocks; A row-major [S][S] in global memory
+__device__ __forceinline__ void chr_gemm(const double* __restrict__ A, int S, int K4, const double* Bs, int nrb, int warp, int g,
+                                         int q, double (&acc)[kChrMaxRB][kChrCols / 8][2]) {
+#pragma unroll
+  for (int i = 0; i < kChrMaxRB; ++i)
+#pragma unroll
+    for (int cb = 0; cb < kChrCols / 8; ++cb) acc[i][cb][0] = acc[i][cb][1] = 0.0;
+#pragma unroll 2
+  for (int k0 = 0; k0 < K4; k0 += 4) {
+    double a[kChrMaxRB];
+#pragma unroll
+    for (int i = 0; i < kChrMaxRB; ++i) {
+      const int row = (warp + i * kChrWarps) * 8 + g;
+      a[i] = (warp + i * kChrWarps < nrb && row < S && k0 + q < S) ? __ldg(A + (size_t)row * S + k0 + q) : 0.0;
+    }
+    double b[kChrCols / 8];
+#pragma unroll
+    for (int cb = 0; cb < kChrCols / 8; ++cb) b[cb] = Bs[(k0 + q) * kChrLD + cb * 8 + g];
+#pragma unroll
+    for (int i = 0; i < kChrMaxRB; ++i)
+      if (warp + i * kChrWarps < nrb) {
+#pragma unroll
+        for (int cb = 0; cb < kChrCols / 8; ++cb) dmma884(acc[i][cb][0], acc[i][cb][1], a[i], b[cb]);
+      }
+  }
+}
+__device__ __forceinline__ void chr_store_acc(double* Cs, int nrb, int warp, int g, int q,
+                                              const double (&acc)[kChrMaxRB][kChrCols / 8][2]) {
+#pragma unroll
+  for (int i = 0; i < kChrMaxRB; ++i)
+    if (warp + i * kChrWarps < nrb) {
+      const int row = (warp + i * kChrWarps) * 8 + g;
+#pragma unroll
+      for (int cb = 0; cb < kChrCols / 8; ++cb)
+        *reinterpret_cast<double2*>(Cs + row * kChrLD + cb * 8 + 2 * q) = make_double2(acc[i][cb][0], acc[i][cb][1]);
+    }
+}
+
+__global__ void __launch_bounds__(kChrWarps * 32, 2) chr_level_kernel(ChrLevelParams p) {
+  extern __shared__ __align__(16) double sm_chr[];
+  const int S = p.S;
+  const int K4 = (S + 7) & ~7;                 // rows of the shared tiles (multiple of 8: row blocks and k-steps)
+  double* Xs = sm_chr;                         // [K4][LD]  the column tile: x, then V^-1 x, then T V^-1 x, then the terms (in place:
+  double* Ws = Xs;                             //           every GEMM reads it completely before its result is stored back)
+  double* tl = Xs + (size_t)K4 * kChrLD;       // [32] rate * t of the column's branch
+  double* cmax = tl + kChrCols;                // [32] column maxima
+  double* cscale = cmax + kChrCols;            // [32]
+  int* cexp = reinterpret_cast<int*>(cscale + kChrCols);   // [32] exponent carried in by the column
+  int* cnode = cexp + kChrCols;                // [32]
+
+  const int tile = p.tile0 + blockIdx.x;
+  const int pt = p.p0 + blockIdx.y;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, q = lane & 3;
+  const int* edges = p.tile_edges + (size_t)tile * kChrCols;
+  const int kind = p.tile_kind[tile];
+  const int first = edges[0];
+  const ModelDev md = p.models[p.branch_model[(size_t)pt * p.nn + first]];
+  const int nrb = K4 >> 3;
+  if (p.skip && p.skip[pt]) return;
+  double* term_pt = p.term + (size_t)blockIdx.y * p.nn * S;
+  int* texp_pt = p.term_exp + (size_t)blockIdx.y * p.nn;
+
+  if (tid < kChrCols) {
+    const int n = edges[tid];
+    cnode[tid] = n;
+    tl[tid] = n >= 0 ? md.rate * p.rate0 * p.brlen[(size_t)pt * p.nn + n] : 0.0;
+    cexp[tid] = 0;
+  }
+  __syncthreads();
+
+  if (kind == 0) {
+    // observed tips: W[:, j] = V^-1[:, state_j]
+    for (int i = tid; i < K4 * kChrCols; i += blockDim.x) {
+      const int j = i / K4, k = i - j * K4;
+      const int n = cnode[j];
+      Ws[k * kChrLD + j] = (n >= 0 && k < S) ? __ldg(md.Vinv + (size_t)k * S + p.leaf_state[n]) : 0.0;
+    }
+  } else {
+    // dense columns: x = the son's conditional likelihoods = product of ITS sons' terms (or a dense leaf's init row)
+    for (int i = tid; i < K4 * kChrCols; i += blockDim.x) {
+      const int j = i / K4, k = i - j * K4;      // consecutive threads read one son's term contiguously
+      const int n = cnode[j];
+      double v = 0.0;
+      if (n >= 0 && k < S) {
+        if (p.leaf_state[n] == -1) v = p.leaf_vec[(size_t)n * S + k];
+        else {
+          v = 1.0;
+          for (int c = p.child_off[n]; c < p.child_off[n + 1]; ++c) v *= term_pt[(size_t)p.children[c] * S + k];
+        }
+      }
+      Xs[k * kChrLD + j] = v;
+    }
+    if (tid < kChrCols) {
+      const int n = cnode[tid];
+      int e = 0;
+      if (n >= 0 && p.leaf_state[n] == -2)
+        for (int c = p.child_off[n]; c < p.child_off[n + 1]; ++c) e += texp_pt[p.children[c]];
+      cexp[tid] = e;
+    }
+    __syncthreads();
+    // the product of several rescaled terms may be small again: bring every column's maximum back to [0.5, 1)
+    if (warp < kChrCols / 8 * 2) {   // 8 warps x 4 columns
+      for (int j = warp * 4; j < warp * 4 + 4; ++j) {
+        double m = 0.0;
+        for (int k = lane; k < S; k += 32) m = fmax(m, fabs(Xs[k * kChrLD + j]));
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+        if (lane == 0) {
+          int sh = 0;
+          const int hi = hi_word(m);
+          if (hi < kScaleThresholdHi && hi >= (1 << 20)) sh = rescale_shift(hi);
+          cscale[j] = pow2(sh);
+          cexp[j] += sh;
+        }
+      }
+    }
+    __syncthreads();
+    for (int i = tid; i < S * kChrCols; i += blockDim.x) {
+      const int k = i / kChrCols, j = i - k * kChrCols;
+      Xs[k * kChrLD + j] *= cscale[j];
+    }
+    __syncthreads();
+    double acc[kChrMaxRB][kChrCols / 8][2];
+    chr_gemm(md.Vinv, S, K4, Xs, nrb, warp, g, q, acc);
+    __syncthreads();
+    chr_store_acc(Ws, nrb, warp, g, q, acc);
+  }
+  __syncthreads();
+  // T(t): exp(re l) on real eigenvalues, the rotation block on conjugate pairs (ChromosomeSubstitutionModel.cpp:821-850)
+  for (int i = tid; i < S * kChrCols; i += blockDim.x) {
+    const int k = i / kChrCols, j = i - k * kChrCols;
+    const int role = md.role[k];
+    const double l = tl[j];
+    if (role == 0) {
+      Ws[k * kChrLD + j] *= exp(md.re[k] * l);
+    } else if (role == 1) {
+      const double ex = exp(md.re[k] * l);
+      double sn, cs;
+      sincos(md.im[k] * l, &sn, &cs);
+      const double w0 = Ws[k * kChrLD + j], w1 = Ws[(k + 1) * kChrLD + j];
+      Ws[k * kChrLD + j] = ex * (cs * w0 + sn * w1);
+      Ws[(k + 1) * kChrLD + j] = ex * (cs * w1 - sn * w0);
+    }
+  }
+  __syncthreads();
+  {
+    double acc[kChrMaxRB][kChrCols / 8][2];
+    chr_gemm(md.V, S, K4, Ws, nrb, warp, g, q, acc);
+    __syncthreads();
+    chr_store_acc(Xs, nrb, warp, g, q, acc);
+  }
+  __syncthreads();
+  // rescale every term to [0.5, 1) by an exact power of two and store it with its exponent
+  if (warp < kChrCols / 8 * 2) {
+    for (int j = warp * 4; j < warp * 4 + 4; ++j) {
+      double m = 0.0;
+      for (int k = lane; k < S; k += 32) m = fmax(m, fabs(Xs[k * kChrLD + j]));
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+      if (lane == 0) {
+        int sh = 0;
+        const int hi = hi_word(m);
+        if (hi < kScaleThresholdHi && hi >= (1 << 20)) sh = rescale_shift(hi);
+        cscale[j] = pow2(sh);
+        const int n = cnode[j];
+        if (n >= 0) texp_pt[n] = cexp[j] + sh;
+      }
+    }
+  }
+  __syncthreads();
+  // an observed tip's term IS a column of P: the reference's per-entry clamp (ChromosomeSubstitutionModel.cpp:903-916) applies
+  // to it exactly; cscale is 1 there unless the whole column is below 2^-256
+  const bool clamp_col = kind == 0 && (md.flags & 4u);
+  for (int i = tid; i < S * kChrCols; i += blockDim.x) {
+    const int j = i / S, k = i - j * S;     // consecutive threads write one term contiguously
+    const int n = cnode[j];
+    if (n < 0) continue;
+    double v = Xs[k * kChrLD + j];
+    if (clamp_col) v = v < 0.0 ? 1e-20 : (v > 1.0 ? 1.0 : v);
+    term_pt[(size_t)n * S + k] = v * cscale[j];
+  }
+}
+
+// root of every point: CLV_root = product of the root's sons' terms; weighted root frequencies (setWeightedRootFreq,
+// DRNonHomogeneousTreeLikelihood.cpp:927-962: with one site, freq_x = L_x / sum L, 1 / S when all are zero) or the given ones;
+// lnL = log sum_x freq_x CLV_root[x] - E ln 2.
+struct ChrRootParams {
+  int S, nn, root, p0;
+  unsigned flags;   // bit1: weighted root frequencies
+  const int* child_off;
+  const int* children;
+  const double* term;
+  const int* term_exp;
+  const int* skip;             // as in ChrLevelParams
+  const double* rootfreq_in;   // [npts][S]
+  double* rootfreq_used;       // [npts][S]
+  const double* weights;       // [1]
+  double* site_lnl;            // [npts]
+  double* out;                 // [npts][stride]
+  int out_stride;
+};
+__global__ void chr_root_kernel(ChrRootParams p) {
+  extern __shared__ double sm_root2[];   // [S] root CLV
+  __shared__ double red[32];
+  const int pt = p.p0 + blockIdx.x, S = p.S;
+  if (p.skip && p.skip[pt]) return;
+  const double* term_pt = p.term + (size_t)blockIdx.x * p.nn * S;
+  int E = 0;
+  for (int c = p.child_off[p.root]; c < p.child_off[p.root + 1]; ++c) E += p.term_exp[(size_t)blockIdx.x * p.nn + p.children[c]];
+  double tot = 0.0;
+  for (int x = threadIdx.x; x < S; x += blockDim.x) {
+    double v = 1.0;
+    for (int c = p.child_off[p.root]; c < p.child_off[p.root + 1]; ++c) v *= term_pt[(size_t)p.children[c] * S + x];
+    sm_root2[x] = v;
+    tot += v;
+  }
+  tot = block_sum(tot, red);
+  __shared__ double tot_s;
+  if (threadIdx.x == 0) tot_s = tot;
+  __syncthreads();
+  double acc = 0.0;
+  for (int x = threadIdx.x; x < S; x += blockDim.x) {
+    const double f = (p.flags & 2u) ? (tot_s == 0.0 ? 1.0 / S : sm_root2[x] / tot_s) : p.rootfreq_in[(size_t)pt * S + x];
+    p.rootfreq_used[(size_t)pt * S + x] = f;
+    acc += f * sm_root2[x];
+  }
+  acc = block_sum(acc, red);
+  if (threadIdx.x == 0) {
+    double L = acc;
+    if (L < 0) L = 0.0;
+    const double lnl = log(L) - (double)E * kLn2;
+    p.site_lnl[pt] = lnl;
+    p.out[(size_t)pt * p.out_stride] = p.weights[0] * lnl;
+  }
+}
+
+// rows of per-point arrays gathered to / scattered from the compact list of the points the guard sends to the table route
+template <typename T>
+__global__ void gather_rows_kernel(const T* src, T* dst, const int* idx, int row_len) {
+  const int r = blockIdx.x;
+  for (int i = threadIdx.x; i < row_len; i += blockDim.x) dst[(size_t)r * row_len + i] = src[(size_t)idx[r] * row_len + i];
+}
+template <typename T>
+__global__ void scatter_rows_kernel(const T* src, T* dst, const int* idx, int row_len, int copy_len) {
+  const int r = blockIdx.x;
+  for (int i = threadIdx.x; i < copy_len; i += blockDim.x) dst[(size_t)idx[r] * row_len + i] = src[(size_t)r * row_len + i];
+}
+
+// guard of the factored route: entries of the P tables of a few probe branches outside [-tol, 1 + tol], per point
+__global__ void chr_guard_kernel(const double* P, int nprobe, int S, double tol, int* bad /*[npts]*/, int p0) {
+  const int pt = blockIdx.x;
+  const double* Pp = P + (size_t)pt * nprobe * S * S;
+  int b = 0;
+  for (size_t i = threadIdx.x; i < (size_t)nprobe * S * S; i += blockDim.x) {
+    const double v = Pp[i];
+    if (!(v >= -tol && v <= 1.0 + tol)) b = 1;
+  }
+  if (__syncthreads_or(b) && threadIdx.x == 0) bad[p0 + pt] = 1;
+}
+
+}  // namespace bppgpu

@@ -443,7 +443,7 @@ using namespace bppgpu;
 // (C linkage comes from the declarations in include/bppgpu.h)
 
 const char* bppgpu_last_error(void) { return last_error().c_str(); }
-int bppgpu_abi_version(void) { return 1; }
+int bppgpu_abi_version(void) { return 2; }
 int bppgpu_sizeof(int which) {
   switch (which) {
     case 0: return (int)sizeof(bppgpu_model_desc);
@@ -580,7 +580,10 @@ int bppgpu_destroy(bppgpu_engine* e) {
                   e->d_upper_exp, e->d_SR, e->d_rexp, e->d_site_lnl, e->d_partials, e->d_partials2, e->d_out,
                   e->prog.d_ops, e->prog.d_childs, e->gprog.d_ops, e->gprog.d_childs, e->d_sibs, e->d_scratch,
                   e->d_dtiptab, e->d_d2tiptab, e->d_dLc, e->d_fam_mask, e->d_fam_part, e->d_fam_packA, e->d_fam_packS, e->d_fam_packL, e->d_fam_packT, e->d_w4c_stream, e->d_w4c_blocks, e->d_w4c_tip_order, e->d_codesC, e->d_w4_desc, e->d_w4_tip_order, e->d_w4_blocks, e->d_w4_stream, e->d_codesT,
-                  e->d_status, e->d_wr_recs};
+                  e->d_status, e->d_wr_recs, e->d_chr_tile_edges, e->d_chr_tile_kind, e->d_chr_leaf_state, e->d_child_off,
+                  e->d_children, e->d_chr_leaf_vec, e->d_chr_term, e->d_chr_term_exp, e->d_chr_bad, e->d_chr_guardP, e->d_chr_probe_t,
+                  e->d_chr_probe_bm, e->d_models_noclamp, e->d_bad_idx, e->d_bad_brlen, e->d_bad_rootfreq, e->d_bad_rootfreq_used,
+                  e->d_bad_site_lnl, e->d_bad_out, e->d_bad_branch_model};
   for (void* p : ptrs) cudaFree(p);
   for (auto& m : e->models) free_model(m);
   if (e->comm && nccl_api().ok) nccl_api().CommDestroy((ncclComm_t)e->comm);
@@ -925,6 +928,8 @@ static int create_impl(const bppgpu_config* cfg, bppgpu_engine* e) {
     }
     BPP_CUDA(dev_alloc(e, &e->d_code_single, (size_t)e->ncodes));
     BPP_CUDA(cudaMemcpy(e->d_code_single, single.data(), e->ncodes * sizeof(int), cudaMemcpyHostToDevice));
+    e->h_code_single = single;
+    e->h_code_table.assign(cfg->code_table, cfg->code_table + (size_t)e->ncodes * S);
   }
   BPP_CUDA(dev_alloc(e, &e->d_weights, (size_t)N));
   BPP_CUDA(dev_alloc(e, &e->d_rates, (size_t)C));
@@ -956,8 +961,40 @@ static int create_impl(const bppgpu_config* cfg, bppgpu_engine* e) {
     size_t fr = 0, tot = 0;
     if (cudaMemGetInfo(&fr, &tot) == cudaSuccess) budget = std::max(budget, fr / 2);
   }
-  e->pchunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)e->npoints, budget / std::max<size_t>(1, (e->path == PATH_POINTS ? 1 : 3) * per_point)));
-  BPP_CUDA(dev_alloc(e, &e->d_P, (size_t)e->pchunk * nn * C * SS));
+  // one character, one class, many points: the factored route needs no tables (they are allocated on demand, for the points
+  // the guard sends to the table route); KEEP_CLVS asks for the per-node arrays, which only the table route has
+  e->chr_factored = e->path == PATH_POINTS && N == 1 && C == 1 && S <= 8 * kChrWarps * kChrMaxRB && !(cfg->flags & BPPGPU_FLAG_KEEP_CLVS) &&
+                    !(getenv("BPPGPU_POINTS_FACTORED") && atoi(getenv("BPPGPU_POINTS_FACTORED")) == 0);
+  if (e->chr_factored) {
+    e->tables_allocated = false;
+    size_t fr = 0, tot = 0;
+    if (cudaMemGetInfo(&fr, &tot) != cudaSuccess) fr = (size_t)8 << 30;
+    const size_t per_pt = (size_t)nn * S * 8 + (size_t)nn * 4;
+    e->fchunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)e->npoints, (fr / 4) / per_pt));
+    BPP_CUDA(dev_alloc(e, &e->d_chr_term, (size_t)e->fchunk * nn * S));
+    BPP_CUDA(dev_alloc(e, &e->d_chr_term_exp, (size_t)e->fchunk * nn));
+    e->gchunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)e->npoints, ((size_t)1 << 30) / (3 * SS * 8)));
+    BPP_CUDA(dev_alloc(e, &e->d_chr_guardP, (size_t)e->gchunk * 3 * SS));
+    BPP_CUDA(dev_alloc(e, &e->d_chr_bad, (size_t)e->npoints));
+    BPP_CUDA(dev_alloc(e, &e->d_chr_probe_t, (size_t)e->npoints * 3));
+    BPP_CUDA(dev_alloc(e, &e->d_chr_probe_bm, (size_t)e->npoints * 3));
+    BPP_CUDA(dev_alloc(e, &e->d_models_noclamp, (size_t)e->nmodels));
+    BPP_CUDA(dev_alloc(e, &e->d_chr_leaf_state, (size_t)nn));
+    BPP_CUDA(dev_alloc(e, &e->d_chr_leaf_vec, (size_t)nn * S));
+    BPP_CUDA(dev_alloc(e, &e->d_child_off, (size_t)nn + 1));
+    BPP_CUDA(dev_alloc(e, &e->d_children, e->children.size()));
+    BPP_CUDA(cudaMemcpy(e->d_child_off, e->child_off.data(), (nn + 1) * sizeof(int), cudaMemcpyHostToDevice));
+    if (!e->children.empty()) BPP_CUDA(cudaMemcpy(e->d_children, e->children.data(), e->children.size() * sizeof(int), cudaMemcpyHostToDevice));
+    const int maxtiles = nn;   // generous: a tile holds at least one edge
+    BPP_CUDA(dev_alloc(e, &e->d_chr_tile_edges, (size_t)maxtiles * kChrCols));
+    BPP_CUDA(dev_alloc(e, &e->d_chr_tile_kind, (size_t)maxtiles));
+    e->h_codes.assign(e->nl, 0);
+    BPP_CUDA(cudaFuncSetAttribute(chr_level_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chr_level_smem(S)));
+    e->pchunk = 1;
+  } else {
+    e->pchunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)e->npoints, budget / std::max<size_t>(1, (e->path == PATH_POINTS ? 1 : 3) * per_point)));
+    BPP_CUDA(dev_alloc(e, &e->d_P, (size_t)e->pchunk * nn * C * SS));
+  }
   if (e->path == PATH_WALK4 && !e->w4c) {
     BPP_CUDA(dev_alloc(e, &e->d_w4_desc, e->w4_desc.size()));
     BPP_CUDA(cudaMemcpy(e->d_w4_desc, e->w4_desc.data(), e->w4_desc.size() * 8, cudaMemcpyHostToDevice));
@@ -991,7 +1028,7 @@ static int create_impl(const bppgpu_config* cfg, bppgpu_engine* e) {
     BPP_CUDA(dev_alloc(e, &e->d_tiptab, (size_t)e->pchunk * e->nl * C * e->ncodes * S));
 
   const size_t clv = (size_t)N * C * S;
-  if (e->keep) {
+  if (e->keep && e->tables_allocated) {
     const size_t mult = e->path == PATH_POINTS ? (size_t)e->pchunk : 1;
     BPP_CUDA(dev_alloc(e, &e->d_keep, mult * e->ni * clv));
     BPP_CUDA(dev_alloc(e, &e->d_keep_exp, mult * e->ni * N * C));
@@ -1163,6 +1200,10 @@ int bppgpu_set_tip_codes(bppgpu_engine* e, int32_t node, const void* codes) {
                            cudaMemcpyHostToDevice, e->stream));
   BPP_CUDA(cudaStreamSynchronize(e->stream));
   e->have_tip[e->leaf_slot[node]] = 1;
+  if (e->chr_factored) {
+    e->h_codes[(size_t)e->leaf_slot[node]] = e->code_bytes == 1 ? *(const unsigned char*)codes : *(const unsigned short*)codes;
+    e->chr_tiles_dirty = true;
+  }
   e->codesT_dirty = true;
   e->last_point = -1;
   return BPPGPU_OK;
@@ -1176,6 +1217,11 @@ int bppgpu_set_all_tip_codes(bppgpu_engine* e, const void* codes) {
   BPP_CUDA(cudaMemcpyAsync(e->d_codes, codes, bytes, cudaMemcpyHostToDevice, e->stream));
   BPP_CUDA(cudaStreamSynchronize(e->stream));
   std::fill(e->have_tip.begin(), e->have_tip.end(), 1);
+  if (e->chr_factored) {
+    for (int l = 0; l < e->nl; ++l)
+      e->h_codes[(size_t)l] = e->code_bytes == 1 ? ((const unsigned char*)codes)[l] : ((const unsigned short*)codes)[l];
+    e->chr_tiles_dirty = true;
+  }
   e->codesT_dirty = true;
   e->last_point = -1;
   return BPPGPU_OK;
@@ -1828,6 +1874,204 @@ static int enqueue_derivs(bppgpu_engine* e, int point, int pl, unsigned want, cu
   return BPPGPU_OK;
 }
 
+// table route buffers of a factored engine, allocated the first time the guard sends a point there
+static int ensure_tables(bppgpu_engine* e) {
+  if (e->tables_allocated) return BPPGPU_OK;
+  const int nn = e->nn, S = e->S, C = e->C;
+  const size_t SS = (size_t)S * S, per_point = (size_t)nn * C * SS * 8;
+  size_t fr = 0, tot = 0;
+  if (cudaMemGetInfo(&fr, &tot) != cudaSuccess) fr = (size_t)8 << 30;
+  const size_t clv = (size_t)e->N * C * S;
+  e->pchunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)e->npoints, (fr / 2) / (5 * per_point + e->ni * clv * 8)));   // + series scratch
+  BPP_CUDA(dev_alloc(e, &e->d_P, (size_t)e->pchunk * nn * C * SS));
+  BPP_CUDA(dev_alloc(e, &e->d_keep, (size_t)e->pchunk * e->ni * clv));
+  BPP_CUDA(dev_alloc(e, &e->d_keep_exp, (size_t)e->pchunk * e->ni * e->N * C));
+  e->tables_allocated = true;
+  return BPPGPU_OK;
+}
+
+// The factored route of a batched-points engine (chr_factored_kernels.cuh): guard, level kernels, root.  `ranges` receives
+// the runs of consecutive points that must go through the table route instead (guard failures, singular generators).
+static int eval_points_factored(bppgpu_engine* e, cudaStream_t st, bool any_real, bool any_complex,
+                                std::vector<std::pair<int, int>>& ranges) {
+  const int nn = e->nn, S = e->S, npts = e->npoints;
+  const size_t SS = (size_t)S * S;
+  // ---- tiles: sons grouped by the height of their subtree, observed tips apart from dense columns -------------------------
+  if (e->chr_tiles_dirty) {
+    std::vector<int> height(nn, 0), leaf_state(nn, -2);
+    std::vector<double> leaf_vec((size_t)nn * S, 0.0);
+    for (int k = nn - 1; k >= 0; --k) {   // reverse pre-order: sons first
+      const int n = e->preorder[k];
+      for (int c = e->child_off[n]; c < e->child_off[n + 1]; ++c) height[n] = std::max(height[n], height[e->children[c]] + 1);
+      if (e->leaf_slot[n] >= 0) {
+        const int code = e->h_codes[(size_t)e->leaf_slot[n]];
+        leaf_state[n] = e->h_code_single[(size_t)code];
+        if (leaf_state[n] < 0) {
+          leaf_state[n] = -1;
+          std::copy(e->h_code_table.begin() + (size_t)code * S, e->h_code_table.begin() + (size_t)(code + 1) * S, leaf_vec.begin() + (size_t)n * S);
+        }
+      }
+    }
+    const int hmax = height[e->root];
+    std::vector<int> edges, kinds;
+    e->chr_level_tile0.assign(1, 0);
+    for (int h = 0; h < hmax; ++h) {
+      for (int kind = 0; kind < 2; ++kind) {
+        int fill = 0;
+        for (int n = 0; n < nn; ++n) {
+          if (n == e->root || height[n] != h) continue;
+          const int kd = (e->leaf_slot[n] >= 0 && leaf_state[n] >= 0) ? 0 : 1;
+          if (kd != kind) continue;
+          if (fill == 0) { edges.resize(edges.size() + kChrCols, -1); kinds.push_back(kind); }
+          edges[edges.size() - kChrCols + fill] = n;
+          fill = (fill + 1) % kChrCols;
+        }
+      }
+      e->chr_level_tile0.push_back((int)kinds.size());
+    }
+    e->chr_ntiles = (int)kinds.size();
+    e->stats.chr_tiles_tip = (int)std::count(kinds.begin(), kinds.end(), 0);
+    e->stats.chr_tiles_dense = (int)std::count(kinds.begin(), kinds.end(), 1);
+    BPP_CUDA(cudaMemcpyAsync(e->d_chr_tile_edges, edges.data(), edges.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+    BPP_CUDA(cudaMemcpyAsync(e->d_chr_tile_kind, kinds.data(), kinds.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+    BPP_CUDA(cudaMemcpyAsync(e->d_chr_leaf_state, leaf_state.data(), nn * sizeof(int), cudaMemcpyHostToDevice, st));
+    BPP_CUDA(cudaMemcpyAsync(e->d_chr_leaf_vec, leaf_vec.data(), leaf_vec.size() * 8, cudaMemcpyHostToDevice, st));
+    BPP_CUDA(cudaStreamSynchronize(st));   // the host vectors go out of scope
+    e->chr_tiles_dirty = false;
+  }
+  // ---- guard --------------------------------------------------------------------------------------------------------------
+  const int probe_node = e->root == 0 ? 1 : 0;
+  e->chr_bad.assign(npts, 0);
+  static const bool guard_on = !(getenv("BPPGPU_POINTS_GUARD") && atoi(getenv("BPPGPU_POINTS_GUARD")) == 0);
+  static const double guard_tol = getenv("BPPGPU_POINTS_GUARD_TOL") ? atof(getenv("BPPGPU_POINTS_GUARD_TOL")) : kChrGuardTol;   // experiments
+  std::vector<double> probe_t((size_t)npts * 3);
+  std::vector<int> probe_bm((size_t)npts * 3);
+  for (int p = 0; p < npts; ++p) {
+    const int slot = e->h_branch_model[(size_t)p * nn + probe_node];
+    if (!(e->models[slot].flags & BPPGPU_MODEL_NONSINGULAR)) e->chr_bad[p] = 1;
+    double tmin = 1e300, tmax = 0.0;
+    for (int n = 0; n < nn; ++n) {
+      if (n == e->root) continue;
+      const double t = e->h_brlen[(size_t)p * nn + n];
+      tmin = std::min(tmin, t);
+      tmax = std::max(tmax, t);
+    }
+    if (!(tmin > 0)) tmin = tmax * 1e-3;
+    probe_t[(size_t)p * 3] = tmin;
+    probe_t[(size_t)p * 3 + 1] = std::sqrt(tmin * tmax);
+    probe_t[(size_t)p * 3 + 2] = tmax;
+    probe_bm[(size_t)p * 3] = probe_bm[(size_t)p * 3 + 1] = probe_bm[(size_t)p * 3 + 2] = slot;
+  }
+  BPP_CUDA(cudaEventRecord(e->ptring_a[e->ptring_head], st));
+  BPP_CUDA(cudaMemcpyAsync(e->d_chr_bad, e->chr_bad.data(), npts * sizeof(int), cudaMemcpyHostToDevice, st));
+  if (guard_on) {
+    BPP_CUDA(cudaMemcpyAsync(e->d_chr_probe_t, probe_t.data(), probe_t.size() * 8, cudaMemcpyHostToDevice, st));
+    BPP_CUDA(cudaMemcpyAsync(e->d_chr_probe_bm, probe_bm.data(), probe_bm.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+    std::vector<ModelDev> md(e->nmodels);
+    for (int m = 0; m < e->nmodels; ++m) {
+      md[m] = to_dev(e->models[m]);
+      md[m].flags &= ~(unsigned)BPPGPU_MODEL_CLAMP01;   // the guard looks at the entries BEFORE the reference's clamp
+    }
+    BPP_CUDA(cudaMemcpyAsync(e->d_models_noclamp, md.data(), md.size() * sizeof(ModelDev), cudaMemcpyHostToDevice, st));
+    BPP_CUDA(cudaStreamSynchronize(st));
+    for (int g0 = 0; g0 < npts; g0 += e->gchunk) {
+      const int np = std::min(e->gchunk, npts - g0);
+      long long launches = 0;
+      int rc = launch_pt(st, e->d_models_noclamp, false, false, any_real, any_complex, false, e->d_chr_probe_bm + (size_t)g0 * 3,
+                         e->d_chr_probe_t + (size_t)g0 * 3, e->d_rates, S, 1, 3, -1, np, BPPGPU_WANT_P, e->d_chr_guardP, nullptr, nullptr,
+                         nullptr, e->d_status, &launches);
+      if (rc) return rc;
+      chr_guard_kernel<<<np, 256, 0, st>>>(e->d_chr_guardP, 3, S, guard_tol, e->d_chr_bad, g0);
+      e->stats.kernel_launches += launches + 1;
+    }
+    BPP_CUDA(cudaMemcpyAsync(e->chr_bad.data(), e->d_chr_bad, npts * sizeof(int), cudaMemcpyDeviceToHost, st));
+    BPP_CUDA(cudaStreamSynchronize(st));
+  }
+  BPP_CUDA(cudaEventRecord(e->ptring_b[e->ptring_head], st));
+  e->ptring_head = (e->ptring_head + 1) % bppgpu_engine::kRing;
+  e->ptring_n = std::min(e->ptring_n + 1, (int)bppgpu_engine::kRing);
+  // ---- levels + root ------------------------------------------------------------------------------------------------------
+  BPP_CUDA(cudaEventRecord(e->ring_a[e->ring_head], st));
+  const size_t smem = chr_level_smem(S);
+  for (int f0 = 0; f0 < npts; f0 += e->fchunk) {
+    const int np = std::min(e->fchunk, npts - f0);
+    ChrLevelParams lp{};
+    lp.models = e->d_models; lp.branch_model = e->d_branch_model; lp.brlen = e->d_brlen;
+    lp.rate0 = e->h_rates[0];
+    lp.S = S; lp.nn = nn; lp.p0 = f0;
+    lp.tile_edges = e->d_chr_tile_edges; lp.tile_kind = e->d_chr_tile_kind;
+    lp.child_off = e->d_child_off; lp.children = e->d_children;
+    lp.leaf_state = e->d_chr_leaf_state; lp.leaf_vec = e->d_chr_leaf_vec;
+    lp.term = e->d_chr_term; lp.term_exp = e->d_chr_term_exp;
+    lp.skip = e->d_chr_bad;
+    for (size_t l = 0; l + 1 < e->chr_level_tile0.size(); ++l) {
+      const int t0 = e->chr_level_tile0[l], nt = e->chr_level_tile0[l + 1] - t0;
+      if (nt <= 0) continue;
+      lp.tile0 = t0;
+      for (int y0 = 0; y0 < np; y0 += 65535) {   // gridDim.y limit
+        ChrLevelParams q = lp;
+        q.p0 = f0 + y0;
+        q.term = e->d_chr_term + (size_t)y0 * nn * S;
+        q.term_exp = e->d_chr_term_exp + (size_t)y0 * nn;
+        chr_level_kernel<<<dim3((unsigned)nt, (unsigned)std::min(65535, np - y0)), kChrWarps * 32, smem, st>>>(q);
+        e->stats.kernel_launches++;
+      }
+    }
+    ChrRootParams rp{};
+    rp.S = S; rp.nn = nn; rp.root = e->root; rp.p0 = f0;
+    rp.flags = (e->flags & BPPGPU_FLAG_WEIGHTED_ROOT) ? 2u : 0u;
+    rp.child_off = e->d_child_off; rp.children = e->d_children;
+    rp.term = e->d_chr_term; rp.term_exp = e->d_chr_term_exp;
+    rp.skip = e->d_chr_bad;
+    rp.rootfreq_in = e->d_rootfreq; rp.rootfreq_used = e->d_rootfreq_used;
+    rp.weights = e->d_weights; rp.site_lnl = e->d_site_lnl; rp.out = e->d_out; rp.out_stride = 1 + 2 * nn;
+    chr_root_kernel<<<np, 256, S * sizeof(double), st>>>(rp);
+    e->stats.kernel_launches++;
+  }
+  BPP_CUDA(cudaGetLastError());
+  BPP_CUDA(cudaEventRecord(e->ring_b[e->ring_head], st));
+  e->ring_head = (e->ring_head + 1) % bppgpu_engine::kRing;
+  e->ring_n = std::min(e->ring_n + 1, (int)bppgpu_engine::kRing);
+  // ---- the points for the table route, as ONE compact range [0, nbad) over gathered copies of their inputs ---------------------
+  ranges.clear();
+  std::vector<int> bad_idx;
+  for (int p = 0; p < npts; ++p)
+    if (e->chr_bad[p]) bad_idx.push_back(p);
+  e->chr_table_points = (long long)bad_idx.size();
+  e->chr_factored_points = npts - e->chr_table_points;
+  e->stats.factored_points = e->chr_factored_points;
+  e->stats.table_points = e->chr_table_points;
+  if (!bad_idx.empty()) {
+    const int nb = (int)bad_idx.size();
+    if (nb > e->nbad_cap) {
+      BPP_CUDA(cudaStreamSynchronize(st));
+      for (void* q : {(void*)e->d_bad_idx, (void*)e->d_bad_brlen, (void*)e->d_bad_rootfreq, (void*)e->d_bad_rootfreq_used, (void*)e->d_bad_site_lnl,
+                      (void*)e->d_bad_out, (void*)e->d_bad_branch_model})
+        cudaFree(q);
+      e->nbad_cap = std::min(npts, std::max(nb, 2 * e->nbad_cap));
+      const size_t c = (size_t)e->nbad_cap;
+      BPP_CUDA(dev_alloc(e, &e->d_bad_idx, c));
+      BPP_CUDA(dev_alloc(e, &e->d_bad_brlen, c * nn));
+      BPP_CUDA(dev_alloc(e, &e->d_bad_branch_model, c * nn));
+      BPP_CUDA(dev_alloc(e, &e->d_bad_rootfreq, c * S));
+      BPP_CUDA(dev_alloc(e, &e->d_bad_rootfreq_used, c * S));
+      BPP_CUDA(dev_alloc(e, &e->d_bad_site_lnl, c * std::max<long long>(1, e->N)));
+      BPP_CUDA(dev_alloc(e, &e->d_bad_out, c * (1 + 2 * nn)));
+    }
+    BPP_CUDA(cudaMemcpyAsync(e->d_bad_idx, bad_idx.data(), nb * sizeof(int), cudaMemcpyHostToDevice, st));
+    BPP_CUDA(cudaStreamSynchronize(st));   // bad_idx goes out of scope
+    gather_rows_kernel<double><<<nb, 128, 0, st>>>(e->d_brlen, e->d_bad_brlen, e->d_bad_idx, nn);
+    gather_rows_kernel<int><<<nb, 128, 0, st>>>(e->d_branch_model, e->d_bad_branch_model, e->d_bad_idx, nn);
+    gather_rows_kernel<double><<<nb, 128, 0, st>>>(e->d_rootfreq, e->d_bad_rootfreq, e->d_bad_idx, S);
+    gather_rows_kernel<double><<<nb, 128, 0, st>>>(e->d_rootfreq, e->d_bad_rootfreq_used, e->d_bad_idx, S);
+    e->stats.kernel_launches += 4;
+    ranges.push_back({0, nb});
+  }
+  e->stats.clv_updates += e->chr_factored_points * e->ni * (long long)S;
+  (void)SS;
+  return BPPGPU_OK;
+}
+
 static int eval_impl(bppgpu_engine* e, unsigned want, cudaStream_t st, bool timed) {
   e->last_point = -1;   // nothing is resident until this evaluation has been enqueued completely
   e->last_want = 0;
@@ -1870,12 +2114,34 @@ static int eval_impl(bppgpu_engine* e, unsigned want, cudaStream_t st, bool time
   unsigned pt_want = BPPGPU_WANT_P | ((want & BPPGPU_EVAL_D1) ? BPPGPU_WANT_DP : 0) | ((want & BPPGPU_EVAL_D2) ? BPPGPU_WANT_D2P : 0);
   if (timed) BPP_CUDA(cudaEventRecord(e->ev0, st));
   BPP_CUDA(cudaMemcpyAsync(e->d_rootfreq_used, e->d_rootfreq, (size_t)e->npoints * S * 8, cudaMemcpyDeviceToDevice, st));
-  for (int p0 = 0; p0 < e->npoints; p0 += e->pchunk) {
-    const int np = std::min(e->pchunk, e->npoints - p0);
+  std::vector<std::pair<int, int>> ranges(1, {0, e->npoints});
+  if (e->chr_factored) {
+    rc = eval_points_factored(e, st, any_real, any_complex, ranges);
+    if (rc) return rc;
+    if (!ranges.empty()) {
+      rc = ensure_tables(e);
+      if (rc) return rc;
+      rc = ensure_scratch(e, any_series, false);
+      if (rc) return rc;
+    }
+    e->last_point = e->npoints - 1;
+  }
+  // per-point arrays the table route reads and writes: the engine's own, or the compact copies of a factored engine
+  const bool compact = e->chr_factored;
+  const int* pa_bm = compact ? e->d_bad_branch_model : e->d_branch_model;
+  const double* pa_brlen = compact ? e->d_bad_brlen : e->d_brlen;
+  const double* pa_rootfreq = compact ? e->d_bad_rootfreq : e->d_rootfreq;
+  double* pa_rootfreq_used = compact ? e->d_bad_rootfreq_used : e->d_rootfreq_used;
+  double* pa_site_lnl = compact ? e->d_bad_site_lnl : e->d_site_lnl;
+  double* pa_out = compact ? e->d_bad_out : e->d_out;
+  for (const auto& range : ranges)
+  for (int p0 = range.first; p0 < range.second; p0 += e->pchunk) {
+    const int np = std::min(e->pchunk, range.second - p0);
+    const bool first_chunk = p0 == ranges.front().first, last_chunk = p0 + np >= ranges.back().second;
     long long launches = 0;
     BPP_CUDA(cudaEventRecord(e->ptring_a[e->ptring_head], st));
-    rc = launch_pt(st, e->d_models, any_series, any_chrd, any_real, any_complex, e->homogeneous_points, e->d_branch_model + (size_t)p0 * nn,
-                   e->d_brlen + (size_t)p0 * nn, e->d_rates, S, C, nn, e->root, np, pt_want, e->d_P, e->d_dP, e->d_d2P,
+    rc = launch_pt(st, e->d_models, any_series, any_chrd, any_real, any_complex, e->homogeneous_points, pa_bm + (size_t)p0 * nn,
+                   pa_brlen + (size_t)p0 * nn, e->d_rates, S, C, nn, e->root, np, pt_want, e->d_P, e->d_dP, e->d_d2P,
                    e->d_scratch, e->d_status, &launches);
     if (rc) return rc;
     BPP_CUDA(cudaEventRecord(e->ptring_b[e->ptring_head], st));
@@ -1955,7 +2221,7 @@ static int eval_impl(bppgpu_engine* e, unsigned want, cudaStream_t st, bool time
     }
     BPP_CUDA(cudaGetLastError());
     if (e->path == PATH_POINTS) {
-      if (p0 == 0) BPP_CUDA(cudaEventRecord(e->ring_a[e->ring_head], st));
+      if (first_chunk) BPP_CUDA(cudaEventRecord(e->ring_a[e->ring_head], st));
       const long long rows = e->N * C;
       for (const Op& op : e->gprog.ops) {
         PointsNodeParams pp{};
@@ -1978,16 +2244,16 @@ static int eval_impl(bppgpu_engine* e, unsigned want, cudaStream_t st, bool time
       pr.flags = ((e->flags & BPPGPU_FLAG_R_SEMANTICS) ? 1u : 0u) | ((e->flags & BPPGPU_FLAG_WEIGHTED_ROOT) ? 2u : 0u);
       pr.N = e->N;
       pr.keep = e->d_keep; pr.keep_exp = e->d_keep_exp; pr.probs = e->d_probs; pr.weights = e->d_weights;
-      pr.rootfreq_in = e->d_rootfreq + (size_t)p0 * S;
-      pr.rootfreq_used = e->d_rootfreq_used + (size_t)p0 * S;
-      pr.site_lnl = e->d_site_lnl + (size_t)p0 * e->N;
-      pr.out = e->d_out + (size_t)p0 * (1 + 2 * nn);
+      pr.rootfreq_in = pa_rootfreq + (size_t)p0 * S;
+      pr.rootfreq_used = pa_rootfreq_used + (size_t)p0 * S;
+      pr.site_lnl = pa_site_lnl + (size_t)p0 * e->N;
+      pr.out = pa_out + (size_t)p0 * (1 + 2 * nn);
       pr.out_stride = 1 + 2 * nn;
       points_root_kernel<<<np, 256, S * sizeof(double), st>>>(pr);
       e->stats.kernel_launches++;
       BPP_CUDA(cudaGetLastError());
       e->stats.clv_updates += (long long)np * e->ni * rows * S;
-      if (p0 + np >= e->npoints) {
+      if (last_chunk) {
         BPP_CUDA(cudaEventRecord(e->ring_b[e->ring_head], st));
         e->ring_head = (e->ring_head + 1) % bppgpu_engine::kRing;
         e->ring_n = std::min(e->ring_n + 1, (int)bppgpu_engine::kRing);
@@ -2013,6 +2279,14 @@ static int eval_impl(bppgpu_engine* e, unsigned want, cudaStream_t st, bool time
     }
   }
   (void)SS;
+  if (compact && !ranges.empty()) {   // results of the table-route points back to their places
+    const int nb = ranges.front().second;
+    scatter_rows_kernel<double><<<nb, 128, 0, st>>>(e->d_bad_out, e->d_out, e->d_bad_idx, 1 + 2 * nn, 1);
+    scatter_rows_kernel<double><<<nb, 128, 0, st>>>(e->d_bad_site_lnl, e->d_site_lnl, e->d_bad_idx, (int)e->N, (int)e->N);
+    scatter_rows_kernel<double><<<nb, 128, 0, st>>>(e->d_bad_rootfreq_used, e->d_rootfreq_used, e->d_bad_idx, S, S);
+    e->stats.kernel_launches += 3;
+    BPP_CUDA(cudaGetLastError());
+  }
   if (e->comm && e->comm_nranks > 1)   // pattern shards: every rank ends up with the whole alignment's lnL, d1, d2
     BPP_NCCL(nccl_api().AllReduce(e->d_out, e->d_out, (size_t)e->npoints * (1 + 2 * nn), ncclDouble, ncclSum, (ncclComm_t)e->comm, st));
   if (timed) BPP_CUDA(cudaEventRecord(e->ev1, st));
@@ -2089,6 +2363,7 @@ int bppgpu_get_clv(bppgpu_engine* e, int32_t point, int32_t node, int32_t which,
   if (node < 0 || node >= e->nn || !clv || point < 0 || point >= e->npoints) BPP_FAIL(BPPGPU_E_INVALID, "bad node / point or null out");
   const size_t clvn = (size_t)e->N * e->C * e->S;
   size_t pt_off = 0;  // slab offset of the point inside the resident chunk (batched-points path)
+  if (e->chr_factored) BPP_FAIL(BPPGPU_E_STATE, "the factored batched-points route keeps no per-node arrays: create the engine with BPPGPU_FLAG_KEEP_CLVS");
   if (e->path == PATH_POINTS) {
     const int chunk0 = ((e->npoints - 1) / e->pchunk) * e->pchunk;
     if (e->last_point < 0 || point < chunk0 || point >= e->npoints)

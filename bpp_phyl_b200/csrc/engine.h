@@ -12,6 +12,7 @@
 #include "dmma_node_kernels.cuh"
 #include "generic_kernels.cuh"
 #include "points_kernels.cuh"
+#include "chr_factored_kernels.cuh"
 #include "pt_dmma_kernels.cuh"
 #include "pt_kernels.cuh"
 #include "walk_kernels.cuh"
@@ -166,6 +167,33 @@ struct bppgpu_engine {
   cudaEvent_t ptring_a[kRing] = {}, ptring_b[kRing] = {};
   int ptring_n = 0, ptring_head = 0;
   size_t bytes_resident = 0;
+  // batched points without P tables (chr_factored_kernels.cuh): one character, one rate class, many parameter points
+  bool chr_factored = false;
+  bool tables_allocated = true;          // d_P / d_keep of the table route (allocated on demand for factored engines)
+  std::vector<unsigned short> h_codes;   // [nl] the single pattern's tip codes (host copy)
+  std::vector<int> h_code_single;        // [ncodes]
+  std::vector<double> h_code_table;      // [ncodes][S]
+  std::vector<int> chr_level_tile0;      // first tile of every level (+ end)
+  int chr_ntiles = 0;
+  bool chr_tiles_dirty = true;
+  int *d_chr_tile_edges = nullptr, *d_chr_tile_kind = nullptr, *d_chr_leaf_state = nullptr, *d_child_off = nullptr, *d_children = nullptr;
+  double* d_chr_leaf_vec = nullptr;      // [nn][S]
+  double* d_chr_term = nullptr;          // [fchunk][nn][S]
+  int* d_chr_term_exp = nullptr;         // [fchunk][nn]
+  int fchunk = 0;                        // points per pass of the factored route
+  int* d_chr_bad = nullptr;              // [npoints] guard verdicts
+  double* d_chr_guardP = nullptr;        // [gchunk][3][S][S]
+  int gchunk = 0;
+  double* d_chr_probe_t = nullptr;       // [npoints][3]
+  int* d_chr_probe_bm = nullptr;         // [npoints][3]
+  bppgpu::ModelDev* d_models_noclamp = nullptr;
+  // compact copies of the per-point inputs / outputs of the points on the table route ("bad" points), [nbad_cap][...]
+  int nbad_cap = 0;
+  int* d_bad_idx = nullptr;
+  double *d_bad_brlen = nullptr, *d_bad_rootfreq = nullptr, *d_bad_rootfreq_used = nullptr, *d_bad_site_lnl = nullptr, *d_bad_out = nullptr;
+  int* d_bad_branch_model = nullptr;
+  std::vector<int> chr_bad;              // host copy of the last guard
+  long long chr_factored_points = 0, chr_table_points = 0;   // of the last evaluation
   // multi-GPU (pattern shards, one engine per GPU): NCCL communicator of the job, set by bppgpu_comm_init
   void* comm = nullptr;           // ncclComm_t
   int comm_rank = 0, comm_nranks = 1;

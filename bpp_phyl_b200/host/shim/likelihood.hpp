@@ -395,7 +395,8 @@ class AbstractHomogeneousTreeLikelihood {
     cfg.child_offsets = off.data(); cfg.children = children.data(); cfg.n_points = nPoints_;
     cfg.n_models = modelSet_ ? (int32_t)modelSet_->getNumberOfModels() : (nModelSlots_ > 0 ? nModelSlots_ : nPoints_);
     cfg.n_codes = (int32_t)chars.size(); cfg.code_bytes = chars.size() > 256 ? 2 : 1; cfg.code_table = table.data();
-    cfg.device = device_; cfg.flags = engineFlags_ | BPPGPU_FLAG_KEEP_CLVS;
+    // a batch of parameter points on one character keeps no per-node arrays: the engine may then apply P(t) in factored form
+    cfg.device = device_; cfg.flags = engineFlags_ | ((nPoints_ > 1 && nPatterns_ == 1 && C == 1) ? 0u : (unsigned)BPPGPU_FLAG_KEEP_CLVS);
     if (engine_) { bppgpu_destroy(engine_); engine_ = nullptr; }
     check(bppgpu_create(&cfg, &engine_), "TreeLikelihood::setData");
     const std::vector<Node*> leaves = tree_->getLeaves();

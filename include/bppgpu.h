@@ -268,6 +268,11 @@ typedef struct bppgpu_stats {
   int64_t hbm_bytes_resident;
   int32_t stack_slots;
   int32_t path;            /* which kernel family ran             */
+  int64_t factored_points; /* batched-points engines, last eval: points evaluated
+                              without P tables (chr_level_kernel) ...             */
+  int64_t table_points;    /* ... and points the guard sent to the table route    */
+  int32_t chr_tiles_tip;   /* column tiles per point: observed-tip tiles (one GEMM) */
+  int32_t chr_tiles_dense; /* ... and dense tiles (two GEMMs)                     */
 } bppgpu_stats;
 int bppgpu_get_stats(bppgpu_engine* e, bppgpu_stats* out);
 

@@ -523,8 +523,55 @@ def test_chromosome_weighted_root_batched_points(S, npts, ntaxa):
     for k, m in enumerate(pts):
         res = cases.oracle_eval(c, model=m, weighted_root=True)
         assert abs(lnl[k] - res.lnl) <= REL * abs(res.lnl)
-        np.testing.assert_allclose(e.root_freqs(k), res.root_freqs, rtol=1e-10, atol=1e-14)
+        # entries near 1e-14 differ between the routes: the table route clamps P < 0 to 1e-20 entry by entry, the factored one cannot
+        np.testing.assert_allclose(e.root_freqs(k), res.root_freqs, rtol=1e-9, atol=1e-12)
     e.close()
+
+
+@pytest.mark.parametrize("S,ntaxa", [(30, 25), (52, 40), (200, 60)])
+def test_factored_points_route_against_the_table_route_and_the_oracle(monkeypatch, S, ntaxa):
+    """chr_level_kernel (P(t) applied as V T(t) V^-1 x on the FP64 tensor cores, no tables) against the table route
+    (BPPGPU_POINTS_FACTORED=0) and the oracle: real and complex spectra, S not a multiple of 8, an unknown count ('X': dense leaf
+    column), the guard sending an ill-conditioned and a singular point to the table route inside the same batch."""
+    capi = _capi()
+    rng = np.random.default_rng(S)
+    r, p = rm.constant_rate()
+    pts = []
+    while len(pts) < 5:
+        m = rm.chromosome(1, S, gain=rng.uniform(0.2, 2), loss=rng.uniform(0.2, 2), dupl=rng.uniform(0.05, 1), demi=rng.uniform(0.05, 1))
+        if m.nonsingular and np.linalg.cond(m.V) < 1e7:
+            pts.append(m)
+    pts.append(rm.chromosome(1, S, gain=0.5, loss=0.0, dupl=0.0))                   # singular generator: Taylor route
+    assert not pts[-1].nonsingular
+    c = cases.make_case(ntaxa, 1, pts[0], r, p, seed=77, rooted=True, mean_brlen=0.1, compress=False)
+    unknown = S                                                                       # the all-ones row of cases' code table
+    some_leaf = sorted(c.codes_by_leaf)[3]
+    c.codes_by_leaf[some_leaf] = np.array([unknown], c.code_dtype)
+    off, ch = c.flat.csr()
+    out = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("BPPGPU_POINTS_FACTORED", mode)
+        e = capi.Engine(S, 1, 1, off, ch, c.flat.root, c.table, n_points=len(pts), n_models=len(pts), flags=capi.FLAG_WEIGHTED_ROOT,
+                        code_bytes=np.dtype(c.code_dtype).itemsize)
+        for lid, codes in c.codes_by_leaf.items():
+            e.set_tip_codes(lid, codes)
+        e.set_pattern_weights(c.weights)
+        e.set_rates(r, p)
+        holders = [cases.to_model_desc(m) for m in pts]
+        for k, h in enumerate(holders):
+            e.set_model(k, h)
+            e.set_branch_lengths(k, c.flat.brlen * (1.0 + 0.1 * k))
+        lnl, _, _ = e.eval()
+        st = e.stats()
+        out[mode] = (lnl.copy(), np.array([e.root_freqs(k) for k in range(len(pts))]), st["factored_points"], st["table_points"])
+        e.close()
+    np.testing.assert_allclose(out["1"][0], out["0"][0], rtol=1e-9)
+    np.testing.assert_allclose(out["1"][1], out["0"][1], rtol=1e-8, atol=1e-12)
+    assert out["1"][2] >= 1 and out["1"][3] >= 1 and out["1"][2] + out["1"][3] == len(pts)   # both routes inside one batch
+    assert out["0"][2] == 0
+    for k, m in enumerate(pts):
+        res = cases.oracle_eval(c, model=m, weighted_root=True, brlen=c.flat.brlen * (1.0 + 0.1 * k))
+        assert abs(out["1"][0][k] - res.lnl) <= REL * abs(res.lnl), k
 
 
 def test_batched_points_path_general_shapes():
