@@ -347,8 +347,8 @@ def run_points(a, w, rank, world, local, K, W, metric, config):
     d2h = npts * 8
 
     def step_e2e():
+        e.set_models(0, mds)                       # every point's eigensystem, host -> device (pinned staging)
         for k in range(npts):
-            e.set_model(k, mds[k])
             e.set_branch_lengths(k, tree.brlen)
         return e.eval(1)[0]
 
@@ -401,10 +401,20 @@ def run_points(a, w, rank, world, local, K, W, metric, config):
                 "e2e": {"value": upd_step / (e2e_ms * 1e-3) if e2e_ms > 0 else None, "unit": "CLV updates/s",
                         "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms,
                         "logl_evals_per_s": npts_total / (e2e_ms * 1e-3) if e2e_ms > 0 else None,
-                        "call": "bppgpu_set_model + bppgpu_set_branch_lengths per point, one bppgpu_eval (host buffers)"},
+                        "call": "bppgpu_set_models (all points) + bppgpu_set_branch_lengths per point, one bppgpu_eval (host buffers); the host "
+                                "eigendecompositions are NOT inside (see host_eigen)"},
                 "gpu_launches": int(st["kernel_launches"]) * K, "launches_per_step": int(st["kernel_launches"]),
                 "roofline": roofline, "clocks": clocks, "fp64_peaks_measured": {"dfma_tflops": dfma_now, "dmma_m8n8k4_tflops": dmma_now},
                 "hbm_resident_bytes": int(st["hbm_bytes_resident"])}
+        # the host side of a model update: ChromosomeSubstitutionModel::updateMatrices / updateEigenMatrices through the C++
+        # shim (bppgpu_host_model), one thread, a few points -- the reference pays this (plus 30 matrix powers) per point and step
+        t0 = time.perf_counter()
+        nh = min(4, npts)
+        for es in pts[:nh]:
+            g_, l_, du_, de_ = es["params"]
+            capi.host_model("Chromosome", 1, S, g_, l_, du_, de_)
+        line["host_eigen"] = {"shim_ms_per_model_one_thread": 1e3 * (time.perf_counter() - t0) / nh, "models_timed": nh,
+                              "note": "outside every timed region; the bench's eigensystems come from numpy (LAPACK) before the run"}
         if world == 1 and not a.no_cpu:
             # the reference's CPU algorithm on a few points, one point per host thread
             from concurrent.futures import ThreadPoolExecutor

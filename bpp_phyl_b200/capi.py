@@ -343,6 +343,11 @@ class Engine:
     def set_model(self, slot, model: _ModelHolder):
         _check(lib().bppgpu_set_model(self._h, C.c_int32(slot), C.byref(model.desc)))
 
+    def set_models(self, first_slot, models):
+        """bppgpu_set_models: a run of slots in one call (pinned staging, one transfer per model)."""
+        arr = (ModelDesc * len(models))(*[m.desc for m in models])
+        _check(lib().bppgpu_set_models(self._h, C.c_int32(first_slot), C.c_int32(len(models)), arr))
+
     def set_branch_models(self, point, slots):
         a = np.ascontiguousarray(slots, np.int32)
         _check(lib().bppgpu_set_branch_models(self._h, C.c_int32(point), _ptr(a, C.c_int32)))

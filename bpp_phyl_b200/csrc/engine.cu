@@ -233,140 +233,127 @@ static int check_device(int device) {
 
 // ---- model upload -------------------------------------------------------------------
 static void free_model(DevModel& m) {
-  if (m.Vp != m.V) { cudaFree(m.Vp); cudaFree(m.Vinvp); cudaFree(m.rep); }
-  cudaFree(m.imp);
-  cudaFree(m.V); cudaFree(m.Vinv); cudaFree(m.re); cudaFree(m.im); cudaFree(m.Q); cudaFree(m.Q2); cudaFree(m.role);
+  cudaFree(m.slab);
+  cudaFree(m.pslab);
   m = DevModel{};
 }
 
-static int upload_model(DevModel& dm, const bppgpu_model_desc* m, int S) {
+// bytes of the host-side image of a model slab: [V | Vinv | Q | Q2 | re | im | role(int, padded to 8 bytes each)]
+static size_t model_slab_doubles(int S) { return (size_t)4 * S * S + 3 * (size_t)S; }
+
+// Fills `img` (host, model_slab_doubles(S) doubles) and the padded / permuted image `pimg` (resized; empty when V .. re serve the
+// tensor-core kernel as they are) from the descriptor; returns flags through dm.  No CUDA call: set_models stages many images.
+static int build_model_image(DevModel& dm, const bppgpu_model_desc* m, int S, bool need_q2, double* img, std::vector<double>& pimg) {
   const size_t SS = (size_t)S * S;
-  // fast path (an optimiser re-sending a model of the same kind every step): same arrays present, real spectrum both
-  // times -> overwrite in place, no allocation
-  {
-    const bool eigen_new = (m->flags & BPPGPU_MODEL_NONSINGULAR) != 0;
-    bool cplx_new = false;
-    if (eigen_new && m->eigen_im)
-      for (int k = 0; k < S; ++k) cplx_new |= m->eigen_im[k] != 0.0;
-    const int Sp0 = (S + 7) & ~7;
-    if (dm.set && dm.S == S && eigen_new && dm.V && !cplx_new && !dm.has_complex && (Sp0 == S || S < 32) &&
-        ((m->generator != nullptr) == (dm.Q != nullptr)) && m->right_eigen && m->left_eigen && m->eigen_re) {
-      dm.flags = m->flags;
-      dm.rate = m->rate;
-      dm.eps = m->taylor_epsilon > 0 ? m->taylor_epsilon : 1e-4;
-      BPP_CUDA(cudaMemcpy(dm.V, m->right_eigen, SS * 8, cudaMemcpyHostToDevice));
-      BPP_CUDA(cudaMemcpy(dm.Vinv, m->left_eigen, SS * 8, cudaMemcpyHostToDevice));
-      BPP_CUDA(cudaMemcpy(dm.re, m->eigen_re, S * 8, cudaMemcpyHostToDevice));
-      if (m->generator) {
-        BPP_CUDA(cudaMemcpy(dm.Q, m->generator, SS * 8, cudaMemcpyHostToDevice));
-        if (m->flags & (BPPGPU_MODEL_CHR_DERIV | 0u) || !(m->flags & BPPGPU_MODEL_NONSINGULAR)) {
-          std::vector<double> q2(SS, 0.0);
-          double l1 = 0.0;
-          for (int i = 0; i < S; ++i)
-            for (int k = 0; k < S; ++k) {
-              const double a = m->generator[(size_t)i * S + k];
-              l1 += std::fabs(a);
-              if (a == 0.0) continue;
-              for (int j = 0; j < S; ++j) q2[(size_t)i * S + j] += a * m->generator[(size_t)k * S + j];
-            }
-          dm.q_l1 = l1;
-          BPP_CUDA(cudaMemcpy(dm.Q2, q2.data(), SS * 8, cudaMemcpyHostToDevice));
-        }
-      }
-      return BPPGPU_OK;
-    }
-  }
-  free_model(dm);
   const bool eigen = (m->flags & BPPGPU_MODEL_NONSINGULAR) != 0;
   if (eigen && (!m->right_eigen || !m->left_eigen || !m->eigen_re))
     BPP_FAIL(BPPGPU_E_INVALID, "model flagged NONSINGULAR needs right_eigen, left_eigen and eigen_re");
   if (!eigen && !m->generator) BPP_FAIL(BPPGPU_E_INVALID, "singular model needs its generator");
-  if ((m->flags & BPPGPU_MODEL_CHR_DERIV) && !m->generator)
-    BPP_FAIL(BPPGPU_E_INVALID, "BPPGPU_MODEL_CHR_DERIV needs the generator");
+  if ((m->flags & BPPGPU_MODEL_CHR_DERIV) && !m->generator) BPP_FAIL(BPPGPU_E_INVALID, "BPPGPU_MODEL_CHR_DERIV needs the generator");
   dm.flags = m->flags;
   dm.rate = m->rate;
   dm.eps = m->taylor_epsilon > 0 ? m->taylor_epsilon : 1e-4;
+  dm.has_complex = 0;
+  dm.has_Q = m->generator != nullptr;
+  double *iV = img, *iVinv = img + SS, *iQ = img + 2 * SS, *iQ2 = img + 3 * SS, *ire = img + 4 * SS, *iim = ire + S;
+  int* irole = reinterpret_cast<int*>(iim + S);
+  std::fill(img, img + model_slab_doubles(S), 0.0);
+  pimg.clear();
   if (eigen) {
-    BPP_CUDA(cudaMalloc(&dm.V, SS * 8));
-    BPP_CUDA(cudaMalloc(&dm.Vinv, SS * 8));
-    BPP_CUDA(cudaMalloc(&dm.re, S * 8));
-    BPP_CUDA(cudaMalloc(&dm.im, S * 8));
-    BPP_CUDA(cudaMalloc(&dm.role, S * 4));
-    BPP_CUDA(cudaMemcpy(dm.V, m->right_eigen, SS * 8, cudaMemcpyHostToDevice));
-    BPP_CUDA(cudaMemcpy(dm.Vinv, m->left_eigen, SS * 8, cudaMemcpyHostToDevice));
-    BPP_CUDA(cudaMemcpy(dm.re, m->eigen_re, S * 8, cudaMemcpyHostToDevice));
-    std::vector<double> im(S, 0.0);
-    std::vector<int> role(S, 0);
+    memcpy(iV, m->right_eigen, SS * 8);
+    memcpy(iVinv, m->left_eigen, SS * 8);
+    memcpy(ire, m->eigen_re, S * 8);
     if (m->eigen_im) {
-      for (int k = 0; k < S; ++k) im[k] = m->eigen_im[k];
+      memcpy(iim, m->eigen_im, S * 8);
       // conjugate pairs are adjacent, the +im member first (JAMA EigenValue convention,
       // AbstractSubstitutionModel.cpp:438-468 walks them the same way)
       for (int k = 0; k < S; ++k) {
-        if (im[k] != 0.0 && role[k] == 0) {
-          if (k + 1 >= S || im[k + 1] == 0.0) BPP_FAIL(BPPGPU_E_INVALID, "unpaired complex eigenvalue at index %d", k);
-          role[k] = 1;
-          role[k + 1] = 2;
+        if (iim[k] != 0.0 && irole[k] == 0) {
+          if (k + 1 >= S || iim[k + 1] == 0.0) BPP_FAIL(BPPGPU_E_INVALID, "unpaired complex eigenvalue at index %d", k);
+          irole[k] = 1;
+          irole[k + 1] = 2;
           dm.has_complex = 1;
         }
       }
     }
-    BPP_CUDA(cudaMemcpy(dm.im, im.data(), S * 8, cudaMemcpyHostToDevice));
-    BPP_CUDA(cudaMemcpy(dm.role, role.data(), S * 4, cudaMemcpyHostToDevice));
     const int Sp = (S + 7) & ~7;
-    if (Sp == S && !dm.has_complex) {
-      dm.Vp = dm.V; dm.Vinvp = dm.Vinv; dm.rep = dm.re;
-    } else if (S >= 32) {
+    if (S >= 32 && (Sp != S || dm.has_complex)) {
       // copies for the DMMA kernel: zero-padded to Sp, eigen-columns permuted so that every conjugate pair starts at an
-      // even index (pairs first, then the real eigenvalues)
+      // even index (pairs first, then the real eigenvalues): [Vp | Vinvp | rep | imp]
       std::vector<int> order;
       for (int k = 0; k < S; ++k)
-        if (role[k] == 1) { order.push_back(k); order.push_back(k + 1); }
+        if (irole[k] == 1) { order.push_back(k); order.push_back(k + 1); }
       for (int k = 0; k < S; ++k)
-        if (role[k] == 0) order.push_back(k);
-      std::vector<double> vp((size_t)Sp * Sp, 0.0), vip((size_t)Sp * Sp, 0.0), rp(Sp, 0.0), ip(Sp, 0.0);
+        if (irole[k] == 0) order.push_back(k);
+      pimg.assign((size_t)2 * Sp * Sp + 2 * Sp, 0.0);
+      double *vp = pimg.data(), *vip = vp + (size_t)Sp * Sp, *rp = vip + (size_t)Sp * Sp, *ip = rp + Sp;
       for (int j = 0; j < S; ++j) {
         const int k = order[j];
         rp[j] = m->eigen_re[k];
-        ip[j] = im[k];
+        ip[j] = iim[k];
         for (int i = 0; i < S; ++i) {
           vp[(size_t)i * Sp + j] = m->right_eigen[(size_t)i * S + k];
           vip[(size_t)j * Sp + i] = m->left_eigen[(size_t)k * S + i];
         }
       }
-      BPP_CUDA(cudaMalloc(&dm.Vp, vp.size() * 8));
-      BPP_CUDA(cudaMalloc(&dm.Vinvp, vip.size() * 8));
-      BPP_CUDA(cudaMalloc(&dm.rep, Sp * 8));
-      BPP_CUDA(cudaMemcpy(dm.Vp, vp.data(), vp.size() * 8, cudaMemcpyHostToDevice));
-      BPP_CUDA(cudaMemcpy(dm.Vinvp, vip.data(), vip.size() * 8, cudaMemcpyHostToDevice));
-      BPP_CUDA(cudaMemcpy(dm.rep, rp.data(), Sp * 8, cudaMemcpyHostToDevice));
-      BPP_CUDA(cudaMalloc(&dm.imp, Sp * 8));
-      BPP_CUDA(cudaMemcpy(dm.imp, ip.data(), Sp * 8, cudaMemcpyHostToDevice));
     }
   }
   if (m->generator) {
-    BPP_CUDA(cudaMalloc(&dm.Q, SS * 8));
-    BPP_CUDA(cudaMalloc(&dm.Q2, SS * 8));
-    BPP_CUDA(cudaMemcpy(dm.Q, m->generator, SS * 8, cudaMemcpyHostToDevice));
-    std::vector<double> q2(SS, 0.0);
+    memcpy(iQ, m->generator, SS * 8);
     double l1 = 0.0;
-    for (int i = 0; i < S; ++i)
-      for (int k = 0; k < S; ++k) {
-        const double a = m->generator[(size_t)i * S + k];
-        l1 += std::fabs(a);
-        if (a == 0.0) continue;
-        for (int j = 0; j < S; ++j) q2[(size_t)i * S + j] += a * m->generator[(size_t)k * S + j];
-      }
+    for (size_t i = 0; i < SS; ++i) l1 += std::fabs(m->generator[i]);
     dm.q_l1 = l1;
-    BPP_CUDA(cudaMemcpy(dm.Q2, q2.data(), SS * 8, cudaMemcpyHostToDevice));
+    if (need_q2 && ((m->flags & BPPGPU_MODEL_CHR_DERIV) || !eigen))   // Q.Q for the Chromosome second derivative (Q^2.P)
+      for (int i = 0; i < S; ++i)
+        for (int k = 0; k < S; ++k) {
+          const double a = m->generator[(size_t)i * S + k];
+          if (a == 0.0) continue;
+          for (int j = 0; j < S; ++j) iQ2[(size_t)i * S + j] += a * m->generator[(size_t)k * S + j];
+        }
   }
+  return BPPGPU_OK;
+}
+
+// device storage of a model slot (first upload, or a change of shape) and the pointers into it
+static int ensure_model_storage(DevModel& dm, int S, bool padded) {
+  const size_t SS = (size_t)S * S;
+  if (!dm.slab || dm.S != S) {   // (only the storage: the scalar fields were just filled by build_model_image)
+    cudaFree(dm.slab);
+    cudaFree(dm.pslab);
+    dm.slab = dm.pslab = nullptr;
+    BPP_CUDA(cudaMalloc(&dm.slab, model_slab_doubles(S) * 8));
+    dm.S = S;
+  }
+  dm.V = dm.slab; dm.Vinv = dm.slab + SS; dm.Q = dm.slab + 2 * SS; dm.Q2 = dm.slab + 3 * SS;
+  dm.re = dm.slab + 4 * SS; dm.im = dm.re + S;
+  dm.role = reinterpret_cast<int*>(dm.im + S);
+  const int Sp = (S + 7) & ~7;
+  if (padded) {
+    if (!dm.pslab) BPP_CUDA(cudaMalloc(&dm.pslab, ((size_t)2 * Sp * Sp + 2 * Sp) * 8));
+    dm.Vp = dm.pslab; dm.Vinvp = dm.pslab + (size_t)Sp * Sp; dm.rep = dm.Vinvp + (size_t)Sp * Sp; dm.imp = dm.rep + Sp;
+  } else if (Sp == S) {
+    dm.Vp = dm.V; dm.Vinvp = dm.Vinv; dm.rep = dm.re; dm.imp = dm.im;
+  } else {
+    dm.Vp = dm.Vinvp = dm.rep = dm.imp = nullptr;   // S < 32 and not a multiple of 8: the CUDA-core P(t) kernel reads V .. re
+  }
+  return BPPGPU_OK;
+}
+
+static int upload_model(DevModel& dm, const bppgpu_model_desc* m, int S, bool need_q2 = true) {
+  std::vector<double> img(model_slab_doubles(S)), pimg;
+  int rc = build_model_image(dm, m, S, need_q2, img.data(), pimg);
+  if (rc) return rc;
+  rc = ensure_model_storage(dm, S, !pimg.empty());
+  if (rc) return rc;
+  BPP_CUDA(cudaMemcpy(dm.slab, img.data(), img.size() * 8, cudaMemcpyHostToDevice));
+  if (!pimg.empty()) BPP_CUDA(cudaMemcpy(dm.pslab, pimg.data(), pimg.size() * 8, cudaMemcpyHostToDevice));
   dm.set = true;
-  dm.S = S;
   return BPPGPU_OK;
 }
 
 static ModelDev to_dev(const DevModel& m) {
   ModelDev d{};
-  d.V = m.V; d.Vinv = m.Vinv; d.re = m.re; d.im = m.im; d.role = m.role; d.Q = m.Q; d.Q2 = m.Q2;
+  d.V = m.V; d.Vinv = m.Vinv; d.re = m.re; d.im = m.im; d.role = m.role; d.Q = m.has_Q ? m.Q : nullptr; d.Q2 = m.has_Q ? m.Q2 : nullptr;
   d.Vp = m.Vp; d.Vinvp = m.Vinvp; d.rep = m.rep; d.imp = m.imp;
   d.rate = m.rate; d.eps = m.eps; d.q_l1 = m.q_l1; d.flags = m.flags; d.has_complex = m.has_complex;
   return d;
@@ -586,6 +573,9 @@ int bppgpu_destroy(bppgpu_engine* e) {
                   e->d_bad_site_lnl, e->d_bad_out, e->d_bad_branch_model};
   for (void* p : ptrs) cudaFree(p);
   for (auto& m : e->models) free_model(m);
+  if (e->h_stage) cudaFreeHost(e->h_stage);
+  if (e->stage_ev[0]) cudaEventDestroy(e->stage_ev[0]);
+  if (e->stage_ev[1]) cudaEventDestroy(e->stage_ev[1]);
   if (e->comm && nccl_api().ok) nccl_api().CommDestroy((ncclComm_t)e->comm);
   e->comm = nullptr;
   if (e->eval_done) cudaEventDestroy(e->eval_done);
@@ -1263,8 +1253,40 @@ int bppgpu_set_model(bppgpu_engine* e, int32_t slot, const bppgpu_model_desc* m)
   if (slot < 0 || slot >= e->nmodels) BPP_FAIL(BPPGPU_E_INVALID, "model slot %d out of range", slot);
   if (m->n_states != e->S) BPP_FAIL(BPPGPU_E_INVALID, "model has %d states, engine %d", m->n_states, e->S);
   BPP_CUDA(cudaStreamSynchronize(e->stream));
-  int rc = upload_model(e->models[slot], m, e->S);
+  int rc = upload_model(e->models[slot], m, e->S, e->path != PATH_POINTS);
   if (rc) return rc;
+  e->models_dirty = true;
+  e->last_point = -1;
+  return BPPGPU_OK;
+}
+
+int bppgpu_set_models(bppgpu_engine* e, int32_t first_slot, int32_t n, const bppgpu_model_desc* descs) {
+  ENGINE_SYNC(e);
+  if (!descs || n < 0 || first_slot < 0 || first_slot + n > e->nmodels) BPP_FAIL(BPPGPU_E_INVALID, "bad slot range or null descriptors");
+  const int S = e->S;
+  const size_t img_doubles = model_slab_doubles(S);
+  // two pinned staging images: model k is packed on the host while model k-1 travels
+  if (!e->h_stage) {
+    BPP_CUDA(cudaMallocHost(&e->h_stage, 2 * img_doubles * 8));
+    BPP_CUDA(cudaEventCreateWithFlags(&e->stage_ev[0], cudaEventDisableTiming));
+    BPP_CUDA(cudaEventCreateWithFlags(&e->stage_ev[1], cudaEventDisableTiming));
+  }
+  std::vector<double> pimg;
+  for (int k = 0; k < n; ++k) {
+    if (descs[k].n_states != S) BPP_FAIL(BPPGPU_E_INVALID, "model %d has %d states, engine %d", k, descs[k].n_states, S);
+    DevModel& dm = e->models[first_slot + k];
+    double* img = e->h_stage + (size_t)(k & 1) * img_doubles;
+    if (k >= 2) BPP_CUDA(cudaEventSynchronize(e->stage_ev[k & 1]));   // the copy that last used this image has left
+    int rc = build_model_image(dm, &descs[k], S, e->path != PATH_POINTS, img, pimg);
+    if (rc) return rc;
+    rc = ensure_model_storage(dm, S, !pimg.empty());
+    if (rc) return rc;
+    BPP_CUDA(cudaMemcpyAsync(dm.slab, img, img_doubles * 8, cudaMemcpyHostToDevice, e->stream));
+    BPP_CUDA(cudaEventRecord(e->stage_ev[k & 1], e->stream));
+    if (!pimg.empty()) BPP_CUDA(cudaMemcpy(dm.pslab, pimg.data(), pimg.size() * 8, cudaMemcpyHostToDevice));   // pageable: synchronous
+    dm.set = true;
+  }
+  BPP_CUDA(cudaStreamSynchronize(e->stream));
   e->models_dirty = true;
   e->last_point = -1;
   return BPPGPU_OK;

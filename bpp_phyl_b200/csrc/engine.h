@@ -23,8 +23,13 @@ namespace bppgpu {
 enum PathKind { PATH_NONE = 0, PATH_WALK4 = 1, PATH_WALKS = 2, PATH_GENERIC = 3, PATH_DMMA = 4, PATH_POINTS = 5 };
 
 struct DevModel {
+  // one device slab per model slot, allocated at the first upload and overwritten by later ones (an optimiser re-sends a model
+  // of the same shape at every step): [V | Vinv | Q | Q2 | re | im | role];  V .. role point into it
+  double* slab = nullptr;
   double *V = nullptr, *Vinv = nullptr, *re = nullptr, *im = nullptr, *Q = nullptr, *Q2 = nullptr;
-  double *Vp = nullptr, *Vinvp = nullptr, *rep = nullptr, *imp = nullptr;  // zero-padded to a multiple of 8 (own storage only if S % 8)
+  double *Vp = nullptr, *Vinvp = nullptr, *rep = nullptr, *imp = nullptr;  // what the tensor-core P(t) kernel reads: V .. itself, or
+  double* pslab = nullptr;                                                 // the padded / pair-permuted copies in `pslab` (S % 8, complex)
+  bool has_Q = false;
   int* role = nullptr;
   double rate = 1.0, eps = 1e-4;
   unsigned flags = 0;
@@ -198,6 +203,8 @@ struct bppgpu_engine {
   void* comm = nullptr;           // ncclComm_t
   int comm_rank = 0, comm_nranks = 1;
   double* d_wr_recs = nullptr;    // [nranks][S + 1] weighted-root records (exponent, S sums), all-gathered
+  double* h_stage = nullptr;        // pinned staging of bppgpu_set_models (two model images)
+  cudaEvent_t stage_ev[2] = {nullptr, nullptr};
   cudaEvent_t eval_done = nullptr;  // recorded at the end of every evaluation on the evaluation's stream
   cudaStream_t last_stream = nullptr;
 };

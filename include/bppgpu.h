@@ -174,6 +174,9 @@ int bppgpu_set_pattern_weights(bppgpu_engine* e, const uint32_t* w);
 int bppgpu_set_rates(bppgpu_engine* e, const double* rates, const double* probs);
 /* model slot (eigensystem copied to the device) */
 int bppgpu_set_model(bppgpu_engine* e, int32_t slot, const bppgpu_model_desc* m);
+/* many slots at once (what an optimiser over a batch of parameter points sends every step): each model is packed into a
+ * pinned staging image and copied asynchronously as ONE contiguous transfer, instead of several pageable copies          */
+int bppgpu_set_models(bppgpu_engine* e, int32_t first_slot, int32_t n, const bppgpu_model_desc* descs);
 /* per point: model slot of the branch above each node (default: slot 0, or slot
  * `point` when n_models == n_points)                                           */
 int bppgpu_set_branch_models(bppgpu_engine* e, int32_t point, const int32_t* slot_of_node);
