@@ -50,6 +50,26 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+# stdout must carry exactly ONE JSON line.  Native libraries write banners to file descriptor 1 whatever Python does (NCCL's
+# "NCCL version ..." from the communicator the engine creates): keep a private copy of the real stdout for the JSON line and
+# point descriptor 1 at stderr for everything else.
+_JSON_OUT = None
+
+
+def _claim_stdout():
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    _claim_stdout()
+    _JSON_OUT.write(json.dumps(line) + "\n")
+    _JSON_OUT.flush()
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -435,7 +455,7 @@ def run_points(a, w, rank, world, local, K, W, metric, config):
             line["cpu_baseline"] = {"value": tree.n_internal * threads * S / dt, "unit": "CLV updates/s", "cores": threads, "kind": "port",
                                     "sample": "%d of %d points, full tree, one point per thread, %.1f s" % (threads, npts_total, dt),
                                     "logl_evals_per_s": threads / dt, "rel_diff_vs_gpu": rel}
-        print(json.dumps(line), flush=True)
+        emit(line)
         log("[rank 0] JSON line printed")
     e.close()
     if world > 1:
@@ -461,6 +481,7 @@ def main():
     ap.add_argument("--no-weak", action="store_true", help="N > 1: skip the weak-scaling job timed after the strong one")
     ap.add_argument("--profile", action="store_true", help="1 warm-up + 1 timed step, no e2e / CPU legs (for ncu only)")
     a = ap.parse_args()
+    _claim_stdout()
     w = dict(WORKLOADS[a.workload])
     if a.patterns:
         w["patterns"] = a.patterns
@@ -515,14 +536,14 @@ def main():
         one = tree.n_internal * (n // threads) * w["C"] * w["S"] / r1["seconds"]
         sample = "%d of %d patterns per step (full tree, tips simulated under the model like the native arm's), %d host threads as " \
                  "independent pattern shards" % (n, w["patterns"], threads)
-        print(json.dumps({"impl": "reference", "metric": metric, "value": val, "unit": "CLV updates/s", "n_gpus": a.gpus,
+        emit({"impl": "reference", "metric": metric, "value": val, "unit": "CLV updates/s", "n_gpus": a.gpus,
                           "steps": K, "warmup": a.warmup, "ms_per_step": 1e3 * dt / K, "higher_is_better": True,
                           "scaling": a.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                           "config": config,
                           "cpu_baseline": {"value": val, "unit": "CLV updates/s", "cores": threads, "kind": "port", "sample": sample,
                                            "one_thread": {"value": one, "cores": 1,
                                                           "sample": "%d patterns, %.2f s" % (n // threads, r1["seconds"])}},
-                          "e2e": {"value": val, "unit": "CLV updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+                          "e2e": {"value": val, "unit": "CLV updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
         return 0
 
     # ---------------- native arm ----------------
@@ -748,7 +769,7 @@ def main():
             line["cpu_baseline"] = cb
             line["parity"] = parity
             log("cpu leg %.1fs" % (time.time() - t0))
-        print(json.dumps(line), flush=True)
+        emit(line)
         log("[rank 0] JSON line printed")
     e.close()
     if world > 1:
