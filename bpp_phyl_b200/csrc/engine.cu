@@ -566,7 +566,7 @@ int bppgpu_destroy(bppgpu_engine* e) {
                   e->d_d2P, e->d_tiptab, e->d_keep, e->d_keep_exp, e->d_gstack, e->d_gstack_exp, e->d_upper,
                   e->d_upper_exp, e->d_SR, e->d_rexp, e->d_site_lnl, e->d_partials, e->d_partials2, e->d_out,
                   e->prog.d_ops, e->prog.d_childs, e->gprog.d_ops, e->gprog.d_childs, e->d_sibs, e->d_scratch,
-                  e->d_dtiptab, e->d_d2tiptab, e->d_dLc, e->d_fam_mask, e->d_fam_part, e->d_fam_packA, e->d_fam_packS, e->d_fam_packL, e->d_fam_packT, e->d_w4c_stream, e->d_w4c_blocks, e->d_w4c_tip_order, e->d_codesC, e->d_w4_desc, e->d_w4_tip_order, e->d_w4_blocks, e->d_w4_stream, e->d_codesT,
+                  e->d_dtiptab, e->d_d2tiptab, e->d_dLc, e->d_fam_mask, e->d_fam_part, e->d_fam_packA, e->d_fam_packS, e->d_fam_packL, e->d_fam_packT, e->d_w4c_stream, e->d_w4c_blocks, e->d_w4c_tip_order, e->d_codesC, e->d_w4c_counter, e->d_w4_desc, e->d_w4_tip_order, e->d_w4_blocks, e->d_w4_stream, e->d_codesT,
                   e->d_status, e->d_wr_recs, e->d_chr_tile_edges, e->d_chr_tile_kind, e->d_chr_leaf_state, e->d_child_off,
                   e->d_children, e->d_chr_leaf_vec, e->d_chr_term, e->d_chr_term_exp, e->d_chr_bad, e->d_chr_guardP, e->d_chr_probe_t,
                   e->d_chr_probe_bm, e->d_models_noclamp, e->d_bad_idx, e->d_bad_brlen, e->d_bad_rootfreq, e->d_bad_rootfreq_used,
@@ -720,7 +720,7 @@ static int create_impl(const bppgpu_config* cfg, bppgpu_engine* e) {
     // program (descriptor words + chunk records) in the kernel-parameter block
     build_program(e, e->prog4c, false, true);
     const int blk_int = C * 128, blk_tip = C * e->ncodes * 32;
-    int max_op = 0;
+    int max_op = 0, max_tips_op = 0;
     bool ok = e->prog4c.nslots <= 63;
     for (const Op& op : e->prog4c.ops) {
       int b = 0, nt = 0;
@@ -730,10 +730,15 @@ static int create_impl(const bppgpu_config* cfg, bppgpu_engine* e) {
         nt += tip;
       }
       max_op = std::max(max_op, b);
-      if (op.nchild > 6 || nt > kW4cMaxTipsPerChunk) ok = false;
+      max_tips_op = std::max(max_tips_op, nt);
+      if (op.nchild > 6) ok = false;
     }
-    int CH = 8192;
+    // chunk geometry: bytes of tables and tip-code rows per ring stage (tuning knobs; a stage must hold the largest op)
+    int CH = getenv("BPPGPU_WALK4_CH") ? std::max(1024, atoi(getenv("BPPGPU_WALK4_CH")) & ~127) : 8192;
     while (CH < max_op) CH *= 2;
+    e->w4c_max_tips = getenv("BPPGPU_WALK4_MAXTIPS") ? std::max(1, std::min(31, atoi(getenv("BPPGPU_WALK4_MAXTIPS")))) : kW4cMaxTipsPerChunk;
+    e->w4c_max_tips = std::max(e->w4c_max_tips, max_tips_op);
+    if (e->w4c_max_tips > 31) ok = false;
     // launch plan.  Patterns per thread PT = 4 / 2 / 1 run 2 / 3 / 4 CTAs (of NW warps, 32 PT NW / C patterns) per SM; measured
     // on the 1024-taxon tree (ms per evaluation): 10.4 / 11.3 / 15.2 at 1M patterns, 1.47 / 1.56 / 1.98 at 125k -- PT = 4 wins at
     // every size that fills the GPU, so the default is ONE segment at the widest PT that has enough CTAs.  A launch is a
@@ -750,14 +755,14 @@ static int create_impl(const bppgpu_config* cfg, bppgpu_engine* e) {
       const int v = atoi(env);
       if (v >= 1 && v <= 4) forced_pt = v;
     }
-    auto fits = [&](int pt) { return walk4c_smem_bytes(CH, e->prog4c.nslots, C, pt, e->w4c_nw) <= 200 * 1024; };
+    auto fits = [&](int pt) { return walk4c_smem_bytes(CH, e->prog4c.nslots, C, pt, e->w4c_nw, e->w4c_max_tips) <= 200 * 1024; };
     if (!fits(1)) ok = false;
     if (ok) {
       const int G = e->w4c_nw / C;
       auto ppc = [&](int pt) { return (long long)G * 32 * pt; };
       auto ctas_per_sm = [&](int pt) {
-        const size_t smem = walk4c_smem_bytes(CH, e->prog4c.nslots, C, pt, e->w4c_nw) + 1024;
-        const int by_regs = e->w4c_nw == 8 ? (pt <= 2 ? 2 : 1) : (pt <= 1 ? 4 : pt <= 3 ? 3 : 2);
+        const size_t smem = walk4c_smem_bytes(CH, e->prog4c.nslots, C, pt, e->w4c_nw, e->w4c_max_tips) + 1024;
+        const int by_regs = e->w4c_nw == 8 ? (pt <= 2 ? 2 : 1) : (pt <= 1 ? 4 : pt <= 3 ? 3 : 2);   // walk4c_min_ctas + registers
         return std::max(1, std::min<int>(by_regs, (int)(227 * 1024 / smem)));
       };
       const double wave_ms[5] = {0, 0.287, 0.315, 0.36, 0.386};   // relative cost of one wave (only ratios matter)
@@ -774,7 +779,7 @@ static int create_impl(const bppgpu_config* cfg, bppgpu_engine* e) {
         int pt = forced_pt;
         while (pt > 1 && !fits(pt)) --pt;
         add_seg(pt, 0, N);
-      } else if (N > 0 && !(getenv("BPPGPU_WALK4_PLAN") && !strcmp(getenv("BPPGPU_WALK4_PLAN"), "split"))) {
+      } else if (N > 0 && !(getenv("BPPGPU_WALK4_PLAN") && !strncmp(getenv("BPPGPU_WALK4_PLAN"), "split", 5))) {
         int big = 4;
         while (big > 1 && (!fits(big) || N < (long long)g_sm_count * ctas_per_sm(big) * ppc(big))) big >>= 1;   // at least one wave
         add_seg(big, 0, N);
@@ -793,7 +798,13 @@ static int create_impl(const bppgpu_config* cfg, bppgpu_engine* e) {
             const double t = k * wave_ms[big] + (rem > 0 ? waves(rem, pt) * wave_ms[pt] : 0.0);
             if (t < best - 1e-12) { best = t; best_k = k; best_pt = pt; }
           }
-        if (best_pt == big) add_seg(big, 0, N);
+        if (const char* pl = getenv("BPPGPU_WALK4_PLAN"))   // "split:<pt>[:<waves below the maximum>]" forces the remainder's PT (experiments)
+          if (strlen(pl) > 6 && pl[5] == ':') {
+            best_pt = std::max(1, std::min(big, atoi(pl + 6)));
+            best_k = kmax;
+            if (const char* c2 = strchr(pl + 6, ':')) best_k = std::max<long long>(0, kmax - atoi(c2 + 1));
+          }
+        if (best_pt == big && best_k == kmax) add_seg(big, 0, N);
         else { add_seg(big, 0, best_k * per_wave); add_seg(best_pt, best_k * per_wave, N); }
       }
       e->w4c_pt = e->w4c_segs.empty() ? 1 : e->w4c_segs[0].pt;
@@ -817,7 +828,7 @@ static int create_impl(const bppgpu_config* cfg, bppgpu_engine* e) {
           b += tip ? blk_tip : blk_int;
           nt += tip;
         }
-        if (nops_in == 31 || used + (size_t)b > (size_t)CH || ntips_in + nt > kW4cMaxTipsPerChunk) close_chunk();
+        if (nops_in == 31 || used + (size_t)b > (size_t)CH || ntips_in + nt > e->w4c_max_tips) close_chunk();
         auto kind4c = [](int k) { return k == CHILD_TIP ? W4C_TIP : k == CHILD_SLOT ? W4C_SLOT : k == CHILD_RSLOT ? W4C_RSL : W4C_REG; };
         int shape = W4C_GENERIC;
         int order[8] = {0, 1, 2, 3, 4, 5, 6, 7};   // order in which the handler consumes the children's table blocks
@@ -1013,6 +1024,8 @@ static int create_impl(const bppgpu_config* cfg, bppgpu_engine* e) {
       parts += sg.grid;
     }
     BPP_CUDA(dev_alloc(e, &e->d_codesC, codes_bytes + 128));
+    BPP_CUDA(dev_alloc(e, &e->d_w4c_counter, 1));
+    BPP_CUDA(cudaMemset(e->d_w4c_counter, 0, sizeof(unsigned)));
   }
   if ((e->path != PATH_WALK4 || e->keep) && e->path != PATH_POINTS)
     BPP_CUDA(dev_alloc(e, &e->d_tiptab, (size_t)e->pchunk * e->nl * C * e->ncodes * S));
@@ -1094,7 +1107,7 @@ static int create_impl(const bppgpu_config* cfg, bppgpu_engine* e) {
 
   if (e->w4c) {
     for (int pt = 1; pt <= 4; ++pt) {   // opt in to the dynamic shared memory of every instantiation a plan may use
-      const size_t smem = walk4c_smem_bytes(e->w4c_CH, e->prog4c.nslots, C, pt, e->w4c_nw);
+      const size_t smem = walk4c_smem_bytes(e->w4c_CH, e->prog4c.nslots, C, pt, e->w4c_nw, e->w4c_max_tips);
       if (smem > 200 * 1024) continue;
       int rc4 = walk4c_dispatch(e, pt, nullptr, 0, smem, nullptr, true);
       if (rc4) return rc4;
@@ -1324,6 +1337,7 @@ int bppgpu_set_root_freqs(bppgpu_engine* e, int32_t point, const double* pi) {
   BPP_CUDA(cudaMemcpyAsync(e->d_rootfreq + (size_t)point * e->S, pi, e->S * 8, cudaMemcpyHostToDevice, e->stream));
   BPP_CUDA(cudaStreamSynchronize(e->stream));
   e->have_rootfreq[point] = 1;
+  e->rootfreq_used_stale = true;
   e->last_point = -1;
   return BPPGPU_OK;
 }
@@ -1513,6 +1527,7 @@ static int enqueue_prune(bppgpu_engine* e, int point, int pl, cudaStream_t st) {
     wp.nslots = e->prog4c.nslots;
     wp.ncodes = e->ncodes;
     wp.ntips = (int)e->w4c_tip_order.size();
+    wp.max_tips = e->w4c_max_tips;
     wp.flags = rflag;
     wp.rootfreq = rootfreq;
     wp.probs = e->d_probs;
@@ -1521,12 +1536,16 @@ static int enqueue_prune(bppgpu_engine* e, int point, int pl, cudaStream_t st) {
     wp.rexp = e->d_rexp;
     wp.site_lnl = site_lnl;
     wp.partials = e->d_partials;
+    wp.parts_total = 0;
+    for (const auto& sg : e->w4c_segs) wp.parts_total += sg.grid;
+    wp.done_counter = e->d_w4c_counter;
+    wp.lnl_out = out;
     for (const auto& sg : e->w4c_segs) {
       wp.codesC = e->d_codesC + sg.codes_off;
       wp.pat0 = sg.pat0;
       wp.pat_end = sg.pat_end;
       wp.part0 = sg.part0;
-      int rc4 = walk4c_dispatch(e, sg.pt, &wp, sg.grid, walk4c_smem_bytes(e->w4c_CH, e->prog4c.nslots, C, sg.pt, e->w4c_nw), st, false);
+      int rc4 = walk4c_dispatch(e, sg.pt, &wp, sg.grid, walk4c_smem_bytes(e->w4c_CH, e->prog4c.nslots, C, sg.pt, e->w4c_nw, e->w4c_max_tips), st, false);
       if (rc4) return rc4;
       nparts += sg.grid;
       e->stats.kernel_launches++;
@@ -1713,8 +1732,10 @@ static int enqueue_prune(bppgpu_engine* e, int point, int pl, cudaStream_t st) {
     e->stats.kernel_launches++;
     nparts = grid_p;
   }
-  finalize_sum_kernel<<<1, 256, 0, st>>>(e->d_partials, nparts, out);
-  e->stats.kernel_launches++;
+  if (!e->w4c) {   // (the chunk-streamed walk adds its partials up itself)
+    finalize_sum_kernel<<<1, 256, 0, st>>>(e->d_partials, nparts, out);
+    e->stats.kernel_launches++;
+  }
   BPP_CUDA(cudaGetLastError());
   long long upd = 0;
   for (const Op& op : e->prog.ops) (void)op, upd += N * C * S;
@@ -2094,7 +2115,7 @@ static int eval_points_factored(bppgpu_engine* e, cudaStream_t st, bool any_real
   return BPPGPU_OK;
 }
 
-static int eval_impl(bppgpu_engine* e, unsigned want, cudaStream_t st, bool timed) {
+static int eval_impl(bppgpu_engine* e, unsigned want, cudaStream_t st, bool timed, double* dev_out = nullptr) {
   e->last_point = -1;   // nothing is resident until this evaluation has been enqueued completely
   e->last_want = 0;
   int rc = check_ready(e);
@@ -2107,7 +2128,7 @@ static int eval_impl(bppgpu_engine* e, unsigned want, cudaStream_t st, bool time
     BPP_FAIL(BPPGPU_E_INVALID, "branch derivatives are not available on the batched-points path (n_points > 1)");
   // an evaluation enqueued on another stream (bppgpu_eval_device) must have finished with the engine's buffers
   if (e->eval_done && e->last_stream && e->last_stream != st) BPP_CUDA(cudaStreamWaitEvent(st, e->eval_done, 0));
-  BPP_CUDA(cudaMemsetAsync(e->d_status, 0, sizeof(int), st));
+  e->status_armed = false;
   rc = ensure_deriv_buffers(e, want);
   if (rc) return rc;
   bool any_series = false, any_chrd = false, any_real = false, any_complex = false;
@@ -2129,13 +2150,20 @@ static int eval_impl(bppgpu_engine* e, unsigned want, cudaStream_t st, bool time
   }
   rc = ensure_scratch(e, any_series, any_chrd && derivs);
   if (rc) return rc;
+  if (any_series || any_chrd) {   // only the series / Chromosome kernels ever raise the status word
+    BPP_CUDA(cudaMemsetAsync(e->d_status, 0, sizeof(int), st));
+    e->status_armed = true;
+  }
   e->stats.kernel_launches = 0;
   e->stats.clv_updates = 0;
   const int S = e->S, C = e->C, nn = e->nn;
   const size_t SS = (size_t)S * S;
   unsigned pt_want = BPPGPU_WANT_P | ((want & BPPGPU_EVAL_D1) ? BPPGPU_WANT_DP : 0) | ((want & BPPGPU_EVAL_D2) ? BPPGPU_WANT_D2P : 0);
   if (timed) BPP_CUDA(cudaEventRecord(e->ev0, st));
-  BPP_CUDA(cudaMemcpyAsync(e->d_rootfreq_used, e->d_rootfreq, (size_t)e->npoints * S * 8, cudaMemcpyDeviceToDevice, st));
+  if (e->rootfreq_used_stale || (e->flags & BPPGPU_FLAG_WEIGHTED_ROOT)) {   // the copy in use differs from the input only with weighted roots
+    BPP_CUDA(cudaMemcpyAsync(e->d_rootfreq_used, e->d_rootfreq, (size_t)e->npoints * S * 8, cudaMemcpyDeviceToDevice, st));
+    e->rootfreq_used_stale = false;
+  }
   std::vector<std::pair<int, int>> ranges(1, {0, e->npoints});
   if (e->chr_factored) {
     rc = eval_points_factored(e, st, any_real, any_complex, ranges);
@@ -2161,7 +2189,13 @@ static int eval_impl(bppgpu_engine* e, unsigned want, cudaStream_t st, bool time
     const int np = std::min(e->pchunk, range.second - p0);
     const bool first_chunk = p0 == ranges.front().first, last_chunk = p0 + np >= ranges.back().second;
     long long launches = 0;
+    // DNA walk, real spectra, plain models: P(t) is built inside the stream-packing launch (pt_pack4c_kernel)
+    bool clamp_or_chr = false;
+    for (int m = 0; m < e->nmodels; ++m)
+      if (e->models[m].set && (e->models[m].flags & (BPPGPU_MODEL_CLAMP01 | BPPGPU_MODEL_CHR_DERIV))) clamp_or_chr = true;
+    const bool fused_pt = e->w4c && S == 4 && !any_series && !any_complex && !clamp_or_chr && pt_want == BPPGPU_WANT_P;
     BPP_CUDA(cudaEventRecord(e->ptring_a[e->ptring_head], st));
+    if (!fused_pt)
     rc = launch_pt(st, e->d_models, any_series, any_chrd, any_real, any_complex, e->homogeneous_points, pa_bm + (size_t)p0 * nn,
                    pa_brlen + (size_t)p0 * nn, e->d_rates, S, C, nn, e->root, np, pt_want, e->d_P, e->d_dP, e->d_d2P,
                    e->d_scratch, e->d_status, &launches);
@@ -2180,10 +2214,22 @@ static int eval_impl(bppgpu_engine* e, unsigned want, cudaStream_t st, bool time
         }
         e->codesT_dirty = false;
       }
-      for (int pl = 0; pl < np; ++pl)
-        pack_stream4c_kernel<<<(unsigned)e->w4c_blocks.size(), 64, 0, st>>>(
-            e->d_w4c_blocks, e->d_P + (size_t)pl * nn * C * SS, e->d_code_table, C, e->ncodes,
-            e->d_w4c_stream + (size_t)pl * e->w4c_stream_bytes);
+      for (int pl = 0; pl < np; ++pl) {
+        if (fused_pt) {
+          PtPack4cParams pk{};
+          pk.blocks = e->d_w4c_blocks; pk.models = e->d_models;
+          pk.branch_model = pa_bm + (size_t)(p0 + pl) * nn;
+          pk.brlen = pa_brlen + (size_t)(p0 + pl) * nn;
+          pk.rates = e->d_rates; pk.code_table = e->d_code_table; pk.C = C; pk.ncodes = e->ncodes;
+          pk.P = e->d_P + (size_t)pl * nn * C * SS;
+          pk.stream = e->d_w4c_stream + (size_t)pl * e->w4c_stream_bytes;
+          pt_pack4c_kernel<<<(unsigned)e->w4c_blocks.size(), 64, 0, st>>>(pk);
+        } else {
+          pack_stream4c_kernel<<<(unsigned)e->w4c_blocks.size(), 64, 0, st>>>(
+              e->d_w4c_blocks, e->d_P + (size_t)pl * nn * C * SS, e->d_code_table, C, e->ncodes,
+              e->d_w4c_stream + (size_t)pl * e->w4c_stream_bytes);
+        }
+      }
       e->stats.kernel_launches += np;
     } else if (e->path == PATH_WALK4) {
       if (e->codesT_dirty && e->N > 0) {
@@ -2309,8 +2355,14 @@ static int eval_impl(bppgpu_engine* e, unsigned want, cudaStream_t st, bool time
     e->stats.kernel_launches += 3;
     BPP_CUDA(cudaGetLastError());
   }
-  if (e->comm && e->comm_nranks > 1)   // pattern shards: every rank ends up with the whole alignment's lnL, d1, d2
-    BPP_NCCL(nccl_api().AllReduce(e->d_out, e->d_out, (size_t)e->npoints * (1 + 2 * nn), ncclDouble, ncclSum, (ncclComm_t)e->comm, st));
+  const size_t row = (size_t)(1 + 2 * nn);
+  // what the caller can read: one point and no derivatives -> the first element only (an 8-byte message, not 16 nn + 8 bytes)
+  const size_t live = (e->npoints == 1 && !derivs) ? 1 : (size_t)e->npoints * row;
+  if (e->comm && e->comm_nranks > 1) {   // pattern shards: every rank ends up with the whole alignment's lnL, d1, d2 -- straight
+    BPP_NCCL(nccl_api().AllReduce(e->d_out, dev_out ? dev_out : e->d_out, live, ncclDouble, ncclSum, (ncclComm_t)e->comm, st));   // into the caller's buffer
+  } else if (dev_out) {
+    BPP_CUDA(cudaMemcpyAsync(dev_out, e->d_out, live * 8, cudaMemcpyDeviceToDevice, st));
+  }
   if (timed) BPP_CUDA(cudaEventRecord(e->ev1, st));
   BPP_CUDA(cudaEventRecord(e->eval_done, st));
   e->last_stream = st;
@@ -2334,7 +2386,7 @@ int bppgpu_eval(bppgpu_engine* e, unsigned want, double* lnl, double* d1, double
   std::vector<double> h((size_t)e->npoints * (1 + 2 * nn));
   BPP_CUDA(cudaMemcpy(h.data(), e->d_out, h.size() * 8, cudaMemcpyDeviceToHost));
   int status = 0;
-  BPP_CUDA(cudaMemcpy(&status, e->d_status, 4, cudaMemcpyDeviceToHost));
+  if (e->status_armed) BPP_CUDA(cudaMemcpy(&status, e->d_status, 4, cudaMemcpyDeviceToHost));
   if (status) BPP_FAIL(BPPGPU_E_NUMERIC, "ChromosomeSubstitutionModel: Taylor series did not reach convergence!");
   for (int p = 0; p < e->npoints; ++p) {
     const double* row = h.data() + (size_t)p * (1 + 2 * nn);
@@ -2349,10 +2401,7 @@ int bppgpu_eval_device(bppgpu_engine* e, unsigned want, double* dev_out, void* c
   ENGINE_ENTER(e);
   if (!dev_out) BPP_FAIL(BPPGPU_E_INVALID, "null dev_out");
   cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : e->stream;
-  int rc = eval_impl(e, want, st, false);
-  if (rc) return rc;
-  BPP_CUDA(cudaMemcpyAsync(dev_out, e->d_out, (size_t)e->npoints * (1 + 2 * e->nn) * 8, cudaMemcpyDeviceToDevice, st));
-  return BPPGPU_OK;
+  return eval_impl(e, want, st, false, dev_out);
 }
 
 // ---- accessors -------------------------------------------------------------------------
@@ -2815,7 +2864,7 @@ int bppgpu_eval_status(bppgpu_engine* e, int32_t* numeric_failure) {
   ENGINE_SYNC(e);
   if (!numeric_failure) BPP_FAIL(BPPGPU_E_INVALID, "null argument");
   int status = 0;
-  BPP_CUDA(cudaMemcpy(&status, e->d_status, 4, cudaMemcpyDeviceToHost));
+  if (e->status_armed) BPP_CUDA(cudaMemcpy(&status, e->d_status, 4, cudaMemcpyDeviceToHost));
   *numeric_failure = status;
   if (status) BPP_FAIL(BPPGPU_E_NUMERIC, "ChromosomeSubstitutionModel: Taylor series did not reach convergence!");
   return BPPGPU_OK;
@@ -2847,7 +2896,7 @@ int bppgpu_eval_multi(bppgpu_engine* const* engines, int32_t n_engines, unsigned
     BPP_CUDA(cudaStreamSynchronize(e->stream));
     BPP_CUDA(cudaMemcpy(h.data(), e->d_out, h.size() * 8, cudaMemcpyDeviceToHost));
     int status = 0;
-    BPP_CUDA(cudaMemcpy(&status, e->d_status, 4, cudaMemcpyDeviceToHost));
+    if (e->status_armed) BPP_CUDA(cudaMemcpy(&status, e->d_status, 4, cudaMemcpyDeviceToHost));
     if (status) BPP_FAIL(BPPGPU_E_NUMERIC, "ChromosomeSubstitutionModel: Taylor series did not reach convergence!");
     for (size_t i = 0; i < tot.size(); ++i) tot[i] += h[i];   // shard order: deterministic
   }

@@ -123,10 +123,11 @@ struct bppgpu_engine {
   std::vector<W4cSeg> w4c_segs;
   std::vector<bppgpu::Pack4cBlock> w4c_blocks;
   std::vector<int> w4c_tip_order;
-  int w4c_CH = 0, w4c_nchunks = 0, w4c_pt = 2, w4c_nw = 8;
+  int w4c_CH = 0, w4c_nchunks = 0, w4c_pt = 2, w4c_nw = 8, w4c_max_tips = 16;
   unsigned char* d_w4c_stream = nullptr;   // [pchunk][nchunks][CH]
   bppgpu::Pack4cBlock* d_w4c_blocks = nullptr;
   int* d_w4c_tip_order = nullptr;
+  unsigned* d_w4c_counter = nullptr;       // CTAs done in the current evaluation (reset by the last one)
   unsigned char* d_codesC = nullptr;       // [grid][ntips][PPC] tip codes as the CTAs stage them
   // CLV storage (one point at a time)
   double* d_keep = nullptr;  // [ni][N][C][S]
@@ -173,6 +174,8 @@ struct bppgpu_engine {
   int ptring_n = 0, ptring_head = 0;
   size_t bytes_resident = 0;
   // batched points without P tables (chr_factored_kernels.cuh): one character, one rate class, many parameter points
+  bool status_armed = false;        // the status word was cleared for the evaluation in flight
+  bool rootfreq_used_stale = true;  // d_rootfreq_used must be refreshed from d_rootfreq
   bool chr_factored = false;
   bool tables_allocated = true;          // d_P / d_keep of the table route (allocated on demand for factored engines)
   std::vector<unsigned short> h_codes;   // [nl] the single pattern's tip codes (host copy)

@@ -53,9 +53,13 @@ struct Walk4cParams {
   const unsigned char* stream;       // [nchunks][CH] this point's table chunks
   const unsigned char* codesC;       // [gridDim.x][ntips][PPC] tip codes, consumption order, one byte per pattern
   int nchunks, CH, nslots, ncodes, ntips;
+  int max_tips;                      // tip-code rows a ring stage has room for (the planner never puts more tips in a chunk)
   unsigned flags;                    // bit0: R semantics at the root
   long long pat0, pat_end;           // this launch covers patterns [pat0, pat_end) (a segment of the engine's pattern list)
   int part0;                         // first slot of `partials` of this launch
+  int parts_total;                   // CTAs of ALL launches of this evaluation: the last one to finish adds the partials up
+  unsigned* done_counter;            // zero between evaluations
+  double* lnl_out;                   // the evaluation's log-likelihood (weighted sum of the site values)
   const double* rootfreq;            // [4]
   const double* probs;               // [C]
   const double* weights;             // [N]
@@ -286,13 +290,16 @@ struct W4cState {
 };
 
 // bytes of one ring stage: the table chunk + the tip-code rows of the chunk's tips
-__host__ __device__ inline size_t walk4c_stage_bytes(int CH, int C, int PT, int NW) {
-  return (size_t)CH + (size_t)kW4cMaxTipsPerChunk * (NW / C) * 32 * PT;
+__host__ __device__ inline size_t walk4c_stage_bytes(int CH, int C, int PT, int NW, int max_tips) {
+  return (size_t)CH + (size_t)max_tips * (NW / C) * 32 * PT;
 }
-// dynamic shared memory of one CTA
-__host__ __device__ inline size_t walk4c_smem_bytes(int CH, int nslots, int C, int PT, int NW) {
-  return (size_t)kW4cStages * walk4c_stage_bytes(CH, C, PT, NW) + (size_t)(nslots > 0 ? nslots : 0) * PT * NW * 32 * 36 +
-         (size_t)PT * NW * 32 * 12 + 128;
+// dynamic shared memory of one CTA: the ring (re-used by the root reduction, which needs 12 bytes per pattern and class), the
+// stack planes, the barriers
+__host__ __device__ inline size_t walk4c_smem_bytes(int CH, int nslots, int C, int PT, int NW, int max_tips) {
+  size_t ring = (size_t)kW4cStages * walk4c_stage_bytes(CH, C, PT, NW, max_tips);
+  const size_t root = (size_t)PT * NW * 32 * 12;
+  if (ring < root) ring = root;
+  return ring + (size_t)(nslots > 0 ? nslots : 0) * PT * NW * 32 * 36 + 128;
 }
 __host__ __device__ constexpr int walk4c_min_ctas(int PT, int NW) { return NW == 8 ? (PT <= 2 ? 2 : 1) : (PT <= 3 ? 3 : 2); }
 
@@ -307,18 +314,20 @@ walk4c_kernel(const __grid_constant__ Walk4cParams prm, const __grid_constant__ 
   __shared__ double red[32];
 
   const int CH = prm.CH;
-  const unsigned SB = (unsigned)CH + kW4cMaxTipsPerChunk * PPC;   // stage bytes
+  const unsigned SB = (unsigned)CH + (unsigned)prm.max_tips * PPC;   // stage bytes
   unsigned char* ring = smem_raw;
   const unsigned ring_s = smem_u32(smem_raw);
-  unsigned char* q0 = smem_raw + (size_t)kW4cStages * SB;
+  size_t ring_bytes = (size_t)kW4cStages * SB;
+  if (ring_bytes < (size_t)PT * NTH * 12) ring_bytes = (size_t)PT * NTH * 12;
+  unsigned char* q0 = smem_raw + ring_bytes;
   const size_t plane = (size_t)(prm.nslots > 0 ? prm.nslots : 0) * PT * NTH;
   W4cState<C_LOG2, PT, NW> s;
   s.stA = smem_u32(q0) + threadIdx.x * 16;
   s.stB = smem_u32(q0 + plane * 16) + threadIdx.x * 16;
   s.ste = smem_u32(q0 + plane * 32) + threadIdx.x * 4;
-  double* rsum = reinterpret_cast<double*>(q0 + plane * 36);          // [C][PPC] class terms of the root reduction
-  int* rexpn = reinterpret_cast<int*>(q0 + plane * 36 + (size_t)PT * NTH * 8);   // [C][PPC]
-  unsigned long long* bars = reinterpret_cast<unsigned long long*>(q0 + plane * 36 + (size_t)PT * NTH * 12);  // full[], empty[]
+  double* rsum = reinterpret_cast<double*>(smem_raw);                 // [C][PPC] class terms of the root reduction: the ring's
+  int* rexpn = reinterpret_cast<int*>(smem_raw + (size_t)PT * NTH * 8);   // [C][PPC]   memory, free once the walk is over
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(q0 + plane * 36);  // full[], empty[]
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int c = warp & (C - 1), g = warp >> C_LOG2;
@@ -409,6 +418,7 @@ walk4c_kernel(const __grid_constant__ Walk4cParams prm, const __grid_constant__ 
   }
 
   // ---- root reduction: L_i = sum_c p_c 2^-(E_c - Emin) sum_x pi_x CLV_root[i][c][x] (association as in walk4_kernel) ----
+  __syncthreads();   // every warp has read its last chunk: the ring is free
   const bool rsem = prm.flags & 1u;
   const double f0 = prm.rootfreq[0], f1 = prm.rootfreq[1], f2 = prm.rootfreq[2], f3 = prm.rootfreq[3];
 #pragma unroll
@@ -449,7 +459,26 @@ walk4c_kernel(const __grid_constant__ Walk4cParams prm, const __grid_constant__ 
     contrib += prm.weights[pat] * lnl;
   }
   const double bs = block_sum(contrib, red);
-  if (tid == 0) prm.partials[prm.part0 + blockIdx.x] = bs;
+  // the CTA that finishes last (over every launch of the evaluation) sums the per-CTA partials in index order: the same
+  // fixed-shape, deterministic reduction a separate finalize launch would do, without the launch
+  __shared__ bool is_last;
+  if (tid == 0) {
+    prm.partials[prm.part0 + blockIdx.x] = bs;
+    __threadfence();
+    const unsigned ticket = atomicAdd(prm.done_counter, 1u);
+    is_last = ticket == (unsigned)prm.parts_total - 1u;
+  }
+  __syncthreads();
+  if (is_last) {
+    __threadfence();
+    double acc = 0.0;
+    for (int i = tid; i < prm.parts_total; i += NTH) acc += __ldcg(prm.partials + i);
+    const double tot = block_sum(acc, red);
+    if (tid == 0) {
+      *prm.lnl_out = tot;
+      *prm.done_counter = 0u;
+    }
+  }
 }
 
 // codes [nl][N] (leaf-slot major) -> codesC [cta][tip in consumption order][PPC]: the rows a CTA stages with its chunks
@@ -484,6 +513,48 @@ __global__ void pack_stream4c_kernel(const Pack4cBlock* blocks, const double* P 
     }
   } else {                   // [class][x][y] = the reference's pxy_ order
     for (int e = threadIdx.x; e < C * 16; e += blockDim.x) out[e] = Pn[e];
+  }
+}
+
+// K1 + K2b fused for the DNA walk (S = 4, real spectra, value only): the CTA of a child block builds the branch's
+// P(t) = V exp(L r_c t) V^-1 for every class -- the arithmetic of pt_eigen_kernel (pt_kernels.cuh), term by term, so the tables are
+// bit-identical -- writes it to the P table (accessors read it there) and lays out its stream block.  One launch instead of two.
+struct PtPack4cParams {
+  const Pack4cBlock* blocks;
+  const ModelDev* models;
+  const int* branch_model;   // [nn] of this point
+  const double* brlen;       // [nn] of this point
+  const double* rates;       // [C]
+  const double* code_table;
+  int C, ncodes;
+  double* P;                 // [nn][C][4][4] of this point
+  unsigned char* stream;
+};
+__global__ void pt_pack4c_kernel(PtPack4cParams p) {
+  __shared__ double Ps[8 * 16];
+  const Pack4cBlock b = p.blocks[blockIdx.x];
+  const ModelDev md = p.models[p.branch_model[b.pnode]];
+  const int C = p.C;
+  for (int e = threadIdx.x; e < C * 16; e += blockDim.x) {
+    const int c = e >> 4, x = (e >> 2) & 3, y = e & 3;
+    const double l = md.rate * (p.brlen[b.pnode] * p.rates[c]);
+    double a0 = 0.0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) a0 = fma(md.V[x * 4 + k] * md.Vinv[k * 4 + y], exp(md.re[k] * l), a0);
+    Ps[e] = a0;
+    p.P[(size_t)b.pnode * C * 16 + e] = a0;
+  }
+  __syncthreads();
+  double* out = reinterpret_cast<double*>(p.stream + b.off);
+  if (b.kind == W4C_TIP) {   // [class][code][x]
+    for (int e = threadIdx.x; e < p.ncodes * C * 4; e += blockDim.x) {
+      const int x = e & 3, code = (e >> 2) % p.ncodes, c = (e >> 2) / p.ncodes;
+      const double* tv = p.code_table + code * 4;
+      const double* pr = Ps + c * 16 + x * 4;
+      out[e] = fma(pr[3], tv[3], fma(pr[2], tv[2], fma(pr[1], tv[1], pr[0] * tv[0])));
+    }
+  } else {
+    for (int e = threadIdx.x; e < C * 16; e += blockDim.x) out[e] = Ps[e];
   }
 }
 
