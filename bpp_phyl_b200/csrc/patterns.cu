@@ -105,7 +105,9 @@ __global__ void pattern_tip_codes_kernel(const T* __restrict__ cols, const long 
   }
 }
 
-// ---- variant "dedup" (BPPGPU_PATTERNS_ALGO=dedup; NOT yet run on a device, default off) -------------------------------------------
+// ---- "dedup" (the default; BPPGPU_PATTERNS_ALGO=radix selects the plain word-by-word sort of every column) -----------------------
+// Measured on 1M sites x 1024 taxa (245k patterns), copies included: 0.240 s against 0.277 s for the plain sort and 0.59 s for the
+// host routine (profiles/r2_patterns_device_vs_host_1Mx1024.json); outputs identical, bit for bit, in every test.
 // Identical columns are merged BEFORE the lexicographic sort: one 64-bit hash per column (equal columns -> equal hashes; a
 // collision between different columns only leaves duplicates for the final run detection to merge), one stable sort of the hashes,
 // run heads by full comparison, and the word-by-word radix sort runs over the unique columns only.
@@ -298,7 +300,7 @@ int bppgpu_site_patterns_device(int device, const uint8_t* columns, int64_t n_si
   cudaStream_t st = 0;
   BPP_CUDA(cudaMemcpyAsync(d.cols, columns, bytes, cudaMemcpyHostToDevice, st));
   const char* algo = getenv("BPPGPU_PATTERNS_ALGO");
-  if (algo && std::string(algo) == "dedup") {   // NOT yet run on a device (see the variant's comment); the default path is below
+  if (!(algo && std::string(algo) == "radix")) {
     uint32_t npd = 0;
     const int rc = site_patterns_dedup(d, n, col_bytes, temp_bytes, st, &npd);
     if (rc) return rc;

@@ -133,10 +133,10 @@ def test_device_patterns_feed_the_engine(built_lib):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("n,ntaxa,nstates,seed", [(1, 3, 4, 0), (500, 5, 2, 2), (3000, 40, 20, 4), (257, 300, 4, 5), (70000, 64, 4, 9)])
-def test_device_patterns_dedup_variant(built_lib, monkeypatch, n, ntaxa, nstates, seed):
-    """BPPGPU_PATTERNS_ALGO=dedup (merge identical columns by hash first, sort only the unique ones): bit-identical to the host
-    routine (first seen green on a B200 at the start of round 2, gpurun_out/r2_t1_pat.log)."""
-    monkeypatch.setenv("BPPGPU_PATTERNS_ALGO", "dedup")
+def test_device_patterns_plain_radix_variant(built_lib, monkeypatch, n, ntaxa, nstates, seed):
+    """The two device algorithms -- "dedup" (default: merge identical columns by hash first, sort only the unique ones) and "radix"
+    (sort every column) -- are bit-identical to the host routine; this test pins the non-default one."""
+    monkeypatch.setenv("BPPGPU_PATTERNS_ALGO", "radix")
     rng = np.random.default_rng(seed)
     alphabet = np.frombuffer(b"ACGTRYKMSWBDHVN-?XQZ", np.uint8)[:nstates]
     check_device(alphabet[rng.integers(nstates, size=(n, ntaxa))])
