@@ -325,6 +325,11 @@ def run_points(a, w, rank, world, local, K, W, metric, config):
     mds = [synth.chromosome_model_desc(es) for es in pts]
     P0, _, _ = capi.pt_batch(mds[0], tree.brlen, capi.WANT_P, device=local)
     codes = synth.simulate_single_character(tree, P0, root_state=23, seed=w["seed"])
+    # ChromosomeNumberMng::rescale_tree (App/ChromosomeNumberMng.cpp:121-147, branchMul_ = 999): the total tree length becomes the
+    # number of distinct chromosome counts in the data before anything is evaluated
+    n_unique = int(len(np.unique(codes)))
+    tree.brlen = tree.brlen * (n_unique / tree.brlen.sum())
+    tree.brlen[tree.root] = 0.0
     e = capi.Engine(S, 1, 1, tree.child_off, tree.children, tree.root, np.eye(S), n_points=npts, n_models=npts, device=local,
                     flags=capi.FLAG_WEIGHTED_ROOT)
     e.set_all_tip_codes(codes)
@@ -413,7 +418,8 @@ def run_points(a, w, rank, world, local, K, W, metric, config):
                 "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": a.scaling, "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic (one chromosome count per taxon simulated down a random rooted tree; parameter points "
                                         "drawn uniformly, numerically defective generators redrawn)",
-                "config": dict(config, points=npts_total, sharding="points/%d (replicas, no collective)" % world),
+                "config": dict(config, points=npts_total, sharding="points/%d (replicas, no collective)" % world,
+                               tree_length="rescaled to the %d distinct counts of the data (rescale_tree)" % n_unique),
                 "logl_evals_per_s": npts_total * K / (ms * 1e-3), "lnl_point0": lnl0,
                 "routes": {"factored_points": nfac, "table_points": ntab,
                            "note": "points whose probe tables leave [0, 1] by more than 1e-8 (where the reference's per-entry clamp would matter) "

@@ -22,10 +22,6 @@
 
 namespace bppgpu {
 
-constexpr int kChrCols = 32;      // columns (branches) per tile
-constexpr int kChrLD = 36;        // leading dimension of the shared column tiles (= 4 mod 16 doubles: conflict-free B fragments)
-constexpr int kChrWarps = 8;
-constexpr int kChrMaxRB = 4;      // row blocks of 8 per warp -> S <= 8 * 8 * 4 = 256
 // Guard: a point takes the factored route when no entry of its probe tables leaves [0, 1] by more than this; entries that do
 // are the ones the reference clamps (ChromosomeSubstitutionModel.cpp:903-916).  Observed tips are exact whatever the guard says
 // (their term is a column of P and is clamped entry by entry); the guard is about internal branches, where the clamp cannot be
@@ -55,44 +51,6 @@ struct ChrLevelParams {
 inline size_t chr_level_smem(int S) {
   const int K4 = (S + 7) & ~7;
   return (size_t)K4 * kChrLD * sizeof(double) + 3 * kChrCols * sizeof(double) + 2 * kChrCols * sizeof(int);
-}
-
-// C[rb][cb] += A[rows of rb][k] . Bs[k][cols of cb]   for this warp's row blocks; A row-major [S][S] in global memory
-__device__ __forceinline__ void chr_gemm(const double* __restrict__ A, int S, int K4, const double* Bs, int nrb, int warp, int g,
-                                         int q, double (&acc)[kChrMaxRB][kChrCols / 8][2]) {
-#pragma unroll
-  for (int i = 0; i < kChrMaxRB; ++i)
-#pragma unroll
-    for (int cb = 0; cb < kChrCols / 8; ++cb) acc[i][cb][0] = acc[i][cb][1] = 0.0;
-#pragma unroll 2
-  for (int k0 = 0; k0 < K4; k0 += 4) {
-    double a[kChrMaxRB];
-#pragma unroll
-    for (int i = 0; i < kChrMaxRB; ++i) {
-      const int row = (warp + i * kChrWarps) * 8 + g;
-      a[i] = (warp + i * kChrWarps < nrb && row < S && k0 + q < S) ? __ldg(A + (size_t)row * S + k0 + q) : 0.0;
-    }
-    double b[kChrCols / 8];
-#pragma unroll
-    for (int cb = 0; cb < kChrCols / 8; ++cb) b[cb] = Bs[(k0 + q) * kChrLD + cb * 8 + g];
-#pragma unroll
-    for (int i = 0; i < kChrMaxRB; ++i)
-      if (warp + i * kChrWarps < nrb) {
-#pragma unroll
-        for (int cb = 0; cb < kChrCols / 8; ++cb) dmma884(acc[i][cb][0], acc[i][cb][1], a[i], b[cb]);
-      }
-  }
-}
-__device__ __forceinline__ void chr_store_acc(double* Cs, int nrb, int warp, int g, int q,
-                                              const double (&acc)[kChrMaxRB][kChrCols / 8][2]) {
-#pragma unroll
-  for (int i = 0; i < kChrMaxRB; ++i)
-    if (warp + i * kChrWarps < nrb) {
-      const int row = (warp + i * kChrWarps) * 8 + g;
-#pragma unroll
-      for (int cb = 0; cb < kChrCols / 8; ++cb)
-        *reinterpret_cast<double2*>(Cs + row * kChrLD + cb * 8 + 2 * q) = make_double2(acc[i][cb][0], acc[i][cb][1]);
-    }
 }
 
 __global__ void __launch_bounds__(kChrWarps * 32, 2) chr_level_kernel(ChrLevelParams p) {

@@ -34,4 +34,56 @@ __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
+// ---- skinny panel GEMM on the FP64 tensor cores -----------------------------------------------------------------------
+// C[M x 32] = A[M x K] . Bs[K x 32]: A row-major in global memory (L2-resident), the 32-column panel of B in shared memory
+// with a leading dimension of 36 doubles (= 4 mod 16: conflict-free B fragments), 8 warps, warp w owns the row blocks
+// w, w + 8, w + 16, w + 24 (M <= 256) times the panel's four column blocks.  Used by chr_level_kernel (columns = the
+// branches of a tree level) and by the series kernel's matrix products (columns = a panel of the right factor).
+constexpr int kChrCols = 32;      // columns (branches) per tile
+constexpr int kChrLD = 36;        // leading dimension of the shared column tiles (= 4 mod 16 doubles: conflict-free B fragments)
+constexpr int kChrWarps = 8;
+constexpr int kChrMaxRB = 4;      // row blocks of 8 per warp -> S <= 8 * 8 * 4 = 256
+// C[rb][cb] += A[rows of rb][k] . Bs[k][cols of cb]   for this warp's row blocks; A row-major [S][S] in global memory
+// COHERENT: A was written earlier by this same kernel (ld.global.cg: L2, never a stale L1 line); otherwise it is read-only for
+// the launch (ld.global.nc)
+template <bool COHERENT = false>
+__device__ __forceinline__ void chr_gemm(const double* __restrict__ A, int S, int K4, const double* Bs, int nrb, int warp, int g,
+                                         int q, double (&acc)[kChrMaxRB][kChrCols / 8][2]) {
+#pragma unroll
+  for (int i = 0; i < kChrMaxRB; ++i)
+#pragma unroll
+    for (int cb = 0; cb < kChrCols / 8; ++cb) acc[i][cb][0] = acc[i][cb][1] = 0.0;
+#pragma unroll 2
+  for (int k0 = 0; k0 < K4; k0 += 4) {
+    double a[kChrMaxRB];
+#pragma unroll
+    for (int i = 0; i < kChrMaxRB; ++i) {
+      const int row = (warp + i * kChrWarps) * 8 + g;
+      const bool in = warp + i * kChrWarps < nrb && row < S && k0 + q < S;
+      a[i] = !in ? 0.0 : (COHERENT ? __ldcg(A + (size_t)row * S + k0 + q) : __ldg(A + (size_t)row * S + k0 + q));   // L2 / read-only path
+    }
+    double b[kChrCols / 8];
+#pragma unroll
+    for (int cb = 0; cb < kChrCols / 8; ++cb) b[cb] = Bs[(k0 + q) * kChrLD + cb * 8 + g];
+#pragma unroll
+    for (int i = 0; i < kChrMaxRB; ++i)
+      if (warp + i * kChrWarps < nrb) {
+#pragma unroll
+        for (int cb = 0; cb < kChrCols / 8; ++cb) dmma884(acc[i][cb][0], acc[i][cb][1], a[i], b[cb]);
+      }
+  }
+}
+__device__ __forceinline__ void chr_store_acc(double* Cs, int nrb, int warp, int g, int q,
+                                              const double (&acc)[kChrMaxRB][kChrCols / 8][2]) {
+#pragma unroll
+  for (int i = 0; i < kChrMaxRB; ++i)
+    if (warp + i * kChrWarps < nrb) {
+      const int row = (warp + i * kChrWarps) * 8 + g;
+#pragma unroll
+      for (int cb = 0; cb < kChrCols / 8; ++cb)
+        *reinterpret_cast<double2*>(Cs + row * kChrLD + cb * 8 + 2 * q) = make_double2(acc[i][cb][0], acc[i][cb][1]);
+    }
+}
+
+
 }  // namespace bppgpu

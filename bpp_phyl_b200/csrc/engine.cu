@@ -415,7 +415,13 @@ static int launch_pt(cudaStream_t st, const ModelDev* d_models, bool any_series,
     sp.pt = pp;
     sp.scratch = scratch;
     sp.status = d_status;
-    pt_series_kernel<<<nmat, threads, 0, st>>>(sp);
+    if (S >= 32 && S <= 8 * kChrWarps * kChrMaxRB) {   // matrix products on the FP64 tensor cores
+      const size_t smem = (size_t)((S + 7) & ~7) * kChrLD * sizeof(double);
+      BPP_CUDA(cudaFuncSetAttribute(pt_series_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+      pt_series_kernel<true><<<nmat, kChrWarps * 32, smem, st>>>(sp);
+    } else {
+      pt_series_kernel<false><<<nmat, threads, 0, st>>>(sp);
+    }
     ++*launches;
   }
   BPP_CUDA(cudaGetLastError());

@@ -14,6 +14,7 @@
 // one thread per element group).  The S>=32 DMMA path is in gemm_kernels.cuh.
 #pragma once
 #include "common.cuh"
+#include "dmma.cuh"
 
 namespace bppgpu {
 
@@ -196,8 +197,11 @@ namespace bppgpu {
 // clamp P<0 -> 1e-20, P>1 -> 1 (:903-916) on P itself.  BPPGPU_MODEL_EXACT_EXPM runs the
 // series to FP64 convergence instead of the reference's truncation.
 //
-// One CTA per matrix, scratch in global memory ([4][S][S] per matrix): a correctness
-// path for the rare singular case, not a throughput kernel.
+// One CTA per matrix, operands in global scratch ([4][S][S] per matrix, L2-resident).  For S >= 32 every matrix product
+// -- the Taylor terms and, above all, the m squarings (m ~ 10 for a Chromosome generator: the reference halves until
+// t * sum|Q_ij| <= 0.5) -- runs on the FP64 tensor cores: mat_mul_dmma walks the right factor in 32-column panels staged in
+// shared memory and takes the left factor's fragments straight from L2 (the skinny panel GEMM of dmma.cuh).  Smaller
+// alphabets keep the CUDA-core loop.
 struct SeriesParams {
   PtParams pt;
   double* scratch;  // [nmat][4][S*S]
@@ -216,7 +220,42 @@ __device__ __forceinline__ void mat_mul(const double* A, const double* B, double
   __syncthreads();
 }
 
+// O = A . B . scale on the tensor cores (blockDim = 256, dynamic shared memory: roundup(S, 8) x 36 doubles); A, B, O distinct.
+// A and B may have been written by this CTA: plain (coherent) loads, and every thread passes the closing barrier.
+__device__ __forceinline__ void mat_mul_dmma(const double* A, const double* B, double* O, int S, double scale, double* Bs) {
+  const int K8 = (S + 7) & ~7, nrb = K8 >> 3;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, q = lane & 3;
+  for (int n0 = 0; n0 < S; n0 += kChrCols) {
+    __syncthreads();   // the previous panel's fragments have been read
+    for (int i = tid; i < K8 * kChrCols; i += blockDim.x) {
+      const int k = i / kChrCols, j = i - k * kChrCols;
+      Bs[k * kChrLD + j] = (k < S && n0 + j < S) ? __ldcg(B + (size_t)k * S + n0 + j) : 0.0;
+    }
+    __syncthreads();
+    double acc[kChrMaxRB][kChrCols / 8][2];
+    chr_gemm<true>(A, S, K8, Bs, nrb, warp, g, q, acc);
+#pragma unroll
+    for (int i = 0; i < kChrMaxRB; ++i)
+      if (warp + i * kChrWarps < nrb) {
+        const int row = (warp + i * kChrWarps) * 8 + g;
+#pragma unroll
+        for (int cb = 0; cb < kChrCols / 8; ++cb) {
+          const int col = n0 + cb * 8 + 2 * q;
+          if (row < S && col < S) O[(size_t)row * S + col] = acc[i][cb][0] * scale;
+          if (row < S && col + 1 < S) O[(size_t)row * S + col + 1] = acc[i][cb][1] * scale;
+        }
+      }
+  }
+  __syncthreads();
+}
+
+template <bool DMMA>
 __global__ void pt_series_kernel(SeriesParams sp) {
+  extern __shared__ __align__(16) double sm_series[];
+  auto mat_mul = [&](const double* A_, const double* B_, double* O_, int S_, double scale_) {
+    if (DMMA) mat_mul_dmma(A_, B_, O_, S_, scale_, sm_series);
+    else bppgpu::mat_mul(A_, B_, O_, S_, scale_);
+  };
   const PtParams& p = sp.pt;
   __shared__ double red_max[32];
   __shared__ int flag;

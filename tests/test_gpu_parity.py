@@ -463,8 +463,18 @@ def test_nonhomogeneous_model_set_per_branch_models(kind, ncat, ntaxa, nsites):
         assert abs(lnl3[0] - c0.lnl) <= REL * abs(c0.lnl)
 
 
+def _generic_singular(S):
+    """a pure-birth chain: upper bidiagonal generator with equal rates -> one Jordan block, not diagonalisable"""
+    Q = np.zeros((S, S))
+    for i in range(S - 1):
+        Q[i, i + 1] = 1.0
+    Q = rm._set_diagonal(Q)
+    m = rm.update_matrices(rm.Model("birth", Q, np.full(S, 1.0 / S), reversible=False, scalable=False))
+    return m
+
+
 @pytest.mark.parametrize("name", ["t92", "gtr", "lg08", "yn98", "chr_eigen", "chr_complex", "chr_complex50", "chr_real200",
-                                  "chr_complex200", "chr_singular", "nonrev4"])
+                                  "chr_complex200", "chr_singular", "chr_singular200", "chr_singular52_exact", "generic_singular40", "nonrev4"])
 def test_pt_batch_interface(name):
     """Interface 1: getPij_t / getdPij_dt / getd2Pij_dt2 for a batch of t."""
     capi = _capi()
@@ -480,7 +490,14 @@ def test_pt_batch_interface(name):
              "chr_complex50": lambda: rm.chromosome(1, 50, gain=1.02, loss=1.90, dupl=0.14, demi=0.95),
              "chr_real200": lambda: rm.chromosome(1, 104, gain=1.0, loss=1.0, dupl=0.01),     # real spectrum, S % 8 == 0
              "chr_complex200": lambda: rm.chromosome(1, 200, gain=0.08, loss=1.06, dupl=0.46, demi=0.06),
-             "chr_singular": lambda: rm.chromosome(1, 20, gain=0.5, loss=0.0, dupl=0.0)}[name]()
+             "chr_singular": lambda: rm.chromosome(1, 20, gain=0.5, loss=0.0, dupl=0.0),
+             # the series route on the FP64 tensor cores (S >= 32: mat_mul_dmma): the reference's adaptive Taylor rule at S = 200,
+             # S not a multiple of 8, and the generic 30-term rule of a non-Chromosome singular generator
+             "chr_singular200": lambda: rm.chromosome(1, 200, gain=0.5, loss=0.0, dupl=0.1),
+             "chr_singular52_exact": lambda: rm.chromosome(1, 52, gain=0.5, loss=0.0, dupl=0.0),
+             "generic_singular40": lambda: _generic_singular(40)}[name]()
+        if name.startswith("chr_singular") or name == "generic_singular40":
+            assert not m.nonsingular
         if name in ("chr_complex50", "chr_complex200"):
             assert m.nonsingular and not m.diagonalizable       # conjugate pairs -> block form on the tensor cores
     ts = np.array([0.0, 1e-6, 0.013, 0.2, 1.0, 4.5])
