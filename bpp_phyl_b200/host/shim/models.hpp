@@ -1,6 +1,6 @@
 // bppgpu shim (see ../bppgpu_shim.hpp): rate distributions, substitution models, omega mixtures, frequency sets, model sets
 #pragma once
-#include "tree.hpp"
+#include "io.hpp"
 
 namespace bppshim {
 

@@ -34,8 +34,42 @@ static void print_model(const char* name, const SubstitutionModel& m, bool comma
          comma ? "," : "");
 }
 
+#include <fstream>
+static double tree_len(const Node* n) {
+  double s = n->hasFather() && n->hasDistanceToFather() ? n->getDistanceToFather() : 0.0;
+  for (size_t i = 0; i < n->getNumberOfSons(); ++i) s += tree_len(n->getSon(i));
+  return s;
+}
+static void io_checks() {
+  // the input side: files -> tree / containers, the same objects the string constructors give
+  const char* dir = getenv("BPPGPU_TEST_TMP") ? getenv("BPPGPU_TEST_TMP") : "/tmp";
+  const std::string base = std::string(dir) + "/bppgpu_io_";
+  { std::ofstream f(base + "t.nwk"); f << "((A:0.01,\n B[a comment]:0.02):0.03,\nC:0.01,D:0.1);\n(ignored);\n"; }
+  { std::ofstream f(base + "s.fa"); f << ">A first\nAAATGG\nCTGTGC\n>B\naaatggctgtgg\n>C\nAAATGGCTGTGA\n>D\nNAATGG-TGTGC\n"; }
+  { std::ofstream f(base + "s.phy"); f << " 2 6\nA  AAATGG\nB  CTG\nTGC\n"; }
+  { std::ofstream f(base + "c.fa"); f << ">a\n7\n>b\n14\n\n>e\nX\n"; }
+  unique_ptr<TreeTemplate<Node> > t(Newick(true).read(base + "t.nwk"));
+  printf("\"IO_tree_leaves\": %zu, \"IO_tree_nodes\": %zu, \"IO_tree_len\": %.17g,\n", t->getLeavesNames().size(), t->getNodes().size(),
+         tree_len(t->getRootNode()));
+  VectorSiteContainer fa(&AlphabetTools::DNA_ALPHABET());
+  Fasta().readSequences(base + "s.fa", fa);
+  printf("\"IO_fasta_n\": %zu, \"IO_fasta_sites\": %zu, \"IO_fasta_name0\": \"%s\", \"IO_fasta_B7\": \"%s\",\n", fa.getNumberOfSequences(),
+         fa.getNumberOfSites(), fa.getSequencesNames()[0].c_str(), fa.getSequence("B")[7].c_str());
+  VectorSiteContainer ph(&AlphabetTools::DNA_ALPHABET());
+  Phylip().readSequences(base + "s.phy", ph);
+  printf("\"IO_phylip_n\": %zu, \"IO_phylip_B5\": \"%s\",\n", ph.getNumberOfSequences(), ph.getSequence("B")[5].c_str());
+  ChromosomeAlphabet chr(1, 30);
+  unique_ptr<VectorSiteContainer> cf(chrFasta::readSequencesFromFile(base + "c.fa", &chr));
+  printf("\"IO_chr_n\": %zu, \"IO_chr_b\": \"%s\", \"IO_chr_e\": \"%s\",\n", cf->getNumberOfSequences(), cf->getSequence("b")[0].c_str(),
+         cf->getSequence("e")[0].c_str());
+  bool threw = false;
+  try { Newick().read(base + "missing.nwk"); } catch (IOException&) { threw = true; }
+  printf("\"IO_missing_throws\": %d,\n", (int)threw);
+}
+
 int main() {
   printf("{\n");
+  io_checks();
   {
     GammaDiscreteRateDistribution g41(4, 1.0), g405(4, 0.5), g8(8, 2.3), g1(1, 0.7);
     Vdouble r;

@@ -47,6 +47,17 @@ def test_gamma_rate_classes(host_doc):
         np.testing.assert_allclose(host_doc[key], rm.gamma_rates(n, a)[0], rtol=1e-13)
 
 
+def test_file_readers_newick_fasta_phylip_chrfasta(host_doc):
+    """SURVEY 8f-4, second half: Newick (multi-line, comments, text after the first ';' ignored -- Io/Newick.cpp:69-92), Fasta
+    (names up to the end of the line, lower case, multi-line), sequential Phylip, the fork's chrFasta (one count per taxon)."""
+    d = host_doc
+    assert d["IO_tree_leaves"] == 4 and d["IO_tree_nodes"] == 6 and abs(d["IO_tree_len"] - 0.17) < 1e-15
+    assert d["IO_fasta_n"] == 4 and d["IO_fasta_sites"] == 12 and d["IO_fasta_name0"] == "A first" and d["IO_fasta_B7"] == "T"
+    assert d["IO_phylip_n"] == 2 and d["IO_phylip_B5"] == "C"
+    assert d["IO_chr_n"] == 3 and d["IO_chr_b"] == "14" and d["IO_chr_e"] == "X"
+    assert d["IO_missing_throws"] == 1
+
+
 def _block_diag(re, im):
     n = len(re)
     D = np.zeros((n, n))
