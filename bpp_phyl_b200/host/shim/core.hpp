@@ -1,6 +1,7 @@
 // bppgpu shim (see ../bppgpu_shim.hpp): exceptions, RowMatrix, NumConstants, host linear algebra and special functions (bpp-core stand-ins)
 #pragma once
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <limits>
 #include <complex>
@@ -12,6 +13,7 @@
 #include <sstream>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../../include/bppgpu.h"
@@ -62,6 +64,29 @@ inline double VERY_TINY() { return 1e-20; }
 
 // ---- host linear algebra (updateMatrices stays on the host, north-star (1)) --------------------------------------
 namespace linalg {
+
+// rows / eigenvalues of the S >= 96 models (codon 61, chromosome ~200) are independent pieces of O(S^2) work: spread them over the
+// host cores.  Every piece writes its own outputs, so the result does not depend on the thread count (BPPGPU_SHIM_THREADS, default
+// min(hardware threads, 16); 1 = serial).
+inline int shim_threads() {
+  static const int n = [] {
+    const char* e = std::getenv("BPPGPU_SHIM_THREADS");
+    int v = e ? std::atoi(e) : (int)std::thread::hardware_concurrency();
+    return std::max(1, std::min(v, 16));
+  }();
+  return n;
+}
+template <class F>
+inline void parallel_for(int n, int min_parallel, F&& body) {
+  const int T = n >= min_parallel ? std::min(shim_threads(), n) : 1;
+  if (T <= 1) { for (int i = 0; i < n; ++i) body(i); return; }
+  std::atomic<int> next(0);   // pieces are handed out one at a time: their costs differ (conjugate pairs, sparse rows)
+  auto work = [&] { for (int i = next.fetch_add(1); i < n; i = next.fetch_add(1)) body(i); };
+  std::vector<std::thread> th;
+  for (int t = 1; t < T; ++t) th.emplace_back(work);
+  work();
+  for (auto& x : th) x.join();
+}
 
 // cyclic Jacobi for a symmetric matrix: A = U diag(w) U^T, columns of U are eigenvectors
 inline void jacobi_symmetric(std::vector<double> a, int n, std::vector<double>& w, std::vector<double>& U) {
@@ -131,20 +156,22 @@ inline bool invert(const std::vector<double>& A, int n, std::vector<double>& inv
   // conditioned eigenvector bases of non-normal generators (chromosome models reach cond(V) ~ 1e5)
   for (int it = 0; it < 2; ++it) {
     std::vector<double> R((size_t)n * n, 0.0);
-    for (int i = 0; i < n; ++i)
+    parallel_for(n, 96, [&](int i) {
       for (int k = 0; k < n; ++k) {
         const double aik = A[(size_t)i * n + k];
         if (aik == 0.0) continue;
         for (int j = 0; j < n; ++j) R[(size_t)i * n + j] -= aik * inv[(size_t)k * n + j];
       }
-    for (int i = 0; i < n; ++i) R[(size_t)i * n + i] += 1.0;
+      R[(size_t)i * n + i] += 1.0;
+    });
     std::vector<double> X(inv);
-    for (int i = 0; i < n; ++i)
+    parallel_for(n, 96, [&](int i) {
       for (int k = 0; k < n; ++k) {
         const double xik = inv[(size_t)i * n + k];
         if (xik == 0.0) continue;
         for (int j = 0; j < n; ++j) X[(size_t)i * n + j] += xik * R[(size_t)k * n + j];
       }
+    });
     for (double v : X)
       if (!std::isfinite(v)) return true;  // keep the unrefined inverse
     inv.swap(X);
@@ -285,37 +312,60 @@ inline bool hessenberg_qr_eigenvalues(std::vector<double> a, int n, std::vector<
   return true;
 }
 
-// complex LU solve of (A - lambda I) x = b, used for inverse iteration
-inline bool solve_shifted(const std::vector<double>& A, int n, std::complex<double> lambda, std::vector<std::complex<double>>& x) {
+// complex LU of (A - lambda I) with partial pivoting, factored ONCE per eigenvalue and reused by every inverse-iteration
+// solve (O(n^3) per eigenvalue at worst, far less on the banded generators of the chromosome models: zero multipliers are
+// skipped and remembered)
+struct ShiftedLU {
   typedef std::complex<double> cd;
-  std::vector<cd> a((size_t)n * n);
-  for (int i = 0; i < n; ++i)
-    for (int j = 0; j < n; ++j) a[(size_t)i * n + j] = cd(A[(size_t)i * n + j]) - (i == j ? lambda : cd(0));
-  for (int col = 0; col < n; ++col) {
-    int piv = col;
-    double best = std::abs(a[(size_t)col * n + col]);
-    for (int r = col + 1; r < n; ++r)
-      if (std::abs(a[(size_t)r * n + col]) > best) { best = std::abs(a[(size_t)r * n + col]); piv = r; }
-    if (best < 1e-300) a[(size_t)piv * n + col] = cd(1e-300);
-    if (piv != col) {
-      for (int k = 0; k < n; ++k) std::swap(a[(size_t)piv * n + k], a[(size_t)col * n + k]);
-      std::swap(x[piv], x[col]);
-    }
-    const cd d = cd(1.0) / a[(size_t)col * n + col];
-    for (int r = col + 1; r < n; ++r) {
-      const cd f = a[(size_t)r * n + col] * d;
-      if (f == cd(0)) continue;
-      for (int k = col; k < n; ++k) a[(size_t)r * n + k] -= f * a[(size_t)col * n + k];
-      x[r] -= f * x[col];
+  int n = 0;
+  std::vector<cd> a;          // U above / on the diagonal, the multipliers of L below it
+  std::vector<int> piv;       // row swapped with `col` at step col
+  std::vector<int> nz_ptr, nz_row;   // rows with a non-zero multiplier, per column
+  void factor(const std::vector<double>& A, int n_, cd lambda) {
+    n = n_;
+    a.resize((size_t)n * n);
+    piv.resize(n);
+    nz_ptr.assign(1, 0);
+    nz_row.clear();
+    for (int i = 0; i < n; ++i)
+      for (int j = 0; j < n; ++j) a[(size_t)i * n + j] = cd(A[(size_t)i * n + j]) - (i == j ? lambda : cd(0));
+    for (int col = 0; col < n; ++col) {
+      int p = col;
+      double best = std::norm(a[(size_t)col * n + col]);
+      for (int r = col + 1; r < n; ++r) {
+        const double v = std::norm(a[(size_t)r * n + col]);
+        if (v > best) { best = v; p = r; }
+      }
+      if (best < 1e-300) a[(size_t)p * n + col] = cd(1e-300);
+      piv[col] = p;
+      if (p != col)   // the multipliers already stored left of `col` stay with their rows: solve() replays swap and elimination in step
+        for (int k = col; k < n; ++k) std::swap(a[(size_t)p * n + k], a[(size_t)col * n + k]);
+      const cd d = cd(1.0) / a[(size_t)col * n + col];
+      for (int r = col + 1; r < n; ++r) {
+        const cd f = a[(size_t)r * n + col] * d;
+        a[(size_t)r * n + col] = f;
+        if (f == cd(0)) continue;
+        nz_row.push_back(r);
+        for (int k = col + 1; k < n; ++k) a[(size_t)r * n + k] -= f * a[(size_t)col * n + k];
+      }
+      nz_ptr.push_back((int)nz_row.size());
     }
   }
-  for (int i = n - 1; i >= 0; --i) {
-    cd s = x[i];
-    for (int k = i + 1; k < n; ++k) s -= a[(size_t)i * n + k] * x[k];
-    x[i] = s / a[(size_t)i * n + i];
+  void solve(std::vector<cd>& x) const {
+    for (int col = 0; col < n; ++col) {
+      if (piv[col] != col) std::swap(x[piv[col]], x[col]);
+      const cd xc = x[col];
+      if (xc == cd(0)) continue;
+      for (int t = nz_ptr[col]; t < nz_ptr[col + 1]; ++t) x[nz_row[t]] -= a[(size_t)nz_row[t] * n + col] * xc;
+    }
+    for (int i = n - 1; i >= 0; --i) {
+      cd s = x[i];
+      const cd* row = &a[(size_t)i * n];
+      for (int k = i + 1; k < n; ++k) s -= row[k] * x[k];
+      x[i] = s / row[i];
+    }
   }
-  return true;
-}
+};
 
 // Real eigen-form of a general real matrix as bpp-core's EigenValue<double> presents it: eigenvalues (re, im) and a
 // REAL matrix V with A V = V D, D block diagonal ([[re, im], [-im, re]] for a conjugate pair, +im member first).
@@ -337,35 +387,44 @@ inline bool eigen_general(const std::vector<double>& A, int n, std::vector<doubl
   double scale = 0.0;
   for (double v : A) scale = std::max(scale, std::fabs(v));
   if (scale == 0.0) scale = 1.0;
-  for (int k = 0; k < n; ++k) {
-    if (im[k] < 0.0) continue;  // second member of a pair: filled with the first
-    const cd lam(re[k], im[k]);
+  std::vector<char> failed(n, 0);
+  const std::vector<double> re0(re), im0(im);   // the QR values: what every piece reads (pieces write re / im of their own pair)
+  parallel_for(n, 96, [&](int k) {
+    if (im0[k] < 0.0) return;  // second member of a pair: filled with the first
+    const cd lam(re0[k], im0[k]);
     // inverse iteration; the eigenvalue itself is refined from the iteration (lambda = shift + <x,x>/<x,y> with
     // (A - shift I) y = x), which recovers the digits the unbalanced QR iteration loses on non-normal generators
     cd lamk = lam;
     std::vector<cd> x(n);
     for (int i = 0; i < n; ++i) x[i] = cd(1.0 + 0.37 * ((i * 7919 + k * 104729) % 101) / 101.0, 0.0);
-    for (int it = 0; it < 5; ++it) {
-      // a shift a few ulps off the current eigenvalue keeps (A - shift I) numerically invertible
+    // two rounds: the first with the QR eigenvalue as the shift, the second with the refined one; each factors once and
+    // iterates on the factors (a shift a few ulps off the eigenvalue keeps (A - shift I) numerically invertible)
+    ShiftedLU lu;
+    for (int round = 0; round < 2; ++round) {
       const double eps = std::max(std::abs(lamk), scale * 1e-3) * 4e-15 * (1.0 + (k % 7));
-      const cd shifted = lamk + cd(eps, im[k] != 0.0 ? eps : 0.0);
-      std::vector<cd> y = x;
-      solve_shifted(A, n, shifted, y);
-      cd xy(0), xx(0);
-      for (int i = 0; i < n; ++i) { xy += std::conj(x[i]) * y[i]; xx += std::conj(x[i]) * x[i]; }
-      double nrm = 0.0;
-      for (auto& v : y) nrm = std::max(nrm, std::abs(v));
-      if (!(nrm > 0.0) || !std::isfinite(nrm)) return false;
-      for (int i = 0; i < n; ++i) x[i] = y[i] / nrm;
-      if (it >= 1 && std::abs(xy) > 0.0) {
-        cd l2 = shifted + xx / xy;
-        if (im[k] == 0.0) l2 = cd(l2.real(), 0.0);
-        if (std::abs(l2 - lam) <= 1e-6 * std::max(std::abs(lam), scale)) lamk = l2;  // stay on this eigenvalue
+      const cd shifted = lamk + cd(eps, im0[k] != 0.0 ? eps : 0.0);
+      lu.factor(A, n, shifted);
+      cd lnew = lamk;
+      for (int it = 0; it < (round == 0 ? 3 : 2); ++it) {
+        std::vector<cd> y = x;
+        lu.solve(y);
+        cd xy(0), xx(0);
+        for (int i = 0; i < n; ++i) { xy += std::conj(x[i]) * y[i]; xx += std::conj(x[i]) * x[i]; }
+        double nrm = 0.0;
+        for (auto& v : y) nrm = std::max(nrm, std::abs(v));
+        if (!(nrm > 0.0) || !std::isfinite(nrm)) { failed[k] = 1; return; }
+        for (int i = 0; i < n; ++i) x[i] = y[i] / nrm;
+        if (it >= 1 && std::abs(xy) > 0.0) {
+          cd l2 = shifted + xx / xy;
+          if (im0[k] == 0.0) l2 = cd(l2.real(), 0.0);
+          if (std::abs(l2 - lam) <= 1e-6 * std::max(std::abs(lam), scale)) lnew = l2;  // stay on this eigenvalue
+        }
       }
+      lamk = lnew;
     }
     re[k] = lamk.real();
-    if (im[k] != 0.0) { im[k] = lamk.imag(); re[k + 1] = lamk.real(); im[k + 1] = -lamk.imag(); }
-    if (im[k] == 0.0) {
+    if (im0[k] != 0.0) { im[k] = lamk.imag(); re[k + 1] = lamk.real(); im[k + 1] = -lamk.imag(); }
+    if (im0[k] == 0.0) {
       // rotate to a real vector
       cd ph(0);
       double best = 0;
@@ -373,24 +432,27 @@ inline bool eigen_general(const std::vector<double>& A, int n, std::vector<doubl
         if (std::abs(v) > best) { best = std::abs(v); ph = v; }
       for (int i = 0; i < n; ++i) V[(size_t)i * n + k] = (x[i] / ph).real();
     } else {
-      if (k + 1 >= n) return false;
+      if (k + 1 >= n) { failed[k] = 1; return; }
       for (int i = 0; i < n; ++i) {
         V[(size_t)i * n + k] = x[i].real();
         V[(size_t)i * n + k + 1] = x[i].imag();
       }
     }
-  }
+  });
+  for (char f : failed)
+    if (f) return false;
   return true;
 }
 
 inline std::vector<double> matmul(const std::vector<double>& A, const std::vector<double>& B, int n) {
   std::vector<double> C((size_t)n * n, 0.0);
-  for (int i = 0; i < n; ++i)
+  parallel_for(n, 96, [&](int i) {
     for (int k = 0; k < n; ++k) {
       const double a = A[(size_t)i * n + k];
       if (a == 0.0) continue;
       for (int j = 0; j < n; ++j) C[(size_t)i * n + j] += a * B[(size_t)k * n + j];
     }
+  });
   return C;
 }
 

@@ -182,12 +182,18 @@ class AbstractSubstitutionModel : public SubstitutionModel {
       if (usable) {
         // the eigen form must reproduce the generator; a (nearly) defective matrix does not and takes the series path,
         // as the reference does when MatrixTools::inv fails (:283-291)
-        std::vector<double> D((size_t)n * n, 0.0);
+        // V D with D block diagonal ([[re, im], [-im, re]] per conjugate pair): column work, then one product
+        std::vector<double> VD((size_t)n * n);
         for (int k = 0; k < n; ++k) {
-          D[(size_t)k * n + k] = eigenValues_[k];
-          if (iEigenValues_[k] > 0 && k + 1 < n) { D[(size_t)k * n + k + 1] = iEigenValues_[k]; D[(size_t)(k + 1) * n + k] = -iEigenValues_[k]; }
+          const double re_k = eigenValues_[k], im_k = iEigenValues_[k];
+          for (int i = 0; i < n; ++i) {
+            double v = V[(size_t)i * n + k] * re_k;
+            if (im_k > 0 && k + 1 < n) v -= V[(size_t)i * n + k + 1] * im_k;           // D[k+1][k] = -im
+            else if (im_k < 0 && k >= 1 && iEigenValues_[k - 1] > 0) v += V[(size_t)i * n + k - 1] * iEigenValues_[k - 1];   // D[k-1][k] = +im
+            VD[(size_t)i * n + k] = v;
+          }
         }
-        const std::vector<double> R = linalg::matmul(linalg::matmul(V, D, n), Vinv, n);
+        const std::vector<double> R = linalg::matmul(VD, Vinv, n);
         double err = 0.0, nrm = 0.0;
         for (int i = 0; i < n; ++i)
           for (int j = 0; j < n; ++j) {
