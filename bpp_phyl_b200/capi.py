@@ -240,8 +240,8 @@ def site_patterns_device(columns, code_bytes=1, tip_codes=True, device=0):
     k = npat.value
     codes = None
     if tip is not None:
-        codes = tip[:k * w].view(np.uint8 if code_bytes == 1 else np.uint16).reshape(w // code_bytes, k).copy()
-    return ps[:k].copy(), wt[:k].copy(), ix, codes
+        codes = tip[:k * w].view(np.uint8 if code_bytes == 1 else np.uint16).reshape(w // code_bytes, k)   # a view: no second copy
+    return ps[:k], wt[:k], ix, codes
 
 
 class _ModelHolder:

@@ -83,18 +83,21 @@ __global__ void __launch_bounds__(kChrWarps * 32, 2) chr_level_kernel(ChrLevelPa
     tl[tid] = n >= 0 ? md.rate * p.rate0 * p.brlen[(size_t)pt * p.nn + n] : 0.0;
     cexp[tid] = 0;
   }
-  __syncthreads();
+  // columns in use (a tile is filled from column 0): only their 8-column blocks go through the tensor cores, and the
+  // element-wise phases stop at the last block in use.  Most levels of a tree hold a handful of branches.
+  const int ncb = (__syncthreads_count(tid < kChrCols && edges[tid] >= 0) + 7) >> 3;
+  const int ncols = ncb * 8;
 
   if (kind == 0) {
     // observed tips: W[:, j] = V^-1[:, state_j]
-    for (int i = tid; i < K4 * kChrCols; i += blockDim.x) {
+    for (int i = tid; i < K4 * ncols; i += blockDim.x) {
       const int j = i / K4, k = i - j * K4;
       const int n = cnode[j];
       Ws[k * kChrLD + j] = (n >= 0 && k < S) ? __ldg(md.Vinv + (size_t)k * S + p.leaf_state[n]) : 0.0;
     }
   } else {
     // dense columns: x = the son's conditional likelihoods = product of ITS sons' terms (or a dense leaf's init row)
-    for (int i = tid; i < K4 * kChrCols; i += blockDim.x) {
+    for (int i = tid; i < K4 * ncols; i += blockDim.x) {
       const int j = i / K4, k = i - j * K4;      // consecutive threads read one son's term contiguously
       const int n = cnode[j];
       double v = 0.0;
@@ -116,7 +119,7 @@ __global__ void __launch_bounds__(kChrWarps * 32, 2) chr_level_kernel(ChrLevelPa
     }
     __syncthreads();
     // the product of several rescaled terms may be small again: bring every column's maximum back to [0.5, 1)
-    if (warp < kChrCols / 8 * 2) {   // 8 warps x 4 columns
+    if (warp * 4 < ncols) {   // 8 warps x 4 columns
       for (int j = warp * 4; j < warp * 4 + 4; ++j) {
         double m = 0.0;
         for (int k = lane; k < S; k += 32) m = fmax(m, fabs(Xs[k * kChrLD + j]));
@@ -132,20 +135,20 @@ __global__ void __launch_bounds__(kChrWarps * 32, 2) chr_level_kernel(ChrLevelPa
       }
     }
     __syncthreads();
-    for (int i = tid; i < S * kChrCols; i += blockDim.x) {
-      const int k = i / kChrCols, j = i - k * kChrCols;
+    for (int i = tid; i < S * ncols; i += blockDim.x) {
+      const int k = i / ncols, j = i - k * ncols;
       Xs[k * kChrLD + j] *= cscale[j];
     }
     __syncthreads();
     double acc[kChrMaxRB][kChrCols / 8][2];
-    chr_gemm(md.Vinv, S, K4, Xs, nrb, warp, g, q, acc);
+    chr_gemm_ncb(ncb, md.Vinv, S, K4, Xs, nrb, warp, g, q, acc);
     __syncthreads();
-    chr_store_acc(Ws, nrb, warp, g, q, acc);
+    chr_store_acc(Ws, nrb, warp, g, q, acc, ncb);
   }
   __syncthreads();
   // T(t): exp(re l) on real eigenvalues, the rotation block on conjugate pairs (ChromosomeSubstitutionModel.cpp:821-850)
-  for (int i = tid; i < S * kChrCols; i += blockDim.x) {
-    const int k = i / kChrCols, j = i - k * kChrCols;
+  for (int i = tid; i < S * ncols; i += blockDim.x) {
+    const int k = i / ncols, j = i - k * ncols;
     const int role = md.role[k];
     const double l = tl[j];
     if (role == 0) {
@@ -162,13 +165,13 @@ __global__ void __launch_bounds__(kChrWarps * 32, 2) chr_level_kernel(ChrLevelPa
   __syncthreads();
   {
     double acc[kChrMaxRB][kChrCols / 8][2];
-    chr_gemm(md.V, S, K4, Ws, nrb, warp, g, q, acc);
+    chr_gemm_ncb(ncb, md.V, S, K4, Ws, nrb, warp, g, q, acc);
     __syncthreads();
-    chr_store_acc(Xs, nrb, warp, g, q, acc);
+    chr_store_acc(Xs, nrb, warp, g, q, acc, ncb);
   }
   __syncthreads();
   // rescale every term to [0.5, 1) by an exact power of two and store it with its exponent
-  if (warp < kChrCols / 8 * 2) {
+  if (warp * 4 < ncols) {
     for (int j = warp * 4; j < warp * 4 + 4; ++j) {
       double m = 0.0;
       for (int k = lane; k < S; k += 32) m = fmax(m, fabs(Xs[k * kChrLD + j]));
@@ -188,7 +191,7 @@ __global__ void __launch_bounds__(kChrWarps * 32, 2) chr_level_kernel(ChrLevelPa
   // an observed tip's term IS a column of P: the reference's per-entry clamp (ChromosomeSubstitutionModel.cpp:903-916) applies
   // to it exactly; cscale is 1 there unless the whole column is below 2^-256
   const bool clamp_col = kind == 0 && (md.flags & 4u);
-  for (int i = tid; i < S * kChrCols; i += blockDim.x) {
+  for (int i = tid; i < S * ncols; i += blockDim.x) {
     const int j = i / S, k = i - j * S;     // consecutive threads write one term contiguously
     const int n = cnode[j];
     if (n < 0) continue;

@@ -45,43 +45,88 @@ constexpr int kChrWarps = 8;
 constexpr int kChrMaxRB = 4;      // row blocks of 8 per warp -> S <= 8 * 8 * 4 = 256
 // C[rb][cb] += A[rows of rb][k] . Bs[k][cols of cb]   for this warp's row blocks; A row-major [S][S] in global memory
 // COHERENT: A was written earlier by this same kernel (ld.global.cg: L2, never a stale L1 line); otherwise it is read-only for
-// the launch (ld.global.nc)
-template <bool COHERENT = false>
-__device__ __forceinline__ void chr_gemm(const double* __restrict__ A, int S, int K4, const double* Bs, int nrb, int warp, int g,
-                                         int q, double (&acc)[kChrMaxRB][kChrCols / 8][2]) {
+// the launch (ld.global.nc).
+// NCB = column blocks of 8 in use (a tree level with 5 branches needs one, not four), KU = k-steps whose A fragments are fetched
+// together.  The A fragments of the NEXT KU k-steps are in flight while the current ones feed the tensor cores (two register
+// sets), so the L2 latency of A -- the only operand that does not sit in shared memory -- is covered by 4 KU loads per lane;
+// a narrow tile has few DMMAs per load and takes a deep KU, a full one the opposite.  Accumulation order over k is the same for
+// every (NCB, KU): results do not depend on them.
+template <bool COHERENT, int NCB, int KU>
+__device__ __forceinline__ void chr_gemm_t(const double* __restrict__ A, int S, int K4, const double* Bs, int nrb, int warp, int g,
+                                           int q, double (&acc)[kChrMaxRB][kChrCols / 8][2]) {
 #pragma unroll
   for (int i = 0; i < kChrMaxRB; ++i)
 #pragma unroll
-    for (int cb = 0; cb < kChrCols / 8; ++cb) acc[i][cb][0] = acc[i][cb][1] = 0.0;
-#pragma unroll 2
-  for (int k0 = 0; k0 < K4; k0 += 4) {
-    double a[kChrMaxRB];
+    for (int cb = 0; cb < NCB; ++cb) acc[i][cb][0] = acc[i][cb][1] = 0.0;
+  const double* arow[kChrMaxRB];
+  bool rok[kChrMaxRB];
 #pragma unroll
-    for (int i = 0; i < kChrMaxRB; ++i) {
-      const int row = (warp + i * kChrWarps) * 8 + g;
-      const bool in = warp + i * kChrWarps < nrb && row < S && k0 + q < S;
-      a[i] = !in ? 0.0 : (COHERENT ? __ldcg(A + (size_t)row * S + k0 + q) : __ldg(A + (size_t)row * S + k0 + q));   // L2 / read-only path
-    }
-    double b[kChrCols / 8];
+  for (int i = 0; i < kChrMaxRB; ++i) {
+    const int row = (warp + i * kChrWarps) * 8 + g;
+    rok[i] = warp + i * kChrWarps < nrb && row < S;
+    arow[i] = A + (size_t)(rok[i] ? row : 0) * S + q;
+  }
+  auto fetch = [&](int kbase, double (&a)[KU][kChrMaxRB]) {
 #pragma unroll
-    for (int cb = 0; cb < kChrCols / 8; ++cb) b[cb] = Bs[(k0 + q) * kChrLD + cb * 8 + g];
+    for (int u = 0; u < KU; ++u) {
+      const int k = kbase + 4 * u;
 #pragma unroll
-    for (int i = 0; i < kChrMaxRB; ++i)
-      if (warp + i * kChrWarps < nrb) {
-#pragma unroll
-        for (int cb = 0; cb < kChrCols / 8; ++cb) dmma884(acc[i][cb][0], acc[i][cb][1], a[i], b[cb]);
+      for (int i = 0; i < kChrMaxRB; ++i) {
+        const bool in = rok[i] && k + q < S;
+        a[u][i] = !in ? 0.0 : (COHERENT ? __ldcg(arow[i] + k) : __ldg(arow[i] + k));   // L2 / read-only path
       }
+    }
+  };
+  auto feed = [&](int kbase, const double (&a)[KU][kChrMaxRB]) {
+#pragma unroll
+    for (int u = 0; u < KU; ++u) {
+      const int k = kbase + 4 * u;
+      if (k < K4) {   // uniform
+        double b[NCB];
+#pragma unroll
+        for (int cb = 0; cb < NCB; ++cb) b[cb] = Bs[(k + q) * kChrLD + cb * 8 + g];
+#pragma unroll
+        for (int i = 0; i < kChrMaxRB; ++i)
+          if (warp + i * kChrWarps < nrb) {
+#pragma unroll
+            for (int cb = 0; cb < NCB; ++cb) dmma884(acc[i][cb][0], acc[i][cb][1], a[u][i], b[cb]);
+          }
+      }
+    }
+  };
+  double a0[KU][kChrMaxRB], a1[KU][kChrMaxRB];
+  fetch(0, a0);
+  for (int k0 = 0; k0 < K4; k0 += 8 * KU) {
+    fetch(k0 + 4 * KU, a1);
+    feed(k0, a0);
+    fetch(k0 + 8 * KU, a0);
+    feed(k0 + 4 * KU, a1);
+  }
+}
+template <bool COHERENT = false>
+__device__ __forceinline__ void chr_gemm(const double* __restrict__ A, int S, int K4, const double* Bs, int nrb, int warp, int g,
+                                         int q, double (&acc)[kChrMaxRB][kChrCols / 8][2]) {
+  chr_gemm_t<COHERENT, kChrCols / 8, 1>(A, S, K4, Bs, nrb, warp, g, q, acc);
+}
+// the same with the number of column blocks chosen at run time (uniform over the CTA)
+__device__ __forceinline__ void chr_gemm_ncb(int ncb, const double* __restrict__ A, int S, int K4, const double* Bs, int nrb, int warp,
+                                             int g, int q, double (&acc)[kChrMaxRB][kChrCols / 8][2]) {
+  switch (ncb) {
+    case 1: chr_gemm_t<false, 1, 4>(A, S, K4, Bs, nrb, warp, g, q, acc); break;
+    case 2: chr_gemm_t<false, 2, 2>(A, S, K4, Bs, nrb, warp, g, q, acc); break;
+    case 3: chr_gemm_t<false, 3, 1>(A, S, K4, Bs, nrb, warp, g, q, acc); break;
+    default: chr_gemm_t<false, 4, 1>(A, S, K4, Bs, nrb, warp, g, q, acc); break;
   }
 }
 __device__ __forceinline__ void chr_store_acc(double* Cs, int nrb, int warp, int g, int q,
-                                              const double (&acc)[kChrMaxRB][kChrCols / 8][2]) {
+                                              const double (&acc)[kChrMaxRB][kChrCols / 8][2], int ncb = kChrCols / 8) {
 #pragma unroll
   for (int i = 0; i < kChrMaxRB; ++i)
     if (warp + i * kChrWarps < nrb) {
       const int row = (warp + i * kChrWarps) * 8 + g;
 #pragma unroll
       for (int cb = 0; cb < kChrCols / 8; ++cb)
-        *reinterpret_cast<double2*>(Cs + row * kChrLD + cb * 8 + 2 * q) = make_double2(acc[i][cb][0], acc[i][cb][1]);
+        if (cb < ncb) *reinterpret_cast<double2*>(Cs + row * kChrLD + cb * 8 + 2 * q) = make_double2(acc[i][cb][0], acc[i][cb][1]);
     }
 }
 

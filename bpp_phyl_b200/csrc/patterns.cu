@@ -21,8 +21,13 @@
 #include <cub/cub.cuh>
 
 #include <algorithm>
+#include <chrono>
 #include <cstdlib>
+#include <cstring>
+#include <mutex>
 #include <string>
+#include <thread>
+#include <vector>
 
 namespace bppgpu {
 namespace {
@@ -106,8 +111,9 @@ __global__ void pattern_tip_codes_kernel(const T* __restrict__ cols, const long 
 }
 
 // ---- "dedup" (the default; BPPGPU_PATTERNS_ALGO=radix selects the plain word-by-word sort of every column) -----------------------
-// Measured on 1M sites x 1024 taxa (245k patterns), copies included: 0.240 s against 0.277 s for the plain sort and 0.59 s for the
-// host routine (profiles/r2_patterns_device_vs_host_1Mx1024.json); outputs identical, bit for bit, in every test.
+// Measured on 1M sites x 1024 taxa (245k patterns): the kernels of this variant take 20 ms, the plain sort 57 ms; the rest of a call
+// is the alignment going in and the tip codes coming out (see staged_copy below), against 0.59 s for the host routine
+// (profiles/r2_patterns_device_vs_host_1Mx1024.json); outputs identical, bit for bit, in every test.
 // Identical columns are merged BEFORE the lexicographic sort: one 64-bit hash per column (equal columns -> equal hashes; a
 // collision between different columns only leaves duplicates for the final run detection to merge), one stable sort of the hashes,
 // run heads by full comparison, and the word-by-word radix sort runs over the unique columns only.
@@ -159,7 +165,9 @@ __global__ void pattern_indices_kernel(const uint32_t* __restrict__ site_to_u, c
   if (i < n) indices[i] = (long long)u_to_pattern[site_to_u[i]];
 }
 
+// every work array comes out of ONE device allocation (a 1M-site call used to pay sixteen cudaMalloc / cudaFree pairs)
 struct DevBufs {
+  uint8_t* slab = nullptr;
   uint8_t* cols = nullptr;
   unsigned long long *keys_a = nullptr, *keys_b = nullptr;
   uint32_t *perm_a = nullptr, *perm_b = nullptr, *head = nullptr, *number = nullptr, *weights = nullptr;
@@ -167,10 +175,136 @@ struct DevBufs {
   void* temp = nullptr;
   uint8_t* tip = nullptr;
   uint32_t *site_to_u = nullptr, *u_site = nullptr, *u_weight = nullptr, *u_to_pattern = nullptr;   // "dedup" variant
-  ~DevBufs() {
-    cudaFree(site_to_u); cudaFree(u_site); cudaFree(u_weight); cudaFree(u_to_pattern);
-    cudaFree(cols); cudaFree(keys_a); cudaFree(keys_b); cudaFree(perm_a); cudaFree(perm_b); cudaFree(head); cudaFree(number);
-    cudaFree(weights); cudaFree(pattern_site); cudaFree(indices); cudaFree(temp); cudaFree(tip);
+  cudaError_t allocate(long long n, size_t col_total, size_t temp_bytes) {
+    size_t off = 0;
+    auto take = [&](size_t bytes) { const size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
+    const size_t o_cols = take(col_total + 8);   // + 8: the aligned fast path never reads past the end, the slack is for safety
+    const size_t o_ka = take((size_t)n * 8), o_kb = take((size_t)n * 8), o_ps = take((size_t)n * 8), o_ix = take((size_t)n * 8);
+    const size_t o_pa = take((size_t)n * 4), o_pb = take((size_t)n * 4), o_hd = take((size_t)n * 4), o_nb = take((size_t)n * 4);
+    const size_t o_w = take((size_t)n * 4), o_su = take((size_t)n * 4), o_us = take((size_t)n * 4), o_uw = take((size_t)n * 4);
+    const size_t o_up = take((size_t)n * 4), o_tmp = take(std::max<size_t>(temp_bytes, 16));
+    const cudaError_t e = cudaMalloc(&slab, off);
+    if (e != cudaSuccess) return e;
+    cols = slab + o_cols;
+    keys_a = reinterpret_cast<unsigned long long*>(slab + o_ka);
+    keys_b = reinterpret_cast<unsigned long long*>(slab + o_kb);
+    pattern_site = reinterpret_cast<long long*>(slab + o_ps);
+    indices = reinterpret_cast<long long*>(slab + o_ix);
+    perm_a = reinterpret_cast<uint32_t*>(slab + o_pa);
+    perm_b = reinterpret_cast<uint32_t*>(slab + o_pb);
+    head = reinterpret_cast<uint32_t*>(slab + o_hd);
+    number = reinterpret_cast<uint32_t*>(slab + o_nb);
+    weights = reinterpret_cast<uint32_t*>(slab + o_w);
+    site_to_u = reinterpret_cast<uint32_t*>(slab + o_su);
+    u_site = reinterpret_cast<uint32_t*>(slab + o_us);
+    u_weight = reinterpret_cast<uint32_t*>(slab + o_uw);
+    u_to_pattern = reinterpret_cast<uint32_t*>(slab + o_up);
+    temp = slab + o_tmp;
+    return cudaSuccess;
+  }
+  ~DevBufs() { cudaFree(slab); cudaFree(tip); }
+};
+
+// ---- pageable host memory <-> device at PCIe speed ------------------------------------------------------------------------------
+// A plain cudaMemcpy of pageable memory is bounded by ONE host thread copying through the driver's staging buffer (about 10 GB/s);
+// the alignment (1 GB for 1M sites x 1024 taxa) and the tip codes coming back are most of this routine's time.  Here kCopyThreads
+// host threads each move their share of the 4 MB chunks through two pinned buffers of their own, on their own stream, so that the
+// host-side memcpy of one chunk overlaps the DMA of the others.  The pinned pool is allocated once per process.  Buffers the
+// runtime already knows (pinned / registered / device / managed) and small ones take the direct copy.
+constexpr size_t kStageChunk = (size_t)4 << 20;
+constexpr int kCopyThreadsMax = 8;
+struct StagePool {
+  std::mutex mu;
+  int device = -1, threads = 0;
+  void* pinned[kCopyThreadsMax][2] = {};
+  cudaStream_t stream[kCopyThreadsMax] = {};
+  cudaEvent_t done[kCopyThreadsMax][2] = {};
+  cudaError_t ensure(int dev) {
+    if (device == dev) return cudaSuccess;
+    if (device >= 0) return cudaErrorInvalidDevice;   // one device per process for the pool; other devices take the direct copy
+    const char* e = getenv("BPPGPU_COPY_THREADS");
+    int t = e ? atoi(e) : std::min(4, std::max(1, (int)std::thread::hardware_concurrency()));
+    t = std::max(1, std::min(t, kCopyThreadsMax));
+    for (int i = 0; i < t; ++i) {
+      cudaError_t r = cudaStreamCreateWithFlags(&stream[i], cudaStreamNonBlocking);
+      for (int k = 0; k < 2 && r == cudaSuccess; ++k) {
+        r = cudaHostAlloc(&pinned[i][k], kStageChunk, cudaHostAllocDefault);
+        if (r == cudaSuccess) r = cudaEventCreateWithFlags(&done[i][k], cudaEventDisableTiming);
+      }
+      if (r != cudaSuccess) return r;
+    }
+    threads = t;
+    device = dev;
+    return cudaSuccess;
+  }
+};
+StagePool g_stage;
+
+// blocking copy; the caller has synchronised the work that produced `src` (device to host) / will launch consumers afterwards
+cudaError_t staged_copy(void* dst, const void* src, size_t bytes, bool h2d, int device) {
+  if (bytes == 0) return cudaSuccess;
+  const void* host = h2d ? src : dst;
+  cudaPointerAttributes at;
+  bool pageable = cudaPointerGetAttributes(&at, host) == cudaSuccess && at.type == cudaMemoryTypeUnregistered;
+  cudaGetLastError();
+  std::unique_lock<std::mutex> lock(g_stage.mu, std::defer_lock);
+  if (pageable && bytes >= 4 * kStageChunk) {
+    lock.lock();
+    if (g_stage.ensure(device) != cudaSuccess) { cudaGetLastError(); pageable = false; }
+  } else {
+    pageable = false;
+  }
+  if (!pageable) return cudaMemcpy(dst, src, bytes, h2d ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost);
+  const size_t nchunks = (bytes + kStageChunk - 1) / kStageChunk;
+  const int T = g_stage.threads;
+  std::vector<cudaError_t> err(T, cudaSuccess);
+  auto worker = [&](int t) {
+    cudaError_t r = cudaSetDevice(device);
+    size_t pend_off = 0, pend_len = 0;   // device to host: the chunk whose DMA is in flight, still to be copied out of its slot
+    int pend_slot = -1, it = 0;
+    for (size_t c = (size_t)t; c < nchunks && r == cudaSuccess; c += (size_t)T, ++it) {
+      const int slot = it & 1;
+      const size_t off = c * kStageChunk, len = std::min(kStageChunk, bytes - off);
+      if (h2d) {
+        r = cudaEventSynchronize(g_stage.done[t][slot]);   // the DMA that last read this slot
+        if (r != cudaSuccess) break;
+        std::memcpy(g_stage.pinned[t][slot], (const char*)src + off, len);
+        r = cudaMemcpyAsync((char*)dst + off, g_stage.pinned[t][slot], len, cudaMemcpyHostToDevice, g_stage.stream[t]);
+        if (r == cudaSuccess) r = cudaEventRecord(g_stage.done[t][slot], g_stage.stream[t]);
+      } else {
+        r = cudaMemcpyAsync(g_stage.pinned[t][slot], (const char*)src + off, len, cudaMemcpyDeviceToHost, g_stage.stream[t]);
+        if (r == cudaSuccess) r = cudaEventRecord(g_stage.done[t][slot], g_stage.stream[t]);
+        if (pend_slot >= 0 && r == cudaSuccess) {
+          r = cudaEventSynchronize(g_stage.done[t][pend_slot]);
+          if (r == cudaSuccess) std::memcpy((char*)dst + pend_off, g_stage.pinned[t][pend_slot], pend_len);
+        }
+        pend_slot = slot; pend_off = off; pend_len = len;
+      }
+    }
+    if (r == cudaSuccess) r = cudaStreamSynchronize(g_stage.stream[t]);
+    if (!h2d && pend_slot >= 0 && r == cudaSuccess) std::memcpy((char*)dst + pend_off, g_stage.pinned[t][pend_slot], pend_len);
+    err[t] = r;
+  };
+  std::vector<std::thread> th;
+  for (int t = 1; t < T; ++t) th.emplace_back(worker, t);
+  worker(0);
+  for (auto& x : th) x.join();
+  for (cudaError_t r : err)
+    if (r != cudaSuccess) return r;
+  return cudaSuccess;
+}
+
+// BPPGPU_PATTERNS_TRACE=1: stage times on stderr (each stage synchronised; for profiling, not for timing a production call)
+struct StageTrace {
+  bool on;
+  std::chrono::steady_clock::time_point t0;
+  StageTrace() : on(getenv("BPPGPU_PATTERNS_TRACE") != nullptr), t0(std::chrono::steady_clock::now()) {}
+  void mark(const char* what) {
+    if (!on) return;
+    cudaDeviceSynchronize();
+    const auto t1 = std::chrono::steady_clock::now();
+    fprintf(stderr, "[bppgpu patterns] %-28s %8.2f ms\n", what, 1e3 * std::chrono::duration<double>(t1 - t0).count());
+    t0 = t1;
   }
 };
 
@@ -189,10 +323,6 @@ int site_patterns_dedup(DevBufs& d, long long n, int col_bytes, size_t temp_byte
     BPP_CUDA(cudaStreamSynchronize(st));
     return BPPGPU_OK;
   };
-  BPP_CUDA(cudaMalloc(&d.site_to_u, (size_t)n * 4));
-  BPP_CUDA(cudaMalloc(&d.u_site, (size_t)n * 4));
-  BPP_CUDA(cudaMalloc(&d.u_weight, (size_t)n * 4));
-  BPP_CUDA(cudaMalloc(&d.u_to_pattern, (size_t)n * 4));
   // 1. merge identical columns: hash, stable sort by hash, run heads by full comparison
   pattern_hash_kernel<<<(unsigned)((n * 32 + 255) / 256), 256, 0, st>>>(d.cols, n, col_bytes, d.keys_a);
   pattern_iota_kernel<<<blocks, 256, 0, st>>>(d.perm_a, n);
@@ -229,12 +359,9 @@ int site_patterns_dedup(DevBufs& d, long long n, int col_bytes, size_t temp_byte
   return BPPGPU_OK;
 }
 
-// copy-out + tip codes for the "dedup" variant (the default path keeps its own, verified, copy of these lines)
-int finish_site_patterns(DevBufs& d, long long np, long long n, int col_bytes, int code_bytes, cudaStream_t st, int64_t* pattern_site,
-                         uint32_t* weights, int64_t* indices, int64_t* n_patterns, void* tip_codes) {
-  BPP_CUDA(cudaMemcpyAsync(pattern_site, d.pattern_site, (size_t)np * 8, cudaMemcpyDeviceToHost, st));
-  BPP_CUDA(cudaMemcpyAsync(weights, d.weights, (size_t)np * 4, cudaMemcpyDeviceToHost, st));
-  BPP_CUDA(cudaMemcpyAsync(indices, d.indices, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+// tip codes + copy-out, both variants
+int finish_site_patterns(DevBufs& d, long long np, long long n, int col_bytes, int code_bytes, cudaStream_t st, int device,
+                         StageTrace& tr, int64_t* pattern_site, uint32_t* weights, int64_t* indices, int64_t* n_patterns, void* tip_codes) {
   if (tip_codes) {
     const int n_leaves = col_bytes / code_bytes;
     BPP_CUDA(cudaMalloc(&d.tip, (size_t)np * (size_t)col_bytes));
@@ -246,9 +373,14 @@ int finish_site_patterns(DevBufs& d, long long np, long long n, int col_bytes, i
       pattern_tip_codes_kernel<uint16_t><<<grid, block, 0, st>>>(reinterpret_cast<const uint16_t*>(d.cols), d.pattern_site, np, n_leaves,
                                                                  reinterpret_cast<uint16_t*>(d.tip));
     BPP_CUDA(cudaGetLastError());
-    BPP_CUDA(cudaMemcpyAsync(tip_codes, d.tip, (size_t)np * (size_t)col_bytes, cudaMemcpyDeviceToHost, st));
   }
   BPP_CUDA(cudaStreamSynchronize(st));
+  tr.mark("tip-code transpose");
+  BPP_CUDA(staged_copy(pattern_site, d.pattern_site, (size_t)np * 8, false, device));
+  BPP_CUDA(staged_copy(weights, d.weights, (size_t)np * 4, false, device));
+  BPP_CUDA(staged_copy(indices, d.indices, (size_t)n * 8, false, device));
+  if (tip_codes) BPP_CUDA(staged_copy(tip_codes, d.tip, (size_t)np * (size_t)col_bytes, false, device));
+  tr.mark("device -> host results");
   *n_patterns = np;
   return BPPGPU_OK;
 }
@@ -280,31 +412,25 @@ int bppgpu_site_patterns_device(int device, const uint8_t* columns, int64_t n_si
 
   const long long n = n_sites;
   const size_t bytes = (size_t)n * (size_t)col_bytes;
+  StageTrace tr;
   DevBufs d;
-  BPP_CUDA(cudaMalloc(&d.cols, bytes + 8));   // + 8: the aligned fast path never reads past the end, the slack is for safety
-  BPP_CUDA(cudaMalloc(&d.keys_a, (size_t)n * 8));
-  BPP_CUDA(cudaMalloc(&d.keys_b, (size_t)n * 8));
-  BPP_CUDA(cudaMalloc(&d.perm_a, (size_t)n * 4));
-  BPP_CUDA(cudaMalloc(&d.perm_b, (size_t)n * 4));
-  BPP_CUDA(cudaMalloc(&d.head, (size_t)n * 4));
-  BPP_CUDA(cudaMalloc(&d.number, (size_t)n * 4));
-  BPP_CUDA(cudaMalloc(&d.weights, (size_t)n * 4));
-  BPP_CUDA(cudaMalloc(&d.pattern_site, (size_t)n * 8));
-  BPP_CUDA(cudaMalloc(&d.indices, (size_t)n * 8));
   size_t temp_sort = 0, temp_scan = 0;
   BPP_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, temp_sort, d.keys_a, d.keys_b, d.perm_a, d.perm_b, (int)n));
   BPP_CUDA(cub::DeviceScan::InclusiveSum(nullptr, temp_scan, d.head, d.number, (int)n));
   const size_t temp_bytes = std::max(temp_sort, temp_scan);
-  BPP_CUDA(cudaMalloc(&d.temp, std::max<size_t>(temp_bytes, 16)));
+  BPP_CUDA(d.allocate(n, bytes, temp_bytes));
+  tr.mark("device allocation");
 
   cudaStream_t st = 0;
-  BPP_CUDA(cudaMemcpyAsync(d.cols, columns, bytes, cudaMemcpyHostToDevice, st));
+  BPP_CUDA(staged_copy(d.cols, columns, bytes, true, device));
+  tr.mark("host -> device alignment");
   const char* algo = getenv("BPPGPU_PATTERNS_ALGO");
   if (!(algo && std::string(algo) == "radix")) {
     uint32_t npd = 0;
     const int rc = site_patterns_dedup(d, n, col_bytes, temp_bytes, st, &npd);
     if (rc) return rc;
-    return finish_site_patterns(d, (long long)npd, n, col_bytes, code_bytes, st, pattern_site, weights, indices, n_patterns, tip_codes);
+    tr.mark("dedup + sort + numbering");
+    return finish_site_patterns(d, (long long)npd, n, col_bytes, code_bytes, st, device, tr, pattern_site, weights, indices, n_patterns, tip_codes);
   }
   const unsigned blocks = (unsigned)((n + 255) / 256);
   pattern_iota_kernel<<<blocks, 256, 0, st>>>(d.perm_a, n);
@@ -329,24 +455,6 @@ int bppgpu_site_patterns_device(int device, const uint8_t* columns, int64_t n_si
   uint32_t np32 = 0;
   BPP_CUDA(cudaMemcpyAsync(&np32, d.number + (n - 1), 4, cudaMemcpyDeviceToHost, st));
   BPP_CUDA(cudaStreamSynchronize(st));
-  const long long np = (long long)np32;
-  BPP_CUDA(cudaMemcpyAsync(pattern_site, d.pattern_site, (size_t)np * 8, cudaMemcpyDeviceToHost, st));
-  BPP_CUDA(cudaMemcpyAsync(weights, d.weights, (size_t)np * 4, cudaMemcpyDeviceToHost, st));
-  BPP_CUDA(cudaMemcpyAsync(indices, d.indices, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
-  if (tip_codes) {
-    const int n_leaves = col_bytes / code_bytes;
-    BPP_CUDA(cudaMalloc(&d.tip, (size_t)np * (size_t)col_bytes));
-    const dim3 grid((unsigned)((np + 31) / 32), (unsigned)((n_leaves + 31) / 32)), block(32, 8);
-    if (grid.y > 65535u) BPP_FAIL(BPPGPU_E_INVALID, "too many leaves for the tip-code transpose");
-    if (code_bytes == 1)
-      pattern_tip_codes_kernel<uint8_t><<<grid, block, 0, st>>>(d.cols, d.pattern_site, np, n_leaves, d.tip);
-    else
-      pattern_tip_codes_kernel<uint16_t><<<grid, block, 0, st>>>(reinterpret_cast<const uint16_t*>(d.cols), d.pattern_site, np, n_leaves,
-                                                                 reinterpret_cast<uint16_t*>(d.tip));
-    BPP_CUDA(cudaGetLastError());
-    BPP_CUDA(cudaMemcpyAsync(tip_codes, d.tip, (size_t)np * (size_t)col_bytes, cudaMemcpyDeviceToHost, st));
-  }
-  BPP_CUDA(cudaStreamSynchronize(st));
-  *n_patterns = np;
-  return BPPGPU_OK;
+  tr.mark("radix sort + numbering");
+  return finish_site_patterns(d, (long long)np32, n, col_bytes, code_bytes, st, device, tr, pattern_site, weights, indices, n_patterns, tip_codes);
 }
