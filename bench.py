@@ -368,7 +368,9 @@ def run_points(a, w, rank, world, local, K, W, metric, config):
     log("[rank %d] timed region done: %.3f ms/step, P(t) %.3f ms, pruning %.3f ms" % (rank, ms / K, st["pt_ms_sum"] / K, st["prune_ms_sum"] / max(1, st["prune_count"])))
     lnl0 = float(out[0].item())
     # e2e: every point's model (host eigensystem) and branch lengths go host -> device, log L of every point comes back
-    h2d = npts * (4 * S * S * 8 + 2 * S * 8 + nn * 8)
+    # per point: the head of the model image [V | V^-1 | re | im | role] (the generator is not read by any route of these models
+    # and does not travel) + the branch lengths
+    h2d = npts * (((2 * S * S + 2 * S + (S + 1) // 2 + 31) // 32 * 32) * 8 + nn * 8)
     d2h = npts * 8
 
     def step_e2e():
@@ -398,14 +400,14 @@ def run_points(a, w, rank, world, local, K, W, metric, config):
         nfac, ntab = int(st["factored_points"]), int(st["table_points"])
         if nfac > 0:
             K8 = (S + 7) // 8 * 8
-            dm_flops = nfac * (st["chr_tiles_tip"] + 2 * st["chr_tiles_dense"]) * (K8 // 8) * 4 * (K8 // 4) * 512.0
+            dm_flops = nfac * (st["chr_cblocks_tip"] + 2 * st["chr_cblocks_dense"]) * (K8 // 8) * (K8 // 4) * 512.0
             ach = dm_flops / (kms * 1e-3) / 1e12 if kms > 0 else None
-            roofline = {"bound": "tensor", "kernel": "chr_level_kernel (one launch per tree level; all levels + root timed together)",
+            roofline = {"bound": "tensor", "kernel": "chr_level_kernel / chr_chain_kernel (one launch per wide tree level, one for the single-tile levels above; all levels + root timed together)",
                         "achieved": ach, "peak": dmma_peak, "unit": "TFLOP/s", "frac": ach / dmma_peak if ach else None, "traffic": None,
                         "kernel_ms": kms, "executed_dmma_flops_per_eval": dm_flops, "guard_ms": pt_ms,
                         "peak_source": "FP64 mma.sync m8n8k4 measured in this run (bppgpu_measure_fp64_peak)",
                         "note": "P(t) is applied in factored form V T(t) V^-1 x, tree level by tree level, as skinny tensor-core GEMMs; "
-                                "flops = DMMAs issued x 512 (column tiles are padded to 32 columns)"}
+                                "flops = DMMAs issued x 512 (only the 8-column blocks in use are issued)"}
         else:
             n_mat = npts * (nn - 1)
             flops = n_mat * (2.0 * S ** 3 + S * S)

@@ -95,6 +95,8 @@ class Stats(C.Structure):
         ("table_points", C.c_int64),
         ("chr_tiles_tip", C.c_int32),
         ("chr_tiles_dense", C.c_int32),
+        ("chr_cblocks_tip", C.c_int32),
+        ("chr_cblocks_dense", C.c_int32),
     ]
 
 

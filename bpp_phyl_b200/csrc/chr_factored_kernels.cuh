@@ -50,11 +50,12 @@ struct ChrLevelParams {
 
 inline size_t chr_level_smem(int S) {
   const int K4 = (S + 7) & ~7;
-  return (size_t)K4 * kChrLD * sizeof(double) + 3 * kChrCols * sizeof(double) + 2 * kChrCols * sizeof(int);
+  return (size_t)K4 * kChrLD * sizeof(double) + 3 * kChrCols * sizeof(double) + 2 * kChrCols * sizeof(int) +
+         (size_t)kChrWarps * kChrRingDoubles * sizeof(double);   // + every warp's ring of A fragments
 }
 
-__global__ void __launch_bounds__(kChrWarps * 32, 2) chr_level_kernel(ChrLevelParams p) {
-  extern __shared__ __align__(16) double sm_chr[];
+// one tile (<= 32 sons of one level) of one point; every thread of the CTA calls it
+__device__ __forceinline__ void chr_tile(const ChrLevelParams& p, double* sm_chr, int tile, int prel) {
   const int S = p.S;
   const int K4 = (S + 7) & ~7;                 // rows of the shared tiles (multiple of 8: row blocks and k-steps)
   double* Xs = sm_chr;                         // [K4][LD]  the column tile: x, then V^-1 x, then T V^-1 x, then the terms (in place:
@@ -64,18 +65,17 @@ __global__ void __launch_bounds__(kChrWarps * 32, 2) chr_level_kernel(ChrLevelPa
   double* cscale = cmax + kChrCols;            // [32]
   int* cexp = reinterpret_cast<int*>(cscale + kChrCols);   // [32] exponent carried in by the column
   int* cnode = cexp + kChrCols;                // [32]
+  double* ring = reinterpret_cast<double*>(cnode + kChrCols) + (size_t)(threadIdx.x >> 5) * kChrRingDoubles;   // this warp's A ring
 
-  const int tile = p.tile0 + blockIdx.x;
-  const int pt = p.p0 + blockIdx.y;
+  const int pt = p.p0 + prel;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, q = lane & 3;
   const int* edges = p.tile_edges + (size_t)tile * kChrCols;
   const int kind = p.tile_kind[tile];
   const int first = edges[0];
   const ModelDev md = p.models[p.branch_model[(size_t)pt * p.nn + first]];
   const int nrb = K4 >> 3;
-  if (p.skip && p.skip[pt]) return;
-  double* term_pt = p.term + (size_t)blockIdx.y * p.nn * S;
-  int* texp_pt = p.term_exp + (size_t)blockIdx.y * p.nn;
+  double* term_pt = p.term + (size_t)prel * p.nn * S;
+  int* texp_pt = p.term_exp + (size_t)prel * p.nn;
 
   if (tid < kChrCols) {
     const int n = edges[tid];
@@ -90,8 +90,9 @@ __global__ void __launch_bounds__(kChrWarps * 32, 2) chr_level_kernel(ChrLevelPa
 
   if (kind == 0) {
     // observed tips: W[:, j] = V^-1[:, state_j]
+    // (the tiles of observed tips are sorted by state: neighbouring columns read neighbouring entries of a row of V^-1)
     for (int i = tid; i < K4 * ncols; i += blockDim.x) {
-      const int j = i / K4, k = i - j * K4;
+      const int k = i / ncols, j = i - k * ncols;
       const int n = cnode[j];
       Ws[k * kChrLD + j] = (n >= 0 && k < S) ? __ldg(md.Vinv + (size_t)k * S + p.leaf_state[n]) : 0.0;
     }
@@ -141,7 +142,7 @@ __global__ void __launch_bounds__(kChrWarps * 32, 2) chr_level_kernel(ChrLevelPa
     }
     __syncthreads();
     double acc[kChrMaxRB][kChrCols / 8][2];
-    chr_gemm_ncb(ncb, md.Vinv, S, K4, Xs, nrb, warp, g, q, acc);
+    chr_gemm_ncb(ncb, md.Vinv, S, K4, Xs, ring, nrb, warp, lane, acc);
     __syncthreads();
     chr_store_acc(Ws, nrb, warp, g, q, acc, ncb);
   }
@@ -165,7 +166,7 @@ __global__ void __launch_bounds__(kChrWarps * 32, 2) chr_level_kernel(ChrLevelPa
   __syncthreads();
   {
     double acc[kChrMaxRB][kChrCols / 8][2];
-    chr_gemm_ncb(ncb, md.V, S, K4, Ws, nrb, warp, g, q, acc);
+    chr_gemm_ncb(ncb, md.V, S, K4, Ws, ring, nrb, warp, lane, acc);
     __syncthreads();
     chr_store_acc(Xs, nrb, warp, g, q, acc, ncb);
   }
@@ -198,6 +199,28 @@ __global__ void __launch_bounds__(kChrWarps * 32, 2) chr_level_kernel(ChrLevelPa
     double v = Xs[k * kChrLD + j];
     if (clamp_col) v = v < 0.0 ? 1e-20 : (v > 1.0 ? 1.0 : v);
     term_pt[(size_t)n * S + k] = v * cscale[j];
+  }
+}
+
+// one launch per tree level: grid (tiles of the level, points)
+__global__ void __launch_bounds__(kChrWarps * 32, 2) chr_level_kernel(ChrLevelParams p) {
+  extern __shared__ __align__(16) double sm_chr[];
+  if (p.skip && p.skip[p.p0 + blockIdx.y]) return;
+  chr_tile(p, sm_chr, p.tile0 + blockIdx.x, blockIdx.y);
+}
+
+// The top of the tree in ONE launch: from the first level on which every later level is a single tile (a handful of branches
+// each -- 43 of the 47 levels of the 500-taxon benchmark tree) a CTA keeps its point and walks the levels itself.  Level-by-level
+// launches stream the V and V^-1 of ALL points (2.6 GB at 4096 points x 200 states) from HBM once per level; here the launch is
+// sized to one CTA per SM (p.chain_smem), so the eigenvectors of the 148 resident points (95 MB) stay in the 126 MB L2 while
+// their CTA goes up the tree, and HBM sees each point once.  The terms written by one level are read back by the same CTA after
+// a block barrier.
+__global__ void __launch_bounds__(kChrWarps * 32, 1) chr_chain_kernel(ChrLevelParams p, int ntiles) {
+  extern __shared__ __align__(16) double sm_chr[];
+  if (p.skip && p.skip[p.p0 + blockIdx.x]) return;
+  for (int t = 0; t < ntiles; ++t) {
+    chr_tile(p, sm_chr, p.tile0 + t, blockIdx.x);
+    __syncthreads();
   }
 }
 

@@ -108,14 +108,92 @@ __device__ __forceinline__ void chr_gemm(const double* __restrict__ A, int S, in
                                          int q, double (&acc)[kChrMaxRB][kChrCols / 8][2]) {
   chr_gemm_t<COHERENT, kChrCols / 8, 1>(A, S, K4, Bs, nrb, warp, g, q, acc);
 }
-// the same with the number of column blocks chosen at run time (uniform over the CTA)
-__device__ __forceinline__ void chr_gemm_ncb(int ncb, const double* __restrict__ A, int S, int K4, const double* Bs, int nrb, int warp,
-                                             int g, int q, double (&acc)[kChrMaxRB][kChrCols / 8][2]) {
+// ---- the same product with A streamed through a warp-private cp.async ring --------------------------------------------------------
+// A warp only ever reads the A rows of its own row blocks, so each warp brings them in by itself: per k-step the 32 rows x 4
+// doubles (1 KB) of its fragments, into a ring of kChrStages slots in shared memory, kChrStages - 1 k-steps ahead of the tensor
+// cores.  The bytes in flight live in shared memory instead of registers (5 KB per warp against 0.25 KB with register double
+// buffering), which is what covers the L2 / HBM latency of A; no block-level barrier sits in the k loop (cp.async.wait_group +
+// __syncwarp).  Fragment reads of the ring are conflict-free (row stride 32 B: bank pair 8 g + 2 q within a half warp).
+// Rows / k beyond S are zero-filled by the copy itself (src-size operand).  Accumulation order over k as in chr_gemm_t.
+constexpr int kChrStages = 6;
+constexpr int kChrRingDoubles = kChrStages * 32 * 4;   // per warp
+__device__ __forceinline__ void cp_async16_zfill(void* smem_dst, const void* gmem_src, int valid_bytes) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(s), "l"(gmem_src), "r"(valid_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async8_zfill(void* smem_dst, const void* gmem_src, int valid_bytes) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(s), "l"(gmem_src), "r"(valid_bytes) : "memory");
+}
+template <int NCB>
+__device__ __forceinline__ void chr_gemm_ring(const double* __restrict__ A, int S, int K4, const double* Bs, double* ring, int nrb,
+                                              int warp, int lane, double (&acc)[kChrMaxRB][kChrCols / 8][2]) {
+  const int g = lane >> 2, q = lane & 3;
+#pragma unroll
+  for (int i = 0; i < kChrMaxRB; ++i)
+#pragma unroll
+    for (int cb = 0; cb < NCB; ++cb) acc[i][cb][0] = acc[i][cb][1] = 0.0;
+  const int nk = K4 >> 2;
+  const bool al16 = (S & 1) == 0 && (reinterpret_cast<size_t>(A) & 15) == 0;   // uniform: 16-byte pieces need aligned rows
+  auto issue = [&](int t, int slot) {
+    double* dst = ring + slot * 128;
+    const int k0 = t * 4;
+    if (al16) {
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int p = lane + 32 * j, r = p >> 1, h = p & 1;
+        const int rb = warp + (r >> 3) * kChrWarps, row = rb * 8 + (r & 7), kc = k0 + 2 * h;
+        int valid = (rb < nrb && row < S) ? (S - kc) * 8 : 0;
+        valid = valid < 0 ? 0 : (valid > 16 ? 16 : valid);
+        cp_async16_zfill(dst + r * 4 + 2 * h, valid ? A + (size_t)row * S + kc : A, valid);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int p = lane + 32 * j, r = p >> 2, c = p & 3;
+        const int rb = warp + (r >> 3) * kChrWarps, row = rb * 8 + (r & 7), kc = k0 + c;
+        const int valid = (rb < nrb && row < S && kc < S) ? 8 : 0;
+        cp_async8_zfill(dst + r * 4 + c, valid ? A + (size_t)row * S + kc : A, valid);
+      }
+    }
+  };
+#pragma unroll
+  for (int t = 0; t < kChrStages - 1; ++t) {
+    if (t < nk) issue(t, t);
+    cp_async_commit();
+  }
+  int slot = 0, fill = kChrStages - 1;   // slot read by this k-step; slot the next copy goes to (the one read one k-step ago)
+  for (int t = 0; t < nk; ++t) {
+    cp_async_wait<kChrStages - 2>();   // this lane's pieces of k-step t have landed ...
+    __syncwarp();                      // ... and so have the other lanes'; everyone is done reading the slot of k-step t - 1
+    if (t + kChrStages - 1 < nk) issue(t + kChrStages - 1, fill);
+    cp_async_commit();
+    const double* as = ring + slot * 128;
+    double a[kChrMaxRB], b[NCB];
+#pragma unroll
+    for (int i = 0; i < kChrMaxRB; ++i) a[i] = as[(i * 8 + g) * 4 + q];
+#pragma unroll
+    for (int cb = 0; cb < NCB; ++cb) b[cb] = Bs[(4 * t + q) * kChrLD + cb * 8 + g];
+#pragma unroll
+    for (int i = 0; i < kChrMaxRB; ++i)
+      if (warp + i * kChrWarps < nrb) {
+#pragma unroll
+        for (int cb = 0; cb < NCB; ++cb) dmma884(acc[i][cb][0], acc[i][cb][1], a[i], b[cb]);
+      }
+    slot = slot + 1 == kChrStages ? 0 : slot + 1;
+    fill = fill + 1 == kChrStages ? 0 : fill + 1;
+  }
+  cp_async_wait<0>();
+  __syncwarp();
+}
+// the number of column blocks chosen at run time (uniform over the CTA)
+__device__ __forceinline__ void chr_gemm_ncb(int ncb, const double* __restrict__ A, int S, int K4, const double* Bs, double* ring, int nrb,
+                                             int warp, int lane, double (&acc)[kChrMaxRB][kChrCols / 8][2]) {
   switch (ncb) {
-    case 1: chr_gemm_t<false, 1, 4>(A, S, K4, Bs, nrb, warp, g, q, acc); break;
-    case 2: chr_gemm_t<false, 2, 2>(A, S, K4, Bs, nrb, warp, g, q, acc); break;
-    case 3: chr_gemm_t<false, 3, 1>(A, S, K4, Bs, nrb, warp, g, q, acc); break;
-    default: chr_gemm_t<false, 4, 1>(A, S, K4, Bs, nrb, warp, g, q, acc); break;
+    case 1: chr_gemm_ring<1>(A, S, K4, Bs, ring, nrb, warp, lane, acc); break;
+    case 2: chr_gemm_ring<2>(A, S, K4, Bs, ring, nrb, warp, lane, acc); break;
+    case 3: chr_gemm_ring<3>(A, S, K4, Bs, ring, nrb, warp, lane, acc); break;
+    default: chr_gemm_ring<4>(A, S, K4, Bs, ring, nrb, warp, lane, acc); break;
   }
 }
 __device__ __forceinline__ void chr_store_acc(double* Cs, int nrb, int warp, int g, int q,

@@ -14,6 +14,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <functional>
+#include <string>
+#include <thread>
 
 #include <dlfcn.h>
 #include <nccl.h>   // declarations only: the library is dlopen()ed at bppgpu_comm_init, so libbppgpu has no link-time NCCL dependency
@@ -238,13 +240,42 @@ static void free_model(DevModel& m) {
   m = DevModel{};
 }
 
-// bytes of the host-side image of a model slab: [V | Vinv | Q | Q2 | re | im | role(int, padded to 8 bytes each)]
-static size_t model_slab_doubles(int S) { return (size_t)4 * S * S + 3 * (size_t)S; }
+// Host-side image of a model slab: [V | Vinv | re | im | role(int) | pad] [Q | Q2].  The head is all an eigen-route model without
+// generator needs, so it travels alone (half the bytes of a batched-points upload).
+static size_t model_head_doubles(int S) { return (((size_t)2 * S * S + 2 * (size_t)S + ((size_t)S + 1) / 2) + 31) & ~(size_t)31; }
+static size_t model_slab_doubles(int S) { return model_head_doubles(S) + (size_t)2 * S * S; }
 
-// Fills `img` (host, model_slab_doubles(S) doubles) and the padded / permuted image `pimg` (resized; empty when V .. re serve the
-// tensor-core kernel as they are) from the descriptor; returns flags through dm.  No CUDA call: set_models stages many images.
-static int build_model_image(DevModel& dm, const bppgpu_model_desc* m, int S, bool need_q2, double* img, std::vector<double>& pimg) {
-  const size_t SS = (size_t)S * S;
+// pslab of a model = [Vp | Vinvp | rep | imp], the copies the tensor-core P(t) kernel reads when S is not a multiple of 8 or the
+// spectrum has conjugate pairs: zero-padded to Sp, eigen-columns permuted so that every pair starts at an even index (pairs first,
+// then the real eigenvalues).  Built on the device from the slab that has just arrived: no second host image, no second copy.
+__global__ void model_permute_kernel(const double* __restrict__ V, const double* __restrict__ Vinv, const double* __restrict__ re,
+                                     const double* __restrict__ im, const int* __restrict__ role, int S, int Sp, double* __restrict__ pslab) {
+  __shared__ int order[256];
+  if (threadIdx.x == 0) {
+    int n = 0;
+    for (int k = 0; k < S; ++k)
+      if (role[k] == 1) { order[n++] = k; order[n++] = k + 1; }
+    for (int k = 0; k < S; ++k)
+      if (role[k] == 0) order[n++] = k;
+  }
+  __syncthreads();
+  double *vp = pslab, *vip = vp + (size_t)Sp * Sp, *rp = vip + (size_t)Sp * Sp, *ip = rp + Sp;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < Sp * Sp; idx += gridDim.x * blockDim.x) {
+    const int i = idx / Sp, j = idx - i * Sp;
+    vp[idx] = (i < S && j < S) ? V[(size_t)i * S + order[j]] : 0.0;     // vp[i][j]   = V[i][order[j]]
+    vip[idx] = (i < S && j < S) ? Vinv[(size_t)order[i] * S + j] : 0.0; // vip[i][j]  = Vinv[order[i]][j]
+  }
+  if (blockIdx.x == 0)
+    for (int j = threadIdx.x; j < Sp; j += blockDim.x) {
+      rp[j] = j < S ? re[order[j]] : 0.0;
+      ip[j] = j < S ? im[order[j]] : 0.0;
+    }
+}
+
+// Fills `img` (host, model_slab_doubles(S) doubles; only the first *used are written and need to travel) from the descriptor and
+// the scalar fields of dm; *padded = the tensor-core kernel needs the permuted copies.  No CUDA call: set_models stages many images.
+static int build_model_image(DevModel& dm, const bppgpu_model_desc* m, int S, bool need_q2, bool keep_q, double* img, size_t* used, bool* padded) {
+  const size_t SS = (size_t)S * S, head = model_head_doubles(S);
   const bool eigen = (m->flags & BPPGPU_MODEL_NONSINGULAR) != 0;
   if (eigen && (!m->right_eigen || !m->left_eigen || !m->eigen_re))
     BPP_FAIL(BPPGPU_E_INVALID, "model flagged NONSINGULAR needs right_eigen, left_eigen and eigen_re");
@@ -254,15 +285,18 @@ static int build_model_image(DevModel& dm, const bppgpu_model_desc* m, int S, bo
   dm.rate = m->rate;
   dm.eps = m->taylor_epsilon > 0 ? m->taylor_epsilon : 1e-4;
   dm.has_complex = 0;
-  dm.has_Q = m->generator != nullptr;
-  double *iV = img, *iVinv = img + SS, *iQ = img + 2 * SS, *iQ2 = img + 3 * SS, *ire = img + 4 * SS, *iim = ire + S;
+  // the generator only travels when a route of this model reads it: series (singular), the Chromosome derivative forms, exact expm
+  const bool want_q = m->generator && (keep_q || !eigen || (m->flags & (BPPGPU_MODEL_CHR_DERIV | BPPGPU_MODEL_CHR_TAYLOR | BPPGPU_MODEL_EXACT_EXPM)));
+  dm.has_Q = want_q;
+  dm.q_l1 = 0.0;
+  double *iV = img, *iVinv = img + SS, *ire = img + 2 * SS, *iim = ire + S, *iQ = img + head, *iQ2 = iQ + SS;
   int* irole = reinterpret_cast<int*>(iim + S);
-  std::fill(img, img + model_slab_doubles(S), 0.0);
-  pimg.clear();
+  *used = want_q ? model_slab_doubles(S) : head;
   if (eigen) {
     memcpy(iV, m->right_eigen, SS * 8);
     memcpy(iVinv, m->left_eigen, SS * 8);
     memcpy(ire, m->eigen_re, S * 8);
+    std::fill(iim, img + head, 0.0);   // im, role, pad
     if (m->eigen_im) {
       memcpy(iim, m->eigen_im, S * 8);
       // conjugate pairs are adjacent, the +im member first (JAMA EigenValue convention,
@@ -276,30 +310,14 @@ static int build_model_image(DevModel& dm, const bppgpu_model_desc* m, int S, bo
         }
       }
     }
-    const int Sp = (S + 7) & ~7;
-    if (S >= 32 && (Sp != S || dm.has_complex)) {
-      // copies for the DMMA kernel: zero-padded to Sp, eigen-columns permuted so that every conjugate pair starts at an
-      // even index (pairs first, then the real eigenvalues): [Vp | Vinvp | rep | imp]
-      std::vector<int> order;
-      for (int k = 0; k < S; ++k)
-        if (irole[k] == 1) { order.push_back(k); order.push_back(k + 1); }
-      for (int k = 0; k < S; ++k)
-        if (irole[k] == 0) order.push_back(k);
-      pimg.assign((size_t)2 * Sp * Sp + 2 * Sp, 0.0);
-      double *vp = pimg.data(), *vip = vp + (size_t)Sp * Sp, *rp = vip + (size_t)Sp * Sp, *ip = rp + Sp;
-      for (int j = 0; j < S; ++j) {
-        const int k = order[j];
-        rp[j] = m->eigen_re[k];
-        ip[j] = iim[k];
-        for (int i = 0; i < S; ++i) {
-          vp[(size_t)i * Sp + j] = m->right_eigen[(size_t)i * S + k];
-          vip[(size_t)j * Sp + i] = m->left_eigen[(size_t)k * S + i];
-        }
-      }
-    }
+  } else {
+    std::fill(img, img + head, 0.0);
   }
-  if (m->generator) {
+  const int Sp = (S + 7) & ~7;
+  *padded = eigen && S >= 32 && Sp <= 256 && (Sp != S || dm.has_complex);   // the sizes the tensor-core P(t) kernel takes
+  if (want_q) {
     memcpy(iQ, m->generator, SS * 8);
+    std::fill(iQ2, iQ2 + SS, 0.0);
     double l1 = 0.0;
     for (size_t i = 0; i < SS; ++i) l1 += std::fabs(m->generator[i]);
     dm.q_l1 = l1;
@@ -324,9 +342,10 @@ static int ensure_model_storage(DevModel& dm, int S, bool padded) {
     BPP_CUDA(cudaMalloc(&dm.slab, model_slab_doubles(S) * 8));
     dm.S = S;
   }
-  dm.V = dm.slab; dm.Vinv = dm.slab + SS; dm.Q = dm.slab + 2 * SS; dm.Q2 = dm.slab + 3 * SS;
-  dm.re = dm.slab + 4 * SS; dm.im = dm.re + S;
+  dm.V = dm.slab; dm.Vinv = dm.slab + SS;
+  dm.re = dm.slab + 2 * SS; dm.im = dm.re + S;
   dm.role = reinterpret_cast<int*>(dm.im + S);
+  dm.Q = dm.slab + model_head_doubles(S); dm.Q2 = dm.Q + SS;
   const int Sp = (S + 7) & ~7;
   if (padded) {
     if (!dm.pslab) BPP_CUDA(cudaMalloc(&dm.pslab, ((size_t)2 * Sp * Sp + 2 * Sp) * 8));
@@ -339,14 +358,28 @@ static int ensure_model_storage(DevModel& dm, int S, bool padded) {
   return BPPGPU_OK;
 }
 
+// the image -> the slot's slab on `st`, then the permuted copies from it (stream order)
+static int send_model_image(DevModel& dm, int S, const double* img, size_t used, bool padded, cudaStream_t st) {
+  BPP_CUDA(cudaMemcpyAsync(dm.slab, img, used * 8, cudaMemcpyHostToDevice, st));
+  if (padded) {
+    const int Sp = (S + 7) & ~7;
+    model_permute_kernel<<<std::min(64, (Sp * Sp + 255) / 256), 256, 0, st>>>(dm.V, dm.Vinv, dm.re, dm.im, dm.role, S, Sp, dm.pslab);
+    BPP_CUDA(cudaGetLastError());
+  }
+  return BPPGPU_OK;
+}
+
 static int upload_model(DevModel& dm, const bppgpu_model_desc* m, int S, bool need_q2 = true) {
-  std::vector<double> img(model_slab_doubles(S)), pimg;
-  int rc = build_model_image(dm, m, S, need_q2, img.data(), pimg);
+  std::vector<double> img(model_slab_doubles(S));
+  size_t used = 0;
+  bool padded = false;
+  int rc = build_model_image(dm, m, S, need_q2, /*keep_q=*/need_q2, img.data(), &used, &padded);
   if (rc) return rc;
-  rc = ensure_model_storage(dm, S, !pimg.empty());
+  rc = ensure_model_storage(dm, S, padded);
   if (rc) return rc;
-  BPP_CUDA(cudaMemcpy(dm.slab, img.data(), img.size() * 8, cudaMemcpyHostToDevice));
-  if (!pimg.empty()) BPP_CUDA(cudaMemcpy(dm.pslab, pimg.data(), pimg.size() * 8, cudaMemcpyHostToDevice));
+  rc = send_model_image(dm, S, img.data(), used, padded, 0);
+  if (rc) return rc;
+  BPP_CUDA(cudaStreamSynchronize(0));   // img goes out of scope
   dm.set = true;
   return BPPGPU_OK;
 }
@@ -580,8 +613,11 @@ int bppgpu_destroy(bppgpu_engine* e) {
   for (void* p : ptrs) cudaFree(p);
   for (auto& m : e->models) free_model(m);
   if (e->h_stage) cudaFreeHost(e->h_stage);
-  if (e->stage_ev[0]) cudaEventDestroy(e->stage_ev[0]);
-  if (e->stage_ev[1]) cudaEventDestroy(e->stage_ev[1]);
+  for (int t = 0; t < bppgpu_engine::kStageThreads; ++t) {
+    if (e->stage_stream[t]) cudaStreamDestroy(e->stage_stream[t]);
+    for (int b = 0; b < 2; ++b)
+      if (e->stage_ev[t][b]) cudaEventDestroy(e->stage_ev[t][b]);
+  }
   if (e->comm && nccl_api().ok) nccl_api().CommDestroy((ncclComm_t)e->comm);
   e->comm = nullptr;
   if (e->eval_done) cudaEventDestroy(e->eval_done);
@@ -997,6 +1033,8 @@ static int create_impl(const bppgpu_config* cfg, bppgpu_engine* e) {
     BPP_CUDA(dev_alloc(e, &e->d_chr_tile_kind, (size_t)maxtiles));
     e->h_codes.assign(e->nl, 0);
     BPP_CUDA(cudaFuncSetAttribute(chr_level_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chr_level_smem(S)));
+    BPP_CUDA(cudaFuncSetAttribute(chr_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)std::max(chr_level_smem(S), (size_t)116 * 1024)));
     e->pchunk = 1;
   } else {
     e->pchunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)e->npoints, budget / std::max<size_t>(1, (e->path == PATH_POINTS ? 1 : 3) * per_point)));
@@ -1283,31 +1321,63 @@ int bppgpu_set_models(bppgpu_engine* e, int32_t first_slot, int32_t n, const bpp
   ENGINE_SYNC(e);
   if (!descs || n < 0 || first_slot < 0 || first_slot + n > e->nmodels) BPP_FAIL(BPPGPU_E_INVALID, "bad slot range or null descriptors");
   const int S = e->S;
-  const size_t img_doubles = model_slab_doubles(S);
-  // two pinned staging images: model k is packed on the host while model k-1 travels
-  if (!e->h_stage) {
-    BPP_CUDA(cudaMallocHost(&e->h_stage, 2 * img_doubles * 8));
-    BPP_CUDA(cudaEventCreateWithFlags(&e->stage_ev[0], cudaEventDisableTiming));
-    BPP_CUDA(cudaEventCreateWithFlags(&e->stage_ev[1], cudaEventDisableTiming));
-  }
-  std::vector<double> pimg;
-  for (int k = 0; k < n; ++k) {
+  for (int k = 0; k < n; ++k)
     if (descs[k].n_states != S) BPP_FAIL(BPPGPU_E_INVALID, "model %d has %d states, engine %d", k, descs[k].n_states, S);
-    DevModel& dm = e->models[first_slot + k];
-    double* img = e->h_stage + (size_t)(k & 1) * img_doubles;
-    if (k >= 2) BPP_CUDA(cudaEventSynchronize(e->stage_ev[k & 1]));   // the copy that last used this image has left
-    int rc = build_model_image(dm, &descs[k], S, e->path != PATH_POINTS, img, pimg);
-    if (rc) return rc;
-    rc = ensure_model_storage(dm, S, !pimg.empty());
-    if (rc) return rc;
-    BPP_CUDA(cudaMemcpyAsync(dm.slab, img, img_doubles * 8, cudaMemcpyHostToDevice, e->stream));
-    BPP_CUDA(cudaEventRecord(e->stage_ev[k & 1], e->stream));
-    if (!pimg.empty()) BPP_CUDA(cudaMemcpy(dm.pslab, pimg.data(), pimg.size() * 8, cudaMemcpyHostToDevice));   // pageable: synchronous
-    dm.set = true;
+  const size_t img_doubles = model_slab_doubles(S);
+  // Several host threads, each with two pinned staging images and a stream of its own: model k is packed on the host while the
+  // previous ones travel, and the packing itself (a few hundred KB of memcpy per model) is spread over the threads -- a batched-
+  // points optimiser re-sends thousands of eigensystems per step (BASELINE config 5), and one thread packing 4096 x 640 KB was
+  // most of that step's end-to-end time.
+  constexpr int kMaxT = bppgpu_engine::kStageThreads;
+  if (!e->h_stage) {
+    BPP_CUDA(cudaMallocHost(&e->h_stage, (size_t)kMaxT * 2 * img_doubles * 8));
+    for (int t = 0; t < kMaxT; ++t) {
+      BPP_CUDA(cudaStreamCreateWithFlags(&e->stage_stream[t], cudaStreamNonBlocking));
+      for (int b = 0; b < 2; ++b) BPP_CUDA(cudaEventCreateWithFlags(&e->stage_ev[t][b], cudaEventDisableTiming));
+    }
   }
-  BPP_CUDA(cudaStreamSynchronize(e->stream));
+  static const int env_threads = getenv("BPPGPU_COPY_THREADS") ? atoi(getenv("BPPGPU_COPY_THREADS")) : 4;
+  const int T = std::max(1, std::min({kMaxT, env_threads, n / 4 + 1, (int)std::max(1u, std::thread::hardware_concurrency())}));
+  std::vector<int> rcs(T, BPPGPU_OK);
+  std::vector<std::string> msgs(T);
+  auto worker = [&](int t) -> int {
+    BPP_CUDA(cudaSetDevice(e->dev));
+    int it = 0;
+    for (int k = t; k < n; k += T, ++it) {
+      DevModel& dm = e->models[first_slot + k];
+      const int b = it & 1;
+      double* img = e->h_stage + ((size_t)t * 2 + b) * img_doubles;
+      BPP_CUDA(cudaEventSynchronize(e->stage_ev[t][b]));   // the copy that last used this image has left
+      size_t used = 0;
+      bool padded = false;
+      int rc = build_model_image(dm, &descs[k], S, e->path != PATH_POINTS, /*keep_q=*/e->path != PATH_POINTS, img, &used, &padded);
+      if (rc) return rc;
+      rc = ensure_model_storage(dm, S, padded);
+      if (rc) return rc;
+      rc = send_model_image(dm, S, img, used, padded, e->stage_stream[t]);
+      if (rc) return rc;
+      BPP_CUDA(cudaEventRecord(e->stage_ev[t][b], e->stage_stream[t]));
+      dm.set = true;
+    }
+    BPP_CUDA(cudaStreamSynchronize(e->stage_stream[t]));
+    return BPPGPU_OK;
+  };
+  auto run = [&](int t) {
+    rcs[t] = worker(t);
+    if (rcs[t]) msgs[t] = last_error();   // the error string is thread-local
+  };
+  std::vector<std::thread> th;
+  for (int t = 1; t < T; ++t) th.emplace_back(run, t);
+  run(0);
+  for (auto& x : th) x.join();
   e->models_dirty = true;
   e->last_point = -1;
+  for (int t = 0; t < T; ++t)
+    if (rcs[t]) {
+      for (int u = 0; u < T; ++u) cudaStreamSynchronize(e->stage_stream[u]);
+      last_error() = msgs[t];
+      return rcs[t];
+    }
   return BPPGPU_OK;
 }
 
@@ -1966,11 +2036,16 @@ static int eval_points_factored(bppgpu_engine* e, cudaStream_t st, bool any_real
     e->chr_level_tile0.assign(1, 0);
     for (int h = 0; h < hmax; ++h) {
       for (int kind = 0; kind < 2; ++kind) {
-        int fill = 0;
+        std::vector<int> members;
         for (int n = 0; n < nn; ++n) {
           if (n == e->root || height[n] != h) continue;
           const int kd = (e->leaf_slot[n] >= 0 && leaf_state[n] >= 0) ? 0 : 1;
-          if (kd != kind) continue;
+          if (kd == kind) members.push_back(n);
+        }
+        // observed tips by state: the columns of a tile then gather neighbouring entries of V^-1 (any order within a level is valid)
+        if (kind == 0) std::stable_sort(members.begin(), members.end(), [&](int a, int b) { return leaf_state[a] < leaf_state[b]; });
+        int fill = 0;
+        for (int n : members) {
           if (fill == 0) { edges.resize(edges.size() + kChrCols, -1); kinds.push_back(kind); }
           edges[edges.size() - kChrCols + fill] = n;
           fill = (fill + 1) % kChrCols;
@@ -1981,6 +2056,12 @@ static int eval_points_factored(bppgpu_engine* e, cudaStream_t st, bool any_real
     e->chr_ntiles = (int)kinds.size();
     e->stats.chr_tiles_tip = (int)std::count(kinds.begin(), kinds.end(), 0);
     e->stats.chr_tiles_dense = (int)std::count(kinds.begin(), kinds.end(), 1);
+    e->stats.chr_cblocks_tip = e->stats.chr_cblocks_dense = 0;
+    for (size_t t = 0; t < kinds.size(); ++t) {
+      int used = 0;
+      for (int j = 0; j < kChrCols; ++j) used += edges[t * kChrCols + j] >= 0;
+      (kinds[t] == 0 ? e->stats.chr_cblocks_tip : e->stats.chr_cblocks_dense) += (used + 7) / 8;
+    }
     BPP_CUDA(cudaMemcpyAsync(e->d_chr_tile_edges, edges.data(), edges.size() * sizeof(int), cudaMemcpyHostToDevice, st));
     BPP_CUDA(cudaMemcpyAsync(e->d_chr_tile_kind, kinds.data(), kinds.size() * sizeof(int), cudaMemcpyHostToDevice, st));
     BPP_CUDA(cudaMemcpyAsync(e->d_chr_leaf_state, leaf_state.data(), nn * sizeof(int), cudaMemcpyHostToDevice, st));
@@ -2053,7 +2134,13 @@ static int eval_points_factored(bppgpu_engine* e, cudaStream_t st, bool any_real
     lp.leaf_state = e->d_chr_leaf_state; lp.leaf_vec = e->d_chr_leaf_vec;
     lp.term = e->d_chr_term; lp.term_exp = e->d_chr_term_exp;
     lp.skip = e->d_chr_bad;
-    for (size_t l = 0; l + 1 < e->chr_level_tile0.size(); ++l) {
+    // first level from which every level is one tile: those go in one chain launch (chr_chain_kernel)
+    static const bool chain_on = !(getenv("BPPGPU_CHR_CHAIN") && atoi(getenv("BPPGPU_CHR_CHAIN")) == 0);
+    const size_t nlev = e->chr_level_tile0.size() - 1;
+    size_t chain0 = nlev;
+    while (chain_on && chain0 > 0 && e->chr_level_tile0[chain0] - e->chr_level_tile0[chain0 - 1] == 1) --chain0;
+    if (nlev - chain0 < 3) chain0 = nlev;   // not worth a different schedule
+    for (size_t l = 0; l < chain0; ++l) {
       const int t0 = e->chr_level_tile0[l], nt = e->chr_level_tile0[l + 1] - t0;
       if (nt <= 0) continue;
       lp.tile0 = t0;
@@ -2065,6 +2152,14 @@ static int eval_points_factored(bppgpu_engine* e, cudaStream_t st, bool any_real
         chr_level_kernel<<<dim3((unsigned)nt, (unsigned)std::min(65535, np - y0)), kChrWarps * 32, smem, st>>>(q);
         e->stats.kernel_launches++;
       }
+    }
+    if (chain0 < nlev) {
+      ChrLevelParams q = lp;
+      q.tile0 = e->chr_level_tile0[chain0];
+      // more than half of an SM's shared memory: one CTA per SM, so that the resident points' eigenvectors fit in L2
+      const size_t chain_smem = std::max(smem, (size_t)116 * 1024);
+      chr_chain_kernel<<<(unsigned)np, kChrWarps * 32, chain_smem, st>>>(q, e->chr_level_tile0[nlev] - q.tile0);
+      e->stats.kernel_launches++;
     }
     ChrRootParams rp{};
     rp.S = S; rp.nn = nn; rp.root = e->root; rp.p0 = f0;

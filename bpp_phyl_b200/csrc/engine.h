@@ -24,7 +24,7 @@ enum PathKind { PATH_NONE = 0, PATH_WALK4 = 1, PATH_WALKS = 2, PATH_GENERIC = 3,
 
 struct DevModel {
   // one device slab per model slot, allocated at the first upload and overwritten by later ones (an optimiser re-sends a model
-  // of the same shape at every step): [V | Vinv | Q | Q2 | re | im | role];  V .. role point into it
+  // of the same shape at every step): [V | Vinv | re | im | role | Q | Q2];  V .. role point into it
   double* slab = nullptr;
   double *V = nullptr, *Vinv = nullptr, *re = nullptr, *im = nullptr, *Q = nullptr, *Q2 = nullptr;
   double *Vp = nullptr, *Vinvp = nullptr, *rep = nullptr, *imp = nullptr;  // what the tensor-core P(t) kernel reads: V .. itself, or
@@ -206,8 +206,10 @@ struct bppgpu_engine {
   void* comm = nullptr;           // ncclComm_t
   int comm_rank = 0, comm_nranks = 1;
   double* d_wr_recs = nullptr;    // [nranks][S + 1] weighted-root records (exponent, S sums), all-gathered
-  double* h_stage = nullptr;        // pinned staging of bppgpu_set_models (two model images)
-  cudaEvent_t stage_ev[2] = {nullptr, nullptr};
+  static constexpr int kStageThreads = 8;
+  double* h_stage = nullptr;        // pinned staging of bppgpu_set_models (two model images per packing thread)
+  cudaStream_t stage_stream[kStageThreads] = {};
+  cudaEvent_t stage_ev[kStageThreads][2] = {};
   cudaEvent_t eval_done = nullptr;  // recorded at the end of every evaluation on the evaluation's stream
   cudaStream_t last_stream = nullptr;
 };

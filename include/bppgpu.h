@@ -276,6 +276,8 @@ typedef struct bppgpu_stats {
   int64_t table_points;    /* ... and points the guard sent to the table route    */
   int32_t chr_tiles_tip;   /* column tiles per point: observed-tip tiles (one GEMM) */
   int32_t chr_tiles_dense; /* ... and dense tiles (two GEMMs)                     */
+  int32_t chr_cblocks_tip;  /* 8-column blocks in use over the tip tiles (a tile runs only those through the tensor cores) */
+  int32_t chr_cblocks_dense; /* ... and over the dense tiles                       */
 } bppgpu_stats;
 int bppgpu_get_stats(bppgpu_engine* e, bppgpu_stats* out);
 

@@ -31,7 +31,7 @@ def test_struct_layouts_match_library(built_lib):
     from bpp_phyl_b200 import capi
     assert ctypes.sizeof(capi.ModelDesc) == built_lib.bppgpu_sizeof(0) == 64
     assert ctypes.sizeof(capi.Config) == built_lib.bppgpu_sizeof(1) == 72
-    assert ctypes.sizeof(capi.Stats) == built_lib.bppgpu_sizeof(2) == 104
+    assert ctypes.sizeof(capi.Stats) == built_lib.bppgpu_sizeof(2) == 112
 
 
 def test_no_cpu_fallback(built_lib):
