@@ -246,6 +246,19 @@ def site_patterns_device(columns, code_bytes=1, tip_codes=True, device=0):
     return ps[:k], wt[:k], ix, codes
 
 
+def site_patterns_device_raw(columns_ptr, n, col_bytes, ps_ptr, wt_ptr, ix_ptr, tip_ptr=None, code_bytes=1, device=0):
+    """bppgpu_site_patterns_device on raw addresses (ints): pinned or device-resident buffers owned by the caller.  Returns the
+    number of patterns; the outputs are in the caller's buffers (capacities as in include/bppgpu.h)."""
+    npat = C.c_int64(0)
+    _check(lib().bppgpu_site_patterns_device(C.c_int(device), C.cast(C.c_void_p(columns_ptr), C.POINTER(C.c_uint8)), C.c_int64(n),
+                                             C.c_int32(max(col_bytes, 1)), C.c_int32(code_bytes),
+                                             C.cast(C.c_void_p(ps_ptr), C.POINTER(C.c_int64)),
+                                             C.cast(C.c_void_p(wt_ptr), C.POINTER(C.c_uint32)),
+                                             C.cast(C.c_void_p(ix_ptr), C.POINTER(C.c_int64)), C.byref(npat),
+                                             None if tip_ptr is None else C.c_void_p(tip_ptr)))
+    return npat.value
+
+
 class _ModelHolder:
     """Keeps the numpy buffers a ModelDesc points at alive."""
 

@@ -46,6 +46,8 @@ struct ChrLevelParams {
   double* term;              // [points of this launch][nn][S] term of the branch above node n, rescaled
   int* term_exp;             // [points of this launch][nn]
   const int* skip;           // [npts] 1 = the point goes through the table route (guard), or nullptr
+  const double* aslab;       // [model slot][V^-1 | V] slab-ordered copies (chr_slab_kernel), slab-streamed kernels only
+  int nst;                   // stages of the slab ring
 };
 
 inline size_t chr_level_smem(int S) {
@@ -54,8 +56,27 @@ inline size_t chr_level_smem(int S) {
          (size_t)kChrWarps * kChrRingDoubles * sizeof(double);   // + every warp's ring of A fragments
 }
 
-// one tile (<= 32 sons of one level) of one point; every thread of the CTA calls it
-__device__ __forceinline__ void chr_tile(const ChrLevelParams& p, double* sm_chr, int tile, int prel) {
+// shared memory of the slab-streamed kernels: the column tile and its per-column scalars as above, then the ring's barriers and slabs
+inline size_t chr_slab_smem(int S, int nst) {
+  const int K8 = (S + 7) & ~7;
+  return (size_t)K8 * kChrLD * sizeof(double) + 3 * kChrCols * sizeof(double) + 2 * kChrCols * sizeof(int) + 2 * 16 * sizeof(unsigned long long) +
+         (size_t)nst * chr_slab_doubles(K8) * sizeof(double);
+}
+constexpr int kChrMaxStages = 16;
+
+// barrier over the threads that work on the tile: the whole CTA, or the consumer warps of a slab-streamed kernel (named barrier 1;
+// the producer warp is not part of it)
+template <bool SLAB>
+__device__ __forceinline__ void chr_sync() {
+  if (SLAB) asm volatile("bar.sync 1, %0;" ::"n"(kChrCons * 32) : "memory");
+  else __syncthreads();
+}
+
+// one tile (<= 32 sons of one level) of one point; every (consumer) thread of the CTA calls it
+template <bool SLAB>
+__device__ __forceinline__ void chr_tile(const ChrLevelParams& p, double* sm_chr, int tile, int prel, ChrRing* rg) {
+  constexpr int NW = SLAB ? kChrCons : kChrWarps;
+  constexpr int NT = NW * 32;
   const int S = p.S;
   const int K4 = (S + 7) & ~7;                 // rows of the shared tiles (multiple of 8: row blocks and k-steps)
   double* Xs = sm_chr;                         // [K4][LD]  the column tile: x, then V^-1 x, then T V^-1 x, then the terms (in place:
@@ -65,7 +86,7 @@ __device__ __forceinline__ void chr_tile(const ChrLevelParams& p, double* sm_chr
   double* cscale = cmax + kChrCols;            // [32]
   int* cexp = reinterpret_cast<int*>(cscale + kChrCols);   // [32] exponent carried in by the column
   int* cnode = cexp + kChrCols;                // [32]
-  double* ring = reinterpret_cast<double*>(cnode + kChrCols) + (size_t)(threadIdx.x >> 5) * kChrRingDoubles;   // this warp's A ring
+  double* ring = SLAB ? nullptr : reinterpret_cast<double*>(cnode + kChrCols) + (size_t)(threadIdx.x >> 5) * kChrRingDoubles;   // this warp's A ring
 
   const int pt = p.p0 + prel;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, q = lane & 3;
@@ -85,20 +106,21 @@ __device__ __forceinline__ void chr_tile(const ChrLevelParams& p, double* sm_chr
   }
   // columns in use (a tile is filled from column 0): only their 8-column blocks go through the tensor cores, and the
   // element-wise phases stop at the last block in use.  Most levels of a tree hold a handful of branches.
-  const int ncb = (__syncthreads_count(tid < kChrCols && edges[tid] >= 0) + 7) >> 3;
+  const int ncb = (__popc(__ballot_sync(0xffffffffu, edges[lane] >= 0)) + 7) >> 3;
   const int ncols = ncb * 8;
+  chr_sync<SLAB>();
 
   if (kind == 0) {
     // observed tips: W[:, j] = V^-1[:, state_j]
     // (the tiles of observed tips are sorted by state: neighbouring columns read neighbouring entries of a row of V^-1)
-    for (int i = tid; i < K4 * ncols; i += blockDim.x) {
+    for (int i = tid; i < K4 * ncols; i += NT) {
       const int k = i / ncols, j = i - k * ncols;
       const int n = cnode[j];
       Ws[k * kChrLD + j] = (n >= 0 && k < S) ? __ldg(md.Vinv + (size_t)k * S + p.leaf_state[n]) : 0.0;
     }
   } else {
     // dense columns: x = the son's conditional likelihoods = product of ITS sons' terms (or a dense leaf's init row)
-    for (int i = tid; i < K4 * ncols; i += blockDim.x) {
+    for (int i = tid; i < K4 * ncols; i += NT) {
       const int j = i / K4, k = i - j * K4;      // consecutive threads read one son's term contiguously
       const int n = cnode[j];
       double v = 0.0;
@@ -118,10 +140,10 @@ __device__ __forceinline__ void chr_tile(const ChrLevelParams& p, double* sm_chr
         for (int c = p.child_off[n]; c < p.child_off[n + 1]; ++c) e += texp_pt[p.children[c]];
       cexp[tid] = e;
     }
-    __syncthreads();
+    chr_sync<SLAB>();
     // the product of several rescaled terms may be small again: bring every column's maximum back to [0.5, 1)
-    if (warp * 4 < ncols) {   // 8 warps x 4 columns
-      for (int j = warp * 4; j < warp * 4 + 4; ++j) {
+    {
+      for (int j = warp; j < ncols; j += NW) {
         double m = 0.0;
         for (int k = lane; k < S; k += 32) m = fmax(m, fabs(Xs[k * kChrLD + j]));
 #pragma unroll
@@ -135,20 +157,21 @@ __device__ __forceinline__ void chr_tile(const ChrLevelParams& p, double* sm_chr
         }
       }
     }
-    __syncthreads();
-    for (int i = tid; i < S * ncols; i += blockDim.x) {
+    chr_sync<SLAB>();
+    for (int i = tid; i < S * ncols; i += NT) {
       const int k = i / ncols, j = i - k * ncols;
       Xs[k * kChrLD + j] *= cscale[j];
     }
-    __syncthreads();
+    chr_sync<SLAB>();
     double acc[kChrMaxRB][kChrCols / 8][2];
-    chr_gemm_ncb(ncb, md.Vinv, S, K4, Xs, ring, nrb, warp, lane, acc);
-    __syncthreads();
-    chr_store_acc(Ws, nrb, warp, g, q, acc, ncb);
+    if (SLAB) chr_gemm_slab_ncb(ncb, *rg, K4, Xs, nrb, warp, lane, acc);
+    else chr_gemm_ncb(ncb, md.Vinv, S, K4, Xs, ring, nrb, warp, lane, acc);
+    chr_sync<SLAB>();
+    chr_store_acc_w<NW>(Ws, nrb, warp, g, q, acc, ncb);
   }
-  __syncthreads();
+  chr_sync<SLAB>();
   // T(t): exp(re l) on real eigenvalues, the rotation block on conjugate pairs (ChromosomeSubstitutionModel.cpp:821-850)
-  for (int i = tid; i < S * ncols; i += blockDim.x) {
+  for (int i = tid; i < S * ncols; i += NT) {
     const int k = i / ncols, j = i - k * ncols;
     const int role = md.role[k];
     const double l = tl[j];
@@ -163,17 +186,18 @@ __device__ __forceinline__ void chr_tile(const ChrLevelParams& p, double* sm_chr
       Ws[(k + 1) * kChrLD + j] = ex * (cs * w1 - sn * w0);
     }
   }
-  __syncthreads();
+  chr_sync<SLAB>();
   {
     double acc[kChrMaxRB][kChrCols / 8][2];
-    chr_gemm_ncb(ncb, md.V, S, K4, Ws, ring, nrb, warp, lane, acc);
-    __syncthreads();
-    chr_store_acc(Xs, nrb, warp, g, q, acc, ncb);
+    if (SLAB) chr_gemm_slab_ncb(ncb, *rg, K4, Ws, nrb, warp, lane, acc);
+    else chr_gemm_ncb(ncb, md.V, S, K4, Ws, ring, nrb, warp, lane, acc);
+    chr_sync<SLAB>();
+    chr_store_acc_w<NW>(Xs, nrb, warp, g, q, acc, ncb);
   }
-  __syncthreads();
+  chr_sync<SLAB>();
   // rescale every term to [0.5, 1) by an exact power of two and store it with its exponent
-  if (warp * 4 < ncols) {
-    for (int j = warp * 4; j < warp * 4 + 4; ++j) {
+  {
+    for (int j = warp; j < ncols; j += NW) {
       double m = 0.0;
       for (int k = lane; k < S; k += 32) m = fmax(m, fabs(Xs[k * kChrLD + j]));
 #pragma unroll
@@ -188,11 +212,11 @@ __device__ __forceinline__ void chr_tile(const ChrLevelParams& p, double* sm_chr
       }
     }
   }
-  __syncthreads();
+  chr_sync<SLAB>();
   // an observed tip's term IS a column of P: the reference's per-entry clamp (ChromosomeSubstitutionModel.cpp:903-916) applies
   // to it exactly; cscale is 1 there unless the whole column is below 2^-256
   const bool clamp_col = kind == 0 && (md.flags & 4u);
-  for (int i = tid; i < S * ncols; i += blockDim.x) {
+  for (int i = tid; i < S * ncols; i += NT) {
     const int j = i / S, k = i - j * S;     // consecutive threads write one term contiguously
     const int n = cnode[j];
     if (n < 0) continue;
@@ -206,7 +230,7 @@ __device__ __forceinline__ void chr_tile(const ChrLevelParams& p, double* sm_chr
 __global__ void __launch_bounds__(kChrWarps * 32, 2) chr_level_kernel(ChrLevelParams p) {
   extern __shared__ __align__(16) double sm_chr[];
   if (p.skip && p.skip[p.p0 + blockIdx.y]) return;
-  chr_tile(p, sm_chr, p.tile0 + blockIdx.x, blockIdx.y);
+  chr_tile<false>(p, sm_chr, p.tile0 + blockIdx.x, blockIdx.y, nullptr);
 }
 
 // The top of the tree in ONE launch: from the first level on which every later level is a single tile (a handful of branches
@@ -219,8 +243,80 @@ __global__ void __launch_bounds__(kChrWarps * 32, 1) chr_chain_kernel(ChrLevelPa
   extern __shared__ __align__(16) double sm_chr[];
   if (p.skip && p.skip[p.p0 + blockIdx.x]) return;
   for (int t = 0; t < ntiles; ++t) {
-    chr_tile(p, sm_chr, p.tile0 + t, blockIdx.x);
+    chr_tile<false>(p, sm_chr, p.tile0 + t, blockIdx.x, nullptr);
     __syncthreads();
+  }
+}
+
+// ---- slab-streamed variants (dmma.cuh: chr_gemm_slab): 7 consumer warps + 1 producer warp ------------------------------------
+__device__ __forceinline__ ChrRing chr_ring_setup(const ChrLevelParams& p, double* sm_chr) {
+  const int K8 = (p.S + 7) & ~7;
+  ChrRing r;
+  r.full = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(sm_chr) + (size_t)K8 * kChrLD * sizeof(double) +
+                                                 3 * kChrCols * sizeof(double) + 2 * kChrCols * sizeof(int));
+  r.empty = r.full + 16;
+  r.slab = reinterpret_cast<double*>(r.empty + 16);
+  r.nst = p.nst;
+  r.stage = 0;
+  r.phase = 0;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < p.nst; ++i) {
+      mbar_init(r.full + i, 1);
+      mbar_init(r.empty + i, kChrCons);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();   // (the only CTA-wide barrier: the producer warp leaves the kernel on its own)
+  return r;
+}
+// the slabs tile `tile` of point `prel` consumes, in its order: [V^-1 | V] for dense columns, V alone for observed tips
+__device__ __forceinline__ void chr_produce_tile(const ChrLevelParams& p, ChrRing& r, int tile, int prel) {
+  const int K8 = (p.S + 7) & ~7;
+  const int first = p.tile_edges[(size_t)tile * kChrCols];
+  const int slot = p.branch_model[(size_t)(p.p0 + prel) * p.nn + first];
+  const bool tips = p.tile_kind[tile] == 0;
+  const double* src = p.aslab + (size_t)slot * 2 * K8 * K8 + (tips ? (size_t)K8 * K8 : 0);
+  chr_ring_produce(r, src, (tips ? 1 : 2) * (K8 >> 3), K8);
+}
+__global__ void __launch_bounds__((kChrCons + 1) * 32, 2) chr_level_slab_kernel(ChrLevelParams p) {
+  extern __shared__ __align__(16) double sm_chr[];
+  if (p.skip && p.skip[p.p0 + blockIdx.y]) return;
+  ChrRing r = chr_ring_setup(p, sm_chr);
+  if ((threadIdx.x >> 5) == kChrCons) {
+    if ((threadIdx.x & 31) == 0) chr_produce_tile(p, r, p.tile0 + blockIdx.x, blockIdx.y);
+    return;
+  }
+  chr_tile<true>(p, sm_chr, p.tile0 + blockIdx.x, blockIdx.y, &r);
+}
+__global__ void __launch_bounds__((kChrCons + 1) * 32, 1) chr_chain_slab_kernel(ChrLevelParams p, int ntiles) {
+  extern __shared__ __align__(16) double sm_chr[];
+  if (p.skip && p.skip[p.p0 + blockIdx.x]) return;
+  ChrRing r = chr_ring_setup(p, sm_chr);
+  if ((threadIdx.x >> 5) == kChrCons) {
+    if ((threadIdx.x & 31) == 0)
+      for (int t = 0; t < ntiles; ++t) chr_produce_tile(p, r, p.tile0 + t, blockIdx.x);
+    return;
+  }
+  for (int t = 0; t < ntiles; ++t) {
+    chr_tile<true>(p, sm_chr, p.tile0 + t, blockIdx.x, &r);
+    chr_sync<true>();
+  }
+}
+
+// slab-ordered copies of a model's V^-1 and V (layout: dmma.cuh, chr_gemm_slab): out[slot] = [V^-1 image | V image], each
+// [K8 / 8 slabs][K8 rows][8 swizzled k-columns], zero-padded.  One CTA row per model slot, built when the models change.
+__global__ void chr_slab_kernel(const ModelDev* models, int S, int K8, double* out) {
+  const ModelDev md = models[blockIdx.y];
+  if (md.V == nullptr || md.Vinv == nullptr) return;
+  double* o = out + (size_t)blockIdx.y * 2 * K8 * K8;
+  const int per = K8 * K8;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < 2 * per; idx += gridDim.x * blockDim.x) {
+    const int mat = idx >= per, e = idx - mat * per;
+    const int ks = e / (K8 * 8), rem = e - ks * (K8 * 8), r = rem >> 3, pos = rem & 7;
+    const int k = ks * 8 + (pos ^ (4 * ((r >> 1) & 1)));
+    const double* M = mat ? md.V : md.Vinv;
+    o[idx] = (r < S && k < S) ? M[(size_t)r * S + k] : 0.0;
   }
 }
 

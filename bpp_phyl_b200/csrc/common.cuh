@@ -39,6 +39,45 @@ __device__ __forceinline__ void st256(double* p, double a, double b, double c, d
   asm volatile("st.global.v4.f64 [%4], {%0,%1,%2,%3};" ::"d"(a), "d"(b), "d"(c), "d"(d), "l"(p) : "memory");
 }
 
+// ---- programmatic dependent launch (one kernel per tree node, hundreds per evaluation) --------------------------------------
+// A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start while its predecessor in the stream is
+// still draining: its CTAs take the SMs the predecessor frees, stage what does not depend on it (P operands), and only then
+// wait for the predecessor's results.  pdl_wait() returns once the predecessor grid has completed and its writes are visible
+// (it returns at once in a kernel launched without the attribute); every kernel of such a chain must call it, so that
+// "my predecessor is complete" implies "all earlier kernels are complete".
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+// ---- mbarrier / TMA bulk copy (PTX ISA 8.x, sm_90+) ------------------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* b, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* b, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* b) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* b, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "W4C_WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra W4C_DONE_%=;\n"
+      "bra W4C_WAIT_%=;\n"
+      "W4C_DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(b)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* b) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(b))
+               : "memory");
+}
+
 // ---- power-of-two rescaling (exact in FP64) ----------------------------------
 // A pattern is rescaled when its largest CLV entry drops below 2^-256; the rule
 // (and therefore every exponent) is identical in oracle/ref_likelihood.py::_rescale.

@@ -186,6 +186,92 @@ __device__ __forceinline__ void chr_gemm_ring(const double* __restrict__ A, int 
   cp_async_wait<0>();
   __syncwarp();
 }
+// ---- the same product with A streamed by the TMA engine in k-slabs ------------------------------------------------------------
+// The warp-private ring above keeps 5 KB per warp in flight in 16-byte pieces from 32 different rows per k-step: the A stream
+// (2 S^2 doubles per tile, nothing else comes from L2) ran at 16 GB/s per SM, and a tile with a handful of columns -- 43 of the 47
+// levels of the 500-taxon benchmark tree -- spent 8x longer waiting for A than on its DMMAs.  Here every model keeps a second copy
+// of V^-1 and V in SLAB order (chr_slab_kernel): slab ks = the K8 rows x 8 k-columns [8 ks, 8 ks + 8) as one contiguous block of
+// K8 x 8 doubles (12.8 KB at S = 200), so a slab is ONE cp.async.bulk.  A producer warp streams the slabs of the CTA's whole tile
+// sequence ([V^-1 | V] per dense tile, V per observed-tip tile) through an mbarrier full/empty ring; it never waits for the
+// element-wise phases between the GEMMs, so the ring is full again when the next product starts.  7 consumer warps (25 row blocks:
+// the busiest warp owns 4 with 7 warps as with 8).  Within a slab the 8 doubles of row r are stored XOR-swizzled,
+// position = kk ^ (4 * ((r >> 1) & 1)): the fragment load a = A[rb * 8 + g][4 h + q] of a half warp (g = 0..3, q = 0..3) then
+// touches 16 distinct bank pairs.  Accumulation order over k as in chr_gemm_t: results are bit-identical to the other variants.
+constexpr int kChrCons = 7;   // consumer warps (warp kChrCons is the producer)
+struct ChrRing {
+  unsigned long long* full;    // [nst] count 1 (+ transaction bytes)
+  unsigned long long* empty;   // [nst] count kChrCons
+  double* slab;                // [nst][K8 * 8]
+  int nst;
+  int stage;
+  unsigned phase;
+};
+__host__ __device__ inline int chr_slab_doubles(int K8) { return K8 * 8; }
+template <int NCB>
+__device__ __forceinline__ void chr_gemm_slab(ChrRing& r, int K8, const double* Bs, int nrb, int warp, int lane,
+                                              double (&acc)[kChrMaxRB][kChrCols / 8][2]) {
+  const int g = lane >> 2, q = lane & 3;
+#pragma unroll
+  for (int i = 0; i < kChrMaxRB; ++i)
+#pragma unroll
+    for (int cb = 0; cb < NCB; ++cb) acc[i][cb][0] = acc[i][cb][1] = 0.0;
+  const int sw = 4 * ((g >> 1) & 1);
+  const int slabD = chr_slab_doubles(K8);
+  const int nslab = K8 >> 3;
+  for (int ks = 0; ks < nslab; ++ks) {
+    mbar_wait(r.full + r.stage, r.phase);
+    const double* as = r.slab + (size_t)r.stage * slabD + g * 8;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      double a[kChrMaxRB], b[NCB];
+#pragma unroll
+      for (int i = 0; i < kChrMaxRB; ++i) a[i] = (warp + i * kChrCons < nrb) ? as[(warp + i * kChrCons) * 64 + ((4 * h + q) ^ sw)] : 0.0;
+#pragma unroll
+      for (int cb = 0; cb < NCB; ++cb) b[cb] = Bs[(8 * ks + 4 * h + q) * kChrLD + cb * 8 + g];
+#pragma unroll
+      for (int i = 0; i < kChrMaxRB; ++i)
+        if (warp + i * kChrCons < nrb) {
+#pragma unroll
+          for (int cb = 0; cb < NCB; ++cb) dmma884(acc[i][cb][0], acc[i][cb][1], a[i], b[cb]);
+        }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(r.empty + r.stage);
+    if (++r.stage == r.nst) { r.stage = 0; r.phase ^= 1u; }
+  }
+}
+__device__ __forceinline__ void chr_gemm_slab_ncb(int ncb, ChrRing& r, int K8, const double* Bs, int nrb, int warp, int lane,
+                                                  double (&acc)[kChrMaxRB][kChrCols / 8][2]) {
+  switch (ncb) {
+    case 1: chr_gemm_slab<1>(r, K8, Bs, nrb, warp, lane, acc); break;
+    case 2: chr_gemm_slab<2>(r, K8, Bs, nrb, warp, lane, acc); break;
+    case 3: chr_gemm_slab<3>(r, K8, Bs, nrb, warp, lane, acc); break;
+    default: chr_gemm_slab<4>(r, K8, Bs, nrb, warp, lane, acc); break;
+  }
+}
+// producer side: n slabs starting at src (contiguous) into the ring; one thread
+__device__ __forceinline__ void chr_ring_produce(ChrRing& r, const double* src, int n, int K8) {
+  const int slabD = chr_slab_doubles(K8);
+  for (int s = 0; s < n; ++s) {
+    mbar_wait(r.empty + r.stage, r.phase ^ 1u);   // (a fresh barrier passes a wait on parity 1: the first lap does not block)
+    mbar_expect_tx(r.full + r.stage, (unsigned)slabD * 8u);
+    bulk_g2s(r.slab + (size_t)r.stage * slabD, src + (size_t)s * slabD, (unsigned)slabD * 8u, r.full + r.stage);
+    if (++r.stage == r.nst) { r.stage = 0; r.phase ^= 1u; }
+  }
+}
+template <int NW>
+__device__ __forceinline__ void chr_store_acc_w(double* Cs, int nrb, int warp, int g, int q,
+                                                const double (&acc)[kChrMaxRB][kChrCols / 8][2], int ncb) {
+#pragma unroll
+  for (int i = 0; i < kChrMaxRB; ++i)
+    if (warp + i * NW < nrb) {
+      const int row = (warp + i * NW) * 8 + g;
+#pragma unroll
+      for (int cb = 0; cb < kChrCols / 8; ++cb)
+        if (cb < ncb) *reinterpret_cast<double2*>(Cs + row * kChrLD + cb * 8 + 2 * q) = make_double2(acc[i][cb][0], acc[i][cb][1]);
+    }
+}
+
 // the number of column blocks chosen at run time (uniform over the CTA)
 __device__ __forceinline__ void chr_gemm_ncb(int ncb, const double* __restrict__ A, int S, int K4, const double* Bs, double* ring, int nrb,
                                              int warp, int lane, double (&acc)[kChrMaxRB][kChrCols / 8][2]) {

@@ -288,9 +288,9 @@ __global__ void __launch_bounds__(fam_threads_kind(KIND), 1) dmma_family_kernel(
     for (int j = 0; j < MS; ++j) ps.code[j] = (has(j) && tip(j)) ? load_code(p.sons[j].codes, p.code_bytes, pat) : 0;
   };
 
-  // ---- prologue: the first NST - 1 items of every warp, operands of every class -------------------------------------------
-#pragma unroll
-  for (int s0 = 0; s0 < NST - 1; ++s0) fetch_next(s0);
+  // ---- prologue: operands of every class (packed once per evaluation, before the first launch of the pass: independent of the
+  // previous father's launch, so they are staged while that launch drains), then the first NST - 1 items of every warp ---------
+  pdl_launch_dependents();
   for (int c = 0; c < C; ++c) {
     double* base = sm_fam + (size_t)c * MATS;
     if (!root) family_stage_async<NT>(base, p.packA + ((size_t)p.father * C + c) * kFamPackA, kFamPackA);
@@ -301,6 +301,9 @@ __global__ void __launch_bounds__(fam_threads_kind(KIND), 1) dmma_family_kernel(
                                kFamPackS);
   }
   cp_async_commit();
+  pdl_wait();   // upper[f] is the previous launches' output
+#pragma unroll
+  for (int s0 = 0; s0 < NST - 1; ++s0) fetch_next(s0);
   PatScal pcur, pnxt;
   load_pat(warp * 8, pnxt);
   cp_async_wait<0>();
@@ -662,14 +665,17 @@ __global__ void __launch_bounds__(prune_threads(S_, KIND, CFG), 1) dmma_prune_ke
     for (int j = 0; j < MS; ++j) code[j] = (has(j) && tip(j)) ? load_code(p.sons[j].codes, p.code_bytes, pat) : 0;
   };
 
-#pragma unroll
-  for (int s0 = 0; s0 < NST - 1; ++s0) fetch_next(s0);
+  // operands first (independent of the previous node's launch: staged while it drains), then the sons' rows
+  pdl_launch_dependents();
   for (int c = 0; c < C; ++c)
 #pragma unroll
     for (int j = 0; j < MS; ++j)
       if (has(j) && !tip(j))
         family_stage_async<NT>(sm_pr + (size_t)c * MATS + (size_t)slot(j) * PACK, p.packL + ((size_t)p.sons[j].node * C + c) * PACK, PACK);
   cp_async_commit();
+  pdl_wait();   // the sons' CLVs are earlier launches' output
+#pragma unroll
+  for (int s0 = 0; s0 < NST - 1; ++s0) fetch_next(s0);
   int ccur[MS], cnxt[MS];
   load_codes(warp * 8, cnxt);
   cp_async_wait<0>();

@@ -63,6 +63,8 @@ std::string& last_error() {
 }
 
 static int g_sm_count = 148;
+static int g_smem_per_sm = 228 * 1024;   // cudaDeviceProp::sharedMemPerMultiprocessor
+static int g_smem_optin = 227 * 1024;    // cudaDeviceProp::sharedMemPerBlockOptin
 
 template <typename T>
 static cudaError_t dev_alloc(bppgpu_engine* e, T** p, size_t n) {
@@ -217,6 +219,8 @@ static int check_device(int device) {
   BPP_CUDA(cudaGetDeviceProperties(&prop, device));
   if (prop.major < 10) BPP_FAIL(BPPGPU_E_CUDA, "device %d is sm_%d%d; libbppgpu is built for sm_100a only", device, prop.major, prop.minor);
   g_sm_count = prop.multiProcessorCount;
+  g_smem_per_sm = (int)prop.sharedMemPerMultiprocessor;
+  g_smem_optin = (int)prop.sharedMemPerBlockOptin;
   // dynamic shared memory above 48 KB is opt-in
   BPP_CUDA(cudaFuncSetAttribute(pt_dmma_kernel<8, 1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
   BPP_CUDA(cudaFuncSetAttribute(pt_dmma_kernel<8, 2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
@@ -231,6 +235,26 @@ static int check_device(int device) {
   BPP_CUDA(cudaFuncSetAttribute(dmma_upper_deriv_kernel<5, 3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   BPP_CUDA(cudaFuncSetAttribute(dmma_upper_deriv_kernel<16, 8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   return BPPGPU_OK;
+}
+
+// ---- programmatic dependent launch of the per-node kernels (common.cuh: pdl_wait / pdl_launch_dependents) -------------------
+// `overlap` = this launch may start while its predecessor in the stream drains.  The first per-node launch of a pass is launched
+// plainly: what precedes it (operand packing) must be complete before any CTA of the chain stages operands.
+static const bool g_pdl_on = getenv("BPPGPU_PDL") && atoi(getenv("BPPGPU_PDL")) != 0;   // opt-in: measured, no gain
+template <typename P>
+static cudaError_t launch_node_kernel(void (*kern)(P), unsigned grid, unsigned threads, size_t smem, cudaStream_t st, bool overlap,
+                                      const P& params) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(threads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = (overlap && g_pdl_on) ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, params);
 }
 
 // ---- model upload -------------------------------------------------------------------
@@ -607,7 +631,7 @@ int bppgpu_destroy(bppgpu_engine* e) {
                   e->prog.d_ops, e->prog.d_childs, e->gprog.d_ops, e->gprog.d_childs, e->d_sibs, e->d_scratch,
                   e->d_dtiptab, e->d_d2tiptab, e->d_dLc, e->d_fam_mask, e->d_fam_part, e->d_fam_packA, e->d_fam_packS, e->d_fam_packL, e->d_fam_packT, e->d_w4c_stream, e->d_w4c_blocks, e->d_w4c_tip_order, e->d_codesC, e->d_w4c_counter, e->d_w4_desc, e->d_w4_tip_order, e->d_w4_blocks, e->d_w4_stream, e->d_codesT,
                   e->d_status, e->d_wr_recs, e->d_chr_tile_edges, e->d_chr_tile_kind, e->d_chr_leaf_state, e->d_child_off,
-                  e->d_children, e->d_chr_leaf_vec, e->d_chr_term, e->d_chr_term_exp, e->d_chr_bad, e->d_chr_guardP, e->d_chr_probe_t,
+                  e->d_children, e->d_chr_leaf_vec, e->d_chr_term, e->d_chr_term_exp, e->d_chr_bad, e->d_chr_guardP, e->d_chr_aslab, e->d_chr_probe_t,
                   e->d_chr_probe_bm, e->d_models_noclamp, e->d_bad_idx, e->d_bad_brlen, e->d_bad_rootfreq, e->d_bad_rootfreq_used,
                   e->d_bad_site_lnl, e->d_bad_out, e->d_bad_branch_model};
   for (void* p : ptrs) cudaFree(p);
@@ -1035,6 +1059,17 @@ static int create_impl(const bppgpu_config* cfg, bppgpu_engine* e) {
     BPP_CUDA(cudaFuncSetAttribute(chr_level_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chr_level_smem(S)));
     BPP_CUDA(cudaFuncSetAttribute(chr_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)std::max(chr_level_smem(S), (size_t)116 * 1024)));
+    {
+      static const bool slab_on = !(getenv("BPPGPU_CHR_SLAB") && atoi(getenv("BPPGPU_CHR_SLAB")) == 0);
+      const int K8 = (S + 7) & ~7;
+      e->chr_slab = slab_on && K8 <= 8 * kChrCons * kChrMaxRB;
+      if (e->chr_slab) {
+        BPP_CUDA(dev_alloc(e, &e->d_chr_aslab, (size_t)e->nmodels * 2 * K8 * K8));
+        const int optin = (int)std::min<size_t>((size_t)g_smem_optin, chr_slab_smem(S, kChrMaxStages));
+        BPP_CUDA(cudaFuncSetAttribute(chr_level_slab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
+        BPP_CUDA(cudaFuncSetAttribute(chr_chain_slab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
+      }
+    }
     e->pchunk = 1;
   } else {
     e->pchunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)e->npoints, budget / std::max<size_t>(1, (e->path == PATH_POINTS ? 1 : 3) * per_point)));
@@ -1313,6 +1348,7 @@ int bppgpu_set_model(bppgpu_engine* e, int32_t slot, const bppgpu_model_desc* m)
   int rc = upload_model(e->models[slot], m, e->S, e->path != PATH_POINTS);
   if (rc) return rc;
   e->models_dirty = true;
+  e->chr_slab_dirty = true;
   e->last_point = -1;
   return BPPGPU_OK;
 }
@@ -1371,6 +1407,7 @@ int bppgpu_set_models(bppgpu_engine* e, int32_t first_slot, int32_t n, const bpp
   run(0);
   for (auto& x : th) x.join();
   e->models_dirty = true;
+  e->chr_slab_dirty = true;
   e->last_point = -1;
   for (int t = 0; t < T; ++t)
     if (rcs[t]) {
@@ -1698,6 +1735,7 @@ static int enqueue_prune(bppgpu_engine* e, int point, int pl, cudaStream_t st) {
     const int grid_e = (int)std::min<long long>((total + 255) / 256, (long long)g_sm_count * 32);
     const int grid_p = (int)((N + 255) / 256);
     const int grid_r = (int)((N * C + 255) / 256);
+    bool prev_chained = false;
     for (const Op& op : e->gprog.ops) {
       GenericParams gp{};
       gp.childs = e->gprog.d_childs + op.child_begin;
@@ -1734,8 +1772,10 @@ static int enqueue_prune(bppgpu_engine* e, int point, int pl, cudaStream_t st) {
         pp.out = e->d_keep + (size_t)op.keep_idx * N * C * S;
         pp.out_exp = e->d_keep_exp + (size_t)op.keep_idx * N * C;
         const int G = e->fam_grid;
+        const bool chained = prev_chained;   // the previous launch of this loop was one of these kernels (it calls pdl_wait itself)
+        prev_chained = true;
         switch (kind) {
-#define BPP_PRUNE(Sv, Kv, Cv) dmma_prune_kernel<Sv, Kv, Cv><<<G, prune_threads(Sv, Kv, Cv), dmma_prune_smem<Sv, Kv, Cv>(C), st>>>(pp)
+#define BPP_PRUNE(Sv, Kv, Cv) BPP_CUDA(launch_node_kernel(dmma_prune_kernel<Sv, Kv, Cv>, G, prune_threads(Sv, Kv, Cv), dmma_prune_smem<Sv, Kv, Cv>(C), st, chained, pp))
 #define BPP_PRUNE_K(Kv) if (S == 64) BPP_PRUNE(64, Kv, 0); else if (e->prune_cfg == 0) BPP_PRUNE(20, Kv, 0); \
                         else if (e->prune_cfg == 1) BPP_PRUNE(20, Kv, 1); else BPP_PRUNE(20, Kv, 2)
           case 0: BPP_PRUNE_K(0); break;
@@ -1763,6 +1803,7 @@ static int enqueue_prune(bppgpu_engine* e, int point, int pl, cudaStream_t st) {
           const dim3 grid((unsigned)std::min<long long>(tiles, std::max(1, g_sm_count * ctas_per_sm / C)), (unsigned)C);
           kern<<<grid, kDmmaNodeWarps * 32, smem, st>>>(dp);
         };
+        prev_chained = false;
         if (S <= 20) {
           const size_t smem = nint * dmma_node_smem_per_child<5, 3>();
           if (rw_env == 1) launch(dmma_node_kernel<5, 3, 1>, 1, smem, 12);
@@ -1777,6 +1818,7 @@ static int enqueue_prune(bppgpu_engine* e, int point, int pl, cudaStream_t st) {
       } else {
         generic_node_kernel<<<grid_e, 256, 0, st>>>(gp);
         generic_scale_kernel<<<grid_r, 256, 0, st>>>(gp);
+        prev_chained = false;
         e->stats.kernel_launches += 2;
       }
     }
@@ -1836,6 +1878,8 @@ static int enqueue_derivs(bppgpu_engine* e, int point, int pl, unsigned want, cu
   const int grid_p = (int)((N + 255) / 256);
   const int grid_r = (int)((N * C + 255) / 256);
   const bool family = e->path == PATH_DMMA && e->family;
+  bool prev_family = false;   // the previous launch was a dmma_family_kernel (programmatic dependent launch chain)
+  cudaError_t fam_err = cudaSuccess;
   auto launch_family = [&](int f) {
     DmmaFamilyParams fp{};
     const size_t clvN = (size_t)N * C * S, expN = (size_t)N * C;
@@ -1878,7 +1922,9 @@ static int enqueue_derivs(bppgpu_engine* e, int point, int pl, unsigned want, cu
     fp.part = e->d_fam_part;
     const bool d2 = (want & BPPGPU_EVAL_D2) != 0;
     const int G = e->fam_grid;
-#define BPP_FAM(NBv, Kv) dmma_family_kernel<NBv, Kv><<<G, fam_threads_kind(Kv), dmma_family_smem<Kv>(C), st>>>(fp)
+    const bool fam_chained = prev_family;
+    prev_family = true;
+#define BPP_FAM(NBv, Kv) fam_err = launch_node_kernel(dmma_family_kernel<NBv, Kv>, G, fam_threads_kind(Kv), dmma_family_smem<Kv>(C), st, fam_chained, fp)
     switch (kind) {
       case 0: if (d2) BPP_FAM(8, 0); else BPP_FAM(5, 0); break;
       case 1: if (d2) BPP_FAM(8, 1); else BPP_FAM(5, 1); break;
@@ -1890,6 +1936,7 @@ static int enqueue_derivs(bppgpu_engine* e, int point, int pl, unsigned want, cu
     e->stats.kernel_launches++;
   };
   auto launch_branch = [&](int n) {
+    prev_family = false;
     const int f = e->parent[n];
     UpperParams up{};
     up.sibs = e->d_sibs + e->sib_off[n];
@@ -1983,6 +2030,7 @@ static int enqueue_derivs(bppgpu_engine* e, int point, int pl, unsigned want, cu
       // the sons of n in one launch (upper[n] is complete: n's own launch precedes this one in pre-order)
       const int k = e->child_off[n + 1] - e->child_off[n];
       if (k >= 1 && k <= kFamMaxSons) launch_family(n);
+      BPP_CUDA(fam_err);
     }
   }
   if (family) {
@@ -2123,6 +2171,26 @@ static int eval_points_factored(bppgpu_engine* e, cudaStream_t st, bool any_real
   // ---- levels + root ------------------------------------------------------------------------------------------------------
   BPP_CUDA(cudaEventRecord(e->ring_a[e->ring_head], st));
   const size_t smem = chr_level_smem(S);
+  // slab-streamed kernels: ring depth from the shared memory left beside the column tile -- two CTAs per SM for the level
+  // launches (several tiles of a point run side by side), one per SM for the chain (148 resident points' eigenvectors fit in L2)
+  int nst_level = 0, nst_chain = 0;
+  if (e->chr_slab) {
+    const int K8 = (S + 7) & ~7;
+    const size_t base = chr_slab_smem(S, 0), slab = (size_t)chr_slab_doubles(K8) * 8;
+    static const int lv_env = getenv("BPPGPU_CHR_NST_LEVEL") ? atoi(getenv("BPPGPU_CHR_NST_LEVEL")) : 0;   // tuning knobs
+    static const int ch_env = getenv("BPPGPU_CHR_NST_CHAIN") ? atoi(getenv("BPPGPU_CHR_NST_CHAIN")) : 0;
+    nst_level = (int)std::min<size_t>(kChrMaxStages, (((size_t)g_smem_per_sm / 2 - 1024) > base ? ((size_t)g_smem_per_sm / 2 - 1024 - base) / slab : 0));
+    nst_chain = (int)std::min<size_t>(kChrMaxStages, ((size_t)g_smem_optin > base ? ((size_t)g_smem_optin - base) / slab : 0));
+    if (nst_level < 2) nst_level = (int)std::min<size_t>(kChrMaxStages, ((size_t)g_smem_optin > base ? ((size_t)g_smem_optin - base) / slab : 0));
+    if (lv_env >= 2) nst_level = std::min(lv_env, nst_chain);
+    if (ch_env >= 2) nst_chain = std::min(ch_env, nst_chain);
+    if (nst_level < 2 || nst_chain < 2) BPP_FAIL(BPPGPU_E_INVALID, "no room for the slab ring at S = %d", S);
+    if (e->chr_slab_dirty) {
+      chr_slab_kernel<<<dim3(8, (unsigned)e->nmodels), 256, 0, st>>>(e->d_models, S, K8, e->d_chr_aslab);
+      e->stats.kernel_launches++;
+      e->chr_slab_dirty = false;
+    }
+  }
   for (int f0 = 0; f0 < npts; f0 += e->fchunk) {
     const int np = std::min(e->fchunk, npts - f0);
     ChrLevelParams lp{};
@@ -2134,6 +2202,7 @@ static int eval_points_factored(bppgpu_engine* e, cudaStream_t st, bool any_real
     lp.leaf_state = e->d_chr_leaf_state; lp.leaf_vec = e->d_chr_leaf_vec;
     lp.term = e->d_chr_term; lp.term_exp = e->d_chr_term_exp;
     lp.skip = e->d_chr_bad;
+    lp.aslab = e->d_chr_aslab;
     // first level from which every level is one tile: those go in one chain launch (chr_chain_kernel)
     static const bool chain_on = !(getenv("BPPGPU_CHR_CHAIN") && atoi(getenv("BPPGPU_CHR_CHAIN")) == 0);
     const size_t nlev = e->chr_level_tile0.size() - 1;
@@ -2149,7 +2218,12 @@ static int eval_points_factored(bppgpu_engine* e, cudaStream_t st, bool any_real
         q.p0 = f0 + y0;
         q.term = e->d_chr_term + (size_t)y0 * nn * S;
         q.term_exp = e->d_chr_term_exp + (size_t)y0 * nn;
-        chr_level_kernel<<<dim3((unsigned)nt, (unsigned)std::min(65535, np - y0)), kChrWarps * 32, smem, st>>>(q);
+        if (e->chr_slab) {
+          q.nst = nst_level;
+          chr_level_slab_kernel<<<dim3((unsigned)nt, (unsigned)std::min(65535, np - y0)), (kChrCons + 1) * 32, chr_slab_smem(S, nst_level), st>>>(q);
+        } else {
+          chr_level_kernel<<<dim3((unsigned)nt, (unsigned)std::min(65535, np - y0)), kChrWarps * 32, smem, st>>>(q);
+        }
         e->stats.kernel_launches++;
       }
     }
@@ -2158,7 +2232,12 @@ static int eval_points_factored(bppgpu_engine* e, cudaStream_t st, bool any_real
       q.tile0 = e->chr_level_tile0[chain0];
       // more than half of an SM's shared memory: one CTA per SM, so that the resident points' eigenvectors fit in L2
       const size_t chain_smem = std::max(smem, (size_t)116 * 1024);
-      chr_chain_kernel<<<(unsigned)np, kChrWarps * 32, chain_smem, st>>>(q, e->chr_level_tile0[nlev] - q.tile0);
+      if (e->chr_slab) {
+        q.nst = nst_chain;
+        chr_chain_slab_kernel<<<(unsigned)np, (kChrCons + 1) * 32, chr_slab_smem(S, nst_chain), st>>>(q, e->chr_level_tile0[nlev] - q.tile0);
+      } else {
+        chr_chain_kernel<<<(unsigned)np, kChrWarps * 32, chain_smem, st>>>(q, e->chr_level_tile0[nlev] - q.tile0);
+      }
       e->stats.kernel_launches++;
     }
     ChrRootParams rp{};

@@ -254,7 +254,8 @@ cudaError_t staged_copy(void* dst, const void* src, size_t bytes, bool h2d, int 
   } else {
     pageable = false;
   }
-  if (!pageable) return cudaMemcpy(dst, src, bytes, h2d ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost);
+  // (cudaMemcpyDefault: the caller's side may also be DEVICE memory -- an alignment already resident, results that stay on the GPU)
+  if (!pageable) return cudaMemcpy(dst, src, bytes, cudaMemcpyDefault);
   const size_t nchunks = (bytes + kStageChunk - 1) / kStageChunk;
   const int T = g_stage.threads;
   std::vector<cudaError_t> err(T, cudaSuccess);

@@ -68,6 +68,8 @@ int bppgpu_site_patterns(const uint8_t* columns, int64_t n_sites, int32_t col_by
  * engine consumes extracted: tip_codes[l * n_patterns + k] = element l of the column of pattern k (elements of `code_bytes`
  * = 1 or 2 bytes, col_bytes / code_bytes leaves; caller-allocated, capacity n_sites * col_bytes bytes; NULL to skip), i.e.
  * row l is what bppgpu_set_tip_codes takes for leaf l.  Results are identical, bit for bit, to bppgpu_site_patterns.
+ * `columns` and every output buffer may be pageable host memory (moved through pinned staging buffers by several host threads),
+ * pinned / registered host memory (one direct DMA each) or DEVICE memory of `device` (device-to-device copies: nothing crosses PCIe).
  * No CPU fallback: BPPGPU_E_CUDA without a usable sm_100a device.                                                   */
 int bppgpu_site_patterns_device(int device, const uint8_t* columns, int64_t n_sites, int32_t col_bytes, int32_t code_bytes,
                                 int64_t* pattern_site, uint32_t* weights, int64_t* indices, int64_t* n_patterns,

@@ -145,6 +145,31 @@ def test_device_patterns_plain_radix_variant(built_lib, monkeypatch, n, ntaxa, n
     check_device(np.full((1000, 9), ord("A"), np.uint8))
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("where", ["pinned", "device"])
+def test_device_patterns_on_pinned_and_device_resident_buffers(built_lib, where):
+    """The alignment and every output buffer may be pinned host memory or device memory (include/bppgpu.h): same bits as the
+    host routine.  (torch only allocates the buffers.)"""
+    import torch
+    from bpp_phyl_b200 import capi
+    rng = np.random.default_rng(11)
+    n, taxa = 600_000, 24                                  # > 4 staging chunks, so the pageable path would take the staged copy
+    base = rng.integers(0, 4, size=(n // 6, taxa)).astype(np.uint8)
+    cols = np.ascontiguousarray(base[rng.integers(len(base), size=n)])
+    ps, w, idx = capi.site_patterns(cols)
+    make = (lambda t: t.pin_memory()) if where == "pinned" else (lambda t: t.cuda())
+    c = make(torch.from_numpy(cols))
+    o_ps, o_ix = make(torch.zeros(n, dtype=torch.int64)), make(torch.zeros(n, dtype=torch.int64))
+    o_w, o_tip = make(torch.zeros(n, dtype=torch.int32)), make(torch.zeros(n * taxa, dtype=torch.uint8))
+    k = capi.site_patterns_device_raw(c.data_ptr(), n, taxa, o_ps.data_ptr(), o_w.data_ptr(), o_ix.data_ptr(), o_tip.data_ptr())
+    torch.cuda.synchronize()
+    assert k == len(ps)
+    np.testing.assert_array_equal(o_ps[:k].cpu().numpy(), ps)
+    np.testing.assert_array_equal(o_w[:k].cpu().numpy().view(np.uint32), w)
+    np.testing.assert_array_equal(o_ix.cpu().numpy(), idx)
+    np.testing.assert_array_equal(o_tip[:k * taxa].cpu().numpy().reshape(taxa, k), cols[ps].T)
+
+
 @pytest.mark.parametrize("ntaxa,nsites,nstates,seed,width", [(4, 17, 4, 0, 1), (9, 300, 2, 1, 1), (25, 800, 4, 2, 1), (12, 200, 4, 3, 3),
                                                          (6, 0, 4, 4, 1), (2, 50, 3, 5, 1)])
 def test_recursive_subtree_patterns_are_bit_exact(built_lib, ntaxa, nsites, nstates, seed, width):

@@ -35,6 +35,35 @@ ps_h, w_h, ix_h = capi.site_patterns(cols)
 t_host = time.perf_counter() - t0
 same = bool(np.array_equal(ps_d, ps_h) and np.array_equal(w_d, w_h) and np.array_equal(ix_d, ix_h)
             and np.array_equal(tips, cols[ps_h].T))
+
+# the same call on PINNED host buffers (one direct DMA each way) and on DEVICE-resident buffers (nothing crosses PCIe): what a
+# caller that keeps its alignment in cudaHostAlloc memory / on the GPU gets (include/bppgpu.h: bppgpu_site_patterns_device)
+import torch  # noqa: E402  (device memory and pinned allocations only)
+
+
+def run_raw(make):
+    c = make(torch.from_numpy(cols))
+    ps = make(torch.empty(n, dtype=torch.int64))
+    wt = make(torch.empty(n, dtype=torch.int32))
+    ix = make(torch.empty(n, dtype=torch.int64))
+    tp = make(torch.empty(n * taxa, dtype=torch.uint8))
+    torch.cuda.synchronize()
+    best, k = 1e30, 0
+    for _ in range(3):
+        t0 = time.perf_counter()
+        k = capi.site_patterns_device_raw(c.data_ptr(), n, taxa, ps.data_ptr(), wt.data_ptr(), ix.data_ptr(), tp.data_ptr())
+        torch.cuda.synchronize()
+        best = min(best, time.perf_counter() - t0)
+    ok = bool(k == len(ps_h) and np.array_equal(ps[:k].cpu().numpy(), ps_h) and np.array_equal(wt[:k].cpu().numpy().view(np.uint32), w_h)
+              and np.array_equal(ix.cpu().numpy(), ix_h) and np.array_equal(tp[:k * taxa].cpu().numpy().reshape(taxa, k), tips))
+    return best, ok
+
+
+t_pin, ok_pin = run_raw(lambda t: t.pin_memory())
+t_res, ok_res = run_raw(lambda t: t.cuda())
 print(json.dumps({"workload": "site patterns %d sites x %d taxa" % (n, taxa), "n_patterns": int(len(ps_h)),
                   "host_s": round(t_host, 4), "device_s_incl_copies": round(t_dev, 4),
-                  "alignment_bytes": int(cols.nbytes), "identical": same}))
+                  "device_s_pinned_buffers": round(t_pin, 4), "device_s_resident_buffers": round(t_res, 4),
+                  "speedup_pageable": round(t_host / t_dev, 2), "speedup_pinned": round(t_host / t_pin, 2),
+                  "speedup_resident": round(t_host / t_res, 2),
+                  "alignment_bytes": int(cols.nbytes), "identical": bool(same and ok_pin and ok_res)}))
