@@ -320,10 +320,16 @@ def run_points(a, w, rank, world, local, K, W, metric, config):
     rng = np.random.default_rng(w["seed"])
     tree = synth.random_tree(w["taxa"], rng, mean_brlen=0.02, rooted=True)
     t0 = time.time()
-    pts = synth.chromosome_points(S, npts, seed=w["seed"] + 1000 * rank)
-    log("[rank %d] %d parameter points (host eigendecompositions) in %.1fs" % (rank, npts, time.time() - t0))
+    # every point drawn from the box stays in the batch, on the route the reference takes for it (synth.chromosome_eigensystem):
+    # eigen form where V can be inverted, Taylor series + squaring otherwise; --well-conditioned restores the round-1 sample
+    pts = synth.chromosome_points(S, npts, seed=w["seed"] + 1000 * rank, well_conditioned_only=a.well_conditioned)
+    n_series = sum(1 for es in pts if es["route"] == "series")
+    n_illcond = sum(1 for es in pts if es["route"] == "eigen" and es["resid"] > 1e-9)
+    good = [k for k, es in enumerate(pts) if es["route"] == "eigen" and es["resid"] <= 1e-9]
+    log("[rank %d] %d parameter points (host eigendecompositions) in %.1fs: %d series route, %d eigen route with |V D V^-1 - Q| > 1e-9 |Q|, %d well-conditioned"
+        % (rank, npts, time.time() - t0, n_series, n_illcond, len(good)))
     mds = [synth.chromosome_model_desc(es) for es in pts]
-    P0, _, _ = capi.pt_batch(mds[0], tree.brlen, capi.WANT_P, device=local)
+    P0, _, _ = capi.pt_batch(mds[good[0]], tree.brlen, capi.WANT_P, device=local)   # the data are simulated under a well-conditioned point
     codes = synth.simulate_single_character(tree, P0, root_state=23, seed=w["seed"])
     # ChromosomeNumberMng::rescale_tree (App/ChromosomeNumberMng.cpp:121-147, branchMul_ = 999): the total tree length becomes the
     # number of distinct chromosome counts in the data before anything is evaluated
@@ -366,11 +372,12 @@ def run_points(a, w, rank, world, local, K, W, metric, config):
     ms = ev0.elapsed_time(ev1)
     st = e.stats()
     log("[rank %d] timed region done: %.3f ms/step, P(t) %.3f ms, pruning %.3f ms" % (rank, ms / K, st["pt_ms_sum"] / K, st["prune_ms_sum"] / max(1, st["prune_count"])))
-    lnl0 = float(out[0].item())
+    lnl0 = float(out[good[0] * (1 + 2 * nn)].item())
     # e2e: every point's model (host eigensystem) and branch lengths go host -> device, log L of every point comes back
     # per point: the head of the model image [V | V^-1 | re | im | role] (the generator is not read by any route of these models
     # and does not travel) + the branch lengths
-    h2d = npts * (((2 * S * S + 2 * S + (S + 1) // 2 + 31) // 32 * 32) * 8 + nn * 8)
+    head = ((2 * S * S + 2 * S + (S + 1) // 2 + 31) // 32 * 32) * 8
+    h2d = (npts - n_series) * head + n_series * (head + 2 * S * S * 8) + npts * nn * 8   # (series models travel with Q and Q^2)
     d2h = npts * 8
 
     def step_e2e():
@@ -419,10 +426,16 @@ def run_points(a, w, rank, world, local, K, W, metric, config):
         line = {"metric": metric, "value": upd_step * K / (ms * 1e-3), "unit": "CLV updates/s", "n_gpus": world, "steps": K,
                 "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": a.scaling, "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic (one chromosome count per taxon simulated down a random rooted tree; parameter points "
-                                        "drawn uniformly, numerically defective generators redrawn)",
+                                        "drawn uniformly from gain, loss in (0, 2), dupl, demi in (0, 1); " +
+                                        ("numerically defective generators redrawn (--well-conditioned)" if a.well_conditioned else
+                                         "every drawn point kept, on the route the reference takes for it") + ")",
                 "config": dict(config, points=npts_total, sharding="points/%d (replicas, no collective)" % world,
                                tree_length="rescaled to the %d distinct counts of the data (rescale_tree)" % n_unique),
                 "logl_evals_per_s": npts_total * K / (ms * 1e-3), "lnl_point0": lnl0,
+                "points_drawn": {"series_route": n_series, "eigen_route_illconditioned": n_illcond, "eigen_route_wellconditioned": len(good),
+                                 "rule": "series = V not invertible (non-finite inverse or cond(V) > 1e15) or no unique null eigenvalue, as "
+                                         "ChromosomeSubstitutionModel.cpp:686-767 decides; ill-conditioned = eigen route whose V D V^-1 misses Q by "
+                                         "more than 1e-9 max|Q| (the reference never checks and still uses it)"},
                 "routes": {"factored_points": nfac, "table_points": ntab,
                            "note": "points whose probe tables leave [0, 1] by more than 1e-8 (where the reference's per-entry clamp would matter) "
                                    "and singular generators take the P-table route"},
@@ -448,10 +461,10 @@ def run_points(a, w, rank, world, local, K, W, metric, config):
             from concurrent.futures import ThreadPoolExecutor
             from oracle import ref_cpu
             ref_cpu.build()
-            threads = min(os.cpu_count() or 1, npts, 16)
+            threads = min(os.cpu_count() or 1, len(good), 16)
 
-            def one(k):
-                es = pts[k]
+            def one(j):
+                es = pts[good[j]]
                 return ref_cpu.eval_raw(S, 1, 1, tree.child_off, tree.children, tree.root, codes, np.eye(S), np.ones(1, np.uint32),
                                         np.ones(1), np.ones(1), es["V"], es["Vinv"], es["ev"], 1.0, tree.brlen, es["pi"], scaled=True,
                                         want=1, nthreads=1, reps=1, ev_im=es["ev_im"], chr_clamp=True, weighted_root=True)
@@ -459,9 +472,10 @@ def run_points(a, w, rank, world, local, K, W, metric, config):
             with ThreadPoolExecutor(threads) as ex:
                 res = list(ex.map(one, range(threads)))
             dt = time.perf_counter() - t0
-            rel = max(abs(res[k]["lnl"] - lnl_host[k]) / abs(res[k]["lnl"]) for k in range(threads))
+            rel = max(abs(res[j]["lnl"] - lnl_host[good[j]]) / abs(res[j]["lnl"]) for j in range(threads))
             line["cpu_baseline"] = {"value": tree.n_internal * threads * S / dt, "unit": "CLV updates/s", "cores": threads, "kind": "port",
-                                    "sample": "%d of %d points, full tree, one point per thread, %.1f s" % (threads, npts_total, dt),
+                                    "sample": "the first %d well-conditioned eigen-route points of %d, full tree, one point per thread, %.1f s"
+                                              % (threads, npts_total, dt),
                                     "logl_evals_per_s": threads / dt, "rel_diff_vs_gpu": rel}
         emit(line)
         log("[rank 0] JSON line printed")
@@ -486,6 +500,8 @@ def main():
                          "weak = every GPU gets the workload's pattern count.  A strong run also times the weak job and reports it "
                          "under the key `weak` of the same line.")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--well-conditioned", action="store_true",
+                    help="chromosome workload: redraw parameter points whose eigen form misses the generator (the round-1 sample)")
     ap.add_argument("--no-weak", action="store_true", help="N > 1: skip the weak-scaling job timed after the strong one")
     ap.add_argument("--profile", action="store_true", help="1 warm-up + 1 timed step, no e2e / CPU legs (for ncu only)")
     a = ap.parse_args()

@@ -289,7 +289,10 @@ __global__ void __launch_bounds__((kChrCons + 1) * 32, 2) chr_level_slab_kernel(
   }
   chr_tile<true>(p, sm_chr, p.tile0 + blockIdx.x, blockIdx.y, &r);
 }
-__global__ void __launch_bounds__((kChrCons + 1) * 32, 1) chr_chain_slab_kernel(ChrLevelParams p, int ntiles) {
+// MINB = CTAs per SM the register budget allows: 2 interleaves two points per SM (the element-wise phases between the products
+// are latency-bound: one CTA leaves the SM idle in them), 1 keeps the 148 resident points' eigenvectors inside L2
+template <int MINB>
+__global__ void __launch_bounds__((kChrCons + 1) * 32, MINB) chr_chain_slab_kernel(ChrLevelParams p, int ntiles) {
   extern __shared__ __align__(16) double sm_chr[];
   if (p.skip && p.skip[p.p0 + blockIdx.x]) return;
   ChrRing r = chr_ring_setup(p, sm_chr);

@@ -575,7 +575,7 @@ constexpr size_t dmma_prune_smem(int C) {
 }
 
 template <int S_, int KIND, int CFG>
-__global__ void __launch_bounds__(prune_threads(S_, KIND, CFG), 1) dmma_prune_kernel(DmmaPruneParams p) {
+__device__ __forceinline__ void dmma_prune_body(const DmmaPruneParams& p, const int cta_index) {
   constexpr bool GEN = KIND == 4;
   constexpr int MS = GEN ? 3 : 2;
   constexpr int KB = prune_kb(S_), NB = prune_nb(S_), NP = prune_np(S_), PACK = prune_pack(S_);
@@ -599,7 +599,7 @@ __global__ void __launch_bounds__(prune_threads(S_, KIND, CFG), 1) dmma_prune_ke
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, q = lane & 3;
   double* rows = sm_pr + (size_t)C * MATS + (size_t)warp * NST * ROWSTAGE;
-  const long long cta0 = (long long)blockIdx.x * p.ppc;
+  const long long cta0 = (long long)cta_index * p.ppc;
   const int ncta = (int)(cta0 + p.ppc < p.N ? p.ppc : p.N - cta0);
   const int prow = p.prow, crow = p.crow;
   const int rowbase = (int)cta0 * prow;
@@ -740,6 +740,25 @@ __global__ void __launch_bounds__(prune_threads(S_, KIND, CFG), 1) dmma_prune_ke
       }
     }
   }
+}
+
+// one node per launch: the CTAs share its pattern range
+template <int S_, int KIND, int CFG>
+__global__ void __launch_bounds__(prune_threads(S_, KIND, CFG), 1) dmma_prune_kernel(DmmaPruneParams p) {
+  dmma_prune_body<S_, KIND, CFG>(p, (int)blockIdx.x);
+}
+
+// All nodes of one tree LEVEL (equal subtree height: independent of each other) with the same kind of sons in ONE launch:
+// CTA b works on node b / ctas_per_node, pattern range b % ctas_per_node.  A 500-taxon tree has ~500 internal nodes on a few dozen
+// levels; a launch per node pays its operand staging, pipeline fill and drain once per node on all 148 SMs, a launch per
+// level once per level (a CTA keeps one node's operands for 148 / n times more rows), and the cherries -- a third of the nodes --
+// are one launch.
+template <int S_, int KIND, int CFG>
+__global__ void __launch_bounds__(prune_threads(S_, KIND, CFG), 1) dmma_prune_level_kernel(const DmmaPruneParams* __restrict__ nodes,
+                                                                                            int ctas_per_node) {
+  const int node = (int)blockIdx.x / ctas_per_node;
+  const DmmaPruneParams p = nodes[node];
+  dmma_prune_body<S_, KIND, CFG>(p, (int)blockIdx.x - node * ctas_per_node);
 }
 
 }  // namespace bppgpu

@@ -631,7 +631,7 @@ int bppgpu_destroy(bppgpu_engine* e) {
                   e->prog.d_ops, e->prog.d_childs, e->gprog.d_ops, e->gprog.d_childs, e->d_sibs, e->d_scratch,
                   e->d_dtiptab, e->d_d2tiptab, e->d_dLc, e->d_fam_mask, e->d_fam_part, e->d_fam_packA, e->d_fam_packS, e->d_fam_packL, e->d_fam_packT, e->d_w4c_stream, e->d_w4c_blocks, e->d_w4c_tip_order, e->d_codesC, e->d_w4c_counter, e->d_w4_desc, e->d_w4_tip_order, e->d_w4_blocks, e->d_w4_stream, e->d_codesT,
                   e->d_status, e->d_wr_recs, e->d_chr_tile_edges, e->d_chr_tile_kind, e->d_chr_leaf_state, e->d_child_off,
-                  e->d_children, e->d_chr_leaf_vec, e->d_chr_term, e->d_chr_term_exp, e->d_chr_bad, e->d_chr_guardP, e->d_chr_aslab, e->d_chr_probe_t,
+                  e->d_children, e->d_chr_leaf_vec, e->d_chr_term, e->d_chr_term_exp, e->d_chr_bad, e->d_chr_guardP, e->d_chr_aslab, e->d_prune_nodes, e->d_chr_probe_t,
                   e->d_chr_probe_bm, e->d_models_noclamp, e->d_bad_idx, e->d_bad_brlen, e->d_bad_rootfreq, e->d_bad_rootfreq_used,
                   e->d_bad_site_lnl, e->d_bad_out, e->d_bad_branch_model};
   for (void* p : ptrs) cudaFree(p);
@@ -1067,7 +1067,8 @@ static int create_impl(const bppgpu_config* cfg, bppgpu_engine* e) {
         BPP_CUDA(dev_alloc(e, &e->d_chr_aslab, (size_t)e->nmodels * 2 * K8 * K8));
         const int optin = (int)std::min<size_t>((size_t)g_smem_optin, chr_slab_smem(S, kChrMaxStages));
         BPP_CUDA(cudaFuncSetAttribute(chr_level_slab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
-        BPP_CUDA(cudaFuncSetAttribute(chr_chain_slab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
+        BPP_CUDA(cudaFuncSetAttribute(chr_chain_slab_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
+        BPP_CUDA(cudaFuncSetAttribute(chr_chain_slab_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
       }
     }
     e->pchunk = 1;
@@ -1170,17 +1171,32 @@ static int create_impl(const bppgpu_config* cfg, bppgpu_engine* e) {
       if (const char* env = getenv("BPPGPU_PRUNE_CFG")) e->prune_cfg = std::min(2, std::max(0, atoi(env)));
 #define BPP_PRUNE_ATTR(Kv) \
       BPP_CUDA(attr(dmma_prune_kernel<20, Kv, 0>, dmma_prune_smem<20, Kv, 0>(C))); \
+      BPP_CUDA(attr(dmma_prune_level_kernel<20, Kv, 0>, dmma_prune_smem<20, Kv, 0>(C))); \
       BPP_CUDA(attr(dmma_prune_kernel<20, Kv, 1>, dmma_prune_smem<20, Kv, 1>(C))); \
       BPP_CUDA(attr(dmma_prune_kernel<20, Kv, 2>, dmma_prune_smem<20, Kv, 2>(C)));
       BPP_PRUNE_ATTR(0) BPP_PRUNE_ATTR(1) BPP_PRUNE_ATTR(2) BPP_PRUNE_ATTR(3)
 #undef BPP_PRUNE_ATTR
       BPP_CUDA(attr(dmma_prune_kernel<20, 4, 0>, dmma_prune_smem<20, 4, 0>(C)));
+      BPP_CUDA(attr(dmma_prune_level_kernel<20, 4, 0>, dmma_prune_smem<20, 4, 0>(C)));
     } else {
       BPP_CUDA(attr(dmma_prune_kernel<64, 0, 0>, dmma_prune_smem<64, 0, 0>(C)));
       BPP_CUDA(attr(dmma_prune_kernel<64, 1, 0>, dmma_prune_smem<64, 1, 0>(C)));
       BPP_CUDA(attr(dmma_prune_kernel<64, 2, 0>, dmma_prune_smem<64, 2, 0>(C)));
       BPP_CUDA(attr(dmma_prune_kernel<64, 3, 0>, dmma_prune_smem<64, 3, 0>(C)));
       BPP_CUDA(attr(dmma_prune_kernel<64, 4, 0>, dmma_prune_smem<64, 4, 0>(C)));
+      BPP_CUDA(attr(dmma_prune_level_kernel<64, 0, 0>, dmma_prune_smem<64, 0, 0>(C)));
+      BPP_CUDA(attr(dmma_prune_level_kernel<64, 1, 0>, dmma_prune_smem<64, 1, 0>(C)));
+      BPP_CUDA(attr(dmma_prune_level_kernel<64, 2, 0>, dmma_prune_smem<64, 2, 0>(C)));
+      BPP_CUDA(attr(dmma_prune_level_kernel<64, 3, 0>, dmma_prune_smem<64, 3, 0>(C)));
+      BPP_CUDA(attr(dmma_prune_level_kernel<64, 4, 0>, dmma_prune_smem<64, 4, 0>(C)));
+    }
+    {
+      // level-batched pruning launches (dmma_prune_level_kernel): one point, every node within the kernels' son limit
+      static const bool lb_on = !(getenv("BPPGPU_LEVEL_BATCH") && atoi(getenv("BPPGPU_LEVEL_BATCH")) == 0);
+      e->level_batch = lb_on && e->npoints == 1 && e->prune_cfg == 0;
+      for (const Op& op : e->gprog.ops)
+        if (op.nchild > kFamMaxSons) e->level_batch = false;
+      if (e->level_batch) BPP_CUDA(dev_alloc(e, &e->d_prune_nodes, e->gprog.ops.size()));
     }
   }
 
@@ -1617,6 +1633,112 @@ static void launch_walkS20(const WalkParams& wp, int grid, size_t smem, cudaStre
 }
 
 // pruning + root reduction of one point (tables of chunk-local index `pl`)
+// S = 20 / 64 pruning pass, one launch per (tree level, kind of sons) instead of one per node (dmma_prune_level_kernel).
+// The node descriptors are built once and cached on the device; they only hold addresses inside buffers that live as long as
+// the engine (checked by signature).
+static int enqueue_prune_levels(bppgpu_engine* e, const double* tiptab, cudaStream_t st) {
+  const int S = e->S, C = e->C;
+  const long long N = e->N;
+  const void* sig[3] = {e->d_keep, tiptab, e->d_fam_packL};
+  if (e->prune_groups.empty() || sig[0] != e->prune_nodes_sig[0] || sig[1] != e->prune_nodes_sig[1] || sig[2] != e->prune_nodes_sig[2]) {
+    const size_t nops = e->gprog.ops.size();
+    // level of a node = height of its subtree (sons first in the post-order program)
+    std::vector<int> height(e->nn, 0), kind_of(nops, 0), level_of(nops, 0);
+    std::vector<DmmaPruneParams> all(nops);
+    for (size_t i = 0; i < nops; ++i) {
+      const Op& op = e->gprog.ops[i];
+      DmmaPruneParams& pp = all[i];
+      pp = DmmaPruneParams{};
+      pp.nson = op.nchild;
+      int kind = op.nchild == 2 ? 0 : 4, h = 0;
+      for (int j = 0; j < op.nchild; ++j) {
+        const Child& ch = e->gprog.childs[op.child_begin + j];
+        PruneSon& ps = pp.sons[j];
+        ps.kind = ch.kind == CHILD_TIP ? CHILD_TIP : CHILD_KEEP;
+        ps.node = ch.pnode;
+        h = std::max(h, height[ch.pnode] + 1);
+        if (ch.kind == CHILD_TIP) {
+          ps.codes = (const char*)e->d_codes + (size_t)ch.idx * N * e->code_bytes;
+          ps.tt = tiptab + (size_t)ch.idx * C * e->ncodes * S;
+          if (kind != 4) kind |= 1 << j;
+        } else {
+          ps.clv = e->d_keep + (size_t)ch.idx * N * C * S;
+          ps.exp = e->d_keep_exp + (size_t)ch.idx * N * C;
+        }
+      }
+      height[op.node] = h;
+      kind_of[i] = kind;
+      level_of[i] = h;
+      pp.S = S; pp.C = C; pp.ncodes = e->ncodes; pp.code_bytes = e->code_bytes;
+      pp.prow = e->clv_class_major ? 1 : C;
+      pp.crow = e->clv_class_major ? (int)N : 1;
+      pp.N = N;
+      pp.packL = e->d_fam_packL;
+      pp.out = e->d_keep + (size_t)op.keep_idx * N * C * S;
+      pp.out_exp = e->d_keep_exp + (size_t)op.keep_idx * N * C;
+    }
+    std::vector<size_t> order(nops);
+    for (size_t i = 0; i < nops; ++i) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) {
+      return level_of[a] != level_of[b] ? level_of[a] < level_of[b] : kind_of[a] < kind_of[b];
+    });
+    e->prune_groups.clear();
+    std::vector<DmmaPruneParams> sorted(nops);
+    const long long G = std::max(1, e->fam_grid);
+    // rows a CTA must have for its warps to fill their row rings (8 rows per warp and item, a few items each)
+    const long long min_ppc = S > 32 ? 256 : 512;
+    for (size_t k = 0; k < nops;) {
+      size_t k1 = k;
+      while (k1 < nops && level_of[order[k1]] == level_of[order[k]] && kind_of[order[k1]] == kind_of[order[k]]) ++k1;
+      const long long n = (long long)(k1 - k);
+      // CTAs per node: the count whose last wave is fullest, a launch's fixed cost (operand staging, fill, drain ~ `fixed` rows'
+      // worth of time) charged once per wave
+      long long best_c = 1;
+      double best_cost = 1e300;
+      const double fixed = 0.15 * (double)N / (double)G;
+      for (long long c = 1; c <= G; ++c) {
+        long long ppc = (N + c - 1) / c;
+        ppc = std::max<long long>(8, (ppc + 7) / 8 * 8);
+        if (c > 1 && ppc < min_ppc) break;
+        const long long ctas = n * ((N + ppc - 1) / ppc);
+        const long long waves = (ctas + G - 1) / G;
+        const double cost = (double)waves * ((double)ppc + fixed);
+        if (cost < best_cost * (1.0 - 1e-9)) { best_cost = cost; best_c = c; }
+      }
+      long long ppc = (N + best_c - 1) / best_c;
+      ppc = std::max<long long>(8, (ppc + 7) / 8 * 8);
+      const int cpn = (int)((N + ppc - 1) / ppc);
+      for (size_t j = k; j < k1; ++j) {
+        sorted[j] = all[order[j]];
+        sorted[j].ppc = (int)ppc;
+      }
+      e->prune_groups.push_back({kind_of[order[k]], (int)k, (int)n, cpn});
+      k = k1;
+    }
+    BPP_CUDA(cudaMemcpyAsync(e->d_prune_nodes, sorted.data(), nops * sizeof(DmmaPruneParams), cudaMemcpyHostToDevice, st));
+    BPP_CUDA(cudaStreamSynchronize(st));   // (`sorted` goes out of scope)
+    for (int i = 0; i < 3; ++i) e->prune_nodes_sig[i] = sig[i];
+  }
+  for (const bppgpu_engine::PruneGroup& g : e->prune_groups) {
+    const DmmaPruneParams* nodes = e->d_prune_nodes + g.first;
+    const unsigned grid = (unsigned)g.count * (unsigned)g.ctas_per_node;
+#define BPP_PRUNE_L(Sv, Kv) dmma_prune_level_kernel<Sv, Kv, 0><<<grid, prune_threads(Sv, Kv, 0), dmma_prune_smem<Sv, Kv, 0>(C), st>>>(nodes, g.ctas_per_node)
+#define BPP_PRUNE_LK(Kv) if (S == 64) BPP_PRUNE_L(64, Kv); else BPP_PRUNE_L(20, Kv)
+    switch (g.kind) {
+      case 0: BPP_PRUNE_LK(0); break;
+      case 1: BPP_PRUNE_LK(1); break;
+      case 2: BPP_PRUNE_LK(2); break;
+      case 3: BPP_PRUNE_LK(3); break;
+      default: BPP_PRUNE_LK(4); break;
+    }
+#undef BPP_PRUNE_LK
+#undef BPP_PRUNE_L
+    e->stats.kernel_launches += 1;
+  }
+  BPP_CUDA(cudaGetLastError());
+  return BPPGPU_OK;
+}
+
 static int enqueue_prune(bppgpu_engine* e, int point, int pl, cudaStream_t st) {
   const int S = e->S, C = e->C, nn = e->nn;
   const long long N = e->N;
@@ -1736,7 +1858,13 @@ static int enqueue_prune(bppgpu_engine* e, int point, int pl, cudaStream_t st) {
     const int grid_p = (int)((N + 255) / 256);
     const int grid_r = (int)((N * C + 255) / 256);
     bool prev_chained = false;
+    const bool by_level = e->level_batch && e->path == PATH_DMMA && (e->family || e->prune64) && pl == 0;
+    if (by_level) {
+      int rcl = enqueue_prune_levels(e, tiptab, st);
+      if (rcl) return rcl;
+    }
     for (const Op& op : e->gprog.ops) {
+      if (by_level) break;
       GenericParams gp{};
       gp.childs = e->gprog.d_childs + op.child_begin;
       gp.nchild = op.nchild;
@@ -2233,8 +2361,14 @@ static int eval_points_factored(bppgpu_engine* e, cudaStream_t st, bool any_real
       // more than half of an SM's shared memory: one CTA per SM, so that the resident points' eigenvectors fit in L2
       const size_t chain_smem = std::max(smem, (size_t)116 * 1024);
       if (e->chr_slab) {
-        q.nst = nst_chain;
-        chr_chain_slab_kernel<<<(unsigned)np, (kChrCons + 1) * 32, chr_slab_smem(S, nst_chain), st>>>(q, e->chr_level_tile0[nlev] - q.tile0);
+        static const int chain_ctas = getenv("BPPGPU_CHR_CHAIN_CTAS") ? atoi(getenv("BPPGPU_CHR_CHAIN_CTAS")) : 2;   // A/B knob
+        if (chain_ctas >= 2) {
+          q.nst = nst_level;
+          chr_chain_slab_kernel<2><<<(unsigned)np, (kChrCons + 1) * 32, chr_slab_smem(S, nst_level), st>>>(q, e->chr_level_tile0[nlev] - q.tile0);
+        } else {
+          q.nst = nst_chain;
+          chr_chain_slab_kernel<1><<<(unsigned)np, (kChrCons + 1) * 32, chr_slab_smem(S, nst_chain), st>>>(q, e->chr_level_tile0[nlev] - q.tile0);
+        }
       } else {
         chr_chain_kernel<<<(unsigned)np, kChrWarps * 32, chain_smem, st>>>(q, e->chr_level_tile0[nlev] - q.tile0);
       }

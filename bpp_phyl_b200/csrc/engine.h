@@ -177,6 +177,12 @@ struct bppgpu_engine {
   bool status_armed = false;        // the status word was cleared for the evaluation in flight
   bool rootfreq_used_stale = true;  // d_rootfreq_used must be refreshed from d_rootfreq
   bool chr_factored = false;
+  // level-batched pruning launches of the fragment-order tensor-core kernels (dmma_prune_level_kernel)
+  bool level_batch = false;
+  bppgpu::DmmaPruneParams* d_prune_nodes = nullptr;   // [internal nodes], grouped by (level, kind of sons)
+  struct PruneGroup { int kind, first, count, ctas_per_node; };
+  std::vector<PruneGroup> prune_groups;
+  const void* prune_nodes_sig[3] = {nullptr, nullptr, nullptr};   // buffers the cached descriptors point into
   bool tables_allocated = true;          // d_P / d_keep of the table route (allocated on demand for factored engines)
   std::vector<unsigned short> h_codes;   // [nl] the single pattern's tip codes (host copy)
   std::vector<int> h_code_single;        // [ncodes]

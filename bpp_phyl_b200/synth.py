@@ -184,34 +184,42 @@ def real_block_form(w, U):
 
 def chromosome_eigensystem(args):
     """Host eigendecomposition of one parameter point (what ChromosomeSubstitutionModel::updateEigenMatrices does per
-    likelihood object: Model/ChromosomeSubstitutionModel.cpp:589-802).  Returns None when the eigen form does not
-    reproduce the generator (numerically defective Q: the reference then uses its Taylor series; such points are not part
-    of the throughput workload)."""
+    likelihood object: Model/ChromosomeSubstitutionModel.cpp:589-802) and the reference's choice of route for it (:686-767):
+    the eigen form V exp(L t) V^-1 when V can be inverted and exactly one eigenvalue is null, the Taylor series otherwise
+    ("route": "eigen" | "series"; like oracle/ref_models.py, an inverse with non-finite entries or cond(V) > 1e15 stands for
+    MatrixTools::inv's ZeroDivisionException).  Every point is returned -- nothing is redrawn; "resid" = max |V D V^-1 - Q| / max |Q|
+    says how well the eigen form a point travels with reproduces its generator (the reference never checks)."""
     n, gain, loss, dupl, demi = args
     Q = chromosome_generator(n, gain, loss, dupl, demi)
-    w, U = np.linalg.eig(Q)
-    re, im, V = real_block_form(w, U)
-    try:
-        Vinv = np.linalg.inv(V)
-    except np.linalg.LinAlgError:
-        return None
-    D = np.diag(re)
-    for k in range(n - 1):
-        if im[k] > 0:
-            D[k, k + 1], D[k + 1, k] = im[k], -im[k]
-    if not np.all(np.isfinite(Vinv)) or np.abs(V @ D @ Vinv - Q).max() > 1e-9 * np.abs(Q).max():
-        return None
-    z = np.argmin(np.abs(re) + np.abs(im))
-    re[z] = 0.0
-    return {"Q": Q, "V": V, "Vinv": Vinv, "ev": re, "ev_im": im, "pi": np.full(n, 1.0 / n), "params": (gain, loss, dupl, demi)}
+    base = {"Q": Q, "pi": np.full(n, 1.0 / n), "params": (gain, loss, dupl, demi), "route": "series", "resid": np.inf}
+    with np.errstate(all="ignore"):
+        w, U = np.linalg.eig(Q)
+        re, im, V = real_block_form(w, U)
+        try:
+            Vinv = np.linalg.inv(V)
+        except np.linalg.LinAlgError:
+            return base
+        if not np.all(np.isfinite(Vinv)) or not np.all(np.isfinite(V)) or np.linalg.cond(V) > 1e15:
+            return base
+        null = (np.abs(re) < 1e-6) & (np.abs(im) < 1e-6)          # NumConstants::SMALL()
+        if null.sum() != 1:
+            return base
+        D = np.diag(re)
+        for k in range(n - 1):
+            if im[k] > 0:
+                D[k, k + 1], D[k + 1, k] = im[k], -im[k]
+        resid = float(np.abs(V @ D @ Vinv - Q).max() / np.abs(Q).max())
+    re[np.argmax(null)] = 0.0
+    return dict(base, V=V, Vinv=Vinv, ev=re, ev_im=im, route="eigen", resid=resid)
 
 
 def chromosome_model_desc(es):
     from . import capi
-    S = len(es["ev"])
-    return capi.model_desc(S, capi.MODEL_DIAGONALIZABLE | capi.MODEL_NONSINGULAR | capi.MODEL_CLAMP01 | capi.MODEL_CHR_DERIV |
-                           capi.MODEL_CHR_TAYLOR if not np.any(es["ev_im"]) else
-                           capi.MODEL_NONSINGULAR | capi.MODEL_CLAMP01 | capi.MODEL_CHR_DERIV | capi.MODEL_CHR_TAYLOR,
+    S = len(es["Q"])
+    chr_flags = capi.MODEL_CLAMP01 | capi.MODEL_CHR_DERIV | capi.MODEL_CHR_TAYLOR
+    if es.get("route", "eigen") == "series":                     # isNonSingular_ false: the reference's Taylor + squaring route
+        return capi.model_desc(S, chr_flags, rate=1.0, Q=es["Q"])
+    return capi.model_desc(S, chr_flags | capi.MODEL_NONSINGULAR | (0 if np.any(es["ev_im"]) else capi.MODEL_DIAGONALIZABLE),
                            rate=1.0, V=es["V"], Vinv=es["Vinv"], ev_re=es["ev"], ev_im=es["ev_im"], Q=es["Q"])
 
 
@@ -223,8 +231,10 @@ def _single_thread_blas():
         pass
 
 
-def chromosome_points(n_states, n_points, seed, workers=None):
-    """`n_points` usable parameter points (gain, loss ~ U(0,2); dupl, demi ~ U(0,1)), eigensystems computed in parallel."""
+def chromosome_points(n_states, n_points, seed, workers=None, well_conditioned_only=False):
+    """`n_points` parameter points drawn uniformly from the box gain, loss ~ U(0,2); dupl, demi ~ U(0,1), eigensystems computed
+    in parallel.  Every drawn point is kept with the route the reference would take for it (chromosome_eigensystem);
+    `well_conditioned_only` restores the round-1 behaviour (points whose eigen form misses Q by more than 1e-9 are redrawn)."""
     import concurrent.futures as cf
     import os
     rng = np.random.default_rng(seed)
@@ -232,9 +242,10 @@ def chromosome_points(n_states, n_points, seed, workers=None):
     with cf.ProcessPoolExecutor(max_workers=workers or (os.cpu_count() or 1), initializer=_single_thread_blas) as ex:
         while len(out) < n_points:
             need = n_points - len(out)
-            args = [(n_states, rng.uniform(0, 2), rng.uniform(0, 2), rng.uniform(0, 1), rng.uniform(0, 1)) for _ in range(int(need * 1.3) + 8)]
+            args = [(n_states, rng.uniform(0, 2), rng.uniform(0, 2), rng.uniform(0, 1), rng.uniform(0, 1))
+                    for _ in range((int(need * 2.6) + 8) if well_conditioned_only else need)]
             for es in ex.map(chromosome_eigensystem, args, chunksize=8):
-                if es is not None and len(out) < n_points:
+                if len(out) < n_points and (not well_conditioned_only or (es["route"] == "eigen" and es["resid"] <= 1e-9)):
                     out.append(es)
     return out
 

@@ -19,7 +19,7 @@ npts = int(sys.argv[2])
 S = 200
 rng = np.random.default_rng(20260105)
 tree = synth.random_tree(500, rng, mean_brlen=0.02, rooted=True)
-pts = synth.chromosome_points(S, npts, seed=20260105)
+pts = synth.chromosome_points(S, npts, seed=20260105, well_conditioned_only=True)
 mds = [synth.chromosome_model_desc(es) for es in pts]
 P0, _, _ = capi.pt_batch(mds[0], tree.brlen, capi.WANT_P)
 codes = synth.simulate_single_character(tree, P0, root_state=23, seed=20260105)
