@@ -50,16 +50,22 @@ struct ChrLevelParams {
   int nst;                   // stages of the slab ring
 };
 
+// per-tile scalars behind the column tile: tl, cmax, cscale [32] doubles; cexp, cnode [32] ints; the sons of every column
+// [32][4] ints (count + up to 3 ids); the point's eigenvalues re, im [K8] doubles and role [K8] ints
+__host__ __device__ inline size_t chr_meta_bytes(int S) {
+  const int K8 = (S + 7) & ~7;
+  return 3 * kChrCols * sizeof(double) + 2 * kChrCols * sizeof(int) + 4 * kChrCols * sizeof(int) + (size_t)K8 * (2 * sizeof(double) + sizeof(int));
+}
 inline size_t chr_level_smem(int S) {
   const int K4 = (S + 7) & ~7;
-  return (size_t)K4 * kChrLD * sizeof(double) + 3 * kChrCols * sizeof(double) + 2 * kChrCols * sizeof(int) +
+  return (size_t)K4 * kChrLD * sizeof(double) + chr_meta_bytes(S) +
          (size_t)kChrWarps * kChrRingDoubles * sizeof(double);   // + every warp's ring of A fragments
 }
 
 // shared memory of the slab-streamed kernels: the column tile and its per-column scalars as above, then the ring's barriers and slabs
 inline size_t chr_slab_smem(int S, int nst) {
   const int K8 = (S + 7) & ~7;
-  return (size_t)K8 * kChrLD * sizeof(double) + 3 * kChrCols * sizeof(double) + 2 * kChrCols * sizeof(int) + 2 * 16 * sizeof(unsigned long long) +
+  return (size_t)K8 * kChrLD * sizeof(double) + chr_meta_bytes(S) + 2 * 16 * sizeof(unsigned long long) +
          (size_t)nst * chr_slab_doubles(K8) * sizeof(double);
 }
 constexpr int kChrMaxStages = 16;
@@ -73,8 +79,9 @@ __device__ __forceinline__ void chr_sync() {
 }
 
 // one tile (<= 32 sons of one level) of one point; every (consumer) thread of the CTA calls it
+// `cached_slot`: the model slot whose eigenvalues sit in shared memory (a chain CTA keeps them over its tiles), -1 = none
 template <bool SLAB>
-__device__ __forceinline__ void chr_tile(const ChrLevelParams& p, double* sm_chr, int tile, int prel, ChrRing* rg) {
+__device__ __forceinline__ void chr_tile(const ChrLevelParams& p, double* sm_chr, int tile, int prel, ChrRing* rg, int& cached_slot) {
   constexpr int NW = SLAB ? kChrCons : kChrWarps;
   constexpr int NT = NW * 32;
   const int S = p.S;
@@ -86,14 +93,19 @@ __device__ __forceinline__ void chr_tile(const ChrLevelParams& p, double* sm_chr
   double* cscale = cmax + kChrCols;            // [32]
   int* cexp = reinterpret_cast<int*>(cscale + kChrCols);   // [32] exponent carried in by the column
   int* cnode = cexp + kChrCols;                // [32]
-  double* ring = SLAB ? nullptr : reinterpret_cast<double*>(cnode + kChrCols) + (size_t)(threadIdx.x >> 5) * kChrRingDoubles;   // this warp's A ring
+  int* cch = cnode + kChrCols;                 // [32][4] sons of the column's node: count, then up to 3 ids (more: read from the CSR lists)
+  double* sre = reinterpret_cast<double*>(cch + 4 * kChrCols);   // [K4] eigenvalues of the point's model: real parts,
+  double* sim = sre + K4;                                        //      imaginary parts,
+  int* srole = reinterpret_cast<int*>(sim + K4);                 //      role (0 real, 1 / 2 the members of a conjugate pair)
+  double* ring = SLAB ? nullptr : reinterpret_cast<double*>(reinterpret_cast<char*>(tl) + chr_meta_bytes(S)) + (size_t)(threadIdx.x >> 5) * kChrRingDoubles;   // this warp's A ring
 
   const int pt = p.p0 + prel;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, q = lane & 3;
   const int* edges = p.tile_edges + (size_t)tile * kChrCols;
   const int kind = p.tile_kind[tile];
   const int first = edges[0];
-  const ModelDev md = p.models[p.branch_model[(size_t)pt * p.nn + first]];
+  const int slot = p.branch_model[(size_t)pt * p.nn + first];
+  const ModelDev md = p.models[slot];
   const int nrb = K4 >> 3;
   double* term_pt = p.term + (size_t)prel * p.nn * S;
   int* texp_pt = p.term_exp + (size_t)prel * p.nn;
@@ -103,6 +115,23 @@ __device__ __forceinline__ void chr_tile(const ChrLevelParams& p, double* sm_chr
     cnode[tid] = n;
     tl[tid] = n >= 0 ? md.rate * p.rate0 * p.brlen[(size_t)pt * p.nn + n] : 0.0;
     cexp[tid] = 0;
+    // the sons of a dense column, once per tile (the products below then issue their term loads back to back instead of walking
+    // child_off -> children -> term for every element)
+    int cnt = 0;
+    if (n >= 0 && kind != 0 && p.leaf_state[n] == -2) {
+      const int c0 = p.child_off[n];
+      cnt = p.child_off[n + 1] - c0;
+      for (int c = 0; c < 3 && c < cnt; ++c) cch[4 * tid + 1 + c] = p.children[c0 + c];
+    }
+    cch[4 * tid] = cnt;
+  }
+  if (slot != cached_slot) {   // (uniform over the CTA) this point's eigenvalues: one coalesced pass, read many times below
+    for (int k = tid; k < K4; k += NT) {
+      sre[k] = k < S ? md.re[k] : 0.0;
+      sim[k] = k < S ? md.im[k] : 0.0;
+      srole[k] = k < S ? md.role[k] : 0;
+    }
+    cached_slot = slot;
   }
   // columns in use (a tile is filled from column 0): only their 8-column blocks go through the tensor cores, and the
   // element-wise phases stop at the last block in use.  Most levels of a tree hold a handful of branches.
@@ -125,10 +154,13 @@ __device__ __forceinline__ void chr_tile(const ChrLevelParams& p, double* sm_chr
       const int n = cnode[j];
       double v = 0.0;
       if (n >= 0 && k < S) {
-        if (p.leaf_state[n] == -1) v = p.leaf_vec[(size_t)n * S + k];
+        const int cnt = cch[4 * j];
+        if (cnt == 0) v = p.leaf_vec[(size_t)n * S + k];   // dense leaf (unknown / ambiguous count)
         else {
-          v = 1.0;
-          for (int c = p.child_off[n]; c < p.child_off[n + 1]; ++c) v *= term_pt[(size_t)p.children[c] * S + k];
+          v = term_pt[(size_t)cch[4 * j + 1] * S + k];    // (same order of the factors as the CSR list)
+          if (cnt > 1) v *= term_pt[(size_t)cch[4 * j + 2] * S + k];
+          if (cnt > 2) v *= term_pt[(size_t)cch[4 * j + 3] * S + k];
+          for (int c = p.child_off[n] + 3; c < p.child_off[n] + cnt; ++c) v *= term_pt[(size_t)p.children[c] * S + k];
         }
       }
       Xs[k * kChrLD + j] = v;
@@ -173,14 +205,14 @@ __device__ __forceinline__ void chr_tile(const ChrLevelParams& p, double* sm_chr
   // T(t): exp(re l) on real eigenvalues, the rotation block on conjugate pairs (ChromosomeSubstitutionModel.cpp:821-850)
   for (int i = tid; i < S * ncols; i += NT) {
     const int k = i / ncols, j = i - k * ncols;
-    const int role = md.role[k];
+    const int role = srole[k];
     const double l = tl[j];
     if (role == 0) {
-      Ws[k * kChrLD + j] *= exp(md.re[k] * l);
+      Ws[k * kChrLD + j] *= exp(sre[k] * l);
     } else if (role == 1) {
-      const double ex = exp(md.re[k] * l);
+      const double ex = exp(sre[k] * l);
       double sn, cs;
-      sincos(md.im[k] * l, &sn, &cs);
+      sincos(sim[k] * l, &sn, &cs);
       const double w0 = Ws[k * kChrLD + j], w1 = Ws[(k + 1) * kChrLD + j];
       Ws[k * kChrLD + j] = ex * (cs * w0 + sn * w1);
       Ws[(k + 1) * kChrLD + j] = ex * (cs * w1 - sn * w0);
@@ -230,7 +262,8 @@ __device__ __forceinline__ void chr_tile(const ChrLevelParams& p, double* sm_chr
 __global__ void __launch_bounds__(kChrWarps * 32, 2) chr_level_kernel(ChrLevelParams p) {
   extern __shared__ __align__(16) double sm_chr[];
   if (p.skip && p.skip[p.p0 + blockIdx.y]) return;
-  chr_tile<false>(p, sm_chr, p.tile0 + blockIdx.x, blockIdx.y, nullptr);
+  int cached = -1;
+  chr_tile<false>(p, sm_chr, p.tile0 + blockIdx.x, blockIdx.y, nullptr, cached);
 }
 
 // The top of the tree in ONE launch: from the first level on which every later level is a single tile (a handful of branches
@@ -242,8 +275,9 @@ __global__ void __launch_bounds__(kChrWarps * 32, 2) chr_level_kernel(ChrLevelPa
 __global__ void __launch_bounds__(kChrWarps * 32, 1) chr_chain_kernel(ChrLevelParams p, int ntiles) {
   extern __shared__ __align__(16) double sm_chr[];
   if (p.skip && p.skip[p.p0 + blockIdx.x]) return;
+  int cached = -1;
   for (int t = 0; t < ntiles; ++t) {
-    chr_tile<false>(p, sm_chr, p.tile0 + t, blockIdx.x, nullptr);
+    chr_tile<false>(p, sm_chr, p.tile0 + t, blockIdx.x, nullptr, cached);
     __syncthreads();
   }
 }
@@ -252,8 +286,7 @@ __global__ void __launch_bounds__(kChrWarps * 32, 1) chr_chain_kernel(ChrLevelPa
 __device__ __forceinline__ ChrRing chr_ring_setup(const ChrLevelParams& p, double* sm_chr) {
   const int K8 = (p.S + 7) & ~7;
   ChrRing r;
-  r.full = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(sm_chr) + (size_t)K8 * kChrLD * sizeof(double) +
-                                                 3 * kChrCols * sizeof(double) + 2 * kChrCols * sizeof(int));
+  r.full = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(sm_chr) + (size_t)K8 * kChrLD * sizeof(double) + chr_meta_bytes(p.S));
   r.empty = r.full + 16;
   r.slab = reinterpret_cast<double*>(r.empty + 16);
   r.nst = p.nst;
@@ -287,7 +320,8 @@ __global__ void __launch_bounds__((kChrCons + 1) * 32, 2) chr_level_slab_kernel(
     if ((threadIdx.x & 31) == 0) chr_produce_tile(p, r, p.tile0 + blockIdx.x, blockIdx.y);
     return;
   }
-  chr_tile<true>(p, sm_chr, p.tile0 + blockIdx.x, blockIdx.y, &r);
+  int cached = -1;
+  chr_tile<true>(p, sm_chr, p.tile0 + blockIdx.x, blockIdx.y, &r, cached);
 }
 // MINB = CTAs per SM the register budget allows: 2 interleaves two points per SM (the element-wise phases between the products
 // are latency-bound: one CTA leaves the SM idle in them), 1 keeps the 148 resident points' eigenvectors inside L2
@@ -301,8 +335,9 @@ __global__ void __launch_bounds__((kChrCons + 1) * 32, MINB) chr_chain_slab_kern
       for (int t = 0; t < ntiles; ++t) chr_produce_tile(p, r, p.tile0 + t, blockIdx.x);
     return;
   }
+  int cached = -1;
   for (int t = 0; t < ntiles; ++t) {
-    chr_tile<true>(p, sm_chr, p.tile0 + t, blockIdx.x, &r);
+    chr_tile<true>(p, sm_chr, p.tile0 + t, blockIdx.x, &r, cached);
     chr_sync<true>();
   }
 }

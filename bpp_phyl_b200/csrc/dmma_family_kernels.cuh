@@ -67,7 +67,8 @@ struct DmmaFamilyParams {
   const double* packS;   // [nn][C][kFamPackS]  stacked P | dP | d2P in fragment order
   const double *rootfreq, *probs, *SR, *weights;
   const int* rexp;
-  double* part;          // [nn][2][gridDim.x]
+  double* part;          // [nn][2][part_stride]
+  int part_stride;       // slots per (branch, sum) of `part` (>= the CTAs that work on one father)
 };
 
 // The B operands in FRAGMENT ORDER.  Column n = 8 nb + 2 q' + h of the stacked operand holds slot t = 2 nb + h of lane
@@ -184,7 +185,7 @@ constexpr size_t dmma_family_smem(int C) {
 // KIND 0..3: a binary father whose son j is a tip iff bit j is set (straight-line code, 12 warps);  KIND 4: one to three
 // sons of any kind decided at run time (the unrooted root, unary nodes; 6 warps).
 template <int NB, int KIND>
-__global__ void __launch_bounds__(fam_threads_kind(KIND), 1) dmma_family_kernel(DmmaFamilyParams p) {
+__device__ __forceinline__ void dmma_family_body(const DmmaFamilyParams& p, const int cta_index) {
   constexpr bool GEN = KIND == 4;
   constexpr int MS = GEN ? 3 : 2;
   constexpr int NMAT = NB == 5 ? 2 : 3;
@@ -209,7 +210,7 @@ __global__ void __launch_bounds__(fam_threads_kind(KIND), 1) dmma_family_kernel(
   const int g = lane >> 2, q = lane & 3;
   double* rows = sm_fam + (size_t)C * MATS + (size_t)warp * NST * ROWSTAGE;
   // pattern indices below are relative to the CTA's first pattern (32-bit); the CTA's base offsets are folded in once
-  const long long cta0 = (long long)blockIdx.x * p.ppc;
+  const long long cta0 = (long long)cta_index * p.ppc;
   const int ncta = (int)(cta0 + p.ppc < p.N ? p.ppc : p.N - cta0);
   const bool root = p.father < 0;
   const double* fup = p.fup;
@@ -448,11 +449,30 @@ __global__ void __launch_bounds__(fam_threads_kind(KIND), 1) dmma_family_kernel(
       const double b1 = block_sum(acc1[j], red);
       const double b2 = block_sum(acc2[j], red);
       if (threadIdx.x == 0) {
-        p.part[((size_t)p.sons[j].node * 2 + 0) * gridDim.x + blockIdx.x] = b1;
-        p.part[((size_t)p.sons[j].node * 2 + 1) * gridDim.x + blockIdx.x] = b2;
+        p.part[((size_t)p.sons[j].node * 2 + 0) * p.part_stride + cta_index] = b1;
+        p.part[((size_t)p.sons[j].node * 2 + 1) * p.part_stride + cta_index] = b2;
       }
     }
   }
+}
+
+// one father per launch
+template <int NB, int KIND>
+__global__ void __launch_bounds__(fam_threads_kind(KIND), 1) dmma_family_kernel(DmmaFamilyParams p) {
+  dmma_family_body<NB, KIND>(p, (int)blockIdx.x);
+}
+// every father of one DEPTH (their upper arrays are complete: written by the launches of the depth above) with the same kind of
+// sons in one launch, as dmma_prune_level_kernel does for the pruning pass
+template <int NB, int KIND>
+__global__ void __launch_bounds__(fam_threads_kind(KIND), 1) dmma_family_level_kernel(const DmmaFamilyParams* __restrict__ fathers,
+                                                                                       int ctas_per_father) {
+  // the descriptor in shared memory: its fields are then read like kernel parameters (no registers held for them)
+  __shared__ DmmaFamilyParams sp;
+  const int f = (int)blockIdx.x / ctas_per_father;
+  if (threadIdx.x < sizeof(DmmaFamilyParams) / 4)
+    reinterpret_cast<int*>(&sp)[threadIdx.x] = reinterpret_cast<const int*>(fathers + f)[threadIdx.x];
+  __syncthreads();
+  dmma_family_body<NB, KIND>(sp, (int)blockIdx.x - f * ctas_per_father);
 }
 
 // block = branch: sums the per-CTA partials of the family kernel into out[1 + n] and out[1 + nn + n]
@@ -757,8 +777,11 @@ template <int S_, int KIND, int CFG>
 __global__ void __launch_bounds__(prune_threads(S_, KIND, CFG), 1) dmma_prune_level_kernel(const DmmaPruneParams* __restrict__ nodes,
                                                                                             int ctas_per_node) {
   const int node = (int)blockIdx.x / ctas_per_node;
-  const DmmaPruneParams p = nodes[node];
+  const DmmaPruneParams p = nodes[node];   // (a copy in registers measured faster than a copy in shared memory: 6.80 vs 6.97 ms on cfg4)
   dmma_prune_body<S_, KIND, CFG>(p, (int)blockIdx.x - node * ctas_per_node);
 }
+
+static_assert(sizeof(DmmaFamilyParams) % 4 == 0 && sizeof(DmmaFamilyParams) / 4 <= 128, "descriptor copy: one int per thread");
+static_assert(sizeof(DmmaPruneParams) % 4 == 0 && sizeof(DmmaPruneParams) / 4 <= 128, "descriptor copy: one int per thread");
 
 }  // namespace bppgpu

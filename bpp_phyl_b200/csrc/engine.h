@@ -183,6 +183,10 @@ struct bppgpu_engine {
   struct PruneGroup { int kind, first, count, ctas_per_node; };
   std::vector<PruneGroup> prune_groups;
   const void* prune_nodes_sig[3] = {nullptr, nullptr, nullptr};   // buffers the cached descriptors point into
+  bppgpu::DmmaFamilyParams* d_family_nodes = nullptr; // [internal nodes], grouped by (depth, kind of sons)
+  std::vector<PruneGroup> family_groups;
+  const void* family_nodes_sig[4] = {nullptr, nullptr, nullptr, nullptr};
+  unsigned family_nodes_want = 0;
   bool tables_allocated = true;          // d_P / d_keep of the table route (allocated on demand for factored engines)
   std::vector<unsigned short> h_codes;   // [nl] the single pattern's tip codes (host copy)
   std::vector<int> h_code_single;        // [ncodes]

@@ -249,8 +249,10 @@ __device__ __forceinline__ void mat_mul_dmma(const double* A, const double* B, d
   __syncthreads();
 }
 
+// (DMMA variant: two CTAs per SM -- one matrix's copy loops between the products wait on L2 while the other's products run:
+//  ncu of the one-CTA version showed the DMMA pipe 34 % active with long-scoreboard stalls on the scratch copies)
 template <bool DMMA>
-__global__ void pt_series_kernel(SeriesParams sp) {
+__global__ void __launch_bounds__(DMMA ? 256 : 1024, DMMA ? 2 : 1) pt_series_kernel(SeriesParams sp) {
   extern __shared__ __align__(16) double sm_series[];
   auto mat_mul = [&](const double* A_, const double* B_, double* O_, int S_, double scale_) {
     if (DMMA) mat_mul_dmma(A_, B_, O_, S_, scale_, sm_series);
