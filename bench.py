@@ -405,7 +405,17 @@ def run_points(a, w, rank, world, local, K, W, metric, config):
         kms = st["prune_ms_sum"] / max(1, st["prune_count"])      # level kernels + root (factored) or node kernels (tables)
         pt_ms = st["pt_ms_sum"] / max(1, K)                        # guard (factored) or all P(t) chunks (tables)
         nfac, ntab = int(st["factored_points"]), int(st["table_points"])
-        if nfac > 0:
+        if ntab > 0:
+            # points on the table route (Taylor series / clamped eigen tables) dominate the batch: the step is the P(t) launches of
+            # those points (pt_series_kernel<DMMA>, pt_dmma_kernel); their DMMA count depends on the terms and squarings of every
+            # branch and is not tallied, so the fraction comes from ncu (profiles/), not from this line
+            roofline = {"bound": "tensor", "kernel": "pt_series_kernel<DMMA> (Taylor + squaring, one CTA per branch matrix) + pt_dmma_kernel of the "
+                                                     "guard-failed points",
+                        "achieved": None, "peak": dmma_peak, "unit": "TFLOP/s", "frac": None, "traffic": None,
+                        "kernel_ms": pt_ms, "peak_source": "FP64 mma.sync m8n8k4 measured in this run (bppgpu_measure_fp64_peak)",
+                        "note": "kernel_ms = all P(t) launches of the step (guard probes + tables of the table-route points), event timed; "
+                                "DMMA pipe of pt_series_kernel<DMMA> in ncu: profiles/r2b_pt_series_dmma_2cta_metrics.csv"}
+        elif nfac > 0:
             K8 = (S + 7) // 8 * 8
             dm_flops = nfac * (st["chr_cblocks_tip"] + 2 * st["chr_cblocks_dense"]) * (K8 // 8) * (K8 // 4) * 512.0
             ach = dm_flops / (kms * 1e-3) / 1e12 if kms > 0 else None

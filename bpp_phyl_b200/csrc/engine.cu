@@ -473,7 +473,7 @@ static int launch_pt(cudaStream_t st, const ModelDev* d_models, bool any_series,
     sp.scratch = scratch;
     sp.status = d_status;
     if (S >= 32 && S <= 8 * kChrWarps * kChrMaxRB) {   // matrix products on the FP64 tensor cores
-      const size_t smem = (size_t)((S + 7) & ~7) * kChrLD * sizeof(double);
+      const size_t smem = (size_t)((S + 7) & ~7) * kChrLD * sizeof(double) + sparse_cols_bytes(S);   // B panel + compressed columns of Q
       BPP_CUDA(cudaFuncSetAttribute(pt_series_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
       pt_series_kernel<true><<<nmat, kChrWarps * 32, smem, st>>>(sp);
     } else {
@@ -1060,7 +1060,7 @@ static int create_impl(const bppgpu_config* cfg, bppgpu_engine* e) {
     BPP_CUDA(cudaFuncSetAttribute(chr_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)std::max(chr_level_smem(S), (size_t)116 * 1024)));
     {
-      static const bool slab_on = !(getenv("BPPGPU_CHR_SLAB") && atoi(getenv("BPPGPU_CHR_SLAB")) == 0);
+      const bool slab_on = !(getenv("BPPGPU_CHR_SLAB") && atoi(getenv("BPPGPU_CHR_SLAB")) == 0);   // read per engine (A/B tests)
       const int K8 = (S + 7) & ~7;
       e->chr_slab = slab_on && K8 <= 8 * kChrCons * kChrMaxRB;
       if (e->chr_slab) {
@@ -1192,7 +1192,7 @@ static int create_impl(const bppgpu_config* cfg, bppgpu_engine* e) {
     }
     {
       // level-batched pruning launches (dmma_prune_level_kernel): one point, every node within the kernels' son limit
-      static const bool lb_on = !(getenv("BPPGPU_LEVEL_BATCH") && atoi(getenv("BPPGPU_LEVEL_BATCH")) == 0);
+      const bool lb_on = !(getenv("BPPGPU_LEVEL_BATCH") && atoi(getenv("BPPGPU_LEVEL_BATCH")) == 0);   // read per engine (A/B tests)
       e->level_batch = lb_on && e->npoints == 1 && e->prune_cfg == 0;
       for (const Op& op : e->gprog.ops)
         if (op.nchild > kFamMaxSons) e->level_batch = false;
@@ -2173,7 +2173,7 @@ static int enqueue_derivs(bppgpu_engine* e, int point, int pl, unsigned want, cu
   // one launch per (depth, kind of sons) when every father is within the family kernel's son limit (dmma_family_level_kernel)
   // (measured on cfg3: 73.6 ms against 70.9 ms for one launch per father -- the derivative launches are long enough (140 us) that
   //  their fixed cost does not matter, so this stays opt-in; the pruning pass, 54 us per launch, gains 8-13 %)
-  static const bool deriv_levels = getenv("BPPGPU_LEVEL_BATCH_DERIV") && atoi(getenv("BPPGPU_LEVEL_BATCH_DERIV")) != 0;
+  const bool deriv_levels = getenv("BPPGPU_LEVEL_BATCH_DERIV") && atoi(getenv("BPPGPU_LEVEL_BATCH_DERIV")) != 0;
   const bool by_level = deriv_levels && family && e->level_batch && pl == 0 && e->d_family_nodes != nullptr;
   if (by_level) {
     const void* sig[4] = {e->d_keep, e->d_upper, e->d_fam_packS, e->d_fam_part};

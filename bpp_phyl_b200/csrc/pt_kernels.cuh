@@ -249,6 +249,62 @@ __device__ __forceinline__ void mat_mul_dmma(const double* A, const double* B, d
   __syncthreads();
 }
 
+// ---- Taylor terms against a SPARSE generator ----------------------------------------------------------------------------
+// term_i = term_{i-1} . Q . v / i is a product with the generator on the right, and a Chromosome generator has at most a handful of
+// non-zeros per column (the states that reach state c by one gain, loss, duplication or demi-duplication, and c itself): the
+// product is ~6 S^2 multiply-adds, not S^3.  The CTA compresses the columns of Q once (kSparseMax entries per column; a denser
+// column stays dense, and more than S / 8 of those make the whole model take the dense tensor-core product) and the series' first phase -- 3 to 6 terms of the ~10 products of
+// a matrix -- runs on them; the squarings stay dense.  Sums run over k ascending like the dense loop (zeros skipped).
+constexpr int kSparseMax = 8;
+struct SparseCols {
+  int* cnt;      // [S]
+  int* row;      // [S][kSparseMax]
+  double* val;   // [S][kSparseMax]
+};
+__host__ __device__ inline size_t sparse_cols_bytes(int S) {
+  return (size_t)S * kSparseMax * (sizeof(double) + sizeof(int)) + (size_t)((S + 1) & ~1) * sizeof(int);
+}
+// returns (uniformly over the CTA) whether every column fits; all threads call
+__device__ __forceinline__ bool sparse_cols_build(const double* Q, int S, SparseCols sc) {
+  __shared__ int too_dense;
+  if (threadIdx.x == 0) too_dense = 0;
+  __syncthreads();
+  for (int c = threadIdx.x; c < S; c += blockDim.x) {
+    int n = 0;
+    for (int k = 0; k < S; ++k) {
+      const double q = Q[(size_t)k * S + c];
+      if (q != 0.0) {
+        if (n < kSparseMax) {
+          sc.row[c * kSparseMax + n] = k;
+          sc.val[c * kSparseMax + n] = q;
+        }
+        ++n;
+      }
+    }
+    // a column with more entries is kept dense (cnt = -1) and costs S multiply-adds per row: the LAST state of a Chromosome model
+    // collects every duplication / demi-duplication that would overshoot the maximal count, i.e. about half of the rows
+    sc.cnt[c] = n > kSparseMax ? -1 : n;
+    if (n > kSparseMax) atomicAdd(&too_dense, 1);
+  }
+  __syncthreads();
+  return too_dense * 8 <= S;   // at most S / 8 dense columns: the product stays well below S^3 / 8
+}
+// O = A . Q . scale with Q given by its compressed columns (A, O distinct; A may have been written by this CTA)
+__device__ __forceinline__ void mat_mul_sparse_right(const double* A, const double* Q, SparseCols sc, double* O, int S, double scale) {
+  for (int e = threadIdx.x; e < S * S; e += blockDim.x) {
+    const int x = e / S, c = e - x * S;
+    const int n = sc.cnt[c];
+    double acc = 0.0;
+    if (n >= 0) {
+      for (int j = 0; j < n; ++j) acc = fma(__ldcg(A + (size_t)x * S + sc.row[c * kSparseMax + j]), sc.val[c * kSparseMax + j], acc);
+    } else {
+      for (int k = 0; k < S; ++k) acc = fma(__ldcg(A + (size_t)x * S + k), Q[(size_t)k * S + c], acc);
+    }
+    O[e] = acc * scale;
+  }
+  __syncthreads();
+}
+
 // (DMMA variant: two CTAs per SM -- one matrix's copy loops between the products wait on L2 while the other's products run:
 //  ncu of the one-CTA version showed the DMMA pipe 34 % active with long-scoreboard stalls on the scratch copies)
 template <bool DMMA>
@@ -295,11 +351,22 @@ __global__ void __launch_bounds__(DMMA ? 256 : 1024, DMMA ? 2 : 1) pt_series_ker
     A[e] = id;
   }
   __syncthreads();
+  // compressed columns of Q behind the tensor-core product's panel (DMMA variant only: that is where the dynamic shared memory is)
+  SparseCols sc{};
+  bool sparse = false;
+  if (DMMA && t != 0.0) {
+    char* sb = reinterpret_cast<char*>(sm_series) + (size_t)((S + 7) & ~7) * kChrLD * sizeof(double);
+    sc.val = reinterpret_cast<double*>(sb);
+    sc.row = reinterpret_cast<int*>(sc.val + (size_t)S * kSparseMax);
+    sc.cnt = sc.row + (size_t)S * kSparseMax;
+    sparse = sparse_cols_build(Q, S, sc);
+  }
   if (t != 0.0) {
     const bool exact = (md.flags & 32u) != 0;
     const int max_terms = chr || exact ? 250 : 29;
     for (int i = 1; i <= max_terms; ++i) {
-      mat_mul(T, Q, B, S, v / (double)i);  // term_i = term_{i-1}.Q.v/i
+      if (sparse) mat_mul_sparse_right(T, Q, sc, B, S, v / (double)i);
+      else mat_mul(T, Q, B, S, v / (double)i);  // term_i = term_{i-1}.Q.v/i
       double mx = 0.0;
       int bad = 0;
       for (int e = threadIdx.x; e < S * S; e += blockDim.x) {

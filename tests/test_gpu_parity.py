@@ -227,6 +227,47 @@ def test_family_kernel_chunks_multifurcation_and_underflow(monkeypatch):
         _check_derivs_and_uppers(c, e, res, uppers=False)
 
 
+@pytest.mark.parametrize("S,ncat,ntaxa,nsites", [(20, 4, 60, 700), (20, 3, 33, 150), (64, 1, 40, 300)])
+def test_level_batched_launches_equal_one_launch_per_node(monkeypatch, S, ncat, ntaxa, nsites):
+    """dmma_prune_level_kernel (one launch per tree level and kind of sons, the default) and dmma_family_level_kernel (opt-in) do
+    the arithmetic of the per-node / per-father launches row by row: lnL, per-site lnL, every lower CLV with its exponents and the
+    derivatives are bit-identical, with far fewer launches.  Includes a multifurcation below the root and ragged pattern counts."""
+    capi = _capi()
+    r, p = rm.gamma_rates(ncat, 0.6) if ncat > 1 else rm.constant_rate()
+    model = rm.lg08() if S == 20 else rm.yn98(2.0, 0.3)
+    c = cases.make_case(ntaxa, nsites, model, r, p, seed=91, mean_brlen=0.2, ambiguity=0.02, compress=False)
+    derivs = S == 20
+    got = {}
+    for mode in ("per_node", "levels", "levels+deriv"):
+        if mode == "levels+deriv" and not derivs:
+            continue
+        monkeypatch.setenv("BPPGPU_LEVEL_BATCH", "0" if mode == "per_node" else "1")
+        monkeypatch.setenv("BPPGPU_LEVEL_BATCH_DERIV", "1" if mode == "levels+deriv" else "0")
+        with cases.make_engine(c, flags=capi.FLAG_KEEP_CLVS) as e:
+            assert e.stats()["path"] == 4
+            lnl, d1, d2 = e.eval(capi.EVAL_LNL | ((capi.EVAL_D1 | capi.EVAL_D2) if derivs else 0))
+            launches = e.stats()["kernel_launches"]
+            site = e.site_lnl()
+            clvs = [e.clv(nid, 0) for nid in range(c.flat.n_nodes) if not c.flat.is_leaf[nid]]
+        got[mode] = (lnl.copy(), None if d1 is None else d1.copy(), None if d2 is None else d2.copy(), site.copy(), clvs, launches)
+    ref = got["per_node"]
+    for mode, g in got.items():
+        if mode == "per_node":
+            continue
+        assert g[0][0] == ref[0][0]
+        np.testing.assert_array_equal(g[3], ref[3])
+        for (a, ea), (b, eb) in zip(g[4], ref[4]):
+            np.testing.assert_array_equal(a, b)
+            np.testing.assert_array_equal(ea, eb)
+        if derivs and mode == "levels":
+            np.testing.assert_array_equal(g[1], ref[1])
+            np.testing.assert_array_equal(g[2], ref[2])
+        elif derivs:   # the per-CTA partial sums of w dL are cut at other pattern boundaries: same terms, another association
+            np.testing.assert_allclose(g[1], ref[1], rtol=1e-12, atol=1e-12)
+            np.testing.assert_allclose(g[2], ref[2], rtol=1e-12, atol=1e-12)
+        assert g[5] < ref[5]
+
+
 def test_s20_three_classes_two_byte_codes_with_derivatives():
     """fragment-order S = 20 kernels with an odd class count (class-major rows: crow = N) and 2-byte tip codes, d1 + d2"""
     capi = _capi()
@@ -589,6 +630,41 @@ def test_factored_points_route_against_the_table_route_and_the_oracle(monkeypatc
     for k, m in enumerate(pts):
         res = cases.oracle_eval(c, model=m, weighted_root=True, brlen=c.flat.brlen * (1.0 + 0.1 * k))
         assert abs(out["1"][0][k] - res.lnl) <= REL * abs(res.lnl), k
+
+
+@pytest.mark.parametrize("S,ntaxa", [(52, 40), (200, 60)])
+def test_slab_streamed_chromosome_kernels_equal_the_fragment_loaded_ones(monkeypatch, S, ntaxa):
+    """chr_level_slab_kernel / chr_chain_slab_kernel (A through the TMA slab ring, 7 consumer warps) accumulate over k in the
+    order of chr_level_kernel / chr_chain_kernel (A fragments from L2): log L and the root frequencies in use are bit-identical."""
+    capi = _capi()
+    rng = np.random.default_rng(S + 1)
+    r, p = rm.constant_rate()
+    pts = []
+    while len(pts) < 6:
+        m = rm.chromosome(1, S, gain=rng.uniform(0.2, 2), loss=rng.uniform(0.2, 2), dupl=rng.uniform(0.05, 1), demi=rng.uniform(0.05, 1))
+        if m.nonsingular and np.linalg.cond(m.V) < 1e7:
+            pts.append(m)
+    c = cases.make_case(ntaxa, 1, pts[0], r, p, seed=78, rooted=True, mean_brlen=0.1, compress=False)
+    off, ch = c.flat.csr()
+    out = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("BPPGPU_CHR_SLAB", mode)
+        e = capi.Engine(S, 1, 1, off, ch, c.flat.root, c.table, n_points=len(pts), n_models=len(pts), flags=capi.FLAG_WEIGHTED_ROOT,
+                        code_bytes=np.dtype(c.code_dtype).itemsize)
+        for lid, codes in c.codes_by_leaf.items():
+            e.set_tip_codes(lid, codes)
+        e.set_pattern_weights(c.weights)
+        e.set_rates(r, p)
+        holders = [cases.to_model_desc(m) for m in pts]
+        for k, h in enumerate(holders):
+            e.set_model(k, h)
+            e.set_branch_lengths(k, c.flat.brlen * (1.0 + 0.07 * k))
+        lnl, _, _ = e.eval()
+        assert e.stats()["factored_points"] == len(pts)
+        out[mode] = (lnl.copy(), np.array([e.root_freqs(k) for k in range(len(pts))]))
+        e.close()
+    np.testing.assert_array_equal(out["1"][0], out["0"][0])
+    np.testing.assert_array_equal(out["1"][1], out["0"][1])
 
 
 def test_batched_points_path_general_shapes():

@@ -1,11 +1,5 @@
 set -x
-timeout 600 python -m pytest tests -m gpu -x -q > gpurun_out/s6_tests.log 2>&1; echo "rc=$?" >> gpurun_out/s6_tests.log
-timeout 300 python bench.py --workload chromosome_500x4096pts --well-conditioned --steps 5 --warmup 3 > gpurun_out/s6_bench_chr_wc.json 2> gpurun_out/s6_bench_chr_wc.err
-BPPGPU_CHR_CHAIN_CTAS=1 timeout 300 python bench.py --workload chromosome_500x4096pts --well-conditioned --steps 5 --warmup 3 --no-cpu 2>&1 >/dev/null | grep "timed region" > gpurun_out/s6_chr_chain_ctas1.txt
-timeout 300 python bench.py --workload codon_200x100k --steps 10 --warmup 3 > gpurun_out/s6_bench_codon.json 2> gpurun_out/s6_bench_codon.err
-timeout 300 python bench.py --workload protein_g4_500x200k --steps 10 --warmup 3 > gpurun_out/s6_bench_protval.json 2> gpurun_out/s6_bench_protval.err
-timeout 300 python bench.py --workload protein_g4_500x200k_d2 --steps 5 --warmup 3 > gpurun_out/s6_bench_prot.json 2> gpurun_out/s6_bench_prot.err
-timeout 300 python bench.py --steps 20 --warmup 5 > gpurun_out/s6_bench_dna.json 2> gpurun_out/s6_bench_dna.err
-timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/s6_launches_codon.csv python bench.py --workload codon_200x100k --profile > gpurun_out/s6_ncu_codon.log 2>&1
-timeout 300 ncu -k regex:"chr_|pt_dmma" --metrics gpu__time_duration.sum --clock-control none -c 40 --csv --log-file gpurun_out/s6_launches_chr.csv python bench.py --workload chromosome_500x4096pts --well-conditioned --profile > gpurun_out/s6_ncu_chr.log 2>&1
+timeout 600 python -m pytest tests -m gpu -x -q -k "pt_batch or series or singular or chr or chromosome or expm or points" > gpurun_out/s8_tests_series.log 2>&1; echo "rc=$?" >> gpurun_out/s8_tests_series.log
+timeout 900 python bench.py --workload chromosome_500x4096pts --steps 2 --warmup 1 > gpurun_out/s8_bench_chr_all.json 2> gpurun_out/s8_bench_chr_all.err
+timeout 600 ncu -k regex:"pt_series" --metrics sm__pipe_tensor_subpipe_dmma_cycles_active.avg.pct_of_peak_sustained_active,gpu__time_duration.sum,sm__warps_active.avg.pct_of_peak_sustained_active --clock-control none -c 1 --csv --log-file gpurun_out/s8_pt_series_sparse.csv python bench.py --workload chromosome_500x4096pts --points 64 --profile > gpurun_out/s8_ncu_series.log 2>&1
 du -sh gpurun_out
