@@ -472,6 +472,8 @@ static int launch_pt(cudaStream_t st, const ModelDev* d_models, bool any_series,
     sp.pt = pp;
     sp.scratch = scratch;
     sp.status = d_status;
+    static const int sparse_env = getenv("BPPGPU_SERIES_SPARSE") ? atoi(getenv("BPPGPU_SERIES_SPARSE")) : 0;
+    sp.sparse_terms = sparse_env;
     if (S >= 32 && S <= 8 * kChrWarps * kChrMaxRB) {   // matrix products on the FP64 tensor cores
       const size_t smem = (size_t)((S + 7) & ~7) * kChrLD * sizeof(double) + sparse_cols_bytes(S);   // B panel + compressed columns of Q
       BPP_CUDA(cudaFuncSetAttribute(pt_series_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
@@ -1389,7 +1391,7 @@ int bppgpu_set_models(bppgpu_engine* e, int32_t first_slot, int32_t n, const bpp
       for (int b = 0; b < 2; ++b) BPP_CUDA(cudaEventCreateWithFlags(&e->stage_ev[t][b], cudaEventDisableTiming));
     }
   }
-  static const int env_threads = getenv("BPPGPU_COPY_THREADS") ? atoi(getenv("BPPGPU_COPY_THREADS")) : 4;
+  static const int env_threads = getenv("BPPGPU_COPY_THREADS") ? atoi(getenv("BPPGPU_COPY_THREADS")) : (std::thread::hardware_concurrency() >= 16 ? 8 : 4);
   const int T = std::max(1, std::min({kMaxT, env_threads, n / 4 + 1, (int)std::max(1u, std::thread::hardware_concurrency())}));
   std::vector<int> rcs(T, BPPGPU_OK);
   std::vector<std::string> msgs(T);
@@ -1454,8 +1456,10 @@ int bppgpu_set_branch_lengths(bppgpu_engine* e, int32_t point, const double* t) 
   if (point < 0 || point >= e->npoints || !t) BPP_FAIL(BPPGPU_E_INVALID, "bad point or null array");
   std::copy(t, t + e->nn, e->h_brlen.begin() + (size_t)point * e->nn);
   e->h_brlen[(size_t)point * e->nn + e->root] = 0.0;  // the root has no branch: its table slot is the identity
-  BPP_CUDA(cudaMemcpyAsync(e->d_brlen + (size_t)point * e->nn, &e->h_brlen[(size_t)point * e->nn], e->nn * 8, cudaMemcpyHostToDevice, e->stream));
-  BPP_CUDA(cudaStreamSynchronize(e->stream));
+  // the device copy is refreshed by the next evaluation, ONE transfer for all the points that changed (a batched-points
+  // optimiser sets thousands of points per step: a copy + synchronisation per point was 60 ms of its end-to-end step)
+  if (e->brlen_dirty_hi <= e->brlen_dirty_lo) { e->brlen_dirty_lo = point; e->brlen_dirty_hi = point + 1; }
+  else { e->brlen_dirty_lo = std::min(e->brlen_dirty_lo, (int)point); e->brlen_dirty_hi = std::max(e->brlen_dirty_hi, (int)point + 1); }
   e->have_brlen[point] = 1;
   e->last_point = -1;
   return BPPGPU_OK;
@@ -2540,6 +2544,11 @@ static int eval_impl(bppgpu_engine* e, unsigned want, cudaStream_t st, bool time
     BPP_CUDA(cudaMemcpyAsync(e->d_models, md.data(), md.size() * sizeof(ModelDev), cudaMemcpyHostToDevice, st));
     BPP_CUDA(cudaStreamSynchronize(st));
     e->models_dirty = false;
+  }
+  if (e->brlen_dirty_hi > e->brlen_dirty_lo) {
+    const size_t off = (size_t)e->brlen_dirty_lo * e->nn, cnt = (size_t)(e->brlen_dirty_hi - e->brlen_dirty_lo) * e->nn;
+    BPP_CUDA(cudaMemcpyAsync(e->d_brlen + off, e->h_brlen.data() + off, cnt * 8, cudaMemcpyHostToDevice, st));   // (pageable source: staged before the call returns)
+    e->brlen_dirty_lo = e->brlen_dirty_hi = 0;
   }
   for (int m = 0; m < e->nmodels; ++m) {
     if (!e->models[m].set) continue;

@@ -77,6 +77,7 @@ struct bppgpu_engine {
   std::vector<bppgpu::DevModel> models;
   bppgpu::ModelDev* d_models = nullptr;
   bool models_dirty = true;
+  int brlen_dirty_lo = 0, brlen_dirty_hi = 0;   // points whose branch lengths changed on the host since the last upload [lo, hi)
   bool homogeneous_points = true;  // every branch of a point uses the same model slot
   std::vector<double> h_rates, h_probs;
   std::vector<double> h_brlen;  // [npoints][nn]

@@ -208,6 +208,7 @@ struct SeriesParams {
   double q_l1_unused;
   int* status;      // set to 1 if the chromosome series did not converge
   int only_chr_deriv;  // 1: matrices of eigen-path models flagged CHR_DERIV: rebuild dP/d2P from P
+  int sparse_terms;    // 1: Taylor terms against the compressed columns of Q (opt-in: measured slower than the tensor-core product)
 };
 
 __device__ __forceinline__ void mat_mul(const double* A, const double* B, double* O, int S, double scale) {
@@ -255,6 +256,9 @@ __device__ __forceinline__ void mat_mul_dmma(const double* A, const double* B, d
 // product is ~6 S^2 multiply-adds, not S^3.  The CTA compresses the columns of Q once (kSparseMax entries per column; a denser
 // column stays dense, and more than S / 8 of those make the whole model take the dense tensor-core product) and the series' first phase -- 3 to 6 terms of the ~10 products of
 // a matrix -- runs on them; the squarings stay dense.  Sums run over k ascending like the dense loop (zeros skipped).
+// MEASURED (cfg5, 33 966 matrices of 200 x 200): 245 ms against 231 ms with every product on the tensor cores -- the gathers of the
+// left factor from L2 (five dependent-latency loads per output) cost more than the 43 % of DMMAs they remove.  Opt-in
+// (BPPGPU_SERIES_SPARSE=1) until the left factor's rows are staged in shared memory.
 constexpr int kSparseMax = 8;
 struct SparseCols {
   int* cnt;      // [S]
@@ -354,7 +358,7 @@ __global__ void __launch_bounds__(DMMA ? 256 : 1024, DMMA ? 2 : 1) pt_series_ker
   // compressed columns of Q behind the tensor-core product's panel (DMMA variant only: that is where the dynamic shared memory is)
   SparseCols sc{};
   bool sparse = false;
-  if (DMMA && t != 0.0) {
+  if (DMMA && sp.sparse_terms && t != 0.0) {
     char* sb = reinterpret_cast<char*>(sm_series) + (size_t)((S + 7) & ~7) * kChrLD * sizeof(double);
     sc.val = reinterpret_cast<double*>(sb);
     sc.row = reinterpret_cast<int*>(sc.val + (size_t)S * kSparseMax);

@@ -1,5 +1,8 @@
 set -x
-timeout 600 python -m pytest tests -m gpu -x -q -k "pt_batch or series or singular or chr or chromosome or expm or points" > gpurun_out/s8_tests_series.log 2>&1; echo "rc=$?" >> gpurun_out/s8_tests_series.log
-timeout 900 python bench.py --workload chromosome_500x4096pts --steps 2 --warmup 1 > gpurun_out/s8_bench_chr_all.json 2> gpurun_out/s8_bench_chr_all.err
-timeout 600 ncu -k regex:"pt_series" --metrics sm__pipe_tensor_subpipe_dmma_cycles_active.avg.pct_of_peak_sustained_active,gpu__time_duration.sum,sm__warps_active.avg.pct_of_peak_sustained_active --clock-control none -c 1 --csv --log-file gpurun_out/s8_pt_series_sparse.csv python bench.py --workload chromosome_500x4096pts --points 64 --profile > gpurun_out/s8_ncu_series.log 2>&1
+timeout 600 python -m pytest tests -m gpu -x -q > gpurun_out/s9_tests.log 2>&1; echo "rc=$?" >> gpurun_out/s9_tests.log
+timeout 120 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/s9_smoke.log 2>&1; echo "rc=$?" >> gpurun_out/s9_smoke.log
+timeout 300 python bench.py --workload chromosome_500x4096pts --well-conditioned --steps 5 --warmup 3 > gpurun_out/s9_bench_chr_wc.json 2> gpurun_out/s9_bench_chr_wc.err
+BPPGPU_COPY_THREADS=4 timeout 300 python bench.py --workload chromosome_500x4096pts --well-conditioned --steps 5 --warmup 3 --no-cpu > gpurun_out/s9_bench_chr_wc_t4.json 2> gpurun_out/s9_bench_chr_wc_t4.err
+timeout 300 python bench.py --steps 20 --warmup 5 > gpurun_out/s9_bench_dna.json 2> gpurun_out/s9_bench_dna.err
+timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/s9_bench_ref.json 2> gpurun_out/s9_bench_ref.err
 du -sh gpurun_out
