@@ -522,3 +522,35 @@ def test_hky85_generator_and_closed_form_transition_probabilities():
         P[2] = [pA * (1 + pY / pR * e1) - pA / pR * e22, pC * (1 - e1), pG * (1 + pY / pR * e1) + pA / pR * e22, pT * (1 - e1)]
         P[3] = [pA * (1 - e1), pC * (1 + pR / pY * e1) - pC / pY * e21, pG * (1 - e1), pT * (1 + pR / pY * e1) + pC / pY * e21]
         np.testing.assert_allclose(rm.pij_t(m, t), P, rtol=0, atol=3e-15)
+
+
+def test_bench_parameter_points_keep_every_draw_on_the_reference_s_route():
+    """bench.py's chromosome workload (synth.chromosome_points): nothing is redrawn; every point carries the route the reference
+    takes for it (ChromosomeSubstitutionModel.cpp:686-767: eigen form when V can be inverted and one eigenvalue is null, Taylor series
+    otherwise) -- the same decision the oracle's update_matrices makes -- and eigen-route points reproduce their generator up to
+    `resid`.  `well_conditioned_only` is the round-1 sample (eigen route, resid <= 1e-9)."""
+    from bpp_phyl_b200 import synth
+    pts = synth.chromosome_points(36, 40, seed=11, workers=2)
+    assert len(pts) == 40
+    routes = {p["route"] for p in pts}
+    assert routes <= {"eigen", "series"}
+    for p in pts:
+        Q = p["Q"]
+        assert np.allclose(Q.sum(axis=1), 0.0, atol=1e-12)
+        if p["route"] == "eigen":
+            n = len(Q)
+            D = np.diag(p["ev"])
+            for k in range(n - 1):
+                if p["ev_im"][k] > 0:
+                    D[k, k + 1], D[k + 1, k] = p["ev_im"][k], -p["ev_im"][k]
+            rec = np.abs(p["V"] @ D @ p["Vinv"] - Q).max() / np.abs(Q).max()
+            assert rec <= max(10 * p["resid"], 1e-6 * (p["resid"] > 1e-9) + 1e-12) or rec <= 1e-9   # (one eigenvalue was set to exactly 0)
+            assert int((np.abs(p["ev"]) + np.abs(p["ev_im"]) == 0).sum()) >= 1
+            gain, loss, dupl, demi = p["params"]
+            m = rm.chromosome(1, n, gain=gain, loss=loss, dupl=dupl, demi=demi)
+            if p["resid"] <= 1e-9:
+                assert m.nonsingular                          # the oracle takes the eigen route for every well-conditioned point
+        else:
+            assert not np.isfinite(p["resid"])
+    good = synth.chromosome_points(36, 12, seed=11, workers=2, well_conditioned_only=True)
+    assert len(good) == 12 and all(p["route"] == "eigen" and p["resid"] <= 1e-9 for p in good)

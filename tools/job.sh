@@ -1,8 +1,4 @@
 set -x
-timeout 600 python -m pytest tests -m gpu -x -q > gpurun_out/s9_tests.log 2>&1; echo "rc=$?" >> gpurun_out/s9_tests.log
-timeout 120 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/s9_smoke.log 2>&1; echo "rc=$?" >> gpurun_out/s9_smoke.log
-timeout 300 python bench.py --workload chromosome_500x4096pts --well-conditioned --steps 5 --warmup 3 > gpurun_out/s9_bench_chr_wc.json 2> gpurun_out/s9_bench_chr_wc.err
-BPPGPU_COPY_THREADS=4 timeout 300 python bench.py --workload chromosome_500x4096pts --well-conditioned --steps 5 --warmup 3 --no-cpu > gpurun_out/s9_bench_chr_wc_t4.json 2> gpurun_out/s9_bench_chr_wc_t4.err
-timeout 300 python bench.py --steps 20 --warmup 5 > gpurun_out/s9_bench_dna.json 2> gpurun_out/s9_bench_dna.err
-timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/s9_bench_ref.json 2> gpurun_out/s9_bench_ref.err
-du -sh gpurun_out
+timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus 2 --steps 20 --warmup 5 > gpurun_out/s10_bench_dna_2gpu.json 2> gpurun_out/s10_bench_dna_2gpu.err
+timeout 300 python -m pytest tests/test_engine_comm.py -m gpu -x -q > gpurun_out/s10_tests_comm.log 2>&1; echo "rc=$?" >> gpurun_out/s10_tests_comm.log
+timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29518 bench.py --gpus 2 --workload protein_g4_500x200k_d2 --steps 5 --warmup 3 --no-weak > gpurun_out/s10_bench_prot_2gpu.json 2> gpurun_out/s10_bench_prot_2gpu.err
