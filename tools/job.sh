@@ -1,4 +1,10 @@
 set -x
-timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus 2 --steps 20 --warmup 5 > gpurun_out/s10_bench_dna_2gpu.json 2> gpurun_out/s10_bench_dna_2gpu.err
-timeout 300 python -m pytest tests/test_engine_comm.py -m gpu -x -q > gpurun_out/s10_tests_comm.log 2>&1; echo "rc=$?" >> gpurun_out/s10_tests_comm.log
-timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29518 bench.py --gpus 2 --workload protein_g4_500x200k_d2 --steps 5 --warmup 3 --no-weak > gpurun_out/s10_bench_prot_2gpu.json 2> gpurun_out/s10_bench_prot_2gpu.err
+timeout 600 ncu -k regex:"walk4c_kernel" --set full --clock-control none -c 1 -o /tmp/w4c python bench.py --profile > gpurun_out/s11_ncu_w4c.log 2>&1
+python tools/ncu_summary.py /tmp/w4c.ncu-rep gpurun_out/s11_walk4c_summary.csv
+timeout 600 ncu -k regex:"dmma_prune_level" --set full --clock-control none --launch-skip 20 -c 6 -o /tmp/p64 python bench.py --workload codon_200x100k --profile > gpurun_out/s11_ncu_p64.log 2>&1
+python tools/ncu_summary.py /tmp/p64.ncu-rep gpurun_out/s11_prune_level64_summary.csv
+timeout 600 ncu -k regex:"dmma_prune_level" --set full --clock-control none --launch-skip 30 -c 6 -o /tmp/p20 python bench.py --workload protein_g4_500x200k --profile > gpurun_out/s11_ncu_p20.log 2>&1
+python tools/ncu_summary.py /tmp/p20.ncu-rep gpurun_out/s11_prune_level20_summary.csv
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file gpurun_out/s11_launches_protval.csv python bench.py --workload protein_g4_500x200k --profile > gpurun_out/s11_ncu_protval.log 2>&1
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 100 --csv --log-file gpurun_out/s11_launches_dna.csv python bench.py --profile > gpurun_out/s11_ncu_dna.log 2>&1
+du -sh gpurun_out
