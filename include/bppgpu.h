@@ -183,7 +183,9 @@ int bppgpu_set_models(bppgpu_engine* e, int32_t first_slot, int32_t n, const bpp
  * `point` when n_models == n_points)                                           */
 int bppgpu_set_branch_models(bppgpu_engine* e, int32_t point, const int32_t* slot_of_node);
 /* per point: length of the branch above each node, indexed by node id; the
- * root's entry is ignored                                                      */
+ * root's entry is ignored.  `t` is copied before the call returns; the device copy
+ * is refreshed by the next evaluation, one transfer for all points set since the
+ * previous one (an optimiser over thousands of points sets them one by one)      */
 int bppgpu_set_branch_lengths(bppgpu_engine* e, int32_t point, const double* t);
 /* per point: root frequencies [S] */
 int bppgpu_set_root_freqs(bppgpu_engine* e, int32_t point, const double* pi);
