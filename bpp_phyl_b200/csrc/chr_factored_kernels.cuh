@@ -46,7 +46,7 @@ struct ChrLevelParams {
   double* term;              // [points of this launch][nn][S] term of the branch above node n, rescaled
   int* term_exp;             // [points of this launch][nn]
   const int* skip;           // [npts] 1 = the point goes through the table route (guard), or nullptr
-  const double* aslab;       // [model slot][V^-1 | V] slab-ordered copies (chr_slab_kernel), slab-streamed kernels only
+  const double* aslab;       // [model slot][V^-1 | V | (V^-1)^T] slab-ordered copies + transpose (chr_slab_kernel), slab-streamed kernels only
   int nst;                   // stages of the slab ring
 };
 
@@ -142,10 +142,21 @@ __device__ __forceinline__ void chr_tile(const ChrLevelParams& p, double* sm_chr
   if (kind == 0) {
     // observed tips: W[:, j] = V^-1[:, state_j]
     // (the tiles of observed tips are sorted by state: neighbouring columns read neighbouring entries of a row of V^-1)
-    for (int i = tid; i < K4 * ncols; i += NT) {
-      const int k = i / ncols, j = i - k * ncols;
-      const int n = cnode[j];
-      Ws[k * kChrLD + j] = (n >= 0 && k < S) ? __ldg(md.Vinv + (size_t)k * S + p.leaf_state[n]) : 0.0;
+    if (SLAB) {
+      // from the TRANSPOSED copy kept next to the slab images: a column of V^-1 is a contiguous row there (coalesced), instead of
+      // S loads 8 S bytes apart
+      const double* vt = p.aslab + (size_t)slot * 3 * K4 * K4 + (size_t)2 * K4 * K4;
+      for (int i = tid; i < K4 * ncols; i += NT) {
+        const int j = i / K4, k = i - j * K4;
+        const int n = cnode[j];
+        Ws[k * kChrLD + j] = n >= 0 ? __ldg(vt + (size_t)p.leaf_state[n] * K4 + k) : 0.0;
+      }
+    } else {
+      for (int i = tid; i < K4 * ncols; i += NT) {
+        const int k = i / ncols, j = i - k * ncols;
+        const int n = cnode[j];
+        Ws[k * kChrLD + j] = (n >= 0 && k < S) ? __ldg(md.Vinv + (size_t)k * S + p.leaf_state[n]) : 0.0;
+      }
     }
   } else {
     // dense columns: x = the son's conditional likelihoods = product of ITS sons' terms (or a dense leaf's init row)
@@ -309,7 +320,7 @@ __device__ __forceinline__ void chr_produce_tile(const ChrLevelParams& p, ChrRin
   const int first = p.tile_edges[(size_t)tile * kChrCols];
   const int slot = p.branch_model[(size_t)(p.p0 + prel) * p.nn + first];
   const bool tips = p.tile_kind[tile] == 0;
-  const double* src = p.aslab + (size_t)slot * 2 * K8 * K8 + (tips ? (size_t)K8 * K8 : 0);
+  const double* src = p.aslab + (size_t)slot * 3 * K8 * K8 + (tips ? (size_t)K8 * K8 : 0);
   chr_ring_produce(r, src, (tips ? 1 : 2) * (K8 >> 3), K8);
 }
 __global__ void __launch_bounds__((kChrCons + 1) * 32, 2) chr_level_slab_kernel(ChrLevelParams p) {
@@ -342,15 +353,21 @@ __global__ void __launch_bounds__((kChrCons + 1) * 32, MINB) chr_chain_slab_kern
   }
 }
 
-// slab-ordered copies of a model's V^-1 and V (layout: dmma.cuh, chr_gemm_slab): out[slot] = [V^-1 image | V image], each
-// [K8 / 8 slabs][K8 rows][8 swizzled k-columns], zero-padded.  One CTA row per model slot, built when the models change.
+// slab-ordered copies of a model's V^-1 and V (layout: dmma.cuh, chr_gemm_slab): out[slot] = [V^-1 image | V image | (V^-1)^T], the
+// images [K8 / 8 slabs][K8 rows][8 swizzled k-columns], zero-padded; the transpose [K8 states][K8] (row s = column s of V^-1: what an
+// observed tip with state s starts from).  One CTA row per model slot, built when the models change.
 __global__ void chr_slab_kernel(const ModelDev* models, int S, int K8, double* out) {
   const ModelDev md = models[blockIdx.y];
   if (md.V == nullptr || md.Vinv == nullptr) return;
-  double* o = out + (size_t)blockIdx.y * 2 * K8 * K8;
+  double* o = out + (size_t)blockIdx.y * 3 * K8 * K8;
   const int per = K8 * K8;
-  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < 2 * per; idx += gridDim.x * blockDim.x) {
-    const int mat = idx >= per, e = idx - mat * per;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < 3 * per; idx += gridDim.x * blockDim.x) {
+    const int mat = idx / per, e = idx - mat * per;
+    if (mat == 2) {
+      const int st = e / K8, k = e - st * K8;
+      o[idx] = (st < S && k < S) ? md.Vinv[(size_t)k * S + st] : 0.0;
+      continue;
+    }
     const int ks = e / (K8 * 8), rem = e - ks * (K8 * 8), r = rem >> 3, pos = rem & 7;
     const int k = ks * 8 + (pos ^ (4 * ((r >> 1) & 1)));
     const double* M = mat ? md.V : md.Vinv;

@@ -1066,7 +1066,7 @@ static int create_impl(const bppgpu_config* cfg, bppgpu_engine* e) {
       const int K8 = (S + 7) & ~7;
       e->chr_slab = slab_on && K8 <= 8 * kChrCons * kChrMaxRB;
       if (e->chr_slab) {
-        BPP_CUDA(dev_alloc(e, &e->d_chr_aslab, (size_t)e->nmodels * 2 * K8 * K8));
+        BPP_CUDA(dev_alloc(e, &e->d_chr_aslab, (size_t)e->nmodels * 3 * K8 * K8));   // [V^-1 | V] slab images + (V^-1)^T
         const int optin = (int)std::min<size_t>((size_t)g_smem_optin, chr_slab_smem(S, kChrMaxStages));
         BPP_CUDA(cudaFuncSetAttribute(chr_level_slab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
         BPP_CUDA(cudaFuncSetAttribute(chr_chain_slab_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));

@@ -204,7 +204,7 @@ struct bppgpu_engine {
   double* d_chr_guardP = nullptr;        // [gchunk][3][S][S]
   bool chr_slab = false;                 // slab-streamed level kernels (TMA ring; dmma.cuh chr_gemm_slab)
   bool chr_slab_dirty = true;            // the slab-ordered copies must be rebuilt from the model slabs
-  double* d_chr_aslab = nullptr;         // [nmodels][V^-1 | V] slab-ordered copies
+  double* d_chr_aslab = nullptr;         // [nmodels][V^-1 | V | (V^-1)^T] slab-ordered copies + transpose
   int gchunk = 0;
   double* d_chr_probe_t = nullptr;       // [npoints][3]
   int* d_chr_probe_bm = nullptr;         // [npoints][3]

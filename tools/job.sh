@@ -1,6 +1,4 @@
 set -x
-K='regex:dmma_|pt_|walk4|generic_|finalize_|tiptab|_pack|pack_|transpose_codes'
-timeout 300 ncu -k "$K" --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file gpurun_out/s12_launches_codon.csv python bench.py --workload codon_200x100k --profile > gpurun_out/s12_ncu_codon.log 2>&1
-timeout 300 ncu -k "$K" --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/s12_launches_protval.csv python bench.py --workload protein_g4_500x200k --profile > gpurun_out/s12_ncu_protval.log 2>&1
-timeout 300 ncu -k "$K" --metrics gpu__time_duration.sum --clock-control none -c 40 --csv --log-file gpurun_out/s12_launches_dna.csv python bench.py --profile > gpurun_out/s12_ncu_dna.log 2>&1
-du -sh gpurun_out
+timeout 600 python -m pytest tests -m gpu -x -q > gpurun_out/s13_tests.log 2>&1; echo "rc=$?" >> gpurun_out/s13_tests.log
+timeout 300 python bench.py --workload chromosome_500x4096pts --well-conditioned --steps 5 --warmup 3 > gpurun_out/s13_bench_chr_wc.json 2> gpurun_out/s13_bench_chr_wc.err
+timeout 120 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/s13_smoke.log 2>&1; echo "rc=$?" >> gpurun_out/s13_smoke.log
