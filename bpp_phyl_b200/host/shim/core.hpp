@@ -399,14 +399,18 @@ inline bool eigen_general(const std::vector<double>& A, int n, std::vector<doubl
     for (int i = 0; i < n; ++i) x[i] = cd(1.0 + 0.37 * ((i * 7919 + k * 104729) % 101) / 101.0, 0.0);
     // two rounds: the first with the QR eigenvalue as the shift, the second with the refined one; each factors once and
     // iterates on the factors (a shift a few ulps off the eigenvalue keeps (A - shift I) numerically invertible)
-    ShiftedLU lu;
+    // the factor's n x n complex workspace lives as long as the thread: a fresh 640 KB allocation per eigenvalue is an mmap /
+    // page-fault / munmap round trip each, and those serialise the worker threads on the process's address-space lock
+    // (measured: 8 threads took as long as one)
+    static thread_local ShiftedLU lu;
     for (int round = 0; round < 2; ++round) {
       const double eps = std::max(std::abs(lamk), scale * 1e-3) * 4e-15 * (1.0 + (k % 7));
       const cd shifted = lamk + cd(eps, im0[k] != 0.0 ? eps : 0.0);
       lu.factor(A, n, shifted);
       cd lnew = lamk;
       for (int it = 0; it < (round == 0 ? 3 : 2); ++it) {
-        std::vector<cd> y = x;
+        static thread_local std::vector<cd> y;
+        y = x;
         lu.solve(y);
         cd xy(0), xx(0);
         for (int i = 0; i < n; ++i) { xy += std::conj(x[i]) * y[i]; xx += std::conj(x[i]) * x[i]; }
