@@ -326,6 +326,8 @@ def run_points(a, w, rank, world, local, K, W, metric, config):
     n_series = sum(1 for es in pts if es["route"] == "series")
     n_illcond = sum(1 for es in pts if es["route"] == "eigen" and es["resid"] > 1e-9)
     good = [k for k, es in enumerate(pts) if es["route"] == "eigen" and es["resid"] <= 1e-9]
+    if not good:   # (a handful of points and none well-conditioned: simulate and sample on whatever has an eigen form)
+        good = [k for k, es in enumerate(pts) if es["route"] == "eigen"] or [0]
     log("[rank %d] %d parameter points (host eigendecompositions) in %.1fs: %d series route, %d eigen route with |V D V^-1 - Q| > 1e-9 |Q|, %d well-conditioned"
         % (rank, npts, time.time() - t0, n_series, n_illcond, len(good)))
     mds = [synth.chromosome_model_desc(es) for es in pts]
